@@ -1,0 +1,348 @@
+"""CPU oracle for the WABBIT block hot path (TEST INFRASTRUCTURE ONLY).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module.  The product package
+``wabbit_b200`` never does; it fails loudly when its CUDA library is missing.
+
+The arithmetic lives in ``orc_*.c`` (plain C, ``-ffp-contract=off``), restating the
+reference Fortran statement by statement; this file holds the tree-level loops
+(block loops, ghost synchronisation on the grid, Runge-Kutta driver, time-step
+control) in NumPy, citing the reference file:line each part follows.
+
+Array convention: ``hvy[b, c, iz, iy, ix]`` C-ordered == Fortran ``hvy(ix,iy,iz,c,b)``.
+2-D runs use ``nz = 1``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import subprocess
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SRCS = ["orc_acm.c", "orc_wavelet.c"]
+
+
+def _lib_path(fast: bool) -> str:
+    return os.path.join(_HERE, "liboracle_fast.so" if fast else "liboracle.so")
+
+
+def build(force: bool = False) -> None:
+    """Compile the C restatement: parity build (no FMA contraction) and timing build."""
+    srcs = [os.path.join(_HERE, s) for s in _SRCS if os.path.exists(os.path.join(_HERE, s))]
+    for fast in (False, True):
+        out = _lib_path(fast)
+        if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in srcs):
+            continue
+        flags = ["-O3", "-march=native", "-fopenmp"] if fast else ["-O2", "-ffp-contract=off", "-fopenmp"]
+        subprocess.check_call(["gcc", "-shared", "-fPIC", "-std=c11", *flags, "-o", out, *srcs, "-lm"])
+
+
+class AcmParams(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("fd", C.c_int32), ("skew", C.c_int32), ("penalization", C.c_int32),
+                ("use_sponge", C.c_int32), ("pad_", C.c_int32),
+                ("c0", C.c_double), ("nu", C.c_double), ("gamma_p", C.c_double), ("C_eta", C.c_double),
+                ("C_sponge", C.c_double), ("u_mean_set", C.c_double * 3),
+                ("CFL", C.c_double), ("CFL_eta", C.c_double), ("CFL_nu", C.c_double)]
+
+
+FD_IDS = {"FD_2nd_central": 2, "FD_4th_central": 4, "FD_6th_central": 6, "FD_4th_central_optimized": 40}
+
+_libs: Dict[bool, C.CDLL] = {}
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+def lib(fast: bool = False) -> C.CDLL:
+    if fast not in _libs:
+        build()
+        L = C.CDLL(_lib_path(fast))
+        L.orc_rhs_acm_3d.argtypes = [C.POINTER(AcmParams), C.c_int, _ip, _dp, _dp, _dp, _dp]
+        L.orc_rhs_acm_2d.argtypes = [C.POINTER(AcmParams), C.c_int, _ip, _dp, _dp, _dp, _dp]
+        L.orc_get_dt_block.argtypes = [C.POINTER(AcmParams), C.c_int, _ip, _dp, _dp]
+        L.orc_get_dt_block.restype = C.c_double
+        L.orc_rk_copy_interior.argtypes = [C.c_int, C.c_int, _ip, C.c_int, _dp, _dp]
+        L.orc_rk_axpy_interior.argtypes = [C.c_int, C.c_int, _ip, C.c_int, _dp, C.c_double, C.c_double, _dp]
+        L.orc_max_abs_interior.argtypes = [C.c_int, C.c_int, _ip, C.c_int, _dp]
+        L.orc_max_abs_interior.restype = C.c_double
+        L.orc_fd_halfwidth.argtypes = [C.c_int]
+        _libs[fast] = L
+    return _libs[fast]
+
+
+def _p(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags.c_contiguous
+    return a.ctypes.data_as(_dp)
+
+
+def _bs(Bs: Sequence[int]):
+    return (C.c_int32 * 3)(*[int(b) for b in Bs])
+
+
+def _d3(v: Sequence[float]):
+    return (C.c_double * 3)(*[float(x) for x in v])
+
+
+# ----------------------------------------------------------------------------- configuration
+BUTCHER_RK4 = np.array([[0.0, 0.0, 0.0, 0.0, 0.0],
+                        [0.5, 0.5, 0.0, 0.0, 0.0],
+                        [0.5, 0.0, 0.5, 0.0, 0.0],
+                        [1.0, 0.0, 0.0, 1.0, 0.0],
+                        [0.0, 1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0]])  # ini_file_to_params.f90:640-646
+
+
+@dataclass
+class Params:
+    """Subset of type_params / type_params_acm the hot path reads (module_params.f90:18-233,
+    module_ACM.f90:56-154).  Defaults are the reference's read_param defaults."""
+    dim: int = 3
+    Bs: Tuple[int, int, int] = (16, 16, 16)
+    g: int = 3
+    g_rhs: int = 2
+    n_eqn: int = 4
+    domain: Tuple[float, float, float] = (1.0, 1.0, 1.0)
+    Jmax: int = 1
+    discretization: str = "FD_4th_central"
+    skew: bool = False
+    penalization: bool = False
+    use_sponge: bool = False
+    c0: float = 10.0
+    nu: float = 1e-1
+    gamma_p: float = 1.0
+    C_eta: float = 1.0
+    C_sponge: float = 1.0e-2
+    u_mean_set: Tuple[float, float, float] = (1.0, 0.0, 0.0)
+    CFL: float = 1.0
+    CFL_eta: float = 0.99
+    CFL_nu: Optional[float] = None
+    dt_fixed: float = 0.0
+    dt_max: float = 0.0
+    time_max: float = 1.0
+    write_method: str = "fixed_freq"
+    write_time: float = 1.0
+    write_time_first: float = 0.0
+    tsave_stats: float = 9999999.9
+    butcher: np.ndarray = field(default_factory=lambda: BUTCHER_RK4.copy())
+
+    def acm(self) -> AcmParams:
+        a = AcmParams()
+        a.dim, a.fd = self.dim, FD_IDS[self.discretization]
+        a.skew, a.penalization, a.use_sponge = int(self.skew), int(self.penalization), int(self.use_sponge)
+        a.c0, a.nu, a.gamma_p, a.C_eta, a.C_sponge = self.c0, self.nu, self.gamma_p, self.C_eta, self.C_sponge
+        a.u_mean_set = (C.c_double * 3)(*self.u_mean_set)
+        a.CFL, a.CFL_eta = self.CFL, self.CFL_eta
+        a.CFL_nu = self.cfl_nu()
+        return a
+
+    def cfl_nu(self) -> float:
+        """module_ACM.f90:367-381 -- default depends on the order digit of the discretization."""
+        if self.CFL_nu is not None:
+            return self.CFL_nu
+        digit = self.discretization[3]
+        den = {"2": 4.000, "4": 5.333, "6": 6.0444}[digit]
+        return 0.95 * 2.79 / (den * float(self.dim))
+
+
+# ----------------------------------------------------------------------------- grid
+@dataclass
+class Grid:
+    """Light data of a single tree: integer block coordinates (ix,iy,iz) at `level` per block.
+
+    Block spacing / origin follow module_treelib.f90:93-98:
+        dx = 2^-J * L / Bs ;  x0 = (ixyz) * Bs * dx          (ixyz zero-based here)
+    """
+    level: np.ndarray   # (Nb,) int
+    ixyz: np.ndarray    # (Nb,3) int, zero-based block coordinates on their own level
+    dim: int = 3
+
+    @property
+    def n(self) -> int:
+        return len(self.level)
+
+    def spacing_origin(self, p: Params, b: int):
+        J = int(self.level[b])
+        dx = np.zeros(3)
+        x0 = np.zeros(3)
+        for d in range(self.dim):
+            dx[d] = 2.0 ** (-J) * p.domain[d] / float(p.Bs[d])
+            x0[d] = float(int(self.ixyz[b, d]) * p.Bs[d]) * dx[d]
+        return x0, dx
+
+    def lookup(self) -> Dict[Tuple[int, int, int, int], int]:
+        return {(int(l), int(i[0]), int(i[1]), int(i[2])): k for k, (l, i) in enumerate(zip(self.level, self.ixyz))}
+
+
+def uniform_grid(J: int, dim: int = 3) -> Grid:
+    n = 2 ** J
+    if dim == 3:
+        iz, iy, ix = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    else:
+        iy, ix = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+        iz = np.zeros_like(ix)
+    ixyz = np.stack([ix.ravel(), iy.ravel(), iz.ravel()], axis=1)
+    return Grid(level=np.full(len(ixyz), J, dtype=np.int64), ixyz=ixyz.astype(np.int64), dim=dim)
+
+
+def alloc(grid: Grid, p: Params, nc: Optional[int] = None) -> np.ndarray:
+    nc = p.n_eqn if nc is None else nc
+    nz = p.Bs[2] + 2 * p.g if p.dim == 3 else 1
+    return np.zeros((grid.n, nc, nz, p.Bs[1] + 2 * p.g, p.Bs[0] + 2 * p.g))
+
+
+def interior(p: Params):
+    g = p.g
+    zs = slice(g, p.Bs[2] + g) if p.dim == 3 else slice(0, 1)
+    return (zs, slice(g, p.Bs[1] + g), slice(g, p.Bs[0] + g))
+
+
+# ----------------------------------------------------------------------------- ghost sync (same level)
+def sync_ghosts_same_level(grid: Grid, p: Params, hvy: np.ndarray, g_minus: int, g_plus: int,
+                           ncomp: Optional[int] = None) -> None:
+    """Same-level, periodic ghost synchronisation (lvl_diff = 0 relations only).
+
+    Receiver boxes: get_indices_of_ghost_patch (neighborhood.f90:158-285): fixed direction '-':
+    g-gminus+1:g, '+': Bs+g+1:Bs+g+gplus, free directions g+1:Bs+g.  Sender boxes: interior
+    strip of matching depth (set_send_bounds, calc_data_bounds.f90:99-146).  A copy, so exact.
+    All 26 (8 in 2-D) relations are exchanged as in sync_ghosts_generic stage 1
+    (synchronize_ghosts_generic.f90:266-339).
+    """
+    look = grid.lookup()
+    g, Bs, dim = p.g, p.Bs, grid.dim
+    nc = hvy.shape[1] if ncomp is None else ncomp
+    dirs = [(dx_, dy_, dz_) for dz_ in ((-1, 0, 1) if dim == 3 else (0,)) for dy_ in (-1, 0, 1) for dx_ in (-1, 0, 1)
+            if (dx_, dy_, dz_) != (0, 0, 0)]
+    src = hvy.copy()  # interiors are never written by a sync; copy keeps the restatement order-free
+
+    def boxes(d, n):
+        if d == 0:
+            return slice(g, n + g), slice(g, n + g)
+        if d < 0:   # my lower ghost  <- neighbour's upper interior strip
+            return slice(g - g_minus, g), slice(n + g - g_minus, n + g)
+        return slice(n + g, n + g + g_plus), slice(g, g + g_plus)
+
+    for b in range(grid.n):
+        J = int(grid.level[b])
+        nblk = 2 ** J
+        for d in dirs:
+            nb_xyz = [(int(grid.ixyz[b, a]) + d[a]) % nblk if a < dim else 0 for a in range(3)]
+            nb = look[(J, nb_xyz[0], nb_xyz[1], nb_xyz[2])]
+            rx, sx = boxes(d[0], Bs[0])
+            ry, sy = boxes(d[1], Bs[1])
+            if dim == 3:
+                rz, sz = boxes(d[2], Bs[2])
+            else:
+                rz = sz = slice(0, 1)
+            hvy[b, :nc, rz, ry, rx] = src[nb, :nc, sz, sy, sx]
+
+
+# ----------------------------------------------------------------------------- RHS / dt / RK
+def rhs_tree(grid: Grid, p: Params, hvy: np.ndarray, rhs: np.ndarray, mask: Optional[np.ndarray] = None,
+             fast: bool = False) -> None:
+    """RHS_wrapper local_stage loop (RHS_wrapper.f90:124-142) -> RHS_ACM -> RHS_{2,3}D_acm."""
+    L = lib(fast)
+    a = p.acm()
+    f = L.orc_rhs_acm_3d if p.dim == 3 else L.orc_rhs_acm_2d
+    for b in range(grid.n):
+        _, dx = grid.spacing_origin(p, b)
+        m = None if mask is None else mask[b if mask.shape[0] > 1 else 0]
+        f(C.byref(a), p.g, _bs(p.Bs), _d3(dx), _p(hvy[b]), _p(rhs[b]), _p(m))
+
+
+LIM_DIVERGED = 1.0e12
+
+
+def divergence_guard(grid: Grid, p: Params, hvy: np.ndarray) -> bool:
+    """integral_stage guard (rhs_ACM.f90:133-146): True if any |u| > 1e12 in a block interior."""
+    L = lib()
+    for b in range(grid.n):
+        if L.orc_max_abs_interior(p.dim, p.g, _bs(p.Bs), hvy.shape[1], _p(hvy[b])) > LIM_DIVERGED:
+            return True
+    return False
+
+
+def calculate_time_step(grid: Grid, p: Params, hvy: np.ndarray, time: float) -> float:
+    """calculate_time_step.f90:19-118 (statistics / probes / backup clauses that are off by default omitted)."""
+    dt = 9.0e9
+    if p.dt_fixed > 0.0:
+        dt = p.dt_fixed
+    else:
+        L = lib()
+        a = p.acm()
+        for b in range(grid.n):
+            _, dx = grid.spacing_origin(p, b)
+            dt = min(dt, L.orc_get_dt_block(C.byref(a), p.g, _bs(p.Bs), _d3(dx), _p(hvy[b])))
+        if p.dt_max > 0.0:
+            dt = min(p.dt_max, dt)
+    if p.write_method == "fixed_time":
+        if (math.fmod(time + dt, p.write_time) < math.fmod(time + 1e-12, p.write_time)
+                and not abs(math.fmod(time, p.write_time)) < 1e-12 and time + 1e-12 > p.write_time_first):
+            dt = p.write_time - math.fmod(time, p.write_time)
+    if abs(p.tsave_stats - 9999999.9) > 1e-3:
+        if (math.fmod(time + dt, p.tsave_stats) < math.fmod(time + 1e-12, p.tsave_stats)
+                and not abs(math.fmod(time, p.tsave_stats)) < 1e-12):
+            dt = p.tsave_stats - math.fmod(time, p.tsave_stats)
+    if time + dt > p.time_max and time <= p.time_max:
+        dt = p.time_max - time
+    return dt
+
+
+def rk_generic(grid: Grid, p: Params, hvy: np.ndarray, work: np.ndarray, time: float,
+               mask: Optional[np.ndarray] = None, sync=None, fast: bool = False) -> float:
+    """RungeKuttaGeneric (runge_kutta_generic.f90:50-154).  `work[slot]` are ghosted arrays like hvy.
+
+    `sync(hvy)` performs sync_ghosts_RHS_tree with g_minus=g_plus=g_rhs; defaults to the same-level sync.
+    Returns dt.  hvy is advanced in place.
+    """
+    L = lib(fast)
+    rk = p.butcher
+    n = rk.shape[0]
+    nc = p.n_eqn
+    Bs = _bs(p.Bs)
+    if sync is None:
+        sync = lambda h: sync_ghosts_same_level(grid, p, h, p.g_rhs, p.g_rhs)
+    sync(hvy)
+    dt = calculate_time_step(grid, p, hvy, time)
+    for b in range(grid.n):
+        L.orc_rk_copy_interior(p.dim, p.g, Bs, nc, _p(work[0][b]), _p(hvy[b]))
+    rhs_tree(grid, p, hvy, work[1], mask, fast)
+    for j in range(2, n):          # Fortran j = 2 .. size(rk,1)-1
+        for b in range(grid.n):
+            L.orc_rk_copy_interior(p.dim, p.g, Bs, nc, _p(hvy[b]), _p(work[0][b]))
+        for l in range(2, j + 1):
+            coef = rk[j - 1, l - 1]
+            if abs(coef) < 1.0e-8:
+                continue
+            for b in range(grid.n):
+                L.orc_rk_axpy_interior(p.dim, p.g, Bs, nc, _p(hvy[b]), dt, coef, _p(work[l - 1][b]))
+        sync(hvy)
+        rhs_tree(grid, p, hvy, work[j], mask, fast)
+    for b in range(grid.n):
+        L.orc_rk_copy_interior(p.dim, p.g, Bs, nc, _p(hvy[b]), _p(work[0][b]))
+        for j in range(2, rk.shape[1] + 1):
+            coef = rk[n - 1, j - 1]
+            if abs(coef) < 1.0e-8:
+                continue
+            L.orc_rk_axpy_interior(p.dim, p.g, Bs, nc, _p(hvy[b]), dt, coef, _p(work[j - 1][b]))
+    return dt
+
+
+# ----------------------------------------------------------------------------- initial conditions
+def inicond_taylor_green(grid: Grid, p: Params, hvy: np.ndarray) -> None:
+    """inicond 'taylor-green-vanRees2011' (inicond_ACM.f90:371-389), set on the whole ghosted block."""
+    g = p.g
+    for b in range(grid.n):
+        x0, dx = grid.spacing_origin(p, b)
+        x = (np.arange(p.Bs[0] + 2 * g) - g).astype(np.float64) * dx[0] + x0[0]
+        y = (np.arange(p.Bs[1] + 2 * g) - g).astype(np.float64) * dx[1] + x0[1]
+        z = (np.arange(p.Bs[2] + 2 * g) - g).astype(np.float64) * dx[2] + x0[2]
+        Z, Y, X = np.meshgrid(z, y, x, indexing="ij")
+        hvy[b, 0] = np.sin(X) * np.cos(Y) * np.cos(Z)
+        hvy[b, 1] = -np.cos(X) * np.sin(Y) * np.cos(Z)
+        hvy[b, 2] = 0.0
+        hvy[b, 3] = (np.cos(2.0 * X) + np.cos(2.0 * Y)) * (np.cos(2.0 * Z) + 2.0) / 16.0
