@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""Benchmark of the WABBIT block hot path on B200: 3-D ACM RK4 block-updates/s.
+
+  python bench.py --gpus N --steps K --warmup W          (N>1: launched under torchrun, one rank per GPU)
+  python bench.py --impl reference ...                    the reference's CPU algorithm on the host cores
+
+A step = one RungeKuttaGeneric time step (4 stages of RHS_3D_acm + ghost synchronisation + stage updates + dt)
+over every block of a periodic, equidistant 3-D Taylor-Green grid (BASELINE.json configs[1]).
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "3D ACM RK4 block-updates/sec"
+UNIT = "block-updates/s"
+TWO_PI = 6.283185307179586
+
+
+def workload_name(a):
+    return f"taylor_green_3d_periodic_uniform_J{a.level}_Bs{a.bs}_FD4_skew_RK4_CDF40"
+
+
+def algorithmic_bytes_per_block_update(Bs: int, g_rhs: int = 2, nc: int = 4, n_mask: int = 0) -> int:
+    """SURVEY.md 8(d) / BASELINE.md 3:  B_rk4 = 8*[23*nc*N + 8*nc*(box_r - N) + 4*n_mask*N]."""
+    N = Bs ** 3
+    box = (Bs + 2 * g_rhs) ** 3
+    return 8 * (23 * nc * N + 8 * nc * (box - N) + 4 * n_mask * N)
+
+
+def make_params(a):
+    from wabbit_b200 import Params
+    return Params(dim=3, domain=(TWO_PI,) * 3, Bs=(a.bs,) * 3, wavelet="CDF40", g=3, g_rhs=2, n_eqn=4, Jmax=a.level,
+                  discretization="FD_4th_central", skew_symmetry=True, c0=10.0, nu=3.125e-3, gamma_p=0.0, CFL=1.0,
+                  u_mean_set=(0.0, 0.0, 0.0), time_max=1.0e9).finalize()
+
+
+def taylor_green_host(p, ixyz, level, out):
+    """inicond 'taylor-green-vanRees2011' (inicond_ACM.f90:371-389) for the blocks listed, into out[k] (ghosted)."""
+    import torch
+    g, Bs = p.g, p.Bs[0]
+    n = Bs + 2 * g
+    t_out = torch.from_numpy(out)
+    lv = torch.from_numpy(level.astype(np.float64))
+    dx = (2.0 ** (-lv)) * p.domain[0] / float(Bs)                      # [nb]
+    idx = torch.arange(n, dtype=torch.float64) - g
+    chunk = 2048
+    for s in range(0, len(level), chunk):
+        e = min(s + chunk, len(level))
+        d = dx[s:e, None]
+        x0 = torch.from_numpy((ixyz[s:e] * Bs).astype(np.float64)) * d  # [m,3]
+        X = (idx[None, :] * d + x0[:, 0:1])[:, None, None, :]
+        Y = (idx[None, :] * d + x0[:, 1:2])[:, None, :, None]
+        Z = (idx[None, :] * d + x0[:, 2:3])[:, :, None, None]
+        t_out[s:e, 0] = torch.sin(X) * torch.cos(Y) * torch.cos(Z)
+        t_out[s:e, 1] = -torch.cos(X) * torch.sin(Y) * torch.cos(Z)
+        t_out[s:e, 2] = 0.0
+        t_out[s:e, 3] = (torch.cos(2.0 * X) + torch.cos(2.0 * Y)) * (torch.cos(2.0 * Z) + 2.0) / 16.0
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        self.marks = {}
+
+    def mark(self, name):
+        self.f.flush()
+        self.marks[name] = os.path.getsize(self.f.name)
+
+    def stop(self):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        self.f.flush()
+        with open(self.f.name) as f:
+            data = f.read()
+        os.unlink(self.f.name)
+        lo, hi = self.marks.get("t0", 0), self.marks.get("t1", len(data))
+        rows = [r for r in data[lo:hi].splitlines() if r.count(",") >= 8]
+        where = "timed_region"
+        if not rows:
+            rows = [r for r in data.splitlines() if r.count(",") >= 8]
+            where = "whole_run"
+        sm, smax, reasons = [], 0.0, set()
+        for r in rows:
+            c = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(c[1]))
+                smax = max(smax, float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax or None, "reasons": sorted(reasons),
+                "samples": len(sm), "sampled": where}
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+def cpu_run(a, level: int, steps: int, warmup: int):
+    """The reference's algorithm on the host cores (oracle C restatement, -O3 -march=native, OpenMP: one worker
+    per core over contiguous SFC chunks of blocks).  Returns (block_updates_per_s, ms_per_step, cores, nblocks)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    po = O.Params(dim=3, Bs=(a.bs,) * 3, g=3, g_rhs=2, domain=(TWO_PI,) * 3, Jmax=level, discretization="FD_4th_central",
+                  skew=True, c0=10.0, nu=3.125e-3, gamma_p=0.0, CFL=1.0, u_mean_set=(0.0, 0.0, 0.0), time_max=1.0e9)
+    grid = O.uniform_grid(level)
+    u = O.alloc(grid, po)
+    O.inicond_taylor_green(grid, po, u)
+    work = np.zeros((5,) + u.shape)
+    nbr, dxb = O.nbr_table(grid), O.dx_table(grid, po)
+    t = 0.0
+    for _ in range(warmup):
+        t += O.rk_step_c(grid, po, u, work, t, nbr, dxb, fast=True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        t += O.rk_step_c(grid, po, u, work, t, nbr, dxb, fast=True)
+    el = time.perf_counter() - t0
+    return grid.n * steps / el, 1e3 * el / steps, cores, grid.n
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    lvl = min(a.level, a.cpu_level)
+    steps = max(1, min(a.steps, 8))
+    warm = max(1, min(a.warmup, 2))
+    v, ms, cores, nb = cpu_run(a, lvl, steps, warm)
+    sample = f"{steps} RK4 steps on {nb} blocks (level {lvl}, Bs={a.bs}) of the {workload_name(a)} workload"
+    line = {
+        "metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": a.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "blocks": nb, "Bs": a.bs, "note": "bounded sample of the workload on the host cores"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample + "; oracle C restatement of the reference Fortran (no Fortran compiler in the image), "
+                                            "-O3 -march=native, OpenMP static chunks of the SFC-ordered block list"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from wabbit_b200 import Forest, WabbitGPU
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    p = make_params(a)
+    forest = Forest.uniform(3, a.level, block_dist="sfc_hilbert", n_ranks=world)
+    nb_global = forest.n_blocks
+    hvy, lvl, ixyz, _ = forest.active(rank)
+    nb_local = len(hvy)
+    stream = torch.cuda.current_stream()
+    sol = WabbitGPU(p, max_blocks=forest.max_blocks, device=local, stream=stream.cuda_stream)
+    if world > 1:
+        from wabbit_b200.multi import attach_exchange
+        attach_exchange(sol, forest, rank, world)
+    else:
+        sol.set_forest(forest, rank)
+
+    # host state in the reference layout hvy_block(nx,ny,nz,4,number_blocks), pinned
+    shape = sol.host_shape()
+    host = torch.empty(shape, dtype=torch.float64, pin_memory=True)
+    h_np = host.numpy()
+    taylor_green_host(p, ixyz, lvl, h_np)
+    ids = hvy
+    sol.upload_ptr(host.data_ptr(), shape[1], hvy_ids=ids)
+    sol.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    t = 0.0
+    it = 0
+    for _ in range(a.warmup):
+        t, it, _dt = sol.timeStep_tree(t, it)
+    # ---------------- timed region: device-resident state
+    sol.profile(True)
+    barrier()
+    if sampler:
+        sampler.mark("t0")
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = sol.launch_count
+    ev0.record(stream)
+    for _ in range(a.steps):
+        t, it, _dt = sol.timeStep_tree(t, it)
+    ev1.record(stream)
+    barrier()
+    if sampler:
+        sampler.mark("t1")
+    launches = sol.launch_count - n0
+    ms = ev0.elapsed_time(ev1)
+    n_stage, stage_ms = sol.profile_read()
+    sol.profile(False)
+    tm = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms = float(tm.item())
+    value = nb_global * a.steps / (ms * 1e-3)
+
+    # ---------------- end to end: host buffers in, host buffers out, every step
+    e2e_steps = max(1, min(a.steps, a.e2e_steps))
+    per_block = int(np.prod(shape[1:])) * 8
+    barrier()
+    w0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        sol.upload_ptr(host.data_ptr(), shape[1], hvy_ids=ids)
+        t, it, _dt = sol.timeStep_tree(t, it)
+        sol.download_ptr(host.data_ptr(), shape[1], hvy_ids=ids, g_sync=p.g)
+    e1.record(stream)
+    barrier()
+    e2e_wall = time.perf_counter() - w0
+    te = torch.tensor([max(e0.elapsed_time(e1) * 1e-3, e2e_wall)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = nb_global * e2e_steps / float(te.item())
+    finite = bool(np.isfinite(h_np[: min(nb_local, 8)]).all())
+
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s (of fallback)"
+        B = algorithmic_bytes_per_block_update(a.bs)
+        # dominant kernel = stage_kernel, 4 launches per step, each processing every local block once:
+        # algorithmic bytes per launch = (B_rk4 / 4) * blocks_per_gpu
+        avg_launch_s = (stage_ms / max(n_stage, 1)) * 1e-3
+        achieved = (B / 4.0) * nb_local / avg_launch_s / 1e9 if n_stage else None
+        traffic = None
+        tr_path = os.path.join(ROOT, "profiles", "stage_kernel_traffic.json")
+        if os.path.exists(tr_path):
+            try:
+                traffic = json.load(open(tr_path)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(a), "blocks": nb_global, "blocks_per_gpu": nb_local, "Bs": a.bs, "nc": 4, "g_rhs": 2,
+                       "host_layout_g": p.g, "block_dist": "sfc_hilbert", "parallelism": f"sfc-partition x{world}",
+                       "l2": "inputs larger than L2 (state array %.0f MB per GPU)" % (nb_local * 4 * a.bs ** 3 * 8 / 1e6),
+                       "finite": finite},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": per_block * nb_local, "d2h_bytes_per_step": per_block * nb_local,
+                    "steps": e2e_steps, "note": "wgpu_upload(host hvy_block) + wgpu_rk_step + wgpu_download(host hvy_block) per step, pinned host memory"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                         "traffic": traffic, "kernel": "stage_kernel<FD4,skew,Bs16>", "launches_timed": n_stage,
+                         "avg_launch_ms": avg_launch_s * 1e3, "algorithmic_bytes_per_block_update": B, "peak_source": peak_src},
+        }
+        if world == 1 and not a.no_cpu:
+            v, cms, cores, nbc = cpu_run(a, min(a.level, a.cpu_level), a.cpu_steps, 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{a.cpu_steps} RK4 steps on {nbc} blocks (level {min(a.level, a.cpu_level)}) of the same workload; "
+                                              "oracle C restatement, -O3 -march=native, OpenMP"}
+        print(json.dumps(line), flush=True)
+    sol.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--level", type=int, default=5, help="equidistant level J: (2^J)^3 blocks")
+    ap.add_argument("--bs", type=int, default=16)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-level", type=int, default=3)
+    ap.add_argument("--cpu-steps", type=int, default=6)
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

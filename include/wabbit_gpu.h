@@ -1,0 +1,157 @@
+/*
+ * wabbit_gpu.h -- C ABI of the B200-resident WABBIT block hot path.
+ *
+ * This is the drop-in boundary: plain pointers, int32 / double scalars, no C++ or torch types.
+ * A Fortran host binds these with ISO_C_BINDING (`bind(C)`, scalars `value`); the binding a WABBIT
+ * maintainer would add is shown in INTEGRATION.md (fortran/module_gpu_bridge.f90).
+ *
+ * Each entry point names the tree-level reference routine it replaces (paths relative to the
+ * reference checkout).  The per-block plugin calls RHS_meta / GET_DT_BLOCK_meta
+ * (LIB/EQUATION/module_physics_metamodule.f90:268,558) are useless granularity for a GPU, so the
+ * boundary sits one level up, at the routines that own the block loops.
+ *
+ * Conventions
+ *   - Heavy arrays on the HOST side keep the reference layout: Fortran column-major
+ *     hvy(nx,ny,nz,ncomp,number_blocks), nx = Bs+2g, x fastest, float64 (LIB/MESH/allocate_forest.f90:228-267).
+ *   - hvy ids and lgt ids are 1-based as in Fortran; -1 means "none".
+ *   - Every function returns 0 on success, else a non-zero WABBIT-style integer code; the message is
+ *     available from wgpu_last_error().  The library never calls exit()/abort().
+ *   - One host thread drives a context (the reference is single-threaded per rank as well).
+ *   - Device arrays are owned by the library and indexed by the SAME hvy_id as the host arrays.
+ */
+#ifndef WABBIT_GPU_H
+#define WABBIT_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WGPU_MAX_STAGES 8   /* rows of the Butcher tableau minus one */
+#define WGPU_NCOLORS 16
+
+/* order_discretization (LIB/EQUATION/ACMnew/rhs_ACM.f90:1014,1137,1344,1461) */
+enum { WGPU_FD_2ND_CENTRAL = 2, WGPU_FD_4TH_CENTRAL = 4, WGPU_FD_6TH_CENTRAL = 6, WGPU_FD_4TH_CENTRAL_OPTIMIZED = 40 };
+
+/* device-resident heavy arrays (LIB/MESH/allocate_forest.f90:228-267) */
+enum { WGPU_HVY_BLOCK = 0, WGPU_HVY_WORK = 1, WGPU_HVY_MASK = 2, WGPU_HVY_TMP = 3 };
+
+/* error codes (0 = ok).  WGPU_ERR_DIVERGED mirrors abort(0409201933) in rhs_ACM.f90:145. */
+enum {
+    WGPU_OK = 0,
+    WGPU_ERR_ARG = 1001,
+    WGPU_ERR_CUDA = 1002,
+    WGPU_ERR_UNSUPPORTED = 1003,
+    WGPU_ERR_NO_DEVICE = 1004,
+    WGPU_ERR_DIVERGED = 409201933
+};
+
+/*
+ * Configuration: the subset of type_params (LIB/PARAMS/module_params.f90:18-233) and type_params_acm
+ * (LIB/EQUATION/ACMnew/module_ACM.f90:56-154) the hot path reads.  Filled by the host from the same
+ * .ini file (LIB/MESH/ini_file_to_params.f90, module_ACM.f90:172-609).
+ */
+typedef struct wgpu_config {
+    int32_t dim;                 /* [Domain] dim: 2 or 3 */
+    int32_t Bs[3];               /* [Blocks] number_block_nodes (even) */
+    int32_t g;                   /* [Blocks] number_ghost_nodes (host layout ghost width) */
+    int32_t g_rhs;               /* [Blocks] number_ghost_nodes_rhs */
+    int32_t n_eqn;               /* [Blocks] number_equations: 3 (2-D) or 4 (3-D) for ACM */
+    int32_t n_mask;              /* components of hvy_mask held on the device: 0, 5 or 6 */
+    int32_t max_blocks;          /* params%number_blocks (per rank) */
+    int32_t Jmax;                /* [Blocks] max_treelevel */
+    int32_t periodic[3];         /* [Domain] periodic_BC */
+    int32_t fd;                  /* WGPU_FD_* */
+    int32_t skew_symmetry;       /* [ACM-new] skew_symmetry */
+    int32_t penalization;        /* [VPM] penalization */
+    int32_t use_sponge;          /* [Sponge] use_sponge */
+    int32_t n_stages;            /* s: the tableau below is (s+1) x (s+1) */
+    int32_t write_method_fixed_time; /* [Time] write_method == "fixed_time" */
+    int32_t device;              /* CUDA device ordinal */
+    double domain[3];            /* [Domain] domain_size */
+    double c0, nu, gamma_p;      /* [ACM-new] */
+    double C_eta;                /* [VPM] C_eta */
+    double C_sponge;             /* [Sponge] C_sponge */
+    double u_mean_set[3];        /* [ACM-new] u_mean_set */
+    double CFL, CFL_eta, CFL_nu; /* [Time] */
+    double dt_fixed, dt_max;     /* [Time] */
+    double time_max;             /* [Time] */
+    double write_time, write_time_first;   /* [Time] */
+    double tsave_stats;          /* [Statistics] tsave_stats (9999999.9 = off) */
+    double butcher[(WGPU_MAX_STAGES + 1) * (WGPU_MAX_STAGES + 1)]; /* row-major (s+1)x(s+1), ini_file_to_params.f90:640-646 */
+} wgpu_config;
+
+typedef struct wgpu_ctx wgpu_ctx;
+
+/* ---- lifecycle: replaces allocate_forest (LIB/MESH/allocate_forest.f90:1) for the device copies ---- */
+int32_t wgpu_create(const wgpu_config *cfg, wgpu_ctx **out);
+int32_t wgpu_destroy(wgpu_ctx *ctx);
+/* copies the last error message of `ctx` (or of a failed wgpu_create if ctx == NULL) into buf */
+int32_t wgpu_last_error(const wgpu_ctx *ctx, char *buf, int32_t len);
+/* all work of this context is issued on `cuda_stream` (a cudaStream_t); NULL = default stream */
+int32_t wgpu_set_stream(wgpu_ctx *ctx, void *cuda_stream);
+int32_t wgpu_synchronize(wgpu_ctx *ctx);
+
+/*
+ * ---- topology upload: consumes what updateMetadata_tree leaves in the forest metadata
+ *      (LIB/MESH/module_forestMetaData.f90:33-56; neighbour slots LIB/TREE/neighborhood.f90:10-22).
+ * hvy_active[n_active]        1-based hvy ids in the order of hvy_active(:,tree_ID)
+ * level[n_active]             mesh level of each active block (lgt_block(lgt_id, IDX_MESH_LVL))
+ * hvy_neighbor                Fortran array hvy_neighbor(ld, 168) of LGT ids (lgt = rank*max_blocks + hvy), -1 = none
+ * rank                        this process' rank (to translate lgt <-> hvy ids)
+ */
+int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_active, const int32_t *level,
+                          const int32_t *hvy_neighbor, int32_t ld, int32_t rank);
+
+/*
+ * ---- data movement between the host's Fortran arrays and the resident device arrays.
+ * host points at element (1,1,1,1,1) of hvy(nx,ny,nz,ncomp_host,number_blocks); blocks listed in hvy_ids
+ * (1-based, n of them) are moved.  `slot` selects hvy_work(:,:,:,:,:,slot) (ignored for other arrays).
+ * Download fills ghost layers of width g_sync (0..g) by running the ghost synchronisation on the fly
+ * (same-level copy; what sync_ghosts_tree would have left there), the rest of the ghost region is untouched.
+ */
+int32_t wgpu_upload(wgpu_ctx *ctx, int32_t array_id, int32_t slot, const int32_t *hvy_ids, int32_t n,
+                    const double *host, int32_t ncomp_host);
+int32_t wgpu_download(wgpu_ctx *ctx, int32_t array_id, int32_t slot, const int32_t *hvy_ids, int32_t n,
+                      double *host, int32_t ncomp_host, int32_t g_sync);
+
+/*
+ * ---- compute ----
+ * wgpu_sync_ghosts: replaces sync_ghosts_RHS_tree / sync_ghosts_tree
+ *   (LIB/MPI/synchronize_ghosts_generic.f90:155-174, 181-343).  Same-level relations are not materialised in HBM
+ *   (the stencil kernels gather them from the neighbour's interior); this call refreshes the level-jump / remote
+ *   patch pool and is a no-op on a uniform single-GPU grid.
+ */
+int32_t wgpu_sync_ghosts(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t g_minus, int32_t g_plus);
+
+/* wgpu_rhs: replaces RHS_wrapper (LIB/TIME/RHS_wrapper.f90:16-260) for physics "ACM-new":
+ *   hvy_work(:,:,:,:,:,dst_slot) = RHS(src), src = hvy_block (src_slot = 0) or hvy_work(..., src_slot).
+ *   Includes the integral_stage divergence guard (rhs_ACM.f90:133-146) -> WGPU_ERR_DIVERGED. */
+int32_t wgpu_rhs(wgpu_ctx *ctx, double time, int32_t src_slot, int32_t dst_slot);
+
+/* wgpu_calculate_time_step: replaces calculate_time_step (LIB/TIME/calculate_time_step.f90:2-125) incl. the
+ *   per-block GET_DT_BLOCK_ACM (module_ACM.f90:617-691) and the global MIN. */
+int32_t wgpu_calculate_time_step(wgpu_ctx *ctx, double time, double *dt);
+
+/* wgpu_rk_step: replaces RungeKuttaGeneric (LIB/TIME/runge_kutta_generic.f90:1-156): ghost sync, dt, all stages,
+ *   final combination; hvy_block is advanced in place on the device.  *dt receives the step taken. */
+int32_t wgpu_rk_step(wgpu_ctx *ctx, double time, int32_t iteration, double *dt);
+
+/* Stage-kernel timing with CUDA events on the context's stream (for the roofline line of bench.py):
+ * wgpu_profile(ctx, 1) starts recording an event pair around every stage-kernel launch (at most 4096 pairs),
+ * wgpu_profile_read synchronises, returns their number and summed duration in milliseconds, and resets. */
+int32_t wgpu_profile(wgpu_ctx *ctx, int32_t enable);
+int32_t wgpu_profile_read(wgpu_ctx *ctx, int32_t *n_launches, double *total_ms);
+
+/* number of kernels launched by this context since creation (bench.py's gpu_launches) */
+int64_t wgpu_launch_count(const wgpu_ctx *ctx);
+/* bytes of device memory held by the context */
+int64_t wgpu_device_bytes(const wgpu_ctx *ctx);
+/* raw device pointer + element count of a resident array (for zero-copy interop, e.g. NCCL via torch) */
+int32_t wgpu_device_pointer(wgpu_ctx *ctx, int32_t array_id, int32_t slot, void **ptr, int64_t *n_doubles);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WABBIT_GPU_H */

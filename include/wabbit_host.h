@@ -1,0 +1,57 @@
+/*
+ * wabbit_host.h -- C ABI of the host-side forest metadata used by the drivers, tests and benchmark
+ * of this repository (libwabbit_host.so, plain C++17, no CUDA).
+ *
+ * In a WABBIT build the octree / light data stay in host Fortran (LIB/TREE, LIB/MESH) and only their
+ * RESULT -- hvy_active, block levels and the 168-slot hvy_neighbor table -- crosses the boundary
+ * through wgpu_set_topology().  No Fortran compiler exists in this image, so this library produces
+ * the same tables for the grids the drivers need (equidistant grids, and grids given as an explicit
+ * list of leaf blocks), with WABBIT's conventions:
+ *   - binary treecode, coarsest digit in the highest bits, digit bit0 -> y, bit1 -> x, bit2 -> z
+ *     (LIB/TREE/module_treelib.f90:793-871),
+ *   - neighbour slots 1-56 same level, 57-112 coarser, 113-168 finer; faces 1-24, edges 25-48,
+ *     corners 49-56 (LIB/TREE/neighborhood.f90:10-22, LIB/MESH/find_neighbors.f90:18-180),
+ *   - lgt_id = rank*number_blocks + hvy_id, 1-based (LIB/MESH/hvy2lgt.f90, lgt2proc.f90),
+ *   - blocks sorted along a space-filling curve (Z or Hilbert) and cut into contiguous chunks,
+ *     one per rank (LIB/MESH/balanceLoad_tree.f90:203-285, 600-715).
+ */
+#ifndef WABBIT_HOST_H
+#define WABBIT_HOST_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct whost_forest whost_forest;
+
+enum { WHOST_SFC_Z = 0, WHOST_SFC_HILBERT = 1 };
+
+/* Equidistant grid on level J (createEquidistantGrid_tree), distributed over n_ranks by the SFC. */
+int32_t whost_create_uniform(int32_t dim, int32_t J, int32_t Jmax, int32_t sfc, int32_t n_ranks, int32_t max_blocks_per_rank,
+                             const int32_t periodic[3], whost_forest **out);
+/* Grid from an explicit list of leaf blocks: level[n], ixyz[3*n] zero-based block coordinates on their level. */
+int32_t whost_create_from_blocks(int32_t dim, int32_t Jmax, int32_t sfc, int32_t n_ranks, int32_t max_blocks_per_rank,
+                                 const int32_t periodic[3], int32_t n, const int32_t *level, const int32_t *ixyz, whost_forest **out);
+int32_t whost_destroy(whost_forest *f);
+
+int32_t whost_n_blocks(const whost_forest *f);                 /* lgt_n */
+int32_t whost_n_active(const whost_forest *f, int32_t rank);   /* hvy_n of a rank */
+/* per rank, in SFC order: hvy ids (1-based), level, zero-based block coordinates, treecode */
+int32_t whost_get_active(const whost_forest *f, int32_t rank, int32_t *hvy_active, int32_t *level, int32_t *ixyz, int64_t *treecode);
+/* hvy_neighbor(max_blocks_per_rank, 168) of a rank, Fortran column-major, lgt ids, -1 = none */
+int32_t whost_get_neighbors(const whost_forest *f, int32_t rank, int32_t *hvy_neighbor);
+/* 1 if every neighbour relation of every block is same-level */
+int32_t whost_is_uniform(const whost_forest *f);
+
+/* treecode helpers (module_treelib.f90:793-871) */
+int64_t whost_encode(int32_t dim, int32_t level, int32_t Jmax, const int32_t ixyz[3]);
+int32_t whost_decode(int32_t dim, int32_t level, int32_t Jmax, int64_t treecode, int32_t ixyz[3]);
+/* position along the space-filling curve of a block (sort key) */
+uint64_t whost_sfc_key(int32_t dim, int32_t sfc, int32_t level, int32_t Jmax, const int32_t ixyz[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

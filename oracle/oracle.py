@@ -24,7 +24,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SRCS = ["orc_acm.c", "orc_wavelet.c"]
+_SRCS = ["orc_acm.c", "orc_tree.c", "orc_wavelet.c"]
 
 
 def _lib_path(fast: bool) -> str:
@@ -70,6 +70,12 @@ def lib(fast: bool = False) -> C.CDLL:
         L.orc_max_abs_interior.argtypes = [C.c_int, C.c_int, _ip, C.c_int, _dp]
         L.orc_max_abs_interior.restype = C.c_double
         L.orc_fd_halfwidth.argtypes = [C.c_int]
+        L.orc_sync_same_level.argtypes = [C.c_int, _ip, C.c_int, C.c_int, _ip, C.c_int, _dp, C.c_int, C.c_int]
+        L.orc_dt_tree.argtypes = [C.POINTER(AcmParams), C.c_int, _dp, C.c_int, C.c_int, _ip, C.c_int, _dp]
+        L.orc_dt_tree.restype = C.c_double
+        L.orc_rhs_tree.argtypes = [C.POINTER(AcmParams), C.c_int, _dp, C.c_int, C.c_int, _ip, C.c_int, _dp, _dp, _dp, C.c_int]
+        L.orc_rk_step_same_level.argtypes = [C.POINTER(AcmParams), C.c_int, _ip, _dp, C.c_int, C.c_int, C.c_int, _ip, C.c_int,
+                                             _dp, _dp, _dp, C.c_int, C.c_double, _dp, C.c_int]
         _libs[fast] = L
     return _libs[fast]
 
@@ -174,6 +180,25 @@ class Grid:
             x0[d] = float(int(self.ixyz[b, d]) * p.Bs[d]) * dx[d]
         return x0, dx
 
+    def same_level_neighbors(self) -> Dict[Tuple[int, int, int], np.ndarray]:
+        """Periodic same-level neighbour block index per direction (every block must have one)."""
+        if getattr(self, "_nbr", None) is None:
+            look = self.lookup()
+            out = {}
+            for dz_ in ((-1, 0, 1) if self.dim == 3 else (0,)):
+                for dy_ in (-1, 0, 1):
+                    for dx_ in (-1, 0, 1):
+                        d = (dx_, dy_, dz_)
+                        idx = np.zeros(self.n, dtype=np.int64)
+                        for b in range(self.n):
+                            J = int(self.level[b])
+                            nblk = 2 ** J
+                            q = [(int(self.ixyz[b, a]) + d[a]) % nblk if a < self.dim else 0 for a in range(3)]
+                            idx[b] = look[(J, q[0], q[1], q[2])]
+                        out[d] = idx
+            self._nbr = out
+        return self._nbr
+
     def lookup(self) -> Dict[Tuple[int, int, int, int], int]:
         return {(int(l), int(i[0]), int(i[1]), int(i[2])): k for k, (l, i) in enumerate(zip(self.level, self.ixyz))}
 
@@ -212,12 +237,11 @@ def sync_ghosts_same_level(grid: Grid, p: Params, hvy: np.ndarray, g_minus: int,
     All 26 (8 in 2-D) relations are exchanged as in sync_ghosts_generic stage 1
     (synchronize_ghosts_generic.f90:266-339).
     """
-    look = grid.lookup()
     g, Bs, dim = p.g, p.Bs, grid.dim
     nc = hvy.shape[1] if ncomp is None else ncomp
     dirs = [(dx_, dy_, dz_) for dz_ in ((-1, 0, 1) if dim == 3 else (0,)) for dy_ in (-1, 0, 1) for dx_ in (-1, 0, 1)
             if (dx_, dy_, dz_) != (0, 0, 0)]
-    src = hvy.copy()  # interiors are never written by a sync; copy keeps the restatement order-free
+    src = hvy  # senders are interior strips, receivers ghost strips: disjoint, so in-place is safe
 
     def boxes(d, n):
         if d == 0:
@@ -226,19 +250,16 @@ def sync_ghosts_same_level(grid: Grid, p: Params, hvy: np.ndarray, g_minus: int,
             return slice(g - g_minus, g), slice(n + g - g_minus, n + g)
         return slice(n + g, n + g + g_plus), slice(g, g + g_plus)
 
-    for b in range(grid.n):
-        J = int(grid.level[b])
-        nblk = 2 ** J
-        for d in dirs:
-            nb_xyz = [(int(grid.ixyz[b, a]) + d[a]) % nblk if a < dim else 0 for a in range(3)]
-            nb = look[(J, nb_xyz[0], nb_xyz[1], nb_xyz[2])]
-            rx, sx = boxes(d[0], Bs[0])
-            ry, sy = boxes(d[1], Bs[1])
-            if dim == 3:
-                rz, sz = boxes(d[2], Bs[2])
-            else:
-                rz = sz = slice(0, 1)
-            hvy[b, :nc, rz, ry, rx] = src[nb, :nc, sz, sy, sx]
+    nbr = grid.same_level_neighbors()
+    for d in dirs:
+        nb = nbr[d]
+        rx, sx = boxes(d[0], Bs[0])
+        ry, sy = boxes(d[1], Bs[1])
+        if dim == 3:
+            rz, sz = boxes(d[2], Bs[2])
+        else:
+            rz = sz = slice(0, 1)
+        hvy[:, :nc, rz, ry, rx] = src[:, :nc, sz, sy, sx][nb]
 
 
 # ----------------------------------------------------------------------------- RHS / dt / RK
@@ -279,6 +300,13 @@ def calculate_time_step(grid: Grid, p: Params, hvy: np.ndarray, time: float) -> 
             dt = min(dt, L.orc_get_dt_block(C.byref(a), p.g, _bs(p.Bs), _d3(dx), _p(hvy[b])))
         if p.dt_max > 0.0:
             dt = min(p.dt_max, dt)
+    return _clip_dt(p, dt, time, apply_dt_max=False)
+
+
+def _clip_dt(p: Params, dt: float, time: float, apply_dt_max: bool = True) -> float:
+    """calculate_time_step.f90:53-118 -- everything after the global MIN."""
+    if apply_dt_max and p.dt_max > 0.0 and not p.dt_fixed > 0.0:
+        dt = min(p.dt_max, dt)
     if p.write_method == "fixed_time":
         if (math.fmod(time + dt, p.write_time) < math.fmod(time + 1e-12, p.write_time)
                 and not abs(math.fmod(time, p.write_time)) < 1e-12 and time + 1e-12 > p.write_time_first):
@@ -346,3 +374,38 @@ def inicond_taylor_green(grid: Grid, p: Params, hvy: np.ndarray) -> None:
         hvy[b, 1] = -np.cos(X) * np.sin(Y) * np.cos(Z)
         hvy[b, 2] = 0.0
         hvy[b, 3] = (np.cos(2.0 * X) + np.cos(2.0 * Y)) * (np.cos(2.0 * Z) + 2.0) / 16.0
+
+
+# ----------------------------------------------------------------------------- C tree loops (orc_tree.c)
+def nbr_table(grid: Grid) -> np.ndarray:
+    """[n,27] same-level neighbour indices, index (dz+1)*9+(dy+1)*3+(dx+1)."""
+    nb = grid.same_level_neighbors()
+    out = np.full((grid.n, 27), -1, dtype=np.int32)
+    for (dx_, dy_, dz_), idx in nb.items():
+        out[:, (dz_ + 1) * 9 + (dy_ + 1) * 3 + (dx_ + 1)] = idx
+    return np.ascontiguousarray(out)
+
+
+def dx_table(grid: Grid, p: Params) -> np.ndarray:
+    return np.ascontiguousarray(np.stack([grid.spacing_origin(p, b)[1] for b in range(grid.n)]))
+
+
+def rk_step_c(grid: Grid, p: Params, hvy: np.ndarray, work: np.ndarray, time: float, nbr: np.ndarray, dxb: np.ndarray,
+              fast: bool = False, mask: Optional[np.ndarray] = None) -> float:
+    """One RungeKuttaGeneric step with every block loop in C/OpenMP (same arithmetic as rk_generic).
+    work: array [s+1, n, nc, nz, ny, nx]."""
+    L = lib(fast)
+    a = p.acm()
+    Bs = _bs(p.Bs)
+    nc = p.n_eqn
+    ip = lambda x: x.ctypes.data_as(_ip)
+    L.orc_sync_same_level(grid.n, ip(nbr), p.dim, p.g, Bs, nc, _p(hvy), p.g_rhs, p.g_rhs)
+    if p.dt_fixed > 0.0:
+        dt = calculate_time_step(grid, p, hvy, time)
+    else:
+        dt_cfl = L.orc_dt_tree(C.byref(a), grid.n, _p(dxb), p.dim, p.g, Bs, nc, _p(hvy))
+        dt = _clip_dt(p, dt_cfl, time)
+    s = p.butcher.shape[0] - 1
+    L.orc_rk_step_same_level(C.byref(a), grid.n, ip(nbr), _p(dxb), p.dim, p.g, p.g_rhs, Bs, nc, _p(hvy), _p(work),
+                             _p(np.ascontiguousarray(p.butcher)), s, dt, _p(mask), 0 if mask is None else mask.shape[1])
+    return dt

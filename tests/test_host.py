@@ -1,0 +1,187 @@
+"""CPU-side checks of the host logic: the C-ABI libraries load and export every declared symbol, the .ini reader,
+and the forest tables (hvy_neighbor conventions) against an independent NumPy restatement."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle as O
+from wabbit_b200 import Forest, Params, _build, _native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(w(?:gpu|host)_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_gpu_library_exports_every_declared_symbol():
+    assert os.path.exists(_build.GPU_LIB), "libwabbit_gpu.so not built (python -m wabbit_b200._build)"
+    lib = C.CDLL(_build.GPU_LIB)   # loading needs no GPU
+    names = _declared("wabbit_gpu.h")
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), n
+    assert set(names) == set(_native.GPU_SYMBOLS), set(names) ^ set(_native.GPU_SYMBOLS)
+
+
+def test_host_library_exports_every_declared_symbol():
+    lib = _native.host_lib()
+    names = _declared("wabbit_host.h")
+    for n in names:
+        assert hasattr(lib, n), n
+    assert set(names) == set(_native.HOST_SYMBOLS)
+
+
+def test_create_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from wabbit_b200 import WabbitAbort, WabbitGPU
+    with pytest.raises(WabbitAbort) as e:
+        WabbitGPU(Params(), max_blocks=8)
+    assert e.value.code == 1004 and "no CPU fallback" in str(e.value)
+
+
+def test_ini_reader(tmp_path):
+    ini = tmp_path / "PARAMS.ini"
+    ini.write_text("""
+; comment
+[Domain]
+dim=3;
+domain_size=6.283185307179586 6.283185307179586 6.283185307179586;
+periodic_BC=1 1 1;
+[Wavelet]
+wavelet=CDF44; some comment
+[Blocks]
+number_block_nodes=16;
+number_ghost_nodes=;
+number_ghost_nodes_rhs=1;
+number_equations=4;
+max_treelevel=4;
+[Time]
+CFL=1.0;
+CFL_nu=;
+write_method=fixed_time;
+write_time=10.0;
+butcher_tableau=(/ 0.0 0.0 0.0
+0.5 0.5 0.0
+0.0 0.0 1.0 /)
+[ACM-new]
+c_0=10;
+nu=3.125000e-03;
+gamma_p=0;
+skew_symmetry=1;
+[Discretization]
+order_discretization=FD_4th_central;
+[VPM]
+penalization=0;
+""")
+    p = Params.from_ini(str(ini))
+    assert p.dim == 3 and p.Bs == (16, 16, 16) and p.wavelet == "CDF44"
+    assert p.g == 6            # CDF44: X-1 + Y-1            (ini_file_to_params.f90:467)
+    assert p.g_rhs == 2        # raised from 1 to the FD4 half width (ini_file_to_params.f90:303-309)
+    assert p.skew_symmetry and not p.penalization and p.n_mask == 0
+    assert abs(p.CFL_nu - 0.95 * 2.79 / (5.333 * 3)) < 1e-15
+    assert p.n_stages == 2 and p.butcher[1] == [0.5, 0.5, 0.0]
+    cfg = p.to_config(64)
+    assert cfg.n_stages == 2 and cfg.butcher[3] == 0.5 and cfg.write_method_fixed_time == 1
+
+
+def test_odd_block_size_rejected():
+    with pytest.raises(ValueError):
+        Params(Bs=(17, 17, 17)).finalize()
+
+
+# slot -> direction, from the lists in get_indices_of_modify_patch (LIB/TREE/neighborhood.f90:75-92)
+def _dir_of_slot(s):
+    d = [0, 0, 0]
+    if s in (1, 2, 3, 4, 25, 26, 29, 30, 33, 34, 37, 38, 49, 51, 53, 55): d[0] = -1
+    if s in (5, 6, 7, 8, 27, 28, 31, 32, 35, 36, 39, 40, 50, 52, 54, 56): d[0] = +1
+    if s in (9, 10, 11, 12, 25, 26, 27, 28, 41, 42, 45, 46, 49, 50, 53, 54): d[1] = -1
+    if s in (13, 14, 15, 16, 29, 30, 31, 32, 43, 44, 47, 48, 51, 52, 55, 56): d[1] = +1
+    if s in (17, 18, 19, 20, 33, 34, 35, 36, 41, 42, 43, 44, 49, 50, 51, 52): d[2] = -1
+    if s in (21, 22, 23, 24, 37, 38, 39, 40, 45, 46, 47, 48, 53, 54, 55, 56): d[2] = +1
+    return d
+
+
+@pytest.mark.parametrize("dim,J,sfc", [(3, 2, "sfc_hilbert"), (3, 3, "sfc_z"), (2, 3, "sfc_hilbert")])
+def test_uniform_forest_neighbors(dim, J, sfc):
+    f = Forest.uniform(dim, J, block_dist=sfc)
+    assert f.is_uniform and f.n_blocks == (2 ** J) ** dim
+    hvy, lvl, ixyz, tc = f.active(0)
+    nb = f.neighbors(0)
+    pos = {tuple(ixyz[k]): int(hvy[k]) for k in range(len(hvy))}
+    n = 2 ** J
+    n_rel = 26 if dim == 3 else 8
+    for k in range(len(hvy)):
+        found = 0
+        for s in range(1, 57):
+            lgt = nb[s - 1, hvy[k] - 1]
+            if lgt < 0:
+                continue
+            d = _dir_of_slot(s)
+            q = tuple(int((ixyz[k, a] + d[a]) % n) if a < dim else 0 for a in range(3))
+            assert pos[q] == lgt, (k, s)
+            found += 1
+        assert found == n_rel
+        assert (nb[56:, hvy[k] - 1] == -1).all()
+    # treecode: digit bit0 -> y, bit1 -> x, bit2 -> z, coarsest digit highest (module_treelib.f90:793-871)
+    lib = _native.host_lib()
+    for k in (0, len(hvy) // 2, len(hvy) - 1):
+        out = (C.c_int32 * 3)()
+        lib.whost_decode(dim, J, J, int(tc[k]), out)
+        assert list(out)[:dim] == list(ixyz[k])[:dim]
+    one = (C.c_int32 * 3)(0, 1, 0)
+    assert lib.whost_encode(3, 1, 1, one) == 1
+    one = (C.c_int32 * 3)(1, 0, 0)
+    assert lib.whost_encode(3, 1, 1, one) == 2
+    one = (C.c_int32 * 3)(0, 0, 1)
+    assert lib.whost_encode(3, 1, 1, one) == 4
+
+
+def test_sfc_is_a_curve():
+    """consecutive blocks along the Hilbert curve are face neighbours; every rank gets a contiguous chunk"""
+    f = Forest.uniform(3, 3, block_dist="sfc_hilbert", n_ranks=4)
+    tot = 0
+    for r in range(4):
+        hvy, lvl, ixyz, tc = f.active(r)
+        tot += len(hvy)
+        assert len(hvy) == 128 and (hvy == np.arange(1, 129)).all()
+        step = np.abs(np.diff(ixyz, axis=0)).sum(axis=1)
+        assert (step == 1).all()
+    assert tot == 512
+
+
+def test_two_level_forest_slots():
+    """2-level grid: one level-1 block refined.  Checks the +56 / +112 slot groups are mutually consistent."""
+    lv, ix = [], []
+    for z in range(2):
+        for y in range(2):
+            for x in range(2):
+                if (x, y, z) == (0, 0, 0):
+                    for c in range(8):
+                        lv.append(2); ix.append((c & 1, (c >> 1) & 1, (c >> 2) & 1))
+                else:
+                    lv.append(1); ix.append((x, y, z))
+    f = Forest.from_blocks(3, 2, lv, ix)
+    assert not f.is_uniform and f.n_blocks == 15
+    hvy, lvl, ixyz, tc = f.active(0)
+    nb = f.neighbors(0)
+    by_id = {int(hvy[k]): (int(lvl[k]), tuple(ixyz[k])) for k in range(len(hvy))}
+    for k in range(len(hvy)):
+        for s in range(1, 169):
+            lgt = nb[s - 1, hvy[k] - 1]
+            if lgt < 0:
+                continue
+            l2, _ = by_id[int(lgt)]
+            grp = (s - 1) // 56
+            assert l2 - lvl[k] == (0, -1, +1)[grp]
+    # the coarse block at (1,0,0) sees 4 finer neighbours across its -x face (slots 113..116) and, periodic, across +x
+    kc = [k for k in range(len(hvy)) if lvl[k] == 1 and tuple(ixyz[k]) == (1, 0, 0)][0]
+    assert (nb[112:116, hvy[kc] - 1] > 0).all() and (nb[116:120, hvy[kc] - 1] > 0).all()
+    assert nb[0, hvy[kc] - 1] == -1

@@ -1,0 +1,519 @@
+// C ABI of libwabbit_gpu.so (include/wabbit_gpu.h): context, resident arrays, topology upload,
+// host<->device block movement and the Runge-Kutta driver that sequences the stage kernels.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "wgpu_internal.cuh"
+
+static std::string g_create_err;
+
+namespace {
+
+int32_t fail(wgpu_ctx *ctx, int32_t code, const std::string &msg)
+{
+    if (ctx) ctx->err = msg;
+    else g_create_err = msg;
+    return code;
+}
+
+template <typename T>
+int32_t dmalloc(wgpu_ctx *ctx, T **p, size_t n)
+{
+    *p = nullptr;
+    if (n == 0) return WGPU_OK;
+    WGPU_CHECK(ctx, cudaMalloc((void **)p, n * sizeof(T)));
+    ctx->dev_bytes += (int64_t)(n * sizeof(T));
+    return WGPU_OK;
+}
+
+// same-level neighbour code of a direction, as assigned by find_neighbor (LIB/MESH/find_neighbors.f90:60-95)
+int same_level_code(const int d[3])
+{
+    const int nzero = (d[0] == 0) + (d[1] == 0) + (d[2] == 0);
+    if (nzero == 2) {
+        int code = 1;
+        for (int i = 0; i < 3; ++i) {
+            if (d[i] != 0) code += 8 * i;
+            if (d[i] == 1) code += 4;
+        }
+        return code;
+    }
+    if (nzero == 1) {
+        int code = 25, apply_free = 1;
+        for (int i = 0; i < 3; ++i) {
+            if (d[i] == 0) code += 8 * (3 - (i + 1));
+            else {
+                if (d[i] == 1) code += apply_free * 2;
+                apply_free++;
+            }
+        }
+        return code;
+    }
+    int code = 49;
+    for (int i = 0; i < 3; ++i)
+        if (d[i] == 1) code += 1 << i;
+    return code;
+}
+
+double *array_ptr(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int *ncomp)
+{
+    const int s = ctx->cfg.n_stages;
+    switch (array_id) {
+    case WGPU_HVY_BLOCK: *ncomp = ctx->nc; return ctx->U;
+    case WGPU_HVY_WORK:
+        *ncomp = ctx->nc;
+        if (slot == 1) return ctx->U;   // hvy_work(...,1) is the copy of the state (runge_kutta_generic.f90:63-67)
+        if (slot >= 2 && slot <= s + 1) return ctx->K[slot - 2];
+        return nullptr;
+    case WGPU_HVY_MASK: *ncomp = ctx->cfg.n_mask; return ctx->MASK;
+    case WGPU_HVY_TMP: *ncomp = ctx->nc; return ctx->TMP;
+    }
+    return nullptr;
+}
+
+void fill_common_args(wgpu_ctx *ctx, StageArgs &a)
+{
+    const wgpu_config &c = ctx->cfg;
+    memset(&a, 0, sizeof(a));
+    a.active = ctx->d_active;
+    a.nbr = ctx->d_nbr;
+    a.level = ctx->d_level;
+    a.pool = ctx->d_pool;
+    a.pool_off = ctx->d_pool_off;
+    for (int l = 0; l < WGPU_MAX_LEVELS; ++l)
+        for (int d = 0; d < 3; ++d) a.dx_lvl[l][d] = ldexp(1.0, -l) * c.domain[d] / (double)c.Bs[d];  // module_treelib.f90:93
+    a.c0 = c.c0;
+    a.nu = c.nu;
+    a.gamma_p = c.gamma_p;
+    a.C_eta_inv = 1.0 / c.C_eta;
+    a.C_sponge_inv = 1.0 / c.C_sponge;
+    for (int d = 0; d < 3; ++d) a.u_mean_set[d] = c.u_mean_set[d];
+    a.use_sponge = c.use_sponge;
+    a.CFL = c.CFL;
+    a.diverged = ctx->d_flags;
+    a.dim_min_axes = c.dim;
+    a.dt_ptr = ctx->d_dt;
+    if (c.n_mask >= 5 && (c.penalization || c.use_sponge)) {
+        a.mask = ctx->MASK;
+        a.n_mask = c.n_mask;
+    }
+}
+
+int32_t ensure_stage(wgpu_ctx *ctx, int64_t elems)
+{
+    if (ctx->stage_elems >= elems) return WGPU_OK;
+    if (ctx->d_stage) {
+        cudaFree(ctx->d_stage);
+        ctx->dev_bytes -= ctx->stage_elems * 8;
+    }
+    ctx->stage_elems = 0;
+    int32_t rc = dmalloc(ctx, &ctx->d_stage, (size_t)elems);
+    if (rc) return rc;
+    ctx->stage_elems = elems;
+    return WGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t wgpu_create(const wgpu_config *cfg, wgpu_ctx **out)
+{
+    if (!cfg || !out) return fail(nullptr, WGPU_ERR_ARG, "wgpu_create: null argument");
+    *out = nullptr;
+    if (cfg->dim != 2 && cfg->dim != 3) return fail(nullptr, WGPU_ERR_ARG, "dim must be 2 or 3");
+    for (int d = 0; d < cfg->dim; ++d)
+        if (cfg->Bs[d] < 2 || (cfg->Bs[d] & 1))   // read_Bs aborts on odd sizes, module_ini_files_parser_mpi.f90:816
+            return fail(nullptr, WGPU_ERR_ARG, "number_block_nodes must be even");
+    if (cfg->n_stages < 1 || cfg->n_stages > WGPU_MAX_STAGES) return fail(nullptr, WGPU_ERR_ARG, "n_stages out of range");
+    if (cfg->max_blocks < 1) return fail(nullptr, WGPU_ERR_ARG, "max_blocks must be positive");
+    if (cfg->Jmax < 0 || cfg->Jmax >= WGPU_MAX_LEVELS) return fail(nullptr, WGPU_ERR_ARG, "Jmax out of range");
+    if (cfg->n_eqn != cfg->dim + 1) return fail(nullptr, WGPU_ERR_UNSUPPORTED, "ACM needs number_equations = dim+1");
+    if (cfg->n_mask != 0 && cfg->n_mask != 5 && cfg->n_mask != 6) return fail(nullptr, WGPU_ERR_ARG, "n_mask must be 0, 5 or 6");
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, WGPU_ERR_NO_DEVICE, "no CUDA device: the WABBIT GPU hot path has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, WGPU_ERR_ARG, "device ordinal out of range");
+
+    wgpu_ctx *ctx = new (std::nothrow) wgpu_ctx();
+    if (!ctx) return fail(nullptr, WGPU_ERR_ARG, "out of host memory");
+    ctx->cfg = *cfg;
+    if (cudaSetDevice(cfg->device) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, WGPU_ERR_CUDA, "cudaSetDevice failed");
+    }
+    ctx->nc = cfg->n_eqn;
+    const int Bz = cfg->dim == 3 ? cfg->Bs[2] : 1;
+    ctx->blk_elems = (int64_t)cfg->Bs[0] * cfg->Bs[1] * Bz;
+    ctx->gblk_elems = (int64_t)(cfg->Bs[0] + 2 * cfg->g) * (cfg->Bs[1] + 2 * cfg->g) * (cfg->dim == 3 ? cfg->Bs[2] + 2 * cfg->g : 1);
+    const size_t n = (size_t)cfg->max_blocks * ctx->nc * ctx->blk_elems;
+
+    int32_t rc = WGPU_OK;
+    auto A = [&](double **p, size_t cnt) {
+        if (rc == WGPU_OK) rc = dmalloc(ctx, p, cnt);
+        if (rc == WGPU_OK && *p) {
+            if (cudaMemset(*p, 0, cnt * sizeof(double)) != cudaSuccess) rc = WGPU_ERR_CUDA;
+        }
+    };
+    A(&ctx->U, n);
+    A(&ctx->UA, n);
+    A(&ctx->UB, n);
+    for (int s = 0; s < cfg->n_stages; ++s) A(&ctx->K[s], n);
+    if (cfg->n_mask > 0) A(&ctx->MASK, (size_t)cfg->max_blocks * cfg->n_mask * ctx->blk_elems);
+    if (rc == WGPU_OK) rc = dmalloc(ctx, &ctx->d_active, (size_t)cfg->max_blocks);
+    if (rc == WGPU_OK) rc = dmalloc(ctx, &ctx->d_nbr, (size_t)cfg->max_blocks * WGPU_NDIR);
+    if (rc == WGPU_OK) rc = dmalloc(ctx, &ctx->d_level, (size_t)cfg->max_blocks);
+    if (rc == WGPU_OK) rc = dmalloc(ctx, &ctx->d_dt, 1);
+    if (rc == WGPU_OK) rc = dmalloc(ctx, &ctx->d_dtmin, 2);
+    if (rc == WGPU_OK) rc = dmalloc(ctx, &ctx->d_flags, 4);
+    if (rc == WGPU_OK && cudaMemset(ctx->d_flags, 0, 4 * sizeof(int)) != cudaSuccess) rc = WGPU_ERR_CUDA;
+    if (rc == WGPU_OK && cudaMallocHost((void **)&ctx->h_pinned, 8 * sizeof(double)) != cudaSuccess) rc = WGPU_ERR_CUDA;
+    if (rc != WGPU_OK) {
+        g_create_err = ctx->err.empty() ? std::string("device allocation failed") : ctx->err;
+        wgpu_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return WGPU_OK;
+}
+
+int32_t wgpu_destroy(wgpu_ctx *ctx)
+{
+    if (!ctx) return WGPU_OK;
+    cudaSetDevice(ctx->cfg.device);
+    cudaDeviceSynchronize();
+    cudaFree(ctx->U);
+    cudaFree(ctx->UA);
+    cudaFree(ctx->UB);
+    for (int s = 0; s < WGPU_MAX_STAGES; ++s) cudaFree(ctx->K[s]);
+    cudaFree(ctx->MASK);
+    cudaFree(ctx->TMP);
+    cudaFree(ctx->d_active);
+    cudaFree(ctx->d_nbr);
+    cudaFree(ctx->d_level);
+    cudaFree(ctx->d_pool);
+    cudaFree(ctx->d_pool_off);
+    cudaFree(ctx->d_dt);
+    cudaFree(ctx->d_dtmin);
+    cudaFree(ctx->d_flags);
+    cudaFree(ctx->d_stage);
+    for (auto &e : ctx->prof_ev) cudaEventDestroy(e);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->h_bounce) cudaFreeHost(ctx->h_bounce);
+    delete ctx;
+    return WGPU_OK;
+}
+
+int32_t wgpu_last_error(const wgpu_ctx *ctx, char *buf, int32_t len)
+{
+    if (!buf || len <= 0) return WGPU_ERR_ARG;
+    const std::string &s = ctx ? ctx->err : g_create_err;
+    snprintf(buf, (size_t)len, "%s", s.c_str());
+    return WGPU_OK;
+}
+
+int32_t wgpu_set_stream(wgpu_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return WGPU_ERR_ARG;
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return WGPU_OK;
+}
+
+int32_t wgpu_synchronize(wgpu_ctx *ctx)
+{
+    if (!ctx) return WGPU_ERR_ARG;
+    WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return WGPU_OK;
+}
+
+int32_t wgpu_profile(wgpu_ctx *ctx, int32_t enable)
+{
+    if (!ctx) return WGPU_ERR_ARG;
+    if (enable && ctx->prof_ev.empty()) {
+        ctx->prof_ev.resize(2 * 4096);
+        for (auto &e : ctx->prof_ev) WGPU_CHECK(ctx, cudaEventCreate(&e));
+    }
+    ctx->profiling = enable != 0;
+    ctx->prof_n = 0;
+    return WGPU_OK;
+}
+
+int32_t wgpu_profile_read(wgpu_ctx *ctx, int32_t *n_launches, double *total_ms)
+{
+    if (!ctx || !n_launches || !total_ms) return WGPU_ERR_ARG;
+    WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    double tot = 0.0;
+    for (int i = 0; i < ctx->prof_n; ++i) {
+        float ms = 0.f;
+        WGPU_CHECK(ctx, cudaEventElapsedTime(&ms, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
+        tot += ms;
+    }
+    *n_launches = ctx->prof_n;
+    *total_ms = tot;
+    ctx->prof_n = 0;
+    return WGPU_OK;
+}
+
+int64_t wgpu_launch_count(const wgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int64_t wgpu_device_bytes(const wgpu_ctx *ctx) { return ctx ? ctx->dev_bytes : 0; }
+
+int32_t wgpu_device_pointer(wgpu_ctx *ctx, int32_t array_id, int32_t slot, void **ptr, int64_t *n_doubles)
+{
+    if (!ctx || !ptr) return WGPU_ERR_ARG;
+    int nc = 0;
+    double *p = array_ptr(ctx, array_id, slot, &nc);
+    if (!p) return fail(ctx, WGPU_ERR_ARG, "wgpu_device_pointer: no such array/slot");
+    *ptr = p;
+    if (n_doubles) *n_doubles = (int64_t)ctx->cfg.max_blocks * nc * ctx->blk_elems;
+    return WGPU_OK;
+}
+
+int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_active, const int32_t *level, const int32_t *hvy_neighbor,
+                          int32_t ld, int32_t rank)
+{
+    if (!ctx || n_active < 0 || (n_active > 0 && (!hvy_active || !level || !hvy_neighbor))) return WGPU_ERR_ARG;
+    const wgpu_config &c = ctx->cfg;
+    const int N = c.max_blocks;
+    if (n_active > N) return fail(ctx, WGPU_ERR_ARG, "more active blocks than max_blocks");
+    ctx->h_active.assign(n_active, 0);
+    ctx->h_nbr.assign((size_t)N * WGPU_NDIR, -1);
+    ctx->h_level.assign(N, 0);
+    for (int k = 0; k < n_active; ++k) {
+        const int hid = hvy_active[k];
+        if (hid < 1 || hid > N) return fail(ctx, WGPU_ERR_ARG, "hvy_active entry out of range");
+        if (level[k] < 0 || level[k] > c.Jmax) return fail(ctx, WGPU_ERR_ARG, "block level out of range");
+        ctx->h_active[k] = hid - 1;
+        ctx->h_level[hid - 1] = (signed char)level[k];
+        for (int dz = -1; dz <= 1; ++dz)
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    if (!dx && !dy && !dz) continue;
+                    if (c.dim == 2 && dz != 0) continue;
+                    const int d[3] = {dx, dy, dz};
+                    const int code = same_level_code(d);   // 1..56
+                    const int nfree = 1 << ((dx == 0) + (dy == 0) + (dz == 0) - (c.dim == 2 ? 1 : 0));
+                    const int lgt = hvy_neighbor[(size_t)(code - 1) * ld + (hid - 1)];
+                    int entry = -1;
+                    if (lgt >= 1) {
+                        const int r = (lgt - 1) / N;           // lgt2proc.f90
+                        if (r != rank) return fail(ctx, WGPU_ERR_UNSUPPORTED, "neighbour on another rank: multi-GPU ghost exchange goes through the patch pool (not built yet)");
+                        entry = (lgt - 1) - r * N;
+                    } else {
+                        // coarser (+56) or finer (+112) neighbours in this direction?
+                        for (int s = 0; s < nfree; ++s) {
+                            if (hvy_neighbor[(size_t)(code - 1 + s + 56) * ld + (hid - 1)] >= 1 ||
+                                hvy_neighbor[(size_t)(code - 1 + s + 112) * ld + (hid - 1)] >= 1)
+                                return fail(ctx, WGPU_ERR_UNSUPPORTED, "level-jump neighbour relations are not built yet");
+                        }
+                    }
+                    ctx->h_nbr[(size_t)(hid - 1) * WGPU_NDIR + (dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)] = entry;
+                }
+    }
+    ctx->n_active = n_active;
+    if (n_active) {
+        WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_active, ctx->h_active.data(), sizeof(int) * n_active, cudaMemcpyHostToDevice, ctx->stream));
+        WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_nbr, ctx->h_nbr.data(), sizeof(int) * ctx->h_nbr.size(), cudaMemcpyHostToDevice, ctx->stream));
+        WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_level, ctx->h_level.data(), (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+        WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->dtmin_valid = false;
+    return WGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ data movement
+static int32_t move_blocks(wgpu_ctx *ctx, bool up, int32_t array_id, int32_t slot, const int32_t *hvy_ids, int32_t n, double *host,
+                           int32_t ncomp_host, int32_t g_sync)
+{
+    if (!ctx || n < 0 || (n > 0 && (!hvy_ids || !host))) return WGPU_ERR_ARG;
+    int nc = 0;
+    double *dev = array_ptr(ctx, array_id, slot, &nc);
+    if (!dev) return fail(ctx, WGPU_ERR_ARG, "no such array/slot on the device");
+    if (ncomp_host < 1) return fail(ctx, WGPU_ERR_ARG, "ncomp_host must be >= 1");
+    const wgpu_config &c = ctx->cfg;
+    if (g_sync < 0 || g_sync > c.g) return fail(ctx, WGPU_ERR_ARG, "g_sync must be in 0..g");
+    for (int d = 0; d < c.dim; ++d)
+        if (g_sync > c.Bs[d]) return fail(ctx, WGPU_ERR_ARG, "g_sync larger than the block");
+    const int64_t per_block = ctx->gblk_elems * ncomp_host;
+    const int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)(256ll << 20) / (per_block * 8)));
+    int32_t rc = ensure_stage(ctx, per_block * chunk + (chunk + 1) / 2 + 8);
+    if (rc) return rc;
+    int *d_ids = (int *)(ctx->d_stage + per_block * chunk);
+    std::vector<int> ids(chunk);
+    for (int s0 = 0; s0 < n; s0 += chunk) {
+        const int m = std::min(chunk, n - s0);
+        for (int i = 0; i < m; ++i) {
+            const int hid = hvy_ids[s0 + i];
+            if (hid < 1 || hid > c.max_blocks) return fail(ctx, WGPU_ERR_ARG, "hvy id out of range");
+            ids[i] = hid - 1;
+        }
+        WGPU_CHECK(ctx, cudaMemcpyAsync(d_ids, ids.data(), sizeof(int) * m, cudaMemcpyHostToDevice, ctx->stream));
+        // consecutive hvy ids are contiguous in the host array: move them as one transfer
+        auto xfer = [&](bool h2d) -> int32_t {
+            int i = 0;
+            while (i < m) {
+                int j = i + 1;
+                while (j < m && ids[j] == ids[j - 1] + 1) ++j;
+                double *h = host + (int64_t)ids[i] * per_block;
+                double *d = ctx->d_stage + (int64_t)i * per_block;
+                const size_t bytes = (size_t)(j - i) * per_block * 8;
+                if (h2d) WGPU_CHECK(ctx, cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+                else WGPU_CHECK(ctx, cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+                i = j;
+            }
+            return WGPU_OK;
+        };
+        if (up) {
+            if ((rc = xfer(true))) return rc;
+            if ((rc = wgpu_launch_extract(ctx, ctx->d_stage, dev, d_ids, m, nc, ncomp_host))) return rc;
+        } else {
+            // ghost layers beyond g_sync (and patches without a same-level source) keep the host's values
+            if (g_sync < c.g || ncomp_host > nc)
+                if ((rc = xfer(true))) return rc;
+            if ((rc = wgpu_launch_export(ctx, dev, ctx->d_stage, d_ids, m, nc, ncomp_host, g_sync))) return rc;
+            if ((rc = xfer(false))) return rc;
+        }
+        // the staging buffer and `ids` are reused by the next chunk
+        WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (up && array_id == WGPU_HVY_BLOCK) ctx->dtmin_valid = false;
+    return WGPU_OK;
+}
+
+int32_t wgpu_upload(wgpu_ctx *ctx, int32_t array_id, int32_t slot, const int32_t *hvy_ids, int32_t n, const double *host, int32_t ncomp_host)
+{
+    return move_blocks(ctx, true, array_id, slot, hvy_ids, n, const_cast<double *>(host), ncomp_host, 0);
+}
+
+int32_t wgpu_download(wgpu_ctx *ctx, int32_t array_id, int32_t slot, const int32_t *hvy_ids, int32_t n, double *host, int32_t ncomp_host,
+                      int32_t g_sync)
+{
+    return move_blocks(ctx, false, array_id, slot, hvy_ids, n, host, ncomp_host, g_sync);
+}
+
+// ------------------------------------------------------------------------------------------------ compute
+int32_t wgpu_sync_ghosts(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t g_minus, int32_t g_plus)
+{
+    if (!ctx) return WGPU_ERR_ARG;
+    int nc = 0;
+    if (!array_ptr(ctx, array_id, slot, &nc)) return fail(ctx, WGPU_ERR_ARG, "no such array/slot on the device");
+    if (g_minus < 0 || g_plus < 0 || g_minus > ctx->cfg.g || g_plus > ctx->cfg.g) return fail(ctx, WGPU_ERR_ARG, "ghost width out of range");
+    // Same-level relations are gathered on the fly by the consumers; there is no level-jump / remote patch in
+    // the topologies accepted by wgpu_set_topology yet, hence nothing to refresh.
+    return WGPU_OK;
+}
+
+static int32_t check_flags(wgpu_ctx *ctx)
+{
+    int flags[4];
+    WGPU_CHECK(ctx, cudaMemcpyAsync(flags, ctx->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
+    WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (flags[0]) {
+        cudaMemsetAsync(ctx->d_flags, 0, sizeof(flags), ctx->stream);
+        return fail(ctx, WGPU_ERR_DIVERGED, "ACM fail: very very large values in state vector.");
+    }
+    return WGPU_OK;
+}
+
+int32_t wgpu_rhs(wgpu_ctx *ctx, double time, int32_t src_slot, int32_t dst_slot)
+{
+    (void)time;
+    if (!ctx) return WGPU_ERR_ARG;
+    if (ctx->cfg.dim != 3) return fail(ctx, WGPU_ERR_UNSUPPORTED, "2-D ACM kernels are not built yet");
+    int nc = 0;
+    const double *src = src_slot == 0 ? ctx->U : array_ptr(ctx, WGPU_HVY_WORK, src_slot, &nc);
+    double *dst = array_ptr(ctx, WGPU_HVY_WORK, dst_slot, &nc);
+    if (!src || !dst || dst_slot < 2) return fail(ctx, WGPU_ERR_ARG, "wgpu_rhs: bad slot");
+    StageArgs a;
+    fill_common_args(ctx, a);
+    a.u_in = src;
+    a.u0 = src;
+    a.k_out = dst;
+    int32_t rc = wgpu_launch_stage(ctx, a);
+    if (rc) return rc;
+    return check_flags(ctx);
+}
+
+static int32_t compute_dt(wgpu_ctx *ctx, double time)
+{
+    int32_t rc;
+    unsigned long long *cur = ctx->d_dtmin + ctx->dtmin_cur, *nxt = ctx->d_dtmin + (ctx->dtmin_cur ^ 1);
+    if (!ctx->dtmin_valid && !(ctx->cfg.dt_fixed > 0.0)) {
+        const unsigned long long inf = 0x7FF0000000000000ULL;
+        WGPU_CHECK(ctx, cudaMemcpyAsync(cur, &inf, 8, cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = wgpu_launch_dtmin(ctx, ctx->U, cur))) return rc;
+    }
+    if ((rc = wgpu_launch_dt_finalize(ctx, time, cur, nxt))) return rc;
+    ctx->dtmin_cur ^= 1;
+    ctx->dtmin_valid = false;
+    return WGPU_OK;
+}
+
+int32_t wgpu_calculate_time_step(wgpu_ctx *ctx, double time, double *dt)
+{
+    if (!ctx || !dt) return WGPU_ERR_ARG;
+    int32_t rc = compute_dt(ctx, time);
+    if (rc) return rc;
+    WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_dt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    *dt = ctx->h_pinned[0];
+    return WGPU_OK;
+}
+
+int32_t wgpu_rk_step(wgpu_ctx *ctx, double time, int32_t iteration, double *dt)
+{
+    (void)iteration;
+    if (!ctx || !dt) return WGPU_ERR_ARG;
+    const wgpu_config &c = ctx->cfg;
+    if (c.dim != 3) return fail(ctx, WGPU_ERR_UNSUPPORTED, "2-D ACM kernels are not built yet");
+    const int s = c.n_stages, ld = s + 1;
+    int32_t rc;
+    // runge_kutta_generic.f90:52-56: ghost sync (fused into the stage kernels) and the time step
+    if ((rc = compute_dt(ctx, time))) return rc;
+    unsigned long long *dtmin_next = ctx->d_dtmin + ctx->dtmin_cur;   // reset to +inf by dt_finalize
+
+    const double *uin = ctx->U;
+    for (int j = 1; j <= s; ++j) {
+        StageArgs a;
+        fill_common_args(ctx, a);
+        a.u_in = uin;
+        a.u0 = ctx->U;
+        const bool last = (j == s);
+        a.k_out = last ? nullptr : ctx->K[j - 1];      // the last slope only enters the final combination
+        // the final state may overwrite U in place (each thread reads u0 only at its own point, halos come from
+        // the stage input) unless the stage input IS U (single-stage schemes): then go through UA and swap
+        double *uout = last ? (uin == ctx->U ? ctx->UA : ctx->U) : ((j & 1) ? ctx->UA : ctx->UB);
+        a.u_out = uout;
+        // row of the tableau that forms u_out: stage j+1 input (row j+1) or the final weights (row s+1)
+        const double *row = c.butcher + (size_t)(last ? s : j) * ld;
+        a.n_prev = 0;
+        for (int l = 1; l < j; ++l) {
+            if (fabs(row[l]) < 1.0e-8) continue;        // runge_kutta_generic.f90:99,144
+            a.k_prev[a.n_prev] = ctx->K[l - 1];
+            a.coef_prev[a.n_prev] = row[l];
+            a.n_prev++;
+        }
+        a.use_self = fabs(row[j]) >= 1.0e-8;
+        a.coef_self = row[j];
+        if (last && !(c.dt_fixed > 0.0)) a.dtmin_bits = dtmin_next;
+        if ((rc = wgpu_launch_stage(ctx, a))) return rc;
+        if (last && uout != ctx->U) std::swap(ctx->U, ctx->UA);
+        uin = uout;
+    }
+    if (!(c.dt_fixed > 0.0)) ctx->dtmin_valid = true;
+    WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_dt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pinned + 1, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    *dt = ctx->h_pinned[0];
+    if (*(int *)(ctx->h_pinned + 1)) {
+        cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), ctx->stream);
+        return fail(ctx, WGPU_ERR_DIVERGED, "ACM fail: very very large values in state vector.");
+    }
+    return WGPU_OK;
+}
+
+}  // extern "C"

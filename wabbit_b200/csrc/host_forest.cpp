@@ -1,0 +1,313 @@
+// libwabbit_host.so -- host-side forest metadata (see include/wabbit_host.h).
+// Plain C++17; produces hvy_active / level / hvy_neighbor(168) tables with WABBIT's conventions.
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <array>
+#include <numeric>
+#include <unordered_map>
+#include <vector>
+
+#include "wabbit_host.h"
+
+namespace {
+
+struct Blk {
+    int level;
+    int ix[3];
+    int64_t tc;
+    uint64_t key;
+    int rank, hvy;   // owner and 1-based hvy id
+};
+
+inline uint64_t pos_hash(int level, const int ix[3])
+{
+    return ((uint64_t)level << 58) ^ ((uint64_t)(uint32_t)ix[2] << 38) ^ ((uint64_t)(uint32_t)ix[1] << 19) ^ (uint64_t)(uint32_t)ix[0];
+}
+
+// Skilling's transposed-axes Hilbert index for `dim` coordinates of `bits` bits each
+uint64_t hilbert_index(int dim, int bits, const int x_in[3])
+{
+    if (bits == 0) return 0;
+    uint32_t X[3] = {(uint32_t)x_in[0], (uint32_t)x_in[1], dim == 3 ? (uint32_t)x_in[2] : 0u};
+    const uint32_t M = 1u << (bits - 1);
+    for (uint32_t Q = M; Q > 1; Q >>= 1) {   // inverse undo
+        const uint32_t P = Q - 1;
+        for (int i = 0; i < dim; ++i) {
+            if (X[i] & Q) X[0] ^= P;
+            else {
+                const uint32_t t = (X[0] ^ X[i]) & P;
+                X[0] ^= t;
+                X[i] ^= t;
+            }
+        }
+    }
+    for (int i = 1; i < dim; ++i) X[i] ^= X[i - 1];   // Gray encode
+    uint32_t t = 0;
+    for (uint32_t Q = M; Q > 1; Q >>= 1)
+        if (X[dim - 1] & Q) t ^= Q - 1;
+    for (int i = 0; i < dim; ++i) X[i] ^= t;
+    uint64_t h = 0;
+    for (int b = bits - 1; b >= 0; --b)
+        for (int i = 0; i < dim; ++i) h = (h << 1) | ((X[i] >> b) & 1u);
+    return h;
+}
+
+}  // namespace
+
+struct whost_forest {
+    int dim, Jmax, sfc, n_ranks, N;
+    int periodic[3];
+    std::vector<Blk> blocks;                       // SFC order
+    std::vector<std::vector<int>> rank_blocks;     // indices into blocks per rank
+    std::unordered_map<uint64_t, int> lookup;
+    std::vector<std::vector<int32_t>> nbr;         // per rank: N*168
+    bool uniform = true;
+
+    int find(int level, const int ix[3]) const
+    {
+        auto it = lookup.find(pos_hash(level, ix));
+        return it == lookup.end() ? -1 : it->second;
+    }
+};
+
+extern "C" {
+
+int64_t whost_encode(int32_t dim, int32_t level, int32_t Jmax, const int32_t ixyz[3])
+{
+    // digit bit0 <- y, bit1 <- x, bit2 <- z ; level bit i of the coordinate goes to digit (i + Jmax - level)
+    int64_t tc = 0;
+    const int p[3] = {ixyz[1], ixyz[0], dim == 3 ? ixyz[2] : 0};
+    for (int d = 0; d < dim; ++d)
+        for (int i = 0; i < level; ++i) tc |= (int64_t)((p[d] >> i) & 1) << ((i + Jmax - level) * dim + d);
+    return tc;
+}
+
+int32_t whost_decode(int32_t dim, int32_t level, int32_t Jmax, int64_t tc, int32_t ixyz[3])
+{
+    int p[3] = {0, 0, 0};
+    for (int d = 0; d < dim; ++d)
+        for (int i = 0; i < level; ++i) p[d] |= (int)((tc >> ((i + Jmax - level) * dim + d)) & 1) << i;
+    ixyz[0] = p[1];
+    ixyz[1] = p[0];
+    ixyz[2] = p[2];
+    return 0;
+}
+
+uint64_t whost_sfc_key(int32_t dim, int32_t sfc, int32_t level, int32_t Jmax, const int32_t ixyz[3])
+{
+    int fine[3];
+    for (int d = 0; d < 3; ++d) fine[d] = d < dim ? ixyz[d] << (Jmax - level) : 0;
+    if (sfc == WHOST_SFC_HILBERT) return hilbert_index(dim, Jmax, fine);
+    return (uint64_t)whost_encode(dim, Jmax, Jmax, fine);   // the treecode is the Z-curve index
+}
+
+static void build(whost_forest *f)
+{
+    const int dim = f->dim;
+    for (auto &b : f->blocks) {
+        b.tc = whost_encode(dim, b.level, f->Jmax, b.ix);
+        b.key = whost_sfc_key(dim, f->sfc, b.level, f->Jmax, b.ix);
+    }
+    std::sort(f->blocks.begin(), f->blocks.end(), [](const Blk &a, const Blk &b) { return a.key < b.key; });
+    const int nb = (int)f->blocks.size();
+    // contiguous chunks: the first (nb mod P) ranks hold one block more (balanceLoad_tree.f90:600-640)
+    f->rank_blocks.assign(f->n_ranks, {});
+    int pos = 0;
+    for (int r = 0; r < f->n_ranks; ++r) {
+        const int cnt = nb / f->n_ranks + (r < nb % f->n_ranks ? 1 : 0);
+        for (int k = 0; k < cnt; ++k, ++pos) {
+            f->blocks[pos].rank = r;
+            f->blocks[pos].hvy = k + 1;
+            f->rank_blocks[r].push_back(pos);
+        }
+    }
+    f->lookup.clear();
+    for (int i = 0; i < nb; ++i) f->lookup[pos_hash(f->blocks[i].level, f->blocks[i].ix)] = i;
+
+    // neighbour search, one direction at a time (find_neighbor, LIB/MESH/find_neighbors.f90:18-180)
+    f->nbr.assign(f->n_ranks, std::vector<int32_t>((size_t)f->N * 168, -1));
+    f->uniform = true;
+    const int vary_tc[3] = {2, 1, 4};   // digit bit of x, y, z
+    for (int i = 0; i < nb; ++i) {
+        const Blk &b = f->blocks[i];
+        int32_t *row = f->nbr[b.rank].data();
+        auto set = [&](int code, int j) { row[(size_t)(code - 1) * f->N + (b.hvy - 1)] = f->blocks[j].rank * f->N + f->blocks[j].hvy; };
+        const int tc_last = b.level > 0 ? (int)((b.tc >> ((f->Jmax - b.level) * dim)) & ((1 << dim) - 1)) : 0;
+        for (int dz = (dim == 3 ? -1 : 0); dz <= (dim == 3 ? 1 : 0); ++dz)
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    if (!dx && !dy && !dz) continue;
+                    const int d[3] = {dx, dy, dz};
+                    const int nzero = (dx == 0) + (dy == 0) + (dz == 0);
+                    int n_free = 1 << nzero;
+                    if (dim == 2) n_free /= 2;
+                    // digits of the (virtual) children touching this side
+                    int append[4] = {0, 0, 0, 0};
+                    int apply_free = 1;
+                    for (int a = 0; a < dim; ++a) {
+                        if (d[a] == 0) {
+                            for (int k = 0; k < 4; ++k) append[k] += vary_tc[a] * ((k / apply_free) % 2);
+                            apply_free += 1;
+                        } else if (d[a] == 1) {
+                            for (int k = 0; k < 4; ++k) append[k] += vary_tc[a];
+                        }
+                    }
+                    // same-level slot code
+                    int code;
+                    if (nzero == 2) {
+                        code = 1;
+                        for (int a = 0; a < 3; ++a) {
+                            if (d[a] != 0) code += 8 * a;
+                            if (d[a] == 1) code += 4;
+                        }
+                    } else if (nzero == 1) {
+                        code = 25;
+                        int af = 1;
+                        for (int a = 0; a < 3; ++a) {
+                            if (d[a] == 0) code += 8 * (2 - a);
+                            else {
+                                if (d[a] == 1) code += af * 2;
+                                af++;
+                            }
+                        }
+                    } else {
+                        code = 49;
+                        for (int a = 0; a < 3; ++a)
+                            if (d[a] == 1) code += 1 << a;
+                    }
+                    int code_coarser = -1;
+                    for (int k = 0; k < n_free; ++k)
+                        if (tc_last == append[k]) code_coarser = code + k;
+
+                    // same level
+                    const int nblk = 1 << b.level;
+                    int p[3] = {0, 0, 0};
+                    bool outside = false;
+                    for (int a = 0; a < dim; ++a) {
+                        p[a] = b.ix[a] + d[a];
+                        if (p[a] < 0 || p[a] >= nblk) {
+                            if (f->periodic[a]) p[a] = (p[a] + nblk) % nblk;
+                            else outside = true;
+                        }
+                    }
+                    if (outside) continue;
+                    int j = f->find(b.level, p);
+                    if (j >= 0) {
+                        set(code, j);
+                        continue;
+                    }
+                    // finer neighbours: neighbour of each virtual child across this side
+                    bool found_finer = false;
+                    if (b.level < f->Jmax) {
+                        for (int k = 0; k < n_free; ++k) {
+                            int q[3] = {0, 0, 0};
+                            const int nblk2 = nblk * 2;
+                            for (int a = 0; a < dim; ++a) {
+                                const int bit = (append[k] & vary_tc[a]) ? 1 : 0;
+                                q[a] = 2 * b.ix[a] + bit + d[a];
+                                q[a] = (q[a] + nblk2) % nblk2;
+                            }
+                            j = f->find(b.level + 1, q);
+                            if (j < 0) break;
+                            set(code + k + 112, j);
+                            found_finer = true;
+                            f->uniform = false;
+                        }
+                    }
+                    if (found_finer) continue;
+                    // coarser neighbour
+                    if (code_coarser != -1 && b.level > 0) {
+                        int q[3] = {p[0] >> 1, p[1] >> 1, p[2] >> 1};
+                        j = f->find(b.level - 1, q);
+                        if (j >= 0) {
+                            set(code_coarser + 56, j);
+                            f->uniform = false;
+                        }
+                    }
+                }
+    }
+}
+
+int32_t whost_create_from_blocks(int32_t dim, int32_t Jmax, int32_t sfc, int32_t n_ranks, int32_t N, const int32_t periodic[3], int32_t n,
+                                 const int32_t *level, const int32_t *ixyz, whost_forest **out)
+{
+    if (!out || (dim != 2 && dim != 3) || n_ranks < 1 || N < 1 || n < 0 || Jmax < 0 || Jmax > 20) return 1;
+    if ((int64_t)n > (int64_t)N * n_ranks) return 2;
+    if ((n + n_ranks - 1) / n_ranks > N) return 2;
+    whost_forest *f = new whost_forest();
+    f->dim = dim;
+    f->Jmax = Jmax;
+    f->sfc = sfc;
+    f->n_ranks = n_ranks;
+    f->N = N;
+    for (int a = 0; a < 3; ++a) f->periodic[a] = periodic ? periodic[a] : 1;
+    f->blocks.resize(n);
+    for (int i = 0; i < n; ++i) {
+        Blk &b = f->blocks[i];
+        b.level = level[i];
+        if (b.level < 0 || b.level > Jmax) {
+            delete f;
+            return 3;
+        }
+        for (int a = 0; a < 3; ++a) b.ix[a] = a < dim ? ixyz[3 * i + a] : 0;
+    }
+    build(f);
+    *out = f;
+    return 0;
+}
+
+int32_t whost_create_uniform(int32_t dim, int32_t J, int32_t Jmax, int32_t sfc, int32_t n_ranks, int32_t N, const int32_t periodic[3],
+                             whost_forest **out)
+{
+    if (J < 0 || J > Jmax) return 3;
+    const int nb1 = 1 << J;
+    const int64_t n = dim == 3 ? (int64_t)nb1 * nb1 * nb1 : (int64_t)nb1 * nb1;
+    std::vector<int32_t> level((size_t)n, J), ixyz((size_t)n * 3, 0);
+    int64_t i = 0;
+    for (int z = 0; z < (dim == 3 ? nb1 : 1); ++z)
+        for (int y = 0; y < nb1; ++y)
+            for (int x = 0; x < nb1; ++x, ++i) {
+                ixyz[3 * i] = x;
+                ixyz[3 * i + 1] = y;
+                ixyz[3 * i + 2] = z;
+            }
+    return whost_create_from_blocks(dim, Jmax, sfc, n_ranks, N, periodic, (int32_t)n, level.data(), ixyz.data(), out);
+}
+
+int32_t whost_destroy(whost_forest *f)
+{
+    delete f;
+    return 0;
+}
+
+int32_t whost_n_blocks(const whost_forest *f) { return f ? (int32_t)f->blocks.size() : 0; }
+int32_t whost_n_active(const whost_forest *f, int32_t rank) { return (f && rank >= 0 && rank < f->n_ranks) ? (int32_t)f->rank_blocks[rank].size() : 0; }
+
+int32_t whost_get_active(const whost_forest *f, int32_t rank, int32_t *hvy_active, int32_t *level, int32_t *ixyz, int64_t *treecode)
+{
+    if (!f || rank < 0 || rank >= f->n_ranks) return 1;
+    int k = 0;
+    for (int i : f->rank_blocks[rank]) {
+        const Blk &b = f->blocks[i];
+        if (hvy_active) hvy_active[k] = b.hvy;
+        if (level) level[k] = b.level;
+        if (ixyz)
+            for (int a = 0; a < 3; ++a) ixyz[3 * k + a] = b.ix[a];
+        if (treecode) treecode[k] = b.tc;
+        ++k;
+    }
+    return 0;
+}
+
+int32_t whost_get_neighbors(const whost_forest *f, int32_t rank, int32_t *hvy_neighbor)
+{
+    if (!f || rank < 0 || rank >= f->n_ranks || !hvy_neighbor) return 1;
+    memcpy(hvy_neighbor, f->nbr[rank].data(), sizeof(int32_t) * f->nbr[rank].size());
+    return 0;
+}
+
+int32_t whost_is_uniform(const whost_forest *f) { return f && f->uniform ? 1 : 0; }
+
+}  // extern "C"

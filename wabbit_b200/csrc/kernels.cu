@@ -1,0 +1,632 @@
+// Hand-written sm_100a kernels of the WABBIT block hot path (3-D ACM time stepping).
+//
+// Data layout in HBM: every heavy array is stored WITHOUT ghost layers, block-major,
+//   A[blk][comp][z][y][x],  x fastest, Bs^3 doubles per component (32 KiB at Bs=16, 128-byte rows).
+// Ghost values are never materialised for same-level neighbours: the stage kernel gathers the
+// halo of a block directly from the neighbours' interiors (or from the patch pool for level-jump /
+// remote patches), which fuses sync_ghosts_RHS_tree into the stencil pass.
+//
+// stage_kernel = one Runge-Kutta stage of RungeKuttaGeneric (LIB/TIME/runge_kutta_generic.f90:72-154):
+//   k_j   = RHS_3D_acm(u_j)                       (LIB/EQUATION/ACMnew/rhs_ACM.f90:927-1779)
+//   u_j+1 = u_0 + sum_l (dt*a_{j+1,l}) k_l        (runge_kutta_generic.f90:90-112), or the final
+//   u     = u_0 + sum_j (dt*b_j) k_j              (runge_kutta_generic.f90:136-154)
+// plus, fused in: the integral_stage divergence guard (rhs_ACM.f90:133-146) and, on the final stage,
+// GET_DT_BLOCK_ACM's max(u^2+v^2+w^2) for the next step (module_ACM.f90:648-665).
+//
+// One CTA per block, Bs x Bs threads, marching in z.  z-planes (4 components, xy-halo included) stream
+// through a shared-memory ring filled with cp.async (LDGSTS) PF planes ahead of the compute front, so
+// the SM keeps several planes of HBM traffic in flight while the FP64 pipe works on the current one.
+#include <math.h>
+
+#include "wgpu_internal.cuh"
+
+namespace {
+
+__device__ __forceinline__ void cp_async16(double *smem, const double *g)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async8(double *smem, const double *g)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Finite-difference tables (rhs_ACM.f90:976-985).  q points at the centre value, q[o] is offset o.
+// Evaluation order follows the reference: left-to-right sums, then *dx_inv.
+// ---------------------------------------------------------------------------------------------
+template <int FD>
+struct St;
+
+template <>
+struct St<2> {
+    static constexpr int H = 1;
+    __device__ static __forceinline__ double d1(const double *q, double dinv) { return (q[1] - q[-1]) * dinv * 0.5; }
+    __device__ static __forceinline__ double d1p(const double *q, const double *r, double dinv)
+    {
+        return (q[1] * r[1] - q[-1] * r[-1]) * dinv * 0.5;
+    }
+    __device__ static __forceinline__ double d2(const double *q, double d2inv) { return (q[-1] - 2.0 * q[0] + q[1]) * d2inv; }
+};
+
+template <>
+struct St<4> {
+    static constexpr int H = 2;
+    static constexpr double a0 = 1.0 / 12.0, a1 = -2.0 / 3.0, a3 = 2.0 / 3.0, a4 = -1.0 / 12.0;
+    static constexpr double b0 = -1.0 / 12.0, b1 = 4.0 / 3.0, b2 = -5.0 / 2.0, b3 = 4.0 / 3.0, b4 = -1.0 / 12.0;
+    __device__ static __forceinline__ double d1(const double *q, double dinv)
+    {
+        return (a0 * q[-2] + a1 * q[-1] + a3 * q[1] + a4 * q[2]) * dinv;
+    }
+    __device__ static __forceinline__ double d1p(const double *q, const double *r, double dinv)
+    {
+        return (a0 * q[-2] * r[-2] + a1 * q[-1] * r[-1] + a3 * q[1] * r[1] + a4 * q[2] * r[2]) * dinv;
+    }
+    __device__ static __forceinline__ double d2(const double *q, double d2inv)
+    {
+        return (b0 * q[-2] + b1 * q[-1] + b2 * q[0] + b3 * q[1] + b4 * q[2]) * d2inv;
+    }
+};
+
+template <>
+struct St<6> {
+    static constexpr int H = 3;
+    static constexpr double a0 = -1.0 / 60.0, a1 = 3.0 / 20.0, a2 = -3.0 / 4.0, a4 = 3.0 / 4.0, a5 = -3.0 / 20.0, a6 = 1.0 / 60.0;
+    static constexpr double b0 = 1.0 / 90.0, b1 = -3.0 / 20.0, b2 = 3.0 / 2.0, b3 = -49.0 / 18.0, b4 = 3.0 / 2.0, b5 = -3.0 / 20.0,
+                            b6 = 1.0 / 90.0;
+    __device__ static __forceinline__ double d1(const double *q, double dinv)
+    {
+        return (a0 * q[-3] + a1 * q[-2] + a2 * q[-1] + a4 * q[1] + a5 * q[2] + a6 * q[3]) * dinv;
+    }
+    __device__ static __forceinline__ double d1p(const double *q, const double *r, double dinv)
+    {
+        return (a0 * q[-3] * r[-3] + a1 * q[-2] * r[-2] + a2 * q[-1] * r[-1] + a4 * q[1] * r[1] + a5 * q[2] * r[2] +
+                a6 * q[3] * r[3]) * dinv;
+    }
+    __device__ static __forceinline__ double d2(const double *q, double d2inv)
+    {
+        return (b0 * q[-3] + b1 * q[-2] + b2 * q[-1] + b3 * q[0] + b4 * q[1] + b5 * q[2] + b6 * q[3]) * d2inv;
+    }
+};
+
+// Tam & Webb optimised 4th-order first derivative, standard 4th-order second derivative (rhs_ACM.f90:978,1461ff)
+template <>
+struct St<40> {
+    static constexpr int H = 3;
+    static constexpr double a0 = -0.02651995, a1 = +0.18941314, a2 = -0.79926643, a4 = 0.79926643, a5 = -0.18941314, a6 = 0.02651995;
+    __device__ static __forceinline__ double d1(const double *q, double dinv)
+    {
+        return (a0 * q[-3] + a1 * q[-2] + a2 * q[-1] + a4 * q[1] + a5 * q[2] + a6 * q[3]) * dinv;
+    }
+    __device__ static __forceinline__ double d1p(const double *q, const double *r, double dinv)
+    {
+        return (a0 * q[-3] * r[-3] + a1 * q[-2] * r[-2] + a2 * q[-1] * r[-1] + a4 * q[1] * r[1] + a5 * q[2] * r[2] +
+                a6 * q[3] * r[3]) * dinv;
+    }
+    __device__ static __forceinline__ double d2(const double *q, double d2inv) { return St<4>::d2(q, d2inv); }
+};
+
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The stage kernel
+// ---------------------------------------------------------------------------------------------
+template <int FD, int BS>
+struct Tile {
+    static constexpr int H = St<FD>::H;
+    static constexpr int XO = (H + 1) & ~1;        // x offset of the interior inside a smem row (even => 16 B aligned)
+    static constexpr int PITCH = BS + 2 * XO;
+    static constexpr int ROWS = BS + 2 * H;
+    static constexpr int PLANE = ROWS * PITCH;     // one component
+    static constexpr int NC = 4;
+    static constexpr int SLOT = NC * PLANE;        // one z-plane, all components
+    static constexpr size_t SMEM_MAX = 227 * 1024;
+    static constexpr size_t SLOT_BYTES = (size_t)SLOT * sizeof(double);
+    // planes in flight ahead of the compute front: 3 if the ring fits in shared memory, else fewer
+    static constexpr int PF = (2 * H + 1 + 3) * SLOT_BYTES <= SMEM_MAX ? 3 : ((2 * H + 1 + 2) * SLOT_BYTES <= SMEM_MAX ? 2 : 1);
+    static constexpr int RING = 2 * H + 1 + PF;
+    static constexpr int NT = BS * BS;
+    static constexpr size_t SMEM = (size_t)RING * SLOT * sizeof(double);
+    static_assert(SMEM <= SMEM_MAX, "plane ring does not fit in shared memory for this (FD, Bs)");
+};
+
+template <int FD, int BS>
+__device__ __forceinline__ void load_plane(const StageArgs &a, double *sm, int q, int b, const int *code, int tid)
+{
+    using T = Tile<FD, BS>;
+    constexpr int H = T::H, XO = T::XO, PITCH = T::PITCH, PLANE = T::PLANE, NC = T::NC, NT = T::NT, HB = BS / 2;
+    const int zp = q - H;
+    double *dst = sm + (q % T::RING) * T::SLOT;
+    const double *uin = a.u_in;
+    constexpr long long CS = (long long)BS * BS * BS;  // component stride
+
+    if (zp < 0 || zp >= BS) {
+        // z-halo plane: only the Bs x Bs interior footprint is needed by a star stencil
+        const int cd = zp < 0 ? code[4] : code[22];   // (0,0,-1) -> 4 ; (0,0,+1) -> 22
+        const int zs = zp < 0 ? BS + zp : zp - BS;
+        const int kz = zp < 0 ? zp + H : zp - BS;
+        if (cd >= 0) {
+            const double *src = uin + ((long long)cd * NC) * CS + (long long)zs * BS * BS;
+            for (int i = tid; i < NC * BS * HB; i += NT) {
+                const int c = i / (BS * HB), r = i % (BS * HB), y = r / HB, xc = r % HB;
+                cp_async16(dst + c * PLANE + (y + H) * PITCH + XO + 2 * xc, src + c * CS + y * BS + 2 * xc);
+            }
+        } else if (cd <= -2) {
+            const double *src = a.pool + a.pool_off[-2 - cd];   // patch (Bs,Bs,H) per component
+            for (int i = tid; i < NC * BS * HB; i += NT) {
+                const int c = i / (BS * HB), r = i % (BS * HB), y = r / HB, xc = r % HB;
+                cp_async16(dst + c * PLANE + (y + H) * PITCH + XO + 2 * xc, src + ((long long)(c * H + kz) * BS + y) * BS + 2 * xc);
+            }
+        } else {
+            for (int i = tid; i < NC * BS * BS; i += NT) {
+                const int c = i / (BS * BS), r = i % (BS * BS), y = r / BS, x = r % BS;
+                dst[c * PLANE + (y + H) * PITCH + XO + x] = 0.0;
+            }
+        }
+        return;
+    }
+
+    // interior plane: rows y = -H .. BS+H-1 (16-byte chunks), then the x halos (8-byte elements)
+    {
+        const int c_ym = code[10], c_yp = code[16];   // (0,-1,0) -> 10 ; (0,+1,0) -> 16
+        const double *own = uin + ((long long)b * NC) * CS + (long long)zp * BS * BS;
+        for (int i = tid; i < NC * T::ROWS * HB; i += NT) {
+            const int c = i / (T::ROWS * HB), r = i % (T::ROWS * HB), row = r / HB, xc = r % HB;
+            const int y = row - H;
+            double *d = dst + c * PLANE + row * PITCH + XO + 2 * xc;
+            if (y >= 0 && y < BS) {
+                cp_async16(d, own + c * CS + y * BS + 2 * xc);
+            } else {
+                const int cd = y < 0 ? c_ym : c_yp;
+                const int ys = y < 0 ? BS + y : y - BS;      // row in the neighbour's interior
+                const int ky = y < 0 ? y + H : y - BS;       // row in the pool patch (Bs,H,Bs)
+                if (cd >= 0)
+                    cp_async16(d, uin + ((long long)cd * NC + c) * CS + (long long)zp * BS * BS + ys * BS + 2 * xc);
+                else if (cd <= -2)
+                    cp_async16(d, a.pool + a.pool_off[-2 - cd] + ((long long)(c * BS + zp) * H + ky) * BS + 2 * xc);
+                else {
+                    d[0] = 0.0;
+                    d[1] = 0.0;
+                }
+            }
+        }
+        const int c_xm = code[12], c_xp = code[14];   // (-1,0,0) -> 12 ; (+1,0,0) -> 14
+        for (int i = tid; i < NC * BS * 2 * H; i += NT) {
+            const int c = i / (BS * 2 * H), r = i % (BS * 2 * H), y = r / (2 * H), e = r % (2 * H);
+            const bool lo = e < H;
+            const int x = lo ? e - H : BS + (e - H);         // -H..-1 or BS..BS+H-1
+            const int cd = lo ? c_xm : c_xp;
+            const int xs = lo ? BS + x : x - BS;
+            const int kx = lo ? e : e - H;                   // column in the pool patch (H,Bs,Bs)
+            double *d = dst + c * PLANE + (y + H) * PITCH + XO + x;
+            if (cd >= 0)
+                cp_async8(d, uin + ((long long)cd * NC + c) * CS + (long long)zp * BS * BS + y * BS + xs);
+            else if (cd <= -2)
+                cp_async8(d, a.pool + a.pool_off[-2 - cd] + ((long long)(c * BS + zp) * BS + y) * H + kx);
+            else
+                d[0] = 0.0;
+        }
+    }
+}
+
+template <int FD, bool SKEW, int BS>
+__global__ void __launch_bounds__(BS *BS, (Tile<FD, BS>::SMEM <= 110 * 1024 ? 2 : 1))
+    stage_kernel(const __grid_constant__ StageArgs a)
+{
+    using T = Tile<FD, BS>;
+    using S = St<FD>;
+    constexpr int H = T::H, XO = T::XO, PITCH = T::PITCH, PLANE = T::PLANE, NC = T::NC, RING = T::RING, SLOT = T::SLOT, PF = T::PF;
+    constexpr int NQ = BS + 2 * H;
+    extern __shared__ __align__(16) double sm[];
+    __shared__ int s_code[WGPU_NDIR];
+    __shared__ double s_red[32];
+
+    const int tid = threadIdx.x;
+    const int tx = tid % BS, ty = tid / BS;
+    const int b = a.active[blockIdx.x];
+    if (tid < WGPU_NDIR) s_code[tid] = a.nbr[b * WGPU_NDIR + tid];
+    __syncthreads();
+
+    // geometry of this block (module_treelib.f90:93): dx = 2^-J * L / Bs
+    const int lvl = a.level[b];
+    const double dx = a.dx_lvl[lvl][0], dy = a.dx_lvl[lvl][1], dz = a.dx_lvl[lvl][2];
+    const double dinv[3] = {1.0 / dx, 1.0 / dy, 1.0 / dz};
+    const double d2inv[3] = {1.0 / (dx * dx), 1.0 / (dy * dy), 1.0 / (dz * dz)};
+    const double dt = a.u_out ? *a.dt_ptr : 0.0;
+    const double c02 = a.c0 * a.c0;
+
+    // prologue: planes 0 .. 2H+PF-1 in flight
+#pragma unroll 1
+    for (int q = 0; q < 2 * H + PF; ++q) {
+        if (q < NQ) load_plane<FD, BS>(a, sm, q, b, s_code, tid);
+        cp_async_commit();
+    }
+
+    const int cidx = (ty + H) * PITCH + XO + tx;
+    constexpr long long CS = (long long)BS * BS * BS;
+    double umag_max = 0.0, uabs_max = 0.0;
+
+#pragma unroll 1
+    for (int z = 0; z < BS; ++z) {
+        // plane q = z+2H must have landed: all but the newest PF-1 groups... groups are committed one per plane,
+        // the newest committed plane is z+2H+PF-1, so waiting for <= PF-1 pending groups completes plane z+2H.
+        cp_async_wait<PF - 1>();
+        __syncthreads();
+        {
+            // refill the slot of plane z-1 (last read in iteration z-1, which every thread has left: barrier above)
+            const int q = z + 2 * H + PF;
+            if (q < NQ) load_plane<FD, BS>(a, sm, q, b, s_code, tid);
+            cp_async_commit();
+        }
+
+        double rhs[4];
+        double ctr[4];
+        {
+            double d1v[3][4];  // [dir][comp]
+            double d2v[3][3];
+            double cv[3][3];   // skew: cv[dir][comp] = d/d(dir) (comp * vel_dir)
+#pragma unroll
+            for (int dir = 0; dir < 3; ++dir) {
+                double qv[4][2 * H + 1];
+#pragma unroll
+                for (int o = -H; o <= H; ++o) {
+                    int off;
+                    if (dir == 0) off = ((z + H) % RING) * SLOT + cidx + o;
+                    else if (dir == 1) off = ((z + H) % RING) * SLOT + cidx + o * PITCH;
+                    else off = ((z + H + o) % RING) * SLOT + cidx;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) qv[c][o + H] = sm[off + c * PLANE];
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) d1v[dir][c] = S::d1(&qv[c][H], dinv[dir]);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) d2v[dir][c] = S::d2(&qv[c][H], d2inv[dir]);
+                if (SKEW) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) cv[dir][c] = S::d1p(&qv[c][H], &qv[dir][H], dinv[dir]);
+                }
+                if (dir == 0) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) ctr[c] = qv[c][H];
+                }
+            }
+            const double u = ctr[0], v = ctr[1], w = ctr[2], p = ctr[3];
+            double penal[3] = {0.0, 0.0, 0.0};
+            const long long g0 = ((long long)b * a.n_mask) * CS + (long long)z * BS * BS + ty * BS + tx;
+            if (a.mask) {
+                // chi = mask(1) * C_eta_apply_inv(int(mask(5)))   rhs_ACM.f90:1192-1195
+                const int color = (int)a.mask[g0 + 4 * CS];
+                const double chi = a.mask[g0] * (color == 0 ? 0.0 : a.C_eta_inv);
+                penal[0] = -chi * (u - a.mask[g0 + 1 * CS]);
+                penal[1] = -chi * (v - a.mask[g0 + 2 * CS]);
+                penal[2] = -chi * (w - a.mask[g0 + 3 * CS]);
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                double adv;
+                if (SKEW)  // rhs_ACM.f90:1199-1201
+                    adv = -0.5 * (cv[0][c] + cv[1][c] + cv[2][c] + u * d1v[0][c] + v * d1v[1][c] + w * d1v[2][c]);
+                else       // rhs_ACM.f90:1249-1251
+                    adv = (-u * d1v[0][c] - v * d1v[1][c] - w * d1v[2][c]);
+                rhs[c] = adv - d1v[c][3] + a.nu * (d2v[0][c] + d2v[1][c] + d2v[2][c]) + penal[c];
+            }
+            rhs[3] = -c02 * (d1v[0][0] + d1v[1][1] + d1v[2][2]) - a.gamma_p * p;   // rhs_ACM.f90:1202
+            if (a.use_sponge && a.mask) {  // rhs_ACM.f90:1734-1753
+                const double spo = a.mask[g0 + 5 * CS] * a.C_sponge_inv;
+                rhs[0] = rhs[0] - (u - a.u_mean_set[0]) * spo;
+                rhs[1] = rhs[1] - (v - a.u_mean_set[1]) * spo;
+                rhs[2] = rhs[2] - (w - a.u_mean_set[2]) * spo;
+                rhs[3] = rhs[3] - p * spo;
+            }
+        }
+        uabs_max = fmax(uabs_max, fmax(fmax(fabs(ctr[0]), fabs(ctr[1])), fmax(fabs(ctr[2]), fabs(ctr[3]))));
+
+        // epilogue: store the slope and form the next stage input / the new state
+        const long long gi = ((long long)b * NC) * CS + (long long)z * BS * BS + ty * BS + tx;
+        double un[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (a.k_out) a.k_out[gi + c * CS] = rhs[c];
+            if (a.u_out) {
+                double acc = (a.u0 == a.u_in) ? ctr[c] : a.u0[gi + c * CS];
+                for (int l = 0; l < a.n_prev; ++l)   // (dt*a_jl)*k_l, increasing l  (runge_kutta_generic.f90:108-110)
+                    acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dt, a.coef_prev[l]), a.k_prev[l][gi + c * CS]));
+                if (a.use_self) acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dt, a.coef_self), rhs[c]));
+                a.u_out[gi + c * CS] = acc;
+                un[c] = acc;
+            }
+        }
+        if (a.dtmin_bits && a.u_out) {
+            // u_mag = u^2 + v^2 + w^2   (module_ACM.f90:651-652), no contraction
+            const double m = __dadd_rn(__dadd_rn(__dmul_rn(un[0], un[0]), __dmul_rn(un[1], un[1])), __dmul_rn(un[2], un[2]));
+            umag_max = fmax(umag_max, m);
+        }
+    }
+    cp_async_wait<0>();
+
+    // block reductions: divergence guard, and the CFL time step of this block for the next step
+    const int lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = (BS * BS + 31) / 32;
+    uabs_max = warp_max(uabs_max);
+    umag_max = warp_max(umag_max);
+    if (lane == 0) s_red[wid] = uabs_max;
+    __syncthreads();
+    if (tid == 0) {
+        double m = 0.0;
+        for (int i = 0; i < NW; ++i) m = fmax(m, s_red[i]);
+        if (m > 1.0e12) atomicExch(a.diverged, 1);   // LIM_DIVERGED, rhs_ACM.f90:134
+    }
+    if (a.dtmin_bits && a.u_out) {
+        __syncthreads();
+        if (lane == 0) s_red[wid] = umag_max;
+        __syncthreads();
+        if (tid == 0) {
+            double m = 0.0;
+            for (int i = 0; i < NW; ++i) m = fmax(m, s_red[i]);
+            // module_ACM.f90:657-665
+            const double u_eigen = __dadd_rn(sqrt(m), sqrt(__dadd_rn(c02, m)));
+            double dxmin = dx;
+            if (a.dim_min_axes > 1) dxmin = fmin(dxmin, dy);
+            if (a.dim_min_axes > 2) dxmin = fmin(dxmin, dz);
+            const double dtb = (u_eigen >= 1.0e-6) ? __ddiv_rn(__dmul_rn(a.CFL, dxmin), u_eigen) : 1.0e-2;
+            atomicMin(a.dtmin_bits, (unsigned long long)__double_as_longlong(dtb));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GET_DT_BLOCK_ACM's block loop as a standalone reduction (used when no fused value is available,
+// e.g. right after an upload):  dtmin = min_b CFL*min(dx_b)/(sqrt(umag_b) + sqrt(c0^2 + umag_b))
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dtmin_kernel(const double *__restrict__ u, const int *__restrict__ active,
+                                                    const signed char *__restrict__ level, StageArgs a, int nc, long long CS,
+                                                    int dim, unsigned long long *dtmin_bits)
+{
+    __shared__ double s_red[8];
+    const int b = active[blockIdx.x];
+    const double *ub = u + (long long)b * nc * CS;
+    double m = 0.0;
+    for (long long i = threadIdx.x; i < CS; i += blockDim.x) {
+        double v = __dadd_rn(__dmul_rn(ub[i], ub[i]), __dmul_rn(ub[i + CS], ub[i + CS]));
+        if (dim == 3) v = __dadd_rn(v, __dmul_rn(ub[i + 2 * CS], ub[i + 2 * CS]));
+        m = fmax(m, v);
+    }
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmax(m, s_red[i]);
+        const int lvl = level[b];
+        double dxmin = a.dx_lvl[lvl][0];
+        for (int d = 1; d < dim; ++d) dxmin = fmin(dxmin, a.dx_lvl[lvl][d]);
+        const double c02 = a.c0 * a.c0;
+        const double u_eigen = __dadd_rn(sqrt(m), sqrt(__dadd_rn(c02, m)));
+        const double dtb = (u_eigen >= 1.0e-6) ? __ddiv_rn(__dmul_rn(a.CFL, dxmin), u_eigen) : 1.0e-2;
+        atomicMin(dtmin_bits, (unsigned long long)__double_as_longlong(dtb));
+    }
+}
+
+// calculate_time_step (LIB/TIME/calculate_time_step.f90:19-118) after the global MIN; single thread.
+struct DtArgs {
+    double time, dt_fixed, dt_max, time_max, write_time, write_time_first, tsave_stats;
+    double nu, CFL_nu, CFL_eta, gamma_p, C_eta, C_sponge, dxmin_finest;
+    int penalization, use_sponge, write_fixed_time;
+};
+
+__global__ void dt_finalize_kernel(DtArgs p, const unsigned long long *dtmin_bits, unsigned long long *dtmin_next, double *dt_out,
+                                   double *dt_host)
+{
+    double dt = 9.0e9;
+    if (p.dt_fixed > 0.0) {
+        dt = p.dt_fixed;
+    } else {
+        dt = fmin(dt, __longlong_as_double((long long)*dtmin_bits));
+        // module_ACM.f90:669-689 (block independent apart from dx, whose minimum is the finest active level)
+        if (p.nu > 1.0e-13) dt = fmin(dt, __ddiv_rn(__dmul_rn(p.CFL_nu, __dmul_rn(p.dxmin_finest, p.dxmin_finest)), p.nu));
+        if (p.gamma_p > 0) dt = fmin(dt, __dmul_rn(p.CFL_eta, p.gamma_p));
+        if (p.penalization) dt = fmin(dt, __dmul_rn(p.CFL_eta, p.C_eta));
+        if (p.use_sponge) dt = fmin(dt, __dmul_rn(p.CFL_eta, p.C_sponge));
+        if (p.dt_max > 0.0) dt = fmin(p.dt_max, dt);
+    }
+    const double time = p.time;
+    if (p.write_fixed_time) {
+        if (fmod(time + dt, p.write_time) < fmod(time + 1e-12, p.write_time) && !(fabs(fmod(time, p.write_time)) < 1e-12) &&
+            time + 1e-12 > p.write_time_first)
+            dt = p.write_time - fmod(time, p.write_time);
+    }
+    if (fabs(p.tsave_stats - 9999999.9) > 1e-3) {
+        if (fmod(time + dt, p.tsave_stats) < fmod(time + 1e-12, p.tsave_stats) && !(fabs(fmod(time, p.tsave_stats)) < 1e-12))
+            dt = p.tsave_stats - fmod(time, p.tsave_stats);
+    }
+    if (time + dt > p.time_max && time <= p.time_max) dt = p.time_max - time;
+    *dt_out = dt;
+    if (dt_host) *dt_host = dt;
+    if (dtmin_next) *dtmin_next = 0x7FF0000000000000ULL;  // +inf
+}
+
+// ---------------------------------------------------------------------------------------------
+// host layout <-> resident layout
+// ---------------------------------------------------------------------------------------------
+// staged: [n][ncomp_host][nz][ny][nx] ghosted (Fortran hvy(:,:,:,:,k)); dst: compact [blk][ncomp_dst][Bs^3]
+__global__ void extract_kernel(const double *__restrict__ staged, double *__restrict__ dst, const int *__restrict__ ids, int ncomp_dst,
+                               int ncomp_host, int Bx, int By, int Bz, int g, int gz)
+{
+    const int i = blockIdx.y;       // which staged block
+    const int c = blockIdx.z;       // component
+    const int nx = Bx + 2 * g, ny = By + 2 * g, nz = Bz + 2 * gz;
+    const long long CS = (long long)Bx * By * Bz;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= CS) return;
+    const int x = e % Bx, y = (e / Bx) % By, z = e / ((long long)Bx * By);
+    const double *s = staged + ((long long)i * ncomp_host + c) * nx * ny * nz;
+    dst[((long long)ids[i] * ncomp_dst + c) * CS + e] = s[((long long)(z + gz) * ny + (y + g)) * nx + (x + g)];
+}
+
+// compact -> ghosted staging, ghost shell of width gs gathered from same-level neighbours (all 26 relations:
+// the copy sync_ghosts_generic stage 1 performs, synchronize_ghosts_generic.f90:266-339)
+__global__ void export_kernel(const double *__restrict__ src, double *__restrict__ staged, const int *__restrict__ ids,
+                              const int *__restrict__ nbr, int ncomp_src, int ncomp_host, int Bx, int By, int Bz, int g, int gz, int gs,
+                              int gsz)
+{
+    const int i = blockIdx.y, c = blockIdx.z;
+    const int b = ids[i];
+    const int nx = Bx + 2 * g, ny = By + 2 * g, nz = Bz + 2 * gz;
+    const int ex = Bx + 2 * gs, ey = By + 2 * gs, ez = Bz + 2 * gsz;
+    const long long n = (long long)ex * ey * ez;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    int x = (int)(e % ex) - gs, y = (int)((e / ex) % ey) - gs, z = (int)(e / ((long long)ex * ey)) - gsz;
+    const int dxi = x < 0 ? -1 : (x >= Bx ? 1 : 0), dyi = y < 0 ? -1 : (y >= By ? 1 : 0), dzi = z < 0 ? -1 : (z >= Bz ? 1 : 0);
+    int sb = b;
+    if (dxi | dyi | dzi) {
+        sb = nbr[b * WGPU_NDIR + (dzi + 1) * 9 + (dyi + 1) * 3 + (dxi + 1)];
+        if (sb < 0) return;   // no direct same-level source: leave the staged value untouched
+    }
+    const int xs = x - dxi * Bx, ys = y - dyi * By, zs = z - dzi * Bz;
+    const long long CS = (long long)Bx * By * Bz;
+    double *d = staged + ((long long)i * ncomp_host + c) * nx * ny * nz;
+    d[((long long)(z + gz) * ny + (y + g)) * nx + (x + g)] = src[((long long)sb * ncomp_src + c) * CS + ((long long)zs * By + ys) * Bx + xs];
+}
+
+template <int FD, bool SKEW, int BS>
+int32_t launch_stage_t(wgpu_ctx *ctx, const StageArgs &a)
+{
+    using T = Tile<FD, BS>;
+    static bool configured = false;
+    if (!configured) {
+        WGPU_CHECK(ctx, cudaFuncSetAttribute(stage_kernel<FD, SKEW, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
+        configured = true;
+    }
+    const bool prof = ctx->profiling && ctx->prof_n < (int)ctx->prof_ev.size() / 2;
+    if (prof) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], ctx->stream);
+    stage_kernel<FD, SKEW, BS><<<ctx->n_active, T::NT, T::SMEM, ctx->stream>>>(a);
+    if (prof) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n++ + 1], ctx->stream);
+    ctx->launches++;
+    WGPU_CHECK(ctx, cudaGetLastError());
+    return WGPU_OK;
+}
+
+template <int FD, bool SKEW>
+int32_t launch_stage_bs(wgpu_ctx *ctx, const StageArgs &a)
+{
+    switch (ctx->cfg.Bs[0]) {
+    case 16: return launch_stage_t<FD, SKEW, 16>(ctx, a);
+    case 18: return launch_stage_t<FD, SKEW, 18>(ctx, a);
+    case 20: return launch_stage_t<FD, SKEW, 20>(ctx, a);
+    default:
+        ctx->err = "3-D stage kernel is instantiated for Bs in {16,18,20}";
+        return WGPU_ERR_UNSUPPORTED;
+    }
+}
+
+template <int FD>
+int32_t launch_stage_skew(wgpu_ctx *ctx, const StageArgs &a)
+{
+    return ctx->cfg.skew_symmetry ? launch_stage_bs<FD, true>(ctx, a) : launch_stage_bs<FD, false>(ctx, a);
+}
+
+}  // namespace
+
+int32_t wgpu_launch_stage(wgpu_ctx *ctx, const StageArgs &a)
+{
+    if (ctx->n_active == 0) return WGPU_OK;
+    switch (ctx->cfg.fd) {
+    case 2: return launch_stage_skew<2>(ctx, a);
+    case 4: return launch_stage_skew<4>(ctx, a);
+    case 6: return launch_stage_skew<6>(ctx, a);
+    case 40: return launch_stage_skew<40>(ctx, a);
+    }
+    ctx->err = "unknown order_discretization id";
+    return WGPU_ERR_UNSUPPORTED;
+}
+
+int32_t wgpu_launch_dtmin(wgpu_ctx *ctx, const double *u, unsigned long long *dtmin_bits)
+{
+    if (ctx->n_active == 0) return WGPU_OK;
+    StageArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int l = 0; l < WGPU_MAX_LEVELS; ++l)
+        for (int d = 0; d < 3; ++d) a.dx_lvl[l][d] = ldexp(1.0, -l) * ctx->cfg.domain[d] / (double)ctx->cfg.Bs[d];
+    a.c0 = ctx->cfg.c0;
+    a.CFL = ctx->cfg.CFL;
+    dtmin_kernel<<<ctx->n_active, 256, 0, ctx->stream>>>(u, ctx->d_active, ctx->d_level, a, ctx->nc, ctx->blk_elems, ctx->cfg.dim, dtmin_bits);
+    ctx->launches++;
+    WGPU_CHECK(ctx, cudaGetLastError());
+    return WGPU_OK;
+}
+
+int32_t wgpu_launch_dt_finalize(wgpu_ctx *ctx, double time, const unsigned long long *dtmin_bits, unsigned long long *dtmin_next)
+{
+    const wgpu_config &c = ctx->cfg;
+    DtArgs p;
+    p.time = time;
+    p.dt_fixed = c.dt_fixed;
+    p.dt_max = c.dt_max;
+    p.time_max = c.time_max;
+    p.write_time = c.write_time;
+    p.write_time_first = c.write_time_first;
+    p.tsave_stats = c.tsave_stats;
+    p.nu = c.nu;
+    p.CFL_nu = c.CFL_nu;
+    p.CFL_eta = c.CFL_eta;
+    p.gamma_p = c.gamma_p;
+    p.C_eta = c.C_eta;
+    p.C_sponge = c.C_sponge;
+    p.penalization = c.penalization;
+    p.use_sponge = c.use_sponge;
+    p.write_fixed_time = c.write_method_fixed_time;
+    int lmax = 0;
+    for (int i = 0; i < ctx->n_active; ++i) lmax = ctx->h_level[ctx->h_active[i]] > lmax ? ctx->h_level[ctx->h_active[i]] : lmax;
+    double dxmin = 1e300;
+    for (int d = 0; d < c.dim; ++d) {
+        const double dx = ldexp(1.0, -lmax) * c.domain[d] / (double)c.Bs[d];
+        dxmin = dx < dxmin ? dx : dxmin;
+    }
+    p.dxmin_finest = dxmin;
+    dt_finalize_kernel<<<1, 1, 0, ctx->stream>>>(p, dtmin_bits, dtmin_next, ctx->d_dt, nullptr);
+    ctx->launches++;
+    WGPU_CHECK(ctx, cudaGetLastError());
+    return WGPU_OK;
+}
+
+int32_t wgpu_launch_extract(wgpu_ctx *ctx, const double *staged, double *dst, const int *d_ids, int n, int ncomp_dst, int ncomp_host)
+{
+    if (n == 0) return WGPU_OK;
+    const wgpu_config &c = ctx->cfg;
+    const int Bz = c.dim == 3 ? c.Bs[2] : 1, gz = c.dim == 3 ? c.g : 0;
+    const int nc = ncomp_dst < ncomp_host ? ncomp_dst : ncomp_host;
+    dim3 grid((unsigned)((ctx->blk_elems + 255) / 256), n, nc);
+    extract_kernel<<<grid, 256, 0, ctx->stream>>>(staged, dst, d_ids, ncomp_dst, ncomp_host, c.Bs[0], c.Bs[1], Bz, c.g, gz);
+    ctx->launches++;
+    WGPU_CHECK(ctx, cudaGetLastError());
+    return WGPU_OK;
+}
+
+int32_t wgpu_launch_export(wgpu_ctx *ctx, const double *src, double *staged, const int *d_ids, int n, int ncomp_src, int ncomp_host,
+                           int g_sync)
+{
+    if (n == 0) return WGPU_OK;
+    const wgpu_config &c = ctx->cfg;
+    const int Bz = c.dim == 3 ? c.Bs[2] : 1, gz = c.dim == 3 ? c.g : 0, gsz = c.dim == 3 ? g_sync : 0;
+    const int nc = ncomp_src < ncomp_host ? ncomp_src : ncomp_host;
+    const long long npts = (long long)(c.Bs[0] + 2 * g_sync) * (c.Bs[1] + 2 * g_sync) * (Bz + 2 * gsz);
+    dim3 grid((unsigned)((npts + 255) / 256), n, nc);
+    export_kernel<<<grid, 256, 0, ctx->stream>>>(src, staged, d_ids, ctx->d_nbr, ncomp_src, ncomp_host, c.Bs[0], c.Bs[1], Bz, c.g, gz,
+                                                 g_sync, gsz);
+    ctx->launches++;
+    WGPU_CHECK(ctx, cudaGetLastError());
+    return WGPU_OK;
+}

@@ -1,0 +1,122 @@
+// Internal definitions shared by the CUDA translation units of libwabbit_gpu.so.
+// Not part of the public C ABI (include/wabbit_gpu.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "wabbit_gpu.h"
+
+#define WGPU_MAX_LEVELS 32
+
+// ------------------------------------------------------------------------------------------------
+// Neighbour direction table.  Device-side the 168-slot hvy_neighbor is folded into 26 directions
+// (index = (dz+1)*9 + (dy+1)*3 + (dx+1), 13 = self) with one int32 "source code" each:
+//    >= 0 : same-level neighbour resident on this GPU: its 0-based block index (gather from its interior)
+//    -1   : no neighbour (non-periodic domain boundary)
+//    <=-2 : patch pool entry  pid = -2 - code  (values prepared by a pre-pass: restriction,
+//           prediction or a remote GPU's pack kernel); pool_off[pid] is the offset in doubles.
+// ------------------------------------------------------------------------------------------------
+#define WGPU_NDIR 27
+
+struct StageArgs {
+    // fields
+    const double *u_in;        // stage input, compact [blk][nc][Bs^3]
+    const double *u0;          // state at start of the step (compact)
+    double *k_out;             // RHS output slot (may be nullptr: not stored)
+    double *u_out;             // next stage input / final state (may be nullptr)
+    const double *k_prev[WGPU_MAX_STAGES];  // earlier slopes entering u_out
+    double coef_prev[WGPU_MAX_STAGES];      // Butcher coefficients (dt applied in-kernel: (dt*a)*k)
+    int n_prev;
+    double coef_self;          // coefficient of the slope computed by this launch
+    int use_self;
+    const double *dt_ptr;      // device scalar
+    const double *mask;        // compact [blk][n_mask][Bs^3] or nullptr
+    int n_mask;
+    // topology
+    const int *active;         // [n_active] 0-based block indices
+    const int *nbr;            // [max_blocks][27]
+    const signed char *level;  // [max_blocks]
+    const double *pool;
+    const long long *pool_off;
+    // physics
+    double dx_lvl[WGPU_MAX_LEVELS][3];
+    double c0, nu, gamma_p, C_eta_inv, C_sponge_inv, u_mean_set[3];
+    int use_sponge;
+    // reductions
+    unsigned long long *dtmin_bits;  // atomicMin target for the NEXT step's CFL dt (final stage only), or nullptr
+    double CFL;
+    int *diverged;                   // set to 1 if any |u_in| > 1e12
+    int dim_min_axes;                // number of axes entering minval(dx(1:dim))
+};
+
+struct wgpu_ctx {
+    wgpu_config cfg;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int64_t dev_bytes = 0;
+
+    int nc = 0;                 // n_eqn
+    int64_t blk_elems = 0;      // Bs^3 (or Bs^2)
+    int64_t gblk_elems = 0;     // (Bs+2g)^3
+
+    // resident arrays (compact interior layout [blk][comp][z][y][x])
+    double *U = nullptr;        // hvy_block
+    double *UA = nullptr, *UB = nullptr;   // stage inputs (ping-pong)
+    double *K[WGPU_MAX_STAGES] = {nullptr};  // hvy_work slots 2..s+1
+    double *MASK = nullptr;
+    double *TMP = nullptr;
+
+    // topology
+    int n_active = 0;
+    int *d_active = nullptr;
+    int *d_nbr = nullptr;
+    signed char *d_level = nullptr;
+    std::vector<int> h_active;
+    std::vector<int> h_nbr;
+    std::vector<signed char> h_level;
+    double *d_pool = nullptr;
+    long long *d_pool_off = nullptr;
+
+    // scalars
+    double *d_dt = nullptr;                   // dt of the current step
+    unsigned long long *d_dtmin = nullptr;    // [2]: CFL dt candidates (bits), ping-pong
+    int dtmin_cur = 0;
+    bool dtmin_valid = false;
+    int *d_flags = nullptr;                   // [0] diverged
+    double *h_pinned = nullptr;               // [0] dt, [1] flags (as int bits)
+
+    // optional event pairs around stage launches
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_ev;   // [2*i], [2*i+1]
+    int prof_n = 0;
+
+    // staging for upload/download
+    double *d_stage = nullptr;
+    int64_t stage_elems = 0;
+    double *h_bounce = nullptr;
+    int64_t bounce_elems = 0;
+};
+
+#define WGPU_CHECK(ctx, call)                                                                  \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                  \
+            return WGPU_ERR_CUDA;                                                              \
+        }                                                                                      \
+    } while (0)
+
+// kernels.cu
+int32_t wgpu_launch_stage(wgpu_ctx *ctx, const StageArgs &a);
+int32_t wgpu_launch_dtmin(wgpu_ctx *ctx, const double *u, unsigned long long *dtmin_bits);
+int32_t wgpu_launch_dt_finalize(wgpu_ctx *ctx, double time, const unsigned long long *dtmin_bits,
+                                unsigned long long *dtmin_next);
+int32_t wgpu_launch_extract(wgpu_ctx *ctx, const double *staged, double *dst, const int *d_ids, int n, int ncomp_dst,
+                            int ncomp_host);
+int32_t wgpu_launch_export(wgpu_ctx *ctx, const double *src, double *staged, const int *d_ids, int n, int ncomp_src,
+                           int ncomp_host, int g_sync);

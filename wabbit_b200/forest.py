@@ -1,0 +1,88 @@
+"""Host forest metadata (light data) -- thin wrapper over libwabbit_host.so (include/wabbit_host.h).
+
+Stands in for what WABBIT's host Fortran (createEquidistantGrid_tree, updateMetadata_tree,
+balanceLoad_tree) leaves in lgt_block / hvy_active / hvy_neighbor.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from ._native import host_lib
+
+SFC = {"sfc_z": 0, "sfc_hilbert": 1}
+
+
+def _i32(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+class Forest:
+    def __init__(self, handle, dim: int, Jmax: int, n_ranks: int, max_blocks: int):
+        self._h = handle
+        self.dim, self.Jmax, self.n_ranks, self.max_blocks = dim, Jmax, n_ranks, max_blocks
+
+    @classmethod
+    def uniform(cls, dim: int, J: int, Jmax: Optional[int] = None, block_dist: str = "sfc_hilbert", n_ranks: int = 1,
+                max_blocks: Optional[int] = None, periodic: Sequence[int] = (1, 1, 1)) -> "Forest":
+        Jmax = J if Jmax is None else Jmax
+        nb = (2 ** J) ** dim
+        max_blocks = max_blocks or -(-nb // n_ranks)
+        h = C.c_void_p()
+        per = np.asarray(periodic, dtype=np.int32)
+        rc = host_lib().whost_create_uniform(dim, J, Jmax, SFC[block_dist], n_ranks, max_blocks, _i32(per), C.byref(h))
+        if rc:
+            raise RuntimeError(f"whost_create_uniform failed with code {rc}")
+        return cls(h, dim, Jmax, n_ranks, max_blocks)
+
+    @classmethod
+    def from_blocks(cls, dim: int, Jmax: int, level, ixyz, block_dist: str = "sfc_hilbert", n_ranks: int = 1,
+                    max_blocks: Optional[int] = None, periodic: Sequence[int] = (1, 1, 1)) -> "Forest":
+        level = np.ascontiguousarray(level, dtype=np.int32)
+        ixyz = np.ascontiguousarray(ixyz, dtype=np.int32).reshape(-1, 3)
+        n = len(level)
+        max_blocks = max_blocks or -(-n // n_ranks)
+        h = C.c_void_p()
+        per = np.asarray(periodic, dtype=np.int32)
+        rc = host_lib().whost_create_from_blocks(dim, Jmax, SFC[block_dist], n_ranks, max_blocks, _i32(per), n, _i32(level),
+                                                 _i32(ixyz), C.byref(h))
+        if rc:
+            raise RuntimeError(f"whost_create_from_blocks failed with code {rc}")
+        return cls(h, dim, Jmax, n_ranks, max_blocks)
+
+    def __del__(self):
+        try:
+            if self._h:
+                host_lib().whost_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @property
+    def n_blocks(self) -> int:
+        return host_lib().whost_n_blocks(self._h)
+
+    def n_active(self, rank: int = 0) -> int:
+        return host_lib().whost_n_active(self._h, rank)
+
+    @property
+    def is_uniform(self) -> bool:
+        return bool(host_lib().whost_is_uniform(self._h))
+
+    def active(self, rank: int = 0):
+        """(hvy_active[1-based], level, ixyz[n,3], treecode) of a rank in SFC order."""
+        n = self.n_active(rank)
+        hvy = np.zeros(n, np.int32)
+        lvl = np.zeros(n, np.int32)
+        ixyz = np.zeros((n, 3), np.int32)
+        tc = np.zeros(n, np.int64)
+        host_lib().whost_get_active(self._h, rank, _i32(hvy), _i32(lvl), _i32(ixyz), tc.ctypes.data_as(C.POINTER(C.c_int64)))
+        return hvy, lvl, ixyz, tc
+
+    def neighbors(self, rank: int = 0) -> np.ndarray:
+        """hvy_neighbor as an array [168, max_blocks] (== Fortran hvy_neighbor(max_blocks,168)), lgt ids, -1 none."""
+        out = np.full((168, self.max_blocks), -1, np.int32)
+        host_lib().whost_get_neighbors(self._h, rank, _i32(out))
+        return out

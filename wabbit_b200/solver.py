@@ -1,0 +1,165 @@
+"""Host-side mirror of WABBIT's tree-level routines for the block hot path, on top of the C ABI.
+
+Method names and argument meaning follow the reference routines they replace
+(LIB/TIME/runge_kutta_generic.f90, LIB/TIME/RHS_wrapper.f90, LIB/TIME/calculate_time_step.f90,
+LIB/TIME/timeStep_tree.f90, LIB/MPI/synchronize_ghosts_generic.f90); errors surface as `WabbitAbort`
+carrying the reference's integer abort code (LIB/MODULE/module_globals.f90:131-161).
+
+Heavy arrays on the host are NumPy arrays `hvy[number_blocks, ncomp, nz, ny, nx]` (C order), i.e. exactly
+the memory of the Fortran array hvy(nx,ny,nz,ncomp,number_blocks).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from ._native import WgpuConfig, gpu_lib
+from .forest import Forest
+from .params import Params
+
+HVY_BLOCK, HVY_WORK, HVY_MASK, HVY_TMP = 0, 1, 2, 3
+
+
+class WabbitAbort(RuntimeError):
+    """The library's equivalent of `call abort(code, msg)`."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+
+
+def _i32(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+class WabbitGPU:
+    """One rank's device-resident forest (one process per GPU)."""
+
+    def __init__(self, params: Params, max_blocks: int, device: int = 0, stream: Optional[int] = None):
+        self.params = params.finalize()
+        self.max_blocks = int(max_blocks)
+        self._lib = gpu_lib()
+        self._cfg: WgpuConfig = params.to_config(self.max_blocks, device)
+        self._ctx = C.c_void_p()
+        rc = self._lib.wgpu_create(C.byref(self._cfg), C.byref(self._ctx))
+        if rc:
+            buf = C.create_string_buffer(512)
+            self._lib.wgpu_last_error(None, buf, 512)
+            self._ctx = None
+            raise WabbitAbort(rc, buf.value.decode())
+        if stream is not None:
+            self._check(self._lib.wgpu_set_stream(self._ctx, C.c_void_p(stream)))
+        self.hvy_active = np.zeros(0, np.int32)
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc: int):
+        if rc:
+            buf = C.create_string_buffer(512)
+            self._lib.wgpu_last_error(self._ctx, buf, 512)
+            raise WabbitAbort(rc, buf.value.decode())
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.wgpu_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        self._check(self._lib.wgpu_synchronize(self._ctx))
+
+    def profile(self, enable: bool = True):
+        self._check(self._lib.wgpu_profile(self._ctx, int(enable)))
+
+    def profile_read(self):
+        """(number of stage-kernel launches recorded, their summed duration in ms)"""
+        n, ms = C.c_int32(), C.c_double()
+        self._check(self._lib.wgpu_profile_read(self._ctx, C.byref(n), C.byref(ms)))
+        return n.value, ms.value
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.wgpu_launch_count(self._ctx))
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self._lib.wgpu_device_bytes(self._ctx))
+
+    def host_shape(self, ncomp: Optional[int] = None):
+        p = self.params
+        nz = p.Bs[2] + 2 * p.g if p.dim == 3 else 1
+        return (self.max_blocks, p.n_eqn if ncomp is None else ncomp, nz, p.Bs[1] + 2 * p.g, p.Bs[0] + 2 * p.g)
+
+    # ------------------------------------------------------------------ topology
+    def set_topology(self, hvy_active: np.ndarray, level: np.ndarray, hvy_neighbor: np.ndarray, rank: int = 0):
+        """Upload what updateMetadata_tree produced: hvy_active (1-based), level per active block and
+        hvy_neighbor[168, max_blocks] (lgt ids)."""
+        hvy_active = np.ascontiguousarray(hvy_active, dtype=np.int32)
+        level = np.ascontiguousarray(level, dtype=np.int32)
+        hvy_neighbor = np.ascontiguousarray(hvy_neighbor, dtype=np.int32)
+        assert hvy_neighbor.shape[0] == 168
+        self._check(self._lib.wgpu_set_topology(self._ctx, len(hvy_active), _i32(hvy_active), _i32(level), _i32(hvy_neighbor),
+                                                hvy_neighbor.shape[1], rank))
+        self.hvy_active = hvy_active.copy()
+
+    def set_forest(self, forest: Forest, rank: int = 0):
+        hvy, lvl, _, _ = forest.active(rank)
+        self.set_topology(hvy, lvl, forest.neighbors(rank), rank)
+
+    # ------------------------------------------------------------------ data movement
+    def _ids(self, hvy_ids):
+        return np.ascontiguousarray(self.hvy_active if hvy_ids is None else hvy_ids, dtype=np.int32)
+
+    def upload(self, host: np.ndarray, array_id: int = HVY_BLOCK, slot: int = 0, hvy_ids: Optional[Sequence[int]] = None):
+        assert host.dtype == np.float64 and host.flags.c_contiguous and host.ndim == 5
+        ids = self._ids(hvy_ids)
+        self._check(self._lib.wgpu_upload(self._ctx, array_id, slot, _i32(ids), len(ids), C.c_void_p(host.ctypes.data), host.shape[1]))
+
+    def download(self, host: np.ndarray, array_id: int = HVY_BLOCK, slot: int = 0, hvy_ids: Optional[Sequence[int]] = None,
+                 g_sync: Optional[int] = None):
+        assert host.dtype == np.float64 and host.flags.c_contiguous and host.ndim == 5
+        ids = self._ids(hvy_ids)
+        gs = self.params.g if g_sync is None else g_sync
+        self._check(self._lib.wgpu_download(self._ctx, array_id, slot, _i32(ids), len(ids), C.c_void_p(host.ctypes.data), host.shape[1], gs))
+
+    def upload_ptr(self, host_ptr: int, ncomp: int, array_id: int = HVY_BLOCK, slot: int = 0, hvy_ids=None):
+        ids = self._ids(hvy_ids)
+        self._check(self._lib.wgpu_upload(self._ctx, array_id, slot, _i32(ids), len(ids), C.c_void_p(host_ptr), ncomp))
+
+    def download_ptr(self, host_ptr: int, ncomp: int, array_id: int = HVY_BLOCK, slot: int = 0, hvy_ids=None, g_sync=None):
+        ids = self._ids(hvy_ids)
+        gs = self.params.g if g_sync is None else g_sync
+        self._check(self._lib.wgpu_download(self._ctx, array_id, slot, _i32(ids), len(ids), C.c_void_p(host_ptr), ncomp, gs))
+
+    # ------------------------------------------------------------------ reference routines
+    def sync_ghosts_RHS_tree(self, g_minus: Optional[int] = None, g_plus: Optional[int] = None):
+        """synchronize_ghosts_generic.f90:155-174"""
+        g = self.params.g_rhs
+        self._check(self._lib.wgpu_sync_ghosts(self._ctx, HVY_BLOCK, 0, g if g_minus is None else g_minus, g if g_plus is None else g_plus))
+
+    def RHS_wrapper(self, time: float, dst_slot: int, src_slot: int = 0):
+        """RHS_wrapper.f90:16 -- hvy_work(:,:,:,:,:,dst_slot) = RHS(hvy_block | hvy_work(...,src_slot))."""
+        self._check(self._lib.wgpu_rhs(self._ctx, float(time), src_slot, dst_slot))
+
+    def calculate_time_step(self, time: float) -> float:
+        """calculate_time_step.f90:2"""
+        dt = C.c_double()
+        self._check(self._lib.wgpu_calculate_time_step(self._ctx, float(time), C.byref(dt)))
+        return dt.value
+
+    def RungeKuttaGeneric(self, time: float, iteration: int = 0) -> float:
+        """runge_kutta_generic.f90:1 -- advances hvy_block by one step on the device, returns dt."""
+        dt = C.c_double()
+        self._check(self._lib.wgpu_rk_step(self._ctx, float(time), int(iteration), C.byref(dt)))
+        return dt.value
+
+    def timeStep_tree(self, time: float, iteration: int):
+        """timeStep_tree.f90:1 -- returns (time+dt, iteration+1, dt)."""
+        dt = self.RungeKuttaGeneric(time, iteration)
+        return time + dt, iteration + 1, dt
