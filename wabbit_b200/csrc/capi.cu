@@ -476,6 +476,14 @@ int32_t wgpu_rk_step(wgpu_ctx *ctx, double time, int32_t iteration, double *dt)
     if ((rc = compute_dt(ctx, time))) return rc;
     unsigned long long *dtmin_next = ctx->d_dtmin + ctx->dtmin_cur;   // reset to +inf by dt_finalize
 
+    // "acc mode": if every stage input only uses the slope of the stage before (a_{j,l} = 0 for l < j-1; true for
+    // RK4 and Euler/Heun/midpoint), no slope has to be stored: the final combination is accumulated stage by stage
+    // in the array K[0] in exactly the reference's order  ((u0 + dt b1 k1) + dt b2 k2) + ...
+    bool subdiag = s >= 2;
+    for (int j = 1; j < s && subdiag; ++j)          // 0-based row j = stage j+1, whose previous slope is column j
+        for (int l = 1; l < j; ++l)
+            if (fabs(c.butcher[(size_t)j * ld + l]) >= 1.0e-8) subdiag = false;
+
     const double *uin = ctx->U;
     for (int j = 1; j <= s; ++j) {
         StageArgs a;
@@ -483,22 +491,40 @@ int32_t wgpu_rk_step(wgpu_ctx *ctx, double time, int32_t iteration, double *dt)
         a.u_in = uin;
         a.u0 = ctx->U;
         const bool last = (j == s);
-        a.k_out = last ? nullptr : ctx->K[j - 1];      // the last slope only enters the final combination
-        // the final state may overwrite U in place (each thread reads u0 only at its own point, halos come from
-        // the stage input) unless the stage input IS U (single-stage schemes): then go through UA and swap
+        // the final state may overwrite U in place (each thread reads its bases only at its own point, halos come
+        // from the stage input) unless the stage input IS U (single-stage schemes): then go through UA and swap
         double *uout = last ? (uin == ctx->U ? ctx->UA : ctx->U) : ((j & 1) ? ctx->UA : ctx->UB);
         a.u_out = uout;
-        // row of the tableau that forms u_out: stage j+1 input (row j+1) or the final weights (row s+1)
-        const double *row = c.butcher + (size_t)(last ? s : j) * ld;
-        a.n_prev = 0;
-        for (int l = 1; l < j; ++l) {
-            if (fabs(row[l]) < 1.0e-8) continue;        // runge_kutta_generic.f90:99,144
-            a.k_prev[a.n_prev] = ctx->K[l - 1];
-            a.coef_prev[a.n_prev] = row[l];
-            a.n_prev++;
+        const double *brow = c.butcher + (size_t)s * ld;          // final weights b_j = butcher(s+1, j+1)
+        if (subdiag) {
+            double *ACC = ctx->K[0];
+            if (!last) {
+                const double *row = c.butcher + (size_t)j * ld;   // row of stage j+1
+                a.use_self = fabs(row[j]) >= 1.0e-8;
+                a.coef_self = row[j];
+                a.acc_in = (j == 1) ? ctx->U : ACC;
+                a.acc_out = ACC;
+                a.use_acc = fabs(brow[j]) >= 1.0e-8;
+                a.coef_acc = brow[j];
+            } else {
+                a.u0 = ACC;                                        // u = acc_{s-1} + (dt b_s) k_s
+                a.use_self = fabs(brow[j]) >= 1.0e-8;
+                a.coef_self = brow[j];
+            }
+        } else {
+            a.k_out = last ? nullptr : ctx->K[j - 1];              // the last slope only enters the final combination
+            // row of the tableau that forms u_out: stage j+1 input (row j+1) or the final weights (row s+1)
+            const double *row = last ? brow : c.butcher + (size_t)j * ld;
+            a.n_prev = 0;
+            for (int l = 1; l < j; ++l) {
+                if (fabs(row[l]) < 1.0e-8) continue;               // runge_kutta_generic.f90:99,144
+                a.k_prev[a.n_prev] = ctx->K[l - 1];
+                a.coef_prev[a.n_prev] = row[l];
+                a.n_prev++;
+            }
+            a.use_self = fabs(row[j]) >= 1.0e-8;
+            a.coef_self = row[j];
         }
-        a.use_self = fabs(row[j]) >= 1.0e-8;
-        a.coef_self = row[j];
         if (last && !(c.dt_fixed > 0.0)) a.dtmin_bits = dtmin_next;
         if ((rc = wgpu_launch_stage(ctx, a))) return rc;
         if (last && uout != ctx->U) std::swap(ctx->U, ctx->UA);

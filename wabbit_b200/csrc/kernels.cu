@@ -143,81 +143,123 @@ struct Tile {
     static_assert(SMEM <= SMEM_MAX, "plane ring does not fit in shared memory for this (FD, Bs)");
 };
 
+// ---------------------------------------------------------------------------------------------
+// Per-block load tables.  Where each row (and each x-halo strip) of a plane comes from does not depend on z, so it
+// is resolved once per block into shared memory: an element offset (into the stage input or into the patch
+// pool) plus the number of elements to add per plane.  The per-plane loader is then a table lookup + cp.async.
+//   variant 0: interior planes  zp = 0..BS-1   (rows y = -H..BS+H-1, plane index zp)
+//   variant 1: z- halo planes   zp = -H..-1    (rows y = 0..BS-1,    plane index zp+H)
+//   variant 2: z+ halo planes   zp = BS..BS+H-1(rows y = 0..BS-1,    plane index zp-BS)
+// ---------------------------------------------------------------------------------------------
+#define LT_POOL (1ull << 63)
+#define LT_SKIP (~0ull)
+#define LT_ZERO (~0ull - 1ull)
+
 template <int FD, int BS>
-__device__ __forceinline__ void load_plane(const StageArgs &a, double *sm, int q, int b, const int *code, int tid)
+struct LoadTables {
+    using T = Tile<FD, BS>;
+    static constexpr int NROW = T::NC * T::ROWS;
+    static constexpr int NXH = T::NC * BS * 2;
+    unsigned long long row_off[3][NROW];
+    unsigned long long x_off[NXH];
+    int row_stride[3][NROW];
+    int x_stride[NXH];
+};
+
+template <int FD, int BS>
+__device__ __forceinline__ void build_tables(const StageArgs &a, LoadTables<FD, BS> &lt, int b, const int *code, int tid)
 {
     using T = Tile<FD, BS>;
-    constexpr int H = T::H, XO = T::XO, PITCH = T::PITCH, PLANE = T::PLANE, NC = T::NC, NT = T::NT, HB = BS / 2;
-    const int zp = q - H;
-    double *dst = sm + (q % T::RING) * T::SLOT;
-    const double *uin = a.u_in;
-    constexpr long long CS = (long long)BS * BS * BS;  // component stride
-
-    if (zp < 0 || zp >= BS) {
-        // z-halo plane: only the Bs x Bs interior footprint is needed by a star stencil
-        const int cd = zp < 0 ? code[4] : code[22];   // (0,0,-1) -> 4 ; (0,0,+1) -> 22
-        const int zs = zp < 0 ? BS + zp : zp - BS;
-        const int kz = zp < 0 ? zp + H : zp - BS;
-        if (cd >= 0) {
-            const double *src = uin + ((long long)cd * NC) * CS + (long long)zs * BS * BS;
-            for (int i = tid; i < NC * BS * HB; i += NT) {
-                const int c = i / (BS * HB), r = i % (BS * HB), y = r / HB, xc = r % HB;
-                cp_async16(dst + c * PLANE + (y + H) * PITCH + XO + 2 * xc, src + c * CS + y * BS + 2 * xc);
+    constexpr int H = T::H, NC = T::NC, NT = T::NT, ROWS = T::ROWS;
+    constexpr long long CS = (long long)BS * BS * BS;
+    using LT = LoadTables<FD, BS>;
+    for (int i = tid; i < 3 * LT::NROW; i += NT) {
+        const int v = i / LT::NROW, rid = i % LT::NROW, c = rid / ROWS, y = rid % ROWS - H;
+        unsigned long long off = LT_SKIP;
+        int stride = BS * BS;
+        if (v == 0) {
+            if (y >= 0 && y < BS) off = ((unsigned long long)b * NC + c) * CS + y * BS;
+            else {
+                const int cd = y < 0 ? code[10] : code[16];       // (0,-1,0) -> 10 ; (0,+1,0) -> 16
+                const int ys = y < 0 ? BS + y : y - BS, ky = y < 0 ? y + H : y - BS;
+                if (cd >= 0) off = ((unsigned long long)cd * NC + c) * CS + ys * BS;
+                else if (cd <= -2) {                              // pool patch (Bs, H, Bs)
+                    off = ((unsigned long long)a.pool_off[-2 - cd] + ((long long)c * BS * H + ky) * BS) | LT_POOL;
+                    stride = H * BS;
+                } else off = LT_ZERO;
             }
-        } else if (cd <= -2) {
-            const double *src = a.pool + a.pool_off[-2 - cd];   // patch (Bs,Bs,H) per component
-            for (int i = tid; i < NC * BS * HB; i += NT) {
-                const int c = i / (BS * HB), r = i % (BS * HB), y = r / HB, xc = r % HB;
-                cp_async16(dst + c * PLANE + (y + H) * PITCH + XO + 2 * xc, src + ((long long)(c * H + kz) * BS + y) * BS + 2 * xc);
-            }
-        } else {
-            for (int i = tid; i < NC * BS * BS; i += NT) {
-                const int c = i / (BS * BS), r = i % (BS * BS), y = r / BS, x = r % BS;
-                dst[c * PLANE + (y + H) * PITCH + XO + x] = 0.0;
-            }
+        } else if (y >= 0 && y < BS) {
+            const int cd = v == 1 ? code[4] : code[22];           // (0,0,-1) -> 4 ; (0,0,+1) -> 22
+            if (cd >= 0) off = ((unsigned long long)cd * NC + c) * CS + (v == 1 ? (long long)(BS - H) * BS * BS : 0) + y * BS;
+            else if (cd <= -2) off = ((unsigned long long)a.pool_off[-2 - cd] + ((long long)c * H * BS + y) * BS) | LT_POOL;  // (Bs,Bs,H)
+            else off = LT_ZERO;
         }
-        return;
+        lt.row_off[v][rid] = off;
+        lt.row_stride[v][rid] = stride;
     }
+    for (int i = tid; i < LT::NXH; i += NT) {
+        const int side = i & 1, cy = i >> 1, c = cy / BS, y = cy % BS;
+        const int cd = side ? code[14] : code[12];                // (+1,0,0) -> 14 ; (-1,0,0) -> 12
+        unsigned long long off;
+        int stride = BS * BS;
+        if (cd >= 0) off = ((unsigned long long)cd * NC + c) * CS + y * BS + (side ? 0 : BS - H);
+        else if (cd <= -2) {                                      // pool patch (H, Bs, Bs)
+            off = ((unsigned long long)a.pool_off[-2 - cd] + ((long long)c * BS * BS + y) * H) | LT_POOL;
+            stride = BS * H;
+        } else off = LT_ZERO;
+        lt.x_off[i] = off;
+        lt.x_stride[i] = stride;
+    }
+}
 
-    // interior plane: rows y = -H .. BS+H-1 (16-byte chunks), then the x halos (8-byte elements)
-    {
-        const int c_ym = code[10], c_yp = code[16];   // (0,-1,0) -> 10 ; (0,+1,0) -> 16
-        const double *own = uin + ((long long)b * NC) * CS + (long long)zp * BS * BS;
-        for (int i = tid; i < NC * T::ROWS * HB; i += NT) {
-            const int c = i / (T::ROWS * HB), r = i % (T::ROWS * HB), row = r / HB, xc = r % HB;
-            const int y = row - H;
-            double *d = dst + c * PLANE + row * PITCH + XO + 2 * xc;
-            if (y >= 0 && y < BS) {
-                cp_async16(d, own + c * CS + y * BS + 2 * xc);
-            } else {
-                const int cd = y < 0 ? c_ym : c_yp;
-                const int ys = y < 0 ? BS + y : y - BS;      // row in the neighbour's interior
-                const int ky = y < 0 ? y + H : y - BS;       // row in the pool patch (Bs,H,Bs)
-                if (cd >= 0)
-                    cp_async16(d, uin + ((long long)cd * NC + c) * CS + (long long)zp * BS * BS + ys * BS + 2 * xc);
-                else if (cd <= -2)
-                    cp_async16(d, a.pool + a.pool_off[-2 - cd] + ((long long)(c * BS + zp) * H + ky) * BS + 2 * xc);
-                else {
+template <int FD, int BS>
+__device__ __forceinline__ void load_plane(const StageArgs &a, const LoadTables<FD, BS> &lt, double *sm, int q, int tid)
+{
+    using T = Tile<FD, BS>;
+    using LT = LoadTables<FD, BS>;
+    constexpr int H = T::H, XO = T::XO, PITCH = T::PITCH, PLANE = T::PLANE, NT = T::NT, HB = BS / 2;
+    const int zp = q - H;
+    const int v = zp < 0 ? 1 : (zp >= BS ? 2 : 0);
+    const int pz = zp < 0 ? zp + H : (zp >= BS ? zp - BS : zp);
+    double *dst = sm + (q % T::RING) * T::SLOT;
+
+#pragma unroll
+    for (int k = 0; k < (LT::NROW * HB + NT - 1) / NT; ++k) {
+        const int i = tid + k * NT;
+        if (i < LT::NROW * HB) {
+            const int rid = i / HB, xc = i % HB;
+            const unsigned long long off = lt.row_off[v][rid];
+            if (off != LT_SKIP) {
+                double *d = dst + rid * PITCH + XO + 2 * xc;       // c*PLANE + row*PITCH == rid*PITCH
+                if (off == LT_ZERO) {
                     d[0] = 0.0;
                     d[1] = 0.0;
+                } else {
+                    const double *base = (off & LT_POOL) ? a.pool : a.u_in;
+                    cp_async16(d, base + (long long)(off & ~LT_POOL) + (long long)pz * lt.row_stride[v][rid] + 2 * xc);
                 }
             }
         }
-        const int c_xm = code[12], c_xp = code[14];   // (-1,0,0) -> 12 ; (+1,0,0) -> 14
-        for (int i = tid; i < NC * BS * 2 * H; i += NT) {
-            const int c = i / (BS * 2 * H), r = i % (BS * 2 * H), y = r / (2 * H), e = r % (2 * H);
-            const bool lo = e < H;
-            const int x = lo ? e - H : BS + (e - H);         // -H..-1 or BS..BS+H-1
-            const int cd = lo ? c_xm : c_xp;
-            const int xs = lo ? BS + x : x - BS;
-            const int kx = lo ? e : e - H;                   // column in the pool patch (H,Bs,Bs)
-            double *d = dst + c * PLANE + (y + H) * PITCH + XO + x;
-            if (cd >= 0)
-                cp_async8(d, uin + ((long long)cd * NC + c) * CS + (long long)zp * BS * BS + y * BS + xs);
-            else if (cd <= -2)
-                cp_async8(d, a.pool + a.pool_off[-2 - cd] + ((long long)(c * BS + zp) * BS + y) * H + kx);
-            else
-                d[0] = 0.0;
+    }
+    if (v == 0) {
+        // x halos: H elements per (component, row, side); 16-byte chunks when H is even, else 8-byte elements
+        constexpr int PER = (H % 2 == 0) ? H / 2 : H;
+#pragma unroll
+        for (int k = 0; k < (LT::NXH * PER + NT - 1) / NT; ++k) {
+            const int i = tid + k * NT;
+            if (i < LT::NXH * PER) {
+                const int sid = i / PER, e = i % PER, side = sid & 1, cy = sid >> 1, c = cy / BS, y = cy % BS;
+                const unsigned long long off = lt.x_off[sid];
+                double *d = dst + c * PLANE + (y + H) * PITCH + XO + (side ? BS : -H);
+                if (off == LT_ZERO) {
+                    if (H % 2 == 0) { d[2 * e] = 0.0; d[2 * e + 1] = 0.0; }
+                    else d[e] = 0.0;
+                } else {
+                    const double *src = ((off & LT_POOL) ? a.pool : a.u_in) + (long long)(off & ~LT_POOL) + (long long)pz * lt.x_stride[sid];
+                    if (H % 2 == 0) cp_async16(d + 2 * e, src + 2 * e);
+                    else cp_async8(d + e, src + e);
+                }
+            }
         }
     }
 }
@@ -233,11 +275,14 @@ __global__ void __launch_bounds__(BS *BS, (Tile<FD, BS>::SMEM <= 110 * 1024 ? 2 
     extern __shared__ __align__(16) double sm[];
     __shared__ int s_code[WGPU_NDIR];
     __shared__ double s_red[32];
+    __shared__ LoadTables<FD, BS> s_lt;
 
     const int tid = threadIdx.x;
     const int tx = tid % BS, ty = tid / BS;
     const int b = a.active[blockIdx.x];
     if (tid < WGPU_NDIR) s_code[tid] = a.nbr[b * WGPU_NDIR + tid];
+    __syncthreads();
+    build_tables<FD, BS>(a, s_lt, b, s_code, tid);
     __syncthreads();
 
     // geometry of this block (module_treelib.f90:93): dx = 2^-J * L / Bs
@@ -245,13 +290,16 @@ __global__ void __launch_bounds__(BS *BS, (Tile<FD, BS>::SMEM <= 110 * 1024 ? 2 
     const double dx = a.dx_lvl[lvl][0], dy = a.dx_lvl[lvl][1], dz = a.dx_lvl[lvl][2];
     const double dinv[3] = {1.0 / dx, 1.0 / dy, 1.0 / dz};
     const double d2inv[3] = {1.0 / (dx * dx), 1.0 / (dy * dy), 1.0 / (dz * dz)};
-    const double dt = a.u_out ? *a.dt_ptr : 0.0;
+    const double dt = (a.u_out || a.acc_out) ? *a.dt_ptr : 0.0;
+    // bases of the two epilogue outputs; when a base is the stage input itself its value is already in smem
+    const bool base_u_global = a.u_out && a.u0 != a.u_in;
+    const bool base_acc_global = a.acc_out && a.acc_in != a.u_in;
     const double c02 = a.c0 * a.c0;
 
     // prologue: planes 0 .. 2H+PF-1 in flight
 #pragma unroll 1
     for (int q = 0; q < 2 * H + PF; ++q) {
-        if (q < NQ) load_plane<FD, BS>(a, sm, q, b, s_code, tid);
+        if (q < NQ) load_plane<FD, BS>(a, s_lt, sm, q, tid);
         cp_async_commit();
     }
 
@@ -268,8 +316,20 @@ __global__ void __launch_bounds__(BS *BS, (Tile<FD, BS>::SMEM <= 110 * 1024 ? 2 
         {
             // refill the slot of plane z-1 (last read in iteration z-1, which every thread has left: barrier above)
             const int q = z + 2 * H + PF;
-            if (q < NQ) load_plane<FD, BS>(a, sm, q, b, s_code, tid);
+            if (q < NQ) load_plane<FD, BS>(a, s_lt, sm, q, tid);
             cp_async_commit();
+        }
+
+        // issue the epilogue's global reads now: their latency hides behind the stencil arithmetic of this plane
+        const long long gi = ((long long)b * NC) * CS + (long long)z * BS * BS + ty * BS + tx;
+        double pre_u[4], pre_acc[4];
+        if (base_u_global) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) pre_u[c] = __ldg(a.u0 + gi + c * CS);
+        }
+        if (base_acc_global) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) pre_acc[c] = a.acc_in[gi + c * CS];
         }
 
         double rhs[4];
@@ -334,19 +394,23 @@ __global__ void __launch_bounds__(BS *BS, (Tile<FD, BS>::SMEM <= 110 * 1024 ? 2 
         }
         uabs_max = fmax(uabs_max, fmax(fmax(fabs(ctr[0]), fabs(ctr[1])), fmax(fabs(ctr[2]), fabs(ctr[3]))));
 
-        // epilogue: store the slope and form the next stage input / the new state
-        const long long gi = ((long long)b * NC) * CS + (long long)z * BS * BS + ty * BS + tx;
+        // epilogue: store the slope, form the next stage input / the new state and the running final combination
         double un[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             if (a.k_out) a.k_out[gi + c * CS] = rhs[c];
             if (a.u_out) {
-                double acc = (a.u0 == a.u_in) ? ctr[c] : a.u0[gi + c * CS];
+                double acc = base_u_global ? pre_u[c] : ctr[c];
                 for (int l = 0; l < a.n_prev; ++l)   // (dt*a_jl)*k_l, increasing l  (runge_kutta_generic.f90:108-110)
                     acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dt, a.coef_prev[l]), a.k_prev[l][gi + c * CS]));
                 if (a.use_self) acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dt, a.coef_self), rhs[c]));
                 a.u_out[gi + c * CS] = acc;
                 un[c] = acc;
+            }
+            if (a.acc_out) {   // runge_kutta_generic.f90:142-153, one term per stage, increasing j
+                double acc = base_acc_global ? pre_acc[c] : ctr[c];
+                if (a.use_acc) acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dt, a.coef_acc), rhs[c]));
+                a.acc_out[gi + c * CS] = acc;
             }
         }
         if (a.dtmin_bits && a.u_out) {

@@ -33,6 +33,12 @@ struct StageArgs {
     int n_prev;
     double coef_self;          // coefficient of the slope computed by this launch
     int use_self;
+    // running final combination ("acc mode", tableaus whose stage inputs only use the previous slope):
+    //   acc_out = acc_in + (dt*coef_acc)*k_this   (acc_in == u_in: take the stage input itself)
+    const double *acc_in;
+    double *acc_out;           // may alias acc_in (each thread reads and writes only its own point)
+    double coef_acc;
+    int use_acc;
     const double *dt_ptr;      // device scalar
     const double *mask;        // compact [blk][n_mask][Bs^3] or nullptr
     int n_mask;
