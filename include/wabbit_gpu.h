@@ -138,6 +138,39 @@ int32_t wgpu_calculate_time_step(wgpu_ctx *ctx, double time, double *dt);
  *   final combination; hvy_block is advanced in place on the device.  *dt receives the step taken. */
 int32_t wgpu_rk_step(wgpu_ctx *ctx, double time, int32_t iteration, double *dt);
 
+/*
+ * ---- multi-GPU (one process per GPU): the Runge-Kutta step split at the points where ranks must talk.
+ * The reference exchanges ghost patches with MPI_Isend/Irecv once per sync (LIB/MPI/xfer_block_data.f90:10-99) and
+ * all-reduces dt with MPI_MIN (LIB/TIME/calculate_time_step.f90:48).  Here the host moves bytes with NCCL
+ * (torch.distributed) between the library's pack kernel and the stage kernels, which read remote halos straight
+ * from the receive buffer ("patch pool") -- there is no unpack pass.
+ *
+ *   wgpu_rk_begin(time)        local CFL candidate -> device scalar (wgpu_dtmin_pointer); host all-reduces it (MIN)
+ *   wgpu_rk_dt(time)           calculate_time_step's clipping, dt stays on the device
+ *   for j = 1..s:  wgpu_pack_halo(j); <host: all-to-all send_buf -> pool>; wgpu_rk_stage(j, WGPU_BLOCKS_ALL)
+ *                  (or stage(j, INTERIOR) overlapped with the exchange, then stage(j, BOUNDARY))
+ *   wgpu_rk_end(&dt)
+ * wgpu_rk_step() is exactly this sequence without the host steps.
+ *
+ * wgpu_set_exchange: face patches this rank receives (block hvy id, direction index (dz+1)*9+(dy+1)*3+(dx+1)) in
+ * the order they arrive in `pool`, and the patches it sends in the order they are laid out in `send_buf`.
+ * Patch = nc x (g_rhs deep strip), laid out as the receiver's ghost strip, x fastest.  pool / send_buf are device
+ * buffers owned by the caller (n_recv resp. n_send patches of wgpu_patch_doubles() doubles).
+ * Must be called after wgpu_set_topology (which accepts neighbours on other ranks only if this call follows).
+ */
+enum { WGPU_BLOCKS_ALL = 0, WGPU_BLOCKS_INTERIOR = 1, WGPU_BLOCKS_BOUNDARY = 2 };
+int64_t wgpu_patch_doubles(const wgpu_ctx *ctx);
+int32_t wgpu_set_exchange(wgpu_ctx *ctx, int32_t n_recv, const int32_t *recv_hvy, const int32_t *recv_dir, double *pool,
+                          int32_t n_send, const int32_t *send_hvy, const int32_t *send_dir, double *send_buf);
+int32_t wgpu_pack_halo(wgpu_ctx *ctx, int32_t stage);
+int32_t wgpu_rk_begin(wgpu_ctx *ctx, double time);
+int32_t wgpu_dtmin_pointer(wgpu_ctx *ctx, void **ptr);
+int32_t wgpu_rk_dt(wgpu_ctx *ctx, double time);
+int32_t wgpu_rk_stage(wgpu_ctx *ctx, int32_t stage, int32_t which_blocks);
+int32_t wgpu_rk_end(wgpu_ctx *ctx, double *dt);
+/* number of blocks in each set (ALL / INTERIOR / BOUNDARY) */
+int32_t wgpu_block_count(const wgpu_ctx *ctx, int32_t which_blocks);
+
 /* Stage-kernel timing with CUDA events on the context's stream (for the roofline line of bench.py):
  * wgpu_profile(ctx, 1) starts recording an event pair around every stage-kernel launch (at most 4096 pairs),
  * wgpu_profile_read synchronises, returns their number and summed duration in milliseconds, and resets. */

@@ -44,6 +44,15 @@ GPU_SYMBOLS = {
     "wgpu_rhs": (C.c_int32, [C.c_void_p, C.c_double, C.c_int32, C.c_int32]),
     "wgpu_calculate_time_step": (C.c_int32, [C.c_void_p, C.c_double, _dp]),
     "wgpu_rk_step": (C.c_int32, [C.c_void_p, C.c_double, C.c_int32, _dp]),
+    "wgpu_patch_doubles": (C.c_int64, [C.c_void_p]),
+    "wgpu_set_exchange": (C.c_int32, [C.c_void_p, C.c_int32, _i32p, _i32p, C.c_void_p, C.c_int32, _i32p, _i32p, C.c_void_p]),
+    "wgpu_pack_halo": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "wgpu_rk_begin": (C.c_int32, [C.c_void_p, C.c_double]),
+    "wgpu_dtmin_pointer": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "wgpu_rk_dt": (C.c_int32, [C.c_void_p, C.c_double]),
+    "wgpu_rk_stage": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32]),
+    "wgpu_rk_end": (C.c_int32, [C.c_void_p, _dp]),
+    "wgpu_block_count": (C.c_int32, [C.c_void_p, C.c_int32]),
     "wgpu_profile": (C.c_int32, [C.c_void_p, C.c_int32]),
     "wgpu_profile_read": (C.c_int32, [C.c_void_p, _i32p, _dp]),
     "wgpu_launch_count": (C.c_int64, [C.c_void_p]),

@@ -196,8 +196,11 @@ int32_t wgpu_destroy(wgpu_ctx *ctx)
     cudaFree(ctx->d_active);
     cudaFree(ctx->d_nbr);
     cudaFree(ctx->d_level);
-    cudaFree(ctx->d_pool);
     cudaFree(ctx->d_pool_off);
+    cudaFree(ctx->d_active_int);
+    cudaFree(ctx->d_active_bnd);
+    cudaFree(ctx->d_send_blk);
+    cudaFree(ctx->d_send_dir);
     cudaFree(ctx->d_dt);
     cudaFree(ctx->d_dtmin);
     cudaFree(ctx->d_flags);
@@ -281,6 +284,7 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
     const int N = c.max_blocks;
     if (n_active > N) return fail(ctx, WGPU_ERR_ARG, "more active blocks than max_blocks");
     ctx->h_active.assign(n_active, 0);
+    ctx->remote_faces.clear();
     ctx->h_nbr.assign((size_t)N * WGPU_NDIR, -1);
     ctx->h_level.assign(N, 0);
     for (int k = 0; k < n_active; ++k) {
@@ -301,8 +305,16 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
                     int entry = -1;
                     if (lgt >= 1) {
                         const int r = (lgt - 1) / N;           // lgt2proc.f90
-                        if (r != rank) return fail(ctx, WGPU_ERR_UNSUPPORTED, "neighbour on another rank: multi-GPU ghost exchange goes through the patch pool (not built yet)");
-                        entry = (lgt - 1) - r * N;
+                        if (r != rank) {
+                            // same-level neighbour on another GPU: resolved to a pool patch by wgpu_set_exchange (faces);
+                            // edges/corners are not needed by the star stencils of the time step
+                            entry = -1;
+                            if ((dx != 0) + (dy != 0) + (dz != 0) == 1) {
+                                ctx->remote_faces.push_back(hid - 1);
+                                ctx->remote_faces.push_back((dz + 1) * 9 + (dy + 1) * 3 + (dx + 1));
+                            }
+                        } else
+                            entry = (lgt - 1) - r * N;
                     } else {
                         // coarser (+56) or finer (+112) neighbours in this direction?
                         for (int s = 0; s < nfree; ++s) {
@@ -315,7 +327,15 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
                 }
     }
     ctx->n_active = n_active;
+    ctx->n_int = n_active;
+    ctx->n_bnd = 0;
+    if (!ctx->d_active_int) {
+        int32_t rc2 = dmalloc(ctx, &ctx->d_active_int, (size_t)N);
+        if (rc2) return rc2;
+        if ((rc2 = dmalloc(ctx, &ctx->d_active_bnd, (size_t)N))) return rc2;
+    }
     if (n_active) {
+        WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_active_int, ctx->h_active.data(), sizeof(int) * n_active, cudaMemcpyHostToDevice, ctx->stream));
         WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_active, ctx->h_active.data(), sizeof(int) * n_active, cudaMemcpyHostToDevice, ctx->stream));
         WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_nbr, ctx->h_nbr.data(), sizeof(int) * ctx->h_nbr.size(), cudaMemcpyHostToDevice, ctx->stream));
         WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_level, ctx->h_level.data(), (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
@@ -433,7 +453,7 @@ int32_t wgpu_rhs(wgpu_ctx *ctx, double time, int32_t src_slot, int32_t dst_slot)
     a.u_in = src;
     a.u0 = src;
     a.k_out = dst;
-    int32_t rc = wgpu_launch_stage(ctx, a);
+    int32_t rc = wgpu_launch_stage(ctx, a, ctx->n_active);
     if (rc) return rc;
     return check_flags(ctx);
 }
@@ -464,18 +484,91 @@ int32_t wgpu_calculate_time_step(wgpu_ctx *ctx, double time, double *dt)
     return WGPU_OK;
 }
 
-int32_t wgpu_rk_step(wgpu_ctx *ctx, double time, int32_t iteration, double *dt)
+// ------------------------------------------------------------------------------------------------ multi-GPU exchange
+static int fd_halo(const wgpu_ctx *ctx) { return ctx->cfg.fd == 2 ? 1 : (ctx->cfg.fd == 4 ? 2 : 3); }
+
+int64_t wgpu_patch_doubles(const wgpu_ctx *ctx)
 {
-    (void)iteration;
-    if (!ctx || !dt) return WGPU_ERR_ARG;
+    if (!ctx) return 0;
+    return (int64_t)ctx->nc * fd_halo(ctx) * ctx->cfg.Bs[0] * ctx->cfg.Bs[1];
+}
+
+int32_t wgpu_block_count(const wgpu_ctx *ctx, int32_t which)
+{
+    if (!ctx) return 0;
+    return which == WGPU_BLOCKS_INTERIOR ? ctx->n_int : (which == WGPU_BLOCKS_BOUNDARY ? ctx->n_bnd : ctx->n_active);
+}
+
+int32_t wgpu_set_exchange(wgpu_ctx *ctx, int32_t n_recv, const int32_t *recv_hvy, const int32_t *recv_dir, double *pool, int32_t n_send,
+                          const int32_t *send_hvy, const int32_t *send_dir, double *send_buf)
+{
+    if (!ctx || n_recv < 0 || n_send < 0) return WGPU_ERR_ARG;
+    if ((n_recv && (!recv_hvy || !recv_dir || !pool)) || (n_send && (!send_hvy || !send_dir || !send_buf))) return WGPU_ERR_ARG;
+    const wgpu_config &c = ctx->cfg;
+    if (c.dim != 3 || c.Bs[0] != c.Bs[1] || c.Bs[0] != c.Bs[2]) return fail(ctx, WGPU_ERR_UNSUPPORTED, "exchange needs cubic 3-D blocks");
+    if ((size_t)n_recv * 2 != ctx->remote_faces.size()) return fail(ctx, WGPU_ERR_ARG, "wgpu_set_exchange: receive list does not cover the remote faces of the topology");
+    const int N = c.max_blocks;
+    const int64_t pd = wgpu_patch_doubles(ctx);
+    std::vector<long long> off(n_recv > 0 ? n_recv : 1);
+    std::vector<char> is_bnd(N, 0);
+    for (int k = 0; k < n_recv; ++k) {
+        const int b = recv_hvy[k] - 1, d = recv_dir[k];
+        if (b < 0 || b >= N || d < 0 || d >= WGPU_NDIR) return fail(ctx, WGPU_ERR_ARG, "wgpu_set_exchange: bad receive entry");
+        ctx->h_nbr[(size_t)b * WGPU_NDIR + d] = -2 - k;
+        off[k] = (long long)k * pd;
+        is_bnd[b] = 1;
+    }
+    std::vector<int> ai, ab;
+    for (int k = 0; k < ctx->n_active; ++k) (is_bnd[ctx->h_active[k]] ? ab : ai).push_back(ctx->h_active[k]);
+    ctx->n_int = (int)ai.size();
+    ctx->n_bnd = (int)ab.size();
+    cudaFree(ctx->d_pool_off);
+    cudaFree(ctx->d_send_blk);
+    cudaFree(ctx->d_send_dir);
+    ctx->d_pool_off = nullptr;
+    ctx->d_send_blk = ctx->d_send_dir = nullptr;
+    int32_t rc;
+    if ((rc = dmalloc(ctx, &ctx->d_pool_off, (size_t)std::max(n_recv, 1)))) return rc;
+    if ((rc = dmalloc(ctx, &ctx->d_send_blk, (size_t)std::max(n_send, 1)))) return rc;
+    if ((rc = dmalloc(ctx, &ctx->d_send_dir, (size_t)std::max(n_send, 1)))) return rc;
+    std::vector<int> sb(std::max(n_send, 1)), sd(std::max(n_send, 1));
+    for (int k = 0; k < n_send; ++k) {
+        sb[k] = send_hvy[k] - 1;
+        sd[k] = send_dir[k];
+        if (sb[k] < 0 || sb[k] >= N || sd[k] < 0 || sd[k] >= WGPU_NDIR) return fail(ctx, WGPU_ERR_ARG, "wgpu_set_exchange: bad send entry");
+    }
+    ctx->n_send = n_send;
+    ctx->d_pool = pool;
+    ctx->d_send_buf = send_buf;
+    WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_pool_off, off.data(), sizeof(long long) * off.size(), cudaMemcpyHostToDevice, ctx->stream));
+    WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_send_blk, sb.data(), sizeof(int) * sb.size(), cudaMemcpyHostToDevice, ctx->stream));
+    WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_send_dir, sd.data(), sizeof(int) * sd.size(), cudaMemcpyHostToDevice, ctx->stream));
+    WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_nbr, ctx->h_nbr.data(), sizeof(int) * ctx->h_nbr.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (!ai.empty()) WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_active_int, ai.data(), sizeof(int) * ai.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (!ab.empty()) WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_active_bnd, ab.data(), sizeof(int) * ab.size(), cudaMemcpyHostToDevice, ctx->stream));
+    WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->remote_faces.clear();
+    return WGPU_OK;
+}
+
+static bool exchange_pending(wgpu_ctx *ctx) { return !ctx->remote_faces.empty(); }
+
+// ------------------------------------------------------------------------------------------------ Runge-Kutta, phase by phase
+int32_t wgpu_rk_begin(wgpu_ctx *ctx, double time)
+{
+    (void)time;
+    if (!ctx) return WGPU_ERR_ARG;
     const wgpu_config &c = ctx->cfg;
     if (c.dim != 3) return fail(ctx, WGPU_ERR_UNSUPPORTED, "2-D ACM kernels are not built yet");
+    if (exchange_pending(ctx)) return fail(ctx, WGPU_ERR_ARG, "topology has neighbours on other ranks: call wgpu_set_exchange first");
+    unsigned long long *cur = ctx->d_dtmin + ctx->dtmin_cur;
+    if (!ctx->dtmin_valid && !(c.dt_fixed > 0.0)) {
+        const unsigned long long inf = 0x7FF0000000000000ULL;
+        WGPU_CHECK(ctx, cudaMemcpyAsync(cur, &inf, 8, cudaMemcpyHostToDevice, ctx->stream));
+        int32_t rc = wgpu_launch_dtmin(ctx, ctx->U, cur);
+        if (rc) return rc;
+    }
     const int s = c.n_stages, ld = s + 1;
-    int32_t rc;
-    // runge_kutta_generic.f90:52-56: ghost sync (fused into the stage kernels) and the time step
-    if ((rc = compute_dt(ctx, time))) return rc;
-    unsigned long long *dtmin_next = ctx->d_dtmin + ctx->dtmin_cur;   // reset to +inf by dt_finalize
-
     // "acc mode": if every stage input only uses the slope of the stage before (a_{j,l} = 0 for l < j-1; true for
     // RK4 and Euler/Heun/midpoint), no slope has to be stored: the final combination is accumulated stage by stage
     // in the array K[0] in exactly the reference's order  ((u0 + dt b1 k1) + dt b2 k2) + ...
@@ -483,54 +576,110 @@ int32_t wgpu_rk_step(wgpu_ctx *ctx, double time, int32_t iteration, double *dt)
     for (int j = 1; j < s && subdiag; ++j)          // 0-based row j = stage j+1, whose previous slope is column j
         for (int l = 1; l < j; ++l)
             if (fabs(c.butcher[(size_t)j * ld + l]) >= 1.0e-8) subdiag = false;
+    ctx->rk_subdiag = subdiag;
+    ctx->rk_uin = ctx->U;
+    ctx->rk_next_stage = 0;   // becomes 1 after wgpu_rk_dt
+    return WGPU_OK;
+}
 
-    const double *uin = ctx->U;
-    for (int j = 1; j <= s; ++j) {
-        StageArgs a;
-        fill_common_args(ctx, a);
-        a.u_in = uin;
-        a.u0 = ctx->U;
-        const bool last = (j == s);
-        // the final state may overwrite U in place (each thread reads its bases only at its own point, halos come
-        // from the stage input) unless the stage input IS U (single-stage schemes): then go through UA and swap
-        double *uout = last ? (uin == ctx->U ? ctx->UA : ctx->U) : ((j & 1) ? ctx->UA : ctx->UB);
-        a.u_out = uout;
-        const double *brow = c.butcher + (size_t)s * ld;          // final weights b_j = butcher(s+1, j+1)
-        if (subdiag) {
-            double *ACC = ctx->K[0];
-            if (!last) {
-                const double *row = c.butcher + (size_t)j * ld;   // row of stage j+1
-                a.use_self = fabs(row[j]) >= 1.0e-8;
-                a.coef_self = row[j];
-                a.acc_in = (j == 1) ? ctx->U : ACC;
-                a.acc_out = ACC;
-                a.use_acc = fabs(brow[j]) >= 1.0e-8;
-                a.coef_acc = brow[j];
-            } else {
-                a.u0 = ACC;                                        // u = acc_{s-1} + (dt b_s) k_s
-                a.use_self = fabs(brow[j]) >= 1.0e-8;
-                a.coef_self = brow[j];
-            }
-        } else {
-            a.k_out = last ? nullptr : ctx->K[j - 1];              // the last slope only enters the final combination
-            // row of the tableau that forms u_out: stage j+1 input (row j+1) or the final weights (row s+1)
-            const double *row = last ? brow : c.butcher + (size_t)j * ld;
-            a.n_prev = 0;
-            for (int l = 1; l < j; ++l) {
-                if (fabs(row[l]) < 1.0e-8) continue;               // runge_kutta_generic.f90:99,144
-                a.k_prev[a.n_prev] = ctx->K[l - 1];
-                a.coef_prev[a.n_prev] = row[l];
-                a.n_prev++;
-            }
+int32_t wgpu_dtmin_pointer(wgpu_ctx *ctx, void **ptr)
+{
+    if (!ctx || !ptr) return WGPU_ERR_ARG;
+    *ptr = ctx->d_dtmin + ctx->dtmin_cur;
+    return WGPU_OK;
+}
+
+int32_t wgpu_rk_dt(wgpu_ctx *ctx, double time)
+{
+    if (!ctx) return WGPU_ERR_ARG;
+    unsigned long long *cur = ctx->d_dtmin + ctx->dtmin_cur, *nxt = ctx->d_dtmin + (ctx->dtmin_cur ^ 1);
+    int32_t rc = wgpu_launch_dt_finalize(ctx, time, cur, nxt);
+    if (rc) return rc;
+    ctx->dtmin_cur ^= 1;
+    ctx->dtmin_valid = false;
+    ctx->rk_next_stage = 1;
+    return WGPU_OK;
+}
+
+static const double *stage_input(wgpu_ctx *ctx, int j)
+{
+    // stage 1 reads U; stage j>1 reads what stage j-1 wrote: UA for even j, UB for odd j
+    return j == 1 ? ctx->U : (((j - 1) & 1) ? ctx->UA : ctx->UB);
+}
+
+int32_t wgpu_pack_halo(wgpu_ctx *ctx, int32_t stage)
+{
+    if (!ctx || stage < 1 || stage > ctx->cfg.n_stages) return WGPU_ERR_ARG;
+    return wgpu_launch_pack(ctx, stage_input(ctx, stage));
+}
+
+int32_t wgpu_rk_stage(wgpu_ctx *ctx, int32_t j, int32_t which)
+{
+    if (!ctx) return WGPU_ERR_ARG;
+    const wgpu_config &c = ctx->cfg;
+    const int s = c.n_stages, ld = s + 1;
+    if (j < 1 || j > s || ctx->rk_next_stage < 1) return fail(ctx, WGPU_ERR_ARG, "wgpu_rk_stage: call wgpu_rk_begin / wgpu_rk_dt first");
+    unsigned long long *dtmin_next = ctx->d_dtmin + ctx->dtmin_cur;   // reset to +inf by dt_finalize
+    const double *uin = stage_input(ctx, j);
+    StageArgs a;
+    fill_common_args(ctx, a);
+    a.u_in = uin;
+    a.u0 = ctx->U;
+    const bool last = (j == s);
+    // the final state may overwrite U in place (each thread reads its bases only at its own point, halos come
+    // from the stage input) unless the stage input IS U (single-stage schemes): then go through UA and swap
+    double *uout = last ? (uin == ctx->U ? ctx->UA : ctx->U) : ((j & 1) ? ctx->UA : ctx->UB);
+    a.u_out = uout;
+    const double *brow = c.butcher + (size_t)s * ld;          // final weights b_j = butcher(s+1, j+1)
+    if (ctx->rk_subdiag) {
+        double *ACC = ctx->K[0];
+        if (!last) {
+            const double *row = c.butcher + (size_t)j * ld;   // row of stage j+1
             a.use_self = fabs(row[j]) >= 1.0e-8;
             a.coef_self = row[j];
+            a.acc_in = (j == 1) ? ctx->U : ACC;
+            a.acc_out = ACC;
+            a.use_acc = fabs(brow[j]) >= 1.0e-8;
+            a.coef_acc = brow[j];
+        } else {
+            a.u0 = ACC;                                        // u = acc_{s-1} + (dt b_s) k_s
+            a.use_self = fabs(brow[j]) >= 1.0e-8;
+            a.coef_self = brow[j];
         }
-        if (last && !(c.dt_fixed > 0.0)) a.dtmin_bits = dtmin_next;
-        if ((rc = wgpu_launch_stage(ctx, a))) return rc;
-        if (last && uout != ctx->U) std::swap(ctx->U, ctx->UA);
-        uin = uout;
+    } else {
+        a.k_out = last ? nullptr : ctx->K[j - 1];              // the last slope only enters the final combination
+        // row of the tableau that forms u_out: stage j+1 input (row j+1) or the final weights (row s+1)
+        const double *row = last ? brow : c.butcher + (size_t)j * ld;
+        a.n_prev = 0;
+        for (int l = 1; l < j; ++l) {
+            if (fabs(row[l]) < 1.0e-8) continue;               // runge_kutta_generic.f90:99,144
+            a.k_prev[a.n_prev] = ctx->K[l - 1];
+            a.coef_prev[a.n_prev] = row[l];
+            a.n_prev++;
+        }
+        a.use_self = fabs(row[j]) >= 1.0e-8;
+        a.coef_self = row[j];
     }
+    if (last && !(c.dt_fixed > 0.0)) a.dtmin_bits = dtmin_next;
+    int nblk = ctx->n_active;
+    if (which == WGPU_BLOCKS_INTERIOR) {
+        a.active = ctx->d_active_int;
+        nblk = ctx->n_int;
+    } else if (which == WGPU_BLOCKS_BOUNDARY) {
+        a.active = ctx->d_active_bnd;
+        nblk = ctx->n_bnd;
+    }
+    return wgpu_launch_stage(ctx, a, nblk);
+}
+
+int32_t wgpu_rk_end(wgpu_ctx *ctx, double *dt)
+{
+    if (!ctx || !dt) return WGPU_ERR_ARG;
+    const wgpu_config &c = ctx->cfg;
+    const int s = c.n_stages;
+    if (stage_input(ctx, s) == ctx->U) std::swap(ctx->U, ctx->UA);   // single-stage scheme: result was written to UA
     if (!(c.dt_fixed > 0.0)) ctx->dtmin_valid = true;
+    ctx->rk_next_stage = 0;
     WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_dt, 8, cudaMemcpyDeviceToHost, ctx->stream));
     WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pinned + 1, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -540,6 +689,21 @@ int32_t wgpu_rk_step(wgpu_ctx *ctx, double time, int32_t iteration, double *dt)
         return fail(ctx, WGPU_ERR_DIVERGED, "ACM fail: very very large values in state vector.");
     }
     return WGPU_OK;
+}
+
+int32_t wgpu_rk_step(wgpu_ctx *ctx, double time, int32_t iteration, double *dt)
+{
+    (void)iteration;
+    if (!ctx || !dt) return WGPU_ERR_ARG;
+    int32_t rc;
+    // runge_kutta_generic.f90:52-56: ghost sync (fused into the stage kernels) and the time step
+    if ((rc = wgpu_rk_begin(ctx, time))) return rc;
+    if ((rc = wgpu_rk_dt(ctx, time))) return rc;
+    for (int j = 1; j <= ctx->cfg.n_stages; ++j) {
+        if ((rc = wgpu_pack_halo(ctx, j))) return rc;   // no-op without remote neighbours
+        if ((rc = wgpu_rk_stage(ctx, j, WGPU_BLOCKS_ALL))) return rc;
+    }
+    return wgpu_rk_end(ctx, dt);
 }
 
 }  // extern "C"

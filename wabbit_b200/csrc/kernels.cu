@@ -565,8 +565,33 @@ __global__ void export_kernel(const double *__restrict__ src, double *__restrict
     d[((long long)(z + gz) * ny + (y + g)) * nx + (x + g)] = src[((long long)sb * ncomp_src + c) * CS + ((long long)zs * By + ys) * Bx + xs];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pack kernel: the sender side of the inter-GPU ghost exchange (send_prepare_external,
+// LIB/MPI/xfer_block_data.f90:106-246, same-level relations).  One CTA per face patch: copies the g_rhs-deep interior
+// strip facing the remote neighbour into the send buffer, already in the layout of the receiver's ghost strip, so the
+// receiver's stage kernel reads it in place.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_kernel(const double *__restrict__ src, double *__restrict__ send, const int *__restrict__ blk,
+                                                   const int *__restrict__ dir, int nc, int Bs, int H)
+{
+    const int i = blockIdx.x;
+    const int b = blk[i], d = dir[i];
+    const int dx = d % 3 - 1, dy = (d / 3) % 3 - 1, dz = d / 9 - 1;   // direction from the SENDER to the receiver
+    // strip extents in the sender's interior
+    const int ex = dx ? H : Bs, ey = dy ? H : Bs, ez = dz ? H : Bs;
+    const int x0 = dx > 0 ? Bs - H : 0, y0 = dy > 0 ? Bs - H : 0, z0 = dz > 0 ? Bs - H : 0;
+    const long long CS = (long long)Bs * Bs * Bs;
+    const int n = ex * ey * ez;
+    double *out = send + (long long)i * nc * n;
+    const double *in = src + (long long)b * nc * CS;
+    for (int e = threadIdx.x; e < nc * n; e += blockDim.x) {
+        const int c = e / n, r = e % n, x = r % ex, y = (r / ex) % ey, z = r / (ex * ey);
+        out[e] = in[c * CS + ((long long)(z0 + z) * Bs + (y0 + y)) * Bs + (x0 + x)];
+    }
+}
+
 template <int FD, bool SKEW, int BS>
-int32_t launch_stage_t(wgpu_ctx *ctx, const StageArgs &a)
+int32_t launch_stage_t(wgpu_ctx *ctx, const StageArgs &a, int n_blocks)
 {
     using T = Tile<FD, BS>;
     static bool configured = false;
@@ -576,7 +601,7 @@ int32_t launch_stage_t(wgpu_ctx *ctx, const StageArgs &a)
     }
     const bool prof = ctx->profiling && ctx->prof_n < (int)ctx->prof_ev.size() / 2;
     if (prof) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], ctx->stream);
-    stage_kernel<FD, SKEW, BS><<<ctx->n_active, T::NT, T::SMEM, ctx->stream>>>(a);
+    stage_kernel<FD, SKEW, BS><<<n_blocks, T::NT, T::SMEM, ctx->stream>>>(a);
     if (prof) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n++ + 1], ctx->stream);
     ctx->launches++;
     WGPU_CHECK(ctx, cudaGetLastError());
@@ -584,12 +609,12 @@ int32_t launch_stage_t(wgpu_ctx *ctx, const StageArgs &a)
 }
 
 template <int FD, bool SKEW>
-int32_t launch_stage_bs(wgpu_ctx *ctx, const StageArgs &a)
+int32_t launch_stage_bs(wgpu_ctx *ctx, const StageArgs &a, int n_blocks)
 {
     switch (ctx->cfg.Bs[0]) {
-    case 16: return launch_stage_t<FD, SKEW, 16>(ctx, a);
-    case 18: return launch_stage_t<FD, SKEW, 18>(ctx, a);
-    case 20: return launch_stage_t<FD, SKEW, 20>(ctx, a);
+    case 16: return launch_stage_t<FD, SKEW, 16>(ctx, a, n_blocks);
+    case 18: return launch_stage_t<FD, SKEW, 18>(ctx, a, n_blocks);
+    case 20: return launch_stage_t<FD, SKEW, 20>(ctx, a, n_blocks);
     default:
         ctx->err = "3-D stage kernel is instantiated for Bs in {16,18,20}";
         return WGPU_ERR_UNSUPPORTED;
@@ -597,21 +622,31 @@ int32_t launch_stage_bs(wgpu_ctx *ctx, const StageArgs &a)
 }
 
 template <int FD>
-int32_t launch_stage_skew(wgpu_ctx *ctx, const StageArgs &a)
+int32_t launch_stage_skew(wgpu_ctx *ctx, const StageArgs &a, int n_blocks)
 {
-    return ctx->cfg.skew_symmetry ? launch_stage_bs<FD, true>(ctx, a) : launch_stage_bs<FD, false>(ctx, a);
+    return ctx->cfg.skew_symmetry ? launch_stage_bs<FD, true>(ctx, a, n_blocks) : launch_stage_bs<FD, false>(ctx, a, n_blocks);
 }
 
 }  // namespace
 
-int32_t wgpu_launch_stage(wgpu_ctx *ctx, const StageArgs &a)
+int32_t wgpu_launch_pack(wgpu_ctx *ctx, const double *src)
 {
-    if (ctx->n_active == 0) return WGPU_OK;
+    if (ctx->n_send == 0) return WGPU_OK;
+    const int H = ctx->cfg.fd == 2 ? 1 : (ctx->cfg.fd == 4 ? 2 : 3);   // halo depth the stage kernel gathers
+    pack_kernel<<<ctx->n_send, 256, 0, ctx->stream>>>(src, ctx->d_send_buf, ctx->d_send_blk, ctx->d_send_dir, ctx->nc, ctx->cfg.Bs[0], H);
+    ctx->launches++;
+    WGPU_CHECK(ctx, cudaGetLastError());
+    return WGPU_OK;
+}
+
+int32_t wgpu_launch_stage(wgpu_ctx *ctx, const StageArgs &a, int n_blocks)
+{
+    if (n_blocks == 0) return WGPU_OK;
     switch (ctx->cfg.fd) {
-    case 2: return launch_stage_skew<2>(ctx, a);
-    case 4: return launch_stage_skew<4>(ctx, a);
-    case 6: return launch_stage_skew<6>(ctx, a);
-    case 40: return launch_stage_skew<40>(ctx, a);
+    case 2: return launch_stage_skew<2>(ctx, a, n_blocks);
+    case 4: return launch_stage_skew<4>(ctx, a, n_blocks);
+    case 6: return launch_stage_skew<6>(ctx, a, n_blocks);
+    case 40: return launch_stage_skew<40>(ctx, a, n_blocks);
     }
     ctx->err = "unknown order_discretization id";
     return WGPU_ERR_UNSUPPORTED;

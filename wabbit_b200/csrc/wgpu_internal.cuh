@@ -85,8 +85,19 @@ struct wgpu_ctx {
     std::vector<int> h_active;
     std::vector<int> h_nbr;
     std::vector<signed char> h_level;
-    double *d_pool = nullptr;
+    double *d_pool = nullptr;          // receive buffer of remote face patches (owned by the caller)
     long long *d_pool_off = nullptr;
+    // multi-GPU exchange
+    std::vector<int> remote_faces;     // (block, dir) pairs with a same-level neighbour on another rank, pending wgpu_set_exchange
+    int n_int = 0, n_bnd = 0;          // interior / boundary split of the active list
+    int *d_active_int = nullptr, *d_active_bnd = nullptr;
+    int n_send = 0;
+    int *d_send_blk = nullptr, *d_send_dir = nullptr;
+    double *d_send_buf = nullptr;
+    // Runge-Kutta step in flight
+    const double *rk_uin = nullptr;
+    int rk_next_stage = 0;
+    bool rk_subdiag = false;
 
     // scalars
     double *d_dt = nullptr;                   // dt of the current step
@@ -118,7 +129,8 @@ struct wgpu_ctx {
     } while (0)
 
 // kernels.cu
-int32_t wgpu_launch_stage(wgpu_ctx *ctx, const StageArgs &a);
+int32_t wgpu_launch_stage(wgpu_ctx *ctx, const StageArgs &a, int n_blocks);
+int32_t wgpu_launch_pack(wgpu_ctx *ctx, const double *src);
 int32_t wgpu_launch_dtmin(wgpu_ctx *ctx, const double *u, unsigned long long *dtmin_bits);
 int32_t wgpu_launch_dt_finalize(wgpu_ctx *ctx, double time, const unsigned long long *dtmin_bits,
                                 unsigned long long *dtmin_next);
