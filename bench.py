@@ -129,7 +129,7 @@ def cpu_run(a, level: int, steps: int, warmup: int):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    os.environ["OMP_NUM_THREADS"] = str(cores)   # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every core
     po = O.Params(dim=3, Bs=(a.bs,) * 3, g=3, g_rhs=2, domain=(TWO_PI,) * 3, Jmax=level, discretization="FD_4th_central",
                   skew=True, c0=10.0, nu=3.125e-3, gamma_p=0.0, CFL=1.0, u_mean_set=(0.0, 0.0, 0.0), time_max=1.0e9)
     grid = O.uniform_grid(level)
@@ -271,13 +271,15 @@ def run_ours(a):
         B = algorithmic_bytes_per_block_update(a.bs)
         # dominant kernel = stage_kernel, 4 launches per step, each processing every local block once:
         # algorithmic bytes per launch = (B_rk4 / 4) * blocks_per_gpu
-        avg_launch_s = (stage_ms / max(n_stage, 1)) * 1e-3
-        achieved = (B / 4.0) * nb_local / avg_launch_s / 1e9 if n_stage else None
+        # (multi-GPU runs split a stage into an interior and a boundary launch; their durations are summed)
+        n_stages = p.n_stages
+        avg_launch_s = (stage_ms / (a.steps * n_stages)) * 1e-3
+        achieved = (B / float(n_stages)) * nb_local / avg_launch_s / 1e9 if n_stage else None
         traffic = None
         tr_path = os.path.join(ROOT, "profiles", "stage_kernel_traffic.json")
         if os.path.exists(tr_path):
             try:
-                traffic = json.load(open(tr_path)).get("dram_bytes_per_launch")
+                traffic = json.load(open(tr_path)).get("dram_bytes_per_block_per_launch") * nb_local
             except Exception:
                 traffic = None
         line = {
@@ -294,7 +296,7 @@ def run_ours(a):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic, "kernel": "stage_kernel<FD4,skew,Bs16>", "launches_timed": n_stage,
-                         "avg_launch_ms": avg_launch_s * 1e3, "algorithmic_bytes_per_block_update": B, "peak_source": peak_src},
+                         "avg_launch_ms": avg_launch_s * 1e3, "algorithmic_bytes_per_launch": (B / float(n_stages)) * nb_local, "algorithmic_bytes_per_block_update": B, "peak_source": peak_src},
         }
         if world == 1 and not a.no_cpu:
             v, cms, cores, nbc = cpu_run(a, min(a.level, a.cpu_level), a.cpu_steps, 1)
