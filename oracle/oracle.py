@@ -409,3 +409,104 @@ def rk_step_c(grid: Grid, p: Params, hvy: np.ndarray, work: np.ndarray, time: fl
     L.orc_rk_step_same_level(C.byref(a), grid.n, ip(nbr), _p(dxb), p.dim, p.g, p.g_rhs, Bs, nc, _p(hvy), _p(work),
                              _p(np.ascontiguousarray(p.butcher)), s, dt, _p(mask), 0 if mask is None else mask.shape[1])
     return dt
+
+
+# ----------------------------------------------------------------------------- wavelets (orc_wavelet.c)
+ORC_FMAX = 12
+
+
+class Wavelet(C.Structure):
+    _fields_ = [("X", C.c_int32), ("Y", C.c_int32),
+                ("hd_lo", C.c_int32), ("hd_hi", C.c_int32), ("gd_lo", C.c_int32), ("gd_hi", C.c_int32),
+                ("hr_lo", C.c_int32), ("hr_hi", C.c_int32), ("gr_lo", C.c_int32), ("gr_hi", C.c_int32),
+                ("g_default", C.c_int32), ("lifted", C.c_int32),
+                ("Nscl", C.c_int32), ("Nscr", C.c_int32), ("Nwcl", C.c_int32), ("Nwcr", C.c_int32),
+                ("Nreconl", C.c_int32), ("Nreconr", C.c_int32),
+                ("HD", C.c_double * (2 * ORC_FMAX + 1)), ("GD", C.c_double * (2 * ORC_FMAX + 1)),
+                ("HR", C.c_double * (2 * ORC_FMAX + 1)), ("GR", C.c_double * (2 * ORC_FMAX + 1))]
+
+    def taps(self, name):
+        lo, hi = getattr(self, name.lower() + "_lo"), getattr(self, name.lower() + "_hi")
+        arr = getattr(self, name)
+        return {k: arr[k + ORC_FMAX] for k in range(lo, hi + 1)}
+
+
+def _wl(fast=False):
+    L = lib(fast)
+    if not hasattr(L, "_wl_ready"):
+        W = C.POINTER(Wavelet)
+        L.orc_setup_wavelet.argtypes = [C.c_char_p, W]
+        L.orc_fwt_block.argtypes = [W, C.c_int, C.c_int, _ip, C.c_int, _dp, _dp]
+        L.orc_iwt_block.argtypes = [W, C.c_int, C.c_int, _ip, C.c_int, _dp, _dp]
+        L.orc_threshold_block.argtypes = [C.c_int, C.c_int, _ip, C.c_int, _dp, C.c_int, C.c_int, C.c_int, _ip, _dp, _dp, _dp]
+        L.orc_prediction.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp]
+        L.orc_refine_block.argtypes = [C.c_int, C.c_int, C.c_int, _ip, C.c_int, _dp, _dp]
+        L.orc_block_linfty.argtypes = [C.c_int, C.c_int, _ip, C.c_int, _dp, _dp]
+        L._wl_ready = True
+    return L
+
+
+def setup_wavelet(name: str) -> Wavelet:
+    w = Wavelet()
+    rc = _wl().orc_setup_wavelet(name.encode(), C.byref(w))
+    if rc:
+        raise ValueError(f"unsupported wavelet {name}")
+    return w
+
+
+EPS_NORMS = {"Linfty": 0, "L1": 1, "L2": 2, "H1": 3}
+
+
+def fwt_tree(w: Wavelet, p: Params, hvy: np.ndarray, out: np.ndarray) -> None:
+    """waveletDecomposition_optimized_block on every block (ghosts of hvy must be synchronised to depth g)."""
+    L = _wl()
+    for b in range(hvy.shape[0]):
+        L.orc_fwt_block(C.byref(w), p.dim, p.g, _bs(p.Bs), hvy.shape[1], _p(hvy[b]), _p(out[b]))
+
+
+def iwt_tree(w: Wavelet, p: Params, hvy_wd: np.ndarray, out: np.ndarray) -> None:
+    L = _wl()
+    for b in range(hvy_wd.shape[0]):
+        L.orc_iwt_block(C.byref(w), p.dim, p.g, _bs(p.Bs), hvy_wd.shape[1], _p(hvy_wd[b]), _p(out[b]))
+
+
+def threshold_tree(p: Params, hvy_wd: np.ndarray, level, eps: float, norm=None, eps_norm: str = "Linfty", thresh_comp=None,
+                   level_ref: int = 0):
+    """threshold_block per block: returns (refinement_status[nb], detail[nb, nc])."""
+    L = _wl()
+    nb, nc = hvy_wd.shape[:2]
+    tc = np.ascontiguousarray(np.ones(nc) if thresh_comp is None else thresh_comp, dtype=np.int32)
+    e = np.full(nc, eps, dtype=np.float64)
+    nrm = None if norm is None else np.ascontiguousarray(norm, dtype=np.float64)
+    det = np.zeros((nb, nc))
+    st = np.zeros(nb, dtype=np.int32)
+    for b in range(nb):
+        st[b] = L.orc_threshold_block(p.dim, p.g, _bs(p.Bs), nc, _p(hvy_wd[b]), int(level[b]), level_ref, EPS_NORMS[eps_norm],
+                                      tc.ctypes.data_as(_ip), _p(e), _p(nrm), _p(det[b]))
+    return st, det
+
+
+def norm_linfty_tree(p: Params, hvy: np.ndarray) -> np.ndarray:
+    """componentWiseNorm_tree, Linfty; the caller applies `norm <= 1e-9 -> 1` (coarseningIndicator_tree.f90:165-167)."""
+    L = _wl()
+    nrm = np.zeros(hvy.shape[1])
+    for b in range(hvy.shape[0]):
+        L.orc_block_linfty(p.dim, p.g, _bs(p.Bs), hvy.shape[1], _p(hvy[b]), _p(nrm))
+    return nrm
+
+
+def prediction(order: int, coarse: np.ndarray) -> np.ndarray:
+    """coarse[nz,ny,nx] -> fine[2nz-1, 2ny-1, 2nx-1]"""
+    c = np.ascontiguousarray(coarse, dtype=np.float64)
+    nz, ny, nx = c.shape
+    fine = np.zeros((2 * nz - 1, 2 * ny - 1, 2 * nx - 1))
+    _wl().orc_prediction(order, nx, ny, nz, _p(c), _p(fine))
+    return fine
+
+
+def refine_block(order: int, p: Params, mother: np.ndarray) -> np.ndarray:
+    """mother[nc,nz,ny,nx] ghosted -> daughters[2^dim, nc, nz, ny, nx] ghosted"""
+    m = np.ascontiguousarray(mother, dtype=np.float64)
+    d = np.zeros((2 ** p.dim,) + m.shape)
+    _wl().orc_refine_block(order, p.dim, p.g, _bs(p.Bs), m.shape[0], _p(m), _p(d))
+    return d

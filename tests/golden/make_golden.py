@@ -45,5 +45,79 @@ def main():
         print(path, os.path.getsize(path), out["t1"].shape, out["t1_iteration"])
 
 
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# TESTING/wavelets: vor_000020000000.h5 --refine-everywhere--> adaptive_CDF40/vor_00100.h5 --coarsen-everywhere-->
+# adaptive_CDFxy/vor_00200.h5 (2-D, Bs=32, 4 levels).  For blocks whose whole neighbourhood is on their own level the
+# ghost layers are plain copies, so the reference's outputs pin `prediction`/refineBlock (CDF40 refine) and the
+# low-pass decomposition filter HD + decimation alignment (CDF44 / CDF42 / CDF22 / CDF62 coarsen) block by block.
+# wavelet_blocks.npz holds, for a few such blocks, the ghosted input assembled from the reference's input file and the
+# reference's output blocks.
+def _grid(d):
+    Bs = int(d["attrs"]["block-size"][0])
+    L = float(d["attrs"]["domain-size"][0])
+    dx = d["spacing"][:, ::-1]            # stored (y,x)
+    x0 = d["origin"][:, ::-1]
+    level = np.rint(np.log2(L / (Bs * dx[:, 0]))).astype(np.int32)
+    ixy = np.rint(x0 / (Bs * dx)).astype(np.int32)
+    return Bs, level, ixy
+
+
+def wavelet_blocks():
+    W = "/root/reference/TESTING/wavelets"
+    d0 = read_wabbit(os.path.join(W, "vor_000020000000.h5"))
+    d1 = read_wabbit(os.path.join(W, "adaptive_CDF40", "vor_00100.h5"))
+    Bs, lv0, ix0 = _grid(d0)
+    _, lv1, ix1 = _grid(d1)
+    look0 = {(int(l), int(i[0]), int(i[1])): k for k, (l, i) in enumerate(zip(lv0, ix0))}
+    look1 = {(int(l), int(i[0]), int(i[1])): k for k, (l, i) in enumerate(zip(lv1, ix1))}
+    coarsened = {w: read_wabbit(os.path.join(W, f"adaptive_{w}", "vor_00200.h5")) for w in ("CDF22", "CDF42", "CDF44", "CDF62")}
+    out = {"Bs": np.array([Bs])}
+    G0, G1 = 3, 6
+    picked = 0
+    for k in range(len(lv0)):
+        J, (bx, by) = int(lv0[k]), ix0[k]
+        n = 2 ** J
+        # the 5x5 neighbourhood must be on the same level: then the 3x3 neighbourhood of every daughter's neighbourhood
+        # is uniform as well
+        nb = {(dx_, dy_): look0.get((J, (bx + dx_) % n, (by + dy_) % n)) for dx_ in (-2, -1, 0, 1, 2) for dy_ in (-2, -1, 0, 1, 2)}
+        if any(v is None for v in nb.values()):
+            continue
+        # ghosted mother, g = 3 (CDF40 refine input)
+        m = np.zeros((Bs + 2 * G0, Bs + 2 * G0))
+        big = np.block([[d0["blocks"][nb[(dx_, dy_)]][:Bs, :Bs] for dx_ in (-1, 0, 1)] for dy_ in (-1, 0, 1)])   # [y,x]
+        m[:, :] = big[Bs - G0:2 * Bs + G0, Bs - G0:2 * Bs + G0]
+        # the reference's four daughters (interiors), digit bit0 -> y, bit1 -> x
+        dau = np.zeros((4, Bs, Bs))
+        for kd in range(4):
+            ox, oy = (kd // 2) % 2, kd % 2
+            dau[kd] = d1["blocks"][look1[(J + 1, 2 * bx + ox, 2 * by + oy)]][:Bs, :Bs]
+        # composite fine field around the four daughters with a 6-wide ring, from the reference's refined files
+        # (the refined data depend on the predictor order X only, and are stored for the unlifted wavelets CDFX0)
+        n1 = 2 * n
+        for X in (2, 4, 6):
+            dX = read_wabbit(os.path.join(W, f"adaptive_CDF{X}0", "vor_00100.h5"))
+            _, lvX, ixX = _grid(dX)
+            lookX = {(int(l), int(i[0]), int(i[1])): q for q, (l, i) in enumerate(zip(lvX, ixX))}
+            fine = np.block([[dX["blocks"][lookX[(J + 1, (2 * bx + ax) % n1, (2 * by + ay) % n1)]][:Bs, :Bs] for ax in (-1, 0, 1, 2)]
+                             for ay in (-1, 0, 1, 2)])
+            out[f"fine_X{X}_{picked}"] = fine[Bs - G1:3 * Bs + G1, Bs - G1:3 * Bs + G1]
+        out[f"mother{picked}"] = m
+        out[f"daughters{picked}"] = dau
+        for w, dc in coarsened.items():
+            _, lvc, ixc = _grid(dc)
+            kc = [q for q in range(len(lvc)) if lvc[q] == J and ixc[q][0] == bx and ixc[q][1] == by][0]
+            out[f"coarse_{w}_{picked}"] = dc["blocks"][kc][:Bs, :Bs]
+        picked += 1
+        if picked == 3:
+            break
+    out["n"] = np.array([picked])
+    path = os.path.join(HERE, "wavelet_blocks.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), picked)
+
+
 if __name__ == "__main__":
     main()
+    wavelet_blocks()
