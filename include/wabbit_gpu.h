@@ -139,6 +139,27 @@ int32_t wgpu_calculate_time_step(wgpu_ctx *ctx, double time, double *dt);
 int32_t wgpu_rk_step(wgpu_ctx *ctx, double time, int32_t iteration, double *dt);
 
 /*
+ * ---- wavelet side (grid adaptation): decomposition, thresholding, reconstruction ----
+ * wgpu_set_wavelet: replaces setup_wavelet (LIB/WAVELETS/module_wavelets.f90:1031-1417) for "CDFXY", X in {2,4,6},
+ *   Y in {0,2,4,6}, Y <= X; returns the default ghost widths g = X-1+max(Y-1,0) and g_rhs = X/2 (ini_file_to_params.f90:467-468).
+ * wgpu_fwt / wgpu_iwt: replace the block loops over waveletDecomposition_optimized_block /
+ *   waveletReconstruction_optimized_block (LIB/WAVELETS/wavelet_decomposition_reconstruction.f90:23,426) together with
+ *   the sync_ghosts_tree that precedes them (LIB/MESH/adapt_tree.f90:403-446, 813-843): dst = transform(src), result in
+ *   spaghetti order (scaling coefficients at interior offsets 0,2,4,..).  src and dst must be different arrays.
+ * wgpu_norm: componentWiseNorm_tree (LIB/OPERATORS/componentWiseNorm_tree.f90:1), norm_id 0 = Linfty; out[n_eqn].
+ * wgpu_threshold: wavelet_renorm_block + threshold_block on a decomposed array (LIB/INDICATORS/threshold_block.f90:1-130,
+ *   module_wavelets.f90:1848-1960): refinement_status[n_active] = -1 iff all(detail <= eps*norm) else 0, in the order of
+ *   hvy_active; eps_norm_id 0 Linfty / 1 L1 / 2 L2 / 3 H1; thresh_comp = params%threshold_state_vector_component;
+ *   norm may be NULL (eps not normalised); detail_out[n_active*n_eqn] may be NULL.
+ */
+int32_t wgpu_set_wavelet(wgpu_ctx *ctx, const char *name, int32_t *g_default, int32_t *g_rhs_default);
+int32_t wgpu_fwt(wgpu_ctx *ctx, int32_t src_id, int32_t src_slot, int32_t dst_id, int32_t dst_slot);
+int32_t wgpu_iwt(wgpu_ctx *ctx, int32_t src_id, int32_t src_slot, int32_t dst_id, int32_t dst_slot);
+int32_t wgpu_norm(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t norm_id, double *out);
+int32_t wgpu_threshold(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t eps_norm_id, int32_t level_ref, const int32_t *thresh_comp,
+                       const double *eps, const double *norm, int32_t *refinement_status, double *detail_out);
+
+/*
  * ---- multi-GPU (one process per GPU): the Runge-Kutta step split at the points where ranks must talk.
  * The reference exchanges ghost patches with MPI_Isend/Irecv once per sync (LIB/MPI/xfer_block_data.f90:10-99) and
  * all-reduces dt with MPI_MIN (LIB/TIME/calculate_time_step.f90:48).  Here the host moves bytes with NCCL

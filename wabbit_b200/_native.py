@@ -44,6 +44,11 @@ GPU_SYMBOLS = {
     "wgpu_rhs": (C.c_int32, [C.c_void_p, C.c_double, C.c_int32, C.c_int32]),
     "wgpu_calculate_time_step": (C.c_int32, [C.c_void_p, C.c_double, _dp]),
     "wgpu_rk_step": (C.c_int32, [C.c_void_p, C.c_double, C.c_int32, _dp]),
+    "wgpu_set_wavelet": (C.c_int32, [C.c_void_p, C.c_char_p, _i32p, _i32p]),
+    "wgpu_fwt": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "wgpu_iwt": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "wgpu_norm": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _dp]),
+    "wgpu_threshold": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _i32p, _dp, _dp, _i32p, _dp]),
     "wgpu_patch_doubles": (C.c_int64, [C.c_void_p]),
     "wgpu_set_exchange": (C.c_int32, [C.c_void_p, C.c_int32, _i32p, _i32p, C.c_void_p, C.c_int32, _i32p, _i32p, C.c_void_p]),
     "wgpu_pack_halo": (C.c_int32, [C.c_void_p, C.c_int32]),

@@ -196,6 +196,11 @@ int32_t wgpu_destroy(wgpu_ctx *ctx)
     cudaFree(ctx->d_active);
     cudaFree(ctx->d_nbr);
     cudaFree(ctx->d_level);
+    cudaFree(ctx->d_det_abs);
+    cudaFree(ctx->d_det_sq);
+    cudaFree(ctx->d_detail_out);
+    cudaFree(ctx->d_status);
+    cudaFree(ctx->d_norm);
     cudaFree(ctx->d_pool_off);
     cudaFree(ctx->d_active_int);
     cudaFree(ctx->d_active_bnd);
@@ -481,6 +486,146 @@ int32_t wgpu_calculate_time_step(wgpu_ctx *ctx, double time, double *dt)
     WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_dt, 8, cudaMemcpyDeviceToHost, ctx->stream));
     WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     *dt = ctx->h_pinned[0];
+    return WGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ wavelets
+// interpolation stencils (module_wavelets.f90:14-20), centred
+static void interp_stencil(int order, double *s)
+{
+    for (int i = 0; i < 2 * order - 1; ++i) s[i] = 0.0;
+    if (order == 2) {
+        s[0] = 1.0 / 2.0; s[1] = 2.0 / 2.0; s[2] = 1.0 / 2.0;
+    } else if (order == 4) {
+        const double v[7] = {-1.0, 0.0, 9.0, 16.0, 9.0, 0.0, -1.0};
+        for (int i = 0; i < 7; ++i) s[i] = v[i] / 16.0;
+    } else {
+        const double v[11] = {3.0, 0.0, -25.0, 0.0, 150.0, 256.0, 150.0, 0.0, -25.0, 0.0, 3.0};
+        for (int i = 0; i < 11; ++i) s[i] = v[i] / 256.0;
+    }
+}
+
+int32_t wgpu_set_wavelet(wgpu_ctx *ctx, const char *name, int32_t *g_default, int32_t *g_rhs_default)
+{
+    if (!ctx || !name) return WGPU_ERR_ARG;
+    if (strlen(name) != 5 || strncmp(name, "CDF", 3) != 0) return fail(ctx, 3006221, "Unkown bi-orthogonal wavelet specified.");
+    const int X = name[3] - '0', Y = name[4] - '0';
+    if ((X != 2 && X != 4 && X != 6) || (Y != 0 && Y != 2 && Y != 4 && Y != 6) || Y > X)
+        return fail(ctx, 3006221, "Unkown bi-orthogonal wavelet specified (supported: CDFXY, X in 2,4,6, Y in 0,2,4,6, Y<=X).");
+    WaveFilters &w = ctx->wavelet;
+    memset(&w, 0, sizeof(w));
+    w.X = X;
+    w.Y = Y;
+    double hr[11], hn[11];
+    interp_stencil(X, hr);                                   // HR = interpolation stencil (module_wavelets.f90:1157-1176)
+    w.hr_lo = -(X - 1);
+    w.hr_hi = X - 1;
+    for (int i = w.hr_lo; i <= w.hr_hi; ++i) w.HR[i + WGPU_FMAX] = hr[i + X - 1];
+    if (Y == 0) {
+        w.hd_lo = w.hd_hi = 0;
+        w.HD[WGPU_FMAX] = 1.0;
+    } else {                                                 // HD = delta + 1/2 sum_j (-1)^j HR(j) h~(i-j)   (:1218-1234)
+        interp_stencil(Y, hn);
+        hn[Y - 1] = 0.0;
+        w.hd_lo = w.hr_lo - (Y - 1);
+        w.hd_hi = w.hr_hi + (Y - 1);
+        for (int i = w.hd_lo; i <= w.hd_hi; ++i) {
+            double v = i == 0 ? 1.0 : 0.0;
+            for (int j = w.hr_lo; j <= w.hr_hi; ++j) {
+                if (i - j < -(Y - 1) || i - j > Y - 1) continue;
+                v = v + ((j % 2 == 0) ? 1.0 : -1.0) * w.HR[j + WGPU_FMAX] * hn[i - j + Y - 1] / 2.0;
+            }
+            w.HD[i + WGPU_FMAX] = v;
+        }
+    }
+    w.gd_lo = w.hr_lo;                                       // GD(i) = (-1)^i HR(i), GR(i) = (-1)^i HD(i)   (:1275-1288)
+    w.gd_hi = w.hr_hi;
+    for (int i = w.gd_lo; i <= w.gd_hi; ++i) w.GD[i + WGPU_FMAX] = ((i % 2 == 0) ? 1.0 : -1.0) * w.HR[i + WGPU_FMAX];
+    w.gr_lo = w.hd_lo;
+    w.gr_hi = w.hd_hi;
+    for (int i = w.gr_lo; i <= w.gr_hi; ++i) w.GR[i + WGPU_FMAX] = ((i % 2 == 0) ? 1.0 : -1.0) * w.HD[i + WGPU_FMAX];
+    if (g_default) *g_default = X - 1 + (Y - 1 > 0 ? Y - 1 : 0);
+    if (g_rhs_default) *g_rhs_default = X / 2;
+    int32_t rc;
+    const size_t n = (size_t)ctx->cfg.max_blocks * ctx->nc;
+    if (!ctx->TMP) {
+        if ((rc = dmalloc(ctx, &ctx->TMP, n * ctx->blk_elems))) return rc;
+        WGPU_CHECK(ctx, cudaMemset(ctx->TMP, 0, n * ctx->blk_elems * sizeof(double)));
+    }
+    if (!ctx->d_det_abs) {
+        if ((rc = dmalloc(ctx, &ctx->d_det_abs, n))) return rc;
+        if ((rc = dmalloc(ctx, &ctx->d_det_sq, n))) return rc;
+        if ((rc = dmalloc(ctx, &ctx->d_detail_out, n))) return rc;
+        if ((rc = dmalloc(ctx, &ctx->d_status, (size_t)ctx->cfg.max_blocks))) return rc;
+        if ((rc = dmalloc(ctx, &ctx->d_norm, 16))) return rc;
+    }
+    ctx->wavelet_set = true;
+    return WGPU_OK;
+}
+
+static int32_t transform(wgpu_ctx *ctx, int32_t src_id, int32_t src_slot, int32_t dst_id, int32_t dst_slot, int inverse)
+{
+    if (!ctx) return WGPU_ERR_ARG;
+    if (!ctx->wavelet_set) return fail(ctx, 1213149, "The cat is angry: Wavelet-setup not yet called?");
+    const wgpu_config &c = ctx->cfg;
+    if (c.dim != 3 || c.Bs[0] != c.Bs[1] || c.Bs[0] != c.Bs[2]) return fail(ctx, WGPU_ERR_UNSUPPORTED, "wavelet kernels: cubic 3-D blocks only so far");
+    if (!ctx->remote_faces.empty() || ctx->n_bnd) return fail(ctx, WGPU_ERR_UNSUPPORTED, "wavelet kernels: neighbours on other ranks are not supported yet");
+    int n1 = 0, n2 = 0;
+    const double *src = array_ptr(ctx, src_id, src_slot, &n1);
+    double *dst = array_ptr(ctx, dst_id, dst_slot, &n2);
+    if (!src || !dst || n1 != ctx->nc || n2 != ctx->nc) return fail(ctx, WGPU_ERR_ARG, "wavelet transform: bad array/slot");
+    if (src == dst) return fail(ctx, WGPU_ERR_ARG, "wavelet transform: src and dst must differ (neighbours read src halos)");
+    if (dst == ctx->U) ctx->dtmin_valid = false;
+    return wgpu_launch_wavelet(ctx, src, dst, inverse);
+}
+
+int32_t wgpu_fwt(wgpu_ctx *ctx, int32_t src_id, int32_t src_slot, int32_t dst_id, int32_t dst_slot)
+{
+    return transform(ctx, src_id, src_slot, dst_id, dst_slot, 0);
+}
+
+int32_t wgpu_iwt(wgpu_ctx *ctx, int32_t src_id, int32_t src_slot, int32_t dst_id, int32_t dst_slot)
+{
+    return transform(ctx, src_id, src_slot, dst_id, dst_slot, 1);
+}
+
+int32_t wgpu_norm(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t norm_id, double *out)
+{
+    if (!ctx || !out) return WGPU_ERR_ARG;
+    if (norm_id != 0) return fail(ctx, WGPU_ERR_UNSUPPORTED, "wgpu_norm: only Linfty is built");
+    if (!ctx->wavelet_set) return fail(ctx, 1213149, "The cat is angry: Wavelet-setup not yet called?");
+    int n1 = 0;
+    const double *src = array_ptr(ctx, array_id, slot, &n1);
+    if (!src || n1 != ctx->nc) return fail(ctx, WGPU_ERR_ARG, "wgpu_norm: bad array/slot");
+    WGPU_CHECK(ctx, cudaMemsetAsync(ctx->d_norm, 0, 16 * sizeof(unsigned long long), ctx->stream));
+    int32_t rc = wgpu_launch_linfty(ctx, src, ctx->d_norm);
+    if (rc) return rc;
+    double h[16];
+    WGPU_CHECK(ctx, cudaMemcpyAsync(h, ctx->d_norm, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < ctx->nc; ++i) out[i] = h[i];
+    return WGPU_OK;
+}
+
+int32_t wgpu_threshold(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t eps_norm_id, int32_t level_ref, const int32_t *thresh_comp,
+                       const double *eps, const double *norm, int32_t *refinement_status, double *detail_out)
+{
+    if (!ctx || !thresh_comp || !eps || !refinement_status) return WGPU_ERR_ARG;
+    if (!ctx->wavelet_set) return fail(ctx, 1213149, "The cat is angry: Wavelet-setup not yet called?");
+    if (eps_norm_id < 0 || eps_norm_id > 3) return fail(ctx, 241024, "ERROR:Unknown wavelet normalization!");
+    if (ctx->nc > 16) return fail(ctx, WGPU_ERR_UNSUPPORTED, "too many components");
+    int n1 = 0;
+    const double *wd = array_ptr(ctx, array_id, slot, &n1);
+    if (!wd || n1 != ctx->nc) return fail(ctx, WGPU_ERR_ARG, "wgpu_threshold: bad array/slot");
+    int32_t rc;
+    if ((rc = wgpu_launch_detail(ctx, wd, eps_norm_id, level_ref))) return rc;
+    double eps_use[16];
+    for (int i = 0; i < ctx->nc; ++i) eps_use[i] = norm ? eps[i] * norm[i] : eps[i];   // threshold_block.f90:111-113
+    if ((rc = wgpu_launch_flags(ctx, thresh_comp, eps_use, ctx->d_status, detail_out ? ctx->d_detail_out : nullptr))) return rc;
+    WGPU_CHECK(ctx, cudaMemcpyAsync(refinement_status, ctx->d_status, sizeof(int) * ctx->n_active, cudaMemcpyDeviceToHost, ctx->stream));
+    if (detail_out)
+        WGPU_CHECK(ctx, cudaMemcpyAsync(detail_out, ctx->d_detail_out, sizeof(double) * (size_t)ctx->n_active * ctx->nc, cudaMemcpyDeviceToHost, ctx->stream));
+    WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return WGPU_OK;
 }
 

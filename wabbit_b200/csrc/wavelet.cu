@@ -1,0 +1,402 @@
+// Wavelet side of the block hot path on sm_100a: biorthogonal CDF decomposition / reconstruction with the ghost
+// synchronisation fused in (halo gathered from the neighbours' interiors), detail norms, thresholding flags and the
+// component-wise Linfty norm.
+//
+// Reference: waveletDecomposition_optimized_block / waveletReconstruction_optimized_block
+//            (LIB/WAVELETS/wavelet_decomposition_reconstruction.f90:23-389, 426-840), setup_wavelet
+//            (LIB/WAVELETS/module_wavelets.f90:1031-1417), wavelet_renorm_block (:1848-1960), threshold_block
+//            (LIB/INDICATORS/threshold_block.f90:1-130), componentWiseNorm_tree (LIB/OPERATORS/componentWiseNorm_tree.f90:63-197).
+//
+// Arithmetic that feeds refinement flags (FWT -> renorm -> max|wc| -> compare) is written with __dmul_rn/__dadd_rn so
+// that nvcc cannot contract it: the reference build has no FMA (LIB/fortran.mk:72-84) and flags must be bit-exact.
+// Every filter is one product per non-zero tap, summed in increasing tap order (the reference's hard-coded and generic
+// branches coincide under this rule).
+//
+// Kernel shape: one CTA per (block, component); the (Bs+2f)^2 input planes (f = filter half width) stream through
+// shared memory (cp.async), each plane is transformed in x then y, the xy-transformed planes sit in a ring of
+// 2f+2 planes from which the z transform emits two output planes every second input plane.  HBM-bound: reads the
+// (Bs+2f)^3 box once (mostly L2 hits for the halo: neighbours are launched back to back in space-filling-curve order),
+// writes Bs^3.
+#include <math.h>
+
+#include "wgpu_internal.cuh"
+
+namespace {
+
+__device__ __forceinline__ void cp_async8(double *smem, const double *g)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// sum over non-zero taps, increasing index, product then add, never contracted
+__device__ __forceinline__ double filt(const double *p, int stride, const double *F, int lo, int hi)
+{
+    double acc = 0.0;
+    bool first = true;
+    for (int k = lo; k <= hi; ++k) {
+        const double c = F[k + WGPU_FMAX];
+        if (c == 0.0) continue;
+        const double t = __dmul_rn(p[k * stride], c);
+        acc = first ? t : __dadd_rn(acc, t);
+        first = false;
+    }
+    return acc;
+}
+
+struct WaveArgs {
+    const double *src;
+    double *dst;
+    const int *active;
+    const int *nbr;
+    int nc, Bs, f;       // f = halo depth gathered = max filter half width of the transform direction
+    int inverse;         // 0: decomposition (HD/GD), 1: reconstruction (HR/GR on zero-stuffed SC/WC)
+    WaveFilters w;
+};
+
+// source of a ghosted coordinate c in [-f, Bs+f): direction -1/0/+1 and local coordinate
+__device__ __forceinline__ void split(int c, int Bs, int &d, int &l)
+{
+    d = c < 0 ? -1 : (c >= Bs ? 1 : 0);
+    l = c - d * Bs;
+}
+
+__global__ void __launch_bounds__(256) wavelet_kernel(const WaveArgs a)
+{
+    extern __shared__ __align__(16) double sm[];
+    const int Bs = a.Bs, f = a.f, n = Bs + 2 * f;
+    const int R = 2 * f + 2;                 // ring of xy-transformed planes
+    double *in0 = sm;                        // [2][n*n] input planes (double buffered)
+    double *xs = in0 + 2 * n * n;            // [n][Bs]  after the x transform
+    double *ring = xs + n * Bs;              // [R][Bs*Bs]
+    __shared__ int s_code[WGPU_NDIR];
+
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int b = a.active[blockIdx.x], c = blockIdx.y;
+    if (tid < WGPU_NDIR) s_code[tid] = tid == 13 ? b : a.nbr[b * WGPU_NDIR + tid];
+    __syncthreads();
+    const long long CS = (long long)Bs * Bs * Bs;
+
+    auto load_plane = [&](int zp, double *dstp) {
+        int dz, lz;
+        split(zp, Bs, dz, lz);
+        for (int i = tid; i < n * n; i += nt) {
+            const int y = i / n - f, x = i % n - f;
+            int dy, ly, dx, lx;
+            split(y, Bs, dy, ly);
+            split(x, Bs, dx, lx);
+            const int sb = s_code[(dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)];
+            if (sb >= 0) cp_async8(dstp + i, a.src + ((long long)sb * a.nc + c) * CS + ((long long)lz * Bs + ly) * Bs + lx);
+            else dstp[i] = 0.0;   // no neighbour (non-periodic boundary)
+        }
+    };
+
+    const double *F0 = a.inverse ? a.w.HR : a.w.HD, *F1 = a.inverse ? a.w.GR : a.w.GD;
+    const int lo0 = a.inverse ? a.w.hr_lo : a.w.hd_lo, hi0 = a.inverse ? a.w.hr_hi : a.w.hd_hi;
+    const int lo1 = a.inverse ? a.w.gr_lo : a.w.gd_lo, hi1 = a.inverse ? a.w.gr_hi : a.w.gd_hi;
+
+    // 1-D transform of a line at interior offset o (0..Bs-1); p points at the line element of offset o.
+    // decomposition: even offsets -> HD (scaling), odd -> GD (wavelet).
+    // reconstruction: u(o) = sum_{k: o+k even} sc(o+k) HR(k) + sum_{k: o+k odd} wc(o+k) GR(k)   (zero stuffing)
+    auto line = [&](const double *p, int stride, int o) -> double {
+        if (!a.inverse) return (o & 1) ? filt(p, stride, F1, lo1, hi1) : filt(p, stride, F0, lo0, hi0);
+        double s0 = 0.0, s1 = 0.0;
+        for (int k = lo0; k <= hi0; ++k)
+            if (((o + k) & 1) == 0) s0 = __dadd_rn(s0, __dmul_rn(p[k * stride], F0[k + WGPU_FMAX]));
+        for (int k = lo1; k <= hi1; ++k)
+            if (((o + k) & 1) != 0) s1 = __dadd_rn(s1, __dmul_rn(p[k * stride], F1[k + WGPU_FMAX]));
+        return __dadd_rn(s0, s1);
+    };
+
+    load_plane(-f, in0);
+    cp_async_commit();
+    for (int q = 0; q < n; ++q) {             // q-th input plane, zp = q - f
+        const int zp = q - f;
+        double *cur = in0 + (q & 1) * n * n;
+        if (q + 1 < n) load_plane(zp + 1, in0 + ((q + 1) & 1) * n * n);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        // x transform: rows y = -f..Bs+f-1, outputs at interior x
+        for (int i = tid; i < n * Bs; i += nt) {
+            const int r = i / Bs, o = i % Bs;
+            xs[i] = line(cur + r * n + f + o, 1, o);
+        }
+        __syncthreads();
+        // y transform on interior x
+        double *rp = ring + (q % R) * Bs * Bs;
+        for (int i = tid; i < Bs * Bs; i += nt) {
+            const int o = i / Bs, x = i % Bs;
+            rp[i] = line(xs + (o + f) * Bs + x, Bs, o);
+        }
+        __syncthreads();
+        // z transform: once the plane zp = k + f + 1 is in the ring (k even), output planes k and k+1 are complete
+        const int k = zp - f - 1;
+        if (k >= 0 && k < Bs && (k & 1) == 0) {
+            for (int i = tid; i < 2 * Bs * Bs; i += nt) {
+                const int o = k + i / (Bs * Bs), xy = i % (Bs * Bs);
+                // ring index of interior plane z is (z + f) % R; walk with explicit modulo
+                double acc;
+                {
+                    // gather the taps through the ring: emulate `line` with a modular stride
+                    const double *F = nullptr;
+                    int lo, hi;
+                    if (!a.inverse) {
+                        F = (o & 1) ? F1 : F0;
+                        lo = (o & 1) ? lo1 : lo0;
+                        hi = (o & 1) ? hi1 : hi0;
+                        double s = 0.0;
+                        bool first = true;
+                        for (int t = lo; t <= hi; ++t) {
+                            const double cf = F[t + WGPU_FMAX];
+                            if (cf == 0.0) continue;
+                            const double v = __dmul_rn(ring[((o + t + f) % R) * Bs * Bs + xy], cf);
+                            s = first ? v : __dadd_rn(s, v);
+                            first = false;
+                        }
+                        acc = s;
+                    } else {
+                        double s0 = 0.0, s1 = 0.0;
+                        for (int t = lo0; t <= hi0; ++t)
+                            if (((o + t) & 1) == 0) s0 = __dadd_rn(s0, __dmul_rn(ring[((o + t + f) % R) * Bs * Bs + xy], F0[t + WGPU_FMAX]));
+                        for (int t = lo1; t <= hi1; ++t)
+                            if (((o + t) & 1) != 0) s1 = __dadd_rn(s1, __dmul_rn(ring[((o + t + f) % R) * Bs * Bs + xy], F1[t + WGPU_FMAX]));
+                        acc = __dadd_rn(s0, s1);
+                    }
+                }
+                a.dst[((long long)b * a.nc + c) * CS + (long long)o * Bs * Bs + xy] = acc;
+            }
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------------------
+// wavelet_renorm_block + threshold_block's detail norms on a decomposed (spaghetti-ordered) array:
+// per block and component max|wc| (pure scaling positions removed), both as max(abs) and max(sqrt(x*x)).
+// ---------------------------------------------------------------------------------------------
+struct DetailArgs {
+    const double *wd;
+    const int *active;
+    const signed char *level;
+    double *det_abs, *det_sq;   // [max_blocks][nc]
+    int nc, Bx, By, Bz, dim;
+    int eps_norm;               // 0 Linfty, 1 L1, 2 L2, 3 H1
+    double fac_lvl[WGPU_MAX_LEVELS];
+    double fdir;
+    int fdir_div;
+};
+
+__global__ void __launch_bounds__(256) detail_kernel(const DetailArgs a)
+{
+    __shared__ double s0[8], s1[8];
+    const int b = a.active[blockIdx.x], c = blockIdx.y;
+    const long long CS = (long long)a.Bx * a.By * a.Bz;
+    const double *p = a.wd + ((long long)b * a.nc + c) * CS;
+    const double fac = a.fac_lvl[a.level[b]];
+    const bool scale = a.eps_norm != 0 && !(a.eps_norm == 3 && a.dim != 3);
+    double m0 = -INFINITY, m1 = -INFINITY;
+    for (long long i = threadIdx.x; i < CS; i += blockDim.x) {
+        const int x = (int)(i % a.Bx), y = (int)((i / a.Bx) % a.By), z = (int)(i / ((long long)a.Bx * a.By));
+        const bool px = !(x & 1), py = !(y & 1), pz = a.dim == 3 ? !(z & 1) : true;
+        double v = p[i];
+        if (px && py && pz) v = 0.0;
+        if (scale) {
+            v = __dmul_rn(v, fac);
+            if (px) v = a.fdir_div ? __ddiv_rn(v, a.fdir) : __dmul_rn(v, a.fdir);
+            if (py) v = a.fdir_div ? __ddiv_rn(v, a.fdir) : __dmul_rn(v, a.fdir);
+            if (a.dim == 3 && pz) v = a.fdir_div ? __ddiv_rn(v, a.fdir) : __dmul_rn(v, a.fdir);
+        }
+        m0 = fmax(m0, fabs(v));
+        m1 = fmax(m1, sqrt(__dmul_rn(v, v)));
+    }
+    m0 = warp_max(m0);
+    m1 = warp_max(m1);
+    if ((threadIdx.x & 31) == 0) {
+        s0[threadIdx.x >> 5] = m0;
+        s1[threadIdx.x >> 5] = m1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) {
+            m0 = fmax(m0, s0[i]);
+            m1 = fmax(m1, s1[i]);
+        }
+        a.det_abs[(long long)b * a.nc + c] = m0;
+        a.det_sq[(long long)b * a.nc + c] = m1;
+    }
+}
+
+// threshold_block.f90:96-121: detail per component (own / joint group / ignored), status = -1 iff all(detail <= eps*norm)
+struct FlagArgs {
+    const int *active;
+    const double *det_abs, *det_sq;
+    int *status;          // [n_active]
+    double *detail_out;   // [n_active][nc] or nullptr
+    int n_active, nc;
+    int thresh_comp[16];
+    double eps_use[16];   // eps * norm
+};
+
+__global__ void flags_kernel(const FlagArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_active) return;
+    const int b = a.active[i];
+    double det[16];
+    int maxgrp = 0;
+    for (int c = 0; c < a.nc; ++c) {
+        det[c] = -1.0;
+        maxgrp = a.thresh_comp[c] > maxgrp ? a.thresh_comp[c] : maxgrp;
+    }
+    for (int l = 2; l <= maxgrp; ++l) {
+        double m = -INFINITY;
+        for (int c = 0; c < a.nc; ++c)
+            if (a.thresh_comp[c] == l) m = fmax(m, a.det_sq[(long long)b * a.nc + c]);
+        for (int c = 0; c < a.nc; ++c)
+            if (a.thresh_comp[c] == l) det[c] = m;
+    }
+    int status = -1;
+    for (int c = 0; c < a.nc; ++c) {
+        if (a.thresh_comp[c] == 1) det[c] = a.det_abs[(long long)b * a.nc + c];
+        if (a.thresh_comp[c] == 0) det[c] = 0.0;
+        if (!(det[c] <= a.eps_use[c])) status = 0;
+        if (a.detail_out) a.detail_out[(long long)i * a.nc + c] = det[c];
+    }
+    a.status[i] = status;
+}
+
+// componentWiseNorm_tree, Linfty: max |u| per component over all active blocks (atomicMax on the bit pattern)
+__global__ void __launch_bounds__(256) linfty_kernel(const double *__restrict__ u, const int *__restrict__ active, int nc, long long CS,
+                                                     unsigned long long *out)
+{
+    __shared__ double s[8];
+    const int b = active[blockIdx.x], c = blockIdx.y;
+    const double *p = u + ((long long)b * nc + c) * CS;
+    double m = 0.0;
+    for (long long i = threadIdx.x; i < CS; i += blockDim.x) m = fmax(m, fabs(p[i]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmax(m, s[i]);
+        atomicMax(out + c, (unsigned long long)__double_as_longlong(m));
+    }
+}
+
+}  // namespace
+
+int32_t wgpu_launch_wavelet(wgpu_ctx *ctx, const double *src, double *dst, int inverse)
+{
+    if (ctx->n_active == 0) return WGPU_OK;
+    const wgpu_config &c = ctx->cfg;
+    WaveArgs a;
+    a.src = src;
+    a.dst = dst;
+    a.active = ctx->d_active;
+    a.nbr = ctx->d_nbr;
+    a.nc = ctx->nc;
+    a.Bs = c.Bs[0];
+    a.inverse = inverse;
+    a.w = ctx->wavelet;
+    const WaveFilters &w = ctx->wavelet;
+    int f = 0;
+    const int b4[4] = {inverse ? -w.hr_lo : -w.hd_lo, inverse ? w.hr_hi : w.hd_hi, inverse ? -w.gr_lo : -w.gd_lo, inverse ? w.gr_hi : w.gd_hi};
+    for (int i = 0; i < 4; ++i) f = b4[i] > f ? b4[i] : f;
+    a.f = f;
+    if (f > a.Bs) {
+        ctx->err = "wavelet filter wider than the block";
+        return WGPU_ERR_UNSUPPORTED;
+    }
+    const int n = a.Bs + 2 * f;
+    const size_t smem = sizeof(double) * ((size_t)2 * n * n + (size_t)n * a.Bs + (size_t)(2 * f + 2) * a.Bs * a.Bs);
+    static size_t configured = 0;
+    if (smem > configured) {
+        WGPU_CHECK(ctx, cudaFuncSetAttribute(wavelet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid(ctx->n_active, ctx->nc);
+    wavelet_kernel<<<grid, 256, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    WGPU_CHECK(ctx, cudaGetLastError());
+    return WGPU_OK;
+}
+
+int32_t wgpu_launch_detail(wgpu_ctx *ctx, const double *wd, int eps_norm, int level_ref)
+{
+    if (ctx->n_active == 0) return WGPU_OK;
+    const wgpu_config &c = ctx->cfg;
+    DetailArgs a;
+    a.wd = wd;
+    a.active = ctx->d_active;
+    a.level = ctx->d_level;
+    a.det_abs = ctx->d_det_abs;
+    a.det_sq = ctx->d_det_sq;
+    a.nc = ctx->nc;
+    a.Bx = c.Bs[0];
+    a.By = c.Bs[1];
+    a.Bz = c.dim == 3 ? c.Bs[2] : 1;
+    a.dim = c.dim;
+    a.eps_norm = eps_norm;
+    a.fdir = 1.0;
+    a.fdir_div = 0;
+    for (int l = 0; l < WGPU_MAX_LEVELS; ++l) {
+        double fac = 1.0;   // module_wavelets.f90:1900-1945
+        if (eps_norm == 1) fac = pow(2.0, (double)((level_ref - l - 1) * c.dim));
+        if (eps_norm == 2) fac = pow(2.0, (double)((level_ref - l - 1) * c.dim) / 2.0);
+        if (eps_norm == 3) fac = pow(2.0, (double)(level_ref - l) * (2.0 - c.dim) / 2.0);
+        a.fac_lvl[l] = fac;
+    }
+    if (eps_norm == 1) { a.fdir = 4.0; a.fdir_div = 1; }
+    if (eps_norm == 2) { a.fdir = 2.0; a.fdir_div = 1; }
+    if (eps_norm == 3) a.fdir = pow(2.0, 2.0 * (c.dim - 2.0) / 3.0);
+    dim3 grid(ctx->n_active, ctx->nc);
+    detail_kernel<<<grid, 256, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    WGPU_CHECK(ctx, cudaGetLastError());
+    return WGPU_OK;
+}
+
+int32_t wgpu_launch_flags(wgpu_ctx *ctx, const int32_t *thresh_comp, const double *eps_use, int *d_status, double *d_detail_out)
+{
+    if (ctx->n_active == 0) return WGPU_OK;
+    FlagArgs a;
+    a.active = ctx->d_active;
+    a.det_abs = ctx->d_det_abs;
+    a.det_sq = ctx->d_det_sq;
+    a.status = d_status;
+    a.detail_out = d_detail_out;
+    a.n_active = ctx->n_active;
+    a.nc = ctx->nc;
+    for (int i = 0; i < 16; ++i) {
+        a.thresh_comp[i] = i < ctx->nc ? thresh_comp[i] : 0;
+        a.eps_use[i] = i < ctx->nc ? eps_use[i] : 0.0;
+    }
+    flags_kernel<<<(ctx->n_active + 127) / 128, 128, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    WGPU_CHECK(ctx, cudaGetLastError());
+    return WGPU_OK;
+}
+
+int32_t wgpu_launch_linfty(wgpu_ctx *ctx, const double *u, unsigned long long *d_out)
+{
+    if (ctx->n_active == 0) return WGPU_OK;
+    dim3 grid(ctx->n_active, ctx->nc);
+    linfty_kernel<<<grid, 256, 0, ctx->stream>>>(u, ctx->d_active, ctx->nc, ctx->blk_elems, d_out);
+    ctx->launches++;
+    WGPU_CHECK(ctx, cudaGetLastError());
+    return WGPU_OK;
+}

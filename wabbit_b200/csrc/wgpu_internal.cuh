@@ -21,6 +21,14 @@
 //           prediction or a remote GPU's pack kernel); pool_off[pid] is the offset in doubles.
 // ------------------------------------------------------------------------------------------------
 #define WGPU_NDIR 27
+#define WGPU_FMAX 12   // largest |tap index| of a wavelet filter
+
+// filter banks of a biorthogonal CDF wavelet (setup_wavelet, LIB/WAVELETS/module_wavelets.f90:1031-1290); tap k at [k+WGPU_FMAX]
+struct WaveFilters {
+    int X, Y;
+    int hd_lo, hd_hi, gd_lo, gd_hi, hr_lo, hr_hi, gr_lo, gr_hi;
+    double HD[2 * WGPU_FMAX + 1], GD[2 * WGPU_FMAX + 1], HR[2 * WGPU_FMAX + 1], GR[2 * WGPU_FMAX + 1];
+};
 
 struct StageArgs {
     // fields
@@ -107,6 +115,14 @@ struct wgpu_ctx {
     int *d_flags = nullptr;                   // [0] diverged
     double *h_pinned = nullptr;               // [0] dt, [1] flags (as int bits)
 
+    // wavelets
+    WaveFilters wavelet;
+    bool wavelet_set = false;
+    double *d_det_abs = nullptr, *d_det_sq = nullptr;   // [max_blocks][nc]
+    int *d_status = nullptr;                            // [max_blocks]
+    double *d_detail_out = nullptr;                     // [max_blocks][nc]
+    unsigned long long *d_norm = nullptr;               // [16]
+
     // optional event pairs around stage launches
     bool profiling = false;
     std::vector<cudaEvent_t> prof_ev;   // [2*i], [2*i+1]
@@ -131,6 +147,11 @@ struct wgpu_ctx {
 // kernels.cu
 int32_t wgpu_launch_stage(wgpu_ctx *ctx, const StageArgs &a, int n_blocks);
 int32_t wgpu_launch_pack(wgpu_ctx *ctx, const double *src);
+// wavelet.cu
+int32_t wgpu_launch_wavelet(wgpu_ctx *ctx, const double *src, double *dst, int inverse);
+int32_t wgpu_launch_detail(wgpu_ctx *ctx, const double *wd, int eps_norm, int level_ref);
+int32_t wgpu_launch_flags(wgpu_ctx *ctx, const int32_t *thresh_comp, const double *eps_use, int *d_status, double *d_detail_out);
+int32_t wgpu_launch_linfty(wgpu_ctx *ctx, const double *u, unsigned long long *d_out);
 int32_t wgpu_launch_dtmin(wgpu_ctx *ctx, const double *u, unsigned long long *dtmin_bits);
 int32_t wgpu_launch_dt_finalize(wgpu_ctx *ctx, double time, const unsigned long long *dtmin_bits,
                                 unsigned long long *dtmin_next);

@@ -159,6 +159,43 @@ class WabbitGPU:
         self._check(self._lib.wgpu_rk_step(self._ctx, float(time), int(iteration), C.byref(dt)))
         return dt.value
 
+    # ------------------------------------------------------------------ wavelet side (adapt_tree's heavy-data loops)
+    EPS_NORMS = {"Linfty": 0, "L1": 1, "L2": 2, "H1": 3}
+
+    def setup_wavelet(self, name: Optional[str] = None):
+        """setup_wavelet (module_wavelets.f90:1031): returns the default (g, g_rhs) of the wavelet."""
+        g, grhs = C.c_int32(), C.c_int32()
+        self._check(self._lib.wgpu_set_wavelet(self._ctx, (name or self.params.wavelet).encode(), C.byref(g), C.byref(grhs)))
+        return g.value, grhs.value
+
+    def waveletDecomposition_tree(self, src=(HVY_BLOCK, 0), dst=(HVY_TMP, 0)):
+        """sync_ghosts_tree + waveletDecomposition_optimized_block on every block (adapt_tree.f90:403-446)."""
+        self._check(self._lib.wgpu_fwt(self._ctx, src[0], src[1], dst[0], dst[1]))
+
+    def waveletReconstruction_tree(self, src=(HVY_TMP, 0), dst=(HVY_BLOCK, 0)):
+        """sync of SC/WC + waveletReconstruction_optimized_block on every block (adapt_tree.f90:813-843)."""
+        self._check(self._lib.wgpu_iwt(self._ctx, src[0], src[1], dst[0], dst[1]))
+
+    def componentWiseNorm_tree(self, array=(HVY_BLOCK, 0), norm: str = "Linfty") -> np.ndarray:
+        out = np.zeros(self.params.n_eqn)
+        self._check(self._lib.wgpu_norm(self._ctx, array[0], array[1], self.EPS_NORMS[norm], out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def threshold_tree(self, array=(HVY_TMP, 0), eps: Optional[float] = None, norm=None, eps_norm: str = "Linfty", thresh_comp=None,
+                       level_ref: int = 0, want_detail: bool = False):
+        """threshold_block on every active block of a decomposed array: refinement_status[n_active] (-1 coarsen / 0 keep)."""
+        nc = self.params.n_eqn
+        tc = np.ascontiguousarray(np.ones(nc) if thresh_comp is None else thresh_comp, dtype=np.int32)
+        e = np.full(nc, self.params.eps if eps is None else eps, dtype=np.float64)
+        nrm = None if norm is None else np.ascontiguousarray(norm, dtype=np.float64)
+        st = np.zeros(len(self.hvy_active), dtype=np.int32)
+        det = np.zeros((len(self.hvy_active), nc)) if want_detail else None
+        dp = C.POINTER(C.c_double)
+        self._check(self._lib.wgpu_threshold(self._ctx, array[0], array[1], self.EPS_NORMS[eps_norm], level_ref, _i32(tc),
+                                             e.ctypes.data_as(dp), None if nrm is None else nrm.ctypes.data_as(dp), _i32(st),
+                                             None if det is None else det.ctypes.data_as(dp)))
+        return (st, det) if want_detail else st
+
     def timeStep_tree(self, time: float, iteration: int):
         """timeStep_tree.f90:1 -- returns (time+dt, iteration+1, dt)."""
         dt = self.RungeKuttaGeneric(time, iteration)
