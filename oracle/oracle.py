@@ -24,7 +24,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SRCS = ["orc_acm.c", "orc_tree.c", "orc_wavelet.c"]
+_SRCS = ["orc_acm.c", "orc_tree.c", "orc_wavelet.c", "orc_sync.c"]
 
 
 def _lib_path(fast: bool) -> str:
@@ -510,3 +510,101 @@ def refine_block(order: int, p: Params, mother: np.ndarray) -> np.ndarray:
     d = np.zeros((2 ** p.dim,) + m.shape)
     _wl().orc_refine_block(order, p.dim, p.g, _bs(p.Bs), m.shape[0], _p(m), _p(d))
     return d
+
+
+# ----------------------------------------------------------------------------- level-jump ghost sync (orc_sync.c)
+def same_level_code(d) -> int:
+    """slot of the same-level neighbour in direction d (find_neighbor, LIB/MESH/find_neighbors.f90:60-95)"""
+    nzero = sum(1 for v in d if v == 0)
+    if nzero == 2:
+        code = 1
+        for i in range(3):
+            if d[i] != 0:
+                code += 8 * i
+            if d[i] == 1:
+                code += 4
+        return code
+    if nzero == 1:
+        code, apply_free = 25, 1
+        for i in range(3):
+            if d[i] == 0:
+                code += 8 * (2 - i)
+            else:
+                if d[i] == 1:
+                    code += apply_free * 2
+                apply_free += 1
+        return code
+    return 49 + sum(1 << i for i in range(3) if d[i] == 1)
+
+
+def neighbor_table168(grid: Grid, Jmax: int, periodic=(1, 1, 1)) -> np.ndarray:
+    """hvy_neighbor[168, nb] (1-based block ids, -1 none) of a leaf grid on one rank -- an independent NumPy restatement
+    of find_neighbor (LIB/MESH/find_neighbors.f90:18-180): same level, else finer (+112), else coarser (+56)."""
+    dim = grid.dim
+    look = grid.lookup()
+    out = np.full((168, grid.n), -1, dtype=np.int32)
+    vary = (2, 1, 4)
+    for b in range(grid.n):
+        J = int(grid.level[b])
+        ix = [int(v) for v in grid.ixyz[b]]
+        tc_last = sum(vary[a] * (ix[a] & 1) for a in range(dim)) if J > 0 else 0
+        for dz in ((-1, 0, 1) if dim == 3 else (0,)):
+            for dy in (-1, 0, 1):
+                for dx in (-1, 0, 1):
+                    d = (dx, dy, dz)
+                    if d == (0, 0, 0):
+                        continue
+                    nfree = 2 ** sum(1 for a in range(dim) if d[a] == 0)
+                    append = [0, 0, 0, 0]
+                    apply_free = 1
+                    for a in range(dim):
+                        if d[a] == 0:
+                            for k in range(4):
+                                append[k] += vary[a] * ((k // apply_free) % 2)
+                            apply_free += 1
+                        elif d[a] == 1:
+                            for k in range(4):
+                                append[k] += vary[a]
+                    code = same_level_code(d)
+                    n = 2 ** J
+                    p = [ix[a] + d[a] for a in range(3)]
+                    if any((p[a] < 0 or p[a] >= n) and not periodic[a] for a in range(dim)):
+                        continue
+                    p = [p[a] % n if a < dim else 0 for a in range(3)]
+                    j = look.get((J, p[0], p[1], p[2]))
+                    if j is not None:
+                        out[code - 1, b] = j + 1
+                        continue
+                    found = False
+                    if J < Jmax:
+                        for k in range(nfree):
+                            q = [((2 * ix[a] + (1 if append[k] & vary[a] else 0) + d[a]) % (2 * n)) if a < dim else 0 for a in range(3)]
+                            j = look.get((J + 1, q[0], q[1], q[2]))
+                            if j is None:
+                                break
+                            out[code - 1 + k + 112, b] = j + 1
+                            found = True
+                    if found:
+                        continue
+                    for k in range(nfree):
+                        if tc_last == append[k] and J > 0:
+                            j = look.get((J - 1, p[0] >> 1, p[1] >> 1, p[2] >> 1))
+                            if j is not None:
+                                out[code - 1 + k + 56, b] = j + 1
+    return out
+
+
+def sync_ghosts_leaf(grid: Grid, p: Params, hvy: np.ndarray, nbr168: np.ndarray, g_minus: int, g_plus: int, order: int,
+                     lifted: bool) -> int:
+    """sync_ghosts_generic("full_leaf", ignore_Filter=.true.) on a leaf grid with level jumps (orc_sync.c)."""
+    L = lib()
+    if not hasattr(L, "_sync_ready"):
+        L.orc_sync_ghosts_leaf.argtypes = [C.c_int, _ip, _ip, C.c_int, C.c_int, _ip, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_sync_ghosts_leaf.restype = C.c_int
+        L.orc_inverse_relation.argtypes = [C.c_int]
+        L.orc_inverse_relation.restype = C.c_int
+        L._sync_ready = True
+    nb = np.ascontiguousarray(nbr168, dtype=np.int32)
+    lv = np.ascontiguousarray(grid.level, dtype=np.int32)
+    return L.orc_sync_ghosts_leaf(grid.n, nb.ctypes.data_as(_ip), lv.ctypes.data_as(_ip), grid.dim, p.g, _bs(p.Bs), hvy.shape[1], _p(hvy),
+                                  g_minus, g_plus, order, int(lifted))
