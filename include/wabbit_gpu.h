@@ -105,6 +105,15 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
                           const int32_t *hvy_neighbor, int32_t ld, int32_t rank);
 
 /*
+ * wgpu_set_treecodes: the numerical binary treecodes of the active blocks (get_tc(lgt_block(lgt_id, IDX_TC_1:IDX_TC_2)),
+ * LIB/TREE/module_treelib.f90:227-239, encoding_b :837-871 with max_level = Jmax), same order as hvy_active / level.
+ * Required BEFORE wgpu_set_topology whenever the grid has coarser / finer neighbour relations: the level-jump ghost
+ * patches (restriction, prediction; LIB/MPI/restrict_predict_data.f90:45-202) locate their sources by block position.
+ * Grids with level jumps also need wgpu_set_wavelet first (the predictor order is the wavelet's, params%order_predictor).
+ */
+int32_t wgpu_set_treecodes(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_active, const int32_t *level, const int64_t *treecode);
+
+/*
  * ---- data movement between the host's Fortran arrays and the resident device arrays.
  * host points at element (1,1,1,1,1) of hvy(nx,ny,nz,ncomp_host,number_blocks); blocks listed in hvy_ids
  * (1-based, n of them) are moved.  `slot` selects hvy_work(:,:,:,:,:,slot) (ignored for other arrays).

@@ -113,3 +113,70 @@ def test_inverse_relation_is_an_involution_on_slots():
         inv = L.orc_inverse_relation(r)
         assert 1 <= inv <= 168 and L.orc_inverse_relation(inv) == r
         assert (inv - 1) // 56 == {0: 0, 1: 2, 2: 1}[(r - 1) // 56]
+
+
+@pytest.mark.parametrize("wavelet,Bs,Jmax,seed", [("CDF40", 16, 3, 5), ("CDF44", 16, 3, 11), ("CDF62", 20, 3, 5)])
+def test_sync_equals_geometric_definition_on_graded_grids(wavelet, Bs, Jmax, seed):
+    """What the GPU path relies on (wabbit_b200/csrc/resolve.cuh): on a graded leaf grid, the reference's staged, table-driven
+    synchronisation (ignore_Filter) gives every ghost point -- faces, edges and corners, full depth g -- the value of the
+    coincident interior point of the leaf that owns it (same level or one finer), else the tensor-product interpolation
+    (x, then y, then z) of the next-coarser lattice, whose points are again owned by leaves of that level or one finer."""
+    from util import graded_blocks
+    w = O.setup_wavelet(wavelet)
+    g, order = w.g_default, w.X
+    A = order // 2 - 1
+    p = O.Params(dim=3, Bs=(Bs,) * 3, g=g, g_rhs=g, n_eqn=1, Jmax=Jmax)
+    lv, ix = graded_blocks(3, 1, Jmax, seed, 0.3)
+    grid = O.Grid(level=lv.astype(np.int64), ixyz=ix.astype(np.int64), dim=3)
+    nbr = O.neighbor_table168(grid, Jmax)
+    rng = np.random.default_rng(seed)
+    u = O.alloc(grid, p, 1)
+    u[:] = rng.standard_normal(u.shape)
+    ref = u.copy()
+    O.sync_ghosts_leaf(grid, p, ref, nbr, g, g, order, bool(w.lifted))
+    look = grid.lookup()
+    cf = {2: [.5, .5], 4: [-1 / 16, 9 / 16, 9 / 16, -1 / 16], 6: [3 / 256, -25 / 256, 150 / 256, 150 / 256, -25 / 256, 3 / 256]}[order]
+
+    def lattice(L, P):
+        n = 2 ** L * Bs
+        P = [q % n for q in P]
+        b = look.get((L,) + tuple(q // Bs for q in P))
+        if b is not None:
+            return u[b, 0, P[2] % Bs + g, P[1] % Bs + g, P[0] % Bs + g]
+        b = look.get((L + 1,) + tuple((2 * q) // Bs for q in P))
+        if b is None:
+            return None
+        return u[b, 0, (2 * P[2]) % Bs + g, (2 * P[1]) % Bs + g, (2 * P[0]) % Bs + g]
+
+    def predicted(L, G, axis=2):
+        if axis < 0:
+            return lattice(L - 1, G)
+        q = G[axis]
+        c = list(G)
+        if q % 2 == 0:
+            c[axis] = q // 2
+            return predicted(L, c, axis - 1)
+        s = None
+        for t in range(order):
+            c[axis] = (q - 1) // 2 - A + t
+            v = predicted(L, c, axis - 1)
+            if v is None:
+                return None
+            s = cf[t] * v if s is None else s + cf[t] * v
+        return s
+
+    checked = {"copy": 0, "pred": 0}
+    for b in range(grid.n):
+        L = int(grid.level[b])
+        for _ in range(40):
+            i = rng.integers(-g, Bs + g, size=3)
+            if all(0 <= q < Bs for q in i):
+                continue
+            G = [int(grid.ixyz[b, a]) * Bs + int(i[a]) for a in range(3)]
+            v, kind = lattice(L, G), "copy"
+            if v is None:
+                v, kind = predicted(L, G), "pred"
+            assert v is not None
+            assert v == ref[b, 0, i[2] + g, i[1] + g, i[0] + g], (b, i, kind)
+            checked[kind] += 1
+    assert checked["copy"] > 100 and checked["pred"] > 100

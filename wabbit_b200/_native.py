@@ -38,6 +38,7 @@ GPU_SYMBOLS = {
     "wgpu_set_stream": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "wgpu_synchronize": (C.c_int32, [C.c_void_p]),
     "wgpu_set_topology": (C.c_int32, [C.c_void_p, C.c_int32, _i32p, _i32p, _i32p, C.c_int32, C.c_int32]),
+    "wgpu_set_treecodes": (C.c_int32, [C.c_void_p, C.c_int32, _i32p, _i32p, _i64p]),
     "wgpu_upload": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, _i32p, C.c_int32, C.c_void_p, C.c_int32]),
     "wgpu_download": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, _i32p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]),
     "wgpu_sync_ghosts": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <new>
 
+#include "resolve.cuh"
 #include "wgpu_internal.cuh"
 
 static std::string g_create_err;
@@ -84,6 +85,8 @@ void fill_common_args(wgpu_ctx *ctx, StageArgs &a)
     a.level = ctx->d_level;
     a.pool = ctx->d_pool;
     a.pool_off = ctx->d_pool_off;
+    a.jpool = ctx->d_jpool;
+    a.jpatch = (long long)ctx->nc * (c.fd == 2 ? 1 : (c.fd == 4 ? 2 : 3)) * c.Bs[0] * c.Bs[1];
     for (int l = 0; l < WGPU_MAX_LEVELS; ++l)
         for (int d = 0; d < 3; ++d) a.dx_lvl[l][d] = ldexp(1.0, -l) * c.domain[d] / (double)c.Bs[d];  // module_treelib.f90:93
     a.c0 = c.c0;
@@ -117,9 +120,102 @@ int32_t ensure_stage(wgpu_ctx *ctx, int64_t elems)
     return WGPU_OK;
 }
 
+// block lookup + level-jump patch lists of the current topology (needs wgpu_set_treecodes and wgpu_set_wavelet)
+int32_t upload_jump_tables(wgpu_ctx *ctx, const std::vector<int> &jump_blk, const std::vector<int> &jump_dir)
+{
+    const wgpu_config &c = ctx->cfg;
+    const int N = c.max_blocks;
+    if (!ctx->wavelet_set)
+        return fail(ctx, WGPU_ERR_ARG, "grid has level jumps: call wgpu_set_wavelet first (the predictor order is the wavelet's)");
+    if (c.dim != 3 || c.Bs[0] != c.Bs[1] || c.Bs[0] != c.Bs[2]) return fail(ctx, WGPU_ERR_UNSUPPORTED, "level jumps need cubic 3-D blocks so far");
+    for (int k = 0; k < ctx->n_active; ++k)
+        if ((int)ctx->h_has_coords.size() != N || !ctx->h_has_coords[ctx->h_active[k]])
+            return fail(ctx, WGPU_ERR_ARG, "grid has level jumps: call wgpu_set_treecodes for the active blocks first");
+    // hash table (level, ix, iy, iz) -> block
+    size_t cap = 64;
+    while (cap < (size_t)ctx->n_active * 2 + 2) cap <<= 1;
+    std::vector<unsigned long long> keys(cap, ~0ull);
+    std::vector<int> vals(cap, -1);
+    for (int k = 0; k < ctx->n_active; ++k) {
+        const int b = ctx->h_active[k];
+        const unsigned long long key = blk_key(ctx->h_level[b], ctx->h_ixyz[3 * b], ctx->h_ixyz[3 * b + 1], ctx->h_ixyz[3 * b + 2]);
+        unsigned h = blk_hash(key) & (unsigned)(cap - 1);
+        while (keys[h] != ~0ull) {
+            if (keys[h] == key) return fail(ctx, WGPU_ERR_ARG, "two active blocks share a treecode");
+            h = (h + 1) & (unsigned)(cap - 1);
+        }
+        keys[h] = key;
+        vals[h] = b;
+    }
+    int32_t rc;
+    if (cap > ctx->hcap) {
+        cudaFree(ctx->d_hkeys);
+        cudaFree(ctx->d_hvals);
+        ctx->d_hkeys = nullptr;
+        ctx->d_hvals = nullptr;
+        if ((rc = dmalloc(ctx, &ctx->d_hkeys, cap))) return rc;
+        if ((rc = dmalloc(ctx, &ctx->d_hvals, cap))) return rc;
+        ctx->hcap = cap;
+    }
+    ctx->hmask = (unsigned)(cap - 1);
+    if (!ctx->d_ixyz && (rc = dmalloc(ctx, &ctx->d_ixyz, (size_t)N * 3))) return rc;
+    const int nj = (int)jump_blk.size();
+    if (nj > ctx->jump_cap) {
+        cudaFree(ctx->d_jump_blk);
+        cudaFree(ctx->d_jump_dir);
+        ctx->d_jump_blk = ctx->d_jump_dir = nullptr;
+        const int want = std::max(nj, std::min(6 * N, 2 * nj));
+        if ((rc = dmalloc(ctx, &ctx->d_jump_blk, (size_t)want))) return rc;
+        if ((rc = dmalloc(ctx, &ctx->d_jump_dir, (size_t)want))) return rc;
+        ctx->jump_cap = want;
+    }
+    const int H = c.fd == 2 ? 1 : (c.fd == 4 ? 2 : 3);
+    const size_t need = (size_t)std::max(nj, 1) * ctx->nc * H * c.Bs[0] * c.Bs[1];
+    if (need > ctx->jpool_cap) {
+        cudaFree(ctx->d_jpool);
+        ctx->d_jpool = nullptr;
+        ctx->dev_bytes -= (int64_t)ctx->jpool_cap * 8;
+        const size_t want = need + need / 2;
+        if ((rc = dmalloc(ctx, &ctx->d_jpool, want))) return rc;
+        ctx->jpool_cap = want;
+    }
+    WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_hkeys, keys.data(), cap * 8, cudaMemcpyHostToDevice, ctx->stream));
+    WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_hvals, vals.data(), cap * 4, cudaMemcpyHostToDevice, ctx->stream));
+    WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_ixyz, ctx->h_ixyz.data(), sizeof(int) * (size_t)N * 3, cudaMemcpyHostToDevice, ctx->stream));
+    if (nj) {
+        WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_jump_blk, jump_blk.data(), sizeof(int) * nj, cudaMemcpyHostToDevice, ctx->stream));
+        WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_jump_dir, jump_dir.data(), sizeof(int) * nj, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));   // the host vectors above go out of scope
+    return WGPU_OK;
+}
+
 }  // namespace
 
 extern "C" {
+
+int32_t wgpu_set_treecodes(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_active, const int32_t *level, const int64_t *treecode)
+{
+    if (!ctx || n_active < 0 || (n_active > 0 && (!hvy_active || !level || !treecode))) return WGPU_ERR_ARG;
+    const wgpu_config &c = ctx->cfg;
+    const int N = c.max_blocks;
+    ctx->h_ixyz.assign((size_t)N * 3, 0);
+    ctx->h_has_coords.assign(N, 0);
+    for (int k = 0; k < n_active; ++k) {
+        const int hid = hvy_active[k], J = level[k];
+        if (hid < 1 || hid > N) return fail(ctx, WGPU_ERR_ARG, "hvy_active entry out of range");
+        if (J < 0 || J > c.Jmax) return fail(ctx, WGPU_ERR_ARG, "block level out of range");
+        // decoding_b (LIB/TREE/module_treelib.f90:793-831): digit bit0 -> y, bit1 -> x, bit2 -> z; level bit i sits in digit i+Jmax-J
+        int p[3] = {0, 0, 0};
+        for (int d = 0; d < c.dim; ++d)
+            for (int i = 0; i < J; ++i) p[d] |= (int)((treecode[k] >> ((i + c.Jmax - J) * c.dim + d)) & 1) << i;
+        ctx->h_ixyz[3 * (size_t)(hid - 1) + 0] = p[1];
+        ctx->h_ixyz[3 * (size_t)(hid - 1) + 1] = p[0];
+        ctx->h_ixyz[3 * (size_t)(hid - 1) + 2] = p[2];
+        ctx->h_has_coords[hid - 1] = 1;
+    }
+    return WGPU_OK;
+}
 
 int32_t wgpu_create(const wgpu_config *cfg, wgpu_ctx **out)
 {
@@ -202,6 +298,12 @@ int32_t wgpu_destroy(wgpu_ctx *ctx)
     cudaFree(ctx->d_status);
     cudaFree(ctx->d_norm);
     cudaFree(ctx->d_pool_off);
+    cudaFree(ctx->d_ixyz);
+    cudaFree(ctx->d_hkeys);
+    cudaFree(ctx->d_hvals);
+    cudaFree(ctx->d_jump_blk);
+    cudaFree(ctx->d_jump_dir);
+    cudaFree(ctx->d_jpool);
     cudaFree(ctx->d_active_int);
     cudaFree(ctx->d_active_bnd);
     cudaFree(ctx->d_send_blk);
@@ -292,6 +394,8 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
     ctx->remote_faces.clear();
     ctx->h_nbr.assign((size_t)N * WGPU_NDIR, -1);
     ctx->h_level.assign(N, 0);
+    ctx->has_jumps = false;
+    std::vector<int> jump_blk, jump_dir;
     for (int k = 0; k < n_active; ++k) {
         const int hid = hvy_active[k];
         if (hid < 1 || hid > N) return fail(ctx, WGPU_ERR_ARG, "hvy_active entry out of range");
@@ -322,10 +426,23 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
                             entry = (lgt - 1) - r * N;
                     } else {
                         // coarser (+56) or finer (+112) neighbours in this direction?
+                        bool jump = false;
                         for (int s = 0; s < nfree; ++s) {
-                            if (hvy_neighbor[(size_t)(code - 1 + s + 56) * ld + (hid - 1)] >= 1 ||
-                                hvy_neighbor[(size_t)(code - 1 + s + 112) * ld + (hid - 1)] >= 1)
-                                return fail(ctx, WGPU_ERR_UNSUPPORTED, "level-jump neighbour relations are not built yet");
+                            const int lc = hvy_neighbor[(size_t)(code - 1 + s + 56) * ld + (hid - 1)];
+                            const int lf = hvy_neighbor[(size_t)(code - 1 + s + 112) * ld + (hid - 1)];
+                            if (lc >= 1 || lf >= 1) jump = true;
+                            if ((lc >= 1 && (lc - 1) / N != rank) || (lf >= 1 && (lf - 1) / N != rank))
+                                return fail(ctx, WGPU_ERR_UNSUPPORTED, "level-jump neighbours on another rank are not supported yet");
+                        }
+                        if (jump) {
+                            ctx->has_jumps = true;
+                            // faces become restriction / prediction patches in the jump pool; the star stencils of the time
+                            // step do not read edges and corners
+                            if ((dx != 0) + (dy != 0) + (dz != 0) == 1) {
+                                entry = -2 - (WGPU_JUMP_PID + (int)jump_blk.size());
+                                jump_blk.push_back(hid - 1);
+                                jump_dir.push_back((dz + 1) * 9 + (dy + 1) * 3 + (dx + 1));
+                            }
                         }
                     }
                     ctx->h_nbr[(size_t)(hid - 1) * WGPU_NDIR + (dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)] = entry;
@@ -334,6 +451,11 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
     ctx->n_active = n_active;
     ctx->n_int = n_active;
     ctx->n_bnd = 0;
+    ctx->n_jump = (int)jump_blk.size();
+    if (ctx->has_jumps) {
+        int32_t rcj = upload_jump_tables(ctx, jump_blk, jump_dir);
+        if (rcj) return rcj;
+    }
     if (!ctx->d_active_int) {
         int32_t rc2 = dmalloc(ctx, &ctx->d_active_int, (size_t)N);
         if (rc2) return rc2;
@@ -458,7 +580,9 @@ int32_t wgpu_rhs(wgpu_ctx *ctx, double time, int32_t src_slot, int32_t dst_slot)
     a.u_in = src;
     a.u0 = src;
     a.k_out = dst;
-    int32_t rc = wgpu_launch_stage(ctx, a, ctx->n_active);
+    int32_t rc = wgpu_launch_jump_fill(ctx, src);   // sync_ghosts_RHS_tree: restriction / prediction face patches
+    if (rc) return rc;
+    rc = wgpu_launch_stage(ctx, a, ctx->n_active);
     if (rc) return rc;
     return check_flags(ctx);
 }
@@ -570,6 +694,7 @@ static int32_t transform(wgpu_ctx *ctx, int32_t src_id, int32_t src_slot, int32_
     const wgpu_config &c = ctx->cfg;
     if (c.dim != 3 || c.Bs[0] != c.Bs[1] || c.Bs[0] != c.Bs[2]) return fail(ctx, WGPU_ERR_UNSUPPORTED, "wavelet kernels: cubic 3-D blocks only so far");
     if (!ctx->remote_faces.empty() || ctx->n_bnd) return fail(ctx, WGPU_ERR_UNSUPPORTED, "wavelet kernels: neighbours on other ranks are not supported yet");
+    if (ctx->has_jumps) return fail(ctx, WGPU_ERR_UNSUPPORTED, "wavelet kernels: grids with level jumps are not supported yet");
     int n1 = 0, n2 = 0;
     const double *src = array_ptr(ctx, src_id, src_slot, &n1);
     double *dst = array_ptr(ctx, dst_id, dst_slot, &n2);
@@ -807,6 +932,10 @@ int32_t wgpu_rk_stage(wgpu_ctx *ctx, int32_t j, int32_t which)
     }
     if (last && !(c.dt_fixed > 0.0)) a.dtmin_bits = dtmin_next;
     int nblk = ctx->n_active;
+    if (which != WGPU_BLOCKS_BOUNDARY) {   // level-jump face patches of this stage input (once per stage)
+        int32_t rcj = wgpu_launch_jump_fill(ctx, uin);
+        if (rcj) return rcj;
+    }
     if (which == WGPU_BLOCKS_INTERIOR) {
         a.active = ctx->d_active_int;
         nblk = ctx->n_int;

@@ -152,6 +152,8 @@ struct Tile {
 //   variant 2: z+ halo planes   zp = BS..BS+H-1(rows y = 0..BS-1,    plane index zp-BS)
 // ---------------------------------------------------------------------------------------------
 #define LT_POOL (1ull << 63)
+#define LT_JPOOL (1ull << 62)
+#define LT_MASK (~(LT_POOL | LT_JPOOL))
 #define LT_SKIP (~0ull)
 #define LT_ZERO (~0ull - 1ull)
 
@@ -165,6 +167,15 @@ struct LoadTables {
     int row_stride[3][NROW];
     int x_stride[NXH];
 };
+
+// element offset of pool patch `code` (<= -2) with the flag of the buffer it lives in: the exchange pool (remote faces)
+// or the jump pool (restriction / prediction patches of jump.cu); offsets inside a patch are added by the caller
+__device__ __forceinline__ unsigned long long pool_base(const StageArgs &a, int code)
+{
+    const int pid = -2 - code;
+    if (pid >= WGPU_JUMP_PID) return ((unsigned long long)(pid - WGPU_JUMP_PID) * (unsigned long long)a.jpatch) | LT_JPOOL;
+    return (unsigned long long)a.pool_off[pid] | LT_POOL;
+}
 
 template <int FD, int BS>
 __device__ __forceinline__ void build_tables(const StageArgs &a, LoadTables<FD, BS> &lt, int b, const int *code, int tid)
@@ -184,14 +195,14 @@ __device__ __forceinline__ void build_tables(const StageArgs &a, LoadTables<FD, 
                 const int ys = y < 0 ? BS + y : y - BS, ky = y < 0 ? y + H : y - BS;
                 if (cd >= 0) off = ((unsigned long long)cd * NC + c) * CS + ys * BS;
                 else if (cd <= -2) {                              // pool patch (Bs, H, Bs)
-                    off = ((unsigned long long)a.pool_off[-2 - cd] + ((long long)c * BS * H + ky) * BS) | LT_POOL;
+                    off = pool_base(a, cd) + ((long long)c * BS * H + ky) * BS;
                     stride = H * BS;
                 } else off = LT_ZERO;
             }
         } else if (y >= 0 && y < BS) {
             const int cd = v == 1 ? code[4] : code[22];           // (0,0,-1) -> 4 ; (0,0,+1) -> 22
             if (cd >= 0) off = ((unsigned long long)cd * NC + c) * CS + (v == 1 ? (long long)(BS - H) * BS * BS : 0) + y * BS;
-            else if (cd <= -2) off = ((unsigned long long)a.pool_off[-2 - cd] + ((long long)c * H * BS + y) * BS) | LT_POOL;  // (Bs,Bs,H)
+            else if (cd <= -2) off = pool_base(a, cd) + ((long long)c * H * BS + y) * BS;  // (Bs,Bs,H)
             else off = LT_ZERO;
         }
         lt.row_off[v][rid] = off;
@@ -204,7 +215,7 @@ __device__ __forceinline__ void build_tables(const StageArgs &a, LoadTables<FD, 
         int stride = BS * BS;
         if (cd >= 0) off = ((unsigned long long)cd * NC + c) * CS + y * BS + (side ? 0 : BS - H);
         else if (cd <= -2) {                                      // pool patch (H, Bs, Bs)
-            off = ((unsigned long long)a.pool_off[-2 - cd] + ((long long)c * BS * BS + y) * H) | LT_POOL;
+            off = pool_base(a, cd) + ((long long)c * BS * BS + y) * H;
             stride = BS * H;
         } else off = LT_ZERO;
         lt.x_off[i] = off;
@@ -235,8 +246,8 @@ __device__ __forceinline__ void load_plane(const StageArgs &a, const LoadTables<
                     d[0] = 0.0;
                     d[1] = 0.0;
                 } else {
-                    const double *base = (off & LT_POOL) ? a.pool : a.u_in;
-                    cp_async16(d, base + (long long)(off & ~LT_POOL) + (long long)pz * lt.row_stride[v][rid] + 2 * xc);
+                    const double *base = (off & LT_POOL) ? a.pool : ((off & LT_JPOOL) ? a.jpool : a.u_in);
+                    cp_async16(d, base + (long long)(off & LT_MASK) + (long long)pz * lt.row_stride[v][rid] + 2 * xc);
                 }
             }
         }
@@ -255,7 +266,8 @@ __device__ __forceinline__ void load_plane(const StageArgs &a, const LoadTables<
                     if (H % 2 == 0) { d[2 * e] = 0.0; d[2 * e + 1] = 0.0; }
                     else d[e] = 0.0;
                 } else {
-                    const double *src = ((off & LT_POOL) ? a.pool : a.u_in) + (long long)(off & ~LT_POOL) + (long long)pz * lt.x_stride[sid];
+                    const double *src = ((off & LT_POOL) ? a.pool : ((off & LT_JPOOL) ? a.jpool : a.u_in)) + (long long)(off & LT_MASK) +
+                                        (long long)pz * lt.x_stride[sid];
                     if (H % 2 == 0) cp_async16(d + 2 * e, src + 2 * e);
                     else cp_async8(d + e, src + e);
                 }

@@ -21,6 +21,7 @@
 //           prediction or a remote GPU's pack kernel); pool_off[pid] is the offset in doubles.
 // ------------------------------------------------------------------------------------------------
 #define WGPU_NDIR 27
+#define WGPU_JUMP_PID (1 << 28)   // pool patch ids >= this are level-jump patches (index = pid - WGPU_JUMP_PID) in the jump pool
 #define WGPU_FMAX 12   // largest |tap index| of a wavelet filter
 
 // filter banks of a biorthogonal CDF wavelet (setup_wavelet, LIB/WAVELETS/module_wavelets.f90:1031-1290); tap k at [k+WGPU_FMAX]
@@ -56,6 +57,8 @@ struct StageArgs {
     const signed char *level;  // [max_blocks]
     const double *pool;
     const long long *pool_off;
+    const double *jpool;       // level-jump face patches (restriction / prediction), patch i at i*jpatch doubles
+    long long jpatch;
     // physics
     double dx_lvl[WGPU_MAX_LEVELS][3];
     double c0, nu, gamma_p, C_eta_inv, C_sponge_inv, u_mean_set[3];
@@ -102,6 +105,20 @@ struct wgpu_ctx {
     int n_send = 0;
     int *d_send_blk = nullptr, *d_send_dir = nullptr;
     double *d_send_buf = nullptr;
+    // block coordinates + device lookup (level, ix, iy, iz) -> block index, for level-jump patches
+    std::vector<int> h_ixyz;           // [max_blocks][3], valid where coords_of[b] != 0
+    std::vector<char> h_has_coords;
+    int *d_ixyz = nullptr;
+    unsigned long long *d_hkeys = nullptr;
+    int *d_hvals = nullptr;
+    unsigned hmask = 0;
+    size_t hcap = 0;
+    // level-jump face patches of the stage kernel (refreshed from the stage input before every stage)
+    int n_jump = 0, jump_cap = 0;
+    int *d_jump_blk = nullptr, *d_jump_dir = nullptr;
+    double *d_jpool = nullptr;
+    size_t jpool_cap = 0;
+    bool has_jumps = false;            // some active block has a coarser / finer neighbour
     // Runge-Kutta step in flight
     const double *rk_uin = nullptr;
     int rk_next_stage = 0;
@@ -147,6 +164,8 @@ struct wgpu_ctx {
 // kernels.cu
 int32_t wgpu_launch_stage(wgpu_ctx *ctx, const StageArgs &a, int n_blocks);
 int32_t wgpu_launch_pack(wgpu_ctx *ctx, const double *src);
+// jump.cu
+int32_t wgpu_launch_jump_fill(wgpu_ctx *ctx, const double *src);
 // wavelet.cu
 int32_t wgpu_launch_wavelet(wgpu_ctx *ctx, const double *src, double *dst, int inverse);
 int32_t wgpu_launch_detail(wgpu_ctx *ctx, const double *wd, int eps_norm, int level_ref);

@@ -108,8 +108,17 @@ class WabbitGPU:
                                                 hvy_neighbor.shape[1], rank))
         self.hvy_active = hvy_active.copy()
 
+    def set_treecodes(self, hvy_active: np.ndarray, level: np.ndarray, treecode: np.ndarray):
+        """Block positions (numerical binary treecodes, module_treelib.f90:837) -- needed for grids with level jumps."""
+        hvy_active = np.ascontiguousarray(hvy_active, dtype=np.int32)
+        level = np.ascontiguousarray(level, dtype=np.int32)
+        treecode = np.ascontiguousarray(treecode, dtype=np.int64)
+        self._check(self._lib.wgpu_set_treecodes(self._ctx, len(hvy_active), _i32(hvy_active), _i32(level),
+                                                 treecode.ctypes.data_as(C.POINTER(C.c_int64))))
+
     def set_forest(self, forest: Forest, rank: int = 0):
-        hvy, lvl, _, _ = forest.active(rank)
+        hvy, lvl, _, tc = forest.active(rank)
+        self.set_treecodes(hvy, lvl, tc)
         self.set_topology(hvy, lvl, forest.neighbors(rank), rank)
 
     # ------------------------------------------------------------------ data movement
