@@ -117,8 +117,9 @@ int32_t wgpu_set_treecodes(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_a
  * ---- data movement between the host's Fortran arrays and the resident device arrays.
  * host points at element (1,1,1,1,1) of hvy(nx,ny,nz,ncomp_host,number_blocks); blocks listed in hvy_ids
  * (1-based, n of them) are moved.  `slot` selects hvy_work(:,:,:,:,:,slot) (ignored for other arrays).
- * Download fills ghost layers of width g_sync (0..g) by running the ghost synchronisation on the fly
- * (same-level copy; what sync_ghosts_tree would have left there), the rest of the ghost region is untouched.
+ * Download fills ghost layers of width g_sync (0..g) by running the ghost synchronisation on the fly (what
+ * sync_ghosts_tree with ignore_Filter would have left there: same-level copy, and on grids with level jumps decimation from finer
+ * and prediction from coarser neighbours for all 26 relations); the rest of the ghost region is untouched.
  */
 int32_t wgpu_upload(wgpu_ctx *ctx, int32_t array_id, int32_t slot, const int32_t *hvy_ids, int32_t n,
                     const double *host, int32_t ncomp_host);
@@ -167,6 +168,28 @@ int32_t wgpu_iwt(wgpu_ctx *ctx, int32_t src_id, int32_t src_slot, int32_t dst_id
 int32_t wgpu_norm(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t norm_id, double *out);
 int32_t wgpu_threshold(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t eps_norm_id, int32_t level_ref, const int32_t *thresh_comp,
                        const double *eps, const double *norm, int32_t *refinement_status, double *detail_out);
+
+/*
+ * ---- refinement / coarsening of heavy data (the light-data side -- which blocks, which free ids -- stays with the host) ----
+ * wgpu_refine: replaces the block loop of refinement_execute_tree -> refineBlock (LIB/MESH/refinementExecute.f90:1-120) on hvy_block:
+ *   every mother (ghosts synchronised on the fly, as the sync_ghosts_tree before refine_tree, LIB/MAIN/main.f90:314-322, with
+ *   ignore_Filter) is interpolated with the wavelet's predictor to 2^dim daughters.  daughter_hvy[i*2^dim + digit], digit bit0 -> y,
+ *   bit1 -> x, bit2 -> z (treecode digit).  Blocks that are not refined either stay in place (n_keep < 0) or move from hvy id
+ *   keep_src[i] to keep_dst[i] (the block_xfer of balanceLoad_tree("refine_post"), LIB/MESH/balanceLoad_tree.f90, on one rank);
+ *   every active block must then be a mother or listed, and no destination slot may be used twice.  hvy_tmp is used as the second buffer and holds the old grid's data afterwards.  The topology on the device
+ *   is the OLD one during the call; upload the new one (wgpu_set_treecodes + wgpu_set_topology) before any other compute call.
+ * wgpu_coarsen: replaces sync_D2M + the mother assembly of executeCoarsening (LIB/MESH/executeCoarsening_tree.f90:125-230): octant
+ *   `digit` of hvy_block(mother) = the scaling coefficients (even spaghetti positions, conversion_routines.f90:149) of the decomposed
+ *   daughter in array (src_id, src_slot) -- the result of wgpu_fwt; the source must not be hvy_block.  A mother may reuse the id of one
+ *   of its daughters.
+ */
+int32_t wgpu_refine(wgpu_ctx *ctx, int32_t n, const int32_t *mother_hvy, const int32_t *daughter_hvy, int32_t n_keep, const int32_t *keep_src,
+                    const int32_t *keep_dst);
+int32_t wgpu_coarsen(wgpu_ctx *ctx, int32_t n, const int32_t *mother_hvy, const int32_t *daughter_hvy, int32_t src_id, int32_t src_slot);
+/* wgpu_move_blocks: the same-rank part of block_xfer (LIB/MPI/block_xfer_nonblocking.f90:16) as used by balanceLoad_tree: hvy_block(dst[i]) =
+ *   hvy_block(src[i]) for all i at once (a permutation is fine).  Every block that must survive has to be listed (identity pairs
+ *   allowed): the move goes through hvy_tmp, which becomes hvy_block.  Upload the new topology afterwards. */
+int32_t wgpu_move_blocks(wgpu_ctx *ctx, int32_t n, const int32_t *src_hvy, const int32_t *dst_hvy);
 
 /*
  * ---- multi-GPU (one process per GPU): the Runge-Kutta step split at the points where ranks must talk.

@@ -118,6 +118,49 @@ def wavelet_blocks():
     print(path, os.path.getsize(path), picked)
 
 
+
+# ------------------------------------------------------------------------------------------------------------------
+# TESTING/acm/3vortices: 2-D ACM, Bs=32, equidistant level 3 (64 blocks), skew-symmetric, restart from the stored
+# {ux,uy,p}_000010000000.h5 (t = 10) and run to t = 20.  three_vortices_t10.npz holds the full restart fields (interior
+# points), three_vortices_FDx_CDFy0.npz strided samples of the reference's t = 20 output and its iteration counter.
+def three_vortices():
+    R = "/root/reference/TESTING/acm/3vortices"
+    out = {}
+    fields = []
+    for name in ("ux", "uy", "p"):
+        d = read_wabbit(os.path.join(R, f"{name}_000010000000.h5"))
+        Bs = int(d["attrs"]["block-size"][0])
+        ixy = np.rint(d["origin"][:, ::-1] / (d["spacing"][:, ::-1] * Bs)).astype(np.int32)
+        order = np.lexsort((ixy[:, 0], ixy[:, 1]))
+        fields.append(d["blocks"][order][:, :Bs, :Bs])
+        out["ixy"] = ixy[order]
+        out["iteration"] = d["attrs"]["iteration"]
+        out["time"] = d["attrs"]["time"]
+        out["level"] = d["level"][order]
+    out["u"] = np.stack(fields, axis=1)
+    path = os.path.join(HERE, "three_vortices_t10.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), out["u"].shape)
+    for case in ("3vorticesEquiFD2_CDF20", "3vorticesEquiFD4_CDF40", "3vorticesEquiFD6_CDF60"):
+        o = {}
+        fields = []
+        for name in ("ux", "uy", "p"):
+            d = read_wabbit(os.path.join(R, case, f"{name}_000020000000.h5"))
+            Bs = int(d["attrs"]["block-size"][0])
+            ixy = np.rint(d["origin"][:, ::-1] / (d["spacing"][:, ::-1] * Bs)).astype(np.int32)
+            order = np.lexsort((ixy[:, 0], ixy[:, 1]))
+            fields.append(d["blocks"][order][:, :Bs:STRIDE, :Bs:STRIDE])
+            o["ixy"] = ixy[order]
+            o["iteration"] = d["attrs"]["iteration"]
+            o["time"] = d["attrs"]["time"]
+        o["u"] = np.stack(fields, axis=1)
+        o["stride"] = np.array([STRIDE])
+        path = os.path.join(HERE, case.replace("3vorticesEqui", "three_vortices_") + ".npz")
+        np.savez_compressed(path, **o)
+        print(path, os.path.getsize(path), o["u"].shape, o["iteration"])
+
+
 if __name__ == "__main__":
     main()
     wavelet_blocks()
+    three_vortices()

@@ -1,0 +1,154 @@
+"""GPU parity of the level-crossing heavy-data kernels (wabbit_b200/csrc/jump.cu) against the oracle:
+download with a fully synchronised ghost shell on graded grids (all 26 relations; copy, decimation, prediction), refineBlock,
+sync_D2M / executeCoarsening, and the reference's unit-test property Coarsen(Refine(u)) = u (unit_test_refineCoarsen.f90:129)."""
+import numpy as np
+import pytest
+
+import oracle as O
+from wabbit_b200 import Forest, WabbitGPU
+from wabbit_b200.solver import HVY_BLOCK, HVY_WORK
+
+from util import graded_blocks, orc_grid, orc_params, relerr, tg_params
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(wavelet, Bs, forest, seed, max_blocks=None):
+    w = O.setup_wavelet(wavelet)
+    p = tg_params(Bs=Bs, J=forest.Jmax, wavelet_g=w.g_default)
+    p.wavelet = wavelet
+    grid = orc_grid(forest)
+    po = orc_params(p)
+    sol = WabbitGPU(p, max_blocks=max_blocks or forest.n_blocks)
+    sol.setup_wavelet(wavelet)
+    sol.set_forest(forest)
+    rng = np.random.default_rng(seed)
+    u = np.zeros(sol.host_shape())
+    u[:grid.n] = rng.standard_normal((grid.n,) + u.shape[1:])
+    return w, p, po, grid, sol, u
+
+
+@pytest.mark.parametrize("wavelet,Bs", [("CDF40", 16), ("CDF44", 16), ("CDF20", 16), ("CDF62", 20)])
+def test_download_with_ghosts_on_graded_grid(wavelet, Bs):
+    lv, ix = graded_blocks(3, 1, 3, seed=7)
+    forest = Forest.from_blocks(3, 3, lv, ix)
+    w, p, po, grid, sol, u = _case(wavelet, Bs, forest, seed=1)
+    nbr = forest.neighbors(0)[:, :grid.n]
+    sol.upload(u)
+    for gs in (p.g, max(p.g_rhs, w.X // 2)):   # the reference's minimum sync depth is X/2 (ini_file_to_params.f90:467-468)
+        got = u.copy()
+        sol.download(got, g_sync=gs)
+        ref = u.copy()
+        O.sync_ghosts_leaf(grid, po, ref, nbr, gs, gs, w.X, bool(w.lifted))
+        assert np.array_equal(got, ref), gs
+    sol.close()
+
+
+def _refine_oracle(w, po, grid, u, nbr):
+    """sync (ignore_Filter) + refineBlock per block: dict (level, ix, iy, iz) -> daughter interior [nc, Bs, Bs, Bs]"""
+    ref = u.copy()
+    if nbr is None:
+        O.sync_ghosts_same_level(grid, po, ref, po.g, po.g)
+    else:
+        O.sync_ghosts_leaf(grid, po, ref, nbr, po.g, po.g, w.X, bool(w.lifted))
+    I = O.interior(po)
+    out = {}
+    for b in range(grid.n):
+        d = O.refine_block(w.X, po, ref[b])
+        L, (x, y, z) = int(grid.level[b]), (int(v) for v in grid.ixyz[b])
+        for k in range(8):
+            q = ((k >> 1) & 1, k & 1, (k >> 2) & 1)
+            out[(L + 1, 2 * x + q[0], 2 * y + q[1], 2 * z + q[2])] = d[k][(slice(None),) + I]
+    return out
+
+
+@pytest.mark.parametrize("wavelet,Bs", [("CDF40", 16), ("CDF44", 16), ("CDF20", 18), ("CDF62", 20)])
+def test_refine_everywhere_uniform(wavelet, Bs):
+    forest = Forest.uniform(3, 1, Jmax=2)
+    w, p, po, grid, sol, u = _case(wavelet, Bs, forest, seed=2, max_blocks=64)
+    sol.upload(u)
+    expect = _refine_oracle(w, po, grid, u[:grid.n], None)
+    new = sol.refine_tree(forest)
+    assert new.n_blocks == 64
+    got = np.zeros(sol.host_shape())
+    sol.download(got, g_sync=0)
+    hvy, lvl, ixyz, _ = new.active(0)
+    I = (slice(None),) + O.interior(po)
+    for h, l, (x, y, z) in zip(hvy, lvl, ixyz):
+        assert np.array_equal(got[h - 1][I], expect[(int(l), int(x), int(y), int(z))])
+    sol.close()
+
+
+def test_refine_everywhere_graded_and_partial():
+    # everywhere on a graded grid: mothers next to coarser blocks are interpolated from predicted ghost nodes
+    lv, ix = graded_blocks(3, 1, 2, seed=4)
+    forest = Forest.from_blocks(3, 3, lv, ix)
+    assert not forest.is_uniform
+    w, p, po, grid, sol, u = _case("CDF40", 16, forest, seed=3, max_blocks=8 * forest.n_blocks)
+    nbr = forest.neighbors(0)[:, :grid.n]
+    sol.upload(u)
+    expect = _refine_oracle(w, po, grid, u[:grid.n], nbr)
+    new = sol.refine_tree(forest)
+    got = np.zeros(sol.host_shape())
+    sol.download(got, g_sync=0)
+    hvy, lvl, ixyz, _ = new.active(0)
+    I = (slice(None),) + O.interior(po)
+    for h, l, (x, y, z) in zip(hvy, lvl, ixyz):
+        assert np.array_equal(got[h - 1][I], expect[(int(l), int(x), int(y), int(z))])
+    sol.close()
+
+    # partial refinement of a uniform grid: blocks that stay keep their data (and move to their new slots)
+    forest = Forest.uniform(3, 2, Jmax=3)
+    w, p, po, grid, sol, u = _case("CDF44", 16, forest, seed=5, max_blocks=64 + 7 * 20)
+    sol.upload(u)
+    expect = _refine_oracle(w, po, grid, u[:grid.n], None)
+    flags = np.zeros(grid.n, np.int32)
+    flags[np.random.default_rng(0).choice(grid.n, 20, replace=False)] = 1
+    new = sol.refine_tree(forest, flags)
+    assert new.n_blocks == 64 + 7 * 20
+    got = np.zeros(sol.host_shape())
+    sol.download(got, g_sync=0)
+    old = {(int(l), int(a), int(b), int(c)): k for k, (l, (a, b, c)) in enumerate(zip(grid.level, grid.ixyz))}
+    hvy, lvl, ixyz, _ = new.active(0)
+    I = (slice(None),) + O.interior(po)
+    for h, l, (x, y, z) in zip(hvy, lvl, ixyz):
+        key = (int(l), int(x), int(y), int(z))
+        if key in old:
+            assert np.array_equal(got[h - 1][I], u[old[key]][I])
+        else:
+            assert np.array_equal(got[h - 1][I], expect[key])
+    sol.close()
+
+
+@pytest.mark.parametrize("wavelet,Bs", [("CDF40", 16), ("CDF44", 16), ("CDF42", 18), ("CDF62", 20)])
+def test_coarsen_of_refine_is_identity_and_matches_oracle(wavelet, Bs):
+    forest = Forest.uniform(3, 1, Jmax=2)
+    w, p, po, grid, sol, u = _case(wavelet, Bs, forest, seed=6, max_blocks=64)
+    sol.upload(u)
+    fine = sol.refine_tree(forest)
+    fine_host = np.zeros(sol.host_shape())
+    sol.download(fine_host, g_sync=p.g)
+    sol.waveletDecomposition_tree(src=(HVY_BLOCK, 0), dst=(HVY_WORK, 2))
+    status = np.full(fine.n_blocks, -1, np.int32)
+    coarse = sol.executeCoarsening_tree(fine, status, decomposed=(HVY_WORK, 2))
+    assert coarse.n_blocks == 8 and coarse.is_uniform
+    got = np.zeros(sol.host_shape())
+    sol.download(got, g_sync=0)
+    hvy, lvl, ixyz, _ = coarse.active(0)
+    I = (slice(None),) + O.interior(po)
+    old = {(int(l), int(a), int(b), int(c)): k for k, (l, (a, b, c)) in enumerate(zip(grid.level, grid.ixyz))}
+    # (1) oracle: decomposition of the refined field, scaling coefficients at even positions -> octants of the mothers
+    fgrid = orc_grid(fine)
+    wd = np.zeros_like(fine_host[:fgrid.n])
+    O.fwt_tree(w, po, fine_host[:fgrid.n], wd)
+    g, h = po.g, Bs // 2
+    for hm, l, (x, y, z) in zip(hvy, lvl, ixyz):
+        exp = np.zeros((4, Bs, Bs, Bs))
+        for k, (fl, (fx, fy, fz)) in enumerate(zip(fgrid.level, fgrid.ixyz)):
+            if (fx // 2, fy // 2, fz // 2) == (x, y, z):
+                qx, qy, qz = fx % 2, fy % 2, fz % 2
+                exp[:, qz * h:(qz + 1) * h, qy * h:(qy + 1) * h, qx * h:(qx + 1) * h] = wd[k][:, g:g + Bs:2, g:g + Bs:2, g:g + Bs:2]
+        assert np.array_equal(got[hm - 1][I], exp)
+        # (2) the reference's property test: Coarsen(Refine(u)) = u to 1e-14
+        assert relerr(got[hm - 1][I], u[old[(int(l), int(x), int(y), int(z))]][I]) <= 1e-14
+    sol.close()

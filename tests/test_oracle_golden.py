@@ -57,3 +57,41 @@ def test_taylor_green_fixture(case):
     err = np.abs(sample(u, p, grid, gold["t1_ixyz"], stride) - gold["t1"]).max()
     # the restatement reproduces the Fortran output to round-off; 1e-12 is the north-star field tolerance
     assert err <= 1e-12, err
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 2-D: TESTING/acm/3vortices/3vorticesEqui*: restart from the stored t = 10 fields (64 blocks of 32^2 on level 3), run to
+# t = 20 (fixed_time output clips the last step).  Pins RHS_2D_acm (FD2/FD4/FD6, skew-symmetric, gamma_p), the 2-D
+# same-level synchronisation (8 relations), RungeKuttaGeneric and calculate_time_step in two dimensions.
+TV_CASES = {"FD4_CDF40": ("FD_4th_central", 3, 2), "FD2_CDF20": ("FD_2nd_central", 1, 1), "FD6_CDF60": ("FD_6th_central", 5, 3)}
+
+
+def three_vortices_setup(case):
+    inp = np.load(os.path.join(GOLD, "three_vortices_t10.npz"))
+    disc, g, g_rhs = TV_CASES[case]
+    p = O.Params(dim=2, Bs=(32, 32, 1), g=g, g_rhs=g_rhs, n_eqn=3, domain=(6.283185307179586,) * 3, Jmax=3, discretization=disc,
+                 skew=True, c0=7.0, nu=5.0e-5, gamma_p=1.0, CFL=1.0, time_max=20.0, write_method="fixed_time", write_time=10.0,
+                 u_mean_set=(0.0, 0.0, 0.0))
+    ixyz = np.concatenate([inp["ixy"], np.zeros((len(inp["ixy"]), 1), np.int32)], axis=1).astype(np.int64)
+    grid = O.Grid(level=inp["level"].astype(np.int64), ixyz=ixyz, dim=2)
+    u = O.alloc(grid, p)
+    u[:, :, 0, g:g + 32, g:g + 32] = inp["u"]
+    return p, grid, u, float(inp["time"][0]), int(inp["iteration"][0])
+
+
+@pytest.mark.parametrize("case", list(TV_CASES))
+def test_three_vortices_2d_fixture(case):
+    gold = np.load(os.path.join(GOLD, f"three_vortices_{case}.npz"))
+    p, grid, u, t, it = three_vortices_setup(case)
+    nbr, dxb = O.nbr_table(grid), O.dx_table(grid, p)
+    work = np.zeros((5,) + u.shape)
+    while t < p.time_max:
+        t += O.rk_step_c(grid, p, u, work, t, nbr, dxb)
+        it += 1
+    assert it == int(gold["iteration"][0])
+    assert t == float(gold["time"][0])
+    s, g = int(gold["stride"][0]), p.g
+    order = {tuple(v): k for k, v in enumerate(grid.ixyz[:, :2])}
+    got = np.stack([u[order[tuple(v)], :, 0, g:g + 32:s, g:g + 32:s] for v in gold["ixy"]])
+    err = np.abs(got - gold["u"]).max()
+    assert err <= 1e-12, err

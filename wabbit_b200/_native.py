@@ -50,6 +50,9 @@ GPU_SYMBOLS = {
     "wgpu_iwt": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "wgpu_norm": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _dp]),
     "wgpu_threshold": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _i32p, _dp, _dp, _i32p, _dp]),
+    "wgpu_refine": (C.c_int32, [C.c_void_p, C.c_int32, _i32p, _i32p, C.c_int32, _i32p, _i32p]),
+    "wgpu_coarsen": (C.c_int32, [C.c_void_p, C.c_int32, _i32p, _i32p, C.c_int32, C.c_int32]),
+    "wgpu_move_blocks": (C.c_int32, [C.c_void_p, C.c_int32, _i32p, _i32p]),
     "wgpu_patch_doubles": (C.c_int64, [C.c_void_p]),
     "wgpu_set_exchange": (C.c_int32, [C.c_void_p, C.c_int32, _i32p, _i32p, C.c_void_p, C.c_int32, _i32p, _i32p, C.c_void_p]),
     "wgpu_pack_halo": (C.c_int32, [C.c_void_p, C.c_int32]),

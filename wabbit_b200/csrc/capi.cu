@@ -125,12 +125,16 @@ int32_t upload_jump_tables(wgpu_ctx *ctx, const std::vector<int> &jump_blk, cons
 {
     const wgpu_config &c = ctx->cfg;
     const int N = c.max_blocks;
-    if (!ctx->wavelet_set)
-        return fail(ctx, WGPU_ERR_ARG, "grid has level jumps: call wgpu_set_wavelet first (the predictor order is the wavelet's)");
-    if (c.dim != 3 || c.Bs[0] != c.Bs[1] || c.Bs[0] != c.Bs[2]) return fail(ctx, WGPU_ERR_UNSUPPORTED, "level jumps need cubic 3-D blocks so far");
-    for (int k = 0; k < ctx->n_active; ++k)
-        if ((int)ctx->h_has_coords.size() != N || !ctx->h_has_coords[ctx->h_active[k]])
-            return fail(ctx, WGPU_ERR_ARG, "grid has level jumps: call wgpu_set_treecodes for the active blocks first");
+    ctx->lookup_ready = false;
+    bool coords = (int)ctx->h_has_coords.size() == N;
+    for (int k = 0; k < ctx->n_active && coords; ++k) coords = ctx->h_has_coords[ctx->h_active[k]] != 0;
+    if (ctx->has_jumps) {
+        if (!ctx->wavelet_set)
+            return fail(ctx, WGPU_ERR_ARG, "grid has level jumps: call wgpu_set_wavelet first (the predictor order is the wavelet's)");
+        if (c.dim != 3 || c.Bs[0] != c.Bs[1] || c.Bs[0] != c.Bs[2]) return fail(ctx, WGPU_ERR_UNSUPPORTED, "level jumps need cubic 3-D blocks so far");
+        if (!coords) return fail(ctx, WGPU_ERR_ARG, "grid has level jumps: call wgpu_set_treecodes for the active blocks first");
+    }
+    if (!coords) return WGPU_OK;   // uniform grid without block positions: nothing that needs the lookup can be called
     // hash table (level, ix, iy, iz) -> block
     size_t cap = 64;
     while (cap < (size_t)ctx->n_active * 2 + 2) cap <<= 1;
@@ -187,6 +191,21 @@ int32_t upload_jump_tables(wgpu_ctx *ctx, const std::vector<int> &jump_blk, cons
         WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_jump_dir, jump_dir.data(), sizeof(int) * nj, cudaMemcpyHostToDevice, ctx->stream));
     }
     WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));   // the host vectors above go out of scope
+    ctx->lookup_ready = true;
+    return WGPU_OK;
+}
+
+int32_t upload_ids(wgpu_ctx *ctx, int which, const std::vector<int> &v)
+{
+    int *&p = ctx->d_idbuf[which];
+    if (v.size() > ctx->idbuf_cap[which]) {
+        cudaFree(p);
+        p = nullptr;
+        int32_t rc = dmalloc(ctx, &p, v.size() + v.size() / 2 + 64);
+        if (rc) return rc;
+        ctx->idbuf_cap[which] = v.size() + v.size() / 2 + 64;
+    }
+    if (!v.empty()) WGPU_CHECK(ctx, cudaMemcpyAsync(p, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice, ctx->stream));
     return WGPU_OK;
 }
 
@@ -304,6 +323,9 @@ int32_t wgpu_destroy(wgpu_ctx *ctx)
     cudaFree(ctx->d_jump_blk);
     cudaFree(ctx->d_jump_dir);
     cudaFree(ctx->d_jpool);
+    cudaFree(ctx->d_idbuf[0]);
+    cudaFree(ctx->d_idbuf[1]);
+    cudaFree(ctx->d_idbuf[2]);
     cudaFree(ctx->d_active_int);
     cudaFree(ctx->d_active_bnd);
     cudaFree(ctx->d_send_blk);
@@ -452,7 +474,7 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
     ctx->n_int = n_active;
     ctx->n_bnd = 0;
     ctx->n_jump = (int)jump_blk.size();
-    if (ctx->has_jumps) {
+    {
         int32_t rcj = upload_jump_tables(ctx, jump_blk, jump_dir);
         if (rcj) return rcj;
     }
@@ -521,7 +543,9 @@ static int32_t move_blocks(wgpu_ctx *ctx, bool up, int32_t array_id, int32_t slo
             // ghost layers beyond g_sync (and patches without a same-level source) keep the host's values
             if (g_sync < c.g || ncomp_host > nc)
                 if ((rc = xfer(true))) return rc;
-            if ((rc = wgpu_launch_export(ctx, dev, ctx->d_stage, d_ids, m, nc, ncomp_host, g_sync))) return rc;
+            if (ctx->has_jumps) rc = wgpu_launch_export_regions(ctx, dev, ctx->d_stage, d_ids, m, nc, ncomp_host, g_sync);
+            else rc = wgpu_launch_export(ctx, dev, ctx->d_stage, d_ids, m, nc, ncomp_host, g_sync);
+            if (rc) return rc;
             if ((rc = xfer(false))) return rc;
         }
         // the staging buffer and `ids` are reused by the next chunk
@@ -570,7 +594,6 @@ int32_t wgpu_rhs(wgpu_ctx *ctx, double time, int32_t src_slot, int32_t dst_slot)
 {
     (void)time;
     if (!ctx) return WGPU_ERR_ARG;
-    if (ctx->cfg.dim != 3) return fail(ctx, WGPU_ERR_UNSUPPORTED, "2-D ACM kernels are not built yet");
     int nc = 0;
     const double *src = src_slot == 0 ? ctx->U : array_ptr(ctx, WGPU_HVY_WORK, src_slot, &nc);
     double *dst = array_ptr(ctx, WGPU_HVY_WORK, dst_slot, &nc);
@@ -754,6 +777,116 @@ int32_t wgpu_threshold(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t ep
     return WGPU_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ refinement / coarsening
+int32_t wgpu_refine(wgpu_ctx *ctx, int32_t n, const int32_t *mother_hvy, const int32_t *daughter_hvy, int32_t n_keep, const int32_t *keep_src,
+                    const int32_t *keep_dst)
+{
+    if (!ctx || n < 0 || (n > 0 && (!mother_hvy || !daughter_hvy)) || (n_keep > 0 && (!keep_src || !keep_dst))) return WGPU_ERR_ARG;
+    if (!ctx->wavelet_set) return fail(ctx, 1213149, "The cat is angry: Wavelet-setup not yet called?");
+    if (!ctx->lookup_ready) return fail(ctx, WGPU_ERR_ARG, "wgpu_refine: call wgpu_set_treecodes + wgpu_set_topology first");
+    const wgpu_config &c = ctx->cfg;
+    if (c.Bs[0] != c.Bs[1] || (c.dim == 3 && c.Bs[0] != c.Bs[2])) return fail(ctx, WGPU_ERR_UNSUPPORTED, "wgpu_refine: cubic blocks only");
+    if (!ctx->remote_faces.empty() || ctx->n_bnd) return fail(ctx, WGPU_ERR_UNSUPPORTED, "wgpu_refine: neighbours on other ranks are not supported yet");
+    const int N = c.max_blocks, nd = 1 << c.dim;
+    std::vector<int> mo(n), da((size_t)n * nd), ksrc, kdst;
+    std::vector<char> is_mother(N, 0), is_active(N, 0), taken(N, 0);
+    for (int k = 0; k < ctx->n_active; ++k) is_active[ctx->h_active[k]] = 1;
+    for (int i = 0; i < n; ++i) {
+        mo[i] = mother_hvy[i] - 1;
+        if (mo[i] < 0 || mo[i] >= N || !is_active[mo[i]] || is_mother[mo[i]]) return fail(ctx, WGPU_ERR_ARG, "wgpu_refine: bad mother id");
+        if (ctx->h_level[mo[i]] >= c.Jmax) return fail(ctx, WGPU_ERR_ARG, "wgpu_refine: mother is on Jmax already");
+        is_mother[mo[i]] = 1;
+    }
+    if (n_keep < 0) {   // every block that is not refined stays where it is
+        for (int k = 0; k < ctx->n_active; ++k)
+            if (!is_mother[ctx->h_active[k]]) {
+                ksrc.push_back(ctx->h_active[k]);
+                kdst.push_back(ctx->h_active[k]);
+            }
+    } else {
+        for (int i = 0; i < n_keep; ++i) {
+            ksrc.push_back(keep_src[i] - 1);
+            kdst.push_back(keep_dst[i] - 1);
+            if (ksrc[i] < 0 || ksrc[i] >= N || !is_active[ksrc[i]] || is_mother[ksrc[i]] || kdst[i] < 0 || kdst[i] >= N)
+                return fail(ctx, WGPU_ERR_ARG, "wgpu_refine: bad keep list entry");
+        }
+    }
+    // the new grid is assembled in the other array: any slot may be a destination, but only once
+    for (int v : kdst) {
+        if (taken[v]) return fail(ctx, WGPU_ERR_ARG, "wgpu_refine: destination slot used twice");
+        taken[v] = 1;
+    }
+    for (size_t i = 0; i < da.size(); ++i) {
+        da[i] = daughter_hvy[i] - 1;
+        if (da[i] < 0 || da[i] >= N || taken[da[i]]) return fail(ctx, WGPU_ERR_ARG, "wgpu_refine: daughter id out of range or destination slot used twice");
+        taken[da[i]] = 1;
+    }
+    int32_t rc;
+    std::vector<int> pairs(ksrc);
+    pairs.insert(pairs.end(), kdst.begin(), kdst.end());
+    if ((rc = upload_ids(ctx, 0, mo)) || (rc = upload_ids(ctx, 1, da)) || (rc = upload_ids(ctx, 2, pairs))) return rc;
+    // daughters and kept blocks are written to the other array, which then becomes hvy_block: one read and one write of
+    // the new grid's data, and no in-place hazard when a slot is reused (refinementExecute.f90: the last daughter overwrites the mother)
+    if ((rc = wgpu_launch_refine(ctx, ctx->U, ctx->TMP, ctx->d_idbuf[0], ctx->d_idbuf[1], n))) return rc;
+    if ((rc = wgpu_launch_copy_blocks(ctx, ctx->U, ctx->TMP, ctx->d_idbuf[2], ctx->d_idbuf[2] + ksrc.size(), (int)ksrc.size()))) return rc;
+    WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    std::swap(ctx->U, ctx->TMP);
+    ctx->dtmin_valid = false;
+    return WGPU_OK;
+}
+
+int32_t wgpu_move_blocks(wgpu_ctx *ctx, int32_t n, const int32_t *src_hvy, const int32_t *dst_hvy)
+{
+    if (!ctx || n < 0 || (n > 0 && (!src_hvy || !dst_hvy))) return WGPU_ERR_ARG;
+    if (!ctx->TMP) return fail(ctx, 1213149, "wgpu_move_blocks needs hvy_tmp as the second buffer: call wgpu_set_wavelet first");
+    const int N = ctx->cfg.max_blocks;
+    std::vector<int> pairs((size_t)2 * n);
+    std::vector<char> taken(N, 0);
+    bool identity = true;
+    for (int i = 0; i < n; ++i) {
+        const int s = src_hvy[i] - 1, d = dst_hvy[i] - 1;
+        if (s < 0 || s >= N || d < 0 || d >= N || taken[d]) return fail(ctx, WGPU_ERR_ARG, "wgpu_move_blocks: id out of range or destination used twice");
+        taken[d] = 1;
+        pairs[i] = s;
+        pairs[(size_t)n + i] = d;
+        identity = identity && s == d;
+    }
+    if (identity) return WGPU_OK;
+    int32_t rc;
+    if ((rc = upload_ids(ctx, 2, pairs))) return rc;
+    if ((rc = wgpu_launch_copy_blocks(ctx, ctx->U, ctx->TMP, ctx->d_idbuf[2], ctx->d_idbuf[2] + n, n))) return rc;
+    WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    std::swap(ctx->U, ctx->TMP);
+    return WGPU_OK;
+}
+
+int32_t wgpu_coarsen(wgpu_ctx *ctx, int32_t n, const int32_t *mother_hvy, const int32_t *daughter_hvy, int32_t src_id, int32_t src_slot)
+{
+    if (!ctx || n < 0 || (n > 0 && (!mother_hvy || !daughter_hvy))) return WGPU_ERR_ARG;
+    const wgpu_config &c = ctx->cfg;
+    if (c.Bs[0] != c.Bs[1] || (c.dim == 3 && c.Bs[0] != c.Bs[2])) return fail(ctx, WGPU_ERR_UNSUPPORTED, "wgpu_coarsen: cubic blocks only");
+    int nc = 0;
+    const double *src = array_ptr(ctx, src_id, src_slot, &nc);
+    if (!src || nc != ctx->nc) return fail(ctx, WGPU_ERR_ARG, "wgpu_coarsen: bad array/slot");
+    if (src == ctx->U) return fail(ctx, WGPU_ERR_ARG, "wgpu_coarsen: the decomposed source must not be hvy_block (a mother may reuse a daughter's slot)");
+    const int N = c.max_blocks, nd = 1 << c.dim;
+    std::vector<int> mo(n), da((size_t)n * nd);
+    for (int i = 0; i < n; ++i) {
+        mo[i] = mother_hvy[i] - 1;
+        if (mo[i] < 0 || mo[i] >= N) return fail(ctx, WGPU_ERR_ARG, "wgpu_coarsen: mother id out of range");
+    }
+    for (size_t i = 0; i < da.size(); ++i) {
+        da[i] = daughter_hvy[i] - 1;
+        if (da[i] < 0 || da[i] >= N) return fail(ctx, WGPU_ERR_ARG, "wgpu_coarsen: daughter id out of range");
+    }
+    int32_t rc;
+    if ((rc = upload_ids(ctx, 0, mo)) || (rc = upload_ids(ctx, 1, da))) return rc;
+    if ((rc = wgpu_launch_coarsen(ctx, src, ctx->U, ctx->d_idbuf[0], ctx->d_idbuf[1], n))) return rc;
+    WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->dtmin_valid = false;
+    return WGPU_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ multi-GPU exchange
 static int fd_halo(const wgpu_ctx *ctx) { return ctx->cfg.fd == 2 ? 1 : (ctx->cfg.fd == 4 ? 2 : 3); }
 
@@ -829,7 +962,6 @@ int32_t wgpu_rk_begin(wgpu_ctx *ctx, double time)
     (void)time;
     if (!ctx) return WGPU_ERR_ARG;
     const wgpu_config &c = ctx->cfg;
-    if (c.dim != 3) return fail(ctx, WGPU_ERR_UNSUPPORTED, "2-D ACM kernels are not built yet");
     if (exchange_pending(ctx)) return fail(ctx, WGPU_ERR_ARG, "topology has neighbours on other ranks: call wgpu_set_exchange first");
     unsigned long long *cur = ctx->d_dtmin + ctx->dtmin_cur;
     if (!ctx->dtmin_valid && !(c.dt_fixed > 0.0)) {

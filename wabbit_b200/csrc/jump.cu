@@ -1,143 +1,212 @@
-// Level-jump face patches for the stage kernel: the lvl_diff = +1 (restriction) and lvl_diff = -1 (prediction) parts of
-// sync_ghosts_RHS_tree (LIB/MPI/synchronize_ghosts_generic.f90:155-174; "full_leaf", ignore_Filter = .true.,
-// g_minus = g_plus = stencil half width), written straight into the patch pool in the layout of the receiver's ghost strip.
+// Kernels that cross mesh levels (all built on fill_region, fill.cuh):
 //
-// Reference: restrict_data / predict_data (LIB/MPI/restrict_predict_data.f90:45-202), prediction
-//            (LIB/WAVELETS/module_wavelets.f90:96-284), set_send_bounds (LIB/MPI/calc_data_bounds.f90:99-146),
-//            get_indices_of_ghost_patch (LIB/TREE/neighborhood.f90:158-331).
+//   jump_fill_kernel     level-jump face patches for the stage kernel: the lvl_diff = +1 (restriction) and lvl_diff = -1
+//                        (prediction) parts of sync_ghosts_RHS_tree (LIB/MPI/synchronize_ghosts_generic.f90:155-174;
+//                        "full_leaf", ignore_Filter = .true.), written into the jump pool in the layout of the receiver's
+//                        ghost strip (restrict_data / predict_data, LIB/MPI/restrict_predict_data.f90:45-202).
+//   export_regions_kernel  resident layout -> ghosted host layout with a g_sync deep, fully synchronised ghost shell on grids
+//                        with level jumps: all 26 relations, copy / decimation / prediction (what sync_ghosts_tree with
+//                        ignore_Filter leaves; xfer_block_data.f90:10-601).
+//   refine_kernel        refineBlock (LIB/MESH/refinementExecute.f90:1-120): prediction of the ghosted mother to 2^dim
+//                        daughters (daughter digit bit0 -> y, bit1 -> x, bit2 -> z), interiors only -- daughter ghosts are
+//                        never stored in HBM.
+//   coarsen_kernel       sync_D2M (LIB/MESH/executeCoarsening_tree.f90:125-230): the scaling coefficients of a decomposed
+//                        daughter (even spaghetti positions) become octant `digit` of its mother.
 //
-// One CTA per (receiver block, face) patch.  The ghost strip is H deep and Bs x Bs wide:
-//   receiver coarser than the neighbours: every strip point coincides with an interior point of one of the four fine
-//     neighbours (decimation, a copy);
-//   receiver finer than the neighbour: the strip is interpolated (x, then y, then z, as the reference) from the box of
-//     coarse-lattice points around it, each of which is the interior value of whichever leaf owns it (see resolve.cuh).
-// HBM traffic: reads ~ the strip's footprint in the neighbours, writes nc*H*Bs^2 doubles per patch.
-#include "resolve.cuh"
+// One CTA per patch / region / (daughter, component).  All of them are HBM-bound gathers of a few hundred to a few thousand
+// points; the arithmetic (prediction) is never contracted so that values are bit-identical to the reference's.
+#include "fill.cuh"
 #include "wgpu_internal.cuh"
 
 namespace {
 
+FillCtx make_fill_ctx(wgpu_ctx *ctx, const double *u)
+{
+    FillCtx f;
+    f.u = u;
+    f.L.keys = ctx->d_hkeys;
+    f.L.vals = ctx->d_hvals;
+    f.L.mask = ctx->hmask;
+    f.nc = ctx->nc;
+    f.Bs = ctx->cfg.Bs[0];
+    f.dim = ctx->cfg.dim;
+    f.order = ctx->wavelet.X;
+    for (int k = 0; k < 3; ++k) f.periodic[k] = ctx->cfg.periodic[k];
+    return f;
+}
+
+template <typename K>
+int32_t ensure_smem(wgpu_ctx *ctx, K kernel, size_t smem, size_t &configured)
+{
+    if (smem > configured) {
+        if (smem > 227 * 1024) {
+            ctx->err = "level-jump kernel: shared memory request exceeds 227 KB (block too large)";
+            return WGPU_ERR_UNSUPPORTED;
+        }
+        WGPU_CHECK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    return WGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ jump patches
 struct JumpArgs {
-    const double *u;
+    FillCtx f;
     double *jpool;
     long long jpatch;
     const int *jblk, *jdir;
     const signed char *level;
     const int *ixyz;
-    BlockLookup L;
-    int nc, Bs, H, order, dim;
-    int periodic[3];
+    int H;
 };
-
-__device__ __forceinline__ double interp1(const double *p, int stride, int order, const double *c)
-{
-    // sum_t c[t] * coarse[start + t], products then sums, left to right (module_wavelets.f90:188-283), never contracted
-    double acc = __dmul_rn(c[0], p[0]);
-    for (int t = 1; t < order; ++t) acc = __dadd_rn(acc, __dmul_rn(c[t], p[t * stride]));
-    return acc;
-}
 
 __global__ void __launch_bounds__(128) jump_fill_kernel(const JumpArgs a)
 {
     extern __shared__ __align__(16) double sm[];
     __shared__ SrcTable T;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int Bs = a.Bs, H = a.H, dim = a.dim;
+    const int Bs = a.f.Bs, H = a.H, dim = a.f.dim;
     const int b = a.jblk[blockIdx.x], dcode = a.jdir[blockIdx.x];
     const int d[3] = {dcode % 3 - 1, (dcode / 3) % 3 - 1, dcode / 9 - 1};
-    const int lvl = a.level[b];
-    const long long CS = (long long)Bs * Bs * (dim == 3 ? Bs : 1);
-    int org[3], ext[3], bx[3];
+    int lo[3], ext[3];
     for (int k = 0; k < 3; ++k) {
-        bx[k] = a.ixyz[3 * b + k];
-        org[k] = d[k] < 0 ? -H : (d[k] > 0 ? Bs : 0);
+        lo[k] = a.ixyz[3 * b + k] * Bs + (d[k] < 0 ? -H : (d[k] > 0 ? Bs : 0));
         ext[k] = d[k] ? H : (k < dim ? Bs : 1);
     }
-    const int npts = ext[0] * ext[1] * ext[2];
-    double *out = a.jpool + (long long)blockIdx.x * a.jpatch;
+    const long long npts = (long long)ext[0] * ext[1] * ext[2];
+    fill_region(a.f, T, sm, a.level[b], lo, ext, a.jpool + (long long)blockIdx.x * a.jpatch, npts, ext[0], (long long)ext[0] * ext[1], 0, a.f.nc,
+                threadIdx.x, blockDim.x);
+}
 
-    // which kind of patch? the level of the leaf that owns the strip
-    int P0[3], lo[3], hi[3];
+// ------------------------------------------------------------------------------------------------ export with ghosts
+struct ExportArgs {
+    FillCtx f;
+    double *staged;         // [n][ncomp_host][nz][ny][nx]
+    const int *ids;
+    const signed char *level;
+    const int *ixyz;
+    int ncomp, ncomp_host, g, gs;
+};
+
+__global__ void __launch_bounds__(128) export_regions_kernel(const ExportArgs a)
+{
+    extern __shared__ __align__(16) double sm[];
+    __shared__ SrcTable T;
+    const int Bs = a.f.Bs, dim = a.f.dim, g = a.g, gs = a.gs;
+    const int r = blockIdx.x, i = blockIdx.y;
+    const int d[3] = {r % 3 - 1, (r / 3) % 3 - 1, r / 9 - 1};
+    if (dim == 2 && d[2] != 0) return;
+    if (gs == 0 && r != 13) return;
+    const int b = a.ids[i];
+    const int nx = Bs + 2 * g, ny = Bs + 2 * g, nz = dim == 3 ? Bs + 2 * g : 1, gz = dim == 3 ? g : 0;
+    int lo[3], ext[3], org[3];
     for (int k = 0; k < 3; ++k) {
-        lo[k] = bx[k] * Bs + org[k];
-        hi[k] = lo[k] + ext[k] - 1;
+        org[k] = d[k] < 0 ? -gs : (d[k] > 0 ? Bs : 0);
+        lo[k] = a.ixyz[3 * b + k] * Bs + org[k];
+        ext[k] = d[k] ? gs : (k < dim ? Bs : 1);
     }
-    src_table_build(T, a.L, lvl, lo, hi, Bs, dim, a.periodic, tid, nt);
-    __syncthreads();
-    {
-        for (int k = 0; k < 3; ++k) P0[k] = lo[k];
-        int sb, so;
-        src_resolve(T, P0, Bs, dim, sb, so);
-        if (sb >= 0) {
-            // same level or finer owner: copy / decimation
-            for (int i = tid; i < a.nc * npts; i += nt) {
-                const int c = i / npts, r = i % npts;
-                const int P[3] = {lo[0] + r % ext[0], lo[1] + (r / ext[0]) % ext[1], lo[2] + r / (ext[0] * ext[1])};
-                src_resolve(T, P, Bs, dim, sb, so);
-                out[i] = sb >= 0 ? a.u[((long long)sb * a.nc + c) * CS + so] : 0.0;
-            }
-            return;
-        }
-    }
-    __syncthreads();
+    const long long sc = (long long)nx * ny * nz;
+    double *out = a.staged + (long long)i * a.ncomp_host * sc + ((long long)(org[2] + gz) * ny + (org[1] + g)) * nx + (org[0] + g);
+    fill_region(a.f, T, sm, a.level[b], lo, ext, out, sc, nx, (long long)nx * ny, 0, a.ncomp, threadIdx.x, blockDim.x);
+}
 
-    // coarser owner: prediction from the level-(lvl-1) lattice
-    const int order = a.order, A = order / 2 - 1;
-    double cf[6];
-    if (order == 2) { cf[0] = 0.5; cf[1] = 0.5; }
-    else if (order == 4) { cf[0] = -1.0 / 16.0; cf[1] = 9.0 / 16.0; cf[2] = 9.0 / 16.0; cf[3] = -1.0 / 16.0; }
-    else { cf[0] = 3.0 / 256.0; cf[1] = -25.0 / 256.0; cf[2] = 150.0 / 256.0; cf[3] = 150.0 / 256.0; cf[4] = -25.0 / 256.0; cf[5] = 3.0 / 256.0; }
-    int clo[3], chi[3], n[3];
+// ------------------------------------------------------------------------------------------------ refineBlock
+struct RefineArgs {
+    FillCtx f;              // f.u = source array (mothers and their neighbours)
+    double *dst;            // compact array that receives the daughters
+    const int *mother;      // [n] 0-based
+    const int *daughter;    // [n][2^dim] 0-based, digit order
+    const signed char *level;
+    const int *ixyz;
+};
+
+// grid (2^dim, n, nc); one daughter component per CTA
+__global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a)
+{
+    extern __shared__ __align__(16) double sm[];
+    __shared__ SrcTable T;
+    const int Bs = a.f.Bs, dim = a.f.dim, order = a.f.order, A = order / 2 - 1, half = Bs / 2;
+    const int digit = blockIdx.x, m = a.mother[blockIdx.y], c = blockIdx.z;
+    const int q[3] = {(digit >> 1) & 1, digit & 1, (digit >> 2) & 1};   // refinementExecute.f90: bit0 -> y, bit1 -> x, bit2 -> z
+    const int lvl = a.level[m];
+    // box of the mother's (ghosted) lattice this daughter is interpolated from: [q*Bs/2 - A, q*Bs/2 + Bs/2 + A]
+    int clo[3], n[3], flo[3], fext[3];
     for (int k = 0; k < 3; ++k) {
         if (k < dim) {
-            clo[k] = (lo[k] >> 1) - A;
-            chi[k] = ((hi[k] + 1) >> 1) + A;
-        } else clo[k] = chi[k] = 0;
-        n[k] = chi[k] - clo[k] + 1;
+            clo[k] = a.ixyz[3 * m + k] * Bs + q[k] * half - A;
+            n[k] = half + 2 * A + 1;
+            flo[k] = 2 * (a.ixyz[3 * m + k] * Bs + q[k] * half);
+            fext[k] = Bs;
+        } else {
+            clo[k] = 0;
+            n[k] = 1;
+            flo[k] = 0;
+            fext[k] = 1;
+        }
     }
-    src_table_build(T, a.L, lvl - 1, clo, chi, Bs, dim, a.periodic, tid, nt);
+    double *cb = sm;
+    double *scratch = cb + (size_t)n[0] * n[1] * n[2] + (size_t)fext[0] * n[1] * n[2] + (size_t)fext[0] * fext[1] * n[2];
+    // the box straddles the mother and up to 2^dim - 1 neighbouring cells: fill it cell by cell
+    const int m0[3] = {a.ixyz[3 * m] * Bs, a.ixyz[3 * m + 1] * Bs, a.ixyz[3 * m + 2] * Bs};
+    for (int part = 0; part < 8; ++part) {
+        int lo[3], ext[3];
+        bool empty = false;
+        for (int k = 0; k < 3; ++k) {
+            const int side = (part >> k) & 1;   // 0: the part inside the mother, 1: the part outside
+            if (k >= dim) {
+                lo[k] = 0;
+                ext[k] = 1;
+                if (side) empty = true;
+                continue;
+            }
+            const int b0 = clo[k], b1 = clo[k] + n[k] - 1;                 // box
+            const int i0 = m0[k], i1 = m0[k] + Bs - 1;                      // mother interior
+            if (!side) {
+                lo[k] = b0 > i0 ? b0 : i0;
+                ext[k] = (b1 < i1 ? b1 : i1) - lo[k] + 1;
+            } else if (q[k] == 0) {                                         // below the mother
+                lo[k] = b0;
+                ext[k] = i0 - b0;
+            } else {                                                        // above
+                lo[k] = i1 + 1;
+                ext[k] = b1 - i1;
+            }
+            if (ext[k] <= 0) empty = true;
+        }
+        if (empty) continue;
+        double *out = cb + ((size_t)(lo[2] - clo[2]) * n[1] + (lo[1] - clo[1])) * n[0] + (lo[0] - clo[0]);
+        fill_region(a.f, T, scratch, lvl, lo, ext, out, 0, n[0], (long long)n[0] * n[1], c, 1, threadIdx.x, blockDim.x);
+    }
     __syncthreads();
-    double *cb = sm;                                   // [n2][n1][n0]
-    double *t1 = cb + n[0] * n[1] * n[2];              // [n2][n1][e0]
-    double *t2 = t1 + ext[0] * n[1] * n[2];            // [n2][e1][e0]
-    for (int c = 0; c < a.nc; ++c) {
-        for (int i = tid; i < n[0] * n[1] * n[2]; i += nt) {
-            const int P[3] = {clo[0] + i % n[0], clo[1] + (i / n[0]) % n[1], clo[2] + i / (n[0] * n[1])};
-            int sb, so;
-            src_resolve(T, P, Bs, dim, sb, so);
-            cb[i] = sb >= 0 ? a.u[((long long)sb * a.nc + c) * CS + so] : 0.0;
-        }
-        __syncthreads();
-        // x
-        for (int i = tid; i < ext[0] * n[1] * n[2]; i += nt) {
-            const int x = i % ext[0], r = i / ext[0];
-            const int G = lo[0] + x;
-            const double *row = cb + r * n[0];
-            t1[i] = (G & 1) ? interp1(row + ((G - 1) >> 1) - clo[0] - A, 1, order, cf) : row[(G >> 1) - clo[0]];
-        }
-        __syncthreads();
-        // y
-        for (int i = tid; i < ext[0] * ext[1] * n[2]; i += nt) {
-            const int x = i % ext[0], y = (i / ext[0]) % ext[1], z = i / (ext[0] * ext[1]);
-            const int G = lo[1] + y;
-            const double *col = t1 + (z * n[1]) * ext[0] + x;
-            t2[i] = (G & 1) ? interp1(col + (((G - 1) >> 1) - clo[1] - A) * ext[0], ext[0], order, cf) : col[((G >> 1) - clo[1]) * ext[0]];
-        }
-        __syncthreads();
-        // z
-        for (int i = tid; i < npts; i += nt) {
-            const int xy = i % (ext[0] * ext[1]), z = i / (ext[0] * ext[1]);
-            double v;
-            if (dim == 3) {
-                const int G = lo[2] + z;
-                const int pl = ext[0] * ext[1];
-                const double *col = t2 + xy;
-                v = (G & 1) ? interp1(col + (((G - 1) >> 1) - clo[2] - A) * pl, pl, order, cf) : col[((G >> 1) - clo[2]) * pl];
-            } else v = t2[xy];
-            out[(long long)c * npts + i] = v;
-        }
-        __syncthreads();
+    const long long CS = (long long)Bs * Bs * (dim == 3 ? Bs : 1);
+    double *out = a.dst + ((long long)a.daughter[blockIdx.y * (1 << dim) + digit] * a.f.nc + c) * CS;
+    predict_from_box(cb, clo, n, flo, fext, order, dim, out, Bs, (long long)Bs * Bs, threadIdx.x, blockDim.x);
+}
+
+// ------------------------------------------------------------------------------------------------ sync_D2M / block copies
+// mother[octant digit] = daughter values at even (scaling-coefficient) positions of `src`
+__global__ void __launch_bounds__(256) coarsen_kernel(const double *__restrict__ src, double *__restrict__ dst, const int *__restrict__ mother,
+                                                      const int *__restrict__ daughter, int nc, int Bs, int dim)
+{
+    const int nd = 1 << dim, half = Bs / 2;
+    const int digit = blockIdx.x, m = mother[blockIdx.y], c = blockIdx.z;
+    const int d = daughter[blockIdx.y * nd + digit];
+    const int q[3] = {(digit >> 1) & 1, digit & 1, (digit >> 2) & 1};
+    const long long CS = (long long)Bs * Bs * (dim == 3 ? Bs : 1);
+    const int hz = dim == 3 ? half : 1;
+    const double *s = src + ((long long)d * nc + c) * CS;
+    double *o = dst + ((long long)m * nc + c) * CS;
+    for (int i = threadIdx.x; i < half * half * hz; i += blockDim.x) {
+        const int x = i % half, y = (i / half) % half, z = i / (half * half);
+        o[((long long)(z + q[2] * hz * (dim == 3)) * Bs + (y + q[1] * half)) * Bs + (x + q[0] * half)] = s[((long long)(2 * z) * Bs + 2 * y) * Bs + 2 * x];
     }
+}
+
+__global__ void __launch_bounds__(256) copy_blocks_kernel(const double *__restrict__ src, double *__restrict__ dst, const int *__restrict__ src_ids,
+                                                          const int *__restrict__ dst_ids, long long per_block)
+{
+    const double2 *s = reinterpret_cast<const double2 *>(src + (long long)src_ids[blockIdx.y] * per_block);
+    double2 *o = reinterpret_cast<double2 *>(dst + (long long)dst_ids[blockIdx.y] * per_block);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_block / 2; i += (long long)gridDim.x * blockDim.x) o[i] = s[i];
 }
 
 }  // namespace
@@ -147,42 +216,106 @@ int32_t wgpu_launch_jump_fill(wgpu_ctx *ctx, const double *src)
     if (ctx->n_jump == 0) return WGPU_OK;
     const wgpu_config &c = ctx->cfg;
     JumpArgs a;
-    a.u = src;
+    a.f = make_fill_ctx(ctx, src);
     a.jpool = ctx->d_jpool;
     a.jblk = ctx->d_jump_blk;
     a.jdir = ctx->d_jump_dir;
     a.level = ctx->d_level;
     a.ixyz = ctx->d_ixyz;
-    a.L.keys = ctx->d_hkeys;
-    a.L.vals = ctx->d_hvals;
-    a.L.mask = ctx->hmask;
-    a.nc = ctx->nc;
-    a.Bs = c.Bs[0];
     a.H = c.fd == 2 ? 1 : (c.fd == 4 ? 2 : 3);
     a.jpatch = (long long)ctx->nc * a.H * c.Bs[0] * (c.dim == 3 ? c.Bs[0] : 1);
-    a.order = ctx->wavelet.X;
-    a.dim = c.dim;
-    for (int k = 0; k < 3; ++k) a.periodic[k] = c.periodic[k];
-    // shared memory of the prediction branch: coarse box + two intermediates, largest over the face orientations
-    const int A = a.order / 2 - 1, Bs = a.Bs, H = a.H;
-    const int nt = Bs / 2 + 1 + 2 * A + 1, nn = H / 2 + 2 + 2 * A + 1;
-    const int e3 = c.dim == 3 ? Bs : 1, n3 = c.dim == 3 ? nt : 1;
     size_t best = 0;
     for (int f = 0; f < c.dim; ++f) {
-        const int n[3] = {f == 0 ? nn : nt, f == 1 ? nn : nt, c.dim == 3 ? (f == 2 ? nn : nt) : 1};
-        const int e[3] = {f == 0 ? H : Bs, f == 1 ? H : Bs, c.dim == 3 ? (f == 2 ? H : Bs) : 1};
-        const size_t s = (size_t)n[0] * n[1] * n[2] + (size_t)e[0] * n[1] * n[2] + (size_t)e[0] * e[1] * n[2];
+        const int e[3] = {f == 0 ? a.H : c.Bs[0], f == 1 ? a.H : c.Bs[0], c.dim == 3 ? (f == 2 ? a.H : c.Bs[0]) : 1};
+        const size_t s = fill_scratch_doubles(e, a.f.order, c.dim);
         best = s > best ? s : best;
     }
-    (void)e3;
-    (void)n3;
-    const size_t smem = best * sizeof(double);
     static size_t configured = 0;
-    if (smem > configured) {
-        WGPU_CHECK(ctx, cudaFuncSetAttribute(jump_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    int32_t rc = ensure_smem(ctx, jump_fill_kernel, best * sizeof(double), configured);
+    if (rc) return rc;
+    jump_fill_kernel<<<ctx->n_jump, 128, best * sizeof(double), ctx->stream>>>(a);
+    ctx->launches++;
+    WGPU_CHECK(ctx, cudaGetLastError());
+    return WGPU_OK;
+}
+
+int32_t wgpu_launch_export_regions(wgpu_ctx *ctx, const double *src, double *staged, const int *d_ids, int n, int ncomp_src, int ncomp_host,
+                                   int g_sync)
+{
+    if (n == 0) return WGPU_OK;
+    const wgpu_config &c = ctx->cfg;
+    ExportArgs a;
+    a.f = make_fill_ctx(ctx, src);
+    a.f.nc = ncomp_src;
+    a.staged = staged;
+    a.ids = d_ids;
+    a.level = ctx->d_level;
+    a.ixyz = ctx->d_ixyz;
+    a.ncomp = ncomp_src < ncomp_host ? ncomp_src : ncomp_host;
+    a.ncomp_host = ncomp_host;
+    a.g = c.g;
+    a.gs = g_sync;
+    size_t best = 0;
+    for (int r = 0; r < 27; ++r) {
+        const int d[3] = {r % 3 - 1, (r / 3) % 3 - 1, r / 9 - 1};
+        if (r == 13 || (c.dim == 2 && d[2])) continue;
+        const int e[3] = {d[0] ? g_sync : c.Bs[0], d[1] ? g_sync : c.Bs[0], c.dim == 3 ? (d[2] ? g_sync : c.Bs[0]) : 1};
+        const size_t s = fill_scratch_doubles(e, a.f.order, c.dim);
+        best = s > best ? s : best;
     }
-    jump_fill_kernel<<<ctx->n_jump, 128, smem, ctx->stream>>>(a);
+    static size_t configured = 0;
+    int32_t rc = ensure_smem(ctx, export_regions_kernel, best * sizeof(double), configured);
+    if (rc) return rc;
+    dim3 grid(27, n);
+    export_regions_kernel<<<grid, 128, best * sizeof(double), ctx->stream>>>(a);
+    ctx->launches++;
+    WGPU_CHECK(ctx, cudaGetLastError());
+    return WGPU_OK;
+}
+
+int32_t wgpu_launch_refine(wgpu_ctx *ctx, const double *src, double *dst, const int *d_mother, const int *d_daughter, int n)
+{
+    if (n == 0) return WGPU_OK;
+    const wgpu_config &c = ctx->cfg;
+    RefineArgs a;
+    a.f = make_fill_ctx(ctx, src);
+    a.dst = dst;
+    a.mother = d_mother;
+    a.daughter = d_daughter;
+    a.level = ctx->d_level;
+    a.ixyz = ctx->d_ixyz;
+    const int A = a.f.order / 2 - 1, Bs = c.Bs[0], half = Bs / 2;
+    const int nn = half + 2 * A + 1;
+    const int n3[3] = {nn, nn, c.dim == 3 ? nn : 1}, fe[3] = {Bs, Bs, c.dim == 3 ? Bs : 1};
+    size_t own = (size_t)n3[0] * n3[1] * n3[2] + (size_t)fe[0] * n3[1] * n3[2] + (size_t)fe[0] * fe[1] * n3[2];
+    const size_t sub = fill_scratch_doubles(n3, a.f.order, c.dim);
+    const size_t smem = (own + sub) * sizeof(double);
+    static size_t configured = 0;
+    int32_t rc = ensure_smem(ctx, refine_kernel, smem, configured);
+    if (rc) return rc;
+    dim3 grid(1 << c.dim, n, ctx->nc);
+    refine_kernel<<<grid, 256, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    WGPU_CHECK(ctx, cudaGetLastError());
+    return WGPU_OK;
+}
+
+int32_t wgpu_launch_coarsen(wgpu_ctx *ctx, const double *src, double *dst, const int *d_mother, const int *d_daughter, int n)
+{
+    if (n == 0) return WGPU_OK;
+    dim3 grid(1 << ctx->cfg.dim, n, ctx->nc);
+    coarsen_kernel<<<grid, 256, 0, ctx->stream>>>(src, dst, d_mother, d_daughter, ctx->nc, ctx->cfg.Bs[0], ctx->cfg.dim);
+    ctx->launches++;
+    WGPU_CHECK(ctx, cudaGetLastError());
+    return WGPU_OK;
+}
+
+int32_t wgpu_launch_copy_blocks(wgpu_ctx *ctx, const double *src, double *dst, const int *d_src_ids, const int *d_dst_ids, int n)
+{
+    if (n == 0) return WGPU_OK;
+    const long long per_block = (long long)ctx->nc * ctx->blk_elems;
+    dim3 grid((unsigned)((per_block / 2 + 255) / 256), n);
+    copy_blocks_kernel<<<grid, 256, 0, ctx->stream>>>(src, dst, d_src_ids, d_dst_ids, per_block);
     ctx->launches++;
     WGPU_CHECK(ctx, cudaGetLastError());
     return WGPU_OK;

@@ -464,6 +464,150 @@ __global__ void __launch_bounds__(BS *BS, (Tile<FD, BS>::SMEM <= 110 * 1024 ? 2 
 }
 
 // ---------------------------------------------------------------------------------------------
+// 2-D stage kernel: RHS_2D_acm (LIB/EQUATION/ACMnew/rhs_ACM.f90:292-922) + the same Runge-Kutta epilogue.
+// One CTA per block; the whole ghosted tile (3 components, Bs+2H squared, at most ~40 KB at Bs=32) is staged in shared memory
+// with the four face halos gathered from the neighbours' interiors (star stencils do not read corners).  Bs is a run-time
+// value (the reference's 2-D cases use 26 and 32).  HBM-bound: reads 3*(Bs^2 + 4*H*Bs) + bases, writes 3*Bs^2 per output.
+// ---------------------------------------------------------------------------------------------
+template <int FD, bool SKEW>
+__global__ void __launch_bounds__(256) stage_kernel_2d(const __grid_constant__ StageArgs a, int BS)
+{
+    using S = St<FD>;
+    constexpr int H = S::H, NC = 3;
+    extern __shared__ __align__(16) double sm[];
+    __shared__ double s_red[8];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int b = a.active[blockIdx.x];
+    const int PITCH = BS + 2 * H, PLANE = PITCH * PITCH;
+    const long long CS = (long long)BS * BS;
+    const int cW = a.nbr[b * WGPU_NDIR + 12], cE = a.nbr[b * WGPU_NDIR + 14], cS = a.nbr[b * WGPU_NDIR + 10], cN = a.nbr[b * WGPU_NDIR + 16];
+
+    // interior + four face strips; corners of the tile are never read
+    for (int i = tid; i < NC * BS * BS; i += nt) {
+        const int c = i / (BS * BS), r = i % (BS * BS), y = r / BS, x = r % BS;
+        sm[c * PLANE + (y + H) * PITCH + x + H] = a.u_in[((long long)b * NC + c) * CS + r];
+    }
+    for (int i = tid; i < NC * 4 * H * BS; i += nt) {
+        const int c = i / (4 * H * BS), r = i % (4 * H * BS), side = r / (H * BS), q = r % (H * BS);
+        int sx, sy, tx, ty, nb;
+        if (side == 0) { const int h = q % H, y = q / H; nb = cW; sx = BS - H + h; sy = y; tx = h; ty = y + H; }
+        else if (side == 1) { const int h = q % H, y = q / H; nb = cE; sx = h; sy = y; tx = BS + H + h; ty = y + H; }
+        else if (side == 2) { const int x = q % BS, h = q / BS; nb = cS; sx = x; sy = BS - H + h; tx = x + H; ty = h; }
+        else { const int x = q % BS, h = q / BS; nb = cN; sx = x; sy = h; tx = x + H; ty = BS + H + h; }
+        sm[c * PLANE + ty * PITCH + tx] = nb >= 0 ? a.u_in[((long long)nb * NC + c) * CS + sy * BS + sx] : 0.0;
+    }
+    __syncthreads();
+
+    const int lvl = a.level[b];
+    const double dx = a.dx_lvl[lvl][0], dy = a.dx_lvl[lvl][1];
+    const double dinv[2] = {1.0 / dx, 1.0 / dy};
+    const double d2inv[2] = {1.0 / (dx * dx), 1.0 / (dy * dy)};
+    const double dt = (a.u_out || a.acc_out) ? *a.dt_ptr : 0.0;
+    const bool base_u_global = a.u_out && a.u0 != a.u_in;
+    const bool base_acc_global = a.acc_out && a.acc_in != a.u_in;
+    const double c02 = a.c0 * a.c0;
+    double umag_max = 0.0, uabs_max = 0.0;
+
+    for (int i = tid; i < BS * BS; i += nt) {
+        const int ty = i / BS, tx = i % BS;
+        const int cidx = (ty + H) * PITCH + tx + H;
+        const long long gi = ((long long)b * NC) * CS + i;
+        double d1v[2][3], d2v[2][2], cv[2][2], ctr[3];
+#pragma unroll
+        for (int dir = 0; dir < 2; ++dir) {
+            double qv[3][2 * H + 1];
+#pragma unroll
+            for (int o = -H; o <= H; ++o) {
+                const int off = cidx + (dir == 0 ? o : o * PITCH);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) qv[c][o + H] = sm[off + c * PLANE];
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) d1v[dir][c] = S::d1(&qv[c][H], dinv[dir]);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) d2v[dir][c] = S::d2(&qv[c][H], d2inv[dir]);
+            if (SKEW) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) cv[dir][c] = S::d1p(&qv[c][H], &qv[dir][H], dinv[dir]);
+            }
+            if (dir == 0) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) ctr[c] = qv[c][H];
+            }
+        }
+        const double u = ctr[0], v = ctr[1], p = ctr[2];
+        double penal[2] = {0.0, 0.0};
+        const long long g0 = ((long long)b * a.n_mask) * CS + i;
+        if (a.mask) {   // rhs_ACM.f90:600-602
+            const int color = (int)a.mask[g0 + 4 * CS];
+            const double chi = a.mask[g0] * (color == 0 ? 0.0 : a.C_eta_inv);
+            penal[0] = -chi * (u - a.mask[g0 + 1 * CS]);
+            penal[1] = -chi * (v - a.mask[g0 + 2 * CS]);
+        }
+        double rhs[3];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            double adv;
+            if (SKEW) adv = -0.5 * (cv[0][c] + cv[1][c] + u * d1v[0][c] + v * d1v[1][c]);   // rhs_ACM.f90:574-576
+            else adv = -u * d1v[0][c] - v * d1v[1][c];                                      // rhs_ACM.f90:604-605
+            rhs[c] = adv - d1v[c][2] + a.nu * (d2v[0][c] + d2v[1][c]) + penal[c];
+        }
+        rhs[2] = -c02 * (d1v[0][0] + d1v[1][1]) - a.gamma_p * p;
+        if (a.use_sponge && a.mask) {   // rhs_ACM.f90:880-892
+            const double spo = a.mask[g0 + 5 * CS] * a.C_sponge_inv;
+            rhs[0] = rhs[0] - (u - a.u_mean_set[0]) * spo;
+            rhs[1] = rhs[1] - (v - a.u_mean_set[1]) * spo;
+            rhs[2] = rhs[2] - p * spo;
+        }
+        uabs_max = fmax(uabs_max, fmax(fmax(fabs(u), fabs(v)), fabs(p)));
+
+        double un[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (a.k_out) a.k_out[gi + c * CS] = rhs[c];
+            if (a.u_out) {
+                double acc = base_u_global ? a.u0[gi + c * CS] : ctr[c];
+                for (int l = 0; l < a.n_prev; ++l)
+                    acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dt, a.coef_prev[l]), a.k_prev[l][gi + c * CS]));
+                if (a.use_self) acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dt, a.coef_self), rhs[c]));
+                a.u_out[gi + c * CS] = acc;
+                un[c] = acc;
+            }
+            if (a.acc_out) {
+                double acc = base_acc_global ? a.acc_in[gi + c * CS] : ctr[c];
+                if (a.use_acc) acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dt, a.coef_acc), rhs[c]));
+                a.acc_out[gi + c * CS] = acc;
+            }
+        }
+        if (a.dtmin_bits && a.u_out) umag_max = fmax(umag_max, __dadd_rn(__dmul_rn(un[0], un[0]), __dmul_rn(un[1], un[1])));
+    }
+
+    const int lane = tid & 31, wid = tid >> 5, NW = nt >> 5;
+    uabs_max = warp_max(uabs_max);
+    umag_max = warp_max(umag_max);
+    if (lane == 0) s_red[wid] = uabs_max;
+    __syncthreads();
+    if (tid == 0) {
+        double m = 0.0;
+        for (int i = 0; i < NW; ++i) m = fmax(m, s_red[i]);
+        if (m > 1.0e12) atomicExch(a.diverged, 1);
+    }
+    if (a.dtmin_bits && a.u_out) {
+        __syncthreads();
+        if (lane == 0) s_red[wid] = umag_max;
+        __syncthreads();
+        if (tid == 0) {
+            double m = 0.0;
+            for (int i = 0; i < NW; ++i) m = fmax(m, s_red[i]);
+            const double u_eigen = __dadd_rn(sqrt(m), sqrt(__dadd_rn(c02, m)));
+            const double dxmin = fmin(dx, dy);
+            const double dtb = (u_eigen >= 1.0e-6) ? __ddiv_rn(__dmul_rn(a.CFL, dxmin), u_eigen) : 1.0e-2;
+            atomicMin(a.dtmin_bits, (unsigned long long)__double_as_longlong(dtb));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // GET_DT_BLOCK_ACM's block loop as a standalone reduction (used when no fused value is available,
 // e.g. right after an upload):  dtmin = min_b CFL*min(dx_b)/(sqrt(umag_b) + sqrt(c0^2 + umag_b))
 // ---------------------------------------------------------------------------------------------
@@ -651,9 +795,56 @@ int32_t wgpu_launch_pack(wgpu_ctx *ctx, const double *src)
     return WGPU_OK;
 }
 
+namespace {
+
+template <int FD, bool SKEW>
+int32_t launch_stage_2d_t(wgpu_ctx *ctx, const StageArgs &a, int n_blocks)
+{
+    const int Bs = ctx->cfg.Bs[0], H = St<FD>::H;
+    const size_t smem = sizeof(double) * 3 * (size_t)(Bs + 2 * H) * (Bs + 2 * H);
+    static size_t configured = 0;
+    if (smem > configured) {
+        if (smem > 227 * 1024) {
+            ctx->err = "2-D stage kernel: block too large for shared memory";
+            return WGPU_ERR_UNSUPPORTED;
+        }
+        WGPU_CHECK(ctx, cudaFuncSetAttribute(stage_kernel_2d<FD, SKEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const bool prof = ctx->profiling && ctx->prof_n < (int)ctx->prof_ev.size() / 2;
+    if (prof) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], ctx->stream);
+    stage_kernel_2d<FD, SKEW><<<n_blocks, 256, smem, ctx->stream>>>(a, Bs);
+    if (prof) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n++ + 1], ctx->stream);
+    ctx->launches++;
+    WGPU_CHECK(ctx, cudaGetLastError());
+    return WGPU_OK;
+}
+
+template <int FD>
+int32_t launch_stage_2d(wgpu_ctx *ctx, const StageArgs &a, int n_blocks)
+{
+    return ctx->cfg.skew_symmetry ? launch_stage_2d_t<FD, true>(ctx, a, n_blocks) : launch_stage_2d_t<FD, false>(ctx, a, n_blocks);
+}
+
+}  // namespace
+
 int32_t wgpu_launch_stage(wgpu_ctx *ctx, const StageArgs &a, int n_blocks)
 {
     if (n_blocks == 0) return WGPU_OK;
+    if (ctx->cfg.dim == 2) {
+        if (ctx->cfg.Bs[0] != ctx->cfg.Bs[1]) {
+            ctx->err = "2-D stage kernel: square blocks only";
+            return WGPU_ERR_UNSUPPORTED;
+        }
+        switch (ctx->cfg.fd) {
+        case 2: return launch_stage_2d<2>(ctx, a, n_blocks);
+        case 4: return launch_stage_2d<4>(ctx, a, n_blocks);
+        case 6: return launch_stage_2d<6>(ctx, a, n_blocks);
+        case 40: return launch_stage_2d<40>(ctx, a, n_blocks);
+        }
+        ctx->err = "unknown order_discretization id";
+        return WGPU_ERR_UNSUPPORTED;
+    }
     switch (ctx->cfg.fd) {
     case 2: return launch_stage_skew<2>(ctx, a, n_blocks);
     case 4: return launch_stage_skew<4>(ctx, a, n_blocks);

@@ -119,6 +119,9 @@ struct wgpu_ctx {
     double *d_jpool = nullptr;
     size_t jpool_cap = 0;
     bool has_jumps = false;            // some active block has a coarser / finer neighbour
+    bool lookup_ready = false;         // block lookup + coordinates of the current topology are on the device
+    int *d_idbuf[3] = {nullptr, nullptr, nullptr};   // scratch id lists (refine / coarsen)
+    size_t idbuf_cap[3] = {0, 0, 0};
     // Runge-Kutta step in flight
     const double *rk_uin = nullptr;
     int rk_next_stage = 0;
@@ -166,6 +169,11 @@ int32_t wgpu_launch_stage(wgpu_ctx *ctx, const StageArgs &a, int n_blocks);
 int32_t wgpu_launch_pack(wgpu_ctx *ctx, const double *src);
 // jump.cu
 int32_t wgpu_launch_jump_fill(wgpu_ctx *ctx, const double *src);
+int32_t wgpu_launch_export_regions(wgpu_ctx *ctx, const double *src, double *staged, const int *d_ids, int n, int ncomp_src, int ncomp_host,
+                                   int g_sync);
+int32_t wgpu_launch_refine(wgpu_ctx *ctx, const double *src, double *dst, const int *d_mother, const int *d_daughter, int n);
+int32_t wgpu_launch_coarsen(wgpu_ctx *ctx, const double *src, double *dst, const int *d_mother, const int *d_daughter, int n);
+int32_t wgpu_launch_copy_blocks(wgpu_ctx *ctx, const double *src, double *dst, const int *d_src_ids, const int *d_dst_ids, int n);
 // wavelet.cu
 int32_t wgpu_launch_wavelet(wgpu_ctx *ctx, const double *src, double *dst, int inverse);
 int32_t wgpu_launch_detail(wgpu_ctx *ctx, const double *wd, int eps_norm, int level_ref);

@@ -20,9 +20,11 @@ def _i32(a):
 
 
 class Forest:
-    def __init__(self, handle, dim: int, Jmax: int, n_ranks: int, max_blocks: int):
+    def __init__(self, handle, dim: int, Jmax: int, n_ranks: int, max_blocks: int, block_dist: str = "sfc_hilbert",
+                 periodic: Sequence[int] = (1, 1, 1)):
         self._h = handle
         self.dim, self.Jmax, self.n_ranks, self.max_blocks = dim, Jmax, n_ranks, max_blocks
+        self.block_dist, self.periodic = block_dist, tuple(int(v) for v in periodic)
 
     @classmethod
     def uniform(cls, dim: int, J: int, Jmax: Optional[int] = None, block_dist: str = "sfc_hilbert", n_ranks: int = 1,
@@ -35,7 +37,7 @@ class Forest:
         rc = host_lib().whost_create_uniform(dim, J, Jmax, SFC[block_dist], n_ranks, max_blocks, _i32(per), C.byref(h))
         if rc:
             raise RuntimeError(f"whost_create_uniform failed with code {rc}")
-        return cls(h, dim, Jmax, n_ranks, max_blocks)
+        return cls(h, dim, Jmax, n_ranks, max_blocks, block_dist, periodic)
 
     @classmethod
     def from_blocks(cls, dim: int, Jmax: int, level, ixyz, block_dist: str = "sfc_hilbert", n_ranks: int = 1,
@@ -50,7 +52,7 @@ class Forest:
                                                  _i32(ixyz), C.byref(h))
         if rc:
             raise RuntimeError(f"whost_create_from_blocks failed with code {rc}")
-        return cls(h, dim, Jmax, n_ranks, max_blocks)
+        return cls(h, dim, Jmax, n_ranks, max_blocks, block_dist, periodic)
 
     def __del__(self):
         try:
