@@ -152,3 +152,29 @@ def test_coarsen_of_refine_is_identity_and_matches_oracle(wavelet, Bs):
         # (2) the reference's property test: Coarsen(Refine(u)) = u to 1e-14
         assert relerr(got[hm - 1][I], u[old[(int(l), int(x), int(y), int(z))]][I]) <= 1e-14
     sol.close()
+
+
+def test_page_locked_host_arrays_take_the_direct_path_with_identical_results():
+    """wgpu_upload / wgpu_download on a page-locked host array (kernels read / write it over PCIe, no staging) == staged path,
+    on a uniform and on a graded grid, for a full and a partial ghost shell."""
+    import torch
+    for graded in (False, True):
+        if graded:
+            lv, ix = graded_blocks(3, 1, 3, seed=9)
+            forest = Forest.from_blocks(3, 3, lv, ix)
+        else:
+            forest = Forest.uniform(3, 2, Jmax=3)
+        w, p, po, grid, sol, u = _case("CDF44", 16, forest, seed=8)
+        pinned = torch.empty(u.shape, dtype=torch.float64, pin_memory=True)
+        pn = pinned.numpy()
+        pn[:] = u
+        n0 = sol.launch_count
+        sol.upload(pn)
+        assert sol.launch_count - n0 == 1          # one kernel, no staging chunks
+        for gs in (0, 2, p.g):
+            a = np.full_like(u, -7.0)
+            sol.download(a, g_sync=gs)
+            pn[:] = -7.0
+            sol.download(pn, g_sync=gs)
+            assert np.array_equal(a, pn), (graded, gs)
+        sol.close()

@@ -119,3 +119,32 @@ def test_full_size_wavelet_properties():
     st, det = sol.threshold_tree(eps=1e-12, want_detail=True)
     assert (st == -1).all() and np.abs(det).max() <= 1e-15
     sol.close()
+
+
+@pytest.mark.parametrize("name", ["CDF20", "CDF22", "CDF40", "CDF42", "CDF44", "CDF60", "CDF62"])
+@pytest.mark.parametrize("Bs", [16, 24])
+def test_fast_and_generic_kernels_agree(name, Bs):
+    """The compile-time specialised transform (wavelet_fast_kernel) and the generic, table-driven one give identical bits,
+    forward and inverse."""
+    import os
+    w, p, po, forest, sol, grid = make(name, Bs, 1)
+    rng = np.random.default_rng(11)
+    u = rng.standard_normal(sol.host_shape())
+    sol.upload(u)
+    out = {}
+    for mode in ("fast", "generic"):
+        if mode == "generic":
+            os.environ["WGPU_WAVELET_GENERIC"] = "1"
+        try:
+            sol.waveletDecomposition_tree()
+            a = np.zeros_like(u)
+            sol.download(a, HVY_TMP, g_sync=0)
+            sol.waveletReconstruction_tree(src=(HVY_TMP, 0), dst=(HVY_WORK, 2))
+            b = np.zeros_like(u)
+            sol.download(b, HVY_WORK, 2, g_sync=0)
+        finally:
+            os.environ.pop("WGPU_WAVELET_GENERIC", None)
+        out[mode] = (a, b)
+    assert np.array_equal(out["fast"][0], out["generic"][0])
+    assert np.array_equal(out["fast"][1], out["generic"][1])
+    sol.close()

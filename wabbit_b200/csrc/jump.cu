@@ -84,7 +84,7 @@ struct ExportArgs {
     const int *ids;
     const signed char *level;
     const int *ixyz;
-    int ncomp, ncomp_host, g, gs;
+    int ncomp, ncomp_host, g, gs, by_id;
 };
 
 __global__ void __launch_bounds__(128) export_regions_kernel(const ExportArgs a)
@@ -92,11 +92,12 @@ __global__ void __launch_bounds__(128) export_regions_kernel(const ExportArgs a)
     extern __shared__ __align__(16) double sm[];
     __shared__ SrcTable T;
     const int Bs = a.f.Bs, dim = a.f.dim, g = a.g, gs = a.gs;
-    const int r = blockIdx.x, i = blockIdx.y;
+    const int r = blockIdx.x;
     const int d[3] = {r % 3 - 1, (r / 3) % 3 - 1, r / 9 - 1};
     if (dim == 2 && d[2] != 0) return;
     if (gs == 0 && r != 13) return;
-    const int b = a.ids[i];
+    const int b = a.ids[blockIdx.y];
+    const int i = a.by_id ? b : blockIdx.y;
     const int nx = Bs + 2 * g, ny = Bs + 2 * g, nz = dim == 3 ? Bs + 2 * g : 1, gz = dim == 3 ? g : 0;
     int lo[3], ext[3], org[3];
     for (int k = 0; k < 3; ++k) {
@@ -240,7 +241,7 @@ int32_t wgpu_launch_jump_fill(wgpu_ctx *ctx, const double *src)
 }
 
 int32_t wgpu_launch_export_regions(wgpu_ctx *ctx, const double *src, double *staged, const int *d_ids, int n, int ncomp_src, int ncomp_host,
-                                   int g_sync)
+                                   int g_sync, int by_id)
 {
     if (n == 0) return WGPU_OK;
     const wgpu_config &c = ctx->cfg;
@@ -255,6 +256,7 @@ int32_t wgpu_launch_export_regions(wgpu_ctx *ctx, const double *src, double *sta
     a.ncomp_host = ncomp_host;
     a.g = c.g;
     a.gs = g_sync;
+    a.by_id = by_id;
     size_t best = 0;
     for (int r = 0; r < 27; ++r) {
         const int d[3] = {r % 3 - 1, (r / 3) % 3 - 1, r / 9 - 1};

@@ -682,9 +682,9 @@ __global__ void dt_finalize_kernel(DtArgs p, const unsigned long long *dtmin_bit
 // ---------------------------------------------------------------------------------------------
 // staged: [n][ncomp_host][nz][ny][nx] ghosted (Fortran hvy(:,:,:,:,k)); dst: compact [blk][ncomp_dst][Bs^3]
 __global__ void extract_kernel(const double *__restrict__ staged, double *__restrict__ dst, const int *__restrict__ ids, int ncomp_dst,
-                               int ncomp_host, int Bx, int By, int Bz, int g, int gz)
+                               int ncomp_host, int Bx, int By, int Bz, int g, int gz, int by_id)
 {
-    const int i = blockIdx.y;       // which staged block
+    const int i = by_id ? ids[blockIdx.y] : blockIdx.y;       // which staged block (by_id: `staged` is the whole host array)
     const int c = blockIdx.z;       // component
     const int nx = Bx + 2 * g, ny = By + 2 * g, nz = Bz + 2 * gz;
     const long long CS = (long long)Bx * By * Bz;
@@ -692,17 +692,18 @@ __global__ void extract_kernel(const double *__restrict__ staged, double *__rest
     if (e >= CS) return;
     const int x = e % Bx, y = (e / Bx) % By, z = e / ((long long)Bx * By);
     const double *s = staged + ((long long)i * ncomp_host + c) * nx * ny * nz;
-    dst[((long long)ids[i] * ncomp_dst + c) * CS + e] = s[((long long)(z + gz) * ny + (y + g)) * nx + (x + g)];
+    dst[((long long)ids[blockIdx.y] * ncomp_dst + c) * CS + e] = s[((long long)(z + gz) * ny + (y + g)) * nx + (x + g)];
 }
 
 // compact -> ghosted staging, ghost shell of width gs gathered from same-level neighbours (all 26 relations:
 // the copy sync_ghosts_generic stage 1 performs, synchronize_ghosts_generic.f90:266-339)
 __global__ void export_kernel(const double *__restrict__ src, double *__restrict__ staged, const int *__restrict__ ids,
                               const int *__restrict__ nbr, int ncomp_src, int ncomp_host, int Bx, int By, int Bz, int g, int gz, int gs,
-                              int gsz)
+                              int gsz, int by_id)
 {
-    const int i = blockIdx.y, c = blockIdx.z;
-    const int b = ids[i];
+    const int c = blockIdx.z;
+    const int b = ids[blockIdx.y];
+    const int i = by_id ? b : blockIdx.y;
     const int nx = Bx + 2 * g, ny = By + 2 * g, nz = Bz + 2 * gz;
     const int ex = Bx + 2 * gs, ey = By + 2 * gs, ez = Bz + 2 * gsz;
     const long long n = (long long)ex * ey * ez;
@@ -904,21 +905,21 @@ int32_t wgpu_launch_dt_finalize(wgpu_ctx *ctx, double time, const unsigned long 
     return WGPU_OK;
 }
 
-int32_t wgpu_launch_extract(wgpu_ctx *ctx, const double *staged, double *dst, const int *d_ids, int n, int ncomp_dst, int ncomp_host)
+int32_t wgpu_launch_extract(wgpu_ctx *ctx, const double *staged, double *dst, const int *d_ids, int n, int ncomp_dst, int ncomp_host, int by_id)
 {
     if (n == 0) return WGPU_OK;
     const wgpu_config &c = ctx->cfg;
     const int Bz = c.dim == 3 ? c.Bs[2] : 1, gz = c.dim == 3 ? c.g : 0;
     const int nc = ncomp_dst < ncomp_host ? ncomp_dst : ncomp_host;
     dim3 grid((unsigned)((ctx->blk_elems + 255) / 256), n, nc);
-    extract_kernel<<<grid, 256, 0, ctx->stream>>>(staged, dst, d_ids, ncomp_dst, ncomp_host, c.Bs[0], c.Bs[1], Bz, c.g, gz);
+    extract_kernel<<<grid, 256, 0, ctx->stream>>>(staged, dst, d_ids, ncomp_dst, ncomp_host, c.Bs[0], c.Bs[1], Bz, c.g, gz, by_id);
     ctx->launches++;
     WGPU_CHECK(ctx, cudaGetLastError());
     return WGPU_OK;
 }
 
 int32_t wgpu_launch_export(wgpu_ctx *ctx, const double *src, double *staged, const int *d_ids, int n, int ncomp_src, int ncomp_host,
-                           int g_sync)
+                           int g_sync, int by_id)
 {
     if (n == 0) return WGPU_OK;
     const wgpu_config &c = ctx->cfg;
@@ -927,7 +928,7 @@ int32_t wgpu_launch_export(wgpu_ctx *ctx, const double *src, double *staged, con
     const long long npts = (long long)(c.Bs[0] + 2 * g_sync) * (c.Bs[1] + 2 * g_sync) * (Bz + 2 * gsz);
     dim3 grid((unsigned)((npts + 255) / 256), n, nc);
     export_kernel<<<grid, 256, 0, ctx->stream>>>(src, staged, d_ids, ctx->d_nbr, ncomp_src, ncomp_host, c.Bs[0], c.Bs[1], Bz, c.g, gz,
-                                                 g_sync, gsz);
+                                                 g_sync, gsz, by_id);
     ctx->launches++;
     WGPU_CHECK(ctx, cudaGetLastError());
     return WGPU_OK;

@@ -18,6 +18,7 @@
 // (Bs+2f)^3 box once (mostly L2 hits for the halo: neighbours are launched back to back in space-filling-curve order),
 // writes Bs^3.
 #include <math.h>
+#include <stdlib.h>
 
 #include "wgpu_internal.cuh"
 
@@ -185,6 +186,247 @@ __global__ void __launch_bounds__(256) wavelet_kernel(const WaveArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fast path: the same transform with everything the compiler can know fixed at compile time -- wavelet (taps become
+// literals, zero taps vanish), block size, halo depth.  One CTA per (block, component), 256 threads.  Every thread produces
+// a (scaling, wavelet) pair of neighbouring outputs from one register window of 2F+2 inputs, so each pass costs
+// ~(taps_HD + taps_GD) multiply-adds per output pair and two vector shared-memory loads per tap pair.  Arithmetic order and
+// rounding are those of the generic kernel above (and of the reference): one product per non-zero tap, summed in increasing
+// tap order, never contracted.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ constexpr double cdf_interp(int order, int i)   // interpolation stencil, i in -(order-1)..(order-1)
+{
+    const int a = i < 0 ? -i : i;
+    if (a == 0) return 1.0;
+    if (order == 2) return a == 1 ? 0.5 : 0.0;
+    if (order == 4) return a == 1 ? 9.0 / 16.0 : (a == 3 ? -1.0 / 16.0 : 0.0);
+    if (order == 6) return a == 1 ? 150.0 / 256.0 : (a == 3 ? -25.0 / 256.0 : (a == 5 ? 3.0 / 256.0 : 0.0));
+    return 0.0;
+}
+__host__ __device__ constexpr double cdf_HR(int X, int k) { return (k < -(X - 1) || k > X - 1) ? 0.0 : cdf_interp(X, k); }
+__host__ __device__ constexpr double cdf_HD(int X, int Y, int k)
+{
+    if (Y == 0) return k == 0 ? 1.0 : 0.0;
+    double v = k == 0 ? 1.0 : 0.0;
+    for (int j = -(X - 1); j <= X - 1; ++j) {
+        const int d = k - j;
+        if (d < -(Y - 1) || d > Y - 1 || d == 0) continue;
+        v = v + ((j % 2 == 0) ? 1.0 : -1.0) * cdf_HR(X, j) * cdf_interp(Y, d) / 2.0;
+    }
+    return v;
+}
+__host__ __device__ constexpr double cdf_GD(int X, int k) { return ((k % 2 == 0) ? 1.0 : -1.0) * cdf_HR(X, k); }
+__host__ __device__ constexpr double cdf_GR(int X, int Y, int k) { return ((k % 2 == 0) ? 1.0 : -1.0) * cdf_HD(X, Y, k); }
+__host__ __device__ constexpr int cdf_hd_half(int X, int Y) { return Y == 0 ? 0 : X - 1 + Y - 1; }
+
+// the two outputs at offsets o (even) and o+1 from the window w[j] = in(o - F + j), j = 0 .. 2F+1
+template <int X, int Y, bool INV, int F>
+__device__ __forceinline__ void pair_out(const double (&w)[2 * F + 2], double &out0, double &out1)
+{
+    constexpr int HDH = cdf_hd_half(X, Y), HRH = X - 1;
+    if (!INV) {
+        double s = 0.0;
+        bool first = true;
+#pragma unroll
+        for (int k = -HDH; k <= HDH; ++k) {          // scaling coefficient at o: HD
+            const double c = cdf_HD(X, Y, k);
+            if (c != 0.0) {
+                const double t = __dmul_rn(w[F + k], c);
+                s = first ? t : __dadd_rn(s, t);
+                first = false;
+            }
+        }
+        out0 = s;
+        s = 0.0;
+        first = true;
+#pragma unroll
+        for (int k = -HRH; k <= HRH; ++k) {          // wavelet coefficient at o+1: GD
+            const double c = cdf_GD(X, k);
+            if (c != 0.0) {
+                const double t = __dmul_rn(w[F + 1 + k], c);
+                s = first ? t : __dadd_rn(s, t);
+                first = false;
+            }
+        }
+        out1 = s;
+    } else {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {                // u(o+p) = sum_{k == p mod 2} HR(k) sc(o+p+k) + sum_{k != p mod 2} GR(k) wc(o+p+k)
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int k = -HRH; k <= HRH; ++k)
+                if (((k + p) & 1) == 0) s0 = __dadd_rn(s0, __dmul_rn(w[F + p + k], cdf_HR(X, k)));
+#pragma unroll
+            for (int k = -HDH; k <= HDH; ++k)
+                if (((k + p) & 1) != 0) s1 = __dadd_rn(s1, __dmul_rn(w[F + p + k], cdf_GR(X, Y, k)));
+            (p ? out1 : out0) = __dadd_rn(s0, s1);
+        }
+    }
+}
+
+template <int X, int Y, int BS, bool INV>
+struct FastCfg {
+    static constexpr int HDH = cdf_hd_half(X, Y), HRH = X - 1;
+    static constexpr int F = HDH > HRH ? HDH : HRH;   // halo depth = widest filter of the transform
+    static constexpr int N = BS + 2 * F;
+    static constexpr int R = 2 * F + 2;
+    static constexpr size_t SMEM = sizeof(double) * ((size_t)2 * N * N + (size_t)N * BS + (size_t)R * BS * BS);
+};
+
+template <int X, int Y, int BS, bool INV>
+__global__ void __launch_bounds__(256) wavelet_fast_kernel(const double *__restrict__ src, double *__restrict__ dst, const int *__restrict__ active,
+                                                           const int *__restrict__ nbr, int nc)
+{
+    using C = FastCfg<X, Y, BS, INV>;
+    constexpr int F = C::F, N = C::N, R = C::R, NT = 256;
+    extern __shared__ __align__(16) double sm[];
+    double *in0 = sm;                       // [2][N*N]
+    double *xs = in0 + 2 * N * N;           // [N][BS]
+    double *ring = xs + N * BS;             // [R][BS*BS]
+    __shared__ int s_code[WGPU_NDIR];
+    const int tid = threadIdx.x;
+    const int b = active[blockIdx.x], c = blockIdx.y;
+    if (tid < WGPU_NDIR) s_code[tid] = tid == 13 ? b : nbr[b * WGPU_NDIR + tid];
+    __syncthreads();
+    constexpr long long CS = (long long)BS * BS * BS;
+    const double *srcc = src + (long long)c * CS;
+
+    auto load_plane = [&](int zp, double *dstp) {
+        const int dz = zp < 0 ? -1 : (zp >= BS ? 1 : 0), lz = zp - dz * BS;
+        if (F % 2 == 0) {
+            // 16-byte chunks: F and BS even, so a chunk never straddles a block boundary and is 16-byte aligned on both sides
+            for (int i = tid; i < N * (N / 2); i += NT) {
+                const int r = i / (N / 2), x = 2 * (i % (N / 2)) - F, y = r - F;
+                const int dy = y < 0 ? -1 : (y >= BS ? 1 : 0), dx = x < 0 ? -1 : (x >= BS ? 1 : 0);
+                const int sb = s_code[(dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)];
+                double *d = dstp + r * N + x + F;
+                if (sb >= 0) {
+                    const unsigned sa = (unsigned)__cvta_generic_to_shared(d);
+                    const double *g = srcc + (long long)sb * nc * CS + ((long long)lz * BS + (y - dy * BS)) * BS + (x - dx * BS);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(g) : "memory");
+                } else {
+                    d[0] = 0.0;
+                    d[1] = 0.0;
+                }
+            }
+        } else {
+            for (int i = tid; i < N * N; i += NT) {
+                const int r = i / N, x = i % N - F, y = r - F;
+                const int dy = y < 0 ? -1 : (y >= BS ? 1 : 0), dx = x < 0 ? -1 : (x >= BS ? 1 : 0);
+                const int sb = s_code[(dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)];
+                if (sb >= 0) cp_async8(dstp + i, srcc + (long long)sb * nc * CS + ((long long)lz * BS + (y - dy * BS)) * BS + (x - dx * BS));
+                else dstp[i] = 0.0;
+            }
+        }
+    };
+
+    load_plane(-F, in0);
+    cp_async_commit();
+#pragma unroll 1
+    for (int q = 0; q < N; ++q) {
+        const int zp = q - F;
+        const double *cur = in0 + (q & 1) * N * N;
+        if (q + 1 < N) load_plane(zp + 1, in0 + ((q + 1) & 1) * N * N);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        // x: rows y = -F .. BS+F-1, output pairs at interior x
+        for (int i = tid; i < N * (BS / 2); i += NT) {
+            const int r = i / (BS / 2), o = 2 * (i % (BS / 2));
+            double w[2 * F + 2];
+            const double2 *p2 = reinterpret_cast<const double2 *>(cur + r * N + o);
+#pragma unroll
+            for (int j = 0; j < F + 1; ++j) {
+                const double2 v = p2[j];
+                w[2 * j] = v.x;
+                w[2 * j + 1] = v.y;
+            }
+            double2 out;
+            pair_out<X, Y, INV, F>(w, out.x, out.y);
+            *reinterpret_cast<double2 *>(xs + r * BS + o) = out;
+        }
+        __syncthreads();
+        // y: output pairs at interior y, all interior x
+        double *rp = ring + (q % R) * BS * BS;
+        for (int i = tid; i < (BS / 2) * BS; i += NT) {
+            const int x = i % BS, o = 2 * (i / BS);
+            double w[2 * F + 2];
+#pragma unroll
+            for (int j = 0; j < 2 * F + 2; ++j) w[j] = xs[(o + j) * BS + x];
+            double o0, o1;
+            pair_out<X, Y, INV, F>(w, o0, o1);
+            rp[o * BS + x] = o0;
+            rp[(o + 1) * BS + x] = o1;
+        }
+        __syncthreads();
+        // z: once plane zp = k + F + 1 is in the ring (k even), output planes k and k+1 are complete
+        const int k = zp - F - 1;
+        if (k >= 0 && k < BS && (k & 1) == 0) {
+            double *out = dst + ((long long)b * nc + c) * CS + (long long)k * BS * BS;
+            int slot0 = k % R;                      // ring slot of input plane k - F  (plane z sits in slot (z + F) % R)
+            for (int i = tid; i < BS * BS; i += NT) {
+                double w[2 * F + 2];
+                int sl = slot0;
+#pragma unroll
+                for (int j = 0; j < 2 * F + 2; ++j) {
+                    w[j] = ring[sl * BS * BS + i];
+                    sl = sl + 1 == R ? 0 : sl + 1;
+                }
+                double o0, o1;
+                pair_out<X, Y, INV, F>(w, o0, o1);
+                out[i] = o0;
+                out[BS * BS + i] = o1;
+            }
+        }
+    }
+    cp_async_wait<0>();
+}
+
+template <int X, int Y, int BS, bool INV>
+int32_t launch_fast_t(wgpu_ctx *ctx, const double *src, double *dst)
+{
+    using C = FastCfg<X, Y, BS, INV>;
+    static bool configured = false;
+    if (!configured) {
+        WGPU_CHECK(ctx, cudaFuncSetAttribute(wavelet_fast_kernel<X, Y, BS, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        configured = true;
+    }
+    dim3 grid(ctx->n_active, ctx->nc);
+    wavelet_fast_kernel<X, Y, BS, INV><<<grid, 256, C::SMEM, ctx->stream>>>(src, dst, ctx->d_active, ctx->d_nbr, ctx->nc);
+    ctx->launches++;
+    WGPU_CHECK(ctx, cudaGetLastError());
+    return WGPU_OK;
+}
+
+template <int X, int Y>
+int32_t launch_fast_bs(wgpu_ctx *ctx, const double *src, double *dst, int inverse, bool &handled)
+{
+    handled = true;
+    switch (ctx->cfg.Bs[0]) {
+    case 16: return inverse ? launch_fast_t<X, Y, 16, true>(ctx, src, dst) : launch_fast_t<X, Y, 16, false>(ctx, src, dst);
+    case 18: return inverse ? launch_fast_t<X, Y, 18, true>(ctx, src, dst) : launch_fast_t<X, Y, 18, false>(ctx, src, dst);
+    case 20: return inverse ? launch_fast_t<X, Y, 20, true>(ctx, src, dst) : launch_fast_t<X, Y, 20, false>(ctx, src, dst);
+    case 24: return inverse ? launch_fast_t<X, Y, 24, true>(ctx, src, dst) : launch_fast_t<X, Y, 24, false>(ctx, src, dst);
+    }
+    handled = false;
+    return WGPU_OK;
+}
+
+int32_t launch_fast(wgpu_ctx *ctx, const double *src, double *dst, int inverse, bool &handled)
+{
+    const int X = ctx->wavelet.X, Y = ctx->wavelet.Y;
+    handled = false;
+    if (getenv("WGPU_WAVELET_GENERIC")) return WGPU_OK;   // tests compare the two paths
+    if (X == 2 && Y == 0) return launch_fast_bs<2, 0>(ctx, src, dst, inverse, handled);
+    if (X == 2 && Y == 2) return launch_fast_bs<2, 2>(ctx, src, dst, inverse, handled);
+    if (X == 4 && Y == 0) return launch_fast_bs<4, 0>(ctx, src, dst, inverse, handled);
+    if (X == 4 && Y == 2) return launch_fast_bs<4, 2>(ctx, src, dst, inverse, handled);
+    if (X == 4 && Y == 4) return launch_fast_bs<4, 4>(ctx, src, dst, inverse, handled);
+    if (X == 6 && Y == 0) return launch_fast_bs<6, 0>(ctx, src, dst, inverse, handled);
+    if (X == 6 && Y == 2) return launch_fast_bs<6, 2>(ctx, src, dst, inverse, handled);
+    return WGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // wavelet_renorm_block + threshold_block's detail norms on a decomposed (spaghetti-ordered) array:
 // per block and component max|wc| (pure scaling positions removed), both as max(abs) and max(sqrt(x*x)).
 // ---------------------------------------------------------------------------------------------
@@ -320,6 +562,11 @@ int32_t wgpu_launch_wavelet(wgpu_ctx *ctx, const double *src, double *dst, int i
     if (f > a.Bs) {
         ctx->err = "wavelet filter wider than the block";
         return WGPU_ERR_UNSUPPORTED;
+    }
+    {
+        bool handled = false;
+        int32_t rc = launch_fast(ctx, src, dst, inverse, handled);
+        if (rc || handled) return rc;
     }
     const int n = a.Bs + 2 * f;
     const size_t smem = sizeof(double) * ((size_t)2 * n * n + (size_t)n * a.Bs + (size_t)(2 * f + 2) * a.Bs * a.Bs);

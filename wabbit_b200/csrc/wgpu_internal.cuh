@@ -170,7 +170,7 @@ int32_t wgpu_launch_pack(wgpu_ctx *ctx, const double *src);
 // jump.cu
 int32_t wgpu_launch_jump_fill(wgpu_ctx *ctx, const double *src);
 int32_t wgpu_launch_export_regions(wgpu_ctx *ctx, const double *src, double *staged, const int *d_ids, int n, int ncomp_src, int ncomp_host,
-                                   int g_sync);
+                                   int g_sync, int by_id);
 int32_t wgpu_launch_refine(wgpu_ctx *ctx, const double *src, double *dst, const int *d_mother, const int *d_daughter, int n);
 int32_t wgpu_launch_coarsen(wgpu_ctx *ctx, const double *src, double *dst, const int *d_mother, const int *d_daughter, int n);
 int32_t wgpu_launch_copy_blocks(wgpu_ctx *ctx, const double *src, double *dst, const int *d_src_ids, const int *d_dst_ids, int n);
@@ -183,6 +183,6 @@ int32_t wgpu_launch_dtmin(wgpu_ctx *ctx, const double *u, unsigned long long *dt
 int32_t wgpu_launch_dt_finalize(wgpu_ctx *ctx, double time, const unsigned long long *dtmin_bits,
                                 unsigned long long *dtmin_next);
 int32_t wgpu_launch_extract(wgpu_ctx *ctx, const double *staged, double *dst, const int *d_ids, int n, int ncomp_dst,
-                            int ncomp_host);
+                            int ncomp_host, int by_id);
 int32_t wgpu_launch_export(wgpu_ctx *ctx, const double *src, double *staged, const int *d_ids, int n, int ncomp_src,
-                           int ncomp_host, int g_sync);
+                           int ncomp_host, int g_sync, int by_id);
