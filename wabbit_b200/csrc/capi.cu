@@ -417,6 +417,7 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
     ctx->h_nbr.assign((size_t)N * WGPU_NDIR, -1);
     ctx->h_level.assign(N, 0);
     ctx->has_jumps = false;
+    ctx->det_cached_for = nullptr;
     std::vector<int> jump_blk, jump_dir;
     for (int k = 0; k < n_active; ++k) {
         const int hid = hvy_active[k];
@@ -531,6 +532,7 @@ static int32_t move_blocks(wgpu_ctx *ctx, bool up, int32_t array_id, int32_t slo
             if (rc) return rc;
             WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
             if (up && array_id == WGPU_HVY_BLOCK) ctx->dtmin_valid = false;
+            if (up) ctx->det_cached_for = nullptr;
             return WGPU_OK;
         }
         cudaGetLastError();   // pageable memory: not an error, take the staged path
@@ -579,6 +581,7 @@ static int32_t move_blocks(wgpu_ctx *ctx, bool up, int32_t array_id, int32_t slo
         WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     }
     if (up && array_id == WGPU_HVY_BLOCK) ctx->dtmin_valid = false;
+    if (up) ctx->det_cached_for = nullptr;
     return WGPU_OK;
 }
 
@@ -625,6 +628,7 @@ int32_t wgpu_rhs(wgpu_ctx *ctx, double time, int32_t src_slot, int32_t dst_slot)
     const double *src = src_slot == 0 ? ctx->U : array_ptr(ctx, WGPU_HVY_WORK, src_slot, &nc);
     double *dst = array_ptr(ctx, WGPU_HVY_WORK, dst_slot, &nc);
     if (!src || !dst || dst_slot < 2) return fail(ctx, WGPU_ERR_ARG, "wgpu_rhs: bad slot");
+    ctx->det_cached_for = nullptr;
     StageArgs a;
     fill_common_args(ctx, a);
     a.u_in = src;
@@ -751,6 +755,7 @@ static int32_t transform(wgpu_ctx *ctx, int32_t src_id, int32_t src_slot, int32_
     if (!src || !dst || n1 != ctx->nc || n2 != ctx->nc) return fail(ctx, WGPU_ERR_ARG, "wavelet transform: bad array/slot");
     if (src == dst) return fail(ctx, WGPU_ERR_ARG, "wavelet transform: src and dst must differ (neighbours read src halos)");
     if (dst == ctx->U) ctx->dtmin_valid = false;
+    ctx->det_cached_for = nullptr;
     return wgpu_launch_wavelet(ctx, src, dst, inverse);
 }
 
@@ -859,6 +864,7 @@ int32_t wgpu_refine(wgpu_ctx *ctx, int32_t n, const int32_t *mother_hvy, const i
     WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     std::swap(ctx->U, ctx->TMP);
     ctx->dtmin_valid = false;
+    ctx->det_cached_for = nullptr;
     return WGPU_OK;
 }
 
@@ -884,6 +890,7 @@ int32_t wgpu_move_blocks(wgpu_ctx *ctx, int32_t n, const int32_t *src_hvy, const
     if ((rc = wgpu_launch_copy_blocks(ctx, ctx->U, ctx->TMP, ctx->d_idbuf[2], ctx->d_idbuf[2] + n, n))) return rc;
     WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     std::swap(ctx->U, ctx->TMP);
+    ctx->det_cached_for = nullptr;
     return WGPU_OK;
 }
 
@@ -1006,6 +1013,7 @@ int32_t wgpu_rk_begin(wgpu_ctx *ctx, double time)
         for (int l = 1; l < j; ++l)
             if (fabs(c.butcher[(size_t)j * ld + l]) >= 1.0e-8) subdiag = false;
     ctx->rk_subdiag = subdiag;
+    ctx->det_cached_for = nullptr;
     ctx->rk_uin = ctx->U;
     ctx->rk_next_stage = 0;   // becomes 1 after wgpu_rk_dt
     return WGPU_OK;

@@ -263,122 +263,224 @@ __device__ __forceinline__ void pair_out(const double (&w)[2 * F + 2], double &o
     }
 }
 
+// one of the two outputs only (P = 0: offset o, P = 1: offset o+1), same arithmetic as pair_out
+template <int X, int Y, bool INV, int F, int P>
+__device__ __forceinline__ void pair_out_one(const double (&w)[2 * F + 2], double &out)
+{
+    constexpr int HDH = cdf_hd_half(X, Y), HRH = X - 1;
+    if (!INV) {
+        double s = 0.0;
+        bool first = true;
+        if (P == 0) {
+#pragma unroll
+            for (int k = -HDH; k <= HDH; ++k) {
+                const double c = cdf_HD(X, Y, k);
+                if (c != 0.0) {
+                    const double t = __dmul_rn(w[F + k], c);
+                    s = first ? t : __dadd_rn(s, t);
+                    first = false;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = -HRH; k <= HRH; ++k) {
+                const double c = cdf_GD(X, k);
+                if (c != 0.0) {
+                    const double t = __dmul_rn(w[F + 1 + k], c);
+                    s = first ? t : __dadd_rn(s, t);
+                    first = false;
+                }
+            }
+        }
+        out = s;
+    } else {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int k = -HRH; k <= HRH; ++k)
+            if (((k + P) & 1) == 0) s0 = __dadd_rn(s0, __dmul_rn(w[F + P + k], cdf_HR(X, k)));
+#pragma unroll
+        for (int k = -HDH; k <= HDH; ++k)
+            if (((k + P) & 1) != 0) s1 = __dadd_rn(s1, __dmul_rn(w[F + P + k], cdf_GR(X, Y, k)));
+        out = __dadd_rn(s0, s1);
+    }
+}
+
 template <int X, int Y, int BS, bool INV>
 struct FastCfg {
     static constexpr int HDH = cdf_hd_half(X, Y), HRH = X - 1;
     static constexpr int F = HDH > HRH ? HDH : HRH;   // halo depth = widest filter of the transform
     static constexpr int N = BS + 2 * F;
-    static constexpr int R = 2 * F + 2;
-    static constexpr size_t SMEM = sizeof(double) * ((size_t)2 * N * N + (size_t)N * BS + (size_t)R * BS * BS);
+    static constexpr int R = 2 * F + 2;               // planes a z output pair looks at
+    static constexpr int NT = ((BS * BS + 31) / 32) * 32;   // one thread per (x, y) column of the block
+    static constexpr int NLD = (F % 2 == 0) ? N * (N / 2) : N * N;   // 16-byte chunks (F even) or 8-byte elements per input plane
+    static constexpr int LPT = (NLD + NT - 1) / NT;   // loads per thread and plane
+    static constexpr size_t SMEM = sizeof(double) * ((size_t)2 * N * N + (size_t)2 * N * BS);
 };
 
+// One CTA per (block, component).  Input planes (xy halo included) stream through a double buffer (cp.async); the x pass
+// writes rows to a second double buffer; every thread then owns one (x, y) column: it computes the y pass for its column and
+// keeps the last 2F+2 y-pass results in REGISTERS (the plane loop is fully unrolled, so the sliding window is pure register
+// renaming), from which the z pass emits a (scaling, wavelet) output pair every second plane -- no shared-memory traffic for z.
+// Threads are mapped to columns so that a warp has one y parity (all scaling rows or all wavelet rows: no divergence).
 template <int X, int Y, int BS, bool INV>
-__global__ void __launch_bounds__(256) wavelet_fast_kernel(const double *__restrict__ src, double *__restrict__ dst, const int *__restrict__ active,
-                                                           const int *__restrict__ nbr, int nc)
+__global__ void __launch_bounds__(FastCfg<X, Y, BS, INV>::NT) wavelet_fast_kernel(const double *__restrict__ src, double *__restrict__ dst,
+                                                                                 const int *__restrict__ active, const int *__restrict__ nbr, int nc,
+                                                                                 double *__restrict__ det_abs, double *__restrict__ det_sq)
 {
     using C = FastCfg<X, Y, BS, INV>;
-    constexpr int F = C::F, N = C::N, R = C::R, NT = 256;
+    constexpr int F = C::F, N = C::N, R = C::R, NT = C::NT, LPT = C::LPT, HALF = BS * BS / 2;
     extern __shared__ __align__(16) double sm[];
     double *in0 = sm;                       // [2][N*N]
-    double *xs = in0 + 2 * N * N;           // [N][BS]
-    double *ring = xs + N * BS;             // [R][BS*BS]
-    __shared__ int s_code[WGPU_NDIR];
+    double *xs0 = in0 + 2 * N * N;          // [2][N][BS]
+    __shared__ long long s_base[WGPU_NDIR]; // element offset of the source block per direction, -1 = none
     const int tid = threadIdx.x;
     const int b = active[blockIdx.x], c = blockIdx.y;
-    if (tid < WGPU_NDIR) s_code[tid] = tid == 13 ? b : nbr[b * WGPU_NDIR + tid];
-    __syncthreads();
     constexpr long long CS = (long long)BS * BS * BS;
-    const double *srcc = src + (long long)c * CS;
+    if (tid < WGPU_NDIR) {
+        const int sb = tid == 13 ? b : nbr[b * WGPU_NDIR + tid];
+        s_base[tid] = sb >= 0 ? ((long long)sb * nc + c) * CS : -1;
+    }
+    // per-thread load descriptors (the same for every plane): destination in the plane buffer, xy part of the direction, offset in the source plane
+    int ld_dst[LPT], ld_src[LPT], ld_dir[LPT];
+#pragma unroll
+    for (int j = 0; j < LPT; ++j) {
+        const int i = tid + j * NT;
+        int r, x;
+        if (F % 2 == 0) { r = i / (N / 2); x = 2 * (i % (N / 2)) - F; }
+        else { r = i / N; x = i % N - F; }
+        const int y = r - F;
+        const int dy = y < 0 ? -1 : (y >= BS ? 1 : 0), dx = x < 0 ? -1 : (x >= BS ? 1 : 0);
+        ld_dst[j] = i < C::NLD ? r * N + x + F : -1;
+        ld_src[j] = (y - dy * BS) * BS + (x - dx * BS);
+        ld_dir[j] = (dy + 1) * 3 + (dx + 1);
+    }
+    __syncthreads();
 
     auto load_plane = [&](int zp, double *dstp) {
-        const int dz = zp < 0 ? -1 : (zp >= BS ? 1 : 0), lz = zp - dz * BS;
-        if (F % 2 == 0) {
-            // 16-byte chunks: F and BS even, so a chunk never straddles a block boundary and is 16-byte aligned on both sides
-            for (int i = tid; i < N * (N / 2); i += NT) {
-                const int r = i / (N / 2), x = 2 * (i % (N / 2)) - F, y = r - F;
-                const int dy = y < 0 ? -1 : (y >= BS ? 1 : 0), dx = x < 0 ? -1 : (x >= BS ? 1 : 0);
-                const int sb = s_code[(dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)];
-                double *d = dstp + r * N + x + F;
-                if (sb >= 0) {
-                    const unsigned sa = (unsigned)__cvta_generic_to_shared(d);
-                    const double *g = srcc + (long long)sb * nc * CS + ((long long)lz * BS + (y - dy * BS)) * BS + (x - dx * BS);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(g) : "memory");
-                } else {
-                    d[0] = 0.0;
-                    d[1] = 0.0;
-                }
-            }
-        } else {
-            for (int i = tid; i < N * N; i += NT) {
-                const int r = i / N, x = i % N - F, y = r - F;
-                const int dy = y < 0 ? -1 : (y >= BS ? 1 : 0), dx = x < 0 ? -1 : (x >= BS ? 1 : 0);
-                const int sb = s_code[(dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)];
-                if (sb >= 0) cp_async8(dstp + i, srcc + (long long)sb * nc * CS + ((long long)lz * BS + (y - dy * BS)) * BS + (x - dx * BS));
-                else dstp[i] = 0.0;
+        const int dz = zp < 0 ? -1 : (zp >= BS ? 1 : 0);
+        const int zoff = (zp - dz * BS) * BS * BS;
+#pragma unroll
+        for (int j = 0; j < LPT; ++j) {
+            if (ld_dst[j] < 0) continue;
+            const long long base = s_base[(dz + 1) * 9 + ld_dir[j]];
+            double *d = dstp + ld_dst[j];
+            if (base >= 0) {
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(d);
+                const double *g = src + base + zoff + ld_src[j];
+                if (F % 2 == 0) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(g) : "memory");
+                else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(g) : "memory");
+            } else {
+                d[0] = 0.0;
+                if (F % 2 == 0) d[1] = 0.0;
             }
         }
     };
 
+    // column of this thread: warps hold one y parity
+    const bool has_col = tid < BS * BS;
+    const int par = tid / HALF, idx = tid % HALF;
+    const int cx = idx % BS, cy = 2 * (idx / BS) + par;
+    double win[R];                          // y-pass results of planes zp-R+1 .. zp of this column; plane z sits in win[(z + F) % R]
+#pragma unroll
+    for (int j = 0; j < R; ++j) win[j] = 0.0;
+    double m0 = 0.0, m1 = 0.0;              // Linfty detail of this (block, component), see below
+    double *outc = dst + ((long long)b * nc + c) * CS + cy * BS + cx;
+
     load_plane(-F, in0);
     cp_async_commit();
+    // plane loop in rounds of R planes, the round fully unrolled: window slots, buffer parities and the z ordering are
+    // compile-time (R is even and q0 is a multiple of R)
 #pragma unroll 1
-    for (int q = 0; q < N; ++q) {
+    for (int q0 = 0; q0 < N; q0 += R) {
+#pragma unroll
+    for (int jq = 0; jq < R; ++jq) {
+        const int q = q0 + jq;
+        if (q >= N) break;
         const int zp = q - F;
-        const double *cur = in0 + (q & 1) * N * N;
-        if (q + 1 < N) load_plane(zp + 1, in0 + ((q + 1) & 1) * N * N);
+        const double *cur = in0 + (jq & 1) * N * N;
+        double *xs = xs0 + (jq & 1) * N * BS;
+        if (q + 1 < N) load_plane(zp + 1, in0 + ((jq + 1) & 1) * N * N);
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
         // x: rows y = -F .. BS+F-1, output pairs at interior x
-        for (int i = tid; i < N * (BS / 2); i += NT) {
-            const int r = i / (BS / 2), o = 2 * (i % (BS / 2));
-            double w[2 * F + 2];
-            const double2 *p2 = reinterpret_cast<const double2 *>(cur + r * N + o);
 #pragma unroll
-            for (int j = 0; j < F + 1; ++j) {
-                const double2 v = p2[j];
-                w[2 * j] = v.x;
-                w[2 * j + 1] = v.y;
-            }
-            double2 out;
-            pair_out<X, Y, INV, F>(w, out.x, out.y);
-            *reinterpret_cast<double2 *>(xs + r * BS + o) = out;
-        }
-        __syncthreads();
-        // y: output pairs at interior y, all interior x
-        double *rp = ring + (q % R) * BS * BS;
-        for (int i = tid; i < (BS / 2) * BS; i += NT) {
-            const int x = i % BS, o = 2 * (i / BS);
-            double w[2 * F + 2];
-#pragma unroll
-            for (int j = 0; j < 2 * F + 2; ++j) w[j] = xs[(o + j) * BS + x];
-            double o0, o1;
-            pair_out<X, Y, INV, F>(w, o0, o1);
-            rp[o * BS + x] = o0;
-            rp[(o + 1) * BS + x] = o1;
-        }
-        __syncthreads();
-        // z: once plane zp = k + F + 1 is in the ring (k even), output planes k and k+1 are complete
-        const int k = zp - F - 1;
-        if (k >= 0 && k < BS && (k & 1) == 0) {
-            double *out = dst + ((long long)b * nc + c) * CS + (long long)k * BS * BS;
-            int slot0 = k % R;                      // ring slot of input plane k - F  (plane z sits in slot (z + F) % R)
-            for (int i = tid; i < BS * BS; i += NT) {
+        for (int i0 = 0; i0 < N * (BS / 2); i0 += NT) {
+            const int i = i0 + tid;
+            if (i < N * (BS / 2)) {
+                const int r = i / (BS / 2), o = 2 * (i % (BS / 2));
                 double w[2 * F + 2];
-                int sl = slot0;
+                const double2 *p2 = reinterpret_cast<const double2 *>(cur + r * N + o);
 #pragma unroll
-                for (int j = 0; j < 2 * F + 2; ++j) {
-                    w[j] = ring[sl * BS * BS + i];
-                    sl = sl + 1 == R ? 0 : sl + 1;
+                for (int j = 0; j < F + 1; ++j) {
+                    const double2 v = p2[j];
+                    w[2 * j] = v.x;
+                    w[2 * j + 1] = v.y;
                 }
-                double o0, o1;
+                double2 out;
+                pair_out<X, Y, INV, F>(w, out.x, out.y);
+                *reinterpret_cast<double2 *>(xs + r * BS + o) = out;
+            }
+        }
+        __syncthreads();
+        if (has_col) {
+            // y: one output of this thread's column (scaling row if cy is even, wavelet row if odd)
+            {
+                double w[2 * F + 2], o0, o1;
+                const double *colp = xs + (cy - par) * BS + cx;     // window of the pair (cy - par, cy - par + 1)
+                if (par == 0) {
+#pragma unroll
+                    for (int j = 0; j < 2 * F + 1; ++j) w[j] = colp[j * BS];
+                    w[2 * F + 1] = 0.0;
+                    pair_out_one<X, Y, INV, F, 0>(w, o0);
+                    win[jq] = o0;
+                } else {
+                    w[0] = 0.0;
+#pragma unroll
+                    for (int j = 1; j < 2 * F + 2; ++j) w[j] = colp[j * BS];
+                    pair_out_one<X, Y, INV, F, 1>(w, o1);
+                    win[jq] = o1;
+                }
+            }
+            // z: once plane zp = k + F + 1 is in the window (k even), output planes k and k+1 of this column are complete
+            const int k = zp - F - 1;          // = q - R + 1: its plane k - F sits in slot (jq + 1) % R
+            if ((jq & 1) && k >= 0 && k < BS) {
+                double w[R], o0, o1;
+#pragma unroll
+                for (int j = 0; j < R; ++j) w[j] = win[(jq + 1 + j) % R];
                 pair_out<X, Y, INV, F>(w, o0, o1);
-                out[i] = o0;
-                out[BS * BS + i] = o1;
+                outc[(long long)k * BS * BS] = o0;
+                outc[(long long)(k + 1) * BS * BS] = o1;
+                if (!INV) {
+                    // threshold_block's Linfty detail, fused: max |wc| and max sqrt(wc*wc) over everything but the pure scaling
+                    // positions (wavelet_renorm_block is the identity for eps_norm = Linfty); sqrt is monotone, taken once at the end
+                    const double v0 = (!(cx & 1) && !(cy & 1)) ? 0.0 : o0;
+                    m0 = fmax(m0, fmax(fabs(v0), fabs(o1)));
+                    m1 = fmax(m1, fmax(__dmul_rn(v0, v0), __dmul_rn(o1, o1)));
+                }
             }
         }
     }
+    }
     cp_async_wait<0>();
+    if (!INV && det_abs) {
+        __shared__ double s0[NT / 32], s1[NT / 32];
+        m0 = warp_max(m0);
+        m1 = warp_max(m1);
+        if ((tid & 31) == 0) {
+            s0[tid >> 5] = m0;
+            s1[tid >> 5] = m1;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int i = 1; i < NT / 32; ++i) {
+                m0 = fmax(m0, s0[i]);
+                m1 = fmax(m1, s1[i]);
+            }
+            det_abs[(long long)b * nc + c] = m0;
+            det_sq[(long long)b * nc + c] = sqrt(m1);
+        }
+    }
 }
 
 template <int X, int Y, int BS, bool INV>
@@ -391,9 +493,11 @@ int32_t launch_fast_t(wgpu_ctx *ctx, const double *src, double *dst)
         configured = true;
     }
     dim3 grid(ctx->n_active, ctx->nc);
-    wavelet_fast_kernel<X, Y, BS, INV><<<grid, 256, C::SMEM, ctx->stream>>>(src, dst, ctx->d_active, ctx->d_nbr, ctx->nc);
+    wavelet_fast_kernel<X, Y, BS, INV><<<grid, C::NT, C::SMEM, ctx->stream>>>(src, dst, ctx->d_active, ctx->d_nbr, ctx->nc, ctx->d_det_abs,
+                                                                             ctx->d_det_sq);
     ctx->launches++;
     WGPU_CHECK(ctx, cudaGetLastError());
+    if (!INV) ctx->det_cached_for = dst;   // Linfty details of `dst` are in d_det_abs / d_det_sq until the array is written again
     return WGPU_OK;
 }
 
@@ -585,6 +689,8 @@ int32_t wgpu_launch_wavelet(wgpu_ctx *ctx, const double *src, double *dst, int i
 int32_t wgpu_launch_detail(wgpu_ctx *ctx, const double *wd, int eps_norm, int level_ref)
 {
     if (ctx->n_active == 0) return WGPU_OK;
+    if (eps_norm == 0 && ctx->det_cached_for == wd) return WGPU_OK;   // computed by the decomposition kernel itself
+    ctx->det_cached_for = nullptr;
     const wgpu_config &c = ctx->cfg;
     DetailArgs a;
     a.wd = wd;

@@ -139,6 +139,7 @@ struct wgpu_ctx {
     WaveFilters wavelet;
     bool wavelet_set = false;
     double *d_det_abs = nullptr, *d_det_sq = nullptr;   // [max_blocks][nc]
+    const double *det_cached_for = nullptr;             // decomposed array whose Linfty details d_det_* currently hold (fused into the FWT)
     int *d_status = nullptr;                            // [max_blocks]
     double *d_detail_out = nullptr;                     // [max_blocks][nc]
     unsigned long long *d_norm = nullptr;               // [16]
