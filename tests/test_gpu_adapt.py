@@ -178,3 +178,38 @@ def test_page_locked_host_arrays_take_the_direct_path_with_identical_results():
             sol.download(pn, g_sync=gs)
             assert np.array_equal(a, pn), (graded, gs)
         sol.close()
+
+
+@pytest.mark.parametrize("wavelet,Bs", [("CDF40", 16), ("CDF44", 16), ("CDF22", 18), ("CDF62", 20), ("CDF20", 24)])
+def test_wavelet_transform_on_graded_grid(wavelet, Bs):
+    """FWT / IWT on a leaf grid with level jumps: ghost values of all 26 relations come from the wavelet jump pool (decimation
+    from finer, prediction from coarser neighbours) and are exactly what the oracle's sync_ghosts_generic(ignore_Filter) leaves,
+    so the coefficients agree bit for bit with sync + waveletDecomposition_optimized_block on the host."""
+    from wabbit_b200.solver import HVY_TMP
+    lv, ix = graded_blocks(3, 1, 3, seed=12)
+    forest = Forest.from_blocks(3, 3, lv, ix)
+    w, p, po, grid, sol, u = _case(wavelet, Bs, forest, seed=13)
+    nbr = forest.neighbors(0)[:, :grid.n]
+    I = (slice(None), slice(None)) + O.interior(po)
+    sol.upload(u)
+    sol.waveletDecomposition_tree((HVY_BLOCK, 0), (HVY_TMP, 0))
+    wd = np.zeros_like(u)
+    sol.download(wd, HVY_TMP, g_sync=0)
+    ref = u[:grid.n].copy()
+    O.sync_ghosts_leaf(grid, po, ref, nbr, po.g, po.g, w.X, bool(w.lifted))
+    wd_ref = np.zeros_like(ref)
+    O.fwt_tree(w, po, ref, wd_ref)
+    assert np.array_equal(wd[:grid.n][I], wd_ref[I])
+    # flags from the fused Linfty details == oracle's threshold_block
+    st, det = sol.threshold_tree((HVY_TMP, 0), eps=0.5, want_detail=True)
+    st_ref, det_ref = O.threshold_tree(po, wd_ref, grid.level, 0.5)
+    assert np.array_equal(det, det_ref) and np.array_equal(st, st_ref)
+    # inverse transform of the coefficient field, ghosts synchronised the same way
+    sol.waveletReconstruction_tree(src=(HVY_TMP, 0), dst=(HVY_WORK, 2))
+    r = np.zeros_like(u)
+    sol.download(r, HVY_WORK, 2, g_sync=0)
+    O.sync_ghosts_leaf(grid, po, wd_ref, nbr, po.g, po.g, w.X, bool(w.lifted))
+    r_ref = np.zeros_like(wd_ref)
+    O.iwt_tree(w, po, wd_ref, r_ref)
+    assert np.array_equal(r[:grid.n][I], r_ref[I])
+    sol.close()

@@ -195,6 +195,62 @@ int32_t upload_jump_tables(wgpu_ctx *ctx, const std::vector<int> &jump_blk, cons
     return WGPU_OK;
 }
 
+// level-jump ghost patches of the wavelet kernels: every (block, direction) whose neighbours are finer or coarser, all 26
+// directions, as deep as the widest wavelet filter; d_wnbr is d_nbr with those directions pointing into the pool
+int32_t upload_wjump_tables(wgpu_ctx *ctx, const std::vector<int> &blk, const std::vector<int> &dir)
+{
+    ctx->n_wjump = 0;
+    if (!ctx->has_jumps) return WGPU_OK;
+    const wgpu_config &c = ctx->cfg;
+    const int N = c.max_blocks, Bs = c.Bs[0];
+    const WaveFilters &w = ctx->wavelet;
+    const int F = std::max(std::max(-w.hd_lo, w.hd_hi), std::max(-w.hr_lo, w.hr_hi));
+    ctx->wjump_depth = F;
+    const int nj = (int)blk.size();
+    std::vector<int> wnbr(ctx->h_nbr);
+    std::vector<long long> off(std::max(nj, 1));
+    long long total = 0;
+    for (int i = 0; i < nj; ++i) {
+        const int d[3] = {dir[i] % 3 - 1, (dir[i] / 3) % 3 - 1, dir[i] / 9 - 1};
+        wnbr[(size_t)blk[i] * WGPU_NDIR + dir[i]] = -2 - i;
+        off[i] = total;
+        total += (long long)ctx->nc * (d[0] ? F : Bs) * (d[1] ? F : Bs) * (d[2] ? F : Bs);
+    }
+    for (size_t i = 0; i < wnbr.size(); ++i)
+        if (wnbr[i] <= -2 - WGPU_JUMP_PID) wnbr[i] = -1;   // stage-kernel patch ids mean nothing here (cannot happen: overwritten above)
+    int32_t rc;
+    if (!ctx->d_wnbr && (rc = dmalloc(ctx, &ctx->d_wnbr, (size_t)N * WGPU_NDIR))) return rc;
+    if (nj > ctx->wjump_cap) {
+        cudaFree(ctx->d_wjump_blk);
+        cudaFree(ctx->d_wjump_dir);
+        cudaFree(ctx->d_woff);
+        ctx->d_wjump_blk = ctx->d_wjump_dir = nullptr;
+        ctx->d_woff = nullptr;
+        const int want = nj + nj / 2 + 64;
+        if ((rc = dmalloc(ctx, &ctx->d_wjump_blk, (size_t)want))) return rc;
+        if ((rc = dmalloc(ctx, &ctx->d_wjump_dir, (size_t)want))) return rc;
+        if ((rc = dmalloc(ctx, &ctx->d_woff, (size_t)want))) return rc;
+        ctx->wjump_cap = want;
+    }
+    if ((size_t)total > ctx->wpool_cap) {
+        cudaFree(ctx->d_wpool);
+        ctx->d_wpool = nullptr;
+        ctx->dev_bytes -= (int64_t)ctx->wpool_cap * 8;
+        const size_t want = (size_t)total + (size_t)total / 4;
+        if ((rc = dmalloc(ctx, &ctx->d_wpool, want))) return rc;
+        ctx->wpool_cap = want;
+    }
+    WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_wnbr, wnbr.data(), sizeof(int) * wnbr.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (nj) {
+        WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_wjump_blk, blk.data(), sizeof(int) * nj, cudaMemcpyHostToDevice, ctx->stream));
+        WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_wjump_dir, dir.data(), sizeof(int) * nj, cudaMemcpyHostToDevice, ctx->stream));
+        WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_woff, off.data(), sizeof(long long) * nj, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->n_wjump = nj;
+    return WGPU_OK;
+}
+
 int32_t upload_ids(wgpu_ctx *ctx, int which, const std::vector<int> &v)
 {
     int *&p = ctx->d_idbuf[which];
@@ -323,6 +379,11 @@ int32_t wgpu_destroy(wgpu_ctx *ctx)
     cudaFree(ctx->d_jump_blk);
     cudaFree(ctx->d_jump_dir);
     cudaFree(ctx->d_jpool);
+    cudaFree(ctx->d_wjump_blk);
+    cudaFree(ctx->d_wjump_dir);
+    cudaFree(ctx->d_wnbr);
+    cudaFree(ctx->d_woff);
+    cudaFree(ctx->d_wpool);
     cudaFree(ctx->d_idbuf[0]);
     cudaFree(ctx->d_idbuf[1]);
     cudaFree(ctx->d_idbuf[2]);
@@ -418,7 +479,7 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
     ctx->h_level.assign(N, 0);
     ctx->has_jumps = false;
     ctx->det_cached_for = nullptr;
-    std::vector<int> jump_blk, jump_dir;
+    std::vector<int> jump_blk, jump_dir, wjump_blk, wjump_dir, no_same;
     for (int k = 0; k < n_active; ++k) {
         const int hid = hvy_active[k];
         if (hid < 1 || hid > N) return fail(ctx, WGPU_ERR_ARG, "hvy_active entry out of range");
@@ -457,6 +518,11 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
                             if ((lc >= 1 && (lc - 1) / N != rank) || (lf >= 1 && (lf - 1) / N != rank))
                                 return fail(ctx, WGPU_ERR_UNSUPPORTED, "level-jump neighbours on another rank are not supported yet");
                         }
+                        // every direction without a same-level neighbour is a candidate for a wavelet ghost patch: besides the
+                        // coarser / finer relations of the table these are the edges and corners that the reference fills through
+                        // the extension of a coarser face neighbour's patch (get_indices_of_ghost_patch, neighborhood.f90:158-331)
+                        no_same.push_back(hid - 1);
+                        no_same.push_back((dz + 1) * 9 + (dy + 1) * 3 + (dx + 1));
                         if (jump) {
                             ctx->has_jumps = true;
                             // faces become restriction / prediction patches in the jump pool; the star stencils of the time
@@ -475,9 +541,27 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
     ctx->n_int = n_active;
     ctx->n_bnd = 0;
     ctx->n_jump = (int)jump_blk.size();
+    if (ctx->has_jumps && (int)ctx->h_has_coords.size() == N) {
+        for (size_t i = 0; i < no_same.size(); i += 2) {
+            const int b = no_same[i], d = no_same[i + 1];
+            if (!ctx->h_has_coords[b]) continue;
+            const int dd[3] = {d % 3 - 1, (d / 3) % 3 - 1, d / 9 - 1};
+            const int nb = 1 << ctx->h_level[b];
+            bool inside = true;
+            for (int a = 0; a < c.dim; ++a) {
+                const int q = ctx->h_ixyz[3 * (size_t)b + a] + dd[a];
+                if ((q < 0 || q >= nb) && !c.periodic[a]) inside = false;
+            }
+            if (inside) {
+                wjump_blk.push_back(b);
+                wjump_dir.push_back(d);
+            }
+        }
+    }
     {
         int32_t rcj = upload_jump_tables(ctx, jump_blk, jump_dir);
         if (rcj) return rcj;
+        if ((rcj = upload_wjump_tables(ctx, wjump_blk, wjump_dir))) return rcj;
     }
     if (!ctx->d_active_int) {
         int32_t rc2 = dmalloc(ctx, &ctx->d_active_int, (size_t)N);
@@ -748,7 +832,6 @@ static int32_t transform(wgpu_ctx *ctx, int32_t src_id, int32_t src_slot, int32_
     const wgpu_config &c = ctx->cfg;
     if (c.dim != 3 || c.Bs[0] != c.Bs[1] || c.Bs[0] != c.Bs[2]) return fail(ctx, WGPU_ERR_UNSUPPORTED, "wavelet kernels: cubic 3-D blocks only so far");
     if (!ctx->remote_faces.empty() || ctx->n_bnd) return fail(ctx, WGPU_ERR_UNSUPPORTED, "wavelet kernels: neighbours on other ranks are not supported yet");
-    if (ctx->has_jumps) return fail(ctx, WGPU_ERR_UNSUPPORTED, "wavelet kernels: grids with level jumps are not supported yet");
     int n1 = 0, n2 = 0;
     const double *src = array_ptr(ctx, src_id, src_slot, &n1);
     double *dst = array_ptr(ctx, dst_id, dst_slot, &n2);

@@ -35,6 +35,8 @@ FillCtx make_fill_ctx(wgpu_ctx *ctx, const double *u)
     return f;
 }
 
+size_t g_jump_fill_smem = 0;   // largest dynamic shared memory jump_fill_kernel has been configured for (two launchers share it)
+
 template <typename K>
 int32_t ensure_smem(wgpu_ctx *ctx, K kernel, size_t smem, size_t &configured)
 {
@@ -53,11 +55,12 @@ int32_t ensure_smem(wgpu_ctx *ctx, K kernel, size_t smem, size_t &configured)
 struct JumpArgs {
     FillCtx f;
     double *jpool;
-    long long jpatch;
+    long long jpatch;          // size of a patch when all have the same (joff == nullptr)
+    const long long *joff;     // offset of every patch in the pool, or nullptr
     const int *jblk, *jdir;
     const signed char *level;
     const int *ixyz;
-    int H;
+    int H;                     // depth of the ghost strip
 };
 
 __global__ void __launch_bounds__(128) jump_fill_kernel(const JumpArgs a)
@@ -73,8 +76,8 @@ __global__ void __launch_bounds__(128) jump_fill_kernel(const JumpArgs a)
         ext[k] = d[k] ? H : (k < dim ? Bs : 1);
     }
     const long long npts = (long long)ext[0] * ext[1] * ext[2];
-    fill_region(a.f, T, sm, a.level[b], lo, ext, a.jpool + (long long)blockIdx.x * a.jpatch, npts, ext[0], (long long)ext[0] * ext[1], 0, a.f.nc,
-                threadIdx.x, blockDim.x);
+    double *out = a.jpool + (a.joff ? a.joff[blockIdx.x] : (long long)blockIdx.x * a.jpatch);
+    fill_region(a.f, T, sm, a.level[b], lo, ext, out, npts, ext[0], (long long)ext[0] * ext[1], 0, a.f.nc, threadIdx.x, blockDim.x);
 }
 
 // ------------------------------------------------------------------------------------------------ export with ghosts
@@ -219,6 +222,7 @@ int32_t wgpu_launch_jump_fill(wgpu_ctx *ctx, const double *src)
     JumpArgs a;
     a.f = make_fill_ctx(ctx, src);
     a.jpool = ctx->d_jpool;
+    a.joff = nullptr;
     a.jblk = ctx->d_jump_blk;
     a.jdir = ctx->d_jump_dir;
     a.level = ctx->d_level;
@@ -231,8 +235,7 @@ int32_t wgpu_launch_jump_fill(wgpu_ctx *ctx, const double *src)
         const size_t s = fill_scratch_doubles(e, a.f.order, c.dim);
         best = s > best ? s : best;
     }
-    static size_t configured = 0;
-    int32_t rc = ensure_smem(ctx, jump_fill_kernel, best * sizeof(double), configured);
+    int32_t rc = ensure_smem(ctx, jump_fill_kernel, best * sizeof(double), g_jump_fill_smem);
     if (rc) return rc;
     jump_fill_kernel<<<ctx->n_jump, 128, best * sizeof(double), ctx->stream>>>(a);
     ctx->launches++;
@@ -318,6 +321,36 @@ int32_t wgpu_launch_copy_blocks(wgpu_ctx *ctx, const double *src, double *dst, c
     const long long per_block = (long long)ctx->nc * ctx->blk_elems;
     dim3 grid((unsigned)((per_block / 2 + 255) / 256), n);
     copy_blocks_kernel<<<grid, 256, 0, ctx->stream>>>(src, dst, d_src_ids, d_dst_ids, per_block);
+    ctx->launches++;
+    WGPU_CHECK(ctx, cudaGetLastError());
+    return WGPU_OK;
+}
+
+int32_t wgpu_launch_wjump_fill(wgpu_ctx *ctx, const double *src)
+{
+    if (ctx->n_wjump == 0) return WGPU_OK;
+    const wgpu_config &c = ctx->cfg;
+    JumpArgs a;
+    a.f = make_fill_ctx(ctx, src);
+    a.jpool = ctx->d_wpool;
+    a.jpatch = 0;
+    a.joff = ctx->d_woff;
+    a.jblk = ctx->d_wjump_blk;
+    a.jdir = ctx->d_wjump_dir;
+    a.level = ctx->d_level;
+    a.ixyz = ctx->d_ixyz;
+    a.H = ctx->wjump_depth;
+    size_t best = 0;
+    for (int r = 0; r < 27; ++r) {
+        const int d[3] = {r % 3 - 1, (r / 3) % 3 - 1, r / 9 - 1};
+        if (r == 13 || (c.dim == 2 && d[2])) continue;
+        const int e[3] = {d[0] ? a.H : c.Bs[0], d[1] ? a.H : c.Bs[0], c.dim == 3 ? (d[2] ? a.H : c.Bs[0]) : 1};
+        const size_t s = fill_scratch_doubles(e, a.f.order, c.dim);
+        best = s > best ? s : best;
+    }
+    int32_t rc = ensure_smem(ctx, jump_fill_kernel, best * sizeof(double), g_jump_fill_smem);
+    if (rc) return rc;
+    jump_fill_kernel<<<ctx->n_wjump, 128, best * sizeof(double), ctx->stream>>>(a);
     ctx->launches++;
     WGPU_CHECK(ctx, cudaGetLastError());
     return WGPU_OK;

@@ -325,20 +325,38 @@ struct FastCfg {
 template <int X, int Y, int BS, bool INV>
 __global__ void __launch_bounds__(FastCfg<X, Y, BS, INV>::NT) wavelet_fast_kernel(const double *__restrict__ src, double *__restrict__ dst,
                                                                                  const int *__restrict__ active, const int *__restrict__ nbr, int nc,
-                                                                                 double *__restrict__ det_abs, double *__restrict__ det_sq)
+                                                                                 double *__restrict__ det_abs, double *__restrict__ det_sq,
+                                                                                 const double *__restrict__ wpool, const long long *__restrict__ woff)
 {
     using C = FastCfg<X, Y, BS, INV>;
     constexpr int F = C::F, N = C::N, R = C::R, NT = C::NT, LPT = C::LPT, HALF = BS * BS / 2;
     extern __shared__ __align__(16) double sm[];
     double *in0 = sm;                       // [2][N*N]
     double *xs0 = in0 + 2 * N * N;          // [2][N][BS]
-    __shared__ long long s_base[WGPU_NDIR]; // element offset of the source block per direction, -1 = none
+    // source of the ghost region of each direction: pointer such that the point with neighbour-local coordinates (lx, ly, lz)
+    // sits at ptr + lz*sz + ly*sy + lx -- the neighbour's interior (same level), or a patch of the wavelet jump pool (level
+    // jumps: decimated / predicted values in the layout of the ghost region), or null (no neighbour)
+    __shared__ const double *s_ptr[WGPU_NDIR];
+    __shared__ int s_sy[WGPU_NDIR], s_sz[WGPU_NDIR];
     const int tid = threadIdx.x;
     const int b = active[blockIdx.x], c = blockIdx.y;
     constexpr long long CS = (long long)BS * BS * BS;
     if (tid < WGPU_NDIR) {
         const int sb = tid == 13 ? b : nbr[b * WGPU_NDIR + tid];
-        s_base[tid] = sb >= 0 ? ((long long)sb * nc + c) * CS : -1;
+        const double *ptr = nullptr;
+        int sy = BS, sz = BS * BS;
+        if (sb >= 0) ptr = src + ((long long)sb * nc + c) * CS;
+        else if (sb <= -2) {
+            const int d[3] = {tid % 3 - 1, (tid / 3) % 3 - 1, tid / 9 - 1};
+            const int ex = d[0] ? F : BS, ey = d[1] ? F : BS, ez = d[2] ? F : BS;
+            const int ox = d[0] < 0 ? BS - F : 0, oy = d[1] < 0 ? BS - F : 0, oz = d[2] < 0 ? BS - F : 0;
+            sy = ex;
+            sz = ex * ey;
+            ptr = wpool + woff[-2 - sb] + (long long)c * ex * ey * ez - ((long long)(oz * ey + oy) * ex + ox);
+        }
+        s_ptr[tid] = ptr;
+        s_sy[tid] = sy;
+        s_sz[tid] = sz;
     }
     // per-thread load descriptors (the same for every plane): destination in the plane buffer, xy part of the direction, offset in the source plane
     int ld_dst[LPT], ld_src[LPT], ld_dir[LPT];
@@ -351,22 +369,23 @@ __global__ void __launch_bounds__(FastCfg<X, Y, BS, INV>::NT) wavelet_fast_kerne
         const int y = r - F;
         const int dy = y < 0 ? -1 : (y >= BS ? 1 : 0), dx = x < 0 ? -1 : (x >= BS ? 1 : 0);
         ld_dst[j] = i < C::NLD ? r * N + x + F : -1;
-        ld_src[j] = (y - dy * BS) * BS + (x - dx * BS);
+        ld_src[j] = ((y - dy * BS) << 8) | (x - dx * BS);   // neighbour-local (ly, lx)
         ld_dir[j] = (dy + 1) * 3 + (dx + 1);
     }
     __syncthreads();
 
     auto load_plane = [&](int zp, double *dstp) {
         const int dz = zp < 0 ? -1 : (zp >= BS ? 1 : 0);
-        const int zoff = (zp - dz * BS) * BS * BS;
+        const int lz = zp - dz * BS;
 #pragma unroll
         for (int j = 0; j < LPT; ++j) {
             if (ld_dst[j] < 0) continue;
-            const long long base = s_base[(dz + 1) * 9 + ld_dir[j]];
+            const int D = (dz + 1) * 9 + ld_dir[j];
+            const double *base = s_ptr[D];
             double *d = dstp + ld_dst[j];
-            if (base >= 0) {
+            if (base) {
                 const unsigned sa = (unsigned)__cvta_generic_to_shared(d);
-                const double *g = src + base + zoff + ld_src[j];
+                const double *g = base + lz * s_sz[D] + (ld_src[j] >> 8) * s_sy[D] + (ld_src[j] & 255);
                 if (F % 2 == 0) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(g) : "memory");
                 else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(g) : "memory");
             } else {
@@ -493,8 +512,12 @@ int32_t launch_fast_t(wgpu_ctx *ctx, const double *src, double *dst)
         configured = true;
     }
     dim3 grid(ctx->n_active, ctx->nc);
-    wavelet_fast_kernel<X, Y, BS, INV><<<grid, C::NT, C::SMEM, ctx->stream>>>(src, dst, ctx->d_active, ctx->d_nbr, ctx->nc, ctx->d_det_abs,
-                                                                             ctx->d_det_sq);
+    if (ctx->has_jumps && C::F != ctx->wjump_depth) {
+        ctx->err = "wavelet kernel: halo depth differs from the depth of the level-jump patches";
+        return WGPU_ERR_UNSUPPORTED;
+    }
+    wavelet_fast_kernel<X, Y, BS, INV><<<grid, C::NT, C::SMEM, ctx->stream>>>(src, dst, ctx->d_active, ctx->has_jumps ? ctx->d_wnbr : ctx->d_nbr, ctx->nc,
+                                                                             ctx->d_det_abs, ctx->d_det_sq, ctx->d_wpool, ctx->d_woff);
     ctx->launches++;
     WGPU_CHECK(ctx, cudaGetLastError());
     if (!INV) ctx->det_cached_for = dst;   // Linfty details of `dst` are in d_det_abs / d_det_sq until the array is written again
@@ -519,7 +542,7 @@ int32_t launch_fast(wgpu_ctx *ctx, const double *src, double *dst, int inverse, 
 {
     const int X = ctx->wavelet.X, Y = ctx->wavelet.Y;
     handled = false;
-    if (getenv("WGPU_WAVELET_GENERIC")) return WGPU_OK;   // tests compare the two paths
+    if (getenv("WGPU_WAVELET_GENERIC") && !ctx->has_jumps) return WGPU_OK;   // tests compare the two paths
     if (X == 2 && Y == 0) return launch_fast_bs<2, 0>(ctx, src, dst, inverse, handled);
     if (X == 2 && Y == 2) return launch_fast_bs<2, 2>(ctx, src, dst, inverse, handled);
     if (X == 4 && Y == 0) return launch_fast_bs<4, 0>(ctx, src, dst, inverse, handled);
@@ -669,8 +692,16 @@ int32_t wgpu_launch_wavelet(wgpu_ctx *ctx, const double *src, double *dst, int i
     }
     {
         bool handled = false;
+        if (ctx->has_jumps) {   // ghost values across level jumps (all 26 relations): decimation / prediction into the wavelet jump pool
+            int32_t rcj = wgpu_launch_wjump_fill(ctx, src);
+            if (rcj) return rcj;
+        }
         int32_t rc = launch_fast(ctx, src, dst, inverse, handled);
         if (rc || handled) return rc;
+        if (ctx->has_jumps) {
+            ctx->err = "wavelet transform on a grid with level jumps: only the specialised kernels (CDF20/22/40/42/44/60/62, Bs 16/18/20/24) are built";
+            return WGPU_ERR_UNSUPPORTED;
+        }
     }
     const int n = a.Bs + 2 * f;
     const size_t smem = sizeof(double) * ((size_t)2 * n * n + (size_t)n * a.Bs + (size_t)(2 * f + 2) * a.Bs * a.Bs);

@@ -118,6 +118,12 @@ struct wgpu_ctx {
     int *d_jump_blk = nullptr, *d_jump_dir = nullptr;
     double *d_jpool = nullptr;
     size_t jpool_cap = 0;
+    // level-jump ghost patches of the wavelet kernels: all 26 relations, wjump_depth deep (the widest wavelet filter)
+    int n_wjump = 0, wjump_cap = 0, wjump_depth = 0;
+    int *d_wjump_blk = nullptr, *d_wjump_dir = nullptr, *d_wnbr = nullptr;
+    long long *d_woff = nullptr;
+    double *d_wpool = nullptr;
+    size_t wpool_cap = 0;
     bool has_jumps = false;            // some active block has a coarser / finer neighbour
     bool lookup_ready = false;         // block lookup + coordinates of the current topology are on the device
     int *d_idbuf[3] = {nullptr, nullptr, nullptr};   // scratch id lists (refine / coarsen)
@@ -170,6 +176,7 @@ int32_t wgpu_launch_stage(wgpu_ctx *ctx, const StageArgs &a, int n_blocks);
 int32_t wgpu_launch_pack(wgpu_ctx *ctx, const double *src);
 // jump.cu
 int32_t wgpu_launch_jump_fill(wgpu_ctx *ctx, const double *src);
+int32_t wgpu_launch_wjump_fill(wgpu_ctx *ctx, const double *src);
 int32_t wgpu_launch_export_regions(wgpu_ctx *ctx, const double *src, double *staged, const int *d_ids, int n, int ncomp_src, int ncomp_host,
                                    int g_sync, int by_id);
 int32_t wgpu_launch_refine(wgpu_ctx *ctx, const double *src, double *dst, const int *d_mother, const int *d_daughter, int n);
