@@ -88,3 +88,39 @@ class Forest:
         out = np.full((168, self.max_blocks), -1, np.int32)
         host_lib().whost_get_neighbors(self._h, rank, _i32(out))
         return out
+
+
+def coarsening_groups(forest: "Forest", status: np.ndarray, Jmin: int = 1):
+    """Host-side adapt logic for ONE coarsening sweep on a leaf grid (stand-in for respectJmaxJmin_tree, ensureCompleteness
+    and ensureGradedness_tree, LIB/MESH/respectJmaxJmin_tree.f90, ensureGradedness_tree.f90:13): returns the final
+    refinement status per active block -- -1 only for blocks whose 2^dim sisters all carry -1, sit above Jmin, and whose
+    mother would not end up two levels coarser than any neighbour that stays.  Light data only; no heavy data is touched."""
+    hvy, lvl, ixyz, _ = forest.active(0)
+    n, dim, nd = len(hvy), forest.dim, 2 ** forest.dim
+    st = np.where((np.asarray(status) == -1) & (lvl > Jmin), -1, 0).astype(np.int32)
+    nbr = forest.neighbors(0)[:, :n]                      # [168, n], 1-based ids (single rank: lgt id == hvy id)
+    pos = {int(h): k for k, h in enumerate(hvy)}
+    key = lambda k: (int(lvl[k]) - 1, int(ixyz[k, 0]) // 2, int(ixyz[k, 1]) // 2, int(ixyz[k, 2]) // 2)
+    changed = True
+    while changed:
+        changed = False
+        groups = {}
+        for k in range(n):
+            if st[k] == -1:
+                groups.setdefault(key(k), []).append(k)
+        for m, ks in groups.items():
+            ok = len(ks) == nd                            # completeness: all sisters are leaves and want to coarsen
+            if ok:
+                for k in ks:                              # gradedness: a finer neighbour must itself coarsen (to this level)
+                    for slot in range(112, 168):
+                        j = nbr[slot, k]
+                        if j >= 1 and st[pos[int(j)]] != -1:
+                            ok = False
+                            break
+                    if not ok:
+                        break
+            if not ok:
+                for k in ks:
+                    st[k] = 0
+                changed = True
+    return st

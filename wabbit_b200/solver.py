@@ -16,7 +16,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from ._native import WgpuConfig, gpu_lib
-from .forest import Forest
+from .forest import Forest, coarsening_groups
 from .params import Params
 
 HVY_BLOCK, HVY_WORK, HVY_MASK, HVY_TMP = 0, 1, 2, 3
@@ -283,6 +283,33 @@ class WabbitGPU:
         self._check(self._lib.wgpu_coarsen(self._ctx, len(mo), _i32(mo), _i32(da), decomposed[0], decomposed[1]))
         self.set_forest(new)
         return new
+
+    def adapt_tree(self, forest: Forest, eps: Optional[float] = None, eps_normalized: bool = True, eps_norm: str = "Linfty",
+                   Jmin: int = 1, force_maxlevel_dealiasing: bool = False, thresh_comp=None):
+        """One coarsening sweep of adapt_tree (LIB/MESH/adapt_tree.f90:11) with indicator "threshold-state-vector" for UNLIFTED
+        wavelets (CDFX0: no coarse extension, no security zone): componentWiseNorm_tree -> ghost synchronisation + wavelet
+        decomposition of every leaf -> threshold_block flags (device), then completeness / gradedness (host light data) and
+        executeCoarsening (device).  The reference's current adapt_tree decomposes the full tree and can remove several levels
+        in one call; this driver removes one level per call (call it again to go further) -- the per-block arithmetic is the same.
+        Returns (new forest, number of blocks before, after)."""
+        w = self.params.wavelet
+        if not (len(w) == 5 and w[4] == "0"):
+            raise WabbitAbort(1003, "adapt_tree: lifted wavelets need the coarse extension, which is not built yet")
+        hvy, lvl, _, _ = forest.active(0)
+        norm = None
+        if eps_normalized:
+            norm = self.componentWiseNorm_tree((HVY_BLOCK, 0), eps_norm)
+            norm[norm <= 1.0e-9] = 1.0                                        # coarseningIndicator_tree.f90:165-167
+        self.waveletDecomposition_tree((HVY_BLOCK, 0), (HVY_WORK, 2))
+        st = self.threshold_tree((HVY_WORK, 2), eps=eps, norm=norm, eps_norm=eps_norm, thresh_comp=thresh_comp, level_ref=forest.Jmax)
+        if force_maxlevel_dealiasing:
+            st = np.where(lvl == forest.Jmax, -1, st)                         # coarseningIndicator_tree.f90:307-309
+        st = coarsening_groups(forest, st, Jmin)
+        n0 = forest.n_blocks
+        if not (st == -1).any():
+            return forest, n0, n0
+        new = self.executeCoarsening_tree(forest, st, decomposed=(HVY_WORK, 2))
+        return new, n0, new.n_blocks
 
     def timeStep_tree(self, time: float, iteration: int):
         """timeStep_tree.f90:1 -- returns (time+dt, iteration+1, dt)."""
