@@ -60,6 +60,20 @@ int same_level_code(const int d[3])
     return code;
 }
 
+// hvy_work slots are allocated on first use: the Runge-Kutta driver needs only slot 2 (as the running final combination) for
+// tableaus whose stage inputs use the previous slope only (RK4, Heun, midpoint, Euler); general tableaus and explicit
+// wgpu_rhs / wgpu_upload / wavelet calls that name a slot allocate it then.  nullptr (+ ctx->err) if the device is out of memory.
+double *ensure_K(wgpu_ctx *ctx, int idx)
+{
+    if (idx < 0 || idx >= ctx->cfg.n_stages) return nullptr;
+    if (!ctx->K[idx]) {
+        const size_t n = (size_t)ctx->cfg.max_blocks * ctx->nc * ctx->blk_elems;
+        if (dmalloc(ctx, &ctx->K[idx], n) != WGPU_OK) return nullptr;
+        if (cudaMemsetAsync(ctx->K[idx], 0, n * sizeof(double), ctx->stream) != cudaSuccess) return nullptr;
+    }
+    return ctx->K[idx];
+}
+
 double *array_ptr(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int *ncomp)
 {
     const int s = ctx->cfg.n_stages;
@@ -68,7 +82,7 @@ double *array_ptr(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int *ncomp)
     case WGPU_HVY_WORK:
         *ncomp = ctx->nc;
         if (slot == 1) return ctx->U;   // hvy_work(...,1) is the copy of the state (runge_kutta_generic.f90:63-67)
-        if (slot >= 2 && slot <= s + 1) return ctx->K[slot - 2];
+        if (slot >= 2 && slot <= s + 1) return ensure_K(ctx, slot - 2);
         return nullptr;
     case WGPU_HVY_MASK: *ncomp = ctx->cfg.n_mask; return ctx->MASK;
     case WGPU_HVY_TMP: *ncomp = ctx->nc; return ctx->TMP;
@@ -334,7 +348,7 @@ int32_t wgpu_create(const wgpu_config *cfg, wgpu_ctx **out)
     A(&ctx->U, n);
     A(&ctx->UA, n);
     A(&ctx->UB, n);
-    for (int s = 0; s < cfg->n_stages; ++s) A(&ctx->K[s], n);
+    A(&ctx->K[0], n);   // further hvy_work slots: on first use (ensure_K)
     if (cfg->n_mask > 0) A(&ctx->MASK, (size_t)cfg->max_blocks * cfg->n_mask * ctx->blk_elems);
     if (rc == WGPU_OK) rc = dmalloc(ctx, &ctx->d_active, (size_t)cfg->max_blocks);
     if (rc == WGPU_OK) rc = dmalloc(ctx, &ctx->d_nbr, (size_t)cfg->max_blocks * WGPU_NDIR);
@@ -1152,7 +1166,8 @@ int32_t wgpu_rk_stage(wgpu_ctx *ctx, int32_t j, int32_t which)
     a.u_out = uout;
     const double *brow = c.butcher + (size_t)s * ld;          // final weights b_j = butcher(s+1, j+1)
     if (ctx->rk_subdiag) {
-        double *ACC = ctx->K[0];
+        double *ACC = ensure_K(ctx, 0);
+        if (!ACC) return fail(ctx, WGPU_ERR_CUDA, "out of device memory for hvy_work");
         if (!last) {
             const double *row = c.butcher + (size_t)j * ld;   // row of stage j+1
             a.use_self = fabs(row[j]) >= 1.0e-8;
@@ -1167,13 +1182,14 @@ int32_t wgpu_rk_stage(wgpu_ctx *ctx, int32_t j, int32_t which)
             a.coef_self = brow[j];
         }
     } else {
-        a.k_out = last ? nullptr : ctx->K[j - 1];              // the last slope only enters the final combination
+        a.k_out = last ? nullptr : ensure_K(ctx, j - 1);       // the last slope only enters the final combination
+        if (!last && !a.k_out) return fail(ctx, WGPU_ERR_CUDA, "out of device memory for hvy_work");
         // row of the tableau that forms u_out: stage j+1 input (row j+1) or the final weights (row s+1)
         const double *row = last ? brow : c.butcher + (size_t)j * ld;
         a.n_prev = 0;
         for (int l = 1; l < j; ++l) {
             if (fabs(row[l]) < 1.0e-8) continue;               // runge_kutta_generic.f90:99,144
-            a.k_prev[a.n_prev] = ctx->K[l - 1];
+            a.k_prev[a.n_prev] = ensure_K(ctx, l - 1);
             a.coef_prev[a.n_prev] = row[l];
             a.n_prev++;
         }
