@@ -319,8 +319,15 @@ def run_ours(a):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{a.cpu_steps} RK4 steps on {nbc} blocks (level {min(a.level, a.cpu_level)}) of the same workload; "
                                               "oracle C restatement, -O3 -march=native, OpenMP"}
-        print(json.dumps(line), flush=True)
     sol.close()
+    if rank == 0:
+        if world == 1 and not a.no_adaptive:
+            try:
+                del host, h_np
+                line["adaptive"] = adaptive_leg(a, local, stream)
+            except Exception as e:      # a secondary figure must not take the headline line down
+                line["adaptive"] = {"error": str(e)}
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -363,6 +370,86 @@ def wavelet_leg(a, sol, nb, stream, barrier, wavelet="CDF44", reps=20):
                          "algorithmic_bytes_per_block": bytes_fwt, "traffic": traffic}}
 
 
+def adaptive_leg(a, device_index, stream, eps=None, J0=5, Jmax=6, cycles=3, max_blocks=150000):
+    """BASELINE config 3's cycle on one GPU (the protocol of performance_test.f90: refine_tree("everywhere") -> timeStep_tree ->
+    adapt_tree), unlifted CDF40 (the coarse extension of lifted wavelets is not built): Taylor-Green + three Gaussian vortex blobs
+    on an equidistant level-J0 grid, coarsened by wavelet thresholding until the grid is stationary, then `cycles` timed cycles.
+    block-updates/s counts the blocks the Runge-Kutta step advances (Nb after refinement, as performance.t's Nb_rhs)."""
+    import torch
+    from wabbit_b200 import Forest, Params, WabbitGPU
+    eps = a.adaptive_eps if eps is None else eps
+    p = Params(dim=3, domain=(TWO_PI,) * 3, Bs=(a.bs,) * 3, wavelet="CDF40", g=3, g_rhs=2, n_eqn=4, Jmax=Jmax,
+               discretization="FD_4th_central", skew_symmetry=True, c0=10.0, nu=3.125e-3, gamma_p=0.0, CFL=1.0,
+               u_mean_set=(0.0, 0.0, 0.0), time_max=1.0e9).finalize()
+    forest = Forest.uniform(3, J0, Jmax=Jmax, max_blocks=max_blocks)
+    hvy, lvl, ixyz, _ = forest.active(0)
+    sol = WabbitGPU(p, max_blocks=max_blocks, device=device_index, stream=stream.cuda_stream)
+    sol.setup_wavelet("CDF40")
+    sol.set_forest(forest)
+    nb0 = len(hvy)
+    shape = (nb0,) + sol.host_shape()[1:]
+    host = torch.empty(shape, dtype=torch.float64, pin_memory=True)
+    h_np = host.numpy()
+    taylor_green_host(p, ixyz, lvl, h_np)
+    # three Gaussian vortex blobs (sigma = 0.15), centres from rng seed 1 (SURVEY 8d, config 3)
+    rng = np.random.default_rng(1)
+    centres = rng.random((3, 3)) * TWO_PI
+    g, Bs = p.g, a.bs
+    n = Bs + 2 * g
+    dx = TWO_PI / (2 ** J0 * Bs)
+    idx = torch.arange(n, dtype=torch.float64) - g
+    for s0 in range(0, nb0, 2048):
+        e = min(s0 + 2048, nb0)
+        x0 = torch.from_numpy((ixyz[s0:e] * Bs).astype(np.float64)) * dx
+        X = (idx[None, :] * dx + x0[:, 0:1])[:, None, None, :]
+        Y = (idx[None, :] * dx + x0[:, 1:2])[:, None, :, None]
+        Z = (idx[None, :] * dx + x0[:, 2:3])[:, :, None, None]
+        for c in centres:
+            r2 = (X - c[0]) ** 2 + (Y - c[1]) ** 2 + (Z - c[2]) ** 2
+            blob = torch.exp(-r2 / (2 * 0.15 ** 2))
+            host[s0:e, 0] += 2.0 * blob
+            host[s0:e, 1] -= blob
+            host[s0:e, 2] += 0.5 * blob
+    sol.upload_ptr(host.data_ptr(), shape[1], hvy_ids=hvy)
+    del host, h_np
+    import gc
+    gc.collect()                                # the page-locked initial-condition array is released before anything is timed
+    torch.cuda.synchronize()
+    sizes = [forest.n_blocks]
+    for _ in range(Jmax):                       # coarsen until the grid is stationary
+        forest, n0, n1 = sol.adapt_tree(forest, eps=eps, Jmin=1)
+        sizes.append(n1)
+        if n1 == n0:
+            break
+    t, it = 0.0, 0
+    recs = []
+    for cyc in range(cycles + 2):               # the first two cycles are the warm-up
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        forest = sol.refine_tree(forest)
+        nb_rhs = forest.n_blocks
+        torch.cuda.synchronize()
+        w1 = time.perf_counter()
+        t, it, _dt = sol.timeStep_tree(t, it)
+        torch.cuda.synchronize()
+        w2 = time.perf_counter()
+        forest, n0, n1 = sol.adapt_tree(forest, eps=eps, Jmin=1)
+        torch.cuda.synchronize()
+        w3 = time.perf_counter()
+        recs.append((nb_rhs, n1, w1 - w0, w2 - w1, w3 - w2))
+    sol.close()
+    recs = recs[2:]
+    tot = sum(r[2] + r[3] + r[4] for r in recs)
+    return {"metric": "adaptive block-updates/s (refine everywhere -> RK4 -> adapt, CDF40, 1 GPU)", "value": sum(r[0] for r in recs) / tot,
+            "unit": UNIT, "eps": eps, "Jmax": Jmax, "blocks_initial_coarsening": sizes, "cycles": len(recs),
+            "blocks_rhs": [r[0] for r in recs], "blocks_after_adapt": [r[1] for r in recs],
+            "ms_refine": [round(r[2] * 1e3, 2) for r in recs], "ms_rk4": [round(r[3] * 1e3, 2) for r in recs],
+            "ms_adapt": [round(r[4] * 1e3, 2) for r in recs],
+            "rk4_block_updates_per_s": sum(r[0] for r in recs) / sum(r[3] for r in recs),
+            "note": "refine / adapt times include the host light-data stand-ins (new forest, neighbour search, topology upload), which "
+                    "stay in host Fortran in a WABBIT build; ms_rk4 is the device-resident time step on the graded grid"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -376,8 +463,16 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=6)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-wavelet", action="store_true", help="skip the secondary FWT + threshold figure")
+    ap.add_argument("--no-adaptive", action="store_true", help="skip the secondary adaptive-cycle figure")
+    ap.add_argument("--adaptive-eps", type=float, default=1.0e-6)
+    ap.add_argument("--adaptive-only", action="store_true", help="run only the adaptive-cycle leg and print its record (development)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
+    if a.adaptive_only:
+        import torch
+        torch.cuda.set_device(0)
+        print(json.dumps(adaptive_leg(a, 0, torch.cuda.current_stream())), flush=True)
+        return
     if a.impl == "reference":
         run_reference(a)
     else:

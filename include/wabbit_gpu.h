@@ -156,7 +156,9 @@ int32_t wgpu_rk_step(wgpu_ctx *ctx, double time, int32_t iteration, double *dt);
  *   waveletReconstruction_optimized_block (LIB/WAVELETS/wavelet_decomposition_reconstruction.f90:23,426) together with
  *   the sync_ghosts_tree that precedes them (LIB/MESH/adapt_tree.f90:403-446, 813-843): dst = transform(src), result in
  *   spaghetti order (scaling coefficients at interior offsets 0,2,4,..).  src and dst must be different arrays.
- * wgpu_norm: componentWiseNorm_tree (LIB/OPERATORS/componentWiseNorm_tree.f90:1), norm_id 0 = Linfty; out[n_eqn].
+ * wgpu_norm: componentWiseNorm_tree (LIB/OPERATORS/componentWiseNorm_tree.f90:1) over the leaf interiors, every component on its own:
+ *   norm_id 0 Linfty (bit-exact), 1 L1, 2 L2, 3 H1 (= L2).  The sums are formed per block in a fixed order on the device and
+ *   added over the blocks in hvy_active order on the host: deterministic, equal to the reference's sequential sum to round-off.
  * wgpu_threshold: wavelet_renorm_block + threshold_block on a decomposed array (LIB/INDICATORS/threshold_block.f90:1-130,
  *   module_wavelets.f90:1848-1960): refinement_status[n_active] = -1 iff all(detail <= eps*norm) else 0, in the order of
  *   hvy_active; eps_norm_id 0 Linfty / 1 L1 / 2 L2 / 3 H1; thresh_comp = params%threshold_state_vector_component;

@@ -40,10 +40,26 @@ int32_t whost_n_blocks(const whost_forest *f);                 /* lgt_n */
 int32_t whost_n_active(const whost_forest *f, int32_t rank);   /* hvy_n of a rank */
 /* per rank, in SFC order: hvy ids (1-based), level, zero-based block coordinates, treecode */
 int32_t whost_get_active(const whost_forest *f, int32_t rank, int32_t *hvy_active, int32_t *level, int32_t *ixyz, int64_t *treecode);
-/* hvy_neighbor(max_blocks_per_rank, 168) of a rank, Fortran column-major, lgt ids, -1 = none */
+/* hvy_neighbor(ld, 168) of a rank, ld = whost_n_active(f, rank) (hvy ids are 1..ld), Fortran column-major, lgt ids
+ * (rank*max_blocks_per_rank + hvy), -1 = none */
 int32_t whost_get_neighbors(const whost_forest *f, int32_t rank, int32_t *hvy_neighbor);
 /* 1 if every neighbour relation of every block is same-level */
 int32_t whost_is_uniform(const whost_forest *f);
+
+/*
+ * Grid adaptation, light data only, single rank (n_ranks == 1).  Stand-ins for the id bookkeeping of refinement_execute_tree +
+ * balanceLoad_tree and for respectJmaxJmin_tree / completeness / ensureGradedness_tree; they produce the id lists that
+ * wgpu_refine / wgpu_move_blocks / wgpu_coarsen consume (all hvy ids 1-based).
+ *   whost_refine : flags[n] > 0 (NULL = everywhere) marks blocks to refine (blocks on Jmax are skipped).  mothers[nm] are old ids,
+ *                  daughters[nm*2^dim] new ids in digit order, keep_src/keep_dst[nk] old -> new ids of the other blocks.
+ *   whost_coarsen: status[n] in: -1 = wants to coarsen; out: final status (-1 only for complete sister groups above Jmin whose
+ *                  finer neighbours coarsen too).  mothers[nm] are new ids, daughters[nm*2^dim] OLD ids in digit order.
+ * Output arrays must hold n entries (daughters: n); returns 2 if the new grid needs more than max_blocks blocks.
+ */
+int32_t whost_refine(const whost_forest *f, const int32_t *flags, int32_t max_blocks, whost_forest **out, int32_t *n_mothers, int32_t *mothers,
+                     int32_t *daughters, int32_t *n_keep, int32_t *keep_src, int32_t *keep_dst);
+int32_t whost_coarsen(const whost_forest *f, int32_t *status, int32_t Jmin, int32_t max_blocks, whost_forest **out, int32_t *n_mothers,
+                      int32_t *mothers, int32_t *daughters, int32_t *n_keep, int32_t *keep_src, int32_t *keep_dst);
 
 /* treecode helpers (module_treelib.f90:793-871) */
 int64_t whost_encode(int32_t dim, int32_t level, int32_t Jmax, const int32_t ixyz[3]);

@@ -148,3 +148,39 @@ def test_fast_and_generic_kernels_agree(name, Bs):
     assert np.array_equal(out["fast"][0], out["generic"][0])
     assert np.array_equal(out["fast"][1], out["generic"][1])
     sol.close()
+
+
+def test_componentwise_norms_l1_l2_on_graded_grid():
+    """componentWiseNorm_tree L1 / L2 (volume-weighted sums over leaf interiors) against a NumPy restatement of
+    componentWiseNorm_tree.f90:150-197, 283-290; Linfty bit-exact."""
+    from util import graded_blocks
+    from wabbit_b200 import Forest, WabbitGPU
+    lv, ix = graded_blocks(3, 1, 3, seed=21)
+    forest = Forest.from_blocks(3, 3, lv, ix)
+    w = O.setup_wavelet("CDF40")
+    from util import tg_params, orc_grid, orc_params
+    p = tg_params(Bs=16, J=3, wavelet_g=3)
+    p.wavelet = "CDF40"
+    po, grid = orc_params(p), orc_grid(forest)
+    sol = WabbitGPU(p, max_blocks=forest.n_blocks)
+    sol.setup_wavelet("CDF40")
+    sol.set_forest(forest)
+    u = np.random.default_rng(2).standard_normal(sol.host_shape())
+    sol.upload(u)
+    I = O.interior(po)
+    l1 = np.zeros(4)
+    l2 = np.zeros(4)
+    for b in range(grid.n):
+        _, dx = grid.spacing_origin(po, b)
+        dv = dx[0] * dx[1] * dx[2]
+        for c in range(4):
+            blk = u[b, c][I]
+            l1[c] += dv * np.abs(blk).sum()
+            l2[c] += dv * (blk ** 2).sum()
+    l2 = np.sqrt(l2)
+    assert np.allclose(sol.componentWiseNorm_tree(norm="L1"), l1, rtol=1e-12, atol=0)
+    assert np.allclose(sol.componentWiseNorm_tree(norm="L2"), l2, rtol=1e-12, atol=0)
+    assert np.array_equal(sol.componentWiseNorm_tree(norm="Linfty"), O.norm_linfty_tree(po, u[:grid.n]))
+    a = sol.componentWiseNorm_tree(norm="L2")
+    assert np.array_equal(a, sol.componentWiseNorm_tree(norm="L2"))      # deterministic
+    sol.close()

@@ -34,7 +34,7 @@ def _stale(out: str, srcs) -> bool:
 def build_host(force: bool = False) -> str:
     srcs = [os.path.join(CSRC, s) for s in HOST_SRCS]
     if force or _stale(HOST_LIB, srcs):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", INCLUDE, "-o", HOST_LIB, *srcs])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-I", INCLUDE, "-o", HOST_LIB, *srcs])
     return HOST_LIB
 
 

@@ -869,11 +869,29 @@ int32_t wgpu_iwt(wgpu_ctx *ctx, int32_t src_id, int32_t src_slot, int32_t dst_id
 int32_t wgpu_norm(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t norm_id, double *out)
 {
     if (!ctx || !out) return WGPU_ERR_ARG;
-    if (norm_id != 0) return fail(ctx, WGPU_ERR_UNSUPPORTED, "wgpu_norm: only Linfty is built");
+    if (norm_id < 0 || norm_id > 3) return fail(ctx, WGPU_ERR_ARG, "wgpu_norm: norm_id must be 0 Linfty, 1 L1, 2 L2 or 3 H1");
     if (!ctx->wavelet_set) return fail(ctx, 1213149, "The cat is angry: Wavelet-setup not yet called?");
     int n1 = 0;
     const double *src = array_ptr(ctx, array_id, slot, &n1);
     if (!src || n1 != ctx->nc) return fail(ctx, WGPU_ERR_ARG, "wgpu_norm: bad array/slot");
+    if (norm_id != 0) {
+        // L1: sum |u| dV; L2 / H1: sqrt(sum u^2 dV)   (componentWiseNorm_tree.f90:150-197, 283-290), dV = prod(dx) of the block's level
+        int32_t rcs = wgpu_launch_blocksum(ctx, src, norm_id != 1, ctx->d_detail_out);
+        if (rcs) return rcs;
+        std::vector<double> part((size_t)ctx->n_active * ctx->nc);
+        WGPU_CHECK(ctx, cudaMemcpyAsync(part.data(), ctx->d_detail_out, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        const wgpu_config &c = ctx->cfg;
+        for (int p = 0; p < ctx->nc; ++p) out[p] = 0.0;
+        for (int k = 0; k < ctx->n_active; ++k) {
+            double dv = 1.0;
+            for (int d = 0; d < c.dim; ++d) dv *= ldexp(1.0, -ctx->h_level[ctx->h_active[k]]) * c.domain[d] / (double)c.Bs[d];
+            for (int p = 0; p < ctx->nc; ++p) out[p] = out[p] + dv * part[(size_t)k * ctx->nc + p];
+        }
+        if (norm_id != 1)
+            for (int p = 0; p < ctx->nc; ++p) out[p] = sqrt(out[p]);
+        return WGPU_OK;
+    }
     WGPU_CHECK(ctx, cudaMemsetAsync(ctx->d_norm, 0, 16 * sizeof(unsigned long long), ctx->stream));
     int32_t rc = wgpu_launch_linfty(ctx, src, ctx->d_norm);
     if (rc) return rc;

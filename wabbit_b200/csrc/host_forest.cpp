@@ -7,6 +7,7 @@
 #include <array>
 #include <numeric>
 #include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "wabbit_host.h"
@@ -61,14 +62,44 @@ struct whost_forest {
     int periodic[3];
     std::vector<Blk> blocks;                       // SFC order
     std::vector<std::vector<int>> rank_blocks;     // indices into blocks per rank
-    std::unordered_map<uint64_t, int> lookup;
+    // open-addressing lookup (level, ix) -> index into blocks; read-only after build(), so the neighbour search can run in parallel
+    std::vector<uint64_t> hkeys;
+    std::vector<int> hvals;
+    uint64_t hmask = 0;
     std::vector<std::vector<int32_t>> nbr;         // per rank: N*168
     bool uniform = true;
 
+    static uint64_t mix(uint64_t k)
+    {
+        k ^= k >> 33;
+        k *= 0xff51afd7ed558ccdULL;
+        k ^= k >> 33;
+        return k;
+    }
+    void lookup_build()
+    {
+        uint64_t cap = 64;
+        while (cap < blocks.size() * 2 + 2) cap <<= 1;
+        hkeys.assign(cap, ~0ull);
+        hvals.assign(cap, -1);
+        hmask = cap - 1;
+        for (int i = 0; i < (int)blocks.size(); ++i) {
+            const uint64_t key = pos_hash(blocks[i].level, blocks[i].ix);
+            uint64_t h = mix(key) & hmask;
+            while (hkeys[h] != ~0ull && hkeys[h] != key) h = (h + 1) & hmask;
+            hkeys[h] = key;
+            hvals[h] = i;
+        }
+    }
     int find(int level, const int ix[3]) const
     {
-        auto it = lookup.find(pos_hash(level, ix));
-        return it == lookup.end() ? -1 : it->second;
+        const uint64_t key = pos_hash(level, ix);
+        uint64_t h = mix(key) & hmask;
+        while (hkeys[h] != ~0ull) {
+            if (hkeys[h] == key) return hvals[h];
+            h = (h + 1) & hmask;
+        }
+        return -1;
     }
 };
 
@@ -123,17 +154,22 @@ static void build(whost_forest *f)
             f->rank_blocks[r].push_back(pos);
         }
     }
-    f->lookup.clear();
-    for (int i = 0; i < nb; ++i) f->lookup[pos_hash(f->blocks[i].level, f->blocks[i].ix)] = i;
+    f->lookup_build();
 
     // neighbour search, one direction at a time (find_neighbor, LIB/MESH/find_neighbors.f90:18-180)
-    f->nbr.assign(f->n_ranks, std::vector<int32_t>((size_t)f->N * 168, -1));
+    // hvy_neighbor(ld, 168) per rank with ld = number of active blocks of the rank (hvy ids are 1..ld): the table costs
+    // 672 B per block instead of 672 B per allocated slot
+    f->nbr.resize(f->n_ranks);
+    for (int r = 0; r < f->n_ranks; ++r) f->nbr[r].assign(f->rank_blocks[r].size() * 168, -1);
     f->uniform = true;
     const int vary_tc[3] = {2, 1, 4};   // digit bit of x, y, z
+    int any_jump = 0;
+#pragma omp parallel for schedule(static) reduction(| : any_jump)
     for (int i = 0; i < nb; ++i) {
         const Blk &b = f->blocks[i];
         int32_t *row = f->nbr[b.rank].data();
-        auto set = [&](int code, int j) { row[(size_t)(code - 1) * f->N + (b.hvy - 1)] = f->blocks[j].rank * f->N + f->blocks[j].hvy; };
+        const size_t ld = f->rank_blocks[b.rank].size();
+        auto set = [&](int code, int j) { row[(size_t)(code - 1) * ld + (b.hvy - 1)] = f->blocks[j].rank * f->N + f->blocks[j].hvy; };
         const int tc_last = b.level > 0 ? (int)((b.tc >> ((f->Jmax - b.level) * dim)) & ((1 << dim) - 1)) : 0;
         for (int dz = (dim == 3 ? -1 : 0); dz <= (dim == 3 ? 1 : 0); ++dz)
             for (int dy = -1; dy <= 1; ++dy)
@@ -213,7 +249,7 @@ static void build(whost_forest *f)
                             if (j < 0) break;
                             set(code + k + 112, j);
                             found_finer = true;
-                            f->uniform = false;
+                            any_jump |= 1;
                         }
                     }
                     if (found_finer) continue;
@@ -223,11 +259,12 @@ static void build(whost_forest *f)
                         j = f->find(b.level - 1, q);
                         if (j >= 0) {
                             set(code_coarser + 56, j);
-                            f->uniform = false;
+                            any_jump |= 1;
                         }
                     }
                 }
     }
+    f->uniform = !any_jump;
 }
 
 int32_t whost_create_from_blocks(int32_t dim, int32_t Jmax, int32_t sfc, int32_t n_ranks, int32_t N, const int32_t periodic[3], int32_t n,
@@ -309,5 +346,150 @@ int32_t whost_get_neighbors(const whost_forest *f, int32_t rank, int32_t *hvy_ne
 }
 
 int32_t whost_is_uniform(const whost_forest *f) { return f && f->uniform ? 1 : 0; }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Grid adaptation, light data only (single rank).  Stand-ins for refinement_execute_tree's id bookkeeping +
+// balanceLoad_tree (LIB/MESH/refinementExecute.f90, balanceLoad_tree.f90) and for respectJmaxJmin_tree / completeness /
+// ensureGradedness_tree (LIB/MESH/ensureGradedness_tree.f90:13) so that the drivers of this repository run at 10^5 blocks
+// without a Python loop.  In a WABBIT build this logic stays in host Fortran.
+// ---------------------------------------------------------------------------------------------------------------------
+static whost_forest *clone_with_blocks(const whost_forest *f, int32_t N, std::vector<Blk> &&blocks)
+{
+    whost_forest *g = new whost_forest();
+    g->dim = f->dim;
+    g->Jmax = f->Jmax;
+    g->sfc = f->sfc;
+    g->n_ranks = 1;
+    g->N = N;
+    for (int a = 0; a < 3; ++a) g->periodic[a] = f->periodic[a];
+    g->blocks = std::move(blocks);
+    build(g);
+    return g;
+}
+
+int32_t whost_refine(const whost_forest *f, const int32_t *flags, int32_t max_blocks, whost_forest **out, int32_t *n_mothers, int32_t *mothers,
+                     int32_t *daughters, int32_t *n_keep, int32_t *keep_src, int32_t *keep_dst)
+{
+    if (!f || !out || f->n_ranks != 1 || !n_mothers || !n_keep) return 1;
+    const int dim = f->dim, nd = 1 << dim, n = (int)f->blocks.size();
+    std::vector<Blk> nb;
+    nb.reserve((size_t)n * nd);
+    std::vector<char> ref(n, 0);
+    for (int k = 0; k < n; ++k) {   // blocks are in SFC order == hvy order on a single rank
+        const Blk &b = f->blocks[k];
+        ref[k] = (!flags || flags[k] > 0) && b.level < f->Jmax;   // respectJmaxJmin_tree
+        if (!ref[k]) {
+            nb.push_back(b);
+            continue;
+        }
+        for (int d = 0; d < nd; ++d) {
+            Blk c = b;
+            c.level = b.level + 1;
+            c.ix[0] = 2 * b.ix[0] + ((d >> 1) & 1);   // digit: bit0 -> y, bit1 -> x, bit2 -> z
+            c.ix[1] = 2 * b.ix[1] + (d & 1);
+            c.ix[2] = dim == 3 ? 2 * b.ix[2] + ((d >> 2) & 1) : 0;
+            nb.push_back(c);
+        }
+    }
+    if ((int64_t)nb.size() > max_blocks) return 2;   // error_OOM of refine_tree
+    whost_forest *g = clone_with_blocks(f, max_blocks, std::move(nb));
+    int nm = 0, nk = 0;
+    for (int k = 0; k < n; ++k) {
+        const Blk &b = f->blocks[k];
+        if (!ref[k]) {
+            if (keep_src) keep_src[nk] = b.hvy;
+            if (keep_dst) keep_dst[nk] = g->blocks[g->find(b.level, b.ix)].hvy;
+            ++nk;
+            continue;
+        }
+        if (mothers) mothers[nm] = b.hvy;
+        for (int d = 0; d < nd; ++d) {
+            const int ix[3] = {2 * b.ix[0] + ((d >> 1) & 1), 2 * b.ix[1] + (d & 1), dim == 3 ? 2 * b.ix[2] + ((d >> 2) & 1) : 0};
+            if (daughters) daughters[(size_t)nm * nd + d] = g->blocks[g->find(b.level + 1, ix)].hvy;
+        }
+        ++nm;
+    }
+    *n_mothers = nm;
+    *n_keep = nk;
+    *out = g;
+    return 0;
+}
+
+int32_t whost_coarsen(const whost_forest *f, int32_t *status, int32_t Jmin, int32_t max_blocks, whost_forest **out, int32_t *n_mothers,
+                      int32_t *mothers, int32_t *daughters, int32_t *n_keep, int32_t *keep_src, int32_t *keep_dst)
+{
+    if (!f || !out || !status || f->n_ranks != 1 || !n_mothers || !n_keep) return 1;
+    const int dim = f->dim, nd = 1 << dim, n = (int)f->blocks.size();
+    const int32_t *nbr = f->nbr[0].data();
+    for (int k = 0; k < n; ++k) status[k] = (status[k] == -1 && f->blocks[k].level > Jmin) ? -1 : 0;
+    auto mkey = [&](const Blk &b) {
+        const int m[3] = {b.ix[0] >> 1, b.ix[1] >> 1, b.ix[2] >> 1};
+        return pos_hash(b.level - 1, m);
+    };
+    bool changed = true;
+    std::unordered_map<uint64_t, std::vector<int>> groups;
+    while (changed) {
+        changed = false;
+        groups.clear();
+        for (int k = 0; k < n; ++k)
+            if (status[k] == -1) groups[mkey(f->blocks[k])].push_back(k);
+        for (auto &kv : groups) {
+            bool ok = (int)kv.second.size() == nd;                     // completeness: all sisters are leaves that want to coarsen
+            for (size_t i = 0; ok && i < kv.second.size(); ++i) {
+                const int k = kv.second[i];
+                for (int slot = 112; slot < 168 && ok; ++slot) {       // gradedness: a finer neighbour must coarsen as well
+                    const int j = nbr[(size_t)slot * n + k];
+                    if (j >= 1 && status[j - 1] != -1) ok = false;
+                }
+            }
+            if (!ok) {
+                for (int k : kv.second) status[k] = 0;
+                changed = true;
+            }
+        }
+    }
+    std::vector<Blk> nb;
+    nb.reserve(n);
+    std::vector<std::pair<uint64_t, Blk>> moth;
+    for (int k = 0; k < n; ++k) {
+        const Blk &b = f->blocks[k];
+        if (status[k] != -1) {
+            nb.push_back(b);
+            continue;
+        }
+        const int d = (b.ix[1] & 1) | ((b.ix[0] & 1) << 1) | ((dim == 3 ? b.ix[2] & 1 : 0) << 2);
+        if (d == 0) {   // one mother per group
+            Blk m = b;
+            m.level = b.level - 1;
+            for (int a = 0; a < 3; ++a) m.ix[a] = b.ix[a] >> 1;
+            nb.push_back(m);
+        }
+    }
+    if ((int64_t)nb.size() > max_blocks) return 2;
+    whost_forest *g = clone_with_blocks(f, max_blocks, std::move(nb));
+    int nm = 0, nk = 0;
+    for (int k = 0; k < n; ++k) {
+        const Blk &b = f->blocks[k];
+        if (status[k] != -1) {
+            if (keep_src) keep_src[nk] = b.hvy;
+            if (keep_dst) keep_dst[nk] = g->blocks[g->find(b.level, b.ix)].hvy;
+            ++nk;
+            continue;
+        }
+        const int d = (b.ix[1] & 1) | ((b.ix[0] & 1) << 1) | ((dim == 3 ? b.ix[2] & 1 : 0) << 2);
+        if (d != 0) continue;
+        const int mix[3] = {b.ix[0] >> 1, b.ix[1] >> 1, b.ix[2] >> 1};
+        if (mothers) mothers[nm] = g->blocks[g->find(b.level - 1, mix)].hvy;
+        for (int dd = 0; dd < nd; ++dd) {
+            const int ix[3] = {2 * mix[0] + ((dd >> 1) & 1), 2 * mix[1] + (dd & 1), dim == 3 ? 2 * mix[2] + ((dd >> 2) & 1) : 0};
+            if (daughters) daughters[(size_t)nm * nd + dd] = f->blocks[f->find(b.level, ix)].hvy;
+        }
+        ++nm;
+    }
+    *n_mothers = nm;
+    *n_keep = nk;
+    *out = g;
+    return 0;
+}
 
 }  // extern "C"

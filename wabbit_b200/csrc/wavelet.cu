@@ -666,7 +666,38 @@ __global__ void __launch_bounds__(256) linfty_kernel(const double *__restrict__ 
     }
 }
 
+// componentWiseNorm_tree, L1 / L2: per (block, component) sum of |u| or u^2 in a fixed order (strided partial sums, shuffle tree,
+// warp partials in order), so the result does not depend on scheduling; the host adds the block sums weighted by the cell volume
+// in the order of hvy_active, as the reference's loop does (componentWiseNorm_tree.f90:150-197)
+__global__ void __launch_bounds__(256) blocksum_kernel(const double *__restrict__ u, const int *__restrict__ active, int nc, long long CS, int squared,
+                                                       double *__restrict__ out)
+{
+    __shared__ double s[8];
+    const int b = active[blockIdx.x], c = blockIdx.y;
+    const double *p = u + ((long long)b * nc + c) * CS;
+    double m = 0.0;
+    for (long long i = threadIdx.x; i < CS; i += blockDim.x) m += squared ? p[i] * p[i] : fabs(p[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m += s[i];
+        out[(long long)blockIdx.x * nc + c] = m;
+    }
+}
+
 }  // namespace
+
+int32_t wgpu_launch_blocksum(wgpu_ctx *ctx, const double *u, int squared, double *d_out)
+{
+    if (ctx->n_active == 0) return WGPU_OK;
+    dim3 grid(ctx->n_active, ctx->nc);
+    blocksum_kernel<<<grid, 256, 0, ctx->stream>>>(u, ctx->d_active, ctx->nc, ctx->blk_elems, squared, d_out);
+    ctx->launches++;
+    WGPU_CHECK(ctx, cudaGetLastError());
+    return WGPU_OK;
+}
 
 int32_t wgpu_launch_wavelet(wgpu_ctx *ctx, const double *src, double *dst, int inverse)
 {

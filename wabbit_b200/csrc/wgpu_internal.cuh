@@ -187,6 +187,7 @@ int32_t wgpu_launch_wavelet(wgpu_ctx *ctx, const double *src, double *dst, int i
 int32_t wgpu_launch_detail(wgpu_ctx *ctx, const double *wd, int eps_norm, int level_ref);
 int32_t wgpu_launch_flags(wgpu_ctx *ctx, const int32_t *thresh_comp, const double *eps_use, int *d_status, double *d_detail_out);
 int32_t wgpu_launch_linfty(wgpu_ctx *ctx, const double *u, unsigned long long *d_out);
+int32_t wgpu_launch_blocksum(wgpu_ctx *ctx, const double *u, int squared, double *d_out);
 int32_t wgpu_launch_dtmin(wgpu_ctx *ctx, const double *u, unsigned long long *dtmin_bits);
 int32_t wgpu_launch_dt_finalize(wgpu_ctx *ctx, double time, const unsigned long long *dtmin_bits,
                                 unsigned long long *dtmin_next);

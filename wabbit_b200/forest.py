@@ -54,6 +54,40 @@ class Forest:
             raise RuntimeError(f"whost_create_from_blocks failed with code {rc}")
         return cls(h, dim, Jmax, n_ranks, max_blocks, block_dist, periodic)
 
+    # ------------------------------------------------------------------ grid adaptation (light data, single rank)
+    def refine(self, flags=None, max_blocks: Optional[int] = None):
+        """New forest with the flagged blocks (None: all below Jmax) replaced by their 2^dim daughters, ordered along the SFC, plus
+        the id lists wgpu_refine consumes: (new_forest, mothers, daughters, keep_src, keep_dst), all 1-based hvy ids."""
+        n, nd = self.n_active(0), 2 ** self.dim
+        N = max_blocks or self.max_blocks
+        fl = None if flags is None else np.ascontiguousarray(flags, dtype=np.int32)
+        mo, da = np.zeros(n, np.int32), np.zeros(n * nd, np.int32)
+        ks, kd = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        nm, nk = C.c_int32(), C.c_int32()
+        h = C.c_void_p()
+        rc = host_lib().whost_refine(self._h, None if fl is None else _i32(fl), N, C.byref(h), C.byref(nm), _i32(mo), _i32(da), C.byref(nk),
+                                     _i32(ks), _i32(kd))
+        if rc:
+            raise MemoryError("refine: the refined grid needs more than max_blocks blocks") if rc == 2 else RuntimeError(f"whost_refine: {rc}")
+        new = Forest(h, self.dim, self.Jmax, 1, N, self.block_dist, self.periodic)
+        return new, mo[:nm.value], da[:nm.value * nd], ks[:nk.value], kd[:nk.value]
+
+    def coarsen(self, status, Jmin: int = 1, max_blocks: Optional[int] = None):
+        """Final refinement status (completeness, gradedness, Jmin) and the coarsened forest with the id lists wgpu_move_blocks /
+        wgpu_coarsen consume: (new_forest, final_status, mothers[new ids], daughters[old ids], keep_src, keep_dst)."""
+        n, nd = self.n_active(0), 2 ** self.dim
+        N = max_blocks or self.max_blocks
+        st = np.ascontiguousarray(status, dtype=np.int32).copy()
+        mo, da = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        ks, kd = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        nm, nk = C.c_int32(), C.c_int32()
+        h = C.c_void_p()
+        rc = host_lib().whost_coarsen(self._h, _i32(st), Jmin, N, C.byref(h), C.byref(nm), _i32(mo), _i32(da), C.byref(nk), _i32(ks), _i32(kd))
+        if rc:
+            raise RuntimeError(f"whost_coarsen: {rc}")
+        new = Forest(h, self.dim, self.Jmax, 1, N, self.block_dist, self.periodic)
+        return new, st, mo[:nm.value], da[:nm.value * nd], ks[:nk.value], kd[:nk.value]
+
     def __del__(self):
         try:
             if self._h:
@@ -84,8 +118,8 @@ class Forest:
         return hvy, lvl, ixyz, tc
 
     def neighbors(self, rank: int = 0) -> np.ndarray:
-        """hvy_neighbor as an array [168, max_blocks] (== Fortran hvy_neighbor(max_blocks,168)), lgt ids, -1 none."""
-        out = np.full((168, self.max_blocks), -1, np.int32)
+        """hvy_neighbor as an array [168, n_active(rank)] (== Fortran hvy_neighbor(1:hvy_n,168)), lgt ids, -1 none."""
+        out = np.empty((168, self.n_active(rank)), np.int32)
         host_lib().whost_get_neighbors(self._h, rank, _i32(out))
         return out
 

@@ -16,7 +16,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from ._native import WgpuConfig, gpu_lib
-from .forest import Forest, coarsening_groups
+from .forest import Forest
 from .params import Params
 
 HVY_BLOCK, HVY_WORK, HVY_MASK, HVY_TMP = 0, 1, 2, 3
@@ -211,75 +211,22 @@ class WabbitGPU:
         active block (the result of refinementIndicator_tree + ensureGradedness_tree, host logic): respectJmaxJmin_tree drops the
         flag of blocks on Jmax, refinement_execute_tree -> refineBlock runs on the device, the new grid is ordered along the
         space-filling curve (balanceLoad_tree) and uploaded.  Returns the new forest."""
-        hvy, lvl, ixyz, _ = forest.active(0)
-        n, dim, nd = len(hvy), forest.dim, 2 ** forest.dim
-        flags = np.ones(n, bool) if refine_flags is None else (np.asarray(refine_flags) > 0)
-        flags = flags & (lvl < forest.Jmax)                                   # respectJmaxJmin_tree.f90
-        new_lvl, new_ix = [], []
-        for k in range(n):
-            if flags[k]:
-                for d in range(nd):                                           # digit: bit0 -> y, bit1 -> x, bit2 -> z
-                    q = ((d >> 1) & 1, d & 1, (d >> 2) & 1)
-                    new_lvl.append(lvl[k] + 1)
-                    new_ix.append((2 * ixyz[k, 0] + q[0], 2 * ixyz[k, 1] + q[1], 2 * ixyz[k, 2] + q[2] if dim == 3 else 0))
-            else:
-                new_lvl.append(lvl[k])
-                new_ix.append(tuple(ixyz[k]))
-        if len(new_lvl) > self.max_blocks:
-            raise WabbitAbort(1909181740, "refine_tree: not enough memory (number_blocks) for the refined grid")   # error_OOM
-        new = Forest.from_blocks(dim, forest.Jmax, new_lvl, new_ix, block_dist=forest.block_dist, max_blocks=self.max_blocks,
-                                 periodic=forest.periodic)
-        nh, nl, nix, _ = new.active(0)
-        where = {(int(l), int(a), int(b), int(c)): int(h) for h, l, (a, b, c) in zip(nh, nl, nix)}
-        mothers, daughters, ksrc, kdst = [], [], [], []
-        for k in range(n):
-            if flags[k]:
-                mothers.append(hvy[k])
-                for d in range(nd):
-                    q = ((d >> 1) & 1, d & 1, (d >> 2) & 1)
-                    daughters.append(where[(int(lvl[k]) + 1, 2 * int(ixyz[k, 0]) + q[0], 2 * int(ixyz[k, 1]) + q[1],
-                                            2 * int(ixyz[k, 2]) + q[2] if dim == 3 else 0)])
-            else:
-                ksrc.append(hvy[k])
-                kdst.append(where[(int(lvl[k]), int(ixyz[k, 0]), int(ixyz[k, 1]), int(ixyz[k, 2]))])
-        mo, da = np.asarray(mothers, np.int32), np.asarray(daughters, np.int32)
-        ks, kd = np.asarray(ksrc, np.int32), np.asarray(kdst, np.int32)
+        try:
+            new, mo, da, ks, kd = forest.refine(refine_flags, max_blocks=self.max_blocks)
+        except MemoryError as e:
+            raise WabbitAbort(1909181740, f"refine_tree: {e}")                  # error_OOM
         self._check(self._lib.wgpu_refine(self._ctx, len(mo), _i32(mo), _i32(da), len(ks), _i32(ks), _i32(kd)))
         self.set_forest(new)
         return new
 
-    def executeCoarsening_tree(self, forest: Forest, coarsen_flags: np.ndarray, decomposed=(HVY_WORK, 2)) -> Forest:
-        """executeCoarsening_tree (LIB/MESH/executeCoarsening_tree.f90): sibling groups whose 2^dim members all carry -1 are merged
-        into their mother, whose octants are the scaling coefficients of the decomposed daughters (array `decomposed`, the
-        output of waveletDecomposition_tree; not hvy_tmp, which serves as the second buffer of the block move).  The flags must already respect completeness and gradedness (host logic).
-        Blocks that stay are moved to their position along the space-filling curve of the new grid.  Returns the new forest."""
-        hvy, lvl, ixyz, _ = forest.active(0)
-        n, dim, nd = len(hvy), forest.dim, 2 ** forest.dim
-        flags = np.asarray(coarsen_flags) == -1
-        look = {(int(l), int(a), int(b), int(c)): k for k, (l, (a, b, c)) in enumerate(zip(lvl, ixyz))}
-        groups = {}
-        for k in range(n):
-            if flags[k] and lvl[k] > 0:
-                groups.setdefault((int(lvl[k]) - 1, int(ixyz[k, 0]) // 2, int(ixyz[k, 1]) // 2, int(ixyz[k, 2]) // 2), []).append(k)
-        merged = {m: ks for m, ks in groups.items() if len(ks) == nd}
-        gone = {k for ks in merged.values() for k in ks}
-        new_lvl = [int(lvl[k]) for k in range(n) if k not in gone] + [m[0] for m in merged]
-        new_ix = [tuple(int(v) for v in ixyz[k]) for k in range(n) if k not in gone] + [m[1:] for m in merged]
-        new = Forest.from_blocks(dim, forest.Jmax, new_lvl, new_ix, block_dist=forest.block_dist, max_blocks=self.max_blocks,
-                                 periodic=forest.periodic)
-        nh, nl, nix, _ = new.active(0)
-        where = {(int(l), int(a), int(b), int(c)): int(h) for h, l, (a, b, c) in zip(nh, nl, nix)}
-        # blocks that stay move to their slots in the new grid first; mothers are then assembled from the daughters' OLD slots
-        # of the decomposed array, which the move does not touch
-        ksrc = np.asarray([hvy[k] for k in range(n) if k not in gone], np.int32)
-        kdst = np.asarray([where[(int(lvl[k]), int(ixyz[k, 0]), int(ixyz[k, 1]), int(ixyz[k, 2]))] for k in range(n) if k not in gone], np.int32)
-        mo = np.asarray([where[m] for m in merged], np.int32)
-        da = np.zeros(len(merged) * nd, np.int32)
-        for i, (m, ks) in enumerate(merged.items()):
-            for d in range(nd):
-                q = ((d >> 1) & 1, d & 1, (d >> 2) & 1)
-                da[i * nd + d] = hvy[look[(m[0] + 1, 2 * m[1] + q[0], 2 * m[2] + q[1], 2 * m[3] + q[2] if dim == 3 else 0)]]
-        self._check(self._lib.wgpu_move_blocks(self._ctx, len(ksrc), _i32(ksrc), _i32(kdst)))
+    def executeCoarsening_tree(self, forest: Forest, coarsen_flags: np.ndarray, decomposed=(HVY_WORK, 2), Jmin: int = 0) -> Forest:
+        """executeCoarsening_tree (LIB/MESH/executeCoarsening_tree.f90): sister groups whose 2^dim members all carry -1 (and pass the
+        completeness / gradedness rules of the host logic) are merged into their mother, whose octants are the scaling coefficients
+        of the decomposed daughters (array `decomposed`, the output of waveletDecomposition_tree; not hvy_tmp, which serves as the
+        second buffer of the block move).  Blocks that stay move to their position along the space-filling curve of the new grid
+        first; the mothers are then assembled from the daughters' OLD slots of the decomposed array, which the move does not touch."""
+        new, st, mo, da, ks, kd = forest.coarsen(coarsen_flags, Jmin, max_blocks=self.max_blocks)
+        self._check(self._lib.wgpu_move_blocks(self._ctx, len(ks), _i32(ks), _i32(kd)))
         self._check(self._lib.wgpu_coarsen(self._ctx, len(mo), _i32(mo), _i32(da), decomposed[0], decomposed[1]))
         self.set_forest(new)
         return new
@@ -304,11 +251,10 @@ class WabbitGPU:
         st = self.threshold_tree((HVY_WORK, 2), eps=eps, norm=norm, eps_norm=eps_norm, thresh_comp=thresh_comp, level_ref=forest.Jmax)
         if force_maxlevel_dealiasing:
             st = np.where(lvl == forest.Jmax, -1, st)                         # coarseningIndicator_tree.f90:307-309
-        st = coarsening_groups(forest, st, Jmin)
         n0 = forest.n_blocks
         if not (st == -1).any():
             return forest, n0, n0
-        new = self.executeCoarsening_tree(forest, st, decomposed=(HVY_WORK, 2))
+        new = self.executeCoarsening_tree(forest, st, decomposed=(HVY_WORK, 2), Jmin=Jmin)
         return new, n0, new.n_blocks
 
     def timeStep_tree(self, time: float, iteration: int):
