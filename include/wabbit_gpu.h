@@ -164,6 +164,13 @@ int32_t wgpu_rk_step(wgpu_ctx *ctx, double time, int32_t iteration, double *dt);
  *   hvy_active; eps_norm_id 0 Linfty / 1 L1 / 2 L2 / 3 H1; thresh_comp = params%threshold_state_vector_component;
  *   norm may be NULL (eps not normalised); detail_out[n_active*n_eqn] may be NULL.
  */
+/* wgpu_coarse_extension: coarse_extension_modify(CE_case="tree") on a leaf grid (LIB/MPI/reconstruction_step.f90:3-100 ->
+ *   coarseExtensionManipulateWC_block / ...SC_block, LIB/WAVELETS/module_wavelets.f90:877-1027): on every block, in every direction
+ *   whose neighbour is coarser, the wavelet coefficients of the decomposed array (wd) are zeroed in a strip Nwcl/Nwcr deep
+ *   (clear_wc) and its scaling coefficients are copied from the array of original values (orig) in a strip Nscl/Nscr deep
+ *   (copy_sc); the sizes are setup_wavelet's (module_wavelets.f90:1368-1417, incl. the widening to 2*FD_max_size).  Interiors
+ *   only: ghost nodes are not stored on the device. */
+int32_t wgpu_coarse_extension(wgpu_ctx *ctx, int32_t wd_id, int32_t wd_slot, int32_t orig_id, int32_t orig_slot, int32_t clear_wc, int32_t copy_sc);
 int32_t wgpu_set_wavelet(wgpu_ctx *ctx, const char *name, int32_t *g_default, int32_t *g_rhs_default);
 int32_t wgpu_fwt(wgpu_ctx *ctx, int32_t src_id, int32_t src_slot, int32_t dst_id, int32_t dst_slot);
 int32_t wgpu_iwt(wgpu_ctx *ctx, int32_t src_id, int32_t src_slot, int32_t dst_id, int32_t dst_slot);

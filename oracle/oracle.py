@@ -608,3 +608,24 @@ def sync_ghosts_leaf(grid: Grid, p: Params, hvy: np.ndarray, nbr168: np.ndarray,
     lv = np.ascontiguousarray(grid.level, dtype=np.int32)
     return L.orc_sync_ghosts_leaf(grid.n, nb.ctypes.data_as(_ip), lv.ctypes.data_as(_ip), grid.dim, p.g, _bs(p.Bs), hvy.shape[1], _p(hvy),
                                   g_minus, g_plus, order, int(lifted))
+
+
+def coarse_extension_modify(grid: Grid, p: Params, w: Wavelet, wd: np.ndarray, orig: np.ndarray, nbr168: np.ndarray, fd_half_width: int = 0,
+                            clear_wc: bool = True, copy_sc: bool = True) -> int:
+    """coarse_extension_modify("tree") on a leaf grid (LIB/MPI/reconstruction_step.f90:3-100): for every block and every relation
+    whose neighbour is coarser, zero the wavelet coefficients / copy the scaling coefficients near the interface.  Nwc includes the
+    widening to 2*FD_max_size of setup_wavelet (module_wavelets.f90:1404-1417).  Returns the number of patches treated."""
+    L = lib()
+    if not hasattr(L, "_ce_ready"):
+        L.orc_ce_modify_block.argtypes = [C.c_int, C.c_int, _ip, C.c_int, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L._ce_ready = True
+    Nwcl = max(w.Nwcl, 2 * fd_half_width)
+    Nwcr = max(w.Nwcr, 2 * fd_half_width)
+    n = 0
+    for b in range(grid.n):
+        for r in range(57, 113):
+            if nbr168[r - 1, b] >= 1:
+                L.orc_ce_modify_block(p.dim, p.g, _bs(p.Bs), wd.shape[1], _p(wd[b]), _p(orig[b]), r, Nwcl, Nwcr, w.Nscl, w.Nscr,
+                                      int(clear_wc), int(copy_sc))
+                n += 1
+    return n

@@ -224,3 +224,53 @@ int orc_sync_ghosts_leaf(int nb, const int32_t *hvy_neighbor, const int32_t *lev
     free(box);
     return moved;
 }
+
+/*
+ * Coarse extension on one decomposed block for one neighbour relation (the neighbour in that relation is coarser):
+ * coarseExtensionManipulateWC_block + coarseExtensionManipulateSC_block (LIB/WAVELETS/module_wavelets.f90:877-959, 963-1027).
+ * wd: [nc][nz][ny][nx] decomposed block in spaghetti order (modified), orig: the values the scaling coefficients are copied from.
+ * WC: every coefficient that is not a pure scaling coefficient is set to 0 in the interior strip (Nwcl / Nwcr deep) AND in the
+ * whole ghost patch of the relation; SC: the pure scaling positions of the interior strip (Nscl / Nscr deep) are copied from orig.
+ */
+void orc_ce_modify_block(int dim, int g, const int32_t Bs32[3], int nc, double *wd, const double *orig, int relation, int Nwcl, int Nwcr,
+                         int Nscl, int Nscr, int clear_wc, int copy_sc)
+{
+    const int Bs[3] = {Bs32[0], Bs32[1], dim == 3 ? Bs32[2] : 1};
+    const int n[3] = {Bs[0] + 2 * g, Bs[1] + 2 * g, dim == 3 ? Bs[2] + 2 * g : 1};
+    const ptrdiff_t sy = n[0], sz = (ptrdiff_t)n[0] * n[1], sc = sz * n[2];
+    const int gv[3] = {g, g, g};
+    if (clear_wc) {
+        for (int i_set = 1; i_set <= 2; ++i_set) {
+            int idx[2][3];
+            if (i_set == 1) {
+                const int Ns[3] = {Nwcl, Nwcl, Nwcl}, Ne[3] = {Nwcr, Nwcr, Nwcr};
+                orc_get_indices_of_modify_patch(g, dim, relation, idx, n, Ns, Ne, gv, gv, +1);
+            } else orc_get_indices_of_ghost_patch(Bs, g, dim, relation, idx, g, g, +1);
+            if (dim == 2) idx[0][2] = idx[1][2] = 1;
+            for (int c = 0; c < nc; ++c)
+                for (int k = idx[0][2]; k <= idx[1][2]; ++k)
+                    for (int j = idx[0][1]; j <= idx[1][1]; ++j)
+                        for (int i = idx[0][0]; i <= idx[1][0]; ++i) {
+                            /* scaling positions are g+1, g+3, ... (1-based) in every direction */
+                            const int scx = ((i - g) & 1) == 1, scy = ((j - g) & 1) == 1, scz = dim == 3 ? ((k - g) & 1) == 1 : 1;
+                            if (!(scx && scy && scz)) wd[c * sc + (k - 1) * sz + (j - 1) * sy + (i - 1)] = 0.0;
+                        }
+        }
+    }
+    if (copy_sc) {
+        int idx[2][3];
+        const int Ns[3] = {Nscl, Nscl, Nscl}, Ne[3] = {Nscr, Nscr, Nscr};
+        orc_get_indices_of_modify_patch(g, dim, relation, idx, n, Ns, Ne, gv, gv, +1);
+        if (dim == 2) idx[0][2] = idx[1][2] = 1;
+        for (int c = 0; c < nc; ++c)
+            for (int k = idx[0][2]; k <= idx[1][2]; ++k)
+                for (int j = idx[0][1]; j <= idx[1][1]; ++j)
+                    for (int i = idx[0][0]; i <= idx[1][0]; ++i) {
+                        const int scx = ((i - g) & 1) == 1, scy = ((j - g) & 1) == 1, scz = dim == 3 ? ((k - g) & 1) == 1 : 1;
+                        if (scx && scy && scz) {
+                            const ptrdiff_t o = c * sc + (k - 1) * sz + (j - 1) * sy + (i - 1);
+                            wd[o] = orig[o];
+                        }
+                    }
+    }
+}

@@ -213,3 +213,39 @@ def test_wavelet_transform_on_graded_grid(wavelet, Bs):
     O.iwt_tree(w, po, wd_ref, r_ref)
     assert np.array_equal(r[:grid.n][I], r_ref[I])
     sol.close()
+
+
+@pytest.mark.parametrize("wavelet,Bs,disc", [("CDF44", 16, "FD_4th_central"), ("CDF42", 18, "FD_6th_central"), ("CDF40", 16, "FD_4th_central"),
+                                             ("CDF62", 20, "FD_4th_central"), ("CDF22", 16, "FD_2nd_central")])
+def test_coarse_extension_modify(wavelet, Bs, disc):
+    """coarse_extension_modify on a graded grid: zeroed wavelet coefficients and copied scaling coefficients in the strips facing
+    coarser neighbours, against the oracle's restatement of coarseExtensionManipulateWC_block / ...SC_block (pure copies: exact)."""
+    from wabbit_b200.solver import HVY_TMP
+    lv, ix = graded_blocks(3, 1, 3, seed=31)
+    forest = Forest.from_blocks(3, 3, lv, ix)
+    w = O.setup_wavelet(wavelet)
+    p = tg_params(Bs=Bs, J=3, wavelet_g=w.g_default, discretization=disc)
+    p.wavelet = wavelet
+    grid, po = orc_grid(forest), orc_params(p)
+    sol = WabbitGPU(p, max_blocks=forest.n_blocks)
+    sol.setup_wavelet(wavelet)
+    sol.set_forest(forest)
+    rng = np.random.default_rng(3)
+    orig = rng.standard_normal(sol.host_shape())
+    wd = rng.standard_normal(sol.host_shape())
+    nbr = forest.neighbors(0)
+    H = {"FD_2nd_central": 1, "FD_4th_central": 2, "FD_6th_central": 3}[disc]
+    I = (slice(None), slice(None)) + O.interior(po)
+    for clear_wc, copy_sc in ((True, True), (True, False), (False, True)):
+        sol.upload(orig)
+        sol.upload(wd, HVY_TMP)
+        sol.coarse_extension_modify((HVY_TMP, 0), (HVY_BLOCK, 0), clear_wc, copy_sc)
+        got = np.zeros_like(wd)
+        sol.download(got, HVY_TMP, g_sync=0)
+        ref = wd.copy()
+        n = O.coarse_extension_modify(grid, po, w, ref, orig, nbr, fd_half_width=H, clear_wc=clear_wc, copy_sc=copy_sc)
+        assert n > 0
+        assert np.array_equal(got[I], ref[I])
+        if clear_wc or w.Nscr > 0:
+            assert not np.array_equal(got[I], wd[I])
+    sol.close()

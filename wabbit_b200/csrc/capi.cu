@@ -393,6 +393,8 @@ int32_t wgpu_destroy(wgpu_ctx *ctx)
     cudaFree(ctx->d_jump_blk);
     cudaFree(ctx->d_jump_dir);
     cudaFree(ctx->d_jpool);
+    cudaFree(ctx->d_ce_blk);
+    cudaFree(ctx->d_ce_dir);
     cudaFree(ctx->d_wjump_blk);
     cudaFree(ctx->d_wjump_dir);
     cudaFree(ctx->d_wnbr);
@@ -493,7 +495,7 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
     ctx->h_level.assign(N, 0);
     ctx->has_jumps = false;
     ctx->det_cached_for = nullptr;
-    std::vector<int> jump_blk, jump_dir, wjump_blk, wjump_dir, no_same;
+    std::vector<int> jump_blk, jump_dir, wjump_blk, wjump_dir, no_same, ce_blk, ce_dir;
     for (int k = 0; k < n_active; ++k) {
         const int hid = hvy_active[k];
         if (hid < 1 || hid > N) return fail(ctx, WGPU_ERR_ARG, "hvy_active entry out of range");
@@ -529,6 +531,10 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
                             const int lc = hvy_neighbor[(size_t)(code - 1 + s + 56) * ld + (hid - 1)];
                             const int lf = hvy_neighbor[(size_t)(code - 1 + s + 112) * ld + (hid - 1)];
                             if (lc >= 1 || lf >= 1) jump = true;
+                            if (lc >= 1 && (ce_blk.empty() || ce_blk.back() != hid - 1 || ce_dir.back() != (dz + 1) * 9 + (dy + 1) * 3 + (dx + 1))) {
+                                ce_blk.push_back(hid - 1);
+                                ce_dir.push_back((dz + 1) * 9 + (dy + 1) * 3 + (dx + 1));
+                            }
                             if ((lc >= 1 && (lc - 1) / N != rank) || (lf >= 1 && (lf - 1) / N != rank))
                                 return fail(ctx, WGPU_ERR_UNSUPPORTED, "level-jump neighbours on another rank are not supported yet");
                         }
@@ -576,6 +582,21 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
         int32_t rcj = upload_jump_tables(ctx, jump_blk, jump_dir);
         if (rcj) return rcj;
         if ((rcj = upload_wjump_tables(ctx, wjump_blk, wjump_dir))) return rcj;
+        ctx->n_ce = 0;
+        if (!ce_blk.empty()) {
+            if ((int)ce_blk.size() > ctx->ce_cap) {
+                cudaFree(ctx->d_ce_blk);
+                cudaFree(ctx->d_ce_dir);
+                ctx->d_ce_blk = ctx->d_ce_dir = nullptr;
+                const size_t want = ce_blk.size() + ce_blk.size() / 2 + 64;
+                if ((rcj = dmalloc(ctx, &ctx->d_ce_blk, want)) || (rcj = dmalloc(ctx, &ctx->d_ce_dir, want))) return rcj;
+                ctx->ce_cap = (int)want;
+            }
+            WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_ce_blk, ce_blk.data(), sizeof(int) * ce_blk.size(), cudaMemcpyHostToDevice, ctx->stream));
+            WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_ce_dir, ce_dir.data(), sizeof(int) * ce_dir.size(), cudaMemcpyHostToDevice, ctx->stream));
+            WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+            ctx->n_ce = (int)ce_blk.size();
+        }
     }
     if (!ctx->d_active_int) {
         int32_t rc2 = dmalloc(ctx, &ctx->d_active_int, (size_t)N);
@@ -922,6 +943,24 @@ int32_t wgpu_threshold(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t ep
         WGPU_CHECK(ctx, cudaMemcpyAsync(detail_out, ctx->d_detail_out, sizeof(double) * (size_t)ctx->n_active * ctx->nc, cudaMemcpyDeviceToHost, ctx->stream));
     WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return WGPU_OK;
+}
+
+int32_t wgpu_coarse_extension(wgpu_ctx *ctx, int32_t wd_id, int32_t wd_slot, int32_t orig_id, int32_t orig_slot, int32_t clear_wc, int32_t copy_sc)
+{
+    if (!ctx) return WGPU_ERR_ARG;
+    if (!ctx->wavelet_set) return fail(ctx, 1213149, "The cat is angry: Wavelet-setup not yet called?");
+    int n1 = 0, n2 = 0;
+    double *wd = array_ptr(ctx, wd_id, wd_slot, &n1);
+    const double *orig = array_ptr(ctx, orig_id, orig_slot, &n2);
+    if (!wd || !orig || n1 != ctx->nc || n2 != ctx->nc || wd == orig) return fail(ctx, WGPU_ERR_ARG, "wgpu_coarse_extension: bad array/slot");
+    // coarse-extension sizes (setup_wavelet, module_wavelets.f90:1368-1417): Nsc from HD, Nwc = Nsc + |GD|, widened to 2*FD_max_size
+    const WaveFilters &w = ctx->wavelet;
+    const int H = ctx->cfg.fd == 2 ? 1 : (ctx->cfg.fd == 4 ? 2 : 3);
+    const int Nscl = std::max(-w.hd_lo - 1, 0), Nscr = w.hd_hi;
+    const int Nwcl = std::max(Nscl - w.gd_lo, 2 * H), Nwcr = std::max(Nscr + w.gd_hi, 2 * H);
+    ctx->det_cached_for = nullptr;
+    if (wd == ctx->U) ctx->dtmin_valid = false;
+    return wgpu_launch_ce(ctx, wd, orig, Nwcl, Nwcr, Nscl, Nscr, clear_wc != 0, copy_sc != 0);
 }
 
 // ------------------------------------------------------------------------------------------------ refinement / coarsening

@@ -213,7 +213,55 @@ __global__ void __launch_bounds__(256) copy_blocks_kernel(const double *__restri
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_block / 2; i += (long long)gridDim.x * blockDim.x) o[i] = s[i];
 }
 
+// coarse extension on the interiors of decomposed blocks (coarseExtensionManipulateWC_block / ...SC_block,
+// LIB/WAVELETS/module_wavelets.f90:877-1027): one CTA per (block, direction with a coarser neighbour).  In the strip facing the
+// neighbour every coefficient that is not a pure scaling coefficient is zeroed (Nwc deep), and the pure scaling positions are
+// copied from the original values (Nsc deep).  The ghost-patch half of the reference routine has no counterpart here: ghost
+// values are never stored, consumers produce them on the fly.
+__global__ void __launch_bounds__(128) ce_kernel(double *__restrict__ wd, const double *__restrict__ orig, const int *__restrict__ blk,
+                                                 const int *__restrict__ dir, int nc, int Bs, int dim, int Nwcl, int Nwcr, int Nscl, int Nscr,
+                                                 int clear_wc, int copy_sc)
+{
+    const int b = blk[blockIdx.x], dc = dir[blockIdx.x];
+    const int d[3] = {dc % 3 - 1, (dc / 3) % 3 - 1, dc / 9 - 1};
+    const long long CS = (long long)Bs * Bs * (dim == 3 ? Bs : 1);
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 0 ? !clear_wc : !copy_sc) continue;
+        const int Nl = pass == 0 ? Nwcl : Nscl, Nr = pass == 0 ? Nwcr : Nscr;
+        int lo[3], ext[3];
+        for (int k = 0; k < 3; ++k) {
+            const int B = k < dim ? Bs : 1;
+            lo[k] = d[k] > 0 ? B - Nr : 0;
+            ext[k] = d[k] < 0 ? Nl : (d[k] > 0 ? Nr : B);
+            if (lo[k] < 0) { ext[k] += lo[k]; lo[k] = 0; }
+            if (ext[k] > B) ext[k] = B;
+        }
+        const int npts = ext[0] * ext[1] * ext[2];
+        if (npts <= 0) continue;
+        for (int i = threadIdx.x; i < nc * npts; i += blockDim.x) {
+            const int c = i / npts, r = i % npts;
+            const int x = lo[0] + r % ext[0], y = lo[1] + (r / ext[0]) % ext[1], z = lo[2] + r / (ext[0] * ext[1]);
+            const bool pure_sc = !(x & 1) && !(y & 1) && (dim == 2 || !(z & 1));
+            const long long o = ((long long)b * nc + c) * CS + ((long long)z * Bs + y) * Bs + x;
+            if (pass == 0) {
+                if (!pure_sc) wd[o] = 0.0;
+            } else if (pure_sc) wd[o] = orig[o];
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace
+
+int32_t wgpu_launch_ce(wgpu_ctx *ctx, double *wd, const double *orig, int Nwcl, int Nwcr, int Nscl, int Nscr, int clear_wc, int copy_sc)
+{
+    if (ctx->n_ce == 0) return WGPU_OK;
+    ce_kernel<<<ctx->n_ce, 128, 0, ctx->stream>>>(wd, orig, ctx->d_ce_blk, ctx->d_ce_dir, ctx->nc, ctx->cfg.Bs[0], ctx->cfg.dim, Nwcl, Nwcr, Nscl,
+                                                   Nscr, clear_wc, copy_sc);
+    ctx->launches++;
+    WGPU_CHECK(ctx, cudaGetLastError());
+    return WGPU_OK;
+}
 
 int32_t wgpu_launch_jump_fill(wgpu_ctx *ctx, const double *src)
 {

@@ -124,6 +124,9 @@ struct wgpu_ctx {
     long long *d_woff = nullptr;
     double *d_wpool = nullptr;
     size_t wpool_cap = 0;
+    // coarse extension: (block, direction) pairs whose neighbour is coarser
+    int n_ce = 0, ce_cap = 0;
+    int *d_ce_blk = nullptr, *d_ce_dir = nullptr;
     bool has_jumps = false;            // some active block has a coarser / finer neighbour
     bool lookup_ready = false;         // block lookup + coordinates of the current topology are on the device
     int *d_idbuf[3] = {nullptr, nullptr, nullptr};   // scratch id lists (refine / coarsen)
@@ -177,6 +180,7 @@ int32_t wgpu_launch_pack(wgpu_ctx *ctx, const double *src);
 // jump.cu
 int32_t wgpu_launch_jump_fill(wgpu_ctx *ctx, const double *src);
 int32_t wgpu_launch_wjump_fill(wgpu_ctx *ctx, const double *src);
+int32_t wgpu_launch_ce(wgpu_ctx *ctx, double *wd, const double *orig, int Nwcl, int Nwcr, int Nscl, int Nscr, int clear_wc, int copy_sc);
 int32_t wgpu_launch_export_regions(wgpu_ctx *ctx, const double *src, double *staged, const int *d_ids, int n, int ncomp_src, int ncomp_host,
                                    int g_sync, int by_id);
 int32_t wgpu_launch_refine(wgpu_ctx *ctx, const double *src, double *dst, const int *d_mother, const int *d_daughter, int n);

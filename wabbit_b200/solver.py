@@ -185,6 +185,10 @@ class WabbitGPU:
         """sync of SC/WC + waveletReconstruction_optimized_block on every block (adapt_tree.f90:813-843)."""
         self._check(self._lib.wgpu_iwt(self._ctx, src[0], src[1], dst[0], dst[1]))
 
+    def coarse_extension_modify(self, wd=(HVY_TMP, 0), orig=(HVY_BLOCK, 0), clear_wc: bool = True, copy_sc: bool = True):
+        """coarse_extension_modify(CE_case="tree") (LIB/MPI/reconstruction_step.f90:3) on the interiors of a decomposed array."""
+        self._check(self._lib.wgpu_coarse_extension(self._ctx, wd[0], wd[1], orig[0], orig[1], int(clear_wc), int(copy_sc)))
+
     def componentWiseNorm_tree(self, array=(HVY_BLOCK, 0), norm: str = "Linfty") -> np.ndarray:
         out = np.zeros(self.params.n_eqn)
         self._check(self._lib.wgpu_norm(self._ctx, array[0], array[1], self.EPS_NORMS[norm], out.ctypes.data_as(C.POINTER(C.c_double))))
