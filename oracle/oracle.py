@@ -595,19 +595,44 @@ def neighbor_table168(grid: Grid, Jmax: int, periodic=(1, 1, 1)) -> np.ndarray:
 
 
 def sync_ghosts_leaf(grid: Grid, p: Params, hvy: np.ndarray, nbr168: np.ndarray, g_minus: int, g_plus: int, order: int,
-                     lifted: bool) -> int:
-    """sync_ghosts_generic("full_leaf", ignore_Filter=.true.) on a leaf grid with level jumps (orc_sync.c)."""
+                     lifted: bool, ignore_filter: bool = True, w: Optional["Wavelet"] = None) -> int:
+    """sync_ghosts_generic("full_leaf") on a leaf grid with level jumps (orc_sync.c).  ignore_filter=True is sync_ghosts_RHS_tree
+    (plain decimation); ignore_filter=False with a lifted wavelet `w` is sync_ghosts_tree's default: the restriction takes its values
+    from the HD-filtered sender (restrict_copy_at_CE, LIB/MPI/restrict_predict_data.f90:121-172)."""
     L = lib()
     if not hasattr(L, "_sync_ready"):
-        L.orc_sync_ghosts_leaf.argtypes = [C.c_int, _ip, _ip, C.c_int, C.c_int, _ip, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_int]
-        L.orc_sync_ghosts_leaf.restype = C.c_int
+        L.orc_sync_ghosts_leaf_ex.argtypes = [C.c_int, _ip, _ip, C.c_int, C.c_int, _ip, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                              C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_sync_ghosts_leaf_ex.restype = C.c_int
         L.orc_inverse_relation.argtypes = [C.c_int]
         L.orc_inverse_relation.restype = C.c_int
         L._sync_ready = True
     nb = np.ascontiguousarray(nbr168, dtype=np.int32)
     lv = np.ascontiguousarray(grid.level, dtype=np.int32)
-    return L.orc_sync_ghosts_leaf(grid.n, nb.ctypes.data_as(_ip), lv.ctypes.data_as(_ip), grid.dim, p.g, _bs(p.Bs), hvy.shape[1], _p(hvy),
-                                  g_minus, g_plus, order, int(lifted))
+    if ignore_filter or not lifted:
+        return L.orc_sync_ghosts_leaf_ex(grid.n, nb.ctypes.data_as(_ip), lv.ctypes.data_as(_ip), grid.dim, p.g, _bs(p.Bs), hvy.shape[1],
+                                         _p(hvy), g_minus, g_plus, order, int(lifted), 1, None, 0, 0, 0, 0)
+    assert w is not None and w.lifted
+    hd = np.array(list(w.HD), dtype=np.float64)
+    return L.orc_sync_ghosts_leaf_ex(grid.n, nb.ctypes.data_as(_ip), lv.ctypes.data_as(_ip), grid.dim, p.g, _bs(p.Bs), hvy.shape[1], _p(hvy),
+                                     g_minus, g_plus, order, 1, 0, _p(hd), w.hd_lo, w.hd_hi, w.Nscl, w.Nscr)
+
+
+def block_filter(p: Params, u: np.ndarray, coef: dict, do_restriction: bool = False) -> np.ndarray:
+    """blockFilterXYZ_vct (module_wavelets.f90:307-401) on one ghosted block u[nc, nz, ny, nx]; coef = {tap: value}."""
+    L = lib()
+    if not hasattr(L, "_bf_ready"):
+        L.orc_block_filter.argtypes = [C.c_int, C.c_int, _ip, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int]
+        L.orc_block_filter.restype = None
+        L._bf_ready = True
+    lo, hi = min(coef), max(coef)
+    cf = np.zeros(2 * ORC_FMAX + 1)
+    for k, v in coef.items():
+        cf[k + ORC_FMAX] = v
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    out = np.zeros_like(u)
+    L.orc_block_filter(p.dim, p.g, _bs(p.Bs), u.shape[0], _p(u), _p(out), _p(cf), lo, hi, int(do_restriction))
+    return out
 
 
 def coarse_extension_modify(grid: Grid, p: Params, w: Wavelet, wd: np.ndarray, orig: np.ndarray, nbr168: np.ndarray, fd_half_width: int = 0,

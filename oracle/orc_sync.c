@@ -149,8 +149,20 @@ void orc_set_send_bounds(const int Bs[3], int g, int dim, int a, int relation, i
  * hvy: [nb][nc][nz][ny][nx] ghosted.  order = predictor order (2,4,6).  lifted: 3 stages, else 2 (restriction in stage 1).
  * Returns the number of patches moved.
  */
-int orc_sync_ghosts_leaf(int nb, const int32_t *hvy_neighbor, const int32_t *level, int dim, int g, const int32_t Bs32[3], int nc,
-                         double *hvy, int gminus, int gplus, int order, int lifted)
+void orc_block_filter(int dim, int g, const int32_t Bs[3], int nc, const double *u, double *uf, const double *coef, int fl_l, int fl_r,
+                      int do_restriction);
+void orc_ce_modify_block(int dim, int g, const int32_t Bs32[3], int nc, double *wd, const double *orig, int relation, int Nwcl, int Nwcr,
+                         int Nscl, int Nscr, int clear_wc, int copy_sc);
+
+/*
+ * ignore_filter = 0 (sync_ghosts_tree's default) with a lifted wavelet: restrict_data takes the decimated values from the HD-filtered
+ * sender block (restrict_copy_at_CE, LIB/MPI/restrict_predict_data.f90:121-172: blockFilterXYZ_vct on the whole block after stage 1,
+ * then, for every relation whose neighbour is coarser or finer, the scaling positions of the Nscl / Nscr strip are copied back from
+ * the unfiltered block).  coefHD[tap + 12], taps hd_lo..hd_hi.
+ */
+int orc_sync_ghosts_leaf_ex(int nb, const int32_t *hvy_neighbor, const int32_t *level, int dim, int g, const int32_t Bs32[3], int nc,
+                            double *hvy, int gminus, int gplus, int order, int lifted, int ignore_filter, const double *coefHD, int hd_lo,
+                            int hd_hi, int Nscl, int Nscr)
 {
     const int Bs[3] = {Bs32[0], Bs32[1], dim == 3 ? Bs32[2] : 1};
     const int nx = Bs[0] + 2 * g, ny = Bs[1] + 2 * g, nz = dim == 3 ? Bs[2] + 2 * g : 1;
@@ -167,6 +179,9 @@ int orc_sync_ghosts_leaf(int nb, const int32_t *hvy_neighbor, const int32_t *lev
     int moved = 0;
     double *res = NULL, *box = NULL;
     size_t res_cap = 0, box_cap = 0;
+    const int use_filter = lifted && !ignore_filter;
+    double *restricted = use_filter ? (double *)malloc(sizeof(double) * (size_t)sb) : NULL;
+    int restricted_id = -1;   /* restricted_hvy_ID of the reference: one filtered block is held at a time */
     for (int istage = 1; istage <= Nstages; ++istage) {
         for (int k = 0; k < nb; ++k)
             for (int i_n = 1; i_n <= 168; ++i_n) {
@@ -189,7 +204,20 @@ int orc_sync_ghosts_leaf(int nb, const int32_t *hvy_neighbor, const int32_t *lev
                                     recv[c * sc + (R[0][2] - 1 + z) * sz + (R[0][1] - 1 + y) * sy + (R[0][0] - 1 + x)] =
                                         send[c * sc + (S[0][2] - 1 + z) * sz + (S[0][1] - 1 + y) * sy + (S[0][0] - 1 + x)];
                 } else if (lvl_diff == +1) {
-                    /* restrict_data, ignore_Filter: res(1:(n+1)/2) = block(ijk1:ijk2:2); then recv = res(buffer) */
+                    /* restrict_data: res(1:(n+1)/2) = block(ijk1:ijk2:2) of the (filtered) sender; then recv = res(buffer) */
+                    if (use_filter) {
+                        if (restricted_id != k) {
+                            orc_block_filter(dim, g, Bs32, nc, send, restricted, coefHD, hd_lo, hd_hi, 1);
+                            for (int j_n = 1; j_n <= 168; ++j_n) {
+                                const int nj = hvy_neighbor[(size_t)(j_n - 1) * nb + k];
+                                if (nj < 1) continue;
+                                const int ld = level[k] - level[nj - 1];
+                                if (ld == -1 || ld == +1) orc_ce_modify_block(dim, g, Bs32, nc, restricted, send, j_n, 0, 0, Nscl, Nscr, 0, 1);
+                            }
+                            restricted_id = k;
+                        }
+                        send = restricted;
+                    }
                     for (int c = 0; c < nc; ++c)
                         for (int z = 0; z < ez; ++z)
                             for (int y = 0; y < ey; ++y)
@@ -222,7 +250,15 @@ int orc_sync_ghosts_leaf(int nb, const int32_t *hvy_neighbor, const int32_t *lev
     }
     free(res);
     free(box);
+    free(restricted);
     return moved;
+}
+
+/* sync_ghosts_generic("full_leaf", ignore_Filter = .true.): sync_ghosts_RHS_tree */
+int orc_sync_ghosts_leaf(int nb, const int32_t *hvy_neighbor, const int32_t *level, int dim, int g, const int32_t Bs32[3], int nc,
+                         double *hvy, int gminus, int gplus, int order, int lifted)
+{
+    return orc_sync_ghosts_leaf_ex(nb, hvy_neighbor, level, dim, g, Bs32, nc, hvy, gminus, gplus, order, lifted, 1, NULL, 0, 0, 0, 0);
 }
 
 /*

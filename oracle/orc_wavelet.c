@@ -108,6 +108,59 @@ static inline double filt(const double *u, ptrdiff_t stride, const double *F, in
 }
 
 /*
+ * blockFilterXYZ_vct (LIB/WAVELETS/module_wavelets.f90:307-401): separable filter of a ghosted block, x then y then z; with
+ * do_restriction only every second interior point (Fortran g+1, g+3, ...) is filtered in a direction, and the later passes read
+ * only those.  The sum starts from 0 and adds u(i+shift)*c(shift) for EVERY shift fl_l..fl_r in increasing order (zero taps
+ * included), as the reference loop does.  u and uf are different arrays [nc][nz][ny][nx]; everything that is not filtered is copied.
+ */
+void orc_block_filter(int dim, int g, const int32_t Bs[3], int nc, const double *u, double *uf, const double *coef, int fl_l, int fl_r,
+                      int do_restriction)
+{
+    const int n[3] = {Bs[0] + 2 * g, Bs[1] + 2 * g, dim == 3 ? Bs[2] + 2 * g : 1};
+    const ptrdiff_t sy = n[0], sz = (ptrdiff_t)n[0] * n[1], sc = sz * n[2];
+    memcpy(uf, u, sizeof(double) * (size_t)sc * nc);
+    if (fl_l == 0 && fl_r == 0 && fabs(coef[ORC_FMAX] - 1.0) <= 1.0e-10) return;
+    int ifs[3], ife[3], ils[3], ile[3];
+    for (int d = 0; d < 3; ++d) {
+        ifs[d] = g + fl_l; ife[d] = Bs[d] + g - 1 + fl_r;    /* 0-based */
+        ils[d] = g; ile[d] = Bs[d] + g - 1;
+    }
+    if (dim == 2) ifs[2] = ife[2] = ils[2] = ile[2] = 0;
+    const int s = do_restriction ? 2 : 1;
+    double *tmp = (double *)malloc(sizeof(double) * (size_t)sc);
+    for (int c = 0; c < nc; ++c) {
+        double *o = uf + c * sc;
+        memcpy(tmp, o, sizeof(double) * (size_t)sc);
+        for (int iz = ifs[2]; iz <= ife[2]; ++iz)
+            for (int iy = ifs[1]; iy <= ife[1]; ++iy)
+                for (int ix = ils[0]; ix <= ile[0]; ix += s) {
+                    double acc = 0.0;
+                    for (int k = fl_l; k <= fl_r; ++k) acc = acc + tmp[iz * sz + iy * sy + ix + k] * coef[k + ORC_FMAX];
+                    o[iz * sz + iy * sy + ix] = acc;
+                }
+        memcpy(tmp, o, sizeof(double) * (size_t)sc);
+        for (int iz = ifs[2]; iz <= ife[2]; ++iz)
+            for (int iy = ils[1]; iy <= ile[1]; iy += s)
+                for (int ix = ils[0]; ix <= ile[0]; ix += s) {
+                    double acc = 0.0;
+                    for (int k = fl_l; k <= fl_r; ++k) acc = acc + tmp[iz * sz + (iy + k) * sy + ix] * coef[k + ORC_FMAX];
+                    o[iz * sz + iy * sy + ix] = acc;
+                }
+        if (dim == 3) {
+            memcpy(tmp, o, sizeof(double) * (size_t)sc);
+            for (int iz = ils[2]; iz <= ile[2]; iz += s)
+                for (int iy = ils[1]; iy <= ile[1]; iy += s)
+                    for (int ix = ils[0]; ix <= ile[0]; ix += s) {
+                        double acc = 0.0;
+                        for (int k = fl_l; k <= fl_r; ++k) acc = acc + tmp[(iz + k) * sz + iy * sy + ix] * coef[k + ORC_FMAX];
+                        o[iz * sz + iy * sy + ix] = acc;
+                    }
+        }
+    }
+    free(tmp);
+}
+
+/*
  * waveletDecomposition_optimized_block: u (ghosts synchronised to depth >= filter size) -> u_d, spaghetti order:
  * SC at interior offsets 0,2,4,... (Fortran g+1, g+3, ...), WC at 1,3,5,...  u_d must be a different array.
  * Only the interior of u_d is meaningful on return (as in the reference).

@@ -43,8 +43,11 @@ def linear_field(grid, p, hvy):
 
 
 @pytest.mark.parametrize("dim", [2, 3])
-@pytest.mark.parametrize("wavelet,Bs", [("CDF40", 16), ("CDF44", 16), ("CDF20", 12), ("CDF62", 20)])
-def test_linear_field_sync_protocol(dim, wavelet, Bs):
+@pytest.mark.parametrize("wavelet,Bs,ignore_filter", [("CDF40", 16, True), ("CDF44", 16, True), ("CDF20", 12, True), ("CDF62", 20, True),
+                                                      ("CDF44", 16, False), ("CDF42", 16, False), ("CDF22", 12, False), ("CDF62", 20, False)])
+def test_linear_field_sync_protocol(dim, wavelet, Bs, ignore_filter):
+    """ignore_filter=True: sync_ghosts_RHS_tree (unit_test_Sync.f90:141); False: sync_ghosts_tree, whose restriction applies the HD
+    filter of a lifted wavelet (unit_test_Sync.f90:136) -- the filter reproduces linear fields, so the protocol holds for both."""
     w = O.setup_wavelet(wavelet)
     g = w.g_default
     order = w.X
@@ -54,12 +57,14 @@ def test_linear_field_sync_protocol(dim, wavelet, Bs):
     nbr = O.neighbor_table168(grid, 2)
     interior = (slice(None), slice(None)) + O.interior(p)
     Jfine = 2
-    for gs in range(g, g_rhs - 1, -1):
+    # with the filter only the full depth is a critical case of the reference's test (unit_test_Sync.f90:205-210): at smaller depths
+    # the filter reads same-level ghost nodes that stage 1 did not fill
+    for gs in (range(g, g_rhs - 1, -1) if ignore_filter else (g,)):
         expected = O.alloc(grid, p)
         linear_field(grid, p, expected)
         u = np.full_like(expected, -1.0)
         u[interior] = expected[interior]
-        n = O.sync_ghosts_leaf(grid, p, u, nbr, gs, gs, order, bool(w.lifted))
+        n = O.sync_ghosts_leaf(grid, p, u, nbr, gs, gs, order, bool(w.lifted), ignore_filter=ignore_filter, w=w)
         assert n > 0
         # points whose stencil crosses the periodic boundary are not comparable (the field jumps there)
         gmin = max(w.hd_hi, w.hr_hi + 1)
@@ -180,3 +185,108 @@ def test_sync_equals_geometric_definition_on_graded_grids(wavelet, Bs, Jmax, see
             assert v == ref[b, 0, i[2] + g, i[1] + g, i[0] + g], (b, i, kind)
             checked[kind] += 1
     assert checked["copy"] > 100 and checked["pred"] > 100
+
+
+def relation_directions(dim):
+    """slot (1..56) -> direction (dx, dy, dz) of the neighbour table (neighborhood.f90:10-22)"""
+    out = {}
+    for dz in ((-1, 0, 1) if dim == 3 else (0,)):
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                d = (dx, dy, dz)
+                if d == (0, 0, 0):
+                    continue
+                nfree = 2 ** (sum(1 for v in d if v == 0) - (1 if dim == 2 else 0))
+                for k in range(nfree):
+                    out[O.same_level_code(d) + k] = d
+    return out
+
+
+@pytest.mark.parametrize("wavelet,Bs,Jmax,seed", [("CDF44", 16, 3, 11), ("CDF42", 16, 3, 3), ("CDF22", 16, 3, 7), ("CDF62", 20, 3, 5)])
+def test_filtered_sync_equals_geometric_definition_on_graded_grids(wavelet, Bs, Jmax, seed):
+    """What the GPU path relies on for sync_ghosts_tree with a lifted wavelet (wabbit_b200/csrc/fill.cuh, restrict_filter_kernel):
+    a ghost point owned by a finer leaf F receives R(F) at the coincident point, where R(F) is the scaling coefficient of the
+    one-level decomposition of F (HD in x, y, z with F's same-level neighbours in its ghosts) -- except inside the Nscl / Nscr strips
+    that face F's coarser or finer neighbours, where it is the plain value; ghost points owned by a same-level leaf are copies and
+    points owned by a coarser leaf are interpolated from the UNFILTERED coarse lattice (the coarse ghost nodes the stencil reaches
+    lie in copy strips).  Compared bit for bit with the oracle's staged, table-driven restatement of the reference."""
+    from util import graded_blocks
+    w = O.setup_wavelet(wavelet)
+    g, order = w.g_default, w.X
+    A = order // 2 - 1
+    p = O.Params(dim=3, Bs=(Bs,) * 3, g=g, g_rhs=g, n_eqn=1, Jmax=Jmax)
+    lv, ix = graded_blocks(3, 1, Jmax, seed, 0.3)
+    grid = O.Grid(level=lv.astype(np.int64), ixyz=ix.astype(np.int64), dim=3)
+    nbr = O.neighbor_table168(grid, Jmax)
+    rng = np.random.default_rng(seed)
+    u = O.alloc(grid, p, 1)
+    u[:] = rng.standard_normal(u.shape)
+    ref = u.copy()
+    O.sync_ghosts_leaf(grid, p, ref, nbr, g, g, order, True, ignore_filter=False, w=w)
+    plain = u.copy()
+    O.sync_ghosts_leaf(grid, p, plain, nbr, g, g, order, True)              # any fill of the non-same-level ghosts will do
+    wd = np.zeros_like(u)
+    O.fwt_tree(w, p, plain, wd)
+    dirs = relation_directions(3)
+    strips = []                                                            # per block: list of (lo[3], hi[3]) copy boxes, interior offsets
+    for b in range(grid.n):
+        boxes = set()
+        for r in range(57, 169):
+            if nbr[r - 1, b] >= 1:
+                d = dirs[(r - 1) % 56 + 1]
+                lo = tuple(0 if d[a] <= 0 else Bs - w.Nscr for a in range(3))
+                hi = tuple(w.Nscl - 1 if d[a] < 0 else Bs - 1 for a in range(3))
+                boxes.add((lo, hi))
+        strips.append(sorted(boxes))
+    look = grid.lookup()
+    cf = {2: [.5, .5], 4: [-1 / 16, 9 / 16, 9 / 16, -1 / 16], 6: [3 / 256, -25 / 256, 150 / 256, 150 / 256, -25 / 256, 3 / 256]}[order]
+    used = {"filtered": 0, "strip": 0}
+
+    def lattice(L, P, filtered):
+        n = 2 ** L * Bs
+        P = [q % n for q in P]
+        b = look.get((L,) + tuple(q // Bs for q in P))
+        if b is not None:
+            return u[b, 0, P[2] % Bs + g, P[1] % Bs + g, P[0] % Bs + g]
+        b = look.get((L + 1,) + tuple((2 * q) // Bs for q in P))
+        if b is None:
+            return None
+        o = [(2 * q) % Bs for q in P]
+        if filtered and not any(all(lo[a] <= o[a] <= hi[a] for a in range(3)) for lo, hi in strips[b]):
+            used["filtered"] += 1
+            return wd[b, 0, o[2] + g, o[1] + g, o[0] + g]
+        used["strip"] += filtered
+        return u[b, 0, o[2] + g, o[1] + g, o[0] + g]
+
+    def predicted(L, G, axis=2):
+        if axis < 0:
+            return lattice(L - 1, G, False)
+        q = G[axis]
+        c = list(G)
+        if q % 2 == 0:
+            c[axis] = q // 2
+            return predicted(L, c, axis - 1)
+        s = None
+        for t in range(order):
+            c[axis] = (q - 1) // 2 - A + t
+            v = predicted(L, c, axis - 1)
+            if v is None:
+                return None
+            s = cf[t] * v if s is None else s + cf[t] * v
+        return s
+
+    checked = {"copy": 0, "pred": 0}
+    for b in range(grid.n):
+        L = int(grid.level[b])
+        for _ in range(60):
+            i = rng.integers(-g, Bs + g, size=3)
+            if all(0 <= q < Bs for q in i):
+                continue
+            G = [int(grid.ixyz[b, a]) * Bs + int(i[a]) for a in range(3)]
+            v, kind = lattice(L, G, True), "copy"
+            if v is None:
+                v, kind = predicted(L, G), "pred"
+            assert v is not None
+            assert v == ref[b, 0, i[2] + g, i[1] + g, i[0] + g], (b, i, kind)
+            checked[kind] += 1
+    assert checked["copy"] > 100 and checked["pred"] > 100 and used["filtered"] > 20 and used["strip"] > 10
