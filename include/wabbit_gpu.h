@@ -135,6 +135,15 @@ int32_t wgpu_download(wgpu_ctx *ctx, int32_t array_id, int32_t slot, const int32
  */
 int32_t wgpu_sync_ghosts(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t g_minus, int32_t g_plus);
 
+/* wgpu_set_ghost_filter: the ignore_Filter switch of sync_ghosts_tree (LIB/MPI/synchronize_ghosts_generic.f90:125-153).  With a lifted
+ *   wavelet (CDFXY, Y > 0) the reference's default synchronisation restricts through the HD filter: a ghost node owned by a finer
+ *   neighbour receives the filtered value, except next to that neighbour's own coarser / finer neighbours, where the plain value is
+ *   copied (restrict_copy_at_CE, LIB/MPI/restrict_predict_data.f90:121-172; blockFilterXYZ_vct, LIB/WAVELETS/module_wavelets.f90:307-401).
+ *   This is the default here too (ignore_filter = 0) for every wavelet-side synchronisation: wgpu_download with g_sync > 0, wgpu_fwt /
+ *   wgpu_iwt and wgpu_refine.  ignore_filter = 1 makes them restrict by plain decimation.  The right-hand side always ignores the
+ *   filter (sync_ghosts_RHS_tree). */
+int32_t wgpu_set_ghost_filter(wgpu_ctx *ctx, int32_t ignore_filter);
+
 /* wgpu_rhs: replaces RHS_wrapper (LIB/TIME/RHS_wrapper.f90:16-260) for physics "ACM-new":
  *   hvy_work(:,:,:,:,:,dst_slot) = RHS(src), src = hvy_block (src_slot = 0) or hvy_work(..., src_slot).
  *   Includes the integral_stage divergence guard (rhs_ACM.f90:133-146) -> WGPU_ERR_DIVERGED. */

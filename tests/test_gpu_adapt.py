@@ -28,29 +28,38 @@ def _case(wavelet, Bs, forest, seed, max_blocks=None):
     return w, p, po, grid, sol, u
 
 
-@pytest.mark.parametrize("wavelet,Bs", [("CDF40", 16), ("CDF44", 16), ("CDF20", 16), ("CDF62", 20)])
-def test_download_with_ghosts_on_graded_grid(wavelet, Bs):
+@pytest.mark.parametrize("wavelet,Bs,ignore_filter", [("CDF40", 16, True), ("CDF44", 16, True), ("CDF20", 16, True), ("CDF62", 20, True),
+                                                      ("CDF44", 16, False), ("CDF42", 18, False), ("CDF22", 16, False), ("CDF62", 20, False),
+                                                      ("CDF44", 24, False)])
+def test_download_with_ghosts_on_graded_grid(wavelet, Bs, ignore_filter):
+    """ignore_filter=False is sync_ghosts_tree's default: with a lifted wavelet the restriction goes through the HD filter
+    (restrict_copy_at_CE); compared at the full depth g (at smaller depths the reference's filter reads ghost nodes it did not fill)."""
     lv, ix = graded_blocks(3, 1, 3, seed=7)
     forest = Forest.from_blocks(3, 3, lv, ix)
     w, p, po, grid, sol, u = _case(wavelet, Bs, forest, seed=1)
     nbr = forest.neighbors(0)[:, :grid.n]
+    sol.set_ghost_filter(ignore_filter)
     sol.upload(u)
-    for gs in (p.g, max(p.g_rhs, w.X // 2)):   # the reference's minimum sync depth is X/2 (ini_file_to_params.f90:467-468)
+    for gs in ((p.g, max(p.g_rhs, w.X // 2)) if ignore_filter else (p.g,)):   # minimum sync depth X/2 (ini_file_to_params.f90:467-468)
         got = u.copy()
         sol.download(got, g_sync=gs)
         ref = u.copy()
-        O.sync_ghosts_leaf(grid, po, ref, nbr, gs, gs, w.X, bool(w.lifted))
+        O.sync_ghosts_leaf(grid, po, ref, nbr, gs, gs, w.X, bool(w.lifted), ignore_filter=ignore_filter, w=w)
         assert np.array_equal(got, ref), gs
+        if not ignore_filter:
+            plain = u.copy()
+            O.sync_ghosts_leaf(grid, po, plain, nbr, gs, gs, w.X, True)
+            assert not np.array_equal(plain, ref)      # the filter does change ghost values on this grid
     sol.close()
 
 
-def _refine_oracle(w, po, grid, u, nbr):
-    """sync (ignore_Filter) + refineBlock per block: dict (level, ix, iy, iz) -> daughter interior [nc, Bs, Bs, Bs]"""
+def _refine_oracle(w, po, grid, u, nbr, ignore_filter=True):
+    """sync_ghosts_tree + refineBlock per block: dict (level, ix, iy, iz) -> daughter interior [nc, Bs, Bs, Bs]"""
     ref = u.copy()
     if nbr is None:
         O.sync_ghosts_same_level(grid, po, ref, po.g, po.g)
     else:
-        O.sync_ghosts_leaf(grid, po, ref, nbr, po.g, po.g, w.X, bool(w.lifted))
+        O.sync_ghosts_leaf(grid, po, ref, nbr, po.g, po.g, w.X, bool(w.lifted), ignore_filter=ignore_filter, w=w)
     I = O.interior(po)
     out = {}
     for b in range(grid.n):
@@ -79,15 +88,18 @@ def test_refine_everywhere_uniform(wavelet, Bs):
     sol.close()
 
 
-def test_refine_everywhere_graded_and_partial():
-    # everywhere on a graded grid: mothers next to coarser blocks are interpolated from predicted ghost nodes
+@pytest.mark.parametrize("wavelet,ignore_filter", [("CDF40", True), ("CDF44", True), ("CDF44", False)])
+def test_refine_everywhere_graded_and_partial(wavelet, ignore_filter):
+    # everywhere on a graded grid: mothers next to coarser blocks are interpolated from predicted ghost nodes, mothers next to
+    # finer blocks from restricted ones (through the HD filter for a lifted wavelet, as the sync_ghosts_tree of main.f90:314)
     lv, ix = graded_blocks(3, 1, 2, seed=4)
     forest = Forest.from_blocks(3, 3, lv, ix)
     assert not forest.is_uniform
-    w, p, po, grid, sol, u = _case("CDF40", 16, forest, seed=3, max_blocks=8 * forest.n_blocks)
+    w, p, po, grid, sol, u = _case(wavelet, 16, forest, seed=3, max_blocks=8 * forest.n_blocks)
     nbr = forest.neighbors(0)[:, :grid.n]
+    sol.set_ghost_filter(ignore_filter)
     sol.upload(u)
-    expect = _refine_oracle(w, po, grid, u[:grid.n], nbr)
+    expect = _refine_oracle(w, po, grid, u[:grid.n], nbr, ignore_filter)
     new = sol.refine_tree(forest)
     got = np.zeros(sol.host_shape())
     sol.download(got, g_sync=0)
@@ -180,23 +192,26 @@ def test_page_locked_host_arrays_take_the_direct_path_with_identical_results():
         sol.close()
 
 
-@pytest.mark.parametrize("wavelet,Bs", [("CDF40", 16), ("CDF44", 16), ("CDF22", 18), ("CDF62", 20), ("CDF20", 24)])
-def test_wavelet_transform_on_graded_grid(wavelet, Bs):
-    """FWT / IWT on a leaf grid with level jumps: ghost values of all 26 relations come from the wavelet jump pool (decimation
-    from finer, prediction from coarser neighbours) and are exactly what the oracle's sync_ghosts_generic(ignore_Filter) leaves,
-    so the coefficients agree bit for bit with sync + waveletDecomposition_optimized_block on the host."""
+@pytest.mark.parametrize("wavelet,Bs,ignore_filter", [("CDF40", 16, True), ("CDF44", 16, True), ("CDF22", 18, True), ("CDF62", 20, True),
+                                                      ("CDF20", 24, True), ("CDF44", 16, False), ("CDF42", 20, False), ("CDF62", 16, False)])
+def test_wavelet_transform_on_graded_grid(wavelet, Bs, ignore_filter):
+    """FWT / IWT on a leaf grid with level jumps: ghost values of all 26 relations come from the wavelet jump pool (restriction
+    from finer -- through the HD filter unless ignore_filter --, prediction from coarser neighbours) and are exactly what the
+    oracle's sync_ghosts_generic leaves, so the coefficients agree bit for bit with sync + waveletDecomposition_optimized_block
+    on the host (the leaf decomposition of wavelet_decompose_full_tree, adapt_tree.f90:403-446)."""
     from wabbit_b200.solver import HVY_TMP
     lv, ix = graded_blocks(3, 1, 3, seed=12)
     forest = Forest.from_blocks(3, 3, lv, ix)
     w, p, po, grid, sol, u = _case(wavelet, Bs, forest, seed=13)
     nbr = forest.neighbors(0)[:, :grid.n]
     I = (slice(None), slice(None)) + O.interior(po)
+    sol.set_ghost_filter(ignore_filter)
     sol.upload(u)
     sol.waveletDecomposition_tree((HVY_BLOCK, 0), (HVY_TMP, 0))
     wd = np.zeros_like(u)
     sol.download(wd, HVY_TMP, g_sync=0)
     ref = u[:grid.n].copy()
-    O.sync_ghosts_leaf(grid, po, ref, nbr, po.g, po.g, w.X, bool(w.lifted))
+    O.sync_ghosts_leaf(grid, po, ref, nbr, po.g, po.g, w.X, bool(w.lifted), ignore_filter=ignore_filter, w=w)
     wd_ref = np.zeros_like(ref)
     O.fwt_tree(w, po, ref, wd_ref)
     assert np.array_equal(wd[:grid.n][I], wd_ref[I])
@@ -208,7 +223,7 @@ def test_wavelet_transform_on_graded_grid(wavelet, Bs):
     sol.waveletReconstruction_tree(src=(HVY_TMP, 0), dst=(HVY_WORK, 2))
     r = np.zeros_like(u)
     sol.download(r, HVY_WORK, 2, g_sync=0)
-    O.sync_ghosts_leaf(grid, po, wd_ref, nbr, po.g, po.g, w.X, bool(w.lifted))
+    O.sync_ghosts_leaf(grid, po, wd_ref, nbr, po.g, po.g, w.X, bool(w.lifted), ignore_filter=ignore_filter, w=w)
     r_ref = np.zeros_like(wd_ref)
     O.iwt_tree(w, po, wd_ref, r_ref)
     assert np.array_equal(r[:grid.n][I], r_ref[I])

@@ -42,6 +42,7 @@ GPU_SYMBOLS = {
     "wgpu_upload": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, _i32p, C.c_int32, C.c_void_p, C.c_int32]),
     "wgpu_download": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, _i32p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]),
     "wgpu_sync_ghosts": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "wgpu_set_ghost_filter": (C.c_int32, [C.c_void_p, C.c_int32]),
     "wgpu_rhs": (C.c_int32, [C.c_void_p, C.c_double, C.c_int32, C.c_int32]),
     "wgpu_calculate_time_step": (C.c_int32, [C.c_void_p, C.c_double, _dp]),
     "wgpu_rk_step": (C.c_int32, [C.c_void_p, C.c_double, C.c_int32, _dp]),

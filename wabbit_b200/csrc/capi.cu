@@ -395,6 +395,10 @@ int32_t wgpu_destroy(wgpu_ctx *ctx)
     cudaFree(ctx->d_jpool);
     cudaFree(ctx->d_ce_blk);
     cudaFree(ctx->d_ce_dir);
+    cudaFree(ctx->d_rst_blk);
+    cudaFree(ctx->d_rst_mask);
+    cudaFree(ctx->d_rmap);
+    cudaFree(ctx->d_rpool);
     cudaFree(ctx->d_wjump_blk);
     cudaFree(ctx->d_wjump_dir);
     cudaFree(ctx->d_wnbr);
@@ -495,13 +499,16 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
     ctx->h_level.assign(N, 0);
     ctx->has_jumps = false;
     ctx->det_cached_for = nullptr;
-    std::vector<int> jump_blk, jump_dir, wjump_blk, wjump_dir, no_same, ce_blk, ce_dir;
+    std::vector<int> jump_blk, jump_dir, wjump_blk, wjump_dir, no_same, ce_blk, ce_dir, rst_blk, rmap(N, -1);
+    std::vector<unsigned> rst_mask;
     for (int k = 0; k < n_active; ++k) {
         const int hid = hvy_active[k];
         if (hid < 1 || hid > N) return fail(ctx, WGPU_ERR_ARG, "hvy_active entry out of range");
         if (level[k] < 0 || level[k] > c.Jmax) return fail(ctx, WGPU_ERR_ARG, "block level out of range");
         ctx->h_active[k] = hid - 1;
         ctx->h_level[hid - 1] = (signed char)level[k];
+        unsigned jump_mask = 0;      // directions with a coarser or finer neighbour
+        bool has_coarser = false;
         for (int dz = -1; dz <= 1; ++dz)
             for (int dy = -1; dy <= 1; ++dy)
                 for (int dx = -1; dx <= 1; ++dx) {
@@ -531,6 +538,7 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
                             const int lc = hvy_neighbor[(size_t)(code - 1 + s + 56) * ld + (hid - 1)];
                             const int lf = hvy_neighbor[(size_t)(code - 1 + s + 112) * ld + (hid - 1)];
                             if (lc >= 1 || lf >= 1) jump = true;
+                            if (lc >= 1) has_coarser = true;
                             if (lc >= 1 && (ce_blk.empty() || ce_blk.back() != hid - 1 || ce_dir.back() != (dz + 1) * 9 + (dy + 1) * 3 + (dx + 1))) {
                                 ce_blk.push_back(hid - 1);
                                 ce_dir.push_back((dz + 1) * 9 + (dy + 1) * 3 + (dx + 1));
@@ -545,6 +553,7 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
                         no_same.push_back((dz + 1) * 9 + (dy + 1) * 3 + (dx + 1));
                         if (jump) {
                             ctx->has_jumps = true;
+                            jump_mask |= 1u << ((dz + 1) * 9 + (dy + 1) * 3 + (dx + 1));
                             // faces become restriction / prediction patches in the jump pool; the star stencils of the time
                             // step do not read edges and corners
                             if ((dx != 0) + (dy != 0) + (dz != 0) == 1) {
@@ -556,6 +565,11 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
                     }
                     ctx->h_nbr[(size_t)(hid - 1) * WGPU_NDIR + (dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)] = entry;
                 }
+        if (has_coarser) {   // this leaf sends restricted data: restrict_copy_at_CE needs its filtered copy
+            rmap[hid - 1] = (int)rst_blk.size();
+            rst_blk.push_back(hid - 1);
+            rst_mask.push_back(jump_mask);
+        }
     }
     ctx->n_active = n_active;
     ctx->n_int = n_active;
@@ -582,6 +596,34 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
         int32_t rcj = upload_jump_tables(ctx, jump_blk, jump_dir);
         if (rcj) return rcj;
         if ((rcj = upload_wjump_tables(ctx, wjump_blk, wjump_dir))) return rcj;
+        ctx->n_rst = 0;
+        if (!rst_blk.empty() && c.dim == 3) {
+            const size_t nr = rst_blk.size();
+            if ((int)nr > ctx->rst_cap) {
+                cudaFree(ctx->d_rst_blk);
+                cudaFree(ctx->d_rst_mask);
+                ctx->d_rst_blk = nullptr;
+                ctx->d_rst_mask = nullptr;
+                const size_t want = nr + nr / 2 + 64;
+                if ((rcj = dmalloc(ctx, &ctx->d_rst_blk, want)) || (rcj = dmalloc(ctx, &ctx->d_rst_mask, want))) return rcj;
+                ctx->rst_cap = (int)want;
+            }
+            const size_t need = nr * ctx->nc * (size_t)(ctx->blk_elems / 8);
+            if (need > ctx->rpool_cap) {
+                cudaFree(ctx->d_rpool);
+                ctx->d_rpool = nullptr;
+                ctx->dev_bytes -= (int64_t)ctx->rpool_cap * 8;
+                const size_t want = need + need / 4;
+                if ((rcj = dmalloc(ctx, &ctx->d_rpool, want))) return rcj;
+                ctx->rpool_cap = want;
+            }
+            if (!ctx->d_rmap && (rcj = dmalloc(ctx, &ctx->d_rmap, (size_t)N))) return rcj;
+            WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_rst_blk, rst_blk.data(), sizeof(int) * nr, cudaMemcpyHostToDevice, ctx->stream));
+            WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_rst_mask, rst_mask.data(), sizeof(unsigned) * nr, cudaMemcpyHostToDevice, ctx->stream));
+            WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_rmap, rmap.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+            WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+            ctx->n_rst = (int)nr;
+        }
         ctx->n_ce = 0;
         if (!ce_blk.empty()) {
             if ((int)ce_blk.size() > ctx->ce_cap) {
@@ -724,6 +766,14 @@ int32_t wgpu_sync_ghosts(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t 
     if (g_minus < 0 || g_plus < 0 || g_minus > ctx->cfg.g || g_plus > ctx->cfg.g) return fail(ctx, WGPU_ERR_ARG, "ghost width out of range");
     // Same-level relations are gathered on the fly by the consumers; there is no level-jump / remote patch in
     // the topologies accepted by wgpu_set_topology yet, hence nothing to refresh.
+    return WGPU_OK;
+}
+
+int32_t wgpu_set_ghost_filter(wgpu_ctx *ctx, int32_t ignore_filter)
+{
+    if (!ctx) return WGPU_ERR_ARG;
+    ctx->ignore_filter = ignore_filter != 0;
+    ctx->det_cached_for = nullptr;
     return WGPU_OK;
 }
 

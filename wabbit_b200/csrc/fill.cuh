@@ -1,8 +1,9 @@
 // fill_region: value of every point of a small box of the level-L lattice on a graded leaf grid, i.e. what the reference's
-// ghost synchronisation (sync_ghosts_generic, "full_leaf", ignore_Filter; LIB/MPI/synchronize_ghosts_generic.f90:181-343)
+// ghost synchronisation (sync_ghosts_generic, "full_leaf"; LIB/MPI/synchronize_ghosts_generic.f90:181-343)
 // leaves in the ghost nodes of a level-L block:
 //   owner leaf on level L     -> copy                      (stage 1; xfer_block_data.f90:395-400)
-//   owner leaf on level L+1   -> decimation                (restrict_data, LIB/MPI/restrict_predict_data.f90:45-115)
+//   owner leaf on level L+1   -> decimation                (restrict_data, LIB/MPI/restrict_predict_data.f90:45-115) of the leaf itself
+//                                (ignore_Filter, unlifted wavelets) or of its HD-filtered copy (FillCtx::rpool)
 //   owner leaf on level L-1   -> prediction x, y, z        (predict_data :174-202; prediction, LIB/WAVELETS/module_wavelets.f90:96-284)
 // The box must lie inside ONE level-L cell (block-sized region), so that all its points share the kind of owner; the
 // coarse lattice points the interpolation touches are resolved the same way one level down (see resolve.cuh).
@@ -14,6 +15,11 @@
 
 struct FillCtx {
     const double *u;      // compact array [blk][nc][Bs^dim]
+    // sync_ghosts_tree with a lifted wavelet (ignore_Filter = .false.): values taken from a finer leaf come from its HD-filtered,
+    // decimated copy (restrict_copy_at_CE, LIB/MPI/restrict_predict_data.f90:121-172), prepared by restrict_filter_kernel:
+    // rpool[rmap[blk]][nc][(Bs/2)^dim]; nullptr = plain decimation (sync_ghosts_RHS_tree, unlifted wavelets)
+    const double *rpool;
+    const int *rmap;
     BlockLookup L;
     int nc, Bs, dim, order;
     int periodic[3];
@@ -94,12 +100,19 @@ __device__ inline int fill_region(const FillCtx &a, SrcTable &T, double *scratch
     int sb, so;
     src_resolve(T, lo, Bs, dim, sb, so);
     if (sb >= 0) {
+        const long long RS = CS >> dim;
         for (int i = tid; i < ncomp * npts; i += nt) {
             const int c = i / npts, r = i % npts;
             const int x = r % ext[0], y = (r / ext[0]) % ext[1], z = r / (ext[0] * ext[1]);
             const int P[3] = {lo[0] + x, lo[1] + y, lo[2] + z};
-            src_resolve(T, P, Bs, dim, sb, so);
-            out[c * sc + z * sz + y * sy + x] = sb >= 0 ? a.u[((long long)sb * a.nc + c0 + c) * CS + so] : 0.0;
+            int ro;
+            src_resolve(T, P, Bs, dim, sb, so, ro);
+            double v = 0.0;
+            if (sb >= 0) {
+                const int ri = (ro >= 0 && a.rpool) ? a.rmap[sb] : -1;
+                v = ri >= 0 ? a.rpool[((long long)ri * a.nc + c0 + c) * RS + ro] : a.u[((long long)sb * a.nc + c0 + c) * CS + so];
+            }
+            out[c * sc + z * sz + y * sy + x] = v;
         }
         return 0;
     }

@@ -15,15 +15,19 @@
 //
 // One CTA per patch / region / (daughter, component).  All of them are HBM-bound gathers of a few hundred to a few thousand
 // points; the arithmetic (prediction) is never contracted so that values are bit-identical to the reference's.
+#include <algorithm>
+
 #include "fill.cuh"
 #include "wgpu_internal.cuh"
 
 namespace {
 
-FillCtx make_fill_ctx(wgpu_ctx *ctx, const double *u)
+FillCtx make_fill_ctx(wgpu_ctx *ctx, const double *u, bool filtered = false)
 {
     FillCtx f;
     f.u = u;
+    f.rpool = filtered ? ctx->d_rpool : nullptr;
+    f.rmap = filtered ? ctx->d_rmap : nullptr;
     f.L.keys = ctx->d_hkeys;
     f.L.vals = ctx->d_hvals;
     f.L.mask = ctx->hmask;
@@ -49,6 +53,81 @@ int32_t ensure_smem(wgpu_ctx *ctx, K kernel, size_t smem, size_t &configured)
         configured = smem;
     }
     return WGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ filtered restriction
+// restrict_copy_at_CE (LIB/MPI/restrict_predict_data.f90:121-172) for every leaf that has a coarser neighbour: blockFilterXYZ_vct with
+// the wavelet's HD filter and do_restriction (LIB/WAVELETS/module_wavelets.f90:307-401: x, then y, then z; only the scaling positions
+// are filtered, each sum starts from 0 and adds u(i+shift)*HD(shift) for every shift in increasing order), then the scaling positions
+// of the Nscl / Nscr strips that face a coarser or finer neighbour are copied back from the unfiltered block
+// (coarseExtensionManipulateSC_block).  The filter reads the leaf's same-level neighbours only: everything it would take from other
+// ghost nodes ends up in a copy strip (tests/test_oracle_sync.py::test_filtered_sync_equals_geometric_definition_on_graded_grids).
+// One CTA per (leaf, component); result: (Bs/2)^3 values in rpool.  x pass from global memory (rows of the leaf and of its same-level
+// neighbours), y and z passes in shared memory.
+struct RestrictArgs {
+    const double *u;
+    double *rpool;
+    const int *rst_blk;
+    const unsigned *rst_mask;
+    const int *nbr;
+    int nc, Bs, F, lo, hi, Nscl, Nscr;
+    double HD[2 * WGPU_FMAX + 1];
+};
+
+__global__ void __launch_bounds__(256) restrict_filter_kernel(const RestrictArgs a)
+{
+    extern __shared__ __align__(16) double sm[];
+    __shared__ int nb[27];
+    const int Bs = a.Bs, F = a.F, half = Bs / 2, n = Bs + 2 * F;
+    const int b = a.rst_blk[blockIdx.x], c = blockIdx.y;
+    const unsigned mask = a.rst_mask[blockIdx.x];
+    const long long CS = (long long)Bs * Bs * Bs;
+    if (threadIdx.x < 27) nb[threadIdx.x] = threadIdx.x == 13 ? b : a.nbr[(long long)b * 27 + threadIdx.x];
+    __syncthreads();
+    double *t1 = sm;                                // [n z][n y][half x]
+    double *t2 = t1 + (size_t)n * n * half;         // [n z][half y][half x]
+    for (int i = threadIdx.x; i < n * n * half; i += blockDim.x) {
+        const int xo = i % half, y = (i / half) % n - F, z = i / (half * n) - F;
+        const int sy = y < 0 ? -1 : (y >= Bs ? 1 : 0), sz = z < 0 ? -1 : (z >= Bs ? 1 : 0);
+        double acc = 0.0;
+        for (int k = a.lo; k <= a.hi; ++k) {
+            const int x = 2 * xo + k;
+            const int sx = x < 0 ? -1 : (x >= Bs ? 1 : 0);
+            const int src = nb[(sz + 1) * 9 + (sy + 1) * 3 + (sx + 1)];
+            const double v = src >= 0 ? a.u[((long long)src * a.nc + c) * CS + ((long long)(z - sz * Bs) * Bs + (y - sy * Bs)) * Bs + (x - sx * Bs)] : 0.0;
+            acc = __dadd_rn(acc, __dmul_rn(v, a.HD[k + WGPU_FMAX]));
+        }
+        t1[i] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n * half * half; i += blockDim.x) {
+        const int xo = i % half, yo = (i / half) % half, z = i / (half * half);
+        double acc = 0.0;
+        for (int k = a.lo; k <= a.hi; ++k) acc = __dadd_rn(acc, __dmul_rn(t1[((size_t)z * n + (2 * yo + F + k)) * half + xo], a.HD[k + WGPU_FMAX]));
+        t2[i] = acc;
+    }
+    __syncthreads();
+    double *out = a.rpool + ((long long)blockIdx.x * a.nc + c) * (CS / 8);
+    const double *own = a.u + ((long long)b * a.nc + c) * CS;
+    for (int i = threadIdx.x; i < half * half * half; i += blockDim.x) {
+        const int xo = i % half, yo = (i / half) % half, zo = i / (half * half);
+        const int p[3] = {2 * xo, 2 * yo, 2 * zo};
+        bool copy = false;
+        for (int d = 0; d < 27 && !copy; ++d) {
+            if (!((mask >> d) & 1u)) continue;
+            const int dd[3] = {d % 3 - 1, (d / 3) % 3 - 1, d / 9 - 1};
+            bool in = true;
+            for (int k = 0; k < 3; ++k) in = in && (dd[k] == 0 || (dd[k] < 0 ? p[k] < a.Nscl : p[k] >= Bs - a.Nscr));
+            copy = in;
+        }
+        double v;
+        if (copy) v = own[((long long)p[2] * Bs + p[1]) * Bs + p[0]];
+        else {
+            v = 0.0;
+            for (int k = a.lo; k <= a.hi; ++k) v = __dadd_rn(v, __dmul_rn(t2[((size_t)(p[2] + F + k) * half + yo) * half + xo], a.HD[k + WGPU_FMAX]));
+        }
+        out[i] = v;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ jump patches
@@ -263,6 +342,40 @@ int32_t wgpu_launch_ce(wgpu_ctx *ctx, double *wd, const double *orig, int Nwcl, 
     return WGPU_OK;
 }
 
+// *active = true if the filtered copies of `src` are in ctx->d_rpool afterwards (lifted wavelet, filter not ignored, level jumps present)
+int32_t wgpu_launch_restrict_filter(wgpu_ctx *ctx, const double *src, int nc_src, bool *active)
+{
+    *active = false;
+    const WaveFilters &w = ctx->wavelet;
+    if (ctx->ignore_filter || !ctx->wavelet_set || w.Y == 0 || ctx->n_rst == 0 || nc_src != ctx->nc) return WGPU_OK;
+    const wgpu_config &c = ctx->cfg;
+    RestrictArgs a;
+    a.u = src;
+    a.rpool = ctx->d_rpool;
+    a.rst_blk = ctx->d_rst_blk;
+    a.rst_mask = ctx->d_rst_mask;
+    a.nbr = ctx->d_nbr;
+    a.nc = ctx->nc;
+    a.Bs = c.Bs[0];
+    a.lo = w.hd_lo;
+    a.hi = w.hd_hi;
+    a.F = std::max(-w.hd_lo, w.hd_hi);
+    a.Nscl = std::max(-w.hd_lo - 1, 0);   // setup_wavelet, module_wavelets.f90:1368-1376
+    a.Nscr = w.hd_hi;
+    for (int k = 0; k < 2 * WGPU_FMAX + 1; ++k) a.HD[k] = w.HD[k];
+    const int n = a.Bs + 2 * a.F, half = a.Bs / 2;
+    const size_t smem = sizeof(double) * ((size_t)n * n * half + (size_t)n * half * half);
+    static size_t configured = 0;
+    int32_t rc = ensure_smem(ctx, restrict_filter_kernel, smem, configured);
+    if (rc) return rc;
+    dim3 grid(ctx->n_rst, ctx->nc);
+    restrict_filter_kernel<<<grid, 256, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    WGPU_CHECK(ctx, cudaGetLastError());
+    *active = true;
+    return WGPU_OK;
+}
+
 int32_t wgpu_launch_jump_fill(wgpu_ctx *ctx, const double *src)
 {
     if (ctx->n_jump == 0) return WGPU_OK;
@@ -296,8 +409,13 @@ int32_t wgpu_launch_export_regions(wgpu_ctx *ctx, const double *src, double *sta
 {
     if (n == 0) return WGPU_OK;
     const wgpu_config &c = ctx->cfg;
+    bool filtered = false;
+    if (g_sync > 0) {   // what sync_ghosts_tree leaves in the ghost nodes: filtered restriction for lifted wavelets
+        int32_t rcf = wgpu_launch_restrict_filter(ctx, src, ncomp_src, &filtered);
+        if (rcf) return rcf;
+    }
     ExportArgs a;
-    a.f = make_fill_ctx(ctx, src);
+    a.f = make_fill_ctx(ctx, src, filtered);
     a.f.nc = ncomp_src;
     a.staged = staged;
     a.ids = d_ids;
@@ -330,8 +448,11 @@ int32_t wgpu_launch_refine(wgpu_ctx *ctx, const double *src, double *dst, const 
 {
     if (n == 0) return WGPU_OK;
     const wgpu_config &c = ctx->cfg;
+    bool filtered = false;   // the sync_ghosts_tree before refine_tree (LIB/MAIN/main.f90:314) applies the restriction filter
+    int32_t rcf = wgpu_launch_restrict_filter(ctx, src, ctx->nc, &filtered);
+    if (rcf) return rcf;
     RefineArgs a;
-    a.f = make_fill_ctx(ctx, src);
+    a.f = make_fill_ctx(ctx, src, filtered);
     a.dst = dst;
     a.mother = d_mother;
     a.daughter = d_daughter;
@@ -378,8 +499,11 @@ int32_t wgpu_launch_wjump_fill(wgpu_ctx *ctx, const double *src)
 {
     if (ctx->n_wjump == 0) return WGPU_OK;
     const wgpu_config &c = ctx->cfg;
+    bool filtered = false;   // sync_TMP_from_all / sync_ghosts_tree before the decomposition: restriction with the HD filter
+    int32_t rcf = wgpu_launch_restrict_filter(ctx, src, ctx->nc, &filtered);
+    if (rcf) return rcf;
     JumpArgs a;
-    a.f = make_fill_ctx(ctx, src);
+    a.f = make_fill_ctx(ctx, src, filtered);
     a.jpool = ctx->d_wpool;
     a.jpatch = 0;
     a.joff = ctx->d_woff;

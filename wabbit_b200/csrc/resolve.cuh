@@ -96,8 +96,10 @@ __device__ inline void src_table_build(SrcTable &T, const BlockLookup &L, int le
 }
 
 // element offset (block index, offset inside the Bs^3 component) of lattice point P; blk = -1 if no leaf of level L or L+1 owns it
-__device__ __forceinline__ void src_resolve(const SrcTable &T, const int P[3], int Bs, int dim, int &blk, int &off)
+// roff >= 0: the owner is one level finer and roff is the point's offset inside a decimated (Bs/2)^dim component (else -1)
+__device__ __forceinline__ void src_resolve(const SrcTable &T, const int P[3], int Bs, int dim, int &blk, int &off, int &roff)
 {
+    roff = -1;
     int seg[3], loc[3];
     for (int a = 0; a < 3; ++a) {
         if (a < dim) {
@@ -116,6 +118,13 @@ __device__ __forceinline__ void src_resolve(const SrcTable &T, const int P[3], i
         const int c = (loc[0] >= half ? 1 : 0) | (loc[1] >= half ? 2 : 0) | ((dim == 3 && loc[2] >= half) ? 4 : 0);
         blk = T.child[e][c];
         for (int a = 0; a < dim; ++a) loc[a] = 2 * loc[a] - (loc[a] >= half ? Bs : 0);
+        roff = ((loc[2] >> 1) * half + (loc[1] >> 1)) * half + (loc[0] >> 1);
     }
     off = (loc[2] * Bs + loc[1]) * Bs + loc[0];
+}
+
+__device__ __forceinline__ void src_resolve(const SrcTable &T, const int P[3], int Bs, int dim, int &blk, int &off)
+{
+    int roff;
+    src_resolve(T, P, Bs, dim, blk, off, roff);
 }

@@ -127,6 +127,14 @@ struct wgpu_ctx {
     // coarse extension: (block, direction) pairs whose neighbour is coarser
     int n_ce = 0, ce_cap = 0;
     int *d_ce_blk = nullptr, *d_ce_dir = nullptr;
+    // HD-filtered restriction of sync_ghosts_tree (lifted wavelets): the blocks that have a coarser neighbour, the directions in which
+    // each of them has a coarser or finer neighbour (bit (dz+1)*9+(dy+1)*3+(dx+1)), and their filtered + decimated copies
+    int n_rst = 0, rst_cap = 0;
+    int *d_rst_blk = nullptr, *d_rmap = nullptr;
+    unsigned *d_rst_mask = nullptr;
+    double *d_rpool = nullptr;
+    size_t rpool_cap = 0;
+    bool ignore_filter = false;        // wavelet-side syncs behave like sync_ghosts_tree(ignore_Filter = .true.)
     bool has_jumps = false;            // some active block has a coarser / finer neighbour
     bool lookup_ready = false;         // block lookup + coordinates of the current topology are on the device
     int *d_idbuf[3] = {nullptr, nullptr, nullptr};   // scratch id lists (refine / coarsen)
@@ -180,6 +188,7 @@ int32_t wgpu_launch_pack(wgpu_ctx *ctx, const double *src);
 // jump.cu
 int32_t wgpu_launch_jump_fill(wgpu_ctx *ctx, const double *src);
 int32_t wgpu_launch_wjump_fill(wgpu_ctx *ctx, const double *src);
+int32_t wgpu_launch_restrict_filter(wgpu_ctx *ctx, const double *src, int nc_src, bool *active);
 int32_t wgpu_launch_ce(wgpu_ctx *ctx, double *wd, const double *orig, int Nwcl, int Nwcr, int Nscl, int Nscr, int clear_wc, int copy_sc);
 int32_t wgpu_launch_export_regions(wgpu_ctx *ctx, const double *src, double *staged, const int *d_ids, int n, int ncomp_src, int ncomp_host,
                                    int g_sync, int by_id);

@@ -146,6 +146,11 @@ class WabbitGPU:
         gs = self.params.g if g_sync is None else g_sync
         self._check(self._lib.wgpu_download(self._ctx, array_id, slot, _i32(ids), len(ids), C.c_void_p(host_ptr), ncomp, gs))
 
+    def set_ghost_filter(self, ignore_filter: bool):
+        """ignore_Filter of sync_ghosts_tree (synchronize_ghosts_generic.f90:125-153): False (default) = restriction through the HD
+        filter of a lifted wavelet in download(g_sync>0) / waveletDecomposition_tree / refine_tree, True = plain decimation."""
+        self._check(self._lib.wgpu_set_ghost_filter(self._ctx, int(bool(ignore_filter))))
+
     # ------------------------------------------------------------------ reference routines
     def sync_ghosts_RHS_tree(self, g_minus: Optional[int] = None, g_plus: Optional[int] = None):
         """synchronize_ghosts_generic.f90:155-174"""
