@@ -229,6 +229,35 @@ int32_t wgpu_move_blocks(wgpu_ctx *ctx, int32_t n, const int32_t *src_hvy, const
  * buffers owned by the caller (n_recv resp. n_send patches of wgpu_patch_doubles() doubles).
  * Must be called after wgpu_set_topology (which accepts neighbours on other ranks only if this call follows).
  */
+/*
+ * Halo blocks: the multi-GPU mode for grids with level jumps and for the wavelet side.  Every block of another rank that appears in
+ * the hvy_neighbor rows of this rank's blocks (any of the 168 relations: same level, coarser, finer) is mirrored in a local slot
+ * behind the rank's own blocks.  The copies are part of the block lookup and of the neighbour tables, so every kernel (stage, level-jump
+ * patches, wavelet transforms, refinement, download with ghosts) runs unchanged; they are never advanced.  The reference moves only
+ * ghost patches (xfer_block_data.f90); whole blocks cost about Bs/(2 g) times the bytes but need no second index space, and the
+ * transfer is hidden behind the blocks that have no halo neighbour.
+ *   wgpu_set_halo            halo_lgt[k] (lgt id = owner_rank*max_blocks + owner_hvy) is mirrored in slot halo_hvy[k] (consecutive slots,
+ *                            in the order the owners' data arrive); send_hvy: own blocks other ranks mirror, in the order they are laid
+ *                            out in send_buf (device memory of the caller, n_send blocks of n_eqn*Bs^dim doubles).  Call it before
+ *                            wgpu_set_treecodes (which then also lists the halo slots) and wgpu_set_topology.
+ *   wgpu_pack_halo(stage)    in halo mode: copies the send blocks of the stage input into send_buf
+ *   wgpu_rk_stage_halo_pointer  where the halo slots of the stage input start: the host receives straight into them (no unpack pass)
+ *   wgpu_pack_blocks / wgpu_halo_pointer   the same for a named array (before wgpu_fwt, wgpu_refine, wgpu_download with ghosts)
+ */
+int32_t wgpu_set_halo(wgpu_ctx *ctx, int32_t n_halo, const int32_t *halo_lgt, const int32_t *halo_hvy, const int32_t *halo_level, int32_t n_send,
+                      const int32_t *send_hvy, double *send_buf);
+int32_t wgpu_pack_blocks(wgpu_ctx *ctx, int32_t array_id, int32_t slot);
+int32_t wgpu_halo_pointer(wgpu_ctx *ctx, int32_t array_id, int32_t slot, void **ptr, int64_t *n_doubles);
+int32_t wgpu_rk_stage_halo_pointer(wgpu_ctx *ctx, int32_t stage, void **ptr, int64_t *n_doubles);
+
+/* wgpu_gather_blocks / wgpu_scatter_blocks: the two local halves of block_xfer (LIB/MPI/block_xfer_nonblocking.f90:16) between ranks, as
+ *   balanceLoad_tree and the gathering of sister blocks before a coarsening need it: whole blocks (interiors) of a resident array are
+ *   packed into / unpacked from a contiguous device buffer of the caller, block k of the list at k*n_eqn*Bs^dim doubles; the host moves
+ *   the buffer between ranks (NCCL).  A block received into a free slot is ordinary local data afterwards (wgpu_move_blocks,
+ *   wgpu_coarsen and wgpu_refine address it by its slot). */
+int32_t wgpu_gather_blocks(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t n, const int32_t *hvy_ids, double *device_buf);
+int32_t wgpu_scatter_blocks(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t n, const int32_t *hvy_ids, const double *device_buf);
+
 enum { WGPU_BLOCKS_ALL = 0, WGPU_BLOCKS_INTERIOR = 1, WGPU_BLOCKS_BOUNDARY = 2 };
 int64_t wgpu_patch_doubles(const wgpu_ctx *ctx);
 int32_t wgpu_set_exchange(wgpu_ctx *ctx, int32_t n_recv, const int32_t *recv_hvy, const int32_t *recv_dir, double *pool,

@@ -142,6 +142,7 @@ int32_t upload_jump_tables(wgpu_ctx *ctx, const std::vector<int> &jump_blk, cons
     ctx->lookup_ready = false;
     bool coords = (int)ctx->h_has_coords.size() == N;
     for (int k = 0; k < ctx->n_active && coords; ++k) coords = ctx->h_has_coords[ctx->h_active[k]] != 0;
+    for (size_t k = 0; k < ctx->h_halo.size() && coords; ++k) coords = ctx->h_has_coords[ctx->h_halo[k]] != 0;
     if (ctx->has_jumps) {
         if (!ctx->wavelet_set)
             return fail(ctx, WGPU_ERR_ARG, "grid has level jumps: call wgpu_set_wavelet first (the predictor order is the wavelet's)");
@@ -151,11 +152,12 @@ int32_t upload_jump_tables(wgpu_ctx *ctx, const std::vector<int> &jump_blk, cons
     if (!coords) return WGPU_OK;   // uniform grid without block positions: nothing that needs the lookup can be called
     // hash table (level, ix, iy, iz) -> block
     size_t cap = 64;
-    while (cap < (size_t)ctx->n_active * 2 + 2) cap <<= 1;
+    const int n_known = ctx->n_active + (int)ctx->h_halo.size();   // blocks resident in HBM: own + halo copies
+    while (cap < (size_t)n_known * 2 + 2) cap <<= 1;
     std::vector<unsigned long long> keys(cap, ~0ull);
     std::vector<int> vals(cap, -1);
-    for (int k = 0; k < ctx->n_active; ++k) {
-        const int b = ctx->h_active[k];
+    for (int k = 0; k < n_known; ++k) {
+        const int b = k < ctx->n_active ? ctx->h_active[k] : ctx->h_halo[k - ctx->n_active];
         const unsigned long long key = blk_key(ctx->h_level[b], ctx->h_ixyz[3 * b], ctx->h_ixyz[3 * b + 1], ctx->h_ixyz[3 * b + 2]);
         unsigned h = blk_hash(key) & (unsigned)(cap - 1);
         while (keys[h] != ~0ull) {
@@ -264,6 +266,9 @@ int32_t upload_wjump_tables(wgpu_ctx *ctx, const std::vector<int> &blk, const st
     ctx->n_wjump = nj;
     return WGPU_OK;
 }
+
+// stage 1 reads U; stage j>1 reads what stage j-1 wrote: UA for even j, UB for odd j
+const double *stage_input_of(wgpu_ctx *ctx, int j) { return j == 1 ? ctx->U : (((j - 1) & 1) ? ctx->UA : ctx->UB); }
 
 int32_t upload_ids(wgpu_ctx *ctx, int which, const std::vector<int> &v)
 {
@@ -395,6 +400,8 @@ int32_t wgpu_destroy(wgpu_ctx *ctx)
     cudaFree(ctx->d_jpool);
     cudaFree(ctx->d_ce_blk);
     cudaFree(ctx->d_ce_dir);
+    cudaFree(ctx->d_halo_send);
+    cudaFree(ctx->d_iota);
     cudaFree(ctx->d_rst_blk);
     cudaFree(ctx->d_rst_mask);
     cudaFree(ctx->d_rmap);
@@ -501,6 +508,9 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
     ctx->det_cached_for = nullptr;
     std::vector<int> jump_blk, jump_dir, wjump_blk, wjump_dir, no_same, ce_blk, ce_dir, rst_blk, rmap(N, -1);
     std::vector<unsigned> rst_mask;
+    std::vector<int> halo_users;      // active blocks with a neighbour in a halo slot (partition-boundary blocks)
+    ctx->halo_fine_neighbor = false;
+    for (size_t k = 0; k < ctx->h_halo.size(); ++k) ctx->h_level[ctx->h_halo[k]] = ctx->halo_level_of[k];
     for (int k = 0; k < n_active; ++k) {
         const int hid = hvy_active[k];
         if (hid < 1 || hid > N) return fail(ctx, WGPU_ERR_ARG, "hvy_active entry out of range");
@@ -508,7 +518,7 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
         ctx->h_active[k] = hid - 1;
         ctx->h_level[hid - 1] = (signed char)level[k];
         unsigned jump_mask = 0;      // directions with a coarser or finer neighbour
-        bool has_coarser = false;
+        bool has_coarser = false, uses_halo = false;
         for (int dz = -1; dz <= 1; ++dz)
             for (int dy = -1; dy <= 1; ++dy)
                 for (int dx = -1; dx <= 1; ++dx) {
@@ -521,7 +531,11 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
                     int entry = -1;
                     if (lgt >= 1) {
                         const int r = (lgt - 1) / N;           // lgt2proc.f90
-                        if (r != rank) {
+                        auto hit = r != rank ? ctx->halo_map.find(lgt) : ctx->halo_map.end();
+                        if (hit != ctx->halo_map.end()) {
+                            entry = hit->second;               // the neighbour's copy lives in a local halo slot
+                            uses_halo = true;
+                        } else if (r != rank) {
                             // same-level neighbour on another GPU: resolved to a pool patch by wgpu_set_exchange (faces);
                             // edges/corners are not needed by the star stencils of the time step
                             entry = -1;
@@ -543,8 +557,14 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
                                 ce_blk.push_back(hid - 1);
                                 ce_dir.push_back((dz + 1) * 9 + (dy + 1) * 3 + (dx + 1));
                             }
-                            if ((lc >= 1 && (lc - 1) / N != rank) || (lf >= 1 && (lf - 1) / N != rank))
-                                return fail(ctx, WGPU_ERR_UNSUPPORTED, "level-jump neighbours on another rank are not supported yet");
+                            for (int pass = 0; pass < 2; ++pass) {
+                                const int l = pass ? lf : lc;
+                                if (l < 1 || (l - 1) / N == rank) continue;
+                                if (!ctx->halo_map.count(l))
+                                    return fail(ctx, WGPU_ERR_UNSUPPORTED, "level-jump neighbour on another rank without a halo copy: call wgpu_set_halo first");
+                                uses_halo = true;
+                                if (pass) ctx->halo_fine_neighbor = true;
+                            }
                         }
                         // every direction without a same-level neighbour is a candidate for a wavelet ghost patch: besides the
                         // coarser / finer relations of the table these are the edges and corners that the reference fills through
@@ -565,6 +585,7 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
                     }
                     ctx->h_nbr[(size_t)(hid - 1) * WGPU_NDIR + (dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)] = entry;
                 }
+        if (uses_halo) halo_users.push_back(hid - 1);
         if (has_coarser) {   // this leaf sends restricted data: restrict_copy_at_CE needs its filtered copy
             rmap[hid - 1] = (int)rst_blk.size();
             rst_blk.push_back(hid - 1);
@@ -574,6 +595,7 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
     ctx->n_active = n_active;
     ctx->n_int = n_active;
     ctx->n_bnd = 0;
+    ctx->halo_bnd.assign(halo_users.begin(), halo_users.end());
     ctx->n_jump = (int)jump_blk.size();
     if (ctx->has_jumps && (int)ctx->h_has_coords.size() == N) {
         for (size_t i = 0; i < no_same.size(); i += 2) {
@@ -645,7 +667,20 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
         if (rc2) return rc2;
         if ((rc2 = dmalloc(ctx, &ctx->d_active_bnd, (size_t)N))) return rc2;
     }
-    if (n_active) {
+    if (!ctx->halo_bnd.empty()) {   // halo mode: partition-boundary blocks wait for the block exchange, the others do not
+        std::vector<char> isb(N, 0);
+        for (int b : ctx->halo_bnd) isb[b] = 1;
+        std::vector<int> ai, ab;
+        for (int k = 0; k < n_active; ++k) (isb[ctx->h_active[k]] ? ab : ai).push_back(ctx->h_active[k]);
+        ctx->n_int = (int)ai.size();
+        ctx->n_bnd = (int)ab.size();
+        if (!ai.empty()) WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_active_int, ai.data(), sizeof(int) * ai.size(), cudaMemcpyHostToDevice, ctx->stream));
+        if (!ab.empty()) WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_active_bnd, ab.data(), sizeof(int) * ab.size(), cudaMemcpyHostToDevice, ctx->stream));
+        WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_active, ctx->h_active.data(), sizeof(int) * n_active, cudaMemcpyHostToDevice, ctx->stream));
+        WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_nbr, ctx->h_nbr.data(), sizeof(int) * ctx->h_nbr.size(), cudaMemcpyHostToDevice, ctx->stream));
+        WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_level, ctx->h_level.data(), (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+        WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    } else if (n_active) {
         WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_active_int, ctx->h_active.data(), sizeof(int) * n_active, cudaMemcpyHostToDevice, ctx->stream));
         WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_active, ctx->h_active.data(), sizeof(int) * n_active, cudaMemcpyHostToDevice, ctx->stream));
         WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_nbr, ctx->h_nbr.data(), sizeof(int) * ctx->h_nbr.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -916,7 +951,10 @@ static int32_t transform(wgpu_ctx *ctx, int32_t src_id, int32_t src_slot, int32_
     if (!ctx->wavelet_set) return fail(ctx, 1213149, "The cat is angry: Wavelet-setup not yet called?");
     const wgpu_config &c = ctx->cfg;
     if (c.dim != 3 || c.Bs[0] != c.Bs[1] || c.Bs[0] != c.Bs[2]) return fail(ctx, WGPU_ERR_UNSUPPORTED, "wavelet kernels: cubic 3-D blocks only so far");
-    if (!ctx->remote_faces.empty() || ctx->n_bnd) return fail(ctx, WGPU_ERR_UNSUPPORTED, "wavelet kernels: neighbours on other ranks are not supported yet");
+    if (!ctx->remote_faces.empty() || (ctx->n_bnd && ctx->halo_bnd.empty()))
+        return fail(ctx, WGPU_ERR_UNSUPPORTED, "wavelet kernels: neighbours on other ranks need halo copies (wgpu_set_halo)");
+    if (ctx->halo_fine_neighbor && !ctx->ignore_filter && ctx->wavelet.Y != 0)
+        return fail(ctx, WGPU_ERR_UNSUPPORTED, "filtered restriction from a finer neighbour on another rank is not supported yet (wgpu_set_ghost_filter(1) or an unlifted wavelet)");
     int n1 = 0, n2 = 0;
     const double *src = array_ptr(ctx, src_id, src_slot, &n1);
     double *dst = array_ptr(ctx, dst_id, dst_slot, &n2);
@@ -1022,7 +1060,10 @@ int32_t wgpu_refine(wgpu_ctx *ctx, int32_t n, const int32_t *mother_hvy, const i
     if (!ctx->lookup_ready) return fail(ctx, WGPU_ERR_ARG, "wgpu_refine: call wgpu_set_treecodes + wgpu_set_topology first");
     const wgpu_config &c = ctx->cfg;
     if (c.Bs[0] != c.Bs[1] || (c.dim == 3 && c.Bs[0] != c.Bs[2])) return fail(ctx, WGPU_ERR_UNSUPPORTED, "wgpu_refine: cubic blocks only");
-    if (!ctx->remote_faces.empty() || ctx->n_bnd) return fail(ctx, WGPU_ERR_UNSUPPORTED, "wgpu_refine: neighbours on other ranks are not supported yet");
+    if (!ctx->remote_faces.empty() || (ctx->n_bnd && ctx->halo_bnd.empty()))
+        return fail(ctx, WGPU_ERR_UNSUPPORTED, "wgpu_refine: neighbours on other ranks need halo copies (wgpu_set_halo)");
+    if (ctx->halo_fine_neighbor && !ctx->ignore_filter && ctx->wavelet.Y != 0)
+        return fail(ctx, WGPU_ERR_UNSUPPORTED, "filtered restriction from a finer neighbour on another rank is not supported yet (wgpu_set_ghost_filter(1) or an unlifted wavelet)");
     const int N = c.max_blocks, nd = 1 << c.dim;
     std::vector<int> mo(n), da((size_t)n * nd), ksrc, kdst;
     std::vector<char> is_mother(N, 0), is_active(N, 0), taken(N, 0);
@@ -1140,6 +1181,118 @@ int32_t wgpu_block_count(const wgpu_ctx *ctx, int32_t which)
     return which == WGPU_BLOCKS_INTERIOR ? ctx->n_int : (which == WGPU_BLOCKS_BOUNDARY ? ctx->n_bnd : ctx->n_active);
 }
 
+int32_t wgpu_set_halo(wgpu_ctx *ctx, int32_t n_halo, const int32_t *halo_lgt, const int32_t *halo_hvy, const int32_t *halo_level, int32_t n_send,
+                      const int32_t *send_hvy, double *send_buf)
+{
+    if (!ctx || n_halo < 0 || n_send < 0) return WGPU_ERR_ARG;
+    if ((n_halo && (!halo_lgt || !halo_hvy || !halo_level)) || (n_send && (!send_hvy || !send_buf))) return WGPU_ERR_ARG;
+    const int N = ctx->cfg.max_blocks;
+    ctx->halo_map.clear();
+    ctx->h_halo.clear();
+    ctx->halo_level_of.clear();
+    for (int k = 0; k < n_halo; ++k) {
+        const int b = halo_hvy[k] - 1;
+        if (b < 0 || b >= N) return fail(ctx, WGPU_ERR_ARG, "wgpu_set_halo: halo slot out of range (max_blocks must hold the own blocks and the halo copies)");
+        if (k && b != ctx->h_halo.back() + 1) return fail(ctx, WGPU_ERR_ARG, "wgpu_set_halo: halo slots must be consecutive, in receive order");
+        if (halo_level[k] < 0 || halo_level[k] > ctx->cfg.Jmax) return fail(ctx, WGPU_ERR_ARG, "wgpu_set_halo: level out of range");
+        ctx->halo_map[halo_lgt[k]] = b;
+        ctx->h_halo.push_back(b);
+        ctx->halo_level_of.push_back((signed char)halo_level[k]);
+    }
+    std::vector<int> sb(std::max(n_send, 1), 0);
+    for (int k = 0; k < n_send; ++k) {
+        sb[k] = send_hvy[k] - 1;
+        if (sb[k] < 0 || sb[k] >= N) return fail(ctx, WGPU_ERR_ARG, "wgpu_set_halo: bad send entry");
+    }
+    int32_t rc;
+    if (n_send > ctx->halo_send_cap) {
+        cudaFree(ctx->d_halo_send);
+        cudaFree(ctx->d_iota);
+        ctx->d_halo_send = ctx->d_iota = nullptr;
+        const int want = n_send + n_send / 2 + 64;
+        if ((rc = dmalloc(ctx, &ctx->d_halo_send, (size_t)want)) || (rc = dmalloc(ctx, &ctx->d_iota, (size_t)want))) return rc;
+        std::vector<int> iota(want);
+        for (int k = 0; k < want; ++k) iota[k] = k;
+        WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_iota, iota.data(), sizeof(int) * want, cudaMemcpyHostToDevice, ctx->stream));
+        WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->halo_send_cap = want;
+    }
+    if (n_send) {
+        WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_halo_send, sb.data(), sizeof(int) * n_send, cudaMemcpyHostToDevice, ctx->stream));
+        WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->n_halo_send = n_send;
+    ctx->d_halo_send_buf = send_buf;
+    ctx->lookup_ready = false;
+    return WGPU_OK;
+}
+
+int32_t wgpu_pack_blocks(wgpu_ctx *ctx, int32_t array_id, int32_t slot)
+{
+    if (!ctx) return WGPU_ERR_ARG;
+    int nc = 0;
+    const double *src = array_ptr(ctx, array_id, slot, &nc);
+    if (!src || nc != ctx->nc) return fail(ctx, WGPU_ERR_ARG, "wgpu_pack_blocks: bad array/slot");
+    return wgpu_launch_copy_blocks(ctx, src, ctx->d_halo_send_buf, ctx->d_halo_send, ctx->d_iota, ctx->n_halo_send);
+}
+
+// whole blocks of a resident array <-> a contiguous device buffer of the caller (block k of the list at k*n_eqn*Bs^dim doubles)
+static int32_t gather_scatter(wgpu_ctx *ctx, bool gather, int32_t array_id, int32_t slot, int32_t n, const int32_t *hvy_ids, double *buf)
+{
+    if (!ctx || n < 0 || (n > 0 && (!hvy_ids || !buf))) return WGPU_ERR_ARG;
+    int nc = 0;
+    double *arr = array_ptr(ctx, array_id, slot, &nc);
+    if (!arr || nc != ctx->nc) return fail(ctx, WGPU_ERR_ARG, "wgpu_gather_blocks / wgpu_scatter_blocks: bad array/slot");
+    if (n == 0) return WGPU_OK;
+    std::vector<int> ids(2 * (size_t)n);
+    for (int k = 0; k < n; ++k) {
+        ids[k] = hvy_ids[k] - 1;
+        ids[n + k] = k;
+        if (ids[k] < 0 || ids[k] >= ctx->cfg.max_blocks) return fail(ctx, WGPU_ERR_ARG, "wgpu_gather_blocks / wgpu_scatter_blocks: hvy id out of range");
+    }
+    int32_t rc = upload_ids(ctx, 2, ids);
+    if (rc) return rc;
+    const int *d_blk = ctx->d_idbuf[2], *d_seq = ctx->d_idbuf[2] + n;
+    rc = gather ? wgpu_launch_copy_blocks(ctx, arr, buf, d_blk, d_seq, n) : wgpu_launch_copy_blocks(ctx, buf, arr, d_seq, d_blk, n);
+    if (rc) return rc;
+    WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));   // the id list is reused by the next call
+    if (!gather) {
+        if (arr == ctx->U) ctx->dtmin_valid = false;
+        ctx->det_cached_for = nullptr;
+    }
+    return WGPU_OK;
+}
+
+int32_t wgpu_gather_blocks(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t n, const int32_t *hvy_ids, double *device_buf)
+{
+    return gather_scatter(ctx, true, array_id, slot, n, hvy_ids, device_buf);
+}
+
+int32_t wgpu_scatter_blocks(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t n, const int32_t *hvy_ids, const double *device_buf)
+{
+    return gather_scatter(ctx, false, array_id, slot, n, hvy_ids, const_cast<double *>(device_buf));
+}
+
+int32_t wgpu_halo_pointer(wgpu_ctx *ctx, int32_t array_id, int32_t slot, void **ptr, int64_t *n_doubles)
+{
+    if (!ctx || !ptr || !n_doubles) return WGPU_ERR_ARG;
+    int nc = 0;
+    double *base = array_ptr(ctx, array_id, slot, &nc);
+    if (!base || nc != ctx->nc) return fail(ctx, WGPU_ERR_ARG, "wgpu_halo_pointer: bad array/slot");
+    *n_doubles = (int64_t)ctx->h_halo.size() * ctx->nc * ctx->blk_elems;
+    *ptr = ctx->h_halo.empty() ? nullptr : base + (int64_t)ctx->h_halo[0] * ctx->nc * ctx->blk_elems;
+    return WGPU_OK;
+}
+
+int32_t wgpu_rk_stage_halo_pointer(wgpu_ctx *ctx, int32_t stage, void **ptr, int64_t *n_doubles)
+{
+    if (!ctx || !ptr || !n_doubles || stage < 1 || stage > ctx->cfg.n_stages) return WGPU_ERR_ARG;
+    double *base = const_cast<double *>(stage_input_of(ctx, stage));
+    *n_doubles = (int64_t)ctx->h_halo.size() * ctx->nc * ctx->blk_elems;
+    *ptr = ctx->h_halo.empty() ? nullptr : base + (int64_t)ctx->h_halo[0] * ctx->nc * ctx->blk_elems;
+    return WGPU_OK;
+}
+
 int32_t wgpu_set_exchange(wgpu_ctx *ctx, int32_t n_recv, const int32_t *recv_hvy, const int32_t *recv_dir, double *pool, int32_t n_send,
                           const int32_t *send_hvy, const int32_t *send_dir, double *send_buf)
 {
@@ -1242,15 +1395,13 @@ int32_t wgpu_rk_dt(wgpu_ctx *ctx, double time)
     return WGPU_OK;
 }
 
-static const double *stage_input(wgpu_ctx *ctx, int j)
-{
-    // stage 1 reads U; stage j>1 reads what stage j-1 wrote: UA for even j, UB for odd j
-    return j == 1 ? ctx->U : (((j - 1) & 1) ? ctx->UA : ctx->UB);
-}
+static const double *stage_input(wgpu_ctx *ctx, int j) { return stage_input_of(ctx, j); }
 
 int32_t wgpu_pack_halo(wgpu_ctx *ctx, int32_t stage)
 {
     if (!ctx || stage < 1 || stage > ctx->cfg.n_stages) return WGPU_ERR_ARG;
+    if (ctx->n_halo_send)   // halo mode: whole blocks for the peers' halo slots
+        return wgpu_launch_copy_blocks(ctx, stage_input(ctx, stage), ctx->d_halo_send_buf, ctx->d_halo_send, ctx->d_iota, ctx->n_halo_send);
     return wgpu_launch_pack(ctx, stage_input(ctx, stage));
 }
 
@@ -1305,7 +1456,9 @@ int32_t wgpu_rk_stage(wgpu_ctx *ctx, int32_t j, int32_t which)
     }
     if (last && !(c.dt_fixed > 0.0)) a.dtmin_bits = dtmin_next;
     int nblk = ctx->n_active;
-    if (which != WGPU_BLOCKS_BOUNDARY) {   // level-jump face patches of this stage input (once per stage)
+    // level-jump face patches of this stage input: once per stage; in halo mode again before the partition-boundary blocks, whose
+    // patches read the halo copies that arrived in the meantime (the patches of interior blocks are rewritten with the same values)
+    if (which != WGPU_BLOCKS_BOUNDARY || !ctx->halo_bnd.empty()) {
         int32_t rcj = wgpu_launch_jump_fill(ctx, uin);
         if (rcj) return rcj;
     }

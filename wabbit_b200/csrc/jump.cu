@@ -488,10 +488,12 @@ int32_t wgpu_launch_copy_blocks(wgpu_ctx *ctx, const double *src, double *dst, c
 {
     if (n == 0) return WGPU_OK;
     const long long per_block = (long long)ctx->nc * ctx->blk_elems;
-    dim3 grid((unsigned)((per_block / 2 + 255) / 256), n);
-    copy_blocks_kernel<<<grid, 256, 0, ctx->stream>>>(src, dst, d_src_ids, d_dst_ids, per_block);
-    ctx->launches++;
-    WGPU_CHECK(ctx, cudaGetLastError());
+    for (int s0 = 0; s0 < n; s0 += 32768) {   // grid.y limit
+        dim3 grid((unsigned)((per_block / 2 + 255) / 256), std::min(32768, n - s0));
+        copy_blocks_kernel<<<grid, 256, 0, ctx->stream>>>(src, dst, d_src_ids + s0, d_dst_ids + s0, per_block);
+        ctx->launches++;
+        WGPU_CHECK(ctx, cudaGetLastError());
+    }
     return WGPU_OK;
 }
 

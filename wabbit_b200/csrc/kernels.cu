@@ -18,6 +18,8 @@
 // the SM keeps several planes of HBM traffic in flight while the FP64 pipe works on the current one.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "wgpu_internal.cuh"
 
 namespace {
@@ -681,45 +683,54 @@ __global__ void dt_finalize_kernel(DtArgs p, const unsigned long long *dtmin_bit
 // host layout <-> resident layout
 // ---------------------------------------------------------------------------------------------
 // staged: [n][ncomp_host][nz][ny][nx] ghosted (Fortran hvy(:,:,:,:,k)); dst: compact [blk][ncomp_dst][Bs^3]
-__global__ void extract_kernel(const double *__restrict__ staged, double *__restrict__ dst, const int *__restrict__ ids, int ncomp_dst,
-                               int ncomp_host, int Bx, int By, int Bz, int g, int gz, int by_id)
+// Both layout kernels are persistent: a capped number of CTAs strides over the work items (block, component, chunk of 256 points).
+// On page-locked host arrays they are PCIe-bound and need few SMs; the cap leaves room for a second transfer kernel in the opposite
+// direction and for the stage kernel of another tree to run at the same time (full-duplex link, see bench.py's end-to-end leg).
+__global__ void __launch_bounds__(256) extract_kernel(const double *__restrict__ staged, double *__restrict__ dst, const int *__restrict__ ids,
+                                                      int n, int nc, int ncomp_dst, int ncomp_host, int Bx, int By, int Bz, int g, int gz, int by_id)
 {
-    const int i = by_id ? ids[blockIdx.y] : blockIdx.y;       // which staged block (by_id: `staged` is the whole host array)
-    const int c = blockIdx.z;       // component
     const int nx = Bx + 2 * g, ny = By + 2 * g, nz = Bz + 2 * gz;
     const long long CS = (long long)Bx * By * Bz;
-    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= CS) return;
-    const int x = e % Bx, y = (e / Bx) % By, z = e / ((long long)Bx * By);
-    const double *s = staged + ((long long)i * ncomp_host + c) * nx * ny * nz;
-    dst[((long long)ids[blockIdx.y] * ncomp_dst + c) * CS + e] = s[((long long)(z + gz) * ny + (y + g)) * nx + (x + g)];
+    const long long nchunk = (CS + blockDim.x - 1) / blockDim.x, total = nchunk * nc * n;
+    for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+        const long long e = (w % nchunk) * blockDim.x + threadIdx.x;
+        if (e >= CS) continue;
+        const int c = (int)((w / nchunk) % nc), k = (int)(w / (nchunk * nc));
+        const int b = ids[k];
+        const int i = by_id ? b : k;       // which staged block (by_id: `staged` is the whole host array)
+        const int x = e % Bx, y = (e / Bx) % By, z = e / ((long long)Bx * By);
+        const double *s = staged + ((long long)i * ncomp_host + c) * nx * ny * nz;
+        dst[((long long)b * ncomp_dst + c) * CS + e] = s[((long long)(z + gz) * ny + (y + g)) * nx + (x + g)];
+    }
 }
 
 // compact -> ghosted staging, ghost shell of width gs gathered from same-level neighbours (all 26 relations:
 // the copy sync_ghosts_generic stage 1 performs, synchronize_ghosts_generic.f90:266-339)
-__global__ void export_kernel(const double *__restrict__ src, double *__restrict__ staged, const int *__restrict__ ids,
-                              const int *__restrict__ nbr, int ncomp_src, int ncomp_host, int Bx, int By, int Bz, int g, int gz, int gs,
-                              int gsz, int by_id)
+__global__ void __launch_bounds__(256) export_kernel(const double *__restrict__ src, double *__restrict__ staged, const int *__restrict__ ids,
+                                                     const int *__restrict__ nbr, int n, int nc, int ncomp_src, int ncomp_host, int Bx, int By, int Bz,
+                                                     int g, int gz, int gs, int gsz, int by_id)
 {
-    const int c = blockIdx.z;
-    const int b = ids[blockIdx.y];
-    const int i = by_id ? b : blockIdx.y;
     const int nx = Bx + 2 * g, ny = By + 2 * g, nz = Bz + 2 * gz;
     const int ex = Bx + 2 * gs, ey = By + 2 * gs, ez = Bz + 2 * gsz;
-    const long long n = (long long)ex * ey * ez;
-    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
-    int x = (int)(e % ex) - gs, y = (int)((e / ex) % ey) - gs, z = (int)(e / ((long long)ex * ey)) - gsz;
-    const int dxi = x < 0 ? -1 : (x >= Bx ? 1 : 0), dyi = y < 0 ? -1 : (y >= By ? 1 : 0), dzi = z < 0 ? -1 : (z >= Bz ? 1 : 0);
-    int sb = b;
-    if (dxi | dyi | dzi) {
-        sb = nbr[b * WGPU_NDIR + (dzi + 1) * 9 + (dyi + 1) * 3 + (dxi + 1)];
-        if (sb < 0) return;   // no direct same-level source: leave the staged value untouched
+    const long long npts = (long long)ex * ey * ez, CS = (long long)Bx * By * Bz;
+    const long long nchunk = (npts + blockDim.x - 1) / blockDim.x, total = nchunk * nc * n;
+    for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+        const long long e = (w % nchunk) * blockDim.x + threadIdx.x;
+        if (e >= npts) continue;
+        const int c = (int)((w / nchunk) % nc), k = (int)(w / (nchunk * nc));
+        const int b = ids[k];
+        const int i = by_id ? b : k;
+        int x = (int)(e % ex) - gs, y = (int)((e / ex) % ey) - gs, z = (int)(e / ((long long)ex * ey)) - gsz;
+        const int dxi = x < 0 ? -1 : (x >= Bx ? 1 : 0), dyi = y < 0 ? -1 : (y >= By ? 1 : 0), dzi = z < 0 ? -1 : (z >= Bz ? 1 : 0);
+        int sb = b;
+        if (dxi | dyi | dzi) {
+            sb = nbr[b * WGPU_NDIR + (dzi + 1) * 9 + (dyi + 1) * 3 + (dxi + 1)];
+            if (sb < 0) continue;   // no direct same-level source: leave the staged value untouched
+        }
+        const int xs = x - dxi * Bx, ys = y - dyi * By, zs = z - dzi * Bz;
+        double *d = staged + ((long long)i * ncomp_host + c) * nx * ny * nz;
+        d[((long long)(z + gz) * ny + (y + g)) * nx + (x + g)] = src[((long long)sb * ncomp_src + c) * CS + ((long long)zs * By + ys) * Bx + xs];
     }
-    const int xs = x - dxi * Bx, ys = y - dyi * By, zs = z - dzi * Bz;
-    const long long CS = (long long)Bx * By * Bz;
-    double *d = staged + ((long long)i * ncomp_host + c) * nx * ny * nz;
-    d[((long long)(z + gz) * ny + (y + g)) * nx + (x + g)] = src[((long long)sb * ncomp_src + c) * CS + ((long long)zs * By + ys) * Bx + xs];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -905,14 +916,28 @@ int32_t wgpu_launch_dt_finalize(wgpu_ctx *ctx, double time, const unsigned long 
     return WGPU_OK;
 }
 
+// CTAs of a layout kernel: a few per SM when the other side is page-locked host memory (PCIe-bound; WGPU_XFER_CTAS overrides), many
+// when it is the device staging buffer (HBM-bound)
+static unsigned xfer_ctas(long long total, int by_id)
+{
+    static int host_cap = 0;
+    if (!host_cap) {
+        const char *e = getenv("WGPU_XFER_CTAS");
+        host_cap = e && atoi(e) > 0 ? atoi(e) : 148 * 4;
+    }
+    const long long cap = by_id ? host_cap : 148 * 32;
+    return (unsigned)(total < cap ? total : cap);
+}
+
 int32_t wgpu_launch_extract(wgpu_ctx *ctx, const double *staged, double *dst, const int *d_ids, int n, int ncomp_dst, int ncomp_host, int by_id)
 {
     if (n == 0) return WGPU_OK;
     const wgpu_config &c = ctx->cfg;
     const int Bz = c.dim == 3 ? c.Bs[2] : 1, gz = c.dim == 3 ? c.g : 0;
     const int nc = ncomp_dst < ncomp_host ? ncomp_dst : ncomp_host;
-    dim3 grid((unsigned)((ctx->blk_elems + 255) / 256), n, nc);
-    extract_kernel<<<grid, 256, 0, ctx->stream>>>(staged, dst, d_ids, ncomp_dst, ncomp_host, c.Bs[0], c.Bs[1], Bz, c.g, gz, by_id);
+    const long long total = ((ctx->blk_elems + 255) / 256) * nc * n;
+    extract_kernel<<<xfer_ctas(total, by_id), 256, 0, ctx->stream>>>(staged, dst, d_ids, n, nc, ncomp_dst, ncomp_host, c.Bs[0], c.Bs[1], Bz, c.g, gz,
+                                                                     by_id);
     ctx->launches++;
     WGPU_CHECK(ctx, cudaGetLastError());
     return WGPU_OK;
@@ -926,9 +951,9 @@ int32_t wgpu_launch_export(wgpu_ctx *ctx, const double *src, double *staged, con
     const int Bz = c.dim == 3 ? c.Bs[2] : 1, gz = c.dim == 3 ? c.g : 0, gsz = c.dim == 3 ? g_sync : 0;
     const int nc = ncomp_src < ncomp_host ? ncomp_src : ncomp_host;
     const long long npts = (long long)(c.Bs[0] + 2 * g_sync) * (c.Bs[1] + 2 * g_sync) * (Bz + 2 * gsz);
-    dim3 grid((unsigned)((npts + 255) / 256), n, nc);
-    export_kernel<<<grid, 256, 0, ctx->stream>>>(src, staged, d_ids, ctx->d_nbr, ncomp_src, ncomp_host, c.Bs[0], c.Bs[1], Bz, c.g, gz,
-                                                 g_sync, gsz, by_id);
+    const long long total = ((npts + 255) / 256) * nc * n;
+    export_kernel<<<xfer_ctas(total, by_id), 256, 0, ctx->stream>>>(src, staged, d_ids, ctx->d_nbr, n, nc, ncomp_src, ncomp_host, c.Bs[0], c.Bs[1], Bz,
+                                                                    c.g, gz, g_sync, gsz, by_id);
     ctx->launches++;
     WGPU_CHECK(ctx, cudaGetLastError());
     return WGPU_OK;

@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "wabbit_gpu.h"
@@ -105,6 +106,17 @@ struct wgpu_ctx {
     int n_send = 0;
     int *d_send_blk = nullptr, *d_send_dir = nullptr;
     double *d_send_buf = nullptr;
+    // halo blocks: copies of blocks owned by other ranks held in local slots (the slots right behind each other, in the order the
+    // owners send them); they are known to the neighbour table and the block lookup but never computed
+    std::unordered_map<int, int> halo_map;   // lgt id (1-based) -> local 0-based block index
+    std::vector<int> h_halo;                 // 0-based block indices of the halo slots, in receive order
+    std::vector<signed char> halo_level_of;  // their mesh levels
+    std::vector<int> halo_bnd;               // active blocks with a neighbour in a halo slot
+    int n_halo_send = 0;
+    int *d_halo_send = nullptr, *d_iota = nullptr;
+    int halo_send_cap = 0;
+    double *d_halo_send_buf = nullptr;       // owned by the caller
+    bool halo_fine_neighbor = false;         // a local block has a FINER neighbour that is a halo block (filtered restriction unavailable)
     // block coordinates + device lookup (level, ix, iy, iz) -> block index, for level-jump patches
     std::vector<int> h_ixyz;           // [max_blocks][3], valid where coords_of[b] != 0
     std::vector<char> h_has_coords;

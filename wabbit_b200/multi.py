@@ -219,3 +219,209 @@ class LockstepGroup:
             dts.append(dt.value)
         assert all(d == dts[0] for d in dts)
         return dts[0]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Halo blocks: the multi-GPU mode for grids with level jumps and for the wavelet side (include/wabbit_gpu.h, wgpu_set_halo)
+# ----------------------------------------------------------------------------------------------------------------------
+def halo_list(forest: Forest, rank: int) -> np.ndarray:
+    """lgt ids (1-based, owner*max_blocks + hvy) of the blocks of other ranks that appear in the 168 neighbour relations of
+    `rank`'s blocks, ascending = sorted by (owner, hvy): the order they arrive in and the order of the halo slots."""
+    N = forest.max_blocks
+    nb = forest.neighbors(rank)
+    ids = np.unique(nb[nb >= 1]).astype(np.int64)
+    return ids[(ids - 1) // N != rank]
+
+
+class HaloPlan:
+    """Which blocks every rank mirrors and which of its own it sends, derived from the replicated light data (no handshake)."""
+
+    def __init__(self, forest: Forest, rank: int, world: int):
+        N = forest.max_blocks
+        self.rank, self.world = rank, world
+        self.n_own = forest.n_active(rank)
+        lists = [halo_list(forest, r) for r in range(world)]
+        mine = lists[rank]
+        self.halo_lgt = mine.astype(np.int32)
+        self.halo_hvy = (self.n_own + 1 + np.arange(len(mine))).astype(np.int32)
+        if self.n_own + len(mine) > N:
+            raise MemoryError(f"rank {rank}: {self.n_own} own blocks + {len(mine)} halo copies exceed max_blocks = {N}")
+        owner = (mine - 1) // N
+        self.recv_counts = [int((owner == p).sum()) for p in range(world)]
+        lvl = np.zeros(len(mine), np.int32)
+        tc = np.zeros(len(mine), np.int64)
+        for p in range(world):
+            sel = owner == p
+            if sel.any():
+                hvy_p, lvl_p, _, tc_p = forest.active(p)
+                assert (hvy_p == np.arange(1, len(hvy_p) + 1)).all()
+                k = (mine[sel] - 1) % N
+                lvl[sel], tc[sel] = lvl_p[k], tc_p[k]
+        self.halo_level, self.halo_tc = lvl, tc
+        send, self.send_counts = [], []
+        for p in range(world):
+            t = lists[p][(lists[p] - 1) // N == rank] if p != rank else np.zeros(0, np.int64)
+            send.append((t - 1) % N + 1)
+            self.send_counts.append(len(t))
+        self.send_hvy = np.concatenate(send).astype(np.int32)
+
+    @property
+    def n_halo(self) -> int:
+        return len(self.halo_lgt)
+
+    @property
+    def n_send(self) -> int:
+        return len(self.send_hvy)
+
+
+class HaloStepper:
+    """One rank of a multi-GPU run on a grid with level jumps: halo copies of the neighbouring blocks of other ranks are refreshed by
+    ONE all-to-all of whole blocks per Runge-Kutta stage (received straight into the halo slots of the stage input), overlapped with
+    the stage kernel on the blocks that have no halo neighbour.  `exchange_array` does the same for a named array before a
+    wavelet-side call (waveletDecomposition_tree, refine_tree, download with ghosts)."""
+
+    def __init__(self, sol, forest: Forest, rank: int, world: int, exchange: Optional[Callable] = None,
+                 allreduce_min: Optional[Callable] = None, overlap: bool = True):
+        import torch
+        self.torch = torch
+        self.sol, self.rank, self.world, self.overlap = sol, rank, world, overlap
+        self.plan = plan = HaloPlan(forest, rank, world)
+        lib, ctx = sol._lib, sol._ctx
+        p = sol.params
+        self.blk = p.n_eqn * int(np.prod([p.Bs[d] for d in range(p.dim)]))
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.send = torch.zeros(max(plan.n_send, 1) * self.blk, dtype=torch.float64, device=self.dev)
+        sol._check(lib.wgpu_set_halo(ctx, plan.n_halo, _i32(plan.halo_lgt), _i32(plan.halo_hvy), _i32(plan.halo_level), plan.n_send,
+                                     _i32(plan.send_hvy), C.c_void_p(self.send.data_ptr())))
+        hvy, lvl, _, tc = forest.active(rank)
+        sol.set_treecodes(np.concatenate([hvy, plan.halo_hvy]), np.concatenate([lvl, plan.halo_level]), np.concatenate([tc, plan.halo_tc]))
+        sol.set_topology(hvy, lvl, forest.neighbors(rank), rank)
+        self.in_splits = [c * self.blk for c in plan.send_counts]
+        self.out_splits = [c * self.blk for c in plan.recv_counts]
+        self._exchange = exchange or MultiGPUStepper._nccl_exchange.__get__(self)
+        self._allreduce_min = allreduce_min or MultiGPUStepper._nccl_min.__get__(self)
+        self.n_int = lib.wgpu_block_count(ctx, 1)
+        self.n_bnd = lib.wgpu_block_count(ctx, 2)
+        self._views: Dict[int, object] = {}
+
+    def _view(self, ptr: int, n: int):
+        if n == 0:
+            return self.torch.zeros(0, dtype=self.torch.float64, device=self.dev)
+        v = self._views.get(ptr)
+        if v is None or v.numel() != n:
+            v = self._views[ptr] = self.torch.as_tensor(_DevPtr(ptr, n), device=self.dev)
+        return v
+
+    def _dtmin_tensor(self):
+        p = C.c_void_p()
+        self.sol._check(self.sol._lib.wgpu_dtmin_pointer(self.sol._ctx, C.byref(p)))
+        return self.torch.as_tensor(_DevPtr(p.value, 1), device=self.dev)
+
+    def stage_halo(self, j: int):
+        p, n = C.c_void_p(), C.c_int64()
+        self.sol._check(self.sol._lib.wgpu_rk_stage_halo_pointer(self.sol._ctx, j, C.byref(p), C.byref(n)))
+        return self._view(p.value or 0, n.value)
+
+    def array_halo(self, array_id: int, slot: int = 0):
+        p, n = C.c_void_p(), C.c_int64()
+        self.sol._check(self.sol._lib.wgpu_halo_pointer(self.sol._ctx, array_id, slot, C.byref(p), C.byref(n)))
+        return self._view(p.value or 0, n.value)
+
+    def exchange_array(self, array_id: int = 0, slot: int = 0):
+        """refresh the halo copies of a named array (blocking)"""
+        self.sol._check(self.sol._lib.wgpu_pack_blocks(self.sol._ctx, array_id, slot))
+        work = self._exchange(self.send, self.array_halo(array_id, slot), self.in_splits, self.out_splits)
+        if work is not None:
+            work.wait()
+
+    def step(self, time: float, iteration: int = 0) -> float:
+        lib, ctx, chk = self.sol._lib, self.sol._ctx, self.sol._check
+        chk(lib.wgpu_rk_begin(ctx, float(time)))
+        if self.world > 1 and not self.sol.params.dt_fixed > 0.0:
+            self._allreduce_min(self._dtmin_tensor())
+        chk(lib.wgpu_rk_dt(ctx, float(time)))
+        for j in range(1, self.sol.params.n_stages + 1):
+            chk(lib.wgpu_pack_halo(ctx, j))
+            work = self._exchange(self.send, self.stage_halo(j), self.in_splits, self.out_splits)
+            if self.overlap and self.n_bnd and self.n_int:
+                chk(lib.wgpu_rk_stage(ctx, j, 1))            # blocks without a halo neighbour while the blocks are in flight
+                if work is not None:
+                    work.wait()
+                chk(lib.wgpu_rk_stage(ctx, j, 2))            # partition-boundary blocks
+            else:
+                if work is not None:
+                    work.wait()
+                chk(lib.wgpu_rk_stage(ctx, j, 0))
+        dt = C.c_double()
+        chk(lib.wgpu_rk_end(ctx, C.byref(dt)))
+        return dt.value
+
+    def timeStep_tree(self, time: float, iteration: int):
+        dt = self.step(time, iteration)
+        return time + dt, iteration + 1, dt
+
+
+def attach_halo(sol, forest: Forest, rank: int, world: int, **kw) -> HaloStepper:
+    """Halo-block mode for `rank`: declare the halo slots, upload the topology and route the time step through HaloStepper."""
+    st = HaloStepper(sol, forest, rank, world, **kw)
+    sol.timeStep_tree = st.timeStep_tree
+    sol.RungeKuttaGeneric = st.step
+    sol.stepper = st
+    return st
+
+
+class HaloLockstepGroup:
+    """Several ranks in halo mode driven by ONE process (contexts on one device), advanced in lockstep; blocks move by device copies.
+    The single-GPU parity test of the halo path."""
+
+    def __init__(self, sols, forest: Forest):
+        import torch
+        self.torch = torch
+        self.world = len(sols)
+        self.st = [HaloStepper(s, forest, r, self.world, exchange=lambda *a: None, allreduce_min=lambda t: None, overlap=False)
+                   for r, s in enumerate(sols)]
+
+    def _move(self, views):
+        W = self.world
+        for r in range(W):
+            so = np.concatenate([[0], np.cumsum(self.st[r].in_splits)])
+            for p in range(W):
+                n = self.st[r].in_splits[p]
+                if n == 0:
+                    continue
+                ro = int(np.sum(self.st[p].out_splits[:r]))
+                views[p][ro:ro + n].copy_(self.st[r].send[int(so[p]):int(so[p]) + n])
+
+    def exchange_array(self, array_id: int = 0, slot: int = 0):
+        for s in self.st:
+            s.sol._check(s.sol._lib.wgpu_pack_blocks(s.sol._ctx, array_id, slot))
+        self._move([s.array_halo(array_id, slot) for s in self.st])
+        self.torch.cuda.synchronize()
+
+    def step(self, time: float, split: bool = False) -> float:
+        torch = self.torch
+        for s in self.st:
+            s.sol._check(s.sol._lib.wgpu_rk_begin(s.sol._ctx, float(time)))
+        if not self.st[0].sol.params.dt_fixed > 0.0:
+            ts = [s._dtmin_tensor() for s in self.st]
+            m = torch.stack([t.to(ts[0].device) for t in ts]).min()
+            for t in ts:
+                t.fill_(m.item())
+        for s in self.st:
+            s.sol._check(s.sol._lib.wgpu_rk_dt(s.sol._ctx, float(time)))
+        for j in range(1, self.st[0].sol.params.n_stages + 1):
+            for s in self.st:
+                s.sol._check(s.sol._lib.wgpu_pack_halo(s.sol._ctx, j))
+            if split:                                        # the overlap order: interior blocks before the halos arrive
+                for s in self.st:
+                    s.sol._check(s.sol._lib.wgpu_rk_stage(s.sol._ctx, j, 1))
+            self._move([s.stage_halo(j) for s in self.st])
+            for s in self.st:
+                s.sol._check(s.sol._lib.wgpu_rk_stage(s.sol._ctx, j, 2 if split else 0))
+        dts = []
+        for s in self.st:
+            dt = C.c_double()
+            s.sol._check(s.sol._lib.wgpu_rk_end(s.sol._ctx, C.byref(dt)))
+            dts.append(dt.value)
+        assert all(d == dts[0] for d in dts)
+        return dts[0]
