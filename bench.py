@@ -531,7 +531,7 @@ def main():
     ap.add_argument("--level", type=int, default=5, help="equidistant level J: (2^J)^3 blocks")
     ap.add_argument("--bs", type=int, default=16)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--e2e-trees", type=int, default=3, help="independent trees in flight in the end-to-end leg (1 = sequential only)")
+    ap.add_argument("--e2e-trees", type=int, default=2, help="independent trees in flight in the end-to-end leg (1 = sequential only)")
     ap.add_argument("--cpu-level", type=int, default=3)
     ap.add_argument("--cpu-steps", type=int, default=6)
     ap.add_argument("--no-cpu", action="store_true")

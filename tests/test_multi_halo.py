@@ -194,3 +194,107 @@ def test_wavelet_side_across_ranks(world, wavelet, ignore_filter):
         off += n
     for s in sols:
         s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,overlap", [(2, True), (3, False)])
+def test_adaptive_cycle_across_ranks_equals_single_rank(world, overlap):
+    """refine_tree("everywhere") -> RK4 step -> adapt_tree (CDF40) with the blocks partitioned over `world` ranks (threads driving one
+    device context each, collectives through ThreadTransport) gives the same grids and bit-identical data as the single-rank driver,
+    which the oracle pins (tests/test_gpu_cycle.py)."""
+    import threading
+    import torch
+    from wabbit_b200 import WabbitGPU
+    from wabbit_b200.multi import DistributedWabbit, ThreadTransport
+    wavelet, Jmax = "CDF40", 4
+    w = O.setup_wavelet(wavelet)
+    lv, ix = graded_blocks(3, 1, 3, seed=5, frac=0.25)
+    MB = 8 * len(lv) + 64
+    p = tg_params(Bs=16, J=Jmax, wavelet_g=w.g_default)
+    p.wavelet = wavelet
+    p.eps = 1.0e-2
+    f1 = Forest.from_blocks(3, Jmax, lv, ix, n_ranks=1, max_blocks=MB)
+    fw = Forest.from_blocks(3, Jmax, lv, ix, n_ranks=world, max_blocks=MB)
+    po = orc_params(p)
+    _, l1, x1, _ = f1.active(0)
+    grid = O.Grid(level=l1.astype(np.int64), ixyz=x1.astype(np.int64), dim=3)
+    u = O.alloc(grid, po)
+    O.inicond_taylor_green(grid, po, u)
+    # strong small-scale content in the low-x half of the domain only: the sweep coarsens part of the grid
+    amp = np.where(x1[:, 0] * 2 < 2 ** l1, 0.05, 1.0e-6)
+    u += amp[:, None, None, None, None] * np.random.default_rng(2).standard_normal(u.shape)
+
+    def run_sequence(drv_refine, drv_step, drv_adapt):
+        out = [drv_refine()]
+        t, it, dt = drv_step(0.0, 0)
+        out.append(dt)
+        out.append(drv_adapt())
+        return out
+
+    # ---- single rank
+    s1 = WabbitGPU(p, max_blocks=MB)
+    s1.setup_wavelet(wavelet)
+    s1.set_forest(f1)
+    host = np.zeros(s1.host_shape())
+    host[:grid.n] = u
+    s1.upload(host)
+    state = {"f": f1}
+
+    def r1():
+        state["f"] = s1.refine_tree(state["f"])
+        return state["f"].n_blocks
+
+    def a1():
+        state["f"], n0, n1 = s1.adapt_tree(state["f"], eps=p.eps, Jmin=1)
+        return (n0, n1)
+
+    ref_seq = run_sequence(r1, s1.timeStep_tree, a1)
+    assert 8 < ref_seq[2][1] < ref_seq[2][0]                   # the sweep coarsens part of the grid
+    _, lf, xf, _ = state["f"].active(0)
+    ref_data = np.zeros(s1.host_shape())
+    s1.download(ref_data, g_sync=0)
+    ref_data = ref_data[:len(lf)].copy()
+    s1.close()
+
+    # ---- `world` ranks
+    sols = []
+    for _ in range(world):
+        s = WabbitGPU(p, max_blocks=MB)
+        s.setup_wavelet(wavelet)
+        sols.append(s)
+    shared = ThreadTransport.Shared(world)
+    offs = np.concatenate([[0], np.cumsum([fw.n_active(r) for r in range(world)])])
+    res, errs = [None] * world, []
+
+    def worker(r):
+        try:
+            torch.cuda.set_device(0)
+            d = DistributedWabbit(sols[r], fw, r, world, transport=ThreadTransport(shared, r), overlap=overlap)
+            n = fw.n_active(r)
+            h = np.zeros(sols[r].host_shape())
+            h[:n] = u[offs[r]:offs[r] + n]
+            sols[r].upload(h)
+            seq = run_sequence(lambda: d.refine_tree().n_blocks, d.timeStep_tree, lambda: d.adapt_tree(eps=p.eps, Jmin=1)[1:])
+            _, l, x, _ = d.forest.active(r)
+            out = np.zeros(sols[r].host_shape())
+            sols[r].download(out, g_sync=0)
+            res[r] = (seq, l, x, out[:len(l)].copy())
+        except BaseException as e:      # noqa: BLE001
+            errs.append((r, repr(e)))
+            shared.barrier.abort()
+
+    th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errs, errs
+    for r in range(world):
+        assert res[r][0][0] == ref_seq[0] and res[r][0][1] == ref_seq[1] and tuple(res[r][0][2]) == tuple(ref_seq[2]), (r, res[r][0], ref_seq)
+    assert np.array_equal(np.concatenate([res[r][1] for r in range(world)]), lf)
+    assert np.array_equal(np.concatenate([res[r][2] for r in range(world)]), xf)
+    got = np.concatenate([res[r][3] for r in range(world)])
+    g = p.g
+    assert np.array_equal(got[:, :, g:-g, g:-g, g:-g], ref_data[:, :, g:-g, g:-g, g:-g])
+    for s in sols:
+        s.close()

@@ -16,7 +16,7 @@ size/metadata handshake is needed (the reference encodes metadata into the messa
 from __future__ import annotations
 
 import ctypes as C
-from typing import Callable, Dict, List, Optional, Tuple
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -425,3 +425,283 @@ class HaloLockstepGroup:
             dts.append(dt.value)
         assert all(d == dts[0] for d in dts)
         return dts[0]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Grid adaptation across ranks: the heavy data of refine_tree / adapt_tree with blocks partitioned over several GPUs
+# ----------------------------------------------------------------------------------------------------------------------
+class NcclTransport:
+    """Collectives of one rank (one process per GPU, torch.distributed / NCCL)."""
+
+    def __init__(self, rank: int, world: int):
+        self.rank, self.world = rank, world
+
+    def alltoall(self, send, recv, in_splits, out_splits, async_op: bool = False):
+        import torch.distributed as dist
+        return dist.all_to_all_single(recv[:sum(out_splits)], send[:sum(in_splits)], out_splits, in_splits, async_op=async_op)
+
+    def allreduce_min_(self, t):
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+
+    def allreduce_max_np(self, a: np.ndarray) -> np.ndarray:
+        import torch
+        import torch.distributed as dist
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.cpu().numpy()
+
+    def allgather_np(self, a: np.ndarray, counts: Sequence[int]) -> np.ndarray:
+        """concatenation over ranks of int32 arrays whose lengths (counts) every rank knows"""
+        import torch
+        import torch.distributed as dist
+        m = max(max(counts), 1)
+        t = torch.zeros(m, dtype=torch.int32).cuda()
+        t[:len(a)] = torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).cuda()
+        out = [torch.zeros(m, dtype=torch.int32).cuda() for _ in range(self.world)]
+        dist.all_gather(out, t)
+        return np.concatenate([o[:c].cpu().numpy() for o, c in zip(out, counts)])
+
+
+class ThreadTransport:
+    """The same collectives between `world` host threads of ONE process (every rank a device context on the same GPU): the
+    single-GPU test harness of the multi-rank drivers."""
+
+    class Shared:
+        def __init__(self, world: int):
+            import threading
+            self.world = world
+            self.barrier = threading.Barrier(world)
+            self.slots = [None] * world
+
+    def __init__(self, shared: "ThreadTransport.Shared", rank: int):
+        self.sh, self.rank, self.world = shared, rank, shared.world
+
+    def _sync(self):
+        import torch
+        torch.cuda.synchronize()
+        self.sh.barrier.wait()
+
+    def alltoall(self, send, recv, in_splits, out_splits, async_op: bool = False):
+        self.sh.slots[self.rank] = (send, in_splits)
+        self._sync()
+        ro = 0
+        for q in range(self.world):
+            s, sp = self.sh.slots[q]
+            so = int(sum(sp[:self.rank]))
+            n = sp[self.rank]
+            assert n == out_splits[q]
+            if n:
+                recv[ro:ro + n].copy_(s[so:so + n])
+            ro += n
+        self._sync()
+        return None
+
+    def allreduce_min_(self, t):
+        self.sh.slots[self.rank] = t
+        self._sync()
+        m = min(float(x.item()) for x in self.sh.slots)
+        self._sync()
+        t.fill_(m)
+
+    def allreduce_max_np(self, a):
+        self.sh.slots[self.rank] = np.asarray(a, dtype=np.float64)
+        self._sync()
+        out = np.max(np.stack(self.sh.slots), axis=0)
+        self._sync()
+        return out
+
+    def allgather_np(self, a, counts):
+        self.sh.slots[self.rank] = np.asarray(a, dtype=np.int32)
+        self._sync()
+        out = np.concatenate(self.sh.slots)
+        self._sync()
+        return out
+
+
+class DistributedWabbit:
+    """One rank of a multi-GPU adaptive run: time step (HaloStepper) plus refine_tree and one coarsening sweep of adapt_tree with the
+    blocks partitioned by the space-filling curve (balanceLoad_tree) over `world` GPUs.  Light data are replicated: every rank derives
+    the same new grid, partition and transfer lists from the all-gathered refinement flags, as WABBIT does from synchronize_lgt_data.
+    Heavy data move as whole blocks: block_xfer (LIB/MPI/block_xfer_nonblocking.f90:16) -> gather kernel + all-to-all + scatter kernel."""
+
+    HVY_BLOCK, HVY_WORK = 0, 1
+
+    def __init__(self, sol, forest: Forest, rank: int, world: int, transport=None, overlap: bool = True):
+        import torch
+        self.torch = torch
+        self.sol, self.rank, self.world = sol, rank, world
+        self.tr = transport or NcclTransport(rank, world)
+        self.overlap = overlap
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        p = sol.params
+        self.blk = p.n_eqn * int(np.prod([p.Bs[d] for d in range(p.dim)]))
+        self.attach(forest)
+
+    # ------------------------------------------------------------------ topology
+    def attach(self, forest: Forest):
+        self.forest = forest
+        self.stepper = HaloStepper(self.sol, forest, self.rank, self.world,
+                                   exchange=lambda s, r, i, o: self.tr.alltoall(s, r, i, o, async_op=True),
+                                   allreduce_min=self.tr.allreduce_min_, overlap=self.overlap)
+        self.counts = [forest.n_active(r) for r in range(self.world)]
+        self.off = np.concatenate([[0], np.cumsum(self.counts)]).astype(np.int64)
+
+    def timeStep_tree(self, time: float, iteration: int):
+        return self.stepper.timeStep_tree(time, iteration)
+
+    def _global_blocks(self, forest: Forest):
+        lv, ix = [], []
+        for r in range(self.world):
+            _, l, x, _ = forest.active(r)
+            lv.append(l)
+            ix.append(x)
+        return np.concatenate(lv), np.concatenate(ix)
+
+    def _shadow(self, forest: Forest) -> Forest:
+        """the same leaves on ONE rank: its block order is the global space-filling-curve order = rank-major order of `forest`"""
+        lv, ix = self._global_blocks(forest)
+        sh = Forest.from_blocks(forest.dim, forest.Jmax, lv, ix, block_dist=forest.block_dist, n_ranks=1, max_blocks=len(lv),
+                                periodic=forest.periodic)
+        _, l2, x2, _ = sh.active(0)
+        assert np.array_equal(l2, lv) and np.array_equal(x2, ix), "global block order is not the space-filling-curve order"
+        return sh
+
+    def _partition(self, shadow: Forest) -> Forest:
+        _, lv, ix, _ = shadow.active(0)
+        return Forest.from_blocks(shadow.dim, shadow.Jmax, lv, ix, block_dist=shadow.block_dist, n_ranks=self.world,
+                                  max_blocks=self.forest.max_blocks, periodic=shadow.periodic)
+
+    # ------------------------------------------------------------------ block transport
+    def _ship(self, array, src_rank, src_slot, dst_rank, first_free: int):
+        """Item k: a block that lives on src_rank[k] in slot src_slot[k] (1-based) of `array` = (array_id, slot) and is needed on
+        dst_rank[k]; the item order is the same on every rank.  Remote blocks are received into free slots from `first_free` on.
+        Returns (local slot of every item with dst_rank == me, in item order; next free slot)."""
+        me, W, torch = self.rank, self.world, self.torch
+        src_rank, src_slot, dst_rank = (np.asarray(a) for a in (src_rank, src_slot, dst_rank))
+        send_ids, in_splits, out_splits = [], [], []
+        mine = dst_rank == me
+        local = np.where(src_rank[mine] == me, src_slot[mine], 0).astype(np.int64)
+        nxt = first_free
+        pos_mine = np.flatnonzero(mine)
+        for q in range(W):
+            s = np.flatnonzero((src_rank == me) & (dst_rank == q)) if q != me else np.zeros(0, np.int64)
+            send_ids.append(src_slot[s])
+            in_splits.append(len(s) * self.blk)
+            r = np.flatnonzero((src_rank[pos_mine] == q)) if q != me else np.zeros(0, np.int64)
+            local[r] = nxt + np.arange(len(r))
+            nxt += len(r)
+            out_splits.append(len(r) * self.blk)
+        if nxt - 1 > self.sol.max_blocks:
+            raise MemoryError(f"rank {me}: block transfer needs {nxt - 1} slots, max_blocks = {self.sol.max_blocks}")
+        send_ids = np.concatenate(send_ids).astype(np.int32) if send_ids else np.zeros(0, np.int32)
+        n_send, n_recv = len(send_ids), nxt - first_free
+        send = torch.empty(max(n_send, 1) * self.blk, dtype=torch.float64, device=self.dev)
+        recv = torch.empty(max(n_recv, 1) * self.blk, dtype=torch.float64, device=self.dev)
+        lib, ctx = self.sol._lib, self.sol._ctx
+        if n_send:
+            self.sol._check(lib.wgpu_gather_blocks(ctx, array[0], array[1], n_send, _i32(send_ids), C.c_void_p(send.data_ptr())))
+        self.tr.alltoall(send, recv, in_splits, out_splits)
+        if n_recv:
+            ids = (first_free + np.arange(n_recv)).astype(np.int32)
+            self.torch.cuda.synchronize()
+            self.sol._check(lib.wgpu_scatter_blocks(ctx, array[0], array[1], n_recv, _i32(ids), C.c_void_p(recv.data_ptr())))
+        return local, nxt
+
+    def _owner(self, off, idx):
+        return np.searchsorted(off[1:], idx, side="right")
+
+    # ------------------------------------------------------------------ refine_tree
+    def refine_tree(self, refine_flags: Optional[np.ndarray] = None) -> Forest:
+        """refine_tree (LIB/MESH/refine_tree.f90:15) across ranks: every rank interpolates its own mothers (ghost nodes from the halo
+        copies), then the new blocks move to their owners in the new partition (balanceLoad_tree).  refine_flags: one +1/0 flag per
+        block of the GLOBAL grid in space-filling-curve order (None = everywhere)."""
+        me, sol = self.rank, self.sol
+        old, ooff = self.forest, self.off
+        self.stepper.exchange_array(0, 0)
+        shadow = self._shadow(old)
+        try:
+            new_sh, mo, da, ks, kd = shadow.refine(refine_flags, max_blocks=self.world * old.max_blocks)
+        except MemoryError as e:
+            raise RuntimeError(f"refine_tree: {e}")
+        new = self._partition(new_sh)
+        noff = np.concatenate([[0], np.cumsum([new.n_active(r) for r in range(self.world)])]).astype(np.int64)
+        nd = 2 ** old.dim
+        mo, da, ks, kd = (a.astype(np.int64) - 1 for a in (mo, da, ks, kd))          # 0-based global indices
+        # blocks derived from my old blocks, in new global order -> intermediate local slots 1..n_tmp
+        my_m = self._owner(ooff, mo) == me
+        my_k = self._owner(ooff, ks) == me
+        d_new = da.reshape(-1, nd)[my_m].ravel()
+        derived = np.sort(np.concatenate([kd[my_k], d_new]))
+        tmp_slot = lambda j: np.searchsorted(derived, j) + 1
+        if len(derived) > sol.max_blocks:
+            raise MemoryError("refine_tree: the refined blocks of this rank do not fit max_blocks")
+        m_loc = (mo[my_m] - ooff[me] + 1).astype(np.int32)
+        sol._check(sol._lib.wgpu_refine(sol._ctx, len(m_loc), _i32(m_loc), _i32(tmp_slot(d_new).astype(np.int32)), int(my_k.sum()),
+                                        _i32((ks[my_k] - ooff[me] + 1).astype(np.int32)), _i32(tmp_slot(kd[my_k]).astype(np.int32))))
+        # every new block: who holds it now (the owner of the old block it derives from) and in which intermediate slot
+        holder = np.empty(new.n_blocks, np.int64)
+        holder[kd] = self._owner(ooff, ks)
+        holder[da] = np.repeat(self._owner(ooff, mo), nd)
+        slot = np.empty(new.n_blocks, np.int64)
+        for r in range(self.world):                         # intermediate slots are ranks' private orderings of contiguous index sets
+            sel = np.flatnonzero(holder == r)
+            slot[sel] = np.arange(1, len(sel) + 1)
+        dst = self._owner(noff, np.arange(new.n_blocks))
+        n_tmp = len(derived)
+        local, _ = self._ship((0, 0), holder, slot, dst, n_tmp + 1)
+        mine_new = np.flatnonzero(dst == me)
+        sol._check(sol._lib.wgpu_move_blocks(sol._ctx, len(mine_new), _i32(local.astype(np.int32)),
+                                             _i32((mine_new - noff[me] + 1).astype(np.int32))))
+        self.attach(new)
+        return new
+
+    # ------------------------------------------------------------------ adapt_tree (one coarsening sweep, unlifted wavelets)
+    def adapt_tree(self, eps: Optional[float] = None, eps_normalized: bool = True, Jmin: int = 1, force_maxlevel_dealiasing: bool = False,
+                   thresh_comp=None):
+        """One coarsening sweep of adapt_tree (LIB/MESH/adapt_tree.f90:11) across ranks, indicator "threshold-state-vector", Linfty norm,
+        unlifted wavelets (as WabbitGPU.adapt_tree): norm -> all-reduce MAX; halo refresh; decomposition + flags per rank; flags
+        all-gathered (synchronize_lgt_data); completeness / gradedness on the replicated light data; sister blocks gathered on the
+        mother's new owner and blocks that stay moved to theirs (block_xfer); mothers assembled from the scaling coefficients.
+        Returns (new forest, number of blocks before, after)."""
+        me, sol = self.rank, self.sol
+        old, ooff = self.forest, self.off
+        w = sol.params.wavelet
+        if not (len(w) == 5 and w[4] == "0"):
+            raise RuntimeError("adapt_tree across ranks: unlifted wavelets only so far")
+        WD = (self.HVY_WORK, 2)
+        norm = None
+        if eps_normalized:
+            norm = self.tr.allreduce_max_np(sol.componentWiseNorm_tree((0, 0), "Linfty"))
+            norm[norm <= 1.0e-9] = 1.0
+        self.stepper.exchange_array(0, 0)
+        sol.waveletDecomposition_tree((0, 0), WD)
+        st = sol.threshold_tree(WD, eps=eps, norm=norm, thresh_comp=thresh_comp, level_ref=old.Jmax)
+        st = self.tr.allgather_np(st, self.counts)
+        lv, _ = self._global_blocks(old)
+        if force_maxlevel_dealiasing:
+            st = np.where(lv == old.Jmax, -1, st)
+        n0 = old.n_blocks
+        if not (st == -1).any():
+            return old, n0, n0
+        shadow = self._shadow(old)
+        new_sh, st_final, mo, da, ks, kd = shadow.coarsen(st, Jmin, max_blocks=n0)
+        if not (st_final == -1).any():
+            return old, n0, n0
+        new = self._partition(new_sh)
+        noff = np.concatenate([[0], np.cumsum([new.n_active(r) for r in range(self.world)])]).astype(np.int64)
+        nd = 2 ** old.dim
+        mo, da, ks, kd = (a.astype(np.int64) - 1 for a in (mo, da, ks, kd))
+        n_own = self.counts[me]
+        # blocks that stay: hvy_block of the old owner -> the new owner
+        loc_k, nxt = self._ship((0, 0), self._owner(ooff, ks), ks - ooff[self._owner(ooff, ks)] + 1, self._owner(noff, kd), n_own + 1)
+        # daughters: decomposed data of the old owner -> the mother's new owner
+        m_rank = np.repeat(self._owner(noff, mo), nd)
+        loc_d, _ = self._ship(WD, self._owner(ooff, da), da - ooff[self._owner(ooff, da)] + 1, m_rank, nxt)
+        kd_mine = kd[self._owner(noff, kd) == me]
+        sol._check(sol._lib.wgpu_move_blocks(sol._ctx, len(kd_mine), _i32(loc_k.astype(np.int32)), _i32((kd_mine - noff[me] + 1).astype(np.int32))))
+        mo_mine = mo[self._owner(noff, mo) == me]
+        sol._check(sol._lib.wgpu_coarsen(sol._ctx, len(mo_mine), _i32((mo_mine - noff[me] + 1).astype(np.int32)), _i32(loc_d.astype(np.int32)),
+                                         WD[0], WD[1]))
+        self.attach(new)
+        return new, n0, new.n_blocks
