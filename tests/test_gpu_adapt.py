@@ -264,3 +264,47 @@ def test_coarse_extension_modify(wavelet, Bs, disc):
         if clear_wc or w.Nscr > 0:
             assert not np.array_equal(got[I], wd[I])
     sol.close()
+
+
+@pytest.mark.parametrize("wavelet,Bs,disc", [("CDF44", 16, "FD_4th_central"), ("CDF42", 18, "FD_4th_central"), ("CDF62", 20, "FD_6th_central")])
+def test_leaf_coarsening_indicator_lifted(wavelet, Bs, disc):
+    """The leaf pass of adapt_tree for a lifted wavelet (wavelet_decompose_full_tree, iteration 0, LIB/MESH/adapt_tree.f90:403-470, and
+    coarseningIndicator_tree): sync_TMP_from_all (restriction through the HD filter) -> waveletDecomposition_optimized_block ->
+    coarse_extension_modify (zero WC / copy SC next to coarser neighbours) -> threshold_block.  Coefficients, details and refinement
+    flags of every leaf equal the oracle's bit for bit."""
+    from wabbit_b200.solver import HVY_TMP
+    lv, ix = graded_blocks(3, 1, 3, seed=41)
+    forest = Forest.from_blocks(3, 3, lv, ix)
+    w = O.setup_wavelet(wavelet)
+    p = tg_params(Bs=Bs, J=3, wavelet_g=w.g_default, discretization=disc)
+    p.wavelet = wavelet
+    grid, po = orc_grid(forest), orc_params(p)
+    sol = WabbitGPU(p, max_blocks=forest.n_blocks)
+    sol.setup_wavelet(wavelet)
+    sol.set_forest(forest)
+    nbr = forest.neighbors(0)[:, :grid.n]
+    H = {"FD_2nd_central": 1, "FD_4th_central": 2, "FD_6th_central": 3}[disc]
+    u = O.alloc(grid, po)
+    O.inicond_taylor_green(grid, po, u)
+    u += 0.01 * np.random.default_rng(4).standard_normal(u.shape)
+    sol.upload(u)
+    norm = sol.componentWiseNorm_tree((HVY_BLOCK, 0))
+    sol.waveletDecomposition_tree((HVY_BLOCK, 0), (HVY_TMP, 0))
+    sol.coarse_extension_modify((HVY_TMP, 0), (HVY_BLOCK, 0))
+    st, det = sol.threshold_tree((HVY_TMP, 0), eps=0.05, norm=norm, want_detail=True, level_ref=3)
+    wd = np.zeros_like(u)
+    sol.download(wd, HVY_TMP, g_sync=0)
+    ref = u.copy()
+    O.sync_ghosts_leaf(grid, po, ref, nbr, po.g, po.g, w.X, True, ignore_filter=False, w=w)
+    wd_ref = np.zeros_like(ref)
+    O.fwt_tree(w, po, ref, wd_ref)
+    n = O.coarse_extension_modify(grid, po, w, wd_ref, ref, nbr, fd_half_width=H)
+    assert n > 0
+    I = (slice(None), slice(None)) + O.interior(po)
+    assert np.array_equal(wd[I], wd_ref[I])
+    norm_ref = O.norm_linfty_tree(po, u)
+    assert np.array_equal(norm, norm_ref)
+    st_ref, det_ref = O.threshold_tree(po, wd_ref, grid.level, 0.05, norm=norm_ref, level_ref=3)
+    assert np.array_equal(det, det_ref) and np.array_equal(st, st_ref)
+    assert 0 < (st == -1).sum() < grid.n
+    sol.close()
