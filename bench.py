@@ -340,7 +340,7 @@ def run_ours(a):
         except Exception as e:      # a secondary figure must not take the headline line down
             adaptive = {"error": repr(e)}
     elif world > 1 and a.adaptive_multi:   # opt-in: a failure on one rank would leave the others waiting in a collective
-        adaptive = adaptive_leg_multi(a, rank, world, local, stream, J0=a.adaptive_level)
+        adaptive = adaptive_leg_multi(a, rank, world, local, stream, J0=a.adaptive_level, Jmax=a.adaptive_level + 1)
     if rank == 0:
         if adaptive is not None:
             line["adaptive"] = adaptive
@@ -539,6 +539,7 @@ def adaptive_leg_multi(a, rank, world, local, stream, eps=None, J0=5, Jmax=6, cy
     p = Params(dim=3, domain=(TWO_PI,) * 3, Bs=(a.bs,) * 3, wavelet="CDF40", g=3, g_rhs=2, n_eqn=4, Jmax=Jmax,
                discretization="FD_4th_central", skew_symmetry=True, c0=10.0, nu=3.125e-3, gamma_p=0.0, CFL=1.0,
                u_mean_set=(0.0, 0.0, 0.0), time_max=1.0e9).finalize()
+    max_blocks_total = max(max_blocks_total, int(1.25 * 8 ** J0))
     mb = int(1.6 * max_blocks_total / world)
     forest = Forest.uniform(3, J0, Jmax=Jmax, n_ranks=world, max_blocks=mb)
     hvy, lvl, ixyz, _ = forest.active(rank)
@@ -637,6 +638,9 @@ def main():
     ap.add_argument("--adaptive-only", action="store_true", help="run only the adaptive-cycle leg and print its record (development)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:   # torchrun exports OMP_NUM_THREADS=1: give the host light-data logic (neighbour search) this rank's share of the cores
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
     if a.adaptive_only:
         import torch
         torch.cuda.set_device(0)

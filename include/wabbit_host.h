@@ -61,6 +61,14 @@ int32_t whost_refine(const whost_forest *f, const int32_t *flags, int32_t max_bl
 int32_t whost_coarsen(const whost_forest *f, int32_t *status, int32_t Jmin, int32_t max_blocks, whost_forest **out, int32_t *n_mothers,
                       int32_t *mothers, int32_t *daughters, int32_t *n_keep, int32_t *keep_src, int32_t *keep_dst);
 
+/* The same for a grid partitioned over any number of ranks: flags / status and every id are 1-based positions in the GLOBAL
+ * space-filling-curve order (= rank-major order of the active lists) of the old resp. new grid; the new grid is partitioned over the
+ * same ranks, at most max_blocks_per_rank blocks each (else 2).  The caller turns positions into (rank, hvy id) with the ranks' counts. */
+int32_t whost_refine_global(const whost_forest *f, const int32_t *flags, int32_t max_blocks_per_rank, whost_forest **out, int32_t *n_mothers,
+                            int32_t *mothers, int32_t *daughters, int32_t *n_keep, int32_t *keep_src, int32_t *keep_dst);
+int32_t whost_coarsen_global(const whost_forest *f, int32_t *status, int32_t Jmin, int32_t max_blocks_per_rank, whost_forest **out,
+                             int32_t *n_mothers, int32_t *mothers, int32_t *daughters, int32_t *n_keep, int32_t *keep_src, int32_t *keep_dst);
+
 /* treecode helpers (module_treelib.f90:793-871) */
 int64_t whost_encode(int32_t dim, int32_t level, int32_t Jmax, const int32_t ixyz[3]);
 int32_t whost_decode(int32_t dim, int32_t level, int32_t Jmax, int64_t treecode, int32_t ixyz[3]);

@@ -185,3 +185,39 @@ def test_two_level_forest_slots():
     kc = [k for k in range(len(hvy)) if lvl[k] == 1 and tuple(ixyz[k]) == (1, 0, 0)][0]
     assert (nb[112:116, hvy[kc] - 1] > 0).all() and (nb[116:120, hvy[kc] - 1] > 0).all()
     assert nb[0, hvy[kc] - 1] == -1
+
+
+@pytest.mark.parametrize("world", [2, 5])
+def test_global_refine_and_coarsen_match_the_single_rank_bookkeeping(world):
+    """whost_refine_global / whost_coarsen_global on a grid partitioned over `world` ranks return, in global space-filling-curve positions,
+    exactly the lists the single-rank routines return in hvy ids (one rank: hvy id == global position), and the same new grid."""
+    from util import graded_blocks
+    lv, ix = graded_blocks(3, 1, 3, seed=9, frac=0.3)
+    n = len(lv)
+    fw = Forest.from_blocks(3, 4, lv, ix, n_ranks=world, max_blocks=8 * n)
+    f1 = Forest.from_blocks(3, 4, lv, ix, n_ranks=1, max_blocks=8 * n)
+
+    def global_blocks(f):
+        l, x = [], []
+        for r in range(f.n_ranks):
+            _, a, b, _ = f.active(r)
+            l.append(a)
+            x.append(b)
+        return np.concatenate(l), np.concatenate(x)
+
+    assert all(np.array_equal(a, b) for a, b in zip(global_blocks(fw), global_blocks(f1)))
+    rng = np.random.default_rng(0)
+    flags = (rng.random(n) < 0.4).astype(np.int32)
+    new_w, *lists_w = fw.refine_global(flags)
+    new_1, *lists_1 = f1.refine(flags, max_blocks=8 * n)
+    assert new_w.n_ranks == world and new_w.n_blocks == new_1.n_blocks
+    assert all(np.array_equal(a, b) for a, b in zip(global_blocks(new_w), global_blocks(new_1)))
+    assert all(np.array_equal(a, b) for a, b in zip(lists_w, lists_1))
+    counts = [new_w.n_active(r) for r in range(world)]
+    assert max(counts) - min(counts) <= 1                                  # balanceLoad_tree: contiguous, equal chunks
+    st = np.where(rng.random(new_w.n_blocks) < 0.8, -1, 0).astype(np.int32)
+    c_w, st_w, *cl_w = new_w.coarsen_global(st, Jmin=1)
+    c_1, st_1, *cl_1 = new_1.coarsen(st, Jmin=1, max_blocks=8 * n)
+    assert np.array_equal(st_w, st_1) and (st_w == -1).any() and c_w.n_blocks == c_1.n_blocks < new_w.n_blocks
+    assert all(np.array_equal(a, b) for a, b in zip(global_blocks(c_w), global_blocks(c_1)))
+    assert all(np.array_equal(a, b) for a, b in zip(cl_w, cl_1))

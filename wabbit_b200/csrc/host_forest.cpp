@@ -353,13 +353,13 @@ int32_t whost_is_uniform(const whost_forest *f) { return f && f->uniform ? 1 : 0
 // ensureGradedness_tree (LIB/MESH/ensureGradedness_tree.f90:13) so that the drivers of this repository run at 10^5 blocks
 // without a Python loop.  In a WABBIT build this logic stays in host Fortran.
 // ---------------------------------------------------------------------------------------------------------------------
-static whost_forest *clone_with_blocks(const whost_forest *f, int32_t N, std::vector<Blk> &&blocks)
+static whost_forest *clone_with_blocks(const whost_forest *f, int32_t N, std::vector<Blk> &&blocks, int n_ranks = 1)
 {
     whost_forest *g = new whost_forest();
     g->dim = f->dim;
     g->Jmax = f->Jmax;
     g->sfc = f->sfc;
-    g->n_ranks = 1;
+    g->n_ranks = n_ranks;
     g->N = N;
     for (int a = 0; a < 3; ++a) g->periodic[a] = f->periodic[a];
     g->blocks = std::move(blocks);
@@ -367,10 +367,29 @@ static whost_forest *clone_with_blocks(const whost_forest *f, int32_t N, std::ve
     return g;
 }
 
+static int32_t refine_impl(const whost_forest *f, const int32_t *flags, int32_t max_blocks, whost_forest **out, int32_t *n_mothers, int32_t *mothers,
+                           int32_t *daughters, int32_t *n_keep, int32_t *keep_src, int32_t *keep_dst, bool global);
+static int32_t coarsen_impl(const whost_forest *f, int32_t *status, int32_t Jmin, int32_t max_blocks, whost_forest **out, int32_t *n_mothers,
+                            int32_t *mothers, int32_t *daughters, int32_t *n_keep, int32_t *keep_src, int32_t *keep_dst, bool global);
+
 int32_t whost_refine(const whost_forest *f, const int32_t *flags, int32_t max_blocks, whost_forest **out, int32_t *n_mothers, int32_t *mothers,
                      int32_t *daughters, int32_t *n_keep, int32_t *keep_src, int32_t *keep_dst)
 {
-    if (!f || !out || f->n_ranks != 1 || !n_mothers || !n_keep) return 1;
+    return refine_impl(f, flags, max_blocks, out, n_mothers, mothers, daughters, n_keep, keep_src, keep_dst, false);
+}
+
+int32_t whost_refine_global(const whost_forest *f, const int32_t *flags, int32_t max_blocks_per_rank, whost_forest **out, int32_t *n_mothers,
+                            int32_t *mothers, int32_t *daughters, int32_t *n_keep, int32_t *keep_src, int32_t *keep_dst)
+{
+    return refine_impl(f, flags, max_blocks_per_rank, out, n_mothers, mothers, daughters, n_keep, keep_src, keep_dst, true);
+}
+
+// global = true: any number of ranks; flags and all ids are 1-based positions in the global space-filling-curve order (rank-major order of
+// the active lists) of the old resp. new grid, and the new grid is partitioned over the same number of ranks
+static int32_t refine_impl(const whost_forest *f, const int32_t *flags, int32_t max_blocks, whost_forest **out, int32_t *n_mothers, int32_t *mothers,
+                           int32_t *daughters, int32_t *n_keep, int32_t *keep_src, int32_t *keep_dst, bool global)
+{
+    if (!f || !out || (!global && f->n_ranks != 1) || !n_mothers || !n_keep) return 1;
     const int dim = f->dim, nd = 1 << dim, n = (int)f->blocks.size();
     std::vector<Blk> nb;
     nb.reserve((size_t)n * nd);
@@ -391,21 +410,26 @@ int32_t whost_refine(const whost_forest *f, const int32_t *flags, int32_t max_bl
             nb.push_back(c);
         }
     }
-    if ((int64_t)nb.size() > max_blocks) return 2;   // error_OOM of refine_tree
-    whost_forest *g = clone_with_blocks(f, max_blocks, std::move(nb));
+    if ((int64_t)nb.size() > (int64_t)max_blocks * (global ? f->n_ranks : 1)) return 2;   // error_OOM of refine_tree
+    whost_forest *g = clone_with_blocks(f, max_blocks, std::move(nb), global ? f->n_ranks : 1);
+    for (int r = 0; r < g->n_ranks; ++r)
+        if ((int)g->rank_blocks[r].size() > max_blocks) {
+            delete g;
+            return 2;
+        }
     int nm = 0, nk = 0;
     for (int k = 0; k < n; ++k) {
         const Blk &b = f->blocks[k];
         if (!ref[k]) {
-            if (keep_src) keep_src[nk] = b.hvy;
-            if (keep_dst) keep_dst[nk] = g->blocks[g->find(b.level, b.ix)].hvy;
+            if (keep_src) keep_src[nk] = global ? k + 1 : b.hvy;
+            if (keep_dst) keep_dst[nk] = global ? g->find(b.level, b.ix) + 1 : g->blocks[g->find(b.level, b.ix)].hvy;
             ++nk;
             continue;
         }
-        if (mothers) mothers[nm] = b.hvy;
+        if (mothers) mothers[nm] = global ? k + 1 : b.hvy;
         for (int d = 0; d < nd; ++d) {
             const int ix[3] = {2 * b.ix[0] + ((d >> 1) & 1), 2 * b.ix[1] + (d & 1), dim == 3 ? 2 * b.ix[2] + ((d >> 2) & 1) : 0};
-            if (daughters) daughters[(size_t)nm * nd + d] = g->blocks[g->find(b.level + 1, ix)].hvy;
+            if (daughters) daughters[(size_t)nm * nd + d] = global ? g->find(b.level + 1, ix) + 1 : g->blocks[g->find(b.level + 1, ix)].hvy;
         }
         ++nm;
     }
@@ -418,9 +442,36 @@ int32_t whost_refine(const whost_forest *f, const int32_t *flags, int32_t max_bl
 int32_t whost_coarsen(const whost_forest *f, int32_t *status, int32_t Jmin, int32_t max_blocks, whost_forest **out, int32_t *n_mothers,
                       int32_t *mothers, int32_t *daughters, int32_t *n_keep, int32_t *keep_src, int32_t *keep_dst)
 {
-    if (!f || !out || !status || f->n_ranks != 1 || !n_mothers || !n_keep) return 1;
+    return coarsen_impl(f, status, Jmin, max_blocks, out, n_mothers, mothers, daughters, n_keep, keep_src, keep_dst, false);
+}
+
+int32_t whost_coarsen_global(const whost_forest *f, int32_t *status, int32_t Jmin, int32_t max_blocks_per_rank, whost_forest **out,
+                             int32_t *n_mothers, int32_t *mothers, int32_t *daughters, int32_t *n_keep, int32_t *keep_src, int32_t *keep_dst)
+{
+    return coarsen_impl(f, status, Jmin, max_blocks_per_rank, out, n_mothers, mothers, daughters, n_keep, keep_src, keep_dst, true);
+}
+
+static int32_t coarsen_impl(const whost_forest *f, int32_t *status, int32_t Jmin, int32_t max_blocks, whost_forest **out, int32_t *n_mothers,
+                            int32_t *mothers, int32_t *daughters, int32_t *n_keep, int32_t *keep_src, int32_t *keep_dst, bool global)
+{
+    if (!f || !out || !status || (!global && f->n_ranks != 1) || !n_mothers || !n_keep) return 1;
     const int dim = f->dim, nd = 1 << dim, n = (int)f->blocks.size();
-    const int32_t *nbr = f->nbr[0].data();
+    // finer neighbours of block k (global position): row of its owner's table, lgt ids -> global positions
+    std::vector<int> roff(f->n_ranks + 1, 0), owner(n), local(n);
+    for (int r = 0; r < f->n_ranks; ++r) {
+        roff[r + 1] = roff[r] + (int)f->rank_blocks[r].size();
+        for (size_t i = 0; i < f->rank_blocks[r].size(); ++i) {
+            owner[f->rank_blocks[r][i]] = r;
+            local[f->rank_blocks[r][i]] = (int)i;
+        }
+    }
+    auto finer = [&](int k, int slot) -> int {   // global position (0-based) of the neighbour in `slot`, or -1
+        const int r = owner[k], ld = (int)f->rank_blocks[r].size();
+        const int lgt = f->nbr[r][(size_t)slot * ld + local[k]];
+        if (lgt < 1) return -1;
+        const int rr = (lgt - 1) / f->N, hv = (lgt - 1) % f->N;
+        return roff[rr] + hv;
+    };
     for (int k = 0; k < n; ++k) status[k] = (status[k] == -1 && f->blocks[k].level > Jmin) ? -1 : 0;
     auto mkey = [&](const Blk &b) {
         const int m[3] = {b.ix[0] >> 1, b.ix[1] >> 1, b.ix[2] >> 1};
@@ -438,8 +489,8 @@ int32_t whost_coarsen(const whost_forest *f, int32_t *status, int32_t Jmin, int3
             for (size_t i = 0; ok && i < kv.second.size(); ++i) {
                 const int k = kv.second[i];
                 for (int slot = 112; slot < 168 && ok; ++slot) {       // gradedness: a finer neighbour must coarsen as well
-                    const int j = nbr[(size_t)slot * n + k];
-                    if (j >= 1 && status[j - 1] != -1) ok = false;
+                    const int j = finer(k, slot);
+                    if (j >= 0 && status[j] != -1) ok = false;
                 }
             }
             if (!ok) {
@@ -465,24 +516,24 @@ int32_t whost_coarsen(const whost_forest *f, int32_t *status, int32_t Jmin, int3
             nb.push_back(m);
         }
     }
-    if ((int64_t)nb.size() > max_blocks) return 2;
-    whost_forest *g = clone_with_blocks(f, max_blocks, std::move(nb));
+    if ((int64_t)nb.size() > (int64_t)max_blocks * (global ? f->n_ranks : 1)) return 2;
+    whost_forest *g = clone_with_blocks(f, max_blocks, std::move(nb), global ? f->n_ranks : 1);
     int nm = 0, nk = 0;
     for (int k = 0; k < n; ++k) {
         const Blk &b = f->blocks[k];
         if (status[k] != -1) {
-            if (keep_src) keep_src[nk] = b.hvy;
-            if (keep_dst) keep_dst[nk] = g->blocks[g->find(b.level, b.ix)].hvy;
+            if (keep_src) keep_src[nk] = global ? k + 1 : b.hvy;
+            if (keep_dst) keep_dst[nk] = global ? g->find(b.level, b.ix) + 1 : g->blocks[g->find(b.level, b.ix)].hvy;
             ++nk;
             continue;
         }
         const int d = (b.ix[1] & 1) | ((b.ix[0] & 1) << 1) | ((dim == 3 ? b.ix[2] & 1 : 0) << 2);
         if (d != 0) continue;
         const int mix[3] = {b.ix[0] >> 1, b.ix[1] >> 1, b.ix[2] >> 1};
-        if (mothers) mothers[nm] = g->blocks[g->find(b.level - 1, mix)].hvy;
+        if (mothers) mothers[nm] = global ? g->find(b.level - 1, mix) + 1 : g->blocks[g->find(b.level - 1, mix)].hvy;
         for (int dd = 0; dd < nd; ++dd) {
             const int ix[3] = {2 * mix[0] + ((dd >> 1) & 1), 2 * mix[1] + (dd & 1), dim == 3 ? 2 * mix[2] + ((dd >> 2) & 1) : 0};
-            if (daughters) daughters[(size_t)nm * nd + dd] = f->blocks[f->find(b.level, ix)].hvy;
+            if (daughters) daughters[(size_t)nm * nd + dd] = global ? f->find(b.level, ix) + 1 : f->blocks[f->find(b.level, ix)].hvy;
         }
         ++nm;
     }

@@ -88,6 +88,37 @@ class Forest:
         new = Forest(h, self.dim, self.Jmax, 1, N, self.block_dist, self.periodic)
         return new, st, mo[:nm.value], da[:nm.value * nd], ks[:nk.value], kd[:nk.value]
 
+    def refine_global(self, flags=None):
+        """refine() for a grid partitioned over any number of ranks: flags and all returned ids are 1-based positions in the global
+        space-filling-curve order (rank-major order of the active lists); the new forest keeps n_ranks and max_blocks."""
+        n, nd = self.n_blocks, 2 ** self.dim
+        fl = None if flags is None else np.ascontiguousarray(flags, dtype=np.int32)
+        mo, da = np.zeros(n, np.int32), np.zeros(n * nd, np.int32)
+        ks, kd = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        nm, nk = C.c_int32(), C.c_int32()
+        h = C.c_void_p()
+        rc = host_lib().whost_refine_global(self._h, None if fl is None else _i32(fl), self.max_blocks, C.byref(h), C.byref(nm), _i32(mo), _i32(da),
+                                            C.byref(nk), _i32(ks), _i32(kd))
+        if rc:
+            raise MemoryError("refine: the refined grid needs more than max_blocks blocks per rank") if rc == 2 else RuntimeError(f"whost_refine_global: {rc}")
+        new = Forest(h, self.dim, self.Jmax, self.n_ranks, self.max_blocks, self.block_dist, self.periodic)
+        return new, mo[:nm.value], da[:nm.value * nd], ks[:nk.value], kd[:nk.value]
+
+    def coarsen_global(self, status, Jmin: int = 1):
+        """coarsen() for a grid partitioned over any number of ranks (global positions, see refine_global)."""
+        n, nd = self.n_blocks, 2 ** self.dim
+        st = np.ascontiguousarray(status, dtype=np.int32).copy()
+        mo, da = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        ks, kd = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        nm, nk = C.c_int32(), C.c_int32()
+        h = C.c_void_p()
+        rc = host_lib().whost_coarsen_global(self._h, _i32(st), Jmin, self.max_blocks, C.byref(h), C.byref(nm), _i32(mo), _i32(da), C.byref(nk),
+                                             _i32(ks), _i32(kd))
+        if rc:
+            raise RuntimeError(f"whost_coarsen_global: {rc}")
+        new = Forest(h, self.dim, self.Jmax, self.n_ranks, self.max_blocks, self.block_dist, self.periodic)
+        return new, st, mo[:nm.value], da[:nm.value * nd], ks[:nk.value], kd[:nk.value]
+
     def __del__(self):
         try:
             if self._h:

@@ -619,12 +619,10 @@ class DistributedWabbit:
         me, sol = self.rank, self.sol
         old, ooff = self.forest, self.off
         self.stepper.exchange_array(0, 0)
-        shadow = self._shadow(old)
         try:
-            new_sh, mo, da, ks, kd = shadow.refine(refine_flags, max_blocks=self.world * old.max_blocks)
+            new, mo, da, ks, kd = old.refine_global(refine_flags)
         except MemoryError as e:
             raise RuntimeError(f"refine_tree: {e}")
-        new = self._partition(new_sh)
         noff = np.concatenate([[0], np.cumsum([new.n_active(r) for r in range(self.world)])]).astype(np.int64)
         nd = 2 ** old.dim
         mo, da, ks, kd = (a.astype(np.int64) - 1 for a in (mo, da, ks, kd))          # 0-based global indices
@@ -684,11 +682,9 @@ class DistributedWabbit:
         n0 = old.n_blocks
         if not (st == -1).any():
             return old, n0, n0
-        shadow = self._shadow(old)
-        new_sh, st_final, mo, da, ks, kd = shadow.coarsen(st, Jmin, max_blocks=n0)
+        new, st_final, mo, da, ks, kd = old.coarsen_global(st, Jmin)
         if not (st_final == -1).any():
             return old, n0, n0
-        new = self._partition(new_sh)
         noff = np.concatenate([[0], np.cumsum([new.n_active(r) for r in range(self.world)])]).astype(np.int64)
         nd = 2 ** old.dim
         mo, da, ks, kd = (a.astype(np.int64) - 1 for a in (mo, da, ks, kd))
