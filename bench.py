@@ -548,7 +548,7 @@ def adaptive_leg_multi(a, rank, world, local, stream, eps=None, J0=5, Jmax=6, cy
     drv = DistributedWabbit(sol, forest, rank, world)
     nb0 = len(hvy)
     shape = (nb0,) + sol.host_shape()[1:]
-    host = torch.empty(shape, dtype=torch.float64, pin_memory=True)
+    host = torch.empty(shape, dtype=torch.float64)     # pageable: with 8 ranks per box the initial condition is not worth 8 x 11 GB of pinned memory
     taylor_green_host(p, ixyz, lvl, host.numpy())
     rng = np.random.default_rng(1)
     centres = rng.random((3, 3)) * TWO_PI
