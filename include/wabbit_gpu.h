@@ -250,6 +250,16 @@ int32_t wgpu_pack_blocks(wgpu_ctx *ctx, int32_t array_id, int32_t slot);
 int32_t wgpu_halo_pointer(wgpu_ctx *ctx, int32_t array_id, int32_t slot, void **ptr, int64_t *n_doubles);
 int32_t wgpu_rk_stage_halo_pointer(wgpu_ctx *ctx, int32_t stage, void **ptr, int64_t *n_doubles);
 
+/* Filtered restriction across ranks (lifted wavelets, wgpu_set_ghost_filter(0)): a block whose FINER neighbour lives on another rank
+ *   needs that neighbour's HD-filtered, decimated copy (restrict_copy_at_CE), which only the owner can form (it reads the fine block's own
+ *   same-level neighbours).  wgpu_set_halo_restrict (after wgpu_set_topology): recv_halo_hvy = halo slots of the finer neighbours, in
+ *   arrival order; send_hvy = own blocks whose copies other ranks need, in the order they are laid out in send_buf (n_eqn*(Bs/2)^dim
+ *   doubles each).  Per synchronisation of an array: wgpu_pack_blocks + all-to-all (the blocks), then wgpu_restrict_pack(array) +
+ *   all-to-all of send_buf into wgpu_restrict_halo_pointer, then the consumer (wgpu_fwt, wgpu_refine, wgpu_download with ghosts). */
+int32_t wgpu_set_halo_restrict(wgpu_ctx *ctx, int32_t n_recv, const int32_t *recv_halo_hvy, int32_t n_send, const int32_t *send_hvy, double *send_buf);
+int32_t wgpu_restrict_pack(wgpu_ctx *ctx, int32_t array_id, int32_t slot);
+int32_t wgpu_restrict_halo_pointer(wgpu_ctx *ctx, void **ptr, int64_t *n_doubles);
+
 /* wgpu_gather_blocks / wgpu_scatter_blocks: the two local halves of block_xfer (LIB/MPI/block_xfer_nonblocking.f90:16) between ranks, as
  *   balanceLoad_tree and the gathering of sister blocks before a coarsening need it: whole blocks (interiors) of a resident array are
  *   packed into / unpacked from a contiguous device buffer of the caller, block k of the list at k*n_eqn*Bs^dim doubles; the host moves

@@ -153,10 +153,11 @@ def test_rk4_on_a_graded_grid_across_ranks(world, split, wavelet):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,wavelet,ignore_filter", [(2, "CDF40", True), (3, "CDF44", True)])
+@pytest.mark.parametrize("world,wavelet,ignore_filter", [(2, "CDF40", True), (3, "CDF44", True), (2, "CDF44", False), (3, "CDF42", False)])
 def test_wavelet_side_across_ranks(world, wavelet, ignore_filter):
     """halo copies refreshed for hvy_block, then on every rank: download with a synchronised ghost shell (all 26 relations, level
-    jumps included) and the wavelet decomposition + flags == the oracle on the global grid, bit for bit"""
+    jumps included) and the wavelet decomposition + flags == the oracle on the global grid, bit for bit.  ignore_filter=False with a
+    lifted wavelet: the HD-filtered copies of finer neighbours owned by other ranks are exchanged as well (wgpu_set_halo_restrict)."""
     from wabbit_b200.solver import HVY_TMP
     w = O.setup_wavelet(wavelet)
     forest = graded_forest(world, seed=21)

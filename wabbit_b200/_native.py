@@ -45,6 +45,9 @@ GPU_SYMBOLS = {
     "wgpu_set_ghost_filter": (C.c_int32, [C.c_void_p, C.c_int32]),
     "wgpu_set_halo": (C.c_int32, [C.c_void_p, C.c_int32, _i32p, _i32p, _i32p, C.c_int32, _i32p, C.c_void_p]),
     "wgpu_pack_blocks": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32]),
+    "wgpu_set_halo_restrict": (C.c_int32, [C.c_void_p, C.c_int32, _i32p, C.c_int32, _i32p, C.c_void_p]),
+    "wgpu_restrict_pack": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32]),
+    "wgpu_restrict_halo_pointer": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), _i64p]),
     "wgpu_gather_blocks": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _i32p, C.c_void_p]),
     "wgpu_scatter_blocks": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _i32p, C.c_void_p]),
     "wgpu_halo_pointer": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), _i64p]),

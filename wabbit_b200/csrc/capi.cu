@@ -401,6 +401,7 @@ int32_t wgpu_destroy(wgpu_ctx *ctx)
     cudaFree(ctx->d_ce_blk);
     cudaFree(ctx->d_ce_dir);
     cudaFree(ctx->d_halo_send);
+    cudaFree(ctx->d_rhalo_send);
     cudaFree(ctx->d_iota);
     cudaFree(ctx->d_rst_blk);
     cudaFree(ctx->d_rst_mask);
@@ -510,6 +511,7 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
     std::vector<unsigned> rst_mask;
     std::vector<int> halo_users;      // active blocks with a neighbour in a halo slot (partition-boundary blocks)
     ctx->halo_fine_neighbor = false;
+    ctx->n_rhalo_recv = ctx->n_rhalo_send = 0;
     for (size_t k = 0; k < ctx->h_halo.size(); ++k) ctx->h_level[ctx->h_halo[k]] = ctx->halo_level_of[k];
     for (int k = 0; k < n_active; ++k) {
         const int hid = hvy_active[k];
@@ -619,6 +621,7 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
         if (rcj) return rcj;
         if ((rcj = upload_wjump_tables(ctx, wjump_blk, wjump_dir))) return rcj;
         ctx->n_rst = 0;
+        ctx->h_rmap.assign(N, -1);
         if (!rst_blk.empty() && c.dim == 3) {
             const size_t nr = rst_blk.size();
             if ((int)nr > ctx->rst_cap) {
@@ -643,6 +646,7 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
             WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_rst_blk, rst_blk.data(), sizeof(int) * nr, cudaMemcpyHostToDevice, ctx->stream));
             WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_rst_mask, rst_mask.data(), sizeof(unsigned) * nr, cudaMemcpyHostToDevice, ctx->stream));
             WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_rmap, rmap.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->h_rmap = rmap;
             WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
             ctx->n_rst = (int)nr;
         }
@@ -953,8 +957,8 @@ static int32_t transform(wgpu_ctx *ctx, int32_t src_id, int32_t src_slot, int32_
     if (c.dim != 3 || c.Bs[0] != c.Bs[1] || c.Bs[0] != c.Bs[2]) return fail(ctx, WGPU_ERR_UNSUPPORTED, "wavelet kernels: cubic 3-D blocks only so far");
     if (!ctx->remote_faces.empty() || (ctx->n_bnd && ctx->halo_bnd.empty()))
         return fail(ctx, WGPU_ERR_UNSUPPORTED, "wavelet kernels: neighbours on other ranks need halo copies (wgpu_set_halo)");
-    if (ctx->halo_fine_neighbor && !ctx->ignore_filter && ctx->wavelet.Y != 0)
-        return fail(ctx, WGPU_ERR_UNSUPPORTED, "filtered restriction from a finer neighbour on another rank is not supported yet (wgpu_set_ghost_filter(1) or an unlifted wavelet)");
+    if (ctx->halo_fine_neighbor && !ctx->n_rhalo_recv && !ctx->ignore_filter && ctx->wavelet.Y != 0)
+        return fail(ctx, WGPU_ERR_UNSUPPORTED, "finer neighbours on another rank: their filtered copies must be exchanged first (wgpu_set_halo_restrict, wgpu_restrict_pack)");
     int n1 = 0, n2 = 0;
     const double *src = array_ptr(ctx, src_id, src_slot, &n1);
     double *dst = array_ptr(ctx, dst_id, dst_slot, &n2);
@@ -1062,8 +1066,8 @@ int32_t wgpu_refine(wgpu_ctx *ctx, int32_t n, const int32_t *mother_hvy, const i
     if (c.Bs[0] != c.Bs[1] || (c.dim == 3 && c.Bs[0] != c.Bs[2])) return fail(ctx, WGPU_ERR_UNSUPPORTED, "wgpu_refine: cubic blocks only");
     if (!ctx->remote_faces.empty() || (ctx->n_bnd && ctx->halo_bnd.empty()))
         return fail(ctx, WGPU_ERR_UNSUPPORTED, "wgpu_refine: neighbours on other ranks need halo copies (wgpu_set_halo)");
-    if (ctx->halo_fine_neighbor && !ctx->ignore_filter && ctx->wavelet.Y != 0)
-        return fail(ctx, WGPU_ERR_UNSUPPORTED, "filtered restriction from a finer neighbour on another rank is not supported yet (wgpu_set_ghost_filter(1) or an unlifted wavelet)");
+    if (ctx->halo_fine_neighbor && !ctx->n_rhalo_recv && !ctx->ignore_filter && ctx->wavelet.Y != 0)
+        return fail(ctx, WGPU_ERR_UNSUPPORTED, "finer neighbours on another rank: their filtered copies must be exchanged first (wgpu_set_halo_restrict, wgpu_restrict_pack)");
     const int N = c.max_blocks, nd = 1 << c.dim;
     std::vector<int> mo(n), da((size_t)n * nd), ksrc, kdst;
     std::vector<char> is_mother(N, 0), is_active(N, 0), taken(N, 0);
@@ -1224,6 +1228,72 @@ int32_t wgpu_set_halo(wgpu_ctx *ctx, int32_t n_halo, const int32_t *halo_lgt, co
     ctx->n_halo_send = n_send;
     ctx->d_halo_send_buf = send_buf;
     ctx->lookup_ready = false;
+    return WGPU_OK;
+}
+
+int32_t wgpu_set_halo_restrict(wgpu_ctx *ctx, int32_t n_recv, const int32_t *recv_halo_hvy, int32_t n_send, const int32_t *send_hvy, double *send_buf)
+{
+    if (!ctx || n_recv < 0 || n_send < 0 || (n_recv && !recv_halo_hvy) || (n_send && (!send_hvy || !send_buf))) return WGPU_ERR_ARG;
+    const int N = ctx->cfg.max_blocks;
+    if ((int)ctx->h_rmap.size() != N) ctx->h_rmap.assign(N, -1);
+    const size_t entry = (size_t)ctx->nc * (size_t)(ctx->blk_elems >> ctx->cfg.dim);
+    const size_t need = ((size_t)ctx->n_rst + n_recv) * entry;
+    int32_t rc;
+    if (need > ctx->rpool_cap) {
+        cudaFree(ctx->d_rpool);
+        ctx->d_rpool = nullptr;
+        ctx->dev_bytes -= (int64_t)ctx->rpool_cap * 8;
+        if ((rc = dmalloc(ctx, &ctx->d_rpool, need + need / 4))) return rc;
+        ctx->rpool_cap = need + need / 4;
+    }
+    if (!ctx->d_rmap && (rc = dmalloc(ctx, &ctx->d_rmap, (size_t)N))) return rc;
+    for (int k = 0; k < n_recv; ++k) {
+        const int b = recv_halo_hvy[k] - 1;
+        if (b < 0 || b >= N) return fail(ctx, WGPU_ERR_ARG, "wgpu_set_halo_restrict: halo slot out of range");
+        ctx->h_rmap[b] = ctx->n_rst + k;
+    }
+    std::vector<int> idx(std::max(n_send, 1), 0);
+    for (int k = 0; k < n_send; ++k) {
+        const int b = send_hvy[k] - 1;
+        if (b < 0 || b >= N || ctx->h_rmap[b] < 0 || ctx->h_rmap[b] >= ctx->n_rst)
+            return fail(ctx, WGPU_ERR_ARG, "wgpu_set_halo_restrict: a block of the send list has no coarser neighbour (no filtered copy exists)");
+        idx[k] = ctx->h_rmap[b];
+    }
+    if (n_send > ctx->rhalo_send_cap) {
+        cudaFree(ctx->d_rhalo_send);
+        ctx->d_rhalo_send = nullptr;
+        if ((rc = dmalloc(ctx, &ctx->d_rhalo_send, (size_t)n_send + n_send / 2 + 64))) return rc;
+        ctx->rhalo_send_cap = n_send + n_send / 2 + 64;
+    }
+    if (n_send) WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_rhalo_send, idx.data(), sizeof(int) * n_send, cudaMemcpyHostToDevice, ctx->stream));
+    WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_rmap, ctx->h_rmap.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+    WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->n_rhalo_recv = n_recv;
+    ctx->n_rhalo_send = n_send;
+    ctx->d_rhalo_send_buf = send_buf;
+    return WGPU_OK;
+}
+
+int32_t wgpu_restrict_pack(wgpu_ctx *ctx, int32_t array_id, int32_t slot)
+{
+    if (!ctx) return WGPU_ERR_ARG;
+    int nc = 0;
+    const double *src = array_ptr(ctx, array_id, slot, &nc);
+    if (!src || nc != ctx->nc) return fail(ctx, WGPU_ERR_ARG, "wgpu_restrict_pack: bad array/slot");
+    bool active = false;
+    int32_t rc = wgpu_launch_restrict_filter(ctx, src, nc, &active);
+    if (rc) return rc;
+    if (!active || ctx->n_rhalo_send == 0) return WGPU_OK;
+    return wgpu_launch_copy_entries(ctx, ctx->d_rpool, ctx->d_rhalo_send_buf, ctx->d_rhalo_send, ctx->n_rhalo_send,
+                                    (long long)ctx->nc * (ctx->blk_elems >> ctx->cfg.dim));
+}
+
+int32_t wgpu_restrict_halo_pointer(wgpu_ctx *ctx, void **ptr, int64_t *n_doubles)
+{
+    if (!ctx || !ptr || !n_doubles) return WGPU_ERR_ARG;
+    const int64_t entry = (int64_t)ctx->nc * (ctx->blk_elems >> ctx->cfg.dim);
+    *n_doubles = (int64_t)ctx->n_rhalo_recv * entry;
+    *ptr = ctx->n_rhalo_recv ? ctx->d_rpool + (int64_t)ctx->n_rst * entry : nullptr;
     return WGPU_OK;
 }
 

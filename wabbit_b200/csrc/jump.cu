@@ -497,6 +497,26 @@ int32_t wgpu_launch_copy_blocks(wgpu_ctx *ctx, const double *src, double *dst, c
     return WGPU_OK;
 }
 
+// dst[k] = src[idx[k]] for entries of per_entry doubles: packs filtered copies for other ranks
+__global__ void __launch_bounds__(256) copy_entries_kernel(const double *__restrict__ src, double *__restrict__ dst, const int *__restrict__ idx,
+                                                           long long per_entry)
+{
+    const double *s = src + (long long)idx[blockIdx.y] * per_entry;
+    double *o = dst + (long long)blockIdx.y * per_entry;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_entry; i += (long long)gridDim.x * blockDim.x) o[i] = s[i];
+}
+
+int32_t wgpu_launch_copy_entries(wgpu_ctx *ctx, const double *src, double *dst, const int *d_src_idx, int n, long long per_entry)
+{
+    for (int s0 = 0; s0 < n; s0 += 32768) {
+        dim3 grid((unsigned)((per_entry + 255) / 256), std::min(32768, n - s0));
+        copy_entries_kernel<<<grid, 256, 0, ctx->stream>>>(src, dst + (long long)s0 * per_entry, d_src_idx + s0, per_entry);
+        ctx->launches++;
+        WGPU_CHECK(ctx, cudaGetLastError());
+    }
+    return WGPU_OK;
+}
+
 int32_t wgpu_launch_wjump_fill(wgpu_ctx *ctx, const double *src)
 {
     if (ctx->n_wjump == 0) return WGPU_OK;

@@ -143,9 +143,14 @@ struct wgpu_ctx {
     // each of them has a coarser or finer neighbour (bit (dz+1)*9+(dy+1)*3+(dx+1)), and their filtered + decimated copies
     int n_rst = 0, rst_cap = 0;
     int *d_rst_blk = nullptr, *d_rmap = nullptr;
+    std::vector<int> h_rmap;           // host copy of d_rmap: block -> rpool entry or -1
     unsigned *d_rst_mask = nullptr;
     double *d_rpool = nullptr;
     size_t rpool_cap = 0;
+    // filtered copies of FINER neighbours owned by other ranks: received behind the rank's own entries of rpool (wgpu_set_halo_restrict)
+    int n_rhalo_recv = 0, n_rhalo_send = 0, rhalo_send_cap = 0;
+    int *d_rhalo_send = nullptr;       // rpool indices of the entries other ranks need
+    double *d_rhalo_send_buf = nullptr;   // owned by the caller
     bool ignore_filter = false;        // wavelet-side syncs behave like sync_ghosts_tree(ignore_Filter = .true.)
     bool has_jumps = false;            // some active block has a coarser / finer neighbour
     bool lookup_ready = false;         // block lookup + coordinates of the current topology are on the device
@@ -207,6 +212,7 @@ int32_t wgpu_launch_export_regions(wgpu_ctx *ctx, const double *src, double *sta
 int32_t wgpu_launch_refine(wgpu_ctx *ctx, const double *src, double *dst, const int *d_mother, const int *d_daughter, int n);
 int32_t wgpu_launch_coarsen(wgpu_ctx *ctx, const double *src, double *dst, const int *d_mother, const int *d_daughter, int n);
 int32_t wgpu_launch_copy_blocks(wgpu_ctx *ctx, const double *src, double *dst, const int *d_src_ids, const int *d_dst_ids, int n);
+int32_t wgpu_launch_copy_entries(wgpu_ctx *ctx, const double *src, double *dst, const int *d_src_idx, int n, long long per_entry);
 // wavelet.cu
 int32_t wgpu_launch_wavelet(wgpu_ctx *ctx, const double *src, double *dst, int inverse);
 int32_t wgpu_launch_detail(wgpu_ctx *ctx, const double *wd, int eps_norm, int level_ref);

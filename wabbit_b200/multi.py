@@ -233,6 +233,14 @@ def halo_list(forest: Forest, rank: int) -> np.ndarray:
     return ids[(ids - 1) // N != rank]
 
 
+def fine_halo_list(forest: Forest, rank: int) -> np.ndarray:
+    """lgt ids of the FINER neighbours (relations 113..168) of `rank`'s blocks that other ranks own, ascending"""
+    N = forest.max_blocks
+    nb = forest.neighbors(rank)[112:168]
+    ids = np.unique(nb[nb >= 1]).astype(np.int64)
+    return ids[(ids - 1) // N != rank]
+
+
 class HaloPlan:
     """Which blocks every rank mirrors and which of its own it sends, derived from the replicated light data (no handshake)."""
 
@@ -241,6 +249,13 @@ class HaloPlan:
         self.rank, self.world = rank, world
         self.n_own = forest.n_active(rank)
         lists = [halo_list(forest, r) for r in range(world)]
+        # filtered copies of finer neighbours (lifted wavelets): who needs whose
+        fl = [fine_halo_list(forest, r) for r in range(world)]
+        self.fine_lgt = fl[rank]
+        self.fine_recv_counts = [int(((fl[rank] - 1) // N == p).sum()) for p in range(world)]
+        fs = [fl[p][(fl[p] - 1) // N == rank] if p != rank else np.zeros(0, np.int64) for p in range(world)]
+        self.fine_send_counts = [len(t) for t in fs]
+        self.fine_send_hvy = ((np.concatenate(fs) - 1) % N + 1).astype(np.int32)
         mine = lists[rank]
         self.halo_lgt = mine.astype(np.int32)
         self.halo_hvy = (self.n_own + 1 + np.arange(len(mine))).astype(np.int32)
@@ -258,6 +273,7 @@ class HaloPlan:
                 k = (mine[sel] - 1) % N
                 lvl[sel], tc[sel] = lvl_p[k], tc_p[k]
         self.halo_level, self.halo_tc = lvl, tc
+        self.fine_recv_hvy = self.halo_hvy[np.searchsorted(mine, self.fine_lgt)].astype(np.int32)   # halo slots of the finer neighbours
         send, self.send_counts = [], []
         for p in range(world):
             t = lists[p][(lists[p] - 1) // N == rank] if p != rank else np.zeros(0, np.int64)
@@ -303,6 +319,16 @@ class HaloStepper:
         self.n_int = lib.wgpu_block_count(ctx, 1)
         self.n_bnd = lib.wgpu_block_count(ctx, 2)
         self._views: Dict[int, object] = {}
+        # lifted wavelet: the filtered copies of finer neighbours on other ranks travel too (restrict_copy_at_CE needs the owner)
+        w = getattr(p, "wavelet", "CDF40")
+        self.lifted = len(w) == 5 and w[4] != "0"
+        self.rblk = p.n_eqn * int(np.prod([p.Bs[d] // 2 for d in range(p.dim)]))
+        if self.lifted and world > 1:
+            self.rsend = torch.zeros(max(len(plan.fine_send_hvy), 1) * self.rblk, dtype=torch.float64, device=self.dev)
+            sol._check(lib.wgpu_set_halo_restrict(ctx, len(plan.fine_recv_hvy), _i32(plan.fine_recv_hvy), len(plan.fine_send_hvy),
+                                                  _i32(plan.fine_send_hvy), C.c_void_p(self.rsend.data_ptr())))
+            self.r_in = [c * self.rblk for c in plan.fine_send_counts]
+            self.r_out = [c * self.rblk for c in plan.fine_recv_counts]
 
     def _view(self, ptr: int, n: int):
         if n == 0:
@@ -327,12 +353,20 @@ class HaloStepper:
         self.sol._check(self.sol._lib.wgpu_halo_pointer(self.sol._ctx, array_id, slot, C.byref(p), C.byref(n)))
         return self._view(p.value or 0, n.value)
 
-    def exchange_array(self, array_id: int = 0, slot: int = 0):
-        """refresh the halo copies of a named array (blocking)"""
+    def exchange_array(self, array_id: int = 0, slot: int = 0, filtered: bool = True):
+        """refresh the halo copies of a named array (blocking); with a lifted wavelet also the filtered copies of the finer neighbours
+        other ranks own (what the next wavelet-side synchronisation of this array restricts from)"""
         self.sol._check(self.sol._lib.wgpu_pack_blocks(self.sol._ctx, array_id, slot))
         work = self._exchange(self.send, self.array_halo(array_id, slot), self.in_splits, self.out_splits)
         if work is not None:
             work.wait()
+        if self.lifted and filtered and self.world > 1:
+            self.sol._check(self.sol._lib.wgpu_restrict_pack(self.sol._ctx, array_id, slot))
+            p, n = C.c_void_p(), C.c_int64()
+            self.sol._check(self.sol._lib.wgpu_restrict_halo_pointer(self.sol._ctx, C.byref(p), C.byref(n)))
+            work = self._exchange(self.rsend, self._view(p.value or 0, n.value), self.r_in, self.r_out)
+            if work is not None:
+                work.wait()
 
     def step(self, time: float, iteration: int = 0) -> float:
         lib, ctx, chk = self.sol._lib, self.sol._ctx, self.sol._check
@@ -397,6 +431,22 @@ class HaloLockstepGroup:
             s.sol._check(s.sol._lib.wgpu_pack_blocks(s.sol._ctx, array_id, slot))
         self._move([s.array_halo(array_id, slot) for s in self.st])
         self.torch.cuda.synchronize()
+        if self.st[0].lifted and self.world > 1:          # filtered copies of finer neighbours on other ranks
+            views = []
+            for s in self.st:
+                s.sol._check(s.sol._lib.wgpu_restrict_pack(s.sol._ctx, array_id, slot))
+                p, n = C.c_void_p(), C.c_int64()
+                s.sol._check(s.sol._lib.wgpu_restrict_halo_pointer(s.sol._ctx, C.byref(p), C.byref(n)))
+                views.append(s._view(p.value or 0, n.value))
+            W = self.world
+            for r in range(W):
+                so = np.concatenate([[0], np.cumsum(self.st[r].r_in)])
+                for q in range(W):
+                    n = self.st[r].r_in[q]
+                    if n:
+                        ro = int(np.sum(self.st[q].r_out[:r]))
+                        views[q][ro:ro + n].copy_(self.st[r].rsend[int(so[q]):int(so[q]) + n])
+            self.torch.cuda.synchronize()
 
     def step(self, time: float, split: bool = False) -> float:
         torch = self.torch
