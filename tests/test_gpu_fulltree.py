@@ -1,0 +1,67 @@
+"""adapt_tree with the full wavelet transformation for lifted wavelets (wabbit_b200/fulltree.py) against the oracle's restatement of
+wavelet_decompose_full_tree / coarseningIndicator_tree / the grid decision / wavelet_reconstruct_full_tree_CEoptimized
+(oracle/fulltree.py): coefficients of every block of the full tree (leaves and mothers), details and flags bit for bit."""
+import numpy as np
+import pytest
+
+import fulltree as OFT
+import oracle as O
+from wabbit_b200 import Forest, WabbitGPU
+from wabbit_b200.fulltree import FullTree, WD
+from wabbit_b200.solver import HVY_BLOCK
+
+from util import graded_blocks, orc_grid, orc_params, tg_params
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(wavelet, Bs, seed, Jmax=3, disc="FD_4th_central", noise=0.05):
+    lv, ix = graded_blocks(3, 1, Jmax, seed, 0.3)
+    forest = Forest.from_blocks(3, Jmax, lv, ix, max_blocks=2 * len(lv) + 16)
+    w = O.setup_wavelet(wavelet)
+    p = tg_params(Bs=Bs, J=Jmax, wavelet_g=w.g_default, discretization=disc)
+    p.wavelet = wavelet
+    grid, po = orc_grid(forest), orc_params(p)
+    sol = WabbitGPU(p, max_blocks=forest.max_blocks)
+    sol.setup_wavelet(wavelet)
+    sol.set_forest(forest)
+    u = O.alloc(grid, po)
+    O.inicond_taylor_green(grid, po, u)
+    # small scales in the low-x half of the domain only: part of the tree is significant, part is not
+    amp = np.where(grid.ixyz[:, 0] * 2 < 2 ** grid.level, noise, 1.0e-7)
+    u += amp[:, None, None, None, None] * np.random.default_rng(seed).standard_normal(u.shape)
+    g = po.g
+    u[:, :, :g] = u[:, :, -g:] = 0.0                      # ghost nodes carry nothing: every value the transform reads is synchronised
+    u[:, :, :, :g] = u[:, :, :, -g:] = 0.0
+    u[:, :, :, :, :g] = u[:, :, :, :, -g:] = 0.0
+    host = np.zeros(sol.host_shape())
+    host[:grid.n] = u
+    sol.upload(host, hvy_ids=np.arange(1, grid.n + 1, dtype=np.int32))
+    H = {"FD_2nd_central": 1, "FD_4th_central": 2, "FD_6th_central": 3}[disc]
+    return w, p, po, forest, grid, sol, u, H
+
+
+@pytest.mark.parametrize("wavelet,Bs", [("CDF44", 16), ("CDF44", 18), ("CDF42", 16), ("CDF62", 16), ("CDF22", 16)])
+def test_full_tree_decomposition_and_flags(wavelet, Bs):
+    w, p, po, forest, grid, sol, u, H = _setup(wavelet, Bs, seed=3)
+    ot = OFT.decompose_full_tree(po, w, grid, u, Jmin=1, fd_half_width=H)
+    norm = O.norm_linfty_tree(po, u)
+    ost = OFT.threshold_full_tree(ot, 0.01, norm=norm, level_ref=forest.Jmax)
+    ft = FullTree(sol, forest, Jmin=1)
+    assert ft.leaf_first == ot.leaf_first and set(ft.slot) == set(ot.blk) and len(ft.slot) > len(ft.leaf)
+    gnorm = sol.componentWiseNorm_tree((HVY_BLOCK, 0))
+    assert np.array_equal(gnorm, norm)
+    st = ft.decompose(eps=0.01, norm=gnorm)
+    keys = sorted(ft.slot, key=lambda k: ft.slot[k])
+    ids = np.array([ft.slot[k] for k in keys], dtype=np.int32)
+    wd = np.zeros(sol.host_shape())
+    sol.download(wd, WD[0], WD[1], hvy_ids=ids, g_sync=0)
+    uu = np.zeros(sol.host_shape())
+    sol.download(uu, HVY_BLOCK, 0, hvy_ids=ids, g_sync=0)
+    I = (slice(None),) + O.interior(po)
+    for k in keys:
+        assert np.array_equal(wd[ft.slot[k] - 1][I], ot.blk[k][I]), k              # decomposed values (hvy_block of the reference)
+        assert np.array_equal(uu[ft.slot[k] - 1][I], ot.tmp[k][I]), k              # original / assembled values (hvy_tmp)
+    assert st == ost
+    assert 0 < sum(1 for v in st.values() if v == -1) < len(st)
+    sol.close()

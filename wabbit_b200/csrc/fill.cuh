@@ -85,9 +85,10 @@ __device__ inline void predict_from_box(double *cb, const int clo[3], const int 
 
 // All threads of the CTA call this.  lo[3]: unwrapped global lattice coordinates (level `lvl`) of the box origin, ext[3] its
 // extents; out[c*sc + z*sz + y*sy + x] receives component c0 + c for c < ncomp.  scratch: fill_scratch_doubles(ext) doubles
-// of shared memory.  T: a SrcTable in shared memory.  Returns 0 copy/decimation, 1 prediction, -1 no owner (zeros written).
+// of shared memory.  T: a SrcTable in shared memory.  Returns 0 copy/decimation, 1 prediction, -1 no owner (zeros written if
+// zero_if_no_owner, else nothing).
 __device__ inline int fill_region(const FillCtx &a, SrcTable &T, double *scratch, int lvl, const int lo[3], const int ext[3], double *out,
-                                  long long sc, long long sy, long long sz, int c0, int ncomp, int tid, int nt)
+                                  long long sc, long long sy, long long sz, int c0, int ncomp, int tid, int nt, bool zero_if_no_owner = false)
 {
     const int Bs = a.Bs, dim = a.dim;
     const long long CS = (long long)Bs * Bs * (dim == 3 ? Bs : 1);
@@ -116,7 +117,15 @@ __device__ inline int fill_region(const FillCtx &a, SrcTable &T, double *scratch
         }
         return 0;
     }
-    if (lvl == 0) return -1;
+    auto no_owner = [&]() {   // pool patches must not keep stale values; the download leaves the host's ghost nodes alone instead
+        if (zero_if_no_owner)
+            for (int i = tid; i < ncomp * npts; i += nt) {
+                const int c = i / npts, r = i % npts;
+                out[c * sc + (r / (ext[0] * ext[1])) * sz + ((r / ext[0]) % ext[1]) * sy + r % ext[0]] = 0.0;
+            }
+        return -1;
+    };
+    if (lvl == 0) return no_owner();
     // coarser owner: prediction from the level-(lvl-1) lattice
     const int order = a.order, A = order / 2 - 1;
     int clo[3], chi[3], n[3];
@@ -133,7 +142,7 @@ __device__ inline int fill_region(const FillCtx &a, SrcTable &T, double *scratch
     {
         const int Pc[3] = {lo[0] >> 1, lo[1] >> 1, lo[2] >> 1};
         src_resolve(T, Pc, Bs, dim, sb, so);
-        if (sb < 0) return -1;                         // outside a non-periodic domain: nothing is written
+        if (sb < 0) return no_owner();                 // outside a non-periodic domain / no such block
     }
     double *cb = scratch;                              // [n2][n1][n0]
     for (int c = 0; c < ncomp; ++c) {

@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(128) jump_fill_kernel(const JumpArgs a)
     }
     const long long npts = (long long)ext[0] * ext[1] * ext[2];
     double *out = a.jpool + (a.joff ? a.joff[blockIdx.x] : (long long)blockIdx.x * a.jpatch);
-    fill_region(a.f, T, sm, a.level[b], lo, ext, out, npts, ext[0], (long long)ext[0] * ext[1], 0, a.f.nc, threadIdx.x, blockDim.x);
+    fill_region(a.f, T, sm, a.level[b], lo, ext, out, npts, ext[0], (long long)ext[0] * ext[1], 0, a.f.nc, threadIdx.x, blockDim.x, true);
 }
 
 // ------------------------------------------------------------------------------------------------ export with ghosts

@@ -194,6 +194,19 @@ class WabbitGPU:
         """coarse_extension_modify(CE_case="tree") (LIB/MPI/reconstruction_step.f90:3) on the interiors of a decomposed array."""
         self._check(self._lib.wgpu_coarse_extension(self._ctx, wd[0], wd[1], orig[0], orig[1], int(clear_wc), int(copy_sc)))
 
+    def wavelet_filter_width(self) -> int:
+        """max |tap index| of the decomposition low-pass filter HD of params.wavelet (setup_wavelet: 0 for unlifted CDFX0)"""
+        w = self.params.wavelet
+        X, Y = int(w[3]), int(w[4])
+        return (X - 1) + (Y - 1) if Y > 0 else 0
+
+    def coarsen_blocks(self, mothers, daughters, decomposed=(HVY_WORK, 2)):
+        """sync_D2M for an explicit list (executeCoarsening_tree.f90:125): hvy_block(mother)[octant] = scaling coefficients of the decomposed
+        daughters (2^dim per mother, treecode digit order)"""
+        mo = np.ascontiguousarray(mothers, dtype=np.int32)
+        da = np.ascontiguousarray(daughters, dtype=np.int32)
+        self._check(self._lib.wgpu_coarsen(self._ctx, len(mo), _i32(mo), _i32(da), decomposed[0], decomposed[1]))
+
     def componentWiseNorm_tree(self, array=(HVY_BLOCK, 0), norm: str = "Linfty") -> np.ndarray:
         out = np.zeros(self.params.n_eqn)
         self._check(self._lib.wgpu_norm(self._ctx, array[0], array[1], self.EPS_NORMS[norm], out.ctypes.data_as(C.POINTER(C.c_double))))
