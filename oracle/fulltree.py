@@ -238,3 +238,147 @@ def threshold_full_tree(t: Tree, eps: float, norm=None, eps_norm: str = "Linfty"
         st[k] = int(L.orc_threshold_block(p.dim, p.g, O._bs(p.Bs), nc, O._p(t.blk[k]), k[0], level_ref, O.EPS_NORMS[eps_norm],
                                           tc.ctypes.data_as(O._ip), O._p(e), O._p(nrm), O._p(det)))
     return st
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# grid decision: respectJmaxJmin_tree + ensureGradedness_tree(check_daughters=.true.) on the full tree
+# ----------------------------------------------------------------------------------------------------------------------
+def finer_neighbors(t: Tree, k: Key):
+    """blocks one level finer that touch block k (relations 113..168 of the full tree's hvy_neighbor)"""
+    out = []
+    for d in dirs(t.dim):
+        nk = nbr_key(k, d, t.dim)
+        for c in children(nk, t.dim):
+            ok = True
+            for a in range(t.dim):
+                off = c[1 + a] & 1
+                if (d[a] > 0 and off != 0) or (d[a] < 0 and off != 1):
+                    ok = False
+            if ok and c in t.blk:
+                out.append(c)
+    return out
+
+
+def decide(t: Tree, st: Dict[Key, int], Jmin: int) -> Dict[Key, int]:
+    """Which blocks are deleted (-1).  respectJmaxJmin_tree (blocks on Jmin stay); then, until nothing changes
+    (ensureGradedness_tree.f90, ensure_completeness_block.f90, statuses only ever move from -1 to "stay", so the result does not depend
+    on the order of the sweep): a block keeps -1 only if all its 2^d sisters have -1 (completeness), none of its daughters stays
+    (check_daughters), and no finer neighbour stays (gradedness)."""
+    st = dict(st)
+    for k in st:
+        if st[k] == -1 and k[0] <= Jmin:
+            st[k] = REF_STAY
+    changed = True
+    while changed:
+        changed = False
+        for k in sorted(st):
+            if st[k] != -1:
+                continue
+            sis = children(parent(k), t.dim)
+            stay = any(s not in st or st[s] != -1 for s in sis)
+            if not stay and not t.is_leaf(k):
+                stay = any(c in st and st[c] != -1 for c in children(k, t.dim))
+            if not stay:
+                stay = any(st[f] != -1 for f in finer_neighbors(t, k))
+            if stay:
+                st[k] = REF_STAY
+                changed = True
+    return st
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# adapt_tree: decomposition, indicator, deletion, coarse extension on the new interfaces, reconstruction
+# ----------------------------------------------------------------------------------------------------------------------
+def ndep2(w: O.Wavelet, fd_half_width: int):
+    """Nrecon and Ndep2 of setup_wavelet incl. the FD widening (module_wavelets.f90:1368-1417)"""
+    dl = max(2 * fd_half_width - w.Nwcl, 0)
+    dr = max(2 * fd_half_width - w.Nwcr, 0)
+    nrl, nrr = w.Nreconl + dl, w.Nreconr + dr
+    d2l = w.Nreconl + max((abs(w.hr_lo) + 1) // 2 - 1, 0) + dl
+    d2r = w.Nreconr + (w.hr_hi + 1) // 2 + dr
+    return nrl, nrr, d2l, d2r
+
+
+def _fill_from_coarse(t: Tree, k: Key, d):
+    """ghost patch of direction d of block k from its coarser leaf neighbour in sync_SCWC_from_MC + coarse_extension_modify (F3): scaling
+    positions take the coincident value of the sender's hvy_tmp, everything else is a wavelet coefficient and is set to zero"""
+    p, dim, g = t.p, t.dim, t.p.g
+    ck = parent(nbr_key(k, d, dim))
+    src = t.tmp[ck]
+    dst = t.blk[k]
+    rng_f, rng_c = [], []
+    for a in range(3):
+        if a >= dim:
+            rng_f.append(np.array([0]))
+            continue
+        B = p.Bs[a]
+        loc = np.arange(-g, 0) if d[a] < 0 else (np.arange(B, B + g) if d[a] > 0 else np.arange(0, B))
+        rng_f.append(loc)
+    n = 2 ** k[0]
+    idx = []
+    for a in range(dim):
+        B = p.Bs[a]
+        glob = (k[1 + a] * B + rng_f[a]) % (n * B)                    # global fine coordinate, periodic
+        even = glob % 2 == 0
+        cloc = glob // 2 - ck[1 + a] * B                               # coordinate inside the coarse sender
+        idx.append((rng_f[a] + g, even, cloc + g))
+    if dim == 3:
+        (fx, ex, cx), (fy, ey, cy), (fz, ez, cz) = idx
+        dst[:, fz[:, None, None], fy[None, :, None], fx[None, None, :]] = 0.0
+        assert ((cx[ex] >= g) & (cx[ex] < g + p.Bs[0])).all() and ((cy[ey] >= g) & (cy[ey] < g + p.Bs[1])).all() and \
+            ((cz[ez] >= g) & (cz[ez] < g + p.Bs[2])).all()          # F3: interior points of the sender
+        dst[:, fz[ez][:, None, None], fy[ey][None, :, None], fx[ex][None, None, :]] = \
+            src[:, cz[ez][:, None, None], cy[ey][None, :, None], cx[ex][None, None, :]]
+    else:
+        (fx, ex, cx), (fy, ey, cy) = idx
+        dst[:, 0, fy[:, None], fx[None, :]] = 0.0
+        assert ((cx[ex] >= g) & (cx[ex] < g + p.Bs[0])).all() and ((cy[ey] >= g) & (cy[ey] < g + p.Bs[1])).all()
+        dst[:, 0, fy[ey][:, None], fx[ex][None, :]] = src[:, 0, cy[ey][:, None], cx[ex][None, :]]
+
+
+def adapt_tree(p: O.Params, w: O.Wavelet, grid: O.Grid, u: np.ndarray, eps: float, Jmin: int = 1, norm=None, eps_norm: str = "Linfty",
+               thresh_comp=None, level_ref: int = 0, force_maxlevel_dealiasing: bool = False, indicator: str = "threshold-state-vector",
+               fd_half_width: int = 0, force_leaf_first: Optional[bool] = None):
+    """adapt_tree (adapt_tree.f90:11-260) for a lifted wavelet with the coarse extension, without security zone.  Returns
+    (new grid, new data [nb, nc, nz, ny, nx] with meaningful interiors, info dict)."""
+    dim = grid.dim
+    t = decompose_full_tree(p, w, grid, u, Jmin, fd_half_width, force_leaf_first)
+    st0 = threshold_full_tree(t, eps, norm, eps_norm, thresh_comp, level_ref, force_maxlevel_dealiasing, indicator)
+    st = decide(t, st0, Jmin)
+    deleted = {k for k in st if st[k] == -1}
+    for k in deleted:                                                   # "any block with -1 can simply be deleted"
+        del t.blk[k]
+        del t.tmp[k]
+    leaves = {k for k in t.blk if t.is_leaf(k)}
+    marked = sorted(k for k in leaves if t.coarse_dirs(k))              # leaves at a coarse/fine interface of the NEW grid
+    nrl, nrr, d2l, d2r = ndep2(w, fd_half_width)
+    assert all(p.Bs[a] >= max(nrl, nrr) for a in range(dim)), "Bs < Nrecon: reconstruction of neighbours is not restated"
+    leaf_only = all(p.Bs[a] >= d2l and p.Bs[a] >= d2r for a in range(dim))
+    # coarse extension on the lasting interfaces: wavelet coefficients only (adapt_tree.f90:222-228)
+    for k in marked:
+        t.ce_modify(k, clear_wc=True, copy_sc=False)
+    levels = [None] if leaf_only else list(range(Jmin, max(k[0] for k in t.blk) + 1))
+    for level in levels:
+        todo = [k for k in marked if level is None or k[0] == level]
+        # sync_SCWC_from_MC: coefficients of the same-level neighbours (leaves or mothers), coarse values at scaling positions
+        for k in todo:
+            t.sync_same_level(k, lambda nk: t.blk.get(nk), p.g)
+            for d in t.coarse_dirs(k):
+                _fill_from_coarse(t, k, d)
+        for k in todo:
+            t.ce_modify(k, clear_wc=True, copy_sc=False)
+        L = O._wl()
+        for k in todo:
+            out = t.blk[k].copy()
+            L.orc_iwt_block(C.byref(w), dim, p.g, O._bs(p.Bs), out.shape[0], O._p(t.blk[k]), O._p(out))
+            t.tmp[k] = out                                            # waveletReconstruction_optimized_block(hvy_block -> hvy_tmp)
+        for k in todo:
+            t.blk[k] = t.tmp[k].copy()                                # hvy_block = hvy_tmp
+        for k in t.blk:                                               # blocks of this level that are not reconstructed: original values
+            if (level is None or k[0] == level) and k not in todo:
+                t.blk[k] = t.tmp[k].copy()
+    keys = sorted(leaves)                                             # prune_fulltree2leafs
+    new_grid = O.Grid(level=np.array([k[0] for k in keys], dtype=np.int64), ixyz=np.array([k[1:] for k in keys], dtype=np.int64), dim=dim)
+    data = np.stack([t.blk[k] for k in keys])
+    return new_grid, data, {"status0": st0, "status": st, "marked": marked, "leaf_only": leaf_only, "leaf_first": t.leaf_first,
+                            "n_deleted": len(deleted)}
