@@ -107,6 +107,7 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
 /*
  * wgpu_set_treecodes: the numerical binary treecodes of the active blocks (get_tc(lgt_block(lgt_id, IDX_TC_1:IDX_TC_2)),
  * LIB/TREE/module_treelib.f90:227-239, encoding_b :837-871 with max_level = Jmax), same order as hvy_active / level.
+ * Blocks listed here but not in the following wgpu_set_topology are known as data sources only (they can be looked up by position).
  * Required BEFORE wgpu_set_topology whenever the grid has coarser / finer neighbour relations: the level-jump ghost
  * patches (restriction, prediction; LIB/MPI/restrict_predict_data.f90:45-202) locate their sources by block position.
  * Grids with level jumps also need wgpu_set_wavelet first (the predictor order is the wavelet's, params%order_predictor).
@@ -183,6 +184,11 @@ int32_t wgpu_coarse_extension(wgpu_ctx *ctx, int32_t wd_id, int32_t wd_slot, int
 int32_t wgpu_set_wavelet(wgpu_ctx *ctx, const char *name, int32_t *g_default, int32_t *g_rhs_default);
 int32_t wgpu_fwt(wgpu_ctx *ctx, int32_t src_id, int32_t src_slot, int32_t dst_id, int32_t dst_slot);
 int32_t wgpu_iwt(wgpu_ctx *ctx, int32_t src_id, int32_t src_slot, int32_t dst_id, int32_t dst_slot);
+/* wgpu_iwt_ce: the reconstruction step of wavelet_reconstruct_full_tree_CEoptimized (LIB/MESH/adapt_tree.f90:686-987) for the active blocks:
+ *   sync_SCWC_from_MC + coarse_extension_modify + waveletReconstruction_optimized_block.  Ghost nodes that face a same-level block take
+ *   that block's coefficients from array wd; ghost nodes that face a coarser leaf take the leaf's value in array `coarse` (hvy_tmp of
+ *   the reference) at the scaling positions and zero elsewhere.  dst may be the `coarse` array (the reference writes hvy_tmp too). */
+int32_t wgpu_iwt_ce(wgpu_ctx *ctx, int32_t wd_id, int32_t wd_slot, int32_t coarse_id, int32_t coarse_slot, int32_t dst_id, int32_t dst_slot);
 int32_t wgpu_norm(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t norm_id, double *out);
 int32_t wgpu_threshold(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t eps_norm_id, int32_t level_ref, const int32_t *thresh_comp,
                        const double *eps, const double *norm, int32_t *refinement_status, double *detail_out);

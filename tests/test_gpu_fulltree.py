@@ -65,3 +65,39 @@ def test_full_tree_decomposition_and_flags(wavelet, Bs):
     assert st == ost
     assert 0 < sum(1 for v in st.values() if v == -1) < len(st)
     sol.close()
+
+
+@pytest.mark.parametrize("wavelet,Bs,indicator", [("CDF44", 16, "threshold-state-vector"), ("CDF44", 18, "threshold-state-vector"),
+                                                   ("CDF42", 16, "threshold-state-vector"), ("CDF44", 16, "everywhere"),
+                                                   ("CDF62", 20, "threshold-state-vector"), ("CDF22", 16, "everywhere")])
+def test_adapt_tree_lifted(wavelet, Bs, indicator):
+    """the whole adapt_tree for a lifted wavelet (decomposition of the full tree, indicator, grid decision, coarse extension on the lasting
+    interfaces, CE-optimised reconstruction, pruning): same new grid as the oracle, data bit for bit; a second adapt_tree changes nothing
+    (the reference's invertibility criterion, unit_test_waveletDecomposition_invertibility.f90)"""
+    w, p, po, forest, grid, sol, u, H = _setup(wavelet, Bs, seed=5)
+    norm = O.norm_linfty_tree(po, u)
+    eps = 0.01
+    og, od, oi = OFT.adapt_tree(po, w, grid, u, eps, Jmin=1, norm=norm, level_ref=forest.Jmax, indicator=indicator, fd_half_width=H)
+    ft = FullTree(sol, forest, Jmin=1)
+    new, info = ft.adapt(eps=eps, norm=sol.componentWiseNorm_tree((HVY_BLOCK, 0)), indicator=indicator)
+    assert info["leaf_first"] == oi["leaf_first"] and info["leaf_only"] == oi["leaf_only"]
+    assert info["status0"] == oi["status0"] and {k: v == -1 for k, v in info["status"].items()} == {k: v == -1 for k, v in oi["status"].items()}
+    assert info["marked"] == oi["marked"] and len(info["marked"]) > 0
+    hvy, lvl, ixyz, _ = new.active(0)
+    okey = {(int(og.level[b]),) + tuple(int(v) for v in og.ixyz[b]): b for b in range(og.n)}
+    keys = [(int(l), int(x[0]), int(x[1]), int(x[2])) for l, x in zip(lvl, ixyz)]
+    assert sorted(keys) == sorted(okey) and 8 <= new.n_blocks < forest.n_blocks
+    got = np.zeros(sol.host_shape())
+    sol.download(got, g_sync=0)
+    I = (slice(None),) + O.interior(po)
+    for h, k in zip(hvy, keys):
+        assert np.array_equal(got[h - 1][I], od[okey[k]][I]), k
+    # adapt(adapt(u)) = adapt(u): with eps = 0 nothing is coarsened any more and the filtered interfaces are a fixed point
+    ft2 = FullTree(sol, new, Jmin=1)
+    new2, info2 = ft2.adapt(eps=0.0, norm=None)
+    assert new2.n_blocks == new.n_blocks
+    got2 = np.zeros(sol.host_shape())
+    sol.download(got2, g_sync=0)
+    a, b = got2[:new.n_blocks][(slice(None),) + I], got[:new.n_blocks][(slice(None),) + I]
+    assert abs(np.sqrt((a ** 2).sum()) / np.sqrt((b ** 2).sum()) - 1.0) <= 1.0e-14 and np.abs(a - b).max() <= 1.0e-13
+    sol.close()

@@ -152,13 +152,16 @@ int32_t upload_jump_tables(wgpu_ctx *ctx, const std::vector<int> &jump_blk, cons
     if (!coords) return WGPU_OK;   // uniform grid without block positions: nothing that needs the lookup can be called
     // hash table (level, ix, iy, iz) -> block
     size_t cap = 64;
-    const int n_known = ctx->n_active + (int)ctx->h_halo.size();   // blocks resident in HBM: own + halo copies
+    // every block wgpu_set_treecodes listed is resident in HBM and can be a source: the active blocks, the halo copies, and blocks a
+    // caller names only as sources (the coarser leaves next to the blocks of a full-tree pass, wabbit_b200/fulltree.py)
+    int n_known = 0;
+    for (int b = 0; b < N; ++b) n_known += ctx->h_has_coords[b] != 0;
     while (cap < (size_t)n_known * 2 + 2) cap <<= 1;
     std::vector<unsigned long long> keys(cap, ~0ull);
     std::vector<int> vals(cap, -1);
-    for (int k = 0; k < n_known; ++k) {
-        const int b = k < ctx->n_active ? ctx->h_active[k] : ctx->h_halo[k - ctx->n_active];
-        const unsigned long long key = blk_key(ctx->h_level[b], ctx->h_ixyz[3 * b], ctx->h_ixyz[3 * b + 1], ctx->h_ixyz[3 * b + 2]);
+    for (int b = 0; b < N; ++b) {
+        if (!ctx->h_has_coords[b]) continue;
+        const unsigned long long key = blk_key(ctx->h_tc_level[b], ctx->h_ixyz[3 * b], ctx->h_ixyz[3 * b + 1], ctx->h_ixyz[3 * b + 2]);
         unsigned h = blk_hash(key) & (unsigned)(cap - 1);
         while (keys[h] != ~0ull) {
             if (keys[h] == key) return fail(ctx, WGPU_ERR_ARG, "two active blocks share a treecode");
@@ -295,6 +298,7 @@ int32_t wgpu_set_treecodes(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_a
     const int N = c.max_blocks;
     ctx->h_ixyz.assign((size_t)N * 3, 0);
     ctx->h_has_coords.assign(N, 0);
+    ctx->h_tc_level.assign(N, 0);
     for (int k = 0; k < n_active; ++k) {
         const int hid = hvy_active[k], J = level[k];
         if (hid < 1 || hid > N) return fail(ctx, WGPU_ERR_ARG, "hvy_active entry out of range");
@@ -307,6 +311,7 @@ int32_t wgpu_set_treecodes(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_a
         ctx->h_ixyz[3 * (size_t)(hid - 1) + 1] = p[0];
         ctx->h_ixyz[3 * (size_t)(hid - 1) + 2] = p[2];
         ctx->h_has_coords[hid - 1] = 1;
+        ctx->h_tc_level[hid - 1] = (signed char)J;
     }
     return WGPU_OK;
 }
@@ -966,7 +971,7 @@ static int32_t transform(wgpu_ctx *ctx, int32_t src_id, int32_t src_slot, int32_
     if (src == dst) return fail(ctx, WGPU_ERR_ARG, "wavelet transform: src and dst must differ (neighbours read src halos)");
     if (dst == ctx->U) ctx->dtmin_valid = false;
     ctx->det_cached_for = nullptr;
-    return wgpu_launch_wavelet(ctx, src, dst, inverse);
+    return wgpu_launch_wavelet(ctx, src, dst, inverse, nullptr);
 }
 
 int32_t wgpu_fwt(wgpu_ctx *ctx, int32_t src_id, int32_t src_slot, int32_t dst_id, int32_t dst_slot)
@@ -977,6 +982,24 @@ int32_t wgpu_fwt(wgpu_ctx *ctx, int32_t src_id, int32_t src_slot, int32_t dst_id
 int32_t wgpu_iwt(wgpu_ctx *ctx, int32_t src_id, int32_t src_slot, int32_t dst_id, int32_t dst_slot)
 {
     return transform(ctx, src_id, src_slot, dst_id, dst_slot, 1);
+}
+
+int32_t wgpu_iwt_ce(wgpu_ctx *ctx, int32_t wd_id, int32_t wd_slot, int32_t coarse_id, int32_t coarse_slot, int32_t dst_id, int32_t dst_slot)
+{
+    if (!ctx) return WGPU_ERR_ARG;
+    if (!ctx->wavelet_set) return fail(ctx, 1213149, "The cat is angry: Wavelet-setup not yet called?");
+    const wgpu_config &c = ctx->cfg;
+    if (c.dim != 3 || c.Bs[0] != c.Bs[1] || c.Bs[0] != c.Bs[2]) return fail(ctx, WGPU_ERR_UNSUPPORTED, "wavelet kernels: cubic 3-D blocks only so far");
+    int n1 = 0, n2 = 0, n3 = 0;
+    const double *src = array_ptr(ctx, wd_id, wd_slot, &n1);
+    const double *crs = array_ptr(ctx, coarse_id, coarse_slot, &n2);
+    double *dst = array_ptr(ctx, dst_id, dst_slot, &n3);
+    if (!src || !crs || !dst || n1 != ctx->nc || n2 != ctx->nc || n3 != ctx->nc || src == dst || src == crs)
+        return fail(ctx, WGPU_ERR_ARG, "wgpu_iwt_ce: bad array/slot (the coefficients must not share an array with the coarse values or the result)");
+    if (!ctx->lookup_ready && ctx->has_jumps) return fail(ctx, WGPU_ERR_ARG, "wgpu_iwt_ce: call wgpu_set_treecodes + wgpu_set_topology first");
+    if (dst == ctx->U) ctx->dtmin_valid = false;
+    ctx->det_cached_for = nullptr;
+    return wgpu_launch_wavelet(ctx, src, dst, 1, crs);
 }
 
 int32_t wgpu_norm(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t norm_id, double *out)

@@ -140,7 +140,40 @@ struct JumpArgs {
     const signed char *level;
     const int *ixyz;
     int H;                     // depth of the ghost strip
+    const double *ce_coarse;   // != nullptr: scaling positions take the coincident value of the coarser leaf in this array, the rest is 0
 };
+
+// Ghost patch of a decomposed block that faces a coarser leaf, as sync_SCWC_from_MC + coarse_extension_modify leave it (adapt_tree.f90:
+// 686-987, reconstruction_step.f90:3-100): the predictor returns the coincident coarse value at scaling positions (even coordinates on
+// the block's lattice) and every other position is a wavelet coefficient, which the coarse extension sets to zero.
+__device__ inline void fill_scwc(const FillCtx &a, const double *uc, SrcTable &T, int lvl, const int lo[3], const int ext[3], double *out,
+                                 long long sc, long long sy, long long sz, int ncomp, int tid, int nt)
+{
+    const int Bs = a.Bs, dim = a.dim;
+    const long long CS = (long long)Bs * Bs * (dim == 3 ? Bs : 1);
+    const int npts = ext[0] * ext[1] * ext[2];
+    int clo[3], chi[3];
+    for (int k = 0; k < 3; ++k) {
+        clo[k] = k < dim ? lo[k] >> 1 : 0;
+        chi[k] = k < dim ? (lo[k] + ext[k] - 1) >> 1 : 0;
+    }
+    __syncthreads();
+    if (lvl > 0) src_table_build(T, a.L, lvl - 1, clo, chi, Bs, dim, a.periodic, tid, nt);
+    __syncthreads();
+    for (int i = tid; i < ncomp * npts; i += nt) {
+        const int c = i / npts, r = i % npts;
+        const int x = r % ext[0], y = (r / ext[0]) % ext[1], z = r / (ext[0] * ext[1]);
+        const int P[3] = {lo[0] + x, lo[1] + y, lo[2] + z};
+        double v = 0.0;
+        if (lvl > 0 && !(P[0] & 1) && !(P[1] & 1) && (dim == 2 || !(P[2] & 1))) {
+            const int Pc[3] = {P[0] >> 1, P[1] >> 1, dim == 3 ? P[2] >> 1 : 0};
+            int sb, so, ro;
+            src_resolve(T, Pc, Bs, dim, sb, so, ro);
+            if (sb >= 0 && ro < 0) v = uc[((long long)sb * a.nc + c) * CS + so];   // owned by a block of level lvl-1 itself
+        }
+        out[c * sc + z * sz + y * sy + x] = v;
+    }
+}
 
 __global__ void __launch_bounds__(128) jump_fill_kernel(const JumpArgs a)
 {
@@ -156,7 +189,8 @@ __global__ void __launch_bounds__(128) jump_fill_kernel(const JumpArgs a)
     }
     const long long npts = (long long)ext[0] * ext[1] * ext[2];
     double *out = a.jpool + (a.joff ? a.joff[blockIdx.x] : (long long)blockIdx.x * a.jpatch);
-    fill_region(a.f, T, sm, a.level[b], lo, ext, out, npts, ext[0], (long long)ext[0] * ext[1], 0, a.f.nc, threadIdx.x, blockDim.x, true);
+    if (a.ce_coarse) fill_scwc(a.f, a.ce_coarse, T, a.level[b], lo, ext, out, npts, ext[0], (long long)ext[0] * ext[1], a.f.nc, threadIdx.x, blockDim.x);
+    else fill_region(a.f, T, sm, a.level[b], lo, ext, out, npts, ext[0], (long long)ext[0] * ext[1], 0, a.f.nc, threadIdx.x, blockDim.x, true);
 }
 
 // ------------------------------------------------------------------------------------------------ export with ghosts
@@ -389,6 +423,7 @@ int32_t wgpu_launch_jump_fill(wgpu_ctx *ctx, const double *src)
     a.level = ctx->d_level;
     a.ixyz = ctx->d_ixyz;
     a.H = c.fd == 2 ? 1 : (c.fd == 4 ? 2 : 3);
+    a.ce_coarse = nullptr;
     a.jpatch = (long long)ctx->nc * a.H * c.Bs[0] * (c.dim == 3 ? c.Bs[0] : 1);
     size_t best = 0;
     for (int f = 0; f < c.dim; ++f) {
@@ -517,16 +552,19 @@ int32_t wgpu_launch_copy_entries(wgpu_ctx *ctx, const double *src, double *dst, 
     return WGPU_OK;
 }
 
-int32_t wgpu_launch_wjump_fill(wgpu_ctx *ctx, const double *src)
+int32_t wgpu_launch_wjump_fill(wgpu_ctx *ctx, const double *src, const double *ce_coarse)
 {
     if (ctx->n_wjump == 0) return WGPU_OK;
     const wgpu_config &c = ctx->cfg;
     bool filtered = false;   // sync_TMP_from_all / sync_ghosts_tree before the decomposition: restriction with the HD filter
-    int32_t rcf = wgpu_launch_restrict_filter(ctx, src, ctx->nc, &filtered);
-    if (rcf) return rcf;
+    if (!ce_coarse) {
+        int32_t rcf = wgpu_launch_restrict_filter(ctx, src, ctx->nc, &filtered);
+        if (rcf) return rcf;
+    }
     JumpArgs a;
     a.f = make_fill_ctx(ctx, src, filtered);
     a.jpool = ctx->d_wpool;
+    a.ce_coarse = ce_coarse;
     a.jpatch = 0;
     a.joff = ctx->d_woff;
     a.jblk = ctx->d_wjump_blk;

@@ -702,7 +702,10 @@ int32_t wgpu_launch_blocksum(wgpu_ctx *ctx, const double *u, int squared, double
     return WGPU_OK;
 }
 
-int32_t wgpu_launch_wavelet(wgpu_ctx *ctx, const double *src, double *dst, int inverse)
+// ce_coarse != nullptr: reconstruction inside wavelet_reconstruct_full_tree_CEoptimized -- the ghost patches that face a coarser leaf
+// hold that leaf's values (array ce_coarse) at the scaling positions and zero wavelet coefficients (sync_SCWC_from_MC +
+// coarse_extension_modify, LIB/MESH/adapt_tree.f90:686-987) instead of restricted / predicted values of `src`
+int32_t wgpu_launch_wavelet(wgpu_ctx *ctx, const double *src, double *dst, int inverse, const double *ce_coarse)
 {
     if (ctx->n_active == 0) return WGPU_OK;
     const wgpu_config &c = ctx->cfg;
@@ -727,7 +730,7 @@ int32_t wgpu_launch_wavelet(wgpu_ctx *ctx, const double *src, double *dst, int i
     {
         bool handled = false;
         if (ctx->has_jumps) {   // ghost values across level jumps (all 26 relations): decimation / prediction into the wavelet jump pool
-            int32_t rcj = wgpu_launch_wjump_fill(ctx, src);
+            int32_t rcj = wgpu_launch_wjump_fill(ctx, src, ce_coarse);
             if (rcj) return rcj;
         }
         int32_t rc = launch_fast(ctx, src, dst, inverse, handled);

@@ -120,6 +120,7 @@ struct wgpu_ctx {
     // block coordinates + device lookup (level, ix, iy, iz) -> block index, for level-jump patches
     std::vector<int> h_ixyz;           // [max_blocks][3], valid where coords_of[b] != 0
     std::vector<char> h_has_coords;
+    std::vector<signed char> h_tc_level;   // level given to wgpu_set_treecodes (also for blocks that are sources only)
     int *d_ixyz = nullptr;
     unsigned long long *d_hkeys = nullptr;
     int *d_hvals = nullptr;
@@ -204,7 +205,7 @@ int32_t wgpu_launch_stage(wgpu_ctx *ctx, const StageArgs &a, int n_blocks);
 int32_t wgpu_launch_pack(wgpu_ctx *ctx, const double *src);
 // jump.cu
 int32_t wgpu_launch_jump_fill(wgpu_ctx *ctx, const double *src);
-int32_t wgpu_launch_wjump_fill(wgpu_ctx *ctx, const double *src);
+int32_t wgpu_launch_wjump_fill(wgpu_ctx *ctx, const double *src, const double *ce_coarse = nullptr);
 int32_t wgpu_launch_restrict_filter(wgpu_ctx *ctx, const double *src, int nc_src, bool *active);
 int32_t wgpu_launch_ce(wgpu_ctx *ctx, double *wd, const double *orig, int Nwcl, int Nwcr, int Nscl, int Nscr, int clear_wc, int copy_sc);
 int32_t wgpu_launch_export_regions(wgpu_ctx *ctx, const double *src, double *staged, const int *d_ids, int n, int ncomp_src, int ncomp_host,
@@ -214,7 +215,7 @@ int32_t wgpu_launch_coarsen(wgpu_ctx *ctx, const double *src, double *dst, const
 int32_t wgpu_launch_copy_blocks(wgpu_ctx *ctx, const double *src, double *dst, const int *d_src_ids, const int *d_dst_ids, int n);
 int32_t wgpu_launch_copy_entries(wgpu_ctx *ctx, const double *src, double *dst, const int *d_src_idx, int n, long long per_entry);
 // wavelet.cu
-int32_t wgpu_launch_wavelet(wgpu_ctx *ctx, const double *src, double *dst, int inverse);
+int32_t wgpu_launch_wavelet(wgpu_ctx *ctx, const double *src, double *dst, int inverse, const double *ce_coarse);
 int32_t wgpu_launch_detail(wgpu_ctx *ctx, const double *wd, int eps_norm, int level_ref);
 int32_t wgpu_launch_flags(wgpu_ctx *ctx, const int32_t *thresh_comp, const double *eps_use, int *d_status, double *d_detail_out);
 int32_t wgpu_launch_linfty(wgpu_ctx *ctx, const double *u, unsigned long long *d_out);

@@ -120,11 +120,15 @@ class FullTree:
         ld = int(ids.max())
         nbr = np.full((168, ld), -1, dtype=np.int32)
         lvl = np.array([k[0] for k in keys], dtype=np.int32)
-        tc = np.zeros(len(keys), dtype=np.int64)
         ix = np.zeros(3, dtype=np.int32)
-        for i, k in enumerate(keys):
+
+        def encode(k):
             ix[:] = k[1:]
-            tc[i] = lib.whost_encode(dim, k[0], self.forest.Jmax, ix.ctypes.data_as(C.POINTER(C.c_int32)))
+            return lib.whost_encode(dim, k[0], self.forest.Jmax, ix.ctypes.data_as(C.POINTER(C.c_int32)))
+
+        tc = np.array([encode(k) for k in keys], dtype=np.int64)
+        coarse = set()                                  # coarser leaves next to the blocks of the pass: known as data sources only
+        for i, k in enumerate(keys):
             s = self.slot[k] - 1
             for d in _dirs(dim):
                 nk = self._nbr_key(k, d)
@@ -134,7 +138,11 @@ class FullTree:
                     ck = _parent(nk)
                     if ck in self.slot:
                         nbr[_code(d) - 1 + 56, s] = self.slot[ck]
-        sol.set_treecodes(ids, lvl, tc)
+                        coarse.add(ck)
+        coarse = sorted(coarse - set(keys))
+        sol.set_treecodes(np.concatenate([ids, np.array([self.slot[k] for k in coarse], dtype=np.int32)]),
+                          np.concatenate([lvl, np.array([k[0] for k in coarse], dtype=np.int32)]),
+                          np.concatenate([tc, np.array([encode(k) for k in coarse], dtype=np.int64)]))
         sol.set_topology(ids, lvl, nbr, 0)
         return keys
 
@@ -176,3 +184,100 @@ class FullTree:
                 flags(keys)
             d2m(level)
         return self.status
+
+
+    # ------------------------------------------------------------------ grid decision (light data)
+    def _finer_neighbors(self, k: Key):
+        out = []
+        for d in _dirs(self.dim):
+            nk = self._nbr_key(k, d)
+            for c in _children(nk, self.dim):
+                if c in self.slot and all((d[a] == 0) or ((c[1 + a] & 1) == (0 if d[a] > 0 else 1)) for a in range(self.dim)):
+                    out.append(c)
+        return out
+
+    def decide(self, st: Dict[Key, int]) -> Dict[Key, int]:
+        """respectJmaxJmin_tree + ensureGradedness_tree(check_daughters) on the full tree (LIB/MESH/ensureGradedness_tree.f90,
+        ensure_completeness_block.f90): a block keeps -1 only if it sits above Jmin, all its sisters carry -1, none of its daughters stays
+        and no finer neighbour stays.  Statuses only move from -1 to "stay", so one monotone sweep to the fixed point."""
+        st = dict(st)
+        dim = self.dim
+        for k in st:
+            if st[k] == -1 and k[0] <= self.Jmin:
+                st[k] = 9                                                  # REF_UNSIGNIFICANT_STAY
+        changed = True
+        while changed:
+            changed = False
+            for k in sorted(st):
+                if st[k] != -1:
+                    continue
+                stay = any(st.get(s_, 0) != -1 for s_ in _children(_parent(k), dim))
+                if not stay and k not in self.leaf:
+                    stay = any(st.get(c, -1) != -1 for c in _children(k, dim) if c in self.slot)
+                if not stay:
+                    stay = any(st[f] != -1 for f in self._finer_neighbors(k))
+                if stay:
+                    st[k] = 9
+                    changed = True
+        return st
+
+    def _ce_sizes(self):
+        """Nrecon and Ndep2 of setup_wavelet incl. the widening to the FD stencil (module_wavelets.f90:1368-1417)"""
+        p = self.sol.params
+        w = p.wavelet
+        X, Y = int(w[3]), int(w[4])
+        F = (X - 1) + (Y - 1)
+        H = {"FD_2nd_central": 1, "FD_4th_central": 2, "FD_6th_central": 3, "FD_4th_central_optimized": 3}[p.discretization]
+        nwl, nwr = (F - 1) + (X - 1), F + (X - 1)
+        dl, dr = max(2 * H - nwl, 0), max(2 * H - nwr, 0)
+        nrl, nrr = nwl + F + dl, nwr + F + dr
+        return nrl, nrr, nrl + max(X // 2 - 1, 0), nrr + X // 2
+
+    # ------------------------------------------------------------------ adapt_tree
+    def adapt(self, eps: Optional[float] = None, norm=None, eps_norm: str = "Linfty", thresh_comp=None, force_maxlevel_dealiasing: bool = False,
+              indicator: str = "threshold-state-vector"):
+        """adapt_tree (LIB/MESH/adapt_tree.f90:11-260) for a lifted wavelet with the coarse extension (useSecurityZone = 0): full-tree
+        decomposition and indicator, grid decision, coarse extension on the lasting coarse/fine interfaces, reconstruction of the leaves at
+        those interfaces (all at once if Bs >= Ndep2, else level by level from coarse to fine), pruning to the leaves, blocks moved to
+        their places along the space-filling curve.  Returns (new forest, info)."""
+        sol, dim = self.sol, self.dim
+        p = sol.params
+        if indicator == "everywhere":
+            self.decompose(threshold=False)
+            st0 = {k: (-1 if k in self.leaf else 0) for k in self.slot}
+        else:
+            st0 = dict(self.decompose(eps=eps, norm=norm, eps_norm=eps_norm, thresh_comp=thresh_comp))
+            if force_maxlevel_dealiasing:
+                st0 = {k: (-1 if k[0] == self.forest.Jmax else v) for k, v in st0.items()}
+        st = self.decide(st0)
+        for k in [k for k in st if st[k] == -1]:
+            del self.slot[k]
+        self.leaf = {k for k in self.slot if not any(c in self.slot for c in _children(k, dim))}
+        marked = [k for k in self.leaf if any(self._nbr_key(k, d) not in self.slot for d in _dirs(dim))]
+        nrl, nrr, d2l, d2r = self._ce_sizes()
+        if any(p.Bs[a] < max(nrl, nrr) for a in range(dim)):
+            raise RuntimeError("adapt_tree: Bs < Nrecon (reconstruction of the neighbours of interface blocks) is not supported")
+        leaf_only = all(p.Bs[a] >= d2l and p.Bs[a] >= d2r for a in range(dim))
+        if marked:
+            if leaf_only:
+                self.set_pass_topology(marked)
+                sol.coarse_extension_modify(WD, (HVY_BLOCK, 0), True, False)
+                sol.waveletReconstruction_CE(WD, (HVY_BLOCK, 0), (HVY_BLOCK, 0))
+            else:
+                self.set_pass_topology(marked)                                # the lasting interfaces first (adapt_tree.f90:222-228):
+                sol.coarse_extension_modify(WD, (HVY_BLOCK, 0), True, False)  # same-level neighbours send coefficients that carry it
+                for level in range(self.Jmin, max(k[0] for k in self.slot) + 1):
+                    todo = [k for k in marked if k[0] == level]
+                    if todo:
+                        self.set_pass_topology(todo)
+                        sol.waveletReconstruction_CE(WD, (HVY_BLOCK, 0), (HVY_BLOCK, 0))
+        # prune_fulltree2leafs + balanceLoad_tree: the leaves move to their slots along the space-filling curve
+        keys = sorted(self.leaf)
+        new = Forest.from_blocks(dim, self.forest.Jmax, np.array([k[0] for k in keys], dtype=np.int32),
+                                 np.array([k[1:] for k in keys], dtype=np.int32), block_dist=self.forest.block_dist, n_ranks=1,
+                                 max_blocks=self.forest.max_blocks, periodic=self.forest.periodic)
+        hvy, lvl, ixyz, _ = new.active(0)
+        src = np.array([self.slot[(int(l), int(x[0]), int(x[1]), int(x[2]))] for l, x in zip(lvl, ixyz)], dtype=np.int32)
+        sol.move_blocks(src, hvy.astype(np.int32))
+        sol.set_forest(new)
+        return new, {"status0": st0, "status": st, "marked": sorted(marked), "leaf_only": leaf_only, "leaf_first": self.leaf_first}

@@ -194,11 +194,22 @@ class WabbitGPU:
         """coarse_extension_modify(CE_case="tree") (LIB/MPI/reconstruction_step.f90:3) on the interiors of a decomposed array."""
         self._check(self._lib.wgpu_coarse_extension(self._ctx, wd[0], wd[1], orig[0], orig[1], int(clear_wc), int(copy_sc)))
 
+    def waveletReconstruction_CE(self, wd=(HVY_WORK, 2), coarse=(HVY_BLOCK, 0), dst=(HVY_BLOCK, 0)):
+        """sync_SCWC_from_MC + coarse_extension_modify + waveletReconstruction_optimized_block on the active blocks
+        (wavelet_reconstruct_full_tree_CEoptimized, adapt_tree.f90:686-987)"""
+        self._check(self._lib.wgpu_iwt_ce(self._ctx, wd[0], wd[1], coarse[0], coarse[1], dst[0], dst[1]))
+
     def wavelet_filter_width(self) -> int:
         """max |tap index| of the decomposition low-pass filter HD of params.wavelet (setup_wavelet: 0 for unlifted CDFX0)"""
         w = self.params.wavelet
         X, Y = int(w[3]), int(w[4])
         return (X - 1) + (Y - 1) if Y > 0 else 0
+
+    def move_blocks(self, src_hvy, dst_hvy):
+        """block_xfer on one rank (wgpu_move_blocks): hvy_block(dst[i]) = hvy_block(src[i]) for all i at once"""
+        s = np.ascontiguousarray(src_hvy, dtype=np.int32)
+        d = np.ascontiguousarray(dst_hvy, dtype=np.int32)
+        self._check(self._lib.wgpu_move_blocks(self._ctx, len(s), _i32(s), _i32(d)))
 
     def coarsen_blocks(self, mothers, daughters, decomposed=(HVY_WORK, 2)):
         """sync_D2M for an explicit list (executeCoarsening_tree.f90:125): hvy_block(mother)[octant] = scaling coefficients of the decomposed
