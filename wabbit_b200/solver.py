@@ -266,15 +266,28 @@ class WabbitGPU:
 
     def adapt_tree(self, forest: Forest, eps: Optional[float] = None, eps_normalized: bool = True, eps_norm: str = "Linfty",
                    Jmin: int = 1, force_maxlevel_dealiasing: bool = False, thresh_comp=None):
-        """One coarsening sweep of adapt_tree (LIB/MESH/adapt_tree.f90:11) with indicator "threshold-state-vector" for UNLIFTED
-        wavelets (CDFX0: no coarse extension, no security zone): componentWiseNorm_tree -> ghost synchronisation + wavelet
+        """adapt_tree (LIB/MESH/adapt_tree.f90:11) with indicator "threshold-state-vector".  Lifted wavelets: the full-tree algorithm with
+        the coarse extension (wabbit_b200/fulltree.py; useSecurityZone = 0).  UNLIFTED wavelets (CDFX0: no coarse extension, no
+        security zone), one coarsening sweep: componentWiseNorm_tree -> ghost synchronisation + wavelet
         decomposition of every leaf -> threshold_block flags (device), then completeness / gradedness (host light data) and
         executeCoarsening (device).  The reference's current adapt_tree decomposes the full tree and can remove several levels
         in one call; this driver removes one level per call (call it again to go further) -- the per-block arithmetic is the same.
         Returns (new forest, number of blocks before, after)."""
         w = self.params.wavelet
         if not (len(w) == 5 and w[4] == "0"):
-            raise WabbitAbort(1003, "adapt_tree: lifted wavelets need the coarse extension, which is not built yet")
+            # lifted wavelets: the reference's full-tree algorithm with the coarse extension (wabbit_b200/fulltree.py), which can remove
+            # several levels in one call; useSecurityZone = 0
+            from .fulltree import FullTree
+            if eps_norm != "Linfty" and eps_normalized:
+                norm_l = self.componentWiseNorm_tree((HVY_BLOCK, 0), eps_norm)
+            else:
+                norm_l = self.componentWiseNorm_tree((HVY_BLOCK, 0), "Linfty") if eps_normalized else None
+            if norm_l is not None:
+                norm_l[norm_l <= 1.0e-9] = 1.0
+            n0 = forest.n_blocks
+            new, _info = FullTree(self, forest, Jmin=Jmin).adapt(eps=self.params.eps if eps is None else eps, norm=norm_l, eps_norm=eps_norm,
+                                                               thresh_comp=thresh_comp, force_maxlevel_dealiasing=force_maxlevel_dealiasing)
+            return new, n0, new.n_blocks
         hvy, lvl, _, _ = forest.active(0)
         norm = None
         if eps_normalized:
