@@ -52,16 +52,17 @@ def test_full_tree_decomposition_and_flags(wavelet, Bs):
     gnorm = sol.componentWiseNorm_tree((HVY_BLOCK, 0))
     assert np.array_equal(gnorm, norm)
     st = ft.decompose(eps=0.01, norm=gnorm)
-    keys = sorted(ft.slot, key=lambda k: ft.slot[k])
-    ids = np.array([ft.slot[k] for k in keys], dtype=np.int32)
+    slot, leaf = ft.slot, ft.leaf
+    keys = sorted(slot, key=lambda k: slot[k])
+    ids = np.array([slot[k] for k in keys], dtype=np.int32)
     wd = np.zeros(sol.host_shape())
     sol.download(wd, WD[0], WD[1], hvy_ids=ids, g_sync=0)
     uu = np.zeros(sol.host_shape())
     sol.download(uu, HVY_BLOCK, 0, hvy_ids=ids, g_sync=0)
     I = (slice(None),) + O.interior(po)
     for k in keys:
-        assert np.array_equal(wd[ft.slot[k] - 1][I], ot.blk[k][I]), k              # decomposed values (hvy_block of the reference)
-        assert np.array_equal(uu[ft.slot[k] - 1][I], ot.tmp[k][I]), k              # original / assembled values (hvy_tmp)
+        assert np.array_equal(wd[slot[k] - 1][I], ot.blk[k][I]), k              # decomposed values (hvy_block of the reference)
+        assert np.array_equal(uu[slot[k] - 1][I], ot.tmp[k][I]), k              # original / assembled values (hvy_tmp)
     assert st == ost
     assert 0 < sum(1 for v in st.values() if v == -1) < len(st)
     sol.close()

@@ -221,3 +221,39 @@ def test_global_refine_and_coarsen_match_the_single_rank_bookkeeping(world):
     assert np.array_equal(st_w, st_1) and (st_w == -1).any() and c_w.n_blocks == c_1.n_blocks < new_w.n_blocks
     assert all(np.array_equal(a, b) for a, b in zip(global_blocks(c_w), global_blocks(c_1)))
     assert all(np.array_equal(a, b) for a, b in zip(cl_w, cl_1))
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_full_tree_light_data_matches_the_oracle(seed):
+    """wabbit_b200/fulltree.py (vectorised host logic of the lifted adapt_tree): tree of leaves + ancestors, treecodes and the grid decision
+    (respectJmaxJmin_tree + ensureGradedness_tree with check_daughters) against the oracle's block-by-block restatement"""
+    import fulltree as OFT
+    import oracle as O
+    from util import graded_blocks
+    from wabbit_b200.fulltree import FullTree, _encode_treecodes
+
+    class FakeSol:
+        max_blocks = 100000
+
+        class params:
+            Bs = (16, 16, 16)
+            wavelet = "CDF44"
+            discretization = "FD_4th_central"
+
+        def wavelet_filter_width(self):
+            return 6
+
+    lv, ix = graded_blocks(3, 1, 4, seed, 0.25)
+    forest = Forest.from_blocks(3, 4, lv, ix, max_blocks=4 * len(lv))
+    ft = FullTree(FakeSol(), forest, Jmin=1)
+    hvy, l, x, tc = forest.active(0)
+    grid = O.Grid(level=l.astype(np.int64), ixyz=x.astype(np.int64), dim=3)
+    t = OFT.Tree(O.Params(dim=3, Bs=(16,) * 3, g=6, n_eqn=1, Jmax=4), O.setup_wavelet("CDF44"), grid, np.zeros((grid.n, 1, 1, 1, 1)), Jmin=1)
+    assert set(ft.slot) == set(t.blk) and ft.leaf == t.leaf and not ft.leaf_first
+    i = ft._find(l.astype(np.int64), x.astype(np.int64))
+    assert (i >= 0).all() and np.array_equal(ft.slots[i], hvy) and np.array_equal(_encode_treecodes(3, ft.level[i], ft.pos[i], 4), tc)
+    st0 = np.where(np.random.default_rng(seed).random(len(ft.code)) < 0.75, -1, 0).astype(np.int32)
+    st = ft.decide(st0)
+    od = OFT.decide(t, ft.status_dict(st0), 1)
+    assert (st == -1).any()
+    assert {k: v == -1 for k, v in ft.status_dict(st).items()} == {k: v == -1 for k, v in od.items()}

@@ -71,155 +71,227 @@ def _children(k: Key, dim: int) -> List[Key]:
     return [(k[0] + 1, 2 * k[1] + ((c >> 1) & 1), 2 * k[2] + (c & 1), 2 * k[3] + ((c >> 2) & 1) if dim == 3 else 0) for c in range(2 ** dim)]
 
 
+def _pack(level, ixyz):
+    """sortable int64 code of a block position (level, ix, iy, iz); arrays in, array out"""
+    level = np.asarray(level, dtype=np.int64)
+    ixyz = np.asarray(ixyz, dtype=np.int64).reshape(-1, 3)
+    return (level << 57) | (ixyz[:, 2] << 38) | (ixyz[:, 1] << 19) | ixyz[:, 0]
+
+
+def _encode_treecodes(dim: int, level: np.ndarray, ixyz: np.ndarray, Jmax: int) -> np.ndarray:
+    """numerical binary treecode (module_treelib.f90:837-871): digit bit0 <- y, bit1 <- x, bit2 <- z; bit i of a coordinate goes to
+    digit i + Jmax - level"""
+    level = level.astype(np.int64)
+    p = [ixyz[:, 1].astype(np.int64), ixyz[:, 0].astype(np.int64), ixyz[:, 2].astype(np.int64)]
+    tc = np.zeros(len(level), dtype=np.int64)
+    for i in range(Jmax):
+        use = i < level
+        sh = (i + Jmax - level) * dim
+        for d in range(dim):
+            tc |= np.where(use, ((p[d] >> i) & 1) << np.where(use, sh + d, 0), 0)
+    return tc
+
+
 class FullTree:
-    """Leaves of `forest` (slots = their hvy ids) plus all ancestors down to Jmin in free slots behind them (init_full_tree)."""
+    """Leaves of `forest` (slots = their hvy ids) plus all ancestors down to Jmin in free slots behind them (init_full_tree).
+    Light data are numpy arrays over the blocks of the tree, sorted by position code; `slot` / `leaf` give dict / set views."""
 
     def __init__(self, sol, forest: Forest, Jmin: int = 1):
         self.sol, self.forest, self.dim, self.Jmin = sol, forest, forest.dim, Jmin
+        dim = self.dim
         hvy, lvl, ixyz, _ = forest.active(0)
-        self.slot: Dict[Key, int] = {}
-        self.leaf = set()
-        for h, l, x in zip(hvy, lvl, ixyz):
-            k = (int(l), int(x[0]), int(x[1]), int(x[2]))
-            self.slot[k] = int(h)
-            self.leaf.add(k)
-        nxt = int(hvy.max()) + 1
-        mothers = set()
-        for k in self.leaf:
-            while k[0] > Jmin:
-                k = _parent(k)
-                if k in mothers:
-                    break
-                mothers.add(k)
-        for k in sorted(mothers):
-            self.slot[k] = nxt
-            nxt += 1
-        if nxt - 1 > sol.max_blocks:
-            raise MemoryError(f"full tree needs {nxt - 1} block slots, max_blocks = {sol.max_blocks}")
-        self.Jmax_active = max(k[0] for k in self.leaf)
-        self.status: Dict[Key, int] = {}
-        self.detail: Dict[Key, np.ndarray] = {}
+        lv, ix = [lvl.astype(np.int64)], [ixyz.astype(np.int64)]
+        cl, cx = lv[0], ix[0]
+        seen = _pack(cl, cx)
+        for _ in range(int(lvl.max()) - Jmin):                     # ancestors, one level at a time
+            up = cl > Jmin
+            pl, px = cl[up] - 1, cx[up] >> 1
+            code, first = np.unique(_pack(pl, px), return_index=True)
+            new = ~np.isin(code, seen)
+            cl, cx = pl[first][new], px[first][new]
+            if len(cl) == 0:
+                break
+            lv.append(cl)
+            ix.append(cx)
+            seen = np.concatenate([seen, code[new]])
+        n_leaf = len(hvy)
+        level = np.concatenate(lv)
+        pos = np.concatenate(ix)
+        is_leaf = np.zeros(len(level), bool)
+        is_leaf[:n_leaf] = True
+        slots = np.zeros(len(level), np.int64)
+        slots[:n_leaf] = hvy
+        m = np.arange(n_leaf, len(level))
+        m_sorted = m[np.argsort(_pack(level[m], pos[m]), kind="stable")]
+        slots[m_sorted] = int(hvy.max()) + 1 + np.arange(len(m))    # mothers: free slots behind the leaves, in position order
+        if slots.max() > sol.max_blocks:
+            raise MemoryError(f"full tree needs {int(slots.max())} block slots, max_blocks = {sol.max_blocks}")
+        self._set_blocks(level, pos, slots, is_leaf)
+        self.Jmax_active = int(lvl.max())
+        self.st = np.zeros(len(level), np.int32)
+        self.det = None
         F = sol.wavelet_filter_width()
         p = sol.params
-        self.leaf_first = all(p.Bs[a] >= 3 * F for a in range(self.dim))
+        self.leaf_first = all(p.Bs[a] >= 3 * F for a in range(dim))
+
+    def _set_blocks(self, level, pos, slots, is_leaf, extra=()):
+        code = _pack(level, pos)
+        o = np.argsort(code)
+        self.code, self.level, self.pos, self.slots, self.is_leaf = code[o], level[o], pos[o], slots[o], is_leaf[o]
+        return o
+
+    # ---- views used by callers and tests
+    def keys(self, idx=None):
+        idx = np.arange(len(self.code)) if idx is None else idx
+        return [(int(l), int(x[0]), int(x[1]), int(x[2])) for l, x in zip(self.level[idx], self.pos[idx])]
+
+    @property
+    def slot(self) -> Dict[Key, int]:
+        return dict(zip(self.keys(), (int(v) for v in self.slots)))
+
+    @property
+    def leaf(self):
+        return set(self.keys(np.flatnonzero(self.is_leaf)))
+
+    def _find(self, level, pos):
+        """index into the tree arrays of the blocks at (level, pos) or -1"""
+        q = _pack(level, pos)
+        i = np.searchsorted(self.code, q)
+        i = np.minimum(i, len(self.code) - 1)
+        return np.where(self.code[i] == q, i, -1)
+
+    def _neighbor_pos(self, idx, d):
+        n = (1 << self.level[idx])[:, None]
+        dd = np.array([d[a] if a < self.dim else 0 for a in range(3)], dtype=np.int64)[None, :]
+        return (self.pos[idx] + dd) % n
 
     # ------------------------------------------------------------------ per-pass topology
-    def _nbr_key(self, k: Key, d) -> Key:
-        n = 2 ** k[0]
-        return (k[0],) + tuple(((k[1 + a] + d[a]) % n) if a < self.dim else 0 for a in range(3))
-
-    def set_pass_topology(self, keys: List[Key]):
-        """neighbour table of a block list: same-level relations to whatever block of the tree sits there (leaf or mother); for leaves,
-        directions without a same-level block become coarser relations (slot + 56), which is where the coarse extension acts"""
+    def set_pass_topology(self, idx: np.ndarray):
+        """neighbour table of a block list (indices into the tree arrays): same-level relations to whatever block of the tree sits there
+        (leaf or mother); for leaves, directions without a same-level block become coarser relations (slot + 56), which is where the
+        coarse extension acts.  Returns the indices in the order of the active list (ascending slot)."""
         sol, dim = self.sol, self.dim
-        lib = host_lib()
-        ids = np.array([self.slot[k] for k in keys], dtype=np.int32)
-        order = np.argsort(ids)
-        keys = [keys[i] for i in order]
-        ids = ids[order]
+        idx = np.asarray(idx)
+        idx = idx[np.argsort(self.slots[idx])]
+        ids = self.slots[idx].astype(np.int32)
         ld = int(ids.max())
         nbr = np.full((168, ld), -1, dtype=np.int32)
-        lvl = np.array([k[0] for k in keys], dtype=np.int32)
-        ix = np.zeros(3, dtype=np.int32)
-
-        def encode(k):
-            ix[:] = k[1:]
-            return lib.whost_encode(dim, k[0], self.forest.Jmax, ix.ctypes.data_as(C.POINTER(C.c_int32)))
-
-        tc = np.array([encode(k) for k in keys], dtype=np.int64)
-        coarse = set()                                  # coarser leaves next to the blocks of the pass: known as data sources only
-        for i, k in enumerate(keys):
-            s = self.slot[k] - 1
-            for d in _dirs(dim):
-                nk = self._nbr_key(k, d)
-                if nk in self.slot:
-                    nbr[_code(d) - 1, s] = self.slot[nk]
-                elif k in self.leaf and k[0] > 0:
-                    ck = _parent(nk)
-                    if ck in self.slot:
-                        nbr[_code(d) - 1 + 56, s] = self.slot[ck]
-                        coarse.add(ck)
-        coarse = sorted(coarse - set(keys))
-        sol.set_treecodes(np.concatenate([ids, np.array([self.slot[k] for k in coarse], dtype=np.int32)]),
-                          np.concatenate([lvl, np.array([k[0] for k in coarse], dtype=np.int32)]),
-                          np.concatenate([tc, np.array([encode(k) for k in coarse], dtype=np.int64)]))
-        sol.set_topology(ids, lvl, nbr, 0)
-        return keys
+        leaf = self.is_leaf[idx] & (self.level[idx] > 0)
+        coarse = []
+        for d in _dirs(dim):
+            npos = self._neighbor_pos(idx, d)
+            j = self._find(self.level[idx], npos)
+            hit = j >= 0
+            nbr[_code(d) - 1, ids[hit] - 1] = self.slots[j[hit]]
+            miss = ~hit & leaf
+            if miss.any():
+                c = self._find(self.level[idx][miss] - 1, npos[miss] >> 1)
+                ok = c >= 0
+                nbr[_code(d) - 1 + 56, ids[miss][ok] - 1] = self.slots[c[ok]]
+                coarse.append(c[ok])
+        extra = np.setdiff1d(np.unique(np.concatenate(coarse)), idx) if coarse else np.zeros(0, np.int64)
+        al = np.concatenate([idx, extra]).astype(np.int64)          # blocks of the pass + coarser leaves known as data sources only
+        tc = _encode_treecodes(dim, self.level[al], self.pos[al], self.forest.Jmax)
+        sol.set_treecodes(self.slots[al].astype(np.int32), self.level[al].astype(np.int32), tc)
+        sol.set_topology(ids, self.level[idx].astype(np.int32), nbr, 0)
+        return idx
 
     # ------------------------------------------------------------------ wavelet_decompose_full_tree + coarseningIndicator_tree
     def decompose(self, eps: Optional[float] = None, norm=None, eps_norm: str = "Linfty", thresh_comp=None, threshold: bool = True):
         sol, dim = self.sol, self.dim
         nd = 2 ** dim
 
-        def flags(keys):
+        def flags(idx):
             if not threshold:
                 return
             st, det = sol.threshold_tree(WD, eps=eps, norm=norm, eps_norm=eps_norm, thresh_comp=thresh_comp, level_ref=self.forest.Jmax,
                                          want_detail=True)
-            for k, s, dd in zip(keys, st, det):
-                self.status[k] = int(s)
-                self.detail[k] = dd
+            if self.det is None:
+                self.det = np.zeros((len(self.code), det.shape[1]))
+            self.st[idx] = st
+            self.det[idx] = det
 
         def d2m(level):
-            ms = sorted({_parent(k) for k in self.slot if k[0] == level and level > self.Jmin} & set(self.slot))
-            if not ms:
+            if level <= self.Jmin:
                 return
-            mo = np.array([self.slot[m] for m in ms], dtype=np.int32)
-            da = np.array([self.slot[c] for m in ms for c in _children(m, dim)], dtype=np.int32)
-            sol.coarsen_blocks(mo, da, WD)
+            kids = np.flatnonzero(self.level == level)
+            if len(kids) == 0:
+                return
+            m = np.unique(self._find(self.level[kids] - 1, self.pos[kids] >> 1))
+            m = m[m >= 0]
+            da = np.zeros((len(m), nd), dtype=np.int32)
+            for c in range(nd):          # treecode digit order: bit0 -> y, bit1 -> x, bit2 -> z
+                off = np.array([(c >> 1) & 1, c & 1, (c >> 2) & 1 if dim == 3 else 0], dtype=np.int64)[None, :]
+                j = self._find(self.level[m] + 1, 2 * self.pos[m] + off)
+                assert (j >= 0).all()
+                da[:, c] = self.slots[j]
+            sol.coarsen_blocks(self.slots[m].astype(np.int32), da.ravel(), WD)
 
         if self.leaf_first:
             sol.set_forest(self.forest)                                   # leaf grid: full synchronisation, filtered restriction
-            keys = [k for _, k in sorted((self.slot[k], k) for k in self.leaf)]
+            leaves = np.flatnonzero(self.is_leaf)
+            leaves = leaves[np.argsort(self.slots[leaves])]
             sol.waveletDecomposition_tree((HVY_BLOCK, 0), WD)
             sol.coarse_extension_modify(WD, (HVY_BLOCK, 0), True, True)
-            flags(keys)
+            flags(leaves)
         for level in range(self.Jmax_active, self.Jmin - 1, -1):
-            todo = [k for k in self.slot if k[0] == level and not (self.leaf_first and k in self.leaf)]
-            if todo:
-                keys = self.set_pass_topology(todo)
+            todo = np.flatnonzero((self.level == level) & ~(self.is_leaf if self.leaf_first else np.zeros(len(self.code), bool)))
+            if len(todo):
+                idx = self.set_pass_topology(todo)
                 sol.waveletDecomposition_tree((HVY_BLOCK, 0), WD)
-                if any(k in self.leaf for k in keys):
+                if self.is_leaf[idx].any():
                     sol.coarse_extension_modify(WD, (HVY_BLOCK, 0), True, True)
-                flags(keys)
+                flags(idx)
             d2m(level)
-        return self.status
+        return self.status_dict(self.st)
 
+    def status_dict(self, st):
+        return dict(zip(self.keys(), (int(v) for v in st)))
 
     # ------------------------------------------------------------------ grid decision (light data)
-    def _finer_neighbors(self, k: Key):
-        out = []
-        for d in _dirs(self.dim):
-            nk = self._nbr_key(k, d)
-            for c in _children(nk, self.dim):
-                if c in self.slot and all((d[a] == 0) or ((c[1 + a] & 1) == (0 if d[a] > 0 else 1)) for a in range(self.dim)):
-                    out.append(c)
-        return out
-
-    def decide(self, st: Dict[Key, int]) -> Dict[Key, int]:
+    def decide(self, st0: np.ndarray) -> np.ndarray:
         """respectJmaxJmin_tree + ensureGradedness_tree(check_daughters) on the full tree (LIB/MESH/ensureGradedness_tree.f90,
         ensure_completeness_block.f90): a block keeps -1 only if it sits above Jmin, all its sisters carry -1, none of its daughters stays
-        and no finer neighbour stays.  Statuses only move from -1 to "stay", so one monotone sweep to the fixed point."""
-        st = dict(st)
-        dim = self.dim
-        for k in st:
-            if st[k] == -1 and k[0] <= self.Jmin:
-                st[k] = 9                                                  # REF_UNSIGNIFICANT_STAY
-        changed = True
-        while changed:
-            changed = False
-            for k in sorted(st):
-                if st[k] != -1:
-                    continue
-                stay = any(st.get(s_, 0) != -1 for s_ in _children(_parent(k), dim))
-                if not stay and k not in self.leaf:
-                    stay = any(st.get(c, -1) != -1 for c in _children(k, dim) if c in self.slot)
-                if not stay:
-                    stay = any(st[f] != -1 for f in self._finer_neighbors(k))
-                if stay:
-                    st[k] = 9
-                    changed = True
-        return st
+        and no finer neighbour stays.  Statuses only move from -1 to "stay" (9), so the fixed point does not depend on the sweep order."""
+        dim, nd = self.dim, 2 ** self.dim
+        st = np.asarray(st0, dtype=np.int32).copy()
+        st[(st == -1) & (self.level <= self.Jmin)] = 9
+        n = len(st)
+        par = self._find(self.level - 1, self.pos >> 1)                 # index of the mother in the tree or -1
+        pcode = _pack(self.level - 1, self.pos >> 1)                    # sisters share it (also when the mother is not in the tree)
+        while True:
+            go = st == -1
+            stay = np.zeros(n, bool)
+            # completeness: all 2^d sisters carry -1
+            uc, inv, cnt = np.unique(pcode[go], return_inverse=True, return_counts=True)
+            tmp = np.zeros(n, bool)
+            tmp[np.flatnonzero(go)] = cnt[inv] < nd
+            stay |= tmp
+            # check_daughters: a daughter that stays keeps its mother
+            has = np.zeros(n, bool)
+            ch = (par >= 0) & (st != -1)
+            has[par[ch]] = True
+            stay |= go & has
+            # gradedness: a finer neighbour that stays keeps this block
+            cand = np.flatnonzero(go & ~stay)
+            if len(cand):
+                bad = np.zeros(len(cand), bool)
+                for d in _dirs(dim):
+                    npos = self._neighbor_pos(cand, d)
+                    free = [a for a in range(dim) if d[a] == 0]
+                    for m in range(2 ** len(free)):
+                        off = np.zeros(3, dtype=np.int64)
+                        for a in range(dim):
+                            if d[a] < 0:
+                                off[a] = 1
+                        for b, a in enumerate(free):
+                            off[a] = (m >> b) & 1
+                        j = self._find(self.level[cand] + 1, 2 * npos + off[None, :])
+                        bad |= (j >= 0) & (st[np.maximum(j, 0)] != -1)
+                stay[cand[bad]] = True
+            if not stay.any():
+                return st
+            st[stay] = 9
 
     def _ce_sizes(self):
         """Nrecon and Ndep2 of setup_wavelet incl. the widening to the FD stencil (module_wavelets.f90:1368-1417)"""
@@ -244,40 +316,45 @@ class FullTree:
         p = sol.params
         if indicator == "everywhere":
             self.decompose(threshold=False)
-            st0 = {k: (-1 if k in self.leaf else 0) for k in self.slot}
+            st0 = np.where(self.is_leaf, -1, 0).astype(np.int32)
         else:
-            st0 = dict(self.decompose(eps=eps, norm=norm, eps_norm=eps_norm, thresh_comp=thresh_comp))
+            self.decompose(eps=eps, norm=norm, eps_norm=eps_norm, thresh_comp=thresh_comp)
+            st0 = self.st.copy()
             if force_maxlevel_dealiasing:
-                st0 = {k: (-1 if k[0] == self.forest.Jmax else v) for k, v in st0.items()}
+                st0[self.level == self.forest.Jmax] = -1
         st = self.decide(st0)
-        for k in [k for k in st if st[k] == -1]:
-            del self.slot[k]
-        self.leaf = {k for k in self.slot if not any(c in self.slot for c in _children(k, dim))}
-        marked = [k for k in self.leaf if any(self._nbr_key(k, d) not in self.slot for d in _dirs(dim))]
+        info = {"status0": self.status_dict(st0), "status": self.status_dict(st)}
+        keep = st != -1
+        self.code, self.level, self.pos, self.slots = self.code[keep], self.level[keep], self.pos[keep], self.slots[keep]
+        par = self._find(self.level - 1, self.pos >> 1)
+        self.is_leaf = np.ones(len(self.code), bool)
+        self.is_leaf[par[par >= 0]] = False
+        leaves = np.flatnonzero(self.is_leaf)
+        at_interface = np.zeros(len(leaves), bool)
+        for d in _dirs(dim):
+            at_interface |= self._find(self.level[leaves], self._neighbor_pos(leaves, d)) < 0
+        marked = leaves[at_interface]
         nrl, nrr, d2l, d2r = self._ce_sizes()
         if any(p.Bs[a] < max(nrl, nrr) for a in range(dim)):
             raise RuntimeError("adapt_tree: Bs < Nrecon (reconstruction of the neighbours of interface blocks) is not supported")
         leaf_only = all(p.Bs[a] >= d2l and p.Bs[a] >= d2r for a in range(dim))
-        if marked:
+        if len(marked):
+            self.set_pass_topology(marked)                                # the lasting interfaces (adapt_tree.f90:222-228): same-level
+            sol.coarse_extension_modify(WD, (HVY_BLOCK, 0), True, False)  # neighbours send coefficients that carry the extension
             if leaf_only:
-                self.set_pass_topology(marked)
-                sol.coarse_extension_modify(WD, (HVY_BLOCK, 0), True, False)
                 sol.waveletReconstruction_CE(WD, (HVY_BLOCK, 0), (HVY_BLOCK, 0))
             else:
-                self.set_pass_topology(marked)                                # the lasting interfaces first (adapt_tree.f90:222-228):
-                sol.coarse_extension_modify(WD, (HVY_BLOCK, 0), True, False)  # same-level neighbours send coefficients that carry it
-                for level in range(self.Jmin, max(k[0] for k in self.slot) + 1):
-                    todo = [k for k in marked if k[0] == level]
-                    if todo:
+                for level in range(self.Jmin, int(self.level.max()) + 1):
+                    todo = marked[self.level[marked] == level]
+                    if len(todo):
                         self.set_pass_topology(todo)
                         sol.waveletReconstruction_CE(WD, (HVY_BLOCK, 0), (HVY_BLOCK, 0))
         # prune_fulltree2leafs + balanceLoad_tree: the leaves move to their slots along the space-filling curve
-        keys = sorted(self.leaf)
-        new = Forest.from_blocks(dim, self.forest.Jmax, np.array([k[0] for k in keys], dtype=np.int32),
-                                 np.array([k[1:] for k in keys], dtype=np.int32), block_dist=self.forest.block_dist, n_ranks=1,
-                                 max_blocks=self.forest.max_blocks, periodic=self.forest.periodic)
+        new = Forest.from_blocks(dim, self.forest.Jmax, self.level[leaves].astype(np.int32), self.pos[leaves].astype(np.int32),
+                                 block_dist=self.forest.block_dist, n_ranks=1, max_blocks=self.forest.max_blocks, periodic=self.forest.periodic)
         hvy, lvl, ixyz, _ = new.active(0)
-        src = np.array([self.slot[(int(l), int(x[0]), int(x[1]), int(x[2]))] for l, x in zip(lvl, ixyz)], dtype=np.int32)
-        sol.move_blocks(src, hvy.astype(np.int32))
+        src = self.slots[self._find(lvl.astype(np.int64), ixyz.astype(np.int64))]
+        sol.move_blocks(src.astype(np.int32), hvy.astype(np.int32))
         sol.set_forest(new)
-        return new, {"status0": st0, "status": st, "marked": sorted(marked), "leaf_only": leaf_only, "leaf_first": self.leaf_first}
+        info.update({"marked": sorted(self.keys(marked)), "leaf_only": leaf_only, "leaf_first": self.leaf_first})
+        return new, info
