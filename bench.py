@@ -334,16 +334,23 @@ def run_ours(a):
     sol.close()
     del host, h_np
     adaptive = None
+    adaptive_lifted = None
     if world == 1 and not a.no_adaptive:
         try:
             adaptive = adaptive_leg(a, local, stream)
         except Exception as e:      # a secondary figure must not take the headline line down
             adaptive = {"error": repr(e)}
+        try:                        # BASELINE config 3 names CDF4,4: the lifted adapt_tree (full-tree algorithm)
+            adaptive_lifted = adaptive_leg(a, local, stream, wavelet="CDF44")
+        except Exception as e:
+            adaptive_lifted = {"error": repr(e)}
     elif world > 1 and a.adaptive_multi:   # opt-in: a failure on one rank would leave the others waiting in a collective
         adaptive = adaptive_leg_multi(a, rank, world, local, stream, J0=a.adaptive_level, Jmax=a.adaptive_level + 1)
     if rank == 0:
         if adaptive is not None:
             line["adaptive"] = adaptive
+        if adaptive_lifted is not None:
+            line["adaptive_cdf44"] = adaptive_lifted
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -447,21 +454,24 @@ def wavelet_leg(a, sol, nb, stream, barrier, wavelet="CDF44", reps=20):
                          "algorithmic_bytes_per_block": bytes_fwt, "traffic": traffic}}
 
 
-def adaptive_leg(a, device_index, stream, eps=None, J0=5, Jmax=6, cycles=3, max_blocks=150000):
+def adaptive_leg(a, device_index, stream, eps=None, J0=5, Jmax=6, cycles=3, max_blocks=None, wavelet="CDF40"):
     """BASELINE config 3's cycle on one GPU (the protocol of performance_test.f90: refine_tree("everywhere") -> timeStep_tree ->
-    adapt_tree), unlifted CDF40 (the coarse extension of lifted wavelets is not built): Taylor-Green + three Gaussian vortex blobs
+    adapt_tree), CDF40 (one coarsening sweep per adapt_tree call) or a lifted wavelet such as CDF44 (the reference's full-tree algorithm
+    with the coarse extension, wabbit_b200/fulltree.py): Taylor-Green + three Gaussian vortex blobs
     on an equidistant level-J0 grid, coarsened by wavelet thresholding until the grid is stationary, then `cycles` timed cycles.
     block-updates/s counts the blocks the Runge-Kutta step advances (Nb after refinement, as performance.t's Nb_rhs)."""
     import torch
     from wabbit_b200 import Forest, Params, WabbitGPU
     eps = a.adaptive_eps if eps is None else eps
-    p = Params(dim=3, domain=(TWO_PI,) * 3, Bs=(a.bs,) * 3, wavelet="CDF40", g=3, g_rhs=2, n_eqn=4, Jmax=Jmax,
+    max_blocks = max_blocks or int(2.5 * 8 ** J0)     # leaves after refinement + the mothers of the full tree, with room to spare
+    lifted = wavelet[4] != "0"
+    p = Params(dim=3, domain=(TWO_PI,) * 3, Bs=(a.bs,) * 3, wavelet=wavelet, g=int(wavelet[3]) - 1 + max(int(wavelet[4]) - 1, 0), g_rhs=2, n_eqn=4, Jmax=Jmax,
                discretization="FD_4th_central", skew_symmetry=True, c0=10.0, nu=3.125e-3, gamma_p=0.0, CFL=1.0,
                u_mean_set=(0.0, 0.0, 0.0), time_max=1.0e9).finalize()
     forest = Forest.uniform(3, J0, Jmax=Jmax, max_blocks=max_blocks)
     hvy, lvl, ixyz, _ = forest.active(0)
     sol = WabbitGPU(p, max_blocks=max_blocks, device=device_index, stream=stream.cuda_stream)
-    sol.setup_wavelet("CDF40")
+    sol.setup_wavelet(wavelet)
     sol.set_forest(forest)
     nb0 = len(hvy)
     shape = (nb0,) + sol.host_shape()[1:]
@@ -517,7 +527,9 @@ def adaptive_leg(a, device_index, stream, eps=None, J0=5, Jmax=6, cycles=3, max_
     sol.close()
     recs = recs[2:]
     tot = sum(r[2] + r[3] + r[4] for r in recs)
-    return {"metric": "adaptive block-updates/s (refine everywhere -> RK4 -> adapt, CDF40, 1 GPU)", "value": sum(r[0] for r in recs) / tot,
+    return {"metric": f"adaptive block-updates/s (refine everywhere -> RK4 -> adapt, {wavelet}, 1 GPU)", "value": sum(r[0] for r in recs) / tot,
+            "adapt_tree": ("full wavelet transformation with coarse extension (lifted wavelet, useSecurityZone=0): all levels in one call"
+                           if lifted else "one coarsening sweep per call (unlifted wavelet)"),
             "unit": UNIT, "eps": eps, "Jmax": Jmax, "blocks_initial_coarsening": sizes, "cycles": len(recs),
             "blocks_rhs": [r[0] for r in recs], "blocks_after_adapt": [r[1] for r in recs],
             "ms_refine": [round(r[2] * 1e3, 2) for r in recs], "ms_rk4": [round(r[3] * 1e3, 2) for r in recs],
@@ -633,6 +645,7 @@ def main():
     ap.add_argument("--no-wavelet", action="store_true", help="skip the secondary FWT + threshold figure")
     ap.add_argument("--no-adaptive", action="store_true", help="skip the secondary adaptive-cycle figure")
     ap.add_argument("--adaptive-eps", type=float, default=1.0e-6)
+    ap.add_argument("--adaptive-wavelet", default="CDF40", help="wavelet of --adaptive-only")
     ap.add_argument("--adaptive-multi", action="store_true", help="N > 1: also run the adaptive cycle across the GPUs (halo blocks + block transport)")
     ap.add_argument("--adaptive-level", type=int, default=5, help="initial equidistant level of the adaptive legs")
     ap.add_argument("--adaptive-only", action="store_true", help="run only the adaptive-cycle leg and print its record (development)")
@@ -644,7 +657,7 @@ def main():
     if a.adaptive_only:
         import torch
         torch.cuda.set_device(0)
-        print(json.dumps(adaptive_leg(a, 0, torch.cuda.current_stream())), flush=True)
+        print(json.dumps(adaptive_leg(a, 0, torch.cuda.current_stream(), wavelet=a.adaptive_wavelet, J0=a.adaptive_level, Jmax=a.adaptive_level + 1)), flush=True)
         return
     if a.impl == "reference":
         run_reference(a)

@@ -69,6 +69,14 @@ int32_t whost_refine_global(const whost_forest *f, const int32_t *flags, int32_t
 int32_t whost_coarsen_global(const whost_forest *f, int32_t *status, int32_t Jmin, int32_t max_blocks_per_rank, whost_forest **out,
                              int32_t *n_mothers, int32_t *mothers, int32_t *daughters, int32_t *n_keep, int32_t *keep_src, int32_t *keep_dst);
 
+/* Full tree (leaves + all ancestors) of adapt_tree's full wavelet transformation (LIB/MESH/adapt_tree.f90:268-545, init_full_tree): blocks as
+ * (level[n], pos[3n]) in any order.  whost_ft_tables: same-level neighbour per direction nb[n][3^dim-1] (dz, dy, dx ascending, periodic), mother
+ * par[n], daughters child[n][2^dim] (column = x + 2y + 4z offset); indices into the list or -1.  whost_ft_decide: respectJmaxJmin_tree +
+ * ensureGradedness_tree(check_daughters) (LIB/MESH/ensureGradedness_tree.f90): status -1 survives only for blocks that are deleted. */
+int32_t whost_ft_tables(int32_t dim, int32_t n, const int32_t *level, const int32_t *pos, int32_t *nb, int32_t *par, int32_t *child);
+int32_t whost_ft_decide(int32_t dim, int32_t n, const int32_t *level, const int32_t *nb, const int32_t *par, const int32_t *child, int32_t Jmin,
+                        int32_t *status);
+
 /* treecode helpers (module_treelib.f90:793-871) */
 int64_t whost_encode(int32_t dim, int32_t level, int32_t Jmax, const int32_t ixyz[3]);
 int32_t whost_decode(int32_t dim, int32_t level, int32_t Jmax, int64_t treecode, int32_t ixyz[3]);

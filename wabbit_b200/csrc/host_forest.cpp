@@ -544,3 +544,112 @@ static int32_t coarsen_impl(const whost_forest *f, int32_t *status, int32_t Jmin
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Full tree (leaves + all ancestors) of adapt_tree's full wavelet transformation: neighbourhood tables and the grid decision.
+// Light data only; stand-ins for updateMetadata_tree on the full tree (LIB/MESH/updateMetadata_tree.f90) and for
+// respectJmaxJmin_tree + ensureGradedness_tree(check_daughters) (LIB/MESH/ensureGradedness_tree.f90, ensure_completeness_block.f90).
+// Blocks are given as (level, ix, iy, iz) in any order; all outputs are indices into that list or -1.
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+// nb[n][3^dim - 1]: same-level neighbour per direction (dz, dy, dx ascending, (0,0,0) skipped; periodic), par[n]: mother,
+// child[n][2^dim]: daughters, column = x offset + 2 * y offset + 4 * z offset
+int32_t whost_ft_tables(int32_t dim, int32_t n, const int32_t *level, const int32_t *pos, int32_t *nb, int32_t *par, int32_t *child)
+{
+    if (n < 0 || (n > 0 && (!level || !pos || !nb || !par || !child))) return 1;
+    std::unordered_map<uint64_t, int> look;
+    look.reserve((size_t)n * 2);
+    for (int i = 0; i < n; ++i) look[pos_hash(level[i], pos + 3 * i)] = i;
+    auto find = [&](int l, const int p[3]) -> int {
+        if (l < 0) return -1;
+        auto it = look.find(pos_hash(l, p));
+        return it == look.end() ? -1 : it->second;
+    };
+    const int nd = 1 << dim, ndir = (dim == 3 ? 27 : 9) - 1;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) {
+        const int l = level[i], nb_l = 1 << l;
+        const int *p = pos + 3 * i;
+        int q = 0;
+        for (int dz = (dim == 3 ? -1 : 0); dz <= (dim == 3 ? 1 : 0); ++dz)
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    if (!dx && !dy && !dz) continue;
+                    const int np[3] = {((p[0] + dx) % nb_l + nb_l) % nb_l, ((p[1] + dy) % nb_l + nb_l) % nb_l,
+                                       dim == 3 ? ((p[2] + dz) % nb_l + nb_l) % nb_l : 0};
+                    nb[(size_t)i * ndir + q++] = find(l, np);
+                }
+        const int pp[3] = {p[0] >> 1, p[1] >> 1, p[2] >> 1};
+        par[i] = find(l - 1, pp);
+        for (int c = 0; c < nd; ++c) {
+            const int cp[3] = {2 * p[0] + (c & 1), 2 * p[1] + ((c >> 1) & 1), dim == 3 ? 2 * p[2] + ((c >> 2) & 1) : 0};
+            child[(size_t)i * nd + c] = find(l + 1, cp);
+        }
+    }
+    return 0;
+}
+
+// status[n] in: -1 = insignificant; out: -1 only for the blocks that are deleted, 9 (REF_UNSIGNIFICANT_STAY) for demoted ones.
+// A block keeps -1 only if it sits above Jmin, all its 2^dim sisters carry -1, none of its daughters stays and none of its finer
+// neighbours (the daughters of its same-level neighbours that touch it) stays.  Statuses only move from -1 to 9: unique fixed point.
+int32_t whost_ft_decide(int32_t dim, int32_t n, const int32_t *level, const int32_t *nb, const int32_t *par, const int32_t *child, int32_t Jmin,
+                        int32_t *status)
+{
+    if (n < 0 || (n > 0 && (!level || !nb || !par || !child || !status))) return 1;
+    const int nd = 1 << dim, ndir = (dim == 3 ? 27 : 9) - 1;
+    // daughters of the neighbour in direction q that touch the block: offset 1 on axes with d < 0, 0 with d > 0, both with d = 0
+    std::vector<std::vector<int>> cols(ndir);
+    {
+        int q = 0;
+        for (int dz = (dim == 3 ? -1 : 0); dz <= (dim == 3 ? 1 : 0); ++dz)
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    if (!dx && !dy && !dz) continue;
+                    const int d[3] = {dx, dy, dz};
+                    for (int c = 0; c < nd; ++c) {
+                        bool ok = true;
+                        for (int a = 0; a < dim; ++a) {
+                            const int off = (c >> a) & 1;
+                            if ((d[a] < 0 && off != 1) || (d[a] > 0 && off != 0)) ok = false;
+                        }
+                        if (ok) cols[q].push_back(c);
+                    }
+                    ++q;
+                }
+    }
+    for (int i = 0; i < n; ++i)
+        if (status[i] == -1 && level[i] <= Jmin) status[i] = 9;
+    bool changed = true;
+    while (changed) {
+        changed = false;
+        for (int i = 0; i < n; ++i) {
+            if (status[i] != -1) continue;
+            bool stay = par[i] < 0;
+            if (!stay)
+                for (int c = 0; c < nd && !stay; ++c) {
+                    const int s = child[(size_t)par[i] * nd + c];
+                    if (s < 0 || status[s] != -1) stay = true;                                   // completeness
+                }
+            for (int c = 0; c < nd && !stay; ++c) {
+                const int s = child[(size_t)i * nd + c];
+                if (s >= 0 && status[s] != -1) stay = true;                                      // check_daughters
+            }
+            for (int q = 0; q < ndir && !stay; ++q) {
+                const int j = nb[(size_t)i * ndir + q];
+                if (j < 0) continue;
+                for (int c : cols[q]) {
+                    const int f = child[(size_t)j * nd + c];
+                    if (f >= 0 && status[f] != -1) { stay = true; break; }                       // gradedness
+                }
+            }
+            if (stay) {
+                status[i] = 9;
+                changed = true;
+            }
+        }
+    }
+    return 0;
+}
+
+}  // extern "C"

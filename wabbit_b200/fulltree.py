@@ -22,6 +22,8 @@ Light data (which blocks exist, their slots, the per-pass neighbour tables) are 
 from __future__ import annotations
 
 import ctypes as C
+import os
+import time
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -130,15 +132,57 @@ class FullTree:
         self.Jmax_active = int(lvl.max())
         self.st = np.zeros(len(level), np.int32)
         self.det = None
+        self.timing = {} if os.environ.get("WABBIT_FT_TIMING") else None
         F = sol.wavelet_filter_width()
         p = sol.params
         self.leaf_first = all(p.Bs[a] >= 3 * F for a in range(dim))
 
-    def _set_blocks(self, level, pos, slots, is_leaf, extra=()):
+    def _set_blocks(self, level, pos, slots, is_leaf):
         code = _pack(level, pos)
         o = np.argsort(code)
         self.code, self.level, self.pos, self.slots, self.is_leaf = code[o], level[o], pos[o], slots[o], is_leaf[o]
+        self._build_tables()
         return o
+
+    def _build_tables(self):
+        """same-level neighbour index per direction, mother index and daughter indices of every block of the tree (or -1): the whole
+        neighbourhood logic of the passes and of the grid decision reads these (libwabbit_host.so: whost_ft_tables)"""
+        dim, n = self.dim, len(self.code)
+        self.dirs = _dirs(dim)
+        self._lvl32 = np.ascontiguousarray(self.level, dtype=np.int32)
+        self._pos32 = np.ascontiguousarray(self.pos, dtype=np.int32)
+        nb = np.zeros((n, len(self.dirs)), np.int32)
+        par = np.zeros(n, np.int32)
+        child = np.zeros((n, 2 ** dim), np.int32)
+        i32 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        rc = host_lib().whost_ft_tables(dim, n, i32(self._lvl32), i32(self._pos32), i32(nb), i32(par), i32(child))
+        if rc:
+            raise RuntimeError(f"whost_ft_tables: {rc}")
+        self.nb, self.par, self.child = nb, par, child
+        self._rows_ready = False
+
+    def _upload_rows(self):
+        """hvy_neighbor rows of EVERY block of the tree, built once per tree state: same-level relations to whatever block sits there
+        (leaf or mother); for leaves, directions without a same-level block become coarser relations (slot + 56), which is where the
+        coarse extension acts.  All blocks are registered as data sources (wgpu_set_treecodes); a pass then only names its active list."""
+        sol, dim = self.sol, self.dim
+        ld = int(self.slots.max())
+        nbr = np.full((168, ld), -1, dtype=np.int32)
+        col = self.slots - 1
+        leaf = self.is_leaf & (self.level > 0)
+        for q, d in enumerate(self.dirs):
+            j = self.nb[:, q]
+            hit = j >= 0
+            nbr[_code(d) - 1, col[hit]] = self.slots[j[hit]]
+            miss = np.flatnonzero(~hit & leaf)
+            if len(miss):
+                c = self._find(self.level[miss] - 1, self._neighbor_pos(miss, d) >> 1)
+                ok = c >= 0
+                nbr[_code(d) - 1 + 56, col[miss[ok]]] = self.slots[c[ok]]
+        self._rows = nbr
+        tc = _encode_treecodes(dim, self.level, self.pos, self.forest.Jmax)
+        sol.set_treecodes(self.slots.astype(np.int32), self._lvl32, tc)
+        self._rows_ready = True
 
     # ---- views used by callers and tests
     def keys(self, idx=None):
@@ -166,38 +210,28 @@ class FullTree:
         return (self.pos[idx] + dd) % n
 
     # ------------------------------------------------------------------ per-pass topology
+    def _tick(self, name, t0):
+        if self.timing is not None:
+            self.sol.synchronize()
+            self.timing[name] = self.timing.get(name, 0.0) + (time.perf_counter() - t0)
+        return time.perf_counter()
+
     def set_pass_topology(self, idx: np.ndarray):
-        """neighbour table of a block list (indices into the tree arrays): same-level relations to whatever block of the tree sits there
-        (leaf or mother); for leaves, directions without a same-level block become coarser relations (slot + 56), which is where the
-        coarse extension acts.  Returns the indices in the order of the active list (ascending slot)."""
-        sol, dim = self.sol, self.dim
+        """a pass = a list of active blocks (indices into the tree arrays) on the tree's neighbour rows.  Returns the indices in the order
+        of the active list (ascending slot)."""
+        t0 = time.perf_counter()
         idx = np.asarray(idx)
         idx = idx[np.argsort(self.slots[idx])]
-        ids = self.slots[idx].astype(np.int32)
-        ld = int(ids.max())
-        nbr = np.full((168, ld), -1, dtype=np.int32)
-        leaf = self.is_leaf[idx] & (self.level[idx] > 0)
-        coarse = []
-        for d in _dirs(dim):
-            npos = self._neighbor_pos(idx, d)
-            j = self._find(self.level[idx], npos)
-            hit = j >= 0
-            nbr[_code(d) - 1, ids[hit] - 1] = self.slots[j[hit]]
-            miss = ~hit & leaf
-            if miss.any():
-                c = self._find(self.level[idx][miss] - 1, npos[miss] >> 1)
-                ok = c >= 0
-                nbr[_code(d) - 1 + 56, ids[miss][ok] - 1] = self.slots[c[ok]]
-                coarse.append(c[ok])
-        extra = np.setdiff1d(np.unique(np.concatenate(coarse)), idx) if coarse else np.zeros(0, np.int64)
-        al = np.concatenate([idx, extra]).astype(np.int64)          # blocks of the pass + coarser leaves known as data sources only
-        tc = _encode_treecodes(dim, self.level[al], self.pos[al], self.forest.Jmax)
-        sol.set_treecodes(self.slots[al].astype(np.int32), self.level[al].astype(np.int32), tc)
-        sol.set_topology(ids, self.level[idx].astype(np.int32), nbr, 0)
+        if not self._rows_ready:
+            self._upload_rows()
+            t0 = self._tick("tree rows (numpy) + wgpu_set_treecodes", t0)
+        self.sol.set_topology(self.slots[idx].astype(np.int32), self._lvl32[idx], self._rows, 0)
+        self._tick("wgpu_set_topology", t0)
         return idx
 
     # ------------------------------------------------------------------ wavelet_decompose_full_tree + coarseningIndicator_tree
-    def decompose(self, eps: Optional[float] = None, norm=None, eps_norm: str = "Linfty", thresh_comp=None, threshold: bool = True):
+    def decompose(self, eps: Optional[float] = None, norm=None, eps_norm: str = "Linfty", thresh_comp=None, threshold: bool = True,
+                  want_dict: bool = True):
         sol, dim = self.sol, self.dim
         nd = 2 ** dim
 
@@ -214,21 +248,20 @@ class FullTree:
         def d2m(level):
             if level <= self.Jmin:
                 return
-            kids = np.flatnonzero(self.level == level)
-            if len(kids) == 0:
+            m = np.flatnonzero((self.level == level - 1) & (self.child[:, 0] >= 0))
+            if len(m) == 0:
                 return
-            m = np.unique(self._find(self.level[kids] - 1, self.pos[kids] >> 1))
-            m = m[m >= 0]
             da = np.zeros((len(m), nd), dtype=np.int32)
             for c in range(nd):          # treecode digit order: bit0 -> y, bit1 -> x, bit2 -> z
-                off = np.array([(c >> 1) & 1, c & 1, (c >> 2) & 1 if dim == 3 else 0], dtype=np.int64)[None, :]
-                j = self._find(self.level[m] + 1, 2 * self.pos[m] + off)
+                col = ((c >> 1) & 1) + 2 * (c & 1) + (4 * ((c >> 2) & 1) if dim == 3 else 0)
+                j = self.child[m, col]
                 assert (j >= 0).all()
                 da[:, c] = self.slots[j]
             sol.coarsen_blocks(self.slots[m].astype(np.int32), da.ravel(), WD)
 
         if self.leaf_first:
             sol.set_forest(self.forest)                                   # leaf grid: full synchronisation, filtered restriction
+            self._rows_ready = False                                      # (registers the leaves only: the tree is re-registered below)
             leaves = np.flatnonzero(self.is_leaf)
             leaves = leaves[np.argsort(self.slots[leaves])]
             sol.waveletDecomposition_tree((HVY_BLOCK, 0), WD)
@@ -238,12 +271,17 @@ class FullTree:
             todo = np.flatnonzero((self.level == level) & ~(self.is_leaf if self.leaf_first else np.zeros(len(self.code), bool)))
             if len(todo):
                 idx = self.set_pass_topology(todo)
+                t0 = time.perf_counter()
                 sol.waveletDecomposition_tree((HVY_BLOCK, 0), WD)
                 if self.is_leaf[idx].any():
                     sol.coarse_extension_modify(WD, (HVY_BLOCK, 0), True, True)
+                t0 = self._tick("fwt + ce kernels", t0)
                 flags(idx)
+                self._tick("threshold", t0)
+            t0 = time.perf_counter()
             d2m(level)
-        return self.status_dict(self.st)
+            self._tick("d2m", t0)
+        return self.status_dict(self.st) if want_dict else None
 
     def status_dict(self, st):
         return dict(zip(self.keys(), (int(v) for v in st)))
@@ -252,46 +290,14 @@ class FullTree:
     def decide(self, st0: np.ndarray) -> np.ndarray:
         """respectJmaxJmin_tree + ensureGradedness_tree(check_daughters) on the full tree (LIB/MESH/ensureGradedness_tree.f90,
         ensure_completeness_block.f90): a block keeps -1 only if it sits above Jmin, all its sisters carry -1, none of its daughters stays
-        and no finer neighbour stays.  Statuses only move from -1 to "stay" (9), so the fixed point does not depend on the sweep order."""
-        dim, nd = self.dim, 2 ** self.dim
-        st = np.asarray(st0, dtype=np.int32).copy()
-        st[(st == -1) & (self.level <= self.Jmin)] = 9
-        n = len(st)
-        par = self._find(self.level - 1, self.pos >> 1)                 # index of the mother in the tree or -1
-        pcode = _pack(self.level - 1, self.pos >> 1)                    # sisters share it (also when the mother is not in the tree)
-        while True:
-            go = st == -1
-            stay = np.zeros(n, bool)
-            # completeness: all 2^d sisters carry -1
-            uc, inv, cnt = np.unique(pcode[go], return_inverse=True, return_counts=True)
-            tmp = np.zeros(n, bool)
-            tmp[np.flatnonzero(go)] = cnt[inv] < nd
-            stay |= tmp
-            # check_daughters: a daughter that stays keeps its mother
-            has = np.zeros(n, bool)
-            ch = (par >= 0) & (st != -1)
-            has[par[ch]] = True
-            stay |= go & has
-            # gradedness: a finer neighbour that stays keeps this block
-            cand = np.flatnonzero(go & ~stay)
-            if len(cand):
-                bad = np.zeros(len(cand), bool)
-                for d in _dirs(dim):
-                    npos = self._neighbor_pos(cand, d)
-                    free = [a for a in range(dim) if d[a] == 0]
-                    for m in range(2 ** len(free)):
-                        off = np.zeros(3, dtype=np.int64)
-                        for a in range(dim):
-                            if d[a] < 0:
-                                off[a] = 1
-                        for b, a in enumerate(free):
-                            off[a] = (m >> b) & 1
-                        j = self._find(self.level[cand] + 1, 2 * npos + off[None, :])
-                        bad |= (j >= 0) & (st[np.maximum(j, 0)] != -1)
-                stay[cand[bad]] = True
-            if not stay.any():
-                return st
-            st[stay] = 9
+        and no finer neighbour stays.  Statuses only move from -1 to "stay" (9), so the fixed point does not depend on the sweep order
+        (libwabbit_host.so: whost_ft_decide)."""
+        st = np.ascontiguousarray(st0, dtype=np.int32).copy()
+        i32 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        rc = host_lib().whost_ft_decide(self.dim, len(st), i32(self._lvl32), i32(self.nb), i32(self.par), i32(self.child), self.Jmin, i32(st))
+        if rc:
+            raise RuntimeError(f"whost_ft_decide: {rc}")
+        return st
 
     def _ce_sizes(self):
         """Nrecon and Ndep2 of setup_wavelet incl. the widening to the FD stencil (module_wavelets.f90:1368-1417)"""
@@ -307,7 +313,7 @@ class FullTree:
 
     # ------------------------------------------------------------------ adapt_tree
     def adapt(self, eps: Optional[float] = None, norm=None, eps_norm: str = "Linfty", thresh_comp=None, force_maxlevel_dealiasing: bool = False,
-              indicator: str = "threshold-state-vector"):
+              indicator: str = "threshold-state-vector", want_info: bool = True):
         """adapt_tree (LIB/MESH/adapt_tree.f90:11-260) for a lifted wavelet with the coarse extension (useSecurityZone = 0): full-tree
         decomposition and indicator, grid decision, coarse extension on the lasting coarse/fine interfaces, reconstruction of the leaves at
         those interfaces (all at once if Bs >= Ndep2, else level by level from coarse to fine), pruning to the leaves, blocks moved to
@@ -315,25 +321,24 @@ class FullTree:
         sol, dim = self.sol, self.dim
         p = sol.params
         if indicator == "everywhere":
-            self.decompose(threshold=False)
+            self.decompose(threshold=False, want_dict=False)
             st0 = np.where(self.is_leaf, -1, 0).astype(np.int32)
         else:
-            self.decompose(eps=eps, norm=norm, eps_norm=eps_norm, thresh_comp=thresh_comp)
+            self.decompose(eps=eps, norm=norm, eps_norm=eps_norm, thresh_comp=thresh_comp, want_dict=False)
             st0 = self.st.copy()
             if force_maxlevel_dealiasing:
                 st0[self.level == self.forest.Jmax] = -1
+        t0 = time.perf_counter()
         st = self.decide(st0)
-        info = {"status0": self.status_dict(st0), "status": self.status_dict(st)}
+        t0 = self._tick("decide", t0)
+        info = {"status0": self.status_dict(st0), "status": self.status_dict(st)} if want_info else {}
         keep = st != -1
         self.code, self.level, self.pos, self.slots = self.code[keep], self.level[keep], self.pos[keep], self.slots[keep]
-        par = self._find(self.level - 1, self.pos >> 1)
-        self.is_leaf = np.ones(len(self.code), bool)
-        self.is_leaf[par[par >= 0]] = False
+        self._build_tables()
+        t0 = self._tick("rebuild tables", t0)
+        self.is_leaf = self.child[:, 0] < 0
         leaves = np.flatnonzero(self.is_leaf)
-        at_interface = np.zeros(len(leaves), bool)
-        for d in _dirs(dim):
-            at_interface |= self._find(self.level[leaves], self._neighbor_pos(leaves, d)) < 0
-        marked = leaves[at_interface]
+        marked = leaves[(self.nb[leaves] < 0).any(axis=1)]
         nrl, nrr, d2l, d2r = self._ce_sizes()
         if any(p.Bs[a] < max(nrl, nrr) for a in range(dim)):
             raise RuntimeError("adapt_tree: Bs < Nrecon (reconstruction of the neighbours of interface blocks) is not supported")
@@ -354,7 +359,12 @@ class FullTree:
                                  block_dist=self.forest.block_dist, n_ranks=1, max_blocks=self.forest.max_blocks, periodic=self.forest.periodic)
         hvy, lvl, ixyz, _ = new.active(0)
         src = self.slots[self._find(lvl.astype(np.int64), ixyz.astype(np.int64))]
+        t0 = self._tick("reconstruction passes + new forest", t0)
         sol.move_blocks(src.astype(np.int32), hvy.astype(np.int32))
         sol.set_forest(new)
-        info.update({"marked": sorted(self.keys(marked)), "leaf_only": leaf_only, "leaf_first": self.leaf_first})
+        self._tick("move_blocks + set_forest", t0)
+        if self.timing is not None:
+            print("FullTree.adapt timing [ms]:", {k: round(v * 1e3, 1) for k, v in self.timing.items()}, flush=True)
+        if want_info:
+            info.update({"marked": sorted(self.keys(marked)), "leaf_only": leaf_only, "leaf_first": self.leaf_first})
         return new, info

@@ -286,7 +286,8 @@ class WabbitGPU:
                 norm_l[norm_l <= 1.0e-9] = 1.0
             n0 = forest.n_blocks
             new, _info = FullTree(self, forest, Jmin=Jmin).adapt(eps=self.params.eps if eps is None else eps, norm=norm_l, eps_norm=eps_norm,
-                                                               thresh_comp=thresh_comp, force_maxlevel_dealiasing=force_maxlevel_dealiasing)
+                                                               thresh_comp=thresh_comp, force_maxlevel_dealiasing=force_maxlevel_dealiasing,
+                                                               want_info=False)
             return new, n0, new.n_blocks
         hvy, lvl, _, _ = forest.active(0)
         norm = None
