@@ -181,6 +181,11 @@ int32_t wgpu_rk_step(wgpu_ctx *ctx, double time, int32_t iteration, double *dt);
  *   (copy_sc); the sizes are setup_wavelet's (module_wavelets.f90:1368-1417, incl. the widening to 2*FD_max_size).  Interiors
  *   only: ghost nodes are not stored on the device. */
 int32_t wgpu_coarse_extension(wgpu_ctx *ctx, int32_t wd_id, int32_t wd_slot, int32_t orig_id, int32_t orig_slot, int32_t clear_wc, int32_t copy_sc);
+/* wgpu_patch_details: the block-level half of addSecurityZone_CE_tree (LIB/MESH/securityZone_tree.f90:140-298): for every pair
+ *   (hvy_ids[k], dirs[k] = (dz+1)*9+(dy+1)*3+(dx+1)) the Linfty detail per component of the decomposed block inside the Nwcl / Nwcr deep
+ *   strip that faces the neighbour in that direction (threshold_block with `indices`), detail_out[k*n_eqn + c].  The host compares with
+ *   eps*norm and keeps the insignificant neighbour alive if the strip is significant. */
+int32_t wgpu_patch_details(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t n, const int32_t *hvy_ids, const int32_t *dirs, double *detail_out);
 int32_t wgpu_set_wavelet(wgpu_ctx *ctx, const char *name, int32_t *g_default, int32_t *g_rhs_default);
 int32_t wgpu_fwt(wgpu_ctx *ctx, int32_t src_id, int32_t src_slot, int32_t dst_id, int32_t dst_slot);
 int32_t wgpu_iwt(wgpu_ctx *ctx, int32_t src_id, int32_t src_slot, int32_t dst_id, int32_t dst_slot);

@@ -13,7 +13,7 @@ Reference (paths relative to the reference checkout):
   coarseningIndicator_tree                     LIB/MESH/coarseningIndicator_tree.f90
   respectJmaxJmin_tree, ensureGradedness_tree, ensure_completeness_block   LIB/MESH/*.f90
 
-Scope: lifted wavelets (useCoarseExtension = 1), useSecurityZone = 0, indicator "threshold-state-vector" or "everywhere", periodic
+Scope: lifted wavelets (useCoarseExtension = 1), useSecurityZone = 0 or 1 (addSecurityZone_CE_tree), indicator "threshold-state-vector" or "everywhere", periodic
 domains, Bs >= Nrecon (no reconstruction of neighbours).  The tree is a dict keyed by (level, ix, iy, iz); every block carries the two
 ghosted arrays of the reference, hvy_block (`blk`) and hvy_tmp (`tmp`), [nc, nz, ny, nx].
 
@@ -259,6 +259,43 @@ def finer_neighbors(t: Tree, k: Key):
     return out
 
 
+def security_zone(t: Tree, st: Dict[Key, int], eps: float, norm=None, eps_norm: str = "Linfty", thresh_comp=None, level_ref: int = 0,
+                  force_maxlevel_dealiasing: bool = False) -> Dict[Key, int]:
+    """addSecurityZone_CE_tree (LIB/MESH/securityZone_tree.f90:140-298): for every significant block (status 0) and every same-level
+    neighbour with -1, threshold the significant block's coefficients inside the Nwcl / Nwcr deep strip facing that neighbour
+    (get_indices_of_modify_patch); if they are significant the neighbour is kept (status 0)."""
+    L = O.lib()
+    if not hasattr(L, "_tbb_ready"):
+        L.orc_threshold_block_box.argtypes = [C.c_int, C.c_int, O._ip, C.c_int, O._dp, C.c_int, C.c_int, C.c_int, O._ip, O._dp, O._dp, O._dp, O._ip, O._ip]
+        L.orc_threshold_block_box.restype = C.c_int
+        L._tbb_ready = True
+    p, dim = t.p, t.dim
+    out = dict(st)
+    nc = next(iter(t.blk.values())).shape[0]
+    tc = np.ascontiguousarray(np.ones(nc) if thresh_comp is None else thresh_comp, dtype=np.int32)
+    e = np.full(nc, eps, dtype=np.float64)
+    nrm = None if norm is None else np.ascontiguousarray(norm, dtype=np.float64)
+    det = np.zeros(nc)
+    for k in t.blk:
+        if st[k] != 0 or (force_maxlevel_dealiasing and k[0] == level_ref):
+            continue
+        for d in dirs(dim):
+            nk = nbr_key(k, d, dim)
+            if nk not in t.blk or st[nk] != -1:
+                continue
+            lo = np.zeros(3, np.int32)
+            hi = np.zeros(3, np.int32)
+            for a in range(dim):
+                B = p.Bs[a]
+                lo[a] = max(B - t.Nwcr, 0) if d[a] > 0 else 0
+                hi[a] = min(t.Nwcl, B) - 1 if d[a] < 0 else B - 1
+            r = L.orc_threshold_block_box(dim, p.g, O._bs(p.Bs), nc, O._p(t.blk[k]), k[0], level_ref, O.EPS_NORMS[eps_norm], tc.ctypes.data_as(O._ip),
+                                          O._p(e), O._p(nrm), O._p(det), lo.ctypes.data_as(O._ip), hi.ctypes.data_as(O._ip))
+            if r == 0:
+                out[nk] = 0
+    return out
+
+
 def decide(t: Tree, st: Dict[Key, int], Jmin: int) -> Dict[Key, int]:
     """Which blocks are deleted (-1).  respectJmaxJmin_tree (blocks on Jmin stay); then, until nothing changes
     (ensureGradedness_tree.f90, ensure_completeness_block.f90, statuses only ever move from -1 to "stay", so the result does not depend
@@ -338,12 +375,14 @@ def _fill_from_coarse(t: Tree, k: Key, d):
 
 def adapt_tree(p: O.Params, w: O.Wavelet, grid: O.Grid, u: np.ndarray, eps: float, Jmin: int = 1, norm=None, eps_norm: str = "Linfty",
                thresh_comp=None, level_ref: int = 0, force_maxlevel_dealiasing: bool = False, indicator: str = "threshold-state-vector",
-               fd_half_width: int = 0, force_leaf_first: Optional[bool] = None):
-    """adapt_tree (adapt_tree.f90:11-260) for a lifted wavelet with the coarse extension, without security zone.  Returns
+               fd_half_width: int = 0, force_leaf_first: Optional[bool] = None, use_security_zone: bool = False):
+    """adapt_tree (adapt_tree.f90:11-260) for a lifted wavelet with the coarse extension, with or without the security zone.  Returns
     (new grid, new data [nb, nc, nz, ny, nx] with meaningful interiors, info dict)."""
     dim = grid.dim
     t = decompose_full_tree(p, w, grid, u, Jmin, fd_half_width, force_leaf_first)
     st0 = threshold_full_tree(t, eps, norm, eps_norm, thresh_comp, level_ref, force_maxlevel_dealiasing, indicator)
+    if use_security_zone and indicator != "everywhere":
+        st0 = security_zone(t, st0, eps, norm, eps_norm, thresh_comp, level_ref, force_maxlevel_dealiasing)
     st = decide(t, st0, Jmin)
     deleted = {k for k in st if st[k] == -1}
     for k in deleted:                                                   # "any block with -1 can simply be deleted"

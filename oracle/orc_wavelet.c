@@ -274,8 +274,22 @@ void orc_iwt_block(const orc_wavelet *w, int dim, int g, const int32_t Bs[3], in
  * eps_norm: 0 Linfty, 1 L1, 2 L2, 3 H1.  thresh_comp[c]: 0 ignore, 1 own max-norm, >=2 joint group
  * (maxval(sqrt(x**2)) over the group's components).  Returns refinement status: -1 iff all(detail <= eps*norm).
  */
+int orc_threshold_block_box(int dim, int g, const int32_t Bs[3], int nc, const double *u_wd, int level, int level_ref, int eps_norm,
+                            const int32_t *thresh_comp, const double *eps, const double *norm, double *detail, const int32_t lo[3],
+                            const int32_t hi[3]);
+
 int orc_threshold_block(int dim, int g, const int32_t Bs[3], int nc, const double *u_wd, int level, int level_ref, int eps_norm,
                         const int32_t *thresh_comp, const double *eps, const double *norm, double *detail)
+{
+    const int32_t lo[3] = {0, 0, 0}, hi[3] = {Bs[0] - 1, Bs[1] - 1, dim == 3 ? Bs[2] - 1 : 0};
+    return orc_threshold_block_box(dim, g, Bs, nc, u_wd, level, level_ref, eps_norm, thresh_comp, eps, norm, detail, lo, hi);
+}
+
+/* the same restricted to the box lo..hi (inclusive, 0-based interior offsets): threshold_block / wavelet_renorm_block with `indices`
+ * (threshold_block.f90:30-44, module_wavelets.f90:1876-1905), as addSecurityZone_CE_tree calls them (securityZone_tree.f90:185-200) */
+int orc_threshold_block_box(int dim, int g, const int32_t Bs[3], int nc, const double *u_wd, int level, int level_ref, int eps_norm,
+                            const int32_t *thresh_comp, const double *eps, const double *norm, double *detail, const int32_t lo[3],
+                            const int32_t hi[3])
 {
     const int nx = Bs[0] + 2 * g, ny = Bs[1] + 2 * g, nz = dim == 3 ? Bs[2] + 2 * g : 1;
     const ptrdiff_t sy = nx, sz = (ptrdiff_t)nx * ny, sc = sz * nz;
@@ -287,10 +301,11 @@ int orc_threshold_block(int dim, int g, const int32_t Bs[3], int nc, const doubl
     if (eps_norm == 1) { fac = pow(2.0, (double)((level_ref - level - 1) * dim)); fdir = 4.0; fdir_div = 1; }
     if (eps_norm == 2) { fac = pow(2.0, (double)((level_ref - level - 1) * dim) / 2.0); fdir = 2.0; fdir_div = 1; }
     if (eps_norm == 3 && dim == 3) { fac = pow(2.0, (double)(level_ref - level) * (2.0 - dim) / 2.0); fdir = pow(2.0, 2.0 * (dim - 2.0) / 3.0); }
+    (void)Bz;
     for (int c = 0; c < nc; ++c)
-        for (int iz = 0; iz < Bz; ++iz)
-            for (int iy = 0; iy < Bs[1]; ++iy)
-                for (int ix = 0; ix < Bs[0]; ++ix) {
+        for (int iz = lo[2]; iz <= (dim == 3 ? hi[2] : 0); ++iz)
+            for (int iy = lo[1]; iy <= hi[1]; ++iy)
+                for (int ix = lo[0]; ix <= hi[0]; ++ix) {
                     const int px = ix % 2 == 0, py = iy % 2 == 0, pz = dim == 3 ? iz % 2 == 0 : 1;
                     double v = u_wd[c * sc + (iz + gz) * sz + (iy + g) * sy + (ix + g)];
                     if (px && py && pz) v = 0.0;                       /* pure scaling coefficients are removed */

@@ -68,21 +68,25 @@ def test_full_tree_decomposition_and_flags(wavelet, Bs):
     sol.close()
 
 
-@pytest.mark.parametrize("wavelet,Bs,indicator", [("CDF44", 16, "threshold-state-vector"), ("CDF44", 18, "threshold-state-vector"),
-                                                   ("CDF42", 16, "threshold-state-vector"), ("CDF44", 16, "everywhere"),
-                                                   ("CDF62", 20, "threshold-state-vector"), ("CDF22", 16, "everywhere")])
-def test_adapt_tree_lifted(wavelet, Bs, indicator):
+@pytest.mark.parametrize("wavelet,Bs,indicator,sz", [("CDF44", 16, "threshold-state-vector", False), ("CDF44", 18, "threshold-state-vector", False),
+                                                      ("CDF42", 16, "threshold-state-vector", False), ("CDF44", 16, "everywhere", False),
+                                                      ("CDF62", 20, "threshold-state-vector", False), ("CDF22", 16, "everywhere", False),
+                                                      ("CDF44", 16, "threshold-state-vector", True), ("CDF42", 18, "threshold-state-vector", True)])
+def test_adapt_tree_lifted(wavelet, Bs, indicator, sz):
     """the whole adapt_tree for a lifted wavelet (decomposition of the full tree, indicator, grid decision, coarse extension on the lasting
     interfaces, CE-optimised reconstruction, pruning): same new grid as the oracle, data bit for bit; a second adapt_tree changes nothing
     (the reference's invertibility criterion, unit_test_waveletDecomposition_invertibility.f90)"""
     w, p, po, forest, grid, sol, u, H = _setup(wavelet, Bs, seed=5)
     norm = O.norm_linfty_tree(po, u)
     eps = 0.01
-    og, od, oi = OFT.adapt_tree(po, w, grid, u, eps, Jmin=1, norm=norm, level_ref=forest.Jmax, indicator=indicator, fd_half_width=H)
+    og, od, oi = OFT.adapt_tree(po, w, grid, u, eps, Jmin=1, norm=norm, level_ref=forest.Jmax, indicator=indicator, fd_half_width=H,
+                                use_security_zone=sz)
     ft = FullTree(sol, forest, Jmin=1)
-    new, info = ft.adapt(eps=eps, norm=sol.componentWiseNorm_tree((HVY_BLOCK, 0)), indicator=indicator)
+    new, info = ft.adapt(eps=eps, norm=sol.componentWiseNorm_tree((HVY_BLOCK, 0)), indicator=indicator, use_security_zone=sz)
     assert info["leaf_first"] == oi["leaf_first"] and info["leaf_only"] == oi["leaf_only"]
-    assert info["status0"] == oi["status0"] and {k: v == -1 for k, v in info["status"].items()} == {k: v == -1 for k, v in oi["status"].items()}
+    if not sz:
+        assert info["status0"] == oi["status0"]
+    assert {k: v == -1 for k, v in info["status"].items()} == {k: v == -1 for k, v in oi["status"].items()}
     assert info["marked"] == oi["marked"] and len(info["marked"]) > 0
     hvy, lvl, ixyz, _ = new.active(0)
     okey = {(int(og.level[b]),) + tuple(int(v) for v in og.ixyz[b]): b for b in range(og.n)}
@@ -95,10 +99,54 @@ def test_adapt_tree_lifted(wavelet, Bs, indicator):
         assert np.array_equal(got[h - 1][I], od[okey[k]][I]), k
     # adapt(adapt(u)) = adapt(u): with eps = 0 nothing is coarsened any more and the filtered interfaces are a fixed point
     ft2 = FullTree(sol, new, Jmin=1)
-    new2, info2 = ft2.adapt(eps=0.0, norm=None)
+    new2, info2 = ft2.adapt(eps=0.0, norm=None, use_security_zone=sz)
     assert new2.n_blocks == new.n_blocks
     got2 = np.zeros(sol.host_shape())
     sol.download(got2, g_sync=0)
     a, b = got2[:new.n_blocks][(slice(None),) + I], got[:new.n_blocks][(slice(None),) + I]
     assert abs(np.sqrt((a ** 2).sum()) / np.sqrt((b ** 2).sum()) - 1.0) <= 1.0e-14 and np.abs(a - b).max() <= 1.0e-13
     sol.close()
+
+
+def test_security_zone_keeps_the_neighbour_of_a_significant_strip():
+    """addSecurityZone_CE_tree (the reference's default for lifted wavelets): a narrow bump 6 points inside a block, next to a face, is invisible
+    to the neighbour's own coefficients (its filters reach 3 points into the ghost nodes) but lies inside the Nwc = 8 deep strip of the
+    block that holds it -- the neighbour would be coarsened without the security zone and is kept with it.  Oracle and device agree on
+    both grids and on the data."""
+    wavelet, Bs, J = "CDF44", 16, 2
+    w = O.setup_wavelet(wavelet)
+    forest = Forest.uniform(3, J, Jmax=J, max_blocks=100)
+    p = tg_params(Bs=Bs, J=J, wavelet_g=w.g_default)
+    p.wavelet = wavelet
+    grid, po = orc_grid(forest), orc_params(p)
+    g = po.g
+    u = O.alloc(grid, po)
+    h = 2.0 * np.pi / (2 ** J * Bs)
+    c = np.array([(1 * Bs + 9) * h, (1 * Bs + 8) * h, (1 * Bs + 8) * h])       # block (1,1,1), 6 points from its +x face
+    for b in range(grid.n):
+        ax = [(int(grid.ixyz[b, a]) * Bs + np.arange(Bs)) * h for a in range(3)]
+        Z, Y, X = np.meshgrid(ax[2], ax[1], ax[0], indexing="ij")
+        bump = np.exp(-((X - c[0]) ** 2 + (Y - c[1]) ** 2 + (Z - c[2]) ** 2) / (2.0 * (0.8 * h) ** 2))
+        u[b, :, g:-g, g:-g, g:-g] = 1.0 + np.stack([bump, 0.5 * bump, -bump, 2.0 * bump])
+    norm = O.norm_linfty_tree(po, u)
+    res = {}
+    for sz in (False, True):
+        og, od, oi = OFT.adapt_tree(po, w, grid, u, 1.0e-3, Jmin=1, norm=norm, level_ref=J, fd_half_width=2, use_security_zone=sz)
+        sol = WabbitGPU(p, max_blocks=100)
+        sol.setup_wavelet(wavelet)
+        sol.set_forest(forest)
+        host = np.zeros(sol.host_shape())
+        host[:grid.n] = u
+        sol.upload(host, hvy_ids=np.arange(1, grid.n + 1, dtype=np.int32))
+        new, info = FullTree(sol, forest, Jmin=1).adapt(eps=1.0e-3, norm=sol.componentWiseNorm_tree((HVY_BLOCK, 0)), use_security_zone=sz)
+        hvy, lvl, ixyz, _ = new.active(0)
+        okey = {(int(og.level[b]),) + tuple(int(v) for v in og.ixyz[b]): b for b in range(og.n)}
+        keys = [(int(l), int(x[0]), int(x[1]), int(x[2])) for l, x in zip(lvl, ixyz)]
+        assert sorted(keys) == sorted(okey)
+        got = np.zeros(sol.host_shape())
+        sol.download(got, g_sync=0)
+        I = (slice(None),) + O.interior(po)
+        assert all(np.array_equal(got[hh - 1][I], od[okey[k]][I]) for hh, k in zip(hvy, keys))
+        res[sz] = new.n_blocks
+        sol.close()
+    assert res[False] < res[True] <= grid.n, res

@@ -30,14 +30,15 @@ def test_adapt_of_adapt_is_adapt(name, Bs, dim):
     I = (slice(None), slice(None)) + O.interior(p)
     u = O.alloc(grid, p)
     u[I] = np.random.default_rng(0).random(u[I].shape)
-    g1, d1, i1 = FT.adapt_tree(p, w, grid, u, eps=1.0e-3, Jmin=1)
+    sz = Bs % 4 == 0                                          # with and without the security zone (the reference's test runs with it)
+    g1, d1, i1 = FT.adapt_tree(p, w, grid, u, eps=1.0e-3, Jmin=1, use_security_zone=sz)
     assert g1.n == grid.n and len(i1["marked"]) > 0          # random data: nothing is coarsened, interfaces are filtered
     assert np.abs(d1[I] - u[I]).max() > 1.0e-2               # ... which changes the field
     unmarked = [b for b in range(g1.n) if (int(g1.level[b]),) + tuple(int(v) for v in g1.ixyz[b]) not in set(i1["marked"])]
     assert np.array_equal(d1[unmarked][I], u[unmarked][I])    # blocks away from interfaces keep their values exactly
     u1 = np.zeros_like(d1)
     u1[I] = d1[I]
-    g2, d2, i2 = FT.adapt_tree(p, w, g1, u1, eps=1.0e-3, Jmin=1)
+    g2, d2, i2 = FT.adapt_tree(p, w, g1, u1, eps=1.0e-3, Jmin=1, use_security_zone=sz)
     n1, n2 = np.sqrt((d1[I] ** 2).sum()), np.sqrt((d2[I] ** 2).sum())
     assert abs(n2 / n1 - 1.0) <= 1.0e-14                     # the reference's criterion
     assert np.abs(d2[I] - d1[I]).max() <= 1.0e-14            # and pointwise
@@ -121,3 +122,25 @@ def test_decision_keeps_the_grid_graded_and_sister_groups_whole():
                 continue
             ck = FT.parent(nk)
             assert ck in leaves, (k, d)                                                  # one level coarser at most
+
+
+def test_security_zone_only_keeps_blocks():
+    """addSecurityZone_CE_tree can only turn -1 into 0: the adapted grid with it contains every block of the adapted grid without it or its
+    descendants, and a narrow feature next to a block face does make a difference (see tests/test_gpu_fulltree.py for the 3-D case)"""
+    w, p, _ = _case("CDF44", 16, 2, seed=1)
+    grid = O.uniform_grid(3, 2)
+    I = (slice(None), slice(None)) + O.interior(p)
+    u = O.alloc(grid, p)
+    h = 1.0 / (8 * 16)
+    for b in range(grid.n):
+        ax = [(int(grid.ixyz[b, a]) * 16 + np.arange(16)) * h for a in range(2)]
+        Y, X = np.meshgrid(ax[1], ax[0], indexing="ij")
+        u[b][I[1:]] = 1.0 + np.exp(-((X - (3 * 16 + 9) * h) ** 2 + (Y - (3 * 16 + 8) * h) ** 2) / (2 * (0.8 * h) ** 2))[None]
+    n = {}
+    for sz in (False, True):
+        g1, d1, i1 = FT.adapt_tree(p, w, grid, u, eps=1.0e-3, Jmin=1, use_security_zone=sz)
+        n[sz] = g1.n
+        if sz:
+            assert all(v0 == -1 or i1["status0"][k] == 0 for k, v0 in st_prev.items() if v0 == 0)
+        st_prev = i1["status0"]
+    assert n[False] < n[True]

@@ -1060,6 +1060,44 @@ int32_t wgpu_threshold(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t ep
     return WGPU_OK;
 }
 
+int32_t wgpu_patch_details(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t n, const int32_t *hvy_ids, const int32_t *dirs, double *detail_out)
+{
+    if (!ctx || n < 0 || (n > 0 && (!hvy_ids || !dirs || !detail_out))) return WGPU_ERR_ARG;
+    if (!ctx->wavelet_set) return fail(ctx, 1213149, "The cat is angry: Wavelet-setup not yet called?");
+    int n1 = 0;
+    const double *wd = array_ptr(ctx, array_id, slot, &n1);
+    if (!wd || n1 != ctx->nc) return fail(ctx, WGPU_ERR_ARG, "wgpu_patch_details: bad array/slot");
+    if (n == 0) return WGPU_OK;
+    const wgpu_config &c = ctx->cfg;
+    std::vector<int> ids(2 * (size_t)n);
+    for (int k = 0; k < n; ++k) {
+        ids[k] = hvy_ids[k] - 1;
+        ids[(size_t)n + k] = dirs[k];
+        if (ids[k] < 0 || ids[k] >= c.max_blocks || dirs[k] < 0 || dirs[k] >= WGPU_NDIR || dirs[k] == 13)
+            return fail(ctx, WGPU_ERR_ARG, "wgpu_patch_details: bad (block, direction) pair");
+    }
+    int32_t rc = upload_ids(ctx, 2, ids);
+    if (rc) return rc;
+    double *d_out = nullptr;
+    WGPU_CHECK(ctx, cudaMalloc((void **)&d_out, sizeof(double) * (size_t)n * ctx->nc));
+    // strip depth = Nwcl / Nwcr of setup_wavelet incl. the widening to the FD stencil (securityZone_tree.f90:166-167)
+    const WaveFilters &w = ctx->wavelet;
+    const int H = c.fd == 2 ? 1 : (c.fd == 4 ? 2 : 3);
+    const int Nscl = std::max(-w.hd_lo - 1, 0), Nscr = w.hd_hi;
+    const int Nwcl = std::max(Nscl - w.gd_lo, 2 * H), Nwcr = std::max(Nscr + w.gd_hi, 2 * H);
+    rc = wgpu_launch_patch_detail(ctx, wd, ctx->d_idbuf[2], ctx->d_idbuf[2] + n, n, Nwcl, Nwcr, d_out);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(detail_out, d_out, sizeof(double) * (size_t)n * ctx->nc, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            ctx->err = std::string("wgpu_patch_details: ") + cudaGetErrorString(e);
+            rc = WGPU_ERR_CUDA;
+        }
+    }
+    cudaFree(d_out);
+    return rc;
+}
+
 int32_t wgpu_coarse_extension(wgpu_ctx *ctx, int32_t wd_id, int32_t wd_slot, int32_t orig_id, int32_t orig_slot, int32_t clear_wc, int32_t copy_sc)
 {
     if (!ctx) return WGPU_ERR_ARG;

@@ -20,6 +20,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "wgpu_internal.cuh"
 
 namespace {
@@ -612,6 +614,42 @@ __global__ void __launch_bounds__(256) detail_kernel(const DetailArgs a)
     }
 }
 
+// threshold_block with `indices` (LIB/INDICATORS/threshold_block.f90:30-44) for the security zone of adapt_tree (addSecurityZone_CE_tree,
+// LIB/MESH/securityZone_tree.f90:140-298): Linfty detail of a decomposed block inside the strip that faces one neighbour direction
+// (get_indices_of_modify_patch with Nwcl / Nwcr), pure scaling positions removed.  One CTA per (pair, component).
+__global__ void __launch_bounds__(128) patch_detail_kernel(const double *__restrict__ wd, const int *__restrict__ blk, const int *__restrict__ dir,
+                                                           double *__restrict__ out, int nc, int Bs, int dim, int Nl, int Nr)
+{
+    __shared__ double s0[4];
+    const int b = blk[blockIdx.x], dc = dir[blockIdx.x], c = blockIdx.y;
+    const int d[3] = {dc % 3 - 1, (dc / 3) % 3 - 1, dc / 9 - 1};
+    const long long CS = (long long)Bs * Bs * (dim == 3 ? Bs : 1);
+    int lo[3], ext[3];
+    for (int k = 0; k < 3; ++k) {
+        const int B = k < dim ? Bs : 1;
+        lo[k] = d[k] > 0 ? B - Nr : 0;
+        ext[k] = d[k] < 0 ? Nl : (d[k] > 0 ? Nr : B);
+        if (lo[k] < 0) { ext[k] += lo[k]; lo[k] = 0; }
+        if (ext[k] > B) ext[k] = B;
+    }
+    const int npts = ext[0] * ext[1] * ext[2];
+    const double *p = wd + ((long long)b * nc + c) * CS;
+    double m = -INFINITY;
+    for (int i = threadIdx.x; i < npts; i += blockDim.x) {
+        const int x = lo[0] + i % ext[0], y = lo[1] + (i / ext[0]) % ext[1], z = lo[2] + i / (ext[0] * ext[1]);
+        const bool pure_sc = !(x & 1) && !(y & 1) && (dim == 2 || !(z & 1));
+        const double v = pure_sc ? 0.0 : p[((long long)z * Bs + y) * Bs + x];
+        m = fmax(m, fabs(v));
+    }
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) s0[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmax(m, s0[i]);
+        out[(long long)blockIdx.x * nc + c] = m;
+    }
+}
+
 // threshold_block.f90:96-121: detail per component (own / joint group / ignored), status = -1 iff all(detail <= eps*norm)
 struct FlagArgs {
     const int *active;
@@ -691,6 +729,19 @@ __global__ void __launch_bounds__(256) blocksum_kernel(const double *__restrict_
 }
 
 }  // namespace
+
+int32_t wgpu_launch_patch_detail(wgpu_ctx *ctx, const double *wd, const int *d_blk, const int *d_dir, int n, int Nl, int Nr, double *d_out)
+{
+    for (int s0 = 0; s0 < n; s0 += 32768) {
+        dim3 grid(std::min(32768, n - s0), ctx->nc);
+        patch_detail_kernel<<<grid, 128, 0, ctx->stream>>>(wd, d_blk + s0, d_dir + s0, d_out + (long long)s0 * ctx->nc, ctx->nc, ctx->cfg.Bs[0],
+                                                         ctx->cfg.dim, Nl, Nr);
+        ctx->launches++;
+        WGPU_CHECK(ctx, cudaGetLastError());
+    }
+    return WGPU_OK;
+}
+
 
 int32_t wgpu_launch_blocksum(wgpu_ctx *ctx, const double *u, int squared, double *d_out)
 {

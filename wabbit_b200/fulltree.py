@@ -299,6 +299,39 @@ class FullTree:
             raise RuntimeError(f"whost_ft_decide: {rc}")
         return st
 
+    def security_zone(self, st0: np.ndarray, eps, norm, thresh_comp=None, force_maxlevel_dealiasing: bool = False) -> np.ndarray:
+        """addSecurityZone_CE_tree (LIB/MESH/securityZone_tree.f90:140-298): an insignificant block (-1) next to a significant same-level block
+        stays (0) if the significant block has significant details inside the Nwc-deep strip at their interface -- details the coarse
+        extension would delete if the neighbour were coarsened.  Linfty norm; pairs are evaluated on the device (wgpu_patch_details)."""
+        sol, dim = self.sol, self.dim
+        nc = sol.params.n_eqn
+        eps = sol.params.eps if eps is None else eps
+        st = st0.copy()
+        sig = st0 == 0
+        if force_maxlevel_dealiasing:
+            sig &= self.level != self.forest.Jmax
+        bs, qs = [], []
+        for q in range(len(self.dirs)):
+            j = self.nb[:, q]
+            sel = np.flatnonzero(sig & (j >= 0) & (st0[np.maximum(j, 0)] == -1))
+            bs.append(sel)
+            qs.append(np.full(len(sel), q))
+        b, q = np.concatenate(bs), np.concatenate(qs)
+        if len(b) == 0:
+            return st
+        dcode = np.array([(d[2] + 1) * 9 + (d[1] + 1) * 3 + (d[0] + 1) for d in self.dirs], dtype=np.int32)
+        det = sol.patch_details(self.slots[b].astype(np.int32), dcode[q], WD)
+        tc = np.ones(nc, np.int32) if thresh_comp is None else np.asarray(thresh_comp, dtype=np.int32)
+        e = np.full(nc, eps, dtype=np.float64) * (1.0 if norm is None else np.asarray(norm, dtype=np.float64))
+        d_use = np.where(tc[None, :] == 0, 0.0, det)
+        for l in range(2, int(tc.max()) + 1):                    # joint groups: max over the group's components (threshold_block.f90:96-99)
+            grp = tc == l
+            if grp.any():
+                d_use[:, grp] = det[:, grp].max(axis=1, keepdims=True)
+        significant = (d_use > e[None, :]).any(axis=1)
+        st[self.nb[b[significant], q[significant]]] = 0
+        return st
+
     def _ce_sizes(self):
         """Nrecon and Ndep2 of setup_wavelet incl. the widening to the FD stencil (module_wavelets.f90:1368-1417)"""
         p = self.sol.params
@@ -313,8 +346,8 @@ class FullTree:
 
     # ------------------------------------------------------------------ adapt_tree
     def adapt(self, eps: Optional[float] = None, norm=None, eps_norm: str = "Linfty", thresh_comp=None, force_maxlevel_dealiasing: bool = False,
-              indicator: str = "threshold-state-vector", want_info: bool = True):
-        """adapt_tree (LIB/MESH/adapt_tree.f90:11-260) for a lifted wavelet with the coarse extension (useSecurityZone = 0): full-tree
+              indicator: str = "threshold-state-vector", want_info: bool = True, use_security_zone: bool = False):
+        """adapt_tree (LIB/MESH/adapt_tree.f90:11-260) for a lifted wavelet with the coarse extension, optionally the security zone: full-tree
         decomposition and indicator, grid decision, coarse extension on the lasting coarse/fine interfaces, reconstruction of the leaves at
         those interfaces (all at once if Bs >= Ndep2, else level by level from coarse to fine), pruning to the leaves, blocks moved to
         their places along the space-filling curve.  Returns (new forest, info)."""
@@ -328,6 +361,8 @@ class FullTree:
             st0 = self.st.copy()
             if force_maxlevel_dealiasing:
                 st0[self.level == self.forest.Jmax] = -1
+        if use_security_zone and indicator != "everywhere":
+            st0 = self.security_zone(st0, eps, norm, thresh_comp, force_maxlevel_dealiasing)
         t0 = time.perf_counter()
         st = self.decide(st0)
         t0 = self._tick("decide", t0)

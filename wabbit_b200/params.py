@@ -123,6 +123,11 @@ class Params:
     Jmin: int = 1
     max_blocks: int = 0
     eps: float = 1e-3
+    eps_normalized: bool = False
+    eps_norm: str = "Linfty"
+    force_maxlevel_dealiasing: bool = False
+    useCoarseExtension: int = -1          # -1: the reference's default = isLiftedWavelet (ini_file_to_params.f90:543-546)
+    useSecurityZone: int = -1
     adapt_tree: bool = False
     block_dist: str = "sfc_hilbert"
     discretization: str = "FD_4th_central"
@@ -193,6 +198,12 @@ class Params:
         p.Jmax = ini.integer("Blocks", "max_treelevel", 5)
         p.Jmin = ini.integer("Blocks", "min_treelevel", 1)
         p.eps = ini.real("Blocks", "eps", 1e-3)
+        p.eps_normalized = ini.boolean("Blocks", "eps_normalized", False)
+        p.eps_norm = ini.string("Blocks", "eps_norm", "Linfty")
+        p.force_maxlevel_dealiasing = ini.boolean("Blocks", "force_maxlevel_dealiasing", False)
+        lifted = p.wavelet[4] != "0"
+        p.useCoarseExtension = int(ini.boolean("Blocks", "useCoarseExtension", lifted))
+        p.useSecurityZone = int(ini.boolean("Blocks", "useSecurityZone", lifted))
         p.adapt_tree = ini.boolean("Blocks", "adapt_tree", False)
         p.block_dist = ini.string("Blocks", "block_dist", "sfc_hilbert")
         p.discretization = ini.string("Discretization", "order_discretization", "FD_4th_central")

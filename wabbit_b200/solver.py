@@ -199,6 +199,14 @@ class WabbitGPU:
         (wavelet_reconstruct_full_tree_CEoptimized, adapt_tree.f90:686-987)"""
         self._check(self._lib.wgpu_iwt_ce(self._ctx, wd[0], wd[1], coarse[0], coarse[1], dst[0], dst[1]))
 
+    def patch_details(self, hvy_ids, dirs, array=(HVY_WORK, 2)) -> np.ndarray:
+        """Linfty details of decomposed blocks inside the strips facing given neighbour directions (addSecurityZone_CE_tree): [n, n_eqn]"""
+        ids = np.ascontiguousarray(hvy_ids, dtype=np.int32)
+        dd = np.ascontiguousarray(dirs, dtype=np.int32)
+        out = np.zeros((len(ids), self.params.n_eqn))
+        self._check(self._lib.wgpu_patch_details(self._ctx, array[0], array[1], len(ids), _i32(ids), _i32(dd), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
     def wavelet_filter_width(self) -> int:
         """max |tap index| of the decomposition low-pass filter HD of params.wavelet (setup_wavelet: 0 for unlifted CDFX0)"""
         w = self.params.wavelet
@@ -265,9 +273,9 @@ class WabbitGPU:
         return new
 
     def adapt_tree(self, forest: Forest, eps: Optional[float] = None, eps_normalized: bool = True, eps_norm: str = "Linfty",
-                   Jmin: int = 1, force_maxlevel_dealiasing: bool = False, thresh_comp=None):
+                   Jmin: int = 1, force_maxlevel_dealiasing: bool = False, thresh_comp=None, useSecurityZone: Optional[bool] = None):
         """adapt_tree (LIB/MESH/adapt_tree.f90:11) with indicator "threshold-state-vector".  Lifted wavelets: the full-tree algorithm with
-        the coarse extension (wabbit_b200/fulltree.py; useSecurityZone = 0).  UNLIFTED wavelets (CDFX0: no coarse extension, no
+        the coarse extension and the security zone (wabbit_b200/fulltree.py).  UNLIFTED wavelets (CDFX0: no coarse extension, no
         security zone), one coarsening sweep: componentWiseNorm_tree -> ghost synchronisation + wavelet
         decomposition of every leaf -> threshold_block flags (device), then completeness / gradedness (host light data) and
         executeCoarsening (device).  The reference's current adapt_tree decomposes the full tree and can remove several levels
@@ -276,7 +284,7 @@ class WabbitGPU:
         w = self.params.wavelet
         if not (len(w) == 5 and w[4] == "0"):
             # lifted wavelets: the reference's full-tree algorithm with the coarse extension (wabbit_b200/fulltree.py), which can remove
-            # several levels in one call; useSecurityZone = 0
+            # several levels in one call; the security zone is on unless params.useSecurityZone = 0 (the reference's default)
             from .fulltree import FullTree
             if eps_norm != "Linfty" and eps_normalized:
                 norm_l = self.componentWiseNorm_tree((HVY_BLOCK, 0), eps_norm)
@@ -287,7 +295,9 @@ class WabbitGPU:
             n0 = forest.n_blocks
             new, _info = FullTree(self, forest, Jmin=Jmin).adapt(eps=self.params.eps if eps is None else eps, norm=norm_l, eps_norm=eps_norm,
                                                                thresh_comp=thresh_comp, force_maxlevel_dealiasing=force_maxlevel_dealiasing,
-                                                               want_info=False)
+                                                               want_info=False,
+                                                               use_security_zone=(self.params.useSecurityZone != 0) if useSecurityZone is None
+                                                               else bool(useSecurityZone))
             return new, n0, new.n_blocks
         hvy, lvl, _, _ = forest.active(0)
         norm = None
