@@ -528,7 +528,7 @@ def adaptive_leg(a, device_index, stream, eps=None, J0=5, Jmax=6, cycles=3, max_
     recs = recs[2:]
     tot = sum(r[2] + r[3] + r[4] for r in recs)
     return {"metric": f"adaptive block-updates/s (refine everywhere -> RK4 -> adapt, {wavelet}, 1 GPU)", "value": sum(r[0] for r in recs) / tot,
-            "adapt_tree": ("full wavelet transformation with coarse extension (lifted wavelet, useSecurityZone=0): all levels in one call"
+            "adapt_tree": ("full wavelet transformation with coarse extension and security zone (lifted wavelet): all levels in one call"
                            if lifted else "one coarsening sweep per call (unlifted wavelet)"),
             "unit": UNIT, "eps": eps, "Jmax": Jmax, "blocks_initial_coarsening": sizes, "cycles": len(recs),
             "blocks_rhs": [r[0] for r in recs], "blocks_after_adapt": [r[1] for r in recs],

@@ -168,7 +168,6 @@ def decompose_full_tree(p: O.Params, w: O.Wavelet, grid: O.Grid, u: np.ndarray, 
     """wavelet_decompose_full_tree (adapt_tree.f90:268-545).  leaf-first (all Bs >= 3*max|HD tap index|): every leaf is decomposed in the
     first pass after a full synchronisation (sync_TMP_from_all: same level, restriction through the HD filter, prediction), then the
     mothers level by level; level-wise otherwise: per level, all blocks of the level together after sync_TMP_from_MF."""
-    assert w.lifted
     t = Tree(p, w, grid, u, Jmin, fd_half_width)
     dim = grid.dim
     F = max(abs(w.hd_lo), w.hd_hi)
@@ -179,14 +178,15 @@ def decompose_full_tree(p: O.Params, w: O.Wavelet, grid: O.Grid, u: np.ndarray, 
         # iteration 0: all leaves carry -1, mothers REF_TMP_EMPTY (they neither send nor receive): a leaf-grid synchronisation
         nbr = O.neighbor_table168(grid, max(int(grid.level.max()), 1) + 8)
         hv = u.copy()
-        O.sync_ghosts_leaf(grid, p, hv, nbr, gs, gs, w.X, True, ignore_filter=False, w=w)
+        O.sync_ghosts_leaf(grid, p, hv, nbr, gs, gs, w.X, bool(w.lifted), ignore_filter=not w.lifted, w=w)
         for b in range(grid.n):
             k = (int(grid.level[b]),) + tuple(int(v) for v in grid.ixyz[b])
             t.blk[k] = hv[b].copy()
         for k in sorted(t.leaf):
             t.fwt(k)
         for k in sorted(t.leaf):
-            t.ce_modify(k)                                  # CE_case="ref", s_ref=-1: leaves only (reconstruction_step.f90:66)
+            if w.lifted:                                    # useCoarseExtension = isLiftedWavelet
+                t.ce_modify(k)                              # CE_case="ref", s_ref=-1: leaves only (reconstruction_step.f90:66)
     level = t.Jmax_active
     while level >= Jmin:
         if leaf_first:
@@ -211,7 +211,7 @@ def decompose_full_tree(p: O.Params, w: O.Wavelet, grid: O.Grid, u: np.ndarray, 
             for k in sorted(todo):
                 t.fwt(k)
             for k in sorted(todo):
-                if k in t.leaf:
+                if k in t.leaf and w.lifted:
                     t.ce_modify(k)
         t.d2m(level)
         level -= 1
@@ -390,6 +390,11 @@ def adapt_tree(p: O.Params, w: O.Wavelet, grid: O.Grid, u: np.ndarray, eps: floa
         del t.tmp[k]
     leaves = {k for k in t.blk if t.is_leaf(k)}
     marked = sorted(k for k in leaves if t.coarse_dirs(k))              # leaves at a coarse/fine interface of the NEW grid
+    if not w.lifted:                                                    # no coarse extension: "restore original values" (adapt_tree.f90:236-241)
+        keys = sorted(leaves)
+        new_grid = O.Grid(level=np.array([k[0] for k in keys], dtype=np.int64), ixyz=np.array([k[1:] for k in keys], dtype=np.int64), dim=dim)
+        return new_grid, np.stack([t.tmp[k] for k in keys]), {"status0": st0, "status": st, "marked": [], "leaf_only": True,
+                                                              "leaf_first": t.leaf_first, "n_deleted": len(deleted)}
     nrl, nrr, d2l, d2r = ndep2(w, fd_half_width)
     assert all(p.Bs[a] >= max(nrl, nrr) for a in range(dim)), "Bs < Nrecon: reconstruction of neighbours is not restated"
     leaf_only = all(p.Bs[a] >= d2l and p.Bs[a] >= d2r for a in range(dim))

@@ -1,4 +1,5 @@
-"""adapt_tree with the full wavelet transformation for LIFTED wavelets, on the device (single rank).
+"""adapt_tree with the full wavelet transformation on the device (single rank): lifted wavelets with the coarse extension, and unlifted
+ones (no coarse extension: the decomposition only drives the indicator, values are kept).
 
 The reference decomposes the whole tree -- leaves and all their ancestors ("mothers") -- from fine to coarse
 (wavelet_decompose_full_tree, LIB/MESH/adapt_tree.f90:268-545), thresholds every block (coarseningIndicator_tree), decides on the
@@ -136,6 +137,7 @@ class FullTree:
         F = sol.wavelet_filter_width()
         p = sol.params
         self.leaf_first = all(p.Bs[a] >= 3 * F for a in range(dim))
+        self.lifted = p.wavelet[4] != "0"          # useCoarseExtension = isLiftedWavelet (ini_file_to_params.f90:543)
 
     def _set_blocks(self, level, pos, slots, is_leaf):
         code = _pack(level, pos)
@@ -265,7 +267,8 @@ class FullTree:
             leaves = np.flatnonzero(self.is_leaf)
             leaves = leaves[np.argsort(self.slots[leaves])]
             sol.waveletDecomposition_tree((HVY_BLOCK, 0), WD)
-            sol.coarse_extension_modify(WD, (HVY_BLOCK, 0), True, True)
+            if self.lifted:
+                sol.coarse_extension_modify(WD, (HVY_BLOCK, 0), True, True)
             flags(leaves)
         for level in range(self.Jmax_active, self.Jmin - 1, -1):
             todo = np.flatnonzero((self.level == level) & ~(self.is_leaf if self.leaf_first else np.zeros(len(self.code), bool)))
@@ -273,7 +276,7 @@ class FullTree:
                 idx = self.set_pass_topology(todo)
                 t0 = time.perf_counter()
                 sol.waveletDecomposition_tree((HVY_BLOCK, 0), WD)
-                if self.is_leaf[idx].any():
+                if self.lifted and self.is_leaf[idx].any():
                     sol.coarse_extension_modify(WD, (HVY_BLOCK, 0), True, True)
                 t0 = self._tick("fwt + ce kernels", t0)
                 flags(idx)
@@ -375,9 +378,11 @@ class FullTree:
         leaves = np.flatnonzero(self.is_leaf)
         marked = leaves[(self.nb[leaves] < 0).any(axis=1)]
         nrl, nrr, d2l, d2r = self._ce_sizes()
-        if any(p.Bs[a] < max(nrl, nrr) for a in range(dim)):
+        if self.lifted and any(p.Bs[a] < max(nrl, nrr) for a in range(dim)):
             raise RuntimeError("adapt_tree: Bs < Nrecon (reconstruction of the neighbours of interface blocks) is not supported")
         leaf_only = all(p.Bs[a] >= d2l and p.Bs[a] >= d2r for a in range(dim))
+        if not self.lifted:
+            marked = marked[:0]      # no coarse extension: every block keeps its original / assembled values (adapt_tree.f90:236-241)
         if len(marked):
             self.set_pass_topology(marked)                                # the lasting interfaces (adapt_tree.f90:222-228): same-level
             sol.coarse_extension_modify(WD, (HVY_BLOCK, 0), True, False)  # neighbours send coefficients that carry the extension

@@ -273,17 +273,20 @@ class WabbitGPU:
         return new
 
     def adapt_tree(self, forest: Forest, eps: Optional[float] = None, eps_normalized: bool = True, eps_norm: str = "Linfty",
-                   Jmin: int = 1, force_maxlevel_dealiasing: bool = False, thresh_comp=None, useSecurityZone: Optional[bool] = None):
-        """adapt_tree (LIB/MESH/adapt_tree.f90:11) with indicator "threshold-state-vector".  Lifted wavelets: the full-tree algorithm with
-        the coarse extension and the security zone (wabbit_b200/fulltree.py).  UNLIFTED wavelets (CDFX0: no coarse extension, no
-        security zone), one coarsening sweep: componentWiseNorm_tree -> ghost synchronisation + wavelet
+                   Jmin: int = 1, force_maxlevel_dealiasing: bool = False, thresh_comp=None, useSecurityZone: Optional[bool] = None,
+                   full_tree: Optional[bool] = None):
+        """adapt_tree (LIB/MESH/adapt_tree.f90:11) with indicator "threshold-state-vector".  full_tree (default for lifted wavelets): the
+        reference's full-tree algorithm, with the coarse extension and the security zone for lifted wavelets (wabbit_b200/fulltree.py).
+        Otherwise (default for unlifted wavelets CDFX0, which have no coarse extension and no security zone) one coarsening sweep:
+        componentWiseNorm_tree -> ghost synchronisation + wavelet
         decomposition of every leaf -> threshold_block flags (device), then completeness / gradedness (host light data) and
         executeCoarsening (device).  The reference's current adapt_tree decomposes the full tree and can remove several levels
         in one call; this driver removes one level per call (call it again to go further) -- the per-block arithmetic is the same.
         Returns (new forest, number of blocks before, after)."""
         w = self.params.wavelet
-        if not (len(w) == 5 and w[4] == "0"):
-            # lifted wavelets: the reference's full-tree algorithm with the coarse extension (wabbit_b200/fulltree.py), which can remove
+        lifted = not (len(w) == 5 and w[4] == "0")
+        if lifted if full_tree is None else full_tree:
+            # the reference's full-tree algorithm (wabbit_b200/fulltree.py; for lifted wavelets with the coarse extension), which can remove
             # several levels in one call; the security zone is on unless params.useSecurityZone = 0 (the reference's default)
             from .fulltree import FullTree
             if eps_norm != "Linfty" and eps_normalized:
@@ -296,7 +299,7 @@ class WabbitGPU:
             new, _info = FullTree(self, forest, Jmin=Jmin).adapt(eps=self.params.eps if eps is None else eps, norm=norm_l, eps_norm=eps_norm,
                                                                thresh_comp=thresh_comp, force_maxlevel_dealiasing=force_maxlevel_dealiasing,
                                                                want_info=False,
-                                                               use_security_zone=(self.params.useSecurityZone != 0) if useSecurityZone is None
+                                                               use_security_zone=(lifted and self.params.useSecurityZone != 0) if useSecurityZone is None
                                                                else bool(useSecurityZone))
             return new, n0, new.n_blocks
         hvy, lvl, _, _ = forest.active(0)
