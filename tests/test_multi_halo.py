@@ -299,3 +299,86 @@ def test_adaptive_cycle_across_ranks_equals_single_rank(world, overlap):
     assert np.array_equal(got[:, :, g:-g, g:-g, g:-g], ref_data[:, :, g:-g, g:-g, g:-g])
     for s in sols:
         s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,Bs,sz", [(2, 16, True), (3, 18, True), (2, 18, False)])
+def test_lifted_adapt_tree_across_ranks_equals_single_rank(world, Bs, sz):
+    """adapt_tree with the full wavelet transformation (CDF44: coarse extension, security zone, CE-optimised reconstruction; Bs=16 level-wise,
+    Bs=18 leaf-first variant) with the tree's blocks owned by `world` ranks: same grid and bit-identical data as the single-rank driver,
+    which the oracle pins (tests/test_gpu_fulltree.py)."""
+    import threading
+    import torch
+    from wabbit_b200 import WabbitGPU
+    from wabbit_b200.multi import DistributedWabbit, ThreadTransport
+    wavelet, Jmax = "CDF44", 3
+    w = O.setup_wavelet(wavelet)
+    lv, ix = graded_blocks(3, 1, 3, seed=5, frac=0.3)
+    MB = 3 * len(lv) + 64
+    p = tg_params(Bs=Bs, J=Jmax, wavelet_g=w.g_default)
+    p.wavelet = wavelet
+    f1 = Forest.from_blocks(3, Jmax, lv, ix, n_ranks=1, max_blocks=MB)
+    fw = Forest.from_blocks(3, Jmax, lv, ix, n_ranks=world, max_blocks=MB)
+    po = orc_params(p)
+    _, l1, x1, _ = f1.active(0)
+    grid = O.Grid(level=l1.astype(np.int64), ixyz=x1.astype(np.int64), dim=3)
+    u = O.alloc(grid, po)
+    O.inicond_taylor_green(grid, po, u)
+    amp = np.where(x1[:, 0] * 2 < 2 ** l1, 0.05, 1.0e-7)
+    u += amp[:, None, None, None, None] * np.random.default_rng(2).standard_normal(u.shape)
+    eps = 0.01
+    s1 = WabbitGPU(p, max_blocks=MB)
+    s1.setup_wavelet(wavelet)
+    s1.set_forest(f1)
+    host = np.zeros(s1.host_shape())
+    host[:grid.n] = u
+    s1.upload(host)
+    new1, n0, n1 = s1.adapt_tree(f1, eps=eps, Jmin=1, useSecurityZone=sz)
+    assert 8 <= n1 < n0
+    _, lf, xf, _ = new1.active(0)
+    ref = np.zeros(s1.host_shape())
+    s1.download(ref, g_sync=0)
+    ref = ref[:n1].copy()
+    s1.close()
+
+    sols = []
+    for _ in range(world):
+        s = WabbitGPU(p, max_blocks=MB)
+        s.setup_wavelet(wavelet)
+        sols.append(s)
+    shared = ThreadTransport.Shared(world)
+    offs = np.concatenate([[0], np.cumsum([fw.n_active(r) for r in range(world)])])
+    res, errs = [None] * world, []
+
+    def worker(r):
+        try:
+            torch.cuda.set_device(0)
+            d = DistributedWabbit(sols[r], fw, r, world, transport=ThreadTransport(shared, r), overlap=False)
+            n = fw.n_active(r)
+            h = np.zeros(sols[r].host_shape())
+            h[:n] = u[offs[r]:offs[r] + n]
+            sols[r].upload(h)
+            new, m0, m1 = d.adapt_tree(eps=eps, Jmin=1, useSecurityZone=sz)
+            _, l, x, _ = d.forest.active(r)
+            out = np.zeros(sols[r].host_shape())
+            sols[r].download(out, g_sync=0)
+            res[r] = (m0, m1, l, x, out[:len(l)].copy())
+        except BaseException as e:      # noqa: BLE001
+            import traceback
+            errs.append((r, traceback.format_exc()))
+            shared.barrier.abort()
+
+    th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errs, errs[0][1]
+    assert all(res[r][0] == n0 and res[r][1] == n1 for r in range(world))
+    assert np.array_equal(np.concatenate([res[r][2] for r in range(world)]), lf)
+    assert np.array_equal(np.concatenate([res[r][3] for r in range(world)]), xf)
+    got = np.concatenate([res[r][4] for r in range(world)])
+    g = p.g
+    assert np.array_equal(got[:, :, g:-g, g:-g, g:-g], ref[:, :, g:-g, g:-g, g:-g])
+    for s in sols:
+        s.close()

@@ -408,3 +408,269 @@ class FullTree:
         if want_info:
             info.update({"marked": sorted(self.keys(marked)), "leaf_only": leaf_only, "leaf_first": self.leaf_first})
         return new, info
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The same algorithm with the blocks partitioned over several GPUs
+# ----------------------------------------------------------------------------------------------------------------------
+class DistributedFullTree(FullTree):
+    """adapt_tree with the full wavelet transformation across ranks.  The tree (light data) is replicated; every leaf lives on its owner
+    in the forest's partition, every mother on the owner of its first daughter, in a free slot behind that rank's leaves.  A pass runs on
+    every rank for the blocks it owns; the same-level neighbours (and, for the reconstruction, the coarser leaves) that other ranks own are
+    shipped as whole blocks into scratch slots first (block_xfer: wgpu_gather_blocks -> all-to-all -> wgpu_scatter_blocks), so the kernels
+    never know about ranks.  Flags are all-gathered (synchronize_lgt_data); the grid decision is computed on every rank."""
+
+    def __init__(self, drv, Jmin: int = 1):
+        # drv: wabbit_b200.multi.DistributedWabbit (sol, forest, rank, world, transport, _ship)
+        self.drv, self.me, self.world = drv, drv.rank, drv.world
+        sol, forest = drv.sol, drv.forest
+        self.sol, self.forest, self.dim, self.Jmin = sol, forest, forest.dim, Jmin
+        dim = self.dim
+        lv, ix, ow, sl = [], [], [], []
+        for r in range(self.world):
+            hvy, lvl, ixyz, _ = forest.active(r)
+            lv.append(lvl.astype(np.int64))
+            ix.append(ixyz.astype(np.int64))
+            ow.append(np.full(len(hvy), r, np.int64))
+            sl.append(hvy.astype(np.int64))
+        level, pos, owner, slots = np.concatenate(lv), np.concatenate(ix), np.concatenate(ow), np.concatenate(sl)
+        n_leaf = len(level)
+        cl, cx = level, pos
+        seen = _pack(cl, cx)
+        ml, mx = [], []
+        for _ in range(int(level.max()) - Jmin):
+            up = cl > Jmin
+            pl, px = cl[up] - 1, cx[up] >> 1
+            code, first = np.unique(_pack(pl, px), return_index=True)
+            new = ~np.isin(code, seen)
+            cl, cx = pl[first][new], px[first][new]
+            if len(cl) == 0:
+                break
+            ml.append(cl)
+            mx.append(cx)
+            seen = np.concatenate([seen, code[new]])
+        level = np.concatenate([level] + ml)
+        pos = np.concatenate([pos] + mx)
+        is_leaf = np.zeros(len(level), bool)
+        is_leaf[:n_leaf] = True
+        owner = np.concatenate([owner, np.full(len(level) - n_leaf, -1, np.int64)])
+        slots = np.concatenate([slots, np.zeros(len(level) - n_leaf, np.int64)])
+        o = self._set_blocks(level, pos, slots, is_leaf)
+        self.owner = owner[o]
+        # mothers: owner = owner of the first daughter, finest level first; slots behind the rank's leaves, in tree order
+        nxt = np.array([forest.n_active(r) + 1 for r in range(self.world)], dtype=np.int64)
+        for L in range(int(self.level.max()) - 1, Jmin - 1, -1):
+            m = np.flatnonzero((self.level == L) & ~self.is_leaf)
+            self.owner[m] = self.owner[self.child[m, 0]]
+            for r in range(self.world):
+                mr = m[self.owner[m] == r]
+                self.slots[mr] = nxt[r] + np.arange(len(mr))
+                nxt[r] += len(mr)
+        self.scratch0 = nxt                                       # first free slot per rank behind leaves and mothers
+        if nxt.max() - 1 > sol.max_blocks:
+            raise MemoryError(f"full tree needs {int(nxt.max()) - 1} block slots on a rank, max_blocks = {sol.max_blocks}")
+        self.Jmax_active = int(self.level[self.is_leaf].max())
+        self.st = np.zeros(len(self.level), np.int32)
+        self.det = None
+        self.timing = None
+        F = sol.wavelet_filter_width()
+        p = sol.params
+        self.leaf_first = all(p.Bs[a] >= 3 * F for a in range(dim))
+        self.lifted = p.wavelet[4] != "0"
+        self._halo_cleared = False
+
+    # ------------------------------------------------------------------ a pass: ship what the owned blocks need, then local tables
+    def _pass(self, active: np.ndarray, need):
+        """active: tree indices of the blocks of the pass (all ranks).  need(idx_of_rank_q) -> list of (array, tree indices of the source
+        blocks rank q reads).  Ships the remote ones, uploads the local topology, returns my active indices in active-list order."""
+        sol, drv, me, W, dim = self.sol, self.drv, self.me, self.world, self.dim
+        if not self._halo_cleared:      # the time stepper's halo slots are dead now; their slots are reused by mothers and copies
+            z = np.zeros(0, np.int32)
+            sol._check(sol._lib.wgpu_set_halo(sol._ctx, 0, z.ctypes.data_as(C.POINTER(C.c_int32)), z.ctypes.data_as(C.POINTER(C.c_int32)),
+                                              z.ctypes.data_as(C.POINTER(C.c_int32)), 0, z.ctypes.data_as(C.POINTER(C.c_int32)), None))
+            self._halo_cleared = True
+        mine_of = [active[self.owner[active] == q] for q in range(W)]
+        lslot = np.where(self.owner == me, self.slots, -1)                  # local slot of every tree block present on this rank
+        nxt = int(self.scratch0[me])
+        needs = [need(mine_of[q]) for q in range(W)]
+        n_arrays = len(needs[0])
+        for a in range(n_arrays):
+            array = needs[0][a][0]
+            src_r, src_s, dst_r, which = [], [], [], []
+            for q in range(W):
+                b = needs[q][a][1]
+                b = np.unique(b[b >= 0])
+                b = b[self.owner[b] != q]
+                src_r.append(self.owner[b])
+                src_s.append(self.slots[b])
+                dst_r.append(np.full(len(b), q, np.int64))
+                which.append(b)
+            src_r, src_s, dst_r, which = (np.concatenate(v) for v in (src_r, src_s, dst_r, which))
+            loc, nxt = drv._ship(array, src_r, src_s, dst_r, nxt)
+            got = which[dst_r == me]
+            lslot[got] = loc
+        mine = mine_of[me]
+        mine = mine[np.argsort(self.slots[mine])]
+        present = np.flatnonzero(lslot >= 0)
+        if len(mine):
+            ids = self.slots[mine].astype(np.int32)
+            ld = int(max(lslot.max(), ids.max()))
+            nbr = np.full((168, ld), -1, dtype=np.int32)
+            leaf = self.is_leaf[mine] & (self.level[mine] > 0)
+            for q, d in enumerate(self.dirs):
+                j = self.nb[mine, q]
+                hit = (j >= 0) & (lslot[np.maximum(j, 0)] >= 0)
+                nbr[_code(d) - 1, ids[hit] - 1] = lslot[j[hit]]
+                miss = (j < 0) & leaf                                     # no same-level block in the tree: a coarser leaf covers it
+                nbr[_code(d) - 1 + 56, ids[miss] - 1] = ids[miss]          # (any valid id: only the relation matters, data go by position)
+            tc = _encode_treecodes(dim, self.level[present], self.pos[present], self.forest.Jmax)
+            sol.set_treecodes(lslot[present].astype(np.int32), self.level[present].astype(np.int32), tc)
+            sol.set_topology(ids, self.level[mine].astype(np.int32), nbr, 0)
+        else:
+            sol.set_topology(np.zeros(0, np.int32), np.zeros(0, np.int32), np.full((168, 1), -1, np.int32), 0)
+        self._lslot = lslot
+        return mine, mine_of
+
+    def _gather_status(self, mine_of, st_local, det_local=None):
+        counts = [len(m) for m in mine_of]
+        st = self.drv.tr.allgather_np(np.asarray(st_local, dtype=np.int32), counts)
+        off = 0
+        for q in range(self.world):
+            m = mine_of[q][np.argsort(self.slots[mine_of[q]])]
+            self.st[m] = st[off:off + len(m)]
+            off += len(m)
+
+    # ------------------------------------------------------------------ decomposition + indicator
+    def decompose(self, eps=None, norm=None, eps_norm: str = "Linfty", thresh_comp=None, threshold: bool = True, want_dict: bool = False):
+        sol, drv, dim, me = self.sol, self.drv, self.dim, self.me
+        nd = 2 ** dim
+        same_level = lambda idx: [((HVY_BLOCK, 0), self.nb[idx].ravel())]
+
+        def flags(mine, mine_of):
+            if not threshold:
+                return
+            st = sol.threshold_tree(WD, eps=eps, norm=norm, eps_norm=eps_norm, thresh_comp=thresh_comp, level_ref=self.forest.Jmax) if len(mine) \
+                else np.zeros(0, np.int32)
+            self._gather_status(mine_of, st)
+
+        def d2m(level):
+            if level <= self.Jmin:
+                return
+            m_all = np.flatnonzero((self.level == level - 1) & (self.child[:, 0] >= 0))
+            if len(m_all) == 0:
+                return
+            # sync_D2M across ranks: the decomposed daughters travel to the owner of their mother
+            cols = [((c >> 1) & 1) + 2 * (c & 1) + (4 * ((c >> 2) & 1) if dim == 3 else 0) for c in range(nd)]   # treecode digit order
+            da = self.child[m_all][:, cols]                                   # [n_m, nd] tree indices
+            src_r, src_s = self.owner[da.ravel()], self.slots[da.ravel()]
+            dst_r = np.repeat(self.owner[m_all], nd)
+            loc, _ = drv._ship(WD, src_r, src_s, dst_r, int(self.scratch0[me]))
+            mine = m_all[self.owner[m_all] == me]
+            if len(mine):
+                sol.coarsen_blocks(self.slots[mine].astype(np.int32), loc.astype(np.int32), WD)
+
+        if self.leaf_first:
+            # leaf pass on the time stepper's topology: halo copies (and filtered copies of finer neighbours) of hvy_block refreshed first
+            drv.stepper.exchange_array(0, 0)
+            sol.waveletDecomposition_tree((HVY_BLOCK, 0), WD)
+            if self.lifted:
+                sol.coarse_extension_modify(WD, (HVY_BLOCK, 0), True, True)
+            leaves = np.flatnonzero(self.is_leaf)
+            mine_of = [leaves[self.owner[leaves] == q] for q in range(self.world)]
+            if threshold:
+                st = sol.threshold_tree(WD, eps=eps, norm=norm, eps_norm=eps_norm, thresh_comp=thresh_comp, level_ref=self.forest.Jmax)
+                self._gather_status(mine_of, st)
+        for level in range(self.Jmax_active, self.Jmin - 1, -1):
+            todo = np.flatnonzero((self.level == level) & ~(self.is_leaf if self.leaf_first else np.zeros(len(self.code), bool)))
+            if len(todo):
+                mine, mine_of = self._pass(todo, same_level)
+                if len(mine):
+                    sol.waveletDecomposition_tree((HVY_BLOCK, 0), WD)
+                    if self.lifted and self.is_leaf[mine].any():
+                        sol.coarse_extension_modify(WD, (HVY_BLOCK, 0), True, True)
+                flags(mine, mine_of)
+            d2m(level)
+        return None
+
+    def security_zone(self, st0, eps, norm, thresh_comp=None, force_maxlevel_dealiasing: bool = False):
+        """addSecurityZone_CE_tree across ranks: every rank evaluates the strips of the significant blocks it owns; the kept neighbours are
+        merged over the ranks (synchronize_lgt_data)."""
+        me = self.me
+        mask = self.owner == me
+        local = FullTree.security_zone(self, np.where(mask | (st0 != 0), st0, 1).astype(np.int32), eps, norm, thresh_comp,
+                                       force_maxlevel_dealiasing)        # blocks of other ranks are not "significant" here (status 1)
+        kept = (st0 == -1) & (local == 0)
+        allk = self.drv.tr.allreduce_max_np(kept.astype(np.float64))
+        st = st0.copy()
+        st[allk > 0] = 0
+        return st
+
+    # ------------------------------------------------------------------ adapt_tree
+    def adapt(self, eps=None, norm=None, eps_norm: str = "Linfty", thresh_comp=None, force_maxlevel_dealiasing: bool = False,
+              indicator: str = "threshold-state-vector", want_info: bool = False, use_security_zone: bool = False):
+        sol, drv, dim, me, W = self.sol, self.drv, self.dim, self.me, self.world
+        p = sol.params
+        if indicator == "everywhere":
+            self.decompose(threshold=False)
+            st0 = np.where(self.is_leaf, -1, 0).astype(np.int32)
+        else:
+            self.decompose(eps=eps, norm=norm, eps_norm=eps_norm, thresh_comp=thresh_comp)
+            st0 = self.st.copy()
+            if force_maxlevel_dealiasing:
+                st0[self.level == self.forest.Jmax] = -1
+        if use_security_zone and indicator != "everywhere":
+            self._lslot_for_patches()
+            st0 = self.security_zone(st0, eps, norm, thresh_comp, force_maxlevel_dealiasing)
+        st = self.decide(st0)
+        keep = st != -1
+        self.code, self.level, self.pos, self.slots, self.owner = (a[keep] for a in (self.code, self.level, self.pos, self.slots, self.owner))
+        self._build_tables()
+        self.is_leaf = self.child[:, 0] < 0
+        leaves = np.flatnonzero(self.is_leaf)
+        marked = leaves[(self.nb[leaves] < 0).any(axis=1)] if self.lifted else leaves[:0]
+        nrl, nrr, d2l, d2r = self._ce_sizes()
+        if self.lifted and any(p.Bs[a] < max(nrl, nrr) for a in range(dim)):
+            raise RuntimeError("adapt_tree: Bs < Nrecon (reconstruction of the neighbours of interface blocks) is not supported")
+        leaf_only = all(p.Bs[a] >= d2l and p.Bs[a] >= d2r for a in range(dim))
+        if len(marked):
+            nothing = lambda idx: [((HVY_BLOCK, 0), np.zeros(0, np.int64))]
+            mine, _ = self._pass(marked, nothing)                              # coarse extension on the lasting interfaces (local data only)
+            if len(mine):
+                sol.coarse_extension_modify(WD, (HVY_BLOCK, 0), True, False)
+
+            def recon_needs(idx):
+                # coefficients of the same-level neighbours; values of the coarser leaves that cover the directions without one
+                coarse = []
+                for q, d in enumerate(self.dirs):
+                    miss = idx[self.nb[idx, q] < 0]
+                    if len(miss):
+                        coarse.append(self._find(self.level[miss] - 1, self._neighbor_pos(miss, d) >> 1))
+                return [(WD, self.nb[idx].ravel()), ((HVY_BLOCK, 0), np.concatenate(coarse) if coarse else np.zeros(0, np.int64))]
+
+            levels = [None] if leaf_only else list(range(self.Jmin, int(self.level.max()) + 1))
+            for level in levels:
+                todo = marked if level is None else marked[self.level[marked] == level]
+                if len(todo):
+                    mine, _ = self._pass(todo, recon_needs)
+                    if len(mine):
+                        sol.waveletReconstruction_CE(WD, (HVY_BLOCK, 0), (HVY_BLOCK, 0))
+        # prune_fulltree2leafs + balanceLoad_tree: the leaves move to their owners / slots in the new partition
+        new = Forest.from_blocks(dim, self.forest.Jmax, self.level[leaves].astype(np.int32), self.pos[leaves].astype(np.int32),
+                                 block_dist=self.forest.block_dist, n_ranks=W, max_blocks=self.forest.max_blocks, periodic=self.forest.periodic)
+        src_r, src_s, dst_r, dst_s = [], [], [], []
+        for r in range(W):
+            hvy, lvl, ixyz, _ = new.active(r)
+            i = self._find(lvl.astype(np.int64), ixyz.astype(np.int64))
+            src_r.append(self.owner[i])
+            src_s.append(self.slots[i])
+            dst_r.append(np.full(len(hvy), r, np.int64))
+            dst_s.append(hvy.astype(np.int64))
+        src_r, src_s, dst_r, dst_s = (np.concatenate(v) for v in (src_r, src_s, dst_r, dst_s))
+        loc, _ = drv._ship((HVY_BLOCK, 0), src_r, src_s, dst_r, int(self.scratch0[me]))
+        sol.move_blocks(loc.astype(np.int32), dst_s[dst_r == me].astype(np.int32))
+        drv.attach(new)
+        return new, {}
+
+    def _lslot_for_patches(self):
+        """wgpu_patch_details addresses blocks by slot: own blocks only (tree slots are the owner's)"""
+        return None
