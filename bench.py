@@ -345,7 +345,7 @@ def run_ours(a):
         except Exception as e:
             adaptive_lifted = {"error": repr(e)}
     elif world > 1 and a.adaptive_multi:   # opt-in: a failure on one rank would leave the others waiting in a collective
-        adaptive = adaptive_leg_multi(a, rank, world, local, stream, J0=a.adaptive_level, Jmax=a.adaptive_level + 1)
+        adaptive = adaptive_leg_multi(a, rank, world, local, stream, J0=a.adaptive_level, Jmax=a.adaptive_level + 1, wavelet=a.adaptive_wavelet)
     if rank == 0:
         if adaptive is not None:
             line["adaptive"] = adaptive
@@ -539,7 +539,7 @@ def adaptive_leg(a, device_index, stream, eps=None, J0=5, Jmax=6, cycles=3, max_
                     "stay in host Fortran in a WABBIT build; ms_rk4 is the device-resident time step on the graded grid"}
 
 
-def adaptive_leg_multi(a, rank, world, local, stream, eps=None, J0=5, Jmax=6, cycles=3, max_blocks_total=150000):
+def adaptive_leg_multi(a, rank, world, local, stream, eps=None, J0=5, Jmax=6, cycles=3, max_blocks_total=150000, wavelet="CDF40"):
     """BASELINE config 3's cycle on `world` GPUs (one process each, NCCL): refine_tree("everywhere") -> timeStep_tree -> adapt_tree with the
     blocks partitioned by the space-filling curve; halo copies of the neighbouring blocks of other ranks, block transport by all-to-all
     (wabbit_b200/multi.py: DistributedWabbit).  Same case and protocol as adaptive_leg."""
@@ -548,7 +548,7 @@ def adaptive_leg_multi(a, rank, world, local, stream, eps=None, J0=5, Jmax=6, cy
     from wabbit_b200 import Forest, Params, WabbitGPU
     from wabbit_b200.multi import DistributedWabbit
     eps = a.adaptive_eps if eps is None else eps
-    p = Params(dim=3, domain=(TWO_PI,) * 3, Bs=(a.bs,) * 3, wavelet="CDF40", g=3, g_rhs=2, n_eqn=4, Jmax=Jmax,
+    p = Params(dim=3, domain=(TWO_PI,) * 3, Bs=(a.bs,) * 3, wavelet=wavelet, g=int(wavelet[3]) - 1 + max(int(wavelet[4]) - 1, 0), g_rhs=2, n_eqn=4, Jmax=Jmax,
                discretization="FD_4th_central", skew_symmetry=True, c0=10.0, nu=3.125e-3, gamma_p=0.0, CFL=1.0,
                u_mean_set=(0.0, 0.0, 0.0), time_max=1.0e9).finalize()
     max_blocks_total = max(max_blocks_total, int(1.25 * 8 ** J0))
@@ -556,7 +556,7 @@ def adaptive_leg_multi(a, rank, world, local, stream, eps=None, J0=5, Jmax=6, cy
     forest = Forest.uniform(3, J0, Jmax=Jmax, n_ranks=world, max_blocks=mb)
     hvy, lvl, ixyz, _ = forest.active(rank)
     sol = WabbitGPU(p, max_blocks=mb, device=local, stream=stream.cuda_stream)
-    sol.setup_wavelet("CDF40")
+    sol.setup_wavelet(wavelet)
     drv = DistributedWabbit(sol, forest, rank, world)
     nb0 = len(hvy)
     shape = (nb0,) + sol.host_shape()[1:]
@@ -618,7 +618,7 @@ def adaptive_leg_multi(a, rank, world, local, stream, eps=None, J0=5, Jmax=6, cy
     dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     tm = tm.cpu().numpy()
     tot = float(tm.sum())
-    return {"metric": f"adaptive block-updates/s (refine everywhere -> RK4 -> adapt, CDF40, {world} GPUs)", "value": sum(r[0] for r in recs) / tot,
+    return {"metric": f"adaptive block-updates/s (refine everywhere -> RK4 -> adapt, {wavelet}, {world} GPUs)", "value": sum(r[0] for r in recs) / tot,
             "unit": UNIT, "eps": eps, "Jmax": Jmax, "blocks_initial_coarsening": sizes, "cycles": len(recs),
             "blocks_rhs": [r[0] for r in recs], "blocks_after_adapt": [r[1] for r in recs],
             "ms_refine": [round(v * 1e3, 2) for v in tm[:, 0]], "ms_rk4": [round(v * 1e3, 2) for v in tm[:, 1]],
@@ -645,7 +645,7 @@ def main():
     ap.add_argument("--no-wavelet", action="store_true", help="skip the secondary FWT + threshold figure")
     ap.add_argument("--no-adaptive", action="store_true", help="skip the secondary adaptive-cycle figure")
     ap.add_argument("--adaptive-eps", type=float, default=1.0e-6)
-    ap.add_argument("--adaptive-wavelet", default="CDF40", help="wavelet of --adaptive-only")
+    ap.add_argument("--adaptive-wavelet", default="CDF40", help="wavelet of --adaptive-only / --adaptive-multi")
     ap.add_argument("--adaptive-multi", action="store_true", help="N > 1: also run the adaptive cycle across the GPUs (halo blocks + block transport)")
     ap.add_argument("--adaptive-level", type=int, default=5, help="initial equidistant level of the adaptive legs")
     ap.add_argument("--adaptive-only", action="store_true", help="run only the adaptive-cycle leg and print its record (development)")
