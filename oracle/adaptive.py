@@ -1,0 +1,167 @@
+"""oracle/adaptive.py -- CPU restatement of WABBIT's adaptive time loop (TEST INFRASTRUCTURE ONLY: imported by tests/ and by
+tests/golden/make_golden.py, never by the product).
+
+Reference (paths relative to the reference checkout):
+  main time loop                 LIB/MAIN/main.f90:305-443      sync_ghosts_tree -> refine_tree -> timeStep_tree -> adapt_tree -> save
+  setInitialCondition_tree       LIB/MESH/setInitialCondition_tree.f90   (read_from_files = 1, adapt_inicond = 1: ONE adapt_tree)
+  refine_tree                    LIB/MESH/refine_tree.f90:7-120
+  refinementIndicator_tree       LIB/INDICATORS/refinementIndicator_tree.f90:14-257   ("everywhere", "significant")
+  respectJmaxJmin_tree           LIB/MESH/respectJmaxJmin_tree.f90
+  ensureGradedness_tree          LIB/MESH/ensureGradedness_tree.f90     (refinement part: a block whose finer neighbour refines, refines)
+  refinement_execute_tree        LIB/MESH/refinementExecute.f90:1-120   (refineBlock: prediction of the ghosted block)
+  componentWiseNorm_tree         LIB/OPERATORS/componentWiseNorm_tree.f90 (Linfty over the interiors of the leaves)
+
+Everything numerical is delegated to the restatements in oracle.py / fulltree.py / orc_*.c.
+
+PINNED by the reference's own regression fixtures TESTING/acm/3vortices/3vorticesAdaptFD4_CDF4{0,2} (tests/test_oracle_adaptive.py):
+the stored grid after adapt_inicond (t = 10) and after the 2281 adaptive time steps to t = 15 -- block lists, refinement statuses
+and iteration counter identical, fields to round-off.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+import oracle as O
+import fulltree as FT
+
+REF_STAY = FT.REF_STAY
+
+
+class AdaptiveRun:
+    """State of one adaptive simulation: leaf grid, ghosted data [nb, nc, nz, ny, nx], refinement status per leaf, time, iteration."""
+
+    def __init__(self, p: O.Params, wavelet: str, grid: O.Grid, u: np.ndarray, time: float, iteration: int, eps: float, Jmin: int = 1,
+                 refinement_indicator: str = "everywhere", use_coarse_extension: Optional[bool] = None,
+                 use_security_zone: Optional[bool] = None, fd_half_width: int = 2, force_maxlevel_dealiasing: bool = False,
+                 thresh_comp=None, eps_normalized: bool = True, eps_norm: str = "Linfty"):
+        self.p, self.w, self.grid, self.u = p, O.setup_wavelet(wavelet), grid, u
+        self.time, self.iteration, self.eps, self.Jmin = time, iteration, eps, Jmin
+        self.refinement_indicator = refinement_indicator
+        self.use_ce = bool(self.w.lifted) if use_coarse_extension is None else use_coarse_extension
+        self.use_sz = bool(self.w.lifted) if use_security_zone is None else use_security_zone
+        self.fd_half_width = fd_half_width
+        self.dealias = force_maxlevel_dealiasing
+        self.thresh_comp = thresh_comp
+        self.eps_normalized, self.eps_norm = eps_normalized, eps_norm
+        self.status = np.zeros(grid.n, dtype=np.int64)
+        self.adapted_once = False
+        self.log = []
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def sync_ghosts_tree(self):
+        """sync_ghosts_tree: all g ghost nodes, restriction through the HD filter for lifted wavelets"""
+        nbr = O.neighbor_table168(self.grid, self.p.Jmax)
+        O.sync_ghosts_leaf(self.grid, self.p, self.u, nbr, self.p.g, self.p.g, self.w.X, bool(self.w.lifted),
+                           ignore_filter=not self.w.lifted, w=self.w)
+
+    def norm(self) -> np.ndarray:
+        """componentWiseNorm_tree(..., "Linfty") on the leaves' interiors; values <= 1e-9 become 1 (coarseningIndicator_tree.f90:66-68)"""
+        if not self.eps_normalized:
+            return np.ones(self.u.shape[1])
+        assert self.eps_norm == "Linfty"
+        it = (slice(None), slice(None)) + O.interior(self.p)
+        n = np.abs(self.u[it]).max(axis=(0, 2, 3, 4))
+        n[n <= 1.0e-9] = 1.0
+        return n
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def adapt_tree(self):
+        g, self.u, info = FT.adapt_tree(self.p, self.w, self.grid, self.u, self.eps, Jmin=self.Jmin, norm=self.norm(), eps_norm=self.eps_norm,
+                                        thresh_comp=self.thresh_comp, level_ref=self.p.Jmax, force_maxlevel_dealiasing=self.dealias,
+                                        fd_half_width=self.fd_half_width, use_security_zone=self.use_sz, use_coarse_extension=self.use_ce)
+        self.grid = g
+        st = info["status"]
+        self.status = np.array([st[(int(l),) + tuple(int(v) for v in x)] for l, x in zip(g.level, g.ixyz)], dtype=np.int64)
+        self.adapted_once = True
+        self.sync_ghosts_tree()                                          # adapt_tree.f90:258
+        return info
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def refine_flags(self, indicator: str) -> np.ndarray:
+        g, dim = self.grid, self.grid.dim
+        if indicator == "everywhere":
+            flag = np.ones(g.n, dtype=np.int64)
+        elif indicator == "significant":
+            assert not np.isin(self.status, (-1, 1)).any()               # abort(241119)
+            flag = np.where(self.status == 0, 1, 0).astype(np.int64)     # 0 -> +1, REF_UNSIGNIFICANT_STAY -> 0
+        else:
+            raise ValueError(indicator)
+        flag[(flag == 1) & (g.level >= self.p.Jmax)] = 0                 # respectJmaxJmin_tree
+        if indicator != "everywhere":                                    # ensureGradedness_tree: monotone 0 -> +1, order-independent
+            key = {(int(l),) + tuple(int(v) for v in x): b for b, (l, x) in enumerate(zip(g.level, g.ixyz))}
+            changed = True
+            while changed:
+                changed = False
+                for k, b in key.items():
+                    if flag[b] != 0:
+                        continue
+                    for d in FT.dirs(dim):
+                        nk = FT.nbr_key(k, d, dim)
+                        if nk in key:
+                            continue                                     # same-level neighbour
+                        hit = False
+                        for c in FT.children(nk, dim):                   # finer neighbours touching k across d
+                            if c in key and flag[key[c]] == 1 and all(
+                                    (d[a] == 0) or (d[a] > 0 and (c[1 + a] & 1) == 0) or (d[a] < 0 and (c[1 + a] & 1) == 1) for a in range(dim)):
+                                hit = True
+                        if hit:
+                            flag[b] = 1
+                            changed = True
+                            break
+        return flag
+
+    def refine_tree(self, indicator: Optional[str] = None):
+        """refine_tree; the caller has synchronised all ghost nodes (main.f90:314)"""
+        indicator = self.refinement_indicator if indicator is None else indicator
+        if indicator == "significant" and not self.adapted_once:
+            indicator = "everywhere"                                     # main.f90:322
+        flag = self.refine_flags(indicator)
+        g, p, dim = self.grid, self.p, self.grid.dim
+        lev, ixyz, data = [], [], []
+        for b in range(g.n):
+            if flag[b] != 1:
+                lev.append(int(g.level[b]))
+                ixyz.append(tuple(int(v) for v in g.ixyz[b]))
+                data.append(self.u[b])
+                continue
+            d = O.refine_block(self.w.X, p, self.u[b])                   # refineBlock: daughters in treecode digit order
+            k = (int(g.level[b]),) + tuple(int(v) for v in g.ixyz[b])
+            for c, ck in enumerate(FT.children(k, dim)):
+                lev.append(ck[0])
+                ixyz.append(ck[1:])
+                data.append(d[self._daughter_slot(c, dim)])
+        order = sorted(range(len(lev)), key=lambda i: (lev[i],) + tuple(ixyz[i]))
+        self.grid = O.Grid(level=np.array([lev[i] for i in order], dtype=np.int64), ixyz=np.array([ixyz[i] for i in order], dtype=np.int64), dim=dim)
+        self.u = np.ascontiguousarray(np.stack([data[i] for i in order]))
+        self.status = np.zeros(self.grid.n, dtype=np.int64)
+        return int(flag.sum())
+
+    @staticmethod
+    def _daughter_slot(c: int, dim: int) -> int:
+        """FT.children numbers daughters by qx + 2 qy + 4 qz; orc_refine_block stores them by treecode digit, qy + 2 qx + 4 qz"""
+        return ((c >> 1) & 1) + 2 * (c & 1) + 4 * ((c >> 2) & 1)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def time_step(self):
+        p, g = self.p, self.grid
+        nbr = O.neighbor_table168(g, p.Jmax)
+
+        def sync(h):
+            O.sync_ghosts_leaf(g, p, h, nbr, p.g_rhs, p.g_rhs, self.w.X, bool(self.w.lifted), ignore_filter=True)
+        work = np.zeros((p.butcher.shape[0] + 1,) + self.u.shape)
+        dt = O.rk_generic(g, p, self.u, work, self.time, sync=sync)
+        self.time += dt
+        self.iteration += 1
+        return dt
+
+    def step(self):
+        """one pass of the main loop (main.f90:305-425)"""
+        self.sync_ghosts_tree()
+        self.refine_tree()
+        nb_rhs = self.grid.n
+        dt = self.time_step()
+        self.adapt_tree()
+        self.log.append((self.iteration, self.time, nb_rhs, self.grid.n, dt))
+        return dt

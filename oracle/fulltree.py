@@ -164,12 +164,16 @@ class Tree:
 
 
 def decompose_full_tree(p: O.Params, w: O.Wavelet, grid: O.Grid, u: np.ndarray, Jmin: int = 1, fd_half_width: int = 0,
-                        force_leaf_first: Optional[bool] = None) -> Tree:
+                        force_leaf_first: Optional[bool] = None, use_coarse_extension: Optional[bool] = None) -> Tree:
     """wavelet_decompose_full_tree (adapt_tree.f90:268-545).  leaf-first (all Bs >= 3*max|HD tap index|): every leaf is decomposed in the
     first pass after a full synchronisation (sync_TMP_from_all: same level, restriction through the HD filter, prediction), then the
     mothers level by level; level-wise otherwise: per level, all blocks of the level together after sync_TMP_from_MF."""
     t = Tree(p, w, grid, u, Jmin, fd_half_width)
     dim = grid.dim
+    # params%useCoarseExtension: default isLiftedWavelet (ini_file_to_params.f90:543); an .ini may switch it on for an unlifted wavelet
+    # (TESTING/acm/3vortices/3vorticesAdaptFD4_CDF40), which then takes the very same code path with Nsc = 0
+    use_ce = bool(w.lifted) if use_coarse_extension is None else bool(use_coarse_extension)
+    t.use_ce = use_ce
     F = max(abs(w.hd_lo), w.hd_hi)
     leaf_first = all(p.Bs[a] >= 3 * F for a in range(dim)) if force_leaf_first is None else force_leaf_first
     t.leaf_first = leaf_first
@@ -185,7 +189,7 @@ def decompose_full_tree(p: O.Params, w: O.Wavelet, grid: O.Grid, u: np.ndarray, 
         for k in sorted(t.leaf):
             t.fwt(k)
         for k in sorted(t.leaf):
-            if w.lifted:                                    # useCoarseExtension = isLiftedWavelet
+            if use_ce:                                      # adapt_tree.f90:479
                 t.ce_modify(k)                              # CE_case="ref", s_ref=-1: leaves only (reconstruction_step.f90:66)
     level = t.Jmax_active
     while level >= Jmin:
@@ -211,7 +215,7 @@ def decompose_full_tree(p: O.Params, w: O.Wavelet, grid: O.Grid, u: np.ndarray, 
             for k in sorted(todo):
                 t.fwt(k)
             for k in sorted(todo):
-                if k in t.leaf and w.lifted:
+                if k in t.leaf and use_ce:
                     t.ce_modify(k)
         t.d2m(level)
         level -= 1
@@ -375,11 +379,12 @@ def _fill_from_coarse(t: Tree, k: Key, d):
 
 def adapt_tree(p: O.Params, w: O.Wavelet, grid: O.Grid, u: np.ndarray, eps: float, Jmin: int = 1, norm=None, eps_norm: str = "Linfty",
                thresh_comp=None, level_ref: int = 0, force_maxlevel_dealiasing: bool = False, indicator: str = "threshold-state-vector",
-               fd_half_width: int = 0, force_leaf_first: Optional[bool] = None, use_security_zone: bool = False):
+               fd_half_width: int = 0, force_leaf_first: Optional[bool] = None, use_security_zone: bool = False,
+               use_coarse_extension: Optional[bool] = None):
     """adapt_tree (adapt_tree.f90:11-260) for a lifted wavelet with the coarse extension, with or without the security zone.  Returns
     (new grid, new data [nb, nc, nz, ny, nx] with meaningful interiors, info dict)."""
     dim = grid.dim
-    t = decompose_full_tree(p, w, grid, u, Jmin, fd_half_width, force_leaf_first)
+    t = decompose_full_tree(p, w, grid, u, Jmin, fd_half_width, force_leaf_first, use_coarse_extension)
     st0 = threshold_full_tree(t, eps, norm, eps_norm, thresh_comp, level_ref, force_maxlevel_dealiasing, indicator)
     if use_security_zone and indicator != "everywhere":
         st0 = security_zone(t, st0, eps, norm, eps_norm, thresh_comp, level_ref, force_maxlevel_dealiasing)
@@ -390,7 +395,7 @@ def adapt_tree(p: O.Params, w: O.Wavelet, grid: O.Grid, u: np.ndarray, eps: floa
         del t.tmp[k]
     leaves = {k for k in t.blk if t.is_leaf(k)}
     marked = sorted(k for k in leaves if t.coarse_dirs(k))              # leaves at a coarse/fine interface of the NEW grid
-    if not w.lifted:                                                    # no coarse extension: "restore original values" (adapt_tree.f90:236-241)
+    if not t.use_ce:                                                    # no coarse extension: "restore original values" (adapt_tree.f90:236-241)
         keys = sorted(leaves)
         new_grid = O.Grid(level=np.array([k[0] for k in keys], dtype=np.int64), ixyz=np.array([k[1:] for k in keys], dtype=np.int64), dim=dim)
         return new_grid, np.stack([t.tmp[k] for k in keys]), {"status0": st0, "status": st, "marked": [], "leaf_only": True,

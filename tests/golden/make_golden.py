@@ -160,7 +160,39 @@ def three_vortices():
         print(path, os.path.getsize(path), o["u"].shape, o["iteration"])
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# TESTING/acm/3vortices/3vorticesAdaptFD4_CDF4{0,2}: the same restart, adaptive (eps = 1e-3, Jmin 1, Jmax 4, refinement
+# indicator "significant", coarse extension and security zone on, c_0 = 5): the stored grid after adapt_inicond (t = 10) and
+# after 2281 adaptive steps (t = 15).  Per file: block levels, zero-based block coordinates, the stored refinement status of
+# every block (0 significant / 9 REF_UNSIGNIFICANT_STAY), iteration, time; the fields in full at t = 10 (25 blocks) and as strided
+# samples at t = 15.
+def three_vortices_adaptive():
+    R = "/root/reference/TESTING/acm/3vortices"
+    for case in ("3vorticesAdaptFD4_CDF40", "3vorticesAdaptFD4_CDF42"):
+        o = {}
+        for tag, key, stride in (("000010000000", "t10", 1), ("000015000000", "t15", 2)):
+            fields = []
+            for name in ("ux", "uy", "p"):
+                d = read_wabbit(os.path.join(R, case, f"{name}_{tag}.h5"))
+                Bs = int(d["attrs"]["block-size"][0])
+                ixy = np.rint(d["origin"][:, ::-1] / (d["spacing"][:, ::-1] * Bs)).astype(np.int32)
+                lvl = d["level"].ravel().astype(np.int32)
+                order = np.lexsort((ixy[:, 1], ixy[:, 0], lvl))
+                fields.append(d["blocks"][order][:, :Bs:stride, :Bs:stride])
+                o[f"{key}_ixy"] = ixy[order]
+                o[f"{key}_level"] = lvl[order]
+                o[f"{key}_status"] = d["refinement_status"].ravel().astype(np.int32)[order]
+                o[f"{key}_iteration"] = d["attrs"]["iteration"]
+                o[f"{key}_time"] = d["attrs"]["time"]
+            o[f"{key}_u"] = np.stack(fields, axis=1)
+            o[f"{key}_stride"] = np.array([stride])
+        path = os.path.join(HERE, case.replace("3vorticesAdapt", "three_vortices_adapt_") + ".npz")
+        np.savez_compressed(path, **o)
+        print(path, os.path.getsize(path), o["t10_u"].shape, o["t15_u"].shape, o["t15_iteration"])
+
+
 if __name__ == "__main__":
     main()
     wavelet_blocks()
     three_vortices()
+    three_vortices_adaptive()

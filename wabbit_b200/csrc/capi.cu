@@ -146,7 +146,7 @@ int32_t upload_jump_tables(wgpu_ctx *ctx, const std::vector<int> &jump_blk, cons
     if (ctx->has_jumps) {
         if (!ctx->wavelet_set)
             return fail(ctx, WGPU_ERR_ARG, "grid has level jumps: call wgpu_set_wavelet first (the predictor order is the wavelet's)");
-        if (c.dim != 3 || c.Bs[0] != c.Bs[1] || c.Bs[0] != c.Bs[2]) return fail(ctx, WGPU_ERR_UNSUPPORTED, "level jumps need cubic 3-D blocks so far");
+        if (c.Bs[0] != c.Bs[1] || (c.dim == 3 && c.Bs[0] != c.Bs[2])) return fail(ctx, WGPU_ERR_UNSUPPORTED, "level jumps need square / cubic blocks so far");
         if (!coords) return fail(ctx, WGPU_ERR_ARG, "grid has level jumps: call wgpu_set_treecodes for the active blocks first");
     }
     if (!coords) return WGPU_OK;   // uniform grid without block positions: nothing that needs the lookup can be called
@@ -233,7 +233,7 @@ int32_t upload_wjump_tables(wgpu_ctx *ctx, const std::vector<int> &blk, const st
         const int d[3] = {dir[i] % 3 - 1, (dir[i] / 3) % 3 - 1, dir[i] / 9 - 1};
         wnbr[(size_t)blk[i] * WGPU_NDIR + dir[i]] = -2 - i;
         off[i] = total;
-        total += (long long)ctx->nc * (d[0] ? F : Bs) * (d[1] ? F : Bs) * (d[2] ? F : Bs);
+        total += (long long)ctx->nc * (d[0] ? F : Bs) * (d[1] ? F : Bs) * (c.dim == 3 ? (d[2] ? F : Bs) : 1);
     }
     for (size_t i = 0; i < wnbr.size(); ++i)
         if (wnbr[i] <= -2 - WGPU_JUMP_PID) wnbr[i] = -1;   // stage-kernel patch ids mean nothing here (cannot happen: overwritten above)
@@ -627,7 +627,7 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
         if ((rcj = upload_wjump_tables(ctx, wjump_blk, wjump_dir))) return rcj;
         ctx->n_rst = 0;
         ctx->h_rmap.assign(N, -1);
-        if (!rst_blk.empty() && c.dim == 3) {
+        if (!rst_blk.empty()) {
             const size_t nr = rst_blk.size();
             if ((int)nr > ctx->rst_cap) {
                 cudaFree(ctx->d_rst_blk);
@@ -638,7 +638,7 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
                 if ((rcj = dmalloc(ctx, &ctx->d_rst_blk, want)) || (rcj = dmalloc(ctx, &ctx->d_rst_mask, want))) return rcj;
                 ctx->rst_cap = (int)want;
             }
-            const size_t need = nr * ctx->nc * (size_t)(ctx->blk_elems / 8);
+            const size_t need = nr * ctx->nc * (size_t)(ctx->blk_elems >> c.dim);
             if (need > ctx->rpool_cap) {
                 cudaFree(ctx->d_rpool);
                 ctx->d_rpool = nullptr;
@@ -959,7 +959,7 @@ static int32_t transform(wgpu_ctx *ctx, int32_t src_id, int32_t src_slot, int32_
     if (!ctx) return WGPU_ERR_ARG;
     if (!ctx->wavelet_set) return fail(ctx, 1213149, "The cat is angry: Wavelet-setup not yet called?");
     const wgpu_config &c = ctx->cfg;
-    if (c.dim != 3 || c.Bs[0] != c.Bs[1] || c.Bs[0] != c.Bs[2]) return fail(ctx, WGPU_ERR_UNSUPPORTED, "wavelet kernels: cubic 3-D blocks only so far");
+    if (c.Bs[0] != c.Bs[1] || (c.dim == 3 && c.Bs[0] != c.Bs[2])) return fail(ctx, WGPU_ERR_UNSUPPORTED, "wavelet kernels: square / cubic blocks only so far");
     if (!ctx->remote_faces.empty() || (ctx->n_bnd && ctx->halo_bnd.empty()))
         return fail(ctx, WGPU_ERR_UNSUPPORTED, "wavelet kernels: neighbours on other ranks need halo copies (wgpu_set_halo)");
     if (ctx->halo_fine_neighbor && !ctx->n_rhalo_recv && !ctx->ignore_filter && ctx->wavelet.Y != 0)
@@ -989,7 +989,7 @@ int32_t wgpu_iwt_ce(wgpu_ctx *ctx, int32_t wd_id, int32_t wd_slot, int32_t coars
     if (!ctx) return WGPU_ERR_ARG;
     if (!ctx->wavelet_set) return fail(ctx, 1213149, "The cat is angry: Wavelet-setup not yet called?");
     const wgpu_config &c = ctx->cfg;
-    if (c.dim != 3 || c.Bs[0] != c.Bs[1] || c.Bs[0] != c.Bs[2]) return fail(ctx, WGPU_ERR_UNSUPPORTED, "wavelet kernels: cubic 3-D blocks only so far");
+    if (c.Bs[0] != c.Bs[1] || (c.dim == 3 && c.Bs[0] != c.Bs[2])) return fail(ctx, WGPU_ERR_UNSUPPORTED, "wavelet kernels: square / cubic blocks only so far");
     int n1 = 0, n2 = 0, n3 = 0;
     const double *src = array_ptr(ctx, wd_id, wd_slot, &n1);
     const double *crs = array_ptr(ctx, coarse_id, coarse_slot, &n2);

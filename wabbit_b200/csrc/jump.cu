@@ -130,6 +130,55 @@ __global__ void __launch_bounds__(256) restrict_filter_kernel(const RestrictArgs
     }
 }
 
+// the same for two-dimensional blocks: x pass from global memory, y pass in shared memory; result (Bs/2)^2 values per (leaf, component)
+__global__ void __launch_bounds__(256) restrict_filter2d_kernel(const RestrictArgs a)
+{
+    extern __shared__ __align__(16) double sm[];
+    __shared__ int nb[9];
+    const int Bs = a.Bs, F = a.F, half = Bs / 2, n = Bs + 2 * F;
+    const int b = a.rst_blk[blockIdx.x], c = blockIdx.y;
+    const unsigned mask = a.rst_mask[blockIdx.x];
+    const long long CS = (long long)Bs * Bs;
+    if (threadIdx.x < 9) nb[threadIdx.x] = threadIdx.x == 4 ? b : a.nbr[(long long)b * 27 + 9 + threadIdx.x];
+    __syncthreads();
+    double *t1 = sm;                                // [n y][half x]
+    for (int i = threadIdx.x; i < n * half; i += blockDim.x) {
+        const int xo = i % half, y = i / half - F;
+        const int sy = y < 0 ? -1 : (y >= Bs ? 1 : 0);
+        double acc = 0.0;
+        for (int k = a.lo; k <= a.hi; ++k) {
+            const int x = 2 * xo + k;
+            const int sx = x < 0 ? -1 : (x >= Bs ? 1 : 0);
+            const int src = nb[(sy + 1) * 3 + (sx + 1)];
+            const double v = src >= 0 ? a.u[((long long)src * a.nc + c) * CS + (long long)(y - sy * Bs) * Bs + (x - sx * Bs)] : 0.0;
+            acc = __dadd_rn(acc, __dmul_rn(v, a.HD[k + WGPU_FMAX]));
+        }
+        t1[i] = acc;
+    }
+    __syncthreads();
+    double *out = a.rpool + ((long long)blockIdx.x * a.nc + c) * (CS / 4);
+    const double *own = a.u + ((long long)b * a.nc + c) * CS;
+    for (int i = threadIdx.x; i < half * half; i += blockDim.x) {
+        const int xo = i % half, yo = i / half;
+        const int p[2] = {2 * xo, 2 * yo};
+        bool copy = false;
+        for (int d = 9; d < 18 && !copy; ++d) {
+            if (!((mask >> d) & 1u)) continue;
+            const int dd[2] = {d % 3 - 1, (d / 3) % 3 - 1};
+            bool in = true;
+            for (int k = 0; k < 2; ++k) in = in && (dd[k] == 0 || (dd[k] < 0 ? p[k] < a.Nscl : p[k] >= Bs - a.Nscr));
+            copy = in;
+        }
+        double v;
+        if (copy) v = own[(long long)p[1] * Bs + p[0]];
+        else {
+            v = 0.0;
+            for (int k = a.lo; k <= a.hi; ++k) v = __dadd_rn(v, __dmul_rn(t1[(size_t)(p[1] + F + k) * half + xo], a.HD[k + WGPU_FMAX]));
+        }
+        out[i] = v;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ jump patches
 struct JumpArgs {
     FillCtx f;
@@ -398,11 +447,22 @@ int32_t wgpu_launch_restrict_filter(wgpu_ctx *ctx, const double *src, int nc_src
     a.Nscr = w.hd_hi;
     for (int k = 0; k < 2 * WGPU_FMAX + 1; ++k) a.HD[k] = w.HD[k];
     const int n = a.Bs + 2 * a.F, half = a.Bs / 2;
+    dim3 grid(ctx->n_rst, ctx->nc);
+    if (c.dim == 2) {
+        const size_t smem2 = sizeof(double) * ((size_t)n * half);
+        static size_t configured2 = 0;
+        int32_t rc2 = ensure_smem(ctx, restrict_filter2d_kernel, smem2, configured2);
+        if (rc2) return rc2;
+        restrict_filter2d_kernel<<<grid, 256, smem2, ctx->stream>>>(a);
+        ctx->launches++;
+        WGPU_CHECK(ctx, cudaGetLastError());
+        *active = true;
+        return WGPU_OK;
+    }
     const size_t smem = sizeof(double) * ((size_t)n * n * half + (size_t)n * half * half);
     static size_t configured = 0;
     int32_t rc = ensure_smem(ctx, restrict_filter_kernel, smem, configured);
     if (rc) return rc;
-    dim3 grid(ctx->n_rst, ctx->nc);
     restrict_filter_kernel<<<grid, 256, smem, ctx->stream>>>(a);
     ctx->launches++;
     WGPU_CHECK(ctx, cudaGetLastError());

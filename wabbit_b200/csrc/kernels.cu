@@ -496,7 +496,15 @@ __global__ void __launch_bounds__(256) stage_kernel_2d(const __grid_constant__ S
         else if (side == 1) { const int h = q % H, y = q / H; nb = cE; sx = h; sy = y; tx = BS + H + h; ty = y + H; }
         else if (side == 2) { const int x = q % BS, h = q / BS; nb = cS; sx = x; sy = BS - H + h; tx = x + H; ty = h; }
         else { const int x = q % BS, h = q / BS; nb = cN; sx = x; sy = h; tx = x + H; ty = BS + H + h; }
-        sm[c * PLANE + ty * PITCH + tx] = nb >= 0 ? a.u_in[((long long)nb * NC + c) * CS + sy * BS + sx] : 0.0;
+        double v = 0.0;
+        if (nb >= 0) v = a.u_in[((long long)nb * NC + c) * CS + sy * BS + sx];
+        else if (nb <= -2) {   // face patch of the jump pool (restriction / prediction across a level jump): x faces (H, Bs), y faces (Bs, H)
+            const unsigned long long base = pool_base(a, nb);
+            const double *pp = (base & LT_POOL) ? a.pool : a.jpool;
+            const int hh = side < 2 ? q % H : q / BS, tt = side < 2 ? q / H : q % BS;
+            v = pp[(long long)(base & LT_MASK) + (side < 2 ? ((long long)c * BS + tt) * H + hh : ((long long)c * H + hh) * BS + tt)];
+        }
+        sm[c * PLANE + ty * PITCH + tx] = v;
     }
     __syncthreads();
 

@@ -188,6 +188,85 @@ __global__ void __launch_bounds__(256) wavelet_kernel(const WaveArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Two-dimensional blocks (dim = 2, TESTING/acm 2-D cases): the same transform without the z pass.  One CTA per (block, component):
+// the ghosted tile (halo depth f) is gathered from the same-level neighbours' interiors or, across level jumps, from the patches of
+// the wavelet jump pool (jump_fill_kernel: decimation / prediction / coarse-extension values in ghost-region layout), then the x pass
+// and the y pass run in shared memory.  Arithmetic as above: one product per non-zero tap, summed in increasing tap order.
+// ---------------------------------------------------------------------------------------------
+struct Wave2dArgs {
+    const double *src;
+    double *dst;
+    const int *active;
+    const int *nbr;            // d_wnbr (codes <= -2: patch of the wavelet jump pool) or d_nbr
+    const double *wpool;
+    const long long *woff;
+    int nc, Bs, f, inverse;
+    WaveFilters w;
+};
+
+__global__ void __launch_bounds__(256) wavelet2d_kernel(const Wave2dArgs a)
+{
+    extern __shared__ __align__(16) double sm[];
+    const int Bs = a.Bs, f = a.f, n = Bs + 2 * f;
+    double *tile = sm;                       // [n][n]
+    double *xs = tile + n * n;               // [n][Bs]
+    __shared__ const double *s_ptr[9];
+    __shared__ int s_sy[9];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int b = a.active[blockIdx.x], c = blockIdx.y;
+    const long long CS = (long long)Bs * Bs;
+    if (tid < 9) {
+        const int D = 9 + tid;               // dz = 0 plane of the 27 directions
+        const int sb = D == 13 ? b : a.nbr[b * WGPU_NDIR + D];
+        const double *ptr = nullptr;
+        int sy = Bs;
+        if (sb >= 0) ptr = a.src + ((long long)sb * a.nc + c) * CS;
+        else if (sb <= -2) {
+            const int d[2] = {tid % 3 - 1, tid / 3 - 1};
+            const int ex = d[0] ? f : Bs, ey = d[1] ? f : Bs;
+            const int ox = d[0] < 0 ? Bs - f : 0, oy = d[1] < 0 ? Bs - f : 0;
+            sy = ex;
+            ptr = a.wpool + a.woff[-2 - sb] + (long long)c * ex * ey - ((long long)oy * ex + ox);
+        }
+        s_ptr[tid] = ptr;
+        s_sy[tid] = sy;
+    }
+    __syncthreads();
+    for (int i = tid; i < n * n; i += nt) {
+        const int y = i / n - f, x = i % n - f;
+        int dy, ly, dx, lx;
+        split(y, Bs, dy, ly);
+        split(x, Bs, dx, lx);
+        const int D = (dy + 1) * 3 + (dx + 1);
+        const double *p = s_ptr[D];
+        tile[i] = p ? p[(long long)ly * s_sy[D] + lx] : 0.0;
+    }
+    __syncthreads();
+    const double *F0 = a.inverse ? a.w.HR : a.w.HD, *F1 = a.inverse ? a.w.GR : a.w.GD;
+    const int lo0 = a.inverse ? a.w.hr_lo : a.w.hd_lo, hi0 = a.inverse ? a.w.hr_hi : a.w.hd_hi;
+    const int lo1 = a.inverse ? a.w.gr_lo : a.w.gd_lo, hi1 = a.inverse ? a.w.gr_hi : a.w.gd_hi;
+    auto line = [&](const double *p, int stride, int o) -> double {
+        if (!a.inverse) return (o & 1) ? filt(p, stride, F1, lo1, hi1) : filt(p, stride, F0, lo0, hi0);
+        double s0 = 0.0, s1 = 0.0;
+        for (int k = lo0; k <= hi0; ++k)
+            if (((o + k) & 1) == 0) s0 = __dadd_rn(s0, __dmul_rn(p[k * stride], F0[k + WGPU_FMAX]));
+        for (int k = lo1; k <= hi1; ++k)
+            if (((o + k) & 1) != 0) s1 = __dadd_rn(s1, __dmul_rn(p[k * stride], F1[k + WGPU_FMAX]));
+        return __dadd_rn(s0, s1);
+    };
+    for (int i = tid; i < n * Bs; i += nt) {
+        const int r = i / Bs, o = i % Bs;
+        xs[i] = line(tile + r * n + f + o, 1, o);
+    }
+    __syncthreads();
+    double *out = a.dst + ((long long)b * a.nc + c) * CS;
+    for (int i = tid; i < Bs * Bs; i += nt) {
+        const int o = i / Bs, x = i % Bs;
+        out[i] = line(xs + (o + f) * Bs + x, Bs, o);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Fast path: the same transform with everything the compiler can know fixed at compile time -- wavelet (taps become
 // literals, zero taps vanish), block size, halo depth.  One CTA per (block, component), 256 threads.  Every thread produces
 // a (scaling, wavelet) pair of neighbouring outputs from one register window of 2F+2 inputs, so each pass costs
@@ -777,6 +856,40 @@ int32_t wgpu_launch_wavelet(wgpu_ctx *ctx, const double *src, double *dst, int i
     if (f > a.Bs) {
         ctx->err = "wavelet filter wider than the block";
         return WGPU_ERR_UNSUPPORTED;
+    }
+    if (c.dim == 2) {
+        if (ctx->has_jumps) {
+            int32_t rcj = wgpu_launch_wjump_fill(ctx, src, ce_coarse);
+            if (rcj) return rcj;
+        }
+        Wave2dArgs q;
+        q.src = src;
+        q.dst = dst;
+        q.active = ctx->d_active;
+        q.nbr = ctx->has_jumps ? ctx->d_wnbr : ctx->d_nbr;
+        q.wpool = ctx->d_wpool;
+        q.woff = ctx->d_woff;
+        q.nc = ctx->nc;
+        q.Bs = c.Bs[0];
+        q.f = ctx->has_jumps ? ctx->wjump_depth : f;     // the patches of the wavelet jump pool are wjump_depth deep
+        q.inverse = inverse;
+        q.w = ctx->wavelet;
+        if (q.f < f || q.f > q.Bs) {
+            ctx->err = "wavelet2d: halo depth does not fit";
+            return WGPU_ERR_UNSUPPORTED;
+        }
+        const int n2 = q.Bs + 2 * q.f;
+        const size_t smem2 = sizeof(double) * ((size_t)n2 * n2 + (size_t)n2 * q.Bs);
+        static size_t configured2 = 0;
+        if (smem2 > configured2) {
+            WGPU_CHECK(ctx, cudaFuncSetAttribute(wavelet2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            configured2 = smem2;
+        }
+        dim3 grid2(ctx->n_active, ctx->nc);
+        wavelet2d_kernel<<<grid2, 256, smem2, ctx->stream>>>(q);
+        ctx->launches++;
+        WGPU_CHECK(ctx, cudaGetLastError());
+        return WGPU_OK;
     }
     {
         bool handled = false;

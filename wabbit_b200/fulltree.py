@@ -137,7 +137,9 @@ class FullTree:
         F = sol.wavelet_filter_width()
         p = sol.params
         self.leaf_first = all(p.Bs[a] >= 3 * F for a in range(dim))
-        self.lifted = p.wavelet[4] != "0"          # useCoarseExtension = isLiftedWavelet (ini_file_to_params.f90:543)
+        # useCoarseExtension: default isLiftedWavelet (ini_file_to_params.f90:543); an .ini may switch it on for an unlifted wavelet, which
+        # then takes the same path with Nsc = 0 (TESTING/acm/3vortices/3vorticesAdaptFD4_CDF40)
+        self.lifted = (p.wavelet[4] != "0") if p.useCoarseExtension < 0 else bool(p.useCoarseExtension)
 
     def _set_blocks(self, level, pos, slots, is_leaf):
         code = _pack(level, pos)
@@ -340,9 +342,9 @@ class FullTree:
         p = self.sol.params
         w = p.wavelet
         X, Y = int(w[3]), int(w[4])
-        F = (X - 1) + (Y - 1)
+        F = (X - 1) + (Y - 1) if Y > 0 else 0          # half width of HD (and of GR)
         H = {"FD_2nd_central": 1, "FD_4th_central": 2, "FD_6th_central": 3, "FD_4th_central_optimized": 3}[p.discretization]
-        nwl, nwr = (F - 1) + (X - 1), F + (X - 1)
+        nwl, nwr = max(F - 1, 0) + (X - 1), F + (X - 1)
         dl, dr = max(2 * H - nwl, 0), max(2 * H - nwr, 0)
         nrl, nrr = nwl + F + dl, nwr + F + dr
         return nrl, nrr, nrl + max(X // 2 - 1, 0), nrr + X // 2
@@ -371,6 +373,7 @@ class FullTree:
         t0 = self._tick("decide", t0)
         info = {"status0": self.status_dict(st0), "status": self.status_dict(st)} if want_info else {}
         keep = st != -1
+        st_kept = st[keep]
         self.code, self.level, self.pos, self.slots = self.code[keep], self.level[keep], self.pos[keep], self.slots[keep]
         self._build_tables()
         t0 = self._tick("rebuild tables", t0)
@@ -398,7 +401,10 @@ class FullTree:
         new = Forest.from_blocks(dim, self.forest.Jmax, self.level[leaves].astype(np.int32), self.pos[leaves].astype(np.int32),
                                  block_dist=self.forest.block_dist, n_ranks=1, max_blocks=self.forest.max_blocks, periodic=self.forest.periodic)
         hvy, lvl, ixyz, _ = new.active(0)
-        src = self.slots[self._find(lvl.astype(np.int64), ixyz.astype(np.int64))]
+        at = self._find(lvl.astype(np.int64), ixyz.astype(np.int64))
+        src = self.slots[at]
+        # lgt_block(:, IDX_REFINE_STS) of the new leaves: 0 significant / 9 REF_UNSIGNIFICANT_STAY, read by the "significant" refinement indicator
+        self.leaf_status = st_kept[at].astype(np.int32)
         t0 = self._tick("reconstruction passes + new forest", t0)
         sol.move_blocks(src.astype(np.int32), hvy.astype(np.int32))
         sol.set_forest(new)
@@ -476,7 +482,7 @@ class DistributedFullTree(FullTree):
         F = sol.wavelet_filter_width()
         p = sol.params
         self.leaf_first = all(p.Bs[a] >= 3 * F for a in range(dim))
-        self.lifted = p.wavelet[4] != "0"
+        self.lifted = (p.wavelet[4] != "0") if p.useCoarseExtension < 0 else bool(p.useCoarseExtension)
         self._halo_cleared = False
 
     # ------------------------------------------------------------------ a pass: ship what the owned blocks need, then local tables

@@ -129,6 +129,7 @@ class Params:
     useCoarseExtension: int = -1          # -1: the reference's default = isLiftedWavelet (ini_file_to_params.f90:543-546)
     useSecurityZone: int = -1
     adapt_tree: bool = False
+    refinement_indicator: str = "everywhere"
     block_dist: str = "sfc_hilbert"
     discretization: str = "FD_4th_central"
     time_max: float = 1.0
@@ -205,6 +206,7 @@ class Params:
         p.useCoarseExtension = int(ini.boolean("Blocks", "useCoarseExtension", lifted))
         p.useSecurityZone = int(ini.boolean("Blocks", "useSecurityZone", lifted))
         p.adapt_tree = ini.boolean("Blocks", "adapt_tree", False)
+        p.refinement_indicator = ini.string("Blocks", "refinement_indicator", "everywhere")
         p.block_dist = ini.string("Blocks", "block_dist", "sfc_hilbert")
         p.discretization = ini.string("Discretization", "order_discretization", "FD_4th_central")
         p.time_max = ini.real("Time", "time_max", 1.0)

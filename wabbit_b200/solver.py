@@ -285,7 +285,9 @@ class WabbitGPU:
         Returns (new forest, number of blocks before, after)."""
         w = self.params.wavelet
         lifted = not (len(w) == 5 and w[4] == "0")
-        if lifted if full_tree is None else full_tree:
+        use_ce = lifted if self.params.useCoarseExtension < 0 else bool(self.params.useCoarseExtension)
+        self.refinement_status = None
+        if use_ce if full_tree is None else full_tree:
             # the reference's full-tree algorithm (wabbit_b200/fulltree.py; for lifted wavelets with the coarse extension), which can remove
             # several levels in one call; the security zone is on unless params.useSecurityZone = 0 (the reference's default)
             from .fulltree import FullTree
@@ -296,11 +298,11 @@ class WabbitGPU:
             if norm_l is not None:
                 norm_l[norm_l <= 1.0e-9] = 1.0
             n0 = forest.n_blocks
-            new, _info = FullTree(self, forest, Jmin=Jmin).adapt(eps=self.params.eps if eps is None else eps, norm=norm_l, eps_norm=eps_norm,
-                                                               thresh_comp=thresh_comp, force_maxlevel_dealiasing=force_maxlevel_dealiasing,
-                                                               want_info=False,
-                                                               use_security_zone=(lifted and self.params.useSecurityZone != 0) if useSecurityZone is None
-                                                               else bool(useSecurityZone))
+            ft = FullTree(self, forest, Jmin=Jmin)
+            sz = (lifted if self.params.useSecurityZone < 0 else bool(self.params.useSecurityZone)) if useSecurityZone is None else bool(useSecurityZone)
+            new, _info = ft.adapt(eps=self.params.eps if eps is None else eps, norm=norm_l, eps_norm=eps_norm, thresh_comp=thresh_comp,
+                                  force_maxlevel_dealiasing=force_maxlevel_dealiasing, want_info=False, use_security_zone=sz)
+            self.refinement_status = ft.leaf_status          # lgt_block(:, IDX_REFINE_STS) after adapt_tree, in the order of new.active(0)
             return new, n0, new.n_blocks
         hvy, lvl, _, _ = forest.active(0)
         norm = None

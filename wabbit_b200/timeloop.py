@@ -1,0 +1,101 @@
+"""The adaptive time loop around the device path: what LIB/MAIN/main.f90:305-443 does per iteration with `adapt_tree = 1`,
+
+    sync_ghosts_tree -> refine_tree(refinement_indicator) -> timeStep_tree (RungeKuttaGeneric) -> adapt_tree
+
+with the heavy data resident on the GPU (WabbitGPU) and the light data (grid, refinement flags) on the host.  The ghost nodes are never
+stored on the device: every consumer (refineBlock, the stage kernels, the wavelet kernels) resolves them on the fly, so the two
+sync_ghosts_tree calls of the reference loop have no counterpart here.
+
+Host light-data logic of this module (stays in host Fortran in a WABBIT build; restated here for the drivers and tests):
+  refinementIndicator_tree    LIB/INDICATORS/refinementIndicator_tree.f90:14-257   "everywhere", "significant"
+  respectJmaxJmin_tree        LIB/MESH/respectJmaxJmin_tree.f90
+  ensureGradedness_tree       LIB/MESH/ensureGradedness_tree.f90 (refinement half: a block whose finer neighbour refines, refines too)
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+from .forest import Forest
+from .solver import WabbitGPU
+
+REF_UNSIGNIFICANT_STAY = 9      # module_globals.f90:28
+
+
+def refinement_flags(forest: Forest, indicator: str, status: Optional[np.ndarray], Jmax: int) -> np.ndarray:
+    """+1 / 0 per active block (order of forest.active(0)): refinementIndicator_tree + respectJmaxJmin_tree + ensureGradedness_tree.
+    `status`: lgt_block(:, IDX_REFINE_STS) left by the last adapt_tree (0 significant, 9 REF_UNSIGNIFICANT_STAY)."""
+    hvy, lvl, ixyz, _ = forest.active(0)
+    n, dim = len(hvy), forest.dim
+    lvl = lvl.astype(np.int64)
+    pos = ixyz.astype(np.int64)
+    if indicator == "everywhere":
+        flag = np.ones(n, np.int32)
+    elif indicator == "significant":
+        if status is None:
+            raise ValueError('refinement indicator "significant" needs the refinement status of the last adapt_tree')
+        if np.isin(status, (-1, 1)).any():
+            raise RuntimeError("241119: I am very confused by what is going on here and do not like it!")
+        flag = (np.asarray(status) == 0).astype(np.int32)
+    else:
+        raise ValueError(f"refinement indicator {indicator!r} is not supported")
+    flag[lvl >= Jmax] = 0
+    if indicator == "everywhere":
+        return flag
+    # gradedness: a block (level L, flag 0) refines if a finer neighbour (level L+1) refines.  Propagate upwards from the finest level:
+    # mark, for every refining block, the (up to 3^dim - 1) positions of level L-1 that touch it and hold a leaf.
+    key = {(int(l), int(p[0]), int(p[1]), int(p[2])): b for b, (l, p) in enumerate(zip(lvl, pos))}
+    changed = True
+    while changed:
+        changed = False
+        for b in np.flatnonzero(flag == 1):
+            L = int(lvl[b])
+            if L == 0:
+                continue
+            nb = 1 << L
+            for dz in ((-1, 0, 1) if dim == 3 else (0,)):
+                for dy in (-1, 0, 1):
+                    for dx in (-1, 0, 1):
+                        q = ((int(pos[b, 0]) + dx) % nb, (int(pos[b, 1]) + dy) % nb, ((int(pos[b, 2]) + dz) % nb) if dim == 3 else 0)
+                        c = key.get((L - 1, q[0] >> 1, q[1] >> 1, q[2] >> 1))
+                        if c is not None and flag[c] == 0:
+                            flag[c] = 1
+                            changed = True
+    return flag
+
+
+class AdaptiveLoop:
+    """One simulation with adapt_tree = 1 on one GPU."""
+
+    def __init__(self, sol: WabbitGPU, forest: Forest, time: float = 0.0, iteration: int = 0, refinement_indicator: Optional[str] = None,
+                 thresh_comp=None):
+        self.sol, self.forest, self.time, self.iteration = sol, forest, time, iteration
+        p = sol.params
+        self.indicator = p.refinement_indicator if refinement_indicator is None else refinement_indicator
+        self.thresh_comp = thresh_comp
+        self.status: Optional[np.ndarray] = None
+        self.log = []
+
+    def adapt_tree(self):
+        p = self.sol.params
+        self.forest, n0, n1 = self.sol.adapt_tree(self.forest, eps=p.eps, eps_normalized=p.eps_normalized, eps_norm=p.eps_norm, Jmin=p.Jmin,
+                                                  force_maxlevel_dealiasing=p.force_maxlevel_dealiasing, thresh_comp=self.thresh_comp)
+        self.status = self.sol.refinement_status
+        return n0, n1
+
+    def refine_tree(self):
+        ind = self.indicator
+        if ind == "significant" and self.status is None:
+            ind = "everywhere"                                   # main.f90:322: adapt_tree was not called yet
+        flags = None if ind == "everywhere" else refinement_flags(self.forest, ind, self.status, self.sol.params.Jmax)
+        self.forest = self.sol.refine_tree(self.forest, flags)
+        self.status = None
+        return self.forest.n_blocks
+
+    def step(self) -> float:
+        nb_rhs = self.refine_tree()
+        self.time, self.iteration, dt = self.sol.timeStep_tree(self.time, self.iteration)
+        self.adapt_tree()
+        self.log.append((self.iteration, self.time, nb_rhs, self.forest.n_blocks, dt))
+        return dt
