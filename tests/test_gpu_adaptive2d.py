@@ -110,6 +110,8 @@ def test_adaptive_run_fixture_2d(wavelet):
         loop.step()
     lvl, pos, u = download_blocks(loop.sol, loop.forest)
     err = AC.compare(AC.gold(wavelet), "t15", lvl, pos, loop.status, u, loop.iteration, loop.time)
+    print(f"\n3vorticesAdaptFD4_{wavelet} on the GPU: {loop.iteration - 3054} adaptive steps, {loop.forest.n_blocks} blocks at t = {loop.time}, "
+          f"max |u - reference| = {err:.3e}, blocks on the RHS grid max {max(r[2] for r in loop.log)}")
     assert err <= 1e-10, err
     loop.sol.close()
 

@@ -100,7 +100,7 @@ void fill_common_args(wgpu_ctx *ctx, StageArgs &a)
     a.pool = ctx->d_pool;
     a.pool_off = ctx->d_pool_off;
     a.jpool = ctx->d_jpool;
-    a.jpatch = (long long)ctx->nc * (c.fd == 2 ? 1 : (c.fd == 4 ? 2 : 3)) * c.Bs[0] * c.Bs[1];
+    a.jpatch = (long long)ctx->nc * (c.fd == 2 ? 1 : (c.fd == 4 ? 2 : 3)) * c.Bs[0] * (c.dim == 3 ? c.Bs[1] : 1);   // = JumpArgs::jpatch (jump.cu)
     for (int l = 0; l < WGPU_MAX_LEVELS; ++l)
         for (int d = 0; d < 3; ++d) a.dx_lvl[l][d] = ldexp(1.0, -l) * c.domain[d] / (double)c.Bs[d];  // module_treelib.f90:93
     a.c0 = c.c0;
