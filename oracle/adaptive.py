@@ -29,13 +29,59 @@ import fulltree as FT
 REF_STAY = FT.REF_STAY
 
 
+def step_cosine(x_rel: np.ndarray, h: float) -> np.ndarray:
+    """step_cosine3 / step_cosine4 (LIB/HELPER/module_helpers.f90:436-470) of x_rel = x - t"""
+    out = 0.5 * (1.0 + np.cos((x_rel + h) * np.pi / (2.0 * h)))
+    out = np.where(x_rel <= -h, 1.0, out)
+    return np.where(x_rel >= h, 0.0, out)
+
+
+class CylinderMask2D:
+    """The six mask components of create_mask_2D_ACM (LIB/EQUATION/ACMnew/create_mask.f90:183-320) for geometry = cylinder (a circle,
+    draw_circle, LIB/EQUATION/insects/module_geometry.f90:315-381, cosine smoothing of width C_smooth * dx_min with dx_min the lattice
+    spacing on Jmax, module_ACM.f90:459-471) plus the p-norm sponge (sponge_2D, sponge.f90), as CREATE_MASK_meta ("all-parts") leaves them
+    on a block: [chi, 0, 0, 0, colour = 1, sponge] at the interior points (the sponge) / the interior and the first upper ghost point (chi);
+    zero elsewhere.  A pure function of the block's position: createMask_tree in 2-D always draws all parts directly."""
+
+    def __init__(self, p: O.Params, center=(10.0, 10.0), radius: float = 0.5, C_smooth: float = 1.5, use_sponge: bool = True, L_sponge: float = 2.0,
+                 p_sponge: float = 8.0):
+        self.p, self.center, self.radius = p, center, radius
+        dx_min = min(2.0 ** (-p.Jmax) * p.domain[d] / float(p.Bs[d]) for d in range(p.dim))
+        self.h = dx_min * C_smooth
+        self.use_sponge, self.L, self.ps = use_sponge, L_sponge, p_sponge
+
+    def block(self, level: int, ixyz) -> np.ndarray:
+        p, g = self.p, self.p.g
+        Bx, By = p.Bs[0], p.Bs[1]
+        m = np.zeros((6, 1, By + 2 * g, Bx + 2 * g))
+        m[4] = 1.0
+        dx = [2.0 ** (-level) * p.domain[d] / float(p.Bs[d]) for d in range(2)]
+        x0 = [float(int(ixyz[d]) * p.Bs[d]) * dx[d] for d in range(2)]
+        x = np.arange(0, Bx + 1, dtype=np.float64) * dx[0] + x0[0]
+        y = np.arange(0, By + 1, dtype=np.float64) * dx[1] + x0[1]
+        dist = np.sqrt((x[None, :] - self.center[0]) ** 2 + (y[:, None] - self.center[1]) ** 2) - self.radius
+        m[0, 0, g:g + By + 1, g:g + Bx + 1] = step_cosine(dist, self.h)
+        if self.use_sponge:
+            off = 0.5 * p.domain[0]
+            xs, ys = x[:Bx] - off, y[:By] - off
+            tmp = -((xs[None, :] ** self.ps + ys[:, None] ** self.ps) ** (1.0 / self.ps) - off)
+            m[5, 0, g:g + By, g:g + Bx] = step_cosine(tmp - 0.5 * self.L, 0.5 * self.L)
+        return m
+
+    def keeps(self, level: int, ixyz) -> bool:
+        """coarseningIndicatorMask_tree: the mask function varies over the block's interior"""
+        p, g = self.p, self.p.g
+        chi = self.block(level, ixyz)[0, 0, g:g + p.Bs[1], g:g + p.Bs[0]]
+        return bool(((chi > 1.0e-12) & (chi < 1.0 - 1.0e-12)).any() or (chi.max() - chi.min()) > 1.0e-12)
+
+
 class AdaptiveRun:
     """State of one adaptive simulation: leaf grid, ghosted data [nb, nc, nz, ny, nx], refinement status per leaf, time, iteration."""
 
     def __init__(self, p: O.Params, wavelet: str, grid: O.Grid, u: np.ndarray, time: float, iteration: int, eps: float, Jmin: int = 1,
                  refinement_indicator: str = "everywhere", use_coarse_extension: Optional[bool] = None,
                  use_security_zone: Optional[bool] = None, fd_half_width: int = 2, force_maxlevel_dealiasing: bool = False,
-                 thresh_comp=None, eps_normalized: bool = True, eps_norm: str = "Linfty"):
+                 thresh_comp=None, eps_normalized: bool = True, eps_norm: str = "Linfty", mask=None, threshold_mask: bool = False):
         self.p, self.w, self.grid, self.u = p, O.setup_wavelet(wavelet), grid, u
         self.time, self.iteration, self.eps, self.Jmin = time, iteration, eps, Jmin
         self.refinement_indicator = refinement_indicator
@@ -45,6 +91,7 @@ class AdaptiveRun:
         self.dealias = force_maxlevel_dealiasing
         self.thresh_comp = thresh_comp
         self.eps_normalized, self.eps_norm = eps_normalized, eps_norm
+        self.mask, self.threshold_mask = mask, threshold_mask        # mask: object with block(level, ixyz) and keeps(level, ixyz)
         self.status = np.zeros(grid.n, dtype=np.int64)
         self.adapted_once = False
         self.log = []
@@ -70,7 +117,8 @@ class AdaptiveRun:
     def adapt_tree(self):
         g, self.u, info = FT.adapt_tree(self.p, self.w, self.grid, self.u, self.eps, Jmin=self.Jmin, norm=self.norm(), eps_norm=self.eps_norm,
                                         thresh_comp=self.thresh_comp, level_ref=self.p.Jmax, force_maxlevel_dealiasing=self.dealias,
-                                        fd_half_width=self.fd_half_width, use_security_zone=self.use_sz, use_coarse_extension=self.use_ce)
+                                        fd_half_width=self.fd_half_width, use_security_zone=self.use_sz, use_coarse_extension=self.use_ce,
+                                        mask_keeps=(lambda k: self.mask.keeps(k[0], k[1:])) if (self.mask is not None and self.threshold_mask) else None)
         self.grid = g
         st = info["status"]
         self.status = np.array([st[(int(l),) + tuple(int(v) for v in x)] for l, x in zip(g.level, g.ixyz)], dtype=np.int64)
@@ -151,10 +199,24 @@ class AdaptiveRun:
         def sync(h):
             O.sync_ghosts_leaf(g, p, h, nbr, p.g_rhs, p.g_rhs, self.w.X, bool(self.w.lifted), ignore_filter=True)
         work = np.zeros((p.butcher.shape[0] + 1,) + self.u.shape)
-        dt = O.rk_generic(g, p, self.u, work, self.time, sync=sync)
+        mask = None if self.mask is None else np.stack([self.mask.block(int(l), x) for l, x in zip(g.level, g.ixyz)])   # createMask_tree
+        dt = O.rk_generic(g, p, self.u, work, self.time, mask=mask, sync=sync)
         self.time += dt
         self.iteration += 1
         return dt
+
+    def adaptive_inicond(self, inicond):
+        """setInitialCondition_tree with inicond_grid_from_file = "no" and adapt_inicond = 1 (setInitialCondition_tree.f90:97-130): the caller
+        starts from the equidistant grid on Jini with the initial condition set; then, until the number of blocks stops changing (at most
+        Jmax - Jmin times): refine everywhere, set the initial condition on the new grid, adapt_tree.  inicond(run) fills run.u."""
+        n_old, it = 9999999, 0
+        while self.grid.n != n_old and it < self.p.Jmax - self.Jmin:
+            n_old = self.grid.n
+            self.refine_tree("everywhere")
+            inicond(self)
+            self.adapt_tree()
+            it += 1
+        return it
 
     def step(self):
         """one pass of the main loop (main.f90:305-425)"""

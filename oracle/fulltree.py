@@ -380,12 +380,20 @@ def _fill_from_coarse(t: Tree, k: Key, d):
 def adapt_tree(p: O.Params, w: O.Wavelet, grid: O.Grid, u: np.ndarray, eps: float, Jmin: int = 1, norm=None, eps_norm: str = "Linfty",
                thresh_comp=None, level_ref: int = 0, force_maxlevel_dealiasing: bool = False, indicator: str = "threshold-state-vector",
                fd_half_width: int = 0, force_leaf_first: Optional[bool] = None, use_security_zone: bool = False,
-               use_coarse_extension: Optional[bool] = None):
+               use_coarse_extension: Optional[bool] = None, mask_keeps=None):
     """adapt_tree (adapt_tree.f90:11-260) for a lifted wavelet with the coarse extension, with or without the security zone.  Returns
     (new grid, new data [nb, nc, nz, ny, nx] with meaningful interiors, info dict)."""
     dim = grid.dim
     t = decompose_full_tree(p, w, grid, u, Jmin, fd_half_width, force_leaf_first, use_coarse_extension)
     st0 = threshold_full_tree(t, eps, norm, eps_norm, thresh_comp, level_ref, force_maxlevel_dealiasing, indicator)
+    if mask_keeps is not None and indicator != "everywhere":
+        # threshold_mask: coarseningIndicatorMask_tree (coarseningIndicator_tree.f90:290-331) -- a block whose mask function is not constant
+        # over its interior stays (status max(status, 0)); blocks on Jmax under force_maxlevel_dealiasing are not asked
+        for k in st0:
+            if force_maxlevel_dealiasing and k[0] == level_ref:
+                continue
+            if st0[k] == -1 and mask_keeps(k):
+                st0[k] = 0
     if use_security_zone and indicator != "everywhere":
         st0 = security_zone(t, st0, eps, norm, eps_norm, thresh_comp, level_ref, force_maxlevel_dealiasing)
     st = decide(t, st0, Jmin)

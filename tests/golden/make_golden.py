@@ -191,8 +191,39 @@ def three_vortices_adaptive():
         print(path, os.path.getsize(path), o["t10_u"].shape, o["t15_u"].shape, o["t15_iteration"])
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# TESTING/acm/acm_CDF44 (acm_cyl.ini): 2-D flow past a cylinder, Bs = 26, CDF44, Jmax = 6, adaptive every step, penalization (C_eta =
+# 1.34e-3, cosine-smoothed circle of radius 0.5 at (10, 10)), p-norm sponge, threshold_mask, force_maxlevel_dealiasing; the stored grids at
+# t = 0 (after the adaptive initial condition), 0.05 (iteration 40) and 0.1 (iteration 82).  Per time: block levels, zero-based block
+# coordinates, refinement statuses, iteration, time, strided samples of ux, uy, p and of the mask function.
+def cylinder_adaptive():
+    R = "/root/reference/TESTING/acm/acm_CDF44"
+    o = {}
+    for tag, key in (("000000000000", "t0"), ("000000050000", "t1"), ("000000100000", "t2")):
+        fields = []
+        for name in ("ux", "uy", "p", "mask"):
+            d = read_wabbit(os.path.join(R, f"{name}_{tag}.h5"))
+            Bs = int(d["attrs"]["block-size"][0])
+            ixy = np.rint(d["origin"][:, ::-1] / (d["spacing"][:, ::-1] * Bs)).astype(np.int32)
+            lvl = d["level"].ravel().astype(np.int32)
+            order = np.lexsort((ixy[:, 1], ixy[:, 0], lvl))
+            fields.append(d["blocks"][order][:, :Bs:2, :Bs:2])
+            o[f"{key}_ixy"] = ixy[order]
+            o[f"{key}_level"] = lvl[order]
+            o[f"{key}_status"] = d["refinement_status"].ravel().astype(np.int32)[order]
+            o[f"{key}_iteration"] = d["attrs"]["iteration"]
+            o[f"{key}_time"] = d["attrs"]["time"]
+        o[f"{key}_u"] = np.stack(fields[:3], axis=1)
+        o[f"{key}_mask"] = fields[3]
+        o[f"{key}_stride"] = np.array([2])
+    path = os.path.join(HERE, "cylinder_adapt_CDF44.npz")
+    np.savez_compressed(path, **o)
+    print(path, os.path.getsize(path), [o[f"{k}_u"].shape for k in ("t0", "t1", "t2")], o["t2_iteration"])
+
+
 if __name__ == "__main__":
     main()
     wavelet_blocks()
     three_vortices()
     three_vortices_adaptive()
+    cylinder_adaptive()
