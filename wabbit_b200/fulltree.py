@@ -351,7 +351,7 @@ class FullTree:
 
     # ------------------------------------------------------------------ adapt_tree
     def adapt(self, eps: Optional[float] = None, norm=None, eps_norm: str = "Linfty", thresh_comp=None, force_maxlevel_dealiasing: bool = False,
-              indicator: str = "threshold-state-vector", want_info: bool = True, use_security_zone: bool = False):
+              indicator: str = "threshold-state-vector", want_info: bool = True, use_security_zone: bool = False, mask_keeps=None):
         """adapt_tree (LIB/MESH/adapt_tree.f90:11-260) for a lifted wavelet with the coarse extension, optionally the security zone: full-tree
         decomposition and indicator, grid decision, coarse extension on the lasting coarse/fine interfaces, reconstruction of the leaves at
         those interfaces (all at once if Bs >= Ndep2, else level by level from coarse to fine), pruning to the leaves, blocks moved to
@@ -366,6 +366,15 @@ class FullTree:
             st0 = self.st.copy()
             if force_maxlevel_dealiasing:
                 st0[self.level == self.forest.Jmax] = -1
+        if mask_keeps is not None and indicator != "everywhere":
+            # threshold_mask (coarseningIndicatorMask_tree, coarseningIndicator_tree.f90:290-331): blocks of the tree whose mask function is
+            # not constant stay; mask_keeps(level, pos) is host geometry code
+            cand = st0 == -1
+            if force_maxlevel_dealiasing:
+                cand &= self.level != self.forest.Jmax
+            ci = np.flatnonzero(cand)
+            if len(ci):
+                st0[ci[np.asarray(mask_keeps(self.level[ci], self.pos[ci]), dtype=bool)]] = 0
         if use_security_zone and indicator != "everywhere":
             st0 = self.security_zone(st0, eps, norm, thresh_comp, force_maxlevel_dealiasing)
         t0 = time.perf_counter()

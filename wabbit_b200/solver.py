@@ -274,7 +274,7 @@ class WabbitGPU:
 
     def adapt_tree(self, forest: Forest, eps: Optional[float] = None, eps_normalized: bool = True, eps_norm: str = "Linfty",
                    Jmin: int = 1, force_maxlevel_dealiasing: bool = False, thresh_comp=None, useSecurityZone: Optional[bool] = None,
-                   full_tree: Optional[bool] = None):
+                   full_tree: Optional[bool] = None, mask_keeps=None):
         """adapt_tree (LIB/MESH/adapt_tree.f90:11) with indicator "threshold-state-vector".  full_tree (default for lifted wavelets): the
         reference's full-tree algorithm, with the coarse extension and the security zone for lifted wavelets (wabbit_b200/fulltree.py).
         Otherwise (default for unlifted wavelets CDFX0, which have no coarse extension and no security zone) one coarsening sweep:
@@ -301,9 +301,12 @@ class WabbitGPU:
             ft = FullTree(self, forest, Jmin=Jmin)
             sz = (lifted if self.params.useSecurityZone < 0 else bool(self.params.useSecurityZone)) if useSecurityZone is None else bool(useSecurityZone)
             new, _info = ft.adapt(eps=self.params.eps if eps is None else eps, norm=norm_l, eps_norm=eps_norm, thresh_comp=thresh_comp,
-                                  force_maxlevel_dealiasing=force_maxlevel_dealiasing, want_info=False, use_security_zone=sz)
+                                  force_maxlevel_dealiasing=force_maxlevel_dealiasing, want_info=False, use_security_zone=sz,
+                                  mask_keeps=mask_keeps)
             self.refinement_status = ft.leaf_status          # lgt_block(:, IDX_REFINE_STS) after adapt_tree, in the order of new.active(0)
             return new, n0, new.n_blocks
+        if mask_keeps is not None:
+            raise ValueError("adapt_tree: threshold_mask needs the full-tree algorithm")
         hvy, lvl, _, _ = forest.active(0)
         norm = None
         if eps_normalized:

@@ -18,7 +18,7 @@ from typing import Optional
 import numpy as np
 
 from .forest import Forest
-from .solver import WabbitGPU
+from .solver import HVY_MASK, WabbitGPU
 
 REF_UNSIGNIFICANT_STAY = 9      # module_globals.f90:28
 
@@ -69,8 +69,10 @@ class AdaptiveLoop:
     """One simulation with adapt_tree = 1 on one GPU."""
 
     def __init__(self, sol: WabbitGPU, forest: Forest, time: float = 0.0, iteration: int = 0, refinement_indicator: Optional[str] = None,
-                 thresh_comp=None):
+                 thresh_comp=None, mask=None, threshold_mask: bool = False):
+        """mask: host geometry object with fill(level, pos) -> hvy_mask rows and keeps(level, pos) -> bool (wabbit_b200.mask)"""
         self.sol, self.forest, self.time, self.iteration = sol, forest, time, iteration
+        self.mask, self.threshold_mask = mask, threshold_mask
         p = sol.params
         self.indicator = p.refinement_indicator if refinement_indicator is None else refinement_indicator
         self.thresh_comp = thresh_comp
@@ -80,7 +82,8 @@ class AdaptiveLoop:
     def adapt_tree(self):
         p = self.sol.params
         self.forest, n0, n1 = self.sol.adapt_tree(self.forest, eps=p.eps, eps_normalized=p.eps_normalized, eps_norm=p.eps_norm, Jmin=p.Jmin,
-                                                  force_maxlevel_dealiasing=p.force_maxlevel_dealiasing, thresh_comp=self.thresh_comp)
+                                                  force_maxlevel_dealiasing=p.force_maxlevel_dealiasing, thresh_comp=self.thresh_comp,
+                                                  mask_keeps=self.mask.keeps if (self.mask is not None and self.threshold_mask) else None)
         self.status = self.sol.refinement_status
         return n0, n1
 
@@ -93,8 +96,32 @@ class AdaptiveLoop:
         self.status = None
         return self.forest.n_blocks
 
+    def createMask_tree(self):
+        """createMask_tree on the current grid (2-D: always all parts, drawn directly): host geometry -> hvy_mask on the device"""
+        if self.mask is None:
+            return
+        hvy, lvl, pos, _ = self.forest.active(0)
+        host = np.zeros(self.sol.host_shape(self.sol.params.n_mask))
+        host[hvy - 1] = self.mask.fill(lvl, pos)
+        self.sol.upload(host, HVY_MASK, 0, hvy_ids=hvy)
+
+    def adaptive_inicond(self, set_inicond) -> int:
+        """setInitialCondition_tree (LIB/MESH/setInitialCondition_tree.f90:97-130) with adapt_inicond = 1 on an auto-generated grid: until the
+        number of blocks stops changing (at most Jmax - Jmin times) refine everywhere, set the initial condition, adapt_tree.
+        set_inicond(loop) uploads the initial condition for loop.forest."""
+        p = self.sol.params
+        n_old, it = 9999999, 0
+        while self.forest.n_blocks != n_old and it < p.Jmax - p.Jmin:
+            n_old = self.forest.n_blocks
+            self.forest = self.sol.refine_tree(self.forest, None)
+            set_inicond(self)
+            self.adapt_tree()
+            it += 1
+        return it
+
     def step(self) -> float:
         nb_rhs = self.refine_tree()
+        self.createMask_tree()
         self.time, self.iteration, dt = self.sol.timeStep_tree(self.time, self.iteration)
         self.adapt_tree()
         self.log.append((self.iteration, self.time, nb_rhs, self.forest.n_blocks, dt))
