@@ -110,6 +110,12 @@ class AdaptiveRun:
         assert self.eps_norm == "Linfty"
         it = (slice(None), slice(None)) + O.interior(self.p)
         n = np.abs(self.u[it]).max(axis=(0, 2, 3, 4))
+        if self.thresh_comp is not None:                                 # componentWiseNorm_tree.f90:119-163: 0 not computed, >= 2 joint
+            tc = np.asarray(self.thresh_comp)
+            n = np.where(tc == 0, -1.0, n)
+            for l in range(2, int(tc.max()) + 1):
+                if (tc == l).any():
+                    n[tc == l] = n[tc == l].max()
         n[n <= 1.0e-9] = 1.0
         return n
 

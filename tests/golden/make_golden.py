@@ -197,28 +197,35 @@ def three_vortices_adaptive():
 # t = 0 (after the adaptive initial condition), 0.05 (iteration 40) and 0.1 (iteration 82).  Per time: block levels, zero-based block
 # coordinates, refinement statuses, iteration, time, strided samples of ux, uy, p and of the mask function.
 def cylinder_adaptive():
-    R = "/root/reference/TESTING/acm/acm_CDF44"
-    o = {}
-    for tag, key in (("000000000000", "t0"), ("000000050000", "t1"), ("000000100000", "t2")):
-        fields = []
-        for name in ("ux", "uy", "p", "mask"):
-            d = read_wabbit(os.path.join(R, f"{name}_{tag}.h5"))
-            Bs = int(d["attrs"]["block-size"][0])
-            ixy = np.rint(d["origin"][:, ::-1] / (d["spacing"][:, ::-1] * Bs)).astype(np.int32)
-            lvl = d["level"].ravel().astype(np.int32)
-            order = np.lexsort((ixy[:, 1], ixy[:, 0], lvl))
-            fields.append(d["blocks"][order][:, :Bs:2, :Bs:2])
-            o[f"{key}_ixy"] = ixy[order]
-            o[f"{key}_level"] = lvl[order]
-            o[f"{key}_status"] = d["refinement_status"].ravel().astype(np.int32)[order]
-            o[f"{key}_iteration"] = d["attrs"]["iteration"]
-            o[f"{key}_time"] = d["attrs"]["time"]
-        o[f"{key}_u"] = np.stack(fields[:3], axis=1)
-        o[f"{key}_mask"] = fields[3]
-        o[f"{key}_stride"] = np.array([2])
-    path = os.path.join(HERE, "cylinder_adapt_CDF44.npz")
-    np.savez_compressed(path, **o)
-    print(path, os.path.getsize(path), [o[f"{k}_u"].shape for k in ("t0", "t1", "t2")], o["t2_iteration"])
+    """acm_CDF44 as described above; acm_CDF40: the same with the unlifted CDF40 (no coarse extension, no security zone);
+    acm_norm_CDF44: Jmax = 5, threshold_state_vector_component = 2 2 1 (joint norm of the velocity), one file at t = 0.2;
+    acm_significant_CDF44: Jmax = 5, refinement_indicator = significant, one file at t = 0.2"""
+    for case, tags in (("acm_CDF44", (("000000000000", "t0"), ("000000050000", "t1"), ("000000100000", "t2"))),
+                       ("acm_CDF40", (("000000000000", "t0"), ("000000050000", "t1"), ("000000100000", "t2"))),
+                       ("acm_norm_CDF44", (("000000000000", "t0"), ("000000200000", "t2"))),
+                       ("acm_significant_CDF44", (("000000000000", "t0"), ("000000200000", "t2")))):
+        R = "/root/reference/TESTING/acm/" + case
+        o = {}
+        for tag, key in tags:
+            fields = []
+            for name in ("ux", "uy", "p", "mask"):
+                d = read_wabbit(os.path.join(R, f"{name}_{tag}.h5"))
+                Bs = int(d["attrs"]["block-size"][0])
+                ixy = np.rint(d["origin"][:, ::-1] / (d["spacing"][:, ::-1] * Bs)).astype(np.int32)
+                lvl = d["level"].ravel().astype(np.int32)
+                order = np.lexsort((ixy[:, 1], ixy[:, 0], lvl))
+                fields.append(d["blocks"][order][:, :Bs:2, :Bs:2])
+                o[f"{key}_ixy"] = ixy[order]
+                o[f"{key}_level"] = lvl[order]
+                o[f"{key}_status"] = d["refinement_status"].ravel().astype(np.int32)[order]
+                o[f"{key}_iteration"] = d["attrs"]["iteration"]
+                o[f"{key}_time"] = d["attrs"]["time"]
+            o[f"{key}_u"] = np.stack(fields[:3], axis=1)
+            o[f"{key}_mask"] = fields[3]
+            o[f"{key}_stride"] = np.array([2])
+        path = os.path.join(HERE, case.replace("acm_", "cylinder_adapt_") + ".npz")
+        np.savez_compressed(path, **o)
+        print(path, os.path.getsize(path), [o[f"{k}_u"].shape for _, k in tags], o["t2_iteration"])
 
 
 if __name__ == "__main__":

@@ -29,14 +29,15 @@ def set_inicond(loop):
     loop.sol.upload(host, HVY_BLOCK, 0, hvy_ids=hvy)
 
 
-def make_loop():
-    p = Params(wavelet="CDF44", eps=CC.EPS, eps_normalized=True, eps_norm="Linfty", Jmin=CC.JMIN, force_maxlevel_dealiasing=True, adapt_tree=True,
-               refinement_indicator="everywhere", **CC.INI).finalize()
+def make_loop(case="CDF44"):
+    c = CC.CASES[case]
+    p = Params(wavelet=c["wavelet"], eps=CC.EPS, eps_normalized=True, eps_norm="Linfty", Jmin=CC.JMIN, force_maxlevel_dealiasing=True, adapt_tree=True,
+               refinement_indicator=c["indicator"], **CC.ini(case)).finalize()
     forest = Forest.uniform(2, CC.JMIN, Jmax=p.Jmax, max_blocks=MAXB)
     sol = WabbitGPU(p, max_blocks=MAXB)
-    sol.setup_wavelet("CDF44")
+    sol.setup_wavelet(c["wavelet"])
     sol.set_forest(forest)
-    loop = AdaptiveLoop(sol, forest, 0.0, 0, mask=CylinderMask2D(p), threshold_mask=True)
+    loop = AdaptiveLoop(sol, forest, 0.0, 0, mask=CylinderMask2D(p), threshold_mask=True, thresh_comp=c["thresh_comp"])
     set_inicond(loop)
     loop.adaptive_inicond(set_inicond)
     return loop
@@ -51,26 +52,29 @@ def state(loop):
     return lvl, pos, loop.status, u, loop.iteration, loop.time, loop.mask.chi(lvl, pos)
 
 
-def test_cylinder_fixture_2d():
-    gd = CC.gold()
-    loop = make_loop()
-    assert CC.compare(gd, "t0", *state(loop)) == 0.0
-    errs, seen = {}, 0
+@pytest.mark.parametrize("case", list(CC.CASES))
+def test_cylinder_fixture_2d(case):
+    c, gd = CC.CASES[case], CC.gold(case)
+    chk = case != "CDF40"      # see test_oracle_cylinder.py
+    loop = make_loop(case)
+    errs = {"t0": CC.compare(gd, "t0", *state(loop), check_status=chk)}
+    assert errs["t0"] == 0.0
+    stops = {k: t for k, t in c["files"].items() if t > 0.0}
     while loop.time < loop.sol.params.time_max:
         loop.step()
-        if abs(loop.time - 0.05) <= 1e-15:
-            errs["t1"] = CC.compare(gd, "t1", *state(loop))
-            seen += 1
-    errs["t2"] = CC.compare(gd, "t2", *state(loop))
-    print(f"\nacm_CDF44 cylinder on the GPU: {loop.iteration} adaptive steps, {loop.forest.n_blocks} blocks at t = {loop.time}, "
+        for k, t in stops.items():
+            if abs(loop.time - t) <= 1e-15:
+                errs[k] = CC.compare(gd, k, *state(loop), check_status=chk)
+    print(f"\nacm_{case} cylinder on the GPU: {loop.iteration} adaptive steps, {loop.forest.n_blocks} blocks at t = {loop.time}, "
           f"max |u - reference| = {errs}, blocks on the RHS grid max {max(r[2] for r in loop.log)}")
-    assert seen == 1 and max(errs.values()) <= 1e-11, errs
+    assert set(errs) == set(c["files"]) and max(errs.values()) <= 1e-11, errs
     loop.sol.close()
 
 
-def test_cylinder_lockstep_2d():
+@pytest.mark.parametrize("case", ["CDF44", "CDF40", "significant_CDF44"])
+def test_cylinder_lockstep_2d(case):
     from test_oracle_cylinder import make_run
-    loop, run = make_loop(), make_run()
+    loop, run = make_loop(case), make_run(case)
     g = run.p.g
     for _ in range(8):
         dt_g, dt_o = loop.step(), run.step()

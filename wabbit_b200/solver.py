@@ -296,6 +296,12 @@ class WabbitGPU:
             else:
                 norm_l = self.componentWiseNorm_tree((HVY_BLOCK, 0), "Linfty") if eps_normalized else None
             if norm_l is not None:
+                if thresh_comp is not None:                  # componentWiseNorm_tree.f90:119-163: 0 not computed, groups >= 2 share their norm
+                    tc = np.asarray(thresh_comp)
+                    norm_l = np.where(tc == 0, -1.0, norm_l)
+                    for l in range(2, int(tc.max()) + 1):
+                        if (tc == l).any():
+                            norm_l[tc == l] = norm_l[tc == l].max()
                 norm_l[norm_l <= 1.0e-9] = 1.0
             n0 = forest.n_blocks
             ft = FullTree(self, forest, Jmin=Jmin)

@@ -83,7 +83,8 @@ class AdaptiveLoop:
         p = self.sol.params
         self.forest, n0, n1 = self.sol.adapt_tree(self.forest, eps=p.eps, eps_normalized=p.eps_normalized, eps_norm=p.eps_norm, Jmin=p.Jmin,
                                                   force_maxlevel_dealiasing=p.force_maxlevel_dealiasing, thresh_comp=self.thresh_comp,
-                                                  mask_keeps=self.mask.keeps if (self.mask is not None and self.threshold_mask) else None)
+                                                  mask_keeps=self.mask.keeps if (self.mask is not None and self.threshold_mask) else None,
+                                                  full_tree=True)     # the reference's algorithm for every wavelet (adapt_tree.f90:11-260)
         self.status = self.sol.refinement_status
         return n0, n1
 
