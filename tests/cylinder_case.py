@@ -23,7 +23,7 @@ CASES = {
                   files={"t0": 0.0, "t1": 0.05, "t2": 0.1}, nb_rhs_max=640),
     # unlifted: useCoarseExtension = useSecurityZone = isLiftedWavelet = 0 -> adapt_tree keeps the original values
     "CDF40": dict(wavelet="CDF40", g=3, Jmax=6, thresh_comp=None, indicator="everywhere", time_max=0.1, write_time=0.05,
-                  files={"t0": 0.0, "t1": 0.05, "t2": 0.1}, nb_rhs_max=640),
+                  files={"t0": 0.0, "t1": 0.05, "t2": 0.1}, nb_rhs_max=604),
     # threshold_state_vector_component = 2 2 1: ux and uy thresholded together with their joint norm
     "norm_CDF44": dict(wavelet="CDF44", g=6, Jmax=5, thresh_comp=(2, 2, 1), indicator="everywhere", time_max=0.2, write_time=0.2,
                        files={"t0": 0.0, "t2": 0.2}, nb_rhs_max=None),
