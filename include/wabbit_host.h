@@ -43,6 +43,8 @@ int32_t whost_get_active(const whost_forest *f, int32_t rank, int32_t *hvy_activ
 /* hvy_neighbor(ld, 168) of a rank, ld = whost_n_active(f, rank) (hvy ids are 1..ld), Fortran column-major, lgt ids
  * (rank*max_blocks_per_rank + hvy), -1 = none */
 int32_t whost_get_neighbors(const whost_forest *f, int32_t rank, int32_t *hvy_neighbor);
+/* the same table without a copy: pointer to the forest's own storage (valid until whost_destroy), or NULL */
+const int32_t *whost_neighbors_ptr(const whost_forest *f, int32_t rank);
 /* 1 if every neighbour relation of every block is same-level */
 int32_t whost_is_uniform(const whost_forest *f);
 

@@ -239,6 +239,7 @@ def test_full_tree_light_data_matches_the_oracle(seed):
             Bs = (16, 16, 16)
             wavelet = "CDF44"
             discretization = "FD_4th_central"
+            useCoarseExtension = -1
 
         def wavelet_filter_width(self):
             return 6

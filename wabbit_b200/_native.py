@@ -91,6 +91,7 @@ HOST_SYMBOLS = {
     "whost_n_active": (C.c_int32, [C.c_void_p, C.c_int32]),
     "whost_get_active": (C.c_int32, [C.c_void_p, C.c_int32, _i32p, _i32p, _i32p, _i64p]),
     "whost_get_neighbors": (C.c_int32, [C.c_void_p, C.c_int32, _i32p]),
+    "whost_neighbors_ptr": (_i32p, [C.c_void_p, C.c_int32]),
     "whost_is_uniform": (C.c_int32, [C.c_void_p]),
     "whost_refine": (C.c_int32, [C.c_void_p, _i32p, C.c_int32, C.POINTER(C.c_void_p), _i32p, _i32p, _i32p, _i32p, _i32p, _i32p]),
     "whost_coarsen": (C.c_int32, [C.c_void_p, _i32p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), _i32p, _i32p, _i32p, _i32p, _i32p, _i32p]),

@@ -134,6 +134,39 @@ int32_t ensure_stage(wgpu_ctx *ctx, int64_t elems)
     return WGPU_OK;
 }
 
+// the (block, direction) lists of the stage kernel's level-jump face patches and room for the patches
+static int32_t upload_jump_lists(wgpu_ctx *ctx, const std::vector<int> &jump_blk, const std::vector<int> &jump_dir)
+{
+    const wgpu_config &c = ctx->cfg;
+    const int N = c.max_blocks, nj = (int)jump_blk.size();
+    int32_t rc;
+    if (nj > ctx->jump_cap) {
+        cudaFree(ctx->d_jump_blk);
+        cudaFree(ctx->d_jump_dir);
+        ctx->d_jump_blk = ctx->d_jump_dir = nullptr;
+        const int want = std::max(nj, std::min(6 * N, 2 * nj));
+        if ((rc = dmalloc(ctx, &ctx->d_jump_blk, (size_t)want))) return rc;
+        if ((rc = dmalloc(ctx, &ctx->d_jump_dir, (size_t)want))) return rc;
+        ctx->jump_cap = want;
+    }
+    const int H = c.fd == 2 ? 1 : (c.fd == 4 ? 2 : 3);
+    const size_t need = (size_t)std::max(nj, 1) * ctx->nc * H * c.Bs[0] * c.Bs[1];
+    if (need > ctx->jpool_cap) {
+        cudaFree(ctx->d_jpool);
+        ctx->d_jpool = nullptr;
+        ctx->dev_bytes -= (int64_t)ctx->jpool_cap * 8;
+        const size_t want = need + need / 2;
+        if ((rc = dmalloc(ctx, &ctx->d_jpool, want))) return rc;
+        ctx->jpool_cap = want;
+    }
+    if (nj) {
+        WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_jump_blk, jump_blk.data(), sizeof(int) * nj, cudaMemcpyHostToDevice, ctx->stream));
+        WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_jump_dir, jump_dir.data(), sizeof(int) * nj, cudaMemcpyHostToDevice, ctx->stream));
+        WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));   // the host vectors may go out of scope
+    }
+    return WGPU_OK;
+}
+
 // block lookup + level-jump patch lists of the current topology (needs wgpu_set_treecodes and wgpu_set_wavelet)
 int32_t upload_jump_tables(wgpu_ctx *ctx, const std::vector<int> &jump_blk, const std::vector<int> &jump_dir)
 {
@@ -150,6 +183,15 @@ int32_t upload_jump_tables(wgpu_ctx *ctx, const std::vector<int> &jump_blk, cons
         if (!coords) return fail(ctx, WGPU_ERR_ARG, "grid has level jumps: call wgpu_set_treecodes for the active blocks first");
     }
     if (!coords) return WGPU_OK;   // uniform grid without block positions: nothing that needs the lookup can be called
+    const int nj = (int)jump_blk.size();
+    int32_t rc;
+    // the lookup table depends on the registered block positions only (wgpu_set_treecodes), not on the active list: the passes of the
+    // full-tree adapt_tree change the active list many times per tree state and reuse it
+    if (!ctx->coords_dirty && ctx->d_hkeys && ctx->d_ixyz) {
+        if ((rc = upload_jump_lists(ctx, jump_blk, jump_dir))) return rc;
+        ctx->lookup_ready = true;
+        return WGPU_OK;
+    }
     // hash table (level, ix, iy, iz) -> block
     size_t cap = 64;
     // every block wgpu_set_treecodes listed is resident in HBM and can be a source: the active blocks, the halo copies, and blocks a
@@ -170,7 +212,6 @@ int32_t upload_jump_tables(wgpu_ctx *ctx, const std::vector<int> &jump_blk, cons
         keys[h] = key;
         vals[h] = b;
     }
-    int32_t rc;
     if (cap > ctx->hcap) {
         cudaFree(ctx->d_hkeys);
         cudaFree(ctx->d_hvals);
@@ -182,34 +223,12 @@ int32_t upload_jump_tables(wgpu_ctx *ctx, const std::vector<int> &jump_blk, cons
     }
     ctx->hmask = (unsigned)(cap - 1);
     if (!ctx->d_ixyz && (rc = dmalloc(ctx, &ctx->d_ixyz, (size_t)N * 3))) return rc;
-    const int nj = (int)jump_blk.size();
-    if (nj > ctx->jump_cap) {
-        cudaFree(ctx->d_jump_blk);
-        cudaFree(ctx->d_jump_dir);
-        ctx->d_jump_blk = ctx->d_jump_dir = nullptr;
-        const int want = std::max(nj, std::min(6 * N, 2 * nj));
-        if ((rc = dmalloc(ctx, &ctx->d_jump_blk, (size_t)want))) return rc;
-        if ((rc = dmalloc(ctx, &ctx->d_jump_dir, (size_t)want))) return rc;
-        ctx->jump_cap = want;
-    }
-    const int H = c.fd == 2 ? 1 : (c.fd == 4 ? 2 : 3);
-    const size_t need = (size_t)std::max(nj, 1) * ctx->nc * H * c.Bs[0] * c.Bs[1];
-    if (need > ctx->jpool_cap) {
-        cudaFree(ctx->d_jpool);
-        ctx->d_jpool = nullptr;
-        ctx->dev_bytes -= (int64_t)ctx->jpool_cap * 8;
-        const size_t want = need + need / 2;
-        if ((rc = dmalloc(ctx, &ctx->d_jpool, want))) return rc;
-        ctx->jpool_cap = want;
-    }
     WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_hkeys, keys.data(), cap * 8, cudaMemcpyHostToDevice, ctx->stream));
     WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_hvals, vals.data(), cap * 4, cudaMemcpyHostToDevice, ctx->stream));
     WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_ixyz, ctx->h_ixyz.data(), sizeof(int) * (size_t)N * 3, cudaMemcpyHostToDevice, ctx->stream));
-    if (nj) {
-        WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_jump_blk, jump_blk.data(), sizeof(int) * nj, cudaMemcpyHostToDevice, ctx->stream));
-        WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_jump_dir, jump_dir.data(), sizeof(int) * nj, cudaMemcpyHostToDevice, ctx->stream));
-    }
     WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));   // the host vectors above go out of scope
+    if ((rc = upload_jump_lists(ctx, jump_blk, jump_dir))) return rc;
+    ctx->coords_dirty = false;
     ctx->lookup_ready = true;
     return WGPU_OK;
 }
@@ -226,12 +245,13 @@ int32_t upload_wjump_tables(wgpu_ctx *ctx, const std::vector<int> &blk, const st
     const int F = std::max(std::max(-w.hd_lo, w.hd_hi), std::max(-w.hr_lo, w.hr_hi));
     ctx->wjump_depth = F;
     const int nj = (int)blk.size();
-    std::vector<int> wnbr(ctx->h_nbr);
+    const size_t r0 = (size_t)ctx->act_lo * WGPU_NDIR, r1 = (size_t)ctx->act_hi * WGPU_NDIR;   // rows of the active id range only
+    std::vector<int> wnbr(ctx->h_nbr.begin() + r0, ctx->h_nbr.begin() + r1);
     std::vector<long long> off(std::max(nj, 1));
     long long total = 0;
     for (int i = 0; i < nj; ++i) {
         const int d[3] = {dir[i] % 3 - 1, (dir[i] / 3) % 3 - 1, dir[i] / 9 - 1};
-        wnbr[(size_t)blk[i] * WGPU_NDIR + dir[i]] = -2 - i;
+        wnbr[(size_t)blk[i] * WGPU_NDIR + dir[i] - r0] = -2 - i;
         off[i] = total;
         total += (long long)ctx->nc * (d[0] ? F : Bs) * (d[1] ? F : Bs) * (c.dim == 3 ? (d[2] ? F : Bs) : 1);
     }
@@ -259,7 +279,7 @@ int32_t upload_wjump_tables(wgpu_ctx *ctx, const std::vector<int> &blk, const st
         if ((rc = dmalloc(ctx, &ctx->d_wpool, want))) return rc;
         ctx->wpool_cap = want;
     }
-    WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_wnbr, wnbr.data(), sizeof(int) * wnbr.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (!wnbr.empty()) WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_wnbr + r0, wnbr.data(), sizeof(int) * wnbr.size(), cudaMemcpyHostToDevice, ctx->stream));
     if (nj) {
         WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_wjump_blk, blk.data(), sizeof(int) * nj, cudaMemcpyHostToDevice, ctx->stream));
         WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_wjump_dir, dir.data(), sizeof(int) * nj, cudaMemcpyHostToDevice, ctx->stream));
@@ -313,6 +333,7 @@ int32_t wgpu_set_treecodes(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_a
         ctx->h_has_coords[hid - 1] = 1;
         ctx->h_tc_level[hid - 1] = (signed char)J;
     }
+    ctx->coords_dirty = true;
     return WGPU_OK;
 }
 
@@ -508,7 +529,19 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
     if (n_active > N) return fail(ctx, WGPU_ERR_ARG, "more active blocks than max_blocks");
     ctx->h_active.assign(n_active, 0);
     ctx->remote_faces.clear();
-    ctx->h_nbr.assign((size_t)N * WGPU_NDIR, -1);
+    // only the rows of the active blocks are read by the kernels: keep the range of active ids up to date, not the whole table (the passes
+    // of the full-tree adapt_tree name a few thousand blocks out of max_blocks many times per call)
+    int act_lo = N, act_hi = 0;
+    for (int k = 0; k < n_active; ++k) {
+        if (hvy_active[k] < 1 || hvy_active[k] > N) return fail(ctx, WGPU_ERR_ARG, "hvy_active entry out of range");
+        act_lo = std::min(act_lo, hvy_active[k] - 1);
+        act_hi = std::max(act_hi, hvy_active[k]);
+    }
+    if (n_active == 0) act_lo = act_hi = 0;
+    if (ctx->h_nbr.size() != (size_t)N * WGPU_NDIR) ctx->h_nbr.assign((size_t)N * WGPU_NDIR, -1);
+    else std::fill(ctx->h_nbr.begin() + (size_t)act_lo * WGPU_NDIR, ctx->h_nbr.begin() + (size_t)act_hi * WGPU_NDIR, -1);
+    ctx->act_lo = act_lo;
+    ctx->act_hi = act_hi;
     ctx->h_level.assign(N, 0);
     ctx->has_jumps = false;
     ctx->det_cached_for = nullptr;
@@ -686,13 +719,15 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
         if (!ai.empty()) WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_active_int, ai.data(), sizeof(int) * ai.size(), cudaMemcpyHostToDevice, ctx->stream));
         if (!ab.empty()) WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_active_bnd, ab.data(), sizeof(int) * ab.size(), cudaMemcpyHostToDevice, ctx->stream));
         WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_active, ctx->h_active.data(), sizeof(int) * n_active, cudaMemcpyHostToDevice, ctx->stream));
-        WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_nbr, ctx->h_nbr.data(), sizeof(int) * ctx->h_nbr.size(), cudaMemcpyHostToDevice, ctx->stream));
+        WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_nbr + (size_t)act_lo * WGPU_NDIR, ctx->h_nbr.data() + (size_t)act_lo * WGPU_NDIR,
+                                        sizeof(int) * (size_t)(act_hi - act_lo) * WGPU_NDIR, cudaMemcpyHostToDevice, ctx->stream));
         WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_level, ctx->h_level.data(), (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
         WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     } else if (n_active) {
         WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_active_int, ctx->h_active.data(), sizeof(int) * n_active, cudaMemcpyHostToDevice, ctx->stream));
         WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_active, ctx->h_active.data(), sizeof(int) * n_active, cudaMemcpyHostToDevice, ctx->stream));
-        WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_nbr, ctx->h_nbr.data(), sizeof(int) * ctx->h_nbr.size(), cudaMemcpyHostToDevice, ctx->stream));
+        WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_nbr + (size_t)act_lo * WGPU_NDIR, ctx->h_nbr.data() + (size_t)act_lo * WGPU_NDIR,
+                                        sizeof(int) * (size_t)(act_hi - act_lo) * WGPU_NDIR, cudaMemcpyHostToDevice, ctx->stream));
         WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->d_level, ctx->h_level.data(), (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
         WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     }

@@ -345,6 +345,12 @@ int32_t whost_get_neighbors(const whost_forest *f, int32_t rank, int32_t *hvy_ne
     return 0;
 }
 
+const int32_t *whost_neighbors_ptr(const whost_forest *f, int32_t rank)
+{
+    if (!f || rank < 0 || rank >= f->n_ranks) return nullptr;
+    return f->nbr[rank].data();
+}
+
 int32_t whost_is_uniform(const whost_forest *f) { return f && f->uniform ? 1 : 0; }
 
 // ---------------------------------------------------------------------------------------------------------------------

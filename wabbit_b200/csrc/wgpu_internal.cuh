@@ -155,6 +155,8 @@ struct wgpu_ctx {
     bool ignore_filter = false;        // wavelet-side syncs behave like sync_ghosts_tree(ignore_Filter = .true.)
     bool has_jumps = false;            // some active block has a coarser / finer neighbour
     bool lookup_ready = false;         // block lookup + coordinates of the current topology are on the device
+    int act_lo = 0, act_hi = 0;        // [act_lo, act_hi): range of block ids of the current active list (rows of nbr / wnbr that are kept up to date)
+    bool coords_dirty = true;          // wgpu_set_treecodes changed the block positions since the lookup table was last uploaded
     int *d_idbuf[3] = {nullptr, nullptr, nullptr};   // scratch id lists (refine / coarsen)
     size_t idbuf_cap[3] = {0, 0, 0};
     // Runge-Kutta step in flight

@@ -171,7 +171,21 @@ class FullTree:
         coarse extension acts.  All blocks are registered as data sources (wgpu_set_treecodes); a pass then only names its active list."""
         sol, dim = self.sol, self.dim
         ld = int(self.slots.max())
-        nbr = np.full((168, ld), -1, dtype=np.int32)
+        # one (168, max_blocks) table per solver, reused by every tree: rows 112..167 (finer relations) are never set here and stay -1
+        N = max(int(getattr(sol, "max_blocks", ld)), ld)
+        nbr = getattr(sol, "_ft_rows", None)
+        if nbr is None or nbr.shape[1] != N:
+            nbr = np.full((168, N), -1, dtype=np.int32)
+            try:
+                sol._ft_rows = nbr
+            except AttributeError:
+                pass
+        else:
+            nbr[:112, :getattr(sol, "_ft_rows_used", N)] = -1
+        try:
+            sol._ft_rows_used = ld
+        except AttributeError:
+            pass
         col = self.slots - 1
         leaf = self.is_leaf & (self.level > 0)
         for q, d in enumerate(self.dirs):
