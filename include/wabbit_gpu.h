@@ -145,6 +145,14 @@ int32_t wgpu_sync_ghosts(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t 
  *   filter (sync_ghosts_RHS_tree). */
 int32_t wgpu_set_ghost_filter(wgpu_ctx *ctx, int32_t ignore_filter);
 
+/* wgpu_set_mask_sphere: replaces, for a (translating) sphere, the per-stage createMask_tree -> CREATE_MASK_meta -> create_mask_3D_ACM ->
+ *   draw_sphere chain (LIB/TIME/RHS_wrapper.f90:51, LIB/MESH/createMask_tree.f90, LIB/EQUATION/ACMnew/create_mask.f90:6-174,
+ *   LIB/EQUATION/insects/module_geometry.f90 draw_sphere) and the hvy_mask reads of the penalization term (rhs_ACM.f90:1192-1195): the
+ *   stage kernel evaluates chi = step_cosine(|x - (center0 + velocity*t)| - radius, smoothing_width) / C_eta and u_s = velocity at the stage
+ *   time t = time + dt*rk_coeffs(j,1) itself, so no mask array is generated, uploaded or read.  enable = 0 returns to hvy_mask.
+ *   3-D, penalization = 1, FD_4th_central. */
+int32_t wgpu_set_mask_sphere(wgpu_ctx *ctx, int32_t enable, const double *center0, const double *velocity, double radius, double smoothing_width);
+
 /* wgpu_rhs: replaces RHS_wrapper (LIB/TIME/RHS_wrapper.f90:16-260) for physics "ACM-new":
  *   hvy_work(:,:,:,:,:,dst_slot) = RHS(src), src = hvy_block (src_slot = 0) or hvy_work(..., src_slot).
  *   Includes the integral_stage divergence guard (rhs_ACM.f90:133-146) -> WGPU_ERR_DIVERGED. */

@@ -75,13 +75,50 @@ class CylinderMask2D:
         return bool(((chi > 1.0e-12) & (chi < 1.0 - 1.0e-12)).any() or (chi.max() - chi.min()) > 1.0e-12)
 
 
+class SphereMask3D:
+    """A sphere drawn by draw_sphere (LIB/EQUATION/insects/module_geometry.f90, 'sphere-fixed' of create_mask_3D_ACM, create_mask.f90:6-174)
+    with cosine smoothing of width C_smooth * dx_min, optionally translating with a constant velocity (SURVEY 8d config 4's synthetic
+    stand-in for a moving body: centre(t) = centre0 + velocity * t, solid velocity u_s = velocity).  Components [chi, u_s(3), colour = 1,
+    sponge = 0]; chi on the interior points and the first upper ghost point, like draw_sphere's loop bounds."""
+
+    def __init__(self, p: O.Params, center=(0.5, 0.5, 0.5), radius: float = 0.15, velocity=(0.0, 0.0, 0.0), C_smooth: float = 1.5):
+        self.p, self.c0, self.R, self.v = p, np.asarray(center, dtype=np.float64), radius, np.asarray(velocity, dtype=np.float64)
+        self.h = C_smooth * min(2.0 ** (-p.Jmax) * p.domain[d] / float(p.Bs[d]) for d in range(3))
+
+    def chi(self, level: int, ixyz, time: float, n_extra: int = 0) -> np.ndarray:
+        p = self.p
+        c = self.c0 + self.v * time
+        ax = []
+        for d in range(3):
+            dx = 2.0 ** (-level) * p.domain[d] / float(p.Bs[d])
+            x0 = float(int(ixyz[d]) * p.Bs[d]) * dx
+            ax.append(np.arange(0, p.Bs[d] + n_extra, dtype=np.float64) * dx + x0)
+        dist = np.sqrt((ax[0][None, None, :] - c[0]) ** 2 + (ax[1][None, :, None] - c[1]) ** 2 + (ax[2][:, None, None] - c[2]) ** 2) - self.R
+        return step_cosine(dist, self.h)
+
+    def block(self, level: int, ixyz, time: float = 0.0) -> np.ndarray:
+        p, g = self.p, self.p.g
+        B = p.Bs
+        m = np.zeros((6, B[2] + 2 * g, B[1] + 2 * g, B[0] + 2 * g))
+        m[4] = 1.0
+        for a in range(3):
+            m[1 + a] = self.v[a]
+        m[0, g:g + B[2] + 1, g:g + B[1] + 1, g:g + B[0] + 1] = self.chi(level, ixyz, time, 1)
+        return m
+
+    def keeps(self, level: int, ixyz, time: float = 0.0) -> bool:
+        chi = self.chi(level, ixyz, time)
+        return bool(((chi > 1.0e-12) & (chi < 1.0 - 1.0e-12)).any() or (chi.max() - chi.min()) > 1.0e-12)
+
+
 class AdaptiveRun:
     """State of one adaptive simulation: leaf grid, ghosted data [nb, nc, nz, ny, nx], refinement status per leaf, time, iteration."""
 
     def __init__(self, p: O.Params, wavelet: str, grid: O.Grid, u: np.ndarray, time: float, iteration: int, eps: float, Jmin: int = 1,
                  refinement_indicator: str = "everywhere", use_coarse_extension: Optional[bool] = None,
                  use_security_zone: Optional[bool] = None, fd_half_width: int = 2, force_maxlevel_dealiasing: bool = False,
-                 thresh_comp=None, eps_normalized: bool = True, eps_norm: str = "Linfty", mask=None, threshold_mask: bool = False):
+                 thresh_comp=None, eps_normalized: bool = True, eps_norm: str = "Linfty", mask=None, threshold_mask: bool = False,
+                 mask_time_dependent: bool = False):
         self.p, self.w, self.grid, self.u = p, O.setup_wavelet(wavelet), grid, u
         self.time, self.iteration, self.eps, self.Jmin = time, iteration, eps, Jmin
         self.refinement_indicator = refinement_indicator
@@ -91,10 +128,14 @@ class AdaptiveRun:
         self.dealias = force_maxlevel_dealiasing
         self.thresh_comp = thresh_comp
         self.eps_normalized, self.eps_norm = eps_normalized, eps_norm
-        self.mask, self.threshold_mask = mask, threshold_mask        # mask: object with block(level, ixyz) and keeps(level, ixyz)
+        self.mask, self.threshold_mask = mask, threshold_mask        # mask: object with block(level, ixyz[, t]) and keeps(level, ixyz[, t])
+        self.mask_time_dependent = mask_time_dependent
         self.status = np.zeros(grid.n, dtype=np.int64)
         self.adapted_once = False
         self.log = []
+
+    def _mt(self):
+        return (self.time,) if self.mask_time_dependent else ()
 
     # ------------------------------------------------------------------------------------------------------------------
     def sync_ghosts_tree(self):
@@ -124,7 +165,7 @@ class AdaptiveRun:
         g, self.u, info = FT.adapt_tree(self.p, self.w, self.grid, self.u, self.eps, Jmin=self.Jmin, norm=self.norm(), eps_norm=self.eps_norm,
                                         thresh_comp=self.thresh_comp, level_ref=self.p.Jmax, force_maxlevel_dealiasing=self.dealias,
                                         fd_half_width=self.fd_half_width, use_security_zone=self.use_sz, use_coarse_extension=self.use_ce,
-                                        mask_keeps=(lambda k: self.mask.keeps(k[0], k[1:])) if (self.mask is not None and self.threshold_mask) else None)
+                                        mask_keeps=(lambda k: self.mask.keeps(k[0], k[1:], *self._mt())) if (self.mask is not None and self.threshold_mask) else None)
         self.grid = g
         st = info["status"]
         self.status = np.array([st[(int(l),) + tuple(int(v) for v in x)] for l, x in zip(g.level, g.ixyz)], dtype=np.int64)
@@ -205,8 +246,12 @@ class AdaptiveRun:
         def sync(h):
             O.sync_ghosts_leaf(g, p, h, nbr, p.g_rhs, p.g_rhs, self.w.X, bool(self.w.lifted), ignore_filter=True)
         work = np.zeros((p.butcher.shape[0] + 1,) + self.u.shape)
-        mask = None if self.mask is None else np.stack([self.mask.block(int(l), x) for l, x in zip(g.level, g.ixyz)])   # createMask_tree
-        dt = O.rk_generic(g, p, self.u, work, self.time, mask=mask, sync=sync)
+        mask, mask_at = None, None
+        if self.mask is not None and self.mask_time_dependent:
+            mask_at = lambda t: np.stack([self.mask.block(int(l), x, t) for l, x in zip(g.level, g.ixyz)])
+        elif self.mask is not None:
+            mask = np.stack([self.mask.block(int(l), x) for l, x in zip(g.level, g.ixyz)])                             # createMask_tree
+        dt = O.rk_generic(g, p, self.u, work, self.time, mask=mask, sync=sync, mask_at=mask_at)
         self.time += dt
         self.iteration += 1
         return dt

@@ -321,7 +321,7 @@ def _clip_dt(p: Params, dt: float, time: float, apply_dt_max: bool = True) -> fl
 
 
 def rk_generic(grid: Grid, p: Params, hvy: np.ndarray, work: np.ndarray, time: float,
-               mask: Optional[np.ndarray] = None, sync=None, fast: bool = False) -> float:
+               mask: Optional[np.ndarray] = None, sync=None, fast: bool = False, mask_at=None) -> float:
     """RungeKuttaGeneric (runge_kutta_generic.f90:50-154).  `work[slot]` are ghosted arrays like hvy.
 
     `sync(hvy)` performs sync_ghosts_RHS_tree with g_minus=g_plus=g_rhs; defaults to the same-level sync.
@@ -338,6 +338,8 @@ def rk_generic(grid: Grid, p: Params, hvy: np.ndarray, work: np.ndarray, time: f
     dt = calculate_time_step(grid, p, hvy, time)
     for b in range(grid.n):
         L.orc_rk_copy_interior(p.dim, p.g, Bs, nc, _p(work[0][b]), _p(hvy[b]))
+    if mask_at is not None:          # time-dependent mask: RHS_wrapper calls createMask_tree at the stage time (RHS_wrapper.f90:51)
+        mask = mask_at(time)
     rhs_tree(grid, p, hvy, work[1], mask, fast)
     for j in range(2, n):          # Fortran j = 2 .. size(rk,1)-1
         for b in range(grid.n):
@@ -349,6 +351,8 @@ def rk_generic(grid: Grid, p: Params, hvy: np.ndarray, work: np.ndarray, time: f
             for b in range(grid.n):
                 L.orc_rk_axpy_interior(p.dim, p.g, Bs, nc, _p(hvy[b]), dt, coef, _p(work[l - 1][b]))
         sync(hvy)
+        if mask_at is not None:
+            mask = mask_at(time + dt * rk[j - 1, 0])                     # t = time + dt*rk_coeffs(j,1), runge_kutta_generic.f90:122
         rhs_tree(grid, p, hvy, work[j], mask, fast)
     for b in range(grid.n):
         L.orc_rk_copy_interior(p.dim, p.g, Bs, nc, _p(hvy[b]), _p(work[0][b]))

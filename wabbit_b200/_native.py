@@ -52,6 +52,7 @@ GPU_SYMBOLS = {
     "wgpu_scatter_blocks": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _i32p, C.c_void_p]),
     "wgpu_halo_pointer": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), _i64p]),
     "wgpu_rk_stage_halo_pointer": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), _i64p]),
+    "wgpu_set_mask_sphere": (C.c_int32, [C.c_void_p, C.c_int32, _dp, _dp, C.c_double, C.c_double]),
     "wgpu_rhs": (C.c_int32, [C.c_void_p, C.c_double, C.c_int32, C.c_int32]),
     "wgpu_calculate_time_step": (C.c_int32, [C.c_void_p, C.c_double, _dp]),
     "wgpu_rk_step": (C.c_int32, [C.c_void_p, C.c_double, C.c_int32, _dp]),

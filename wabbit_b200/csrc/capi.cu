@@ -118,7 +118,18 @@ void fill_common_args(wgpu_ctx *ctx, StageArgs &a)
         a.mask = ctx->MASK;
         a.n_mask = c.n_mask;
     }
+    if (ctx->geom && c.penalization) {   // analytic mask: chi and u_s are evaluated in the kernel (the sponge, if any, still comes from hvy_mask)
+        a.geom = ctx->geom;
+        a.ixyz = ctx->d_ixyz;
+        for (int d = 0; d < 3; ++d) {
+            a.g_c0[d] = ctx->g_c0[d];
+            a.g_v[d] = ctx->g_v[d];
+        }
+        a.g_R = ctx->g_R;
+        a.g_h = ctx->g_h;
+    }
 }
+
 
 int32_t ensure_stage(wgpu_ctx *ctx, int64_t elems)
 {
@@ -310,6 +321,26 @@ int32_t upload_ids(wgpu_ctx *ctx, int which, const std::vector<int> &v)
 }  // namespace
 
 extern "C" {
+
+int32_t wgpu_set_mask_sphere(wgpu_ctx *ctx, int32_t enable, const double *center0, const double *velocity, double radius, double smoothing_width)
+{
+    if (!ctx) return WGPU_ERR_ARG;
+    if (!enable) {
+        ctx->geom = 0;
+        return WGPU_OK;
+    }
+    if (!center0 || !velocity || !(radius > 0.0) || !(smoothing_width > 0.0)) return fail(ctx, WGPU_ERR_ARG, "wgpu_set_mask_sphere: bad geometry");
+    if (ctx->cfg.dim != 3 || !ctx->cfg.penalization) return fail(ctx, WGPU_ERR_ARG, "wgpu_set_mask_sphere: needs dim = 3 and penalization = 1");
+    for (int d = 0; d < 3; ++d) {
+        ctx->g_c0[d] = center0[d];
+        ctx->g_v[d] = velocity[d];
+    }
+    ctx->g_R = radius;
+    ctx->g_h = smoothing_width;
+    ctx->geom = 1;
+    return WGPU_OK;
+}
+
 
 int32_t wgpu_set_treecodes(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_active, const int32_t *level, const int64_t *treecode)
 {
@@ -870,7 +901,6 @@ static int32_t check_flags(wgpu_ctx *ctx)
 
 int32_t wgpu_rhs(wgpu_ctx *ctx, double time, int32_t src_slot, int32_t dst_slot)
 {
-    (void)time;
     if (!ctx) return WGPU_ERR_ARG;
     int nc = 0;
     const double *src = src_slot == 0 ? ctx->U : array_ptr(ctx, WGPU_HVY_WORK, src_slot, &nc);
@@ -882,6 +912,8 @@ int32_t wgpu_rhs(wgpu_ctx *ctx, double time, int32_t src_slot, int32_t dst_slot)
     a.u_in = src;
     a.u0 = src;
     a.k_out = dst;
+    a.t0 = time;
+    a.t_cj = 0.0;
     int32_t rc = wgpu_launch_jump_fill(ctx, src);   // sync_ghosts_RHS_tree: restriction / prediction face patches
     if (rc) return rc;
     rc = wgpu_launch_stage(ctx, a, ctx->n_active);
@@ -1516,8 +1548,8 @@ static bool exchange_pending(wgpu_ctx *ctx) { return !ctx->remote_faces.empty();
 // ------------------------------------------------------------------------------------------------ Runge-Kutta, phase by phase
 int32_t wgpu_rk_begin(wgpu_ctx *ctx, double time)
 {
-    (void)time;
     if (!ctx) return WGPU_ERR_ARG;
+    ctx->rk_time = time;
     const wgpu_config &c = ctx->cfg;
     if (exchange_pending(ctx)) return fail(ctx, WGPU_ERR_ARG, "topology has neighbours on other ranks: call wgpu_set_exchange first");
     unsigned long long *cur = ctx->d_dtmin + ctx->dtmin_cur;
@@ -1583,6 +1615,9 @@ int32_t wgpu_rk_stage(wgpu_ctx *ctx, int32_t j, int32_t which)
     fill_common_args(ctx, a);
     a.u_in = uin;
     a.u0 = ctx->U;
+    a.t0 = ctx->rk_time;
+    a.t_cj = c.butcher[(size_t)(j - 1) * ld];                  // t = time + dt*rk_coeffs(j,1), runge_kutta_generic.f90:78,122
+    if (a.geom && !ctx->lookup_ready) return fail(ctx, WGPU_ERR_ARG, "analytic mask: call wgpu_set_treecodes + wgpu_set_topology first");
     const bool last = (j == s);
     // the final state may overwrite U in place (each thread reads its bases only at its own point, halos come
     // from the stage input) unless the stage input IS U (single-stage schemes): then go through UA and swap

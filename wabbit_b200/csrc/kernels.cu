@@ -278,7 +278,7 @@ __device__ __forceinline__ void load_plane(const StageArgs &a, const LoadTables<
     }
 }
 
-template <int FD, bool SKEW, int BS>
+template <int FD, bool SKEW, int BS, bool GEOM>
 __global__ void __launch_bounds__(BS *BS, (Tile<FD, BS>::SMEM <= 110 * 1024 ? 2 : 1))
     stage_kernel(const __grid_constant__ StageArgs a)
 {
@@ -309,6 +309,19 @@ __global__ void __launch_bounds__(BS *BS, (Tile<FD, BS>::SMEM <= 110 * 1024 ? 2 
     const bool base_u_global = a.u_out && a.u0 != a.u_in;
     const bool base_acc_global = a.acc_out && a.acc_in != a.u_in;
     const double c02 = a.c0 * a.c0;
+    // GEOM: the mask function of a translating sphere at this thread's (x, y) column (draw_sphere, LIB/EQUATION/insects/module_geometry.f90;
+    // step_cosine4, LIB/HELPER/module_helpers.f90): coordinates x = i*dx + x0 and the squared distance in the reference's operation order
+    double gxy2 = 0.0, gz0 = 0.0, gcz = 0.0;
+    if (GEOM) {
+        const double ts = __dadd_rn(a.t0, __dmul_rn(a.t_cj, *a.dt_ptr));
+        const double cx = __dadd_rn(a.g_c0[0], __dmul_rn(a.g_v[0], ts)), cy = __dadd_rn(a.g_c0[1], __dmul_rn(a.g_v[1], ts));
+        gcz = __dadd_rn(a.g_c0[2], __dmul_rn(a.g_v[2], ts));
+        const double x = __dadd_rn(__dmul_rn((double)tx, dx), __dmul_rn((double)(a.ixyz[3 * b] * BS), dx));
+        const double y = __dadd_rn(__dmul_rn((double)ty, dy), __dmul_rn((double)(a.ixyz[3 * b + 1] * BS), dy));
+        gz0 = __dmul_rn((double)(a.ixyz[3 * b + 2] * BS), dz);
+        const double ex = __dsub_rn(x, cx), ey = __dsub_rn(y, cy);
+        gxy2 = __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
+    }
 
     // prologue: planes 0 .. 2H+PF-1 in flight
 #pragma unroll 1
@@ -380,7 +393,17 @@ __global__ void __launch_bounds__(BS *BS, (Tile<FD, BS>::SMEM <= 110 * 1024 ? 2 
             const double u = ctr[0], v = ctr[1], w = ctr[2], p = ctr[3];
             double penal[3] = {0.0, 0.0, 0.0};
             const long long g0 = ((long long)b * a.n_mask) * CS + (long long)z * BS * BS + ty * BS + tx;
-            if (a.mask) {
+            if (GEOM) {
+                const double ez = __dsub_rn(__dadd_rn(__dmul_rn((double)z, dz), gz0), gcz);
+                const double dist = __dsub_rn(sqrt(__dadd_rn(gxy2, __dmul_rn(ez, ez))), a.g_R);
+                double m = 0.0;
+                if (dist <= -a.g_h) m = 1.0;
+                else if (dist < a.g_h) m = 0.5 * (1.0 + cos((dist + a.g_h) * 3.14159265358979323846 / (2.0 * a.g_h)));
+                const double chi = m * a.C_eta_inv;
+                penal[0] = -chi * (u - a.g_v[0]);
+                penal[1] = -chi * (v - a.g_v[1]);
+                penal[2] = -chi * (w - a.g_v[2]);
+            } else if (a.mask) {
                 // chi = mask(1) * C_eta_apply_inv(int(mask(5)))   rhs_ACM.f90:1192-1195
                 const int color = (int)a.mask[g0 + 4 * CS];
                 const double chi = a.mask[g0] * (color == 0 ? 0.0 : a.C_eta_inv);
@@ -772,12 +795,20 @@ int32_t launch_stage_t(wgpu_ctx *ctx, const StageArgs &a, int n_blocks)
     using T = Tile<FD, BS>;
     static bool configured = false;
     if (!configured) {
-        WGPU_CHECK(ctx, cudaFuncSetAttribute(stage_kernel<FD, SKEW, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
+        WGPU_CHECK(ctx, cudaFuncSetAttribute(stage_kernel<FD, SKEW, BS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
+        if (FD == 4) WGPU_CHECK(ctx, cudaFuncSetAttribute(stage_kernel<FD, SKEW, BS, (FD == 4)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
         configured = true;
     }
     const bool prof = ctx->profiling && ctx->prof_n < (int)ctx->prof_ev.size() / 2;
     if (prof) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], ctx->stream);
-    stage_kernel<FD, SKEW, BS><<<n_blocks, T::NT, T::SMEM, ctx->stream>>>(a);
+    if (a.geom) {
+        if (FD != 4) {
+            ctx->err = "analytic mask: the stage kernel is instantiated for FD_4th_central only";
+            return WGPU_ERR_UNSUPPORTED;
+        }
+        stage_kernel<FD, SKEW, BS, (FD == 4)><<<n_blocks, T::NT, T::SMEM, ctx->stream>>>(a);
+    } else
+        stage_kernel<FD, SKEW, BS, false><<<n_blocks, T::NT, T::SMEM, ctx->stream>>>(a);
     if (prof) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n++ + 1], ctx->stream);
     ctx->launches++;
     WGPU_CHECK(ctx, cudaGetLastError());

@@ -69,6 +69,11 @@ struct StageArgs {
     double CFL;
     int *diverged;                   // set to 1 if any |u_in| > 1e12
     int dim_min_axes;                // number of axes entering minval(dx(1:dim))
+    // analytic mask (wgpu_set_mask_sphere): the penalization term of a translating sphere evaluated in the kernel instead of read from hvy_mask
+    int geom;                        // 0: mask arrays, 1: sphere
+    const int *ixyz;                 // [max_blocks][3] block coordinates on their level
+    double g_c0[3], g_v[3], g_R, g_h;
+    double t0, t_cj;                 // stage time = t0 + t_cj * dt
 };
 
 struct wgpu_ctx {
@@ -156,12 +161,15 @@ struct wgpu_ctx {
     bool has_jumps = false;            // some active block has a coarser / finer neighbour
     bool lookup_ready = false;         // block lookup + coordinates of the current topology are on the device
     int act_lo = 0, act_hi = 0;        // [act_lo, act_hi): range of block ids of the current active list (rows of nbr / wnbr that are kept up to date)
+    int geom = 0;                      // analytic mask geometry (0 none, 1 sphere) and its parameters
+    double g_c0[3] = {0, 0, 0}, g_v[3] = {0, 0, 0}, g_R = 0, g_h = 1;
     bool coords_dirty = true;          // wgpu_set_treecodes changed the block positions since the lookup table was last uploaded
     int *d_idbuf[3] = {nullptr, nullptr, nullptr};   // scratch id lists (refine / coarsen)
     size_t idbuf_cap[3] = {0, 0, 0};
     // Runge-Kutta step in flight
     const double *rk_uin = nullptr;
     int rk_next_stage = 0;
+    double rk_time = 0.0;              // time at the start of the step in flight (stage times of the analytic mask)
     bool rk_subdiag = false;
 
     // scalars

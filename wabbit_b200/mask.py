@@ -63,3 +63,43 @@ class CylinderMask2D:
         not constant over the block's interior"""
         c = self.chi(level, pos).reshape(len(level), -1)
         return ((c > 1.0e-12) & (c < 1.0 - 1.0e-12)).any(axis=1) | ((c.max(axis=1) - c.min(axis=1)) > 1.0e-12)
+
+
+class SphereMask3D:
+    """A sphere (draw_sphere, 'sphere-fixed' of create_mask_3D_ACM) with cosine smoothing, optionally translating with a constant velocity
+    (SURVEY 8d config 4's synthetic moving body: centre(t) = centre0 + velocity * t, u_s = velocity).  On the device the mask is evaluated
+    inside the stage kernel (`attach`: wgpu_set_mask_sphere) -- nothing is generated, uploaded or read per stage; the host only needs
+    `keeps` for threshold_mask (light data)."""
+    analytic = True
+
+    def __init__(self, p: Params, center=(0.5, 0.5, 0.5), radius: float = 0.15, velocity=(0.0, 0.0, 0.0), C_smooth: float = 1.5):
+        if p.dim != 3:
+            raise ValueError("SphereMask3D is three-dimensional")
+        self.p, self.c0, self.R, self.v = p, np.asarray(center, dtype=np.float64), radius, np.asarray(velocity, dtype=np.float64)
+        self.h = C_smooth * min(2.0 ** (-p.Jmax) * p.domain[d] / float(p.Bs[d]) for d in range(3))
+
+    def attach(self, sol):
+        sol.set_mask_sphere(self.c0, self.v, self.R, self.h)
+
+    def keeps(self, level, pos, time: float = 0.0) -> np.ndarray:
+        """threshold_mask: True where the mask function varies over the block's interior.  Blocks whose bounding box does not come within
+        the smoothing width of the sphere's surface are constant and are skipped; the others are evaluated point by point."""
+        p = self.p
+        level, pos = np.asarray(level), np.asarray(pos)
+        c = self.c0 + self.v * time
+        n = len(level)
+        dx = np.stack([2.0 ** (-level.astype(np.float64)) * p.domain[d] / float(p.Bs[d]) for d in range(3)], axis=1)
+        lo = pos[:, :3] * np.asarray(p.Bs[:3])[None, :] * dx
+        hi = lo + (np.asarray(p.Bs[:3])[None, :] - 1) * dx
+        near = np.clip(c[None, :], lo, hi)                                        # closest / farthest lattice-box points to the centre
+        far = np.where(np.abs(lo - c[None, :]) > np.abs(hi - c[None, :]), lo, hi)
+        dmin = np.sqrt(((near - c[None, :]) ** 2).sum(axis=1)) - self.R
+        dmax = np.sqrt(((far - c[None, :]) ** 2).sum(axis=1)) - self.R
+        cand = np.flatnonzero((dmin < self.h + dx.max(axis=1)) & (dmax > -self.h - dx.max(axis=1)))
+        out = np.zeros(n, bool)
+        for i in cand:
+            ax = [np.arange(p.Bs[d], dtype=np.float64) * dx[i, d] + float(int(pos[i, d]) * p.Bs[d]) * dx[i, d] for d in range(3)]
+            dist = np.sqrt((ax[0][None, None, :] - c[0]) ** 2 + (ax[1][None, :, None] - c[1]) ** 2 + (ax[2][:, None, None] - c[2]) ** 2) - self.R
+            chi = _step_cosine(dist, self.h)
+            out[i] = bool(((chi > 1.0e-12) & (chi < 1.0 - 1.0e-12)).any() or (chi.max() - chi.min()) > 1.0e-12)
+        return out

@@ -151,6 +151,17 @@ class WabbitGPU:
         filter of a lifted wavelet in download(g_sync>0) / waveletDecomposition_tree / refine_tree, True = plain decimation."""
         self._check(self._lib.wgpu_set_ghost_filter(self._ctx, int(bool(ignore_filter))))
 
+    def set_mask_sphere(self, center0=None, velocity=(0.0, 0.0, 0.0), radius: float = 0.0, smoothing_width: float = 0.0):
+        """analytic penalization mask of a (translating) sphere evaluated inside the stage kernel (wgpu_set_mask_sphere); center0 = None
+        switches back to the hvy_mask array"""
+        dp = C.POINTER(C.c_double)
+        if center0 is None:
+            self._check(self._lib.wgpu_set_mask_sphere(self._ctx, 0, None, None, 0.0, 0.0))
+            return
+        c = np.ascontiguousarray(center0, dtype=np.float64)
+        v = np.ascontiguousarray(velocity, dtype=np.float64)
+        self._check(self._lib.wgpu_set_mask_sphere(self._ctx, 1, c.ctypes.data_as(dp), v.ctypes.data_as(dp), float(radius), float(smoothing_width)))
+
     # ------------------------------------------------------------------ reference routines
     def sync_ghosts_RHS_tree(self, g_minus: Optional[int] = None, g_plus: Optional[int] = None):
         """synchronize_ghosts_generic.f90:155-174"""

@@ -73,6 +73,9 @@ class AdaptiveLoop:
         """mask: host geometry object with fill(level, pos) -> hvy_mask rows and keeps(level, pos) -> bool (wabbit_b200.mask)"""
         self.sol, self.forest, self.time, self.iteration = sol, forest, time, iteration
         self.mask, self.threshold_mask = mask, threshold_mask
+        self.mask_time_dependent = mask is not None and bool(np.any(getattr(mask, "v", 0.0)))
+        if mask is not None and getattr(mask, "analytic", False):
+            mask.attach(sol)                                 # evaluated inside the stage kernel: no hvy_mask traffic
         p = sol.params
         self.indicator = p.refinement_indicator if refinement_indicator is None else refinement_indicator
         self.thresh_comp = thresh_comp
@@ -83,10 +86,15 @@ class AdaptiveLoop:
         p = self.sol.params
         self.forest, n0, n1 = self.sol.adapt_tree(self.forest, eps=p.eps, eps_normalized=p.eps_normalized, eps_norm=p.eps_norm, Jmin=p.Jmin,
                                                   force_maxlevel_dealiasing=p.force_maxlevel_dealiasing, thresh_comp=self.thresh_comp,
-                                                  mask_keeps=self.mask.keeps if (self.mask is not None and self.threshold_mask) else None,
+                                                  mask_keeps=self._mask_keeps() if (self.mask is not None and self.threshold_mask) else None,
                                                   full_tree=True)     # the reference's algorithm for every wavelet (adapt_tree.f90:11-260)
         self.status = self.sol.refinement_status
         return n0, n1
+
+    def _mask_keeps(self):
+        if self.mask_time_dependent:
+            return lambda level, pos: self.mask.keeps(level, pos, self.time)
+        return self.mask.keeps
 
     def refine_tree(self):
         ind = self.indicator
@@ -99,7 +107,7 @@ class AdaptiveLoop:
 
     def createMask_tree(self):
         """createMask_tree on the current grid (2-D: always all parts, drawn directly): host geometry -> hvy_mask on the device"""
-        if self.mask is None:
+        if self.mask is None or getattr(self.mask, "analytic", False):
             return
         hvy, lvl, pos, _ = self.forest.active(0)
         host = np.zeros(self.sol.host_shape(self.sol.params.n_mask))
