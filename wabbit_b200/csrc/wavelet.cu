@@ -311,7 +311,7 @@ __device__ __forceinline__ void pair_out(const double (&w)[2 * F + 2], double &o
         for (int k = -HDH; k <= HDH; ++k) {          // scaling coefficient at o: HD
             const double c = cdf_HD(X, Y, k);
             if (c != 0.0) {
-                const double t = __dmul_rn(w[F + k], c);
+                const double t = c == 1.0 ? w[F + k] : __dmul_rn(w[F + k], c);   // x*1 == x exactly
                 s = first ? t : __dadd_rn(s, t);
                 first = false;
             }
@@ -323,7 +323,7 @@ __device__ __forceinline__ void pair_out(const double (&w)[2 * F + 2], double &o
         for (int k = -HRH; k <= HRH; ++k) {          // wavelet coefficient at o+1: GD
             const double c = cdf_GD(X, k);
             if (c != 0.0) {
-                const double t = __dmul_rn(w[F + 1 + k], c);
+                const double t = c == 1.0 ? w[F + 1 + k] : __dmul_rn(w[F + 1 + k], c);
                 s = first ? t : __dadd_rn(s, t);
                 first = false;
             }
@@ -335,7 +335,7 @@ __device__ __forceinline__ void pair_out(const double (&w)[2 * F + 2], double &o
             double s0 = 0.0, s1 = 0.0;
 #pragma unroll
             for (int k = -HRH; k <= HRH; ++k)
-                if (((k + p) & 1) == 0) s0 = __dadd_rn(s0, __dmul_rn(w[F + p + k], cdf_HR(X, k)));
+                if (((k + p) & 1) == 0) s0 = __dadd_rn(s0, cdf_HR(X, k) == 1.0 ? w[F + p + k] : __dmul_rn(w[F + p + k], cdf_HR(X, k)));
 #pragma unroll
             for (int k = -HDH; k <= HDH; ++k)
                 if (((k + p) & 1) != 0) s1 = __dadd_rn(s1, __dmul_rn(w[F + p + k], cdf_GR(X, Y, k)));
@@ -357,7 +357,7 @@ __device__ __forceinline__ void pair_out_one(const double (&w)[2 * F + 2], doubl
             for (int k = -HDH; k <= HDH; ++k) {
                 const double c = cdf_HD(X, Y, k);
                 if (c != 0.0) {
-                    const double t = __dmul_rn(w[F + k], c);
+                    const double t = c == 1.0 ? w[F + k] : __dmul_rn(w[F + k], c);   // x*1 == x exactly
                     s = first ? t : __dadd_rn(s, t);
                     first = false;
                 }
@@ -367,7 +367,7 @@ __device__ __forceinline__ void pair_out_one(const double (&w)[2 * F + 2], doubl
             for (int k = -HRH; k <= HRH; ++k) {
                 const double c = cdf_GD(X, k);
                 if (c != 0.0) {
-                    const double t = __dmul_rn(w[F + 1 + k], c);
+                    const double t = c == 1.0 ? w[F + 1 + k] : __dmul_rn(w[F + 1 + k], c);
                     s = first ? t : __dadd_rn(s, t);
                     first = false;
                 }
@@ -378,7 +378,7 @@ __device__ __forceinline__ void pair_out_one(const double (&w)[2 * F + 2], doubl
         double s0 = 0.0, s1 = 0.0;
 #pragma unroll
         for (int k = -HRH; k <= HRH; ++k)
-            if (((k + P) & 1) == 0) s0 = __dadd_rn(s0, __dmul_rn(w[F + P + k], cdf_HR(X, k)));
+            if (((k + P) & 1) == 0) s0 = __dadd_rn(s0, cdf_HR(X, k) == 1.0 ? w[F + P + k] : __dmul_rn(w[F + P + k], cdf_HR(X, k)));
 #pragma unroll
         for (int k = -HDH; k <= HDH; ++k)
             if (((k + P) & 1) != 0) s1 = __dadd_rn(s1, __dmul_rn(w[F + P + k], cdf_GR(X, Y, k)));
@@ -395,7 +395,7 @@ struct FastCfg {
     static constexpr int NT = ((BS * BS + 31) / 32) * 32;   // one thread per (x, y) column of the block
     static constexpr int NLD = (F % 2 == 0) ? N * (N / 2) : N * N;   // 16-byte chunks (F even) or 8-byte elements per input plane
     static constexpr int LPT = (NLD + NT - 1) / NT;   // loads per thread and plane
-    static constexpr size_t SMEM = sizeof(double) * ((size_t)2 * N * N + (size_t)2 * N * BS);
+    static constexpr size_t SMEM = sizeof(double) * ((size_t)4 * N * N + (size_t)2 * N * BS);   // two plane pairs in flight + the x-pass rows of a pair
 };
 
 // One CTA per (block, component).  Input planes (xy halo included) stream through a double buffer (cp.async); the x pass
@@ -404,7 +404,7 @@ struct FastCfg {
 // renaming), from which the z pass emits a (scaling, wavelet) output pair every second plane -- no shared-memory traffic for z.
 // Threads are mapped to columns so that a warp has one y parity (all scaling rows or all wavelet rows: no divergence).
 #ifndef WFAST_MINB
-#define WFAST_MINB 1   // minimum resident CTAs per SM requested for Bs = 16 (register cap); 1 = let ptxas choose (64 registers, 4 CTAs)
+#define WFAST_MINB 3   // minimum resident CTAs per SM requested for Bs = 16 (register cap <= 80): measured best for the two-planes-per-barrier loop
 #endif
 template <int X, int Y, int BS, bool INV>
 __global__ void __launch_bounds__(FastCfg<X, Y, BS, INV>::NT, (BS == 16 ? WFAST_MINB : 1)) wavelet_fast_kernel(const double *__restrict__ src, double *__restrict__ dst,
@@ -415,8 +415,8 @@ __global__ void __launch_bounds__(FastCfg<X, Y, BS, INV>::NT, (BS == 16 ? WFAST_
     using C = FastCfg<X, Y, BS, INV>;
     constexpr int F = C::F, N = C::N, R = C::R, NT = C::NT, LPT = C::LPT, HALF = BS * BS / 2;
     extern __shared__ __align__(16) double sm[];
-    double *in0 = sm;                       // [2][N*N]
-    double *xs0 = in0 + 2 * N * N;          // [2][N][BS]
+    double *in0 = sm;                       // [2 pairs][2 planes][N*N]
+    double *xs0 = in0 + 4 * N * N;          // [2 planes][N][BS]
     // source of the ghost region of each direction: pointer such that the point with neighbour-local coordinates (lx, ly, lz)
     // sits at ptr + lz*sz + ly*sy + lx -- the neighbour's interior (same level), or a patch of the wavelet jump pool (level
     // jumps: decimated / predicted values in the layout of the ghost region), or null (no neighbour)
@@ -457,6 +457,16 @@ __global__ void __launch_bounds__(FastCfg<X, Y, BS, INV>::NT, (BS == 16 ? WFAST_
         ld_dir[j] = (dy + 1) * 3 + (dx + 1);
     }
     __syncthreads();
+    // the planes of the block's own z range (dz = 0: BS of the N planes) read through per-thread pointers prepared once
+    const double *ld_g0[LPT];
+    int ld_sz0[LPT];
+#pragma unroll
+    for (int j = 0; j < LPT; ++j) {
+        const int D = 9 + ld_dir[j];
+        const double *base = ld_dst[j] >= 0 ? s_ptr[D] : nullptr;
+        ld_g0[j] = base ? base + (ld_src[j] >> 8) * s_sy[D] + (ld_src[j] & 255) : nullptr;
+        ld_sz0[j] = s_sz[D];
+    }
 
     auto load_plane = [&](int zp, double *dstp) {
         const int dz = zp < 0 ? -1 : (zp >= BS ? 1 : 0);
@@ -464,12 +474,16 @@ __global__ void __launch_bounds__(FastCfg<X, Y, BS, INV>::NT, (BS == 16 ? WFAST_
 #pragma unroll
         for (int j = 0; j < LPT; ++j) {
             if (ld_dst[j] < 0) continue;
-            const int D = (dz + 1) * 9 + ld_dir[j];
-            const double *base = s_ptr[D];
             double *d = dstp + ld_dst[j];
-            if (base) {
+            const double *g;
+            if (dz == 0) g = ld_g0[j] ? ld_g0[j] + lz * ld_sz0[j] : nullptr;
+            else {
+                const int D = (dz + 1) * 9 + ld_dir[j];
+                const double *base = s_ptr[D];
+                g = base ? base + lz * s_sz[D] + (ld_src[j] >> 8) * s_sy[D] + (ld_src[j] & 255) : nullptr;
+            }
+            if (g) {
                 const unsigned sa = (unsigned)__cvta_generic_to_shared(d);
-                const double *g = base + lz * s_sz[D] + (ld_src[j] >> 8) * s_sy[D] + (ld_src[j] & 255);
                 if (F % 2 == 0) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(g) : "memory");
                 else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(g) : "memory");
             } else {
@@ -486,34 +500,41 @@ __global__ void __launch_bounds__(FastCfg<X, Y, BS, INV>::NT, (BS == 16 ? WFAST_
     double win[R];                          // y-pass results of planes zp-R+1 .. zp of this column; plane z sits in win[(z + F) % R]
 #pragma unroll
     for (int j = 0; j < R; ++j) win[j] = 0.0;
-    double m0 = 0.0, m1 = 0.0;              // Linfty detail of this (block, component), see below
+    double m0 = 0.0;                        // Linfty detail of this (block, component), see below
+    const bool pure_col = !(cx & 1) && !(cy & 1);   // o0 of this column is a pure scaling coefficient: not a detail
     double *outc = dst + ((long long)b * nc + c) * CS + cy * BS + cx;
 
     load_plane(-F, in0);
+    load_plane(-F + 1, in0 + N * N);
     cp_async_commit();
-    // plane loop in rounds of R planes, the round fully unrolled: window slots, buffer parities and the z ordering are
-    // compile-time (R is even and q0 is a multiple of R)
+    // plane loop, two planes per barrier pair (N and R are even): x pass of both planes, barrier, y pass of both planes into the register
+    // window, z pass.  Rounds of R planes are fully unrolled so that the window slots and the z ordering are compile-time.
 #pragma unroll 1
     for (int q0 = 0; q0 < N; q0 += R) {
 #pragma unroll
-    for (int jq = 0; jq < R; ++jq) {
+    for (int jq = 0; jq < R; jq += 2) {
         const int q = q0 + jq;
         if (q >= N) break;
         const int zp = q - F;
-        const double *cur = in0 + (jq & 1) * N * N;
-        double *xs = xs0 + (jq & 1) * N * BS;
-        if (q + 1 < N) load_plane(zp + 1, in0 + ((jq + 1) & 1) * N * N);
+        const int pp = (q >> 1) & 1;
+        const double *cur = in0 + pp * 2 * N * N;
+        if (q + 2 < N) {
+            double *nxt = in0 + (pp ^ 1) * 2 * N * N;
+            load_plane(zp + 2, nxt);
+            load_plane(zp + 3, nxt + N * N);
+        }
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
-        // x: rows y = -F .. BS+F-1, output pairs at interior x
+        // x: rows y = -F .. BS+F-1 of both planes, output pairs at interior x
 #pragma unroll
-        for (int i0 = 0; i0 < N * (BS / 2); i0 += NT) {
+        for (int i0 = 0; i0 < 2 * N * (BS / 2); i0 += NT) {
             const int i = i0 + tid;
-            if (i < N * (BS / 2)) {
-                const int r = i / (BS / 2), o = 2 * (i % (BS / 2));
+            if (i < 2 * N * (BS / 2)) {
+                const int pl = i / (N * (BS / 2)), ii = i % (N * (BS / 2));
+                const int r = ii / (BS / 2), o = 2 * (ii % (BS / 2));
                 double w[2 * F + 2];
-                const double2 *p2 = reinterpret_cast<const double2 *>(cur + r * N + o);
+                const double2 *p2 = reinterpret_cast<const double2 *>(cur + pl * N * N + r * N + o);
 #pragma unroll
                 for (int j = 0; j < F + 1; ++j) {
                     const double2 v = p2[j];
@@ -522,44 +543,45 @@ __global__ void __launch_bounds__(FastCfg<X, Y, BS, INV>::NT, (BS == 16 ? WFAST_
                 }
                 double2 out;
                 pair_out<X, Y, INV, F>(w, out.x, out.y);
-                *reinterpret_cast<double2 *>(xs + r * BS + o) = out;
+                *reinterpret_cast<double2 *>(xs0 + pl * N * BS + r * BS + o) = out;
             }
         }
         __syncthreads();
         if (has_col) {
-            // y: one output of this thread's column (scaling row if cy is even, wavelet row if odd)
-            {
+            // y: one output per plane of this thread's column (scaling row if cy is even, wavelet row if odd)
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl) {
                 double w[2 * F + 2], o0, o1;
-                const double *colp = xs + (cy - par) * BS + cx;     // window of the pair (cy - par, cy - par + 1)
+                const double *colp = xs0 + pl * N * BS + (cy - par) * BS + cx;     // window of the pair (cy - par, cy - par + 1)
                 if (par == 0) {
 #pragma unroll
                     for (int j = 0; j < 2 * F + 1; ++j) w[j] = colp[j * BS];
                     w[2 * F + 1] = 0.0;
                     pair_out_one<X, Y, INV, F, 0>(w, o0);
-                    win[jq] = o0;
+                    win[jq + pl] = o0;
                 } else {
                     w[0] = 0.0;
 #pragma unroll
                     for (int j = 1; j < 2 * F + 2; ++j) w[j] = colp[j * BS];
                     pair_out_one<X, Y, INV, F, 1>(w, o1);
-                    win[jq] = o1;
+                    win[jq + pl] = o1;
                 }
             }
-            // z: once plane zp = k + F + 1 is in the window (k even), output planes k and k+1 of this column are complete
-            const int k = zp - F - 1;          // = q - R + 1: its plane k - F sits in slot (jq + 1) % R
-            if ((jq & 1) && k >= 0 && k < BS) {
+            // z: once plane zp + 1 = k + F + 1 is in the window (k even), output planes k and k+1 of this column are complete
+            const int k = q - 2 * F;           // its plane k - F sits in slot (jq + 2) % R
+            if (k >= 0 && k < BS) {
                 double w[R], o0, o1;
 #pragma unroll
-                for (int j = 0; j < R; ++j) w[j] = win[(jq + 1 + j) % R];
+                for (int j = 0; j < R; ++j) w[j] = win[(jq + 2 + j) % R];
                 pair_out<X, Y, INV, F>(w, o0, o1);
                 outc[(long long)k * BS * BS] = o0;
                 outc[(long long)(k + 1) * BS * BS] = o1;
                 if (!INV) {
                     // threshold_block's Linfty detail, fused: max |wc| and max sqrt(wc*wc) over everything but the pure scaling
                     // positions (wavelet_renorm_block is the identity for eps_norm = Linfty); sqrt is monotone, taken once at the end
-                    const double v0 = (!(cx & 1) && !(cy & 1)) ? 0.0 : o0;
-                    m0 = fmax(m0, fmax(fabs(v0), fabs(o1)));
-                    m1 = fmax(m1, fmax(__dmul_rn(v0, v0), __dmul_rn(o1, o1)));
+                    // (max sqrt(wc*wc) = sqrt(fl(max|wc|^2)): squaring and rounding are monotone, so it is formed once from m0 at the end)
+                    m0 = fmax(m0, fabs(o1));
+                    if (!pure_col) m0 = fmax(m0, fabs(o0));
                 }
             }
         }
@@ -567,21 +589,14 @@ __global__ void __launch_bounds__(FastCfg<X, Y, BS, INV>::NT, (BS == 16 ? WFAST_
     }
     cp_async_wait<0>();
     if (!INV && det_abs) {
-        __shared__ double s0[NT / 32], s1[NT / 32];
+        __shared__ double s0[NT / 32];
         m0 = warp_max(m0);
-        m1 = warp_max(m1);
-        if ((tid & 31) == 0) {
-            s0[tid >> 5] = m0;
-            s1[tid >> 5] = m1;
-        }
+        if ((tid & 31) == 0) s0[tid >> 5] = m0;
         __syncthreads();
         if (tid == 0) {
-            for (int i = 1; i < NT / 32; ++i) {
-                m0 = fmax(m0, s0[i]);
-                m1 = fmax(m1, s1[i]);
-            }
+            for (int i = 1; i < NT / 32; ++i) m0 = fmax(m0, s0[i]);
             det_abs[(long long)b * nc + c] = m0;
-            det_sq[(long long)b * nc + c] = sqrt(m1);
+            det_sq[(long long)b * nc + c] = sqrt(__dmul_rn(m0, m0));
         }
     }
 }
