@@ -138,11 +138,20 @@ class AdaptiveRun:
         return (self.time,) if self.mask_time_dependent else ()
 
     # ------------------------------------------------------------------------------------------------------------------
+    def _nbr(self):
+        """hvy_neighbor of the current grid (updateMetadata_tree), computed once per grid"""
+        if getattr(self, "_nbr_of", None) is not self.grid:
+            self._nbr_tab, self._nbr_of = O.neighbor_table168(self.grid, self.p.Jmax), self.grid
+        return self._nbr_tab
+
     def sync_ghosts_tree(self):
-        """sync_ghosts_tree: all g ghost nodes, restriction through the HD filter for lifted wavelets"""
-        nbr = O.neighbor_table168(self.grid, self.p.Jmax)
-        O.sync_ghosts_leaf(self.grid, self.p, self.u, nbr, self.p.g, self.p.g, self.w.X, bool(self.w.lifted),
+        """sync_ghosts_tree: all g ghost nodes, restriction through the HD filter for lifted wavelets (idempotent: repeated calls on
+        unchanged data are skipped)"""
+        if getattr(self, "_synced", None) is self.u:
+            return
+        O.sync_ghosts_leaf(self.grid, self.p, self.u, self._nbr(), self.p.g, self.p.g, self.w.X, bool(self.w.lifted),
                            ignore_filter=not self.w.lifted, w=self.w)
+        self._synced = self.u
 
     def norm(self) -> np.ndarray:
         """componentWiseNorm_tree(..., "Linfty") on the leaves' interiors; values <= 1e-9 become 1 (coarseningIndicator_tree.f90:66-68)"""
@@ -241,7 +250,8 @@ class AdaptiveRun:
     # ------------------------------------------------------------------------------------------------------------------
     def time_step(self):
         p, g = self.p, self.grid
-        nbr = O.neighbor_table168(g, p.Jmax)
+        nbr = self._nbr()
+        self._synced = None                                              # the step changes the data
 
         def sync(h):
             O.sync_ghosts_leaf(g, p, h, nbr, p.g_rhs, p.g_rhs, self.w.X, bool(self.w.lifted), ignore_filter=True)

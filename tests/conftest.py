@@ -27,3 +27,43 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The long oracle runs against the reference's adaptive fixtures (2281-step 3vortices runs, the four cylinder runs: 1 - 4 minutes of CPU
+# each) start in worker processes as soon as the collection is known and run while the other CPU tests execute; the tests that own them
+# (test_oracle_adaptive.py, test_oracle_cylinder.py) collect the results.  Selecting one of them alone works the same way.
+_BG = {"pool": None, "futures": {}}
+
+
+def background(kind, key, fn):
+    """result of the background job (kind, key); computed inline if the job was not started"""
+    fut = _BG["futures"].get((kind, key))
+    return fut.result() if fut is not None else fn(key)
+
+
+def pytest_collection_finish(session):
+    names = {it.name.split("[")[0] for it in session.items}
+    want_adaptive = "test_adaptive_run_fixture" in names
+    want_cylinder = "test_cylinder_fixtures" in names
+    if not (want_adaptive or want_cylinder) or _BG["pool"] is not None:
+        return
+    import concurrent.futures as cf
+    import multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    _BG["pool"] = cf.ProcessPoolExecutor(max_workers=6, mp_context=mp.get_context("spawn"))
+    if want_adaptive:
+        import test_oracle_adaptive as TA
+        for w in ("CDF40", "CDF42"):
+            _BG["futures"][("adaptive", w)] = _BG["pool"].submit(TA._full_run, w)
+    if want_cylinder:
+        import cylinder_case as CC
+        import test_oracle_cylinder as TC
+        for c in CC.CASES:
+            _BG["futures"][("cylinder", c)] = _BG["pool"].submit(TC._run_case, c)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if _BG["pool"] is not None:
+        _BG["pool"].shutdown(wait=False, cancel_futures=True)
+        _BG["pool"] = None

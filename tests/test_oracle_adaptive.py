@@ -10,11 +10,9 @@
       inside the time stepper and the time-step control on a graded grid: iteration counter (5335) and final time identical, block
       list (61 / 58 blocks on levels 2-4) and statuses identical, fields <= 1e-12.
 
-Both wavelets run in parallel worker processes (about 4 minutes of CPU each).
+Both wavelets run in worker processes that conftest.py starts at collection time (about 4 minutes of CPU each), in parallel with the
+rest of the CPU suite.
 """
-import concurrent.futures as cf
-import multiprocessing as mp
-
 import numpy as np
 import pytest
 
@@ -58,8 +56,8 @@ def _full_run(wavelet):
 
 
 def test_adaptive_run_fixture():
-    with cf.ProcessPoolExecutor(max_workers=2, mp_context=mp.get_context("spawn")) as ex:
-        results = list(ex.map(_full_run, ["CDF40", "CDF42"]))
+    from conftest import background
+    results = [background("adaptive", w, _full_run) for w in ("CDF40", "CDF42")]     # started at collection time (conftest.py)
     for wavelet, level, ixyz, status, u, iteration, time, nb_rhs_max in results:
         err = AC.compare(AC.gold(wavelet), "t15", level, ixyz, status, u, iteration, time)
         assert err <= 1e-12, (wavelet, err)

@@ -8,9 +8,6 @@ in RHS_2D_acm, create_mask_2D_ACM (circle with cosine smoothing, p-norm sponge),
 force_maxlevel_dealiasing, the CFL_eta time-step limit, the adaptive initial condition (setInitialCondition_tree) and the lifted CDF44
 wavelet with Bs = 26.
 """
-import concurrent.futures as cf
-import multiprocessing as mp
-
 import numpy as np
 
 import adaptive as A
@@ -56,9 +53,9 @@ def _run_case(case):
 
 
 def test_cylinder_fixtures():
-    """the four variants in parallel worker processes (1 - 2 minutes of CPU each)"""
-    with cf.ProcessPoolExecutor(max_workers=4, mp_context=mp.get_context("spawn")) as ex:
-        results = list(ex.map(_run_case, list(CC.CASES)))
+    """the four variants run in worker processes started by conftest.py (1 - 2 minutes of CPU each)"""
+    from conftest import background
+    results = [background("cylinder", c, _run_case) for c in CC.CASES]               # started at collection time (conftest.py)
     for case, errs, nb_rhs_max in results:
         assert set(errs) == set(CC.CASES[case]["files"]), (case, errs)
         assert errs["t0"] == 0.0 and max(errs.values()) <= 1e-12, (case, errs)
