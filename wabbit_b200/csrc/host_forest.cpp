@@ -564,13 +564,28 @@ extern "C" {
 int32_t whost_ft_tables(int32_t dim, int32_t n, const int32_t *level, const int32_t *pos, int32_t *nb, int32_t *par, int32_t *child)
 {
     if (n < 0 || (n > 0 && (!level || !pos || !nb || !par || !child))) return 1;
-    std::unordered_map<uint64_t, int> look;
-    look.reserve((size_t)n * 2);
-    for (int i = 0; i < n; ++i) look[pos_hash(level[i], pos + 3 * i)] = i;
+    // open-addressing lookup (level, position) -> index: read-only after the fill, so the search below runs in parallel
+    size_t cap = 64;
+    while (cap < (size_t)n * 2 + 2) cap <<= 1;
+    const uint64_t hmask = cap - 1;
+    std::vector<uint64_t> hkeys(cap, ~0ull);
+    std::vector<int> hvals(cap, -1);
+    for (int i = 0; i < n; ++i) {
+        const uint64_t key = pos_hash(level[i], pos + 3 * i);
+        uint64_t h = whost_forest::mix(key) & hmask;
+        while (hkeys[h] != ~0ull && hkeys[h] != key) h = (h + 1) & hmask;
+        hkeys[h] = key;
+        hvals[h] = i;
+    }
     auto find = [&](int l, const int p[3]) -> int {
         if (l < 0) return -1;
-        auto it = look.find(pos_hash(l, p));
-        return it == look.end() ? -1 : it->second;
+        const uint64_t key = pos_hash(l, p);
+        uint64_t h = whost_forest::mix(key) & hmask;
+        while (hkeys[h] != ~0ull) {
+            if (hkeys[h] == key) return hvals[h];
+            h = (h + 1) & hmask;
+        }
+        return -1;
     };
     const int nd = 1 << dim, ndir = (dim == 3 ? 27 : 9) - 1;
 #pragma omp parallel for schedule(static)
