@@ -11,7 +11,8 @@ from wabbit_b200.solver import HVY_BLOCK, HVY_TMP  # noqa: E402
 
 wavelet = sys.argv[1] if len(sys.argv) > 1 else "CDF44"
 J = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-p = Params(dim=3, domain=(6.283185307179586,) * 3, Bs=(16,) * 3, wavelet=wavelet, g=6, g_rhs=2, n_eqn=4, Jmax=J, discretization="FD_4th_central",
+BS = int(sys.argv[3]) if len(sys.argv) > 3 else 16
+p = Params(dim=3, domain=(6.283185307179586,) * 3, Bs=(BS,) * 3, wavelet=wavelet, g=6, g_rhs=2, n_eqn=4, Jmax=J, discretization="FD_4th_central",
            skew_symmetry=True, c0=10.0, nu=3.125e-3, gamma_p=0.0, CFL=1.0, u_mean_set=(0.0, 0.0, 0.0), time_max=1.0e9).finalize()
 forest = Forest.uniform(3, J)
 stream = torch.cuda.current_stream()
@@ -35,6 +36,6 @@ for inverse in (False, True):
     e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 20
-    B = 8 * 4 * ((16 + 12) ** 3 + 16 ** 3) + 32
-    print(f"{wavelet} {'IWT' if inverse else 'FWT'} {forest.n_blocks} blocks: {ms:.3f} ms per launch, {B * forest.n_blocks / ms / 1e6:.0f} GB/s algorithmic", flush=True)
+    B = 8 * 4 * ((BS + 12) ** 3 + BS ** 3) + 32
+    print(f"{wavelet} Bs={BS} {'IWT' if inverse else 'FWT'} {forest.n_blocks} blocks: {ms:.3f} ms per launch, {B * forest.n_blocks / ms / 1e6:.0f} GB/s algorithmic", flush=True)
 sol.close()

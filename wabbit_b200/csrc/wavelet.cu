@@ -403,11 +403,14 @@ struct FastCfg {
 // keeps the last 2F+2 y-pass results in REGISTERS (the plane loop is fully unrolled, so the sliding window is pure register
 // renaming), from which the z pass emits a (scaling, wavelet) output pair every second plane -- no shared-memory traffic for z.
 // Threads are mapped to columns so that a warp has one y parity (all scaling rows or all wavelet rows: no divergence).
+#ifndef WFAST_MINB_BIG
+#define WFAST_MINB_BIG 2   // Bs = 18, 20 (352 / 416 threads per CTA): two resident CTAs instead of the one ptxas would settle for
+#endif
 #ifndef WFAST_MINB
 #define WFAST_MINB 3   // minimum resident CTAs per SM requested for Bs = 16 (register cap <= 80): measured best for the two-planes-per-barrier loop
 #endif
 template <int X, int Y, int BS, bool INV>
-__global__ void __launch_bounds__(FastCfg<X, Y, BS, INV>::NT, (BS == 16 ? WFAST_MINB : 1)) wavelet_fast_kernel(const double *__restrict__ src, double *__restrict__ dst,
+__global__ void __launch_bounds__(FastCfg<X, Y, BS, INV>::NT, (BS == 16 ? WFAST_MINB : (BS <= 20 ? WFAST_MINB_BIG : 1))) wavelet_fast_kernel(const double *__restrict__ src, double *__restrict__ dst,
                                                                                  const int *__restrict__ active, const int *__restrict__ nbr, int nc,
                                                                                  double *__restrict__ det_abs, double *__restrict__ det_sq,
                                                                                  const double *__restrict__ wpool, const long long *__restrict__ woff)
