@@ -23,10 +23,10 @@ pytestmark = pytest.mark.gpu
 
 
 def _params(**kw):
-    d = dict(SC.INI)
+    d = dict(SC.INI, wavelet="CDF44", skew_symmetry=True, eps=SC.EPS, eps_normalized=True, eps_norm="Linfty", Jmin=SC.JMIN,
+             force_maxlevel_dealiasing=True, adapt_tree=True, refinement_indicator="everywhere")
     d.update(kw)
-    return Params(wavelet="CDF44", skew_symmetry=True, eps=SC.EPS, eps_normalized=True, eps_norm="Linfty", Jmin=SC.JMIN,
-                  force_maxlevel_dealiasing=True, adapt_tree=True, refinement_indicator="everywhere", **d).finalize()
+    return Params(**d).finalize()
 
 
 def _field(og, po, seed):
@@ -135,3 +135,90 @@ def test_adaptive_sphere_lockstep():
         assert abs(dt_g - dt_o) <= 1e-13 * dt_o
         assert same() <= 1e-12
     sol.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_adaptive_sphere_across_ranks_equals_single_rank(world):
+    """the adaptive loop with the moving-sphere mask (threshold_mask) and the "significant" refinement indicator with the blocks
+    partitioned over `world` ranks (threads driving one device context each, collectives through ThreadTransport): same grids, refinement
+    statuses and dt, bit-identical data as the single-rank loop, which the oracle pins above"""
+    import threading
+    import torch
+    from wabbit_b200.multi import DistributedWabbit, ThreadTransport
+    from wabbit_b200.timeloop import DistributedAdaptiveLoop
+    p = _params(refinement_indicator="significant")
+    MAXB = 2400
+    forest = Forest.uniform(3, SC.JMIN, Jmax=p.Jmax, max_blocks=MAXB)
+    sol = WabbitGPU(p, max_blocks=MAXB)
+    sol.setup_wavelet("CDF44")
+    sol.set_forest(forest)
+    loop = AdaptiveLoop(sol, forest, 0.0, 0, mask=SphereMask3D(p, **SC.SPHERE), threshold_mask=True)
+
+    def set_inicond(lp):
+        hvy, _, _, _ = lp.forest.active(0)
+        host = np.zeros((int(hvy.max()),) + sol.host_shape()[1:])
+        host[hvy - 1, 0] = 1.0
+        sol.upload(host, HVY_BLOCK, 0, hvy_ids=hvy)
+    set_inicond(loop)
+    loop.adaptive_inicond(set_inicond)
+    loop.step()                                      # a flow with structure around the sphere
+    hvy, l0, x0, _ = loop.forest.active(0)
+    u0 = np.zeros((len(hvy),) + sol.host_shape()[1:])
+    sol.download(u0, g_sync=0)
+    st0, t0, it0 = loop.status.copy(), loop.time, loop.iteration
+    nsteps = 2
+    for _ in range(nsteps):
+        loop.step()
+    _, lf, xf, _ = loop.forest.active(0)
+    ref = np.zeros((len(lf),) + sol.host_shape()[1:])
+    sol.download(ref, g_sync=0)
+    ref_log, ref_status = list(loop.log[-nsteps:]), loop.status.copy()
+    assert len(np.unique(lf)) > 1 and (ref_status == 0).any() and (ref_status == 9).any()
+    sol.close()
+
+    fw = Forest.from_blocks(3, p.Jmax, l0, x0, n_ranks=world, max_blocks=MAXB)
+    offs = np.concatenate([[0], np.cumsum([fw.n_active(r) for r in range(world)])])
+    sols = []
+    for _ in range(world):
+        s = WabbitGPU(p, max_blocks=MAXB)
+        s.setup_wavelet("CDF44")
+        sols.append(s)
+    shared = ThreadTransport.Shared(world)
+    res, errs = [None] * world, []
+
+    def worker(r):
+        try:
+            torch.cuda.set_device(0)
+            d = DistributedWabbit(sols[r], fw, r, world, transport=ThreadTransport(shared, r), overlap=False)
+            n = fw.n_active(r)
+            h = np.zeros((max(n, 1),) + sols[r].host_shape()[1:])
+            h[:n] = u0[offs[r]:offs[r] + n]
+            sols[r].upload(h, hvy_ids=np.arange(1, n + 1, dtype=np.int32))
+            lp = DistributedAdaptiveLoop(d, t0, it0, mask=SphereMask3D(p, **SC.SPHERE), threshold_mask=True)
+            lp.status = st0.copy()
+            for _ in range(nsteps):
+                lp.step()
+            _, l, x, _ = d.forest.active(r)
+            out = np.zeros((max(len(l), 1),) + sols[r].host_shape()[1:])
+            sols[r].download(out, g_sync=0, hvy_ids=np.arange(1, len(l) + 1, dtype=np.int32))
+            res[r] = (list(lp.log), lp.status.copy(), l, x, out[:len(l)].copy())
+        except BaseException as e:      # noqa: BLE001
+            errs.append((r, repr(e)))
+            shared.barrier.abort()
+
+    th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errs, errs
+    for r in range(world):
+        assert res[r][0] == ref_log, (r, res[r][0], ref_log)
+        assert np.array_equal(res[r][1], ref_status)
+    assert np.array_equal(np.concatenate([res[r][2] for r in range(world)]), lf)
+    assert np.array_equal(np.concatenate([res[r][3] for r in range(world)]), xf)
+    got = np.concatenate([res[r][4] for r in range(world)])
+    g = p.g
+    assert np.array_equal(got[:, :, g:-g, g:-g, g:-g], ref[:, :, g:-g, g:-g, g:-g])
+    for s in sols:
+        s.close()

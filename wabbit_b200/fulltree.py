@@ -636,7 +636,7 @@ class DistributedFullTree(FullTree):
 
     # ------------------------------------------------------------------ adapt_tree
     def adapt(self, eps=None, norm=None, eps_norm: str = "Linfty", thresh_comp=None, force_maxlevel_dealiasing: bool = False,
-              indicator: str = "threshold-state-vector", want_info: bool = False, use_security_zone: bool = False):
+              indicator: str = "threshold-state-vector", want_info: bool = False, use_security_zone: bool = False, mask_keeps=None):
         sol, drv, dim, me, W = self.sol, self.drv, self.dim, self.me, self.world
         p = sol.params
         if indicator == "everywhere":
@@ -647,11 +647,19 @@ class DistributedFullTree(FullTree):
             st0 = self.st.copy()
             if force_maxlevel_dealiasing:
                 st0[self.level == self.forest.Jmax] = -1
+        if mask_keeps is not None and indicator != "everywhere":      # threshold_mask: replicated light data, as on one rank
+            cand = st0 == -1
+            if force_maxlevel_dealiasing:
+                cand &= self.level != self.forest.Jmax
+            ci = np.flatnonzero(cand)
+            if len(ci):
+                st0[ci[np.asarray(mask_keeps(self.level[ci], self.pos[ci]), dtype=bool)]] = 0
         if use_security_zone and indicator != "everywhere":
             self._lslot_for_patches()
             st0 = self.security_zone(st0, eps, norm, thresh_comp, force_maxlevel_dealiasing)
         st = self.decide(st0)
         keep = st != -1
+        st_kept = st[keep]
         self.code, self.level, self.pos, self.slots, self.owner = (a[keep] for a in (self.code, self.level, self.pos, self.slots, self.owner))
         self._build_tables()
         self.is_leaf = self.child[:, 0] < 0
@@ -686,15 +694,17 @@ class DistributedFullTree(FullTree):
         # prune_fulltree2leafs + balanceLoad_tree: the leaves move to their owners / slots in the new partition
         new = Forest.from_blocks(dim, self.forest.Jmax, self.level[leaves].astype(np.int32), self.pos[leaves].astype(np.int32),
                                  block_dist=self.forest.block_dist, n_ranks=W, max_blocks=self.forest.max_blocks, periodic=self.forest.periodic)
-        src_r, src_s, dst_r, dst_s = [], [], [], []
+        src_r, src_s, dst_r, dst_s, stat = [], [], [], [], []
         for r in range(W):
             hvy, lvl, ixyz, _ = new.active(r)
             i = self._find(lvl.astype(np.int64), ixyz.astype(np.int64))
+            stat.append(st_kept[i])
             src_r.append(self.owner[i])
             src_s.append(self.slots[i])
             dst_r.append(np.full(len(hvy), r, np.int64))
             dst_s.append(hvy.astype(np.int64))
         src_r, src_s, dst_r, dst_s = (np.concatenate(v) for v in (src_r, src_s, dst_r, dst_s))
+        self.leaf_status = np.concatenate(stat).astype(np.int32)      # refinement status of the new leaves, global space-filling-curve order
         loc, _ = drv._ship((HVY_BLOCK, 0), src_r, src_s, dst_r, int(self.scratch0[me]))
         sol.move_blocks(loc.astype(np.int32), dst_s[dst_r == me].astype(np.int32))
         drv.attach(new)

@@ -706,7 +706,7 @@ class DistributedWabbit:
 
     # ------------------------------------------------------------------ adapt_tree (one coarsening sweep, unlifted wavelets)
     def adapt_tree(self, eps: Optional[float] = None, eps_normalized: bool = True, Jmin: int = 1, force_maxlevel_dealiasing: bool = False,
-                   thresh_comp=None, useSecurityZone: Optional[bool] = None):
+                   thresh_comp=None, useSecurityZone: Optional[bool] = None, mask_keeps=None, full_tree: Optional[bool] = None):
         """One coarsening sweep of adapt_tree (LIB/MESH/adapt_tree.f90:11) across ranks, indicator "threshold-state-vector", Linfty norm,
         unlifted wavelets (as WabbitGPU.adapt_tree): norm -> all-reduce MAX; halo refresh; decomposition + flags per rank; flags
         all-gathered (synchronize_lgt_data); completeness / gradedness on the replicated light data; sister blocks gathered on the
@@ -715,18 +715,25 @@ class DistributedWabbit:
         me, sol = self.rank, self.sol
         old, ooff = self.forest, self.off
         w = sol.params.wavelet
-        if not (len(w) == 5 and w[4] == "0"):
-            # lifted wavelets: the reference's full-tree algorithm with coarse extension and security zone (fulltree.py)
+        lifted = not (len(w) == 5 and w[4] == "0")
+        use_ce = lifted if sol.params.useCoarseExtension < 0 else bool(sol.params.useCoarseExtension)
+        self.refinement_status = None
+        if use_ce if full_tree is None else full_tree:
+            # the reference's full-tree algorithm (coarse extension and security zone for lifted wavelets; fulltree.py)
             from .fulltree import DistributedFullTree
             norm = None
             if eps_normalized:
                 norm = self.tr.allreduce_max_np(sol.componentWiseNorm_tree((0, 0), "Linfty"))
                 norm[norm <= 1.0e-9] = 1.0
             n0 = old.n_blocks
-            sz = sol.params.useSecurityZone != 0 if useSecurityZone is None else bool(useSecurityZone)
-            new, _ = DistributedFullTree(self, Jmin=Jmin).adapt(eps=sol.params.eps if eps is None else eps, norm=norm, thresh_comp=thresh_comp,
-                                                               force_maxlevel_dealiasing=force_maxlevel_dealiasing, use_security_zone=sz)
+            sz = (lifted if sol.params.useSecurityZone < 0 else bool(sol.params.useSecurityZone)) if useSecurityZone is None else bool(useSecurityZone)
+            ft = DistributedFullTree(self, Jmin=Jmin)
+            new, _ = ft.adapt(eps=sol.params.eps if eps is None else eps, norm=norm, thresh_comp=thresh_comp,
+                              force_maxlevel_dealiasing=force_maxlevel_dealiasing, use_security_zone=sz, mask_keeps=mask_keeps)
+            self.refinement_status = ft.leaf_status              # global space-filling-curve order, the same on every rank
             return new, n0, new.n_blocks
+        if mask_keeps is not None:
+            raise ValueError("adapt_tree: threshold_mask needs the full-tree algorithm")
         WD = (self.HVY_WORK, 2)
         norm = None
         if eps_normalized:

@@ -24,12 +24,13 @@ REF_UNSIGNIFICANT_STAY = 9      # module_globals.f90:28
 
 
 def refinement_flags(forest: Forest, indicator: str, status: Optional[np.ndarray], Jmax: int) -> np.ndarray:
-    """+1 / 0 per active block (order of forest.active(0)): refinementIndicator_tree + respectJmaxJmin_tree + ensureGradedness_tree.
+    """+1 / 0 per block in the global space-filling-curve order (forest.active(0) on one rank): refinementIndicator_tree +
+    respectJmaxJmin_tree + ensureGradedness_tree.
     `status`: lgt_block(:, IDX_REFINE_STS) left by the last adapt_tree (0 significant, 9 REF_UNSIGNIFICANT_STAY)."""
-    hvy, lvl, ixyz, _ = forest.active(0)
-    n, dim = len(hvy), forest.dim
-    lvl = lvl.astype(np.int64)
-    pos = ixyz.astype(np.int64)
+    parts = [forest.active(r) for r in range(forest.n_ranks)]          # global order = rank-major order of the active lists
+    lvl = np.concatenate([q[1] for q in parts]).astype(np.int64)
+    pos = np.concatenate([q[2] for q in parts]).astype(np.int64)
+    n, dim = len(lvl), forest.dim
     if indicator == "everywhere":
         flag = np.ones(n, np.int32)
     elif indicator == "significant":
@@ -134,4 +135,46 @@ class AdaptiveLoop:
         self.time, self.iteration, dt = self.sol.timeStep_tree(self.time, self.iteration)
         self.adapt_tree()
         self.log.append((self.iteration, self.time, nb_rhs, self.forest.n_blocks, dt))
+        return dt
+
+
+class DistributedAdaptiveLoop:
+    """The same loop with the blocks partitioned over ranks (wabbit_b200.multi.DistributedWabbit: halo blocks + block transport); the light
+    data -- flags, statuses, the mask indicator -- are replicated, so every rank takes the same grid decisions."""
+
+    def __init__(self, drv, time: float = 0.0, iteration: int = 0, refinement_indicator: Optional[str] = None, thresh_comp=None, mask=None,
+                 threshold_mask: bool = False):
+        self.drv, self.time, self.iteration = drv, time, iteration
+        p = drv.sol.params
+        self.indicator = p.refinement_indicator if refinement_indicator is None else refinement_indicator
+        self.thresh_comp, self.mask, self.threshold_mask = thresh_comp, mask, threshold_mask
+        self.mask_time_dependent = mask is not None and bool(np.any(getattr(mask, "v", 0.0)))
+        if mask is not None:
+            if not getattr(mask, "analytic", False):
+                raise ValueError("DistributedAdaptiveLoop: only masks evaluated on the device (wabbit_b200.mask.SphereMask3D) are supported")
+            mask.attach(drv.sol)
+        self.status: Optional[np.ndarray] = None
+        self.log = []
+
+    def adapt_tree(self):
+        p = self.drv.sol.params
+        keeps = None
+        if self.mask is not None and self.threshold_mask:
+            keeps = (lambda level, pos: self.mask.keeps(level, pos, self.time)) if self.mask_time_dependent else self.mask.keeps
+        _, n0, n1 = self.drv.adapt_tree(eps=p.eps, eps_normalized=p.eps_normalized, Jmin=p.Jmin,
+                                        force_maxlevel_dealiasing=p.force_maxlevel_dealiasing, thresh_comp=self.thresh_comp, mask_keeps=keeps,
+                                        full_tree=True)
+        self.status = self.drv.refinement_status
+        return n0, n1
+
+    def step(self) -> float:
+        ind = self.indicator
+        if ind == "significant" and self.status is None:
+            ind = "everywhere"
+        flags = None if ind == "everywhere" else refinement_flags(self.drv.forest, ind, self.status, self.drv.sol.params.Jmax)
+        nb_rhs = self.drv.refine_tree(flags).n_blocks
+        self.status = None
+        self.time, self.iteration, dt = self.drv.timeStep_tree(self.time, self.iteration)
+        self.adapt_tree()
+        self.log.append((self.iteration, self.time, nb_rhs, self.drv.forest.n_blocks, dt))
         return dt
