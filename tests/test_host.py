@@ -258,3 +258,29 @@ def test_full_tree_light_data_matches_the_oracle(seed):
     od = OFT.decide(t, ft.status_dict(st0), 1)
     assert (st == -1).any()
     assert {k: v == -1 for k, v in ft.status_dict(st).items()} == {k: v == -1 for k, v in od.items()}
+
+
+def test_refinement_flags_do_not_depend_on_the_partition():
+    """refinementIndicator_tree("significant") + respectJmaxJmin_tree + ensureGradedness_tree on replicated light data: the flags in
+    global space-filling-curve order are the same for 1, 2 and 3 ranks and equal to the oracle's restatement"""
+    import adaptive as A
+    import oracle as O
+    from util import graded_blocks
+    from wabbit_b200.timeloop import refinement_flags
+    lv, ix = graded_blocks(3, 1, 4, 11, 0.3)
+    rng = np.random.default_rng(3)
+    f1 = Forest.from_blocks(3, 5, lv, ix, n_ranks=1, max_blocks=4 * len(lv))
+    _, l1, x1, _ = f1.active(0)
+    status = np.where(rng.random(len(l1)) < 0.3, 0, 9).astype(np.int32)
+    ref = refinement_flags(f1, "significant", status, 5)
+    assert 0 < ref.sum() < len(ref) and (ref[status == 9] == 1).any()          # gradedness promoted some insignificant blocks
+    for world in (2, 3):
+        fw = Forest.from_blocks(3, 5, lv, ix, n_ranks=world, max_blocks=4 * len(lv))
+        assert np.array_equal(refinement_flags(fw, "significant", status, 5), ref)
+    # the oracle's formulation (from the coarse block's point of view)
+    po = O.Params(dim=3, Bs=(16, 16, 16), g=3, Jmax=5)
+    grid = O.Grid(level=l1.astype(np.int64), ixyz=x1.astype(np.int64), dim=3)
+    run = A.AdaptiveRun(po, "CDF40", grid, np.zeros((grid.n, 1, 1, 1, 1)), 0.0, 0, 1e-3, refinement_indicator="significant")
+    run.status = status.astype(np.int64)
+    assert np.array_equal(run.refine_flags("significant"), ref)
+    assert np.array_equal(refinement_flags(f1, "everywhere", None, 3), (l1 < 3).astype(np.int32))
