@@ -607,13 +607,22 @@ def adaptive_leg_multi(a, rank, world, local, stream, eps=None, J0=5, Jmax=6, cy
     eps = a.adaptive_eps if eps is None else eps
     p = Params(dim=3, domain=(TWO_PI,) * 3, Bs=(a.bs,) * 3, wavelet=wavelet, g=int(wavelet[3]) - 1 + max(int(wavelet[4]) - 1, 0), g_rhs=2, n_eqn=4, Jmax=Jmax,
                discretization="FD_4th_central", skew_symmetry=True, c0=10.0, nu=3.125e-3, gamma_p=0.0, CFL=1.0,
-               u_mean_set=(0.0, 0.0, 0.0), time_max=1.0e9).finalize()
+               u_mean_set=(0.0, 0.0, 0.0), time_max=1.0e9)
+    sphere = None
+    if a.adaptive_sphere:      # BASELINE config 4's kind of run: volume penalization of a translating sphere, mask evaluated in the stage kernel
+        p.penalization, p.C_eta = True, 1.0e-3
+    p = p.finalize()
+    if a.adaptive_sphere:
+        from wabbit_b200.mask import SphereMask3D
+        sphere = SphereMask3D(p, center=(3.0, 3.1, 3.2), radius=0.8, velocity=(0.5, 0.3, -0.2))
     max_blocks_total = max(max_blocks_total, int(1.25 * 8 ** J0))
     mb = int(1.6 * max_blocks_total / world)
     forest = Forest.uniform(3, J0, Jmax=Jmax, n_ranks=world, max_blocks=mb)
     hvy, lvl, ixyz, _ = forest.active(rank)
     sol = WabbitGPU(p, max_blocks=mb, device=local, stream=stream.cuda_stream)
     sol.setup_wavelet(wavelet)
+    if sphere is not None:
+        sphere.attach(sol)
     drv = DistributedWabbit(sol, forest, rank, world)
     nb0 = len(hvy)
     shape = (nb0,) + sol.host_shape()[1:]
@@ -646,13 +655,15 @@ def adaptive_leg_multi(a, rank, world, local, stream, eps=None, J0=5, Jmax=6, cy
         dist.barrier()
         torch.cuda.synchronize()
 
+    t, it = 0.0, 0
+    keeps = (lambda level, pos: sphere.keeps(level, pos, t)) if sphere is not None else None      # threshold_mask follows the sphere
+    extra = dict(mask_keeps=keeps, full_tree=True) if sphere is not None else {}
     sizes = [forest.n_blocks]
     for _ in range(Jmax):
-        _f, n0, n1 = drv.adapt_tree(eps=eps, Jmin=1)
+        _f, n0, n1 = drv.adapt_tree(eps=eps, Jmin=1, **extra)
         sizes.append(n1)
         if n1 == n0:
             break
-    t, it = 0.0, 0
     recs = []
     for cyc in range(cycles + 2):
         sync()
@@ -663,7 +674,7 @@ def adaptive_leg_multi(a, rank, world, local, stream, eps=None, J0=5, Jmax=6, cy
         t, it, _dt = drv.timeStep_tree(t, it)
         sync()
         w2 = time.perf_counter()
-        _f, n0, n1 = drv.adapt_tree(eps=eps, Jmin=1)
+        _f, n0, n1 = drv.adapt_tree(eps=eps, Jmin=1, **extra)
         sync()
         w3 = time.perf_counter()
         recs.append((nb_rhs, n1, w1 - w0, w2 - w1, w3 - w2))
@@ -675,7 +686,9 @@ def adaptive_leg_multi(a, rank, world, local, stream, eps=None, J0=5, Jmax=6, cy
     dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     tm = tm.cpu().numpy()
     tot = float(tm.sum())
-    return {"metric": f"adaptive block-updates/s (refine everywhere -> RK4 -> adapt, {wavelet}, {world} GPUs)", "value": sum(r[0] for r in recs) / tot,
+    what = "refine everywhere -> RK4 with the penalization mask of a translating sphere -> adapt with threshold_mask" if sphere is not None \
+        else "refine everywhere -> RK4 -> adapt"
+    return {"metric": f"adaptive block-updates/s ({what}, {wavelet}, {world} GPUs)", "value": sum(r[0] for r in recs) / tot,
             "unit": UNIT, "eps": eps, "Jmax": Jmax, "blocks_initial_coarsening": sizes, "cycles": len(recs),
             "blocks_rhs": [r[0] for r in recs], "blocks_after_adapt": [r[1] for r in recs],
             "ms_refine": [round(v * 1e3, 2) for v in tm[:, 0]], "ms_rk4": [round(v * 1e3, 2) for v in tm[:, 1]],
@@ -704,6 +717,7 @@ def main():
     ap.add_argument("--adaptive-eps", type=float, default=1.0e-6)
     ap.add_argument("--adaptive-wavelet", default="CDF40", help="wavelet of --adaptive-only / --adaptive-multi")
     ap.add_argument("--adaptive-multi", action="store_true", help="N > 1: also run the adaptive cycle across the GPUs (halo blocks + block transport)")
+    ap.add_argument("--adaptive-sphere", action="store_true", help="--adaptive-multi with volume penalization of a translating sphere (config 4's kind of run)")
     ap.add_argument("--adaptive-level", type=int, default=5, help="initial equidistant level of the adaptive legs")
     ap.add_argument("--adaptive-only", action="store_true", help="run only the adaptive-cycle leg and print its record (development)")
     a = ap.parse_args()
