@@ -111,7 +111,7 @@ class AdaptiveLoop:
         if self.mask is None or getattr(self.mask, "analytic", False):
             return
         hvy, lvl, pos, _ = self.forest.active(0)
-        host = np.zeros(self.sol.host_shape(self.sol.params.n_mask))
+        host = np.zeros((int(hvy.max()),) + self.sol.host_shape(self.sol.params.n_mask)[1:])     # rows 1 .. max hvy id only
         host[hvy - 1] = self.mask.fill(lvl, pos)
         self.sol.upload(host, HVY_MASK, 0, hvy_ids=hvy)
 
