@@ -284,3 +284,40 @@ def test_refinement_flags_do_not_depend_on_the_partition():
     run.status = status.astype(np.int64)
     assert np.array_equal(run.refine_flags("significant"), ref)
     assert np.array_equal(refinement_flags(f1, "everywhere", None, 3), (l1 < 3).astype(np.int32))
+
+
+def test_host_mask_generators_match_the_oracle():
+    """wabbit_b200.mask (product host code, vectorised over blocks) against the oracle's per-block restatement of create_mask_2D_ACM /
+    draw_sphere: the six mask components bit for bit, the threshold_mask indicator identical"""
+    import adaptive as A
+    import cylinder_case as CC
+    import oracle as O
+    import sphere_case as SC
+    from wabbit_b200 import Params
+    from wabbit_b200.mask import CylinderMask2D, SphereMask3D
+    rng = np.random.default_rng(0)
+    # 2-D cylinder + p-norm sponge (acm_cyl.ini)
+    p = Params(wavelet="CDF44", **CC.INI).finalize()
+    po = O.Params(skew=False, **CC.INI)
+    m, mo = CylinderMask2D(p), A.CylinderMask2D(po)
+    lv = rng.integers(1, 7, 120)
+    pos = np.stack([np.append(rng.integers(0, 2 ** l, 2), 0) for l in lv])
+    pos[:60] = np.stack([[(2 ** l) // 2 - rng.integers(0, 2), (2 ** l) // 2 - rng.integers(0, 2), 0] for l in lv[:60]])   # around the cylinder
+    f, k = m.fill(lv, pos), m.keeps(lv, pos)
+    for i, (l, x) in enumerate(zip(lv, pos)):
+        assert np.array_equal(f[i], mo.block(int(l), x))
+        assert bool(k[i]) == mo.keeps(int(l), x)
+    assert 0 < k.sum() < len(k)
+    # 3-D translating sphere
+    p3 = Params(wavelet="CDF44", skew_symmetry=True, **SC.INI).finalize()
+    po3 = O.Params(skew=True, **SC.INI)
+    s, so = SphereMask3D(p3, **SC.SPHERE), A.SphereMask3D(po3, **SC.SPHERE)
+    assert s.h == so.h
+    lv = rng.integers(1, 5, 200)
+    pos = np.stack([rng.integers(0, 2 ** l, 3) for l in lv])
+    pos[:120] = np.stack([np.clip((np.array(SC.SPHERE["center"]) * 2 ** l).astype(int) + rng.integers(-1, 2, 3), 0, 2 ** l - 1) for l in lv[:120]])
+    for t in (0.0, 0.137):
+        k = s.keeps(lv, pos, t)
+        ko = np.array([so.keeps(int(l), x, t) for l, x in zip(lv, pos)])
+        assert np.array_equal(k, ko)
+        assert 0 < k.sum() < len(k)
