@@ -136,3 +136,36 @@ def test_save_data_of_an_oracle_run_equals_the_reference_output(tmp_path):
     err = AC.compare(gd, "t10", d["level"].ravel(), ixy, d["refinement_status"].ravel(), u, int(d["attrs"]["iteration"][0]), float(d["attrs"]["time"][0]))
     assert err <= 1e-15
     assert np.array_equal(d["treecode"].ravel(), tc)
+
+
+def test_product_reader_round_trip_and_reference_files(tmp_path):
+    """wabbit_b200.h5io.read_wabbit_field / read_state (the restart side): own files round-trip; where the reference checkout exists, its
+    chunked files read the same as with the independent test reader"""
+    rng = np.random.default_rng(0)
+    nb, Bs = 7, (8, 6, 4)
+    level = rng.integers(1, 4, nb).astype(np.int32)
+    ixyz = np.stack([rng.integers(0, 2 ** l, 3) for l in level])
+    field = rng.standard_normal((nb, Bs[2] + 1, Bs[1] + 1, Bs[0] + 1))
+    tc = rng.integers(0, 1 << 40, nb)
+    paths = []
+    for name in ("ux", "uy"):
+        path = str(tmp_path / f"{name}_000000500000.h5")
+        h5io.write_wabbit_field(path, field if name == "ux" else 2 * field, level, ixyz, tc, dim=3, Bs=Bs, domain=(1.0, 2.0, 3.0), time=0.5, iteration=12,
+                                max_level=5, refinement_status=np.arange(nb))
+        paths.append(path)
+    d = h5io.read_wabbit_field(paths[0])
+    assert np.array_equal(d["blocks"], field) and np.array_equal(d["level"], level) and np.array_equal(d["ixyz"], ixyz)
+    assert np.array_equal(d["treecode"], tc) and np.array_equal(d["refinement_status"], np.arange(nb)) and d["Bs"] == [8, 6, 4]
+    st = h5io.read_state(paths, g=3)
+    assert st["hvy"].shape == (nb, 2, 4 + 6, 6 + 6, 8 + 6) and st["time"] == 0.5 and st["iteration"] == 12
+    assert np.array_equal(st["hvy"][:, 1, 3:7, 3:9, 3:11], 2 * field[:, :4, :6, :8]) and st["hvy"][:, :, :3].max() == 0.0
+    if os.path.exists(REF):
+        o, r = h5lite.read_wabbit(REF), h5io.read_wabbit_field(REF)
+        assert np.array_equal(o["blocks"], r["blocks"]) and np.array_equal(o["level"].ravel(), r["level"])
+        assert np.array_equal(o["treecode"].ravel(), r["treecode"]) and np.array_equal(o["refinement_status"].ravel(), r["refinement_status"])
+        assert all(np.array_equal(o["attrs"][k], r["attrs"][k]) for k in o["attrs"])
+        ref3d = "/root/reference/TESTING/acm/taylorGreen/taylorGreenEqui_FD4_CDF40/ux_000010000000.h5"
+        o, r = h5lite.read_wabbit(ref3d), h5io.read_wabbit_field(ref3d)
+        assert np.array_equal(o["blocks"], r["blocks"]) and r["dim"] == 3
+        want = np.rint(o["origin"][:, ::-1] / (o["spacing"][:, ::-1] * r["Bs"][0])).astype(np.int64)
+        assert np.array_equal(r["ixyz"], want)

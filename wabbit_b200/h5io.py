@@ -1,4 +1,4 @@
-"""Writer for WABBIT's field files: what saveHDF5_tree leaves on disk (LIB/MESH/InputOutput.f90:237-280, 322-764;
+"""Writer and reader for WABBIT's field files: what saveHDF5_tree leaves on disk (LIB/MESH/InputOutput.f90:237-280, 322-764;
 LIB/MODULE/module_hdf5_wrapper.f90), so that the reference's own tools (wabbit-post, the python-tools, ParaView readers) and a restart
 (`read_from_files = 1`) can consume what the device path produced.
 
@@ -195,3 +195,158 @@ def save_data(directory: str, field_names: Sequence[str], hvy: np.ndarray, level
                            refinement_status=refinement_status, periodic=p.periodic)
         paths.append(path)
     return paths
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Reader (readHDF5vct_tree's file side, LIB/MESH/InputOutput.f90:322-764): restart from field files -- the reference's (chunked) or ours
+# ----------------------------------------------------------------------------------------------------------------------
+class _File:
+    """the subset of the classic HDF5 format WABBIT's files use: superblock v0, symbol-table groups, v1 object headers (with continuation
+    blocks), contiguous / compact / chunked (v1 B-tree, unfiltered) datasets, v1 attributes of integer and floating-point type"""
+
+    def __init__(self, path: str):
+        with open(path, "rb") as f:
+            self.b = b = f.read()
+        if b[:8] != b"\x89HDF\r\n\x1a\n" or b[8] != 0:
+            raise ValueError(f"{path}: not a classic (superblock version 0) HDF5 file")
+        btree, heap = struct.unpack_from("<QQ", b, 80)
+        if b[heap:heap + 4] != b"HEAP":
+            raise ValueError(f"{path}: root group has no local heap")
+        self.names: Dict[str, int] = {}
+        self._group(btree, struct.unpack_from("<Q", b, heap + 24)[0])
+
+    def _group(self, node: int, seg: int):
+        b = self.b
+        if b[node:node + 4] == b"TREE":
+            n = struct.unpack_from("<H", b, node + 6)[0]
+            for i in range(n):
+                self._group(struct.unpack_from("<Q", b, node + 32 + 16 * i)[0], seg)
+        elif b[node:node + 4] == b"SNOD":
+            for i in range(struct.unpack_from("<H", b, node + 6)[0]):
+                off, hdr = struct.unpack_from("<QQ", b, node + 8 + 40 * i)
+                self.names[b[seg + off:b.index(b"\x00", seg + off)].decode()] = hdr
+        else:
+            raise ValueError("corrupt group structure")
+
+    def _msgs(self, hdr: int):
+        b = self.b
+        version, nmsg = b[hdr], struct.unpack_from("<H", b, hdr + 2)[0]
+        if version != 1:
+            raise ValueError("only version-1 object headers are supported")
+        todo, out = [(hdr + 16, struct.unpack_from("<I", b, hdr + 8)[0])], []
+        while todo and len(out) < nmsg:
+            p, n = todo.pop(0)
+            end = p + n
+            while p + 8 <= end and len(out) < nmsg:
+                t, size = struct.unpack_from("<HH", b, p)
+                if t == 0x10:
+                    todo.append(struct.unpack_from("<QQ", b, p + 8))
+                out.append((t, p + 8))
+                p += 8 + size
+        return out
+
+    def _dtype(self, p: int) -> np.dtype:
+        cls, size = self.b[p] & 15, struct.unpack_from("<I", self.b, p + 4)[0]
+        order = ">" if self.b[p + 1] & 1 else "<"
+        if cls == 0:
+            return np.dtype(f"{order}{'i' if self.b[p + 1] & 8 else 'u'}{size}")
+        if cls == 1:
+            return np.dtype(f"{order}f{size}")
+        raise ValueError(f"datatype class {cls} is not supported")
+
+    def _shape(self, p: int):
+        version, rank = self.b[p], self.b[p + 1]
+        return tuple(struct.unpack_from("<Q", self.b, p + (8 if version == 1 else 4) + 8 * i)[0] for i in range(rank))
+
+    def dataset(self, name: str) -> np.ndarray:
+        b = self.b
+        shape = dt = lay = None
+        for t, p in self._msgs(self.names[name]):
+            if t == 1:
+                shape = self._shape(p)
+            elif t == 3:
+                dt = self._dtype(p)
+            elif t == 8:
+                lay = p
+        if b[lay] != 3:
+            raise ValueError("only version-3 layout messages are supported")
+        n = int(np.prod(shape))
+        if b[lay + 1] == 1:
+            return np.frombuffer(b, dt, n, struct.unpack_from("<Q", b, lay + 2)[0]).reshape(shape).astype(dt.newbyteorder("="))
+        if b[lay + 1] == 0:
+            return np.frombuffer(b, dt, n, lay + 4).reshape(shape).astype(dt.newbyteorder("="))
+        rank1 = b[lay + 2]
+        cdims = struct.unpack_from(f"<{rank1}I", b, lay + 11)[:-1]
+        out = np.zeros(shape, dt.newbyteorder("="))
+        self._chunks(struct.unpack_from("<Q", b, lay + 3)[0], rank1, cdims, dt, out)
+        return out
+
+    def _chunks(self, node: int, rank1: int, cdims, dt, out):
+        b = self.b
+        level, n = b[node + 5], struct.unpack_from("<H", b, node + 6)[0]
+        ksz = 8 + 8 * rank1
+        for i in range(n):
+            k = node + 24 + i * (ksz + 8)
+            nbytes, filt = struct.unpack_from("<II", b, k)
+            child = struct.unpack_from("<Q", b, k + ksz)[0]
+            if level:
+                self._chunks(child, rank1, cdims, dt, out)
+                continue
+            if filt:
+                raise ValueError("filtered chunks are not supported")
+            offs = struct.unpack_from(f"<{rank1}Q", b, k + 8)[:-1]
+            c = np.frombuffer(b, dt, nbytes // dt.itemsize, child).reshape(cdims)
+            sl = tuple(slice(o, min(o + e, s)) for o, e, s in zip(offs, cdims, out.shape))
+            out[sl] = c[tuple(slice(0, s.stop - s.start) for s in sl)]
+
+    def attributes(self, name: str) -> Dict[str, np.ndarray]:
+        b, res = self.b, {}
+        for t, p in self._msgs(self.names[name]):
+            if t != 0x0C:
+                continue
+            if b[p] != 1:
+                raise ValueError("only version-1 attribute messages are supported")
+            nsz, dsz, ssz = struct.unpack_from("<HHH", b, p + 2)
+            up = lambda v: (v + 7) & ~7
+            q = p + 8
+            key = b[q:q + nsz].split(b"\x00")[0].decode()
+            dt = self._dtype(q + up(nsz))
+            shape = self._shape(q + up(nsz) + up(dsz)) if ssz >= 8 else ()
+            res[key] = np.frombuffer(b, dt, int(np.prod(shape)) if shape else 1, q + up(nsz) + up(dsz) + up(ssz)).astype(dt.newbyteorder("="))
+        return res
+
+
+def read_wabbit_field(path: str) -> dict:
+    """One field file: blocks [Nb, (Bz+1,) By+1, Bx+1], level [Nb], ixyz [Nb, 3] (zero-based block coordinates recovered from origin /
+    spacing), treecode [Nb], refinement_status [Nb], and the attributes (time, iteration, block-size, domain-size, max_level, dim, ...)"""
+    f = _File(path)
+    a = f.attributes("blocks")
+    dim = int(a["dim"][0]) if "dim" in a else f.dataset("coords_origin").shape[1]
+    Bs = [int(v) for v in a["block-size"]]
+    origin, spacing = f.dataset("coords_origin"), f.dataset("coords_spacing")
+    ixyz = np.zeros((origin.shape[0], 3), dtype=np.int64)
+    for d in range(dim):                                       # the file stores (z,) y, x
+        ixyz[:, d] = np.rint(origin[:, dim - 1 - d] / (spacing[:, dim - 1 - d] * Bs[d]))
+    out = {"blocks": f.dataset("blocks"), "level": f.dataset("level").ravel().astype(np.int32), "ixyz": ixyz,
+           "treecode": f.dataset("block_treecode_num").ravel().astype(np.int64), "attrs": a, "dim": dim, "Bs": Bs}
+    out["refinement_status"] = f.dataset("refinement_status").ravel().astype(np.int32) if "refinement_status" in f.names else None
+    return out
+
+
+def read_state(paths: Sequence[str], g: int) -> dict:
+    """readHDF5vct_tree for a list of field files on the same grid (`input_files` of the .ini): the state vector as a ghosted host array
+    [Nb, ncomp, nz, ny, nx] (interiors filled, ghost nodes zero -- to be synchronised by the consumer) + the light data of the grid"""
+    first = read_wabbit_field(paths[0])
+    dim, Bs, nb = first["dim"], first["Bs"], len(first["level"])
+    nz = Bs[2] + 2 * g if dim == 3 else 1
+    hvy = np.zeros((nb, len(paths), nz, Bs[1] + 2 * g, Bs[0] + 2 * g))
+    for c, path in enumerate(paths):
+        d = first if c == 0 else read_wabbit_field(path)
+        if not (np.array_equal(d["level"], first["level"]) and np.array_equal(d["ixyz"], first["ixyz"])):
+            raise ValueError(f"{path}: not on the grid of {paths[0]}")
+        if dim == 3:
+            hvy[:, c, g:g + Bs[2], g:g + Bs[1], g:g + Bs[0]] = d["blocks"][:, :Bs[2], :Bs[1], :Bs[0]]
+        else:
+            hvy[:, c, 0, g:g + Bs[1], g:g + Bs[0]] = d["blocks"][:, :Bs[1], :Bs[0]]
+    return {"hvy": hvy, "level": first["level"], "ixyz": first["ixyz"], "treecode": first["treecode"], "time": float(first["attrs"]["time"][0]),
+            "iteration": int(first["attrs"]["iteration"][0]), "refinement_status": first["refinement_status"], "attrs": first["attrs"]}
