@@ -164,59 +164,60 @@ static void build(whost_forest *f)
     f->uniform = true;
     const int vary_tc[3] = {2, 1, 4};   // digit bit of x, y, z
     int any_jump = 0;
+    // direction-major: for one direction all blocks write into (at most 9) rows of the column-major table at consecutive positions
+    // (blocks are in space-filling-curve order = hvy order), instead of every block scattering its ~30 entries over 168 rows
+    for (int dz = (dim == 3 ? -1 : 0); dz <= (dim == 3 ? 1 : 0); ++dz)
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                if (!dx && !dy && !dz) continue;
+                const int d[3] = {dx, dy, dz};
+                const int nzero = (dx == 0) + (dy == 0) + (dz == 0);
+                int n_free = 1 << nzero;
+                if (dim == 2) n_free /= 2;
+                // digits of the (virtual) children touching this side
+                int append[4] = {0, 0, 0, 0};
+                int apply_free = 1;
+                for (int a = 0; a < dim; ++a) {
+                    if (d[a] == 0) {
+                        for (int k = 0; k < 4; ++k) append[k] += vary_tc[a] * ((k / apply_free) % 2);
+                        apply_free += 1;
+                    } else if (d[a] == 1) {
+                        for (int k = 0; k < 4; ++k) append[k] += vary_tc[a];
+                    }
+                }
+                // same-level slot code
+                int code;
+                if (nzero == 2) {
+                    code = 1;
+                    for (int a = 0; a < 3; ++a) {
+                        if (d[a] != 0) code += 8 * a;
+                        if (d[a] == 1) code += 4;
+                    }
+                } else if (nzero == 1) {
+                    code = 25;
+                    int af = 1;
+                    for (int a = 0; a < 3; ++a) {
+                        if (d[a] == 0) code += 8 * (2 - a);
+                        else {
+                            if (d[a] == 1) code += af * 2;
+                            af++;
+                        }
+                    }
+                } else {
+                    code = 49;
+                    for (int a = 0; a < 3; ++a)
+                        if (d[a] == 1) code += 1 << a;
+                }
 #pragma omp parallel for schedule(static) reduction(| : any_jump)
-    for (int i = 0; i < nb; ++i) {
-        const Blk &b = f->blocks[i];
-        int32_t *row = f->nbr[b.rank].data();
-        const size_t ld = f->rank_blocks[b.rank].size();
-        auto set = [&](int code, int j) { row[(size_t)(code - 1) * ld + (b.hvy - 1)] = f->blocks[j].rank * f->N + f->blocks[j].hvy; };
-        const int tc_last = b.level > 0 ? (int)((b.tc >> ((f->Jmax - b.level) * dim)) & ((1 << dim) - 1)) : 0;
-        for (int dz = (dim == 3 ? -1 : 0); dz <= (dim == 3 ? 1 : 0); ++dz)
-            for (int dy = -1; dy <= 1; ++dy)
-                for (int dx = -1; dx <= 1; ++dx) {
-                    if (!dx && !dy && !dz) continue;
-                    const int d[3] = {dx, dy, dz};
-                    const int nzero = (dx == 0) + (dy == 0) + (dz == 0);
-                    int n_free = 1 << nzero;
-                    if (dim == 2) n_free /= 2;
-                    // digits of the (virtual) children touching this side
-                    int append[4] = {0, 0, 0, 0};
-                    int apply_free = 1;
-                    for (int a = 0; a < dim; ++a) {
-                        if (d[a] == 0) {
-                            for (int k = 0; k < 4; ++k) append[k] += vary_tc[a] * ((k / apply_free) % 2);
-                            apply_free += 1;
-                        } else if (d[a] == 1) {
-                            for (int k = 0; k < 4; ++k) append[k] += vary_tc[a];
-                        }
-                    }
-                    // same-level slot code
-                    int code;
-                    if (nzero == 2) {
-                        code = 1;
-                        for (int a = 0; a < 3; ++a) {
-                            if (d[a] != 0) code += 8 * a;
-                            if (d[a] == 1) code += 4;
-                        }
-                    } else if (nzero == 1) {
-                        code = 25;
-                        int af = 1;
-                        for (int a = 0; a < 3; ++a) {
-                            if (d[a] == 0) code += 8 * (2 - a);
-                            else {
-                                if (d[a] == 1) code += af * 2;
-                                af++;
-                            }
-                        }
-                    } else {
-                        code = 49;
-                        for (int a = 0; a < 3; ++a)
-                            if (d[a] == 1) code += 1 << a;
-                    }
+                for (int i = 0; i < nb; ++i) {
+                    const Blk &b = f->blocks[i];
+                    int32_t *row = f->nbr[b.rank].data();
+                    const size_t ld = f->rank_blocks[b.rank].size();
+                    auto set = [&](int cd, int j) { row[(size_t)(cd - 1) * ld + (b.hvy - 1)] = f->blocks[j].rank * f->N + f->blocks[j].hvy; };
+                    const int tc_last = b.level > 0 ? (int)((b.tc >> ((f->Jmax - b.level) * dim)) & ((1 << dim) - 1)) : 0;
                     int code_coarser = -1;
                     for (int k = 0; k < n_free; ++k)
                         if (tc_last == append[k]) code_coarser = code + k;
-
                     // same level
                     const int nblk = 1 << b.level;
                     int p[3] = {0, 0, 0};
@@ -263,7 +264,7 @@ static void build(whost_forest *f)
                         }
                     }
                 }
-    }
+            }
     f->uniform = !any_jump;
 }
 
