@@ -76,6 +76,12 @@ int32_t whost_coarsen_global(const whost_forest *f, int32_t *status, int32_t Jmi
  * par[n], daughters child[n][2^dim] (column = x + 2y + 4z offset); indices into the list or -1.  whost_ft_decide: respectJmaxJmin_tree +
  * ensureGradedness_tree(check_daughters) (LIB/MESH/ensureGradedness_tree.f90): status -1 survives only for blocks that are deleted. */
 int32_t whost_ft_tables(int32_t dim, int32_t n, const int32_t *level, const int32_t *pos, int32_t *nb, int32_t *par, int32_t *child);
+/* hvy_neighbor rows [168][ld] (column = slot - 1) of every block of the full tree for the passes of the full-tree adapt_tree: same-level
+ * relations from nb (row dir_code[q] - 1, dir_code = the slot code of find_neighbor for direction q); for blocks flagged in `leaf`,
+ * directions without a same-level block get the coarser relation (row + 56) to the covering block one level up.  Unset entries keep
+ * their value (preset -1). */
+int32_t whost_ft_rows(int32_t dim, int32_t n, const int32_t *level, const int32_t *pos, const int32_t *nb, const int32_t *slots,
+                      const int32_t *leaf, const int32_t *dir_code, int64_t ld, int32_t *rows);
 int32_t whost_ft_decide(int32_t dim, int32_t n, const int32_t *level, const int32_t *nb, const int32_t *par, const int32_t *child, int32_t Jmin,
                         int32_t *status);
 

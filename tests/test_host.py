@@ -253,6 +253,20 @@ def test_full_tree_light_data_matches_the_oracle(seed):
     assert set(ft.slot) == set(t.blk) and ft.leaf == t.leaf and not ft.leaf_first
     i = ft._find(l.astype(np.int64), x.astype(np.int64))
     assert (i >= 0).all() and np.array_equal(ft.slots[i], hvy) and np.array_equal(_encode_treecodes(3, ft.level[i], ft.pos[i], 4), tc)
+    # the neighbour rows of the tree passes (whost_ft_rows) against their numpy formulation; a second tree reuses the solver's buffer
+    sol = ft.sol
+    sol.set_treecodes = lambda *a: None
+    ft._upload_rows()
+    assert ft._rows.shape[1] == sol.max_blocks and np.array_equal(ft._rows[:, :int(ft.slots.max())], ft._rows_numpy(int(ft.slots.max())))
+    assert (ft._rows[:, int(ft.slots.max()):] == -1).all() and (ft._rows[:56] >= 0).any() and (ft._rows[56:112] >= 0).any()
+    keep = np.ones(len(ft.code), bool)
+    keep[np.flatnonzero(ft.is_leaf)[::3]] = False                      # some other tree state on the same solver
+    ft2 = FullTree(sol, forest, Jmin=1)
+    ft2.code, ft2.level, ft2.pos, ft2.slots, ft2.is_leaf = (a[keep] for a in (ft.code, ft.level, ft.pos, ft.slots, ft.is_leaf))
+    ft2._build_tables()
+    ft2.is_leaf = ft2.child[:, 0] < 0
+    ft2._upload_rows()
+    assert ft2._rows is ft._rows and np.array_equal(ft2._rows[:, :int(ft2.slots.max())], ft2._rows_numpy(int(ft2.slots.max())))
     st0 = np.where(np.random.default_rng(seed).random(len(ft.code)) < 0.75, -1, 0).astype(np.int32)
     st = ft.decide(st0)
     od = OFT.decide(t, ft.status_dict(st0), 1)

@@ -99,6 +99,7 @@ HOST_SYMBOLS = {
     "whost_refine_global": (C.c_int32, [C.c_void_p, _i32p, C.c_int32, C.POINTER(C.c_void_p), _i32p, _i32p, _i32p, _i32p, _i32p, _i32p]),
     "whost_coarsen_global": (C.c_int32, [C.c_void_p, _i32p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), _i32p, _i32p, _i32p, _i32p, _i32p, _i32p]),
     "whost_ft_tables": (C.c_int32, [C.c_int32, C.c_int32, _i32p, _i32p, _i32p, _i32p, _i32p]),
+    "whost_ft_rows": (C.c_int32, [C.c_int32, C.c_int32, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, C.c_int64, _i32p]),
     "whost_ft_decide": (C.c_int32, [C.c_int32, C.c_int32, _i32p, _i32p, _i32p, _i32p, C.c_int32, _i32p]),
     "whost_encode": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, _i32p]),
     "whost_decode": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, _i32p]),

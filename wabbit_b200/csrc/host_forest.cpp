@@ -612,6 +612,64 @@ int32_t whost_ft_tables(int32_t dim, int32_t n, const int32_t *level, const int3
     return 0;
 }
 
+// hvy_neighbor rows of every block of a full tree (wabbit_b200/fulltree.py: _upload_rows): same-level relations to whatever block sits
+// there (row dir_code[q] - 1); for the blocks flagged in `leaf`, directions without a same-level block become a coarser relation
+// (row dir_code[q] - 1 + 56) to the block one level up that covers the neighbour position.  rows: [168][ld] int32, column = slot - 1;
+// entries that are not set keep their value (the caller presets -1).  Direction-major, so the writes stream.
+int32_t whost_ft_rows(int32_t dim, int32_t n, const int32_t *level, const int32_t *pos, const int32_t *nb, const int32_t *slots,
+                      const int32_t *leaf, const int32_t *dir_code, int64_t ld, int32_t *rows)
+{
+    if (n < 0 || ld < 0 || (n > 0 && (!level || !pos || !nb || !slots || !leaf || !dir_code || !rows))) return 1;
+    size_t cap = 64;
+    while (cap < (size_t)n * 2 + 2) cap <<= 1;
+    const uint64_t hmask = cap - 1;
+    std::vector<uint64_t> hkeys(cap, ~0ull);
+    std::vector<int> hvals(cap, -1);
+    for (int i = 0; i < n; ++i) {
+        if (slots[i] < 1 || slots[i] > ld) return 2;
+        const uint64_t key = pos_hash(level[i], pos + 3 * i);
+        uint64_t h = whost_forest::mix(key) & hmask;
+        while (hkeys[h] != ~0ull && hkeys[h] != key) h = (h + 1) & hmask;
+        hkeys[h] = key;
+        hvals[h] = i;
+    }
+    auto find = [&](int l, const int p[3]) -> int {
+        if (l < 0) return -1;
+        const uint64_t key = pos_hash(l, p);
+        uint64_t h = whost_forest::mix(key) & hmask;
+        while (hkeys[h] != ~0ull) {
+            if (hkeys[h] == key) return hvals[h];
+            h = (h + 1) & hmask;
+        }
+        return -1;
+    };
+    const int ndir = (dim == 3 ? 27 : 9) - 1;
+    int q = 0;
+    for (int dz = (dim == 3 ? -1 : 0); dz <= (dim == 3 ? 1 : 0); ++dz)
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                if (!dx && !dy && !dz) continue;
+                const int d[3] = {dx, dy, dz};
+                int32_t *same = rows + (size_t)(dir_code[q] - 1) * ld, *coarse = rows + (size_t)(dir_code[q] - 1 + 56) * ld;
+#pragma omp parallel for schedule(static)
+                for (int i = 0; i < n; ++i) {
+                    const int j = nb[(size_t)i * ndir + q];
+                    if (j >= 0) {
+                        same[slots[i] - 1] = slots[j];
+                    } else if (leaf[i]) {
+                        const int l = level[i], nb_l = 1 << l;
+                        const int *p = pos + 3 * i;
+                        const int cp[3] = {(((p[0] + d[0]) % nb_l + nb_l) % nb_l) >> 1, (((p[1] + d[1]) % nb_l + nb_l) % nb_l) >> 1,
+                                           dim == 3 ? ((((p[2] + d[2]) % nb_l + nb_l) % nb_l) >> 1) : 0};
+                        const int c = find(l - 1, cp);
+                        if (c >= 0) coarse[slots[i] - 1] = slots[c];
+                    }
+                }
+                ++q;
+            }
+    return 0;
+}
+
 // status[n] in: -1 = insignificant; out: -1 only for the blocks that are deleted, 9 (REF_UNSIGNIFICANT_STAY) for demoted ones.
 // A block keeps -1 only if it sits above Jmin, all its 2^dim sisters carry -1, none of its daughters stays and none of its finer
 // neighbours (the daughters of its same-level neighbours that touch it) stays.  Statuses only move from -1 to 9: unique fixed point.

@@ -186,6 +186,22 @@ class FullTree:
             sol._ft_rows_used = ld
         except AttributeError:
             pass
+        leaf = np.ascontiguousarray(self.is_leaf & (self.level > 0), dtype=np.int32)
+        codes = np.array([_code(d) for d in self.dirs], dtype=np.int32)
+        slots32 = np.ascontiguousarray(self.slots, dtype=np.int32)
+        i32 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        rc = host_lib().whost_ft_rows(dim, len(self.code), i32(self._lvl32), i32(self._pos32), i32(self.nb), i32(slots32), i32(leaf), i32(codes),
+                                      nbr.shape[1], i32(nbr))
+        if rc:
+            raise RuntimeError(f"whost_ft_rows: {rc}")
+        self._rows = nbr
+        tc = _encode_treecodes(dim, self.level, self.pos, self.forest.Jmax)
+        sol.set_treecodes(self.slots.astype(np.int32), self._lvl32, tc)
+        self._rows_ready = True
+
+    def _rows_numpy(self, ld: int) -> np.ndarray:
+        """the table of _upload_rows in numpy (reference formulation of whost_ft_rows, used by tests/test_host.py)"""
+        nbr = np.full((168, ld), -1, dtype=np.int32)
         col = self.slots - 1
         leaf = self.is_leaf & (self.level > 0)
         for q, d in enumerate(self.dirs):
@@ -197,10 +213,7 @@ class FullTree:
                 c = self._find(self.level[miss] - 1, self._neighbor_pos(miss, d) >> 1)
                 ok = c >= 0
                 nbr[_code(d) - 1 + 56, col[miss[ok]]] = self.slots[c[ok]]
-        self._rows = nbr
-        tc = _encode_treecodes(dim, self.level, self.pos, self.forest.Jmax)
-        sol.set_treecodes(self.slots.astype(np.int32), self._lvl32, tc)
-        self._rows_ready = True
+        return nbr
 
     # ---- views used by callers and tests
     def keys(self, idx=None):
