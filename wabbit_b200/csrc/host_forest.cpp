@@ -225,7 +225,7 @@ static void build(whost_forest *f)
                     for (int a = 0; a < dim; ++a) {
                         p[a] = b.ix[a] + d[a];
                         if (p[a] < 0 || p[a] >= nblk) {
-                            if (f->periodic[a]) p[a] = (p[a] + nblk) % nblk;
+                            if (f->periodic[a]) p[a] = (p[a] + nblk) & (nblk - 1);
                             else outside = true;
                         }
                     }
@@ -244,7 +244,7 @@ static void build(whost_forest *f)
                             for (int a = 0; a < dim; ++a) {
                                 const int bit = (append[k] & vary_tc[a]) ? 1 : 0;
                                 q[a] = 2 * b.ix[a] + bit + d[a];
-                                q[a] = (q[a] + nblk2) % nblk2;
+                                q[a] = (q[a] + nblk2) & (nblk2 - 1);
                             }
                             j = f->find(b.level + 1, q);
                             if (j < 0) break;
@@ -598,8 +598,8 @@ int32_t whost_ft_tables(int32_t dim, int32_t n, const int32_t *level, const int3
             for (int dy = -1; dy <= 1; ++dy)
                 for (int dx = -1; dx <= 1; ++dx) {
                     if (!dx && !dy && !dz) continue;
-                    const int np[3] = {((p[0] + dx) % nb_l + nb_l) % nb_l, ((p[1] + dy) % nb_l + nb_l) % nb_l,
-                                       dim == 3 ? ((p[2] + dz) % nb_l + nb_l) % nb_l : 0};
+                    const int m_l = nb_l - 1;   // nb_l is a power of two: periodic wrap by masking
+                    const int np[3] = {(p[0] + dx) & m_l, (p[1] + dy) & m_l, dim == 3 ? ((p[2] + dz) & m_l) : 0};
                     nb[(size_t)i * ndir + q++] = find(l, np);
                 }
         const int pp[3] = {p[0] >> 1, p[1] >> 1, p[2] >> 1};
@@ -659,8 +659,8 @@ int32_t whost_ft_rows(int32_t dim, int32_t n, const int32_t *level, const int32_
                     } else if (leaf[i]) {
                         const int l = level[i], nb_l = 1 << l;
                         const int *p = pos + 3 * i;
-                        const int cp[3] = {(((p[0] + d[0]) % nb_l + nb_l) % nb_l) >> 1, (((p[1] + d[1]) % nb_l + nb_l) % nb_l) >> 1,
-                                           dim == 3 ? ((((p[2] + d[2]) % nb_l + nb_l) % nb_l) >> 1) : 0};
+                        const int m_l = nb_l - 1;
+                        const int cp[3] = {((p[0] + d[0]) & m_l) >> 1, ((p[1] + d[1]) & m_l) >> 1, dim == 3 ? (((p[2] + d[2]) & m_l) >> 1) : 0};
                         const int c = find(l - 1, cp);
                         if (c >= 0) coarse[slots[i] - 1] = slots[c];
                     }
