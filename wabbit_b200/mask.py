@@ -97,9 +97,11 @@ class SphereMask3D:
         dmax = np.sqrt(((far - c[None, :]) ** 2).sum(axis=1)) - self.R
         cand = np.flatnonzero((dmin < self.h + dx.max(axis=1)) & (dmax > -self.h - dx.max(axis=1)))
         out = np.zeros(n, bool)
-        for i in cand:
-            ax = [np.arange(p.Bs[d], dtype=np.float64) * dx[i, d] + float(int(pos[i, d]) * p.Bs[d]) * dx[i, d] for d in range(3)]
-            dist = np.sqrt((ax[0][None, None, :] - c[0]) ** 2 + (ax[1][None, :, None] - c[1]) ** 2 + (ax[2][:, None, None] - c[2]) ** 2) - self.R
-            chi = _step_cosine(dist, self.h)
-            out[i] = bool(((chi > 1.0e-12) & (chi < 1.0 - 1.0e-12)).any() or (chi.max() - chi.min()) > 1.0e-12)
+        for s0 in range(0, len(cand), 128):                          # point-by-point evaluation, 128 candidate blocks at a time
+            ii = cand[s0:s0 + 128]
+            ax = [np.arange(p.Bs[d], dtype=np.float64)[None, :] * dx[ii, d][:, None]
+                  + ((pos[ii, d] * p.Bs[d]).astype(np.float64) * dx[ii, d])[:, None] for d in range(3)]
+            dist = np.sqrt((ax[0][:, None, None, :] - c[0]) ** 2 + (ax[1][:, None, :, None] - c[1]) ** 2 + (ax[2][:, :, None, None] - c[2]) ** 2) - self.R
+            chi = _step_cosine(dist, self.h).reshape(len(ii), -1)
+            out[ii] = ((chi > 1.0e-12) & (chi < 1.0 - 1.0e-12)).any(axis=1) | ((chi.max(axis=1) - chi.min(axis=1)) > 1.0e-12)
         return out

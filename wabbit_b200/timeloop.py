@@ -45,24 +45,31 @@ def refinement_flags(forest: Forest, indicator: str, status: Optional[np.ndarray
     if indicator == "everywhere":
         return flag
     # gradedness: a block (level L, flag 0) refines if a finer neighbour (level L+1) refines.  Propagate upwards from the finest level:
-    # mark, for every refining block, the (up to 3^dim - 1) positions of level L-1 that touch it and hold a leaf.
-    key = {(int(l), int(p[0]), int(p[1]), int(p[2])): b for b, (l, p) in enumerate(zip(lvl, pos))}
-    changed = True
-    while changed:
-        changed = False
-        for b in np.flatnonzero(flag == 1):
-            L = int(lvl[b])
-            if L == 0:
-                continue
-            nb = 1 << L
-            for dz in ((-1, 0, 1) if dim == 3 else (0,)):
-                for dy in (-1, 0, 1):
-                    for dx in (-1, 0, 1):
-                        q = ((int(pos[b, 0]) + dx) % nb, (int(pos[b, 1]) + dy) % nb, ((int(pos[b, 2]) + dz) % nb) if dim == 3 else 0)
-                        c = key.get((L - 1, q[0] >> 1, q[1] >> 1, q[2] >> 1))
-                        if c is not None and flag[c] == 0:
-                            flag[c] = 1
-                            changed = True
+    # every refining block marks the (up to 3^dim - 1) leaves of level L-1 that touch it; vectorised over the refining blocks, lookups
+    # by position code (sorted array + searchsorted), repeated until nothing changes
+    from .fulltree import _pack
+    code = _pack(lvl, pos)
+    order = np.argsort(code)
+    code_sorted = code[order]
+    dirs = [(dx, dy, dz) for dz in ((-1, 0, 1) if dim == 3 else (0,)) for dy in (-1, 0, 1) for dx in (-1, 0, 1) if (dx, dy, dz) != (0, 0, 0)]
+    front = np.flatnonzero((flag == 1) & (lvl > 0))
+    while len(front):
+        L = lvl[front]
+        mask = (np.int64(1) << L) - 1
+        hit = []
+        for d in dirs:
+            q = (pos[front] + np.array(d, dtype=np.int64)[None, :]) & mask[:, None]
+            if dim == 2:
+                q[:, 2] = 0
+            ck = _pack(L - 1, q >> 1)
+            k = np.minimum(np.searchsorted(code_sorted, ck), n - 1)
+            ok = code_sorted[k] == ck
+            hit.append(order[k[ok]])
+        cand = np.unique(np.concatenate(hit))
+        new = cand[flag[cand] == 0]
+        new = new[lvl[new] < Jmax]                       # (always true: a leaf with a finer neighbour is below Jmax)
+        flag[new] = 1
+        front = new[lvl[new] > 0]
     return flag
 
 
