@@ -335,3 +335,95 @@ def test_host_mask_generators_match_the_oracle():
         ko = np.array([so.keeps(int(l), x, t) for l, x in zip(lv, pos)])
         assert np.array_equal(k, ko)
         assert 0 < k.sum() < len(k)
+
+
+def test_full_tree_adapt_host_path_runs_without_a_device():
+    """the host side of FullTree.adapt (tree tables, neighbour rows through whost_ft_rows, pass topologies, grid decision, pruning, new
+    forest, move lists) driven end to end with a device stand-in that records the calls and answers the flag queries at random: the
+    light-data logic must produce a complete, graded leaf grid and consistent id lists whatever the flags are"""
+    from util import graded_blocks
+    from wabbit_b200.fulltree import FullTree
+
+    class NullSol:
+        max_blocks = 20000
+
+        class params:
+            Bs = (16, 16, 16)
+            wavelet = "CDF44"
+            discretization = "FD_4th_central"
+            useCoarseExtension = -1
+            n_eqn = 4
+            eps = 1e-3
+
+        def __init__(self):
+            self.rng = np.random.default_rng(4)
+            self.calls = []
+            self.hvy_active = np.zeros(0, np.int32)
+
+        def wavelet_filter_width(self):
+            return 6
+
+        def set_treecodes(self, hvy, level, tc):
+            assert len(hvy) == len(level) == len(tc) and hvy.min() >= 1 and hvy.max() <= self.max_blocks
+            self.calls.append("treecodes")
+
+        def set_topology(self, hvy, level, rows, rank):
+            assert rows.shape[0] == 168 and rows.flags.c_contiguous and rows.dtype == np.int32 and hvy.max() <= rows.shape[1]
+            act = rows[:, np.asarray(hvy) - 1]
+            assert act.max() <= rows.shape[1] and ((act >= 1) | (act == -1)).all()
+            self.hvy_active = np.asarray(hvy)
+            self.calls.append("topology")
+
+        def set_forest(self, forest, rank=0):
+            self.hvy_active = forest.active(0)[0]
+            self.calls.append("forest")
+
+        def waveletDecomposition_tree(self, *a):
+            self.calls.append("fwt")
+
+        def coarse_extension_modify(self, *a):
+            self.calls.append("ce")
+
+        def waveletReconstruction_CE(self, *a):
+            self.calls.append("iwt_ce")
+
+        def coarsen_blocks(self, mothers, daughters, *a):
+            assert len(daughters) == 8 * len(mothers) and len(set(daughters.tolist())) == len(daughters)
+            self.calls.append("d2m")
+
+        def threshold_tree(self, *a, **k):
+            n = len(self.hvy_active)
+            return np.where(self.rng.random(n) < 0.97, -1, 0).astype(np.int32), self.rng.random((n, 4))
+
+        def patch_details(self, ids, dirs, *a):
+            return self.rng.random((len(ids), 4)) * 1.1e-3          # a few pairs exceed eps * norm: the security zone acts
+
+        def move_blocks(self, src, dst):
+            assert len(src) == len(dst) and len(set(dst.tolist())) == len(dst) and len(set(src.tolist())) == len(src)
+            self.moved = (np.asarray(src), np.asarray(dst))
+            self.calls.append("move")
+
+        def synchronize(self):
+            pass
+
+    lv, ix = graded_blocks(3, 1, 4, 9, 0.3)
+    forest = Forest.from_blocks(3, 4, lv, ix, max_blocks=NullSol.max_blocks)
+    sol = NullSol()
+    ft = FullTree(sol, forest, Jmin=1)
+    new, info = ft.adapt(eps=1e-3, norm=np.ones(4), use_security_zone=True, want_info=False,
+                         mask_keeps=lambda level, pos: (np.asarray(pos)[:, 0] == 0))
+    assert {"treecodes", "topology", "fwt", "ce", "d2m", "move", "forest"} <= set(sol.calls)
+    hvy, l, x, _ = new.active(0)
+    assert 8 <= new.n_blocks < forest.n_blocks and np.array_equal(np.sort(sol.moved[1]), hvy)
+    # complete and graded: every point of the domain is covered exactly once, neighbouring leaves differ by at most one level
+    vol = (1.0 / 8.0 ** l.astype(np.float64)).sum()
+    assert abs(vol - 1.0) < 1e-12
+    nb = new.neighbors(0)
+    assert ((nb[:56] >= 1).sum(axis=0) + (nb[56:112] >= 1).any(axis=0) + (nb[112:] >= 1).any(axis=0) > 0).all()
+    assert len(ft.leaf_status) == new.n_blocks and set(np.unique(ft.leaf_status)) <= {0, 9}
+    # the blocks the mask indicator named never disappear below their level: a kept block's position is still covered at >= its level
+    kept = {(int(a), int(b[0]), int(b[1]), int(b[2])) for a, b in zip(l, x)}
+    _, l0, x0, _ = forest.active(0)
+    for a, b in zip(l0, x0):
+        if b[0] == 0:
+            assert (int(a), int(b[0]), int(b[1]), int(b[2])) in kept
