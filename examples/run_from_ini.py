@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""Run an adaptive 2-D ACM case from a WABBIT parameter file on one GPU and write WABBIT field files:
+
+    python examples/run_from_ini.py /path/to/TESTING/acm/acm_CDF44/acm_cyl.ini --out out/
+
+What main.f90 does for `adapt_tree = 1`, `inicond = meanflow`, `read_from_files = 0` (LIB/MAIN/main.f90:85-443): READ_PARAMETERS, the
+adaptive initial condition (setInitialCondition_tree), then per time step refine_tree -> createMask_tree -> RungeKuttaGeneric -> adapt_tree,
+saving `ux uy p mask` at t = 0 and at every multiple of `write_time` (write_method = fixed_time).  The same sequence as
+tests/test_gpu_cylinder2d.py, which compares its results with the files the reference wrote for this .ini; `--plan` stops before the first
+device call (parameter / mask / grid summary only; runs without a GPU).
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from wabbit_b200 import Forest, Params  # noqa: E402
+from wabbit_b200 import h5io  # noqa: E402
+from wabbit_b200.mask import mask_from_ini  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("ini")
+    ap.add_argument("--out", default="out")
+    ap.add_argument("--max-blocks", type=int, default=4000)
+    ap.add_argument("--plan", action="store_true", help="parse, build the mask generator and the initial grid, print the plan, stop")
+    a = ap.parse_args()
+
+    p = Params.from_ini(a.ini)
+    if p.dim != 2 or p.inicond != "meanflow":
+        raise SystemExit("this example covers dim = 2, inicond = meanflow (the TESTING/acm cylinder cases)")
+    mask = mask_from_ini(a.ini, p)
+    forest = Forest.uniform(2, p.Jmin, Jmax=p.Jmax, max_blocks=a.max_blocks)
+    print(f"{a.ini}: {p.wavelet}, Bs = {p.Bs[0]}, g = {p.g}, Jmin..Jmax = {p.Jmin}..{p.Jmax}, eps = {p.eps}, refinement {p.refinement_indicator}, "
+          f"penalization = {p.penalization} ({type(mask).__name__ if mask is not None else 'no mask'}), sponge = {p.use_sponge}, "
+          f"time_max = {p.time_max}, write_time = {p.write_time}; initial grid {forest.n_blocks} blocks on level {p.Jmin}")
+    if a.plan:
+        return
+
+    from wabbit_b200 import WabbitGPU
+    from wabbit_b200.solver import HVY_BLOCK
+    from wabbit_b200.timeloop import AdaptiveLoop
+    os.makedirs(a.out, exist_ok=True)
+    sol = WabbitGPU(p, max_blocks=a.max_blocks)
+    sol.setup_wavelet(p.wavelet)
+    sol.set_forest(forest)
+    loop = AdaptiveLoop(sol, forest, 0.0, 0, mask=mask, threshold_mask=mask is not None)
+
+    def set_inicond(lp):                      # inicond = meanflow (inicond_ACM.f90:285-288): u = u_mean_set, p = 0
+        hvy, _, _, _ = lp.forest.active(0)
+        host = np.zeros((int(hvy.max()),) + sol.host_shape()[1:])
+        for d in range(p.dim):
+            host[hvy - 1, d] = p.u_mean_set[d]
+        sol.upload(host, HVY_BLOCK, 0, hvy_ids=hvy)
+
+    def save():
+        hvy, lvl, pos, tc = loop.forest.active(0)
+        host = np.zeros((int(hvy.max()),) + sol.host_shape()[1:])
+        sol.download(host, g_sync=p.g)                         # ghost nodes as sync_ghosts_tree leaves them: the files hold one of them
+        status = loop.status if loop.status is not None else np.zeros(len(hvy), np.int32)
+        paths = h5io.save_data(a.out, ("ux", "uy", "p"), host[hvy - 1], lvl, pos, tc, p, loop.time, loop.iteration, refinement_status=status)
+        if mask is not None:
+            chi = mask.fill(lvl, pos)[:, :1]
+            paths += h5io.save_data(a.out, ("mask",), chi, lvl, pos, tc, p, loop.time, loop.iteration, refinement_status=status)
+        print(f"t = {loop.time:.6f} it = {loop.iteration} Nb = {loop.forest.n_blocks}: wrote {[os.path.basename(q) for q in paths]}")
+
+    set_inicond(loop)
+    loop.adaptive_inicond(set_inicond)
+    save()
+    while loop.time < p.time_max:
+        loop.step()
+        if p.write_method == "fixed_time" and abs(loop.time / p.write_time - round(loop.time / p.write_time)) <= 1e-12:
+            save()
+    if not (p.write_method == "fixed_time"):
+        save()
+    sol.close()
+
+
+if __name__ == "__main__":
+    main()

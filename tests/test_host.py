@@ -427,3 +427,84 @@ def test_full_tree_adapt_host_path_runs_without_a_device():
     for a, b in zip(l0, x0):
         if b[0] == 0:
             assert (int(a), int(b[0]), int(b[1]), int(b[2])) in kept
+
+
+def test_params_and_mask_from_the_reference_ini_format(tmp_path):
+    """the .ini interface of the path: Params.from_ini + mask_from_ini on a parameter file in the reference's format (the keys of
+    TESTING/acm/acm_CDF44/acm_cyl.ini that the path reads; where the reference checkout exists, that very file)"""
+    import cylinder_case as CC
+    from wabbit_b200 import Params
+    from wabbit_b200.mask import CylinderMask2D, mask_from_ini
+    text = """
+[Domain]
+dim=2;
+domain_size=20 20;
+periodic_BC=1 1;
+[Blocks]
+number_block_nodes=26;
+number_ghost_nodes=;
+number_equations=3;
+eps=1.0e-3;
+max_treelevel=6;
+min_treelevel=;
+adapt_tree=1;
+refinement_indicator=everywhere;
+eps_normalized=1;
+eps_norm=Linfty;
+threshold_mask=1;
+force_maxlevel_dealiasing=1;
+[Wavelet]
+wavelet=CDF44;
+[Time]
+time_max=0.1;
+CFL=1.5;
+CFL_eta=0.99;
+write_method=fixed_time;
+write_time=0.05;
+[ACM-new]
+c_0=12.5;
+nu=0.0;
+gamma_p=0;
+u_mean_set=0.0 -1.0 0.0;
+inicond=meanflow;
+[Sponge]
+use_sponge=1;
+sponge_type=p-norm;
+p_sponge=8.0;
+L_sponge=2.0;
+C_sponge=8.0e-3;
+[Discretization]
+order_discretization=FD_4th_central;
+[VPM]
+penalization=1;
+smoothing_type=cosine; hester, discontinuous/dis, cosine/cos
+C_eta=1.34e-3;
+geometry=cylinder;
+x_cntr=10.0 10.0 0;
+length=1.0;
+"""
+    paths = [str(tmp_path / "acm_cyl.ini")]
+    open(paths[0], "w").write(text)
+    if os.path.exists("/root/reference/TESTING/acm/acm_CDF44/acm_cyl.ini"):
+        paths.append("/root/reference/TESTING/acm/acm_CDF44/acm_cyl.ini")
+    for path in paths:
+        p = Params.from_ini(path)
+        for k, v in CC.INI.items():
+            got = getattr(p, k)
+            if k == "domain":
+                assert tuple(got[:2]) == v[:2]
+            else:
+                assert (tuple(got) if isinstance(v, tuple) else got) == v, (k, got, v)
+        got = (p.wavelet, p.eps, p.eps_normalized, p.eps_norm, p.Jmin, p.force_maxlevel_dealiasing, p.adapt_tree, p.refinement_indicator)
+        assert got == ("CDF44", 1.0e-3, True, "Linfty", 1, True, True, "everywhere")
+        assert p.useCoarseExtension == 1 and p.useSecurityZone == 1 and p.n_mask == 6 and not p.skew_symmetry
+        m, ref = mask_from_ini(path, p), CylinderMask2D(p)
+        assert isinstance(m, CylinderMask2D) and (m.c, m.R, m.h, m.L, m.ps) == ((10.0, 10.0), 0.5, ref.h, 2.0, 8.0)
+        lv = np.array([5, 5, 3]); pos = np.array([[15, 15, 0], [16, 16, 0], [0, 0, 0]])
+        assert np.array_equal(m.fill(lv, pos), ref.fill(lv, pos))
+    # the example driver parses the same file and plans the run without touching a device
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "examples", "run_from_ini.py"), paths[0], "--plan"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "CylinderMask2D" in out.stdout and "Jmin..Jmax = 1..6" in out.stdout, out.stderr

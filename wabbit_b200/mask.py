@@ -105,3 +105,29 @@ class SphereMask3D:
             chi = _step_cosine(dist, self.h).reshape(len(ii), -1)
             out[ii] = ((chi > 1.0e-12) & (chi < 1.0 - 1.0e-12)).any(axis=1) | ((chi.max(axis=1) - chi.min(axis=1)) > 1.0e-12)
         return out
+
+
+def mask_from_ini(path: str, p: Params):
+    """The mask generator for the [VPM] / [Sponge] sections of a WABBIT parameter file (READ_PARAMETERS_ACM, LIB/EQUATION/ACMnew/
+    module_ACM.f90:290-345: geometry, x_cntr, R_cyl = 0.5, C_smooth = 1.5, smoothing_type = cos; sponge_type, L_sponge, p_sponge = 20) or None
+    without penalization.  Supported: geometry = cylinder / circle (2-D, cosine smoothing, p-norm sponge) and sphere-fixed (3-D)."""
+    from .params import IniFile
+    if not p.penalization:
+        return None
+    ini = IniFile(path)
+    geometry = ini.string("VPM", "geometry", "cylinder").strip().lower()
+    x_cntr = ini.vector("VPM", "x_cntr", [0.5 * p.domain[0], 0.5 * p.domain[1], 0.5 * p.domain[2]])
+    x_cntr = (list(x_cntr) + [0.0, 0.0, 0.0])[:3]
+    R = ini.real("VPM", "R_cyl", 0.5)
+    C_smooth = ini.real("VPM", "C_smooth", 1.5)
+    smoothing = ini.string("VPM", "smoothing_type", "cos").strip().lower()
+    if smoothing not in ("cos", "cosine"):
+        raise ValueError(f"smoothing_type {smoothing!r} is not supported (cosine only)")
+    if geometry in ("cylinder", "circle"):
+        if p.use_sponge and ini.string("Sponge", "sponge_type", "rect").strip().lower() != "p-norm":
+            raise ValueError("only the p-norm sponge is supported")
+        return CylinderMask2D(p, x_cntr=tuple(x_cntr[:2]), R_cyl=R, C_smooth=C_smooth, L_sponge=ini.real("Sponge", "L_sponge", 0.0),
+                              p_sponge=ini.real("Sponge", "p_sponge", 20.0))
+    if geometry == "sphere-fixed":
+        return SphereMask3D(p, center=tuple(x_cntr), radius=R, C_smooth=C_smooth)
+    raise ValueError(f"geometry {geometry!r} is not supported")
