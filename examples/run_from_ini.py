@@ -49,7 +49,8 @@ def main():
     sol = WabbitGPU(p, max_blocks=a.max_blocks)
     sol.setup_wavelet(p.wavelet)
     sol.set_forest(forest)
-    loop = AdaptiveLoop(sol, forest, 0.0, 0, mask=mask, threshold_mask=mask is not None)
+    tc = p.threshold_state_vector_component or None
+    loop = AdaptiveLoop(sol, forest, 0.0, 0, mask=mask, threshold_mask=mask is not None and p.threshold_mask, thresh_comp=tc)
 
     def set_inicond(lp):                      # inicond = meanflow (inicond_ACM.f90:285-288): u = u_mean_set, p = 0
         hvy, _, _, _ = lp.forest.active(0)

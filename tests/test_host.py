@@ -498,6 +498,7 @@ length=1.0;
         got = (p.wavelet, p.eps, p.eps_normalized, p.eps_norm, p.Jmin, p.force_maxlevel_dealiasing, p.adapt_tree, p.refinement_indicator)
         assert got == ("CDF44", 1.0e-3, True, "Linfty", 1, True, True, "everywhere")
         assert p.useCoarseExtension == 1 and p.useSecurityZone == 1 and p.n_mask == 6 and not p.skew_symmetry
+        assert p.threshold_mask and p.threshold_state_vector_component in ((), (1, 1, 1))
         m, ref = mask_from_ini(path, p), CylinderMask2D(p)
         assert isinstance(m, CylinderMask2D) and (m.c, m.R, m.h, m.L, m.ps) == ((10.0, 10.0), 0.5, ref.h, 2.0, 8.0)
         lv = np.array([5, 5, 3]); pos = np.array([[15, 15, 0], [16, 16, 0], [0, 0, 0]])

@@ -130,6 +130,8 @@ class Params:
     useSecurityZone: int = -1
     adapt_tree: bool = False
     refinement_indicator: str = "everywhere"
+    threshold_state_vector_component: Tuple[int, ...] = ()      # () = all components with their own norm (ini_file_to_params.f90:548-552)
+    threshold_mask: bool = False
     block_dist: str = "sfc_hilbert"
     discretization: str = "FD_4th_central"
     time_max: float = 1.0
@@ -207,6 +209,8 @@ class Params:
         p.useSecurityZone = int(ini.boolean("Blocks", "useSecurityZone", lifted))
         p.adapt_tree = ini.boolean("Blocks", "adapt_tree", False)
         p.refinement_indicator = ini.string("Blocks", "refinement_indicator", "everywhere")
+        p.threshold_state_vector_component = tuple(ini.vector("Blocks", "threshold_state_vector_component", [], int))
+        p.threshold_mask = ini.boolean("Blocks", "threshold_mask", False)
         p.block_dist = ini.string("Blocks", "block_dist", "sfc_hilbert")
         p.discretization = ini.string("Discretization", "order_discretization", "FD_4th_central")
         p.time_max = ini.real("Time", "time_max", 1.0)
