@@ -509,3 +509,25 @@ length=1.0;
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, os.path.join(root, "examples", "run_from_ini.py"), paths[0], "--plan"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "CylinderMask2D" in out.stdout and "Jmin..Jmax = 1..6" in out.stdout, out.stderr
+
+
+def test_refinement_flags_2d_on_the_adapted_three_vortices_grid():
+    """the "significant" refinement flags on the 2-D grid the reference stores after adapt_inicond (tests/golden), statuses as stored:
+    equal to the oracle's restatement of refinementIndicator_tree + ensureGradedness_tree"""
+    import adaptive as A
+    import adaptive_case as AC
+    import oracle as O
+    from wabbit_b200.timeloop import refinement_flags
+    gd = AC.gold("CDF42")
+    lv, ixy, status = gd["t10_level"], gd["t10_ixy"], gd["t10_status"]
+    ixyz = np.concatenate([ixy, np.zeros((len(ixy), 1), np.int32)], axis=1)
+    f = Forest.from_blocks(2, 4, lv.astype(np.int32), ixyz.astype(np.int32), max_blocks=400)
+    _, l, x, _ = f.active(0)
+    at = {(int(a), int(b[0]), int(b[1])): i for i, (a, b) in enumerate(zip(lv, ixy))}
+    st = np.array([status[at[(int(a), int(b[0]), int(b[1]))]] for a, b in zip(l, x)])
+    got = refinement_flags(f, "significant", st, 4)
+    grid = O.Grid(level=l.astype(np.int64), ixyz=x.astype(np.int64), dim=2)
+    po = O.Params(dim=2, Bs=(32, 32, 1), g=4, n_eqn=3, Jmax=4)
+    run = A.AdaptiveRun(po, "CDF42", grid, np.zeros((grid.n, 1, 1, 1, 1)), 10.0, 0, 1e-3, refinement_indicator="significant")
+    run.status = st.astype(np.int64)
+    assert np.array_equal(got, run.refine_flags("significant")) and 0 < got.sum() < len(got)
