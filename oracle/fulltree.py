@@ -28,6 +28,7 @@ prepare_ghost_synch_metadata and is spelled out where it is used):
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from typing import Dict, Optional, Tuple
 
 import numpy as np
@@ -38,6 +39,7 @@ Key = Tuple[int, int, int, int]
 REF_STAY = 9      # REF_UNSIGNIFICANT_STAY, module_globals.f90:25-32
 
 
+@functools.lru_cache(maxsize=None)
 def dirs(dim):
     return [(dx, dy, dz) for dz in ((-1, 0, 1) if dim == 3 else (0,)) for dy in (-1, 0, 1) for dx in (-1, 0, 1) if (dx, dy, dz) != (0, 0, 0)]
 

@@ -15,6 +15,7 @@ Array convention: ``hvy[b, c, iz, iy, ix]`` C-ordered == Fortran ``hvy(ix,iy,iz,
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import math
 import os
 import subprocess
@@ -518,6 +519,11 @@ def refine_block(order: int, p: Params, mother: np.ndarray) -> np.ndarray:
 
 # ----------------------------------------------------------------------------- level-jump ghost sync (orc_sync.c)
 def same_level_code(d) -> int:
+    return _same_level_code(tuple(int(v) for v in d))
+
+
+@functools.lru_cache(maxsize=None)
+def _same_level_code(d) -> int:
     """slot of the same-level neighbour in direction d (find_neighbor, LIB/MESH/find_neighbors.f90:60-95)"""
     nzero = sum(1 for v in d if v == 0)
     if nzero == 2:
