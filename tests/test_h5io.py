@@ -169,3 +169,24 @@ def test_product_reader_round_trip_and_reference_files(tmp_path):
         assert np.array_equal(o["blocks"], r["blocks"]) and r["dim"] == 3
         want = np.rint(o["origin"][:, ::-1] / (o["spacing"][:, ::-1] * r["Bs"][0])).astype(np.int64)
         assert np.array_equal(r["ixyz"], want)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/TESTING/acm/taylorGreen"), reason="reference checkout not present")
+def test_rewriting_a_3d_reference_fixture(tmp_path):
+    """the 3-D layout (blocks [Nb, Bz+1, By+1, Bx+1], origin / spacing stored z, y, x): a Taylor-Green fixture re-written and read back"""
+    ref = "/root/reference/TESTING/acm/taylorGreen/taylorGreenEqui_FD4_CDF40/p_000010000000.h5"
+    r = h5io.read_wabbit_field(ref)
+    a = r["attrs"]
+    path = str(tmp_path / "p.h5")
+    h5io.write_wabbit_field(path, r["blocks"], r["level"], r["ixyz"], r["treecode"], dim=3, Bs=r["Bs"], domain=tuple(a["domain-size"]),
+                            time=float(a["time"][0]), iteration=int(a["iteration"][0]), max_level=int(a["max_level"][0]),
+                            refinement_status=r["refinement_status"], periodic=a["periodic_BC"], symmetry=a["symmetry_BC"])
+    src, new = h5lite.H5Lite(ref), h5lite.H5Lite(path)
+    for name in ("blocks", "block_treecode_num", "level", "coords_origin", "coords_spacing", "refinement_status"):
+        x, y = src.read(name), new.read(name)
+        assert np.array_equal(x.reshape(y.shape), y), name
+    an = new.attrs("blocks")
+    for k in a:
+        assert np.array_equal(a[k], an[k]), k
+    st = h5io.read_state([path], g=3)
+    assert st["hvy"].shape[1:] == (1, 26, 26, 26) and st["iteration"] == int(a["iteration"][0])
