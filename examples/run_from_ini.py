@@ -3,8 +3,8 @@
 
     python examples/run_from_ini.py /path/to/TESTING/acm/acm_CDF44/acm_cyl.ini --out out/
 
-What main.f90 does for `adapt_tree = 1`, `inicond = meanflow`, `read_from_files = 0` (LIB/MAIN/main.f90:85-443): READ_PARAMETERS, the
-adaptive initial condition (setInitialCondition_tree), then per time step refine_tree -> createMask_tree -> RungeKuttaGeneric -> adapt_tree,
+What main.f90 does for `adapt_tree = 1` (LIB/MAIN/main.f90:85-443): READ_PARAMETERS, the initial condition (setInitialCondition_tree:
+`inicond = meanflow` on an adaptively generated grid, or `read_from_files = 1` with `input_files` + one adapt_tree), then per time step refine_tree -> createMask_tree -> RungeKuttaGeneric -> adapt_tree,
 saving `ux uy p mask` at t = 0 and at every multiple of `write_time` (write_method = fixed_time).  The same sequence as
 tests/test_gpu_cylinder2d.py, which compares its results with the files the reference wrote for this .ini; `--plan` stops before the first
 device call (parameter / mask / grid summary only; runs without a GPU).
@@ -28,17 +28,26 @@ def main():
     ap.add_argument("ini")
     ap.add_argument("--out", default="out")
     ap.add_argument("--max-blocks", type=int, default=4000)
+    ap.add_argument("--input-dir", default="", help="directory of the input_files of a restart (default: next to the .ini)")
     ap.add_argument("--plan", action="store_true", help="parse, build the mask generator and the initial grid, print the plan, stop")
     a = ap.parse_args()
 
     p = Params.from_ini(a.ini)
-    if p.dim != 2 or p.inicond != "meanflow":
-        raise SystemExit("this example covers dim = 2, inicond = meanflow (the TESTING/acm cylinder cases)")
+    if p.dim != 2 or not (p.read_from_files or p.inicond == "meanflow"):
+        raise SystemExit("this example covers dim = 2 with inicond = meanflow or read_from_files = 1 (the TESTING/acm 2-D cases)")
     mask = mask_from_ini(a.ini, p)
-    forest = Forest.uniform(2, p.Jmin, Jmax=p.Jmax, max_blocks=a.max_blocks)
+    state = None
+    if p.read_from_files:                        # setInitialCondition_tree, read_from_files = 1: readHDF5vct_tree(input_files)
+        base = a.input_dir if a.input_dir else os.path.dirname(os.path.abspath(a.ini))
+        state = h5io.read_state([os.path.join(base, f) for f in p.input_files], p.g)
+        forest = Forest.from_blocks(2, p.Jmax, state["level"], state["ixyz"].astype(np.int32), max_blocks=a.max_blocks)
+        print(f"restart from {p.input_files}: t = {state['time']}, iteration = {state['iteration']}, {forest.n_blocks} blocks on levels "
+              f"{int(state['level'].min())}..{int(state['level'].max())}")
+    else:
+        forest = Forest.uniform(2, p.Jmin, Jmax=p.Jmax, max_blocks=a.max_blocks)
     print(f"{a.ini}: {p.wavelet}, Bs = {p.Bs[0]}, g = {p.g}, Jmin..Jmax = {p.Jmin}..{p.Jmax}, eps = {p.eps}, refinement {p.refinement_indicator}, "
           f"penalization = {p.penalization} ({type(mask).__name__ if mask is not None else 'no mask'}), sponge = {p.use_sponge}, "
-          f"time_max = {p.time_max}, write_time = {p.write_time}; initial grid {forest.n_blocks} blocks on level {p.Jmin}")
+          f"time_max = {p.time_max}, write_time = {p.write_time}; initial grid {forest.n_blocks} blocks")
     if a.plan:
         return
 
@@ -50,7 +59,8 @@ def main():
     sol.setup_wavelet(p.wavelet)
     sol.set_forest(forest)
     tc = p.threshold_state_vector_component or None
-    loop = AdaptiveLoop(sol, forest, 0.0, 0, mask=mask, threshold_mask=mask is not None and p.threshold_mask, thresh_comp=tc)
+    t0, it0 = (state["time"], state["iteration"]) if state is not None else (0.0, 0)
+    loop = AdaptiveLoop(sol, forest, t0, it0, mask=mask, threshold_mask=mask is not None and p.threshold_mask, thresh_comp=tc)
 
     def set_inicond(lp):                      # inicond = meanflow (inicond_ACM.f90:285-288): u = u_mean_set, p = 0
         hvy, _, _, _ = lp.forest.active(0)
@@ -70,14 +80,26 @@ def main():
             paths += h5io.save_data(a.out, ("mask",), chi, lvl, pos, tc, p, loop.time, loop.iteration, refinement_status=status)
         print(f"t = {loop.time:.6f} it = {loop.iteration} Nb = {loop.forest.n_blocks}: wrote {[os.path.basename(q) for q in paths]}")
 
-    set_inicond(loop)
-    loop.adaptive_inicond(set_inicond)
+    if state is not None:
+        hvy, lvl, pos, _ = forest.active(0)                   # the forest orders the blocks along the space-filling curve
+        at = {(int(l), int(x[0]), int(x[1])): b for b, (l, x) in enumerate(zip(state["level"], state["ixyz"]))}
+        order = np.array([at[(int(l), int(x[0]), int(x[1]))] for l, x in zip(lvl, pos)])
+        host = np.zeros((int(hvy.max()),) + sol.host_shape()[1:])
+        host[hvy - 1] = state["hvy"][order]
+        sol.upload(host, HVY_BLOCK, 0, hvy_ids=hvy)
+        if p.adapt_inicond:
+            loop.adapt_tree()
+    else:
+        set_inicond(loop)
+        loop.adaptive_inicond(set_inicond)
     save()
+    saved_at = loop.time
     while loop.time < p.time_max:
         loop.step()
         if p.write_method == "fixed_time" and abs(loop.time / p.write_time - round(loop.time / p.write_time)) <= 1e-12:
             save()
-    if not (p.write_method == "fixed_time"):
+            saved_at = loop.time
+    if saved_at != loop.time:                                  # the final state (main.f90 saves when the run ends)
         save()
     sol.close()
 

@@ -509,6 +509,19 @@ length=1.0;
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, os.path.join(root, "examples", "run_from_ini.py"), paths[0], "--plan"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "CylinderMask2D" in out.stdout and "Jmin..Jmax = 1..6" in out.stdout, out.stderr
+    # a restart (read_from_files = 1): field files written by h5io, named in the .ini, read back and planned
+    from wabbit_b200 import h5io
+    lv = np.array([1, 1, 1, 1], np.int32)
+    ix = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]])
+    for name in ("ux", "uy", "p"):
+        h5io.write_wabbit_field(str(tmp_path / f"{name}_000002000000.h5"), np.zeros((4, 27, 27)), lv, ix, np.arange(4), dim=2, Bs=(26, 26, 1),
+                                domain=(20.0, 20.0, 1.0), time=2.0, iteration=77, max_level=6)
+    rpath = str(tmp_path / "restart.ini")
+    open(rpath, "w").write(text + "[Physics]\nread_from_files=1;\ninput_files=ux_000002000000.h5 uy_000002000000.h5 p_000002000000.h5;\n")
+    pr = Params.from_ini(rpath)
+    assert pr.read_from_files and pr.input_files == ("ux_000002000000.h5", "uy_000002000000.h5", "p_000002000000.h5") and pr.adapt_inicond
+    out = subprocess.run([sys.executable, os.path.join(root, "examples", "run_from_ini.py"), rpath, "--plan"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "t = 2.0, iteration = 77, 4 blocks" in out.stdout, out.stdout + out.stderr
 
 
 def test_refinement_flags_2d_on_the_adapted_three_vortices_grid():

@@ -132,6 +132,9 @@ class Params:
     refinement_indicator: str = "everywhere"
     threshold_state_vector_component: Tuple[int, ...] = ()      # () = all components with their own norm (ini_file_to_params.f90:548-552)
     threshold_mask: bool = False
+    adapt_inicond: bool = False
+    read_from_files: bool = False
+    input_files: Tuple[str, ...] = ()
     block_dist: str = "sfc_hilbert"
     discretization: str = "FD_4th_central"
     time_max: float = 1.0
@@ -211,6 +214,9 @@ class Params:
         p.refinement_indicator = ini.string("Blocks", "refinement_indicator", "everywhere")
         p.threshold_state_vector_component = tuple(ini.vector("Blocks", "threshold_state_vector_component", [], int))
         p.threshold_mask = ini.boolean("Blocks", "threshold_mask", False)
+        p.adapt_inicond = ini.boolean("Blocks", "adapt_inicond", p.adapt_tree)
+        p.read_from_files = ini.boolean("Physics", "read_from_files", False)
+        p.input_files = tuple(ini.string("Physics", "input_files", "").split())
         p.block_dist = ini.string("Blocks", "block_dist", "sfc_hilbert")
         p.discretization = ini.string("Discretization", "order_discretization", "FD_4th_central")
         p.time_max = ini.real("Time", "time_max", 1.0)
