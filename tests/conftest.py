@@ -13,6 +13,18 @@ def pytest_configure(config):
 
 
 def _have_gpu() -> bool:
+    """A CUDA device, asked of the CUDA runtime itself (libcudart's cudaGetDeviceCount), so that a box with a GPU but a broken torch
+    does not silently skip the parity suite; torch is the fallback probe."""
+    import ctypes
+    for name in ("libcudart.so", "libcudart.so.12", "/usr/local/cuda/lib64/libcudart.so"):
+        try:
+            rt = ctypes.CDLL(name)
+            n = ctypes.c_int(0)
+            if rt.cudaGetDeviceCount(ctypes.byref(n)) == 0:
+                return n.value > 0
+            return False
+        except OSError:
+            continue
     try:
         import torch
         return torch.cuda.is_available()
@@ -22,7 +34,13 @@ def _have_gpu() -> bool:
 
 def pytest_collection_modifyitems(config, items):
     if _have_gpu():
+        try:
+            import torch  # noqa: F401  (the GPU tests use torch for pinned memory / streams)
+        except Exception as e:      # a GPU box without a working torch must fail loudly, not look green
+            raise pytest.UsageError(f"a CUDA device is present but torch cannot be imported ({e}): the -m gpu parity suite cannot run")
         return
+    if os.environ.get("WABBIT_REQUIRE_GPU"):
+        raise pytest.UsageError("WABBIT_REQUIRE_GPU is set but no CUDA device was found")
     skip = pytest.mark.skip(reason="no CUDA device in this container")
     for item in items:
         if "gpu" in item.keywords:

@@ -157,6 +157,30 @@ def test_sfc_is_a_curve():
     assert tot == 512
 
 
+def test_hilbert_partition_matches_the_reference_fixture_files():
+    """the per-rank block lists (`procs`) of files the reference wrote with 4 / 8 MPI ranks -- 2-D adaptive cylinder
+    runs, 3-D equidistant and adaptive grids -- equal the contiguous chunks of our space-filling-curve order (treecode_to_hilbertcode_2D/3D,
+    balanceLoad_tree.f90:203-285, 600-715).  Fixture: tests/golden/partition_procs.npz (tests/golden/make_partition_golden.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "partition_procs.npz"))
+    lib = _native.host_lib()
+    for k, name in enumerate(g["files"]):
+        dim, Jmax = int(g[f"f{k}_dim"][0]), int(g[f"f{k}_Jmax"][0])
+        procs, level, tc = g[f"f{k}_procs"], g[f"f{k}_level"], g[f"f{k}_treecode"]
+        P = int(procs.max()) + 1
+        ixyz = np.zeros((len(level), 3), np.int32)
+        for i in range(len(level)):
+            buf = (C.c_int32 * 3)()
+            lib.whost_decode(dim, int(level[i]), Jmax, int(tc[i]), buf)
+            ixyz[i] = list(buf)
+        f = Forest.from_blocks(dim, Jmax, level, ixyz, block_dist="sfc_hilbert", n_ranks=P)
+        want = {(int(l), int(t)): int(r) for l, t, r in zip(level, tc, procs)}
+        for r in range(P):
+            _, lv, _, t = f.active(r)
+            got = {want[(int(l), int(tt))] for l, tt in zip(lv, t)}
+            assert got == {r}, (str(name), r, got)
+
+
 def test_two_level_forest_slots():
     """2-level grid: one level-1 block refined.  Checks the +56 / +112 slot groups are mutually consistent."""
     lv, ix = [], []

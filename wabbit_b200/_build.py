@@ -34,7 +34,9 @@ def _stale(out: str, srcs) -> bool:
 def build_host(force: bool = False) -> str:
     srcs = [os.path.join(CSRC, s) for s in HOST_SRCS]
     if force or _stale(HOST_LIB, srcs):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-I", INCLUDE, "-o", HOST_LIB, *srcs])
+        tmp = f"{HOST_LIB}.{os.getpid()}.tmp"      # several ranks may get here at once: build aside, then rename atomically
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-I", INCLUDE, "-o", tmp, *srcs])
+        os.replace(tmp, HOST_LIB)
     return HOST_LIB
 
 
@@ -42,7 +44,9 @@ def build_gpu(force: bool = False) -> str:
     srcs = [os.path.join(CSRC, s) for s in GPU_SRCS]
     if force or _stale(GPU_LIB, srcs):
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-        subprocess.check_call([nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-o", GPU_LIB, *srcs])
+        tmp = f"{GPU_LIB}.{os.getpid()}.tmp"
+        subprocess.check_call([nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-o", tmp, *srcs])
+        os.replace(tmp, GPU_LIB)
     return GPU_LIB
 
 

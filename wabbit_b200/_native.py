@@ -132,8 +132,6 @@ def gpu_lib() -> C.CDLL:
 def host_lib() -> C.CDLL:
     global _host
     if _host is None:
-        path = _build.HOST_LIB
-        if not os.path.exists(path):
-            _build.build_host()
+        path = _build.build_host()        # rebuilds when missing OR older than its sources / headers (the .so is not tracked by git)
         _host = _bind(C.CDLL(path), HOST_SYMBOLS)
     return _host

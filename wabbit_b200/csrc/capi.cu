@@ -111,6 +111,7 @@ void fill_common_args(wgpu_ctx *ctx, StageArgs &a)
     for (int d = 0; d < 3; ++d) a.u_mean_set[d] = c.u_mean_set[d];
     a.use_sponge = c.use_sponge;
     a.CFL = c.CFL;
+    a.CFL_nu = c.CFL_nu;
     a.diverged = ctx->d_flags;
     a.dim_min_axes = c.dim;
     a.dt_ptr = ctx->d_dt;

@@ -27,32 +27,36 @@ inline uint64_t pos_hash(int level, const int ix[3])
     return ((uint64_t)level << 58) ^ ((uint64_t)(uint32_t)ix[2] << 38) ^ ((uint64_t)(uint32_t)ix[1] << 19) ^ (uint64_t)(uint32_t)ix[0];
 }
 
-// Skilling's transposed-axes Hilbert index for `dim` coordinates of `bits` bits each
-uint64_t hilbert_index(int dim, int bits, const int x_in[3])
+// WABBIT's Hilbert curve (treecode_to_hilbertcode_2D / _3D, LIB/MESH/treecode_to_hilbertcode_2D.f90, ..._3D.f90:11; the pattern automaton of
+// M. Bader, "Space-Filling Curves", 2012, p. 115): walking down the treecode, the digit of level k is mapped to its position in the current
+// basic pattern (4 patterns in 2-D, 12 in 3-D; the first is pattern 1) and the pattern of level k+1 follows from the pattern and the digit of
+// level k.  The position replaces the digit in place: the Hilbert code of a block on level J has its digit k at bit (Jmax - k) * dim, zeros
+// behind, exactly like the numerical treecode, which is what balanceLoad_tree sorts by (balanceLoad_tree.f90:225-250).  The two tables per
+// dimension are the reference's (rows: pattern 1.., columns: treecode digit); tests/test_host.py pins them against the per-rank block
+// lists of the reference's multi-rank fixture files.
+const unsigned char HIL2_NEXT[4][4] = {{2, 4, 1, 1}, {1, 2, 3, 2}, {3, 3, 2, 4}, {4, 1, 4, 3}};
+const unsigned char HIL2_POS[4][4] = {{0, 3, 1, 2}, {0, 1, 3, 2}, {2, 1, 3, 0}, {2, 3, 1, 0}};
+const unsigned char HIL3_NEXT[12][8] = {{3, 5, 8, 5, 4, 11, 8, 11},  {12, 3, 12, 7, 6, 4, 6, 7}, {5, 12, 1, 2, 9, 9, 1, 2},   {10, 10, 1, 2, 11, 6, 1, 2},
+                                        {1, 6, 7, 6, 3, 3, 10, 10},  {4, 4, 9, 9, 5, 2, 5, 8},   {2, 5, 10, 5, 2, 11, 9, 11}, {12, 1, 12, 10, 6, 1, 6, 9},
+                                        {7, 8, 3, 3, 7, 8, 11, 6},   {7, 8, 5, 12, 7, 8, 4, 4},  {4, 4, 9, 9, 1, 12, 7, 12},  {11, 2, 11, 8, 3, 3, 10, 10}};
+const unsigned char HIL3_POS[12][8] = {{0, 1, 3, 2, 7, 6, 4, 5}, {6, 7, 5, 4, 1, 0, 2, 3}, {0, 7, 1, 6, 3, 4, 2, 5}, {4, 3, 5, 2, 7, 0, 6, 1},
+                                       {0, 3, 7, 4, 1, 2, 6, 5}, {2, 1, 5, 6, 3, 0, 4, 7}, {4, 5, 7, 6, 3, 2, 0, 1}, {2, 3, 1, 0, 5, 4, 6, 7},
+                                       {2, 5, 3, 4, 1, 6, 0, 7}, {6, 1, 7, 0, 5, 2, 4, 3}, {6, 5, 1, 2, 7, 4, 0, 3}, {4, 7, 3, 0, 5, 6, 2, 1}};
+
+uint64_t hilbert_code(int dim, int level, int Jmax, int64_t tc)
 {
-    if (bits == 0) return 0;
-    uint32_t X[3] = {(uint32_t)x_in[0], (uint32_t)x_in[1], dim == 3 ? (uint32_t)x_in[2] : 0u};
-    const uint32_t M = 1u << (bits - 1);
-    for (uint32_t Q = M; Q > 1; Q >>= 1) {   // inverse undo
-        const uint32_t P = Q - 1;
-        for (int i = 0; i < dim; ++i) {
-            if (X[i] & Q) X[0] ^= P;
-            else {
-                const uint32_t t = (X[0] ^ X[i]) & P;
-                X[0] ^= t;
-                X[i] ^= t;
-            }
-        }
+    const unsigned dmask = (1u << dim) - 1u;
+    uint64_t code = 0;
+    int pattern = 1, prev = 0;
+    for (int k = 1; k <= level; ++k) {
+        const int sh = (Jmax - k) * dim;
+        const int digit = (int)((uint64_t)tc >> sh) & (int)dmask;
+        if (k > 1) pattern = dim == 3 ? HIL3_NEXT[pattern - 1][prev] : HIL2_NEXT[pattern - 1][prev];
+        const uint64_t pos = dim == 3 ? HIL3_POS[pattern - 1][digit] : HIL2_POS[pattern - 1][digit];
+        code |= pos << sh;
+        prev = digit;
     }
-    for (int i = 1; i < dim; ++i) X[i] ^= X[i - 1];   // Gray encode
-    uint32_t t = 0;
-    for (uint32_t Q = M; Q > 1; Q >>= 1)
-        if (X[dim - 1] & Q) t ^= Q - 1;
-    for (int i = 0; i < dim; ++i) X[i] ^= t;
-    uint64_t h = 0;
-    for (int b = bits - 1; b >= 0; --b)
-        for (int i = 0; i < dim; ++i) h = (h << 1) | ((X[i] >> b) & 1u);
-    return h;
+    return code;
 }
 
 }  // namespace
@@ -128,10 +132,9 @@ int32_t whost_decode(int32_t dim, int32_t level, int32_t Jmax, int64_t tc, int32
 
 uint64_t whost_sfc_key(int32_t dim, int32_t sfc, int32_t level, int32_t Jmax, const int32_t ixyz[3])
 {
-    int fine[3];
-    for (int d = 0; d < 3; ++d) fine[d] = d < dim ? ixyz[d] << (Jmax - level) : 0;
-    if (sfc == WHOST_SFC_HILBERT) return hilbert_index(dim, Jmax, fine);
-    return (uint64_t)whost_encode(dim, Jmax, Jmax, fine);   // the treecode is the Z-curve index
+    const int64_t tc = whost_encode(dim, level, Jmax, ixyz);
+    if (sfc == WHOST_SFC_HILBERT) return hilbert_code(dim, level, Jmax, tc);
+    return (uint64_t)tc;   // sfc_z: the position on the Z curve is the treecode itself (balanceLoad_tree.f90:204-222)
 }
 
 static void build(whost_forest *f)

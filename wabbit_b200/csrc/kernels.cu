@@ -482,7 +482,9 @@ __global__ void __launch_bounds__(BS *BS, (Tile<FD, BS>::SMEM <= 110 * 1024 ? 2 
             double dxmin = dx;
             if (a.dim_min_axes > 1) dxmin = fmin(dxmin, dy);
             if (a.dim_min_axes > 2) dxmin = fmin(dxmin, dz);
-            const double dtb = (u_eigen >= 1.0e-6) ? __ddiv_rn(__dmul_rn(a.CFL, dxmin), u_eigen) : 1.0e-2;
+            double dtb = (u_eigen >= 1.0e-6) ? __ddiv_rn(__dmul_rn(a.CFL, dxmin), u_eigen) : 1.0e-2;
+            // explicit diffusion, with THIS block's dx (module_ACM.f90:669-671): folded in before the MIN over blocks and ranks
+            if (a.nu > 1.0e-13) dtb = fmin(dtb, __ddiv_rn(__dmul_rn(a.CFL_nu, __dmul_rn(dxmin, dxmin)), a.nu));
             atomicMin(a.dtmin_bits, (unsigned long long)__double_as_longlong(dtb));
         }
     }
@@ -634,7 +636,8 @@ __global__ void __launch_bounds__(256) stage_kernel_2d(const __grid_constant__ S
             for (int i = 0; i < NW; ++i) m = fmax(m, s_red[i]);
             const double u_eigen = __dadd_rn(sqrt(m), sqrt(__dadd_rn(c02, m)));
             const double dxmin = fmin(dx, dy);
-            const double dtb = (u_eigen >= 1.0e-6) ? __ddiv_rn(__dmul_rn(a.CFL, dxmin), u_eigen) : 1.0e-2;
+            double dtb = (u_eigen >= 1.0e-6) ? __ddiv_rn(__dmul_rn(a.CFL, dxmin), u_eigen) : 1.0e-2;
+            if (a.nu > 1.0e-13) dtb = fmin(dtb, __ddiv_rn(__dmul_rn(a.CFL_nu, __dmul_rn(dxmin, dxmin)), a.nu));   // module_ACM.f90:669-671
             atomicMin(a.dtmin_bits, (unsigned long long)__double_as_longlong(dtb));
         }
     }
@@ -667,7 +670,8 @@ __global__ void __launch_bounds__(256) dtmin_kernel(const double *__restrict__ u
         for (int d = 1; d < dim; ++d) dxmin = fmin(dxmin, a.dx_lvl[lvl][d]);
         const double c02 = a.c0 * a.c0;
         const double u_eigen = __dadd_rn(sqrt(m), sqrt(__dadd_rn(c02, m)));
-        const double dtb = (u_eigen >= 1.0e-6) ? __ddiv_rn(__dmul_rn(a.CFL, dxmin), u_eigen) : 1.0e-2;
+        double dtb = (u_eigen >= 1.0e-6) ? __ddiv_rn(__dmul_rn(a.CFL, dxmin), u_eigen) : 1.0e-2;
+        if (a.nu > 1.0e-13) dtb = fmin(dtb, __ddiv_rn(__dmul_rn(a.CFL_nu, __dmul_rn(dxmin, dxmin)), a.nu));   // module_ACM.f90:669-671
         atomicMin(dtmin_bits, (unsigned long long)__double_as_longlong(dtb));
     }
 }
@@ -675,7 +679,7 @@ __global__ void __launch_bounds__(256) dtmin_kernel(const double *__restrict__ u
 // calculate_time_step (LIB/TIME/calculate_time_step.f90:19-118) after the global MIN; single thread.
 struct DtArgs {
     double time, dt_fixed, dt_max, time_max, write_time, write_time_first, tsave_stats;
-    double nu, CFL_nu, CFL_eta, gamma_p, C_eta, C_sponge, dxmin_finest;
+    double CFL_eta, gamma_p, C_eta, C_sponge;
     int penalization, use_sponge, write_fixed_time;
 };
 
@@ -687,8 +691,8 @@ __global__ void dt_finalize_kernel(DtArgs p, const unsigned long long *dtmin_bit
         dt = p.dt_fixed;
     } else {
         dt = fmin(dt, __longlong_as_double((long long)*dtmin_bits));
-        // module_ACM.f90:669-689 (block independent apart from dx, whose minimum is the finest active level)
-        if (p.nu > 1.0e-13) dt = fmin(dt, __ddiv_rn(__dmul_rn(p.CFL_nu, __dmul_rn(p.dxmin_finest, p.dxmin_finest)), p.nu));
+        // module_ACM.f90:673-689: the block-independent limits.  The diffusion limit CFL_nu dx^2 / nu depends on the block's dx and is part
+        // of the per-block candidate (stage_kernel / dtmin_kernel), so that it takes part in the MIN over the blocks of ALL ranks
         if (p.gamma_p > 0) dt = fmin(dt, __dmul_rn(p.CFL_eta, p.gamma_p));
         if (p.penalization) dt = fmin(dt, __dmul_rn(p.CFL_eta, p.C_eta));
         if (p.use_sponge) dt = fmin(dt, __dmul_rn(p.CFL_eta, p.C_sponge));
@@ -915,6 +919,8 @@ int32_t wgpu_launch_dtmin(wgpu_ctx *ctx, const double *u, unsigned long long *dt
         for (int d = 0; d < 3; ++d) a.dx_lvl[l][d] = ldexp(1.0, -l) * ctx->cfg.domain[d] / (double)ctx->cfg.Bs[d];
     a.c0 = ctx->cfg.c0;
     a.CFL = ctx->cfg.CFL;
+    a.nu = ctx->cfg.nu;
+    a.CFL_nu = ctx->cfg.CFL_nu;
     dtmin_kernel<<<ctx->n_active, 256, 0, ctx->stream>>>(u, ctx->d_active, ctx->d_level, a, ctx->nc, ctx->blk_elems, ctx->cfg.dim, dtmin_bits);
     ctx->launches++;
     WGPU_CHECK(ctx, cudaGetLastError());
@@ -932,8 +938,6 @@ int32_t wgpu_launch_dt_finalize(wgpu_ctx *ctx, double time, const unsigned long 
     p.write_time = c.write_time;
     p.write_time_first = c.write_time_first;
     p.tsave_stats = c.tsave_stats;
-    p.nu = c.nu;
-    p.CFL_nu = c.CFL_nu;
     p.CFL_eta = c.CFL_eta;
     p.gamma_p = c.gamma_p;
     p.C_eta = c.C_eta;
@@ -941,14 +945,6 @@ int32_t wgpu_launch_dt_finalize(wgpu_ctx *ctx, double time, const unsigned long 
     p.penalization = c.penalization;
     p.use_sponge = c.use_sponge;
     p.write_fixed_time = c.write_method_fixed_time;
-    int lmax = 0;
-    for (int i = 0; i < ctx->n_active; ++i) lmax = ctx->h_level[ctx->h_active[i]] > lmax ? ctx->h_level[ctx->h_active[i]] : lmax;
-    double dxmin = 1e300;
-    for (int d = 0; d < c.dim; ++d) {
-        const double dx = ldexp(1.0, -lmax) * c.domain[d] / (double)c.Bs[d];
-        dxmin = dx < dxmin ? dx : dxmin;
-    }
-    p.dxmin_finest = dxmin;
     dt_finalize_kernel<<<1, 1, 0, ctx->stream>>>(p, dtmin_bits, dtmin_next, ctx->d_dt, nullptr);
     ctx->launches++;
     WGPU_CHECK(ctx, cudaGetLastError());

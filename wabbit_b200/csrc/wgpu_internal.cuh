@@ -66,7 +66,7 @@ struct StageArgs {
     int use_sponge;
     // reductions
     unsigned long long *dtmin_bits;  // atomicMin target for the NEXT step's CFL dt (final stage only), or nullptr
-    double CFL;
+    double CFL, CFL_nu;
     int *diverged;                   // set to 1 if any |u_in| > 1e12
     int dim_min_axes;                // number of axes entering minval(dx(1:dim))
     // analytic mask (wgpu_set_mask_sphere): the penalization term of a translating sphere evaluated in the kernel instead of read from hvy_mask

@@ -50,7 +50,8 @@ class CylinderMask2D:
         n = len(level)
         m = np.zeros((n, 6, 1, p.Bs[1] + 2 * g, p.Bs[0] + 2 * g))
         m[:, 4] = 1.0
-        m[:, 0, 0, g:g + p.Bs[1] + 1, g:g + p.Bs[0] + 1] = self.chi(level, pos, 1)
+        if p.penalization:                 # create_mask_2D_ACM draws the geometry only with penalization = 1; the sponge is independent of it
+            m[:, 0, 0, g:g + p.Bs[1] + 1, g:g + p.Bs[0] + 1] = self.chi(level, pos, 1)
         if p.use_sponge:
             off = 0.5 * p.domain[0]
             x, y = self._coords(level, pos, 0)
@@ -61,6 +62,8 @@ class CylinderMask2D:
     def keeps(self, level, pos) -> np.ndarray:
         """threshold_mask (coarseningIndicatorMask_tree, LIB/MESH/coarseningIndicator_tree.f90:290-331): True where the mask function is
         not constant over the block's interior"""
+        if not self.p.penalization:
+            return np.zeros(len(level), bool)          # chi is identically zero
         c = self.chi(level, pos).reshape(len(level), -1)
         return ((c > 1.0e-12) & (c < 1.0 - 1.0e-12)).any(axis=1) | ((c.max(axis=1) - c.min(axis=1)) > 1.0e-12)
 
@@ -110,11 +113,17 @@ class SphereMask3D:
 def mask_from_ini(path: str, p: Params):
     """The mask generator for the [VPM] / [Sponge] sections of a WABBIT parameter file (READ_PARAMETERS_ACM, LIB/EQUATION/ACMnew/
     module_ACM.f90:290-345: geometry, x_cntr, R_cyl = 0.5, C_smooth = 1.5, smoothing_type = cos; sponge_type, L_sponge, p_sponge = 20) or None
-    without penalization.  Supported: geometry = cylinder / circle (2-D, cosine smoothing, p-norm sponge) and sphere-fixed (3-D)."""
+    with neither penalization nor a sponge.  The sponge does not depend on penalization (create_mask.f90: `if (params_acm%use_sponge)`), so
+    penalization = 0 with use_sponge = 1 returns a generator whose chi is zero.  Supported: geometry = cylinder / circle (2-D, cosine
+    smoothing, p-norm sponge) and sphere-fixed (3-D, no sponge)."""
     from .params import IniFile
-    if not p.penalization:
+    if not (p.penalization or p.use_sponge):
         return None
     ini = IniFile(path)
+    if not p.penalization:
+        if p.dim != 2 or ini.string("Sponge", "sponge_type", "rect").strip().lower() != "p-norm":
+            raise ValueError("use_sponge = 1 without penalization: only the 2-D p-norm sponge is supported")
+        return CylinderMask2D(p, L_sponge=ini.real("Sponge", "L_sponge", 0.0), p_sponge=ini.real("Sponge", "p_sponge", 20.0))
     geometry = ini.string("VPM", "geometry", "cylinder").strip().lower()
     x_cntr = ini.vector("VPM", "x_cntr", [0.5 * p.domain[0], 0.5 * p.domain[1], 0.5 * p.domain[2]])
     x_cntr = (list(x_cntr) + [0.0, 0.0, 0.0])[:3]

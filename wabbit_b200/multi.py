@@ -93,6 +93,16 @@ def _i32(a):
     return a.ctypes.data_as(C.POINTER(C.c_int32))
 
 
+def _require_torch_stream(sol, torch):
+    """torch.distributed orders a collective against torch's CURRENT stream, the library issues its pack / stage kernels on the context's
+    stream: the two must be the same stream (or both the legacy default stream), otherwise pack -> all-to-all -> stage would race."""
+    cur = int(torch.cuda.current_stream().cuda_stream)
+    mine = int(getattr(sol, "stream", 0))
+    if mine != cur:
+        raise RuntimeError(f"the WabbitGPU context works on stream {mine:#x} but torch's current stream is {cur:#x}: create the context with "
+                           "stream=torch.cuda.current_stream().cuda_stream (collectives are ordered against torch's current stream)")
+
+
 class MultiGPUStepper:
     """RungeKuttaGeneric across ranks.  `exchange(send, recv, send_counts, recv_counts) -> handle-with-wait()` moves
     the patches; the default uses torch.distributed all_to_all_single (NCCL).  `allreduce_min(tensor)` reduces dt."""
@@ -102,6 +112,8 @@ class MultiGPUStepper:
         import torch
         self.torch = torch
         self.sol, self.rank, self.world, self.overlap = sol, rank, world, overlap
+        if exchange is None and world > 1:
+            _require_torch_stream(sol, torch)
         self.plan = ExchangePlan(forest, rank, world)
         lib, ctx = sol._lib, sol._ctx
         hvy, lvl, _, _ = forest.active(rank)
@@ -301,6 +313,8 @@ class HaloStepper:
         import torch
         self.torch = torch
         self.sol, self.rank, self.world, self.overlap = sol, rank, world, overlap
+        if exchange is None and world > 1:
+            _require_torch_stream(sol, torch)
         self.plan = plan = HaloPlan(forest, rank, world)
         lib, ctx = sol._lib, sol._ctx
         p = sol.params
@@ -501,6 +515,13 @@ class NcclTransport:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.cpu().numpy()
 
+    def allreduce_sum_np(self, a: np.ndarray) -> np.ndarray:
+        import torch
+        import torch.distributed as dist
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
     def allgather_np(self, a: np.ndarray, counts: Sequence[int]) -> np.ndarray:
         """concatenation over ranks of int32 arrays whose lengths (counts) every rank knows"""
         import torch
@@ -561,6 +582,13 @@ class ThreadTransport:
         self._sync()
         return out
 
+    def allreduce_sum_np(self, a):
+        self.sh.slots[self.rank] = np.asarray(a, dtype=np.float64)
+        self._sync()
+        out = np.sum(np.stack(self.sh.slots), axis=0)      # rank order: the same on every rank
+        self._sync()
+        return out
+
     def allgather_np(self, a, counts):
         self.sh.slots[self.rank] = np.asarray(a, dtype=np.int32)
         self._sync()
@@ -581,6 +609,8 @@ class DistributedWabbit:
         import torch
         self.torch = torch
         self.sol, self.rank, self.world = sol, rank, world
+        if transport is None and world > 1:
+            _require_torch_stream(sol, torch)
         self.tr = transport or NcclTransport(rank, world)
         self.overlap = overlap
         self.dev = torch.device("cuda", torch.cuda.current_device())
@@ -705,8 +735,22 @@ class DistributedWabbit:
         return new
 
     # ------------------------------------------------------------------ adapt_tree (one coarsening sweep, unlifted wavelets)
+    def global_norm(self, eps_norm: str = "Linfty", thresh_comp=None) -> np.ndarray:
+        """componentWiseNorm_tree over all ranks: MPI_MAX for Linfty, MPI_SUM of the ranks' partial sums for L1 / L2 / H1
+        (componentWiseNorm_tree.f90:283-326), then the threshold_state_vector_component treatment shared with the single-rank driver."""
+        from .solver import threshold_norm
+        loc = self.sol.componentWiseNorm_tree((0, 0), eps_norm)
+        if eps_norm == "Linfty":
+            nrm = self.tr.allreduce_max_np(loc)
+        elif eps_norm == "L1":
+            nrm = self.tr.allreduce_sum_np(loc)
+        else:                                                # L2 / H1: sqrt of the summed squares
+            nrm = np.sqrt(self.tr.allreduce_sum_np(loc * loc))
+        return threshold_norm(nrm, thresh_comp)
+
     def adapt_tree(self, eps: Optional[float] = None, eps_normalized: bool = True, Jmin: int = 1, force_maxlevel_dealiasing: bool = False,
-                   thresh_comp=None, useSecurityZone: Optional[bool] = None, mask_keeps=None, full_tree: Optional[bool] = None):
+                   thresh_comp=None, useSecurityZone: Optional[bool] = None, mask_keeps=None, full_tree: Optional[bool] = None,
+                   eps_norm: str = "Linfty"):
         """One coarsening sweep of adapt_tree (LIB/MESH/adapt_tree.f90:11) across ranks, indicator "threshold-state-vector", Linfty norm,
         unlifted wavelets (as WabbitGPU.adapt_tree): norm -> all-reduce MAX; halo refresh; decomposition + flags per rank; flags
         all-gathered (synchronize_lgt_data); completeness / gradedness on the replicated light data; sister blocks gathered on the
@@ -721,27 +765,21 @@ class DistributedWabbit:
         if use_ce if full_tree is None else full_tree:
             # the reference's full-tree algorithm (coarse extension and security zone for lifted wavelets; fulltree.py)
             from .fulltree import DistributedFullTree
-            norm = None
-            if eps_normalized:
-                norm = self.tr.allreduce_max_np(sol.componentWiseNorm_tree((0, 0), "Linfty"))
-                norm[norm <= 1.0e-9] = 1.0
+            norm = self.global_norm(eps_norm, thresh_comp) if eps_normalized else None
             n0 = old.n_blocks
             sz = (lifted if sol.params.useSecurityZone < 0 else bool(sol.params.useSecurityZone)) if useSecurityZone is None else bool(useSecurityZone)
             ft = DistributedFullTree(self, Jmin=Jmin)
-            new, _ = ft.adapt(eps=sol.params.eps if eps is None else eps, norm=norm, thresh_comp=thresh_comp,
+            new, _ = ft.adapt(eps=sol.params.eps if eps is None else eps, norm=norm, eps_norm=eps_norm, thresh_comp=thresh_comp,
                               force_maxlevel_dealiasing=force_maxlevel_dealiasing, use_security_zone=sz, mask_keeps=mask_keeps)
             self.refinement_status = ft.leaf_status              # global space-filling-curve order, the same on every rank
             return new, n0, new.n_blocks
         if mask_keeps is not None:
             raise ValueError("adapt_tree: threshold_mask needs the full-tree algorithm")
         WD = (self.HVY_WORK, 2)
-        norm = None
-        if eps_normalized:
-            norm = self.tr.allreduce_max_np(sol.componentWiseNorm_tree((0, 0), "Linfty"))
-            norm[norm <= 1.0e-9] = 1.0
+        norm = self.global_norm(eps_norm, thresh_comp) if eps_normalized else None
         self.stepper.exchange_array(0, 0)
         sol.waveletDecomposition_tree((0, 0), WD)
-        st = sol.threshold_tree(WD, eps=eps, norm=norm, thresh_comp=thresh_comp, level_ref=old.Jmax)
+        st = sol.threshold_tree(WD, eps=eps, norm=norm, eps_norm=eps_norm, thresh_comp=thresh_comp, level_ref=old.Jmax)
         st = self.tr.allgather_np(st, self.counts)
         lv, _ = self._global_blocks(old)
         if force_maxlevel_dealiasing:

@@ -22,6 +22,22 @@ from .params import Params
 HVY_BLOCK, HVY_WORK, HVY_MASK, HVY_TMP = 0, 1, 2, 3
 
 
+def threshold_norm(norm, thresh_comp=None):
+    """The norm adapt_tree divides the details by (eps_normalized): componentWiseNorm_tree's treatment of
+    threshold_state_vector_component (componentWiseNorm_tree.f90:119-163: components with 0 are not computed, components of a group >= 2
+    share the group's maximum) and coarseningIndicator_tree.f90:165-167 (norm <= 1e-9 -> 1).  `norm` is the plain per-component norm,
+    already reduced over all ranks.  One helper for the single-rank and the multi-rank driver."""
+    norm = np.array(norm, dtype=np.float64, copy=True)
+    if thresh_comp is not None:
+        tc = np.asarray(thresh_comp)
+        norm = np.where(tc == 0, -1.0, norm)
+        for l in range(2, int(tc.max()) + 1):
+            if (tc == l).any():
+                norm[tc == l] = norm[tc == l].max()
+    norm[norm <= 1.0e-9] = 1.0
+    return norm
+
+
 class WabbitAbort(RuntimeError):
     """The library's equivalent of `call abort(code, msg)`."""
 
@@ -49,6 +65,7 @@ class WabbitGPU:
             self._lib.wgpu_last_error(None, buf, 512)
             self._ctx = None
             raise WabbitAbort(rc, buf.value.decode())
+        self.stream = 0 if stream is None else int(stream)          # cudaStream_t all work of this context is issued on (0 = legacy default)
         if stream is not None:
             self._check(self._lib.wgpu_set_stream(self._ctx, C.c_void_p(stream)))
         self.hvy_active = np.zeros(0, np.int32)
@@ -307,13 +324,7 @@ class WabbitGPU:
             else:
                 norm_l = self.componentWiseNorm_tree((HVY_BLOCK, 0), "Linfty") if eps_normalized else None
             if norm_l is not None:
-                if thresh_comp is not None:                  # componentWiseNorm_tree.f90:119-163: 0 not computed, groups >= 2 share their norm
-                    tc = np.asarray(thresh_comp)
-                    norm_l = np.where(tc == 0, -1.0, norm_l)
-                    for l in range(2, int(tc.max()) + 1):
-                        if (tc == l).any():
-                            norm_l[tc == l] = norm_l[tc == l].max()
-                norm_l[norm_l <= 1.0e-9] = 1.0
+                norm_l = threshold_norm(norm_l, thresh_comp)
             n0 = forest.n_blocks
             ft = FullTree(self, forest, Jmin=Jmin)
             sz = (lifted if self.params.useSecurityZone < 0 else bool(self.params.useSecurityZone)) if useSecurityZone is None else bool(useSecurityZone)

@@ -168,7 +168,7 @@ class DistributedAdaptiveLoop:
         keeps = None
         if self.mask is not None and self.threshold_mask:
             keeps = (lambda level, pos: self.mask.keeps(level, pos, self.time)) if self.mask_time_dependent else self.mask.keeps
-        _, n0, n1 = self.drv.adapt_tree(eps=p.eps, eps_normalized=p.eps_normalized, Jmin=p.Jmin,
+        _, n0, n1 = self.drv.adapt_tree(eps=p.eps, eps_normalized=p.eps_normalized, eps_norm=p.eps_norm, Jmin=p.Jmin,
                                         force_maxlevel_dealiasing=p.force_maxlevel_dealiasing, thresh_comp=self.thresh_comp, mask_keeps=keeps,
                                         full_tree=True)
         self.status = self.drv.refinement_status
