@@ -115,6 +115,31 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
 int32_t wgpu_set_treecodes(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_active, const int32_t *level, const int64_t *treecode);
 
 /*
+ * wgpu_set_grid / wgpu_set_active: the device-native alternative to wgpu_set_treecodes + wgpu_set_topology ("topology on
+ * device"): the neighbour search of find_neighbors / updateNeighbors_tree (LIB/MESH/find_neighbors.f90:18-180, updateNeighbors_tree.f90)
+ * runs on the GPU.  The host names the RESIDENT blocks -- hvy id, mesh level, numerical treecode (get_tc(lgt_block(:, IDX_TC_1:IDX_TC_2))) --
+ * and the active list; no hvy_neighbor table is needed.  A position hash is built on the device and one thread per (active block,
+ * direction) establishes the relation exactly as find_neighbor does (same level / finer / coarser, incl. the last-digit rule for coarser edge
+ * and corner neighbours); the gather tables of the stencil and wavelet kernels, the level-jump patch lists, the coarse-extension list, the
+ * senders of restricted data and the interior / partition-boundary split follow by stable compaction in the order of the active list.
+ *   Resident blocks that are not active are data sources only: halo copies of other ranks' blocks (the slots wgpu_set_halo declared),
+ *   and, for the passes of adapt_tree's full wavelet transformation, all blocks of the full tree (leaves + mothers, init_full_tree):
+ *   register the tree once with wgpu_set_grid, then name each pass's blocks with wgpu_set_active (wavelet_decompose_full_tree's level
+ *   loop, adapt_tree.f90:268-545).  A leaf next to a refined region then finds the region's mother on its own level, as
+ *   sync_TMP_from_MF provides it.  An entry with hvy id <= 0 names a block that exists but whose data are not resident on this rank: it
+ *   takes part in the relations (a leaf next to it is "next to a coarser block": the coarse extension applies) but is never read.
+ * wgpu_topology_tables / wgpu_topology_list: read the derived tables back (tests, debugging): nbr27 / wnbr27 [max_blocks][27] gather codes
+ *   (>= 0 block index, -1 none, <= -2 pool patch), counts[8] = n_active, n_jump, n_wjump, n_ce, n_rst, n_interior, n_boundary, has_jumps;
+ *   list `which`: 0 stage-kernel face patches (block, dir), 1 wavelet ghost patches (block, dir), 2 coarse extension (block, dir),
+ *   3 restriction senders (block, direction mask), 4 interior blocks, 5 partition-boundary blocks; 0-based block indices.
+ */
+int32_t wgpu_set_grid(wgpu_ctx *ctx, int32_t n_resident, const int32_t *hvy_ids, const int32_t *level, const int64_t *treecode, int32_t n_active,
+                      const int32_t *hvy_active);
+int32_t wgpu_set_active(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_active);
+int32_t wgpu_topology_tables(wgpu_ctx *ctx, int32_t *nbr27, int32_t *wnbr27, int32_t *counts);
+int32_t wgpu_topology_list(wgpu_ctx *ctx, int32_t which, int32_t n, int32_t *out_a, int32_t *out_b);
+
+/*
  * ---- data movement between the host's Fortran arrays and the resident device arrays.
  * host points at element (1,1,1,1,1) of hvy(nx,ny,nz,ncomp_host,number_blocks); blocks listed in hvy_ids
  * (1-based, n of them) are moved.  `slot` selects hvy_work(:,:,:,:,:,slot) (ignored for other arrays).

@@ -48,6 +48,15 @@ const int32_t *whost_neighbors_ptr(const whost_forest *f, int32_t rank);
 /* 1 if every neighbour relation of every block is same-level */
 int32_t whost_is_uniform(const whost_forest *f);
 
+/* Halo plan of a rank from the block positions (no hvy_neighbor table needed): the blocks of other ranks that appear in a neighbour relation
+ * (same level / finer / coarser, find_neighbor's cases) of the rank's blocks, ascending lgt id, with level, treecode and a flag for finer
+ * neighbours (whose HD-filtered copies travel as well, restrict_copy_at_CE); the own blocks (hvy ids) the peers mirror, peer-major and hvy
+ * ascending, and those among them that are finer neighbours of a peer's block.  recv_counts / send_counts / fine_send_counts: n_ranks entries.
+ * The reference derives the same per synchronisation in prepare_ghost_synch_metadata (LIB/MPI/synchronize_ghosts_generic.f90:352-694). */
+int32_t whost_halo_plan(const whost_forest *f, int32_t rank, int32_t *n_halo, int32_t *halo_lgt, int32_t *halo_level, int64_t *halo_tc,
+                        int32_t *halo_fine, int32_t *recv_counts, int32_t *n_send, int32_t *send_hvy, int32_t *send_counts, int32_t *n_fine_send,
+                        int32_t *fine_send_hvy, int32_t *fine_send_counts);
+
 /*
  * Grid adaptation, light data only, single rank (n_ranks == 1).  Stand-ins for the id bookkeeping of refinement_execute_tree +
  * balanceLoad_tree and for respectJmaxJmin_tree / completeness / ensureGradedness_tree; they produce the id lists that

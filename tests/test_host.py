@@ -387,16 +387,17 @@ def test_full_tree_adapt_host_path_runs_without_a_device():
         def wavelet_filter_width(self):
             return 6
 
-        def set_treecodes(self, hvy, level, tc):
+        def set_grid(self, hvy, level, tc, active=None):
             assert len(hvy) == len(level) == len(tc) and hvy.min() >= 1 and hvy.max() <= self.max_blocks
-            self.calls.append("treecodes")
+            assert len(set(hvy.tolist())) == len(hvy)
+            self.known = set(hvy.tolist())
+            self.calls.append("grid")
+            self.set_active(hvy if active is None else active)
 
-        def set_topology(self, hvy, level, rows, rank):
-            assert rows.shape[0] == 168 and rows.flags.c_contiguous and rows.dtype == np.int32 and hvy.max() <= rows.shape[1]
-            act = rows[:, np.asarray(hvy) - 1]
-            assert act.max() <= rows.shape[1] and ((act >= 1) | (act == -1)).all()
+        def set_active(self, hvy):
+            assert set(np.asarray(hvy).tolist()) <= self.known
             self.hvy_active = np.asarray(hvy)
-            self.calls.append("topology")
+            self.calls.append("active")
 
         def set_forest(self, forest, rank=0):
             self.hvy_active = forest.active(0)[0]
@@ -436,7 +437,7 @@ def test_full_tree_adapt_host_path_runs_without_a_device():
     ft = FullTree(sol, forest, Jmin=1)
     new, info = ft.adapt(eps=1e-3, norm=np.ones(4), use_security_zone=True, want_info=False,
                          mask_keeps=lambda level, pos: (np.asarray(pos)[:, 0] == 0))
-    assert {"treecodes", "topology", "fwt", "ce", "d2m", "move", "forest"} <= set(sol.calls)
+    assert {"grid", "active", "fwt", "ce", "d2m", "move", "forest"} <= set(sol.calls)
     hvy, l, x, _ = new.active(0)
     assert 8 <= new.n_blocks < forest.n_blocks and np.array_equal(np.sort(sol.moved[1]), hvy)
     # complete and graded: every point of the domain is covered exactly once, neighbouring leaves differ by at most one level
@@ -568,3 +569,21 @@ def test_refinement_flags_2d_on_the_adapted_three_vortices_grid():
     run = A.AdaptiveRun(po, "CDF42", grid, np.zeros((grid.n, 1, 1, 1, 1)), 10.0, 0, 1e-3, refinement_indicator="significant")
     run.status = st.astype(np.int64)
     assert np.array_equal(got, run.refine_flags("significant")) and 0 < got.sum() < len(got)
+
+
+@pytest.mark.parametrize("dim,world,seed", [(3, 2, 1), (3, 3, 5), (3, 8, 2), (2, 4, 3)])
+def test_halo_plan_from_positions_equals_the_plan_from_the_neighbour_tables(dim, world, seed):
+    """whost_halo_plan (block positions, the rank's own blocks only, relations taken as symmetric) against the plan read off the 168-slot
+    hvy_neighbor tables of ALL ranks: halo blocks, send lists per peer, and the finer-neighbour sub-lists."""
+    from util import graded_blocks
+    from wabbit_b200.multi import HaloPlan, HaloPlanFromTables
+    lv, ix = graded_blocks(dim, 2, 4 if dim == 3 else 5, seed, 0.3)
+    forest = Forest.from_blocks(dim, 5, lv, ix, n_ranks=world, max_blocks=len(lv))
+    for r in range(world):
+        a, b = HaloPlan(forest, r, world), HaloPlanFromTables(forest, r, world)
+        assert np.array_equal(a.halo_lgt, b.halo_lgt) and np.array_equal(a.halo_hvy, b.halo_hvy)
+        assert a.recv_counts == b.recv_counts and a.send_counts == b.send_counts
+        assert np.array_equal(a.send_hvy, b.send_hvy)
+        assert np.array_equal(a.fine_lgt, b.fine_lgt) and np.array_equal(a.fine_recv_hvy, b.fine_recv_hvy)
+        assert a.fine_recv_counts == b.fine_recv_counts and a.fine_send_counts == b.fine_send_counts
+        assert np.array_equal(a.fine_send_hvy, b.fine_send_hvy)

@@ -60,6 +60,10 @@ GPU_SYMBOLS = {
     "wgpu_fwt": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "wgpu_iwt": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "wgpu_iwt_ce": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "wgpu_set_grid": (C.c_int32, [C.c_void_p, C.c_int32, _i32p, _i32p, _i64p, C.c_int32, _i32p]),
+    "wgpu_set_active": (C.c_int32, [C.c_void_p, C.c_int32, _i32p]),
+    "wgpu_topology_tables": (C.c_int32, [C.c_void_p, _i32p, _i32p, _i32p]),
+    "wgpu_topology_list": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, _i32p, _i32p]),
     "wgpu_norm": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _dp]),
     "wgpu_threshold": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _i32p, _dp, _dp, _i32p, _dp]),
     "wgpu_patch_details": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _i32p, _i32p, _dp]),
@@ -94,6 +98,7 @@ HOST_SYMBOLS = {
     "whost_get_neighbors": (C.c_int32, [C.c_void_p, C.c_int32, _i32p]),
     "whost_neighbors_ptr": (_i32p, [C.c_void_p, C.c_int32]),
     "whost_is_uniform": (C.c_int32, [C.c_void_p]),
+    "whost_halo_plan": (C.c_int32, [C.c_void_p, C.c_int32, _i32p, _i32p, _i32p, _i64p, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p]),
     "whost_refine": (C.c_int32, [C.c_void_p, _i32p, C.c_int32, C.POINTER(C.c_void_p), _i32p, _i32p, _i32p, _i32p, _i32p, _i32p]),
     "whost_coarsen": (C.c_int32, [C.c_void_p, _i32p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), _i32p, _i32p, _i32p, _i32p, _i32p, _i32p]),
     "whost_refine_global": (C.c_int32, [C.c_void_p, _i32p, C.c_int32, C.POINTER(C.c_void_p), _i32p, _i32p, _i32p, _i32p, _i32p, _i32p]),

@@ -418,8 +418,8 @@ int32_t wgpu_create(const wgpu_config *cfg, wgpu_ctx **out)
     if (rc == WGPU_OK) rc = dmalloc(ctx, &ctx->d_level, (size_t)cfg->max_blocks);
     if (rc == WGPU_OK) rc = dmalloc(ctx, &ctx->d_dt, 1);
     if (rc == WGPU_OK) rc = dmalloc(ctx, &ctx->d_dtmin, 2);
-    if (rc == WGPU_OK) rc = dmalloc(ctx, &ctx->d_flags, 4);
-    if (rc == WGPU_OK && cudaMemset(ctx->d_flags, 0, 4 * sizeof(int)) != cudaSuccess) rc = WGPU_ERR_CUDA;
+    if (rc == WGPU_OK) rc = dmalloc(ctx, &ctx->d_flags, 8);
+    if (rc == WGPU_OK && cudaMemset(ctx->d_flags, 0, 8 * sizeof(int)) != cudaSuccess) rc = WGPU_ERR_CUDA;
     if (rc == WGPU_OK && cudaMallocHost((void **)&ctx->h_pinned, 8 * sizeof(double)) != cudaSuccess) rc = WGPU_ERR_CUDA;
     if (rc != WGPU_OK) {
         g_create_err = ctx->err.empty() ? std::string("device allocation failed") : ctx->err;
@@ -470,6 +470,11 @@ int32_t wgpu_destroy(wgpu_ctx *ctx)
     cudaFree(ctx->d_wnbr);
     cudaFree(ctx->d_woff);
     cudaFree(ctx->d_wpool);
+    cudaFree(ctx->d_bflag);
+    cudaFree(ctx->d_rel);
+    cudaFree(ctx->d_cnt);
+    cudaFree(ctx->d_topo_in);
+    cudaFree(ctx->d_halo_ids);
     cudaFree(ctx->d_idbuf[0]);
     cudaFree(ctx->d_idbuf[1]);
     cudaFree(ctx->d_idbuf[2]);
@@ -561,6 +566,8 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
     if (n_active > N) return fail(ctx, WGPU_ERR_ARG, "more active blocks than max_blocks");
     ctx->h_active.assign(n_active, 0);
     ctx->remote_faces.clear();
+    ctx->topo_on_device = false;
+    ctx->rmap_on_device = false;
     // only the rows of the active blocks are read by the kernels: keep the range of active ids up to date, not the whole table (the passes
     // of the full-tree adapt_tree name a few thousand blocks out of max_blocks many times per call)
     int act_lo = N, act_hi = 0;
@@ -894,7 +901,7 @@ static int32_t check_flags(wgpu_ctx *ctx)
     WGPU_CHECK(ctx, cudaMemcpyAsync(flags, ctx->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
     WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     if (flags[0]) {
-        cudaMemsetAsync(ctx->d_flags, 0, sizeof(flags), ctx->stream);
+        cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream);
         return fail(ctx, WGPU_ERR_DIVERGED, "ACM fail: very very large values in state vector.");
     }
     return WGPU_OK;
@@ -1376,6 +1383,28 @@ int32_t wgpu_set_halo_restrict(wgpu_ctx *ctx, int32_t n_recv, const int32_t *rec
         ctx->rpool_cap = need + need / 4;
     }
     if (!ctx->d_rmap && (rc = dmalloc(ctx, &ctx->d_rmap, (size_t)N))) return rc;
+    if (ctx->rmap_on_device) {   // the block -> rpool map was derived on the device (wgpu_set_grid): extend / query it there
+        std::vector<int> r0(n_recv), s0(n_send);
+        for (int k = 0; k < n_recv; ++k) {
+            r0[k] = recv_halo_hvy[k] - 1;
+            if (r0[k] < 0 || r0[k] >= N) return fail(ctx, WGPU_ERR_ARG, "wgpu_set_halo_restrict: halo slot out of range");
+        }
+        for (int k = 0; k < n_send; ++k) {
+            s0[k] = send_hvy[k] - 1;
+            if (s0[k] < 0 || s0[k] >= N) return fail(ctx, WGPU_ERR_ARG, "wgpu_set_halo_restrict: send block out of range");
+        }
+        if (n_send > ctx->rhalo_send_cap) {
+            cudaFree(ctx->d_rhalo_send);
+            ctx->d_rhalo_send = nullptr;
+            if ((rc = dmalloc(ctx, &ctx->d_rhalo_send, (size_t)n_send + n_send / 2 + 64))) return rc;
+            ctx->rhalo_send_cap = n_send + n_send / 2 + 64;
+        }
+        if ((rc = wgpu_topology_halo_restrict(ctx, r0, s0))) return rc;
+        ctx->n_rhalo_recv = n_recv;
+        ctx->n_rhalo_send = n_send;
+        ctx->d_rhalo_send_buf = send_buf;
+        return WGPU_OK;
+    }
     for (int k = 0; k < n_recv; ++k) {
         const int b = recv_halo_hvy[k] - 1;
         if (b < 0 || b >= N) return fail(ctx, WGPU_ERR_ARG, "wgpu_set_halo_restrict: halo slot out of range");
@@ -1687,7 +1716,7 @@ int32_t wgpu_rk_end(wgpu_ctx *ctx, double *dt)
     WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     *dt = ctx->h_pinned[0];
     if (*(int *)(ctx->h_pinned + 1)) {
-        cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), ctx->stream);
+        cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream);
         return fail(ctx, WGPU_ERR_DIVERGED, "ACM fail: very very large values in state vector.");
     }
     return WGPU_OK;

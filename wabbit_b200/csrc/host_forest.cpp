@@ -70,7 +70,8 @@ struct whost_forest {
     std::vector<uint64_t> hkeys;
     std::vector<int> hvals;
     uint64_t hmask = 0;
-    std::vector<std::vector<int32_t>> nbr;         // per rank: N*168
+    std::vector<std::vector<int32_t>> nbr;         // per rank: ld*168, built on first use (ensure_neighbors): the device derives its own
+    bool nbr_ready = false;                        // topology from the block positions (wgpu_set_grid), so most forests never need it
     bool uniform = true;
 
     static uint64_t mix(uint64_t k)
@@ -158,7 +159,18 @@ static void build(whost_forest *f)
         }
     }
     f->lookup_build();
+    // every leaf on one level <=> every neighbour relation is same-level (the grid is complete)
+    f->uniform = true;
+    for (int i = 1; i < nb; ++i)
+        if (f->blocks[i].level != f->blocks[0].level) f->uniform = false;
+    f->nbr_ready = false;
+}
 
+static void ensure_neighbors(const whost_forest *cf)
+{
+    whost_forest *f = const_cast<whost_forest *>(cf);
+    if (f->nbr_ready) return;
+    const int dim = f->dim, nb = (int)f->blocks.size();
     // neighbour search, one direction at a time (find_neighbor, LIB/MESH/find_neighbors.f90:18-180)
     // hvy_neighbor(ld, 168) per rank with ld = number of active blocks of the rank (hvy ids are 1..ld): the table costs
     // 672 B per block instead of 672 B per allocated slot
@@ -268,7 +280,8 @@ static void build(whost_forest *f)
                     }
                 }
             }
-    f->uniform = !any_jump;
+    (void)any_jump;
+    f->nbr_ready = true;
 }
 
 int32_t whost_create_from_blocks(int32_t dim, int32_t Jmax, int32_t sfc, int32_t n_ranks, int32_t N, const int32_t periodic[3], int32_t n,
@@ -345,6 +358,7 @@ int32_t whost_get_active(const whost_forest *f, int32_t rank, int32_t *hvy_activ
 int32_t whost_get_neighbors(const whost_forest *f, int32_t rank, int32_t *hvy_neighbor)
 {
     if (!f || rank < 0 || rank >= f->n_ranks || !hvy_neighbor) return 1;
+    ensure_neighbors(f);
     memcpy(hvy_neighbor, f->nbr[rank].data(), sizeof(int32_t) * f->nbr[rank].size());
     return 0;
 }
@@ -352,10 +366,130 @@ int32_t whost_get_neighbors(const whost_forest *f, int32_t rank, int32_t *hvy_ne
 const int32_t *whost_neighbors_ptr(const whost_forest *f, int32_t rank)
 {
     if (!f || rank < 0 || rank >= f->n_ranks) return nullptr;
+    ensure_neighbors(f);
     return f->nbr[rank].data();
 }
 
 int32_t whost_is_uniform(const whost_forest *f) { return f && f->uniform ? 1 : 0; }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Halo plan of one rank, from the block positions (no 168-slot table): which blocks of other ranks appear in a neighbour relation of the
+// rank's blocks (same level, finer, coarser: find_neighbor's three cases, LIB/MESH/find_neighbors.f90:60-180) and which of its own blocks
+// the peers mirror.  Relations are symmetric (A sees B on its level <=> B sees A; A sees the finer B <=> B sees the coarser A), so both
+// lists follow from the rank's own blocks.  The reference derives the same information per synchronisation from hvy_neighbor in
+// prepare_ghost_synch_metadata (LIB/MPI/synchronize_ghosts_generic.f90:352-694).
+//   halo_*      blocks of other ranks, ascending lgt id (= owner-major, hvy ascending: the order they arrive in and of the halo slots);
+//               halo_fine[k] = 1 if the block is a FINER neighbour of one of the rank's blocks (its filtered copy travels too)
+//   send_*      own blocks (hvy ids) the peers mirror, peer-major, hvy ascending; fine_send_*: own blocks that are finer neighbours of a
+//               peer's block
+// Output arrays hold whost_n_blocks entries at most (send lists: n_ranks * n_active(rank)); counts arrays hold n_ranks entries.
+// ---------------------------------------------------------------------------------------------------------------------
+int32_t whost_halo_plan(const whost_forest *f, int32_t rank, int32_t *n_halo, int32_t *halo_lgt, int32_t *halo_level, int64_t *halo_tc,
+                        int32_t *halo_fine, int32_t *recv_counts, int32_t *n_send, int32_t *send_hvy, int32_t *send_counts, int32_t *n_fine_send,
+                        int32_t *fine_send_hvy, int32_t *fine_send_counts)
+{
+    if (!f || rank < 0 || rank >= f->n_ranks || !n_halo || !n_send || !n_fine_send || !recv_counts || !send_counts || !fine_send_counts) return 1;
+    const int dim = f->dim, W = f->n_ranks, nchild = 1 << dim;
+    const std::vector<int> &mine = f->rank_blocks[rank];
+    const int nm = (int)mine.size(), ntot = (int)f->blocks.size();
+    // per foreign block: bit0 related, bit1 finer neighbour of one of mine; per (own block, peer): bit0 related, bit1 the own block is the finer one
+    std::vector<unsigned char> foreign(ntot, 0), own((size_t)nm * W, 0);
+#pragma omp parallel for schedule(static)
+    for (int m = 0; m < nm; ++m) {
+        const Blk &b = f->blocks[mine[m]];
+        const int nblk = 1 << b.level;
+        auto mark = [&](int j, bool j_is_finer, bool j_is_coarser) {
+            const Blk &o = f->blocks[j];
+            if (o.rank == rank) return;
+            unsigned char v = 1 | (j_is_finer ? 2 : 0);
+            if ((foreign[j] & v) != v) {
+#pragma omp atomic
+                foreign[j] |= v;
+            }
+            own[(size_t)m * W + o.rank] |= 1 | (j_is_coarser ? 2 : 0);
+        };
+        for (int dz = (dim == 3 ? -1 : 0); dz <= (dim == 3 ? 1 : 0); ++dz)
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    if (!dx && !dy && !dz) continue;
+                    const int d[3] = {dx, dy, dz};
+                    int p[3] = {0, 0, 0};
+                    bool outside = false;
+                    for (int a = 0; a < dim; ++a) {
+                        p[a] = b.ix[a] + d[a];
+                        if (p[a] < 0 || p[a] >= nblk) {
+                            if (f->periodic[a]) p[a] = (p[a] + nblk) & (nblk - 1);
+                            else outside = true;
+                        }
+                    }
+                    if (outside) continue;
+                    int j = f->find(b.level, p);
+                    if (j >= 0) {
+                        mark(j, false, false);
+                        continue;
+                    }
+                    bool finer = false;
+                    if (b.level < f->Jmax) {
+                        const int nblk2 = nblk * 2;
+                        for (int c = 0; c < nchild; ++c) {   // virtual daughters that touch this side
+                            bool touches = true;
+                            int q[3] = {0, 0, 0};
+                            for (int a = 0; a < dim; ++a) {
+                                const int bit = (c >> a) & 1;
+                                if ((d[a] > 0 && !bit) || (d[a] < 0 && bit)) touches = false;
+                                q[a] = (2 * b.ix[a] + bit + d[a] + nblk2) & (nblk2 - 1);
+                            }
+                            if (!touches) continue;
+                            j = f->find(b.level + 1, q);
+                            if (j >= 0) {
+                                mark(j, true, false);
+                                finer = true;
+                            }
+                        }
+                    }
+                    if (finer || b.level == 0) continue;
+                    const int q[3] = {p[0] >> 1, p[1] >> 1, p[2] >> 1};
+                    j = f->find(b.level - 1, q);
+                    if (j >= 0) mark(j, false, true);
+                }
+    }
+    for (int r = 0; r < W; ++r) recv_counts[r] = send_counts[r] = fine_send_counts[r] = 0;
+    int nh = 0;
+    for (int r = 0; r < W; ++r) {   // blocks are stored rank by rank in hvy order: ascending lgt id
+        if (r == rank) continue;
+        for (int j : f->rank_blocks[r]) {
+            if (!foreign[j]) continue;
+            const Blk &o = f->blocks[j];
+            if (halo_lgt) halo_lgt[nh] = o.rank * f->N + o.hvy;
+            if (halo_level) halo_level[nh] = o.level;
+            if (halo_tc) halo_tc[nh] = o.tc;
+            if (halo_fine) halo_fine[nh] = (foreign[j] & 2) ? 1 : 0;
+            ++nh;
+            ++recv_counts[r];
+        }
+    }
+    *n_halo = nh;
+    int ns = 0, nf = 0;
+    for (int r = 0; r < W; ++r) {
+        if (r == rank) continue;
+        for (int m = 0; m < nm; ++m) {
+            const unsigned char v = own[(size_t)m * W + r];
+            if (v & 1) {
+                if (send_hvy) send_hvy[ns] = f->blocks[mine[m]].hvy;
+                ++ns;
+                ++send_counts[r];
+            }
+            if (v & 2) {
+                if (fine_send_hvy) fine_send_hvy[nf] = f->blocks[mine[m]].hvy;
+                ++nf;
+                ++fine_send_counts[r];
+            }
+        }
+    }
+    *n_send = ns;
+    *n_fine_send = nf;
+    return 0;
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Grid adaptation, light data only (single rank).  Stand-ins for refinement_execute_tree's id bookkeeping +
@@ -466,6 +600,7 @@ static int32_t coarsen_impl(const whost_forest *f, int32_t *status, int32_t Jmin
 {
     if (!f || !out || !status || (!global && f->n_ranks != 1) || !n_mothers || !n_keep) return 1;
     const int dim = f->dim, nd = 1 << dim, n = (int)f->blocks.size();
+    ensure_neighbors(f);
     // finer neighbours of block k (global position): row of its owner's table, lgt ids -> global positions
     std::vector<int> roff(f->n_ranks + 1, 0), owner(n), local(n);
     for (int r = 0; r < f->n_ranks; ++r) {

@@ -430,7 +430,11 @@ int32_t wgpu_launch_restrict_filter(wgpu_ctx *ctx, const double *src, int nc_src
 {
     *active = false;
     const WaveFilters &w = ctx->wavelet;
-    if (ctx->ignore_filter || !ctx->wavelet_set || w.Y == 0 || ctx->n_rst == 0 || nc_src != ctx->nc) return WGPU_OK;
+    if (ctx->ignore_filter || !ctx->wavelet_set || w.Y == 0 || (ctx->n_rst == 0 && ctx->n_rhalo_recv == 0) || nc_src != ctx->nc) return WGPU_OK;
+    if (ctx->n_rst == 0) {   // no block of this rank sends restricted data, but filtered copies of finer neighbours arrived from other ranks
+        *active = true;
+        return WGPU_OK;
+    }
     const wgpu_config &c = ctx->cfg;
     RestrictArgs a;
     a.u = src;

@@ -90,6 +90,7 @@ __device__ inline void src_table_build(SrcTable &T, const BlockLookup &L, int le
                     v = blk_lookup(L, level + 1, 2 * bc[0] + (c & 1), 2 * bc[1] + ((c >> 1) & 1), dim == 3 ? 2 * bc[2] + ((c >> 2) & 1) : 0);
             }
         }
+        if (v < -1) v = -1;   // known by position only (wgpu_set_grid with hvy id <= 0): no data here
         if (k == 0) T.blk[e] = v;
         else T.child[e][k - 1] = v;
     }

@@ -164,6 +164,18 @@ struct wgpu_ctx {
     int geom = 0;                      // analytic mask geometry (0 none, 1 sphere) and its parameters
     double g_c0[3] = {0, 0, 0}, g_v[3] = {0, 0, 0}, g_R = 0, g_h = 1;
     bool coords_dirty = true;          // wgpu_set_treecodes changed the block positions since the lookup table was last uploaded
+    // topology derived on the device (topology.cu: wgpu_set_grid / wgpu_set_active)
+    bool topo_on_device = false;       // the current tables come from wgpu_set_grid (block lookup, level, positions are registered on the device)
+    bool rmap_on_device = false;       // d_rmap was filled on the device (h_rmap is not kept)
+    unsigned char *d_bflag = nullptr;  // [max_blocks] bit0 registered, bit1 halo copy
+    unsigned char *d_rel = nullptr;    // [n_active][27] relation of the active blocks
+    size_t rel_cap = 0;
+    long long *d_cnt = nullptr;        // per-block counts / scanned offsets of the list compaction
+    size_t cnt_cap = 0;
+    char *d_topo_in = nullptr;         // staging of the (id, level, treecode) lists
+    size_t topo_in_cap = 0;
+    int *d_halo_ids = nullptr;
+    size_t halo_ids_cap = 0;
     int *d_idbuf[3] = {nullptr, nullptr, nullptr};   // scratch id lists (refine / coarsen)
     size_t idbuf_cap[3] = {0, 0, 0};
     // Runge-Kutta step in flight
@@ -177,7 +189,7 @@ struct wgpu_ctx {
     unsigned long long *d_dtmin = nullptr;    // [2]: CFL dt candidates (bits), ping-pong
     int dtmin_cur = 0;
     bool dtmin_valid = false;
-    int *d_flags = nullptr;                   // [0] diverged
+    int *d_flags = nullptr;                   // [8]: [0] diverged, [2..4] topology.cu (duplicate position, jump flags, bad send list)
     double *h_pinned = nullptr;               // [0] dt, [1] flags (as int bits)
 
     // wavelets
@@ -224,6 +236,8 @@ int32_t wgpu_launch_refine(wgpu_ctx *ctx, const double *src, double *dst, const 
 int32_t wgpu_launch_coarsen(wgpu_ctx *ctx, const double *src, double *dst, const int *d_mother, const int *d_daughter, int n);
 int32_t wgpu_launch_copy_blocks(wgpu_ctx *ctx, const double *src, double *dst, const int *d_src_ids, const int *d_dst_ids, int n);
 int32_t wgpu_launch_copy_entries(wgpu_ctx *ctx, const double *src, double *dst, const int *d_src_idx, int n, long long per_entry);
+// topology.cu
+int32_t wgpu_topology_halo_restrict(wgpu_ctx *ctx, const std::vector<int> &recv0, const std::vector<int> &send0);
 // wavelet.cu
 int32_t wgpu_launch_wavelet(wgpu_ctx *ctx, const double *src, double *dst, int inverse, const double *ce_coarse);
 int32_t wgpu_launch_detail(wgpu_ctx *ctx, const double *wd, int eps_norm, int level_ref);

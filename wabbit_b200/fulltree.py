@@ -248,16 +248,21 @@ class FullTree:
         return time.perf_counter()
 
     def set_pass_topology(self, idx: np.ndarray):
-        """a pass = a list of active blocks (indices into the tree arrays) on the tree's neighbour rows.  Returns the indices in the order
-        of the active list (ascending slot)."""
+        """a pass = a list of active blocks (indices into the tree arrays).  The whole tree -- leaves and mothers -- is registered on the
+        device once per tree state (wgpu_set_grid: position hash, neighbour relations derived on the GPU); a pass then only names its
+        active list (wgpu_set_active).  Returns the indices in the order of the active list (ascending slot)."""
         t0 = time.perf_counter()
         idx = np.asarray(idx)
         idx = idx[np.argsort(self.slots[idx])]
+        act = self.slots[idx].astype(np.int32)
         if not self._rows_ready:
-            self._upload_rows()
-            t0 = self._tick("tree rows (numpy) + wgpu_set_treecodes", t0)
-        self.sol.set_topology(self.slots[idx].astype(np.int32), self._lvl32[idx], self._rows, 0)
-        self._tick("wgpu_set_topology", t0)
+            tc = _encode_treecodes(self.dim, self.level, self.pos, self.forest.Jmax)
+            self.sol.set_grid(self.slots.astype(np.int32), self._lvl32, tc, act)
+            self._rows_ready = True
+            self._tick("wgpu_set_grid (tree)", t0)
+        else:
+            self.sol.set_active(act)
+            self._tick("wgpu_set_active", t0)
         return idx
 
     # ------------------------------------------------------------------ wavelet_decompose_full_tree + coarseningIndicator_tree
@@ -553,23 +558,11 @@ class DistributedFullTree(FullTree):
             lslot[got] = loc
         mine = mine_of[me]
         mine = mine[np.argsort(self.slots[mine])]
-        present = np.flatnonzero(lslot >= 0)
-        if len(mine):
-            ids = self.slots[mine].astype(np.int32)
-            ld = int(max(lslot.max(), ids.max()))
-            nbr = np.full((168, ld), -1, dtype=np.int32)
-            leaf = self.is_leaf[mine] & (self.level[mine] > 0)
-            for q, d in enumerate(self.dirs):
-                j = self.nb[mine, q]
-                hit = (j >= 0) & (lslot[np.maximum(j, 0)] >= 0)
-                nbr[_code(d) - 1, ids[hit] - 1] = lslot[j[hit]]
-                miss = (j < 0) & leaf                                     # no same-level block in the tree: a coarser leaf covers it
-                nbr[_code(d) - 1 + 56, ids[miss] - 1] = ids[miss]          # (any valid id: only the relation matters, data go by position)
-            tc = _encode_treecodes(dim, self.level[present], self.pos[present], self.forest.Jmax)
-            sol.set_treecodes(lslot[present].astype(np.int32), self.level[present].astype(np.int32), tc)
-            sol.set_topology(ids, self.level[mine].astype(np.int32), nbr, 0)
-        else:
-            sol.set_topology(np.zeros(0, np.int32), np.zeros(0, np.int32), np.full((168, 1), -1, np.int32), 0)
+        # every block of the tree is registered by position (resident ones with their local slot, the others with slot 0 = "exists, no data
+        # here"); the relations of the pass's blocks are derived on the device
+        if getattr(self, "_tc_all", None) is None or len(self._tc_all) != len(self.code):
+            self._tc_all = _encode_treecodes(dim, self.level, self.pos, self.forest.Jmax)
+        sol.set_grid(np.maximum(lslot, 0).astype(np.int32), self._lvl32, self._tc_all, self.slots[mine].astype(np.int32))
         self._lslot = lslot
         return mine, mine_of
 

@@ -254,14 +254,59 @@ def fine_halo_list(forest: Forest, rank: int) -> np.ndarray:
 
 
 class HaloPlan:
-    """Which blocks every rank mirrors and which of its own it sends, derived from the replicated light data (no handshake)."""
+    """Which blocks every rank mirrors and which of its own it sends, derived from the replicated light data (no handshake): computed in
+    libwabbit_host.so from the block positions (whost_halo_plan; relations are symmetric, so a rank's own blocks give both lists)."""
+
+    def __init__(self, forest: Forest, rank: int, world: int):
+        from ._native import host_lib
+        N = forest.max_blocks
+        self.rank, self.world = rank, world
+        self.n_own = forest.n_active(rank)
+        ntot, W = forest.n_blocks, forest.n_ranks
+        assert W == world
+        cap_h, cap_s = max(ntot - self.n_own, 1), max(self.n_own * max(W - 1, 1), 1)
+        lgt, lvl, fine = np.zeros(cap_h, np.int32), np.zeros(cap_h, np.int32), np.zeros(cap_h, np.int32)
+        tc = np.zeros(cap_h, np.int64)
+        send, fsend = np.zeros(cap_s, np.int32), np.zeros(cap_s, np.int32)
+        rc_, sc_, fc_ = np.zeros(W, np.int32), np.zeros(W, np.int32), np.zeros(W, np.int32)
+        nh, ns, nf = C.c_int32(), C.c_int32(), C.c_int32()
+        rc = host_lib().whost_halo_plan(forest._h, rank, C.byref(nh), _i32(lgt), _i32(lvl), tc.ctypes.data_as(C.POINTER(C.c_int64)), _i32(fine),
+                                        _i32(rc_), C.byref(ns), _i32(send), _i32(sc_), C.byref(nf), _i32(fsend), _i32(fc_))
+        if rc:
+            raise RuntimeError(f"whost_halo_plan: {rc}")
+        nh, ns, nf = nh.value, ns.value, nf.value
+        if self.n_own + nh > N:
+            raise MemoryError(f"rank {rank}: {self.n_own} own blocks + {nh} halo copies exceed max_blocks = {N}")
+        self.halo_lgt, self.halo_level, self.halo_tc = lgt[:nh].copy(), lvl[:nh].copy(), tc[:nh].copy()
+        self.halo_hvy = (self.n_own + 1 + np.arange(nh)).astype(np.int32)
+        self.recv_counts = [int(v) for v in rc_]
+        self.send_hvy, self.send_counts = send[:ns].copy(), [int(v) for v in sc_]
+        # filtered copies of finer neighbours (lifted wavelets): who needs whose
+        isf = fine[:nh] != 0
+        self.fine_lgt = self.halo_lgt[isf].astype(np.int64)
+        self.fine_recv_hvy = self.halo_hvy[isf].astype(np.int32)
+        owner = (self.halo_lgt.astype(np.int64) - 1) // N
+        self.fine_recv_counts = [int((isf & (owner == p)).sum()) for p in range(world)]
+        self.fine_send_hvy, self.fine_send_counts = fsend[:nf].copy(), [int(v) for v in fc_]
+
+    @property
+    def n_halo(self) -> int:
+        return len(self.halo_lgt)
+
+    @property
+    def n_send(self) -> int:
+        return len(self.send_hvy)
+
+
+class HaloPlanFromTables:
+    """The same plan read off the 168-slot hvy_neighbor tables of every rank (the formulation the C++ plan is checked against in
+    tests/test_host.py)."""
 
     def __init__(self, forest: Forest, rank: int, world: int):
         N = forest.max_blocks
         self.rank, self.world = rank, world
         self.n_own = forest.n_active(rank)
         lists = [halo_list(forest, r) for r in range(world)]
-        # filtered copies of finer neighbours (lifted wavelets): who needs whose
         fl = [fine_halo_list(forest, r) for r in range(world)]
         self.fine_lgt = fl[rank]
         self.fine_recv_counts = [int(((fl[rank] - 1) // N == p).sum()) for p in range(world)]
@@ -271,35 +316,15 @@ class HaloPlan:
         mine = lists[rank]
         self.halo_lgt = mine.astype(np.int32)
         self.halo_hvy = (self.n_own + 1 + np.arange(len(mine))).astype(np.int32)
-        if self.n_own + len(mine) > N:
-            raise MemoryError(f"rank {rank}: {self.n_own} own blocks + {len(mine)} halo copies exceed max_blocks = {N}")
         owner = (mine - 1) // N
         self.recv_counts = [int((owner == p).sum()) for p in range(world)]
-        lvl = np.zeros(len(mine), np.int32)
-        tc = np.zeros(len(mine), np.int64)
-        for p in range(world):
-            sel = owner == p
-            if sel.any():
-                hvy_p, lvl_p, _, tc_p = forest.active(p)
-                assert (hvy_p == np.arange(1, len(hvy_p) + 1)).all()
-                k = (mine[sel] - 1) % N
-                lvl[sel], tc[sel] = lvl_p[k], tc_p[k]
-        self.halo_level, self.halo_tc = lvl, tc
-        self.fine_recv_hvy = self.halo_hvy[np.searchsorted(mine, self.fine_lgt)].astype(np.int32)   # halo slots of the finer neighbours
+        self.fine_recv_hvy = self.halo_hvy[np.searchsorted(mine, self.fine_lgt)].astype(np.int32)
         send, self.send_counts = [], []
         for p in range(world):
             t = lists[p][(lists[p] - 1) // N == rank] if p != rank else np.zeros(0, np.int64)
             send.append((t - 1) % N + 1)
             self.send_counts.append(len(t))
         self.send_hvy = np.concatenate(send).astype(np.int32)
-
-    @property
-    def n_halo(self) -> int:
-        return len(self.halo_lgt)
-
-    @property
-    def n_send(self) -> int:
-        return len(self.send_hvy)
 
 
 class HaloStepper:
@@ -324,8 +349,14 @@ class HaloStepper:
         sol._check(lib.wgpu_set_halo(ctx, plan.n_halo, _i32(plan.halo_lgt), _i32(plan.halo_hvy), _i32(plan.halo_level), plan.n_send,
                                      _i32(plan.send_hvy), C.c_void_p(self.send.data_ptr())))
         hvy, lvl, _, tc = forest.active(rank)
-        sol.set_treecodes(np.concatenate([hvy, plan.halo_hvy]), np.concatenate([lvl, plan.halo_level]), np.concatenate([tc, plan.halo_tc]))
-        sol.set_topology(hvy, lvl, forest.neighbors(rank), rank)
+        # own blocks + halo copies are the resident blocks; the neighbour relations are derived on the device (wgpu_set_grid);
+        # WABBIT_HOST_TOPOLOGY=1: the Fortran-facing route through the 168-slot hvy_neighbor table instead
+        import os
+        if os.environ.get("WABBIT_HOST_TOPOLOGY"):
+            sol.set_treecodes(np.concatenate([hvy, plan.halo_hvy]), np.concatenate([lvl, plan.halo_level]), np.concatenate([tc, plan.halo_tc]))
+            sol.set_topology(hvy, lvl, forest.neighbors(rank), rank)
+        else:
+            sol.set_grid(np.concatenate([hvy, plan.halo_hvy]), np.concatenate([lvl, plan.halo_level]), np.concatenate([tc, plan.halo_tc]), hvy)
         self.in_splits = [c * self.blk for c in plan.send_counts]
         self.out_splits = [c * self.blk for c in plan.recv_counts]
         self._exchange = exchange or MultiGPUStepper._nccl_exchange.__get__(self)

@@ -133,10 +133,53 @@ class WabbitGPU:
         self._check(self._lib.wgpu_set_treecodes(self._ctx, len(hvy_active), _i32(hvy_active), _i32(level),
                                                  treecode.ctypes.data_as(C.POINTER(C.c_int64))))
 
-    def set_forest(self, forest: Forest, rank: int = 0):
+    def set_grid(self, hvy_ids: np.ndarray, level: np.ndarray, treecode: np.ndarray, hvy_active: Optional[np.ndarray] = None):
+        """Topology derived on the device (wgpu_set_grid): the resident blocks (hvy id, level, treecode) and the active list; no hvy_neighbor
+        table.  hvy_active None: every resident block that is not a halo copy declared by wgpu_set_halo is active."""
+        hvy_ids = np.ascontiguousarray(hvy_ids, dtype=np.int32)
+        level = np.ascontiguousarray(level, dtype=np.int32)
+        treecode = np.ascontiguousarray(treecode, dtype=np.int64)
+        act = hvy_ids if hvy_active is None else np.ascontiguousarray(hvy_active, dtype=np.int32)
+        self._check(self._lib.wgpu_set_grid(self._ctx, len(hvy_ids), _i32(hvy_ids), _i32(level), treecode.ctypes.data_as(C.POINTER(C.c_int64)),
+                                            len(act), _i32(act)))
+        self.hvy_active = act.copy()
+
+    def set_active(self, hvy_active: np.ndarray):
+        """the active list of a pass on the blocks registered by set_grid (wgpu_set_active)"""
+        act = np.ascontiguousarray(hvy_active, dtype=np.int32)
+        self._check(self._lib.wgpu_set_active(self._ctx, len(act), _i32(act)))
+        self.hvy_active = act.copy()
+
+    def topology_tables(self):
+        """(nbr27, wnbr27, counts dict, lists dict) of the current topology, read back from the device (tests)"""
+        N = self.max_blocks
+        nbr = np.zeros((N, 27), np.int32)
+        wnbr = np.full((N, 27), -1, np.int32)
+        cnt = np.zeros(8, np.int32)
+        self._check(self._lib.wgpu_topology_tables(self._ctx, _i32(nbr), _i32(wnbr), _i32(cnt)))
+        names = ("n_active", "n_jump", "n_wjump", "n_ce", "n_rst", "n_int", "n_bnd", "has_jumps")
+        counts = dict(zip(names, (int(v) for v in cnt)))
+        lists = {}
+        for which, (name, key) in enumerate((("jump", "n_jump"), ("wjump", "n_wjump"), ("ce", "n_ce"), ("rst", "n_rst"), ("int", "n_int"), ("bnd", "n_bnd"))):
+            n = counts[key]
+            a, b = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32)
+            self._check(self._lib.wgpu_topology_list(self._ctx, which, n, _i32(a), _i32(b)))
+            lists[name] = (a[:n], b[:n])
+        return nbr, wnbr, counts, lists
+
+    def set_forest(self, forest: Forest, rank: int = 0, host_tables: Optional[bool] = None):
+        """Upload a grid.  Default: the topology is derived on the device from the block positions (wgpu_set_grid); host_tables = True (or
+        WABBIT_HOST_TOPOLOGY=1) takes the Fortran-facing route instead: the 168-slot hvy_neighbor table of updateMetadata_tree through
+        wgpu_set_treecodes + wgpu_set_topology."""
+        import os
         hvy, lvl, _, tc = forest.active(rank)
-        self.set_treecodes(hvy, lvl, tc)
-        self.set_topology(hvy, lvl, forest.neighbors(rank), rank)
+        if host_tables is None:
+            host_tables = bool(os.environ.get("WABBIT_HOST_TOPOLOGY"))
+        if host_tables or forest.n_ranks > 1:
+            self.set_treecodes(hvy, lvl, tc)
+            self.set_topology(hvy, lvl, forest.neighbors(rank), rank)
+        else:
+            self.set_grid(hvy, lvl, tc)
 
     # ------------------------------------------------------------------ data movement
     def _ids(self, hvy_ids):
