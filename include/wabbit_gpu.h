@@ -325,6 +325,42 @@ int32_t wgpu_rk_end(wgpu_ctx *ctx, double *dt);
 /* number of blocks in each set (ALL / INTERIOR / BOUNDARY) */
 int32_t wgpu_block_count(const wgpu_ctx *ctx, int32_t which_blocks);
 
+/*
+ * ---- multi-GPU inside the library: NCCL over NVLink on a communicator the library owns (multigpu.cu).  One process per GPU.
+ * The reference's counterparts: MPI_Isend / Irecv of ghost patches (LIB/MPI/xfer_block_data.f90:10-99), MPI_Allreduce(MIN) of dt
+ * (LIB/TIME/calculate_time_step.f90:48), block_xfer (LIB/MPI/block_xfer_nonblocking.f90:16), synchronize_lgt_data (LIB/MESH/).
+ *   wgpu_comm_unique_id      rank 0: a 128-byte id (ncclGetUniqueId); the host broadcasts it (MPI_Bcast) ...
+ *   wgpu_comm_init           ... and every rank joins (ncclCommInitRank).  NCCL is loaded at run time (dlopen).
+ *   wgpu_comm_set_counts     per-peer counts [world] of the exchange declared last: face patches (wgpu_set_exchange) or halo blocks
+ *                            (wgpu_set_halo), and of the filtered copies of wgpu_set_halo_restrict (may be NULL)
+ *   wgpu_rk_steps            n_steps of RungeKuttaGeneric back to back (the N_dt_per_grid loop of LIB/POSTPROCESSING/performance_test.f90:
+ *                            194-199): time, dt and the divergence flag stay on the device, dt's MIN over ranks is an ncclAllReduce on the
+ *                            device scalar, every stage = pack -> grouped ncclSend / ncclRecv on a second stream, straight into the patch pool
+ *                            resp. the halo slots of the stage input || stage kernel on interior blocks -> stage kernel on partition-boundary
+ *                            blocks.  One host synchronisation at the end: *time_out = time after the last step, *dt_last its dt.
+ *                            Works without a communicator (single GPU) as well.
+ *   wgpu_exchange_array      refresh the halo copies (and, filtered != 0 with a lifted wavelet, the filtered copies of finer neighbours)
+ *                            of a named array: before wgpu_fwt, wgpu_refine, wgpu_download with ghosts
+ *   wgpu_ship_blocks         block_xfer between ranks.  Item k: a block in slot src_slot[k] (1-based) of the array on rank src_rank[k] is
+ *                            needed on dst_rank[k]; all ranks pass the same lists.  Remote blocks are received straight into the free slots
+ *                            first_free, first_free + 1, ... (peer-major, item order); local_slot[] receives the local slot of every item with
+ *                            dst_rank == me (item order), *next_free the first slot still free.
+ *   wgpu_comm_allreduce      small host arrays (norms, flags): op 0 MAX, 1 MIN, 2 SUM
+ *   wgpu_comm_allgatherv_i32 concatenation over ranks of int32 lists whose lengths every rank knows (refinement flags)
+ */
+int32_t wgpu_comm_unique_id(char *id128);
+int32_t wgpu_comm_init(wgpu_ctx *ctx, const char *id128, int32_t rank, int32_t world);
+int32_t wgpu_comm_destroy(wgpu_ctx *ctx);
+int32_t wgpu_comm_info(const wgpu_ctx *ctx, int32_t *rank, int32_t *world);
+int32_t wgpu_comm_set_counts(wgpu_ctx *ctx, const int32_t *send_counts, const int32_t *recv_counts, const int32_t *restrict_send_counts,
+                             const int32_t *restrict_recv_counts);
+int32_t wgpu_rk_steps(wgpu_ctx *ctx, double time, int32_t n_steps, double *time_out, double *dt_last);
+int32_t wgpu_exchange_array(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t filtered);
+int32_t wgpu_ship_blocks(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t n_items, const int32_t *src_rank, const int32_t *src_slot,
+                         const int32_t *dst_rank, int32_t first_free, int32_t *local_slot, int32_t *next_free);
+int32_t wgpu_comm_allreduce(wgpu_ctx *ctx, double *inout, int32_t n, int32_t op);
+int32_t wgpu_comm_allgatherv_i32(wgpu_ctx *ctx, const int32_t *mine, const int32_t *counts, int32_t *out);
+
 /* Stage-kernel timing with CUDA events on the context's stream (for the roofline line of bench.py):
  * wgpu_profile(ctx, 1) starts recording an event pair around every stage-kernel launch (at most 4096 pairs),
  * wgpu_profile_read synchronises, returns their number and summed duration in milliseconds, and resets. */

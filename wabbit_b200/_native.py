@@ -64,6 +64,16 @@ GPU_SYMBOLS = {
     "wgpu_set_active": (C.c_int32, [C.c_void_p, C.c_int32, _i32p]),
     "wgpu_topology_tables": (C.c_int32, [C.c_void_p, _i32p, _i32p, _i32p]),
     "wgpu_topology_list": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, _i32p, _i32p]),
+    "wgpu_comm_unique_id": (C.c_int32, [C.c_char_p]),
+    "wgpu_comm_init": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_int32, C.c_int32]),
+    "wgpu_comm_destroy": (C.c_int32, [C.c_void_p]),
+    "wgpu_comm_info": (C.c_int32, [C.c_void_p, _i32p, _i32p]),
+    "wgpu_comm_set_counts": (C.c_int32, [C.c_void_p, _i32p, _i32p, _i32p, _i32p]),
+    "wgpu_rk_steps": (C.c_int32, [C.c_void_p, C.c_double, C.c_int32, _dp, _dp]),
+    "wgpu_exchange_array": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    "wgpu_ship_blocks": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _i32p, _i32p, _i32p, C.c_int32, _i32p, _i32p]),
+    "wgpu_comm_allreduce": (C.c_int32, [C.c_void_p, _dp, C.c_int32, C.c_int32]),
+    "wgpu_comm_allgatherv_i32": (C.c_int32, [C.c_void_p, _i32p, _i32p, _i32p]),
     "wgpu_norm": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _dp]),
     "wgpu_threshold": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _i32p, _dp, _dp, _i32p, _dp]),
     "wgpu_patch_details": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _i32p, _i32p, _dp]),

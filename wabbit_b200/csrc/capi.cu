@@ -418,6 +418,7 @@ int32_t wgpu_create(const wgpu_config *cfg, wgpu_ctx **out)
     if (rc == WGPU_OK) rc = dmalloc(ctx, &ctx->d_level, (size_t)cfg->max_blocks);
     if (rc == WGPU_OK) rc = dmalloc(ctx, &ctx->d_dt, 1);
     if (rc == WGPU_OK) rc = dmalloc(ctx, &ctx->d_dtmin, 2);
+    if (rc == WGPU_OK) rc = dmalloc(ctx, &ctx->d_time, 2);
     if (rc == WGPU_OK) rc = dmalloc(ctx, &ctx->d_flags, 8);
     if (rc == WGPU_OK && cudaMemset(ctx->d_flags, 0, 8 * sizeof(int)) != cudaSuccess) rc = WGPU_ERR_CUDA;
     if (rc == WGPU_OK && cudaMallocHost((void **)&ctx->h_pinned, 8 * sizeof(double)) != cudaSuccess) rc = WGPU_ERR_CUDA;
@@ -435,6 +436,7 @@ int32_t wgpu_destroy(wgpu_ctx *ctx)
     if (!ctx) return WGPU_OK;
     cudaSetDevice(ctx->cfg.device);
     cudaDeviceSynchronize();
+    wgpu_comm_destroy(ctx);
     cudaFree(ctx->U);
     cudaFree(ctx->UA);
     cudaFree(ctx->UB);
@@ -484,6 +486,7 @@ int32_t wgpu_destroy(wgpu_ctx *ctx)
     cudaFree(ctx->d_send_dir);
     cudaFree(ctx->d_dt);
     cudaFree(ctx->d_dtmin);
+    cudaFree(ctx->d_time);
     cudaFree(ctx->d_flags);
     cudaFree(ctx->d_stage);
     for (auto &e : ctx->prof_ev) cudaEventDestroy(e);
@@ -1646,6 +1649,7 @@ int32_t wgpu_rk_stage(wgpu_ctx *ctx, int32_t j, int32_t which)
     a.u_in = uin;
     a.u0 = ctx->U;
     a.t0 = ctx->rk_time;
+    a.t0_ptr = ctx->time_on_device ? ctx->d_time : nullptr;
     a.t_cj = c.butcher[(size_t)(j - 1) * ld];                  // t = time + dt*rk_coeffs(j,1), runge_kutta_generic.f90:78,122
     if (a.geom && !ctx->lookup_ready) return fail(ctx, WGPU_ERR_ARG, "analytic mask: call wgpu_set_treecodes + wgpu_set_topology first");
     const bool last = (j == s);
@@ -1703,14 +1707,25 @@ int32_t wgpu_rk_stage(wgpu_ctx *ctx, int32_t j, int32_t which)
     return wgpu_launch_stage(ctx, a, nblk);
 }
 
-int32_t wgpu_rk_end(wgpu_ctx *ctx, double *dt)
+}  // extern "C"
+
+// end-of-step bookkeeping without the host read-back of dt and of the divergence flag (wgpu_rk_steps reads them once after the last step)
+int32_t wgpu_rk_end_nosync(wgpu_ctx *ctx)
 {
-    if (!ctx || !dt) return WGPU_ERR_ARG;
     const wgpu_config &c = ctx->cfg;
     const int s = c.n_stages;
     if (stage_input(ctx, s) == ctx->U) std::swap(ctx->U, ctx->UA);   // single-stage scheme: result was written to UA
     if (!(c.dt_fixed > 0.0)) ctx->dtmin_valid = true;
     ctx->rk_next_stage = 0;
+    return WGPU_OK;
+}
+
+extern "C" {
+
+int32_t wgpu_rk_end(wgpu_ctx *ctx, double *dt)
+{
+    if (!ctx || !dt) return WGPU_ERR_ARG;
+    wgpu_rk_end_nosync(ctx);
     WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_dt, 8, cudaMemcpyDeviceToHost, ctx->stream));
     WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pinned + 1, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));

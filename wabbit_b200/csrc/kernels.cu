@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(BS *BS, (Tile<FD, BS>::SMEM <= 110 * 1024 ? 2 
     // step_cosine4, LIB/HELPER/module_helpers.f90): coordinates x = i*dx + x0 and the squared distance in the reference's operation order
     double gxy2 = 0.0, gz0 = 0.0, gcz = 0.0;
     if (GEOM) {
-        const double ts = __dadd_rn(a.t0, __dmul_rn(a.t_cj, *a.dt_ptr));
+        const double ts = __dadd_rn(a.t0_ptr ? *a.t0_ptr : a.t0, __dmul_rn(a.t_cj, *a.dt_ptr));
         const double cx = __dadd_rn(a.g_c0[0], __dmul_rn(a.g_v[0], ts)), cy = __dadd_rn(a.g_c0[1], __dmul_rn(a.g_v[1], ts));
         gcz = __dadd_rn(a.g_c0[2], __dmul_rn(a.g_v[2], ts));
         const double x = __dadd_rn(__dmul_rn((double)tx, dx), __dmul_rn((double)(a.ixyz[3 * b] * BS), dx));
@@ -681,6 +681,7 @@ struct DtArgs {
     double time, dt_fixed, dt_max, time_max, write_time, write_time_first, tsave_stats;
     double CFL_eta, gamma_p, C_eta, C_sponge;
     int penalization, use_sponge, write_fixed_time;
+    double *time_dev;   // != nullptr: the time lives on the device (wgpu_rk_steps): read it here and advance it by dt
 };
 
 __global__ void dt_finalize_kernel(DtArgs p, const unsigned long long *dtmin_bits, unsigned long long *dtmin_next, double *dt_out,
@@ -698,7 +699,7 @@ __global__ void dt_finalize_kernel(DtArgs p, const unsigned long long *dtmin_bit
         if (p.use_sponge) dt = fmin(dt, __dmul_rn(p.CFL_eta, p.C_sponge));
         if (p.dt_max > 0.0) dt = fmin(p.dt_max, dt);
     }
-    const double time = p.time;
+    const double time = p.time_dev ? *p.time_dev : p.time;
     if (p.write_fixed_time) {
         if (fmod(time + dt, p.write_time) < fmod(time + 1e-12, p.write_time) && !(fabs(fmod(time, p.write_time)) < 1e-12) &&
             time + 1e-12 > p.write_time_first)
@@ -710,6 +711,7 @@ __global__ void dt_finalize_kernel(DtArgs p, const unsigned long long *dtmin_bit
     }
     if (time + dt > p.time_max && time <= p.time_max) dt = p.time_max - time;
     *dt_out = dt;
+    if (p.time_dev) p.time_dev[1] = time + dt;   // [0] stays the time at the start of the step (stage times of the analytic mask)
     if (dt_host) *dt_host = dt;
     if (dtmin_next) *dtmin_next = 0x7FF0000000000000ULL;  // +inf
 }
@@ -932,6 +934,7 @@ int32_t wgpu_launch_dt_finalize(wgpu_ctx *ctx, double time, const unsigned long 
     const wgpu_config &c = ctx->cfg;
     DtArgs p;
     p.time = time;
+    p.time_dev = ctx->time_on_device ? ctx->d_time : nullptr;
     p.dt_fixed = c.dt_fixed;
     p.dt_max = c.dt_max;
     p.time_max = c.time_max;

@@ -74,6 +74,7 @@ struct StageArgs {
     const int *ixyz;                 // [max_blocks][3] block coordinates on their level
     double g_c0[3], g_v[3], g_R, g_h;
     double t0, t_cj;                 // stage time = t0 + t_cj * dt
+    const double *t0_ptr;            // != nullptr: t0 is read from the device (wgpu_rk_steps)
 };
 
 struct wgpu_ctx {
@@ -186,6 +187,8 @@ struct wgpu_ctx {
 
     // scalars
     double *d_dt = nullptr;                   // dt of the current step
+    double *d_time = nullptr;                 // [2]: time at the start of the step in flight / after it (wgpu_rk_steps keeps the time on the device)
+    bool time_on_device = false;
     unsigned long long *d_dtmin = nullptr;    // [2]: CFL dt candidates (bits), ping-pong
     int dtmin_cur = 0;
     bool dtmin_valid = false;
@@ -200,6 +203,16 @@ struct wgpu_ctx {
     int *d_status = nullptr;                            // [max_blocks]
     double *d_detail_out = nullptr;                     // [max_blocks][nc]
     unsigned long long *d_norm = nullptr;               // [16]
+
+    // multi-GPU inside the library (multigpu.cu): the NCCL communicator, the per-peer counts of the declared exchange, a second stream
+    void *comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
+    std::vector<int> send_counts, recv_counts, rsend_counts, rrecv_counts;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_pack = nullptr, ev_xchg = nullptr;
+    double *d_comm_scratch = nullptr;
+    double *d_xbuf = nullptr;          // send buffer of wgpu_ship_blocks / scratch of the light-data collectives
+    size_t xbuf_cap = 0;
 
     // optional event pairs around stage launches
     bool profiling = false;
@@ -222,6 +235,8 @@ struct wgpu_ctx {
         }                                                                                      \
     } while (0)
 
+// capi.cu
+int32_t wgpu_rk_end_nosync(wgpu_ctx *ctx);
 // kernels.cu
 int32_t wgpu_launch_stage(wgpu_ctx *ctx, const StageArgs &a, int n_blocks);
 int32_t wgpu_launch_pack(wgpu_ctx *ctx, const double *src);

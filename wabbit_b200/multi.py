@@ -112,7 +112,7 @@ class MultiGPUStepper:
         import torch
         self.torch = torch
         self.sol, self.rank, self.world, self.overlap = sol, rank, world, overlap
-        if exchange is None and world > 1:
+        if exchange is None and world > 1 and getattr(sol, "comm_world", 1) != world:
             _require_torch_stream(sol, torch)
         self.plan = ExchangePlan(forest, rank, world)
         lib, ctx = sol._lib, sol._ctx
@@ -127,6 +127,10 @@ class MultiGPUStepper:
                                          _i32(self.plan.send_dir), C.c_void_p(self.send.data_ptr())))
         self.in_splits = [c * self.pd for c in self.plan.send_counts]
         self.out_splits = [c * self.pd for c in self.plan.recv_counts]
+        # the context owns an NCCL communicator (WabbitGPU.comm_init): the whole step runs inside the library (wgpu_rk_steps)
+        self.in_library = exchange is None and getattr(sol, "comm_world", 1) == world and world > 1
+        if self.in_library:
+            sol.comm_set_counts(self.plan.send_counts, self.plan.recv_counts)
         self._exchange = exchange or self._nccl_exchange
         self._allreduce_min = allreduce_min or self._nccl_min
         self.n_int = lib.wgpu_block_count(ctx, 1)
@@ -146,7 +150,19 @@ class MultiGPUStepper:
         self.sol._check(self.sol._lib.wgpu_dtmin_pointer(self.sol._ctx, C.byref(p)))
         return self.torch.as_tensor(_DevPtr(p.value, 1), device=self.pool.device)
 
+    def steps(self, time: float, n_steps: int):
+        """n_steps back to back inside the library (device-resident time and dt, one host read-back): (time after, last dt)"""
+        if self.in_library or self.world == 1:
+            return self.sol.RungeKuttaSteps(time, n_steps)
+        dt = 0.0
+        for _ in range(n_steps):
+            dt = self.step(time)
+            time += dt
+        return time, dt
+
     def step(self, time: float, iteration: int = 0) -> float:
+        if self.in_library:
+            return self.sol.RungeKuttaSteps(time, 1)[1]
         lib, ctx, chk = self.sol._lib, self.sol._ctx, self.sol._check
         chk(lib.wgpu_rk_begin(ctx, float(time)))
         if self.world > 1 and not self.sol.params.dt_fixed > 0.0:
@@ -338,7 +354,8 @@ class HaloStepper:
         import torch
         self.torch = torch
         self.sol, self.rank, self.world, self.overlap = sol, rank, world, overlap
-        if exchange is None and world > 1:
+        self.in_library = exchange is None and getattr(sol, "comm_world", 1) == world and world > 1
+        if exchange is None and world > 1 and not self.in_library:
             _require_torch_stream(sol, torch)
         self.plan = plan = HaloPlan(forest, rank, world)
         lib, ctx = sol._lib, sol._ctx
@@ -374,6 +391,11 @@ class HaloStepper:
                                                   _i32(plan.fine_send_hvy), C.c_void_p(self.rsend.data_ptr())))
             self.r_in = [c * self.rblk for c in plan.fine_send_counts]
             self.r_out = [c * self.rblk for c in plan.fine_recv_counts]
+        if self.in_library:
+            if self.lifted:
+                sol.comm_set_counts(plan.send_counts, plan.recv_counts, plan.fine_send_counts, plan.fine_recv_counts)
+            else:
+                sol.comm_set_counts(plan.send_counts, plan.recv_counts)
 
     def _view(self, ptr: int, n: int):
         if n == 0:
@@ -401,6 +423,9 @@ class HaloStepper:
     def exchange_array(self, array_id: int = 0, slot: int = 0, filtered: bool = True):
         """refresh the halo copies of a named array (blocking); with a lifted wavelet also the filtered copies of the finer neighbours
         other ranks own (what the next wavelet-side synchronisation of this array restricts from)"""
+        if self.in_library:
+            self.sol._check(self.sol._lib.wgpu_exchange_array(self.sol._ctx, array_id, slot, int(bool(filtered))))
+            return
         self.sol._check(self.sol._lib.wgpu_pack_blocks(self.sol._ctx, array_id, slot))
         work = self._exchange(self.send, self.array_halo(array_id, slot), self.in_splits, self.out_splits)
         if work is not None:
@@ -413,7 +438,18 @@ class HaloStepper:
             if work is not None:
                 work.wait()
 
+    def steps(self, time: float, n_steps: int):
+        if self.in_library or self.world == 1:
+            return self.sol.RungeKuttaSteps(time, n_steps)
+        dt = 0.0
+        for _ in range(n_steps):
+            dt = self.step(time)
+            time += dt
+        return time, dt
+
     def step(self, time: float, iteration: int = 0) -> float:
+        if self.in_library:
+            return self.sol.RungeKuttaSteps(time, 1)[1]
         lib, ctx, chk = self.sol._lib, self.sol._ctx, self.sol._check
         chk(lib.wgpu_rk_begin(ctx, float(time)))
         if self.world > 1 and not self.sol.params.dt_fixed > 0.0:
@@ -565,6 +601,41 @@ class NcclTransport:
         return np.concatenate([o[:c].cpu().numpy() for o, c in zip(out, counts)])
 
 
+class LibTransport:
+    """The collectives of one rank on the NCCL communicator the library owns (WabbitGPU.comm_init): no torch.distributed on the data path."""
+
+    def __init__(self, sol):
+        self.sol, self.rank, self.world = sol, sol.comm_rank, sol.comm_world
+
+    def _reduce(self, a, op):
+        a = np.ascontiguousarray(a, dtype=np.float64).copy()
+        out = []
+        for s0 in range(0, a.size, 4096):                     # the library reduces at most 4096 doubles per call
+            part = np.ascontiguousarray(a.ravel()[s0:s0 + 4096])
+            self.sol._check(self.sol._lib.wgpu_comm_allreduce(self.sol._ctx, part.ctypes.data_as(C.POINTER(C.c_double)), part.size, op))
+            out.append(part)
+        return np.concatenate(out).reshape(a.shape) if out else a
+
+    def allreduce_max_np(self, a):
+        return self._reduce(a, 0)
+
+    def allreduce_sum_np(self, a):
+        return self._reduce(a, 2)
+
+    def allreduce_min_(self, t):
+        raise RuntimeError("the dt reduction runs inside wgpu_rk_steps")
+
+    def allgather_np(self, a, counts):
+        a = np.ascontiguousarray(a, dtype=np.int32)
+        cnt = np.ascontiguousarray(counts, dtype=np.int32)
+        out = np.zeros(int(cnt.sum()), np.int32)
+        self.sol._check(self.sol._lib.wgpu_comm_allgatherv_i32(self.sol._ctx, _i32(a), _i32(cnt), _i32(out)))
+        return out
+
+    def alltoall(self, *a, **k):
+        raise RuntimeError("block transport runs inside wgpu_ship_blocks / wgpu_exchange_array")
+
+
 class ThreadTransport:
     """The same collectives between `world` host threads of ONE process (every rank a device context on the same GPU): the
     single-GPU test harness of the multi-rank drivers."""
@@ -640,9 +711,10 @@ class DistributedWabbit:
         import torch
         self.torch = torch
         self.sol, self.rank, self.world = sol, rank, world
-        if transport is None and world > 1:
+        self.in_library = transport is None and getattr(sol, "comm_world", 1) == world and world > 1
+        if transport is None and world > 1 and not self.in_library:
             _require_torch_stream(sol, torch)
-        self.tr = transport or NcclTransport(rank, world)
+        self.tr = transport or (LibTransport(sol) if self.in_library else NcclTransport(rank, world))
         self.overlap = overlap
         self.dev = torch.device("cuda", torch.cuda.current_device())
         p = sol.params
@@ -652,9 +724,12 @@ class DistributedWabbit:
     # ------------------------------------------------------------------ topology
     def attach(self, forest: Forest):
         self.forest = forest
-        self.stepper = HaloStepper(self.sol, forest, self.rank, self.world,
-                                   exchange=lambda s, r, i, o: self.tr.alltoall(s, r, i, o, async_op=True),
-                                   allreduce_min=self.tr.allreduce_min_, overlap=self.overlap)
+        if self.in_library:
+            self.stepper = HaloStepper(self.sol, forest, self.rank, self.world, overlap=self.overlap)
+        else:
+            self.stepper = HaloStepper(self.sol, forest, self.rank, self.world,
+                                       exchange=lambda s, r, i, o: self.tr.alltoall(s, r, i, o, async_op=True),
+                                       allreduce_min=self.tr.allreduce_min_, overlap=self.overlap)
         self.counts = [forest.n_active(r) for r in range(self.world)]
         self.off = np.concatenate([[0], np.cumsum(self.counts)]).astype(np.int64)
 
@@ -690,6 +765,13 @@ class DistributedWabbit:
         Returns (local slot of every item with dst_rank == me, in item order; next free slot)."""
         me, W, torch = self.rank, self.world, self.torch
         src_rank, src_slot, dst_rank = (np.asarray(a) for a in (src_rank, src_slot, dst_rank))
+        if self.in_library:                     # block_xfer inside the library: gather -> ncclSend / ncclRecv straight into the free slots
+            sr, ss, dr = (np.ascontiguousarray(a, dtype=np.int32) for a in (src_rank, src_slot, dst_rank))
+            loc = np.zeros(max(int((dr == me).sum()), 1), np.int32)
+            nf = C.c_int32()
+            self.sol._check(self.sol._lib.wgpu_ship_blocks(self.sol._ctx, array[0], array[1], len(sr), _i32(sr), _i32(ss), _i32(dr), int(first_free),
+                                                           _i32(loc), C.byref(nf)))
+            return loc[:int((dr == me).sum())].astype(np.int64), nf.value
         send_ids, in_splits, out_splits = [], [], []
         mine = dst_rank == me
         local = np.where(src_rank[mine] == me, src_slot[mine], 0).astype(np.int64)

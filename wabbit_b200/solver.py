@@ -238,6 +238,41 @@ class WabbitGPU:
         self._check(self._lib.wgpu_calculate_time_step(self._ctx, float(time), C.byref(dt)))
         return dt.value
 
+    # ------------------------------------------------------------------ multi-GPU inside the library (NCCL communicator owned by the context)
+    comm_rank, comm_world = 0, 1
+
+    def comm_init(self, rank: int, world: int, broadcast=None):
+        """Join the library's NCCL communicator (wgpu_comm_unique_id on rank 0 + wgpu_comm_init).  `broadcast(buf: bytearray)` must leave rank
+        0's 128 bytes in buf on every rank (a Fortran host: MPI_Bcast); default: torch.distributed."""
+        if world < 2:
+            return
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            self._check(self._lib.wgpu_comm_unique_id(buf))
+        if broadcast is None:
+            import torch
+            import torch.distributed as dist
+            t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).cuda()
+            dist.broadcast(t, 0)
+            raw = bytes(t.cpu().numpy().tobytes())
+        else:
+            ba = bytearray(buf.raw)
+            broadcast(ba)
+            raw = bytes(ba)
+        self._check(self._lib.wgpu_comm_init(self._ctx, raw, int(rank), int(world)))
+        self.comm_rank, self.comm_world = int(rank), int(world)
+
+    def comm_set_counts(self, send_counts, recv_counts, rsend_counts=None, rrecv_counts=None):
+        a = [None if v is None else np.ascontiguousarray(v, dtype=np.int32) for v in (send_counts, recv_counts, rsend_counts, rrecv_counts)]
+        self._check(self._lib.wgpu_comm_set_counts(self._ctx, *[None if v is None else _i32(v) for v in a]))
+
+    def RungeKuttaSteps(self, time: float, n_steps: int = 1):
+        """n_steps of RungeKuttaGeneric back to back with time, dt and the divergence flag resident on the device (wgpu_rk_steps: the
+        N_dt_per_grid loop of performance_test.f90); across ranks if the context has a communicator.  Returns (time after, last dt)."""
+        t, dt = C.c_double(), C.c_double()
+        self._check(self._lib.wgpu_rk_steps(self._ctx, float(time), int(n_steps), C.byref(t), C.byref(dt)))
+        return t.value, dt.value
+
     def RungeKuttaGeneric(self, time: float, iteration: int = 0) -> float:
         """runge_kutta_generic.f90:1 -- advances hvy_block by one step on the device, returns dt."""
         dt = C.c_double()
