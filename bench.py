@@ -702,7 +702,10 @@ def adaptive_leg_multi(a, rank, world, local, stream, eps=None, J0=5, Jmax=6, cy
             if n1 == n0:
                 break
         recs = []
+        from wabbit_b200 import multi as _mg
         for cyc in range(cycles + 2):
+            if cyc == 2 and _mg.TIMING is not None:
+                _mg.TIMING.clear()
             sync()
             w0 = time.perf_counter()
             nb_rhs = drv.refine_tree().n_blocks
@@ -715,6 +718,8 @@ def adaptive_leg_multi(a, rank, world, local, stream, eps=None, J0=5, Jmax=6, cy
             sync()
             w3 = time.perf_counter()
             recs.append((nb_rhs, n1, w1 - w0, w2 - w1, w3 - w2))
+        if _mg.TIMING is not None and rank == 0:
+            rec["phase_ms_per_cycle_rank0"] = {k: round(v * 1e3 / cycles, 2) for k, v in sorted(_mg.TIMING.items())}
         per_rank = [drv.forest.n_active(r) for r in range(world)]
         n_halo, n_int, n_bnd = drv.stepper.plan.n_halo, drv.stepper.n_int, drv.stepper.n_bnd
         # checksum of the final grid: the block list (level, treecode) in space-filling-curve order, identical for every GPU count, and the

@@ -84,6 +84,12 @@ int32_t whost_coarsen_global(const whost_forest *f, int32_t *status, int32_t Jmi
  * (level[n], pos[3n]) in any order.  whost_ft_tables: same-level neighbour per direction nb[n][3^dim-1] (dz, dy, dx ascending, periodic), mother
  * par[n], daughters child[n][2^dim] (column = x + 2y + 4z offset); indices into the list or -1.  whost_ft_decide: respectJmaxJmin_tree +
  * ensureGradedness_tree(check_daughters) (LIB/MESH/ensureGradedness_tree.f90): status -1 survives only for blocks that are deleted. */
+/* whost_ft_build: init_full_tree's light-data half -- the leaves plus all their ancestors down to Jmin, sorted by position code
+ * (level << 57 | z << 38 | y << 19 | x); leaf_of[i] = index into the input list, -1 for a mother.  Returns 2 if cap is too small.
+ * whost_encode_many: numerical treecodes (encoding_b) of a list of blocks. */
+int32_t whost_ft_build(int32_t dim, int32_t Jmin, int32_t n_leaf, const int32_t *level, const int32_t *pos, int32_t cap, int32_t *n_out,
+                       int32_t *level_out, int32_t *pos_out, int32_t *leaf_of);
+int32_t whost_encode_many(int32_t dim, int32_t Jmax, int32_t n, const int32_t *level, const int32_t *pos, int64_t *tc);
 int32_t whost_ft_tables(int32_t dim, int32_t n, const int32_t *level, const int32_t *pos, int32_t *nb, int32_t *par, int32_t *child);
 /* hvy_neighbor rows [168][ld] (column = slot - 1) of every block of the full tree for the passes of the full-tree adapt_tree: same-level
  * relations from nb (row dir_code[q] - 1, dir_code = the slot code of find_neighbor for direction q); for blocks flagged in `leaf`,
@@ -93,6 +99,10 @@ int32_t whost_ft_rows(int32_t dim, int32_t n, const int32_t *level, const int32_
                       const int32_t *leaf, const int32_t *dir_code, int64_t ld, int32_t *rows);
 int32_t whost_ft_decide(int32_t dim, int32_t n, const int32_t *level, const int32_t *nb, const int32_t *par, const int32_t *child, int32_t Jmin,
                         int32_t *status);
+/* the (significant block, direction) pairs addSecurityZone_CE_tree examines (LIB/MESH/securityZone_tree.f90:140-298): sig[i] != 0 and the
+ * same-level neighbour nb[i][q] exists with status -1.  Direction-major, blocks ascending; returns the number of pairs (-2: cap too small). */
+int32_t whost_ft_security_pairs(int32_t dim, int32_t n, const int32_t *nb, const int32_t *status, const uint8_t *sig, int32_t cap, int32_t *blk,
+                                int32_t *dir);
 
 /* treecode helpers (module_treelib.f90:793-871) */
 int64_t whost_encode(int32_t dim, int32_t level, int32_t Jmax, const int32_t ixyz[3]);

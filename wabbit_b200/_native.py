@@ -113,9 +113,12 @@ HOST_SYMBOLS = {
     "whost_coarsen": (C.c_int32, [C.c_void_p, _i32p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), _i32p, _i32p, _i32p, _i32p, _i32p, _i32p]),
     "whost_refine_global": (C.c_int32, [C.c_void_p, _i32p, C.c_int32, C.POINTER(C.c_void_p), _i32p, _i32p, _i32p, _i32p, _i32p, _i32p]),
     "whost_coarsen_global": (C.c_int32, [C.c_void_p, _i32p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), _i32p, _i32p, _i32p, _i32p, _i32p, _i32p]),
+    "whost_ft_build": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _i32p, _i32p, C.c_int32, _i32p, _i32p, _i32p, _i32p]),
+    "whost_encode_many": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _i32p, _i32p, _i64p]),
     "whost_ft_tables": (C.c_int32, [C.c_int32, C.c_int32, _i32p, _i32p, _i32p, _i32p, _i32p]),
     "whost_ft_rows": (C.c_int32, [C.c_int32, C.c_int32, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, C.c_int64, _i32p]),
     "whost_ft_decide": (C.c_int32, [C.c_int32, C.c_int32, _i32p, _i32p, _i32p, _i32p, C.c_int32, _i32p]),
+    "whost_ft_security_pairs": (C.c_int32, [C.c_int32, C.c_int32, _i32p, _i32p, C.POINTER(C.c_uint8), C.c_int32, _i32p, _i32p]),
     "whost_encode": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, _i32p]),
     "whost_decode": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, _i32p]),
     "whost_sfc_key": (C.c_uint64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _i32p]),

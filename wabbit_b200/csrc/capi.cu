@@ -795,9 +795,13 @@ static int32_t move_blocks(wgpu_ctx *ctx, bool up, int32_t array_id, int32_t slo
         // Page-locked host arrays (cudaHostRegister / cudaMallocHost on the whole hvy array): the layout kernels read / write the
         // host array directly over PCIe -- only interiors (+ the g_sync shell on download) cross the bus instead of the whole ghosted
         // box ((Bs+2g)^3 / Bs^3 = 2.6x at Bs=16, g=3), and there is no staging copy.
+        // (asked of the first listed block, not of the array's base address: a caller may pass the address block 1 WOULD have while only a
+        // window of the array exists in memory)
         cudaPointerAttributes attr;
-        if (cudaPointerGetAttributes(&attr, host) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
-            double *hdev = (double *)attr.devicePointer;
+        const int64_t first_off = n > 0 ? (int64_t)(hvy_ids[0] - 1) * per_block : 0;
+        if (n > 0 && hvy_ids[0] >= 1 && cudaPointerGetAttributes(&attr, host + first_off) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+            attr.devicePointer) {
+            double *hdev = (double *)attr.devicePointer - first_off;
             std::vector<int> ids(n);
             for (int i = 0; i < n; ++i) {
                 if (hvy_ids[i] < 1 || hvy_ids[i] > c.max_blocks) return fail(ctx, WGPU_ERR_ARG, "hvy id out of range");

@@ -700,24 +700,60 @@ extern "C" {
 
 // nb[n][3^dim - 1]: same-level neighbour per direction (dz, dy, dx ascending, (0,0,0) skipped; periodic), par[n]: mother,
 // child[n][2^dim]: daughters, column = x offset + 2 * y offset + 4 * z offset
-int32_t whost_ft_tables(int32_t dim, int32_t n, const int32_t *level, const int32_t *pos, int32_t *nb, int32_t *par, int32_t *child)
-{
-    if (n < 0 || (n > 0 && (!level || !pos || !nb || !par || !child))) return 1;
-    // open-addressing lookup (level, position) -> index: read-only after the fill, so the search below runs in parallel
-    size_t cap = 64;
-    while (cap < (size_t)n * 2 + 2) cap <<= 1;
-    const uint64_t hmask = cap - 1;
-    std::vector<uint64_t> hkeys(cap, ~0ull);
-    std::vector<int> hvals(cap, -1);
-    for (int i = 0; i < n; ++i) {
-        const uint64_t key = pos_hash(level[i], pos + 3 * i);
-        uint64_t h = whost_forest::mix(key) & hmask;
-        while (hkeys[h] != ~0ull && hkeys[h] != key) h = (h + 1) & hmask;
-        hkeys[h] = key;
-        hvals[h] = i;
+// (level, position) -> index lookup for a list of tree blocks: one dense array per level when the levels are shallow enough (8^Jmax entries:
+// 1 MB at level 6, direct addressing, cache resident), else open addressing
+struct TreeIndex {
+    int dim = 3, lmax = 0;
+    bool dense = false;
+    std::vector<size_t> base;          // dense: offset of level l
+    std::vector<int> cell;
+    std::vector<uint64_t> hkeys;
+    std::vector<int> hvals;
+    uint64_t hmask = 0;
+
+    bool build(int dim_, int n, const int32_t *level, const int32_t *pos)
+    {
+        dim = dim_;
+        lmax = 0;
+        for (int i = 0; i < n; ++i) lmax = std::max(lmax, (int)level[i]);
+        size_t total = 0;
+        base.assign(lmax + 2, 0);
+        for (int l = 0; l <= lmax; ++l) {
+            base[l] = total;
+            total += (size_t)1 << (l * dim);
+        }
+        dense = total <= ((size_t)1 << 25);
+        if (dense) {
+            cell.assign(total, -1);
+            for (int i = 0; i < n; ++i) {
+                int &c = cell[slot(level[i], pos + 3 * i)];
+                if (c >= 0) return false;   // duplicate position
+                c = i;
+            }
+            return true;
+        }
+        size_t cap = 64;
+        while (cap < (size_t)n * 2 + 2) cap <<= 1;
+        hmask = cap - 1;
+        hkeys.assign(cap, ~0ull);
+        hvals.assign(cap, -1);
+        for (int i = 0; i < n; ++i) {
+            const uint64_t key = pos_hash(level[i], pos + 3 * i);
+            uint64_t h = whost_forest::mix(key) & hmask;
+            while (hkeys[h] != ~0ull && hkeys[h] != key) h = (h + 1) & hmask;
+            hkeys[h] = key;
+            hvals[h] = i;
+        }
+        return true;
     }
-    auto find = [&](int l, const int p[3]) -> int {
-        if (l < 0) return -1;
+    size_t slot(int l, const int p[3]) const
+    {
+        return base[l] + ((((size_t)(dim == 3 ? p[2] : 0) << l) | (size_t)p[1]) << l | (size_t)p[0]);
+    }
+    int find(int l, const int p[3]) const
+    {
+        if (l < 0 || l > lmax) return -1;
+        if (dense) return cell[slot(l, p)];
         const uint64_t key = pos_hash(l, p);
         uint64_t h = whost_forest::mix(key) & hmask;
         while (hkeys[h] != ~0ull) {
@@ -725,9 +761,16 @@ int32_t whost_ft_tables(int32_t dim, int32_t n, const int32_t *level, const int3
             h = (h + 1) & hmask;
         }
         return -1;
-    };
+    }
+};
+
+int32_t whost_ft_tables(int32_t dim, int32_t n, const int32_t *level, const int32_t *pos, int32_t *nb, int32_t *par, int32_t *child)
+{
+    if (n < 0 || (n > 0 && (!level || !pos || !nb || !par || !child))) return 1;
+    TreeIndex T;
+    if (!T.build(dim, n, level, pos)) return 3;
     const int nd = 1 << dim, ndir = (dim == 3 ? 27 : 9) - 1;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n > 20000)
     for (int i = 0; i < n; ++i) {
         const int l = level[i], nb_l = 1 << l;
         const int *p = pos + 3 * i;
@@ -738,15 +781,99 @@ int32_t whost_ft_tables(int32_t dim, int32_t n, const int32_t *level, const int3
                     if (!dx && !dy && !dz) continue;
                     const int m_l = nb_l - 1;   // nb_l is a power of two: periodic wrap by masking
                     const int np[3] = {(p[0] + dx) & m_l, (p[1] + dy) & m_l, dim == 3 ? ((p[2] + dz) & m_l) : 0};
-                    nb[(size_t)i * ndir + q++] = find(l, np);
+                    nb[(size_t)i * ndir + q++] = T.find(l, np);
                 }
         const int pp[3] = {p[0] >> 1, p[1] >> 1, p[2] >> 1};
-        par[i] = find(l - 1, pp);
+        par[i] = T.find(l - 1, pp);
         for (int c = 0; c < nd; ++c) {
             const int cp[3] = {2 * p[0] + (c & 1), 2 * p[1] + ((c >> 1) & 1), dim == 3 ? 2 * p[2] + ((c >> 2) & 1) : 0};
-            child[(size_t)i * nd + c] = find(l + 1, cp);
+            child[(size_t)i * nd + c] = T.find(l + 1, cp);
         }
     }
+    return 0;
+}
+
+// the (significant block, direction) pairs addSecurityZone_CE_tree examines (LIB/MESH/securityZone_tree.f90:140-298): block i is significant
+// (sig[i] != 0), its same-level neighbour in direction q exists and is insignificant (status -1).  Pairs come out direction-major (all blocks
+// of direction 0 first), blocks ascending: blk[k], dir[k] (index q into the direction list of whost_ft_tables).  Returns the count.
+int32_t whost_ft_security_pairs(int32_t dim, int32_t n, const int32_t *nb, const int32_t *status, const uint8_t *sig, int32_t cap, int32_t *blk,
+                                int32_t *dir)
+{
+    if (n < 0 || (n > 0 && (!nb || !status || !sig))) return -1;
+    const int ndir = (dim == 3 ? 27 : 9) - 1;
+    int64_t k = 0;
+    for (int q = 0; q < ndir; ++q)
+        for (int i = 0; i < n; ++i) {
+            if (!sig[i]) continue;
+            const int j = nb[(size_t)i * ndir + q];
+            if (j < 0 || status[j] != -1) continue;
+            if (k < cap) {
+                blk[k] = i;
+                dir[k] = q;
+            }
+            ++k;
+        }
+    return k > cap ? -2 : (int32_t)k;
+}
+
+// init_full_tree (LIB/MESH/adapt_tree.f90:268-330, the light-data half): all ancestors of the leaves down to Jmin are added; the tree comes back
+// sorted by position code (level << 57 | z << 38 | y << 19 | x), leaf_of[i] = index of the block in the input list or -1 for a mother.
+int32_t whost_ft_build(int32_t dim, int32_t Jmin, int32_t n_leaf, const int32_t *level, const int32_t *pos, int32_t cap, int32_t *n_out,
+                       int32_t *level_out, int32_t *pos_out, int32_t *leaf_of)
+{
+    if (n_leaf < 0 || !n_out || (n_leaf > 0 && (!level || !pos)) || !level_out || !pos_out || !leaf_of) return 1;
+    (void)dim;
+    auto code_of = [](int l, const int *p) {
+        return ((uint64_t)l << 57) | ((uint64_t)(uint32_t)p[2] << 38) | ((uint64_t)(uint32_t)p[1] << 19) | (uint64_t)(uint32_t)p[0];
+    };
+    std::vector<std::pair<uint64_t, int>> all;
+    all.reserve((size_t)n_leaf + n_leaf / 6 + 16);
+    for (int i = 0; i < n_leaf; ++i) all.emplace_back(code_of(level[i], pos + 3 * i), i);
+    // ancestors, one level at a time: parents of the newest layer that are not in the tree yet
+    std::vector<uint64_t> layer(all.size());
+    for (size_t i = 0; i < all.size(); ++i) layer[i] = all[i].first;
+    std::vector<uint64_t> seen(layer);
+    std::sort(seen.begin(), seen.end());
+    while (!layer.empty()) {
+        std::vector<uint64_t> par;
+        par.reserve(layer.size() / 4 + 8);
+        for (uint64_t c : layer) {
+            const int l = (int)(c >> 57);
+            if (l <= Jmin) continue;
+            const int p[3] = {(int)(c & 0x7FFFF) >> 1, (int)((c >> 19) & 0x7FFFF) >> 1, (int)((c >> 38) & 0x7FFFF) >> 1};
+            par.push_back(code_of(l - 1, p));
+        }
+        std::sort(par.begin(), par.end());
+        par.erase(std::unique(par.begin(), par.end()), par.end());
+        std::vector<uint64_t> fresh;
+        fresh.reserve(par.size());
+        for (uint64_t c : par)
+            if (!std::binary_search(seen.begin(), seen.end(), c)) fresh.push_back(c);
+        for (uint64_t c : fresh) all.emplace_back(c, -1);
+        std::vector<uint64_t> merged(seen.size() + fresh.size());
+        std::merge(seen.begin(), seen.end(), fresh.begin(), fresh.end(), merged.begin());
+        seen.swap(merged);
+        layer.swap(fresh);
+    }
+    if ((int64_t)all.size() > cap) return 2;
+    std::sort(all.begin(), all.end());
+    for (size_t i = 0; i < all.size(); ++i) {
+        const uint64_t c = all[i].first;
+        level_out[i] = (int)(c >> 57);
+        pos_out[3 * i] = (int)(c & 0x7FFFF);
+        pos_out[3 * i + 1] = (int)((c >> 19) & 0x7FFFF);
+        pos_out[3 * i + 2] = (int)((c >> 38) & 0x7FFFF);
+        leaf_of[i] = all[i].second;
+    }
+    *n_out = (int32_t)all.size();
+    return 0;
+}
+
+// numerical treecodes of many blocks at once (encoding_b, LIB/TREE/module_treelib.f90:837-871)
+int32_t whost_encode_many(int32_t dim, int32_t Jmax, int32_t n, const int32_t *level, const int32_t *pos, int64_t *tc)
+{
+    if (n < 0 || (n > 0 && (!level || !pos || !tc))) return 1;
+    for (int i = 0; i < n; ++i) tc[i] = whost_encode(dim, level[i], Jmax, pos + 3 * i);
     return 0;
 }
 
@@ -838,17 +965,18 @@ int32_t whost_ft_decide(int32_t dim, int32_t n, const int32_t *level, const int3
     }
     for (int i = 0; i < n; ++i)
         if (status[i] == -1 && level[i] <= Jmin) status[i] = 9;
-    bool changed = true;
-    while (changed) {
-        changed = false;
-        for (int i = 0; i < n; ++i) {
+    // Every rule looks at the block's own level (sisters) or one level finer (daughters, finer neighbours), and statuses only move from -1
+    // to 9: one sweep from the finest level to the coarsest -- first the rules that read the finer level, then completeness -- reaches the
+    // fixed point the reference iterates to.
+    int lmax = 0;
+    for (int i = 0; i < n; ++i) lmax = std::max(lmax, (int)level[i]);
+    std::vector<std::vector<int>> by_level(lmax + 1);
+    for (int i = 0; i < n; ++i) by_level[level[i]].push_back(i);
+    for (int l = lmax; l >= 0; --l) {
+        const std::vector<int> &B = by_level[l];
+        for (int i : B) {
             if (status[i] != -1) continue;
             bool stay = par[i] < 0;
-            if (!stay)
-                for (int c = 0; c < nd && !stay; ++c) {
-                    const int s = child[(size_t)par[i] * nd + c];
-                    if (s < 0 || status[s] != -1) stay = true;                                   // completeness
-                }
             for (int c = 0; c < nd && !stay; ++c) {
                 const int s = child[(size_t)i * nd + c];
                 if (s >= 0 && status[s] != -1) stay = true;                                      // check_daughters
@@ -861,11 +989,20 @@ int32_t whost_ft_decide(int32_t dim, int32_t n, const int32_t *level, const int3
                     if (f >= 0 && status[f] != -1) { stay = true; break; }                       // gradedness
                 }
             }
-            if (stay) {
-                status[i] = 9;
-                changed = true;
-            }
+            if (stay) status[i] = 9;
         }
+        for (int i : B) {                                                                         // completeness: decided per sister group
+            if (status[i] != -1) continue;
+            bool stay = false;
+            for (int c = 0; c < nd && !stay; ++c) {
+                const int s = child[(size_t)par[i] * nd + c];
+                if (s < 0 || (status[s] != -1 && status[s] != -3)) stay = true;
+            }
+            // mark the verdict without disturbing the sisters' view of this round: -3 = "-1, but the group stays"
+            if (stay) status[i] = -3;
+        }
+        for (int i : B)
+            if (status[i] == -3) status[i] = 9;
     }
     return 0;
 }

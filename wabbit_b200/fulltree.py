@@ -81,9 +81,40 @@ def _pack(level, ixyz):
     return (level << 57) | (ixyz[:, 2] << 38) | (ixyz[:, 1] << 19) | ixyz[:, 0]
 
 
+def _build_tree(dim: int, Jmin: int, level: np.ndarray, pos: np.ndarray):
+    """leaves + all ancestors down to Jmin, sorted by position code: (level[n], pos[n,3], leaf_of[n]) as int64 / index into the input or -1
+    (libwabbit_host.so: whost_ft_build)"""
+    lv = np.ascontiguousarray(level, dtype=np.int32)
+    px = np.ascontiguousarray(pos, dtype=np.int32).reshape(-1, 3)
+    cap = len(lv) + len(lv) // 4 + 64
+    i32 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    while True:
+        lo, po, lf = np.zeros(cap, np.int32), np.zeros((cap, 3), np.int32), np.zeros(cap, np.int32)
+        n = C.c_int32()
+        rc = host_lib().whost_ft_build(dim, Jmin, len(lv), i32(lv), i32(px), cap, C.byref(n), i32(lo), i32(po), i32(lf))
+        if rc == 2:
+            cap *= 2
+            continue
+        if rc:
+            raise RuntimeError(f"whost_ft_build: {rc}")
+        n = n.value
+        return lo[:n].astype(np.int64), po[:n].astype(np.int64), lf[:n].astype(np.int64)
+
+
 def _encode_treecodes(dim: int, level: np.ndarray, ixyz: np.ndarray, Jmax: int) -> np.ndarray:
     """numerical binary treecode (module_treelib.f90:837-871): digit bit0 <- y, bit1 <- x, bit2 <- z; bit i of a coordinate goes to
-    digit i + Jmax - level"""
+    digit i + Jmax - level (libwabbit_host.so: whost_encode_many)"""
+    lv = np.ascontiguousarray(level, dtype=np.int32)
+    px = np.ascontiguousarray(ixyz, dtype=np.int32).reshape(-1, 3)
+    out = np.zeros(len(lv), np.int64)
+    i32 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    if host_lib().whost_encode_many(dim, Jmax, len(lv), i32(lv), i32(px), out.ctypes.data_as(C.POINTER(C.c_int64))):
+        raise RuntimeError("whost_encode_many failed")
+    return out
+
+
+def _encode_treecodes_numpy(dim: int, level: np.ndarray, ixyz: np.ndarray, Jmax: int) -> np.ndarray:
+    """the same in numpy (reference formulation for tests/test_host.py)"""
     level = level.astype(np.int64)
     p = [ixyz[:, 1].astype(np.int64), ixyz[:, 0].astype(np.int64), ixyz[:, 2].astype(np.int64)]
     tc = np.zeros(len(level), dtype=np.int64)
@@ -103,33 +134,15 @@ class FullTree:
         self.sol, self.forest, self.dim, self.Jmin = sol, forest, forest.dim, Jmin
         dim = self.dim
         hvy, lvl, ixyz, _ = forest.active(0)
-        lv, ix = [lvl.astype(np.int64)], [ixyz.astype(np.int64)]
-        cl, cx = lv[0], ix[0]
-        seen = _pack(cl, cx)
-        for _ in range(int(lvl.max()) - Jmin):                     # ancestors, one level at a time
-            up = cl > Jmin
-            pl, px = cl[up] - 1, cx[up] >> 1
-            code, first = np.unique(_pack(pl, px), return_index=True)
-            new = ~np.isin(code, seen)
-            cl, cx = pl[first][new], px[first][new]
-            if len(cl) == 0:
-                break
-            lv.append(cl)
-            ix.append(cx)
-            seen = np.concatenate([seen, code[new]])
-        n_leaf = len(hvy)
-        level = np.concatenate(lv)
-        pos = np.concatenate(ix)
-        is_leaf = np.zeros(len(level), bool)
-        is_leaf[:n_leaf] = True
+        # init_full_tree: leaves (slots = their hvy ids) + ancestors; mothers get the free slots behind the leaves, in position order
+        level, pos, leaf_of = _build_tree(dim, Jmin, lvl, ixyz)
+        is_leaf = leaf_of >= 0
         slots = np.zeros(len(level), np.int64)
-        slots[:n_leaf] = hvy
-        m = np.arange(n_leaf, len(level))
-        m_sorted = m[np.argsort(_pack(level[m], pos[m]), kind="stable")]
-        slots[m_sorted] = int(hvy.max()) + 1 + np.arange(len(m))    # mothers: free slots behind the leaves, in position order
+        slots[is_leaf] = hvy[leaf_of[is_leaf]]
+        slots[~is_leaf] = int(hvy.max()) + 1 + np.arange(int((~is_leaf).sum()))
         if slots.max() > sol.max_blocks:
             raise MemoryError(f"full tree needs {int(slots.max())} block slots, max_blocks = {sol.max_blocks}")
-        self._set_blocks(level, pos, slots, is_leaf)
+        self._set_blocks(level, pos, slots, is_leaf, presorted=True)
         self.Jmax_active = int(lvl.max())
         self.st = np.zeros(len(level), np.int32)
         self.det = None
@@ -141,9 +154,9 @@ class FullTree:
         # then takes the same path with Nsc = 0 (TESTING/acm/3vortices/3vorticesAdaptFD4_CDF40)
         self.lifted = (p.wavelet[4] != "0") if p.useCoarseExtension < 0 else bool(p.useCoarseExtension)
 
-    def _set_blocks(self, level, pos, slots, is_leaf):
+    def _set_blocks(self, level, pos, slots, is_leaf, presorted: bool = False):
         code = _pack(level, pos)
-        o = np.argsort(code)
+        o = np.arange(len(code)) if presorted else np.argsort(code)
         self.code, self.level, self.pos, self.slots, self.is_leaf = code[o], level[o], pos[o], slots[o], is_leaf[o]
         self._build_tables()
         return o
@@ -347,13 +360,20 @@ class FullTree:
         sig = st0 == 0
         if force_maxlevel_dealiasing:
             sig &= self.level != self.forest.Jmax
-        bs, qs = [], []
-        for q in range(len(self.dirs)):
-            j = self.nb[:, q]
-            sel = np.flatnonzero(sig & (j >= 0) & (st0[np.maximum(j, 0)] == -1))
-            bs.append(sel)
-            qs.append(np.full(len(sel), q))
-        b, q = np.concatenate(bs), np.concatenate(qs)
+        i32 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        sig8 = np.ascontiguousarray(sig, dtype=np.uint8)
+        st32 = np.ascontiguousarray(st0, dtype=np.int32)
+        cap = max(4 * int(sig8.sum()) + 64, 1024)
+        while True:
+            b, q = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+            k = host_lib().whost_ft_security_pairs(dim, len(st32), i32(self.nb), i32(st32), sig8.ctypes.data_as(C.POINTER(C.c_uint8)), cap, i32(b), i32(q))
+            if k == -2:
+                cap *= 4
+                continue
+            if k < 0:
+                raise RuntimeError("whost_ft_security_pairs failed")
+            b, q = b[:k].astype(np.int64), q[:k].astype(np.int64)
+            break
         if len(b) == 0:
             return st
         dcode = np.array([(d[2] + 1) * 9 + (d[1] + 1) * 3 + (d[0] + 1) for d in self.dirs], dtype=np.int32)
@@ -469,6 +489,9 @@ class DistributedFullTree(FullTree):
 
     def __init__(self, drv, Jmin: int = 1):
         # drv: wabbit_b200.multi.DistributedWabbit (sol, forest, rank, world, transport, _ship)
+        from .multi import tick
+        self._tk = tick
+        _t_init = tick("adapt: tree init (numpy + tables)").__enter__()
         self.drv, self.me, self.world = drv, drv.rank, drv.world
         sol, forest = drv.sol, drv.forest
         self.sol, self.forest, self.dim, self.Jmin = sol, forest, forest.dim, Jmin
@@ -480,30 +503,14 @@ class DistributedFullTree(FullTree):
             ix.append(ixyz.astype(np.int64))
             ow.append(np.full(len(hvy), r, np.int64))
             sl.append(hvy.astype(np.int64))
-        level, pos, owner, slots = np.concatenate(lv), np.concatenate(ix), np.concatenate(ow), np.concatenate(sl)
-        n_leaf = len(level)
-        cl, cx = level, pos
-        seen = _pack(cl, cx)
-        ml, mx = [], []
-        for _ in range(int(level.max()) - Jmin):
-            up = cl > Jmin
-            pl, px = cl[up] - 1, cx[up] >> 1
-            code, first = np.unique(_pack(pl, px), return_index=True)
-            new = ~np.isin(code, seen)
-            cl, cx = pl[first][new], px[first][new]
-            if len(cl) == 0:
-                break
-            ml.append(cl)
-            mx.append(cx)
-            seen = np.concatenate([seen, code[new]])
-        level = np.concatenate([level] + ml)
-        pos = np.concatenate([pos] + mx)
-        is_leaf = np.zeros(len(level), bool)
-        is_leaf[:n_leaf] = True
-        owner = np.concatenate([owner, np.full(len(level) - n_leaf, -1, np.int64)])
-        slots = np.concatenate([slots, np.zeros(len(level) - n_leaf, np.int64)])
-        o = self._set_blocks(level, pos, slots, is_leaf)
-        self.owner = owner[o]
+        l0, p0, o0, s0 = np.concatenate(lv), np.concatenate(ix), np.concatenate(ow), np.concatenate(sl)
+        level, pos, leaf_of = _build_tree(dim, Jmin, l0, p0)
+        is_leaf = leaf_of >= 0
+        owner = np.full(len(level), -1, np.int64)
+        slots = np.zeros(len(level), np.int64)
+        owner[is_leaf], slots[is_leaf] = o0[leaf_of[is_leaf]], s0[leaf_of[is_leaf]]
+        self._set_blocks(level, pos, slots, is_leaf, presorted=True)
+        self.owner = owner
         # mothers: owner = owner of the first daughter, finest level first; slots behind the rank's leaves, in tree order
         nxt = np.array([forest.n_active(r) + 1 for r in range(self.world)], dtype=np.int64)
         for L in range(int(self.level.max()) - 1, Jmin - 1, -1):
@@ -525,6 +532,7 @@ class DistributedFullTree(FullTree):
         self.leaf_first = all(p.Bs[a] >= 3 * F for a in range(dim))
         self.lifted = (p.wavelet[4] != "0") if p.useCoarseExtension < 0 else bool(p.useCoarseExtension)
         self._halo_cleared = False
+        _t_init.__exit__()
 
     # ------------------------------------------------------------------ a pass: ship what the owned blocks need, then local tables
     def _pass(self, active: np.ndarray, need):
@@ -536,11 +544,13 @@ class DistributedFullTree(FullTree):
             sol._check(sol._lib.wgpu_set_halo(sol._ctx, 0, z.ctypes.data_as(C.POINTER(C.c_int32)), z.ctypes.data_as(C.POINTER(C.c_int32)),
                                               z.ctypes.data_as(C.POINTER(C.c_int32)), 0, z.ctypes.data_as(C.POINTER(C.c_int32)), None))
             self._halo_cleared = True
+        _t = self._tk("adapt: pass lists (numpy)").__enter__()
         mine_of = [active[self.owner[active] == q] for q in range(W)]
         lslot = np.where(self.owner == me, self.slots, -1)                  # local slot of every tree block present on this rank
         nxt = int(self.scratch0[me])
         needs = [need(mine_of[q]) for q in range(W)]
         n_arrays = len(needs[0])
+        _t.__exit__()
         for a in range(n_arrays):
             array = needs[0][a][0]
             src_r, src_s, dst_r, which = [], [], [], []
@@ -553,7 +563,8 @@ class DistributedFullTree(FullTree):
                 dst_r.append(np.full(len(b), q, np.int64))
                 which.append(b)
             src_r, src_s, dst_r, which = (np.concatenate(v) for v in (src_r, src_s, dst_r, which))
-            loc, nxt = drv._ship(array, src_r, src_s, dst_r, nxt)
+            with self._tk("adapt: pass ship", sol):
+                loc, nxt = drv._ship(array, src_r, src_s, dst_r, nxt)
             got = which[dst_r == me]
             lslot[got] = loc
         mine = mine_of[me]
@@ -562,7 +573,8 @@ class DistributedFullTree(FullTree):
         # here"); the relations of the pass's blocks are derived on the device
         if getattr(self, "_tc_all", None) is None or len(self._tc_all) != len(self.code):
             self._tc_all = _encode_treecodes(dim, self.level, self.pos, self.forest.Jmax)
-        sol.set_grid(np.maximum(lslot, 0).astype(np.int32), self._lvl32, self._tc_all, self.slots[mine].astype(np.int32))
+        with self._tk("adapt: pass set_grid", sol):
+            sol.set_grid(np.maximum(lslot, 0).astype(np.int32), self._lvl32, self._tc_all, self.slots[mine].astype(np.int32))
         self._lslot = lslot
         return mine, mine_of
 
@@ -584,9 +596,10 @@ class DistributedFullTree(FullTree):
         def flags(mine, mine_of):
             if not threshold:
                 return
-            st = sol.threshold_tree(WD, eps=eps, norm=norm, eps_norm=eps_norm, thresh_comp=thresh_comp, level_ref=self.forest.Jmax) if len(mine) \
-                else np.zeros(0, np.int32)
-            self._gather_status(mine_of, st)
+            with self._tk("adapt: threshold + allgather", sol):
+                st = sol.threshold_tree(WD, eps=eps, norm=norm, eps_norm=eps_norm, thresh_comp=thresh_comp, level_ref=self.forest.Jmax) if len(mine) \
+                    else np.zeros(0, np.int32)
+                self._gather_status(mine_of, st)
 
         def d2m(level):
             if level <= self.Jmin:
@@ -599,30 +612,34 @@ class DistributedFullTree(FullTree):
             da = self.child[m_all][:, cols]                                   # [n_m, nd] tree indices
             src_r, src_s = self.owner[da.ravel()], self.slots[da.ravel()]
             dst_r = np.repeat(self.owner[m_all], nd)
-            loc, _ = drv._ship(WD, src_r, src_s, dst_r, int(self.scratch0[me]))
-            mine = m_all[self.owner[m_all] == me]
-            if len(mine):
-                sol.coarsen_blocks(self.slots[mine].astype(np.int32), loc.astype(np.int32), WD)
+            with self._tk("adapt: d2m ship + coarsen", sol):
+                loc, _ = drv._ship(WD, src_r, src_s, dst_r, int(self.scratch0[me]))
+                mine = m_all[self.owner[m_all] == me]
+                if len(mine):
+                    sol.coarsen_blocks(self.slots[mine].astype(np.int32), loc.astype(np.int32), WD)
 
         if self.leaf_first:
             # leaf pass on the time stepper's topology: halo copies (and filtered copies of finer neighbours) of hvy_block refreshed first
-            drv.stepper.exchange_array(0, 0)
-            sol.waveletDecomposition_tree((HVY_BLOCK, 0), WD)
-            if self.lifted:
-                sol.coarse_extension_modify(WD, (HVY_BLOCK, 0), True, True)
+            with self._tk("adapt: leaf pass (exchange + fwt + ce)", sol):
+                drv.stepper.exchange_array(0, 0)
+                sol.waveletDecomposition_tree((HVY_BLOCK, 0), WD)
+                if self.lifted:
+                    sol.coarse_extension_modify(WD, (HVY_BLOCK, 0), True, True)
             leaves = np.flatnonzero(self.is_leaf)
             mine_of = [leaves[self.owner[leaves] == q] for q in range(self.world)]
             if threshold:
-                st = sol.threshold_tree(WD, eps=eps, norm=norm, eps_norm=eps_norm, thresh_comp=thresh_comp, level_ref=self.forest.Jmax)
-                self._gather_status(mine_of, st)
+                with self._tk("adapt: threshold + allgather", sol):
+                    st = sol.threshold_tree(WD, eps=eps, norm=norm, eps_norm=eps_norm, thresh_comp=thresh_comp, level_ref=self.forest.Jmax)
+                    self._gather_status(mine_of, st)
         for level in range(self.Jmax_active, self.Jmin - 1, -1):
             todo = np.flatnonzero((self.level == level) & ~(self.is_leaf if self.leaf_first else np.zeros(len(self.code), bool)))
             if len(todo):
                 mine, mine_of = self._pass(todo, same_level)
                 if len(mine):
-                    sol.waveletDecomposition_tree((HVY_BLOCK, 0), WD)
-                    if self.lifted and self.is_leaf[mine].any():
-                        sol.coarse_extension_modify(WD, (HVY_BLOCK, 0), True, True)
+                    with self._tk("adapt: fwt + ce kernels", sol):
+                        sol.waveletDecomposition_tree((HVY_BLOCK, 0), WD)
+                        if self.lifted and self.is_leaf[mine].any():
+                            sol.coarse_extension_modify(WD, (HVY_BLOCK, 0), True, True)
                 flags(mine, mine_of)
             d2m(level)
         return None
@@ -662,12 +679,16 @@ class DistributedFullTree(FullTree):
                 st0[ci[np.asarray(mask_keeps(self.level[ci], self.pos[ci]), dtype=bool)]] = 0
         if use_security_zone and indicator != "everywhere":
             self._lslot_for_patches()
-            st0 = self.security_zone(st0, eps, norm, thresh_comp, force_maxlevel_dealiasing)
-        st = self.decide(st0)
+            with self._tk("adapt: security zone", sol):
+                st0 = self.security_zone(st0, eps, norm, thresh_comp, force_maxlevel_dealiasing)
+        with self._tk("adapt: decide"):
+            st = self.decide(st0)
+        _t = self._tk("adapt: prune + tables").__enter__()
         keep = st != -1
         st_kept = st[keep]
         self.code, self.level, self.pos, self.slots, self.owner = (a[keep] for a in (self.code, self.level, self.pos, self.slots, self.owner))
         self._build_tables()
+        _t.__exit__()
         self.is_leaf = self.child[:, 0] < 0
         leaves = np.flatnonzero(self.is_leaf)
         marked = leaves[(self.nb[leaves] < 0).any(axis=1)] if self.lifted else leaves[:0]
@@ -675,6 +696,7 @@ class DistributedFullTree(FullTree):
         if self.lifted and any(p.Bs[a] < max(nrl, nrr) for a in range(dim)):
             raise RuntimeError("adapt_tree: Bs < Nrecon (reconstruction of the neighbours of interface blocks) is not supported")
         leaf_only = all(p.Bs[a] >= d2l and p.Bs[a] >= d2r for a in range(dim))
+        _t_rec = self._tk("adapt: CE + reconstruction passes", sol).__enter__()
         if len(marked):
             nothing = lambda idx: [((HVY_BLOCK, 0), np.zeros(0, np.int64))]
             mine, _ = self._pass(marked, nothing)                              # coarse extension on the lasting interfaces (local data only)
@@ -697,7 +719,9 @@ class DistributedFullTree(FullTree):
                     mine, _ = self._pass(todo, recon_needs)
                     if len(mine):
                         sol.waveletReconstruction_CE(WD, (HVY_BLOCK, 0), (HVY_BLOCK, 0))
+        _t_rec.__exit__()
         # prune_fulltree2leafs + balanceLoad_tree: the leaves move to their owners / slots in the new partition
+        _t = self._tk("adapt: new forest + lists").__enter__()
         new = Forest.from_blocks(dim, self.forest.Jmax, self.level[leaves].astype(np.int32), self.pos[leaves].astype(np.int32),
                                  block_dist=self.forest.block_dist, n_ranks=W, max_blocks=self.forest.max_blocks, periodic=self.forest.periodic)
         src_r, src_s, dst_r, dst_s, stat = [], [], [], [], []
@@ -711,9 +735,12 @@ class DistributedFullTree(FullTree):
             dst_s.append(hvy.astype(np.int64))
         src_r, src_s, dst_r, dst_s = (np.concatenate(v) for v in (src_r, src_s, dst_r, dst_s))
         self.leaf_status = np.concatenate(stat).astype(np.int32)      # refinement status of the new leaves, global space-filling-curve order
-        loc, _ = drv._ship((HVY_BLOCK, 0), src_r, src_s, dst_r, int(self.scratch0[me]))
-        sol.move_blocks(loc.astype(np.int32), dst_s[dst_r == me].astype(np.int32))
-        drv.attach(new)
+        _t.__exit__()
+        with self._tk("adapt: final ship + move", sol):
+            loc, _ = drv._ship((HVY_BLOCK, 0), src_r, src_s, dst_r, int(self.scratch0[me]))
+            sol.move_blocks(loc.astype(np.int32), dst_s[dst_r == me].astype(np.int32))
+        with self._tk("adapt: attach (halo plan + set_grid)", sol):
+            drv.attach(new)
         return new, {}
 
     def _lslot_for_patches(self):

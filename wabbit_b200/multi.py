@@ -93,6 +93,31 @@ def _i32(a):
     return a.ctypes.data_as(C.POINTER(C.c_int32))
 
 
+# phase timers of the multi-rank drivers (WABBIT_MG_TIMING=1): wall time per named phase, device synchronised at both ends
+import os as _os
+import time as _time
+TIMING = {} if _os.environ.get("WABBIT_MG_TIMING") else None
+
+
+class tick:
+    def __init__(self, name, sol=None):
+        self.name, self.sol = name, sol
+
+    def __enter__(self):
+        if TIMING is not None:
+            if self.sol is not None:
+                self.sol.synchronize()
+            self.t0 = _time.perf_counter()
+        return self
+
+    def __exit__(self, *a):
+        if TIMING is not None:
+            if self.sol is not None:
+                self.sol.synchronize()
+            TIMING[self.name] = TIMING.get(self.name, 0.0) + (_time.perf_counter() - self.t0)
+        return False
+
+
 def _require_torch_stream(sol, torch):
     """torch.distributed orders a collective against torch's CURRENT stream, the library issues its pack / stage kernels on the context's
     stream: the two must be the same stream (or both the legacy default stream), otherwise pack -> all-to-all -> stage would race."""
@@ -811,11 +836,14 @@ class DistributedWabbit:
         block of the GLOBAL grid in space-filling-curve order (None = everywhere)."""
         me, sol = self.rank, self.sol
         old, ooff = self.forest, self.off
-        self.stepper.exchange_array(0, 0)
+        with tick("refine: exchange_array", sol):
+            self.stepper.exchange_array(0, 0)
         try:
-            new, mo, da, ks, kd = old.refine_global(refine_flags)
+            with tick("refine: refine_global (host)"):
+                new, mo, da, ks, kd = old.refine_global(refine_flags)
         except MemoryError as e:
             raise RuntimeError(f"refine_tree: {e}")
+        t_np = tick("refine: id lists (numpy)").__enter__()
         noff = np.concatenate([[0], np.cumsum([new.n_active(r) for r in range(self.world)])]).astype(np.int64)
         nd = 2 ** old.dim
         mo, da, ks, kd = (a.astype(np.int64) - 1 for a in (mo, da, ks, kd))          # 0-based global indices
@@ -828,8 +856,11 @@ class DistributedWabbit:
         if len(derived) > sol.max_blocks:
             raise MemoryError("refine_tree: the refined blocks of this rank do not fit max_blocks")
         m_loc = (mo[my_m] - ooff[me] + 1).astype(np.int32)
-        sol._check(sol._lib.wgpu_refine(sol._ctx, len(m_loc), _i32(m_loc), _i32(tmp_slot(d_new).astype(np.int32)), int(my_k.sum()),
-                                        _i32((ks[my_k] - ooff[me] + 1).astype(np.int32)), _i32(tmp_slot(kd[my_k]).astype(np.int32))))
+        t_np.__exit__()
+        with tick("refine: wgpu_refine", sol):
+            sol._check(sol._lib.wgpu_refine(sol._ctx, len(m_loc), _i32(m_loc), _i32(tmp_slot(d_new).astype(np.int32)), int(my_k.sum()),
+                                            _i32((ks[my_k] - ooff[me] + 1).astype(np.int32)), _i32(tmp_slot(kd[my_k]).astype(np.int32))))
+        t_np = tick("refine: id lists (numpy)").__enter__()
         # every new block: who holds it now (the owner of the old block it derives from) and in which intermediate slot
         holder = np.empty(new.n_blocks, np.int64)
         holder[kd] = self._owner(ooff, ks)
@@ -840,11 +871,15 @@ class DistributedWabbit:
             slot[sel] = np.arange(1, len(sel) + 1)
         dst = self._owner(noff, np.arange(new.n_blocks))
         n_tmp = len(derived)
-        local, _ = self._ship((0, 0), holder, slot, dst, n_tmp + 1)
+        t_np.__exit__()
+        with tick("refine: ship", sol):
+            local, _ = self._ship((0, 0), holder, slot, dst, n_tmp + 1)
         mine_new = np.flatnonzero(dst == me)
-        sol._check(sol._lib.wgpu_move_blocks(sol._ctx, len(mine_new), _i32(local.astype(np.int32)),
-                                             _i32((mine_new - noff[me] + 1).astype(np.int32))))
-        self.attach(new)
+        with tick("refine: move_blocks", sol):
+            sol._check(sol._lib.wgpu_move_blocks(sol._ctx, len(mine_new), _i32(local.astype(np.int32)),
+                                                 _i32((mine_new - noff[me] + 1).astype(np.int32))))
+        with tick("refine: attach (halo plan + set_grid)", sol):
+            self.attach(new)
         return new
 
     # ------------------------------------------------------------------ adapt_tree (one coarsening sweep, unlifted wavelets)
@@ -878,7 +913,8 @@ class DistributedWabbit:
         if use_ce if full_tree is None else full_tree:
             # the reference's full-tree algorithm (coarse extension and security zone for lifted wavelets; fulltree.py)
             from .fulltree import DistributedFullTree
-            norm = self.global_norm(eps_norm, thresh_comp) if eps_normalized else None
+            with tick("adapt: norm", sol):
+                norm = self.global_norm(eps_norm, thresh_comp) if eps_normalized else None
             n0 = old.n_blocks
             sz = (lifted if sol.params.useSecurityZone < 0 else bool(sol.params.useSecurityZone)) if useSecurityZone is None else bool(useSecurityZone)
             ft = DistributedFullTree(self, Jmin=Jmin)
