@@ -30,7 +30,8 @@ def _case(wavelet, Bs, forest, seed, max_blocks=None):
 
 @pytest.mark.parametrize("wavelet,Bs,ignore_filter", [("CDF40", 16, True), ("CDF44", 16, True), ("CDF20", 16, True), ("CDF62", 20, True),
                                                       ("CDF44", 16, False), ("CDF42", 18, False), ("CDF22", 16, False), ("CDF62", 20, False),
-                                                      ("CDF44", 24, False)])
+                                                      ("CDF44", 24, False), ("CDF44", 22, False), ("CDF44", 26, False), ("CDF42", 32, False),
+                                                      ("CDF40", 28, True)])
 def test_download_with_ghosts_on_graded_grid(wavelet, Bs, ignore_filter):
     """ignore_filter=False is sync_ghosts_tree's default: with a lifted wavelet the restriction goes through the HD filter
     (restrict_copy_at_CE); compared at the full depth g (at smaller depths the reference's filter reads ghost nodes it did not fill)."""
@@ -71,7 +72,7 @@ def _refine_oracle(w, po, grid, u, nbr, ignore_filter=True):
     return out
 
 
-@pytest.mark.parametrize("wavelet,Bs", [("CDF40", 16), ("CDF44", 16), ("CDF20", 18), ("CDF62", 20)])
+@pytest.mark.parametrize("wavelet,Bs", [("CDF40", 16), ("CDF44", 16), ("CDF20", 18), ("CDF62", 20), ("CDF44", 26), ("CDF40", 32)])
 def test_refine_everywhere_uniform(wavelet, Bs):
     forest = Forest.uniform(3, 1, Jmax=2)
     w, p, po, grid, sol, u = _case(wavelet, Bs, forest, seed=2, max_blocks=64)
@@ -193,7 +194,8 @@ def test_page_locked_host_arrays_take_the_direct_path_with_identical_results():
 
 
 @pytest.mark.parametrize("wavelet,Bs,ignore_filter", [("CDF40", 16, True), ("CDF44", 16, True), ("CDF22", 18, True), ("CDF62", 20, True),
-                                                      ("CDF20", 24, True), ("CDF44", 16, False), ("CDF42", 20, False), ("CDF62", 16, False)])
+                                                      ("CDF20", 24, True), ("CDF44", 16, False), ("CDF42", 20, False), ("CDF62", 16, False),
+                                                      ("CDF44", 22, False), ("CDF44", 26, False), ("CDF40", 32, True), ("CDF42", 28, False)])
 def test_wavelet_transform_on_graded_grid(wavelet, Bs, ignore_filter):
     """FWT / IWT on a leaf grid with level jumps: ghost values of all 26 relations come from the wavelet jump pool (restriction
     from finer -- through the HD filter unless ignore_filter --, prediction from coarser neighbours) and are exactly what the

@@ -41,7 +41,7 @@ def _setup(wavelet, Bs, seed, Jmax=3, disc="FD_4th_central", noise=0.05):
     return w, p, po, forest, grid, sol, u, H
 
 
-@pytest.mark.parametrize("wavelet,Bs", [("CDF44", 16), ("CDF44", 18), ("CDF42", 16), ("CDF62", 16), ("CDF22", 16)])
+@pytest.mark.parametrize("wavelet,Bs", [("CDF44", 16), ("CDF44", 18), ("CDF42", 16), ("CDF62", 16), ("CDF22", 16), ("CDF44", 22), ("CDF42", 26)])
 def test_full_tree_decomposition_and_flags(wavelet, Bs):
     w, p, po, forest, grid, sol, u, H = _setup(wavelet, Bs, seed=3)
     ot = OFT.decompose_full_tree(po, w, grid, u, Jmin=1, fd_half_width=H)
@@ -72,7 +72,8 @@ def test_full_tree_decomposition_and_flags(wavelet, Bs):
                                                       ("CDF42", 16, "threshold-state-vector", False), ("CDF44", 16, "everywhere", False),
                                                       ("CDF62", 20, "threshold-state-vector", False), ("CDF22", 16, "everywhere", False),
                                                       ("CDF44", 16, "threshold-state-vector", True), ("CDF42", 18, "threshold-state-vector", True),
-                                                      ("CDF40", 16, "threshold-state-vector", False), ("CDF60", 18, "threshold-state-vector", False)])
+                                                      ("CDF40", 16, "threshold-state-vector", False), ("CDF60", 18, "threshold-state-vector", False),
+                                                      ("CDF44", 22, "threshold-state-vector", True), ("CDF44", 26, "threshold-state-vector", False)])
 def test_adapt_tree_lifted(wavelet, Bs, indicator, sz):
     """the whole adapt_tree with the full wavelet transformation (decomposition of the full tree, indicator, grid decision; for lifted
     wavelets coarse extension on the lasting interfaces and CE-optimised reconstruction; pruning): same new grid as the oracle, data bit

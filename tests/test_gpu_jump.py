@@ -37,7 +37,8 @@ def _setup(wavelet, Bs, J0, Jmax, seed, discretization="FD_4th_central", skew=Tr
 
 @pytest.mark.parametrize("wavelet,Bs,disc,skew", [("CDF40", 16, "FD_4th_central", True), ("CDF44", 16, "FD_4th_central", False),
                                                    ("CDF20", 16, "FD_2nd_central", True), ("CDF62", 20, "FD_6th_central", True),
-                                                   ("CDF44", 18, "FD_4th_central_optimized", True)])
+                                                   ("CDF44", 18, "FD_4th_central_optimized", True), ("CDF44", 22, "FD_4th_central", True),
+                                                   ("CDF40", 26, "FD_6th_central", False)])
 def test_rhs_with_level_jumps(wavelet, Bs, disc, skew):
     w, p, po, forest, grid, nbr, sol, u = _setup(wavelet, Bs, 1, 3, seed=5, discretization=disc, skew=skew)
     sol.upload(u)

@@ -70,9 +70,38 @@ def test_rhs_parity(disc, skew, Bs):
     sol.close()
 
 
+@pytest.mark.parametrize("disc,skew,Bs", [("FD_4th_central", True, 22), ("FD_4th_central", False, 26), ("FD_6th_central", True, 24),
+                                          ("FD_2nd_central", True, 32), ("FD_4th_central_optimized", False, 28), ("FD_4th_central", True, 14)])
+def test_rhs_parity_any_even_block_size(disc, skew, Bs):
+    """the reference accepts every even Bs (read_Bs, module_ini_files_parser_mpi.f90:816; its 3-D penalized fixture uses 26): sizes
+    without a specialised instance run through stage_kernel_any (run-time Bs, xy tiles)"""
+    test_rhs_parity(disc, skew, Bs)
+
+
+def test_generic_stage_kernel_equals_the_specialised_one(monkeypatch):
+    """WGPU_STAGE_GENERIC routes Bs = 16 through stage_kernel_any: the same RK4 steps, dt bit-identical, fields to round-off"""
+    outs = []
+    for generic in (False, True):
+        if generic:
+            monkeypatch.setenv("WGPU_STAGE_GENERIC", "1")
+        p = tg_params(Bs=16, J=2, wavelet_g=3, discretization="FD_4th_central", skew=True)
+        forest, sol, grid, po = setup_case(p, 2)
+        u = O.alloc(grid, po)
+        O.inicond_taylor_green(grid, po, u)
+        sol.upload(u)
+        dts = [sol.RungeKuttaGeneric(0.0, 0)]
+        dts.append(sol.RungeKuttaGeneric(dts[0], 1))
+        out = np.zeros_like(u)
+        sol.download(out, g_sync=0)
+        outs.append((dts, out))
+        sol.close()
+    assert outs[0][0] == outs[1][0]
+    assert relerr(interior(p, outs[1][1]), interior(p, outs[0][1])) <= 1e-13
+
+
 @pytest.mark.parametrize("sponge", [False, True])
-def test_rhs_penalization_sponge(sponge):
-    p = tg_params(Bs=16, J=2, wavelet_g=3, skew=False, penalization=True, use_sponge=sponge, C_eta=1.3e-3, C_sponge=2.0e-2)
+def test_rhs_penalization_sponge(sponge, Bs=16):
+    p = tg_params(Bs=Bs, J=2, wavelet_g=3, skew=False, penalization=True, use_sponge=sponge, C_eta=1.3e-3, C_sponge=2.0e-2)
     p.u_mean_set = (1.0, 0.5, -0.25)
     p.gamma_p = 1.0
     forest, sol, grid, po = setup_case(p, 2)
@@ -93,7 +122,13 @@ def test_rhs_penalization_sponge(sponge):
     sol.close()
 
 
-@pytest.mark.parametrize("disc,Bs", [("FD_4th_central", 16), ("FD_6th_central", 18), ("FD_2nd_central", 20)])
+def test_rhs_penalization_sponge_bs26():
+    """the block size of the reference's 3-D penalized fixture (TESTING/acm/bumblebeeFlowEquiFD4_CDF40/PARAMS.ini: Bs = 26)"""
+    test_rhs_penalization_sponge(True, Bs=26)
+
+
+@pytest.mark.parametrize("disc,Bs", [("FD_4th_central", 16), ("FD_6th_central", 18), ("FD_2nd_central", 20), ("FD_4th_central", 26),
+                                     ("FD_6th_central", 22)])
 def test_rk4_steps_parity(disc, Bs):
     """RungeKuttaGeneric: same dt (bit-exact: max-reduction + IEEE sqrt/div) and fields within 1e-12 over several steps."""
     p = tg_params(Bs=Bs, J=2, wavelet_g=3, discretization=disc, skew=True)

@@ -71,6 +71,7 @@ struct RestrictArgs {
     const unsigned *rst_mask;
     const int *nbr;
     int nc, Bs, F, lo, hi, Nscl, Nscr;
+    int XC;                  // decimated x positions per CTA (blockIdx.z selects the chunk): bounds the shared memory for large blocks
     double HD[2 * WGPU_FMAX + 1];
 };
 
@@ -84,10 +85,11 @@ __global__ void __launch_bounds__(256) restrict_filter_kernel(const RestrictArgs
     const long long CS = (long long)Bs * Bs * Bs;
     if (threadIdx.x < 27) nb[threadIdx.x] = threadIdx.x == 13 ? b : a.nbr[(long long)b * 27 + threadIdx.x];
     __syncthreads();
-    double *t1 = sm;                                // [n z][n y][half x]
-    double *t2 = t1 + (size_t)n * n * half;         // [n z][half y][half x]
-    for (int i = threadIdx.x; i < n * n * half; i += blockDim.x) {
-        const int xo = i % half, y = (i / half) % n - F, z = i / (half * n) - F;
+    const int XC = a.XC, x0 = blockIdx.z * XC, xc = min(XC, half - x0);   // this CTA's decimated x positions [x0, x0 + xc)
+    double *t1 = sm;                                // [n z][n y][xc x]
+    double *t2 = t1 + (size_t)n * n * XC;           // [n z][half y][xc x]
+    for (int i = threadIdx.x; i < n * n * xc; i += blockDim.x) {
+        const int xl = i % xc, xo = x0 + xl, y = (i / xc) % n - F, z = i / (xc * n) - F;
         const int sy = y < 0 ? -1 : (y >= Bs ? 1 : 0), sz = z < 0 ? -1 : (z >= Bs ? 1 : 0);
         double acc = 0.0;
         for (int k = a.lo; k <= a.hi; ++k) {
@@ -97,20 +99,20 @@ __global__ void __launch_bounds__(256) restrict_filter_kernel(const RestrictArgs
             const double v = src >= 0 ? a.u[((long long)src * a.nc + c) * CS + ((long long)(z - sz * Bs) * Bs + (y - sy * Bs)) * Bs + (x - sx * Bs)] : 0.0;
             acc = __dadd_rn(acc, __dmul_rn(v, a.HD[k + WGPU_FMAX]));
         }
-        t1[i] = acc;
+        t1[((size_t)(z + F) * n + (y + F)) * xc + xl] = acc;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n * half * half; i += blockDim.x) {
-        const int xo = i % half, yo = (i / half) % half, z = i / (half * half);
+    for (int i = threadIdx.x; i < n * half * xc; i += blockDim.x) {
+        const int xl = i % xc, yo = (i / xc) % half, z = i / (xc * half);
         double acc = 0.0;
-        for (int k = a.lo; k <= a.hi; ++k) acc = __dadd_rn(acc, __dmul_rn(t1[((size_t)z * n + (2 * yo + F + k)) * half + xo], a.HD[k + WGPU_FMAX]));
-        t2[i] = acc;
+        for (int k = a.lo; k <= a.hi; ++k) acc = __dadd_rn(acc, __dmul_rn(t1[((size_t)z * n + (2 * yo + F + k)) * xc + xl], a.HD[k + WGPU_FMAX]));
+        t2[((size_t)z * half + yo) * xc + xl] = acc;
     }
     __syncthreads();
     double *out = a.rpool + ((long long)blockIdx.x * a.nc + c) * (CS / 8);
     const double *own = a.u + ((long long)b * a.nc + c) * CS;
-    for (int i = threadIdx.x; i < half * half * half; i += blockDim.x) {
-        const int xo = i % half, yo = (i / half) % half, zo = i / (half * half);
+    for (int i = threadIdx.x; i < half * half * xc; i += blockDim.x) {
+        const int xl = i % xc, xo = x0 + xl, yo = (i / xc) % half, zo = i / (xc * half);
         const int p[3] = {2 * xo, 2 * yo, 2 * zo};
         bool copy = false;
         for (int d = 0; d < 27 && !copy; ++d) {
@@ -124,9 +126,9 @@ __global__ void __launch_bounds__(256) restrict_filter_kernel(const RestrictArgs
         if (copy) v = own[((long long)p[2] * Bs + p[1]) * Bs + p[0]];
         else {
             v = 0.0;
-            for (int k = a.lo; k <= a.hi; ++k) v = __dadd_rn(v, __dmul_rn(t2[((size_t)(p[2] + F + k) * half + yo) * half + xo], a.HD[k + WGPU_FMAX]));
+            for (int k = a.lo; k <= a.hi; ++k) v = __dadd_rn(v, __dmul_rn(t2[((size_t)(p[2] + F + k) * half + yo) * xc + xl], a.HD[k + WGPU_FMAX]));
         }
-        out[i] = v;
+        out[((size_t)zo * half + yo) * half + xo] = v;
     }
 }
 
@@ -449,6 +451,7 @@ int32_t wgpu_launch_restrict_filter(wgpu_ctx *ctx, const double *src, int nc_src
     a.F = std::max(-w.hd_lo, w.hd_hi);
     a.Nscl = std::max(-w.hd_lo - 1, 0);   // setup_wavelet, module_wavelets.f90:1368-1376
     a.Nscr = w.hd_hi;
+    a.XC = 0;
     for (int k = 0; k < 2 * WGPU_FMAX + 1; ++k) a.HD[k] = w.HD[k];
     const int n = a.Bs + 2 * a.F, half = a.Bs / 2;
     dim3 grid(ctx->n_rst, ctx->nc);
@@ -463,7 +466,11 @@ int32_t wgpu_launch_restrict_filter(wgpu_ctx *ctx, const double *src, int nc_src
         *active = true;
         return WGPU_OK;
     }
-    const size_t smem = sizeof(double) * ((size_t)n * n * half + (size_t)n * half * half);
+    // all decimated x positions in one CTA if the two intermediates fit into ~100 KB (two CTAs per SM), else chunks of x (independent)
+    a.XC = half;
+    while (a.XC > 1 && sizeof(double) * ((size_t)n * n * a.XC + (size_t)n * half * a.XC) > 100 * 1024) a.XC = (a.XC + 1) / 2;
+    grid.z = (half + a.XC - 1) / a.XC;
+    const size_t smem = sizeof(double) * ((size_t)n * n * a.XC + (size_t)n * half * a.XC);
     static size_t configured = 0;
     int32_t rc = ensure_smem(ctx, restrict_filter_kernel, smem, configured);
     if (rc) return rc;

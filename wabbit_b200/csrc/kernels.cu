@@ -491,6 +491,216 @@ __global__ void __launch_bounds__(BS *BS, (Tile<FD, BS>::SMEM <= 110 * 1024 ? 2 
 }
 
 // ---------------------------------------------------------------------------------------------
+// stage_kernel_any<FD, SKEW>: the same stage for ANY even block size (the reference accepts every even Bs, read_Bs in
+// LIB/PARAMS/module_ini_files_parser_mpi.f90:816; its own 3-D penalized fixture uses Bs = 26).  The fast kernels above fix Bs at compile time
+// (16 / 18 / 20: the CTA shape, the shared-memory ring and the cp.async tables depend on it); this one takes Bs at run time: a CTA of 256
+// threads owns an xy tile of T x T points (T = ceil(Bs / ceil(Bs / 16)) <= 16, so Bs = 26 runs as 2 x 2 tiles of 13) and marches in z
+// through a ring of 2H + 1 planes (4 components, tile + xy halo).  Every ring entry is resolved per element: own block, face neighbour's
+// interior, exchange-pool / jump-pool patch (the layouts of build_tables above) or zero.  Same arithmetic, same epilogue, same fused
+// reductions (the CFL candidate of a block is the MIN over its tiles' candidates: dt is monotone in max|u|).  HBM-bound like the fast
+// kernels, but with plain loads and two barriers per plane: the fall-back, not the headline.
+// ---------------------------------------------------------------------------------------------
+template <int FD, bool SKEW>
+__global__ void __launch_bounds__(256, 2) stage_kernel_any(const __grid_constant__ StageArgs a, int BS, int T, int NTILE)
+{
+    using S = St<FD>;
+    constexpr int H = S::H, NC = 4;
+    extern __shared__ __align__(16) double sm[];
+    __shared__ int s_code[WGPU_NDIR];
+    __shared__ double s_red[8];
+    const int PW = T + 2 * H, PLANE = PW * PW, SLOT = NC * PLANE;
+    constexpr int RING = 2 * H + 1;
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x % (NTILE * NTILE), bi = blockIdx.x / (NTILE * NTILE);
+    const int tx0 = (tile % NTILE) * T, ty0 = (tile / NTILE) * T;
+    const int b = a.active[bi];
+    if (tid < WGPU_NDIR) s_code[tid] = a.nbr[b * WGPU_NDIR + tid];
+    __syncthreads();
+    const long long CS = (long long)BS * BS * BS;
+
+    // value of component c at block-local lattice point (gx, gy, gz), gz in [-H, BS+H), at most one coordinate outside [0, BS)
+    auto fetch = [&](int c, int gx, int gy, int gz) -> double {
+        int cd, dirx = 0, diry = 0, dirz = 0;
+        if (gx < 0) dirx = -1; else if (gx >= BS) dirx = 1;
+        if (gy < 0) diry = -1; else if (gy >= BS) diry = 1;
+        if (gz < 0) dirz = -1; else if (gz >= BS) dirz = 1;
+        if (!(dirx | diry | dirz)) return a.u_in[((long long)b * NC + c) * CS + ((long long)gz * BS + gy) * BS + gx];
+        cd = s_code[(dirz + 1) * 9 + (diry + 1) * 3 + (dirx + 1)];
+        if (cd >= 0) {
+            const int x = gx - dirx * BS, y = gy - diry * BS, z = gz - dirz * BS;
+            return a.u_in[((long long)cd * NC + c) * CS + ((long long)z * BS + y) * BS + x];
+        }
+        if (cd == -1) return 0.0;
+        const unsigned long long base = pool_base(a, cd);
+        const double *pp = (base & LT_POOL) ? a.pool : a.jpool;
+        long long o;
+        if (dirx) o = (((long long)c * BS + gz) * BS + gy) * H + (dirx < 0 ? gx + H : gx - BS);          // (H, Bs, Bs)
+        else if (diry) o = (((long long)c * BS + gz) * H + (diry < 0 ? gy + H : gy - BS)) * BS + gx;     // (Bs, H, Bs)
+        else o = (((long long)c * H + (dirz < 0 ? gz + H : gz - BS)) * BS + gy) * BS + gx;               // (Bs, Bs, H)
+        return pp[(long long)(base & LT_MASK) + o];
+    };
+    auto load_plane = [&](int q) {   // q = gz + H
+        const int gz = q - H;
+        double *dst = sm + (q % RING) * SLOT;
+        const bool zin = gz >= 0 && gz < BS;
+        for (int i = tid; i < SLOT; i += 256) {
+            const int c = i / PLANE, r = i % PLANE, yy = r / PW, xx = r % PW;
+            const int gx = tx0 + xx - H, gy = ty0 + yy - H;
+            const bool xin = gx >= 0 && gx < BS, yin = gy >= 0 && gy < BS;
+            const bool xt = xx >= H && xx < H + T, yt = yy >= H && yy < H + T;     // inside the tile proper
+            // needed: tile points (any z), and on interior planes the x / y halos of the tile (star stencil: no corners)
+            bool need = xt && yt && xin && yin;
+            // x halo of the tile: gy must lie inside the block (and vice versa); the last tile may overhang the block: stay within BS + H
+            if (zin && xt != yt) need = (xt ? xin : yin) && gx < BS + H && gy < BS + H;
+            dst[i] = need ? fetch(c, gx, gy, gz) : 0.0;
+        }
+    };
+
+    const int lx = tid % 16, ly = tid / 16;
+    const bool act = lx < T && ly < T && tx0 + lx < BS && ty0 + ly < BS;
+    const int tx = tx0 + lx, ty = ty0 + ly;
+    const int lvl = a.level[b];
+    const double dx = a.dx_lvl[lvl][0], dy = a.dx_lvl[lvl][1], dz = a.dx_lvl[lvl][2];
+    const double dinv[3] = {1.0 / dx, 1.0 / dy, 1.0 / dz};
+    const double d2inv[3] = {1.0 / (dx * dx), 1.0 / (dy * dy), 1.0 / (dz * dz)};
+    const double dt = (a.u_out || a.acc_out) ? *a.dt_ptr : 0.0;
+    const bool base_u_global = a.u_out && a.u0 != a.u_in;
+    const bool base_acc_global = a.acc_out && a.acc_in != a.u_in;
+    const double c02 = a.c0 * a.c0;
+    double gxy2 = 0.0, gz0 = 0.0, gcz = 0.0;
+    if (a.geom) {   // translating sphere, as in the fast kernel (draw_sphere's operation order)
+        const double ts = __dadd_rn(a.t0_ptr ? *a.t0_ptr : a.t0, __dmul_rn(a.t_cj, *a.dt_ptr));
+        const double cx = __dadd_rn(a.g_c0[0], __dmul_rn(a.g_v[0], ts)), cy = __dadd_rn(a.g_c0[1], __dmul_rn(a.g_v[1], ts));
+        gcz = __dadd_rn(a.g_c0[2], __dmul_rn(a.g_v[2], ts));
+        const double x = __dadd_rn(__dmul_rn((double)tx, dx), __dmul_rn((double)(a.ixyz[3 * b] * BS), dx));
+        const double y = __dadd_rn(__dmul_rn((double)ty, dy), __dmul_rn((double)(a.ixyz[3 * b + 1] * BS), dy));
+        gz0 = __dmul_rn((double)(a.ixyz[3 * b + 2] * BS), dz);
+        const double ex = __dsub_rn(x, cx), ey = __dsub_rn(y, cy);
+        gxy2 = __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
+    }
+    for (int q = 0; q < 2 * H; ++q) load_plane(q);
+    const int cidx = (ly + H) * PW + lx + H;
+    double umag_max = 0.0, uabs_max = 0.0;
+#pragma unroll 1
+    for (int z = 0; z < BS; ++z) {
+        load_plane(z + 2 * H);
+        __syncthreads();
+        if (act) {
+            const long long gi = ((long long)b * NC) * CS + (long long)z * BS * BS + ty * BS + tx;
+            double rhs[4], ctr[4];
+            double d1v[3][4], d2v[3][3], cv[3][3];
+#pragma unroll
+            for (int dir = 0; dir < 3; ++dir) {
+                double qv[4][2 * H + 1];
+#pragma unroll
+                for (int o = -H; o <= H; ++o) {
+                    int off;
+                    if (dir == 0) off = ((z + H) % RING) * SLOT + cidx + o;
+                    else if (dir == 1) off = ((z + H) % RING) * SLOT + cidx + o * PW;
+                    else off = ((z + H + o) % RING) * SLOT + cidx;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) qv[c][o + H] = sm[off + c * PLANE];
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) d1v[dir][c] = S::d1(&qv[c][H], dinv[dir]);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) d2v[dir][c] = S::d2(&qv[c][H], d2inv[dir]);
+                if (SKEW) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) cv[dir][c] = S::d1p(&qv[c][H], &qv[dir][H], dinv[dir]);
+                }
+                if (dir == 0) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) ctr[c] = qv[c][H];
+                }
+            }
+            const double u = ctr[0], v = ctr[1], w = ctr[2], p = ctr[3];
+            double penal[3] = {0.0, 0.0, 0.0};
+            const long long g0 = ((long long)b * a.n_mask) * CS + (long long)z * BS * BS + ty * BS + tx;
+            if (a.geom) {
+                const double ez = __dsub_rn(__dadd_rn(__dmul_rn((double)z, dz), gz0), gcz);
+                const double dist = __dsub_rn(sqrt(__dadd_rn(gxy2, __dmul_rn(ez, ez))), a.g_R);
+                double m = 0.0;
+                if (dist <= -a.g_h) m = 1.0;
+                else if (dist < a.g_h) m = 0.5 * (1.0 + cos((dist + a.g_h) * 3.14159265358979323846 / (2.0 * a.g_h)));
+                const double chi = m * a.C_eta_inv;
+                penal[0] = -chi * (u - a.g_v[0]);
+                penal[1] = -chi * (v - a.g_v[1]);
+                penal[2] = -chi * (w - a.g_v[2]);
+            } else if (a.mask) {
+                const int color = (int)a.mask[g0 + 4 * CS];
+                const double chi = a.mask[g0] * (color == 0 ? 0.0 : a.C_eta_inv);
+                penal[0] = -chi * (u - a.mask[g0 + 1 * CS]);
+                penal[1] = -chi * (v - a.mask[g0 + 2 * CS]);
+                penal[2] = -chi * (w - a.mask[g0 + 3 * CS]);
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                double adv;
+                if (SKEW) adv = -0.5 * (cv[0][c] + cv[1][c] + cv[2][c] + u * d1v[0][c] + v * d1v[1][c] + w * d1v[2][c]);
+                else adv = (-u * d1v[0][c] - v * d1v[1][c] - w * d1v[2][c]);
+                rhs[c] = adv - d1v[c][3] + a.nu * (d2v[0][c] + d2v[1][c] + d2v[2][c]) + penal[c];
+            }
+            rhs[3] = -c02 * (d1v[0][0] + d1v[1][1] + d1v[2][2]) - a.gamma_p * p;
+            if (a.use_sponge && a.mask) {
+                const double spo = a.mask[g0 + 5 * CS] * a.C_sponge_inv;
+                rhs[0] = rhs[0] - (u - a.u_mean_set[0]) * spo;
+                rhs[1] = rhs[1] - (v - a.u_mean_set[1]) * spo;
+                rhs[2] = rhs[2] - (w - a.u_mean_set[2]) * spo;
+                rhs[3] = rhs[3] - p * spo;
+            }
+            uabs_max = fmax(uabs_max, fmax(fmax(fabs(ctr[0]), fabs(ctr[1])), fmax(fabs(ctr[2]), fabs(ctr[3]))));
+            double un[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (a.k_out) a.k_out[gi + c * CS] = rhs[c];
+                if (a.u_out) {
+                    double acc = base_u_global ? a.u0[gi + c * CS] : ctr[c];
+                    for (int l = 0; l < a.n_prev; ++l) acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dt, a.coef_prev[l]), a.k_prev[l][gi + c * CS]));
+                    if (a.use_self) acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dt, a.coef_self), rhs[c]));
+                    a.u_out[gi + c * CS] = acc;
+                    un[c] = acc;
+                }
+                if (a.acc_out) {
+                    double acc = base_acc_global ? a.acc_in[gi + c * CS] : ctr[c];
+                    if (a.use_acc) acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dt, a.coef_acc), rhs[c]));
+                    a.acc_out[gi + c * CS] = acc;
+                }
+            }
+            if (a.dtmin_bits && a.u_out)
+                umag_max = fmax(umag_max, __dadd_rn(__dadd_rn(__dmul_rn(un[0], un[0]), __dmul_rn(un[1], un[1])), __dmul_rn(un[2], un[2])));
+        }
+        __syncthreads();   // plane z leaves the ring in the next iteration
+    }
+    const int lane = tid & 31, wid = tid >> 5;
+    uabs_max = warp_max(uabs_max);
+    umag_max = warp_max(umag_max);
+    if (lane == 0) s_red[wid] = uabs_max;
+    __syncthreads();
+    if (tid == 0) {
+        double m = 0.0;
+        for (int i = 0; i < 8; ++i) m = fmax(m, s_red[i]);
+        if (m > 1.0e12) atomicExch(a.diverged, 1);
+    }
+    if (a.dtmin_bits && a.u_out) {
+        __syncthreads();
+        if (lane == 0) s_red[wid] = umag_max;
+        __syncthreads();
+        if (tid == 0) {
+            double m = 0.0;
+            for (int i = 0; i < 8; ++i) m = fmax(m, s_red[i]);
+            const double u_eigen = __dadd_rn(sqrt(m), sqrt(__dadd_rn(c02, m)));
+            double dxmin = dx;
+            if (a.dim_min_axes > 1) dxmin = fmin(dxmin, dy);
+            if (a.dim_min_axes > 2) dxmin = fmin(dxmin, dz);
+            double dtb = (u_eigen >= 1.0e-6) ? __ddiv_rn(__dmul_rn(a.CFL, dxmin), u_eigen) : 1.0e-2;
+            if (a.nu > 1.0e-13) dtb = fmin(dtb, __ddiv_rn(__dmul_rn(a.CFL_nu, __dmul_rn(dxmin, dxmin)), a.nu));
+            atomicMin(a.dtmin_bits, (unsigned long long)__double_as_longlong(dtb));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // 2-D stage kernel: RHS_2D_acm (LIB/EQUATION/ACMnew/rhs_ACM.f90:292-922) + the same Runge-Kutta epilogue.
 // One CTA per block; the whole ghosted tile (3 components, Bs+2H squared, at most ~40 KB at Bs=32) is staged in shared memory
 // with the four face halos gathered from the neighbours' interiors (star stencils do not read corners).  Bs is a run-time
@@ -821,16 +1031,42 @@ int32_t launch_stage_t(wgpu_ctx *ctx, const StageArgs &a, int n_blocks)
     return WGPU_OK;
 }
 
+// any other even block size: run-time Bs, xy tiles of at most 16 x 16 points
+template <int FD, bool SKEW>
+int32_t launch_stage_any(wgpu_ctx *ctx, const StageArgs &a, int n_blocks)
+{
+    const int Bs = ctx->cfg.Bs[0];
+    if (Bs != ctx->cfg.Bs[1] || Bs != ctx->cfg.Bs[2]) {
+        ctx->err = "3-D stage kernel: cubic blocks only";
+        return WGPU_ERR_UNSUPPORTED;
+    }
+    constexpr int H = St<FD>::H;
+    const int ntile = (Bs + 15) / 16, T = (Bs + ntile - 1) / ntile;
+    const size_t smem = sizeof(double) * (size_t)(2 * H + 1) * 4 * (T + 2 * H) * (T + 2 * H);
+    static bool configured = false;
+    if (!configured) {
+        WGPU_CHECK(ctx, cudaFuncSetAttribute(stage_kernel_any<FD, SKEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        configured = true;
+    }
+    const bool prof = ctx->profiling && ctx->prof_n < (int)ctx->prof_ev.size() / 2;
+    if (prof) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], ctx->stream);
+    const long long grid = (long long)n_blocks * ntile * ntile;
+    stage_kernel_any<FD, SKEW><<<(unsigned)grid, 256, smem, ctx->stream>>>(a, Bs, T, ntile);
+    if (prof) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n++ + 1], ctx->stream);
+    ctx->launches++;
+    WGPU_CHECK(ctx, cudaGetLastError());
+    return WGPU_OK;
+}
+
 template <int FD, bool SKEW>
 int32_t launch_stage_bs(wgpu_ctx *ctx, const StageArgs &a, int n_blocks)
 {
+    if (getenv("WGPU_STAGE_GENERIC")) return launch_stage_any<FD, SKEW>(ctx, a, n_blocks);   // tests compare the two paths
     switch (ctx->cfg.Bs[0]) {
     case 16: return launch_stage_t<FD, SKEW, 16>(ctx, a, n_blocks);
     case 18: return launch_stage_t<FD, SKEW, 18>(ctx, a, n_blocks);
     case 20: return launch_stage_t<FD, SKEW, 20>(ctx, a, n_blocks);
-    default:
-        ctx->err = "3-D stage kernel is instantiated for Bs in {16,18,20}";
-        return WGPU_ERR_UNSUPPORTED;
+    default: return launch_stage_any<FD, SKEW>(ctx, a, n_blocks);
     }
 }
 

@@ -64,7 +64,10 @@ struct WaveArgs {
     const double *src;
     double *dst;
     const int *active;
-    const int *nbr;
+    const int *nbr;      // d_nbr, or d_wnbr on grids with level jumps (codes <= -2: patch of the wavelet jump pool)
+    const double *wpool;
+    const long long *woff;
+    int fw;              // depth of the pool patches (wjump_depth >= f)
     int nc, Bs, f;       // f = halo depth gathered = max filter half width of the transform direction
     int inverse;         // 0: decomposition (HD/GD), 1: reconstruction (HR/GR on zero-stuffed SC/WC)
     WaveFilters w;
@@ -103,7 +106,14 @@ __global__ void __launch_bounds__(256) wavelet_kernel(const WaveArgs a)
             split(x, Bs, dx, lx);
             const int sb = s_code[(dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)];
             if (sb >= 0) cp_async8(dstp + i, a.src + ((long long)sb * a.nc + c) * CS + ((long long)lz * Bs + ly) * Bs + lx);
-            else dstp[i] = 0.0;   // no neighbour (non-periodic boundary)
+            else if (sb <= -2) {
+                // ghost patch across a level jump (jump_fill_kernel: decimation / prediction / coarse-extension values), fw deep, laid out
+                // like the ghost region: extents (dx ? fw : Bs, ...), origin at Bs - fw on the low sides
+                const int fw = a.fw;
+                const int ex = dx ? fw : Bs, ey = dy ? fw : Bs, ez = dz ? fw : Bs;
+                const int ox = dx < 0 ? Bs - fw : 0, oy = dy < 0 ? Bs - fw : 0, oz = dz < 0 ? Bs - fw : 0;
+                cp_async8(dstp + i, a.wpool + a.woff[-2 - sb] + (long long)c * ex * ey * ez + ((long long)(lz - oz) * ey + (ly - oy)) * ex + (lx - ox));
+            } else dstp[i] = 0.0;   // no neighbour (non-periodic boundary)
         }
     };
 
@@ -644,7 +654,7 @@ int32_t launch_fast(wgpu_ctx *ctx, const double *src, double *dst, int inverse, 
 {
     const int X = ctx->wavelet.X, Y = ctx->wavelet.Y;
     handled = false;
-    if (getenv("WGPU_WAVELET_GENERIC") && !ctx->has_jumps) return WGPU_OK;   // tests compare the two paths
+    if (getenv("WGPU_WAVELET_GENERIC")) return WGPU_OK;   // tests compare the two paths
     if (X == 2 && Y == 0) return launch_fast_bs<2, 0>(ctx, src, dst, inverse, handled);
     if (X == 2 && Y == 2) return launch_fast_bs<2, 2>(ctx, src, dst, inverse, handled);
     if (X == 4 && Y == 0) return launch_fast_bs<4, 0>(ctx, src, dst, inverse, handled);
@@ -862,6 +872,9 @@ int32_t wgpu_launch_wavelet(wgpu_ctx *ctx, const double *src, double *dst, int i
     a.dst = dst;
     a.active = ctx->d_active;
     a.nbr = ctx->d_nbr;
+    a.wpool = ctx->d_wpool;
+    a.woff = ctx->d_woff;
+    a.fw = 0;
     a.nc = ctx->nc;
     a.Bs = c.Bs[0];
     a.inverse = inverse;
@@ -917,13 +930,22 @@ int32_t wgpu_launch_wavelet(wgpu_ctx *ctx, const double *src, double *dst, int i
         }
         int32_t rc = launch_fast(ctx, src, dst, inverse, handled);
         if (rc || handled) return rc;
+        // any other (wavelet, even Bs): the table-driven kernel, ghost patches across level jumps read from the same pool
         if (ctx->has_jumps) {
-            ctx->err = "wavelet transform on a grid with level jumps: only the specialised kernels (CDF20/22/40/42/44/60/62, Bs 16/18/20/24) are built";
-            return WGPU_ERR_UNSUPPORTED;
+            a.nbr = ctx->d_wnbr;
+            a.fw = ctx->wjump_depth;
+            if (a.fw < f) {
+                ctx->err = "wavelet transform: the ghost patches are shallower than the filter";
+                return WGPU_ERR_UNSUPPORTED;
+            }
         }
     }
     const int n = a.Bs + 2 * f;
     const size_t smem = sizeof(double) * ((size_t)2 * n * n + (size_t)n * a.Bs + (size_t)(2 * f + 2) * a.Bs * a.Bs);
+    if (smem > 227 * 1024) {
+        ctx->err = "wavelet transform: block too large for the shared-memory ring of the table-driven kernel";
+        return WGPU_ERR_UNSUPPORTED;
+    }
     static size_t configured = 0;
     if (smem > configured) {
         WGPU_CHECK(ctx, cudaFuncSetAttribute(wavelet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -361,6 +361,7 @@ class FullTree:
         if force_maxlevel_dealiasing:
             sig &= self.level != self.forest.Jmax
         i32 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        t0 = time.perf_counter()
         sig8 = np.ascontiguousarray(sig, dtype=np.uint8)
         st32 = np.ascontiguousarray(st0, dtype=np.int32)
         cap = max(4 * int(sig8.sum()) + 64, 1024)
@@ -377,7 +378,12 @@ class FullTree:
         if len(b) == 0:
             return st
         dcode = np.array([(d[2] + 1) * 9 + (d[1] + 1) * 3 + (d[0] + 1) for d in self.dirs], dtype=np.int32)
+        if getattr(self, "timing", None) is not None:
+            t0 = self._tick(f"  sz: pairs (host)", t0)
         det = sol.patch_details(self.slots[b].astype(np.int32), dcode[q], WD)
+        if getattr(self, "timing", None) is not None:
+            self.timing["  sz: n_pairs"] = len(b)
+            t0 = self._tick("  sz: wgpu_patch_details", t0)
         tc = np.ones(nc, np.int32) if thresh_comp is None else np.asarray(thresh_comp, dtype=np.int32)
         e = np.full(nc, eps, dtype=np.float64) * (1.0 if norm is None else np.asarray(norm, dtype=np.float64))
         d_use = np.where(tc[None, :] == 0, 0.0, det)
@@ -427,9 +433,10 @@ class FullTree:
             ci = np.flatnonzero(cand)
             if len(ci):
                 st0[ci[np.asarray(mask_keeps(self.level[ci], self.pos[ci]), dtype=bool)]] = 0
+        t0 = time.perf_counter()
         if use_security_zone and indicator != "everywhere":
             st0 = self.security_zone(st0, eps, norm, thresh_comp, force_maxlevel_dealiasing)
-        t0 = time.perf_counter()
+            t0 = self._tick("security zone", t0)
         st = self.decide(st0)
         t0 = self._tick("decide", t0)
         info = {"status0": self.status_dict(st0), "status": self.status_dict(st)} if want_info else {}

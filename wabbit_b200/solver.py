@@ -397,6 +397,17 @@ class WabbitGPU:
             # the reference's full-tree algorithm (wabbit_b200/fulltree.py; for lifted wavelets with the coarse extension), which can remove
             # several levels in one call; the security zone is on unless params.useSecurityZone = 0 (the reference's default)
             from .fulltree import FullTree
+            import os
+            import time as _time
+            _tm = {} if os.environ.get("WABBIT_FT_TIMING") else None
+            _t0 = _time.perf_counter()
+
+            def _lap(name):
+                nonlocal _t0
+                if _tm is not None:
+                    self.synchronize()
+                    _tm[name] = round((_time.perf_counter() - _t0) * 1e3, 2)
+                    _t0 = _time.perf_counter()
             if eps_norm != "Linfty" and eps_normalized:
                 norm_l = self.componentWiseNorm_tree((HVY_BLOCK, 0), eps_norm)
             else:
@@ -404,12 +415,17 @@ class WabbitGPU:
             if norm_l is not None:
                 norm_l = threshold_norm(norm_l, thresh_comp)
             n0 = forest.n_blocks
+            _lap("norm")
             ft = FullTree(self, forest, Jmin=Jmin)
+            _lap("FullTree init")
             sz = (lifted if self.params.useSecurityZone < 0 else bool(self.params.useSecurityZone)) if useSecurityZone is None else bool(useSecurityZone)
             new, _info = ft.adapt(eps=self.params.eps if eps is None else eps, norm=norm_l, eps_norm=eps_norm, thresh_comp=thresh_comp,
                                   force_maxlevel_dealiasing=force_maxlevel_dealiasing, want_info=False, use_security_zone=sz,
                                   mask_keeps=mask_keeps)
             self.refinement_status = ft.leaf_status          # lgt_block(:, IDX_REFINE_STS) after adapt_tree, in the order of new.active(0)
+            _lap("ft.adapt")
+            if _tm is not None:
+                print("adapt_tree phases [ms]:", _tm, flush=True)
             return new, n0, new.n_blocks
         if mask_keeps is not None:
             raise ValueError("adapt_tree: threshold_mask needs the full-tree algorithm")
