@@ -472,6 +472,7 @@ int32_t wgpu_destroy(wgpu_ctx *ctx)
     cudaFree(ctx->d_wnbr);
     cudaFree(ctx->d_woff);
     cudaFree(ctx->d_wpool);
+    cudaFree(ctx->d_pd_out);
     cudaFree(ctx->d_bflag);
     cudaFree(ctx->d_rel);
     cudaFree(ctx->d_cnt);
@@ -1160,8 +1161,15 @@ int32_t wgpu_patch_details(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_
     }
     int32_t rc = upload_ids(ctx, 2, ids);
     if (rc) return rc;
-    double *d_out = nullptr;
-    WGPU_CHECK(ctx, cudaMalloc((void **)&d_out, sizeof(double) * (size_t)n * ctx->nc));
+    if ((size_t)n * ctx->nc > ctx->pd_cap) {   // persistent scratch: cudaMalloc / cudaFree per call cost more than the kernel
+        cudaFree(ctx->d_pd_out);
+        ctx->d_pd_out = nullptr;
+        ctx->pd_cap = 0;
+        const size_t want = (size_t)n * ctx->nc + (size_t)n * ctx->nc / 2 + 1024;
+        if ((rc = dmalloc(ctx, &ctx->d_pd_out, want))) return rc;
+        ctx->pd_cap = want;
+    }
+    double *d_out = ctx->d_pd_out;
     // strip depth = Nwcl / Nwcr of setup_wavelet incl. the widening to the FD stencil (securityZone_tree.f90:166-167)
     const WaveFilters &w = ctx->wavelet;
     const int H = c.fd == 2 ? 1 : (c.fd == 4 ? 2 : 3);
@@ -1176,7 +1184,6 @@ int32_t wgpu_patch_details(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_
             rc = WGPU_ERR_CUDA;
         }
     }
-    cudaFree(d_out);
     return rc;
 }
 

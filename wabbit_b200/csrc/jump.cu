@@ -285,18 +285,21 @@ struct RefineArgs {
     const int *daughter;    // [n][2^dim] 0-based, digit order
     const signed char *level;
     const int *ixyz;
+    int nslab, fz;          // the daughter's z range is cut into nslab slabs of fz planes (one CTA each): bounds the shared memory for large blocks
 };
 
-// grid (2^dim, n, nc); one daughter component per CTA
+// grid (2^dim * nslab, n, nc); one z slab of one daughter component per CTA
 __global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a)
 {
     extern __shared__ __align__(16) double sm[];
     __shared__ SrcTable T;
     const int Bs = a.f.Bs, dim = a.f.dim, order = a.f.order, A = order / 2 - 1, half = Bs / 2;
-    const int digit = blockIdx.x, m = a.mother[blockIdx.y], c = blockIdx.z;
+    const int digit = blockIdx.x % (1 << dim), slab = blockIdx.x >> dim, m = a.mother[blockIdx.y], c = blockIdx.z;
     const int q[3] = {(digit >> 1) & 1, digit & 1, (digit >> 2) & 1};   // refinementExecute.f90: bit0 -> y, bit1 -> x, bit2 -> z
     const int lvl = a.level[m];
-    // box of the mother's (ghosted) lattice this daughter is interpolated from: [q*Bs/2 - A, q*Bs/2 + Bs/2 + A]
+    // box of the mother's (ghosted) lattice this daughter is interpolated from: [q*Bs/2 - A, q*Bs/2 + Bs/2 + A]; along z only the part
+    // this slab of the daughter (fine planes [slab*fz, slab*fz + fz)) needs
+    const int last = dim == 3 ? 2 : -1, z0 = slab * a.fz, fzn = min(a.fz, Bs - z0);
     int clo[3], n[3], flo[3], fext[3];
     for (int k = 0; k < 3; ++k) {
         if (k < dim) {
@@ -304,6 +307,12 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a)
             n[k] = half + 2 * A + 1;
             flo[k] = 2 * (a.ixyz[3 * m + k] * Bs + q[k] * half);
             fext[k] = Bs;
+            if (k == last && a.nslab > 1) {
+                flo[k] += z0;
+                fext[k] = fzn;
+                clo[k] = (flo[k] >> 1) - A;
+                n[k] = ((flo[k] + fzn - 1 + 1) >> 1) + A - clo[k] + 1;
+            }
         } else {
             clo[k] = 0;
             n[k] = 1;
@@ -331,7 +340,7 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a)
             if (!side) {
                 lo[k] = b0 > i0 ? b0 : i0;
                 ext[k] = (b1 < i1 ? b1 : i1) - lo[k] + 1;
-            } else if (q[k] == 0) {                                         // below the mother
+            } else if (b0 < i0) {                                           // below the mother (a box reaches out on one side only)
                 lo[k] = b0;
                 ext[k] = i0 - b0;
             } else {                                                        // above
@@ -346,7 +355,7 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a)
     }
     __syncthreads();
     const long long CS = (long long)Bs * Bs * (dim == 3 ? Bs : 1);
-    double *out = a.dst + ((long long)a.daughter[blockIdx.y * (1 << dim) + digit] * a.f.nc + c) * CS;
+    double *out = a.dst + ((long long)a.daughter[blockIdx.y * (1 << dim) + digit] * a.f.nc + c) * CS + (a.nslab > 1 ? (long long)z0 * Bs * Bs : 0);
     predict_from_box(cb, clo, n, flo, fext, order, dim, out, Bs, (long long)Bs * Bs, threadIdx.x, blockDim.x);
 }
 
@@ -566,14 +575,25 @@ int32_t wgpu_launch_refine(wgpu_ctx *ctx, const double *src, double *dst, const 
     a.ixyz = ctx->d_ixyz;
     const int A = a.f.order / 2 - 1, Bs = c.Bs[0], half = Bs / 2;
     const int nn = half + 2 * A + 1;
-    const int n3[3] = {nn, nn, c.dim == 3 ? nn : 1}, fe[3] = {Bs, Bs, c.dim == 3 ? Bs : 1};
-    size_t own = (size_t)n3[0] * n3[1] * n3[2] + (size_t)fe[0] * n3[1] * n3[2] + (size_t)fe[0] * fe[1] * n3[2];
-    const size_t sub = fill_scratch_doubles(n3, a.f.order, c.dim);
-    const size_t smem = (own + sub) * sizeof(double);
+    // z slabs of the daughter until the coarse box and the two intermediates of the prediction fit into ~110 KB (two CTAs per SM)
+    a.nslab = 1;
+    a.fz = Bs;
+    size_t smem = 0;
+    for (;;) {
+        const int nz = c.dim == 3 ? (a.nslab == 1 ? nn : a.fz / 2 + 2 * A + 2) : 1;
+        const int n3[3] = {nn, nn, nz}, fe[3] = {Bs, Bs, c.dim == 3 ? a.fz : 1};
+        const size_t own = (size_t)n3[0] * n3[1] * n3[2] + (size_t)fe[0] * n3[1] * n3[2] + (size_t)fe[0] * fe[1] * n3[2];
+        const size_t sub = fill_scratch_doubles(n3, a.f.order, c.dim);
+        smem = (own + sub) * sizeof(double);
+        if (smem <= 110 * 1024 || c.dim == 2 || a.fz <= 4) break;
+        a.nslab *= 2;
+        a.fz = (Bs / a.nslab + 1) & ~1;          // even slabs: fine plane 2i coincides with coarse plane i
+    }
+    a.nslab = c.dim == 3 ? (Bs + a.fz - 1) / a.fz : 1;
     static size_t configured = 0;
     int32_t rc = ensure_smem(ctx, refine_kernel, smem, configured);
     if (rc) return rc;
-    dim3 grid(1 << c.dim, n, ctx->nc);
+    dim3 grid((1 << c.dim) * a.nslab, n, ctx->nc);
     refine_kernel<<<grid, 256, smem, ctx->stream>>>(a);
     ctx->launches++;
     WGPU_CHECK(ctx, cudaGetLastError());

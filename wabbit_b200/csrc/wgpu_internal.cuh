@@ -177,6 +177,8 @@ struct wgpu_ctx {
     size_t topo_in_cap = 0;
     int *d_halo_ids = nullptr;
     size_t halo_ids_cap = 0;
+    double *d_pd_out = nullptr;        // result scratch of wgpu_patch_details
+    size_t pd_cap = 0;
     int *d_idbuf[3] = {nullptr, nullptr, nullptr};   // scratch id lists (refine / coarsen)
     size_t idbuf_cap[3] = {0, 0, 0};
     // Runge-Kutta step in flight
