@@ -292,10 +292,22 @@ int32_t wgpu_rk_steps(wgpu_ctx *ctx, double time, int32_t n_steps, double *time_
                 continue;
             }
             if ((rc = stage_exchange(ctx, j))) return rc;
-            if (ctx->n_bnd && ctx->n_int) {
-                if ((rc = wgpu_rk_stage(ctx, j, WGPU_BLOCKS_INTERIOR))) return rc;   // while the patches / blocks are in flight
+            if (ctx->n_bnd && ctx->n_int && ctx->n_jump == 0) {
+                // uniform grid: the partition-boundary blocks run on the communication stream right behind the exchange, CONCURRENTLY with
+                // the interior blocks on the main stream (the two launches share the SMs: one tail instead of two partial last waves);
+                // the next stage's pack waits for both
+                if ((rc = wgpu_rk_stage(ctx, j, WGPU_BLOCKS_INTERIOR))) return rc;
+                cudaStream_t main_stream = ctx->stream;
+                ctx->stream = ctx->comm_stream;
+                rc = wgpu_rk_stage(ctx, j, WGPU_BLOCKS_BOUNDARY);
+                ctx->stream = main_stream;
+                if (rc) return rc;
+                WGPU_CHECK(ctx, cudaEventRecord(ctx->ev_xchg, ctx->comm_stream));
                 WGPU_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_xchg, 0));
-                if ((rc = wgpu_rk_stage(ctx, j, WGPU_BLOCKS_BOUNDARY))) return rc;
+            } else if (ctx->n_bnd && ctx->n_int) {
+                if ((rc = wgpu_rk_stage(ctx, j, WGPU_BLOCKS_INTERIOR))) return rc;   // while the blocks are in flight
+                WGPU_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_xchg, 0));
+                if ((rc = wgpu_rk_stage(ctx, j, WGPU_BLOCKS_BOUNDARY))) return rc;   // (level-jump patches are refreshed in between: same stream)
             } else {
                 WGPU_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_xchg, 0));
                 if ((rc = wgpu_rk_stage(ctx, j, WGPU_BLOCKS_ALL))) return rc;
