@@ -151,6 +151,16 @@ int32_t wgpu_upload(wgpu_ctx *ctx, int32_t array_id, int32_t slot, const int32_t
                     const double *host, int32_t ncomp_host);
 int32_t wgpu_download(wgpu_ctx *ctx, int32_t array_id, int32_t slot, const int32_t *hvy_ids, int32_t n,
                       double *host, int32_t ncomp_host, int32_t g_sync);
+/* wgpu_set_transfer_mode: how a PAGE-LOCKED 3-D host array crosses PCIe, per direction (no reference counterpart: the reference's
+ *   hvy arrays never leave host memory; this is the cost of the drop-in boundary of RungeKuttaGeneric, runge_kutta_generic.f90:136-154).
+ *   1 (default): copy engines -- for every interior xy plane the contiguous span first..last interior node is moved by DMA
+ *      (cudaMemcpy3DAsync, rows of (Bs-1)*nx+Bs doubles) and a layout kernel converts between that and the resident arrays; uploads and
+ *      downloads of different contexts run concurrently at the full rate of each direction.  A download with g_sync = 0 then also writes
+ *      the x ghost nodes that lie between the interior rows: with the same-level x neighbour's values (what sync_ghosts would put
+ *      there), or 0 where no such neighbour is resident on this GPU.  Ghost nodes are invalid after a time step in the reference too.
+ *   0: the layout kernels read / write the host array directly (zero-copy); exactly the interiors (+ the g_sync shell) are touched.
+ *   Pageable host arrays, 2-D, g_sync > 0 and ncomp_host != the array's component count always take the other paths. */
+int32_t wgpu_set_transfer_mode(wgpu_ctx *ctx, int32_t upload_mode, int32_t download_mode);
 
 /*
  * ---- compute ----

@@ -181,6 +181,7 @@ def test_page_locked_host_arrays_take_the_direct_path_with_identical_results():
         pinned = torch.empty(u.shape, dtype=torch.float64, pin_memory=True)
         pn = pinned.numpy()
         pn[:] = u
+        sol.set_transfer_mode(False, False)        # zero-copy layout kernels (the copy engines: next test)
         n0 = sol.launch_count
         sol.upload(pn)
         assert sol.launch_count - n0 == 1          # one kernel, no staging chunks
@@ -190,6 +191,43 @@ def test_page_locked_host_arrays_take_the_direct_path_with_identical_results():
             pn[:] = -7.0
             sol.download(pn, g_sync=gs)
             assert np.array_equal(a, pn), (graded, gs)
+        sol.close()
+
+
+@pytest.mark.parametrize("Bs,wavelet", [(16, "CDF44"), (18, "CDF40"), (22, "CDF42")])
+def test_copy_engine_transfers_of_page_locked_host_arrays(Bs, wavelet):
+    """default path of wgpu_upload / wgpu_download(g_sync=0) for page-locked 3-D arrays (wgpu_set_transfer_mode): plane spans by DMA + a
+    layout kernel.  Interiors are exact; on a download the x ghost nodes between the interior rows hold the same-level neighbour's values;
+    nothing outside the spans is touched."""
+    import torch
+    for graded in (False, True):
+        if graded:
+            lv, ix = graded_blocks(3, 1, 3, seed=9)
+            forest = Forest.from_blocks(3, 3, lv, ix)
+        else:
+            forest = Forest.uniform(3, 2, Jmax=3)
+        w, p, po, grid, sol, u = _case(wavelet, Bs, forest, seed=8)
+        g, n = p.g, grid.n
+        pinned = torch.empty(u.shape, dtype=torch.float64, pin_memory=True)
+        pn = pinned.numpy()
+        pn[:] = u
+        sol.upload(pn)                                         # copy engines
+        a = np.full_like(u, -7.0)
+        sol.download(a, g_sync=0)                              # pageable: staged path
+        I = (slice(0, n), slice(None)) + O.interior(po)
+        assert np.array_equal(a[I], u[I]), graded
+        pn[:] = -7.0
+        sol.download(pn, g_sync=0)                             # copy engines
+        assert np.array_equal(pn[I], u[I]), graded
+        span = np.zeros(u.shape[2:], dtype=bool)               # [z, y, x]: the nodes a plane span covers
+        flat = span[g:g + Bs].reshape(Bs, -1)
+        nx = Bs + 2 * g
+        flat[:, g * nx + g: (g + Bs - 1) * nx + g + Bs] = True
+        assert (pn[:n][:, :, ~span] == -7.0).all(), graded
+        if not graded:
+            ref = u.copy()
+            O.sync_ghosts_leaf(grid, po, ref, forest.neighbors(0)[:, :n], g, g, w.X, True)
+            assert np.array_equal(pn[:n][:, :, span], ref[:n][:, :, span])
         sol.close()
 
 

@@ -380,7 +380,9 @@ int32_t wgpu_create(const wgpu_config *cfg, wgpu_ctx **out)
     if (cfg->n_stages < 1 || cfg->n_stages > WGPU_MAX_STAGES) return fail(nullptr, WGPU_ERR_ARG, "n_stages out of range");
     if (cfg->max_blocks < 1) return fail(nullptr, WGPU_ERR_ARG, "max_blocks must be positive");
     if (cfg->Jmax < 0 || cfg->Jmax >= WGPU_MAX_LEVELS) return fail(nullptr, WGPU_ERR_ARG, "Jmax out of range");
-    if (cfg->n_eqn != cfg->dim + 1) return fail(nullptr, WGPU_ERR_UNSUPPORTED, "ACM needs number_equations = dim+1");
+    // the wavelet side (decomposition, thresholding, refinement, coarsening, ghost synchronisation) works for any number of components --
+    // post_compression_unit_test.f90 runs it with number_equations = 1; the ACM time stepper needs dim + 1 (checked where it starts)
+    if (cfg->n_eqn < 1 || cfg->n_eqn > 16) return fail(nullptr, WGPU_ERR_UNSUPPORTED, "number_equations must be in 1..16");
     if (cfg->n_mask != 0 && cfg->n_mask != 5 && cfg->n_mask != 6) return fail(nullptr, WGPU_ERR_ARG, "n_mask must be 0, 5 or 6");
 
     int ndev = 0;
@@ -490,6 +492,12 @@ int32_t wgpu_destroy(wgpu_ctx *ctx)
     cudaFree(ctx->d_time);
     cudaFree(ctx->d_flags);
     cudaFree(ctx->d_stage);
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(ctx->d_span[k]);
+        if (ctx->ev_dma[k]) cudaEventDestroy(ctx->ev_dma[k]);
+        if (ctx->ev_lay[k]) cudaEventDestroy(ctx->ev_lay[k]);
+    }
+    if (ctx->dma_stream) cudaStreamDestroy(ctx->dma_stream);
     for (auto &e : ctx->prof_ev) cudaEventDestroy(e);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->h_bounce) cudaFreeHost(ctx->h_bounce);
@@ -778,6 +786,81 @@ int32_t wgpu_set_topology(wgpu_ctx *ctx, int32_t n_active, const int32_t *hvy_ac
     return WGPU_OK;
 }
 
+// Copy-engine path of wgpu_upload / wgpu_download(g_sync = 0) for page-locked host arrays in 3-D (see span_unpack_kernel): chunks of blocks
+// are double-buffered so that the DMA of chunk k+1 runs while the layout kernel works on chunk k.  `ids`: 0-based block indices (also in
+// d_idbuf[0]).
+static int32_t move_blocks_dma(wgpu_ctx *ctx, bool up, double *dev, int nc, const std::vector<int> &ids, double *host)
+{
+    const wgpu_config &c = ctx->cfg;
+    const int n = (int)ids.size();
+    const int Bx = c.Bs[0], By = c.Bs[1], Bz = c.Bs[2], g = c.g, nx = Bx + 2 * g, ny = By + 2 * g, nz = Bz + 2 * g;
+    const size_t plane_pitch = (size_t)nx * ny * 8, span = ((size_t)(By - 1) * nx + Bx) * 8, pitch = (span + 255) & ~(size_t)255;
+    const size_t per_block = pitch * Bz * nc;
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, ((size_t)64 << 20) / per_block));
+    if (ctx->span_cap < per_block * chunk) {
+        for (int s = 0; s < 2; ++s) {
+            cudaFree(ctx->d_span[s]);
+            ctx->d_span[s] = nullptr;
+            WGPU_CHECK(ctx, cudaMalloc((void **)&ctx->d_span[s], per_block * chunk));
+        }
+        ctx->dev_bytes += 2 * (int64_t)(per_block * chunk) - 2 * (int64_t)ctx->span_cap;
+        ctx->span_cap = per_block * chunk;
+    }
+    if (!ctx->dma_stream) {
+        WGPU_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->dma_stream, cudaStreamNonBlocking));
+        for (int s = 0; s < 2; ++s) {
+            WGPU_CHECK(ctx, cudaEventCreateWithFlags(&ctx->ev_dma[s], cudaEventDisableTiming));
+            WGPU_CHECK(ctx, cudaEventCreateWithFlags(&ctx->ev_lay[s], cudaEventDisableTiming));
+        }
+    }
+    const int64_t host_block = ctx->gblk_elems * nc;
+    auto dma = [&](int s0, int m, char *stg) -> int32_t {
+        int i = 0;
+        while (i < m) {      // consecutive hvy ids are contiguous in the host array: one 3-D copy per run
+            int j = i + 1;
+            while (j < m && ids[s0 + j] == ids[s0 + j - 1] + 1) ++j;
+            cudaMemcpy3DParms p = {};
+            cudaPitchedPtr hp = make_cudaPitchedPtr(host + (int64_t)ids[s0 + i] * host_block, plane_pitch, plane_pitch, (size_t)nz);
+            cudaPitchedPtr dp = make_cudaPitchedPtr(stg + (size_t)i * per_block, pitch, pitch, (size_t)Bz);
+            const cudaPos hpos = make_cudaPos(((size_t)g * nx + g) * 8, (size_t)g, 0), dpos = make_cudaPos(0, 0, 0);
+            p.srcPtr = up ? hp : dp;
+            p.srcPos = up ? hpos : dpos;
+            p.dstPtr = up ? dp : hp;
+            p.dstPos = up ? dpos : hpos;
+            p.extent = make_cudaExtent(span, (size_t)Bz, (size_t)nc * (j - i));
+            p.kind = up ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+            WGPU_CHECK(ctx, cudaMemcpy3DAsync(&p, ctx->dma_stream));
+            i = j;
+        }
+        return WGPU_OK;
+    };
+    int32_t rc;
+    // the staging buffers are free (every call ends synchronised); the device array must be complete before the first pack reads it /
+    // may be overwritten once earlier work on the context's stream is done: the layout kernels run on that stream
+    int k = 0;
+    for (int s0 = 0; s0 < n; s0 += chunk, ++k) {
+        const int m = std::min(chunk, n - s0), s = k & 1;
+        if (up) {
+            if (k >= 2) WGPU_CHECK(ctx, cudaStreamWaitEvent(ctx->dma_stream, ctx->ev_lay[s], 0));
+            if ((rc = dma(s0, m, ctx->d_span[s]))) return rc;
+            WGPU_CHECK(ctx, cudaEventRecord(ctx->ev_dma[s], ctx->dma_stream));
+            WGPU_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_dma[s], 0));
+            if ((rc = wgpu_launch_span_unpack(ctx, (const double *)ctx->d_span[s], dev, ctx->d_idbuf[0] + s0, m, nc, (long long)(pitch / 8), ctx->stream))) return rc;
+            WGPU_CHECK(ctx, cudaEventRecord(ctx->ev_lay[s], ctx->stream));
+        } else {
+            if (k >= 2) WGPU_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_dma[s], 0));
+            if ((rc = wgpu_launch_span_pack(ctx, dev, (double *)ctx->d_span[s], ctx->d_idbuf[0] + s0, m, nc, (long long)(pitch / 8), ctx->stream))) return rc;
+            WGPU_CHECK(ctx, cudaEventRecord(ctx->ev_lay[s], ctx->stream));
+            WGPU_CHECK(ctx, cudaStreamWaitEvent(ctx->dma_stream, ctx->ev_lay[s], 0));
+            if ((rc = dma(s0, m, ctx->d_span[s]))) return rc;
+            WGPU_CHECK(ctx, cudaEventRecord(ctx->ev_dma[s], ctx->dma_stream));
+        }
+    }
+    WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->dma_stream));
+    return WGPU_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ data movement
 static int32_t move_blocks(wgpu_ctx *ctx, bool up, int32_t array_id, int32_t slot, const int32_t *hvy_ids, int32_t n, double *host,
                            int32_t ncomp_host, int32_t g_sync)
@@ -810,6 +893,14 @@ static int32_t move_blocks(wgpu_ctx *ctx, bool up, int32_t array_id, int32_t slo
             }
             int32_t rc = upload_ids(ctx, 0, ids);
             if (rc) return rc;
+            if (ctx->xfer_dma[up ? 0 : 1] && c.dim == 3 && g_sync == 0 && ncomp_host == nc && n >= 8) {
+                // copy engines: interior plane spans by DMA + a layout kernel (both directions of the link at full rate at once); the x ghost
+                // nodes between the interior rows of the host array receive their same-level neighbours' values on a download
+                if ((rc = move_blocks_dma(ctx, up, dev, nc, ids, host))) return rc;
+                if (up && array_id == WGPU_HVY_BLOCK) ctx->dtmin_valid = false;
+                if (up) ctx->det_cached_for = nullptr;
+                return WGPU_OK;
+            }
             for (int s0 = 0; s0 < n && !rc; s0 += 32768) {   // grid.y limit
                 const int m = std::min(32768, n - s0);
                 if (up) rc = wgpu_launch_extract(ctx, hdev, dev, ctx->d_idbuf[0] + s0, m, nc, ncomp_host, 1);
@@ -872,6 +963,14 @@ static int32_t move_blocks(wgpu_ctx *ctx, bool up, int32_t array_id, int32_t slo
     return WGPU_OK;
 }
 
+int32_t wgpu_set_transfer_mode(wgpu_ctx *ctx, int32_t upload_mode, int32_t download_mode)
+{
+    if (!ctx || upload_mode < 0 || upload_mode > 1 || download_mode < 0 || download_mode > 1) return WGPU_ERR_ARG;
+    ctx->xfer_dma[0] = upload_mode;
+    ctx->xfer_dma[1] = download_mode;
+    return WGPU_OK;
+}
+
 int32_t wgpu_upload(wgpu_ctx *ctx, int32_t array_id, int32_t slot, const int32_t *hvy_ids, int32_t n, const double *host, int32_t ncomp_host)
 {
     return move_blocks(ctx, true, array_id, slot, hvy_ids, n, const_cast<double *>(host), ncomp_host, 0);
@@ -918,6 +1017,7 @@ static int32_t check_flags(wgpu_ctx *ctx)
 int32_t wgpu_rhs(wgpu_ctx *ctx, double time, int32_t src_slot, int32_t dst_slot)
 {
     if (!ctx) return WGPU_ERR_ARG;
+    if (ctx->nc != ctx->cfg.dim + 1) return fail(ctx, WGPU_ERR_UNSUPPORTED, "ACM needs number_equations = dim+1");
     int nc = 0;
     const double *src = src_slot == 0 ? ctx->U : array_ptr(ctx, WGPU_HVY_WORK, src_slot, &nc);
     double *dst = array_ptr(ctx, WGPU_HVY_WORK, dst_slot, &nc);
@@ -940,6 +1040,7 @@ int32_t wgpu_rhs(wgpu_ctx *ctx, double time, int32_t src_slot, int32_t dst_slot)
 static int32_t compute_dt(wgpu_ctx *ctx, double time)
 {
     int32_t rc;
+    if (ctx->nc != ctx->cfg.dim + 1) return fail(ctx, WGPU_ERR_UNSUPPORTED, "ACM needs number_equations = dim+1");
     unsigned long long *cur = ctx->d_dtmin + ctx->dtmin_cur, *nxt = ctx->d_dtmin + (ctx->dtmin_cur ^ 1);
     if (!ctx->dtmin_valid && !(ctx->cfg.dt_fixed > 0.0)) {
         const unsigned long long inf = 0x7FF0000000000000ULL;
@@ -1593,6 +1694,7 @@ static bool exchange_pending(wgpu_ctx *ctx) { return !ctx->remote_faces.empty();
 int32_t wgpu_rk_begin(wgpu_ctx *ctx, double time)
 {
     if (!ctx) return WGPU_ERR_ARG;
+    if (ctx->nc != ctx->cfg.dim + 1) return fail(ctx, WGPU_ERR_UNSUPPORTED, "ACM needs number_equations = dim+1");
     ctx->rk_time = time;
     const wgpu_config &c = ctx->cfg;
     if (exchange_pending(ctx)) return fail(ctx, WGPU_ERR_ARG, "topology has neighbours on other ranks: call wgpu_set_exchange first");

@@ -18,6 +18,8 @@
 //
 // NCCL is loaded at run time (dlopen, the copy torch already loaded if there is one): the library itself loads without NCCL.
 #include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -176,7 +178,12 @@ int32_t wgpu_comm_init(wgpu_ctx *ctx, const char *id128, int32_t rank, int32_t w
     ctx->recv_counts.assign(world, 0);
     ctx->rsend_counts.assign(world, 0);
     ctx->rrecv_counts.assign(world, 0);
-    WGPU_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    {
+        // highest priority: the exchange (and the boundary blocks behind it) must not queue behind the interior blocks' CTAs
+        int lo = 0, hi = 0;
+        WGPU_CHECK(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        WGPU_CHECK(ctx, cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, hi));
+    }
     WGPU_CHECK(ctx, cudaEventCreateWithFlags(&ctx->ev_pack, cudaEventDisableTiming));
     WGPU_CHECK(ctx, cudaEventCreateWithFlags(&ctx->ev_xchg, cudaEventDisableTiming));
     WGPU_CHECK(ctx, cudaMalloc((void **)&ctx->d_comm_scratch, 4096 * 8));
@@ -259,9 +266,41 @@ static int32_t stage_exchange(wgpu_ctx *ctx, int j)
     return WGPU_OK;
 }
 
+// WGPU_MG_TRACE=1: timestamps (CUDA events) of the phases of the LAST step of a wgpu_rk_steps call, printed by rank 0 to stderr
+struct MgTrace {
+    std::vector<cudaEvent_t> ev;
+    std::vector<std::string> name;
+    bool on = false;
+    void mark(const char *n, cudaStream_t s)
+    {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        ev.push_back(e);
+        name.push_back(n);
+    }
+    void dump()
+    {
+        if (!on || ev.empty()) return;
+        cudaEventSynchronize(ev.back());
+        fprintf(stderr, "wgpu_rk_steps trace (last step), ms since step start:\n");
+        for (size_t i = 0; i < ev.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[0], ev[i]);
+            fprintf(stderr, "  %8.3f  %s\n", ms, name[i].c_str());
+            }
+        for (auto e : ev) cudaEventDestroy(e);
+        ev.clear();
+        name.clear();
+    }
+};
+
 int32_t wgpu_rk_steps(wgpu_ctx *ctx, double time, int32_t n_steps, double *time_out, double *dt_last)
 {
     if (!ctx || n_steps < 1) return WGPU_ERR_ARG;
+    MgTrace tr;
+    const bool want_trace = getenv("WGPU_MG_TRACE") && ctx->comm_rank == 0 && n_steps > 3;
     const wgpu_config &c = ctx->cfg;
     const bool multi = ctx->comm && ctx->comm_world > 1;
     NcclApi *api = multi ? nccl_api() : nullptr;
@@ -273,6 +312,8 @@ int32_t wgpu_rk_steps(wgpu_ctx *ctx, double time, int32_t n_steps, double *time_
         ~Reset() { c->time_on_device = false; }
     } reset{ctx};
     for (int step = 0; step < n_steps; ++step) {
+        tr.on = want_trace && step == n_steps - 1;
+        tr.mark("step start", ctx->stream);
         if (step > 0) {
             advance_time_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_time);
             ctx->launches++;
@@ -285,8 +326,10 @@ int32_t wgpu_rk_steps(wgpu_ctx *ctx, double time, int32_t n_steps, double *time_
             NCCL_CHECK(ctx, api, api->AllReduce(p, p, 1, NCCL_UINT64, NCCL_MIN, ctx->comm, ctx->stream));
         }
         if ((rc = wgpu_rk_dt(ctx, time))) return rc;
+        tr.mark("dt all-reduced + finalised", ctx->stream);
         for (int j = 1; j <= c.n_stages; ++j) {
             if ((rc = wgpu_pack_halo(ctx, j))) return rc;
+            tr.mark("  packed", ctx->stream);
             if (!multi) {
                 if ((rc = wgpu_rk_stage(ctx, j, WGPU_BLOCKS_ALL))) return rc;
                 continue;
@@ -296,12 +339,15 @@ int32_t wgpu_rk_steps(wgpu_ctx *ctx, double time, int32_t n_steps, double *time_
                 // uniform grid: the partition-boundary blocks run on the communication stream right behind the exchange, CONCURRENTLY with
                 // the interior blocks on the main stream (the two launches share the SMs: one tail instead of two partial last waves);
                 // the next stage's pack waits for both
+                tr.mark("  exchange done (comm stream)", ctx->comm_stream);
                 if ((rc = wgpu_rk_stage(ctx, j, WGPU_BLOCKS_INTERIOR))) return rc;
+                tr.mark("  interior done", ctx->stream);
                 cudaStream_t main_stream = ctx->stream;
                 ctx->stream = ctx->comm_stream;
                 rc = wgpu_rk_stage(ctx, j, WGPU_BLOCKS_BOUNDARY);
                 ctx->stream = main_stream;
                 if (rc) return rc;
+                tr.mark("  boundary done (comm stream)", ctx->comm_stream);
                 WGPU_CHECK(ctx, cudaEventRecord(ctx->ev_xchg, ctx->comm_stream));
                 WGPU_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_xchg, 0));
             } else if (ctx->n_bnd && ctx->n_int) {
@@ -314,7 +360,9 @@ int32_t wgpu_rk_steps(wgpu_ctx *ctx, double time, int32_t n_steps, double *time_
             }
         }
         if ((rc = wgpu_rk_end_nosync(ctx))) return rc;
+        tr.mark("step end", ctx->stream);
     }
+    tr.dump();
     WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_dt, 8, cudaMemcpyDeviceToHost, ctx->stream));
     WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pinned + 1, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pinned + 2, ctx->d_time + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));

@@ -226,6 +226,13 @@ struct wgpu_ctx {
     int64_t stage_elems = 0;
     double *h_bounce = nullptr;
     int64_t bounce_elems = 0;
+    // copy-engine transfers of page-locked host arrays (move_blocks_dma): mode per direction (0: SM-issued zero-copy kernels, 1: DMA of
+    // plane spans + a layout kernel), two staging buffers, a stream per direction
+    int xfer_dma[2] = {1, 1};          // [0] upload, [1] download
+    char *d_span[2] = {nullptr, nullptr};
+    size_t span_cap = 0;
+    cudaStream_t dma_stream = nullptr;
+    cudaEvent_t ev_dma[2] = {nullptr, nullptr}, ev_lay[2] = {nullptr, nullptr};
 };
 
 #define WGPU_CHECK(ctx, call)                                                                  \
@@ -269,3 +276,5 @@ int32_t wgpu_launch_extract(wgpu_ctx *ctx, const double *staged, double *dst, co
                             int ncomp_host, int by_id);
 int32_t wgpu_launch_export(wgpu_ctx *ctx, const double *src, double *staged, const int *d_ids, int n, int ncomp_src,
                            int ncomp_host, int g_sync, int by_id);
+int32_t wgpu_launch_span_unpack(wgpu_ctx *ctx, const double *stg, double *dst, const int *d_ids, int n, int nc, long long pitch, cudaStream_t st);
+int32_t wgpu_launch_span_pack(wgpu_ctx *ctx, const double *src, double *stg, const int *d_ids, int n, int nc, long long pitch, cudaStream_t st);

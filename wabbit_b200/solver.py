@@ -206,6 +206,11 @@ class WabbitGPU:
         gs = self.params.g if g_sync is None else g_sync
         self._check(self._lib.wgpu_download(self._ctx, array_id, slot, _i32(ids), len(ids), C.c_void_p(host_ptr), ncomp, gs))
 
+    def set_transfer_mode(self, upload_dma: bool = True, download_dma: bool = True):
+        """page-locked 3-D host arrays: copy engines (plane spans by DMA + a layout kernel, default) or zero-copy layout kernels, per direction
+        (wgpu_set_transfer_mode)"""
+        self._check(self._lib.wgpu_set_transfer_mode(self._ctx, int(bool(upload_dma)), int(bool(download_dma))))
+
     def set_ghost_filter(self, ignore_filter: bool):
         """ignore_Filter of sync_ghosts_tree (synchronize_ghosts_generic.f90:125-153): False (default) = restriction through the HD
         filter of a lifted wavelet in download(g_sync>0) / waveletDecomposition_tree / refine_tree, True = plain decimation."""
