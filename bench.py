@@ -331,13 +331,14 @@ def run_ours(a):
                        "finite": finite, "checksum": checksum},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * a.bs ** 3 * 8 * nb_local, "d2h_bytes_per_step": 4 * a.bs ** 3 * 8 * nb_local,
                     "steps": e2e_steps * e2e_trees, "trees_in_flight": e2e_trees, "sequential_value": e2e_seq,
+                    "transfer": "copy engines: interior plane spans by cudaMemcpy3DAsync (1.35x the interior bytes at Bs=16, g=3) + layout kernels, "
+                                "double-buffered in 16 MB chunks (wgpu_set_transfer_mode default)",
                     "note": "wgpu_upload(host hvy_block) + wgpu_rk_step + wgpu_download(host hvy_block, g_sync=0) per step: "
-                            "RungeKuttaGeneric's contract -- interiors of the Fortran-layout host array in, interiors out, ghost nodes "
-                            "untouched (runge_kutta_generic.f90:136-154); the host arrays are page-locked, so the layout kernels read / "
-                            "write their interior rows directly over PCIe.  value: `trees_in_flight` independent trees of the forest (each "
+                            "RungeKuttaGeneric's contract -- interiors of the page-locked Fortran-layout host array in, interiors out "
+                            "(runge_kutta_generic.f90:136-154).  value: `trees_in_flight` independent trees of the forest (each "
                             "with its own host array, device context and stream, driven by its own host thread), every step of every tree "
-                            "doing its own upload and download, so that one tree's download overlaps another's upload on the full-duplex "
-                            "link; sequential_value: one tree, upload -> step -> download back to back"},
+                            "doing its own upload and download; transfers of one direction take turns, so one tree's download runs against "
+                            "another's upload on the full-duplex link; sequential_value: one tree, upload -> step -> download back to back"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
@@ -773,8 +774,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--level", type=int, default=5, help="equidistant level J: (2^J)^3 blocks")
     ap.add_argument("--bs", type=int, default=16)
-    ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--e2e-trees", type=int, default=2, help="independent trees in flight in the end-to-end leg (1 = sequential only)")
+    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--e2e-trees", type=int, default=3, help="independent trees in flight in the end-to-end leg (1 = sequential only)")
     ap.add_argument("--cpu-level", type=int, default=3)
     ap.add_argument("--cpu-steps", type=int, default=6)
     ap.add_argument("--no-cpu", action="store_true")

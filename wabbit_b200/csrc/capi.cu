@@ -2,9 +2,11 @@
 // host<->device block movement and the Runge-Kutta driver that sequences the stage kernels.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <new>
 
 #include "resolve.cuh"
@@ -796,7 +798,8 @@ static int32_t move_blocks_dma(wgpu_ctx *ctx, bool up, double *dev, int nc, cons
     const int Bx = c.Bs[0], By = c.Bs[1], Bz = c.Bs[2], g = c.g, nx = Bx + 2 * g, ny = By + 2 * g, nz = Bz + 2 * g;
     const size_t plane_pitch = (size_t)nx * ny * 8, span = ((size_t)(By - 1) * nx + Bx) * 8, pitch = (span + 255) & ~(size_t)255;
     const size_t per_block = pitch * Bz * nc;
-    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, ((size_t)64 << 20) / per_block));
+    static const size_t chunk_mb = getenv("WGPU_DMA_CHUNK_MB") && atoi(getenv("WGPU_DMA_CHUNK_MB")) > 0 ? (size_t)atoi(getenv("WGPU_DMA_CHUNK_MB")) : 16;
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, (chunk_mb << 20) / per_block));
     if (ctx->span_cap < per_block * chunk) {
         for (int s = 0; s < 2; ++s) {
             cudaFree(ctx->d_span[s]);
@@ -835,6 +838,11 @@ static int32_t move_blocks_dma(wgpu_ctx *ctx, bool up, double *dev, int nc, cons
         return WGPU_OK;
     };
     int32_t rc;
+    // One transfer per direction at a time in this process: two contexts (trees) that reach their uploads together would share the H2D
+    // rate and then their downloads the D2H rate, and stay in phase for ever; taking turns costs nothing (the link is busy either way)
+    // and shifts them so that one tree's download runs against the other's upload -- both directions of the link in use.
+    static std::mutex link[2];
+    std::lock_guard<std::mutex> turn(link[up ? 0 : 1]);
     // the staging buffers are free (every call ends synchronised); the device array must be complete before the first pack reads it /
     // may be overwritten once earlier work on the context's stream is done: the layout kernels run on that stream
     int k = 0;
