@@ -327,7 +327,9 @@ def run_ours(a):
                        "host_layout_g": p.g, "block_dist": "sfc_hilbert", "parallelism": f"sfc-partition x{world}",
                        "l2": "inputs larger than L2 (state array %.0f MB per GPU)" % (nb_local * 4 * a.bs ** 3 * 8 / 1e6),
                        "stepping": "K steps issued back to back inside the library (wgpu_rk_steps), time / dt device-resident, one host read-back",
-                       "transport": ("NCCL send/recv inside libwabbit_gpu.so on its own communicator, overlapped with the interior blocks" if world > 1 else "none"),
+                       "transport": (("pack kernel stores the face patches straight into the receivers' pools over NVLink (CUDA IPC) + a flag per peer"
+                                      if sol.comm_transport() == "peer stores" else "NCCL send/recv inside libwabbit_gpu.so on its own communicator")
+                                     + ", overlapped with the interior blocks" if world > 1 else "none"),
                        "finite": finite, "checksum": checksum},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * a.bs ** 3 * 8 * nb_local, "d2h_bytes_per_step": 4 * a.bs ** 3 * 8 * nb_local,
                     "steps": e2e_steps * e2e_trees, "trees_in_flight": e2e_trees, "sequential_value": e2e_seq,

@@ -364,6 +364,14 @@ int32_t wgpu_comm_destroy(wgpu_ctx *ctx);
 int32_t wgpu_comm_info(const wgpu_ctx *ctx, int32_t *rank, int32_t *world);
 int32_t wgpu_comm_set_counts(wgpu_ctx *ctx, const int32_t *send_counts, const int32_t *recv_counts, const int32_t *restrict_send_counts,
                              const int32_t *restrict_recv_counts);
+/* wgpu_comm_set_transport / wgpu_comm_transport: how the face patches of wgpu_set_exchange travel inside wgpu_rk_steps (the reference's
+ *   MPI_Isend / Irecv of xfer_block_data.f90:10-99).  1 (default): PEER STORES -- wgpu_comm_set_counts exports the library's receive pools
+ *   by CUDA IPC, the pack kernel writes every patch straight into the receiver's pool over NVLink and releases a flag per peer, the
+ *   receiver acquires the flags in front of its partition-boundary blocks (no send buffer, no NCCL kernel).  0: grouped ncclSend / ncclRecv.
+ *   If peer access or IPC is unavailable on any rank, every rank uses NCCL (agreed by an all-reduce); wgpu_comm_transport reports which
+ *   transport is active (1 peer stores, 0 NCCL).  Set before wgpu_comm_set_counts. */
+int32_t wgpu_comm_set_transport(wgpu_ctx *ctx, int32_t peer_stores);
+int32_t wgpu_comm_transport(const wgpu_ctx *ctx);
 int32_t wgpu_rk_steps(wgpu_ctx *ctx, double time, int32_t n_steps, double *time_out, double *dt_last);
 int32_t wgpu_exchange_array(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t filtered);
 int32_t wgpu_ship_blocks(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t n_items, const int32_t *src_rank, const int32_t *src_slot,

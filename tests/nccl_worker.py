@@ -1,6 +1,7 @@
 """Worker of tests/test_gpu_nccl.py: one process per GPU (torchrun), the library's own NCCL communicator.  Every rank also computes the
 single-rank result on its own GPU and compares its share bit for bit:
-  uniform   RK4 steps on an equidistant grid, face patches (MultiGPUStepper, wgpu_rk_steps)
+  uniform   RK4 steps on an equidistant grid, face patches (MultiGPUStepper, wgpu_rk_steps): peer stores over NVLink (CUDA IPC) when available
+  uniform_nccl   the same with grouped ncclSend / ncclRecv (wgpu_comm_set_transport(0))
   graded    RK4 steps on a graded grid, halo blocks (HaloStepper, wgpu_rk_steps), then download with a synchronised ghost shell
   cycle     refine_tree -> RK4 -> adapt_tree with the lifted full-tree algorithm (DistributedWabbit: wgpu_ship_blocks, wgpu_exchange_array)
 Exit code 0 = all ranks agree with the single-rank driver."""
@@ -48,7 +49,7 @@ def main():
         g = p.g
         return a[:, :, g:-g, g:-g, g:-g]
 
-    if what == "uniform":
+    if what in ("uniform", "uniform_nccl"):
         p = tg_params(Bs=16, J=3)
         f1, fw = Forest.uniform(3, 3), Forest.uniform(3, 3, n_ranks=world)
         u = state(p, f1)
@@ -61,18 +62,23 @@ def main():
         s1.close()
         s = make(p, fw.max_blocks)
         s.comm_init(rank, world)
+        if what == "uniform_nccl":
+            s.comm_set_transport(False)
         st = attach_exchange(s, fw, rank, world)
         assert st.in_library
+        if what == "uniform_nccl":
+            assert s.comm_transport() == "nccl"
         off = sum(fw.n_active(r) for r in range(rank))
         n = fw.n_active(rank)
         h = np.zeros(s.host_shape())
         h[:n] = u[off:off + n]
         s.upload(h)
-        t2, dt2 = st.steps(0.0, 3)
+        t2, dt2 = st.steps(0.0, 2)
+        t2, dt2 = st.steps(t2, 1)          # a second call: the stage sequence numbers of the peer-store exchange carry on
         out = np.zeros(s.host_shape())
         s.download(out, g_sync=0)
         ok = (t1 == t2) and (dt1 == dt2) and np.array_equal(interior(p, out[:n]), interior(p, ref[off:off + n]))
-        print(f"rank {rank}: uniform t={t2!r} dt={dt2!r} int/bnd={st.n_int}/{st.n_bnd} ok={ok}", flush=True)
+        print(f"rank {rank}: uniform t={t2!r} dt={dt2!r} int/bnd={st.n_int}/{st.n_bnd} transport={s.comm_transport()} ok={ok}", flush=True)
         s.close()
     elif what == "graded":
         wavelet = "CDF44"

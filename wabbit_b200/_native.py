@@ -70,6 +70,8 @@ GPU_SYMBOLS = {
     "wgpu_comm_destroy": (C.c_int32, [C.c_void_p]),
     "wgpu_comm_info": (C.c_int32, [C.c_void_p, _i32p, _i32p]),
     "wgpu_comm_set_counts": (C.c_int32, [C.c_void_p, _i32p, _i32p, _i32p, _i32p]),
+    "wgpu_comm_set_transport": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "wgpu_comm_transport": (C.c_int32, [C.c_void_p]),
     "wgpu_rk_steps": (C.c_int32, [C.c_void_p, C.c_double, C.c_int32, _dp, _dp]),
     "wgpu_exchange_array": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
     "wgpu_ship_blocks": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _i32p, _i32p, _i32p, C.c_int32, _i32p, _i32p]),

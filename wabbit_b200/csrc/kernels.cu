@@ -1058,6 +1058,62 @@ __global__ void __launch_bounds__(256) pack_kernel(const double *__restrict__ sr
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pack + put: the exchange itself, fused into the pack kernel.  One CTA per face patch writes the strip straight into the RECEIVER's patch
+// pool over NVLink (peer memory opened through CUDA IPC, multigpu.cu), in the layout of the receiver's ghost strip.  The last CTA to finish
+// the patches of a peer releases that peer's flag word (value = stage sequence number); wait_flags_kernel on the receiver acquires it in
+// front of the partition-boundary blocks.  No send buffer, no NCCL kernel, no unpack: one store per ghost value crosses the link.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_put_kernel(const double *__restrict__ src, const int *__restrict__ blk, const int *__restrict__ dir,
+                                                       const int *__restrict__ peer, const int *__restrict__ idx, double *const *__restrict__ put_base,
+                                                       unsigned *const *__restrict__ put_flag, unsigned *__restrict__ done,
+                                                       const int *__restrict__ n_to_peer, unsigned seq, int nc, int Bs, int H)
+{
+    const int i = blockIdx.x;
+    const int b = blk[i], d = dir[i], p = peer[i];
+    const int dx = d % 3 - 1, dy = (d / 3) % 3 - 1, dz = d / 9 - 1;
+    const int ex = dx ? H : Bs, ey = dy ? H : Bs, ez = dz ? H : Bs;
+    const int x0 = dx > 0 ? Bs - H : 0, y0 = dy > 0 ? Bs - H : 0, z0 = dz > 0 ? Bs - H : 0;
+    const long long CS = (long long)Bs * Bs * Bs;
+    const int n = ex * ey * ez;
+    double *out = put_base[p] + (long long)idx[i] * nc * n;
+    const double *in = src + (long long)b * nc * CS;
+    for (int e = threadIdx.x; e < nc * n; e += blockDim.x) {
+        const int c = e / n, r = e % n, x = r % ex, y = (r / ex) % ey, z = r / (ex * ey);
+        out[e] = in[c * CS + ((long long)(z0 + z) * Bs + (y0 + y)) * Bs + (x0 + x)];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(&done[p], 1u);
+        if (prev + 1u == (unsigned)n_to_peer[p]) {
+            done[p] = 0;               // every CTA of this launch for peer p has passed: ready for the next launch
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(put_flag[p]), "r"(seq) : "memory");
+        }
+    }
+}
+
+// one thread per peer: spin until the peer's patches of stage `seq` have landed (bounded: 5 s, then flags[5] = 1 and the step reports it)
+__global__ void wait_flags_kernel(const unsigned *flags, const int *__restrict__ recv_cnt, int world, unsigned seq, int *err)
+{
+    const int p = threadIdx.x;
+    if (p >= world || recv_cnt[p] == 0) return;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        unsigned v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + p) : "memory");
+        if ((int)(v - seq) >= 0) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 5000000000ull) {
+            *err = 1;
+            break;
+        }
+        __nanosleep(200);
+    }
+}
+
 template <int FD, bool SKEW, int BS>
 int32_t launch_stage_t(wgpu_ctx *ctx, const StageArgs &a, int n_blocks)
 {
@@ -1136,6 +1192,26 @@ int32_t wgpu_launch_pack(wgpu_ctx *ctx, const double *src)
     if (ctx->n_send == 0) return WGPU_OK;
     const int H = ctx->cfg.fd == 2 ? 1 : (ctx->cfg.fd == 4 ? 2 : 3);   // halo depth the stage kernel gathers
     pack_kernel<<<ctx->n_send, 256, 0, ctx->stream>>>(src, ctx->d_send_buf, ctx->d_send_blk, ctx->d_send_dir, ctx->nc, ctx->cfg.Bs[0], H);
+    ctx->launches++;
+    WGPU_CHECK(ctx, cudaGetLastError());
+    return WGPU_OK;
+}
+
+int32_t wgpu_launch_pack_put(wgpu_ctx *ctx, const double *src, int parity, unsigned seq, cudaStream_t st)
+{
+    if (ctx->n_send == 0) return WGPU_OK;
+    const int H = ctx->cfg.fd == 2 ? 1 : (ctx->cfg.fd == 4 ? 2 : 3);
+    pack_put_kernel<<<ctx->n_send, 256, 0, st>>>(src, ctx->d_send_blk, ctx->d_send_dir, ctx->d_send_peer, ctx->d_send_idx,
+                                                          ctx->d_put_base + (size_t)parity * ctx->comm_world, ctx->d_put_flag, ctx->d_done,
+                                                          ctx->d_n_to_peer, seq, ctx->nc, ctx->cfg.Bs[0], H);
+    ctx->launches++;
+    WGPU_CHECK(ctx, cudaGetLastError());
+    return WGPU_OK;
+}
+
+int32_t wgpu_launch_wait_flags(wgpu_ctx *ctx, unsigned seq, cudaStream_t st)
+{
+    wait_flags_kernel<<<1, ((ctx->comm_world + 31) / 32) * 32, 0, st>>>((const unsigned *)ctx->p2p_mem, ctx->d_recv_cnt, ctx->comm_world, seq, ctx->d_flags + 5);
     ctx->launches++;
     WGPU_CHECK(ctx, cudaGetLastError());
     return WGPU_OK;

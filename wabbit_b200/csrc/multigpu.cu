@@ -23,6 +23,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "wgpu_internal.cuh"
@@ -32,7 +33,7 @@ namespace {
 typedef struct { char internal[128]; } nccl_id_t;
 typedef void *nccl_comm_t;
 enum { NCCL_SUM = 0, NCCL_MAX = 2, NCCL_MIN = 3 };
-enum { NCCL_INT32 = 2, NCCL_UINT64 = 5, NCCL_FLOAT64 = 8 };
+enum { NCCL_INT8 = 0, NCCL_INT32 = 2, NCCL_UINT64 = 5, NCCL_FLOAT64 = 8 };
 
 struct NcclApi {
     void *lib = nullptr;
@@ -143,6 +144,123 @@ int32_t ensure_buf(wgpu_ctx *ctx, double **p, size_t *cap, size_t need)
     return WGPU_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ peer stores (CUDA IPC over NVLink)
+void p2p_teardown(wgpu_ctx *ctx)
+{
+    for (void *b : ctx->p2p_peer)
+        if (b) cudaIpcCloseMemHandle(b);
+    ctx->p2p_peer.clear();
+    cudaFree(ctx->p2p_mem);
+    cudaFree(ctx->d_put_base);
+    cudaFree(ctx->d_put_flag);
+    cudaFree(ctx->d_send_peer);
+    cudaFree(ctx->d_send_idx);
+    cudaFree(ctx->d_n_to_peer);
+    cudaFree(ctx->d_recv_cnt);
+    cudaFree(ctx->d_done);
+    ctx->p2p_mem = nullptr;
+    ctx->d_put_base = nullptr;
+    ctx->d_put_flag = nullptr;
+    ctx->d_send_peer = ctx->d_send_idx = ctx->d_n_to_peer = ctx->d_recv_cnt = nullptr;
+    ctx->d_done = nullptr;
+    ctx->p2p_on = false;
+    cudaGetLastError();
+}
+
+size_t round256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// Collective over the communicator (called from wgpu_comm_set_counts on every rank).  Any failure on any rank (no peer access, IPC not
+// permitted in this container, ...) leaves every rank on the NCCL path: the outcome is agreed by an all-reduce.
+int32_t p2p_setup(wgpu_ctx *ctx)
+{
+    NcclApi *api = nccl_api();
+    const int W = ctx->comm_world, me = ctx->comm_rank;
+    p2p_teardown(ctx);
+    ctx->p2p_seq = 0;
+    const long long pd = wgpu_patch_doubles(ctx);
+    long long n_recv = 0;
+    for (int p = 0; p < W; ++p) n_recv += ctx->recv_counts[p];
+    int ok = ctx->p2p_want && !(getenv("WGPU_P2P") && atoi(getenv("WGPU_P2P")) == 0) ? 1 : 0;
+    const size_t flag_bytes = round256((size_t)W * 4), pool_bytes = round256((size_t)std::max<long long>(n_recv, 1) * pd * 8);
+    cudaIpcMemHandle_t handle;
+    memset(&handle, 0, sizeof(handle));
+    if (ok && cudaMalloc((void **)&ctx->p2p_mem, flag_bytes + 2 * pool_bytes) != cudaSuccess) ok = 0;
+    if (ok && cudaMemset(ctx->p2p_mem, 0, flag_bytes) != cudaSuccess) ok = 0;
+    if (ok && cudaIpcGetMemHandle(&handle, ctx->p2p_mem) != cudaSuccess) ok = 0;
+    cudaGetLastError();
+    // all-gather: [64 B handle][ok][n_recv][recv_counts[W]]
+    const size_t rec = (64 + 8 + 4 * (size_t)W + 15) & ~(size_t)15;
+    std::vector<char> all(rec * W, 0);
+    {
+        char *mine = all.data() + rec * me;
+        memcpy(mine, &handle, 64);
+        int head[2] = {ok, (int)n_recv};
+        memcpy(mine + 64, head, 8);
+        memcpy(mine + 72, ctx->recv_counts.data(), 4 * (size_t)W);
+    }
+    int32_t rc;
+    if ((rc = ensure_buf(ctx, &ctx->d_xbuf, &ctx->xbuf_cap, rec * W / 8 + 2))) return rc;
+    char *d = (char *)ctx->d_xbuf;
+    WGPU_CHECK(ctx, cudaMemcpyAsync(d + rec * me, all.data() + rec * me, rec, cudaMemcpyHostToDevice, ctx->stream));
+    NCCL_CHECK(ctx, api, api->AllGather(d + rec * me, d, rec, NCCL_INT8, ctx->comm, ctx->stream));
+    WGPU_CHECK(ctx, cudaMemcpyAsync(all.data(), d, rec * W, cudaMemcpyDeviceToHost, ctx->stream));
+    WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int p = 0; p < W; ++p) ok = ok && *(int *)(all.data() + rec * p + 64);
+    ctx->p2p_peer.assign(W, nullptr);
+    if (ok)
+        for (int p = 0; p < W && ok; ++p) {
+            if (p == me || ctx->send_counts[p] == 0) continue;
+            cudaIpcMemHandle_t h;
+            memcpy(&h, all.data() + rec * p, 64);
+            if (cudaIpcOpenMemHandle(&ctx->p2p_peer[p], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                ctx->p2p_peer[p] = nullptr;
+                ok = 0;
+            }
+        }
+    cudaGetLastError();
+    double agreed = ok;
+    if ((rc = wgpu_comm_allreduce(ctx, &agreed, 1, 1))) return rc;   // MIN
+    if (agreed < 0.5) {
+        p2p_teardown(ctx);
+        return WGPU_OK;
+    }
+    // where my patches go in every peer's pools, my flag word there, and the peer / running index of every send patch (peer-major order)
+    std::vector<double *> put_base(2 * (size_t)W, nullptr);
+    std::vector<unsigned *> put_flag(W, nullptr);
+    std::vector<int> send_peer, send_idx;
+    for (int p = 0; p < W; ++p) {
+        if (ctx->p2p_peer[p]) {
+            const char *rp = all.data() + rec * p;
+            const int n_recv_p = *(int *)(rp + 68);
+            const int *rc_p = (const int *)(rp + 72);
+            long long off = 0;
+            for (int r = 0; r < me; ++r) off += rc_p[r];
+            const size_t pool_p = round256((size_t)std::max(n_recv_p, 1) * pd * 8);
+            char *base = (char *)ctx->p2p_peer[p];
+            for (int q = 0; q < 2; ++q) put_base[(size_t)q * W + p] = (double *)(base + flag_bytes + q * pool_p) + off * pd;
+            put_flag[p] = (unsigned *)base + me;
+        }
+        for (int k = 0; k < ctx->send_counts[p]; ++k) {
+            send_peer.push_back(p);
+            send_idx.push_back(k);
+        }
+    }
+    auto up = [&](auto **dp, const auto &v) -> bool {
+        using T = typename std::remove_reference<decltype(v[0])>::type;
+        const size_t n = std::max<size_t>(v.size(), 1);
+        if (cudaMalloc((void **)dp, n * sizeof(T)) != cudaSuccess) return false;
+        return v.empty() || cudaMemcpy(*dp, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) == cudaSuccess;
+    };
+    bool good = up(&ctx->d_put_base, put_base) && up(&ctx->d_put_flag, put_flag) && up(&ctx->d_send_peer, send_peer) && up(&ctx->d_send_idx, send_idx) &&
+                up(&ctx->d_n_to_peer, ctx->send_counts) && up(&ctx->d_recv_cnt, ctx->recv_counts);
+    good = good && cudaMalloc((void **)&ctx->d_done, 4 * (size_t)W) == cudaSuccess && cudaMemset(ctx->d_done, 0, 4 * (size_t)W) == cudaSuccess;
+    if (!good) return mg_fail(ctx, WGPU_ERR_CUDA, "peer-store exchange: out of device memory for the tables");
+    ctx->p2p_flag_bytes = flag_bytes;
+    ctx->p2p_pool_bytes = pool_bytes;
+    ctx->p2p_on = true;
+    return WGPU_OK;
+}
+
 __global__ void advance_time_kernel(double *t) { t[0] = t[1]; }
 
 }  // namespace
@@ -207,6 +325,7 @@ int32_t wgpu_comm_destroy(wgpu_ctx *ctx)
     ctx->ev_pack = ctx->ev_xchg = nullptr;
     cudaFree(ctx->d_comm_scratch);
     ctx->d_comm_scratch = nullptr;
+    p2p_teardown(ctx);
     cudaFree(ctx->d_xbuf);
     ctx->d_xbuf = nullptr;
     ctx->xbuf_cap = 0;
@@ -235,6 +354,35 @@ int32_t wgpu_comm_set_counts(wgpu_ctx *ctx, const int32_t *send_counts, const in
     const long long want_s = halo ? ctx->n_halo_send : ctx->n_send, want_r = halo ? (long long)ctx->h_halo.size() : -1;
     if (ns != want_s || (want_r >= 0 && nr != want_r))
         return mg_fail(ctx, WGPU_ERR_ARG, "wgpu_comm_set_counts: the counts do not add up to the lists of wgpu_set_halo / wgpu_set_exchange");
+    if (halo || W < 2) {
+        p2p_teardown(ctx);
+        return WGPU_OK;
+    }
+    return p2p_setup(ctx);      // face patches: try the peer-store transport (collective; falls back to NCCL send / recv on every rank)
+}
+
+int32_t wgpu_comm_set_transport(wgpu_ctx *ctx, int32_t peer_stores)
+{
+    if (!ctx) return WGPU_ERR_ARG;
+    ctx->p2p_want = peer_stores ? 1 : 0;     // takes effect at the next wgpu_comm_set_counts
+    return WGPU_OK;
+}
+
+int32_t wgpu_comm_transport(const wgpu_ctx *ctx) { return ctx && ctx->p2p_on ? 1 : 0; }
+
+// peer-store variant of stage_exchange: the pack kernel IS the send; it runs on the (high-priority) communication stream, next to the interior
+// blocks the main stream starts at once, followed by the wait for the peers' flags and then the partition-boundary blocks
+static int32_t stage_exchange_p2p(wgpu_ctx *ctx, int j)
+{
+    const unsigned seq = ++ctx->p2p_seq;
+    const int q = (int)(seq & 1u);
+    int32_t rc;
+    WGPU_CHECK(ctx, cudaEventRecord(ctx->ev_pack, ctx->stream));                  // the stage input is complete
+    WGPU_CHECK(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_pack, 0));
+    if ((rc = wgpu_launch_pack_put(ctx, j == 1 ? ctx->U : (((j - 1) & 1) ? ctx->UA : ctx->UB), q, seq, ctx->comm_stream))) return rc;
+    if ((rc = wgpu_launch_wait_flags(ctx, seq, ctx->comm_stream))) return rc;
+    ctx->d_pool = (double *)(ctx->p2p_mem + ctx->p2p_flag_bytes + (size_t)q * ctx->p2p_pool_bytes);
+    WGPU_CHECK(ctx, cudaEventRecord(ctx->ev_xchg, ctx->comm_stream));
     return WGPU_OK;
 }
 
@@ -309,8 +457,13 @@ int32_t wgpu_rk_steps(wgpu_ctx *ctx, double time, int32_t n_steps, double *time_
     ctx->time_on_device = true;
     struct Reset {
         wgpu_ctx *c;
-        ~Reset() { c->time_on_device = false; }
-    } reset{ctx};
+        double *pool;
+        ~Reset()
+        {
+            c->time_on_device = false;
+            c->d_pool = pool;          // the peer-store transport points the stage kernels at the library's own pools
+        }
+    } reset{ctx, ctx->d_pool};
     for (int step = 0; step < n_steps; ++step) {
         tr.on = want_trace && step == n_steps - 1;
         tr.mark("step start", ctx->stream);
@@ -328,13 +481,17 @@ int32_t wgpu_rk_steps(wgpu_ctx *ctx, double time, int32_t n_steps, double *time_
         if ((rc = wgpu_rk_dt(ctx, time))) return rc;
         tr.mark("dt all-reduced + finalised", ctx->stream);
         for (int j = 1; j <= c.n_stages; ++j) {
-            if ((rc = wgpu_pack_halo(ctx, j))) return rc;
-            tr.mark("  packed", ctx->stream);
-            if (!multi) {
-                if ((rc = wgpu_rk_stage(ctx, j, WGPU_BLOCKS_ALL))) return rc;
-                continue;
+            if (multi && ctx->p2p_on) {
+                if ((rc = stage_exchange_p2p(ctx, j))) return rc;
+            } else {
+                if ((rc = wgpu_pack_halo(ctx, j))) return rc;
+                tr.mark("  packed", ctx->stream);
+                if (!multi) {
+                    if ((rc = wgpu_rk_stage(ctx, j, WGPU_BLOCKS_ALL))) return rc;
+                    continue;
+                }
+                if ((rc = stage_exchange(ctx, j))) return rc;
             }
-            if ((rc = stage_exchange(ctx, j))) return rc;
             if (ctx->n_bnd && ctx->n_int && ctx->n_jump == 0) {
                 // uniform grid: the partition-boundary blocks run on the communication stream right behind the exchange, CONCURRENTLY with
                 // the interior blocks on the main stream (the two launches share the SMs: one tail instead of two partial last waves);
@@ -366,9 +523,14 @@ int32_t wgpu_rk_steps(wgpu_ctx *ctx, double time, int32_t n_steps, double *time_
     WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_dt, 8, cudaMemcpyDeviceToHost, ctx->stream));
     WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pinned + 1, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pinned + 2, ctx->d_time + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pinned + 3, ctx->d_flags + 5, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     if (dt_last) *dt_last = ctx->h_pinned[0];
     if (time_out) *time_out = ctx->h_pinned[2];
+    if (*(int *)(ctx->h_pinned + 3)) {
+        cudaMemsetAsync(ctx->d_flags + 5, 0, sizeof(int), ctx->stream);
+        return mg_fail(ctx, WGPU_ERR_CUDA, "peer-store exchange: a peer's ghost patches did not arrive within 5 s");
+    }
     if (*(int *)(ctx->h_pinned + 1)) {
         cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream);
         return mg_fail(ctx, WGPU_ERR_DIVERGED, "ACM fail: very very large values in state vector.");

@@ -216,6 +216,21 @@ struct wgpu_ctx {
     double *d_xbuf = nullptr;          // send buffer of wgpu_ship_blocks / scratch of the light-data collectives
     size_t xbuf_cap = 0;
 
+    // face-patch exchange by peer stores over NVLink (multigpu.cu: p2p_setup): the library owns the receive pools (two, alternating per
+    // stage) and a flag word per peer in ONE allocation exported by CUDA IPC; the pack kernel writes every patch straight into the
+    // receiver's pool and the last CTA per peer releases that peer's flag; the receiver spins on its flags in front of the boundary blocks
+    bool p2p_on = false;
+    int p2p_want = 1;                  // wgpu_comm_set_transport: 1 peer stores when available, 0 NCCL send / recv
+    char *p2p_mem = nullptr;
+    size_t p2p_flag_bytes = 0, p2p_pool_bytes = 0;
+    std::vector<void *> p2p_peer;      // opened allocations of the peers this rank sends to
+    double **d_put_base = nullptr;     // [2][world] where this rank's patches start in peer p's pool q
+    unsigned **d_put_flag = nullptr;   // [world] this rank's flag word on peer p
+    int *d_send_peer = nullptr, *d_send_idx = nullptr, *d_n_to_peer = nullptr, *d_recv_cnt = nullptr;
+    unsigned *d_done = nullptr;        // [world] CTAs of the running pack launch that have finished, per peer
+    unsigned p2p_seq = 0;              // stages exchanged so far (flag value of the next one = p2p_seq + 1)
+    double *d_pool_user = nullptr;     // the caller's pool of wgpu_set_exchange (used by the NCCL / host-driven paths)
+
     // optional event pairs around stage launches
     bool profiling = false;
     std::vector<cudaEvent_t> prof_ev;   // [2*i], [2*i+1]
@@ -249,6 +264,8 @@ int32_t wgpu_rk_end_nosync(wgpu_ctx *ctx);
 // kernels.cu
 int32_t wgpu_launch_stage(wgpu_ctx *ctx, const StageArgs &a, int n_blocks);
 int32_t wgpu_launch_pack(wgpu_ctx *ctx, const double *src);
+int32_t wgpu_launch_pack_put(wgpu_ctx *ctx, const double *src, int parity, unsigned seq, cudaStream_t st);
+int32_t wgpu_launch_wait_flags(wgpu_ctx *ctx, unsigned seq, cudaStream_t st);
 // jump.cu
 int32_t wgpu_launch_jump_fill(wgpu_ctx *ctx, const double *src);
 int32_t wgpu_launch_wjump_fill(wgpu_ctx *ctx, const double *src, const double *ce_coarse = nullptr);

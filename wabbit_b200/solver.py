@@ -271,6 +271,14 @@ class WabbitGPU:
         a = [None if v is None else np.ascontiguousarray(v, dtype=np.int32) for v in (send_counts, recv_counts, rsend_counts, rrecv_counts)]
         self._check(self._lib.wgpu_comm_set_counts(self._ctx, *[None if v is None else _i32(v) for v in a]))
 
+    def comm_set_transport(self, peer_stores: bool):
+        """face-patch exchange inside wgpu_rk_steps: peer stores over NVLink (CUDA IPC, default) or grouped ncclSend / ncclRecv; call before the
+        exchange is attached (wgpu_comm_set_transport)"""
+        self._check(self._lib.wgpu_comm_set_transport(self._ctx, int(bool(peer_stores))))
+
+    def comm_transport(self) -> str:
+        return "peer stores" if self._lib.wgpu_comm_transport(self._ctx) else "nccl"
+
     def RungeKuttaSteps(self, time: float, n_steps: int = 1):
         """n_steps of RungeKuttaGeneric back to back with time, dt and the divergence flag resident on the device (wgpu_rk_steps: the
         N_dt_per_grid loop of performance_test.f90); across ranks if the context has a communicator.  Returns (time after, last dt)."""
