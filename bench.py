@@ -384,7 +384,17 @@ def run_ours(a):
             legs = [l for l in legs if l[0] in a.adaptive_legs.split(",")]
         for name, bs, j0, sph in legs:
             adaptive_lifted[name] = adaptive_leg_multi(a, rank, world, local, stream, J0=j0, Jmax=j0 + 1, wavelet="CDF44", bs=bs, sphere_on=sph)
+    compression = None
+    if not a.no_compression:
+        idx = list(range(51)) if a.compression_full else (list(range(0, 51, 5)) if world == 1 else list(range(0, 51, 10)))
+        compression = {f"J{a.compression_level}": compression_leg(a, rank, world, local, stream, a.compression_level, eps_idx=idx)}
+        if a.compression_full or world >= 4:      # ~10^5.4 blocks: the protocol's J = 6 needs the memory of >= 4 GPUs for the full tree
+            compression[f"J{a.compression_level + 1}"] = compression_leg(a, rank, world, local, stream, a.compression_level + 1,
+                                                                          wavelets=("CDF40", "CDF42", "CDF44") if a.compression_full else ("CDF44",),
+                                                                          eps_idx=idx if a.compression_full else [20, 30, 40])
     if rank == 0:
+        if compression is not None:
+            line["compression"] = compression
         if adaptive is not None:
             line["adaptive"] = adaptive
         if adaptive_lifted is not None:
@@ -768,6 +778,68 @@ def adaptive_leg_multi(a, rank, world, local, stream, eps=None, J0=5, Jmax=6, cy
     return rec
 
 
+def compression_leg(a, rank, world, local, stream, J, wavelets=("CDF40", "CDF42", "CDF44"), eps_idx=None, bs=16):
+    """BASELINE config 5: the protocol of post_compression_unit_test.f90:107-215 (wabbit_b200/compression.py) -- one component, Gauss blob on the
+    equidistant level-J grid, adapt_tree (full wavelet transformation; coarse extension + security zone for the lifted wavelets), Nb,
+    refineToEquidistant_tree, relative errors -- for a spread of the protocol's 51 thresholds (all of them with --compression-full), on
+    `world` GPUs.  value: blocks of the equidistant grid pushed through adapt_tree + refineToEquidistant_tree per second."""
+    import torch
+    import torch.distributed as dist
+    from wabbit_b200 import Forest, WabbitGPU
+    from wabbit_b200 import compression as CP
+    eps_idx = list(range(0, 51, 5)) if eps_idx is None else list(eps_idx)
+    eps_list = [float(CP.EPS_SWEEP[i]) for i in eps_idx]
+    nb0 = 8 ** J
+    out = {"metric": "blocks/s through the compression protocol (adapt_tree + refineToEquidistant_tree, 1 component)", "unit": "blocks/s",
+           "level": J, "blocks": nb0, "Bs": bs, "n_gpus": world, "eps": eps_list}
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    t_all = 0.0
+    for wv in wavelets:
+        sol = None
+        try:
+            p = CP.compression_params(wv, bs, J)
+            mb = int((1.4 if world == 1 else 2.0) * nb0 / world) + (0 if world == 1 else 8192)
+            forest = Forest.uniform(3, J, Jmax=J, n_ranks=world, max_blocks=mb)
+            sol = WabbitGPU(p, max_blocks=mb, device=local, stream=stream.cuda_stream)
+            sol.setup_wavelet(wv)
+            drv = None
+            if world > 1:
+                from wabbit_b200.multi import DistributedWabbit
+                sol.comm_init(rank, world)
+                drv = DistributedWabbit(sol, forest, rank, world)
+            else:
+                sol.set_forest(forest)
+            test = CP.CompressionTest(sol, forest, drv)
+            test.run(eps_list[len(eps_list) // 2:len(eps_list) // 2 + 1], sync=sync)       # warm-up
+            recs = test.run(eps_list, sync=sync)
+            tm = torch.tensor([[r["ms_adapt"], r["ms_refine"]] for r in recs], dtype=torch.float64, device=torch.device("cuda", local))
+            if world > 1:
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            tm = tm.cpu().numpy()
+            t = float(tm.sum()) * 1e-3
+            t_all += t
+            out[wv] = {"value": nb0 * len(recs) / t, "Nb": [r["Nb"] for r in recs], "err_L2": [float("%.6e" % r["err_L2"]) for r in recs],
+                       "err_Linfty": [float("%.6e" % r["err_Linfty"]) for r in recs], "ms_adapt": [round(float(v), 1) for v in tm[:, 0]],
+                       "ms_refine": [round(float(v), 1) for v in tm[:, 1]]}
+        except Exception as e:      # noqa: BLE001 -- a secondary figure must not take the headline line down
+            import traceback
+            out[wv] = {"error": repr(e), "traceback": traceback.format_exc()[-1200:]}
+        finally:
+            if sol is not None:
+                try:
+                    sol.close()
+                except Exception:
+                    pass
+    n_ok = sum(len(eps_list) for wv in wavelets if "value" in out.get(wv, {}))
+    out["value"] = nb0 * n_ok / t_all if t_all > 0 else None
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -783,6 +855,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-wavelet", action="store_true", help="skip the secondary FWT + threshold figure")
     ap.add_argument("--no-adaptive", action="store_true", help="skip the secondary adaptive-cycle figure")
+    ap.add_argument("--no-compression", action="store_true", help="skip the compression-protocol figure (BASELINE config 5)")
+    ap.add_argument("--compression-level", type=int, default=5)
+    ap.add_argument("--compression-full", action="store_true", help="all 51 thresholds, three wavelets, levels J and J+1")
     ap.add_argument("--adaptive-eps", type=float, default=1.0e-6)
     ap.add_argument("--adaptive-wavelet", default="CDF40", help="wavelet of --adaptive-only / --adaptive-multi")
     ap.add_argument("--adaptive-legs", default="", help="N > 1: comma list out of Bs16,Bs16_sphere,Bs18 (default: all three)")
