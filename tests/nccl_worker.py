@@ -4,6 +4,7 @@ single-rank result on its own GPU and compares its share bit for bit:
   uniform_nccl   the same with grouped ncclSend / ncclRecv (wgpu_comm_set_transport(0))
   graded    RK4 steps on a graded grid, halo blocks (HaloStepper, wgpu_rk_steps), then download with a synchronised ghost shell
   cycle     refine_tree -> RK4 -> adapt_tree with the lifted full-tree algorithm (DistributedWabbit: wgpu_ship_blocks, wgpu_exchange_array)
+  compression   the protocol of post_compression_unit_test.f90 (adapt_tree from the equidistant grid + refineToEquidistant_tree, one component)
 Exit code 0 = all ranks agree with the single-rank driver."""
 import os
 import sys
@@ -165,6 +166,45 @@ def main():
         ok = (nb1 == nb2) and (dt1 == dt2) and (n0, n1) == (m0, m1) and np.array_equal(l, lf[off2:off2 + len(l)]) and \
             np.array_equal(x, xf[off2:off2 + len(l)]) and np.array_equal(interior(p, out[:len(l)]), interior(p, ref[off2:off2 + len(l)]))
         print(f"rank {rank}: cycle {wavelet} Bs={Bs} blocks {nb2} -> {m1} (single rank {nb1} -> {n1}) dt={dt2!r} ok={ok}", flush=True)
+        s.close()
+    elif what == "compression":
+        # BASELINE config 5 (post_compression_unit_test.f90): adapt_tree with the full wavelet transformation from the equidistant grid, then
+        # refineToEquidistant_tree, one component -- across ranks inside the library against the single-rank driver, bit for bit
+        from wabbit_b200 import compression as CP
+        wavelet, Jmax, eps = sys.argv[2], int(sys.argv[3]), float(sys.argv[4])
+        p = CP.compression_params(wavelet, 16, Jmax)
+        mb = 2 * 8 ** Jmax
+        f1 = Forest.uniform(3, Jmax, Jmax=Jmax, max_blocks=mb)
+        fw = Forest.uniform(3, Jmax, Jmax=Jmax, n_ranks=world, max_blocks=mb)
+        hvy, l1, x1, _ = f1.active(0)
+        g = p.g
+        s1 = make(p, mb, wavelet)
+        s1.set_forest(f1)
+        u = np.zeros(s1.host_shape())
+        u[:len(hvy), 0, g:-g, g:-g, g:-g] = CP.set_block_testing_data(16, l1, x1)
+        s1.upload(u)
+        fa, n0, nb1 = s1.adapt_tree(f1, eps=eps, Jmin=1, full_tree=True)
+        fr = CP.refineToEquidistant_tree(s1, fa, Jmax)
+        ref = np.zeros(s1.host_shape())
+        s1.download(ref, g_sync=0)
+        s1.close()
+        s = make(p, mb, wavelet)
+        s.comm_init(rank, world)
+        d = DistributedWabbit(s, fw, rank, world)
+        assert d.in_library
+        off = sum(fw.n_active(r) for r in range(rank))
+        n = fw.n_active(rank)
+        h = np.zeros(s.host_shape())
+        h[:n] = u[off:off + n]
+        s.upload(h)
+        _, m0, nb2 = d.adapt_tree(eps=eps, Jmin=1, full_tree=True)
+        CP.refineToEquidistant_tree(d, None, Jmax)
+        out = np.zeros(s.host_shape())
+        s.download(out, g_sync=0)
+        off2 = sum(d.forest.n_active(r) for r in range(rank))
+        n2 = d.forest.n_active(rank)
+        ok = nb1 == nb2 and d.forest.n_blocks == 8 ** Jmax and np.array_equal(interior(p, out[:n2]), interior(p, ref[off2:off2 + n2]))
+        print(f"rank {rank}: compression {wavelet} J={Jmax} eps={eps} Nb {nb2} (single rank {nb1}) ok={ok}", flush=True)
         s.close()
     else:
         raise SystemExit(f"unknown case {what}")

@@ -37,7 +37,8 @@ def _run(world, *args):
 
 
 @pytest.mark.skipif(_n_devices() < 2, reason="needs >= 2 CUDA devices")
-@pytest.mark.parametrize("case", [("uniform",), ("uniform_nccl",), ("graded",), ("cycle", "CDF44", "16"), ("cycle", "CDF44", "18"), ("cycle", "CDF40", "16")],
+@pytest.mark.parametrize("case", [("uniform",), ("uniform_nccl",), ("graded",), ("cycle", "CDF44", "16"), ("cycle", "CDF44", "18"), ("cycle", "CDF40", "16"),
+                                  ("compression", "CDF42", "4", "1e-6"), ("compression", "CDF44", "4", "1.0"), ("compression", "CDF40", "4", "1e-2")],
                          ids=lambda c: "-".join(c))
 def test_nccl_path_equals_single_rank(case):
     world = min(_n_devices(), 4)

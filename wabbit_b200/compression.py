@@ -91,33 +91,39 @@ class CompressionTest:
     the device straight into / against the resident hvy_block (torch elementwise float64 on the library's device pointer)."""
 
     def __init__(self, sol, forest, drv=None):
-        import ctypes as C
         import torch
-        from .multi import _DevPtr
         self.sol, self.drv, self.torch = sol, drv, torch
         self.rank = drv.rank if drv is not None else 0
         self.forest0 = forest
         p = sol.params
         self.Bs, self.Jmax = p.Bs[0], forest.Jmax
         assert p.dim == 3 and p.n_eqn == 1
-        ptr, n = C.c_void_p(), C.c_int64()
-        sol._check(sol._lib.wgpu_device_pointer(sol._ctx, 0, 0, C.byref(ptr), C.byref(n)))
         self.dev = torch.device("cuda", torch.cuda.current_device())
-        Bs = self.Bs
-        self.U = torch.as_tensor(_DevPtr(ptr.value, n.value), device=self.dev).view(sol.max_blocks, Bs, Bs, Bs)
+        self.forest = forest
         self.stream = torch.cuda.ExternalStream(sol.stream) if sol.stream else torch.cuda.current_stream()
 
     def _forest(self):
         return self.drv.forest if self.drv is not None else self.forest
 
+    def _hvy_block(self):
+        """the resident hvy_block as a torch view; fetched anew every time: refinement and block moves write into the second buffer, which
+        then BECOMES hvy_block (the device pointer changes)"""
+        import ctypes as C
+        from .multi import _DevPtr
+        sol, Bs = self.sol, self.Bs
+        ptr, n = C.c_void_p(), C.c_int64()
+        sol._check(sol._lib.wgpu_device_pointer(sol._ctx, 0, 0, C.byref(ptr), C.byref(n)))
+        return self.torch.as_tensor(_DevPtr(ptr.value, n.value), device=self.dev).view(sol.max_blocks, Bs, Bs, Bs)
+
     def _each_chunk(self, fn, chunk=4096):
         hvy, lvl, ixyz, _ = self._forest().active(self.rank)
         assert (np.diff(hvy) == 1).all() if len(hvy) > 1 else True
+        U = self._hvy_block()
         with self.torch.cuda.stream(self.stream):
             for s0 in range(0, len(hvy), chunk):
                 e = min(s0 + chunk, len(hvy))
                 exact = set_block_testing_data(self.Bs, lvl[s0:e], ixyz[s0:e], self.torch, self.dev)
-                fn(self.U[int(hvy[s0]) - 1:int(hvy[s0]) - 1 + (e - s0)], exact)
+                fn(U[int(hvy[s0]) - 1:int(hvy[s0]) - 1 + (e - s0)], exact)
 
     def create_data(self):
         self._each_chunk(lambda blk, exact: blk.copy_(exact))

@@ -558,22 +558,23 @@ class DistributedFullTree(FullTree):
         needs = [need(mine_of[q]) for q in range(W)]
         n_arrays = len(needs[0])
         _t.__exit__()
+        # a block may be read from several arrays in one pass (coefficients as the same-level neighbour of one block, values as the coarser
+        # neighbour of another): it has ONE local slot, so every array of the pass ships the union of the blocks any of them needs
+        src_r, src_s, dst_r, which = [], [], [], []
+        for q in range(W):
+            b = np.concatenate([needs[q][a][1] for a in range(n_arrays)]) if n_arrays else np.zeros(0, np.int64)
+            b = np.unique(b[b >= 0])
+            b = b[self.owner[b] != q]
+            src_r.append(self.owner[b])
+            src_s.append(self.slots[b])
+            dst_r.append(np.full(len(b), q, np.int64))
+            which.append(b)
+        src_r, src_s, dst_r, which = (np.concatenate(v) for v in (src_r, src_s, dst_r, which))
+        first = nxt
         for a in range(n_arrays):
-            array = needs[0][a][0]
-            src_r, src_s, dst_r, which = [], [], [], []
-            for q in range(W):
-                b = needs[q][a][1]
-                b = np.unique(b[b >= 0])
-                b = b[self.owner[b] != q]
-                src_r.append(self.owner[b])
-                src_s.append(self.slots[b])
-                dst_r.append(np.full(len(b), q, np.int64))
-                which.append(b)
-            src_r, src_s, dst_r, which = (np.concatenate(v) for v in (src_r, src_s, dst_r, which))
             with self._tk("adapt: pass ship", sol):
-                loc, nxt = drv._ship(array, src_r, src_s, dst_r, nxt)
-            got = which[dst_r == me]
-            lslot[got] = loc
+                loc, nxt = drv._ship(needs[0][a][0], src_r, src_s, dst_r, first)
+            lslot[which[dst_r == me]] = loc
         mine = mine_of[me]
         mine = mine[np.argsort(self.slots[mine])]
         # every block of the tree is registered by position (resident ones with their local slot, the others with slot 0 = "exists, no data
