@@ -500,6 +500,7 @@ int32_t wgpu_destroy(wgpu_ctx *ctx)
         if (ctx->ev_lay[k]) cudaEventDestroy(ctx->ev_lay[k]);
     }
     if (ctx->dma_stream) cudaStreamDestroy(ctx->dma_stream);
+    wgpu_tma_release(ctx);
     for (auto &e : ctx->prof_ev) cudaEventDestroy(e);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->h_bounce) cudaFreeHost(ctx->h_bounce);
@@ -990,6 +991,20 @@ int32_t wgpu_download(wgpu_ctx *ctx, int32_t array_id, int32_t slot, const int32
     return move_blocks(ctx, false, array_id, slot, hvy_ids, n, host, ncomp_host, g_sync);
 }
 
+// what the launcher may assume about the blocks of a stage launch (StageArgs::plain_hint): 1 all of them have six resident same-level face
+// neighbours (periodic domain, no level jump, no face patch of another rank), -1 none has (the partition-boundary list of the face-patch
+// exchange), 0 mixed / unknown
+static int plain_hint(const wgpu_ctx *ctx, int which)
+{
+    const wgpu_config &c = ctx->cfg;
+    const bool periodic = c.periodic[0] && c.periodic[1] && (c.dim < 3 || c.periodic[2]);
+    const bool face_patches = ctx->n_bnd > 0 && ctx->h_halo.empty() && ctx->n_halo_send == 0;
+    if (which == WGPU_BLOCKS_BOUNDARY && face_patches) return -1;
+    if (!periodic || ctx->has_jumps || ctx->n_jump > 0) return 0;
+    if (which == WGPU_BLOCKS_INTERIOR) return 1;
+    return ctx->n_bnd > 0 ? 0 : 1;
+}
+
 // ------------------------------------------------------------------------------------------------ compute
 int32_t wgpu_sync_ghosts(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t g_minus, int32_t g_plus)
 {
@@ -1040,6 +1055,7 @@ int32_t wgpu_rhs(wgpu_ctx *ctx, double time, int32_t src_slot, int32_t dst_slot)
     a.t_cj = 0.0;
     int32_t rc = wgpu_launch_jump_fill(ctx, src);   // sync_ghosts_RHS_tree: restriction / prediction face patches
     if (rc) return rc;
+    a.plain_hint = plain_hint(ctx, WGPU_BLOCKS_ALL);
     rc = wgpu_launch_stage(ctx, a, ctx->n_active);
     if (rc) return rc;
     return check_flags(ctx);
@@ -1825,6 +1841,7 @@ int32_t wgpu_rk_stage(wgpu_ctx *ctx, int32_t j, int32_t which)
         a.active = ctx->d_active_bnd;
         nblk = ctx->n_bnd;
     }
+    a.plain_hint = plain_hint(ctx, which);
     return wgpu_launch_stage(ctx, a, nblk);
 }
 

@@ -16,10 +16,12 @@
 // One CTA per block, Bs x Bs threads, marching in z.  z-planes (4 components, xy-halo included) stream
 // through a shared-memory ring filled with cp.async (LDGSTS) PF planes ahead of the compute front, so
 // the SM keeps several planes of HBM traffic in flight while the FP64 pipe works on the current one.
+#include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
 
 #include <algorithm>
+#include <unordered_map>
 
 #include "wgpu_internal.cuh"
 
@@ -297,6 +299,8 @@ __global__ void __launch_bounds__(BS *BS, (Tile<FD, BS>::SMEM <= 110 * 1024 ? 2 
     const int b = a.active[blockIdx.x];
     if (tid < WGPU_NDIR) s_code[tid] = a.nbr[b * WGPU_NDIR + tid];
     __syncthreads();
+    // second launch behind stage_kernel_tma: that kernel has advanced every block whose six face neighbours are resident same-level blocks
+    if (a.skip_plain && (s_code[12] | s_code[14] | s_code[10] | s_code[16] | s_code[4] | s_code[22]) >= 0) return;
     build_tables<FD, BS>(a, s_lt, b, s_code, tid);
     __syncthreads();
 
@@ -485,6 +489,314 @@ __global__ void __launch_bounds__(BS *BS, (Tile<FD, BS>::SMEM <= 110 * 1024 ? 2 
             if (a.dim_min_axes > 2) dxmin = fmin(dxmin, dz);
             double dtb = (u_eigen >= 1.0e-6) ? __ddiv_rn(__dmul_rn(a.CFL, dxmin), u_eigen) : 1.0e-2;
             // explicit diffusion, with THIS block's dx (module_ACM.f90:669-671): folded in before the MIN over blocks and ranks
+            if (a.nu > 1.0e-13) dtb = fmin(dtb, __ddiv_rn(__dmul_rn(a.CFL_nu, __dmul_rn(dxmin, dxmin)), a.nu));
+            atomicMin(a.dtmin_bits, (unsigned long long)__double_as_longlong(dtb));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage_kernel_tma<FD, SKEW, BS, GEOM>: the same stage with the plane ring filled by the TMA unit instead of per-thread cp.async.
+// For a block whose six face neighbours are resident same-level blocks ("plain": every block of an equidistant periodic grid, the
+// interior blocks of a partition, the blocks away from level jumps on a graded grid) every source of a z-plane is a dense box of the
+// resident array A[blk*NC + c][z][y][x], described by three tensor maps (boxes Bs x Bs, Bs x H and XW x Bs).  ONE thread issues the
+// bulk tensor copies of a plane -- per component: the block's own plane, the y-/y+ halo rows and the x-/x+ halo columns from the four
+// neighbours; for the 2H z-halo planes the neighbour's plane -- onto the plane's mbarrier (expect_tx = the plane's bytes); the other
+// 255 threads issue no load instruction at all and wait on the mbarrier's phase before they read the plane.  Shared-memory layout of a
+// plane, per component (RS doubles): [ROWS = Bs+2H rows][Bs] (y halo rows in place, pitch Bs: TMA writes dense boxes) followed by the
+// x- and x+ halo columns as [Bs][XW] each; the x-direction taps of the threads next to the block's x faces read those through four
+// loop-invariant offsets.  Blocks that are not plain leave at once; stage_kernel (above) takes them in a second launch (skip_plain).
+// ---------------------------------------------------------------------------------------------
+template <int FD, int BS, int SLACK_ = 1>
+struct TmaTile {
+    static constexpr int H = St<FD>::H;
+    static constexpr int XW = (H + 1) & ~1;          // x halo columns moved per side (16-byte multiple)
+    static constexpr int ROWS = BS + 2 * H;
+    static constexpr int NC = 4;
+    static constexpr int RS = ROWS * BS + 2 * BS * XW;   // one component of one plane
+    static constexpr int SLOT = NC * RS;
+    static constexpr int PF = 3;                     // planes in flight ahead of the compute front
+    static constexpr int SLACK = SLACK_;             // extra ring slots: a slot is refilled SLACK iterations after its plane died (0: block barrier per plane)
+    static constexpr int RING = 2 * H + 1 + PF + SLACK;
+    static constexpr int NT = BS * BS;
+    static constexpr int NW = NT / 32;
+    static constexpr size_t SMEM = (size_t)RING * SLOT * sizeof(double) + 1024;   // + alignment slack
+    static constexpr unsigned BYTES_PLANE = NC * (BS * BS + 2 * H * BS + 2 * XW * BS) * 8;
+    static constexpr unsigned BYTES_ZHALO = NC * BS * BS * 8;
+    static_assert((BS * 8) % 128 == 0, "TMA destinations must stay 128-byte aligned: rows of a multiple of 16 doubles");
+};
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap *map, unsigned long long *bar, double *dst, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(dst)),
+                 "l"((unsigned long long)map), "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+
+template <int FD, bool SKEW, int BS, bool GEOM, int SLACK>
+__global__ void __launch_bounds__(BS *BS, 2)
+    stage_kernel_tma(const __grid_constant__ StageArgs a, const __grid_constant__ CUtensorMap tm_int, const __grid_constant__ CUtensorMap tm_y,
+                     const __grid_constant__ CUtensorMap tm_x)
+{
+    using T = TmaTile<FD, BS, SLACK>;
+    using S = St<FD>;
+    constexpr int H = T::H, XW = T::XW, ROWS = T::ROWS, RS = T::RS, NC = T::NC, RING = T::RING, SLOT = T::SLOT, PF = T::PF;
+    constexpr int NQ = BS + 2 * H, NW = T::NW;
+    extern __shared__ double sm_raw[];
+    __shared__ __align__(8) unsigned long long s_full[RING], s_empty[RING];
+    __shared__ int s_code[WGPU_NDIR];
+    __shared__ double s_red[32];
+    double *sm = (double *)(((unsigned long long)sm_raw + 1023ull) & ~1023ull);
+
+    const int tid = threadIdx.x;
+    const int tx = tid % BS, ty = tid / BS;
+    const int lane = tid & 31, wid = tid >> 5;
+    const int b = a.active[blockIdx.x];
+    if (tid < WGPU_NDIR) s_code[tid] = a.nbr[b * WGPU_NDIR + tid];
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < RING; ++s) {
+            mbar_init(&s_full[s], 1);        // the arrive.expect_tx of warp 0; the bytes of all warps' copies complete the phase
+            mbar_init(&s_empty[s], NW);      // one arrival per warp when it has read the slot's plane for the last time
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if ((s_code[12] | s_code[14] | s_code[10] | s_code[16] | s_code[4] | s_code[22]) < 0) return;   // not plain: stage_kernel takes this block
+
+    // lane 0 of EVERY warp issues its share of plane q's copies (20 boxes of an interior plane, 4 of a z-halo plane, dealt round robin over
+    // the warps), after all warps have released the slot's previous plane
+    auto issue = [&](int q) {
+        const int s = q % RING, zp = q - H;
+        double *dst = sm + s * SLOT;
+        unsigned long long *bar = &s_full[s];
+        if (SLACK > 0 && q >= RING) mbar_wait(&s_empty[s], ((q / RING) - 1) & 1);
+        if (zp >= 0 && zp < BS) {
+            if (wid == 0) mbar_expect_tx(bar, T::BYTES_PLANE);
+            for (int i = wid; i < 5 * NC; i += NW) {
+                const int c = i / 5, kind = i % 5;
+                double *d = dst + c * RS;
+                // neighbour codes are read from shared memory here (lane 0 only) instead of living in registers through the plane loop
+                if (kind == 0) tma_load_4d(&tm_int, bar, d + H * BS, 0, 0, zp, b * NC + c);
+                else if (kind == 1) tma_load_4d(&tm_y, bar, d, 0, BS - H, zp, s_code[10] * NC + c);
+                else if (kind == 2) tma_load_4d(&tm_y, bar, d + (H + BS) * BS, 0, 0, zp, s_code[16] * NC + c);
+                else if (kind == 3) tma_load_4d(&tm_x, bar, d + ROWS * BS, BS - XW, 0, zp, s_code[12] * NC + c);
+                else tma_load_4d(&tm_x, bar, d + ROWS * BS + BS * XW, 0, 0, zp, s_code[14] * NC + c);
+            }
+        } else {
+            const int nb = zp < 0 ? s_code[4] : s_code[22], zz = zp < 0 ? BS + zp : zp - BS;
+            if (wid == 0) mbar_expect_tx(bar, T::BYTES_ZHALO);
+            if (wid < NC) tma_load_4d(&tm_int, bar, dst + wid * RS + H * BS, 0, 0, zz, nb * NC + wid);
+        }
+    };
+
+    if (lane == 0) {
+#pragma unroll 1
+        for (int q = 0; q < 2 * H + PF; ++q)
+            if (q < NQ) issue(q);
+    }
+    __syncwarp();
+
+    const int lvl = a.level[b];
+    const double dx = a.dx_lvl[lvl][0], dy = a.dx_lvl[lvl][1], dz = a.dx_lvl[lvl][2];
+    const double dinv[3] = {1.0 / dx, 1.0 / dy, 1.0 / dz};
+    const double d2inv[3] = {1.0 / (dx * dx), 1.0 / (dy * dy), 1.0 / (dz * dz)};
+    const double dt = (a.u_out || a.acc_out) ? *a.dt_ptr : 0.0;
+    const bool base_u_global = a.u_out && a.u0 != a.u_in;
+    const bool base_acc_global = a.acc_out && a.acc_in != a.u_in;
+    const double c02 = a.c0 * a.c0;
+    double gxy2 = 0.0, gz0 = 0.0, gcz = 0.0;
+    if (GEOM) {
+        const double ts = __dadd_rn(a.t0_ptr ? *a.t0_ptr : a.t0, __dmul_rn(a.t_cj, *a.dt_ptr));
+        const double cx = __dadd_rn(a.g_c0[0], __dmul_rn(a.g_v[0], ts)), cy = __dadd_rn(a.g_c0[1], __dmul_rn(a.g_v[1], ts));
+        gcz = __dadd_rn(a.g_c0[2], __dmul_rn(a.g_v[2], ts));
+        const double x = __dadd_rn(__dmul_rn((double)tx, dx), __dmul_rn((double)(a.ixyz[3 * b] * BS), dx));
+        const double y = __dadd_rn(__dmul_rn((double)ty, dy), __dmul_rn((double)(a.ixyz[3 * b + 1] * BS), dy));
+        gz0 = __dmul_rn((double)(a.ixyz[3 * b + 2] * BS), dz);
+        const double ex = __dsub_rn(x, cx), ey = __dsub_rn(y, cy);
+        gxy2 = __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
+    }
+
+    // offsets inside a component region: centre, and the x-direction taps (the x halo columns live behind the rows)
+    const int cidx = (ty + H) * BS + tx;
+    int xo[2 * H + 1];
+#pragma unroll
+    for (int o = -H; o <= H; ++o) {
+        const int x = tx + o;
+        xo[o + H] = x < 0 ? ROWS * BS + ty * XW + (XW + x) : (x >= BS ? ROWS * BS + BS * XW + ty * XW + (x - BS) : cidx + o);
+    }
+    constexpr long long CS = (long long)BS * BS * BS;
+    double umag_max = 0.0, uabs_max = 0.0;
+
+#pragma unroll
+    for (int q = 0; q < 2 * H; ++q) mbar_wait(&s_full[q], 0);      // the first iteration reads planes 0 .. 2H; it waits for plane 2H itself
+
+#pragma unroll 1
+    for (int z = 0; z < BS; ++z) {
+        if (SLACK == 0) __syncthreads();               // every thread has left iteration z-1: the slot of its oldest plane is free
+        if (lane == 0) {
+            const int q = z + 2 * H + PF;
+            if (q < NQ) issue(q);
+        }
+        __syncwarp();
+        mbar_wait(&s_full[(z + 2 * H) % RING], ((z + 2 * H) / RING) & 1);   // plane z+2H has landed (planes z .. z+2H-1 were waited for earlier)
+
+        const long long gi = ((long long)b * NC) * CS + (long long)z * BS * BS + ty * BS + tx;
+        double pre_u[4], pre_acc[4];
+        if (base_u_global) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) pre_u[c] = __ldg(a.u0 + gi + c * CS);
+        }
+        if (base_acc_global) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) pre_acc[c] = a.acc_in[gi + c * CS];
+        }
+
+        double rhs[4];
+        double ctr[4];
+        {
+            double d1v[3][4];
+            double d2v[3][3];
+            double cv[3][3];
+#pragma unroll
+            for (int dir = 0; dir < 3; ++dir) {
+                double qv[4][2 * H + 1];
+#pragma unroll
+                for (int o = -H; o <= H; ++o) {
+                    int off;
+                    if (dir == 0) off = ((z + H) % RING) * SLOT + xo[o + H];
+                    else if (dir == 1) off = ((z + H) % RING) * SLOT + cidx + o * BS;
+                    else off = ((z + H + o) % RING) * SLOT + cidx;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) qv[c][o + H] = sm[off + c * RS];
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) d1v[dir][c] = S::d1(&qv[c][H], dinv[dir]);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) d2v[dir][c] = S::d2(&qv[c][H], d2inv[dir]);
+                if (SKEW) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) cv[dir][c] = S::d1p(&qv[c][H], &qv[dir][H], dinv[dir]);
+                }
+                if (dir == 0) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) ctr[c] = qv[c][H];
+                }
+            }
+            const double u = ctr[0], v = ctr[1], w = ctr[2], p = ctr[3];
+            double penal[3] = {0.0, 0.0, 0.0};
+            const long long g0 = ((long long)b * a.n_mask) * CS + (long long)z * BS * BS + ty * BS + tx;
+            if (GEOM) {
+                const double ez = __dsub_rn(__dadd_rn(__dmul_rn((double)z, dz), gz0), gcz);
+                const double dist = __dsub_rn(sqrt(__dadd_rn(gxy2, __dmul_rn(ez, ez))), a.g_R);
+                double m = 0.0;
+                if (dist <= -a.g_h) m = 1.0;
+                else if (dist < a.g_h) m = 0.5 * (1.0 + cos((dist + a.g_h) * 3.14159265358979323846 / (2.0 * a.g_h)));
+                const double chi = m * a.C_eta_inv;
+                penal[0] = -chi * (u - a.g_v[0]);
+                penal[1] = -chi * (v - a.g_v[1]);
+                penal[2] = -chi * (w - a.g_v[2]);
+            } else if (a.mask) {
+                const int color = (int)a.mask[g0 + 4 * CS];
+                const double chi = a.mask[g0] * (color == 0 ? 0.0 : a.C_eta_inv);
+                penal[0] = -chi * (u - a.mask[g0 + 1 * CS]);
+                penal[1] = -chi * (v - a.mask[g0 + 2 * CS]);
+                penal[2] = -chi * (w - a.mask[g0 + 3 * CS]);
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                double adv;
+                if (SKEW) adv = -0.5 * (cv[0][c] + cv[1][c] + cv[2][c] + u * d1v[0][c] + v * d1v[1][c] + w * d1v[2][c]);
+                else adv = (-u * d1v[0][c] - v * d1v[1][c] - w * d1v[2][c]);
+                rhs[c] = adv - d1v[c][3] + a.nu * (d2v[0][c] + d2v[1][c] + d2v[2][c]) + penal[c];
+            }
+            rhs[3] = -c02 * (d1v[0][0] + d1v[1][1] + d1v[2][2]) - a.gamma_p * p;
+            if (a.use_sponge && a.mask) {
+                const double spo = a.mask[g0 + 5 * CS] * a.C_sponge_inv;
+                rhs[0] = rhs[0] - (u - a.u_mean_set[0]) * spo;
+                rhs[1] = rhs[1] - (v - a.u_mean_set[1]) * spo;
+                rhs[2] = rhs[2] - (w - a.u_mean_set[2]) * spo;
+                rhs[3] = rhs[3] - p * spo;
+            }
+        }
+        uabs_max = fmax(uabs_max, fmax(fmax(fabs(ctr[0]), fabs(ctr[1])), fmax(fabs(ctr[2]), fabs(ctr[3]))));
+
+        double un[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (a.k_out) a.k_out[gi + c * CS] = rhs[c];
+            if (a.u_out) {
+                double acc = base_u_global ? pre_u[c] : ctr[c];
+                for (int l = 0; l < a.n_prev; ++l)
+                    acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dt, a.coef_prev[l]), a.k_prev[l][gi + c * CS]));
+                if (a.use_self) acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dt, a.coef_self), rhs[c]));
+                a.u_out[gi + c * CS] = acc;
+                un[c] = acc;
+            }
+            if (a.acc_out) {
+                double acc = base_acc_global ? pre_acc[c] : ctr[c];
+                if (a.use_acc) acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dt, a.coef_acc), rhs[c]));
+                a.acc_out[gi + c * CS] = acc;
+            }
+        }
+        if (a.dtmin_bits && a.u_out) {
+            const double m = __dadd_rn(__dadd_rn(__dmul_rn(un[0], un[0]), __dmul_rn(un[1], un[1])), __dmul_rn(un[2], un[2]));
+            umag_max = fmax(umag_max, m);
+        }
+        if (SLACK > 0) {
+            __syncwarp();                              // every lane has consumed its reads of plane z: this warp releases the slot
+            if (lane == 0) mbar_arrive(&s_empty[z % RING]);
+        }
+    }
+
+    uabs_max = warp_max(uabs_max);
+    umag_max = warp_max(umag_max);
+    if (lane == 0) s_red[wid] = uabs_max;
+    __syncthreads();
+    if (tid == 0) {
+        double m = 0.0;
+        for (int i = 0; i < NW; ++i) m = fmax(m, s_red[i]);
+        if (m > 1.0e12) atomicExch(a.diverged, 1);
+    }
+    if (a.dtmin_bits && a.u_out) {
+        __syncthreads();
+        if (lane == 0) s_red[wid] = umag_max;
+        __syncthreads();
+        if (tid == 0) {
+            double m = 0.0;
+            for (int i = 0; i < NW; ++i) m = fmax(m, s_red[i]);
+            const double u_eigen = __dadd_rn(sqrt(m), sqrt(__dadd_rn(c02, m)));
+            double dxmin = dx;
+            if (a.dim_min_axes > 1) dxmin = fmin(dxmin, dy);
+            if (a.dim_min_axes > 2) dxmin = fmin(dxmin, dz);
+            double dtb = (u_eigen >= 1.0e-6) ? __ddiv_rn(__dmul_rn(a.CFL, dxmin), u_eigen) : 1.0e-2;
             if (a.nu > 1.0e-13) dtb = fmin(dtb, __ddiv_rn(__dmul_rn(a.CFL_nu, __dmul_rn(dxmin, dxmin)), a.nu));
             atomicMin(a.dtmin_bits, (unsigned long long)__double_as_longlong(dtb));
         }
@@ -1114,6 +1426,52 @@ __global__ void wait_flags_kernel(const unsigned *flags, const int *__restrict__
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// tensor maps of a resident array for stage_kernel_tma (cuTensorMapEncodeTiled through the runtime's driver entry point: libcuda is not
+// linked).  Rank 4: x, y, z, (block * NC + component); boxes Bs x Bs (a plane), Bs x H (y halo rows), XW x Bs (x halo columns).
+// ---------------------------------------------------------------------------------------------
+struct TmaMaps {
+    CUtensorMap m[3];
+};
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+const TmaMaps *tma_maps(wgpu_ctx *ctx, const double *base, int BS, int H)
+{
+    typedef std::unordered_map<const void *, TmaMaps> Cache;
+    if (!ctx->tma_cache) ctx->tma_cache = new Cache();
+    Cache &cache = *(Cache *)ctx->tma_cache;
+    auto it = cache.find(base);
+    if (it != cache.end()) return &it->second;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return nullptr;
+    const int XW = (H + 1) & ~1;
+    const cuuint64_t dims[4] = {(cuuint64_t)BS, (cuuint64_t)BS, (cuuint64_t)BS, (cuuint64_t)ctx->nc * (cuuint64_t)ctx->cfg.max_blocks};
+    const cuuint64_t strides[3] = {(cuuint64_t)BS * 8, (cuuint64_t)BS * BS * 8, (cuuint64_t)BS * BS * BS * 8};
+    const cuuint32_t boxes[3][4] = {{(cuuint32_t)BS, (cuuint32_t)BS, 1, 1}, {(cuuint32_t)BS, (cuuint32_t)H, 1, 1}, {(cuuint32_t)XW, (cuuint32_t)BS, 1, 1}};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    TmaMaps t;
+    for (int k = 0; k < 3; ++k)
+        if (enc(&t.m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void *)base, dims, strides, boxes[k], estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return nullptr;
+    return &cache.emplace(base, t).first->second;
+}
+
 template <int FD, bool SKEW, int BS>
 int32_t launch_stage_t(wgpu_ctx *ctx, const StageArgs &a, int n_blocks)
 {
@@ -1126,16 +1484,50 @@ int32_t launch_stage_t(wgpu_ctx *ctx, const StageArgs &a, int n_blocks)
     }
     const bool prof = ctx->profiling && ctx->prof_n < (int)ctx->prof_ev.size() / 2;
     if (prof) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], ctx->stream);
-    if (a.geom) {
-        if (FD != 4) {
-            ctx->err = "analytic mask: the stage kernel is instantiated for FD_4th_central only";
-            return WGPU_ERR_UNSUPPORTED;
+    if (a.geom && FD != 4) {
+        ctx->err = "analytic mask: the stage kernel is instantiated for FD_4th_central only";
+        return WGPU_ERR_UNSUPPORTED;
+    }
+    StageArgs rest = a;
+    bool rest_needed = true;
+    if constexpr (FD == 4 && BS == 16) {
+        // plain blocks through the TMA kernel; whatever it leaves (blocks at level jumps, partition or domain boundaries) through the
+        // cp.async kernel with skip_plain.  plain_hint: 1 every block of this launch is plain, -1 none is (skip the TMA launch)
+        // Measured on B200 (32 768 blocks, RK4 step): cp.async kernel 21.1 ms; TMA with one issuing thread and the block barrier 21.6 ms; TMA
+        // with the copies dealt over the warps and per-slot empty barriers (no block barrier) 26.9 ms -- the 16-byte-wide x-halo boxes and
+        // 20 small copies per plane cost the TMA unit more than the loader instructions cost the SMs.  Opt-in: WGPU_STAGE_TMA=1 (block barrier,
+        // shared issue) or 2 (empty barriers).
+        static const int mode = getenv("WGPU_STAGE_TMA") ? atoi(getenv("WGPU_STAGE_TMA")) : 0;
+        const TmaMaps *tm = (mode > 0 && a.plain_hint >= 0) ? tma_maps(ctx, a.u_in, BS, St<FD>::H) : nullptr;
+        if (tm) {
+            static bool tconf = false;
+            if (!tconf) {
+                WGPU_CHECK(ctx, cudaFuncSetAttribute(stage_kernel_tma<FD, SKEW, BS, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmaTile<FD, BS, 0>::SMEM));
+                WGPU_CHECK(ctx, cudaFuncSetAttribute(stage_kernel_tma<FD, SKEW, BS, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmaTile<FD, BS, 0>::SMEM));
+                WGPU_CHECK(ctx, cudaFuncSetAttribute(stage_kernel_tma<FD, SKEW, BS, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmaTile<FD, BS, 1>::SMEM));
+                WGPU_CHECK(ctx, cudaFuncSetAttribute(stage_kernel_tma<FD, SKEW, BS, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmaTile<FD, BS, 1>::SMEM));
+                tconf = true;
+            }
+            constexpr int NT = TmaTile<FD, BS, 0>::NT;
+            if (mode == 1) {
+                if (a.geom) stage_kernel_tma<FD, SKEW, BS, true, 0><<<n_blocks, NT, TmaTile<FD, BS, 0>::SMEM, ctx->stream>>>(a, tm->m[0], tm->m[1], tm->m[2]);
+                else stage_kernel_tma<FD, SKEW, BS, false, 0><<<n_blocks, NT, TmaTile<FD, BS, 0>::SMEM, ctx->stream>>>(a, tm->m[0], tm->m[1], tm->m[2]);
+            } else {
+                if (a.geom) stage_kernel_tma<FD, SKEW, BS, true, 1><<<n_blocks, NT, TmaTile<FD, BS, 1>::SMEM, ctx->stream>>>(a, tm->m[0], tm->m[1], tm->m[2]);
+                else stage_kernel_tma<FD, SKEW, BS, false, 1><<<n_blocks, NT, TmaTile<FD, BS, 1>::SMEM, ctx->stream>>>(a, tm->m[0], tm->m[1], tm->m[2]);
+            }
+            ctx->launches++;
+            WGPU_CHECK(ctx, cudaGetLastError());
+            rest.skip_plain = 1;
+            rest_needed = a.plain_hint <= 0;
         }
-        stage_kernel<FD, SKEW, BS, (FD == 4)><<<n_blocks, T::NT, T::SMEM, ctx->stream>>>(a);
-    } else
-        stage_kernel<FD, SKEW, BS, false><<<n_blocks, T::NT, T::SMEM, ctx->stream>>>(a);
+    }
+    if (rest_needed) {
+        if (a.geom) stage_kernel<FD, SKEW, BS, (FD == 4)><<<n_blocks, T::NT, T::SMEM, ctx->stream>>>(rest);
+        else stage_kernel<FD, SKEW, BS, false><<<n_blocks, T::NT, T::SMEM, ctx->stream>>>(rest);
+        ctx->launches++;
+    }
     if (prof) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n++ + 1], ctx->stream);
-    ctx->launches++;
     WGPU_CHECK(ctx, cudaGetLastError());
     return WGPU_OK;
 }
@@ -1383,4 +1775,10 @@ int32_t wgpu_launch_span_pack(wgpu_ctx *ctx, const double *src, double *stg, con
     ctx->launches++;
     WGPU_CHECK(ctx, cudaGetLastError());
     return WGPU_OK;
+}
+
+void wgpu_tma_release(wgpu_ctx *ctx)
+{
+    if (ctx->tma_cache) delete (std::unordered_map<const void *, TmaMaps> *)ctx->tma_cache;
+    ctx->tma_cache = nullptr;
 }

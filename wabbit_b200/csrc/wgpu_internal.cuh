@@ -73,6 +73,8 @@ struct StageArgs {
     int geom;                        // 0: mask arrays, 1: sphere
     const int *ixyz;                 // [max_blocks][3] block coordinates on their level
     double g_c0[3], g_v[3], g_R, g_h;
+    int skip_plain;                  // leave blocks whose six face neighbours are resident same-level blocks (stage_kernel_tma took them)
+    int plain_hint;                  // 1: every block of this launch is such a block, -1: none is, 0: unknown / mixed
     double t0, t_cj;                 // stage time = t0 + t_cj * dt
     const double *t0_ptr;            // != nullptr: t0 is read from the device (wgpu_rk_steps)
 };
@@ -231,6 +233,8 @@ struct wgpu_ctx {
     unsigned p2p_seq = 0;              // stages exchanged so far (flag value of the next one = p2p_seq + 1)
     double *d_pool_user = nullptr;     // the caller's pool of wgpu_set_exchange (used by the NCCL / host-driven paths)
 
+    void *tma_cache = nullptr;         // tensor maps of the resident arrays (kernels.cu: tma_maps)
+
     // optional event pairs around stage launches
     bool profiling = false;
     std::vector<cudaEvent_t> prof_ev;   // [2*i], [2*i+1]
@@ -263,6 +267,7 @@ struct wgpu_ctx {
 int32_t wgpu_rk_end_nosync(wgpu_ctx *ctx);
 // kernels.cu
 int32_t wgpu_launch_stage(wgpu_ctx *ctx, const StageArgs &a, int n_blocks);
+void wgpu_tma_release(wgpu_ctx *ctx);
 int32_t wgpu_launch_pack(wgpu_ctx *ctx, const double *src);
 int32_t wgpu_launch_pack_put(wgpu_ctx *ctx, const double *src, int parity, unsigned seq, cudaStream_t st);
 int32_t wgpu_launch_wait_flags(wgpu_ctx *ctx, unsigned seq, cudaStream_t st);
