@@ -384,6 +384,9 @@ def run_ours(a):
             legs = [l for l in legs if l[0] in a.adaptive_legs.split(",")]
         for name, bs, j0, sph in legs:
             adaptive_lifted[name] = adaptive_leg_multi(a, rank, world, local, stream, J0=j0, Jmax=j0 + 1, wavelet="CDF44", bs=bs, sphere_on=sph)
+    weak = None
+    if world == 8 and not a.no_weak:
+        weak = weak_scaling_leg(a, rank, world, local, stream)
     compression = None
     if not a.no_compression:
         idx = list(range(51)) if a.compression_full else (list(range(0, 51, 5)) if world == 1 else list(range(0, 51, 10)))
@@ -393,6 +396,8 @@ def run_ours(a):
                                                                           wavelets=("CDF40", "CDF42", "CDF44") if a.compression_full else ("CDF44",),
                                                                           eps_idx=idx if a.compression_full else [20, 30, 40])
     if rank == 0:
+        if weak is not None:
+            line["weak_scaling"] = weak
         if compression is not None:
             line["compression"] = compression
         if adaptive is not None:
@@ -778,6 +783,80 @@ def adaptive_leg_multi(a, rank, world, local, stream, eps=None, J0=5, Jmax=6, cy
     return rec
 
 
+def weak_scaling_leg(a, rank, world, local, stream):
+    """The N = 1 workload on EVERY GPU: the equidistant grid one level finer (8^(J+1) blocks) over 8 GPUs = 32 768 blocks per GPU, the same
+    per-GPU work as the headline's single-GPU run (an octree's block count only tiles the GPUs evenly for N = 1 and N = 8).  Taylor-Green
+    evaluated on the device straight into the resident hvy_block; same stepper (wgpu_rk_steps), same checksum convention."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from wabbit_b200 import Forest, WabbitGPU
+    from wabbit_b200.multi import _DevPtr, attach_exchange
+    level = a.level + 1
+    a2 = argparse.Namespace(**vars(a))
+    a2.level = level
+    p = make_params(a2)
+    rec = {"metric": METRIC, "unit": UNIT, "scaling": "weak", "level": level, "blocks": 8 ** level, "blocks_per_gpu": 8 ** level // world, "n_gpus": world}
+    sol = None
+    try:
+        forest = Forest.uniform(3, level, block_dist="sfc_hilbert", n_ranks=world)
+        hvy, lvl, ixyz, _ = forest.active(rank)
+        sol = WabbitGPU(p, max_blocks=forest.max_blocks, device=local, stream=stream.cuda_stream)
+        sol.comm_init(rank, world)
+        attach_exchange(sol, forest, rank, world)
+        ptr, n = C.c_void_p(), C.c_int64()
+        sol._check(sol._lib.wgpu_device_pointer(sol._ctx, 0, 0, C.byref(ptr), C.byref(n)))
+        dev = torch.device("cuda", local)
+        Bs = a.bs
+        U = torch.as_tensor(_DevPtr(ptr.value, n.value), device=dev).view(sol.max_blocks, 4, Bs, Bs, Bs)
+        dx = TWO_PI / (2 ** level * Bs)
+        idx = torch.arange(Bs, dtype=torch.float64, device=dev)
+        assert (np.diff(hvy) == 1).all()
+        for s0 in range(0, len(hvy), 4096):
+            e = min(s0 + 4096, len(hvy))
+            x0 = torch.from_numpy((ixyz[s0:e] * Bs).astype(np.float64)).to(dev) * dx
+            X = (idx[None, :] * dx + x0[:, 0:1])[:, None, None, :]
+            Y = (idx[None, :] * dx + x0[:, 1:2])[:, None, :, None]
+            Z = (idx[None, :] * dx + x0[:, 2:3])[:, :, None, None]
+            blk = U[int(hvy[s0]) - 1:int(hvy[s0]) - 1 + (e - s0)]
+            blk[:, 0] = torch.sin(X) * torch.cos(Y) * torch.cos(Z)
+            blk[:, 1] = -torch.cos(X) * torch.sin(Y) * torch.cos(Z)
+            blk[:, 2] = 0.0
+            blk[:, 3] = (torch.cos(2.0 * X) + torch.cos(2.0 * Y)) * (torch.cos(2.0 * Z) + 2.0) / 16.0
+        torch.cuda.synchronize()
+        steps = max(1, min(a.steps, 20))
+        t, _ = sol.stepper.steps(0.0, a.warmup)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        t, _dt = sol.stepper.steps(t, steps)
+        e1.record(stream)
+        dist.barrier()
+        torch.cuda.synchronize()
+        tm = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms = float(tm.item())
+        sol.setup_wavelet("CDF40")
+        tck = torch.tensor(list(sol.componentWiseNorm_tree((0, 0), "Linfty")), dtype=torch.float64, device=dev)
+        dist.all_reduce(tck, op=dist.ReduceOp.MAX)
+        rec.update({"value": 8 ** level * steps / (ms * 1e-3), "per_gpu_value": 8 ** level * steps / (ms * 1e-3) / world, "steps": steps,
+                    "ms_per_step": ms / steps, "transport": sol.comm_transport(),
+                    "checksum": {"time": t, "linfty": [float(v).hex() for v in tck.cpu().tolist()]},
+                    "note": "weak-scaling efficiency = per_gpu_value / the N = 1 line's value (same 32 768 blocks per GPU)"})
+    except Exception as e:      # noqa: BLE001 -- a secondary figure must not take the headline line down
+        import traceback
+        rec["error"] = repr(e)
+        rec["traceback"] = traceback.format_exc()[-1200:]
+    finally:
+        if sol is not None:
+            try:
+                sol.close()
+            except Exception:
+                pass
+    return rec
+
+
 def compression_leg(a, rank, world, local, stream, J, wavelets=("CDF40", "CDF42", "CDF44"), eps_idx=None, bs=16):
     """BASELINE config 5: the protocol of post_compression_unit_test.f90:107-215 (wabbit_b200/compression.py) -- one component, Gauss blob on the
     equidistant level-J grid, adapt_tree (full wavelet transformation; coarse extension + security zone for the lifted wavelets), Nb,
@@ -855,6 +934,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-wavelet", action="store_true", help="skip the secondary FWT + threshold figure")
     ap.add_argument("--no-adaptive", action="store_true", help="skip the secondary adaptive-cycle figure")
+    ap.add_argument("--no-weak", action="store_true", help="N = 8: skip the weak-scaling record (one level finer, 32 768 blocks per GPU)")
     ap.add_argument("--no-compression", action="store_true", help="skip the compression-protocol figure (BASELINE config 5)")
     ap.add_argument("--compression-level", type=int, default=5)
     ap.add_argument("--compression-full", action="store_true", help="all 51 thresholds, three wavelets, levels J and J+1")

@@ -171,6 +171,25 @@ int32_t wgpu_set_transfer_mode(wgpu_ctx *ctx, int32_t upload_mode, int32_t downl
  */
 int32_t wgpu_sync_ghosts(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t g_minus, int32_t g_plus);
 
+/*
+ * ---- mask function and statistics on the device (the physics module's CREATE_MASK / STATISTICS entry points for the ACM module)
+ * wgpu_create_mask: createMask_tree -> create_mask_2D_ACM / create_mask_3D_ACM (LIB/MESH/createMask_tree.f90, LIB/EQUATION/ACMnew/
+ *   create_mask.f90:6-320) for the closed-form geometries: WGPU_GEOM_CYLINDER (2-D "cylinder" / "circle", draw_circle) with the p-norm sponge
+ *   of sponge_2D (LIB/EQUATION/ACMnew/sponge.f90) and WGPU_GEOM_SPHERE (3-D, draw_sphere; centre(t) = center0 + velocity * time, u_s = velocity),
+ *   cosine smoothing of width `smoothing_width` (= C_smooth * dx_min, module_ACM.f90:459-471).  Writes the six components [chi, u_s(3),
+ *   colour = 1, sponge] of every active block's interior into the resident hvy_mask; nothing crosses PCIe.  chi is drawn only with
+ *   penalization = 1, the sponge only with use_sponge = 1 (as the reference).  Other geometries (insects, STL): fill hvy_mask with wgpu_upload.
+ * wgpu_statistics: the integral_stage + post_stage reductions of STATISTICS_ACM (LIB/EQUATION/ACMnew/statistics_ACM.f90:138-430) over the
+ *   active blocks (and over the ranks of the communicator): out[0..2] mean flow * volume, [3] e_kin, [4] ACM energy, [5] mask volume (colour 1),
+ *   [6] sponge volume, [7..9] penalization power (solid input, solid dissipation, sponge), [10..12] force on colour 1, [13] max |u|^2,
+ *   [14] / [15] max / min of div(u) outside the solid (with_divergence = 1: one RHS evaluation into hvy_work slot 2, whose pressure row is
+ *   -c0^2 div(u) - gamma_p p; else 0), [16..18] residual velocity in the solid (sum over blocks of max * dV, as the reference).  out: 19 doubles.
+ */
+enum { WGPU_GEOM_CYLINDER = 1, WGPU_GEOM_SPHERE = 2 };
+int32_t wgpu_create_mask(wgpu_ctx *ctx, double time, int32_t geometry, const double *center0, const double *velocity, double radius,
+                         double smoothing_width, double L_sponge, double p_sponge);
+int32_t wgpu_statistics(wgpu_ctx *ctx, double time, int32_t with_divergence, double *out);
+
 /* wgpu_set_ghost_filter: the ignore_Filter switch of sync_ghosts_tree (LIB/MPI/synchronize_ghosts_generic.f90:125-153).  With a lifted
  *   wavelet (CDFXY, Y > 0) the reference's default synchronisation restricts through the HD filter: a ghost node owned by a finer
  *   neighbour receives the filtered value, except next to that neighbour's own coarser / finer neighbours, where the plain value is

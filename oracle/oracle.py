@@ -664,3 +664,64 @@ def coarse_extension_modify(grid: Grid, p: Params, w: Wavelet, wd: np.ndarray, o
                                       int(clear_wc), int(copy_sc))
                 n += 1
     return n
+
+
+FD1 = {"FD_2nd_central": (1, [-0.5, 0.0, 0.5]), "FD_4th_central": (2, [1.0 / 12.0, -2.0 / 3.0, 0.0, 2.0 / 3.0, -1.0 / 12.0]),
+       "FD_6th_central": (3, [-1.0 / 60.0, 3.0 / 20.0, -3.0 / 4.0, 0.0, 3.0 / 4.0, -3.0 / 20.0, 1.0 / 60.0])}
+
+
+def statistics_acm(grid: Grid, p: Params, hvy: np.ndarray, mask: Optional[np.ndarray] = None) -> dict:
+    """The integral_stage of STATISTICS_ACM (LIB/EQUATION/ACMnew/statistics_ACM.f90:138-368) summed over the blocks (post_stage, :396-430), numpy.
+    hvy: ghost-synchronised state [nb, nc, nz, ny, nx]; mask: hvy_mask [nb, 6, nz, ny, nx] or None.  compute_divergence: central differences of
+    the module's discretization (LIB/OPERATORS/divergence.f90), set to zero where mask(1) > 0."""
+    dim, g = p.dim, p.g
+    I = interior(p)
+    H, a = FD1[p.discretization]
+    out = {k: 0.0 for k in ("meanflow_x", "meanflow_y", "meanflow_z", "e_kin", "ACM_energy", "mask_volume", "sponge_volume", "penal_power_solid_input",
+                            "penal_power_solid_dissipation", "penal_power_sponge", "force_x", "force_y", "force_z", "umag", "div_max", "div_min",
+                            "u_residual_x", "u_residual_y", "u_residual_z")}
+    C_eta_inv, C_sp_inv = 1.0 / p.C_eta, 1.0 / p.C_sponge
+    names = "xyz"
+    for b in range(grid.n):
+        dx = [2.0 ** (-float(grid.level[b])) * p.domain[d] / float(p.Bs[d]) for d in range(dim)]
+        dV = float(np.prod(dx))
+        u = hvy[b]
+        vel = [u[d][I] for d in range(dim)]
+        pr = u[dim][I]
+        for d in range(dim):
+            out["meanflow_" + names[d]] += float(vel[d].sum()) * dV
+        ek = 0.5 * sum(float((v * v).sum()) for v in vel)
+        out["e_kin"] += ek * dV
+        out["ACM_energy"] += (0.5 * float((pr * pr).sum()) / p.c0 ** 2 + ek) * dV
+        out["umag"] = max(out["umag"], float(sum(v * v for v in vel).max()))
+        div = np.zeros_like(pr)
+        for d in range(dim):
+            ax = {0: 2, 1: 1, 2: 0}[d]             # u[c, z, y, x]: x is the last axis (nz = 1 in 2-D)
+            comp = u[d]
+            acc = np.zeros_like(pr)
+            for k, coef in enumerate(a):
+                if coef == 0.0:
+                    continue
+                sl = list(I)
+                s0 = sl[ax]
+                sl[ax] = slice(s0.start + k - H, s0.stop + k - H)
+                acc = acc + coef * comp[tuple(sl)]
+            div = div + acc / dx[d]
+        if mask is not None:
+            chi = mask[b][0][I]
+            div = np.where(chi > 0.0, 0.0, div)
+        out["div_max"] = max(out["div_max"], float(div.max()))
+        out["div_min"] = min(out["div_min"], float(div.min()))
+        if mask is not None and (p.penalization or p.use_sponge):
+            us = [mask[b][1 + d][I] for d in range(dim)]
+            sp = mask[b][5][I] if (p.use_sponge and mask.shape[1] > 5) else np.zeros_like(chi)
+            out["mask_volume"] += float(chi.sum()) * dV
+            out["sponge_volume"] += float(sp.sum()) * dV
+            out["penal_power_solid_input"] += float((sum(us[d] * (vel[d] - us[d]) for d in range(dim)) * chi * C_eta_inv).sum()) * dV
+            out["penal_power_solid_dissipation"] += float((sum((vel[d] - us[d]) ** 2 for d in range(dim)) * chi * C_eta_inv).sum()) * dV
+            if p.use_sponge:
+                out["penal_power_sponge"] += float(((sum(vel[d] * (vel[d] - p.u_mean_set[d]) for d in range(dim)) + pr * pr / p.c0 ** 2) * sp * C_sp_inv).sum()) * dV
+            for d in range(dim):
+                out["force_" + names[d]] += float((chi * (vel[d] - us[d]) * C_eta_inv).sum()) * dV
+                out["u_residual_" + names[d]] += float((np.abs(vel[d] - us[d]) * chi).max()) * dV
+    return out

@@ -1,0 +1,89 @@
+"""Device-side mask function and statistics: wgpu_create_mask against the host / oracle generators of create_mask_2D_ACM
+(cylinder + p-norm sponge) and create_mask_3D_ACM (sphere), wgpu_statistics against the oracle's numpy restatement of STATISTICS_ACM's
+integral stage (oracle.statistics_acm; pinned on the CPU by the analytic Taylor-Green integrals, tests/test_oracle_statistics.py)."""
+import numpy as np
+import pytest
+
+import adaptive as OA
+import oracle as O
+from wabbit_b200 import Forest, Params, WabbitGPU
+from wabbit_b200.mask import CylinderMask2D, SphereMask3D
+from wabbit_b200.solver import HVY_MASK
+
+from util import graded_blocks, orc_grid, orc_params, tg_params
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(a, b, tol=1e-12):
+    return abs(a - b) <= tol * max(abs(a), abs(b), 1e-30) + 1e-13
+
+
+def test_sphere_mask_and_statistics_3d():
+    lv, ix = graded_blocks(3, 1, 3, seed=4)
+    forest = Forest.from_blocks(3, 3, lv, ix)
+    p = tg_params(Bs=16, J=3)
+    p.penalization, p.C_eta = True, 1.0e-2
+    p = p.finalize()
+    po = orc_params(p)
+    grid = orc_grid(forest)
+    sol = WabbitGPU(p, max_blocks=forest.n_blocks)
+    sol.set_forest(forest)
+    u = O.alloc(grid, po)
+    O.inicond_taylor_green(grid, po, u)
+    u += 0.05 * np.random.default_rng(1).standard_normal(u.shape)
+    sol.upload(u)
+    sph = SphereMask3D(p, center=(3.0, 3.1, 3.2), radius=0.9, velocity=(0.5, 0.3, -0.2))
+    osph = OA.SphereMask3D(po, center=(3.0, 3.1, 3.2), radius=0.9, velocity=(0.5, 0.3, -0.2))
+    t = 0.37
+    sph.fill_device(sol, t)
+    got = np.zeros((grid.n, 6) + u.shape[2:])
+    sol.download(got, HVY_MASK, g_sync=0)
+    ref = np.stack([osph.block(int(l), x, t) for l, x in zip(grid.level, grid.ixyz)])
+    I = (slice(None), slice(None)) + O.interior(po)
+    assert np.abs(got[I] - ref[I]).max() <= 1e-14 and ref[I][:, 0].max() == 1.0 and 0.0 < ref[I][:, 0].mean() < 0.2
+    # statistics: the oracle reads the ghost-synchronised state and the same mask
+    synced = u.copy()
+    O.sync_ghosts_leaf(grid, po, synced, forest.neighbors(0)[:, :grid.n], po.g, po.g, 4, True)
+    want = O.statistics_acm(grid, po, synced, ref)
+    have = sol.statistics_ACM(t, with_divergence=True)
+    for k in want:
+        tol = 1e-9 if k.startswith("div") else 1e-12          # the divergence is recovered from the pressure row of the RHS (c0^2 = 100)
+        assert _close(have[k], want[k], tol), (k, have[k], want[k])
+    assert want["mask_volume"] > 1.0 and abs(want["force_x"]) > 0.0 and want["div_max"] > 0.0
+    sol.close()
+
+
+def test_cylinder_mask_sponge_and_statistics_2d():
+    p = Params(dim=2, domain=(20.0, 20.0, 0.0), Bs=(26, 26, 1), wavelet="CDF44", g=6, g_rhs=2, n_eqn=3, Jmax=4, discretization="FD_4th_central",
+               skew_symmetry=True, c0=20.0, nu=1.0e-2, gamma_p=1.0, CFL=1.0, u_mean_set=(1.0, 0.0, 0.0), time_max=1.0e9)
+    p.penalization, p.C_eta, p.use_sponge, p.C_sponge = True, 1.0e-3, True, 1.0e-2
+    p = p.finalize()
+    forest = Forest.uniform(2, 3, Jmax=4)
+    sol = WabbitGPU(p, max_blocks=forest.n_blocks)
+    sol.set_forest(forest)
+    hvy, lvl, ixyz, _ = forest.active(0)
+    cyl = CylinderMask2D(p, x_cntr=(9.0, 10.5), R_cyl=1.0, C_smooth=1.5, L_sponge=2.0, p_sponge=20.0)
+    cyl.fill_device(sol, 0.0)
+    got = np.zeros((len(hvy), 6, 1, 26 + 12, 26 + 12))
+    sol.download(got, HVY_MASK, g_sync=0)
+    ref = cyl.fill(lvl, ixyz)
+    g = p.g
+    assert np.abs(got[:, :, :, g:-g, g:-g] - ref[:, :, :, g:-g, g:-g]).max() <= 1e-13
+    assert ref[:, 5].max() == 1.0 and ref[:, 0].max() == 1.0
+    po = orc_params(p)
+    grid = orc_grid(forest)
+    u = O.alloc(grid, po)
+    rng = np.random.default_rng(3)
+    u[:] = rng.standard_normal(u.shape) * 0.1
+    u[:, 0] += 1.0
+    sol.upload(u)
+    synced = u.copy()
+    O.sync_ghosts_same_level(grid, po, synced, g, g)
+    want = O.statistics_acm(grid, po, synced, ref)
+    have = sol.statistics_ACM(0.0, with_divergence=True)
+    for k in want:
+        tol = 1e-8 if k.startswith("div") else 1e-12
+        assert _close(have[k], want[k], tol), (k, have[k], want[k])
+    assert want["sponge_volume"] > 10.0 and want["penal_power_sponge"] != 0.0 and want["force_x"] > 0.0
+    sol.close()

@@ -494,6 +494,7 @@ int32_t wgpu_destroy(wgpu_ctx *ctx)
     cudaFree(ctx->d_time);
     cudaFree(ctx->d_flags);
     cudaFree(ctx->d_stage);
+    cudaFree(ctx->d_stat);
     for (int k = 0; k < 2; ++k) {
         cudaFree(ctx->d_span[k]);
         if (ctx->ev_dma[k]) cudaEventDestroy(ctx->ev_dma[k]);
@@ -1059,6 +1060,83 @@ int32_t wgpu_rhs(wgpu_ctx *ctx, double time, int32_t src_slot, int32_t dst_slot)
     rc = wgpu_launch_stage(ctx, a, ctx->n_active);
     if (rc) return rc;
     return check_flags(ctx);
+}
+
+// ------------------------------------------------------------------------------------------------ mask function and statistics on the device
+int32_t wgpu_create_mask(wgpu_ctx *ctx, double time, int32_t geometry, const double *center0, const double *velocity, double radius,
+                         double smoothing_width, double L_sponge, double p_sponge)
+{
+    if (!ctx || !center0) return WGPU_ERR_ARG;
+    const wgpu_config &c = ctx->cfg;
+    if (!ctx->MASK || c.n_mask < 5) return fail(ctx, WGPU_ERR_ARG, "wgpu_create_mask: the context has no hvy_mask (n_mask = 0)");
+    if (geometry != WGPU_GEOM_CYLINDER && geometry != WGPU_GEOM_SPHERE) return fail(ctx, WGPU_ERR_UNSUPPORTED, "wgpu_create_mask: geometry must be cylinder (1) or sphere (2)");
+    if ((geometry == WGPU_GEOM_CYLINDER) != (c.dim == 2)) return fail(ctx, WGPU_ERR_ARG, "wgpu_create_mask: cylinder is 2-D, sphere is 3-D");
+    if (c.penalization && !(smoothing_width > 0.0)) return fail(ctx, WGPU_ERR_ARG, "wgpu_create_mask: smoothing width must be positive");
+    if (!ctx->lookup_ready || !ctx->d_ixyz) return fail(ctx, WGPU_ERR_ARG, "wgpu_create_mask: block positions unknown (wgpu_set_treecodes / wgpu_set_grid first)");
+    MaskGeom gm;
+    memset(&gm, 0, sizeof(gm));
+    gm.penalization = c.penalization;
+    gm.use_sponge = c.use_sponge && c.n_mask > 5;
+    for (int d = 0; d < 3; ++d) {
+        gm.domain[d] = c.domain[d];
+        gm.c0[d] = d < c.dim ? center0[d] : 0.0;
+        gm.v[d] = (velocity && d < c.dim) ? velocity[d] : 0.0;
+    }
+    gm.R = radius;
+    gm.h = smoothing_width;
+    gm.L_sponge = L_sponge;
+    gm.p_sponge = p_sponge;
+    if (gm.use_sponge && !(L_sponge > 0.0 && p_sponge >= 1.0)) return fail(ctx, WGPU_ERR_ARG, "wgpu_create_mask: sponge needs L_sponge > 0 and p_sponge >= 1");
+    return wgpu_launch_create_mask(ctx, gm, time);
+}
+
+int32_t wgpu_statistics(wgpu_ctx *ctx, double time, int32_t with_divergence, double *out)
+{
+    if (!ctx || !out) return WGPU_ERR_ARG;
+    const wgpu_config &c = ctx->cfg;
+    if (ctx->nc != c.dim + 1) return fail(ctx, WGPU_ERR_UNSUPPORTED, "ACM needs number_equations = dim+1");
+    int32_t rc;
+    if (!ctx->d_stat && (rc = dmalloc(ctx, &ctx->d_stat, ((size_t)c.max_blocks + 1) * WGPU_NSTAT))) return rc;
+    const double *rhs = nullptr;
+    if (with_divergence) {
+        if ((rc = wgpu_rhs(ctx, time, 0, 2))) return rc;          // hvy_work(:,:,:,:,:,2) <- RHS(hvy_block): its pressure row carries div(u)
+        int ncw = 0;
+        rhs = array_ptr(ctx, WGPU_HVY_WORK, 2, &ncw);
+    }
+    StatArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    for (int d = 0; d < 3; ++d) {
+        sa.domain[d] = c.domain[d];
+        sa.u_mean_set[d] = c.u_mean_set[d];
+    }
+    sa.c0 = c.c0;
+    sa.gamma_p = c.gamma_p;
+    sa.C_eta_inv = 1.0 / c.C_eta;
+    sa.C_sponge_inv = 1.0 / c.C_sponge;
+    sa.use_sponge = c.use_sponge;
+    const double *mask = (c.n_mask >= 5 && (c.penalization || c.use_sponge)) ? ctx->MASK : nullptr;
+    double *d_out = ctx->d_stat + (size_t)c.max_blocks * WGPU_NSTAT;
+    if ((rc = wgpu_launch_stats(ctx, ctx->U, rhs, mask, sa, ctx->d_stat, d_out))) return rc;
+    WGPU_CHECK(ctx, cudaMemcpyAsync(out, d_out, sizeof(double) * WGPU_NSTAT, cudaMemcpyDeviceToHost, ctx->stream));
+    WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!with_divergence) out[14] = out[15] = 0.0;
+    if (ctx->comm && ctx->comm_world > 1) {      // the MPI_Allreduce calls of the post_stage (statistics_ACM.f90:396-430): SUM, MAX, MIN
+        double sums[16], mx[2], mn[1];
+        for (int k = 0; k < 13; ++k) sums[k] = out[k];
+        for (int k = 0; k < 3; ++k) sums[13 + k] = out[16 + k];
+        mx[0] = out[13];
+        mx[1] = out[14];
+        mn[0] = out[15];
+        if ((rc = wgpu_comm_allreduce(ctx, sums, 16, 2))) return rc;
+        if ((rc = wgpu_comm_allreduce(ctx, mx, 2, 0))) return rc;
+        if ((rc = wgpu_comm_allreduce(ctx, mn, 1, 1))) return rc;
+        for (int k = 0; k < 13; ++k) out[k] = sums[k];
+        for (int k = 0; k < 3; ++k) out[16 + k] = sums[13 + k];
+        out[13] = mx[0];
+        out[14] = mx[1];
+        out[15] = mn[0];
+    }
+    return WGPU_OK;
 }
 
 static int32_t compute_dt(wgpu_ctx *ctx, double time)

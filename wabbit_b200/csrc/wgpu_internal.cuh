@@ -79,6 +79,17 @@ struct StageArgs {
     const double *t0_ptr;            // != nullptr: t0 is read from the device (wgpu_rk_steps)
 };
 
+#define WGPU_NSTAT 19
+// closed-form mask geometry of create_mask_kernel (statistics.cu)
+struct MaskGeom {
+    int penalization, use_sponge;
+    double domain[3], c0[3], v[3], R, h, L_sponge, p_sponge;
+};
+struct StatArgs {
+    double domain[3], c0, gamma_p, C_eta_inv, C_sponge_inv, u_mean_set[3];
+    int use_sponge;
+};
+
 struct wgpu_ctx {
     wgpu_config cfg;
     cudaStream_t stream = nullptr;
@@ -233,6 +244,7 @@ struct wgpu_ctx {
     unsigned p2p_seq = 0;              // stages exchanged so far (flag value of the next one = p2p_seq + 1)
     double *d_pool_user = nullptr;     // the caller's pool of wgpu_set_exchange (used by the NCCL / host-driven paths)
 
+    double *d_stat = nullptr;          // [max_blocks + 1][WGPU_NSTAT]: per-block partial statistics, the result behind them
     void *tma_cache = nullptr;         // tensor maps of the resident arrays (kernels.cu: tma_maps)
 
     // optional event pairs around stage launches
@@ -284,6 +296,9 @@ int32_t wgpu_launch_copy_blocks(wgpu_ctx *ctx, const double *src, double *dst, c
 int32_t wgpu_launch_copy_entries(wgpu_ctx *ctx, const double *src, double *dst, const int *d_src_idx, int n, long long per_entry);
 // topology.cu
 int32_t wgpu_topology_halo_restrict(wgpu_ctx *ctx, const std::vector<int> &recv0, const std::vector<int> &send0);
+// statistics.cu
+int32_t wgpu_launch_create_mask(wgpu_ctx *ctx, const MaskGeom &gm, double time);
+int32_t wgpu_launch_stats(wgpu_ctx *ctx, const double *u, const double *rhs, const double *mask, const StatArgs &sa, double *d_part, double *d_out);
 // wavelet.cu
 int32_t wgpu_launch_wavelet(wgpu_ctx *ctx, const double *src, double *dst, int inverse, const double *ce_coarse);
 int32_t wgpu_launch_detail(wgpu_ctx *ctx, const double *wd, int eps_norm, int level_ref);

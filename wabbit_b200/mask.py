@@ -59,6 +59,10 @@ class CylinderMask2D:
             m[:, 5, 0, g:g + p.Bs[1], g:g + p.Bs[0]] = _step_cosine(tmp - 0.5 * self.L, 0.5 * self.L)
         return m
 
+    def fill_device(self, sol, time: float = 0.0):
+        """the same six components evaluated on the device straight into the resident hvy_mask (wgpu_create_mask): no host array, no upload"""
+        sol.create_mask_device(time, "cylinder", self.c, (0.0, 0.0), self.R, self.h, self.L, self.ps)
+
     def keeps(self, level, pos) -> np.ndarray:
         """threshold_mask (coarseningIndicatorMask_tree, LIB/MESH/coarseningIndicator_tree.f90:290-331): True where the mask function is
         not constant over the block's interior"""
@@ -83,6 +87,11 @@ class SphereMask3D:
 
     def attach(self, sol):
         sol.set_mask_sphere(self.c0, self.v, self.R, self.h)
+
+    def fill_device(self, sol, time: float = 0.0):
+        """the six mask components at `time` written into the resident hvy_mask on the device (wgpu_create_mask) -- for consumers that read
+        hvy_mask (statistics, a stage kernel without the in-kernel mask)"""
+        sol.create_mask_device(time, "sphere", self.c0, self.v, self.R, self.h)
 
     def keeps(self, level, pos, time: float = 0.0) -> np.ndarray:
         """threshold_mask: True where the mask function varies over the block's interior.  Blocks whose bounding box does not come within

@@ -228,6 +228,25 @@ class WabbitGPU:
         self._check(self._lib.wgpu_set_mask_sphere(self._ctx, 1, c.ctypes.data_as(dp), v.ctypes.data_as(dp), float(radius), float(smoothing_width)))
 
     # ------------------------------------------------------------------ reference routines
+    STAT_NAMES = ("meanflow_x", "meanflow_y", "meanflow_z", "e_kin", "ACM_energy", "mask_volume", "sponge_volume", "penal_power_solid_input",
+                  "penal_power_solid_dissipation", "penal_power_sponge", "force_x", "force_y", "force_z", "umag", "div_max", "div_min",
+                  "u_residual_x", "u_residual_y", "u_residual_z")
+
+    def create_mask_device(self, time: float, geometry: str, center, velocity=(0.0, 0.0, 0.0), radius: float = 0.5, smoothing_width: float = 0.0,
+                           L_sponge: float = 0.0, p_sponge: float = 20.0):
+        """createMask_tree for a closed-form geometry evaluated on the device into the resident hvy_mask (wgpu_create_mask): "cylinder" (2-D,
+        with the p-norm sponge) or "sphere" (3-D, optionally translating)"""
+        gid = {"cylinder": 1, "circle": 1, "sphere": 2, "sphere-fixed": 2}[geometry]
+        c = (C.c_double * 3)(*(list(center) + [0.0, 0.0, 0.0])[:3])
+        v = (C.c_double * 3)(*(list(velocity) + [0.0, 0.0, 0.0])[:3])
+        self._check(self._lib.wgpu_create_mask(self._ctx, float(time), gid, c, v, float(radius), float(smoothing_width), float(L_sponge), float(p_sponge)))
+
+    def statistics_ACM(self, time: float = 0.0, with_divergence: bool = True) -> dict:
+        """STATISTICS_ACM's integral quantities reduced on the device (and over the ranks of the communicator): wgpu_statistics"""
+        out = (C.c_double * 19)()
+        self._check(self._lib.wgpu_statistics(self._ctx, float(time), int(bool(with_divergence)), out))
+        return dict(zip(self.STAT_NAMES, [float(x) for x in out]))
+
     def sync_ghosts_RHS_tree(self, g_minus: Optional[int] = None, g_plus: Optional[int] = None):
         """synchronize_ghosts_generic.f90:155-174"""
         g = self.params.g_rhs
