@@ -28,6 +28,7 @@ def test_sphere_mask_and_statistics_3d():
     po = orc_params(p)
     grid = orc_grid(forest)
     sol = WabbitGPU(p, max_blocks=forest.n_blocks)
+    sol.setup_wavelet("CDF40")                 # the predictor order of the level-jump ghost patches
     sol.set_forest(forest)
     u = O.alloc(grid, po)
     O.inicond_taylor_green(grid, po, u)
