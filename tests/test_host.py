@@ -2,6 +2,7 @@
 and the forest tables (hvy_neighbor conventions) against an independent NumPy restatement."""
 import ctypes as C
 import os
+import sys
 import re
 
 import numpy as np
@@ -27,6 +28,30 @@ def test_gpu_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert set(names) == set(_native.GPU_SYMBOLS), set(names) ^ set(_native.GPU_SYMBOLS)
+
+
+def test_fortran_bridge_matches_the_header():
+    """fortran/module_gpu_bridge.f90 (the bind(C) module a WABBIT maintainer adds; no Fortran compiler here) is exactly what
+    fortran/gen_bridge.py generates from include/wabbit_gpu.h: one interface per exported function, the wgpu_config mirror in the header's
+    field order and types -- which is also the ctypes mirror's layout, byte for byte."""
+    sys.path.insert(0, os.path.join(ROOT, "fortran"))
+    import gen_bridge
+    text = gen_bridge.generate()
+    assert open(gen_bridge.OUT).read() == text, "regenerate: python fortran/gen_bridge.py"
+    names = _declared("wabbit_gpu.h")
+    for n in names:
+        assert f'bind(C, name="{n}")' in text, n
+    fields = gen_bridge.parse_config(gen_bridge.strip_comments(open(gen_bridge.HEADER).read()))
+    cty = {"int32_t": C.c_int32, "double": C.c_double}
+    mirror = _native.WgpuConfig._fields_
+    assert [f[0] for f in fields] == [m[0] for m in mirror]
+    size = 0
+    for (name, ctype, count), (mname, mtype) in zip(fields, mirror):
+        n = 1 if count is None else eval(count.replace("WGPU_MAX_STAGES", str(_native.WGPU_MAX_STAGES)))
+        want = cty[ctype] if count is None else cty[ctype] * n
+        assert C.sizeof(mtype) == C.sizeof(want) and (mtype is want or mtype._type_ is cty[ctype]), name
+        size += C.sizeof(want)
+    assert C.sizeof(_native.WgpuConfig) == size        # no padding: 20 x int32 before the first double
 
 
 def test_host_library_exports_every_declared_symbol():
