@@ -365,8 +365,9 @@ int32_t wgpu_block_count(const wgpu_ctx *ctx, int32_t which_blocks);
  *   wgpu_rk_steps            n_steps of RungeKuttaGeneric back to back (the N_dt_per_grid loop of LIB/POSTPROCESSING/performance_test.f90:
  *                            194-199): time, dt and the divergence flag stay on the device, dt's MIN over ranks is an ncclAllReduce on the
  *                            device scalar, every stage = pack -> grouped ncclSend / ncclRecv on a second stream, straight into the patch pool
- *                            resp. the halo slots of the stage input || stage kernel on interior blocks -> stage kernel on partition-boundary
- *                            blocks.  One host synchronisation at the end: *time_out = time after the last step, *dt_last its dt.
+ *                            resp. the halo slots of the stage input (face patches by default: the pack kernel stores them into the peers'
+ *                            pools over NVLink, see wgpu_comm_set_transport) || stage kernel on interior blocks -> stage kernel on
+ *                            partition-boundary blocks.  One host synchronisation at the end: *time_out = time after the last step, *dt_last its dt.
  *                            Works without a communicator (single GPU) as well.
  *   wgpu_exchange_array      refresh the halo copies (and, filtered != 0 with a lifted wavelet, the filtered copies of finer neighbours)
  *                            of a named array: before wgpu_fwt, wgpu_refine, wgpu_download with ghosts
