@@ -152,8 +152,8 @@ def run_reference(a):
     if rank != 0:
         return
     lvl = min(a.level, a.cpu_level)
-    steps = max(1, min(a.steps, 8))
-    warm = max(1, min(a.warmup, 2))
+    steps = max(1, min(a.steps, 6))
+    warm = 1
     v, ms, cores, nb = cpu_run(a, lvl, steps, warm)
     sample = f"{steps} RK4 steps on {nb} blocks (level {lvl}, Bs={a.bs}) of the {workload_name(a)} workload"
     line = {
@@ -728,9 +728,14 @@ def adaptive_leg_multi(a, rank, world, local, stream, eps=None, J0=5, Jmax=6, cy
                 break
         recs = []
         from wabbit_b200 import multi as _mg
+        prof = None
         for cyc in range(cycles + 2):
             if cyc == 2 and _mg.TIMING is not None:
                 _mg.TIMING.clear()
+            if cyc == 2 and rank == 0 and os.environ.get("WABBIT_PROFILE"):      # development: where the host time of a cycle goes
+                import cProfile
+                prof = cProfile.Profile()
+                prof.enable()
             sync()
             w0 = time.perf_counter()
             nb_rhs = drv.refine_tree().n_blocks
@@ -743,6 +748,13 @@ def adaptive_leg_multi(a, rank, world, local, stream, eps=None, J0=5, Jmax=6, cy
             sync()
             w3 = time.perf_counter()
             recs.append((nb_rhs, n1, w1 - w0, w2 - w1, w3 - w2))
+        if prof is not None:
+            import io
+            import pstats
+            prof.disable()
+            buf = io.StringIO()
+            pstats.Stats(prof, stream=buf).sort_stats("tottime").print_stats(45)
+            print(buf.getvalue(), file=sys.stderr, flush=True)
         if _mg.TIMING is not None and rank == 0:
             rec["phase_ms_per_cycle_rank0"] = {k: round(v * 1e3 / cycles, 2) for k, v in sorted(_mg.TIMING.items())}
         per_rank = [drv.forest.n_active(r) for r in range(world)]
@@ -929,8 +941,8 @@ def main():
     ap.add_argument("--bs", type=int, default=16)
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--e2e-trees", type=int, default=3, help="independent trees in flight in the end-to-end leg (1 = sequential only)")
-    ap.add_argument("--cpu-level", type=int, default=3)
-    ap.add_argument("--cpu-steps", type=int, default=6)
+    ap.add_argument("--cpu-level", type=int, default=4, help="level of the CPU arm's bounded sample (4: 4096 blocks, ~1 s per RK4 step on 16 cores)")
+    ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-wavelet", action="store_true", help="skip the secondary FWT + threshold figure")
     ap.add_argument("--no-adaptive", action="store_true", help="skip the secondary adaptive-cycle figure")
