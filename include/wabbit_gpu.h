@@ -248,6 +248,10 @@ int32_t wgpu_coarse_extension(wgpu_ctx *ctx, int32_t wd_id, int32_t wd_slot, int
  *   strip that faces the neighbour in that direction (threshold_block with `indices`), detail_out[k*n_eqn + c].  The host compares with
  *   eps*norm and keeps the insignificant neighbour alive if the strip is significant. */
 int32_t wgpu_patch_details(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t n, const int32_t *hvy_ids, const int32_t *dirs, double *detail_out);
+/* wgpu_patch_details_norm: the same with the coefficients renormalised for eps_norm = L1 / L2 / H1 first (wavelet_renorm_block,
+ *   LIB/WAVELETS/module_wavelets.f90:1900-1945; eps_norm_id as in wgpu_threshold: 0 Linfty, 1 L1, 2 L2, 3 H1; level_ref = Jmax) */
+int32_t wgpu_patch_details_norm(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t eps_norm_id, int32_t level_ref, int32_t n,
+                                const int32_t *hvy_ids, const int32_t *dirs, double *detail_out);
 int32_t wgpu_set_wavelet(wgpu_ctx *ctx, const char *name, int32_t *g_default, int32_t *g_rhs_default);
 int32_t wgpu_fwt(wgpu_ctx *ctx, int32_t src_id, int32_t src_slot, int32_t dst_id, int32_t dst_slot);
 int32_t wgpu_iwt(wgpu_ctx *ctx, int32_t src_id, int32_t src_slot, int32_t dst_id, int32_t dst_slot);

@@ -110,7 +110,33 @@ def test_adapt_tree_lifted(wavelet, Bs, indicator, sz):
     sol.close()
 
 
-def test_security_zone_keeps_the_neighbour_of_a_significant_strip():
+@pytest.mark.parametrize("wavelet,Bs,eps_norm", [("CDF44", 16, "L2"), ("CDF42", 18, "L1"), ("CDF44", 16, "H1")])
+def test_adapt_tree_lifted_security_zone_other_norms(wavelet, Bs, eps_norm):
+    """the security zone with eps_norm = L1 / L2 / H1: the strips' coefficients are renormalised as threshold_block does (wavelet_renorm_block)
+    before they are compared with eps * norm (wgpu_patch_details_norm) -- same grid decision and data as the oracle"""
+    w, p, po, forest, grid, sol, u, H = _setup(wavelet, Bs, seed=7)
+    norm = sol.componentWiseNorm_tree((HVY_BLOCK, 0), eps_norm)
+    eps = 0.02
+    og, od, oi = OFT.adapt_tree(po, w, grid, u, eps, Jmin=1, norm=norm, eps_norm=eps_norm, level_ref=forest.Jmax, fd_half_width=H, use_security_zone=True)
+    _, _, oi0 = OFT.adapt_tree(po, w, grid, u, eps, Jmin=1, norm=norm, eps_norm=eps_norm, level_ref=forest.Jmax, fd_half_width=H, use_security_zone=False)
+    ft = FullTree(sol, forest, Jmin=1)
+    new, info = ft.adapt(eps=eps, norm=norm, eps_norm=eps_norm, use_security_zone=True)
+    assert {k: v == -1 for k, v in info["status"].items()} == {k: v == -1 for k, v in oi["status"].items()}
+    hvy, lvl, ixyz, _ = new.active(0)
+    okey = {(int(og.level[b]),) + tuple(int(v) for v in og.ixyz[b]): b for b in range(og.n)}
+    keys = [(int(l), int(x[0]), int(x[1]), int(x[2])) for l, x in zip(lvl, ixyz)]
+    assert sorted(keys) == sorted(okey) and 8 <= new.n_blocks < forest.n_blocks
+    got = np.zeros(sol.host_shape())
+    sol.download(got, g_sync=0)
+    I = (slice(None),) + O.interior(po)
+    for h, k in zip(hvy, keys):
+        assert np.array_equal(got[h - 1][I], od[okey[k]][I]), k
+    print(eps_norm, "blocks", forest.n_blocks, "->", new.n_blocks, "kept by the security zone:", oi0["n_deleted"] - oi["n_deleted"])
+    sol.close()
+
+
+@pytest.mark.parametrize("eps_norm,eps", [("Linfty", 1.0e-3), ("L2", 1.0e-3)])
+def test_security_zone_keeps_the_neighbour_of_a_significant_strip(eps_norm, eps):
     """addSecurityZone_CE_tree (the reference's default for lifted wavelets): a narrow bump 6 points inside a block, next to a face, is invisible
     to the neighbour's own coefficients (its filters reach 3 points into the ghost nodes) but lies inside the Nwc = 8 deep strip of the
     block that holds it -- the neighbour would be coarsened without the security zone and is kept with it.  Oracle and device agree on
@@ -130,17 +156,19 @@ def test_security_zone_keeps_the_neighbour_of_a_significant_strip():
         Z, Y, X = np.meshgrid(ax[2], ax[1], ax[0], indexing="ij")
         bump = np.exp(-((X - c[0]) ** 2 + (Y - c[1]) ** 2 + (Z - c[2]) ** 2) / (2.0 * (0.8 * h) ** 2))
         u[b, :, g:-g, g:-g, g:-g] = 1.0 + np.stack([bump, 0.5 * bump, -bump, 2.0 * bump])
-    norm = O.norm_linfty_tree(po, u)
     res = {}
     for sz in (False, True):
-        og, od, oi = OFT.adapt_tree(po, w, grid, u, 1.0e-3, Jmin=1, norm=norm, level_ref=J, fd_half_width=2, use_security_zone=sz)
         sol = WabbitGPU(p, max_blocks=100)
         sol.setup_wavelet(wavelet)
         sol.set_forest(forest)
         host = np.zeros(sol.host_shape())
         host[:grid.n] = u
         sol.upload(host, hvy_ids=np.arange(1, grid.n + 1, dtype=np.int32))
-        new, info = FullTree(sol, forest, Jmin=1).adapt(eps=1.0e-3, norm=sol.componentWiseNorm_tree((HVY_BLOCK, 0)), use_security_zone=sz)
+        norm = sol.componentWiseNorm_tree((HVY_BLOCK, 0), eps_norm)
+        if eps_norm == "Linfty":
+            assert np.array_equal(norm, O.norm_linfty_tree(po, u))
+        og, od, oi = OFT.adapt_tree(po, w, grid, u, eps, Jmin=1, norm=norm, eps_norm=eps_norm, level_ref=J, fd_half_width=2, use_security_zone=sz)
+        new, info = FullTree(sol, forest, Jmin=1).adapt(eps=eps, norm=norm, eps_norm=eps_norm, use_security_zone=sz)
         hvy, lvl, ixyz, _ = new.active(0)
         okey = {(int(og.level[b]),) + tuple(int(v) for v in og.ixyz[b]): b for b in range(og.n)}
         keys = [(int(l), int(x[0]), int(x[1]), int(x[2])) for l, x in zip(lvl, ixyz)]
@@ -151,4 +179,5 @@ def test_security_zone_keeps_the_neighbour_of_a_significant_strip():
         assert all(np.array_equal(got[hh - 1][I], od[okey[k]][I]) for hh, k in zip(hvy, keys))
         res[sz] = new.n_blocks
         sol.close()
+    print(eps_norm, eps, res)
     assert res[False] < res[True] <= grid.n, res

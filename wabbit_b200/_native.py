@@ -82,6 +82,7 @@ GPU_SYMBOLS = {
     "wgpu_norm": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _dp]),
     "wgpu_threshold": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _i32p, _dp, _dp, _i32p, _dp]),
     "wgpu_patch_details": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _i32p, _i32p, _dp]),
+    "wgpu_patch_details_norm": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _i32p, _i32p, _dp]),
     "wgpu_coarse_extension": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "wgpu_refine": (C.c_int32, [C.c_void_p, C.c_int32, _i32p, _i32p, C.c_int32, _i32p, _i32p]),
     "wgpu_coarsen": (C.c_int32, [C.c_void_p, C.c_int32, _i32p, _i32p, C.c_int32, C.c_int32]),

@@ -1348,7 +1348,14 @@ int32_t wgpu_threshold(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t ep
 
 int32_t wgpu_patch_details(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t n, const int32_t *hvy_ids, const int32_t *dirs, double *detail_out)
 {
+    return wgpu_patch_details_norm(ctx, array_id, slot, 0, 0, n, hvy_ids, dirs, detail_out);
+}
+
+int32_t wgpu_patch_details_norm(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t eps_norm_id, int32_t level_ref, int32_t n, const int32_t *hvy_ids,
+                                const int32_t *dirs, double *detail_out)
+{
     if (!ctx || n < 0 || (n > 0 && (!hvy_ids || !dirs || !detail_out))) return WGPU_ERR_ARG;
+    if (eps_norm_id < 0 || eps_norm_id > 3) return fail(ctx, WGPU_ERR_ARG, "wgpu_patch_details_norm: eps_norm must be 0 (Linfty), 1 (L1), 2 (L2) or 3 (H1)");
     if (!ctx->wavelet_set) return fail(ctx, 1213149, "The cat is angry: Wavelet-setup not yet called?");
     int n1 = 0;
     const double *wd = array_ptr(ctx, array_id, slot, &n1);
@@ -1378,7 +1385,7 @@ int32_t wgpu_patch_details(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_
     const int H = c.fd == 2 ? 1 : (c.fd == 4 ? 2 : 3);
     const int Nscl = std::max(-w.hd_lo - 1, 0), Nscr = w.hd_hi;
     const int Nwcl = std::max(Nscl - w.gd_lo, 2 * H), Nwcr = std::max(Nscr + w.gd_hi, 2 * H);
-    rc = wgpu_launch_patch_detail(ctx, wd, ctx->d_idbuf[2], ctx->d_idbuf[2] + n, n, Nwcl, Nwcr, d_out);
+    rc = wgpu_launch_patch_detail(ctx, wd, ctx->d_idbuf[2], ctx->d_idbuf[2] + n, n, Nwcl, Nwcr, d_out, eps_norm_id, level_ref);
     if (!rc) {
         cudaError_t e = cudaMemcpyAsync(detail_out, d_out, sizeof(double) * (size_t)n * ctx->nc, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

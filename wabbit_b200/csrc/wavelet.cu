@@ -724,8 +724,17 @@ __global__ void __launch_bounds__(256) detail_kernel(const DetailArgs a)
 // threshold_block with `indices` (LIB/INDICATORS/threshold_block.f90:30-44) for the security zone of adapt_tree (addSecurityZone_CE_tree,
 // LIB/MESH/securityZone_tree.f90:140-298): Linfty detail of a decomposed block inside the strip that faces one neighbour direction
 // (get_indices_of_modify_patch with Nwcl / Nwcr), pure scaling positions removed.  One CTA per (pair, component).
+// wavelet_renorm_block inside the strip (eps_norm L1 / L2 / H1; module_wavelets.f90:1900-1945): the per-level factor and the per-direction
+// factor of the pure directions, exactly as detail_kernel applies them to the whole block
+struct PatchNorm {
+    int eps_norm, fdir_div;
+    double fdir;
+    double fac_lvl[WGPU_MAX_LEVELS];
+};
+
 __global__ void __launch_bounds__(128) patch_detail_kernel(const double *__restrict__ wd, const int *__restrict__ blk, const int *__restrict__ dir,
-                                                           double *__restrict__ out, int nc, int Bs, int dim, int Nl, int Nr)
+                                                           double *__restrict__ out, int nc, int Bs, int dim, int Nl, int Nr,
+                                                           const signed char *__restrict__ level, const PatchNorm pn)
 {
     __shared__ double s0[4];
     const int b = blk[blockIdx.x], dc = dir[blockIdx.x], c = blockIdx.y;
@@ -741,11 +750,19 @@ __global__ void __launch_bounds__(128) patch_detail_kernel(const double *__restr
     }
     const int npts = ext[0] * ext[1] * ext[2];
     const double *p = wd + ((long long)b * nc + c) * CS;
+    const bool scale = pn.eps_norm != 0 && !(pn.eps_norm == 3 && dim != 3);
+    const double fac = scale ? pn.fac_lvl[level[b]] : 1.0;
     double m = -INFINITY;
     for (int i = threadIdx.x; i < npts; i += blockDim.x) {
         const int x = lo[0] + i % ext[0], y = lo[1] + (i / ext[0]) % ext[1], z = lo[2] + i / (ext[0] * ext[1]);
-        const bool pure_sc = !(x & 1) && !(y & 1) && (dim == 2 || !(z & 1));
-        const double v = pure_sc ? 0.0 : p[((long long)z * Bs + y) * Bs + x];
+        const bool px = !(x & 1), py = !(y & 1), pz = dim == 3 ? !(z & 1) : true;
+        double v = (px && py && pz) ? 0.0 : p[((long long)z * Bs + y) * Bs + x];
+        if (scale) {
+            v = __dmul_rn(v, fac);
+            if (px) v = pn.fdir_div ? __ddiv_rn(v, pn.fdir) : __dmul_rn(v, pn.fdir);
+            if (py) v = pn.fdir_div ? __ddiv_rn(v, pn.fdir) : __dmul_rn(v, pn.fdir);
+            if (dim == 3 && pz) v = pn.fdir_div ? __ddiv_rn(v, pn.fdir) : __dmul_rn(v, pn.fdir);
+        }
         m = fmax(m, fabs(v));
     }
     m = warp_max(m);
@@ -837,12 +854,32 @@ __global__ void __launch_bounds__(256) blocksum_kernel(const double *__restrict_
 
 }  // namespace
 
-int32_t wgpu_launch_patch_detail(wgpu_ctx *ctx, const double *wd, const int *d_blk, const int *d_dir, int n, int Nl, int Nr, double *d_out)
+static void renorm_factors(const wgpu_config &c, int eps_norm, int level_ref, double *fac_lvl, double *fdir, int *fdir_div)
 {
+    *fdir = 1.0;
+    *fdir_div = 0;
+    for (int l = 0; l < WGPU_MAX_LEVELS; ++l) {
+        double fac = 1.0;   // module_wavelets.f90:1900-1945
+        if (eps_norm == 1) fac = pow(2.0, (double)((level_ref - l - 1) * c.dim));
+        if (eps_norm == 2) fac = pow(2.0, (double)((level_ref - l - 1) * c.dim) / 2.0);
+        if (eps_norm == 3) fac = pow(2.0, (double)(level_ref - l) * (2.0 - c.dim) / 2.0);
+        fac_lvl[l] = fac;
+    }
+    if (eps_norm == 1) { *fdir = 4.0; *fdir_div = 1; }
+    if (eps_norm == 2) { *fdir = 2.0; *fdir_div = 1; }
+    if (eps_norm == 3) *fdir = pow(2.0, 2.0 * (c.dim - 2.0) / 3.0);
+}
+
+int32_t wgpu_launch_patch_detail(wgpu_ctx *ctx, const double *wd, const int *d_blk, const int *d_dir, int n, int Nl, int Nr, double *d_out, int eps_norm,
+                                 int level_ref)
+{
+    PatchNorm pn;
+    pn.eps_norm = eps_norm;
+    renorm_factors(ctx->cfg, eps_norm, level_ref, pn.fac_lvl, &pn.fdir, &pn.fdir_div);
     for (int s0 = 0; s0 < n; s0 += 32768) {
         dim3 grid(std::min(32768, n - s0), ctx->nc);
         patch_detail_kernel<<<grid, 128, 0, ctx->stream>>>(wd, d_blk + s0, d_dir + s0, d_out + (long long)s0 * ctx->nc, ctx->nc, ctx->cfg.Bs[0],
-                                                         ctx->cfg.dim, Nl, Nr);
+                                                         ctx->cfg.dim, Nl, Nr, ctx->d_level, pn);
         ctx->launches++;
         WGPU_CHECK(ctx, cudaGetLastError());
     }
@@ -976,18 +1013,7 @@ int32_t wgpu_launch_detail(wgpu_ctx *ctx, const double *wd, int eps_norm, int le
     a.Bz = c.dim == 3 ? c.Bs[2] : 1;
     a.dim = c.dim;
     a.eps_norm = eps_norm;
-    a.fdir = 1.0;
-    a.fdir_div = 0;
-    for (int l = 0; l < WGPU_MAX_LEVELS; ++l) {
-        double fac = 1.0;   // module_wavelets.f90:1900-1945
-        if (eps_norm == 1) fac = pow(2.0, (double)((level_ref - l - 1) * c.dim));
-        if (eps_norm == 2) fac = pow(2.0, (double)((level_ref - l - 1) * c.dim) / 2.0);
-        if (eps_norm == 3) fac = pow(2.0, (double)(level_ref - l) * (2.0 - c.dim) / 2.0);
-        a.fac_lvl[l] = fac;
-    }
-    if (eps_norm == 1) { a.fdir = 4.0; a.fdir_div = 1; }
-    if (eps_norm == 2) { a.fdir = 2.0; a.fdir_div = 1; }
-    if (eps_norm == 3) a.fdir = pow(2.0, 2.0 * (c.dim - 2.0) / 3.0);
+    renorm_factors(c, eps_norm, level_ref, a.fac_lvl, &a.fdir, &a.fdir_div);
     dim3 grid(ctx->n_active, ctx->nc);
     detail_kernel<<<grid, 256, 0, ctx->stream>>>(a);
     ctx->launches++;

@@ -302,7 +302,8 @@ int32_t wgpu_launch_stats(wgpu_ctx *ctx, const double *u, const double *rhs, con
 // wavelet.cu
 int32_t wgpu_launch_wavelet(wgpu_ctx *ctx, const double *src, double *dst, int inverse, const double *ce_coarse);
 int32_t wgpu_launch_detail(wgpu_ctx *ctx, const double *wd, int eps_norm, int level_ref);
-int32_t wgpu_launch_patch_detail(wgpu_ctx *ctx, const double *wd, const int *d_blk, const int *d_dir, int n, int Nl, int Nr, double *d_out);
+int32_t wgpu_launch_patch_detail(wgpu_ctx *ctx, const double *wd, const int *d_blk, const int *d_dir, int n, int Nl, int Nr, double *d_out, int eps_norm,
+                                 int level_ref);
 int32_t wgpu_launch_flags(wgpu_ctx *ctx, const int32_t *thresh_comp, const double *eps_use, int *d_status, double *d_detail_out);
 int32_t wgpu_launch_linfty(wgpu_ctx *ctx, const double *u, unsigned long long *d_out);
 int32_t wgpu_launch_blocksum(wgpu_ctx *ctx, const double *u, int squared, double *d_out);

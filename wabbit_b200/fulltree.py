@@ -349,10 +349,11 @@ class FullTree:
             raise RuntimeError(f"whost_ft_decide: {rc}")
         return st
 
-    def security_zone(self, st0: np.ndarray, eps, norm, thresh_comp=None, force_maxlevel_dealiasing: bool = False) -> np.ndarray:
+    def security_zone(self, st0: np.ndarray, eps, norm, thresh_comp=None, force_maxlevel_dealiasing: bool = False, eps_norm: str = "Linfty") -> np.ndarray:
         """addSecurityZone_CE_tree (LIB/MESH/securityZone_tree.f90:140-298): an insignificant block (-1) next to a significant same-level block
         stays (0) if the significant block has significant details inside the Nwc-deep strip at their interface -- details the coarse
-        extension would delete if the neighbour were coarsened.  Linfty norm; pairs are evaluated on the device (wgpu_patch_details)."""
+        extension would delete if the neighbour were coarsened.  The pairs are evaluated on the device (wgpu_patch_details_norm: coefficients
+        renormalised for eps_norm as threshold_block does)."""
         sol, dim = self.sol, self.dim
         nc = sol.params.n_eqn
         eps = sol.params.eps if eps is None else eps
@@ -380,7 +381,7 @@ class FullTree:
         dcode = np.array([(d[2] + 1) * 9 + (d[1] + 1) * 3 + (d[0] + 1) for d in self.dirs], dtype=np.int32)
         if getattr(self, "timing", None) is not None:
             t0 = self._tick(f"  sz: pairs (host)", t0)
-        det = sol.patch_details(self.slots[b].astype(np.int32), dcode[q], WD)
+        det = sol.patch_details(self.slots[b].astype(np.int32), dcode[q], WD, eps_norm=eps_norm, level_ref=self.forest.Jmax)
         if getattr(self, "timing", None) is not None:
             self.timing["  sz: n_pairs"] = len(b)
             t0 = self._tick("  sz: wgpu_patch_details", t0)
@@ -435,7 +436,7 @@ class FullTree:
                 st0[ci[np.asarray(mask_keeps(self.level[ci], self.pos[ci]), dtype=bool)]] = 0
         t0 = time.perf_counter()
         if use_security_zone and indicator != "everywhere":
-            st0 = self.security_zone(st0, eps, norm, thresh_comp, force_maxlevel_dealiasing)
+            st0 = self.security_zone(st0, eps, norm, thresh_comp, force_maxlevel_dealiasing, eps_norm)
             t0 = self._tick("security zone", t0)
         st = self.decide(st0)
         t0 = self._tick("decide", t0)
@@ -652,13 +653,13 @@ class DistributedFullTree(FullTree):
             d2m(level)
         return None
 
-    def security_zone(self, st0, eps, norm, thresh_comp=None, force_maxlevel_dealiasing: bool = False):
+    def security_zone(self, st0, eps, norm, thresh_comp=None, force_maxlevel_dealiasing: bool = False, eps_norm: str = "Linfty"):
         """addSecurityZone_CE_tree across ranks: every rank evaluates the strips of the significant blocks it owns; the kept neighbours are
         merged over the ranks (synchronize_lgt_data)."""
         me = self.me
         mask = self.owner == me
         local = FullTree.security_zone(self, np.where(mask | (st0 != 0), st0, 1).astype(np.int32), eps, norm, thresh_comp,
-                                       force_maxlevel_dealiasing)        # blocks of other ranks are not "significant" here (status 1)
+                                       force_maxlevel_dealiasing, eps_norm)        # blocks of other ranks are not "significant" here (status 1)
         kept = (st0 == -1) & (local == 0)
         allk = self.drv.tr.allreduce_max_np(kept.astype(np.float64))
         st = st0.copy()
@@ -688,7 +689,7 @@ class DistributedFullTree(FullTree):
         if use_security_zone and indicator != "everywhere":
             self._lslot_for_patches()
             with self._tk("adapt: security zone", sol):
-                st0 = self.security_zone(st0, eps, norm, thresh_comp, force_maxlevel_dealiasing)
+                st0 = self.security_zone(st0, eps, norm, thresh_comp, force_maxlevel_dealiasing, eps_norm)
         with self._tk("adapt: decide"):
             st = self.decide(st0)
         _t = self._tk("adapt: prune + tables").__enter__()

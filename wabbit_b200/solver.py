@@ -337,12 +337,14 @@ class WabbitGPU:
         (wavelet_reconstruct_full_tree_CEoptimized, adapt_tree.f90:686-987)"""
         self._check(self._lib.wgpu_iwt_ce(self._ctx, wd[0], wd[1], coarse[0], coarse[1], dst[0], dst[1]))
 
-    def patch_details(self, hvy_ids, dirs, array=(HVY_WORK, 2)) -> np.ndarray:
-        """Linfty details of decomposed blocks inside the strips facing given neighbour directions (addSecurityZone_CE_tree): [n, n_eqn]"""
+    def patch_details(self, hvy_ids, dirs, array=(HVY_WORK, 2), eps_norm: str = "Linfty", level_ref: int = 0) -> np.ndarray:
+        """details of decomposed blocks inside the strips facing given neighbour directions (addSecurityZone_CE_tree), renormalised for
+        eps_norm: [n, n_eqn]"""
         ids = np.ascontiguousarray(hvy_ids, dtype=np.int32)
         dd = np.ascontiguousarray(dirs, dtype=np.int32)
         out = np.zeros((len(ids), self.params.n_eqn))
-        self._check(self._lib.wgpu_patch_details(self._ctx, array[0], array[1], len(ids), _i32(ids), _i32(dd), out.ctypes.data_as(C.POINTER(C.c_double))))
+        self._check(self._lib.wgpu_patch_details_norm(self._ctx, array[0], array[1], self.EPS_NORMS[eps_norm], int(level_ref), len(ids), _i32(ids), _i32(dd),
+                                                      out.ctypes.data_as(C.POINTER(C.c_double))))
         return out
 
     def wavelet_filter_width(self) -> int:
