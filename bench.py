@@ -379,7 +379,8 @@ def run_ours(a):
         # BASELINE configs 3 / 4 (the north-star target): 3-D adaptive ACM, CDF44, coarsening + refinement every step, all GPUs
         adaptive_lifted = {}
         J0 = a.adaptive_level if a.adaptive_level > 0 else (6 if world >= 4 else 5)     # 8^6 = 262 144 initial blocks need >= 4 GPUs' memory
-        legs = [("Bs16", 16, J0, False), ("Bs16_sphere", 16, J0, True), ("Bs18", 18, J0 if world >= 4 or J0 < 6 else J0 - 1, False)]
+        # Bs = 18 on level 6 needs 26 GB per resident array and rank at 4 GPUs (max_blocks = 2 * 8^6 / 4 + 8192): level 6 from 8 GPUs on
+        legs = [("Bs16", 16, J0, False), ("Bs16_sphere", 16, J0, True), ("Bs18", 18, J0 if (world >= 8 or J0 < 6) else J0 - 1, False)]
         if a.adaptive_legs:
             legs = [l for l in legs if l[0] in a.adaptive_legs.split(",")]
         for name, bs, j0, sph in legs:
