@@ -281,7 +281,7 @@ __device__ __forceinline__ void load_plane(const StageArgs &a, const LoadTables<
     }
 }
 
-template <int FD, bool SKEW, int BS, bool GEOM>
+template <int FD, bool SKEW, int BS, bool GEOM, bool SKIP_PLAIN = false>
 __global__ void __launch_bounds__(BS *BS, (Tile<FD, BS>::SMEM <= 110 * 1024 ? 2 : 1))
     stage_kernel(const __grid_constant__ StageArgs a)
 {
@@ -297,10 +297,14 @@ __global__ void __launch_bounds__(BS *BS, (Tile<FD, BS>::SMEM <= 110 * 1024 ? 2 
     const int tid = threadIdx.x;
     const int tx = tid % BS, ty = tid / BS;
     const int b = a.active[blockIdx.x];
+    if (SKIP_PLAIN) {
+        // second launch behind stage_kernel_tma: that kernel has advanced every block whose six face neighbours are resident same-level blocks
+        // (a template variant: an early return in the default instance costs it 36 bytes of spills and 9 % of its speed with the in-kernel mask)
+        const int *nb = a.nbr + b * WGPU_NDIR;
+        if ((nb[12] | nb[14] | nb[10] | nb[16] | nb[4] | nb[22]) >= 0) return;
+    }
     if (tid < WGPU_NDIR) s_code[tid] = a.nbr[b * WGPU_NDIR + tid];
     __syncthreads();
-    // second launch behind stage_kernel_tma: that kernel has advanced every block whose six face neighbours are resident same-level blocks
-    if (a.skip_plain && (s_code[12] | s_code[14] | s_code[10] | s_code[16] | s_code[4] | s_code[22]) >= 0) return;
     build_tables<FD, BS>(a, s_lt, b, s_code, tid);
     __syncthreads();
 
@@ -1520,6 +1524,22 @@ int32_t launch_stage_t(wgpu_ctx *ctx, const StageArgs &a, int n_blocks)
             WGPU_CHECK(ctx, cudaGetLastError());
             rest.skip_plain = 1;
             rest_needed = a.plain_hint <= 0;
+        }
+    }
+    if (rest_needed) {
+        if constexpr (FD == 4 && BS == 16) {
+            if (rest.skip_plain) {
+                static bool sconf = false;
+                if (!sconf) {
+                    WGPU_CHECK(ctx, cudaFuncSetAttribute(stage_kernel<FD, SKEW, BS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
+                    WGPU_CHECK(ctx, cudaFuncSetAttribute(stage_kernel<FD, SKEW, BS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
+                    sconf = true;
+                }
+                if (a.geom) stage_kernel<FD, SKEW, BS, true, true><<<n_blocks, T::NT, T::SMEM, ctx->stream>>>(rest);
+                else stage_kernel<FD, SKEW, BS, false, true><<<n_blocks, T::NT, T::SMEM, ctx->stream>>>(rest);
+                ctx->launches++;
+                rest_needed = false;
+            }
         }
     }
     if (rest_needed) {

@@ -73,10 +73,10 @@ struct StageArgs {
     int geom;                        // 0: mask arrays, 1: sphere
     const int *ixyz;                 // [max_blocks][3] block coordinates on their level
     double g_c0[3], g_v[3], g_R, g_h;
-    int skip_plain;                  // leave blocks whose six face neighbours are resident same-level blocks (stage_kernel_tma took them)
-    int plain_hint;                  // 1: every block of this launch is such a block, -1: none is, 0: unknown / mixed
     double t0, t_cj;                 // stage time = t0 + t_cj * dt
     const double *t0_ptr;            // != nullptr: t0 is read from the device (wgpu_rk_steps)
+    int skip_plain;                  // leave blocks whose six face neighbours are resident same-level blocks (stage_kernel_tma took them)
+    int plain_hint;                  // 1: every block of this launch is such a block, -1: none is, 0: unknown / mixed
 };
 
 #define WGPU_NSTAT 19
