@@ -153,6 +153,49 @@ def test_rk4_on_a_graded_grid_across_ranks(world, split, wavelet):
 
 
 @pytest.mark.gpu
+def test_diffusion_limited_dt_with_the_finest_level_on_one_rank_only():
+    """GET_DT_BLOCK applies every limit per block before the MPI_MIN (module_ACM.f90:617-691): with a large viscosity the limit CFL_nu dx^2 / nu
+    of the finest blocks binds, and those blocks live on ONE rank here -- every rank must still take the same, oracle-identical dt."""
+    from wabbit_b200 import Forest
+    world, wavelet = 2, "CDF40"
+    w = O.setup_wavelet(wavelet)
+    # level 1 everywhere, one corner block refined to level 2 and one of its children to level 3: the finest blocks sit at the start of the curve
+    leaves = {(1, x, y, z) for x in range(2) for y in range(2) for z in range(2)}
+
+    def refine(k):
+        leaves.remove(k)
+        L, x, y, z = k
+        for c in range(8):
+            leaves.add((L + 1, 2 * x + (c & 1), 2 * y + ((c >> 1) & 1), 2 * z + ((c >> 2) & 1)))
+    refine((1, 0, 0, 0))
+    refine((2, 0, 0, 0))
+    ks = sorted(leaves)
+    forest = Forest.from_blocks(3, 3, np.array([k[0] for k in ks], np.int32), np.array([k[1:] for k in ks], np.int32), n_ranks=world,
+                                max_blocks=4 * len(ks) + 64)
+    finest = [int((forest.active(r)[1] == 3).sum()) for r in range(world)]
+    assert min(finest) == 0 < max(finest), finest
+    p = tg_params(Bs=16, J=3, wavelet_g=w.g_default)
+    p.wavelet, p.nu = wavelet, 0.5
+    p = p.finalize()
+    sols, grp = _make_ranks(forest, world, p, wavelet)
+    po, grid, nbr = _global_oracle(forest, world, p)
+    u = O.alloc(grid, po)
+    O.inicond_taylor_green(grid, po, u)
+    _scatter(sols, forest, u)
+    work = [O.alloc(grid, po) for _ in range(5)]
+    sync = lambda h: O.sync_ghosts_leaf(grid, po, h, nbr, p.g_rhs, p.g_rhs, w.X, bool(w.lifted))
+    t = 0.0
+    for it in range(2):
+        dt = grp.step(t)
+        dt_ref = O.rk_generic(grid, po, u, work, t, sync=sync)
+        dx_min = p.domain[0] / (2 ** 3 * 16)
+        assert dt == dt_ref and abs(dt - p.CFL_nu * dx_min ** 2 / p.nu) <= 1e-15, (dt, dt_ref)     # the diffusion limit of level 3 binds
+        t += dt
+    for s in sols:
+        s.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("world,wavelet,ignore_filter", [(2, "CDF40", True), (3, "CDF44", True), (2, "CDF44", False), (3, "CDF42", False)])
 def test_wavelet_side_across_ranks(world, wavelet, ignore_filter):
     """halo copies refreshed for hvy_block, then on every rank: download with a synchronised ghost shell (all 26 relations, level
