@@ -411,7 +411,12 @@ def adapt_tree(p: O.Params, w: O.Wavelet, grid: O.Grid, u: np.ndarray, eps: floa
         return new_grid, np.stack([t.tmp[k] for k in keys]), {"status0": st0, "status": st, "marked": [], "leaf_only": True,
                                                               "leaf_first": t.leaf_first, "n_deleted": len(deleted)}
     nrl, nrr, d2l, d2r = ndep2(w, fd_half_width)
-    assert all(p.Bs[a] >= max(nrl, nrr) for a in range(dim)), "Bs < Nrecon: reconstruction of neighbours is not restated"
+    if any(p.Bs[a] < max(nrl, nrr) for a in range(dim)):
+        # Bs < Nrecon (adapt_tree.f90:771-803, reconstruct_neighbors): the modified coefficients of an interface block reach into its same-level
+        # neighbours' reconstruction, so the leaves that have a marked same-level neighbour are reconstructed as well
+        mset = set(marked)
+        extra = [k for k in sorted(leaves) if k not in mset and any(nbr_key(k, d, dim) in mset for d in dirs(dim))]
+        marked = sorted(mset | set(extra))
     leaf_only = all(p.Bs[a] >= d2l and p.Bs[a] >= d2r for a in range(dim))
     # coarse extension on the lasting interfaces: wavelet coefficients only (adapt_tree.f90:222-228)
     for k in marked:

@@ -73,7 +73,9 @@ def test_full_tree_decomposition_and_flags(wavelet, Bs):
                                                       ("CDF62", 20, "threshold-state-vector", False), ("CDF22", 16, "everywhere", False),
                                                       ("CDF44", 16, "threshold-state-vector", True), ("CDF42", 18, "threshold-state-vector", True),
                                                       ("CDF40", 16, "threshold-state-vector", False), ("CDF60", 18, "threshold-state-vector", False),
-                                                      ("CDF44", 22, "threshold-state-vector", True), ("CDF44", 26, "threshold-state-vector", False)])
+                                                      ("CDF44", 22, "threshold-state-vector", True), ("CDF44", 26, "threshold-state-vector", False),
+                                                      # Bs < Nrecon (adapt_tree.f90:771-803): the same-level neighbours of interface blocks are reconstructed too
+                                                      ("CDF44", 14, "threshold-state-vector", False), ("CDF62", 16, "threshold-state-vector", True)])
 def test_adapt_tree_lifted(wavelet, Bs, indicator, sz):
     """the whole adapt_tree with the full wavelet transformation (decomposition of the full tree, indicator, grid decision; for lifted
     wavelets coarse extension on the lasting interfaces and CE-optimised reconstruction; pruning): same new grid as the oracle, data bit

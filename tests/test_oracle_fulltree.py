@@ -24,7 +24,7 @@ def _case(name, Bs, dim, seed, Jmax=3, nc=1):
 
 
 @pytest.mark.parametrize("name,Bs,dim", [("CDF44", 16, 2), ("CDF44", 16, 3), ("CDF44", 18, 3), ("CDF42", 16, 2), ("CDF22", 8, 2),
-                                         ("CDF62", 18, 2), ("CDF44", 20, 2)])
+                                         ("CDF62", 18, 2), ("CDF44", 20, 2), ("CDF62", 16, 2), ("CDF44", 14, 2)])     # the last two: Bs < Nrecon
 def test_adapt_of_adapt_is_adapt(name, Bs, dim):
     w, p, grid = _case(name, Bs, dim, seed=7, Jmax=3 if dim == 2 else 2)
     I = (slice(None), slice(None)) + O.interior(p)

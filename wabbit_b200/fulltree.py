@@ -396,6 +396,16 @@ class FullTree:
         st[self.nb[b[significant], q[significant]]] = 0
         return st
 
+    def _with_marked_neighbours(self, marked: np.ndarray) -> np.ndarray:
+        """Bs < Nrecon (adapt_tree.f90:771-803, reconstruct_neighbors): the leaves with a same-level neighbour that is marked for reconstruction
+        are reconstructed as well (the modified coefficients of an interface block reach into their reconstruction)"""
+        is_marked = np.zeros(len(self.code), bool)
+        is_marked[marked] = True
+        leaves = np.flatnonzero(self.is_leaf & ~is_marked)
+        nb = self.nb[leaves]
+        hit = (np.where(nb >= 0, is_marked[np.maximum(nb, 0)], False)).any(axis=1)
+        return np.sort(np.concatenate([marked, leaves[hit]]))
+
     def _ce_sizes(self):
         """Nrecon and Ndep2 of setup_wavelet incl. the widening to the FD stencil (module_wavelets.f90:1368-1417)"""
         p = self.sol.params
@@ -450,11 +460,11 @@ class FullTree:
         leaves = np.flatnonzero(self.is_leaf)
         marked = leaves[(self.nb[leaves] < 0).any(axis=1)]
         nrl, nrr, d2l, d2r = self._ce_sizes()
-        if self.lifted and any(p.Bs[a] < max(nrl, nrr) for a in range(dim)):
-            raise RuntimeError("adapt_tree: Bs < Nrecon (reconstruction of the neighbours of interface blocks) is not supported")
         leaf_only = all(p.Bs[a] >= d2l and p.Bs[a] >= d2r for a in range(dim))
         if not self.lifted:
             marked = marked[:0]      # no coarse extension: every block keeps its original / assembled values (adapt_tree.f90:236-241)
+        elif any(p.Bs[a] < max(nrl, nrr) for a in range(dim)):
+            marked = self._with_marked_neighbours(marked)
         if len(marked):
             self.set_pass_topology(marked)                                # the lasting interfaces (adapt_tree.f90:222-228): same-level
             sol.coarse_extension_modify(WD, (HVY_BLOCK, 0), True, False)  # neighbours send coefficients that carry the extension
@@ -703,7 +713,7 @@ class DistributedFullTree(FullTree):
         marked = leaves[(self.nb[leaves] < 0).any(axis=1)] if self.lifted else leaves[:0]
         nrl, nrr, d2l, d2r = self._ce_sizes()
         if self.lifted and any(p.Bs[a] < max(nrl, nrr) for a in range(dim)):
-            raise RuntimeError("adapt_tree: Bs < Nrecon (reconstruction of the neighbours of interface blocks) is not supported")
+            marked = self._with_marked_neighbours(marked)
         leaf_only = all(p.Bs[a] >= d2l and p.Bs[a] >= d2r for a in range(dim))
         _t_rec = self._tk("adapt: CE + reconstruction passes", sol).__enter__()
         if len(marked):
