@@ -378,9 +378,8 @@ def run_ours(a):
     elif world > 1 and not a.no_adaptive:
         # BASELINE configs 3 / 4 (the north-star target): 3-D adaptive ACM, CDF44, coarsening + refinement every step, all GPUs
         adaptive_lifted = {}
-        J0 = a.adaptive_level if a.adaptive_level > 0 else (6 if world >= 4 else 5)     # 8^6 = 262 144 initial blocks need >= 4 GPUs' memory
-        # Bs = 18 on level 6 needs 26 GB per resident array and rank at 4 GPUs (max_blocks = 2 * 8^6 / 4 + 8192): level 6 from 8 GPUs on
-        legs = [("Bs16", 16, J0, False), ("Bs16_sphere", 16, J0, True), ("Bs18", 18, J0 if (world >= 8 or J0 < 6) else J0 - 1, False)]
+        J0 = a.adaptive_level if a.adaptive_level > 0 else (6 if world >= 8 else 5)     # 8^6 = 262 144 initial blocks (18 GB per resident array and rank at 4 GPUs): from 8 GPUs on
+        legs = [("Bs16", 16, J0, False), ("Bs16_sphere", 16, J0, True), ("Bs18", 18, J0, False)]
         if a.adaptive_legs:
             legs = [l for l in legs if l[0] in a.adaptive_legs.split(",")]
         for name, bs, j0, sph in legs:
@@ -954,7 +953,7 @@ def main():
     ap.add_argument("--adaptive-eps", type=float, default=1.0e-6)
     ap.add_argument("--adaptive-wavelet", default="CDF40", help="wavelet of --adaptive-only / --adaptive-multi")
     ap.add_argument("--adaptive-legs", default="", help="N > 1: comma list out of Bs16,Bs16_sphere,Bs18 (default: all three)")
-    ap.add_argument("--adaptive-level", type=int, default=0, help="initial equidistant level of the adaptive legs (0: 5 on 1-2 GPUs, 6 from 4 GPUs on)")
+    ap.add_argument("--adaptive-level", type=int, default=0, help="initial equidistant level of the adaptive legs (0: 5 up to 4 GPUs, 6 from 8 GPUs on)")
     ap.add_argument("--adaptive-only", action="store_true", help="run only the adaptive-cycle leg and print its record (development)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
