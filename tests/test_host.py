@@ -445,7 +445,7 @@ def test_full_tree_adapt_host_path_runs_without_a_device():
             n = len(self.hvy_active)
             return np.where(self.rng.random(n) < 0.97, -1, 0).astype(np.int32), self.rng.random((n, 4))
 
-        def patch_details(self, ids, dirs, *a):
+        def patch_details(self, ids, dirs, *a, **kw):
             return self.rng.random((len(ids), 4)) * 1.1e-3          # a few pairs exceed eps * norm: the security zone acts
 
         def move_blocks(self, src, dst):

@@ -393,7 +393,13 @@ int32_t whost_halo_plan(const whost_forest *f, int32_t rank, int32_t *n_halo, in
     const std::vector<int> &mine = f->rank_blocks[rank];
     const int nm = (int)mine.size(), ntot = (int)f->blocks.size();
     // per foreign block: bit0 related, bit1 finer neighbour of one of mine; per (own block, peer): bit0 related, bit1 the own block is the finer one
+    // (every own block writes only its own row of `own`; marks of foreign blocks are collected per thread and merged: the loop over the
+    // own blocks -- ~60 hash lookups each -- runs on the rank's share of the host cores)
     std::vector<unsigned char> foreign(ntot, 0), own((size_t)nm * W, 0);
+#pragma omp parallel
+    {
+    std::vector<std::pair<int, unsigned char>> marks;
+#pragma omp for schedule(static) nowait
     for (int m = 0; m < nm; ++m) {
         const Blk &b = f->blocks[mine[m]];
         const int nblk = 1 << b.level;
@@ -401,7 +407,7 @@ int32_t whost_halo_plan(const whost_forest *f, int32_t rank, int32_t *n_halo, in
             const Blk &o = f->blocks[j];
             if (o.rank == rank) return;
             unsigned char v = 1 | (j_is_finer ? 2 : 0);
-            foreign[j] |= v;
+            marks.emplace_back(j, v);
             own[(size_t)m * W + o.rank] |= 1 | (j_is_coarser ? 2 : 0);
         };
         for (int dz = (dim == 3 ? -1 : 0); dz <= (dim == 3 ? 1 : 0); ++dz)
@@ -448,6 +454,9 @@ int32_t whost_halo_plan(const whost_forest *f, int32_t rank, int32_t *n_halo, in
                     j = f->find(b.level - 1, q);
                     if (j >= 0) mark(j, false, true);
                 }
+    }
+#pragma omp critical
+    for (const auto &mk : marks) foreign[mk.first] |= mk.second;
     }
     for (int r = 0; r < W; ++r) recv_counts[r] = send_counts[r] = fine_send_counts[r] = 0;
     int nh = 0;

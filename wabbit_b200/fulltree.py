@@ -572,10 +572,14 @@ class DistributedFullTree(FullTree):
         # a block may be read from several arrays in one pass (coefficients as the same-level neighbour of one block, values as the coarser
         # neighbour of another): it has ONE local slot, so every array of the pass ships the union of the blocks any of them needs
         src_r, src_s, dst_r, which = [], [], [], []
+        seen = np.zeros(len(self.code), bool)
         for q in range(W):
             b = np.concatenate([needs[q][a][1] for a in range(n_arrays)]) if n_arrays else np.zeros(0, np.int64)
-            b = np.unique(b[b >= 0])
+            b = b[b >= 0]
             b = b[self.owner[b] != q]
+            seen[:] = False                      # sorted unique by a mark array: no sort of the 26-neighbour lists
+            seen[b] = True
+            b = np.flatnonzero(seen)
             src_r.append(self.owner[b])
             src_s.append(self.slots[b])
             dst_r.append(np.full(len(b), q, np.int64))
