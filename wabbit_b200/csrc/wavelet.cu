@@ -405,7 +405,11 @@ struct FastCfg {
     static constexpr int NT = ((BS * BS + 31) / 32) * 32;   // one thread per (x, y) column of the block
     static constexpr int NLD = (F % 2 == 0) ? N * (N / 2) : N * N;   // 16-byte chunks (F even) or 8-byte elements per input plane
     static constexpr int LPT = (NLD + NT - 1) / NT;   // loads per thread and plane
-    static constexpr size_t SMEM = sizeof(double) * ((size_t)4 * N * N + (size_t)2 * N * BS);   // two plane pairs in flight + the x-pass rows of a pair
+    // row pitches with an odd number of 16-byte slots modulo 128 bytes: two rows handled by one quarter warp of 128-bit accesses (x pass: two
+    // output pairs per thread) then hit disjoint banks
+    static constexpr int NP = N + 2 + (((N + 2) / 2) % 2 == 0 ? 2 : 0);      // input planes
+    static constexpr int XP = BS + 2 + (((BS + 2) / 2) % 2 == 0 ? 2 : 0);    // x-pass rows
+    static constexpr size_t SMEM = sizeof(double) * ((size_t)6 * N * NP + (size_t)4 * N * XP);   // three plane pairs (one read, two in flight) + the x-pass rows of two pairs
 };
 
 // One CTA per (block, component).  Input planes (xy halo included) stream through a double buffer (cp.async); the x pass
@@ -426,10 +430,10 @@ __global__ void __launch_bounds__(FastCfg<X, Y, BS, INV>::NT, (BS == 16 ? WFAST_
                                                                                  const double *__restrict__ wpool, const long long *__restrict__ woff)
 {
     using C = FastCfg<X, Y, BS, INV>;
-    constexpr int F = C::F, N = C::N, R = C::R, NT = C::NT, LPT = C::LPT, HALF = BS * BS / 2;
+    constexpr int F = C::F, N = C::N, R = C::R, NT = C::NT, LPT = C::LPT, HALF = BS * BS / 2, NP = C::NP, XP = C::XP;
     extern __shared__ __align__(16) double sm[];
-    double *in0 = sm;                       // [2 pairs][2 planes][N*N]
-    double *xs0 = in0 + 4 * N * N;          // [2 planes][N][BS]
+    double *in0 = sm;                       // [3 pairs][2 planes][N][NP]
+    double *xs0 = in0 + 6 * N * NP;         // [2 pairs][2 planes][N][XP]
     // source of the ghost region of each direction: pointer such that the point with neighbour-local coordinates (lx, ly, lz)
     // sits at ptr + lz*sz + ly*sy + lx -- the neighbour's interior (same level), or a patch of the wavelet jump pool (level
     // jumps: decimated / predicted values in the layout of the ghost region), or null (no neighbour)
@@ -465,7 +469,7 @@ __global__ void __launch_bounds__(FastCfg<X, Y, BS, INV>::NT, (BS == 16 ? WFAST_
         else { r = i / N; x = i % N - F; }
         const int y = r - F;
         const int dy = y < 0 ? -1 : (y >= BS ? 1 : 0), dx = x < 0 ? -1 : (x >= BS ? 1 : 0);
-        ld_dst[j] = i < C::NLD ? r * N + x + F : -1;
+        ld_dst[j] = i < C::NLD ? r * NP + x + F : -1;
         ld_src[j] = ((y - dy * BS) << 8) | (x - dx * BS);   // neighbour-local (ly, lx)
         ld_dir[j] = (dy + 1) * 3 + (dx + 1);
     }
@@ -517,82 +521,105 @@ __global__ void __launch_bounds__(FastCfg<X, Y, BS, INV>::NT, (BS == 16 ? WFAST_
     const bool pure_col = !(cx & 1) && !(cy & 1);   // o0 of this column is a pure scaling coefficient: not a detail
     double *outc = dst + ((long long)b * nc + c) * CS + cy * BS + cx;
 
+    // Plane loop, two planes per iteration and ONE block barrier per iteration: iteration P runs the x pass of plane pair P (input ring ->
+    // x-pass rows) and, software-pipelined behind it, the y and z passes of pair P-1 (x-pass rows of the previous iteration -> register
+    // window -> output).  The x-pass rows are double-buffered, the input planes triple-buffered: the barrier at the top of an iteration
+    // orders (i) the cp.async data of pair P, (ii) the x-pass rows written in iteration P-1 before their readers, and (iii) the end of every
+    // thread's reads of the buffers that are refilled next -- pair P+2 is issued AFTER the barrier into the buffer pair P-1 occupied.
+    // Rounds of R planes are fully unrolled so that the window slots and the z ordering are compile-time.
     load_plane(-F, in0);
-    load_plane(-F + 1, in0 + N * N);
+    load_plane(-F + 1, in0 + N * NP);
     cp_async_commit();
-    // plane loop, two planes per barrier pair (N and R are even): x pass of both planes, barrier, y pass of both planes into the register
-    // window, z pass.  Rounds of R planes are fully unrolled so that the window slots and the z ordering are compile-time.
+    load_plane(-F + 2, in0 + 2 * N * NP);
+    load_plane(-F + 3, in0 + 3 * N * NP);
+    cp_async_commit();
 #pragma unroll 1
-    for (int q0 = 0; q0 < N; q0 += R) {
+    for (int q0 = 0; q0 <= N; q0 += R) {
 #pragma unroll
     for (int jq = 0; jq < R; jq += 2) {
         const int q = q0 + jq;
-        if (q >= N) break;
+        if (q > N) break;
         const int zp = q - F;
-        const int pp = (q >> 1) & 1;
-        const double *cur = in0 + pp * 2 * N * N;
-        if (q + 2 < N) {
-            double *nxt = in0 + (pp ^ 1) * 2 * N * N;
-            load_plane(zp + 2, nxt);
-            load_plane(zp + 3, nxt + N * N);
-        }
-        cp_async_commit();
+        const int P = q >> 1;
         cp_async_wait<1>();
         __syncthreads();
-        // x: rows y = -F .. BS+F-1 of both planes, output pairs at interior x
+        if (q + 4 < N) {
+            double *nxt = in0 + ((P + 2) % 3) * 2 * N * NP;
+            load_plane(zp + 4, nxt);
+            load_plane(zp + 5, nxt + N * NP);
+        }
+        cp_async_commit();
+        if (q < N) {
+            // x: rows y = -F .. BS+F-1 of both planes of pair P; every thread forms TWO adjacent output pairs from one window of 2F+4 values
+            // (F+2 128-bit loads instead of 2(F+1): the kernel is bound by shared-memory wavefronts, profiles/r5_wavelet_fast_kernel.txt)
+            const double *cur = in0 + (P % 3) * 2 * N * NP;
+            double *xw = xs0 + (P & 1) * 2 * N * XP;
+            constexpr int PR = BS / 2, QR = (PR + 1) / 2;       // output pairs per row, items (of two pairs) per row
 #pragma unroll
-        for (int i0 = 0; i0 < 2 * N * (BS / 2); i0 += NT) {
-            const int i = i0 + tid;
-            if (i < 2 * N * (BS / 2)) {
-                const int pl = i / (N * (BS / 2)), ii = i % (N * (BS / 2));
-                const int r = ii / (BS / 2), o = 2 * (ii % (BS / 2));
-                double w[2 * F + 2];
-                const double2 *p2 = reinterpret_cast<const double2 *>(cur + pl * N * N + r * N + o);
+            for (int i0 = 0; i0 < 2 * N * QR; i0 += NT) {
+                const int i = i0 + tid;
+                if (i < 2 * N * QR) {
+                    const int pl = i / (N * QR), ii = i % (N * QR);
+                    const int r = ii / QR, pi = 2 * (ii % QR), o = 2 * pi;
+                    double w[2 * F + 4];
+                    const double2 *p2 = reinterpret_cast<const double2 *>(cur + pl * N * NP + r * NP + o);
 #pragma unroll
-                for (int j = 0; j < F + 1; ++j) {
-                    const double2 v = p2[j];
-                    w[2 * j] = v.x;
-                    w[2 * j + 1] = v.y;
+                    for (int j = 0; j < F + 2; ++j) {
+                        const double2 v = p2[j];
+                        w[2 * j] = v.x;
+                        w[2 * j + 1] = v.y;
+                    }
+                    double wa[2 * F + 2], wb[2 * F + 2];
+#pragma unroll
+                    for (int j = 0; j < 2 * F + 2; ++j) {
+                        wa[j] = w[j];
+                        wb[j] = w[j + 2];
+                    }
+                    double2 out;
+                    pair_out<X, Y, INV, F>(wa, out.x, out.y);
+                    *reinterpret_cast<double2 *>(xw + pl * N * XP + r * XP + o) = out;
+                    if (PR % 2 == 0 || pi + 1 < PR) {
+                        pair_out<X, Y, INV, F>(wb, out.x, out.y);
+                        *reinterpret_cast<double2 *>(xw + pl * N * XP + r * XP + o + 2) = out;
+                    }
                 }
-                double2 out;
-                pair_out<X, Y, INV, F>(w, out.x, out.y);
-                *reinterpret_cast<double2 *>(xs0 + pl * N * BS + r * BS + o) = out;
             }
         }
-        __syncthreads();
-        if (has_col) {
-            // y: one output per plane of this thread's column (scaling row if cy is even, wavelet row if odd)
+        if (has_col && q >= 2) {
+            // y of pair P-1 (planes q-2, q-1): one output per plane of this thread's column (scaling row if cy is even, wavelet row if odd)
+            const double *xr = xs0 + ((P - 1) & 1) * 2 * N * XP;
+            const int jy = (jq + R - 2) % R;              // window slots of planes q-2, q-1 (compile-time after unrolling)
 #pragma unroll
             for (int pl = 0; pl < 2; ++pl) {
                 double w[2 * F + 2], o0, o1;
-                const double *colp = xs0 + pl * N * BS + (cy - par) * BS + cx;     // window of the pair (cy - par, cy - par + 1)
+                const double *colp = xr + pl * N * XP + (cy - par) * XP + cx;     // window of the pair (cy - par, cy - par + 1)
                 if (par == 0) {
 #pragma unroll
-                    for (int j = 0; j < 2 * F + 1; ++j) w[j] = colp[j * BS];
+                    for (int j = 0; j < 2 * F + 1; ++j) w[j] = colp[j * XP];
                     w[2 * F + 1] = 0.0;
                     pair_out_one<X, Y, INV, F, 0>(w, o0);
-                    win[jq + pl] = o0;
+                    win[jy + pl] = o0;
                 } else {
                     w[0] = 0.0;
 #pragma unroll
-                    for (int j = 1; j < 2 * F + 2; ++j) w[j] = colp[j * BS];
+                    for (int j = 1; j < 2 * F + 2; ++j) w[j] = colp[j * XP];
                     pair_out_one<X, Y, INV, F, 1>(w, o1);
-                    win[jq + pl] = o1;
+                    win[jy + pl] = o1;
                 }
             }
-            // z: once plane zp + 1 = k + F + 1 is in the window (k even), output planes k and k+1 of this column are complete
-            const int k = q - 2 * F;           // its plane k - F sits in slot (jq + 2) % R
+            // z: once plane (q-2) + 1 = k + F + 1 is in the window (k even), output planes k and k+1 of this column are complete
+            const int k = q - 2 - 2 * F;       // its plane k - F sits in slot (jy + 2) % R = jq % R
             if (k >= 0 && k < BS) {
                 double w[R], o0, o1;
 #pragma unroll
-                for (int j = 0; j < R; ++j) w[j] = win[(jq + 2 + j) % R];
+                for (int j = 0; j < R; ++j) w[j] = win[(jq + j) % R];
                 pair_out<X, Y, INV, F>(w, o0, o1);
                 outc[(long long)k * BS * BS] = o0;
                 outc[(long long)(k + 1) * BS * BS] = o1;
                 if (!INV) {
-                    // threshold_block's Linfty detail, fused: max |wc| and max sqrt(wc*wc) over everything but the pure scaling
-                    // positions (wavelet_renorm_block is the identity for eps_norm = Linfty); sqrt is monotone, taken once at the end
-                    // (max sqrt(wc*wc) = sqrt(fl(max|wc|^2)): squaring and rounding are monotone, so it is formed once from m0 at the end)
+                    // threshold_block's Linfty detail, fused: max |wc| over everything but the pure scaling positions (wavelet_renorm_block is
+                    // the identity for eps_norm = Linfty); max sqrt(wc*wc) = sqrt(fl(max|wc|^2)) (squaring and rounding are monotone): formed
+                    // once from m0 at the end
                     m0 = fmax(m0, fabs(o1));
                     if (!pure_col) m0 = fmax(m0, fabs(o0));
                 }
