@@ -420,6 +420,9 @@ struct FastCfg {
 #ifndef WFAST_MINB_BIG
 #define WFAST_MINB_BIG 2   // Bs = 18, 20 (352 / 416 threads per CTA): two resident CTAs instead of the one ptxas would settle for
 #endif
+#ifndef WFAST_XPT
+#define WFAST_XPT 2    // output pairs per thread in the x pass (one window of 2F + 2 XPT values): 4 needs more than 80 registers
+#endif
 #ifndef WFAST_MINB
 #define WFAST_MINB 3   // minimum resident CTAs per SM requested for Bs = 16 (register cap <= 80): measured best for the two-planes-per-barrier loop
 #endif
@@ -550,37 +553,37 @@ __global__ void __launch_bounds__(FastCfg<X, Y, BS, INV>::NT, (BS == 16 ? WFAST_
         }
         cp_async_commit();
         if (q < N) {
-            // x: rows y = -F .. BS+F-1 of both planes of pair P; every thread forms TWO adjacent output pairs from one window of 2F+4 values
-            // (F+2 128-bit loads instead of 2(F+1): the kernel is bound by shared-memory wavefronts, profiles/r5_wavelet_fast_kernel.txt)
+            // x: rows y = -F .. BS+F-1 of both planes of pair P; every thread forms XPT adjacent output pairs from one window of 2F + 2 XPT values
+            // (F + XPT 128-bit loads instead of XPT (F+1): the kernel is bound by shared-memory wavefronts, profiles/r5_wavelet_fast_kernel.txt)
             const double *cur = in0 + (P % 3) * 2 * N * NP;
             double *xw = xs0 + (P & 1) * 2 * N * XP;
-            constexpr int PR = BS / 2, QR = (PR + 1) / 2;       // output pairs per row, items (of two pairs) per row
+            constexpr int PR = BS / 2, XPT = WFAST_XPT, QR = (PR + XPT - 1) / XPT;       // output pairs per row, pairs per thread, items per row
 #pragma unroll
             for (int i0 = 0; i0 < 2 * N * QR; i0 += NT) {
                 const int i = i0 + tid;
                 if (i < 2 * N * QR) {
                     const int pl = i / (N * QR), ii = i % (N * QR);
-                    const int r = ii / QR, pi = 2 * (ii % QR), o = 2 * pi;
-                    double w[2 * F + 4];
+                    const int r = ii / QR, pi = XPT * (ii % QR), o = 2 * pi;
+                    double w[2 * F + 2 * XPT];
                     const double2 *p2 = reinterpret_cast<const double2 *>(cur + pl * N * NP + r * NP + o);
 #pragma unroll
-                    for (int j = 0; j < F + 2; ++j) {
-                        const double2 v = p2[j];
-                        w[2 * j] = v.x;
-                        w[2 * j + 1] = v.y;
+                    for (int j = 0; j < F + XPT; ++j) {
+                        if (o + 2 * j < NP) {                       // the last item of a row may hold fewer than XPT pairs: stay inside the row
+                            const double2 v = p2[j];
+                            w[2 * j] = v.x;
+                            w[2 * j + 1] = v.y;
+                        } else w[2 * j] = w[2 * j + 1] = 0.0;
                     }
-                    double wa[2 * F + 2], wb[2 * F + 2];
 #pragma unroll
-                    for (int j = 0; j < 2 * F + 2; ++j) {
-                        wa[j] = w[j];
-                        wb[j] = w[j + 2];
-                    }
-                    double2 out;
-                    pair_out<X, Y, INV, F>(wa, out.x, out.y);
-                    *reinterpret_cast<double2 *>(xw + pl * N * XP + r * XP + o) = out;
-                    if (PR % 2 == 0 || pi + 1 < PR) {
-                        pair_out<X, Y, INV, F>(wb, out.x, out.y);
-                        *reinterpret_cast<double2 *>(xw + pl * N * XP + r * XP + o + 2) = out;
+                    for (int t = 0; t < XPT; ++t) {
+                        if (PR % XPT == 0 || pi + t < PR) {
+                            double wt[2 * F + 2];
+#pragma unroll
+                            for (int j = 0; j < 2 * F + 2; ++j) wt[j] = w[j + 2 * t];
+                            double2 out;
+                            pair_out<X, Y, INV, F>(wt, out.x, out.y);
+                            *reinterpret_cast<double2 *>(xw + pl * N * XP + r * XP + o + 2 * t) = out;
+                        }
                     }
                 }
             }
