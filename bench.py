@@ -959,7 +959,7 @@ def main():
     a.warmup = max(a.warmup, 3)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:   # torchrun exports OMP_NUM_THREADS=1: give the host light-data logic (neighbour search) this rank's share of the cores
-        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
+        os.environ["OMP_NUM_THREADS"] = os.environ.get("WABBIT_OMP_THREADS") or str(max(1, (os.cpu_count() or 1) // world))
     if a.adaptive_only:
         import torch
         torch.cuda.set_device(0)
