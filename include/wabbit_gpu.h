@@ -403,6 +403,17 @@ int32_t wgpu_ship_blocks(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t 
 int32_t wgpu_comm_allreduce(wgpu_ctx *ctx, double *inout, int32_t n, int32_t op);
 int32_t wgpu_comm_allgatherv_i32(wgpu_ctx *ctx, const int32_t *mine, const int32_t *counts, int32_t *out);
 
+/*
+ * wgpu_rkc_step: RungeKuttaChebychev (LIB/TIME/runge_kutta_chebychev.f90:6-146; time_step_method = RungeKuttaChebychev in timeStep_tree.f90:38):
+ *   one step of the s-stage scheme (s >= 4, else code 1715929 as the reference) with the coefficient rows mu(s,1:s), mu_tilde, nu, gamma_tilde,
+ *   c of the host's tables (setup_RKC_coefficients, or the RKC_custom_scheme of the parameter file): calculate_time_step, F0 = rhs(y00),
+ *   y1 = y0 + mu~_1 dt F0, then for i = 2..s  F1 = rhs(y1) at tau = time + c(i-1) dt  and
+ *   y2 = (1 - mu_i - nu_i) y00 + mu_i y1 + nu_i y0 + mu~_i dt F1 + gamma~_i dt F0  (evaluated left to right, uncontracted).  Six registers as the
+ *   reference: hvy_block, two stage inputs and hvy_work slots 2..4.  Ghost synchronisation is fused into every right-hand side.  One rank.
+ */
+int32_t wgpu_rkc_step(wgpu_ctx *ctx, double time, int32_t iteration, int32_t s, const double *mu, const double *mu_tilde, const double *nu,
+                      const double *gamma_tilde, const double *c, double *dt);
+
 /* Stage-kernel timing with CUDA events on the context's stream (for the roofline line of bench.py):
  * wgpu_profile(ctx, 1) starts recording an event pair around every stage-kernel launch (at most 4096 pairs),
  * wgpu_profile_read synchronises, returns their number and summed duration in milliseconds, and resets. */

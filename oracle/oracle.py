@@ -666,6 +666,35 @@ def coarse_extension_modify(grid: Grid, p: Params, w: Wavelet, wd: np.ndarray, o
     return n
 
 
+def rkc_step(grid: Grid, p: Params, hvy: np.ndarray, time: float, mu, mu_tilde, nu, gamma_tilde, c, mask: Optional[np.ndarray] = None, sync=None) -> float:
+    """RungeKuttaChebychev (LIB/TIME/runge_kutta_chebychev.f90:6-146), numpy on the whole ghosted arrays (interiors are what counts; ghost nodes
+    are re-synchronised before every right-hand side).  mu .. c: rows s of the coefficient tables (setup_RKC_coefficients, :180 ff, or the
+    RKC_custom_scheme of the parameter file), 0-based here.  Evaluation order of the main formula as the Fortran expression: left to right.
+    hvy is advanced in place; returns dt."""
+    s = len(mu)
+    if s < 4:
+        raise ValueError("runge-kutta-chebychev: s cannot be less than 4")          # abort(1715929)
+    if sync is None:
+        sync = lambda h: sync_ghosts_same_level(grid, p, h, p.g_rhs, p.g_rhs)
+    sync(hvy)
+    dt = calculate_time_step(grid, p, hvy, time)
+    y00 = hvy.copy()
+    y0 = hvy.copy()
+    F0 = np.zeros_like(hvy)
+    rhs_tree(grid, p, hvy, F0, mask)
+    y1 = y0 + mu_tilde[0] * dt * F0
+    y2 = y1
+    for i in range(1, s):                       # Fortran i = 2 .. s
+        sync(y1)
+        F1 = np.zeros_like(hvy)
+        rhs_tree(grid, p, y1, F1, mask)
+        y2 = (1.0 - mu[i] - nu[i]) * y00 + mu[i] * y1 + nu[i] * y0 + mu_tilde[i] * dt * F1 + gamma_tilde[i] * dt * F0
+        if i < s - 1:
+            y0, y1 = y1, y2
+    hvy[:] = y2
+    return dt
+
+
 FD1 = {"FD_2nd_central": (1, [-0.5, 0.0, 0.5]), "FD_4th_central": (2, [1.0 / 12.0, -2.0 / 3.0, 0.0, 2.0 / 3.0, -1.0 / 12.0]),
        "FD_6th_central": (3, [-1.0 / 60.0, 3.0 / 20.0, -3.0 / 4.0, 0.0, 3.0 / 4.0, -3.0 / 20.0, 1.0 / 60.0])}
 

@@ -234,3 +234,27 @@ if __name__ == "__main__":
     three_vortices()
     three_vortices_adaptive()
     cylinder_adaptive()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Runge-Kutta-Chebychev coefficient tables (LIB/TIME/runge_kutta_chebychev.f90: setup_RKC_coefficients): the rows s = 4, 6, 10, 20 of
+# mu, mu_tilde, nu, gamma_tilde, c as the reference's source lists them (damping eps = 10) -> rkc_coefficients.npz
+def rkc_tables(stages=(4, 6, 10, 20)):
+    import re
+    src = open("/root/reference/LIB/TIME/runge_kutta_chebychev.f90").read()
+    out = {}
+    for s in stages:
+        m = re.search(r"\n\s*s=%d\n(.*?)(?=\n\s*! -{10,}|\nend subroutine)" % s, src, flags=re.S)
+        body = m.group(1)
+        for name in ("mu", "mu_tilde", "nu", "gamma_tilde", "c"):
+            mm = re.search(r"\b%s\(s,1:%d\)=\(/(.*?)/\)" % (name, s), body, flags=re.S)
+            vals = [float(v.replace("_rk", "")) for v in re.findall(r"[-+]?\d\.\d+e[-+]\d+_rk", mm.group(1))]
+            assert len(vals) == s, (s, name, len(vals))
+            out[f"s{s}_{name}"] = np.array(vals)
+    path = os.path.join(HERE, "rkc_coefficients.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), sorted(out)[:5])
+
+
+if __name__ == "__main__":
+    rkc_tables()

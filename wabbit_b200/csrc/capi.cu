@@ -1945,6 +1945,65 @@ int32_t wgpu_rk_end_nosync(wgpu_ctx *ctx)
 
 extern "C" {
 
+// ------------------------------------------------------------------------------------------------ Runge-Kutta-Chebychev
+int32_t wgpu_rkc_step(wgpu_ctx *ctx, double time, int32_t iteration, int32_t s, const double *mu, const double *mu_tilde, const double *nu,
+                      const double *gamma_tilde, const double *c, double *dt)
+{
+    (void)iteration;
+    if (!ctx || !mu || !mu_tilde || !nu || !gamma_tilde || !c || !dt) return WGPU_ERR_ARG;
+    if (s < 4) return fail(ctx, 1715929, "runge-kutta-chebychev: s cannot be less than 4");
+    if (ctx->nc != ctx->cfg.dim + 1) return fail(ctx, WGPU_ERR_UNSUPPORTED, "ACM needs number_equations = dim+1");
+    if (ctx->comm && ctx->comm_world > 1) return fail(ctx, WGPU_ERR_UNSUPPORTED, "wgpu_rkc_step: one rank only so far");
+    if (exchange_pending(ctx)) return fail(ctx, WGPU_ERR_ARG, "topology has neighbours on other ranks");
+    int32_t rc;
+    if ((rc = compute_dt(ctx, time))) return rc;            // calculate_time_step: dt stays on the device
+    // six registers, as the reference (runge_kutta_chebychev.f90:26-27): y00 = hvy_block; y0, y1, y2 rotate; F0, F1 swap
+    const size_t n = (size_t)ctx->cfg.max_blocks * ctx->nc * ctx->blk_elems;
+    for (int k = 0; k < 3; ++k)
+        if (!ctx->K[k]) {
+            if ((rc = dmalloc(ctx, &ctx->K[k], n))) return rc;
+            WGPU_CHECK(ctx, cudaMemsetAsync(ctx->K[k], 0, n * sizeof(double), ctx->stream));
+        }
+    double *F0 = ctx->K[0], *F1 = ctx->K[1];
+    double *y1 = ctx->UA, *y2 = ctx->UB, *spare = ctx->K[2];
+    ctx->det_cached_for = nullptr;
+    auto rhs_of = [&](const double *src, double *dst, double t_cj) -> int32_t {
+        StageArgs a;
+        fill_common_args(ctx, a);
+        a.u_in = src;
+        a.u0 = src;
+        a.k_out = dst;
+        a.t0 = time;
+        a.t_cj = t_cj;                                       // tau = time + c(i-1) * dt for an explicitly time-dependent mask
+        int32_t r = wgpu_launch_jump_fill(ctx, src);         // sync_ghosts_RHS_tree
+        if (r) return r;
+        a.plain_hint = plain_hint(ctx, WGPU_BLOCKS_ALL);
+        return wgpu_launch_stage(ctx, a, ctx->n_active);
+    };
+    if ((rc = rhs_of(ctx->U, F0, 0.0))) return rc;                                                   // F0 = rhs(y00)
+    if ((rc = wgpu_launch_rkc_combine(ctx, y1, ctx->U, ctx->U, ctx->U, F0, F0, 0.0, 0.0, 0.0, mu_tilde[0], 0.0, 0))) return rc;   // y1 = y0 + mu~_1 dt F0
+    const double *y0c = ctx->U;                                                                      // y0 = y00 before the first rotation
+    for (int i = 1; i < s; ++i) {                                                                    // Fortran i = 2 .. s
+        if ((rc = rhs_of(y1, F1, c[i - 1]))) return rc;                                              // F1 = rhs(y1) at tau = time + c(i-1) dt
+        if ((rc = wgpu_launch_rkc_combine(ctx, y2, ctx->U, y1, y0c, F1, F0, 1.0 - mu[i] - nu[i], mu[i], nu[i], mu_tilde[i], gamma_tilde[i], 1))) return rc;
+        if (i < s - 1) {                                                                             // y0 <- y1 <- y2; the old y0 buffer is the next y2
+            double *old0 = (y0c == ctx->U) ? spare : const_cast<double *>(y0c);
+            y0c = y1;
+            y1 = y2;
+            y2 = old0;
+        }
+    }
+    // u = y2: the array that holds it becomes hvy_block (pointer swap, as the single-stage path of the Runge-Kutta driver)
+    if (y2 == ctx->UA) std::swap(ctx->U, ctx->UA);
+    else if (y2 == ctx->UB) std::swap(ctx->U, ctx->UB);
+    else std::swap(ctx->U, ctx->K[2]);
+    ctx->dtmin_valid = false;
+    WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_dt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    *dt = ctx->h_pinned[0];
+    return check_flags(ctx);
+}
+
 int32_t wgpu_rk_end(wgpu_ctx *ctx, double *dt)
 {
     if (!ctx || !dt) return WGPU_ERR_ARG;

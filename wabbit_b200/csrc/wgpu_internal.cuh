@@ -280,6 +280,8 @@ int32_t wgpu_rk_end_nosync(wgpu_ctx *ctx);
 // kernels.cu
 int32_t wgpu_launch_stage(wgpu_ctx *ctx, const StageArgs &a, int n_blocks);
 void wgpu_tma_release(wgpu_ctx *ctx);
+int32_t wgpu_launch_rkc_combine(wgpu_ctx *ctx, double *out, const double *y00, const double *y1, const double *y0, const double *f1, const double *f0,
+                                double cA, double cB, double cC, double cD, double cE, int mode);
 int32_t wgpu_launch_pack(wgpu_ctx *ctx, const double *src);
 int32_t wgpu_launch_pack_put(wgpu_ctx *ctx, const double *src, int parity, unsigned seq, cudaStream_t st);
 int32_t wgpu_launch_wait_flags(wgpu_ctx *ctx, unsigned seq, cudaStream_t st);

@@ -305,6 +305,16 @@ class WabbitGPU:
         self._check(self._lib.wgpu_rk_steps(self._ctx, float(time), int(n_steps), C.byref(t), C.byref(dt)))
         return t.value, dt.value
 
+    def RungeKuttaChebychev(self, time: float, iteration: int, mu, mu_tilde, nu, gamma_tilde, c) -> float:
+        """RungeKuttaChebychev (runge_kutta_chebychev.f90:6) with the host's coefficient rows of length s (wgpu_rkc_step); returns dt"""
+        arr = [np.ascontiguousarray(v, dtype=np.float64) for v in (mu, mu_tilde, nu, gamma_tilde, c)]
+        s = len(arr[0])
+        assert all(len(a) == s for a in arr)
+        dt = C.c_double()
+        dp = C.POINTER(C.c_double)
+        self._check(self._lib.wgpu_rkc_step(self._ctx, float(time), int(iteration), s, *[a.ctypes.data_as(dp) for a in arr], C.byref(dt)))
+        return dt.value
+
     def RungeKuttaGeneric(self, time: float, iteration: int = 0) -> float:
         """runge_kutta_generic.f90:1 -- advances hvy_block by one step on the device, returns dt."""
         dt = C.c_double()
