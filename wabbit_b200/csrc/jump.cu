@@ -91,12 +91,19 @@ __global__ void __launch_bounds__(256) restrict_filter_kernel(const RestrictArgs
     for (int i = threadIdx.x; i < n * n * xc; i += blockDim.x) {
         const int xl = i % xc, xo = x0 + xl, y = (i / xc) % n - F, z = i / (xc * n) - F;
         const int sy = y < 0 ? -1 : (y >= Bs ? 1 : 0), sz = z < 0 ? -1 : (z >= Bs ? 1 : 0);
+        // the row (y, z) of the ghosted block lives in up to three blocks (x neighbours): their row pointers, shifted so that every one of them
+        // is indexed by the block-local x of the ghosted row (the kernel is bound by the index arithmetic of this loop, not by its loads)
+        const long long row = ((long long)(z - sz * Bs) * Bs + (y - sy * Bs)) * Bs;
+        const int *nbrow = nb + (sz + 1) * 9 + (sy + 1) * 3;
+        const int sm1 = nbrow[0], s00 = nbrow[1], sp1 = nbrow[2];
+        const double *pm = sm1 >= 0 ? a.u + ((long long)sm1 * a.nc + c) * CS + row + Bs : nullptr;     // x in [-Bs, 0)
+        const double *p0 = s00 >= 0 ? a.u + ((long long)s00 * a.nc + c) * CS + row : nullptr;          // x in [0, Bs)
+        const double *pp = sp1 >= 0 ? a.u + ((long long)sp1 * a.nc + c) * CS + row - Bs : nullptr;     // x in [Bs, 2 Bs)
         double acc = 0.0;
         for (int k = a.lo; k <= a.hi; ++k) {
             const int x = 2 * xo + k;
-            const int sx = x < 0 ? -1 : (x >= Bs ? 1 : 0);
-            const int src = nb[(sz + 1) * 9 + (sy + 1) * 3 + (sx + 1)];
-            const double v = src >= 0 ? a.u[((long long)src * a.nc + c) * CS + ((long long)(z - sz * Bs) * Bs + (y - sy * Bs)) * Bs + (x - sx * Bs)] : 0.0;
+            const double *ptr = x < 0 ? pm : (x >= Bs ? pp : p0);
+            const double v = ptr ? ptr[x] : 0.0;
             acc = __dadd_rn(acc, __dmul_rn(v, a.HD[k + WGPU_FMAX]));
         }
         t1[((size_t)(z + F) * n + (y + F)) * xc + xl] = acc;
