@@ -414,6 +414,15 @@ int32_t wgpu_comm_allgatherv_i32(wgpu_ctx *ctx, const int32_t *mine, const int32
 int32_t wgpu_rkc_step(wgpu_ctx *ctx, double time, int32_t iteration, int32_t s, const double *mu, const double *mu_tilde, const double *nu,
                       const double *gamma_tilde, const double *c, double *dt);
 
+/*
+ * wgpu_filter: filter_wrapper (LIB/TIME/filter_wrapper.f90:1-78) on the resident hvy_block: filter_type = "explicit_3pt" ... "explicit_21pt" or
+ *   "superviscosity_2nd" ... "_20th" (the binomial stencils of generate_superviscosity_stencil, + identity), applied with blockFilterXYZ_vct
+ *   (LIB/WAVELETS/module_wavelets.f90:307-401: x, then y, then z; every sum starts from 0 and adds the shifts in increasing order) to the components
+ *   with filter_component[c] != 0 (NULL: all) of every active block, or only of the blocks on Jmax / all but those.  Ghost values are gathered
+ *   on the fly as sync_ghosts_tree leaves them.  Error codes 251106 / 251107 / 251108 as the reference.  3-D.
+ */
+int32_t wgpu_filter(wgpu_ctx *ctx, const char *filter_type, const int32_t *filter_component, int32_t only_maxlevel, int32_t all_except_maxlevel);
+
 /* Stage-kernel timing with CUDA events on the context's stream (for the roofline line of bench.py):
  * wgpu_profile(ctx, 1) starts recording an event pair around every stage-kernel launch (at most 4096 pairs),
  * wgpu_profile_read synchronises, returns their number and summed duration in milliseconds, and resets. */

@@ -695,6 +695,50 @@ def rkc_step(grid: Grid, p: Params, hvy: np.ndarray, time: float, mu, mu_tilde, 
     return dt
 
 
+def superviscosity_stencil(filter_type: str) -> dict:
+    """The stencil filter_wrapper applies (LIB/TIME/filter_wrapper.f90:28-62, generate_superviscosity_stencil :82-104): binomial coefficients with
+    alternating sign, normalised by the sum of their absolute values, negated for explicit_5pt / 9pt / 13pt / 17pt / 21pt, plus the identity.
+    {shift: coefficient}."""
+    import re
+    m = re.match(r"explicit_(\d+)pt$", filter_type)
+    if m:
+        order = int(m.group(1)) - 1
+    else:
+        m = re.match(r"superviscosity_(\d+)(?:nd|th)$", filter_type)
+        if not m:
+            raise ValueError("ERROR: Filter not known: " + filter_type)          # abort(251107)
+        order = int(m.group(1))
+    if order < 2 or order > 20 or order % 2:
+        raise ValueError("ERROR: Filter not known: " + filter_type)
+    a = order // 2
+    st = np.array([(-1.0) ** (k + a) * float(math.comb(2 * a, a + k)) for k in range(-a, a + 1)])
+    st = st / np.abs(st).sum()
+    if a % 2 == 0:
+        st = -st
+    st[a] = st[a] + 1.0
+    return {k: float(st[k + a]) for k in range(-a, a + 1)}
+
+
+def filter_wrapper(grid: Grid, p: Params, hvy: np.ndarray, filter_type: str, filter_component=None, only_maxlevel: bool = False,
+                   all_except_maxlevel: bool = False) -> None:
+    """filter_wrapper (LIB/TIME/filter_wrapper.f90:1-78) on ghost-synchronised data, in place: blockFilterXYZ_vct per selected block and component"""
+    if only_maxlevel and all_except_maxlevel:
+        raise ValueError("251106")
+    coef = superviscosity_stencil(filter_type)
+    if max(coef) > p.g:
+        raise ValueError("251108")
+    I = interior(p)
+    for b in range(grid.n):
+        lvl = int(grid.level[b])
+        if (only_maxlevel and lvl < p.Jmax) or (all_except_maxlevel and lvl == p.Jmax):
+            continue
+        for c in range(hvy.shape[1]):
+            if filter_component is not None and not filter_component[c]:
+                continue
+            out = block_filter(p, hvy[b, c:c + 1], coef)
+            hvy[b, c][I] = out[0][I]
+
+
 FD1 = {"FD_2nd_central": (1, [-0.5, 0.0, 0.5]), "FD_4th_central": (2, [1.0 / 12.0, -2.0 / 3.0, 0.0, 2.0 / 3.0, -1.0 / 12.0]),
        "FD_6th_central": (3, [-1.0 / 60.0, 3.0 / 20.0, -3.0 / 4.0, 0.0, 3.0 / 4.0, -3.0 / 20.0, 1.0 / 60.0])}
 

@@ -45,3 +45,15 @@ def test_rkc_step_converges_with_second_order_towards_rk4(s):
     e1 = np.abs(run(h, True) - run(h, False)).max()
     e2 = np.abs(run(h / 2, True) - run(h / 2, False)).max()
     assert 1e-12 < e2 < e1 < 1e-4 and 6.0 <= e1 / e2 <= 10.0, (e1, e2, e1 / e2)      # local error O(dt^3)
+
+
+def test_superviscosity_stencils_known_answers():
+    """generate_superviscosity_stencil + the sign convention and the added identity of filter_wrapper.f90:28-62"""
+    assert list(O.superviscosity_stencil("explicit_3pt").values()) == [0.25, 0.5, 0.25]
+    assert list(O.superviscosity_stencil("explicit_5pt").values()) == [-1 / 16, 4 / 16, 10 / 16, 4 / 16, -1 / 16]
+    assert O.superviscosity_stencil("superviscosity_6th") == O.superviscosity_stencil("explicit_7pt")
+    for t in ("explicit_9pt", "explicit_13pt", "explicit_21pt"):
+        c = O.superviscosity_stencil(t)
+        assert abs(sum(c.values()) - 1.0) <= 1e-15 and c[0] > 0.5 and all(abs(c[k] - c[-k]) == 0.0 for k in c)
+    with pytest.raises(ValueError):
+        O.superviscosity_stencil("explicit_4pt")

@@ -42,6 +42,7 @@ GPU_SYMBOLS = {
     "wgpu_upload": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, _i32p, C.c_int32, C.c_void_p, C.c_int32]),
     "wgpu_download": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, _i32p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]),
     "wgpu_set_transfer_mode": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32]),
+    "wgpu_filter": (C.c_int32, [C.c_void_p, C.c_char_p, _i32p, C.c_int32, C.c_int32]),
     "wgpu_rkc_step": (C.c_int32, [C.c_void_p, C.c_double, C.c_int32, C.c_int32, _dp, _dp, _dp, _dp, _dp, _dp]),
     "wgpu_create_mask": (C.c_int32, [C.c_void_p, C.c_double, C.c_int32, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_double]),
     "wgpu_statistics": (C.c_int32, [C.c_void_p, C.c_double, C.c_int32, _dp]),

@@ -2004,6 +2004,46 @@ int32_t wgpu_rkc_step(wgpu_ctx *ctx, double time, int32_t iteration, int32_t s, 
     return check_flags(ctx);
 }
 
+// ------------------------------------------------------------------------------------------------ explicit filter
+int32_t wgpu_filter(wgpu_ctx *ctx, const char *filter_type, const int32_t *filter_component, int32_t only_maxlevel, int32_t all_except_maxlevel)
+{
+    if (!ctx || !filter_type) return WGPU_ERR_ARG;
+    if (only_maxlevel && all_except_maxlevel)
+        return fail(ctx, 251106, "ERROR: Do you want to filter only on max level or all except max level??? Choose one, not both.");
+    // filter_wrapper.f90:28-60: explicit_(2n+1)pt == superviscosity_(2n)th, n = 1..10
+    int order = 0;
+    int pts = 0, ord = 0;
+    if (sscanf(filter_type, "explicit_%dpt", &pts) == 1 && pts >= 3 && pts <= 21 && (pts & 1)) order = pts - 1;
+    else if (sscanf(filter_type, "superviscosity_%d", &ord) == 1 && ord >= 2 && ord <= 20 && !(ord & 1)) order = ord;
+    if (!order) return fail(ctx, 251107, std::string("ERROR: Filter not known: ") + filter_type);
+    const int a = order / 2;
+    if (a > ctx->cfg.g) return fail(ctx, 251108, "ERROR: Nice filter you've selected there, but its stencil size exceeds the ghost layer thickness. Increase g.");
+    // generate_superviscosity_stencil (filter_wrapper.f90:82-104): (-1)^(k+a) binom(2a, a+k), normalised by the sum of the absolute values; negated
+    // for the orders 4, 8, 12, ...; then stencil(0) + 1
+    double st[2 * WGPU_FMAX + 1], sum_abs = 0.0;
+    for (int k = -a; k <= a; ++k) {
+        double binom = 1.0;
+        for (int j = 1; j <= a + k; ++j) binom = binom * (double)(2 * a - (a + k) + j) / (double)j;     // exact for these sizes
+        binom = floor(binom + 0.5);
+        st[k + a] = (((k + a) & 1) ? -1.0 : 1.0) * binom;
+        sum_abs += fabs(st[k + a]);
+    }
+    for (int k = 0; k <= 2 * a; ++k) st[k] = st[k] / sum_abs;
+    if ((order / 2) % 2 == 0)
+        for (int k = 0; k <= 2 * a; ++k) st[k] = -st[k];
+    st[a] = st[a] + 1.0;
+    unsigned mask = 0;
+    for (int c = 0; c < ctx->nc; ++c)
+        if (!filter_component || filter_component[c]) mask |= 1u << c;
+    if (!ctx->TMP) return fail(ctx, WGPU_ERR_ARG, "wgpu_filter: no second buffer (hvy_tmp)");
+    int32_t rc = wgpu_launch_blockfilter(ctx, ctx->U, ctx->TMP, st, a, mask, only_maxlevel ? 1 : (all_except_maxlevel ? 2 : 0));
+    if (rc) return rc;
+    std::swap(ctx->U, ctx->TMP);          // the filtered array becomes hvy_block
+    ctx->dtmin_valid = false;
+    ctx->det_cached_for = nullptr;
+    return WGPU_OK;
+}
+
 int32_t wgpu_rk_end(wgpu_ctx *ctx, double *dt)
 {
     if (!ctx || !dt) return WGPU_ERR_ARG;

@@ -69,8 +69,13 @@ struct WaveArgs {
     const long long *woff;
     int fw;              // depth of the pool patches (wjump_depth >= f)
     int nc, Bs, f;       // f = halo depth gathered = max filter half width of the transform direction
-    int inverse;         // 0: decomposition (HD/GD), 1: reconstruction (HR/GR on zero-stuffed SC/WC)
+    int inverse;         // 0: decomposition (HD/GD), 1: reconstruction (HR/GR on zero-stuffed SC/WC), 2: plain filter (blockFilterXYZ_vct with
+                         //    the stencil in w.HD[hd_lo..hd_hi]: every point, x then y then z, sums from 0 in increasing shift order)
     WaveFilters w;
+    // mode 2 (filter_wrapper, LIB/TIME/filter_wrapper.f90): which blocks / components are filtered; the others are copied
+    const signed char *level;
+    int Jmax, level_mode;    // 0 every block, 1 only blocks on Jmax (filter_only_maxlevel), 2 all except those (filter_all_except_maxlevel)
+    unsigned comp_mask;      // bit c: component c is filtered (filter_component)
 };
 
 // source of a ghosted coordinate c in [-f, Bs+f): direction -1/0/+1 and local coordinate
@@ -95,6 +100,16 @@ __global__ void __launch_bounds__(256) wavelet_kernel(const WaveArgs a)
     if (tid < WGPU_NDIR) s_code[tid] = tid == 13 ? b : a.nbr[b * WGPU_NDIR + tid];
     __syncthreads();
     const long long CS = (long long)Bs * Bs * Bs;
+    if (a.inverse == 2) {
+        const int lv = a.level[b];
+        const bool skip = !((a.comp_mask >> c) & 1u) || (a.level_mode == 1 && lv < a.Jmax) || (a.level_mode == 2 && lv == a.Jmax);
+        if (skip) {      // this block / component is not filtered: it keeps its values
+            const double *sp = a.src + ((long long)b * a.nc + c) * CS;
+            double *dp = a.dst + ((long long)b * a.nc + c) * CS;
+            for (long long i = tid; i < CS; i += nt) dp[i] = sp[i];
+            return;
+        }
+    }
 
     auto load_plane = [&](int zp, double *dstp) {
         int dz, lz;
@@ -117,14 +132,20 @@ __global__ void __launch_bounds__(256) wavelet_kernel(const WaveArgs a)
         }
     };
 
-    const double *F0 = a.inverse ? a.w.HR : a.w.HD, *F1 = a.inverse ? a.w.GR : a.w.GD;
-    const int lo0 = a.inverse ? a.w.hr_lo : a.w.hd_lo, hi0 = a.inverse ? a.w.hr_hi : a.w.hd_hi;
-    const int lo1 = a.inverse ? a.w.gr_lo : a.w.gd_lo, hi1 = a.inverse ? a.w.gr_hi : a.w.gd_hi;
+    const bool inv = a.inverse == 1;
+    const double *F0 = inv ? a.w.HR : a.w.HD, *F1 = inv ? a.w.GR : a.w.GD;
+    const int lo0 = inv ? a.w.hr_lo : a.w.hd_lo, hi0 = inv ? a.w.hr_hi : a.w.hd_hi;
+    const int lo1 = inv ? a.w.gr_lo : a.w.gd_lo, hi1 = inv ? a.w.gr_hi : a.w.gd_hi;
 
     // 1-D transform of a line at interior offset o (0..Bs-1); p points at the line element of offset o.
     // decomposition: even offsets -> HD (scaling), odd -> GD (wavelet).
     // reconstruction: u(o) = sum_{k: o+k even} sc(o+k) HR(k) + sum_{k: o+k odd} wc(o+k) GR(k)   (zero stuffing)
     auto line = [&](const double *p, int stride, int o) -> double {
+        if (a.inverse == 2) {
+            double s = 0.0;
+            for (int k = lo0; k <= hi0; ++k) s = __dadd_rn(s, __dmul_rn(p[k * stride], F0[k + WGPU_FMAX]));
+            return s;
+        }
         if (!a.inverse) return (o & 1) ? filt(p, stride, F1, lo1, hi1) : filt(p, stride, F0, lo0, hi0);
         double s0 = 0.0, s1 = 0.0;
         for (int k = lo0; k <= hi0; ++k)
@@ -167,7 +188,11 @@ __global__ void __launch_bounds__(256) wavelet_kernel(const WaveArgs a)
                     // gather the taps through the ring: emulate `line` with a modular stride
                     const double *F = nullptr;
                     int lo, hi;
-                    if (!a.inverse) {
+                    if (a.inverse == 2) {
+                        double s = 0.0;
+                        for (int t = lo0; t <= hi0; ++t) s = __dadd_rn(s, __dmul_rn(ring[((o + t + f) % R) * Bs * Bs + xy], F0[t + WGPU_FMAX]));
+                        acc = s;
+                    } else if (!a.inverse) {
                         F = (o & 1) ? F1 : F0;
                         lo = (o & 1) ? lo1 : lo0;
                         hi = (o & 1) ? hi1 : hi0;
@@ -930,6 +955,8 @@ int32_t wgpu_launch_blocksum(wgpu_ctx *ctx, const double *u, int squared, double
 // ce_coarse != nullptr: reconstruction inside wavelet_reconstruct_full_tree_CEoptimized -- the ghost patches that face a coarser leaf
 // hold that leaf's values (array ce_coarse) at the scaling positions and zero wavelet coefficients (sync_SCWC_from_MC +
 // coarse_extension_modify, LIB/MESH/adapt_tree.f90:686-987) instead of restricted / predicted values of `src`
+static size_t g_wavelet_kernel_smem = 0;   // largest dynamic shared memory wavelet_kernel has been configured for (two launchers share the kernel)
+
 int32_t wgpu_launch_wavelet(wgpu_ctx *ctx, const double *src, double *dst, int inverse, const double *ce_coarse)
 {
     if (ctx->n_active == 0) return WGPU_OK;
@@ -1013,10 +1040,74 @@ int32_t wgpu_launch_wavelet(wgpu_ctx *ctx, const double *src, double *dst, int i
         ctx->err = "wavelet transform: block too large for the shared-memory ring of the table-driven kernel";
         return WGPU_ERR_UNSUPPORTED;
     }
-    static size_t configured = 0;
-    if (smem > configured) {
+    if (smem > g_wavelet_kernel_smem) {
         WGPU_CHECK(ctx, cudaFuncSetAttribute(wavelet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        g_wavelet_kernel_smem = smem;
+    }
+    dim3 grid(ctx->n_active, ctx->nc);
+    wavelet_kernel<<<grid, 256, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    WGPU_CHECK(ctx, cudaGetLastError());
+    return WGPU_OK;
+}
+
+// filter_wrapper's block loop (LIB/TIME/filter_wrapper.f90:62-77): blockFilterXYZ_vct with a symmetric stencil of half width `half` on the selected
+// blocks / components, src -> dst (everything else copied); ghost values as sync_ghosts_tree leaves them (same level: neighbour interiors, level
+// jumps: the wavelet jump pool).  3-D, table-driven kernel (the filter runs once per filter_freq time steps).
+int32_t wgpu_launch_blockfilter(wgpu_ctx *ctx, const double *src, double *dst, const double *stencil, int half, unsigned comp_mask, int level_mode)
+{
+    if (ctx->n_active == 0) return WGPU_OK;
+    const wgpu_config &c = ctx->cfg;
+    if (c.dim != 3) {
+        ctx->err = "filter: three-dimensional blocks only";
+        return WGPU_ERR_UNSUPPORTED;
+    }
+    if (half < 1 || half > WGPU_FMAX || half > c.Bs[0]) {
+        ctx->err = "filter: stencil half width out of range";
+        return WGPU_ERR_UNSUPPORTED;
+    }
+    WaveArgs a;
+    memset(&a, 0, sizeof(a));
+    a.src = src;
+    a.dst = dst;
+    a.active = ctx->d_active;
+    a.nbr = ctx->d_nbr;
+    a.wpool = ctx->d_wpool;
+    a.woff = ctx->d_woff;
+    a.nc = ctx->nc;
+    a.Bs = c.Bs[0];
+    a.f = half;
+    a.inverse = 2;
+    a.w.hd_lo = -half;
+    a.w.hd_hi = half;
+    for (int k = -half; k <= half; ++k) a.w.HD[k + WGPU_FMAX] = stencil[k + half];
+    a.level = ctx->d_level;
+    a.Jmax = c.Jmax;
+    a.level_mode = level_mode;
+    a.comp_mask = comp_mask;
+    if (ctx->has_jumps) {
+        if (!ctx->wavelet_set) {
+            ctx->err = "filter on a grid with level jumps: call wgpu_set_wavelet first (the ghost synchronisation is the wavelet's)";
+            return WGPU_ERR_ARG;
+        }
+        int32_t rcj = wgpu_launch_wjump_fill(ctx, src, nullptr);
+        if (rcj) return rcj;
+        a.nbr = ctx->d_wnbr;
+        a.fw = ctx->wjump_depth;
+        if (a.fw < half) {
+            ctx->err = "filter: the ghost patches of the wavelet are shallower than the filter stencil";
+            return WGPU_ERR_UNSUPPORTED;
+        }
+    }
+    const int n = a.Bs + 2 * half;
+    const size_t smem = sizeof(double) * ((size_t)2 * n * n + (size_t)n * a.Bs + (size_t)(2 * half + 2) * a.Bs * a.Bs);
+    if (smem > 227 * 1024) {
+        ctx->err = "filter: block too large for the shared-memory ring";
+        return WGPU_ERR_UNSUPPORTED;
+    }
+    if (smem > g_wavelet_kernel_smem) {
+        WGPU_CHECK(ctx, cudaFuncSetAttribute(wavelet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        g_wavelet_kernel_smem = smem;
     }
     dim3 grid(ctx->n_active, ctx->nc);
     wavelet_kernel<<<grid, 256, smem, ctx->stream>>>(a);

@@ -303,6 +303,7 @@ int32_t wgpu_launch_create_mask(wgpu_ctx *ctx, const MaskGeom &gm, double time);
 int32_t wgpu_launch_stats(wgpu_ctx *ctx, const double *u, const double *rhs, const double *mask, const StatArgs &sa, double *d_part, double *d_out);
 // wavelet.cu
 int32_t wgpu_launch_wavelet(wgpu_ctx *ctx, const double *src, double *dst, int inverse, const double *ce_coarse);
+int32_t wgpu_launch_blockfilter(wgpu_ctx *ctx, const double *src, double *dst, const double *stencil, int half, unsigned comp_mask, int level_mode);
 int32_t wgpu_launch_detail(wgpu_ctx *ctx, const double *wd, int eps_norm, int level_ref);
 int32_t wgpu_launch_patch_detail(wgpu_ctx *ctx, const double *wd, const int *d_blk, const int *d_dir, int n, int Nl, int Nr, double *d_out, int eps_norm,
                                  int level_ref);

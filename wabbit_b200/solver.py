@@ -305,6 +305,11 @@ class WabbitGPU:
         self._check(self._lib.wgpu_rk_steps(self._ctx, float(time), int(n_steps), C.byref(t), C.byref(dt)))
         return t.value, dt.value
 
+    def filter_wrapper(self, filter_type: str, filter_component=None, only_maxlevel: bool = False, all_except_maxlevel: bool = False):
+        """filter_wrapper (LIB/TIME/filter_wrapper.f90): explicit binomial filter of the resident hvy_block (wgpu_filter)"""
+        fc = None if filter_component is None else _i32(np.ascontiguousarray(filter_component, dtype=np.int32))
+        self._check(self._lib.wgpu_filter(self._ctx, filter_type.encode(), fc, int(bool(only_maxlevel)), int(bool(all_except_maxlevel))))
+
     def RungeKuttaChebychev(self, time: float, iteration: int, mu, mu_tilde, nu, gamma_tilde, c) -> float:
         """RungeKuttaChebychev (runge_kutta_chebychev.f90:6) with the host's coefficient rows of length s (wgpu_rkc_step); returns dt"""
         arr = [np.ascontiguousarray(v, dtype=np.float64) for v in (mu, mu_tilde, nu, gamma_tilde, c)]
