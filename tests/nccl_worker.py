@@ -60,6 +60,9 @@ def main():
         t1, dt1 = s1.RungeKuttaSteps(0.0, 3)
         ref = np.zeros_like(u)
         s1.download(ref, g_sync=0)
+        t1b, dt1b = s1.RungeKuttaSteps(t1, 1)
+        ref_b = np.zeros_like(u)
+        s1.download(ref_b, g_sync=0)
         s1.close()
         s = make(p, fw.max_blocks)
         s.comm_init(rank, world)
@@ -79,7 +82,12 @@ def main():
         out = np.zeros(s.host_shape())
         s.download(out, g_sync=0)
         ok = (t1 == t2) and (dt1 == dt2) and np.array_equal(interior(p, out[:n]), interior(p, ref[off:off + n]))
-        print(f"rank {rank}: uniform t={t2!r} dt={dt2!r} int/bnd={st.n_int}/{st.n_bnd} transport={s.comm_transport()} ok={ok}", flush=True)
+        # the exchange declared a second time on the same communicator (pools re-exported, peers re-mapped), then one more step
+        st = attach_exchange(s, fw, rank, world)
+        t3, dt3 = st.steps(t2, 1)
+        s.download(out, g_sync=0)
+        ok = ok and (t3 == t1b) and (dt3 == dt1b) and np.array_equal(interior(p, out[:n]), interior(p, ref_b[off:off + n]))
+        print(f"rank {rank}: uniform t={t3!r} dt={dt3!r} int/bnd={st.n_int}/{st.n_bnd} transport={s.comm_transport()} ok={ok}", flush=True)
         s.close()
     elif what == "graded":
         wavelet = "CDF44"

@@ -2035,7 +2035,12 @@ int32_t wgpu_filter(wgpu_ctx *ctx, const char *filter_type, const int32_t *filte
     unsigned mask = 0;
     for (int c = 0; c < ctx->nc; ++c)
         if (!filter_component || filter_component[c]) mask |= 1u << c;
-    if (!ctx->TMP) return fail(ctx, WGPU_ERR_ARG, "wgpu_filter: no second buffer (hvy_tmp)");
+    if (!ctx->TMP) {                      // hvy_tmp: normally allocated by wgpu_set_wavelet
+        const size_t n = (size_t)ctx->cfg.max_blocks * ctx->nc * ctx->blk_elems;
+        int32_t rca = dmalloc(ctx, &ctx->TMP, n);
+        if (rca) return rca;
+        WGPU_CHECK(ctx, cudaMemsetAsync(ctx->TMP, 0, n * sizeof(double), ctx->stream));
+    }
     int32_t rc = wgpu_launch_blockfilter(ctx, ctx->U, ctx->TMP, st, a, mask, only_maxlevel ? 1 : (all_except_maxlevel ? 2 : 0));
     if (rc) return rc;
     std::swap(ctx->U, ctx->TMP);          // the filtered array becomes hvy_block

@@ -175,6 +175,17 @@ int32_t p2p_setup(wgpu_ctx *ctx)
 {
     NcclApi *api = nccl_api();
     const int W = ctx->comm_world, me = ctx->comm_rank;
+    int32_t rc;
+    if (ctx->p2p_on) {
+        // a second exchange on the same communicator: every rank first unmaps its peers' pools, and only when ALL have done so (a collective)
+        // are the pools freed -- memory must not be freed while another process still has it mapped
+        for (void *&b : ctx->p2p_peer) {
+            if (b) cudaIpcCloseMemHandle(b);
+            b = nullptr;
+        }
+        double closed = 1.0;
+        if ((rc = wgpu_comm_allreduce(ctx, &closed, 1, 1))) return rc;
+    }
     p2p_teardown(ctx);
     ctx->p2p_seq = 0;
     const long long pd = wgpu_patch_doubles(ctx);
@@ -198,7 +209,6 @@ int32_t p2p_setup(wgpu_ctx *ctx)
         memcpy(mine + 64, head, 8);
         memcpy(mine + 72, ctx->recv_counts.data(), 4 * (size_t)W);
     }
-    int32_t rc;
     if ((rc = ensure_buf(ctx, &ctx->d_xbuf, &ctx->xbuf_cap, rec * W / 8 + 2))) return rc;
     char *d = (char *)ctx->d_xbuf;
     WGPU_CHECK(ctx, cudaMemcpyAsync(d + rec * me, all.data() + rec * me, rec, cudaMemcpyHostToDevice, ctx->stream));
