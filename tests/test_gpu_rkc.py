@@ -64,3 +64,41 @@ def test_rkc_rejects_fewer_than_four_stages():
         sol.RungeKuttaChebychev(0.0, 0, *[np.ones(3)] * 5)
     assert e.value.code == 1715929
     sol.close()
+
+
+def test_time_step_tree_dispatches_on_the_parameter_file_keys():
+    """timeStep_tree with time_step_method = RungeKuttaChebychev (custom-scheme rows) and a filter every 2nd iteration == the direct calls"""
+    from wabbit_b200 import WabbitAbort
+    forest = Forest.uniform(3, 1, Jmax=2)
+    outs = []
+    for mode in ("params", "direct"):
+        p = tg_params(Bs=16, J=2)
+        if mode == "params":
+            p.time_step_method, p.rkc_s, p.RKC_custom_scheme = "RungeKuttaChebychev", 4, True
+            p.RKC_mu, p.RKC_mu_tilde, p.RKC_nu, p.RKC_gamma_tilde, p.RKC_c = (tuple(v) for v in coeffs(4))
+            p.filter_type, p.filter_freq, p.filter_component = "explicit_5pt", 2, (1, 1, 1, 0)
+        sol = WabbitGPU(p, max_blocks=forest.n_blocks)
+        sol.setup_wavelet("CDF40")
+        sol.set_forest(forest)
+        u = np.zeros(sol.host_shape())
+        u[:] = np.random.default_rng(3).standard_normal(u.shape) * 0.1
+        sol.upload(u)
+        t, it = 0.0, 0
+        for _ in range(2):
+            if mode == "params":
+                t, it, dt = sol.timeStep_tree(t, it)
+            else:
+                dt = sol.RungeKuttaChebychev(t, it, *coeffs(4))
+                t, it = t + dt, it + 1
+                if it % 2 == 0:
+                    sol.filter_wrapper("explicit_5pt", [1, 1, 1, 0])
+        out = np.zeros_like(u)
+        sol.download(out, g_sync=0)
+        outs.append((t, it, out))
+        if mode == "direct":
+            sol.params.time_step_method = "Krylov"
+            with pytest.raises(WabbitAbort):
+                sol.timeStep_tree(t, it)
+        sol.close()
+    assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1] == 2
+    assert np.array_equal(outs[0][2], outs[1][2])

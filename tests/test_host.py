@@ -612,3 +612,23 @@ def test_halo_plan_from_positions_equals_the_plan_from_the_neighbour_tables(dim,
         assert np.array_equal(a.fine_lgt, b.fine_lgt) and np.array_equal(a.fine_recv_hvy, b.fine_recv_hvy)
         assert a.fine_recv_counts == b.fine_recv_counts and a.fine_send_counts == b.fine_send_counts
         assert np.array_equal(a.fine_send_hvy, b.fine_send_hvy)
+
+
+def test_ini_keys_of_the_chebychev_integrator_and_the_filter(tmp_path):
+    """[Time] time_step_method / s / RKC_custom_scheme + rows, [Discretization] filter_* (ini_file_to_params.f90:176-184, 592, 627-636)"""
+    rows = {"RKC_mu": "0.0 0.5 1.6267817221296652 1.3145584466517715", "RKC_mu_tilde": "0.288421052631579 0.1442105263157895 0.4691980966984508 0.3791463309290373",
+            "RKC_nu": "0.0 -1.0 -0.0770074187990374 -0.2024615056742501", "RKC_gamma_tilde": "0.0 -0.0 -0.2790201699301438 -0.1583434112210081",
+            "RKC_c": "0.288421052631579 0.288421052631579 0.6371654626762986 1.0"}
+    ini = tmp_path / "p.ini"
+    ini.write_text("[Domain]\ndim=3;\n[Blocks]\nnumber_block_nodes=16;\nnumber_equations=4;\n[Time]\ntime_step_method=RungeKuttaChebychev;\ns=4;\n"
+                   "RKC_custom_scheme=1;\n" + "".join(f"{k}={v};\n" for k, v in rows.items()) +
+                   "[Discretization]\norder_discretization=FD_4th_central;\nfilter_type=explicit_5pt;\nfilter_freq=10;\nfilter_component=1 1 1 0;\n")
+    p = Params.from_ini(str(ini))
+    assert p.time_step_method == "RungeKuttaChebychev" and p.rkc_s == 4 and p.RKC_custom_scheme
+    mu, mut, nu, gt, c = p.rkc_coefficients()
+    assert len(mu) == 4 and mu[1] == 0.5 and c[-1] == 1.0 and mut[0] == c[0]
+    assert p.filter_type == "explicit_5pt" and p.filter_freq == 10 and p.filter_component == (1, 1, 1, 0) and not p.filter_only_maxlevel
+    q = Params()
+    assert q.time_step_method == "RungeKuttaGeneric" and q.filter_type == "no_filter"
+    with pytest.raises(ValueError):
+        q.rkc_coefficients()

@@ -149,6 +149,19 @@ class Params:
     write_time_first: float = 0.0
     tsave_stats: float = 9999999.9
     butcher: List[List[float]] = field(default_factory=lambda: [r[:] for r in BUTCHER_RK4])
+    time_step_method: str = "RungeKuttaGeneric"          # or "RungeKuttaChebychev" (timeStep_tree.f90:26-58)
+    rkc_s: int = 4                                        # [Time] s: stages of the Chebychev scheme
+    RKC_custom_scheme: bool = False                       # [Time] RKC_custom_scheme: the coefficient rows come from the parameter file
+    RKC_mu: Tuple[float, ...] = ()
+    RKC_mu_tilde: Tuple[float, ...] = ()
+    RKC_nu: Tuple[float, ...] = ()
+    RKC_gamma_tilde: Tuple[float, ...] = ()
+    RKC_c: Tuple[float, ...] = ()
+    filter_type: str = "no_filter"                        # [Discretization] filter_type (filter_wrapper.f90)
+    filter_freq: int = -1
+    filter_only_maxlevel: bool = False
+    filter_all_except_maxlevel: bool = False
+    filter_component: Tuple[int, ...] = ()                # () = every component
     c0: float = 10.0
     nu: float = 1e-1
     gamma_p: float = 1.0
@@ -183,6 +196,18 @@ class Params:
     @property
     def n_stages(self) -> int:
         return len(self.butcher) - 1
+
+    def rkc_coefficients(self):
+        """rows s of mu, mu_tilde, nu, gamma_tilde, c for RungeKuttaChebychev.  The tabulated schemes live in the reference's Fortran
+        (setup_RKC_coefficients, 4 400 lines of generated tables, passed to wgpu_rkc_step by the Fortran host); this mirror takes them from the
+        parameter file (RKC_custom_scheme = 1, the reference's own mechanism, ini_file_to_params.f90:629-636)."""
+        if not self.RKC_custom_scheme:
+            raise ValueError("RungeKuttaChebychev: give the coefficient rows with RKC_custom_scheme = 1 (RKC_mu, RKC_mu_tilde, RKC_nu, "
+                             "RKC_gamma_tilde, RKC_c in [Time])")
+        rows = tuple(np.asarray(getattr(self, k), dtype=np.float64) for k in ("RKC_mu", "RKC_mu_tilde", "RKC_nu", "RKC_gamma_tilde", "RKC_c"))
+        if any(len(r) != self.rkc_s for r in rows):
+            raise ValueError(f"RungeKuttaChebychev: every coefficient row needs s = {self.rkc_s} values")
+        return rows
 
     @classmethod
     def from_ini(cls, path: str) -> "Params":
@@ -231,6 +256,21 @@ class Params:
         p.write_time_first = ini.real("Time", "write_time_first", 0.0)
         p.tsave_stats = ini.real("Statistics", "tsave_stats", 9999999.9)
         p.butcher = ini.matrix("Time", "butcher_tableau", [r[:] for r in BUTCHER_RK4])
+        p.time_step_method = ini.string("Time", "time_step_method", "RungeKuttaGeneric")       # ini_file_to_params.f90:592
+        p.rkc_s = ini.integer("Time", "s", 4)                                                  # :627
+        p.RKC_custom_scheme = ini.boolean("Time", "RKC_custom_scheme", False)                  # :629-636
+        if p.RKC_custom_scheme:
+            for key in ("RKC_mu", "RKC_mu_tilde", "RKC_nu", "RKC_gamma_tilde", "RKC_c"):
+                v = tuple(ini.vector("Time", key, []))
+                if len(v) < p.rkc_s:
+                    raise ValueError(f"[Time] {key} needs s = {p.rkc_s} values")
+                setattr(p, key, v[:p.rkc_s])
+        p.filter_type = ini.string("Discretization", "filter_type", "no_filter")              # :176-184
+        p.filter_only_maxlevel = ini.boolean("Discretization", "filter_only_maxlevel", False)
+        p.filter_all_except_maxlevel = ini.boolean("Discretization", "filter_all_except_maxlevel", False)
+        if p.filter_type != "no_filter":
+            p.filter_freq = ini.integer("Discretization", "filter_freq", -1)
+            p.filter_component = tuple(int(x) for x in ini.vector("Discretization", "filter_component", [], int))
         p.c0 = ini.real("ACM-new", "c_0", 10.0)
         p.nu = ini.real("ACM-new", "nu", 1e-1)
         p.gamma_p = ini.real("ACM-new", "gamma_p", 1.0)

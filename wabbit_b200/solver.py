@@ -494,6 +494,17 @@ class WabbitGPU:
         return new, n0, new.n_blocks
 
     def timeStep_tree(self, time: float, iteration: int):
-        """timeStep_tree.f90:1 -- returns (time+dt, iteration+1, dt)."""
-        dt = self.RungeKuttaGeneric(time, iteration)
-        return time + dt, iteration + 1, dt
+        """timeStep_tree.f90:1-60 -- dispatch on time_step_method, then filter_wrapper every filter_freq iterations (main.f90:370-373); returns
+        (time+dt, iteration+1, dt)."""
+        p = self.params
+        method = p.time_step_method.strip().lower()
+        if method == "rungekuttageneric":
+            dt = self.RungeKuttaGeneric(time, iteration)
+        elif method == "rungekuttachebychev":
+            dt = self.RungeKuttaChebychev(time, iteration, *p.rkc_coefficients())
+        else:
+            raise WabbitAbort(19101816, "time_step_method is unkown: " + p.time_step_method)
+        iteration += 1
+        if p.filter_type != "no_filter" and p.filter_freq > 0 and iteration % p.filter_freq == 0:
+            self.filter_wrapper(p.filter_type, p.filter_component or None, p.filter_only_maxlevel, p.filter_all_except_maxlevel)
+        return time + dt, iteration, dt
