@@ -48,8 +48,8 @@ def pytest_collection_modifyitems(config, items):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# The long oracle runs against the reference's adaptive fixtures (2281-step 3vortices runs, the four cylinder runs: 1 - 4 minutes of CPU
-# each) start in worker processes as soon as the collection is known and run while the other CPU tests execute; the tests that own them
+# The long oracle runs against the reference's fixtures (2281-step 3vortices runs, the four cylinder runs, the Taylor-Green runs: 0.5 - 5
+# minutes of CPU each) start in worker processes as soon as the collection is known and run while the other CPU tests execute; the tests that own them
 # (test_oracle_adaptive.py, test_oracle_cylinder.py) collect the results.  Selecting one of them alone works the same way.
 _BG = {"pool": None, "futures": {}}
 
@@ -64,12 +64,13 @@ def pytest_collection_finish(session):
     names = {it.name.split("[")[0] for it in session.items}
     want_adaptive = "test_adaptive_run_fixture" in names
     want_cylinder = "test_cylinder_fixtures" in names
+    want_tg = "test_taylor_green_fixture" in names and (want_adaptive or want_cylinder)      # alone they run inline, one after the other
     if not (want_adaptive or want_cylinder) or _BG["pool"] is not None:
         return
     import concurrent.futures as cf
     import multiprocessing as mp
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    _BG["pool"] = cf.ProcessPoolExecutor(max_workers=6, mp_context=mp.get_context("spawn"))
+    _BG["pool"] = cf.ProcessPoolExecutor(max_workers=7, mp_context=mp.get_context("spawn"))
     if want_adaptive:
         import test_oracle_adaptive as TA
         for w in ("CDF40", "CDF42"):
@@ -79,6 +80,10 @@ def pytest_collection_finish(session):
         import test_oracle_cylinder as TC
         for c in CC.CASES:
             _BG["futures"][("cylinder", c)] = _BG["pool"].submit(TC._run_case, c)
+    if want_tg:                      # queued behind the long jobs: done well before the adaptive runs are
+        import test_oracle_golden as TG
+        for c in sorted(TG.CASES, key=lambda c: -TG.CASES[c]["g"]):
+            _BG["futures"][("taylor_green", c)] = _BG["pool"].submit(TG._tg_run, c)
 
 
 def pytest_sessionfinish(session, exitstatus):

@@ -37,24 +37,34 @@ def sample(u, p, grid, gold_ixyz, stride):
     return np.stack(out)
 
 
-@pytest.mark.parametrize("case", list(CASES))
-def test_taylor_green_fixture(case):
+def _tg_run(case):
+    """the run of one Taylor-Green case (a worker process started by conftest.py at collection time, or inline): the sampled initial
+    condition, the number of steps, the final time and the sampled final fields"""
     gold = np.load(os.path.join(GOLD, f"taylor_green_{case}.npz"))
     p = tg_params(case)
     grid = O.uniform_grid(1)
     u = O.alloc(grid, p)
     O.inicond_taylor_green(grid, p, u)
     stride = int(gold["stride"][0])
-    # initial condition (inicond_ACM.f90:371-389)
-    assert np.abs(sample(u, p, grid, gold["t0_ixyz"], stride) - gold["t0"]).max() <= 1e-15
+    s0 = sample(u, p, grid, gold["t0_ixyz"], stride)
     work = [O.alloc(grid, p) for _ in range(5)]
     t, it = 0.0, 0
     while t < p.time_max:
         t += O.rk_generic(grid, p, u, work, t)
         it += 1
+    return s0, it, t, sample(u, p, grid, gold["t1_ixyz"], stride)
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_taylor_green_fixture(case):
+    from conftest import background
+    gold = np.load(os.path.join(GOLD, f"taylor_green_{case}.npz"))
+    s0, it, t, s1 = background("taylor_green", case, _tg_run)
+    # initial condition (inicond_ACM.f90:371-389)
+    assert np.abs(s0 - gold["t0"]).max() <= 1e-15
     assert it == int(gold["t1_iteration"][0])
     assert abs(t - float(gold["t1_time"][0])) < 1e-12
-    err = np.abs(sample(u, p, grid, gold["t1_ixyz"], stride) - gold["t1"]).max()
+    err = np.abs(s1 - gold["t1"]).max()
     # the restatement reproduces the Fortran output to round-off; 1e-12 is the north-star field tolerance
     assert err <= 1e-12, err
 
