@@ -53,8 +53,8 @@ def children(k: Key, dim: int):
 
 
 def nbr_key(k: Key, d, dim: int) -> Key:
-    n = 2 ** k[0]
-    return (k[0],) + tuple(((k[1 + a] + d[a]) % n) if a < dim else 0 for a in range(3))
+    m = (1 << k[0]) - 1                                   # periodic: modulo 2^level
+    return (k[0], (k[1] + d[0]) & m, (k[2] + d[1]) & m, ((k[3] + d[2]) & m) if dim == 3 else 0)
 
 
 class Tree:

@@ -54,7 +54,8 @@ class AcmParams(C.Structure):
 FD_IDS = {"FD_2nd_central": 2, "FD_4th_central": 4, "FD_6th_central": 6, "FD_4th_central_optimized": 40}
 
 _libs: Dict[bool, C.CDLL] = {}
-_dp = C.POINTER(C.c_double)
+_dp = C.c_void_p                      # double* arguments: takes the typed pointers of _p and the plain addresses of _pb
+_dpp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
 
 
@@ -85,11 +86,24 @@ def _p(a: Optional[np.ndarray]):
     if a is None:
         return None
     assert a.dtype == np.float64 and a.flags.c_contiguous
-    return a.ctypes.data_as(_dp)
+    return a.ctypes.data_as(_dpp)
+
+
+def _pb(a: np.ndarray):
+    """addresses of a[0], a[1], ... (the per-block loops call C once per block: one .ctypes object per array instead of one per block).
+    Plain integers: the caller keeps `a` alive."""
+    assert a.dtype == np.float64 and a.flags.c_contiguous
+    base, st = a.ctypes.data, a.strides[0]
+    return [base + b * st for b in range(a.shape[0])]
+
+
+@functools.lru_cache(maxsize=None)
+def _bs_cached(Bs):
+    return (C.c_int32 * 3)(*Bs)
 
 
 def _bs(Bs: Sequence[int]):
-    return (C.c_int32 * 3)(*[int(b) for b in Bs])
+    return _bs_cached(tuple(int(b) for b in Bs))          # read-only in every C routine
 
 
 def _d3(v: Sequence[float]):
@@ -268,12 +282,14 @@ def rhs_tree(grid: Grid, p: Params, hvy: np.ndarray, rhs: np.ndarray, mask: Opti
              fast: bool = False) -> None:
     """RHS_wrapper local_stage loop (RHS_wrapper.f90:124-142) -> RHS_ACM -> RHS_{2,3}D_acm."""
     L = lib(fast)
-    a = p.acm()
+    a = C.byref(p.acm())
     f = L.orc_rhs_acm_3d if p.dim == 3 else L.orc_rhs_acm_2d
+    Bs, ph, pr = _bs(p.Bs), _pb(hvy), _pb(rhs)
+    pm = None if mask is None else _pb(mask)
     for b in range(grid.n):
         _, dx = grid.spacing_origin(p, b)
-        m = None if mask is None else mask[b if mask.shape[0] > 1 else 0]
-        f(C.byref(a), p.g, _bs(p.Bs), _d3(dx), _p(hvy[b]), _p(rhs[b]), _p(m))
+        m = None if pm is None else pm[b if len(pm) > 1 else 0]
+        f(a, p.g, Bs, _d3(dx), ph[b], pr[b], m)
 
 
 LIM_DIVERGED = 1.0e12
@@ -295,10 +311,10 @@ def calculate_time_step(grid: Grid, p: Params, hvy: np.ndarray, time: float) -> 
         dt = p.dt_fixed
     else:
         L = lib()
-        a = p.acm()
+        a, Bs, ph = C.byref(p.acm()), _bs(p.Bs), _pb(hvy)
         for b in range(grid.n):
             _, dx = grid.spacing_origin(p, b)
-            dt = min(dt, L.orc_get_dt_block(C.byref(a), p.g, _bs(p.Bs), _d3(dx), _p(hvy[b])))
+            dt = min(dt, L.orc_get_dt_block(a, p.g, Bs, _d3(dx), ph[b]))
         if p.dt_max > 0.0:
             dt = min(p.dt_max, dt)
     return _clip_dt(p, dt, time, apply_dt_max=False)
@@ -337,31 +353,32 @@ def rk_generic(grid: Grid, p: Params, hvy: np.ndarray, work: np.ndarray, time: f
         sync = lambda h: sync_ghosts_same_level(grid, p, h, p.g_rhs, p.g_rhs)
     sync(hvy)
     dt = calculate_time_step(grid, p, hvy, time)
+    ph, pw = _pb(hvy), [_pb(w_) for w_ in work]
     for b in range(grid.n):
-        L.orc_rk_copy_interior(p.dim, p.g, Bs, nc, _p(work[0][b]), _p(hvy[b]))
+        L.orc_rk_copy_interior(p.dim, p.g, Bs, nc, pw[0][b], ph[b])
     if mask_at is not None:          # time-dependent mask: RHS_wrapper calls createMask_tree at the stage time (RHS_wrapper.f90:51)
         mask = mask_at(time)
     rhs_tree(grid, p, hvy, work[1], mask, fast)
     for j in range(2, n):          # Fortran j = 2 .. size(rk,1)-1
         for b in range(grid.n):
-            L.orc_rk_copy_interior(p.dim, p.g, Bs, nc, _p(hvy[b]), _p(work[0][b]))
+            L.orc_rk_copy_interior(p.dim, p.g, Bs, nc, ph[b], pw[0][b])
         for l in range(2, j + 1):
             coef = rk[j - 1, l - 1]
             if abs(coef) < 1.0e-8:
                 continue
             for b in range(grid.n):
-                L.orc_rk_axpy_interior(p.dim, p.g, Bs, nc, _p(hvy[b]), dt, coef, _p(work[l - 1][b]))
+                L.orc_rk_axpy_interior(p.dim, p.g, Bs, nc, ph[b], dt, coef, pw[l - 1][b])
         sync(hvy)
         if mask_at is not None:
             mask = mask_at(time + dt * rk[j - 1, 0])                     # t = time + dt*rk_coeffs(j,1), runge_kutta_generic.f90:122
         rhs_tree(grid, p, hvy, work[j], mask, fast)
     for b in range(grid.n):
-        L.orc_rk_copy_interior(p.dim, p.g, Bs, nc, _p(hvy[b]), _p(work[0][b]))
+        L.orc_rk_copy_interior(p.dim, p.g, Bs, nc, ph[b], pw[0][b])
         for j in range(2, rk.shape[1] + 1):
             coef = rk[n - 1, j - 1]
             if abs(coef) < 1.0e-8:
                 continue
-            L.orc_rk_axpy_interior(p.dim, p.g, Bs, nc, _p(hvy[b]), dt, coef, _p(work[j - 1][b]))
+            L.orc_rk_axpy_interior(p.dim, p.g, Bs, nc, ph[b], dt, coef, pw[j - 1][b])
     return dt
 
 
@@ -547,6 +564,33 @@ def _same_level_code(d) -> int:
     return 49 + sum(1 << i for i in range(3) if d[i] == 1)
 
 
+@functools.lru_cache(maxsize=None)
+def _relations(dim: int):
+    """per direction: (d, slot of the same-level relation, number of finer neighbours, their treecode digits) -- find_neighbor's
+    direction bookkeeping, which does not depend on the block"""
+    vary = (2, 1, 4)
+    out = []
+    for dz in ((-1, 0, 1) if dim == 3 else (0,)):
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                d = (dx, dy, dz)
+                if d == (0, 0, 0):
+                    continue
+                nfree = 2 ** sum(1 for a in range(dim) if d[a] == 0)
+                append = [0, 0, 0, 0]
+                apply_free = 1
+                for a in range(dim):
+                    if d[a] == 0:
+                        for k in range(4):
+                            append[k] += vary[a] * ((k // apply_free) % 2)
+                        apply_free += 1
+                    elif d[a] == 1:
+                        for k in range(4):
+                            append[k] += vary[a]
+                out.append((d, same_level_code(d), nfree, tuple(append)))
+    return tuple(out)
+
+
 def neighbor_table168(grid: Grid, Jmax: int, periodic=(1, 1, 1)) -> np.ndarray:
     """hvy_neighbor[168, nb] (1-based block ids, -1 none) of a leaf grid on one rank -- an independent NumPy restatement
     of find_neighbor (LIB/MESH/find_neighbors.f90:18-180): same level, else finer (+112), else coarser (+56)."""
@@ -554,53 +598,37 @@ def neighbor_table168(grid: Grid, Jmax: int, periodic=(1, 1, 1)) -> np.ndarray:
     look = grid.lookup()
     out = np.full((168, grid.n), -1, dtype=np.int32)
     vary = (2, 1, 4)
+    rel = _relations(dim)
+    levels, ixyz = grid.level.tolist(), grid.ixyz.tolist()
     for b in range(grid.n):
-        J = int(grid.level[b])
-        ix = [int(v) for v in grid.ixyz[b]]
+        J, ix = levels[b], ixyz[b]
         tc_last = sum(vary[a] * (ix[a] & 1) for a in range(dim)) if J > 0 else 0
-        for dz in ((-1, 0, 1) if dim == 3 else (0,)):
-            for dy in (-1, 0, 1):
-                for dx in (-1, 0, 1):
-                    d = (dx, dy, dz)
-                    if d == (0, 0, 0):
-                        continue
-                    nfree = 2 ** sum(1 for a in range(dim) if d[a] == 0)
-                    append = [0, 0, 0, 0]
-                    apply_free = 1
-                    for a in range(dim):
-                        if d[a] == 0:
-                            for k in range(4):
-                                append[k] += vary[a] * ((k // apply_free) % 2)
-                            apply_free += 1
-                        elif d[a] == 1:
-                            for k in range(4):
-                                append[k] += vary[a]
-                    code = same_level_code(d)
-                    n = 2 ** J
-                    p = [ix[a] + d[a] for a in range(3)]
-                    if any((p[a] < 0 or p[a] >= n) and not periodic[a] for a in range(dim)):
-                        continue
-                    p = [p[a] % n if a < dim else 0 for a in range(3)]
-                    j = look.get((J, p[0], p[1], p[2]))
+        n = 2 ** J
+        for d, code, nfree, append in rel:
+            p = [ix[a] + d[a] for a in range(3)]
+            if any((p[a] < 0 or p[a] >= n) and not periodic[a] for a in range(dim)):
+                continue
+            p = [p[a] % n if a < dim else 0 for a in range(3)]
+            j = look.get((J, p[0], p[1], p[2]))
+            if j is not None:
+                out[code - 1, b] = j + 1
+                continue
+            found = False
+            if J < Jmax:
+                for k in range(nfree):
+                    q = [((2 * ix[a] + (1 if append[k] & vary[a] else 0) + d[a]) % (2 * n)) if a < dim else 0 for a in range(3)]
+                    j = look.get((J + 1, q[0], q[1], q[2]))
+                    if j is None:
+                        break
+                    out[code - 1 + k + 112, b] = j + 1
+                    found = True
+            if found:
+                continue
+            for k in range(nfree):
+                if tc_last == append[k] and J > 0:
+                    j = look.get((J - 1, p[0] >> 1, p[1] >> 1, p[2] >> 1))
                     if j is not None:
-                        out[code - 1, b] = j + 1
-                        continue
-                    found = False
-                    if J < Jmax:
-                        for k in range(nfree):
-                            q = [((2 * ix[a] + (1 if append[k] & vary[a] else 0) + d[a]) % (2 * n)) if a < dim else 0 for a in range(3)]
-                            j = look.get((J + 1, q[0], q[1], q[2]))
-                            if j is None:
-                                break
-                            out[code - 1 + k + 112, b] = j + 1
-                            found = True
-                    if found:
-                        continue
-                    for k in range(nfree):
-                        if tc_last == append[k] and J > 0:
-                            j = look.get((J - 1, p[0] >> 1, p[1] >> 1, p[2] >> 1))
-                            if j is not None:
-                                out[code - 1 + k + 56, b] = j + 1
+                        out[code - 1 + k + 56, b] = j + 1
     return out
 
 

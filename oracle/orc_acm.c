@@ -69,7 +69,7 @@ static const double b_FD6[7] = {1.0 / 90.0, -3.0 / 20.0, 3.0 / 2.0, -49.0 / 18.0
 #define D1P_7(A, c, d) ((A[0] * P(c, -3) * P(d, -3) + A[1] * P(c, -2) * P(d, -2) + A[2] * P(c, -1) * P(d, -1) + A[4] * P(c, 1) * P(d, 1) + A[5] * P(c, 2) * P(d, 2) + A[6] * P(c, 3) * P(d, 3)) * dinv)
 #define D2_7(B, c) ((B[0] * P(c, -3) + B[1] * P(c, -2) + B[2] * P(c, -1) + B[3] * P(c, 0) + B[4] * P(c, 1) + B[5] * P(c, 2) + B[6] * P(c, 3)) * d2inv)
 
-static inline double d1(int fd, const double *const *ph, ptrdiff_t idx, ptrdiff_t s, double dinv, int c)
+static inline __attribute__((always_inline)) double d1(const int fd, const double *const *ph, ptrdiff_t idx, ptrdiff_t s, double dinv, int c)
 {
     switch (fd) {
     case 2: return D1_2(c);
@@ -78,7 +78,7 @@ static inline double d1(int fd, const double *const *ph, ptrdiff_t idx, ptrdiff_
     default: return D1_7(a_TW4, c);
     }
 }
-static inline double d1p(int fd, const double *const *ph, ptrdiff_t idx, ptrdiff_t s, double dinv, int c, int d)
+static inline __attribute__((always_inline)) double d1p(const int fd, const double *const *ph, ptrdiff_t idx, ptrdiff_t s, double dinv, int c, int d)
 {
     switch (fd) {
     case 2: return D1P_2(c, d);
@@ -87,7 +87,7 @@ static inline double d1p(int fd, const double *const *ph, ptrdiff_t idx, ptrdiff
     default: return D1P_7(a_TW4, c, d);
     }
 }
-static inline double d2(int fd, const double *const *ph, ptrdiff_t idx, ptrdiff_t s, double d2inv, int c)
+static inline __attribute__((always_inline)) double d2(const int fd, const double *const *ph, ptrdiff_t idx, ptrdiff_t s, double d2inv, int c)
 {
     switch (fd) {
     case 2: return D2_2(c);
@@ -104,8 +104,10 @@ int orc_fd_halfwidth(int fd) { return fd == 2 ? 1 : (fd == 4 ? 2 : 3); }
  * mask may be NULL: equivalent to chi == 0 and sponge mask == 0 everywhere
  * (the reference multiplies by mask(:,:,:,1)=0, which only adds a signed zero).
  */
-void orc_rhs_acm_3d(const orc_acm_params *p, int g, const int32_t Bs[3], const double dx[3],
-                    const double *phi, double *rhs, const double *mask)
+/* The body is compiled once per stencil family and skew flag (fd, skew are literal constants at every call site below, so the selection
+ * inside d1 / d1p / d2 folds away); the arithmetic is the same statement sequence for every instance. */
+static inline __attribute__((always_inline)) void rhs_acm_3d_body(const int fd, const int skew, const orc_acm_params *p, int g, const int32_t Bs[3],
+                                                                  const double dx[3], const double *phi, double *rhs, const double *mask)
 {
     const int nx = Bs[0] + 2 * g, ny = Bs[1] + 2 * g, nz = Bs[2] + 2 * g;
     const ptrdiff_t sx = 1, sy = nx, sz = (ptrdiff_t)nx * ny, sc = (ptrdiff_t)nx * ny * nz;
@@ -116,7 +118,6 @@ void orc_rhs_acm_3d(const orc_acm_params *p, int g, const int32_t Bs[3], const d
     double C_eta_apply_inv[ORC_NCOLORS + 1];
     for (int c = 0; c <= ORC_NCOLORS; ++c) C_eta_apply_inv[c] = 1.0 / p->C_eta;
     C_eta_apply_inv[0] = 0.0;
-    const int fd = p->fd;
 
     for (int iz = g; iz < Bs[2] + g; ++iz)
         for (int iy = g; iy < Bs[1] + g; ++iy)
@@ -144,7 +145,7 @@ void orc_rhs_acm_3d(const orc_acm_params *p, int g, const int32_t Bs[3], const d
                     penalz = -chi * (w - mask[idx + 3 * sc]);
                 }
 
-                if (p->skew) {
+                if (skew) {
                     const double uu_dx = d1p(fd, ph, idx, sx, dx_inv, 0, 0), uv_dy = d1p(fd, ph, idx, sy, dy_inv, 0, 1), uw_dz = d1p(fd, ph, idx, sz, dz_inv, 0, 2);
                     const double vu_dx = d1p(fd, ph, idx, sx, dx_inv, 1, 0), vv_dy = d1p(fd, ph, idx, sy, dy_inv, 1, 1), vw_dz = d1p(fd, ph, idx, sz, dz_inv, 1, 2);
                     const double wu_dx = d1p(fd, ph, idx, sx, dx_inv, 2, 0), wv_dy = d1p(fd, ph, idx, sy, dy_inv, 2, 1), ww_dz = d1p(fd, ph, idx, sz, dz_inv, 2, 2);
@@ -177,12 +178,26 @@ void orc_rhs_acm_3d(const orc_acm_params *p, int g, const int32_t Bs[3], const d
     }
 }
 
+#define ORC_FD_DISPATCH(body)                                                                     \
+    switch (p->fd) {                                                                             \
+    case 2: if (p->skew) body(2, 1, p, g, Bs, dx, phi, rhs, mask); else body(2, 0, p, g, Bs, dx, phi, rhs, mask); break;   \
+    case 4: if (p->skew) body(4, 1, p, g, Bs, dx, phi, rhs, mask); else body(4, 0, p, g, Bs, dx, phi, rhs, mask); break;   \
+    case 6: if (p->skew) body(6, 1, p, g, Bs, dx, phi, rhs, mask); else body(6, 0, p, g, Bs, dx, phi, rhs, mask); break;   \
+    default: if (p->skew) body(40, 1, p, g, Bs, dx, phi, rhs, mask); else body(40, 0, p, g, Bs, dx, phi, rhs, mask); break; \
+    }
+
+void orc_rhs_acm_3d(const orc_acm_params *p, int g, const int32_t Bs[3], const double dx[3],
+                    const double *phi, double *rhs, const double *mask)
+{
+    ORC_FD_DISPATCH(rhs_acm_3d_body)
+}
+
 /*
  * RHS_2D_acm, p_eqn_model='acm', no lamballais geometry (rhs_ACM.f90:292-922).
  * phi(nx,ny,3) = (ux, uy, p).
  */
-void orc_rhs_acm_2d(const orc_acm_params *p, int g, const int32_t Bs[3], const double dx[3],
-                    const double *phi, double *rhs, const double *mask)
+static inline __attribute__((always_inline)) void rhs_acm_2d_body(const int fd, const int skew, const orc_acm_params *p, int g, const int32_t Bs[3],
+                                                                  const double dx[3], const double *phi, double *rhs, const double *mask)
 {
     const int nx = Bs[0] + 2 * g, ny = Bs[1] + 2 * g;
     const ptrdiff_t sx = 1, sy = nx, sc = (ptrdiff_t)nx * ny;
@@ -193,7 +208,6 @@ void orc_rhs_acm_2d(const orc_acm_params *p, int g, const int32_t Bs[3], const d
     double C_eta_apply_inv[ORC_NCOLORS + 1];
     for (int c = 0; c <= ORC_NCOLORS; ++c) C_eta_apply_inv[c] = 1.0 / p->C_eta;
     C_eta_apply_inv[0] = 0.0;
-    const int fd = p->fd;
 
     for (int iy = g; iy < Bs[1] + g; ++iy)
         for (int ix = g; ix < Bs[0] + g; ++ix) {
@@ -211,7 +225,7 @@ void orc_rhs_acm_2d(const orc_acm_params *p, int g, const int32_t Bs[3], const d
                 penalx = -mask[idx] * C_eta_apply_inv[color] * (ph[0][idx] - mask[idx + 1 * sc]);
                 penaly = -mask[idx] * C_eta_apply_inv[color] * (ph[1][idx] - mask[idx + 2 * sc]);
             }
-            if (p->skew) {
+            if (skew) {
                 const double uu_dx = d1p(fd, ph, idx, sx, dx_inv, 0, 0), uv_dy = d1p(fd, ph, idx, sy, dy_inv, 0, 1);
                 const double vu_dx = d1p(fd, ph, idx, sx, dx_inv, 1, 0), vv_dy = d1p(fd, ph, idx, sy, dy_inv, 1, 1);
                 /* rhs_ACM.f90:574-576 */
@@ -236,6 +250,12 @@ void orc_rhs_acm_2d(const orc_acm_params *p, int g, const int32_t Bs[3], const d
                 rhs[idx + 2 * sc] = rhs[idx + 2 * sc] - ph[2][idx] * spo;
             }
     }
+}
+
+void orc_rhs_acm_2d(const orc_acm_params *p, int g, const int32_t Bs[3], const double dx[3],
+                    const double *phi, double *rhs, const double *mask)
+{
+    ORC_FD_DISPATCH(rhs_acm_2d_body)
 }
 
 /* GET_DT_BLOCK_ACM (module_ACM.f90:617-691), without passive scalars. */
