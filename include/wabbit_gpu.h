@@ -184,11 +184,17 @@ int32_t wgpu_sync_ghosts(wgpu_ctx *ctx, int32_t array_id, int32_t slot, int32_t 
  *   [6] sponge volume, [7..9] penalization power (solid input, solid dissipation, sponge), [10..12] force on colour 1, [13] max |u|^2,
  *   [14] / [15] max / min of div(u) outside the solid (with_divergence = 1: one RHS evaluation into hvy_work slot 2, whose pressure row is
  *   -c0^2 div(u) - gamma_p p; else 0), [16..18] residual velocity in the solid (sum over blocks of max * dV, as the reference).  out: 19 doubles.
+ *   flags: WGPU_STAT_DIVERGENCE (1) as above; WGPU_STAT_VORTICITY (2) adds, on one rank, [19] enstrophy, [20] max |vorticity|, [21] helicity
+ *   (3-D; 0 in 2-D), [22] dissipation = -nu * integral of u . laplace(u) (0 for nu = 0) -- compute_vorticity and compute_dissipation
+ *   (LIB/OPERATORS/compute_vorticity.f90:3-67, compute_dissipation.f90:5-78; statistics_ACM.f90:371-387) with the discretization's first- and
+ *   second-derivative stencils on ghost-synchronised copies of the blocks (level jumps: the wavelet's predictor, wgpu_set_wavelet).
+ *   out: 23 doubles with WGPU_STAT_VORTICITY.
  */
+enum { WGPU_STAT_DIVERGENCE = 1, WGPU_STAT_VORTICITY = 2 };
 enum { WGPU_GEOM_CYLINDER = 1, WGPU_GEOM_SPHERE = 2 };
 int32_t wgpu_create_mask(wgpu_ctx *ctx, double time, int32_t geometry, const double *center0, const double *velocity, double radius,
                          double smoothing_width, double L_sponge, double p_sponge);
-int32_t wgpu_statistics(wgpu_ctx *ctx, double time, int32_t with_divergence, double *out);
+int32_t wgpu_statistics(wgpu_ctx *ctx, double time, int32_t flags, double *out);
 
 /* wgpu_set_ghost_filter: the ignore_Filter switch of sync_ghosts_tree (LIB/MPI/synchronize_ghosts_generic.f90:125-153).  With a lifted
  *   wavelet (CDFXY, Y > 0) the reference's default synchronisation restricts through the HD filter: a ghost node owned by a finer

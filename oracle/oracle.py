@@ -771,6 +771,59 @@ FD1 = {"FD_2nd_central": (1, [-0.5, 0.0, 0.5]), "FD_4th_central": (2, [1.0 / 12.
        "FD_6th_central": (3, [-1.0 / 60.0, 3.0 / 20.0, -3.0 / 4.0, 0.0, 3.0 / 4.0, -3.0 / 20.0, 1.0 / 60.0])}
 
 
+FD2 = {"FD_2nd_central": (1, [1.0, -2.0, 1.0]), "FD_4th_central": (2, [-1.0 / 12.0, 16.0 / 12.0, -30.0 / 12.0, 16.0 / 12.0, -1.0 / 12.0]),
+       "FD_6th_central": (3, [2.0 / 180.0, -27.0 / 180.0, 270.0 / 180.0, -490.0 / 180.0, 270.0 / 180.0, -27.0 / 180.0, 2.0 / 180.0])}
+# FD1_C2/C4/C6, FD2_C2/C4/C6 of LIB/OPERATORS/module_operators.f90:25-33
+
+
+def _fd_sum(comp: np.ndarray, I, ax: int, H: int, coef) -> np.ndarray:
+    """sum(FD(s:e) * u(i+s:i+e)) on the interior along array axis ax: every tap (the zero centre included), in increasing tap order from 0 --
+    the Fortran SUM of the array product (compute_vorticity.f90:40-45, compute_dissipation.f90:41-69)"""
+    acc = np.zeros_like(comp[I])
+    for k, c in enumerate(coef):
+        sl = list(I)
+        s0 = sl[ax]
+        sl[ax] = slice(s0.start + k - H, s0.stop + k - H)
+        acc = acc + c * comp[tuple(sl)]
+    return acc
+
+
+def vorticity_statistics_acm(grid: Grid, p: Params, hvy: np.ndarray) -> dict:
+    """enstrophy, max_vort, helicity and dissipation of STATISTICS_ACM (statistics_ACM.f90:371-387): compute_vorticity (LIB/OPERATORS/
+    compute_vorticity.f90:3-67) and compute_dissipation (compute_dissipation.f90:5-78) on the ghost-synchronised state with the module's
+    first- and second-derivative stencils, block sums times dV, over the whole domain (penalized regions included).
+    hvy: [nb, nc, nz, ny, nx]."""
+    dim = p.dim
+    I = interior(p)
+    H1, a1 = FD1[p.discretization]
+    H2, a2 = FD2[p.discretization]
+    AX = {0: 2, 1: 1, 2: 0}                        # u[c, z, y, x]: x is the last axis
+    out = {"enstrophy": 0.0, "max_vort": 0.0, "helicity": 0.0, "dissipation": 0.0}
+    for b in range(grid.n):
+        dx = [2.0 ** (-float(grid.level[b])) * p.domain[d] / float(p.Bs[d]) for d in range(dim)]
+        dV = float(np.prod(dx))
+        u = hvy[b]
+        d1 = lambda c, d: _fd_sum(u[c], I, AX[d], H1, a1) * (1.0 / dx[d])          # noqa: E731
+        if dim == 2:
+            vor = [d1(1, 0) - d1(0, 1)]                                              # v_dx - u_dy
+            out["max_vort"] = max(out["max_vort"], float(np.abs(vor[0]).max()))
+        else:
+            vor = [d1(2, 1) - d1(1, 2), d1(0, 2) - d1(2, 0), d1(1, 0) - d1(0, 1)]    # (w_dy - v_dz, u_dz - w_dx, v_dx - u_dy)
+            out["max_vort"] = max(out["max_vort"], float(np.sqrt(vor[0] ** 2 + vor[1] ** 2 + vor[2] ** 2).max()))
+            out["helicity"] += 0.5 * float(sum((vor[c] * u[c][I]).sum() for c in range(3))) * dV
+        out["enstrophy"] += 0.5 * float(sum((v * v).sum() for v in vor)) * dV
+        if p.nu > 0.0:
+            eps = np.zeros_like(u[0][I])
+            for c in range(dim):
+                lap = None
+                for d in range(dim):
+                    t = _fd_sum(u[c], I, AX[d], H2, a2) * (1.0 / dx[d] ** 2)
+                    lap = t if lap is None else lap + t
+                eps = eps + u[c][I] * lap
+            out["dissipation"] -= p.nu * float(eps.sum()) * dV
+    return out
+
+
 def statistics_acm(grid: Grid, p: Params, hvy: np.ndarray, mask: Optional[np.ndarray] = None) -> dict:
     """The integral_stage of STATISTICS_ACM (LIB/EQUATION/ACMnew/statistics_ACM.f90:138-368) summed over the blocks (post_stage, :396-430), numpy.
     hvy: ghost-synchronised state [nb, nc, nz, ny, nx]; mask: hvy_mask [nb, 6, nz, ny, nx] or None.  compute_divergence: central differences of

@@ -52,6 +52,39 @@ def test_sphere_mask_and_statistics_3d():
         tol = 1e-9 if k.startswith("div") else 1e-12          # the divergence is recovered from the pressure row of the RHS (c0^2 = 100)
         assert _close(have[k], want[k], tol), (k, have[k], want[k])
     assert want["mask_volume"] > 1.0 and abs(want["force_x"]) > 0.0 and want["div_max"] > 0.0
+    _check_vorticity_entries(sol, grid, po, synced, t)
+    sol.close()
+
+
+def _check_vorticity_entries(sol, grid, po, synced, t=0.0):
+    """enstrophy / max_vort / helicity / dissipation (WGPU_STAT_VORTICITY) against oracle.vorticity_statistics_acm on the synchronised state;
+    the other 19 entries do not change with the flag"""
+    want = O.vorticity_statistics_acm(grid, po, synced)
+    have = sol.statistics_ACM(t, with_divergence=False, with_vorticity=True)
+    base = sol.statistics_ACM(t, with_divergence=False)
+    assert set(have) == set(base) | set(want) and all(have[k] == base[k] for k in base)
+    scale = want["enstrophy"]
+    assert scale > 0.0 and want["max_vort"] > 0.0 and (po.dim == 2 or want["helicity"] != 0.0) and want["dissipation"] != 0.0
+    for k in want:
+        assert abs(have[k] - want[k]) <= 1e-12 * max(abs(want[k]), scale if k == "helicity" else 0.0), (k, have[k], want[k])
+
+
+@pytest.mark.parametrize("disc,g,Bs", [("FD_6th_central", 3, 16), ("FD_2nd_central", 3, 18), ("FD_4th_central", 3, 22)])
+def test_vorticity_statistics_on_equidistant_grids(disc, g, Bs):
+    forest = Forest.uniform(3, 2, Jmax=2)
+    p = tg_params(Bs=Bs, J=2)
+    p.discretization, p.g, p.g_rhs = disc, g, g
+    p = p.finalize()
+    po, grid = orc_params(p), orc_grid(forest)
+    sol = WabbitGPU(p, max_blocks=forest.n_blocks)
+    sol.set_forest(forest)
+    u = O.alloc(grid, po)
+    O.inicond_taylor_green(grid, po, u)
+    u += 0.05 * np.random.default_rng(5).standard_normal(u.shape)
+    sol.upload(u)
+    synced = u.copy()
+    O.sync_ghosts_same_level(grid, po, synced, po.g, po.g)
+    _check_vorticity_entries(sol, grid, po, synced)
     sol.close()
 
 
@@ -87,4 +120,5 @@ def test_cylinder_mask_sponge_and_statistics_2d():
         tol = 1e-8 if k.startswith("div") else 1e-12
         assert _close(have[k], want[k], tol), (k, have[k], want[k])
     assert want["sponge_volume"] > 10.0 and want["penal_power_sponge"] != 0.0 and want["force_x"] > 0.0
+    _check_vorticity_entries(sol, grid, po, synced)
     sol.close()

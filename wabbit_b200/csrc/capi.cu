@@ -1090,11 +1090,14 @@ int32_t wgpu_create_mask(wgpu_ctx *ctx, double time, int32_t geometry, const dou
     return wgpu_launch_create_mask(ctx, gm, time);
 }
 
-int32_t wgpu_statistics(wgpu_ctx *ctx, double time, int32_t with_divergence, double *out)
+int32_t wgpu_statistics(wgpu_ctx *ctx, double time, int32_t flags, double *out)
 {
-    if (!ctx || !out) return WGPU_ERR_ARG;
+    if (!ctx || !out || flags < 0 || flags > 3) return WGPU_ERR_ARG;
     const wgpu_config &c = ctx->cfg;
     if (ctx->nc != c.dim + 1) return fail(ctx, WGPU_ERR_UNSUPPORTED, "ACM needs number_equations = dim+1");
+    const bool with_divergence = flags & WGPU_STAT_DIVERGENCE, with_vorticity = flags & WGPU_STAT_VORTICITY;
+    if (with_vorticity && ctx->comm && ctx->comm_world > 1)
+        return fail(ctx, WGPU_ERR_UNSUPPORTED, "statistics: the vorticity-based entries are computed on one rank only");
     int32_t rc;
     if (!ctx->d_stat && (rc = dmalloc(ctx, &ctx->d_stat, ((size_t)c.max_blocks + 1) * WGPU_NSTAT))) return rc;
     const double *rhs = nullptr;
@@ -1116,8 +1119,44 @@ int32_t wgpu_statistics(wgpu_ctx *ctx, double time, int32_t with_divergence, dou
     sa.use_sponge = c.use_sponge;
     const double *mask = (c.n_mask >= 5 && (c.penalization || c.use_sponge)) ? ctx->MASK : nullptr;
     double *d_out = ctx->d_stat + (size_t)c.max_blocks * WGPU_NSTAT;
-    if ((rc = wgpu_launch_stats(ctx, ctx->U, rhs, mask, sa, ctx->d_stat, d_out))) return rc;
-    WGPU_CHECK(ctx, cudaMemcpyAsync(out, d_out, sizeof(double) * WGPU_NSTAT, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = wgpu_launch_stats(ctx, ctx->U, rhs, mask, sa, ctx->d_stat))) return rc;
+    if (with_vorticity && ctx->n_active) {
+        // compute_vorticity / compute_dissipation read ghost nodes: ghosted copies of the velocity components (the download path's export
+        // kernels: what sync_ghosts_tree leaves, level jumps included), a chunk of blocks at a time through the staging buffer
+        VortArgs va;
+        memset(&va, 0, sizeof(va));
+        for (int d = 0; d < 3; ++d) va.domain[d] = c.domain[d];
+        va.nu = c.nu;
+        va.H = c.fd == 2 ? 1 : (c.fd == 4 ? 2 : 3);
+        if (va.H > c.g) return fail(ctx, WGPU_ERR_ARG, "statistics: fewer ghost nodes than the stencil half width");
+        {   // FD1_C2 / C4 / C6 / CTW4 and FD2_C2 / C4 / C6 (the optimized scheme takes FD2_C4), module_operators.f90:23-33, 385-389: taps -H..H
+            const double c2[3] = {-0.5, 0.0, 0.5}, c4[5] = {1.0 / 12.0, -8.0 / 12.0, 0.0, 8.0 / 12.0, -1.0 / 12.0};
+            const double c6[7] = {-1.0 / 60.0, 9.0 / 60.0, -45.0 / 60.0, 0.0, 45.0 / 60.0, -9.0 / 60.0, 1.0 / 60.0};
+            const double tw[7] = {-0.02651995, 0.18941314, -0.79926643, 0.0, 0.79926643, -0.18941314, 0.02651995};
+            const double s2[3] = {1.0, -2.0, 1.0}, s4[5] = {-1.0 / 12.0, 16.0 / 12.0, -30.0 / 12.0, 16.0 / 12.0, -1.0 / 12.0};
+            const double s6[7] = {2.0 / 180.0, -27.0 / 180.0, 270.0 / 180.0, -490.0 / 180.0, 270.0 / 180.0, -27.0 / 180.0, 2.0 / 180.0};
+            const double *f1 = c.fd == 2 ? c2 : (c.fd == 4 ? c4 : (c.fd == 6 ? c6 : tw));
+            for (int t = 0; t < 2 * va.H + 1; ++t) va.fd1[t] = f1[t];
+            if (c.fd == 2) for (int t = 0; t < 3; ++t) va.fd2[t] = s2[t];
+            else if (c.fd == 6) for (int t = 0; t < 7; ++t) va.fd2[t] = s6[t];
+            else for (int t = 0; t < 5; ++t) va.fd2[t + va.H - 2] = s4[t];          // FD2_C4, centred in the 2H+1 taps
+        }
+        const int64_t per_block = ctx->gblk_elems * c.dim;
+        const int n = ctx->n_active;
+        const int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)(256ll << 20) / (per_block * 8)));
+        if ((rc = ensure_stage(ctx, per_block * chunk))) return rc;
+        WGPU_CHECK(ctx, cudaMemsetAsync(ctx->d_stage, 0, sizeof(double) * (size_t)per_block * chunk, ctx->stream));   // no neighbour: zeros
+        for (int s0 = 0; s0 < n; s0 += chunk) {
+            const int m = std::min(chunk, n - s0);
+            if (ctx->has_jumps) rc = wgpu_launch_export_regions(ctx, ctx->U, ctx->d_stage, ctx->d_active + s0, m, ctx->nc, c.dim, va.H, 0);
+            else rc = wgpu_launch_export(ctx, ctx->U, ctx->d_stage, ctx->d_active + s0, m, ctx->nc, c.dim, va.H, 0);
+            if (rc) return rc;
+            if ((rc = wgpu_launch_vort_stats(ctx, ctx->d_stage, ctx->d_active + s0, m, c.dim, va, ctx->d_stat + (size_t)s0 * WGPU_NSTAT))) return rc;
+        }
+    }
+    if ((rc = wgpu_launch_stats_final(ctx, ctx->d_stat, d_out))) return rc;
+    const int n_out = with_vorticity ? WGPU_NSTAT : 19;
+    WGPU_CHECK(ctx, cudaMemcpyAsync(out, d_out, sizeof(double) * n_out, cudaMemcpyDeviceToHost, ctx->stream));
     WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     if (!with_divergence) out[14] = out[15] = 0.0;
     if (ctx->comm && ctx->comm_world > 1) {      // the MPI_Allreduce calls of the post_stage (statistics_ACM.f90:396-430): SUM, MAX, MIN

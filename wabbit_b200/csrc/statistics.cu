@@ -8,6 +8,10 @@
 //   stats_block_kernel   the integral_stage of STATISTICS_ACM (LIB/EQUATION/ACMnew/statistics_ACM.f90:138-368), per block: mean flow, kinetic and
 //                        ACM energy, max |u|^2, divergence extrema (outside the solid), mask / sponge volume, penalization power, residual
 //                        velocity, force on colour 1 -- each block's sums times its dV;
+//   vort_block_kernel    enstrophy, max |vorticity|, helicity and dissipation of the same routine (statistics_ACM.f90:371-387): compute_vorticity
+//                        (LIB/OPERATORS/compute_vorticity.f90:3-67) and compute_dissipation (compute_dissipation.f90:5-78) with the first- and
+//                        second-derivative stencils of the discretization (module_operators.f90:23-33) on ghosted copies of the blocks (the
+//                        export kernels' staging layout: ghost nodes as sync_ghosts_tree leaves them, level jumps included);
 //   stats_final_kernel   the sum / max / min over the blocks in list order (deterministic), the post_stage's MPI reductions follow in capi.cu.
 #include <math.h>
 
@@ -157,10 +161,76 @@ __global__ void __launch_bounds__(256) stats_block_kernel(const double *__restri
         o[16] = r0 * dV;
         o[17] = r1 * dV;
         o[18] = r2 * dV;
+        o[19] = o[20] = o[21] = o[22] = 0.0;               // vort_block_kernel's entries
     }
 }
 
-// entry k of the result: sum over the blocks in list order (k < 13, 16..18), max (13, 14), min (15)
+// staged: [k][ncomp][nz][ny][nx] ghosted copies (g ghost nodes, the innermost H synchronised) of the blocks ids[0..m); writes entries 19..22 of
+// out[k0 + k][WGPU_NSTAT]: 0.5 sum |omega|^2 dV, max |omega|, 0.5 sum omega.u dV (3-D), -nu sum u.lap(u) dV (nu > 0)
+__global__ void __launch_bounds__(256) vort_block_kernel(const double *__restrict__ staged, const int *__restrict__ ids, const signed char *__restrict__ level,
+                                                         int ncomp, int Bx, int By, int Bz, int g, int dim, VortArgs va, double *__restrict__ out)
+{
+    __shared__ double red[8];
+    const int k = blockIdx.x, b = ids[k];
+    const int gz = dim == 3 ? g : 0;
+    const int nx = Bx + 2 * g, ny = By + 2 * g, nz = Bz + 2 * gz;
+    const long long GS = (long long)nx * ny * nz;
+    const double *u0 = staged + (long long)k * ncomp * GS, *u1 = u0 + GS, *u2 = u0 + 2 * GS;
+    const double sc = ldexp(1.0, -(int)level[b]);
+    const double hx = sc * va.domain[0] / (double)Bx, hy = sc * va.domain[1] / (double)By, hz = dim == 3 ? sc * va.domain[2] / (double)Bz : 1.0;
+    const double dV = dim == 3 ? hx * hy * hz : hx * hy;
+    const double dx_inv = 1.0 / hx, dy_inv = 1.0 / hy, dz_inv = 1.0 / hz;
+    const double dx2_inv = 1.0 / (hx * hx), dy2_inv = 1.0 / (hy * hy), dz2_inv = 1.0 / (hz * hz);
+    const int H = va.H;
+    // sum(FD(s:e) * u(i+s:i+e)): every tap, from 0 in increasing tap order, no contraction
+    auto fd = [&](const double *cf, const double *q, long long st) -> double {
+        double s = 0.0;
+        for (int t = -H; t <= H; ++t) s = __dadd_rn(s, __dmul_rn(cf[t + H], q[t * st]));
+        return s;
+    };
+    double enst = 0.0, vmax = 0.0, hel = 0.0, dis = 0.0;
+    const long long CS = (long long)Bx * By * Bz;
+    for (long long e = threadIdx.x; e < CS; e += blockDim.x) {
+        const int ix = (int)(e % Bx), iy = (int)((e / Bx) % By), iz = (int)(e / ((long long)Bx * By));
+        const long long i = ((long long)(iz + gz) * ny + (iy + g)) * nx + (ix + g);
+        const long long sy = nx, sz = (long long)nx * ny;
+        const double u_dy = __dmul_rn(fd(va.fd1, u0 + i, sy), dy_inv), v_dx = __dmul_rn(fd(va.fd1, u1 + i, 1), dx_inv);
+        if (dim == 3) {
+            const double u_dz = __dmul_rn(fd(va.fd1, u0 + i, sz), dz_inv), v_dz = __dmul_rn(fd(va.fd1, u1 + i, sz), dz_inv);
+            const double w_dx = __dmul_rn(fd(va.fd1, u2 + i, 1), dx_inv), w_dy = __dmul_rn(fd(va.fd1, u2 + i, sy), dy_inv);
+            const double o0 = w_dy - v_dz, o1 = u_dz - w_dx, o2 = v_dx - u_dy;
+            const double m2 = o0 * o0 + o1 * o1 + o2 * o2;
+            enst += m2;
+            vmax = fmax(vmax, sqrt(m2));
+            hel += o0 * u0[i] + o1 * u1[i] + o2 * u2[i];
+        } else {
+            const double o2 = v_dx - u_dy;
+            enst += o2 * o2;
+            vmax = fmax(vmax, fabs(o2));
+        }
+        if (va.nu > 0.0) {
+            double lu = __dmul_rn(fd(va.fd2, u0 + i, 1), dx2_inv) + __dmul_rn(fd(va.fd2, u0 + i, sy), dy2_inv);
+            double lv = __dmul_rn(fd(va.fd2, u1 + i, 1), dx2_inv) + __dmul_rn(fd(va.fd2, u1 + i, sy), dy2_inv);
+            if (dim == 3) {
+                lu = lu + __dmul_rn(fd(va.fd2, u0 + i, sz), dz2_inv);
+                lv = lv + __dmul_rn(fd(va.fd2, u1 + i, sz), dz2_inv);
+                const double lw = __dmul_rn(fd(va.fd2, u2 + i, 1), dx2_inv) + __dmul_rn(fd(va.fd2, u2 + i, sy), dy2_inv) +
+                                  __dmul_rn(fd(va.fd2, u2 + i, sz), dz2_inv);
+                dis += u0[i] * lu + u1[i] * lv + u2[i] * lw;
+            } else dis += u0[i] * lu + u1[i] * lv;
+        }
+    }
+    const double t0 = block_sum(enst, red), t1 = block_max(vmax, red), t2 = block_sum(hel, red), t3 = block_sum(dis, red);
+    if (threadIdx.x == 0) {
+        double *o = out + (long long)k * WGPU_NSTAT;
+        o[19] = 0.5 * t0 * dV;
+        o[20] = t1;
+        o[21] = 0.5 * t2 * dV;
+        o[22] = -va.nu * t3 * dV;
+    }
+}
+
+// entry k of the result: sum over the blocks in list order (k < 13, 16..19, 21, 22), max (13, 14, 20), min (15)
 __global__ void stats_final_kernel(const double *__restrict__ part, int nb, double *__restrict__ out)
 {
     const int k = threadIdx.x;
@@ -168,7 +238,7 @@ __global__ void stats_final_kernel(const double *__restrict__ part, int nb, doub
     double acc = (k == 14) ? -1.0e300 : (k == 15 ? 1.0e300 : 0.0);
     for (int i = 0; i < nb; ++i) {
         const double v = part[(long long)i * WGPU_NSTAT + k];
-        if (k == 13 || k == 14) acc = fmax(acc, v);
+        if (k == 13 || k == 14 || k == 20) acc = fmax(acc, v);
         else if (k == 15) acc = fmin(acc, v);
         else acc += v;
     }
@@ -188,14 +258,32 @@ int32_t wgpu_launch_create_mask(wgpu_ctx *ctx, const MaskGeom &gm, double time)
     return WGPU_OK;
 }
 
-int32_t wgpu_launch_stats(wgpu_ctx *ctx, const double *u, const double *rhs, const double *mask, const StatArgs &sa, double *d_part, double *d_out)
+int32_t wgpu_launch_stats(wgpu_ctx *ctx, const double *u, const double *rhs, const double *mask, const StatArgs &sa, double *d_part)
 {
     const wgpu_config &c = ctx->cfg;
-    if (ctx->n_active)
-        stats_block_kernel<<<ctx->n_active, 256, 0, ctx->stream>>>(u, rhs, mask, ctx->d_active, ctx->d_level, ctx->nc, c.n_mask, c.Bs[0], c.Bs[1],
-                                                                  c.dim == 3 ? c.Bs[2] : 1, c.dim, sa, d_part);
+    if (ctx->n_active == 0) return WGPU_OK;
+    stats_block_kernel<<<ctx->n_active, 256, 0, ctx->stream>>>(u, rhs, mask, ctx->d_active, ctx->d_level, ctx->nc, c.n_mask, c.Bs[0], c.Bs[1],
+                                                              c.dim == 3 ? c.Bs[2] : 1, c.dim, sa, d_part);
+    ctx->launches++;
+    WGPU_CHECK(ctx, cudaGetLastError());
+    return WGPU_OK;
+}
+
+// m ghosted blocks in `staged` (ids = d_active + k0): entries 19..22 of d_part[k0 .. k0 + m)
+int32_t wgpu_launch_vort_stats(wgpu_ctx *ctx, const double *staged, const int *d_ids, int m, int ncomp, const VortArgs &va, double *d_part)
+{
+    const wgpu_config &c = ctx->cfg;
+    if (m == 0) return WGPU_OK;
+    vort_block_kernel<<<m, 256, 0, ctx->stream>>>(staged, d_ids, ctx->d_level, ncomp, c.Bs[0], c.Bs[1], c.dim == 3 ? c.Bs[2] : 1, c.g, c.dim, va, d_part);
+    ctx->launches++;
+    WGPU_CHECK(ctx, cudaGetLastError());
+    return WGPU_OK;
+}
+
+int32_t wgpu_launch_stats_final(wgpu_ctx *ctx, const double *d_part, double *d_out)
+{
     stats_final_kernel<<<1, 32, 0, ctx->stream>>>(d_part, ctx->n_active, d_out);
-    ctx->launches += 2;
+    ctx->launches++;
     WGPU_CHECK(ctx, cudaGetLastError());
     return WGPU_OK;
 }

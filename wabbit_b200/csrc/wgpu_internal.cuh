@@ -79,7 +79,7 @@ struct StageArgs {
     int plain_hint;                  // 1: every block of this launch is such a block, -1: none is, 0: unknown / mixed
 };
 
-#define WGPU_NSTAT 19
+#define WGPU_NSTAT 23
 // closed-form mask geometry of create_mask_kernel (statistics.cu)
 struct MaskGeom {
     int penalization, use_sponge;
@@ -88,6 +88,10 @@ struct MaskGeom {
 struct StatArgs {
     double domain[3], c0, gamma_p, C_eta_inv, C_sponge_inv, u_mean_set[3];
     int use_sponge;
+};
+struct VortArgs {            // vort_block_kernel: FD1 / FD2 taps -H..H of the discretization (module_operators.f90:23-33)
+    double domain[3], nu, fd1[7], fd2[7];
+    int H;
 };
 
 struct wgpu_ctx {
@@ -300,7 +304,9 @@ int32_t wgpu_launch_copy_entries(wgpu_ctx *ctx, const double *src, double *dst, 
 int32_t wgpu_topology_halo_restrict(wgpu_ctx *ctx, const std::vector<int> &recv0, const std::vector<int> &send0);
 // statistics.cu
 int32_t wgpu_launch_create_mask(wgpu_ctx *ctx, const MaskGeom &gm, double time);
-int32_t wgpu_launch_stats(wgpu_ctx *ctx, const double *u, const double *rhs, const double *mask, const StatArgs &sa, double *d_part, double *d_out);
+int32_t wgpu_launch_stats(wgpu_ctx *ctx, const double *u, const double *rhs, const double *mask, const StatArgs &sa, double *d_part);
+int32_t wgpu_launch_vort_stats(wgpu_ctx *ctx, const double *staged, const int *d_ids, int m, int ncomp, const VortArgs &va, double *d_part);
+int32_t wgpu_launch_stats_final(wgpu_ctx *ctx, const double *d_part, double *d_out);
 // wavelet.cu
 int32_t wgpu_launch_wavelet(wgpu_ctx *ctx, const double *src, double *dst, int inverse, const double *ce_coarse);
 int32_t wgpu_launch_blockfilter(wgpu_ctx *ctx, const double *src, double *dst, const double *stencil, int half, unsigned comp_mask, int level_mode);

@@ -241,11 +241,15 @@ class WabbitGPU:
         v = (C.c_double * 3)(*(list(velocity) + [0.0, 0.0, 0.0])[:3])
         self._check(self._lib.wgpu_create_mask(self._ctx, float(time), gid, c, v, float(radius), float(smoothing_width), float(L_sponge), float(p_sponge)))
 
-    def statistics_ACM(self, time: float = 0.0, with_divergence: bool = True) -> dict:
-        """STATISTICS_ACM's integral quantities reduced on the device (and over the ranks of the communicator): wgpu_statistics"""
-        out = (C.c_double * 19)()
-        self._check(self._lib.wgpu_statistics(self._ctx, float(time), int(bool(with_divergence)), out))
-        return dict(zip(self.STAT_NAMES, [float(x) for x in out]))
+    VORT_STAT_NAMES = ("enstrophy", "max_vort", "helicity", "dissipation")
+
+    def statistics_ACM(self, time: float = 0.0, with_divergence: bool = True, with_vorticity: bool = False) -> dict:
+        """STATISTICS_ACM's integral quantities reduced on the device (and over the ranks of the communicator): wgpu_statistics.
+        with_vorticity adds enstrophy / max_vort / helicity / dissipation (statistics_ACM.f90:371-387; one rank)"""
+        out = (C.c_double * 23)()
+        self._check(self._lib.wgpu_statistics(self._ctx, float(time), int(bool(with_divergence)) | (2 if with_vorticity else 0), out))
+        names = self.STAT_NAMES + (self.VORT_STAT_NAMES if with_vorticity else ())
+        return dict(zip(names, [float(x) for x in out]))
 
     def sync_ghosts_RHS_tree(self, g_minus: Optional[int] = None, g_plus: Optional[int] = None):
         """synchronize_ghosts_generic.f90:155-174"""
