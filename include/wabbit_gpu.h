@@ -420,6 +420,20 @@ int32_t wgpu_comm_allgatherv_i32(wgpu_ctx *ctx, const int32_t *mine, const int32
 int32_t wgpu_rkc_step(wgpu_ctx *ctx, double time, int32_t iteration, int32_t s, const double *mu, const double *mu_tilde, const double *nu,
                       const double *gamma_tilde, const double *c, double *dt);
 
+/* wgpu_krylov_step: timeStep_tree -> krylov_time_stepper (time_step_method = "Krylov", LIB/TIME/krylov.f90:1-190): the exponential integrator
+ *   u(t + dt) = u + dt phi_1(dt J) F(u) on the Krylov space of the Jacobian (finite differences of the right-hand side with
+ *   eps = |u| sqrt(epsilon)).  calculate_time_step, M right-hand sides (ghost synchronisation fused), Arnoldi with modified Gram-Schmidt on
+ *   the block interiors (wabbit_norm / scalarproduct, :500-595; every scalar product is read by the host, as the reference's MPI_Allreduce),
+ *   the matrix exponential of the augmented Hessenberg matrix on the host (wgpu_expm_pade), error estimate |beta h(M+1,M) phi(M,M+2)|.
+ *   M_max = params%M_krylov (M_max + 3 registers of the size of hvy_block are allocated on first use); dynamic = 1
+ *   (krylov_subspace_dimension = "dynamic"): stop at the first M with err <= err_threshold, and at M_max shrink dt by 0.9 until it is.
+ *   Outputs: dt (possibly shrunk), M_used, err (what the reference appends to krylov_err.t).  One rank.
+ * wgpu_expm_pade: expM_pade -> DGPADM (krylov.f90:193-396; Expokit): exp(H) of an m x m matrix (row- or column-major alike), degree-6 Pade
+ *   fraction with scaling and squaring.  Host code, no device needed. */
+int32_t wgpu_krylov_step(wgpu_ctx *ctx, double time, int32_t iteration, int32_t M_max, int32_t dynamic, double err_threshold, double *dt,
+                         int32_t *M_used, double *err);
+int32_t wgpu_expm_pade(const double *H, int32_t m, double *E);
+
 /*
  * wgpu_filter: filter_wrapper (LIB/TIME/filter_wrapper.f90:1-78) on the resident hvy_block: filter_type = "explicit_3pt" ... "explicit_21pt" or
  *   "superviscosity_2nd" ... "_20th" (the binomial stencils of generate_superviscosity_stencil, + identity), applied with blockFilterXYZ_vct

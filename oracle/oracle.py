@@ -723,6 +723,100 @@ def rkc_step(grid: Grid, p: Params, hvy: np.ndarray, time: float, mu, mu_tilde, 
     return dt
 
 
+def expm_pade(H: np.ndarray, ideg: int = 6) -> np.ndarray:
+    """exp(H) as expM_pade computes it (LIB/TIME/krylov.f90:193-226 -> DGPADM of Expokit, R. Sidje, ACM TOMS 24 (1998), restated from the
+    published algorithm): scaling by 2^ns with ns = max(0, int(log2 |H|_inf) + 2), the irreducible (ideg, ideg) Pade fraction
+    exp(A) ~ I + 2 (E - O)^-1 O with E / O the even / odd part of sum_k c_k A^k, c_k = c_(k-1) (ideg + 1 - k) / (k (2 ideg + 1 - k)),
+    ns squarings."""
+    H = np.asarray(H, dtype=np.float64)
+    m = H.shape[0]
+    hnorm = float(np.abs(H).sum(axis=1).max())
+    if hnorm == 0.0:
+        return np.eye(m)
+    ns = max(0, int(math.log(hnorm) / math.log(2.0)) + 2)
+    A = H * (1.0 / 2.0 ** ns)
+    c = [1.0]
+    for k in range(1, ideg + 1):
+        c.append(c[-1] * float(ideg + 1 - k) / float(k * (2 * ideg + 1 - k)))
+    A2 = A @ A
+    I = np.eye(m)
+    # Horner in A^2: even part c0 + c2 A^2 + ..., odd part (c1 + c3 A^2 + ...) A
+    ev = c[ideg - (ideg % 2)] * I
+    for k in range(ideg - (ideg % 2) - 2, -1, -2):
+        ev = ev @ A2 + c[k] * I
+    od = c[ideg - 1 + (ideg % 2)] * I
+    for k in range(ideg - 3 + (ideg % 2), 0, -2):
+        od = od @ A2 + c[k] * I
+    od = od @ A
+    E = I + 2.0 * np.linalg.solve(ev - od, od)
+    for _ in range(ns):
+        E = E @ E
+    return E
+
+
+def krylov_step(grid: Grid, p: Params, hvy: np.ndarray, time: float, M_max: int = 12, dynamic: bool = False, err_threshold: float = 1.0e-3,
+                mask: Optional[np.ndarray] = None, sync=None, dot=None):
+    """krylov_time_stepper (LIB/TIME/krylov.f90:1-190): the exponential integrator u(t+dt) = u + dt phi_1(dt J) F(u) on the Krylov space of
+    the Jacobian J (finite differences of the right-hand side with eps = |u| sqrt(epsilon)), Arnoldi with modified Gram-Schmidt on the block
+    interiors (wabbit_norm, scalarproduct :500-595), phi_1 from the matrix exponential of the augmented Hessenberg matrix, error estimate
+    |beta h_(M+1,M) phi(M, M+2)|; "dynamic": stop at the first M with err <= threshold, and at M_max shrink dt by 0.9 until it is.
+    hvy is advanced in place; returns (dt, M_iter, err)."""
+    if sync is None:
+        sync = lambda h: sync_ghosts_same_level(grid, p, h, p.g_rhs, p.g_rhs)
+    I = (slice(None), slice(None)) + interior(p)
+    if dot is None:                                # scalarproduct; a caller may pass another summation order (see tests/test_oracle_krylov.py)
+        dot = lambda a, b: float((a[I] * b[I]).sum())
+    epsm = float(np.finfo(np.float64).eps)
+    sync(hvy)
+    dt = calculate_time_step(grid, p, hvy, time)
+    normv = math.sqrt(dot(hvy, hvy))
+    if normv < epsm:
+        normv = 1.0
+    eps = normv * math.sqrt(epsm)
+    R = np.zeros_like(hvy)
+    rhs_tree(grid, p, hvy, R, mask)
+    beta = math.sqrt(dot(R, R))
+    if beta < epsm:
+        beta = 1.0
+    V = [R / beta]
+    H = np.zeros((M_max + 2, M_max + 2))
+    phi = np.zeros((M_max + 2, M_max + 2))
+    err, M_iter = 0.0, 0
+    for M_iter in range(1, M_max + 1):
+        P = hvy + eps * V[M_iter - 1]
+        sync(P)
+        W = np.zeros_like(hvy)
+        rhs_tree(grid, p, P, W, mask)
+        W = (W - R) / eps
+        for it in range(1, M_iter + 1):
+            H[it - 1, M_iter - 1] = dot(V[it - 1], W)
+            W = W - H[it - 1, M_iter - 1] * V[it - 1]
+        H[M_iter, M_iter - 1] = math.sqrt(dot(W, W))
+        V.append(W / H[M_iter, M_iter - 1])
+        if dynamic or M_iter == M_max:
+            h_klein = H[M_iter, M_iter - 1]
+            Ht = np.zeros((M_iter + 2, M_iter + 2))
+            Ht[:M_iter, :M_iter] = H[:M_iter, :M_iter]
+            Ht[0, M_iter] = 1.0
+            Ht[M_iter, M_iter + 1] = 1.0
+            phi[:] = 0.0
+            phi[:M_iter + 2, :M_iter + 2] = expm_pade(dt * Ht)
+            phi[M_iter, M_iter] = h_klein * phi[M_iter - 1, M_iter + 1]
+            err = abs(beta * phi[M_iter, M_iter])
+            if dynamic and M_iter == M_max and err > err_threshold:
+                while err > err_threshold:
+                    dt = 0.90 * dt
+                    phi[:] = 0.0
+                    phi[:M_iter + 2, :M_iter + 2] = expm_pade(dt * Ht)
+                    phi[M_iter, M_iter] = h_klein * phi[M_iter - 1, M_iter + 1]
+                    err = abs(beta * phi[M_iter, M_iter])
+            if err <= err_threshold or M_iter == M_max:
+                break
+    for it in range(1, M_iter + 2):
+        hvy[:] = hvy + beta * V[it - 1] * phi[it - 1, M_iter]
+    return dt, M_iter, err
+
+
 def superviscosity_stencil(filter_type: str) -> dict:
     """The stencil filter_wrapper applies (LIB/TIME/filter_wrapper.f90:28-62, generate_superviscosity_stencil :82-104): binomial coefficients with
     alternating sign, normalised by the sum of their absolute values, negated for explicit_5pt / 9pt / 13pt / 17pt / 21pt, plus the identity.

@@ -96,7 +96,7 @@ def test_time_step_tree_dispatches_on_the_parameter_file_keys():
         sol.download(out, g_sync=0)
         outs.append((t, it, out))
         if mode == "direct":
-            sol.params.time_step_method = "Krylov"
+            sol.params.time_step_method = "Leapfrog"
             with pytest.raises(WabbitAbort):
                 sol.timeStep_tree(t, it)
         sol.close()

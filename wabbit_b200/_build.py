@@ -16,7 +16,7 @@ INCLUDE = os.path.join(ROOT, "include")
 GPU_LIB = os.path.join(HERE, "libwabbit_gpu.so")
 HOST_LIB = os.path.join(HERE, "libwabbit_host.so")
 
-GPU_SRCS = ["capi.cu", "kernels.cu", "wavelet.cu", "jump.cu", "topology.cu", "multigpu.cu", "statistics.cu"]
+GPU_SRCS = ["capi.cu", "kernels.cu", "wavelet.cu", "jump.cu", "topology.cu", "multigpu.cu", "statistics.cu", "krylov.cu"]
 HOST_SRCS = ["host_forest.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--threads", "6", "-ldl"]

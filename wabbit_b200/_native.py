@@ -44,6 +44,8 @@ GPU_SYMBOLS = {
     "wgpu_set_transfer_mode": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32]),
     "wgpu_filter": (C.c_int32, [C.c_void_p, C.c_char_p, _i32p, C.c_int32, C.c_int32]),
     "wgpu_rkc_step": (C.c_int32, [C.c_void_p, C.c_double, C.c_int32, C.c_int32, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "wgpu_krylov_step": (C.c_int32, [C.c_void_p, C.c_double, C.c_int32, C.c_int32, C.c_int32, C.c_double, _dp, C.POINTER(C.c_int32), _dp]),
+    "wgpu_expm_pade": (C.c_int32, [_dp, C.c_int32, _dp]),
     "wgpu_create_mask": (C.c_int32, [C.c_void_p, C.c_double, C.c_int32, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_double]),
     "wgpu_statistics": (C.c_int32, [C.c_void_p, C.c_double, C.c_int32, _dp]),
     "wgpu_sync_ghosts": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

@@ -445,6 +445,8 @@ int32_t wgpu_destroy(wgpu_ctx *ctx)
     cudaFree(ctx->UA);
     cudaFree(ctx->UB);
     for (int s = 0; s < WGPU_MAX_STAGES; ++s) cudaFree(ctx->K[s]);
+    for (double *p : ctx->kry) cudaFree(p);
+    cudaFree(ctx->d_kry_part);
     cudaFree(ctx->MASK);
     cudaFree(ctx->TMP);
     cudaFree(ctx->d_active);
@@ -2040,6 +2042,126 @@ int32_t wgpu_rkc_step(wgpu_ctx *ctx, double time, int32_t iteration, int32_t s, 
     WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_dt, 8, cudaMemcpyDeviceToHost, ctx->stream));
     WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     *dt = ctx->h_pinned[0];
+    return check_flags(ctx);
+}
+
+// ------------------------------------------------------------------------------------------------ Krylov exponential integrator
+int32_t wgpu_krylov_step(wgpu_ctx *ctx, double time, int32_t iteration, int32_t M_max, int32_t dynamic, double err_threshold, double *dt,
+                         int32_t *M_used, double *err_out)
+{
+    (void)iteration;
+    if (!ctx || !dt) return WGPU_ERR_ARG;
+    if (M_max < 1 || M_max > 62) return fail(ctx, WGPU_ERR_ARG, "krylov: M_krylov must be in 1..62");
+    if (ctx->nc != ctx->cfg.dim + 1) return fail(ctx, WGPU_ERR_UNSUPPORTED, "ACM needs number_equations = dim+1");
+    if (ctx->comm && ctx->comm_world > 1) return fail(ctx, WGPU_ERR_UNSUPPORTED, "wgpu_krylov_step: one rank only so far");
+    if (exchange_pending(ctx)) return fail(ctx, WGPU_ERR_ARG, "topology has neighbours on other ranks");
+    int32_t rc;
+    // M_max + 3 registers, as the reference (allocate_forest.f90:98): the Krylov vectors 1..M_max, slot M_max+1 (the Arnoldi work vector, which
+    // becomes vector M_max+1 in place), the perturbed state and the reference right-hand side
+    const size_t n = (size_t)ctx->cfg.max_blocks * ctx->nc * ctx->blk_elems;
+    while ((int)ctx->kry.size() < M_max + 3) {
+        double *p = nullptr;
+        if ((rc = dmalloc(ctx, &p, n))) return rc;
+        WGPU_CHECK(ctx, cudaMemsetAsync(p, 0, n * sizeof(double), ctx->stream));
+        ctx->kry.push_back(p);
+    }
+    if (!ctx->d_kry_part && (rc = dmalloc(ctx, &ctx->d_kry_part, (size_t)ctx->cfg.max_blocks + 1))) return rc;
+    double **V = ctx->kry.data();
+    double *W = V[M_max], *P = V[M_max + 1], *R = V[M_max + 2];
+    double *d_res = ctx->d_kry_part + ctx->cfg.max_blocks;
+    ctx->det_cached_for = nullptr;
+    auto rhs_of = [&](const double *src, double *dst) -> int32_t {
+        StageArgs a;
+        fill_common_args(ctx, a);
+        a.u_in = src;
+        a.u0 = src;
+        a.k_out = dst;
+        a.t0 = time;
+        a.t_cj = 0.0;
+        int32_t r = wgpu_launch_jump_fill(ctx, src);         // sync_ghosts_RHS_tree
+        if (r) return r;
+        a.plain_hint = plain_hint(ctx, WGPU_BLOCKS_ALL);
+        return wgpu_launch_stage(ctx, a, ctx->n_active);
+    };
+    auto dot = [&](const double *x, const double *y, double *res) -> int32_t {      // scalarproduct + get_sum_all: the host needs the value
+        int32_t r = wgpu_launch_kry_dot(ctx, x, y, ctx->d_kry_part, d_res);
+        if (r) return r;
+        WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pinned, d_res, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        *res = ctx->h_pinned[0];
+        return WGPU_OK;
+    };
+    if ((rc = compute_dt(ctx, time))) return rc;             // calculate_time_step
+    WGPU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_dt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    double dtv = ctx->h_pinned[0];
+    const double epsm = 2.220446049250313e-16;               // epsilon(1.0_rk)
+    double normv, beta, h;
+    if ((rc = dot(ctx->U, ctx->U, &normv))) return rc;
+    normv = sqrt(normv);
+    if (normv < epsm) normv = 1.0;
+    const double eps = normv * sqrt(epsm);
+    if ((rc = rhs_of(ctx->U, R))) return rc;
+    if ((rc = check_flags(ctx))) return rc;
+    if ((rc = dot(R, R, &beta))) return rc;
+    beta = sqrt(beta);
+    if (beta < epsm) beta = 1.0;
+    if ((rc = wgpu_launch_kry_axpy(ctx, V[0], R, R, 0, beta, 0.0))) return rc;
+    const int LD = M_max + 2;
+    std::vector<double> H((size_t)LD * LD, 0.0), phi((size_t)LD * LD, 0.0), Ht, Ex;
+    double err = 0.0;
+    int M_iter = 0;
+    auto phi_of = [&](int M, double h_klein) -> int32_t {    // expM_pade(dt * H_tmp) of the augmented (M+2)^2 matrix, then the error entry
+        const int m = M + 2;
+        Ht.assign((size_t)m * m, 0.0);
+        Ex.assign((size_t)m * m, 0.0);
+        for (int i = 0; i < M; ++i)
+            for (int j = 0; j < M; ++j) Ht[(size_t)i * m + j] = dtv * H[(size_t)i * LD + j];
+        Ht[(size_t)0 * m + M] = dtv * 1.0;
+        Ht[(size_t)M * m + M + 1] = dtv * 1.0;
+        int32_t r = wgpu_expm_pade(Ht.data(), m, Ex.data());
+        if (r) return fail(ctx, 240917, "error in computing exp(t*H)");
+        std::fill(phi.begin(), phi.end(), 0.0);
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < m; ++j) phi[(size_t)i * LD + j] = Ex[(size_t)i * m + j];
+        phi[(size_t)M * LD + M] = h_klein * phi[(size_t)(M - 1) * LD + M + 1];
+        err = fabs(beta * phi[(size_t)M * LD + M]);
+        return WGPU_OK;
+    };
+    for (M_iter = 1; M_iter <= M_max; ++M_iter) {
+        if ((rc = wgpu_launch_kry_axpy(ctx, P, ctx->U, V[M_iter - 1], 1, eps, 0.0))) return rc;      // perturbed state
+        if ((rc = rhs_of(P, W))) return rc;
+        if ((rc = wgpu_launch_kry_axpy(ctx, W, W, R, 2, eps, 0.0))) return rc;                       // linearization
+        for (int it = 1; it <= M_iter; ++it) {                                                       // Arnoldi, modified Gram-Schmidt
+            if ((rc = dot(V[it - 1], W, &h))) return rc;
+            H[(size_t)(it - 1) * LD + (M_iter - 1)] = h;
+            if ((rc = wgpu_launch_kry_axpy(ctx, W, W, V[it - 1], 3, h, 0.0))) return rc;
+        }
+        if ((rc = dot(W, W, &h))) return rc;
+        h = sqrt(h);
+        H[(size_t)M_iter * LD + (M_iter - 1)] = h;
+        if ((rc = wgpu_launch_kry_axpy(ctx, V[M_iter], W, W, 0, h, 0.0))) return rc;                 // M_iter = M_max: in place
+        if (dynamic || M_iter == M_max) {
+            if ((rc = phi_of(M_iter, h))) return rc;
+            if (dynamic && M_iter == M_max && err > err_threshold) {
+                // the largest subspace and the error is still too large: decrease the time step
+                int guard = 0;
+                while (err > err_threshold && guard++ < 2000) {
+                    dtv = 0.90 * dtv;
+                    if ((rc = phi_of(M_iter, h))) return rc;
+                }
+            }
+            if (err <= err_threshold || M_iter == M_max) break;
+        }
+    }
+    if (M_iter > M_max) M_iter = M_max;
+    for (int it = 1; it <= M_iter + 1; ++it)
+        if ((rc = wgpu_launch_kry_axpy(ctx, ctx->U, ctx->U, V[it - 1], 4, beta, phi[(size_t)(it - 1) * LD + M_iter]))) return rc;
+    ctx->dtmin_valid = false;
+    WGPU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    *dt = dtv;
+    if (M_used) *M_used = M_iter;
+    if (err_out) *err_out = err;
     return check_flags(ctx);
 }
 

@@ -249,6 +249,8 @@ struct wgpu_ctx {
     double *d_pool_user = nullptr;     // the caller's pool of wgpu_set_exchange (used by the NCCL / host-driven paths)
 
     double *d_stat = nullptr;          // [max_blocks + 1][WGPU_NSTAT]: per-block partial statistics, the result behind them
+    std::vector<double *> kry;         // wgpu_krylov_step: M_krylov + 3 registers (Krylov vectors, perturbed state, reference right-hand side)
+    double *d_kry_part = nullptr;      // [max_blocks + 1]: per-block partial scalar products, the result behind them
     void *tma_cache = nullptr;         // tensor maps of the resident arrays (kernels.cu: tma_maps)
 
     // optional event pairs around stage launches
@@ -307,6 +309,8 @@ int32_t wgpu_launch_create_mask(wgpu_ctx *ctx, const MaskGeom &gm, double time);
 int32_t wgpu_launch_stats(wgpu_ctx *ctx, const double *u, const double *rhs, const double *mask, const StatArgs &sa, double *d_part);
 int32_t wgpu_launch_vort_stats(wgpu_ctx *ctx, const double *staged, const int *d_ids, int m, int ncomp, const VortArgs &va, double *d_part);
 int32_t wgpu_launch_stats_final(wgpu_ctx *ctx, const double *d_part, double *d_out);
+int32_t wgpu_launch_kry_dot(wgpu_ctx *ctx, const double *x, const double *y, double *d_part, double *d_out);
+int32_t wgpu_launch_kry_axpy(wgpu_ctx *ctx, double *dst, const double *x, const double *y, int op, double a, double b);
 // wavelet.cu
 int32_t wgpu_launch_wavelet(wgpu_ctx *ctx, const double *src, double *dst, int inverse, const double *ce_coarse);
 int32_t wgpu_launch_blockfilter(wgpu_ctx *ctx, const double *src, double *dst, const double *stencil, int half, unsigned comp_mask, int level_mode);

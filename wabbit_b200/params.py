@@ -157,6 +157,9 @@ class Params:
     RKC_nu: Tuple[float, ...] = ()
     RKC_gamma_tilde: Tuple[float, ...] = ()
     RKC_c: Tuple[float, ...] = ()
+    M_krylov: int = 12                                    # [Time] M_krylov, krylov_err_threshold, krylov_subspace_dimension (module_params.f90:23-34)
+    krylov_err_threshold: float = 1.0e-3
+    krylov_subspace_dimension: str = "fixed"
     filter_type: str = "no_filter"                        # [Discretization] filter_type (filter_wrapper.f90)
     filter_freq: int = -1
     filter_only_maxlevel: bool = False
@@ -265,6 +268,9 @@ class Params:
                 if len(v) < p.rkc_s:
                     raise ValueError(f"[Time] {key} needs s = {p.rkc_s} values")
                 setattr(p, key, v[:p.rkc_s])
+        p.M_krylov = ini.integer("Time", "M_krylov", 12)                                       # ini_file_to_params.f90:593-595
+        p.krylov_err_threshold = ini.real("Time", "krylov_err_threshold", 1.0e-3)
+        p.krylov_subspace_dimension = ini.string("Time", "krylov_subspace_dimension", "fixed")
         p.filter_type = ini.string("Discretization", "filter_type", "no_filter")              # :176-184
         p.filter_only_maxlevel = ini.boolean("Discretization", "filter_only_maxlevel", False)
         p.filter_all_except_maxlevel = ini.boolean("Discretization", "filter_all_except_maxlevel", False)

@@ -314,6 +314,15 @@ class WabbitGPU:
         fc = None if filter_component is None else _i32(np.ascontiguousarray(filter_component, dtype=np.int32))
         self._check(self._lib.wgpu_filter(self._ctx, filter_type.encode(), fc, int(bool(only_maxlevel)), int(bool(all_except_maxlevel))))
 
+    def krylov_time_stepper(self, time: float, iteration: int, M_krylov: int = 12, dynamic: bool = False, err_threshold: float = 1.0e-3):
+        """krylov_time_stepper (LIB/TIME/krylov.f90:1) on the device (wgpu_krylov_step); returns (dt, M_iter, err) -- the last two are what
+        the reference appends to krylov_err.t"""
+        dt, err, M = C.c_double(), C.c_double(), C.c_int32()
+        self._check(self._lib.wgpu_krylov_step(self._ctx, float(time), int(iteration), int(M_krylov), int(bool(dynamic)), float(err_threshold),
+                                               C.byref(dt), C.byref(M), C.byref(err)))
+        self.krylov_log = (float(dt.value), int(M.value), float(err.value))
+        return self.krylov_log
+
     def RungeKuttaChebychev(self, time: float, iteration: int, mu, mu_tilde, nu, gamma_tilde, c) -> float:
         """RungeKuttaChebychev (runge_kutta_chebychev.f90:6) with the host's coefficient rows of length s (wgpu_rkc_step); returns dt"""
         arr = [np.ascontiguousarray(v, dtype=np.float64) for v in (mu, mu_tilde, nu, gamma_tilde, c)]
@@ -506,6 +515,8 @@ class WabbitGPU:
             dt = self.RungeKuttaGeneric(time, iteration)
         elif method == "rungekuttachebychev":
             dt = self.RungeKuttaChebychev(time, iteration, *p.rkc_coefficients())
+        elif method == "krylov":
+            dt = self.krylov_time_stepper(time, iteration, p.M_krylov, p.krylov_subspace_dimension.strip().lower() == "dynamic", p.krylov_err_threshold)[0]
         else:
             raise WabbitAbort(19101816, "time_step_method is unkown: " + p.time_step_method)
         iteration += 1
