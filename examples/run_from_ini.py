@@ -61,6 +61,8 @@ def main():
     tc = p.threshold_state_vector_component or None
     t0, it0 = (state["time"], state["iteration"]) if state is not None else (0.0, 0)
     loop = AdaptiveLoop(sol, forest, t0, it0, mask=mask, threshold_mask=mask is not None and p.threshold_mask, thresh_comp=tc)
+    if p.nsave_stats != 99999999 or abs(p.tsave_stats - 9999999.9) > 1e-3:        # [Statistics] nsave_stats / tsave_stats: the *.t files
+        loop.stats_dir = a.out
 
     def set_inicond(lp):                      # inicond = meanflow (inicond_ACM.f90:285-288): u = u_mean_set, p = 0
         hvy, _, _, _ = lp.forest.active(0)

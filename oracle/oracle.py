@@ -92,9 +92,15 @@ def _p(a: Optional[np.ndarray]):
 def _pb(a: np.ndarray):
     """addresses of a[0], a[1], ... (the per-block loops call C once per block: one .ctypes object per array instead of one per block).
     Plain integers: the caller keeps `a` alive."""
-    assert a.dtype == np.float64 and a.flags.c_contiguous
-    base, st = a.ctypes.data, a.strides[0]
-    return [base + b * st for b in range(a.shape[0])]
+    assert a.dtype == np.float64
+    if a.flags.c_contiguous:
+        base, st = a.ctypes.data, a.strides[0]
+        return [base + b * st for b in range(a.shape[0])]
+    out = []
+    for b in range(a.shape[0]):                    # e.g. a strided selection of blocks: every block itself must be contiguous
+        assert a[b].flags.c_contiguous
+        out.append(a[b].ctypes.data)
+    return out
 
 
 @functools.lru_cache(maxsize=None)

@@ -122,3 +122,42 @@ def test_cylinder_mask_sponge_and_statistics_2d():
     assert want["sponge_volume"] > 10.0 and want["penal_power_sponge"] != 0.0 and want["force_x"] > 0.0
     _check_vorticity_entries(sol, grid, po, synced)
     sol.close()
+
+
+def test_time_loop_writes_the_t_files(tmp_path):
+    """AdaptiveLoop.statistics (main.f90:388-397): every nsave_stats iterations the device statistics go to the *.t files -- rows in the
+    reference's format whose numbers are the ones statistics_ACM returns for the state after the time step"""
+    from wabbit_b200.timeloop import AdaptiveLoop
+    p = tg_params(Bs=16, J=3, wavelet_g=6)
+    p.wavelet, p.penalization, p.C_eta, p.nsave_stats, p.eps = "CDF44", True, 1.0e-2, 1, 1.0e-3
+    p = p.finalize()
+    forest = Forest.uniform(3, 2, Jmax=3, max_blocks=600)
+    sol = WabbitGPU(p, max_blocks=600)
+    sol.setup_wavelet("CDF44")
+    sol.set_forest(forest)
+    po, grid = orc_params(p), orc_grid(forest)
+    u = O.alloc(grid, po)
+    O.inicond_taylor_green(grid, po, u)
+    host = np.zeros(sol.host_shape())
+    host[:grid.n] = u
+    sol.upload(host)
+    loop = AdaptiveLoop(sol, forest, 0.0, 0, refinement_indicator="everywhere", mask=SphereMask3D(p, center=(3.0, 3.1, 3.2), radius=0.9))
+    loop.stats_dir = str(tmp_path)
+    seen = []
+    orig = loop.statistics
+    loop.statistics = lambda dt: seen.append(orig(dt)) or seen[-1]
+    for _ in range(2):
+        loop.step()
+    assert len(seen) == 2 and all(s is not None for s in seen)
+    rows = {f.name: [[float(x) for x in line.split(";")] for line in f.read_text().splitlines()] for f in tmp_path.iterdir()}
+    assert set(rows) == {"umag.t", "CFL.t", "meanflow.t", "div.t", "forces.t", "mask_volume.t", "penal_power.t", "u_residual.t", "e_kin.t",
+                         "enstrophy.t", "helicity.t", "dissipation.t"}
+    assert all(len(r) == 2 for r in rows.values())
+    for k, s in enumerate(seen):
+        assert abs(rows["e_kin.t"][k][1] - s["e_kin"]) <= 1e-8 * s["e_kin"] and abs(rows["enstrophy.t"][k][1] - s["enstrophy"]) <= 1e-8 * s["enstrophy"]
+        assert abs(rows["mask_volume.t"][k][1] - s["mask_volume"]) <= 1e-8 * s["mask_volume"]
+    vol = 4.0 / 3.0 * np.pi * 0.9 ** 3
+    assert abs(seen[0]["mask_volume"] - vol) <= 0.15 * vol                     # smoothed sphere on the level-3 lattice
+    assert abs(seen[0]["e_kin"] - (2.0 * np.pi) ** 3 / 8.0) <= 0.05 * (2.0 * np.pi) ** 3 / 8.0 and seen[0]["enstrophy"] > 0.0
+    assert abs(rows["e_kin.t"][0][0] - loop.log[0][1]) <= 1e-8 * loop.log[0][1] and rows["e_kin.t"][1][0] > rows["e_kin.t"][0][0]
+    sol.close()

@@ -632,3 +632,29 @@ def test_ini_keys_of_the_chebychev_integrator_and_the_filter(tmp_path):
     assert q.time_step_method == "RungeKuttaGeneric" and q.filter_type == "no_filter"
     with pytest.raises(ValueError):
         q.rkc_coefficients()
+
+
+def test_t_files_have_the_reference_row_format(tmp_path):
+    """module_t_files.f90:177-201: '(n-1 (es15.8,";"), es15.8)' per row; the statistics trigger of main.f90:392"""
+    from wabbit_b200 import tfiles
+    assert tfiles.format_row([0.5, -1.25e-3, 1.0e10]) == " 5.00000000E-01;-1.25000000E-03; 1.00000000E+10"
+    p = Params(dim=3, n_eqn=4, nu=1.0e-2, c0=10.0)
+    p.penalization, p.C_eta = True, 1.0e-3
+    names = ("meanflow_x", "meanflow_y", "meanflow_z", "e_kin", "ACM_energy", "mask_volume", "sponge_volume", "penal_power_solid_input",
+             "penal_power_solid_dissipation", "penal_power_sponge", "force_x", "force_y", "force_z", "umag", "div_max", "div_min", "u_residual_x",
+             "u_residual_y", "u_residual_z", "enstrophy", "max_vort", "helicity", "dissipation")
+    stats = {k: float(i + 1) for i, k in enumerate(names)}
+    for t in (0.0, 0.1):
+        tfiles.write_statistics_acm(stats, t, 1.0e-3, p, 0.05, str(tmp_path))
+    files = sorted(f.name for f in tmp_path.iterdir())
+    assert files == sorted(["umag.t", "CFL.t", "meanflow.t", "div.t", "forces.t", "mask_volume.t", "penal_power.t", "u_residual.t", "e_kin.t",
+                            "enstrophy.t", "helicity.t", "dissipation.t"])
+    rows = (tmp_path / "enstrophy.t").read_text().splitlines()
+    assert rows == [" 0.00000000E+00; 2.00000000E+01; 2.10000000E+01", " 1.00000000E-01; 2.00000000E+01; 2.10000000E+01"]
+    umag = [float(x) for x in (tmp_path / "umag.t").read_text().splitlines()[0].split(";")]
+    assert umag[1] == np.sqrt(14.0).round(8) or abs(umag[1] - np.sqrt(14.0)) < 1e-8
+    assert abs(umag[4] - (np.sqrt(14.0) + np.sqrt(100.0 + 14.0))) < 1e-7
+    cfl = [float(x) for x in (tmp_path / "CFL.t").read_text().splitlines()[0].split(";")]
+    assert abs(cfl[2] - 1.0e-3 * 1.0e-2 / 0.05 ** 2) < 1e-10 and abs(cfl[3] - 1.0) < 1e-8
+    assert tfiles.statistics_due(10, 0.33, 5, 9999999.9) and not tfiles.statistics_due(11, 0.33, 5, 9999999.9)
+    assert tfiles.statistics_due(11, 0.4, 99999999, 0.2) and not tfiles.statistics_due(11, 0.41, 99999999, 0.2)

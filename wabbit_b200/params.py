@@ -148,6 +148,7 @@ class Params:
     write_time: float = 1.0
     write_time_first: float = 0.0
     tsave_stats: float = 9999999.9
+    nsave_stats: int = 99999999                           # [Statistics] nsave_stats (ini_file_to_params.f90:188)
     butcher: List[List[float]] = field(default_factory=lambda: [r[:] for r in BUTCHER_RK4])
     time_step_method: str = "RungeKuttaGeneric"          # or "RungeKuttaChebychev" (timeStep_tree.f90:26-58)
     rkc_s: int = 4                                        # [Time] s: stages of the Chebychev scheme
@@ -258,6 +259,7 @@ class Params:
         p.write_time = ini.real("Time", "write_time", 1.0)
         p.write_time_first = ini.real("Time", "write_time_first", 0.0)
         p.tsave_stats = ini.real("Statistics", "tsave_stats", 9999999.9)
+        p.nsave_stats = ini.integer("Statistics", "nsave_stats", 99999999)
         p.butcher = ini.matrix("Time", "butcher_tableau", [r[:] for r in BUTCHER_RK4])
         p.time_step_method = ini.string("Time", "time_step_method", "RungeKuttaGeneric")       # ini_file_to_params.f90:592
         p.rkc_s = ini.integer("Time", "s", 4)                                                  # :627

@@ -136,10 +136,30 @@ class AdaptiveLoop:
             it += 1
         return it
 
+    stats_dir: Optional[str] = None      # where the *.t files go; None: no statistics
+
+    def statistics(self, dt: float) -> Optional[dict]:
+        """main.f90:388-397: statistics_wrapper every nsave_stats iterations / tsave_stats time units, after the time step and before the grid
+        is coarsened; the rows go to the *.t files of `stats_dir` (wabbit_b200.tfiles)"""
+        from . import tfiles
+        p = self.sol.params
+        if self.stats_dir is None or not tfiles.statistics_due(self.iteration, self.time, p.nsave_stats, p.tsave_stats):
+            return None
+        if self.mask is not None and getattr(self.mask, "analytic", False):
+            self.mask.fill_device(self.sol, self.time)       # the statistics kernel reads hvy_mask; the stage kernel does not need it
+        else:
+            self.createMask_tree()
+        stats = self.sol.statistics_ACM(self.time, with_divergence=True, with_vorticity=True)
+        _, lvl, _, _ = self.forest.active(0)
+        dx_min = min(2.0 ** (-int(np.max(lvl))) * p.domain[d] / float(p.Bs[d]) for d in range(p.dim))
+        tfiles.write_statistics_acm(stats, self.time, dt, p, dx_min, self.stats_dir)
+        return stats
+
     def step(self) -> float:
         nb_rhs = self.refine_tree()
         self.createMask_tree()
         self.time, self.iteration, dt = self.sol.timeStep_tree(self.time, self.iteration)
+        self.statistics(dt)
         self.adapt_tree()
         self.log.append((self.iteration, self.time, nb_rhs, self.forest.n_blocks, dt))
         return dt
