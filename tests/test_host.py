@@ -658,3 +658,14 @@ def test_t_files_have_the_reference_row_format(tmp_path):
     assert abs(cfl[2] - 1.0e-3 * 1.0e-2 / 0.05 ** 2) < 1e-10 and abs(cfl[3] - 1.0) < 1e-8
     assert tfiles.statistics_due(10, 0.33, 5, 9999999.9) and not tfiles.statistics_due(11, 0.33, 5, 9999999.9)
     assert tfiles.statistics_due(11, 0.4, 99999999, 0.2) and not tfiles.statistics_due(11, 0.41, 99999999, 0.2)
+
+
+def test_is_it_time_to_save_data():
+    """LIB/IO/save_data.f90:255-288 (the filter also runs right before data are saved, main.f90:370)"""
+    p = Params(write_method="fixed_freq")
+    p.write_freq = 4
+    assert p.is_it_time_to_save_data(0.3, 8) and not p.is_it_time_to_save_data(0.3, 9)
+    q = Params(write_method="fixed_time", write_time=0.5)
+    assert q.is_it_time_to_save_data(1.5, 7) and q.is_it_time_to_save_data(0.5 - 1e-14, 7) and not q.is_it_time_to_save_data(0.7, 7)
+    q.write_time_first = 1.0
+    assert not q.is_it_time_to_save_data(0.5, 7) and q.is_it_time_to_save_data(1.0, 7)

@@ -147,6 +147,7 @@ class Params:
     write_method: str = "fixed_freq"
     write_time: float = 1.0
     write_time_first: float = 0.0
+    write_freq: int = 25                                  # [Time] write_freq (write_method = fixed_freq)
     tsave_stats: float = 9999999.9
     nsave_stats: int = 99999999                           # [Statistics] nsave_stats (ini_file_to_params.f90:188)
     butcher: List[List[float]] = field(default_factory=lambda: [r[:] for r in BUTCHER_RK4])
@@ -200,6 +201,17 @@ class Params:
     @property
     def n_stages(self) -> int:
         return len(self.butcher) - 1
+
+    def is_it_time_to_save_data(self, time: float, iteration: int) -> bool:
+        """is_it_time_to_save_data (LIB/IO/save_data.f90:255-288) without the wall-clock clause"""
+        import math
+        due = False
+        if self.write_method == "fixed_freq":
+            due = self.write_freq > 0 and iteration % self.write_freq == 0
+        elif self.write_method == "fixed_time":
+            m = math.fmod(time, self.write_time)
+            due = abs(m) < 1.0e-12 or abs(m - self.write_time) < 1.0e-12
+        return due and not time + 1.0e-12 < self.write_time_first
 
     def rkc_coefficients(self):
         """rows s of mu, mu_tilde, nu, gamma_tilde, c for RungeKuttaChebychev.  The tabulated schemes live in the reference's Fortran
@@ -258,6 +270,7 @@ class Params:
         p.write_method = ini.string("Time", "write_method", "fixed_freq")
         p.write_time = ini.real("Time", "write_time", 1.0)
         p.write_time_first = ini.real("Time", "write_time_first", 0.0)
+        p.write_freq = ini.integer("Time", "write_freq", 25)
         p.tsave_stats = ini.real("Statistics", "tsave_stats", 9999999.9)
         p.nsave_stats = ini.integer("Statistics", "nsave_stats", 99999999)
         p.butcher = ini.matrix("Time", "butcher_tableau", [r[:] for r in BUTCHER_RK4])

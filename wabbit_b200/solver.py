@@ -507,7 +507,7 @@ class WabbitGPU:
         return new, n0, new.n_blocks
 
     def timeStep_tree(self, time: float, iteration: int):
-        """timeStep_tree.f90:1-60 -- dispatch on time_step_method, then filter_wrapper every filter_freq iterations (main.f90:370-373); returns
+        """timeStep_tree.f90:1-60 -- dispatch on time_step_method, then filter_wrapper every filter_freq iterations and before data are saved (main.f90:368-374); returns
         (time+dt, iteration+1, dt)."""
         p = self.params
         method = p.time_step_method.strip().lower()
@@ -520,6 +520,6 @@ class WabbitGPU:
         else:
             raise WabbitAbort(19101816, "time_step_method is unkown: " + p.time_step_method)
         iteration += 1
-        if p.filter_type != "no_filter" and p.filter_freq > 0 and iteration % p.filter_freq == 0:
+        if p.filter_type != "no_filter" and ((p.filter_freq > 0 and iteration % p.filter_freq == 0) or p.is_it_time_to_save_data(time + dt, iteration)):
             self.filter_wrapper(p.filter_type, p.filter_component or None, p.filter_only_maxlevel, p.filter_all_except_maxlevel)
         return time + dt, iteration, dt
