@@ -598,8 +598,62 @@ def _relations(dim: int):
 
 
 def neighbor_table168(grid: Grid, Jmax: int, periodic=(1, 1, 1)) -> np.ndarray:
-    """hvy_neighbor[168, nb] (1-based block ids, -1 none) of a leaf grid on one rank -- an independent NumPy restatement
-    of find_neighbor (LIB/MESH/find_neighbors.f90:18-180): same level, else finer (+112), else coarser (+56)."""
+    """hvy_neighbor[168, nb] (1-based block ids, -1 none) of a leaf grid on one rank -- find_neighbor (LIB/MESH/find_neighbors.f90:18-180) for
+    all blocks at once: same level, else finer (+112), else coarser (+56).  Lookups by binary search in the sorted (level, ix, iy, iz) keys."""
+    dim, n = grid.dim, grid.n
+    if n < 64:                                     # a handful of blocks: the block loop is quicker than 26 vector passes
+        return neighbor_table168_loop(grid, Jmax, periodic)
+    out = np.full((168, n), -1, dtype=np.int32)
+    vary = (2, 1, 4)
+    J = grid.level.astype(np.int64)
+    ix = grid.ixyz.astype(np.int64)
+    key = lambda lv, x, y, z: (lv << 60) | (x << 40) | (y << 20) | z          # noqa: E731  (levels < 8, coordinates < 2^20)
+    keys = key(J, ix[:, 0], ix[:, 1], ix[:, 2])
+    order = np.argsort(keys, kind="stable")
+    skeys = keys[order]
+
+    def look(lv, q):
+        k = key(lv, q[0], q[1], q[2])
+        pos = np.minimum(np.searchsorted(skeys, k), n - 1)
+        return np.where(skeys[pos] == k, order[pos], -1)
+    N = np.int64(1) << J
+    tc_last = np.where(J > 0, sum(vary[a] * (ix[:, a] & 1) for a in range(dim)), 0)
+    cols = np.arange(n)
+    zero = np.zeros(n, dtype=np.int64)
+    for d, code, nfree, append in _relations(dim):
+        p = [ix[:, a] + d[a] if a < dim else zero for a in range(3)]
+        ok = np.ones(n, dtype=bool)
+        for a in range(dim):
+            if not periodic[a]:
+                ok &= (p[a] >= 0) & (p[a] < N)
+        p = [p[a] % N if a < dim else zero for a in range(3)]
+        same = np.where(ok, look(J, p), -1)
+        hit = same >= 0
+        out[code - 1, cols[hit]] = same[hit] + 1
+        todo = ok & ~hit
+        found = np.zeros(n, dtype=bool)
+        alive = todo & (J < Jmax)
+        for k in range(nfree):
+            if not alive.any():
+                break
+            q = [((2 * ix[:, a] + (1 if append[k] & vary[a] else 0) + d[a]) % (2 * N)) if a < dim else zero for a in range(3)]
+            fin = np.where(alive, look(J + 1, q), -1)
+            alive = alive & (fin >= 0)                      # the reference stops at the first missing finer neighbour
+            out[code - 1 + k + 112, cols[alive]] = fin[alive] + 1
+            found |= alive
+        rest = todo & ~found & (J > 0)
+        if rest.any():
+            crs = look(J - 1, [p[0] >> 1, p[1] >> 1, p[2] >> 1])
+            for k in range(nfree):
+                m = rest & (tc_last == append[k]) & (crs >= 0)
+                out[code - 1 + k + 56, cols[m]] = crs[m] + 1
+    return out
+
+
+def neighbor_table168_loop(grid: Grid, Jmax: int, periodic=(1, 1, 1)) -> np.ndarray:
+    """hvy_neighbor[168, nb] (1-based block ids, -1 none) of a leaf grid on one rank -- an independent restatement of find_neighbor
+    (LIB/MESH/find_neighbors.f90:18-180), block by block: same level, else finer (+112), else coarser (+56).  neighbor_table168 is the same
+    search for all blocks at once (tests/test_oracle_tree.py compares the two)."""
     dim = grid.dim
     look = grid.lookup()
     out = np.full((168, grid.n), -1, dtype=np.int32)

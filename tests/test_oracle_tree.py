@@ -28,3 +28,19 @@ def test_c_tree_loops_equal_numpy_loops():
     O.rk_step_c(grid, p, u2, w2, t, nbr, dxb, fast=False)
     O.rk_step_c(grid, p, u3, w2, t, nbr, dxb, fast=True)
     assert np.abs(u2 - u3).max() < 1e-12
+
+
+def test_neighbour_table_for_all_blocks_at_once_equals_the_block_loop():
+    """oracle.neighbor_table168 (sorted keys + binary search) against the block-by-block restatement of find_neighbor, on graded 2-D / 3-D
+    grids, with Jmax at and above the finest level present, periodic and not"""
+    import numpy as np
+    import oracle as O
+    from util import graded_blocks
+    for dim, J0, Jm, seed in [(2, 1, 4, 1), (3, 1, 3, 2), (2, 2, 5, 7), (3, 1, 2, 9)]:
+        lv, ix = graded_blocks(dim, J0, Jm, seed)
+        g = O.Grid(level=lv.astype(np.int64), ixyz=ix.astype(np.int64), dim=dim)
+        for Jmax in (int(lv.max()), int(lv.max()) + 3):
+            for per in ((1, 1, 1), (0, 1, 0)):
+                assert np.array_equal(O.neighbor_table168(g, Jmax, per), O.neighbor_table168_loop(g, Jmax, per)), (dim, seed, Jmax, per)
+    for g, J in ((O.uniform_grid(0, 3), 3), (O.uniform_grid(2, 2), 2)):
+        assert np.array_equal(O.neighbor_table168(g, J), O.neighbor_table168_loop(g, J))
