@@ -87,9 +87,11 @@ typedef struct wgpu_ctx wgpu_ctx;
 /* ---- lifecycle: replaces allocate_forest (LIB/MESH/allocate_forest.f90:1) for the device copies ---- */
 int32_t wgpu_create(const wgpu_config *cfg, wgpu_ctx **out);
 int32_t wgpu_destroy(wgpu_ctx *ctx);
-/* copies the last error message of `ctx` (or of a failed wgpu_create if ctx == NULL) into buf */
+/* wgpu_last_error: copies the last error message of `ctx` (or of a failed wgpu_create if ctx == NULL) into buf -- the text the reference passes
+ * to abort(code, msg) (LIB/MODULE/module_globals.f90:131-150); the library returns the code instead of stopping the program */
 int32_t wgpu_last_error(const wgpu_ctx *ctx, char *buf, int32_t len);
-/* all work of this context is issued on `cuda_stream` (a cudaStream_t); NULL = default stream */
+/* wgpu_set_stream / wgpu_synchronize (no reference counterpart): all work of this context is issued on `cuda_stream` (a cudaStream_t);
+ * NULL = default stream */
 int32_t wgpu_set_stream(wgpu_ctx *ctx, void *cuda_stream);
 int32_t wgpu_synchronize(wgpu_ctx *ctx);
 
@@ -443,17 +445,19 @@ int32_t wgpu_expm_pade(const double *H, int32_t m, double *E);
  */
 int32_t wgpu_filter(wgpu_ctx *ctx, const char *filter_type, const int32_t *filter_component, int32_t only_maxlevel, int32_t all_except_maxlevel);
 
-/* Stage-kernel timing with CUDA events on the context's stream (for the roofline line of bench.py):
+/* Stage-kernel timing with CUDA events on the context's stream (for the roofline line of bench.py; the reference times the same region on the
+ * host with toc("timestep (RHS wrapper)"), LIB/TIMING/module_timing.f90:76, runge_kutta_generic.f90:71-73, 125-127):
  * wgpu_profile(ctx, 1) starts recording an event pair around every stage-kernel launch (at most 4096 pairs),
  * wgpu_profile_read synchronises, returns their number and summed duration in milliseconds, and resets. */
 int32_t wgpu_profile(wgpu_ctx *ctx, int32_t enable);
 int32_t wgpu_profile_read(wgpu_ctx *ctx, int32_t *n_launches, double *total_ms);
 
-/* number of kernels launched by this context since creation (bench.py's gpu_launches) */
+/* wgpu_launch_count (no reference counterpart): number of kernels launched by this context since creation (bench.py's gpu_launches) */
 int64_t wgpu_launch_count(const wgpu_ctx *ctx);
-/* bytes of device memory held by the context */
+/* wgpu_device_bytes: bytes of device memory held by the context (the reference prints its heavy-data footprint in allocate_forest.f90:228-267) */
 int64_t wgpu_device_bytes(const wgpu_ctx *ctx);
-/* raw device pointer + element count of a resident array (for zero-copy interop, e.g. NCCL via torch) */
+/* wgpu_device_pointer (no reference counterpart): raw device pointer + element count of a resident array (for zero-copy interop, e.g. NCCL
+ * via torch) */
 int32_t wgpu_device_pointer(wgpu_ctx *ctx, int32_t array_id, int32_t slot, void **ptr, int64_t *n_doubles);
 
 #ifdef __cplusplus
