@@ -1,5 +1,5 @@
-"""The reference's 2-D adaptive regression case TESTING/acm/3vortices/3vorticesAdaptFD4_CDF4{0,2} (PARAMS_3vortices.ini), shared by the
-oracle pin (test_oracle_adaptive.py) and the GPU run (test_gpu_adaptive2d.py).
+"""The reference's 2-D adaptive regression cases TESTING/acm/3vortices/3vorticesAdaptFD{2,4,6}_CDF{20,22,40,42,60,62} (PARAMS_3vortices.ini),
+shared by the oracle pin (test_oracle_adaptive.py: all six) and the GPU run (test_gpu_adaptive2d.py: FD4_CDF40 / FD4_CDF42).
 
   restart from {ux,uy,p}_000010000000.h5 (64 blocks of 32^2 on level 3, t = 10, iteration 3054)
   adapt_inicond = 1 -> one adapt_tree;  then main.f90's loop (sync -> refine_tree("significant") -> RK4 -> adapt_tree) to t = 15
@@ -25,8 +25,25 @@ def restart_fields():
     return inp["level"].astype(np.int64), ixyz, inp["u"], float(inp["time"][0]), int(inp["iteration"][0])
 
 
-def gold(wavelet: str):
-    return np.load(os.path.join(GOLD, f"three_vortices_adapt_FD4_{wavelet}.npz"))
+# every adaptive 3vortices case of the reference: directory 3vorticesAdapt<key>, (wavelet, order_discretization); the parameter files differ in
+# these two entries only.  g = the wavelet's ghost nodes (setup_wavelet), g_rhs = the stencil half width.
+CASES = {"FD4_CDF40": ("CDF40", "FD_4th_central"), "FD4_CDF42": ("CDF42", "FD_4th_central"), "FD2_CDF20": ("CDF20", "FD_2nd_central"),
+         "FD2_CDF22": ("CDF22", "FD_2nd_central"), "FD6_CDF60": ("CDF60", "FD_6th_central"), "FD6_CDF62": ("CDF62", "FD_6th_central")}
+FD_HALF_WIDTH = {"FD_2nd_central": 1, "FD_4th_central": 2, "FD_6th_central": 3}
+CASE_G = {"FD4_CDF40": 3, "FD4_CDF42": 4, "FD2_CDF20": 1, "FD2_CDF22": 2, "FD6_CDF60": 5, "FD6_CDF62": 6}
+
+
+def case_ini(case: str) -> dict:
+    ini = dict(INI)
+    ini["discretization"] = CASES[case][1]
+    ini["g_rhs"] = FD_HALF_WIDTH[CASES[case][1]]
+    return ini
+
+
+def gold(name: str):
+    """the stored files of a case ("FD2_CDF22", ...; a bare wavelet name means the FD4 case)"""
+    case = name if name in CASES else "FD4_" + name
+    return np.load(os.path.join(GOLD, f"three_vortices_adapt_{case}.npz"))
 
 
 def compare(gd, key: str, level, ixyz, status, interiors, iteration=None, time=None):

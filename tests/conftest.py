@@ -73,8 +73,8 @@ def pytest_collection_finish(session):
     _BG["pool"] = cf.ProcessPoolExecutor(max_workers=7, mp_context=mp.get_context("spawn"))
     if want_adaptive:
         import test_oracle_adaptive as TA
-        for w in ("CDF40", "CDF42"):
-            _BG["futures"][("adaptive", w)] = _BG["pool"].submit(TA._full_run, w)
+        for c in TA.full_run_cases():
+            _BG["futures"][("adaptive", c)] = _BG["pool"].submit(TA._full_run, c)
     if want_cylinder:
         import cylinder_case as CC
         import test_oracle_cylinder as TC

@@ -161,14 +161,16 @@ def three_vortices():
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# TESTING/acm/3vortices/3vorticesAdaptFD4_CDF4{0,2}: the same restart, adaptive (eps = 1e-3, Jmin 1, Jmax 4, refinement
+# TESTING/acm/3vortices/3vorticesAdaptFD{2,4,6}_CDF{20,22,40,42,60,62} (the parameter files differ in wavelet and order_discretization only):
+# the same restart, adaptive (eps = 1e-3, Jmin 1, Jmax 4, refinement
 # indicator "significant", coarse extension and security zone on, c_0 = 5): the stored grid after adapt_inicond (t = 10) and
 # after 2281 adaptive steps (t = 15).  Per file: block levels, zero-based block coordinates, the stored refinement status of
 # every block (0 significant / 9 REF_UNSIGNIFICANT_STAY), iteration, time; the fields in full at t = 10 (25 blocks) and as strided
 # samples at t = 15.
-def three_vortices_adaptive():
+def three_vortices_adaptive(cases=("3vorticesAdaptFD4_CDF40", "3vorticesAdaptFD4_CDF42", "3vorticesAdaptFD2_CDF20", "3vorticesAdaptFD2_CDF22",
+                                   "3vorticesAdaptFD6_CDF60", "3vorticesAdaptFD6_CDF62")):
     R = "/root/reference/TESTING/acm/3vortices"
-    for case in ("3vorticesAdaptFD4_CDF40", "3vorticesAdaptFD4_CDF42"):
+    for case in cases:
         o = {}
         for tag, key, stride in (("000010000000", "t10", 1), ("000015000000", "t15", 2)):
             fields = []
