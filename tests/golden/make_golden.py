@@ -260,3 +260,39 @@ def rkc_tables(stages=(4, 6, 10, 20)):
 
 if __name__ == "__main__":
     rkc_tables()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# TESTING/wavelets, whole files (runtests.py, group "adaptive"): vor_000020000000.h5 (2-D, Bs = 32, 112 blocks on levels 2-5, one
+# component) --wabbit-post --refine-everywhere--> adaptive_CDFX0/vor_00100.h5 (448 blocks) --wabbit-post --coarsen-everywhere-->
+# adaptive_CDFXY/vor_00200.h5 (112 blocks) for the seven wavelets CDF20 / 22 / 40 / 42 / 44 / 60 / 62 (sparse_to_dense.f90:183-235:
+# sync_ghosts_tree, refine_tree("everywhere") resp. adapt_tree("everywhere"), useCoarseExtension = useSecurityZone = isLiftedWavelet).
+# wavelet_files.npz: the input in full; of every output the block list, strided samples (every 4th / 2nd point) and, for the refined
+# files, the SHA-256 of the float64 interiors in (level, ix, iy) order -- the oracle reproduces those bit for bit.
+def wavelet_files():
+    import hashlib
+    W = "/root/reference/TESTING/wavelets"
+
+    def load(path):
+        d = read_wabbit(path)
+        Bs, level, ixy = _grid(d)
+        order = np.lexsort((ixy[:, 1], ixy[:, 0], level))
+        return Bs, level[order], ixy[order], np.ascontiguousarray(d["blocks"][order][:, :Bs, :Bs])
+    Bs, lv, ix, blk = load(os.path.join(W, "vor_000020000000.h5"))
+    out = {"Bs": np.array([Bs]), "in_level": lv, "in_ixy": ix, "in_blocks": blk}
+    for X in (2, 4, 6):
+        _, lv1, ix1, b1 = load(os.path.join(W, f"adaptive_CDF{X}0", "vor_00100.h5"))
+        out[f"refined_X{X}_level"], out[f"refined_X{X}_ixy"] = lv1, ix1
+        out[f"refined_X{X}_sample"] = b1[:, ::4, ::4]
+        out[f"refined_X{X}_sha256"] = np.frombuffer(hashlib.sha256(b1.astype("<f8").tobytes()).digest(), dtype=np.uint8)
+    for w in ("CDF20", "CDF22", "CDF40", "CDF42", "CDF44", "CDF60", "CDF62"):
+        _, lv2, ix2, b2 = load(os.path.join(W, f"adaptive_{w}", "vor_00200.h5"))
+        out[f"coarsened_{w}_level"], out[f"coarsened_{w}_ixy"] = lv2, ix2
+        out[f"coarsened_{w}_sample"] = b2[:, ::2, ::2]
+    path = os.path.join(HERE, "wavelet_files.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path))
+
+
+if __name__ == "__main__":
+    wavelet_files()
