@@ -942,6 +942,32 @@ def _fd_sum(comp: np.ndarray, I, ax: int, H: int, coef) -> np.ndarray:
     return acc
 
 
+def vorticity_block(p: Params, u: np.ndarray, dx) -> list:
+    """compute_vorticity (LIB/OPERATORS/compute_vorticity.f90:3-67) on the interior of one ghost-synchronised block u[c, z, y, x]:
+    [v_dx - u_dy] in 2-D, [w_dy - v_dz, u_dz - w_dx, v_dx - u_dy] in 3-D.  Pinned bit for bit by the vor / vorabs files the reference saved
+    next to its regression fields (tests/test_oracle_derived_fields.py)."""
+    I = interior(p)
+    H1, a1 = FD1[p.discretization]
+    AX = {0: 2, 1: 1, 2: 0}                        # u[c, z, y, x]: x is the last axis
+    d1 = lambda c, d: _fd_sum(u[c], I, AX[d], H1, a1) * (1.0 / dx[d])          # noqa: E731
+    if p.dim == 2:
+        return [d1(1, 0) - d1(0, 1)]
+    return [d1(2, 1) - d1(1, 2), d1(0, 2) - d1(2, 0), d1(1, 0) - d1(0, 1)]
+
+
+def divergence_block(p: Params, u: np.ndarray, dx) -> np.ndarray:
+    """divergence (LIB/OPERATORS/divergence.f90) on the interior of one ghost-synchronised block: u_dx + v_dy (+ w_dz), the first-derivative
+    stencil of the discretization; pinned bit for bit by the div files of the reference's 3vortices cases"""
+    I = interior(p)
+    H1, a1 = FD1[p.discretization]
+    AX = {0: 2, 1: 1, 2: 0}
+    out = None
+    for d in range(p.dim):
+        t = _fd_sum(u[d], I, AX[d], H1, a1) * (1.0 / dx[d])
+        out = t if out is None else out + t
+    return out
+
+
 def vorticity_statistics_acm(grid: Grid, p: Params, hvy: np.ndarray) -> dict:
     """enstrophy, max_vort, helicity and dissipation of STATISTICS_ACM (statistics_ACM.f90:371-387): compute_vorticity (LIB/OPERATORS/
     compute_vorticity.f90:3-67) and compute_dissipation (compute_dissipation.f90:5-78) on the ghost-synchronised state with the module's
@@ -957,12 +983,10 @@ def vorticity_statistics_acm(grid: Grid, p: Params, hvy: np.ndarray) -> dict:
         dx = [2.0 ** (-float(grid.level[b])) * p.domain[d] / float(p.Bs[d]) for d in range(dim)]
         dV = float(np.prod(dx))
         u = hvy[b]
-        d1 = lambda c, d: _fd_sum(u[c], I, AX[d], H1, a1) * (1.0 / dx[d])          # noqa: E731
+        vor = vorticity_block(p, u, dx)
         if dim == 2:
-            vor = [d1(1, 0) - d1(0, 1)]                                              # v_dx - u_dy
             out["max_vort"] = max(out["max_vort"], float(np.abs(vor[0]).max()))
         else:
-            vor = [d1(2, 1) - d1(1, 2), d1(0, 2) - d1(2, 0), d1(1, 0) - d1(0, 1)]    # (w_dy - v_dz, u_dz - w_dx, v_dx - u_dy)
             out["max_vort"] = max(out["max_vort"], float(np.sqrt(vor[0] ** 2 + vor[1] ** 2 + vor[2] ** 2).max()))
             out["helicity"] += 0.5 * float(sum((vor[c] * u[c][I]).sum() for c in range(3))) * dV
         out["enstrophy"] += 0.5 * float(sum((v * v).sum() for v in vor)) * dV
@@ -1002,19 +1026,7 @@ def statistics_acm(grid: Grid, p: Params, hvy: np.ndarray, mask: Optional[np.nda
         out["e_kin"] += ek * dV
         out["ACM_energy"] += (0.5 * float((pr * pr).sum()) / p.c0 ** 2 + ek) * dV
         out["umag"] = max(out["umag"], float(sum(v * v for v in vel).max()))
-        div = np.zeros_like(pr)
-        for d in range(dim):
-            ax = {0: 2, 1: 1, 2: 0}[d]             # u[c, z, y, x]: x is the last axis (nz = 1 in 2-D)
-            comp = u[d]
-            acc = np.zeros_like(pr)
-            for k, coef in enumerate(a):
-                if coef == 0.0:
-                    continue
-                sl = list(I)
-                s0 = sl[ax]
-                sl[ax] = slice(s0.start + k - H, s0.stop + k - H)
-                acc = acc + coef * comp[tuple(sl)]
-            div = div + acc / dx[d]
+        div = divergence_block(p, u, dx)
         if mask is not None:
             chi = mask[b][0][I]
             div = np.where(chi > 0.0, 0.0, div)

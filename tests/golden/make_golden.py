@@ -188,6 +188,18 @@ def three_vortices_adaptive(cases=("3vorticesAdaptFD4_CDF40", "3vorticesAdaptFD4
                 o[f"{key}_time"] = d["attrs"]["time"]
             o[f"{key}_u"] = np.stack(fields, axis=1)
             o[f"{key}_stride"] = np.array([stride])
+            # the derived fields the reference saved with the state (field_names vor, div: compute_vorticity / divergence with the case's
+            # stencils on the synchronised state, PREPARE_SAVE_DATA_ACM): every 2nd point; at t = 15 together with the full velocity of the
+            # two cases FD4_CDF42 / FD6_CDF62 (the strided samples above cannot be differentiated)
+            for name in ("vor", "div"):
+                d = read_wabbit(os.path.join(R, case, f"{name}_{tag}.h5"))
+                o[f"{key}_{name}"] = d["blocks"][order][:, :Bs:2, :Bs:2]
+            if key == "t15" and case in ("3vorticesAdaptFD4_CDF42", "3vorticesAdaptFD6_CDF62"):
+                full = []
+                for name in ("ux", "uy"):
+                    d = read_wabbit(os.path.join(R, case, f"{name}_{tag}.h5"))
+                    full.append(d["blocks"][order][:, :Bs, :Bs])
+                o["t15_velocity"] = np.stack(full, axis=1)
         path = os.path.join(HERE, case.replace("3vorticesAdapt", "three_vortices_adapt_") + ".npz")
         np.savez_compressed(path, **o)
         print(path, os.path.getsize(path), o["t10_u"].shape, o["t15_u"].shape, o["t15_iteration"])
@@ -296,3 +308,39 @@ def wavelet_files():
 
 if __name__ == "__main__":
     wavelet_files()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# TESTING/acm/bumblebeeFlowEquiFD4_CDF40 (3-D, Bs = 26, level 1 = 8 blocks, periodic, FD_4th_central): the reference saved |vorticity|
+# (field "vorabs": compute_vorticity_abs, LIB/OPERATORS/compute_vorticity.f90:70-123) next to ux, uy, uz.  The flow itself needs the insect
+# module, but the derived field is a golden vector for the vorticity operator: vorabs_3d.npz holds, at t = 2, two blocks' velocity with a
+# two-point halo taken from their (periodic) neighbours and the reference's vorabs of those blocks.
+def vorabs_3d():
+    Bd = "/root/reference/TESTING/acm/bumblebeeFlowEquiFD4_CDF40"
+    tag, H = "000002000000", 2
+
+    def load(name):
+        d = read_wabbit(os.path.join(Bd, f"{name}_{tag}.h5"))
+        Bs = int(d["attrs"]["block-size"][0])
+        ixyz = np.rint(d["origin"][:, ::-1] / (d["spacing"][:, ::-1] * Bs)).astype(np.int64)
+        return Bs, {tuple(int(v) for v in x): d["blocks"][k][:Bs, :Bs, :Bs] for k, x in enumerate(ixyz)}, float(d["spacing"][0, 0])
+    Bs, ux, dx = load("ux")
+    _, uy, _ = load("uy")
+    _, uz, _ = load("uz")
+    _, va, _ = load("vorabs")
+    out = {"Bs": np.array([Bs]), "H": np.array([H]), "dx": np.array([dx])}
+    for j, blk in enumerate(((0, 0, 0), (1, 0, 1))):
+        comp = []
+        for f in (ux, uy, uz):
+            big = np.block([[[f[((blk[0] + ax) % 2, (blk[1] + ay) % 2, (blk[2] + az) % 2)] for ax in (-1, 0, 1)] for ay in (-1, 0, 1)]
+                            for az in (-1, 0, 1)])                      # [z, y, x]
+            comp.append(big[Bs - H:2 * Bs + H, Bs - H:2 * Bs + H, Bs - H:2 * Bs + H])
+        out[f"u{j}"] = np.stack(comp)
+        out[f"vorabs{j}"] = va[blk]
+    path = os.path.join(HERE, "vorabs_3d.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), float(out["vorabs0"].max()))
+
+
+if __name__ == "__main__":
+    vorabs_3d()
