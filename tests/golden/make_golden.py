@@ -344,3 +344,29 @@ def vorabs_3d():
 
 if __name__ == "__main__":
     vorabs_3d()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# TESTING/acm/3vortices/3vorticesEqui*/log.original.txt: the reference's own log of the equidistant runs, one line per time step
+# ("RUN: it= 3055 time= 10.003239697 ... dt= 3.2E-03"): the time after every one of the 3073 steps to nine decimals -- a golden vector
+# for calculate_time_step along the whole run.  three_vortices_log_times.npz: iteration and time per step and case.
+def three_vortices_logs():
+    import re
+    R = "/root/reference/TESTING/acm/3vortices"
+    out = {}
+    for case in ("FD2_CDF20", "FD4_CDF40", "FD6_CDF60"):
+        it, tm = [], []
+        for line in open(os.path.join(R, f"3vorticesEqui{case}", "log.original.txt"), errors="replace"):
+            m = re.match(r"RUN: it=\s*(\d+) time=\s*([0-9.]+) ", line)
+            if m:
+                it.append(int(m.group(1)))
+                tm.append(float(m.group(2)))
+        out[f"{case}_iteration"], out[f"{case}_time"] = np.array(it, dtype=np.int64), np.array(tm)
+        print(case, len(it), it[0], it[-1], tm[-1])
+    path = os.path.join(HERE, "three_vortices_log_times.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path))
+
+
+if __name__ == "__main__":
+    three_vortices_logs()

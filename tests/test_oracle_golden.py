@@ -95,11 +95,18 @@ def test_three_vortices_2d_fixture(case):
     p, grid, u, t, it = three_vortices_setup(case)
     nbr, dxb = O.nbr_table(grid), O.dx_table(grid, p)
     work = np.zeros((5,) + u.shape)
+    times = []
     while t < p.time_max:
         t += O.rk_step_c(grid, p, u, work, t, nbr, dxb)
         it += 1
+        times.append(t)
     assert it == int(gold["iteration"][0])
     assert t == float(gold["time"][0])
+    # the reference's own log of this run (log.original.txt: "RUN: it= .. time= 10.003239697 ..") -- the time after EVERY step, printed to
+    # nine decimals: calculate_time_step is pinned along the whole run, not only by the final iteration counter
+    log = np.load(os.path.join(GOLD, "three_vortices_log_times.npz"))
+    assert len(times) == len(log[f"{case}_time"]) and int(log[f"{case}_iteration"][-1]) == it
+    assert np.abs(np.array(times) - log[f"{case}_time"]).max() <= 5.0e-10 + 1e-13
     s, g = int(gold["stride"][0]), p.g
     order = {tuple(v): k for k, v in enumerate(grid.ixyz[:, :2])}
     got = np.stack([u[order[tuple(v)], :, 0, g:g + 32:s, g:g + 32:s] for v in gold["ixy"]])
