@@ -71,3 +71,29 @@ def test_refine_then_coarsen_everywhere_reproduces_the_reference_files(wavelet):
     assert coarse.shape[0] == 112 and sorted(_keys(gc.level, gc.ixyz)) == sorted(_keys(G["in_level"], G["in_ixy"]))     # the input grid is back
     err = float(np.abs(coarse[:, ::2, ::2] - G[f"coarsened_{wavelet}_sample"]).max())
     assert err <= (4.0e-15 if w.lifted else 0.0), err
+
+
+# what the reference printed when it set up the wavelets of its equidistant 3vortices runs (TESTING/acm/3vortices/3vorticesEqui*/
+# log.original.txt:131-141 -- "Increased Nwc to consider FD-stencil size", "Coarse extension will copy SC / delete WC (L,R)", the filters)
+SETUP_LOG = {
+    ("CDF20", 1): dict(Nsc=(0, 0), Nwc=(2, 2), GD=(-1, [-5.0e-1, 1.0, -5.0e-1]), HR=(-1, [5.0e-1, 1.0, 5.0e-1])),
+    ("CDF40", 2): dict(Nsc=(0, 0), Nwc=(4, 4), GD=(-3, [6.25e-2, 0.0, -5.625e-1, 1.0, -5.625e-1, 0.0, 6.25e-2]),
+                       HR=(-3, [-6.25e-2, 0.0, 5.625e-1, 1.0, 5.625e-1, 0.0, -6.25e-2])),
+    ("CDF60", 3): dict(Nsc=(0, 0), Nwc=(6, 6),
+                       GD=(-5, [-1.1719e-2, 0.0, 9.7656e-2, 0.0, -5.8594e-1, 1.0, -5.8594e-1, 0.0, 9.7656e-2, 0.0, -1.1719e-2]),
+                       HR=(-5, [1.1719e-2, 0.0, -9.7656e-2, 0.0, 5.8594e-1, 1.0, 5.8594e-1, 0.0, -9.7656e-2, 0.0, 1.1719e-2])),
+}
+
+
+@pytest.mark.parametrize("wavelet,fd_half", list(SETUP_LOG))
+def test_wavelet_setup_matches_what_the_reference_logged(wavelet, fd_half):
+    w, ref = O.setup_wavelet(wavelet), SETUP_LOG[(wavelet, fd_half)]
+    assert (w.Nscl, w.Nscr) == ref["Nsc"]
+    assert (max(w.Nwcl, 2 * fd_half), max(w.Nwcr, 2 * fd_half)) == ref["Nwc"]          # the widening of module_wavelets.f90:1404-1417
+    F = (len(w.GD) - 1) // 2
+    for name, lo_hi in (("GD", (w.gd_lo, w.gd_hi)), ("HR", (w.hr_lo, w.hr_hi))):
+        lo, vals = ref[name]
+        assert lo_hi == (lo, -lo)
+        mine = [getattr(w, name)[k + F] for k in range(lo, -lo + 1)]
+        assert np.allclose(mine, vals, rtol=0.0, atol=5.1e-6)                           # printed with five significant digits
+    assert (w.hd_lo, w.hd_hi, w.HD[F]) == (0, 0, 1.0) and (w.gr_lo, w.gr_hi, w.GR[F]) == (0, 0, 1.0)
