@@ -57,3 +57,18 @@ def test_superviscosity_stencils_known_answers():
         assert abs(sum(c.values()) - 1.0) <= 1e-15 and c[0] > 0.5 and all(abs(c[k] - c[-k]) == 0.0 for k in c)
     with pytest.raises(ValueError):
         O.superviscosity_stencil("explicit_4pt")
+
+
+def test_closed_form_of_the_tabulated_scheme():
+    """wabbit_b200.params.rkc2_coefficients (what the Python mirror uses without RKC_custom_scheme): the damped second-order scheme of
+    Sommeijer, Shampine & Verwer with eps = 10 IS the reference's table (setup_RKC_coefficients) -- to 3e-15 on the sampled rows"""
+    import os
+    from wabbit_b200.params import rkc2_coefficients
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rkc_coefficients.npz"))
+    for s in (4, 6, 10, 20):
+        for name, mine in zip(("mu", "mu_tilde", "nu", "gamma_tilde", "c"), rkc2_coefficients(s)):
+            assert np.abs(mine - gold[f"s{s}_{name}"]).max() <= 3e-15, (s, name)
+    # consistency (order conditions of the scheme): c_s = 1, c_j increasing
+    for s in (5, 12, 33):
+        c = rkc2_coefficients(s)[4]
+        assert abs(c[-1] - 1.0) <= 1e-13 and np.all(np.diff(c[1:]) > 0.0)

@@ -109,6 +109,37 @@ def wavelet_ghosts(wavelet: str) -> Tuple[int, int, int, int]:
     return X, Y, X - 1 + max(Y - 1, 0), X // 2
 
 
+def rkc2_coefficients(s: int, eps: float = 10.0):
+    """mu, mu_tilde, nu, gamma_tilde, c (each of length s, entry j-1 for stage j) of the damped second-order Runge-Kutta-Chebychev scheme:
+    w0 = 1 + eps / s^2, w1 = T_s'(w0) / T_s''(w0), b_j = T_j''(w0) / T_j'(w0)^2 (b_0 = b_2, b_1 = 1 / w0), a_j = 1 - b_j T_j(w0),
+    mu_j = 2 b_j w0 / b_(j-1), nu_j = -b_j / b_(j-2), mu~_1 = b_1 w1, mu~_j = 2 b_j w1 / b_(j-1), gamma~_j = -a_(j-1) mu~_j,
+    c_1 = mu~_1, c_j = w1 T_j''(w0) / T_j'(w0)."""
+    if s < 2:
+        raise ValueError("runge-kutta-chebychev: s must be at least 2")
+    w0 = 1.0 + eps / float(s) ** 2
+    T, dT, ddT = [1.0, w0], [0.0, 1.0], [0.0, 0.0]
+    for k in range(2, s + 1):
+        T.append(2.0 * w0 * T[k - 1] - T[k - 2])
+        dT.append(2.0 * T[k - 1] + 2.0 * w0 * dT[k - 1] - dT[k - 2])
+        ddT.append(4.0 * dT[k - 1] + 2.0 * w0 * ddT[k - 1] - ddT[k - 2])
+    w1 = dT[s] / ddT[s]
+    b = [0.0] * (s + 1)
+    for j in range(2, s + 1):
+        b[j] = ddT[j] / dT[j] ** 2
+    b[0], b[1] = b[2], 1.0 / w0
+    a = [1.0 - b[j] * T[j] for j in range(s + 1)]
+    mu, mut, nu, gt, c = (np.zeros(s) for _ in range(5))
+    mut[0] = b[1] * w1
+    c[0] = mut[0]
+    for j in range(2, s + 1):
+        mu[j - 1] = 2.0 * b[j] * w0 / b[j - 1]
+        nu[j - 1] = -b[j] / b[j - 2]
+        mut[j - 1] = 2.0 * b[j] * w1 / b[j - 1]
+        gt[j - 1] = -a[j - 1] * mut[j - 1]
+        c[j - 1] = w1 * ddT[j] / dT[j]
+    return mu, mut, nu, gt, c
+
+
 @dataclass
 class Params:
     dim: int = 3
@@ -214,12 +245,13 @@ class Params:
         return due and not time + 1.0e-12 < self.write_time_first
 
     def rkc_coefficients(self):
-        """rows s of mu, mu_tilde, nu, gamma_tilde, c for RungeKuttaChebychev.  The tabulated schemes live in the reference's Fortran
-        (setup_RKC_coefficients, 4 400 lines of generated tables, passed to wgpu_rkc_step by the Fortran host); this mirror takes them from the
-        parameter file (RKC_custom_scheme = 1, the reference's own mechanism, ini_file_to_params.f90:629-636)."""
+        """rows s of mu, mu_tilde, nu, gamma_tilde, c for RungeKuttaChebychev: from the parameter file with RKC_custom_scheme = 1
+        (ini_file_to_params.f90:629-636), else the tabulated scheme of setup_RKC_coefficients (runge_kutta_chebychev.f90:180 ff) -- which is
+        the second-order Chebychev scheme of Sommeijer, Shampine & Verwer (RKC, 1998) with damping eps = 10, evaluated here in closed form;
+        it reproduces the reference's tables to 3e-15 (tests/test_oracle_rkc.py compares the sampled rows s = 4, 6, 10, 20).  A Fortran host
+        passes its own table rows to wgpu_rkc_step."""
         if not self.RKC_custom_scheme:
-            raise ValueError("RungeKuttaChebychev: give the coefficient rows with RKC_custom_scheme = 1 (RKC_mu, RKC_mu_tilde, RKC_nu, "
-                             "RKC_gamma_tilde, RKC_c in [Time])")
+            return rkc2_coefficients(self.rkc_s)
         rows = tuple(np.asarray(getattr(self, k), dtype=np.float64) for k in ("RKC_mu", "RKC_mu_tilde", "RKC_nu", "RKC_gamma_tilde", "RKC_c"))
         if any(len(r) != self.rkc_s for r in rows):
             raise ValueError(f"RungeKuttaChebychev: every coefficient row needs s = {self.rkc_s} values")
