@@ -670,3 +670,51 @@ def test_is_it_time_to_save_data():
     assert q.is_it_time_to_save_data(1.5, 7) and q.is_it_time_to_save_data(0.5 - 1e-14, 7) and not q.is_it_time_to_save_data(0.7, 7)
     q.write_time_first = 1.0
     assert not q.is_it_time_to_save_data(0.5, 7) and q.is_it_time_to_save_data(1.0, 7)
+
+
+def test_time_step_tree_dispatch_logic_without_a_device():
+    """WabbitGPU.timeStep_tree (timeStep_tree.f90:26-58, main.f90:368-374) driven with a stand-in for the device calls: which integrator runs,
+    when the filter runs (every filter_freq iterations, and right before data are saved), what an unknown method raises"""
+    from wabbit_b200 import WabbitAbort
+    from wabbit_b200.solver import WabbitGPU
+
+    class Fake:
+        def __init__(self, p):
+            self.params, self.calls = p, []
+
+        def RungeKuttaGeneric(self, t, it):
+            self.calls.append("rk")
+            return 0.25
+
+        def RungeKuttaChebychev(self, t, it, *rows):
+            assert len(rows) == 5 and all(len(r) == self.params.rkc_s for r in rows)
+            self.calls.append("rkc")
+            return 0.25
+
+        def krylov_time_stepper(self, t, it, M, dynamic, thr):
+            self.calls.append(("krylov", M, dynamic, thr))
+            return 0.25, M, 0.0
+
+        def filter_wrapper(self, ftype, comp, only, allbut):
+            self.calls.append(("filter", ftype, comp))
+
+    p = Params()
+    f = Fake(p)
+    assert WabbitGPU.timeStep_tree(f, 1.0, 7) == (1.25, 8, 0.25) and f.calls == ["rk"]
+    p = Params(write_method="fixed_time", write_time=0.5)
+    p.time_step_method, p.rkc_s, p.filter_type, p.filter_freq, p.filter_component = "RungeKuttaChebychev", 6, "explicit_7pt", 3, (1, 1, 0, 0)
+    f = Fake(p)
+    t, it = 0.0, 0
+    for _ in range(4):                      # iterations 1..4, times 0.25 .. 1.0: filter at iteration 3 and at the save times 0.5 and 1.0
+        t, it, _ = WabbitGPU.timeStep_tree(f, t, it)
+    assert f.calls == ["rkc", "rkc", ("filter", "explicit_7pt", (1, 1, 0, 0)), "rkc", ("filter", "explicit_7pt", (1, 1, 0, 0)), "rkc",
+                       ("filter", "explicit_7pt", (1, 1, 0, 0))]
+    p = Params()
+    p.time_step_method, p.M_krylov, p.krylov_subspace_dimension, p.krylov_err_threshold = "krylov", 9, "dynamic", 1e-5
+    f = Fake(p)
+    WabbitGPU.timeStep_tree(f, 0.0, 0)
+    assert f.calls == [("krylov", 9, True, 1e-5)]
+    p.time_step_method = "Leapfrog"
+    with pytest.raises(WabbitAbort) as e:
+        WabbitGPU.timeStep_tree(Fake(p), 0.0, 0)
+    assert e.value.code == 19101816
