@@ -718,3 +718,35 @@ def test_time_step_tree_dispatch_logic_without_a_device():
     with pytest.raises(WabbitAbort) as e:
         WabbitGPU.timeStep_tree(Fake(p), 0.0, 0)
     assert e.value.code == 19101816
+
+
+REF_ACM = "/root/reference/TESTING/acm"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_ACM), reason="the reference checkout exists in the build container only")
+def test_every_acm_parameter_file_of_the_reference_parses():
+    """Params.from_ini on all parameter files under TESTING/acm: wavelet, ghost nodes (setup_wavelet's value for the wavelet), stencil and
+    block size as the directory names say; mask_from_ini gives the cylinder generator for the cylinder cases and refuses the insect"""
+    import glob
+    import re
+    from wabbit_b200.mask import CylinderMask2D, mask_from_ini
+    g_of = {"CDF20": 1, "CDF22": 2, "CDF40": 3, "CDF42": 4, "CDF44": 6, "CDF60": 5, "CDF62": 6}
+    files = [f for f in sorted(glob.glob(os.path.join(REF_ACM, "**", "*.ini"), recursive=True)) if "kinematics" not in f]
+    assert len(files) >= 17
+    for f in files:
+        p = Params.from_ini(f)
+        case = os.path.basename(os.path.dirname(f))
+        m = re.search(r"(CDF\d\d)", case)
+        assert m and p.wavelet == m.group(1) and p.g == g_of[p.wavelet], (case, p.wavelet, p.g)
+        fd = re.search(r"FD(\d)", case)
+        if fd:
+            assert p.discretization == {"2": "FD_2nd_central", "4": "FD_4th_central", "6": "FD_6th_central"}[fd.group(1)]
+        assert p.time_step_method == "RungeKuttaGeneric" and p.filter_type in ("no_filter", "")
+        if case.startswith("acm_"):
+            assert p.dim == 2 and tuple(p.Bs[:2]) == (26, 26) and p.penalization and p.use_sponge
+            assert isinstance(mask_from_ini(f, p), CylinderMask2D)
+        elif case.startswith("bumblebee"):
+            with pytest.raises(ValueError):
+                mask_from_ini(f, p)
+        else:
+            assert mask_from_ini(f, p) is None
